@@ -1,0 +1,292 @@
+/*
+ * obgpu_scan.h -- C-ABI of the B200-native columnar-scan path (libobgpu_scan.so).
+ *
+ * This is the drop-in boundary for OceanBase's micro-block decode / pushed-down filter /
+ * projection path.  The reference has no C plugin ABI for storage operators: the
+ * path sits behind C++ abstract classes.  Every entry point below therefore names the reference
+ * C++ method it stands in for; the thin C++ adapter (oceanbase_b200/host/) and the binding a
+ * maintainer would add inside the reference tree translate 1:1.
+ *
+ * Conventions (match the reference, deps/oblib/src/lib/ob_errno.h):
+ *   - every function returns int: 0 == OB_SUCCESS, negative OB_* codes otherwise; no exceptions;
+ *   - OBGPU_NOT_SUPPORTED means "caller falls back to its retrograde path", exactly like
+ *     ObMicroBlockDecoder::filter_pushdown_filter (encoding/ob_micro_block_decoder.cpp:1734-1747);
+ *   - plain pointers and sizes only; output buffers are caller-owned;
+ *   - handles are not thread-safe; one ctx per worker thread (one CUDA stream each), many ctxs may
+ *     run concurrently (ObIMicroBlockReader: one reader per scanner per worker thread).
+ *   - there is NO CPU fallback: if no CUDA device is usable every call fails with OBGPU_ERR_SYS.
+ */
+#ifndef OBGPU_SCAN_H_
+#define OBGPU_SCAN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- error codes: values of the reference's OB_* codes (lib/ob_errno.h:27-108) ------------- */
+#define OBGPU_SUCCESS 0
+#define OBGPU_ERROR (-4000)
+#define OBGPU_INVALID_ARGUMENT (-4002)
+#define OBGPU_INIT_TWICE (-4005)
+#define OBGPU_NOT_INIT (-4006)
+#define OBGPU_NOT_SUPPORTED (-4007)
+#define OBGPU_ITER_END (-4008)
+#define OBGPU_ALLOCATE_MEMORY_FAILED (-4013)
+#define OBGPU_INNER_STAT_ERROR (-4014)
+#define OBGPU_ERR_SYS (-4015)
+#define OBGPU_ERR_UNEXPECTED (-4016)
+#define OBGPU_SIZE_OVERFLOW (-4019)
+#define OBGPU_BUF_NOT_ENOUGH (-4024)
+#define OBGPU_INVALID_DATA (-4070)
+#define OBGPU_PHYSIC_CHECKSUM_ERROR (-4108)
+
+/* ---- sql::ObWhiteFilterOperatorType (sql/engine/basic/ob_pushdown_filter.h:388-401) --------- */
+enum {
+  OBGPU_WHITE_OP_EQ = 0,
+  OBGPU_WHITE_OP_LE = 1,
+  OBGPU_WHITE_OP_LT = 2,
+  OBGPU_WHITE_OP_GE = 3,
+  OBGPU_WHITE_OP_GT = 4,
+  OBGPU_WHITE_OP_NE = 5,
+  OBGPU_WHITE_OP_BT = 6,
+  OBGPU_WHITE_OP_IN = 7,
+  OBGPU_WHITE_OP_NU = 8,
+  OBGPU_WHITE_OP_NN = 9,
+  OBGPU_WHITE_OP_MAX = 10
+};
+
+/* ---- ObColumnHeader::Type (blocksstable/ob_block_sstable_struct.h:203-216) ------------------ */
+enum {
+  OBGPU_ENC_RAW = 0,
+  OBGPU_ENC_DICT = 1,
+  OBGPU_ENC_RLE = 2,
+  OBGPU_ENC_CONST = 3,
+  OBGPU_ENC_INTEGER_BASE_DIFF = 4
+};
+
+/* ---- ObObjType values the path accepts (common/object/ob_obj_type.h) ------------------------ */
+enum {
+  OBGPU_OBJ_TINYINT = 1, OBGPU_OBJ_SMALLINT = 2, OBGPU_OBJ_MEDIUMINT = 3, OBGPU_OBJ_INT32 = 4,
+  OBGPU_OBJ_INT = 5, OBGPU_OBJ_UTINYINT = 6, OBGPU_OBJ_USMALLINT = 7, OBGPU_OBJ_UMEDIUMINT = 8,
+  OBGPU_OBJ_UINT32 = 9, OBGPU_OBJ_UINT64 = 10, OBGPU_OBJ_DATETIME = 17, OBGPU_OBJ_TIMESTAMP = 18,
+  OBGPU_OBJ_DATE = 19, OBGPU_OBJ_TIME = 20, OBGPU_OBJ_YEAR = 21, OBGPU_OBJ_VARCHAR = 22,
+  OBGPU_OBJ_CHAR = 23
+};
+
+typedef struct obgpu_ctx obgpu_ctx;       /* per worker thread: device, stream, staging arenas */
+typedef struct obgpu_batch obgpu_batch;   /* a page batch: N micro-blocks resident in HBM       */
+typedef struct obgpu_result obgpu_result; /* device-resident result of one fused scan           */
+
+/* =============================================================================================
+ * Context
+ * ============================================================================================= */
+int obgpu_ctx_create(int device, obgpu_ctx **out);
+void obgpu_ctx_destroy(obgpu_ctx *ctx);
+/* Use an existing CUDA stream (cudaStream_t as void*) instead of the ctx-owned one, e.g. torch's
+ * current stream so that torch.cuda.Event timing sees the kernels. NULL restores the owned stream. */
+int obgpu_ctx_set_stream(obgpu_ctx *ctx, void *cuda_stream);
+int obgpu_ctx_synchronize(obgpu_ctx *ctx);
+/* Last CUDA / validation error text for this ctx (never NULL). */
+const char *obgpu_ctx_last_error(const obgpu_ctx *ctx);
+/* Number of kernels this ctx has launched so far (bench.py's gpu_launches). */
+int64_t obgpu_ctx_launch_count(const obgpu_ctx *ctx);
+
+/* =============================================================================================
+ * Page batch = what ObSSTableRowScanner::open_cur_data_block hands to the reader one block at a
+ * time (access/ob_sstable_row_scanner.cpp:256; ObIMicroBlockReader::init,
+ * blocksstable/ob_imicro_block_reader.h:295), submitted many blocks per call.
+ *
+ * `image` holds n reference-format PAX micro-blocks (post-decompress ObMicroBlockData buffers);
+ * block i occupies [offsets[i], offsets[i] + sizes[i]). offsets must be 16-byte aligned (the
+ * blocks are moved with TMA bulk copies). image_on_device == 0: host memory (pinned for
+ * asynchronous copies), copied to HBM here; != 0: already a device pointer that outlives the
+ * batch (block cache resident in HBM) -- only the descriptor tables are uploaded.
+ * Headers are validated on the host (magic, version, row store type, sizes) the way
+ * ObMicroBlockHeader::is_valid / get_micro_metas do (ob_micro_block_header.cpp:53-61,
+ * encoding/ob_micro_block_decoder.cpp:363-388); `header_view` (optional, host memory, same
+ * layout as image) lets the caller keep a host copy of a device-resident image for that parse.
+ * ============================================================================================= */
+int obgpu_batch_open(obgpu_ctx *ctx, const void *image, int64_t image_size,
+                     const int64_t *offsets, const int64_t *sizes, int32_t n_blocks,
+                     int32_t image_on_device, const void *header_view, obgpu_batch **out);
+void obgpu_batch_close(obgpu_batch *batch);
+/* ObIMicroBlockReader::get_row_count / column count for block i; total over the batch. */
+int obgpu_batch_block_info(const obgpu_batch *batch, int32_t block, int64_t *row_count,
+                           int32_t *column_count);
+int obgpu_batch_total_rows(const obgpu_batch *batch, int64_t *total_rows);
+
+/* =============================================================================================
+ * Filter tree = sql::ObPushdownFilterExecutor tree flattened in post-order
+ * (sql/engine/basic/ob_pushdown_filter.cpp:1551-1624): leaves are ObWhiteFilterExecutor
+ * (op, one column, constants), inner nodes AND / OR over their n_children preceding sub-results.
+ * ============================================================================================= */
+enum { OBGPU_NODE_WHITE = 0, OBGPU_NODE_AND = 1, OBGPU_NODE_OR = 2 };
+
+typedef struct obgpu_filter_param {
+  int64_t i64;      /* integer-class constant (sign/zero extended to 64 bit by the caller)   */
+  const char *ptr;  /* string-class constant                                                 */
+  uint32_t len;
+  int32_t is_null;  /* NULL constant => leaf is all-false unless op is NU/NN
+                       (encoding/ob_micro_block_decoder.cpp:1713-1715)                       */
+} obgpu_filter_param;
+
+typedef struct obgpu_filter_node {
+  int32_t kind;        /* OBGPU_NODE_*                                                        */
+  int32_t op;          /* leaf: OBGPU_WHITE_OP_*                                              */
+  int32_t col;         /* leaf: column store index inside the micro-block (col_offsets.at(0)) */
+  int32_t param_begin; /* leaf: first constant in obgpu_filter.params                          */
+  int32_t n_params;    /* leaf: 1 (cmp), 2 (BT), k (IN), 0 (NU/NN)                             */
+  int32_t n_children;  /* AND/OR: >= 2                                                        */
+} obgpu_filter_node;
+
+typedef struct obgpu_filter {
+  const obgpu_filter_node *nodes; /* post-order, root last */
+  int32_t n_nodes;
+  const obgpu_filter_param *params;
+  int32_t n_params;
+} obgpu_filter;
+
+/* =============================================================================================
+ * Fused scan over the whole batch: filter (ObMicroBlockDecoder::filter_pushdown_filter,
+ * encoding/ob_micro_block_decoder.cpp:1680) -> selection bitmap (common::ObBitmap) -> row ids
+ * (ObBitmap::get_row_ids, lib/container/ob_bitmap.cpp:540) -> projection
+ * (ObMicroBlockDecoder::get_rows / decode_vector, :2473) in ONE kernel, blocks in index order,
+ * rows ascending inside a block. Output is dense over the selected rows of the batch.
+ * ============================================================================================= */
+typedef struct obgpu_scan_spec {
+  const obgpu_filter *filter;  /* NULL: no predicate, every row selected                       */
+  const int32_t *proj_cols;    /* column store indexes to project                              */
+  int32_t n_proj;
+  int32_t want_row_ids;        /* also emit block-relative int32 row ids of the selected rows  */
+  uint64_t string_base;        /* address string pointers are rebased to: ptr = string_base +
+                                  byte offset of the cell inside `image` (VEC_DISCRETE ptrs_
+                                  point into the caller's block buffer, rule 8c.6)             */
+  int64_t max_selected_rows;   /* capacity of the dense output in rows; 0 = every row of the
+                                  batch. If the filter selects more, obgpu_result_info_get
+                                  returns OBGPU_BUF_NOT_ENOUGH with the needed selected_rows
+                                  filled in and the caller re-runs with a larger capacity.    */
+} obgpu_scan_spec;
+
+int obgpu_scan(obgpu_batch *batch, const obgpu_scan_spec *spec, obgpu_result **out);
+void obgpu_result_free(obgpu_result *res);
+
+typedef struct obgpu_result_info {
+  int64_t total_rows;     /* input rows scanned                                  */
+  int64_t selected_rows;  /* rows passing the filter                             */
+  int32_t n_blocks;
+  int32_t n_proj;
+} obgpu_result_info;
+
+/* Synchronises the ctx stream and reads back the totals. */
+int obgpu_result_info_get(obgpu_result *res, obgpu_result_info *info);
+
+/* Column i of the projection, device pointers (valid until obgpu_result_free):
+ *   integer class : data = elem_len-byte values [selected_rows] (VEC_FIXED data_), aux = NULL
+ *   string class  : data = uint64 pointers [selected_rows] (VEC_DISCRETE ptrs_), aux = int32 lens_
+ *   nulls         : sql::ObBitVector image, LSB-first uint64 words over the dense row index
+ * For a NULL row the payload slot is zero (the reference leaves it unwritten, rule 8c.1). */
+typedef struct obgpu_result_col {
+  void *data;
+  void *aux;
+  uint64_t *nulls;
+  int32_t elem_len;   /* 8 / 4 / 1 for integer classes, 8 (pointer) for strings */
+  int32_t is_string;
+  int32_t has_null;   /* valid after obgpu_result_info_get */
+  int32_t obj_type;
+} obgpu_result_col;
+int obgpu_result_col_get(obgpu_result *res, int32_t i, obgpu_result_col *col);
+
+/* Per-block prefix of selected rows: sel_offset[b] .. sel_offset[b+1] is block b's slice of the
+ * dense output (n_blocks + 1 int64 entries, device pointer), plus the packed per-block selection
+ * bitmap (bit r of block b at word bitmap_word_offset[b] + r/32, uint32 words, LSB first). */
+int obgpu_result_block_tables(obgpu_result *res, const int64_t **sel_offset_dev,
+                              const uint32_t **bitmap_words_dev,
+                              const int64_t **bitmap_word_offset_dev, const int32_t **row_ids_dev);
+
+/* Device -> host copies of a dense window [row_begin, row_begin + row_count) of column i.
+ * host_aux / host_nulls may be NULL. host_nulls receives (row_count + 63) / 64 words re-based so
+ * that bit 0 is row_begin. */
+int obgpu_result_fetch_col(obgpu_result *res, int32_t i, int64_t row_begin, int64_t row_count,
+                           void *host_data, void *host_aux, uint64_t *host_nulls);
+int obgpu_result_fetch_sel_offsets(obgpu_result *res, int64_t *host_sel_offset /* n_blocks+1 */);
+int obgpu_result_fetch_row_ids(obgpu_result *res, int64_t row_begin, int64_t row_count,
+                               int32_t *host_row_ids);
+/* common::ObBitmap image (one byte 0x00/0x01 per row) of block b, rows [start, start+count). */
+int obgpu_result_fetch_bitmap(obgpu_result *res, int32_t block, int64_t start, int64_t count,
+                              uint8_t *host_bitmap_bytes);
+
+/* =============================================================================================
+ * Reference-granularity calls (one micro-block, one leaf, one <=batch-size projection). They run
+ * the same device code on a one-block batch; the adapter serves them from a prefetched batch.
+ * ============================================================================================= */
+/* ObIMicroBlockDecoder::filter_pushdown_filter(parent, ObWhiteFilterExecutor&, pd_filter_info,
+ * result_bitmap) -- encoding/ob_imicro_block_decoder.h:27-73. result_bitmap: count bytes 0/1. */
+int obgpu_filter_white(obgpu_batch *batch, int32_t block, int32_t col, int32_t op,
+                       const obgpu_filter_param *params, int32_t n_params, int64_t start,
+                       int64_t count, uint8_t *result_bitmap);
+/* ObPushdownFilterExecutor::execute over a tree (ob_pushdown_filter.cpp:1551). */
+int obgpu_filter_tree(obgpu_batch *batch, int32_t block, const obgpu_filter *filter,
+                      int64_t start, int64_t count, uint8_t *result_bitmap);
+/* common::ObBitmap::get_row_ids(row_ids, row_count, from, to, limit, id_offset)
+ * (lib/container/ob_bitmap.cpp:540-561); *from is advanced like the reference does. */
+int obgpu_bitmap_to_row_ids(obgpu_ctx *ctx, const uint8_t *bitmap, int64_t bitmap_size,
+                            int64_t *from, int64_t to, int64_t limit, int64_t id_offset,
+                            int32_t *row_ids, int64_t *row_count);
+/* ObMicroBlockDecoder::get_rows -> ObIColumnDecoder::decode_vector into a VEC_FIXED vector
+ * (encoding/ob_micro_block_decoder.cpp:2473-2544): data[(vec_offset + i) * elem_len] = value of
+ * row_ids[i]; nulls = ObBitVector words (bit vec_offset + i). */
+int obgpu_project_fixed(obgpu_batch *batch, int32_t block, int32_t col, const int32_t *row_ids,
+                        int64_t row_cap, int64_t vec_offset, void *data, int32_t elem_len,
+                        uint64_t *nulls, int32_t *has_null);
+/* ... into a VEC_DISCRETE vector: ptrs[vec_offset + i] = string_base + cell offset in image. */
+int obgpu_project_discrete(obgpu_batch *batch, int32_t block, int32_t col, const int32_t *row_ids,
+                           int64_t row_cap, int64_t vec_offset, uint64_t string_base,
+                           uint64_t *ptrs, int32_t *lens, uint64_t *nulls, int32_t *has_null);
+
+/* =============================================================================================
+ * Writer: host-side PAX micro-block encoder producing reference-format blocks
+ * (ObMicroBlockEncoder::build_block, encoding/ob_micro_block_encoder.cpp:561-721) for a forced
+ * per-column encoding.  Used to build SSTables for tests / benchmarks and by the compaction
+ * writer.  Column inputs are column-major arrays over the rows of the table.
+ * ============================================================================================= */
+typedef struct obgpu_col_input {
+  int32_t obj_type;        /* OBGPU_OBJ_*                                                      */
+  int32_t encoding;        /* OBGPU_ENC_*                                                      */
+  const int64_t *i64;      /* integer classes: value per row                                   */
+  const uint8_t *is_null;  /* optional: 1 => NULL                                              */
+  const char *str_heap;    /* string classes: bytes                                            */
+  const int64_t *str_off;  /*   nrows + 1 offsets into str_heap                                */
+  int32_t byte_packing_only; /* 1 => ObMicroBlockEncoderOpt.enable_bit_packing_ == false       */
+  int32_t reserved;
+} obgpu_col_input;
+
+/* Upper bound of the encoded size of a block of nrows rows. */
+int64_t obgpu_writer_block_bound(const obgpu_col_input *cols, int32_t n_cols, int64_t row_begin,
+                                 int64_t nrows);
+/* Encode rows [row_begin, row_begin + nrows) into one micro-block. */
+int obgpu_writer_encode_block(const obgpu_col_input *cols, int32_t n_cols,
+                              int32_t rowkey_col_cnt, int64_t row_begin, int64_t nrows,
+                              void *out, int64_t out_cap, int64_t *out_size);
+/* Encode total_rows rows as consecutive blocks of rows_per_block rows (last one shorter). The
+ * encoded blocks are held by the returned handle; export packs them into one image where block i
+ * starts at offsets[i] (aligned to `align`, a power of two >= 16, padding zeroed) and is sizes[i]
+ * bytes long. n_threads <= 0 uses all hardware threads. */
+typedef struct obgpu_table_image obgpu_table_image;
+int obgpu_writer_encode_table(const obgpu_col_input *cols, int32_t n_cols, int32_t rowkey_col_cnt,
+                              int64_t total_rows, int64_t rows_per_block, int32_t align,
+                              int32_t n_threads, obgpu_table_image **out);
+int obgpu_table_image_info(const obgpu_table_image *img, int64_t *image_size, int32_t *n_blocks);
+int obgpu_table_image_export(const obgpu_table_image *img, void *image, int64_t image_cap,
+                             int64_t *offsets, int64_t *sizes, int32_t tables_cap);
+void obgpu_table_image_free(obgpu_table_image *img);
+
+/* Library self-description (build id, arch) for logs. */
+const char *obgpu_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OBGPU_SCAN_H_ */

@@ -1,0 +1,128 @@
+"""ctypes binding of libobgpu_scan.so (include/obgpu_scan.h). Fails loudly when the library is
+missing: the product has no CPU path."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+lib_path = os.path.join(_HERE, "csrc", "libobgpu_scan.so")
+
+OB_SUCCESS = 0
+OB_INVALID_ARGUMENT = -4002
+OB_NOT_SUPPORTED = -4007
+OB_ERR_SYS = -4015
+OB_BUF_NOT_ENOUGH = -4024
+OB_INVALID_DATA = -4070
+
+(WHITE_OP_EQ, WHITE_OP_LE, WHITE_OP_LT, WHITE_OP_GE, WHITE_OP_GT, WHITE_OP_NE, WHITE_OP_BT,
+ WHITE_OP_IN, WHITE_OP_NU, WHITE_OP_NN) = range(10)
+ENC_RAW, ENC_DICT, ENC_RLE, ENC_CONST, ENC_INTEGER_BASE_DIFF = range(5)
+OBJ_TINYINT, OBJ_SMALLINT, OBJ_MEDIUMINT, OBJ_INT32, OBJ_INT = 1, 2, 3, 4, 5
+OBJ_UTINYINT, OBJ_USMALLINT, OBJ_UMEDIUMINT, OBJ_UINT32, OBJ_UINT64 = 6, 7, 8, 9, 10
+OBJ_DATETIME, OBJ_TIMESTAMP, OBJ_DATE, OBJ_TIME, OBJ_YEAR, OBJ_VARCHAR, OBJ_CHAR = 17, 18, 19, 20, 21, 22, 23
+NODE_WHITE, NODE_AND, NODE_OR = 0, 1, 2
+
+
+class ObGpuError(RuntimeError):
+    def __init__(self, code, what, detail=""):
+        self.code = code
+        super().__init__(f"{what} failed: OB error {code}" + (f" ({detail})" if detail else ""))
+
+
+class FilterParam(C.Structure):
+    _fields_ = [("i64", C.c_int64), ("ptr", C.c_char_p), ("len", C.c_uint32), ("is_null", C.c_int32)]
+
+
+class FilterNode(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("op", C.c_int32), ("col", C.c_int32), ("param_begin", C.c_int32),
+                ("n_params", C.c_int32), ("n_children", C.c_int32)]
+
+
+class Filter(C.Structure):
+    _fields_ = [("nodes", C.POINTER(FilterNode)), ("n_nodes", C.c_int32),
+                ("params", C.POINTER(FilterParam)), ("n_params", C.c_int32)]
+
+
+class ScanSpec(C.Structure):
+    _fields_ = [("filter", C.POINTER(Filter)), ("proj_cols", C.POINTER(C.c_int32)), ("n_proj", C.c_int32),
+                ("want_row_ids", C.c_int32), ("string_base", C.c_uint64), ("max_selected_rows", C.c_int64)]
+
+
+class ResultInfo(C.Structure):
+    _fields_ = [("total_rows", C.c_int64), ("selected_rows", C.c_int64), ("n_blocks", C.c_int32),
+                ("n_proj", C.c_int32)]
+
+
+class ResultCol(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("aux", C.c_void_p), ("nulls", C.c_void_p), ("elem_len", C.c_int32),
+                ("is_string", C.c_int32), ("has_null", C.c_int32), ("obj_type", C.c_int32)]
+
+
+class ColInput(C.Structure):
+    _fields_ = [("obj_type", C.c_int32), ("encoding", C.c_int32), ("i64", C.c_void_p), ("is_null", C.c_void_p),
+                ("str_heap", C.c_void_p), ("str_off", C.c_void_p), ("byte_packing_only", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+def declared_signatures():
+    """name -> (restype, argtypes) for every symbol include/obgpu_scan.h declares."""
+    vp, i32, i64, u64 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64
+    P = C.POINTER
+    return {
+        "obgpu_ctx_create": (C.c_int, [C.c_int, P(vp)]),
+        "obgpu_ctx_destroy": (None, [vp]),
+        "obgpu_ctx_set_stream": (C.c_int, [vp, vp]),
+        "obgpu_ctx_synchronize": (C.c_int, [vp]),
+        "obgpu_ctx_last_error": (C.c_char_p, [vp]),
+        "obgpu_ctx_launch_count": (i64, [vp]),
+        "obgpu_batch_open": (C.c_int, [vp, vp, i64, vp, vp, i32, i32, vp, P(vp)]),
+        "obgpu_batch_close": (None, [vp]),
+        "obgpu_batch_block_info": (C.c_int, [vp, i32, P(i64), P(i32)]),
+        "obgpu_batch_total_rows": (C.c_int, [vp, P(i64)]),
+        "obgpu_scan": (C.c_int, [vp, P(ScanSpec), P(vp)]),
+        "obgpu_result_free": (None, [vp]),
+        "obgpu_result_info_get": (C.c_int, [vp, P(ResultInfo)]),
+        "obgpu_result_col_get": (C.c_int, [vp, i32, P(ResultCol)]),
+        "obgpu_result_block_tables": (C.c_int, [vp, P(vp), P(vp), P(vp), P(vp)]),
+        "obgpu_result_fetch_col": (C.c_int, [vp, i32, i64, i64, vp, vp, vp]),
+        "obgpu_result_fetch_sel_offsets": (C.c_int, [vp, vp]),
+        "obgpu_result_fetch_row_ids": (C.c_int, [vp, i64, i64, vp]),
+        "obgpu_result_fetch_bitmap": (C.c_int, [vp, i32, i64, i64, vp]),
+        "obgpu_filter_white": (C.c_int, [vp, i32, i32, i32, P(FilterParam), i32, i64, i64, vp]),
+        "obgpu_filter_tree": (C.c_int, [vp, i32, P(Filter), i64, i64, vp]),
+        "obgpu_bitmap_to_row_ids": (C.c_int, [vp, vp, i64, P(i64), i64, i64, i64, vp, P(i64)]),
+        "obgpu_project_fixed": (C.c_int, [vp, i32, i32, vp, i64, i64, vp, i32, vp, P(i32)]),
+        "obgpu_project_discrete": (C.c_int, [vp, i32, i32, vp, i64, i64, u64, vp, vp, vp, P(i32)]),
+        "obgpu_writer_block_bound": (i64, [P(ColInput), i32, i64, i64]),
+        "obgpu_writer_encode_block": (C.c_int, [P(ColInput), i32, i32, i64, i64, vp, i64, P(i64)]),
+        "obgpu_writer_encode_table": (C.c_int, [P(ColInput), i32, i32, i64, i64, i32, i32, P(vp)]),
+        "obgpu_table_image_info": (C.c_int, [vp, P(i64), P(i32)]),
+        "obgpu_table_image_export": (C.c_int, [vp, vp, i64, vp, vp, i32]),
+        "obgpu_table_image_free": (None, [vp]),
+        "obgpu_version": (C.c_char_p, []),
+    }
+
+
+def _load():
+    if not os.path.exists(lib_path):
+        raise ImportError(
+            f"{lib_path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc -gencode arch=compute_100a,code=sm_100a). oceanbase_b200 has no CPU fallback.")
+    L = C.CDLL(lib_path)
+    for name, (res, args) in declared_signatures().items():
+        fn = getattr(L, name)  # AttributeError => the library does not export the declared ABI
+        fn.restype = res
+        fn.argtypes = args
+    return L
+
+
+lib = _load()
+
+
+def check(code, what, ctx=None):
+    if code != OB_SUCCESS:
+        detail = ""
+        try:
+            detail = (lib.obgpu_ctx_last_error(ctx) or b"").decode()
+        except Exception:  # pragma: no cover
+            pass
+        raise ObGpuError(code, what, detail)

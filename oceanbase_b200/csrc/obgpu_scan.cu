@@ -1,0 +1,1467 @@
+// libobgpu_scan.so -- fused micro-block scan kernels (sm_100a) and the C-ABI around them.
+//
+// One launch processes a whole page batch (thousands of ~16 KiB micro-blocks):
+//   CTA  <- ticket (atomic)                  : logical block index in scan order
+//   TMA bulk copy (cp.async.bulk + mbarrier) : block image HBM -> shared memory, one transaction
+//   filter      : white-filter tree per row, predicate-on-dictionary for DICT/RLE columns,
+//                 warp ballot -> packed selection bitmap (K4/K6/K9/K14)
+//   compaction  : popcount prefix over ballot words -> ascending selected-row list
+//   look-back   : decoupled look-back over per-block counts -> dense output offset (single pass,
+//                 the block image is read from HBM exactly once)
+//   projection  : decode selected rows of each projected column straight from shared memory,
+//                 coalesced 8-byte stores into the dense VEC_FIXED / VEC_DISCRETE buffers (K1-K8)
+//
+// Reference control flow this replaces (per block, per <=256-row batch, per column virtual calls):
+//   ObIMicroBlockRowScanner::apply_filter        blocksstable/ob_micro_block_row_scanner.cpp:361,927
+//   ObPushdownFilterExecutor::execute            sql/engine/basic/ob_pushdown_filter.cpp:1551-1624
+//   ObMicroBlockDecoder::filter_pushdown_filter  encoding/ob_micro_block_decoder.cpp:1680-1755
+//   ObBitmap::get_row_ids                        deps/oblib/src/lib/container/ob_bitmap.cpp:540
+//   ObMicroBlockDecoder::get_rows                encoding/ob_micro_block_decoder.cpp:2473-2544
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/obgpu_scan.h"
+#include "ob_format.h"
+#include "scan_device.cuh"
+
+using namespace obdev;
+
+// =================================================================================================
+// Kernel parameter block
+// =================================================================================================
+struct FilterNodeDev {
+  int8_t kind;
+  int8_t slot;       // dictionary-bitset slot of a leaf (-1: none)
+  int16_t used_idx;  // leaf: index into ScanParams::used_col
+  int16_t op;
+  int16_t param_begin;
+  int16_t n_params;
+  int16_t n_children;
+};
+
+struct ParamDev {
+  int64_t i64;
+  uint32_t heap_off;
+  uint32_t len;
+};
+
+constexpr int kParamHeap = 768;
+
+struct ScanParams {
+  const uint8_t *image;
+  const uint64_t *blk_off;    // [n_blocks] byte offset of block i in image
+  const uint32_t *blk_size;   // [n_blocks] exact block size
+  const int64_t *bm_word_off; // [n_blocks + 1] prefix of ceil(rows / 32)
+  int32_t n_blocks;
+  int32_t n_used;
+  int32_t used_col[kMaxUsedCols];
+  int32_t n_nodes;
+  int32_t simple_shape;       // 1: root is AND over leaves only, 2: OR over leaves only, 0: generic
+  FilterNodeDev nodes[kMaxNodes];
+  ParamDev params[kMaxParams];
+  uint8_t param_heap[kParamHeap];
+  int32_t n_slots;
+  int32_t bitset_words;       // words per slot
+  int32_t n_proj;
+  int32_t want_row_ids;
+  int16_t proj_used[kMaxProj];
+  void *out_data[kMaxProj];
+  int32_t *out_lens[kMaxProj];
+  uint32_t *out_nulls[kMaxProj];
+  int32_t *has_null;          // [kMaxProj]
+  uint64_t string_base;
+  uint32_t *bitmap_words;
+  int64_t *sel_offset;        // [n_blocks + 1]
+  int32_t *row_ids;
+  unsigned long long *tile_state;
+  int32_t *ticket;
+  int32_t *status;
+  int64_t out_cap;
+  // shared-memory layout (bytes from the dynamic smem base)
+  uint32_t smem_sel, smem_bm, smem_wpre, smem_bitset, smem_desc, smem_total;
+  uint32_t rows_cap;
+};
+
+// =================================================================================================
+// PTX helpers: mbarrier + TMA bulk copy, acquire/release descriptor access
+// =================================================================================================
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+constexpr unsigned long long kTileAgg = 1ull << 62;
+constexpr unsigned long long kTilePrefix = 2ull << 62;
+constexpr unsigned long long kTileValueMask = (1ull << 62) - 1ull;
+
+// Decoupled look-back executed by one warp. Returns the exclusive prefix of `cnt` over tiles.
+__device__ __forceinline__ int64_t lookback(unsigned long long *state, int tile, int64_t cnt, int lane) {
+  if (tile == 0) {
+    if (lane == 0) st_release(&state[0], kTilePrefix | (unsigned long long)cnt);
+    return 0;
+  }
+  if (lane == 0) st_release(&state[tile], kTileAgg | (unsigned long long)cnt);
+  int64_t excl = 0;
+  int idx = tile - 1;
+  for (;;) {
+    const int my = idx - lane;
+    unsigned long long s = kTilePrefix;  // tiles before 0 behave as an empty inclusive prefix
+    if (my >= 0) {
+      do { s = ld_acquire(&state[my]); } while ((s >> 62) == 0);
+    }
+    const bool is_prefix = (s >> 62) == 2;
+    const unsigned pmask = __ballot_sync(0xffffffffu, is_prefix);
+    const int first = __ffs(pmask) - 1;  // nearest predecessor holding an inclusive prefix
+    int64_t v = (pmask == 0 || lane <= first) ? (int64_t)(s & kTileValueMask) : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    excl += v;
+    if (pmask) break;
+    idx -= 32;
+  }
+  if (lane == 0) st_release(&state[tile], kTilePrefix | (unsigned long long)(excl + cnt));
+  return excl;
+}
+
+// =================================================================================================
+// Predicate evaluation
+// =================================================================================================
+__device__ __forceinline__ bool int_pred(const ScanParams &p, const FilterNodeDev &nd, const ColDesc &d,
+                                         uint64_t v) {
+  const int64_t a = cmp_image(d, v);
+  const bool sgn = d.sc == 1;
+  auto cmp3 = [&](int64_t c) -> int {
+    if (sgn) return a < c ? -1 : (a > c ? 1 : 0);
+    const uint64_t ua = (uint64_t)a, uc = (uint64_t)c;
+    return ua < uc ? -1 : (ua > uc ? 1 : 0);
+  };
+  const int op = nd.op;
+  if (op <= OP_NE) return cmp_to_bool(op, cmp3(p.params[nd.param_begin].i64));
+  if (op == OP_BT) return cmp3(p.params[nd.param_begin].i64) >= 0 && cmp3(p.params[nd.param_begin + 1].i64) <= 0;
+  if (op == OP_IN) {
+    for (int i = 0; i < nd.n_params; ++i)
+      if (cmp3(p.params[nd.param_begin + i].i64) == 0) return true;
+    return false;
+  }
+  return false;
+}
+
+__device__ __forceinline__ bool str_pred(const ScanParams &p, const FilterNodeDev &nd, const uint8_t *s,
+                                         uint32_t cell, uint32_t len) {
+  auto cmp3 = [&](int k) -> int {
+    const ParamDev &pp = p.params[nd.param_begin + k];
+    return str_cmp(s, cell, len, p.param_heap + pp.heap_off, pp.len);
+  };
+  const int op = nd.op;
+  if (op <= OP_NE) return cmp_to_bool(op, cmp3(0));
+  if (op == OP_BT) return cmp3(0) >= 0 && cmp3(1) <= 0;
+  if (op == OP_IN) {
+    for (int i = 0; i < nd.n_params; ++i)
+      if (cmp3(i) == 0) return true;
+    return false;
+  }
+  return false;
+}
+
+__device__ __forceinline__ bool eval_leaf(const ScanParams &p, const BlockView &b, const ColDesc *descs,
+                                          const uint32_t *bitsets, const FilterNodeDev &nd, uint32_t row) {
+  const int op = nd.op;
+  if (op == OP_FALSE) return false;
+  if (op == OP_TRUE) return true;
+  const ColDesc &d = descs[nd.used_idx];
+  if (d.type == COL_DICT || d.type == COL_RLE) {
+    uint32_t ref = ref_of(b.s, d, row);
+    if (ref > d.dict_count + 1) ref = d.dict_count + 1;
+    return (bitsets[nd.slot * p.bitset_words + (ref >> 5)] >> (ref & 31)) & 1u;
+  }
+  bool is_null;
+  if (d.sc == 5) {
+    uint32_t cell, len;
+    str_cell(b, d, row, cell, len, is_null);
+    if (op == OP_NU) return is_null;
+    if (op == OP_NN) return !is_null;
+    return !is_null && str_pred(p, nd, b.s, cell, len);
+  }
+  const uint64_t v = int_cell(b, d, row, is_null);
+  if (op == OP_NU) return is_null;
+  if (op == OP_NN) return !is_null;
+  return !is_null && int_pred(p, nd, d, v);
+}
+
+__device__ __forceinline__ bool eval_tree(const ScanParams &p, const BlockView &b, const ColDesc *descs,
+                                          const uint32_t *bitsets, uint32_t row) {
+  if (p.simple_shape == 1) {
+    for (int i = 0; i < p.n_nodes - 1; ++i)
+      if (!eval_leaf(p, b, descs, bitsets, p.nodes[i], row)) return false;
+    return true;
+  }
+  if (p.simple_shape == 2) {
+    for (int i = 0; i < p.n_nodes - 1; ++i)
+      if (eval_leaf(p, b, descs, bitsets, p.nodes[i], row)) return true;
+    return false;
+  }
+  uint32_t stack = 0;
+  for (int i = 0; i < p.n_nodes; ++i) {
+    const FilterNodeDev &nd = p.nodes[i];
+    bool r;
+    if (nd.kind == NODE_WHITE) {
+      r = eval_leaf(p, b, descs, bitsets, nd, row);
+    } else {
+      const uint32_t m = (1u << nd.n_children) - 1u;
+      const uint32_t top = stack & m;
+      r = nd.kind == NODE_AND ? top == m : top != 0;
+      stack >>= nd.n_children;
+    }
+    stack = (stack << 1) | (r ? 1u : 0u);
+  }
+  return stack & 1u;
+}
+
+// Predicate over the dictionary of a DICT / RLE column -> bitset over refs (bit count = NULL ref).
+__device__ __forceinline__ void build_dict_bitset(const ScanParams &p, const BlockView &b, const ColDesc &d,
+                                                  const FilterNodeDev &nd, uint32_t *bits, int warp, int lane) {
+  const uint32_t n = d.dict_count + 2;
+  const int op = nd.op;
+  for (uint32_t base = (uint32_t)warp * 32u; base < n; base += kWarps * 32u) {
+    const uint32_t idx = base + (uint32_t)lane;
+    bool r = false;
+    if (idx < d.dict_count) {
+      if (op == OP_NN) r = true;
+      else if (op == OP_NU) r = false;
+      else if (d.sc == 5) {
+        uint32_t cell, len;
+        dict_str(b.s, d, idx, cell, len);
+        r = str_pred(p, nd, b.s, cell, len);
+      } else {
+        r = int_pred(p, nd, d, dict_int(b.s, d, idx));
+      }
+    } else if (idx == d.dict_count) {
+      r = op == OP_NU;
+    }
+    const uint32_t word = __ballot_sync(0xffffffffu, r);
+    if (lane == 0) bits[base >> 5] = word;
+  }
+}
+
+// =================================================================================================
+// Block-wide helpers
+// =================================================================================================
+// Loads block `tile` into shared memory with one TMA bulk transaction; all threads return once the
+// bytes have landed. `bar` must have been initialised by thread 0 (count 1) before the call.
+__device__ __forceinline__ void load_block(uint8_t *smem, const uint8_t *src, uint32_t bytes16, uint64_t *bar,
+                                           uint32_t parity) {
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar, bytes16);
+    tma_bulk_g2s(smem, src, bytes16, bar);
+  }
+  mbar_wait(bar, parity);
+}
+
+// =================================================================================================
+// Fused scan kernel: one CTA per micro-block (logical order by ticket)
+// =================================================================================================
+extern __shared__ __align__(128) uint8_t g_smem[];
+
+__global__ void __launch_bounds__(kThreads) obgpu_scan_kernel(const __grid_constant__ ScanParams p) {
+  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ int s_tile;
+  __shared__ uint32_t s_warp_sum[kWarps];
+  __shared__ long long s_base;
+  __shared__ uint32_t s_cnt;
+  __shared__ BlockView s_view;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint8_t *sblk = g_smem;
+  uint16_t *sel = reinterpret_cast<uint16_t *>(g_smem + p.smem_sel);
+  uint32_t *bm = reinterpret_cast<uint32_t *>(g_smem + p.smem_bm);
+  uint32_t *wpre = reinterpret_cast<uint32_t *>(g_smem + p.smem_wpre);
+  uint32_t *bitsets = reinterpret_cast<uint32_t *>(g_smem + p.smem_bitset);
+  ColDesc *descs = reinterpret_cast<ColDesc *>(g_smem + p.smem_desc);
+
+  if (tid == 0) {
+    s_tile = atomicAdd(p.ticket, 1);
+    mbar_init(&s_bar, 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  const int tile = s_tile;
+  if (tile >= p.n_blocks) return;
+
+  // ---- 1. stage the block ----------------------------------------------------------------------
+  const uint32_t size = p.blk_size[tile];
+  load_block(sblk, p.image + p.blk_off[tile], (size + 15u) & ~15u, &s_bar, 0);
+
+  // ---- 2. parse header, build column descriptors ------------------------------------------------
+  if (tid == 0) {
+    BlockView v;
+    parse_block(sblk, size, v);
+    if (v.ok && v.row_count > p.rows_cap) v.ok = 0;
+    s_view = v;
+  }
+  __syncthreads();
+  BlockView b = s_view;
+  b.s = sblk;
+  bool bad = !b.ok;
+  if (!bad && tid < p.n_used) {
+    ColDesc d;
+    build_col_desc(b, p.used_col[tid], d);
+    descs[tid] = d;
+  }
+  __syncthreads();
+  if (!bad) {
+    for (int i = 0; i < p.n_used; ++i) bad |= !descs[i].ok;
+  }
+  if (bad) {
+    // Unsupported / corrupt block: publish a zero count so later tiles are not blocked, flag it.
+    if (tid == 0) atomicOr(p.status, b.ok ? ST_UNSUPPORTED : ST_CORRUPT);
+    if (warp == 0) {
+      const int64_t excl = lookback(p.tile_state, tile, 0, lane);
+      if (lane == 0) {
+        p.sel_offset[tile] = excl;
+        if (tile == p.n_blocks - 1) p.sel_offset[p.n_blocks] = excl;
+      }
+    }
+    return;
+  }
+  const uint32_t rows = b.row_count;
+  const uint32_t nwords = (rows + 31u) >> 5;
+
+  // ---- 3. predicate over dictionaries ------------------------------------------------------------
+  if (p.n_slots > 0) {
+    for (int i = 0; i < p.n_nodes; ++i) {
+      const FilterNodeDev &nd = p.nodes[i];
+      if (nd.kind != NODE_WHITE || nd.slot < 0) continue;
+      const ColDesc &d = descs[nd.used_idx];
+      if (d.type == COL_DICT || d.type == COL_RLE)
+        build_dict_bitset(p, b, d, nd, bitsets + nd.slot * p.bitset_words, warp, lane);
+    }
+    __syncthreads();
+  }
+
+  // ---- 4. filter -> ballot words (the packed selection bitmap) ------------------------------------
+  uint32_t *gbm = p.bitmap_words + p.bm_word_off[tile];
+  uint32_t my_cnt = 0;
+  for (uint32_t g = (uint32_t)warp; g < nwords; g += kWarps) {
+    const uint32_t row = g * 32u + (uint32_t)lane;
+    bool pr = row < rows;
+    if (pr && p.n_nodes > 0) pr = eval_tree(p, b, descs, bitsets, row);
+    const uint32_t word = __ballot_sync(0xffffffffu, pr);
+    if (lane == 0) {
+      bm[g] = word;
+      gbm[g] = word;
+      my_cnt += __popc(word);
+    }
+  }
+  if (lane == 0) s_warp_sum[warp] = my_cnt;
+  __syncthreads();
+
+  // ---- 5. exclusive prefix of popcounts over words; total ----------------------------------------
+  {
+    const uint32_t per = (nwords + kThreads - 1) / kThreads;
+    const uint32_t w0 = (uint32_t)tid * per;
+    uint32_t local = 0;
+    for (uint32_t k = 0; k < per; ++k) {
+      const uint32_t w = w0 + k;
+      if (w < nwords) local += __popc(bm[w]);
+    }
+    uint32_t inc = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    __shared__ uint32_t s_scan[kWarps];
+    if (lane == 31) s_scan[warp] = inc;
+    __syncthreads();
+    uint32_t warp_off = 0;
+    for (int k = 0; k < warp; ++k) warp_off += s_scan[k];
+    uint32_t run = warp_off + inc - local;
+    for (uint32_t k = 0; k < per; ++k) {
+      const uint32_t w = w0 + k;
+      if (w < nwords) {
+        wpre[w] = run;
+        run += __popc(bm[w]);
+      }
+    }
+    if (tid == kThreads - 1) s_cnt = run;
+  }
+  __syncthreads();
+  const uint32_t cnt = s_cnt;
+
+  // ---- 6. look-back (warp 0) overlapped with building the selected-row list (other warps) --------
+  if (warp == 0) {
+    const int64_t excl = lookback(p.tile_state, tile, (int64_t)cnt, lane);
+    if (lane == 0) {
+      s_base = excl;
+      p.sel_offset[tile] = excl;
+      if (tile == p.n_blocks - 1) p.sel_offset[p.n_blocks] = excl + (int64_t)cnt;
+    }
+  }
+  for (uint32_t g = (uint32_t)warp; g < nwords; g += kWarps) {
+    const uint32_t word = bm[g];
+    if ((word >> lane) & 1u) sel[wpre[g] + __popc(word & ((1u << lane) - 1u))] = (uint16_t)(g * 32u + lane);
+  }
+  __syncthreads();
+  const int64_t base = s_base;
+  if (cnt == 0 || p.n_proj + p.want_row_ids == 0) return;
+  if (base + (int64_t)cnt > p.out_cap) {
+    if (tid == 0) atomicOr(p.status, ST_OVERFLOW);
+    return;
+  }
+
+  // ---- 7. projection ------------------------------------------------------------------------------
+  const uint64_t blk_addr = p.string_base + p.blk_off[tile];
+  for (uint32_t j = (uint32_t)tid; j < cnt; j += kThreads) {
+    const uint32_t row = sel[j];
+    const int64_t o = base + (int64_t)j;
+    if (p.want_row_ids) p.row_ids[o] = (int32_t)row;
+    for (int c = 0; c < p.n_proj; ++c) {
+      const ColDesc &d = descs[p.proj_used[c]];
+      bool is_null;
+      if (d.sc == 5) {
+        uint32_t cell, len;
+        str_cell(b, d, row, cell, len, is_null);
+        reinterpret_cast<uint64_t *>(p.out_data[c])[o] = is_null ? 0ull : blk_addr + cell;
+        p.out_lens[c][o] = is_null ? 0 : (int32_t)len;
+      } else {
+        const uint64_t v = int_cell(b, d, row, is_null);
+        const uint64_t vv = is_null ? 0ull : v;
+        if (d.elem_len == 8) reinterpret_cast<uint64_t *>(p.out_data[c])[o] = vv;
+        else if (d.elem_len == 4) reinterpret_cast<uint32_t *>(p.out_data[c])[o] = (uint32_t)vv;
+        else reinterpret_cast<uint8_t *>(p.out_data[c])[o] = (uint8_t)vv;
+      }
+      if (is_null) {
+        atomicOr(&p.out_nulls[c][o >> 5], 1u << (o & 31));
+        p.has_null[c] = 1;
+      }
+    }
+  }
+}
+
+// =================================================================================================
+// Single-block kernels for the reference-granularity entry points
+// =================================================================================================
+struct BlockOpParams {
+  const uint8_t *image;
+  uint64_t blk_off;
+  uint32_t blk_size;
+  int32_t *status;
+};
+
+// ObBitmap byte image of a filter tree over rows [start, start + count) of one block.
+__global__ void __launch_bounds__(kThreads) obgpu_filter_block_kernel(const __grid_constant__ ScanParams p,
+                                                                      int tile, int64_t start, int64_t count,
+                                                                      uint8_t *out_bytes) {
+  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ BlockView s_view;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint8_t *sblk = g_smem;
+  uint32_t *bitsets = reinterpret_cast<uint32_t *>(g_smem + p.smem_bitset);
+  ColDesc *descs = reinterpret_cast<ColDesc *>(g_smem + p.smem_desc);
+  if (tid == 0) {
+    mbar_init(&s_bar, 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  const uint32_t size = p.blk_size[tile];
+  load_block(sblk, p.image + p.blk_off[tile], (size + 15u) & ~15u, &s_bar, 0);
+  if (tid == 0) {
+    BlockView v;
+    parse_block(sblk, size, v);
+    s_view = v;
+  }
+  __syncthreads();
+  BlockView b = s_view;
+  b.s = sblk;
+  bool bad = !b.ok || start < 0 || start + count > (int64_t)b.row_count;
+  if (!bad && tid < p.n_used) {
+    ColDesc d;
+    build_col_desc(b, p.used_col[tid], d);
+    descs[tid] = d;
+  }
+  __syncthreads();
+  if (!bad)
+    for (int i = 0; i < p.n_used; ++i) bad |= !descs[i].ok;
+  if (bad) {
+    if (tid == 0) atomicOr(p.status, b.ok ? ST_UNSUPPORTED : ST_CORRUPT);
+    return;
+  }
+  for (int i = 0; i < p.n_nodes; ++i) {
+    const FilterNodeDev &nd = p.nodes[i];
+    if (nd.kind != NODE_WHITE || nd.slot < 0) continue;
+    const ColDesc &d = descs[nd.used_idx];
+    if (d.type == COL_DICT || d.type == COL_RLE)
+      build_dict_bitset(p, b, d, nd, bitsets + nd.slot * p.bitset_words, warp, lane);
+  }
+  __syncthreads();
+  for (int64_t i = tid; i < count; i += kThreads)
+    out_bytes[i] = eval_tree(p, b, descs, bitsets, (uint32_t)(start + i)) ? 1 : 0;
+}
+
+// decode_vector of one column for caller-supplied row ids (ObVectorDecodeCtx shape).
+__global__ void __launch_bounds__(kThreads) obgpu_project_block_kernel(
+    const __grid_constant__ ScanParams p, int tile, const int32_t *row_ids, int64_t row_cap, int64_t vec_offset,
+    void *data, int32_t *lens, uint32_t *nulls, int32_t elem_len) {
+  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ BlockView s_view;
+  const int tid = threadIdx.x;
+  uint8_t *sblk = g_smem;
+  ColDesc *descs = reinterpret_cast<ColDesc *>(g_smem + p.smem_desc);
+  if (tid == 0) {
+    mbar_init(&s_bar, 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  const uint32_t size = p.blk_size[tile];
+  load_block(sblk, p.image + p.blk_off[tile], (size + 15u) & ~15u, &s_bar, 0);
+  if (tid == 0) {
+    BlockView v;
+    parse_block(sblk, size, v);
+    s_view = v;
+    if (v.ok) {
+      ColDesc d;
+      build_col_desc(v, p.used_col[0], d);
+      descs[0] = d;
+    }
+  }
+  __syncthreads();
+  BlockView b = s_view;
+  b.s = sblk;
+  if (!b.ok || !descs[0].ok) {
+    if (tid == 0) atomicOr(p.status, b.ok ? ST_UNSUPPORTED : ST_CORRUPT);
+    return;
+  }
+  const ColDesc &d = descs[0];
+  if ((d.sc == 5) != (lens != nullptr) || (d.sc != 5 && d.elem_len != elem_len)) {
+    if (tid == 0) atomicOr(p.status, ST_UNSUPPORTED);
+    return;
+  }
+  const uint64_t blk_addr = p.string_base + p.blk_off[tile];
+  for (int64_t i = tid; i < row_cap; i += kThreads) {
+    const int32_t r = row_ids[i];
+    if (r < 0 || (uint32_t)r >= b.row_count) {
+      atomicOr(p.status, ST_CORRUPT);
+      continue;
+    }
+    const int64_t o = vec_offset + i;
+    bool is_null;
+    if (d.sc == 5) {
+      uint32_t cell, len;
+      str_cell(b, d, (uint32_t)r, cell, len, is_null);
+      if (!is_null) {
+        reinterpret_cast<uint64_t *>(data)[o] = blk_addr + cell;
+        lens[o] = (int32_t)len;
+      }
+    } else {
+      const uint64_t v = int_cell(b, d, (uint32_t)r, is_null);
+      if (!is_null) {
+        if (elem_len == 8) reinterpret_cast<uint64_t *>(data)[o] = v;
+        else if (elem_len == 4) reinterpret_cast<uint32_t *>(data)[o] = (uint32_t)v;
+        else reinterpret_cast<uint8_t *>(data)[o] = (uint8_t)v;
+      }
+    }
+    if (is_null) {
+      atomicOr(&nulls[o >> 5], 1u << (o & 31));
+      p.has_null[0] = 1;
+    }
+  }
+}
+
+// ObBitmap::get_row_ids: ascending ids of set bytes in [from, to), at most `limit`.
+__global__ void __launch_bounds__(kThreads) obgpu_bitmap_row_ids_kernel(const uint8_t *bytes, int64_t from,
+                                                                        int64_t to, int64_t limit,
+                                                                        int64_t id_offset, int32_t *row_ids,
+                                                                        int64_t *out_count) {
+  __shared__ uint32_t s_scan[kWarps];
+  __shared__ long long s_running;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_running = 0;
+  __syncthreads();
+  for (int64_t base = from; base < to; base += kThreads) {
+    const long long running = s_running;
+    if (running >= limit) break;
+    const int64_t i = base + tid;
+    const bool set = i < to && bytes[i] != 0;
+    const uint32_t word = __ballot_sync(0xffffffffu, set);
+    if (lane == 0) s_scan[warp] = __popc(word);
+    __syncthreads();
+    uint32_t off = 0, total = 0;
+    for (int k = 0; k < kWarps; ++k) {
+      if (k < warp) off += s_scan[k];
+      total += s_scan[k];
+    }
+    if (set) {
+      const long long pos = running + off + __popc(word & ((1u << lane) - 1u));
+      if (pos < limit) row_ids[pos] = (int32_t)(i - id_offset);
+    }
+    __syncthreads();
+    if (tid == 0) s_running = running + total;
+    __syncthreads();
+  }
+  if (tid == 0) *out_count = s_running < limit ? s_running : limit;
+}
+
+// =================================================================================================
+// Host side
+// =================================================================================================
+#define CUDA_TRY(ctx, expr)                                                                       \
+  do {                                                                                            \
+    cudaError_t e__ = (expr);                                                                     \
+    if (e__ != cudaSuccess) {                                                                     \
+      (ctx)->err = std::string(#expr) + ": " + cudaGetErrorString(e__);                           \
+      return e__ == cudaErrorMemoryAllocation ? OBGPU_ALLOCATE_MEMORY_FAILED : OBGPU_ERR_SYS;     \
+    }                                                                                             \
+  } while (0)
+
+struct obgpu_ctx {
+  int device = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  int64_t launches = 0;
+  int max_smem_optin = 0;
+  int *h_pinned = nullptr;  // small pinned staging (status, totals)
+};
+
+struct obgpu_batch {
+  obgpu_ctx *ctx = nullptr;
+  const uint8_t *d_image = nullptr;
+  bool own_image = false;
+  int64_t image_size = 0;
+  int32_t n_blocks = 0;
+  std::vector<int64_t> offsets, sizes;
+  std::vector<uint32_t> row_count;
+  std::vector<int32_t> col_count;
+  std::vector<int64_t> bm_word_off;  // n + 1
+  int64_t total_rows = 0;
+  uint32_t max_block_bytes = 0, max_rows = 0, max_cols = 0;
+  std::vector<uint32_t> col_max_dict;  // per store index: max dict count + 2 over blocks
+  std::vector<uint8_t> col_types;      // per store index: ObObjType (0xff: differs between blocks)
+  // device tables (one allocation)
+  void *d_tables = nullptr;
+  uint64_t *d_blk_off = nullptr;
+  uint32_t *d_blk_size = nullptr;
+  int64_t *d_bm_word_off = nullptr;
+};
+
+struct ResultCol {
+  void *data = nullptr;
+  int32_t *lens = nullptr;
+  uint32_t *nulls = nullptr;
+  int32_t elem_len = 8;
+  int32_t is_string = 0;
+  int32_t obj_type = 0;
+};
+
+struct obgpu_result {
+  obgpu_batch *batch = nullptr;
+  obgpu_ctx *ctx = nullptr;
+  void *arena = nullptr;
+  size_t arena_bytes = 0;
+  int32_t n_proj = 0;
+  ResultCol cols[kMaxProj];
+  int32_t *d_has_null = nullptr;
+  int32_t *d_status = nullptr;
+  int64_t *d_sel_offset = nullptr;
+  uint32_t *d_bitmap = nullptr;
+  int32_t *d_row_ids = nullptr;
+  int64_t cap = 0;
+  bool info_valid = false;
+  obgpu_result_info info{};
+  int32_t has_null[kMaxProj] = {0};
+  int32_t status = 0;
+};
+
+static thread_local std::string g_last_global_err;
+
+extern "C" {
+
+const char *obgpu_version(void) { return "obgpu_scan 0.1 (sm_100a, cuda " "12.9" ")"; }
+
+int obgpu_ctx_create(int device, obgpu_ctx **out) {
+  if (!out) return OBGPU_INVALID_ARGUMENT;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) {
+    g_last_global_err = "no usable CUDA device (this library has no CPU fallback)";
+    return OBGPU_ERR_SYS;
+  }
+  obgpu_ctx *c = new (std::nothrow) obgpu_ctx();
+  if (!c) return OBGPU_ALLOCATE_MEMORY_FAILED;
+  c->device = device;
+  if (cudaSetDevice(device) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete c;
+    return OBGPU_ERR_SYS;
+  }
+  c->stream = c->own_stream;
+  cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  cudaMallocHost(&c->h_pinned, 4096);
+  // keep freed result arenas in the stream-ordered pool: steady-state scans do no cudaMalloc
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    uint64_t thr = UINT64_MAX;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  cudaFuncSetAttribute(obgpu_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin);
+  cudaFuncSetAttribute(obgpu_filter_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin);
+  cudaFuncSetAttribute(obgpu_project_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin);
+  *out = c;
+  return OBGPU_SUCCESS;
+}
+
+void obgpu_ctx_destroy(obgpu_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+  delete ctx;
+}
+
+int obgpu_ctx_set_stream(obgpu_ctx *ctx, void *cuda_stream) {
+  if (!ctx) return OBGPU_INVALID_ARGUMENT;
+  ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+  return OBGPU_SUCCESS;
+}
+
+int obgpu_ctx_synchronize(obgpu_ctx *ctx) {
+  if (!ctx) return OBGPU_INVALID_ARGUMENT;
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return OBGPU_SUCCESS;
+}
+
+const char *obgpu_ctx_last_error(const obgpu_ctx *ctx) {
+  return ctx ? ctx->err.c_str() : g_last_global_err.c_str();
+}
+
+int64_t obgpu_ctx_launch_count(const obgpu_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+// ---- batch ------------------------------------------------------------------------------------
+static uint32_t rd32h(const uint8_t *p) { uint32_t v; memcpy(&v, p, 4); return v; }
+static uint16_t rd16h(const uint8_t *p) { uint16_t v; memcpy(&v, p, 2); return v; }
+
+int obgpu_batch_open(obgpu_ctx *ctx, const void *image, int64_t image_size, const int64_t *offsets,
+                     const int64_t *sizes, int32_t n_blocks, int32_t image_on_device, const void *header_view,
+                     obgpu_batch **out) {
+  if (!ctx || !image || !offsets || !sizes || n_blocks <= 0 || !out || image_size <= 0)
+    return OBGPU_INVALID_ARGUMENT;
+  const uint8_t *host = image_on_device ? (const uint8_t *)header_view : (const uint8_t *)image;
+  if (!host) {
+    ctx->err = "device-resident image needs a host header_view";
+    return OBGPU_INVALID_ARGUMENT;
+  }
+  cudaSetDevice(ctx->device);
+  obgpu_batch *b = new (std::nothrow) obgpu_batch();
+  if (!b) return OBGPU_ALLOCATE_MEMORY_FAILED;
+  b->ctx = ctx;
+  b->n_blocks = n_blocks;
+  b->image_size = image_size;
+  b->offsets.assign(offsets, offsets + n_blocks);
+  b->sizes.assign(sizes, sizes + n_blocks);
+  b->row_count.resize((size_t)n_blocks);
+  b->col_count.resize((size_t)n_blocks);
+  b->bm_word_off.resize((size_t)n_blocks + 1);
+  int ret = OBGPU_SUCCESS;
+  int64_t words = 0;
+  for (int32_t i = 0; i < n_blocks && ret == OBGPU_SUCCESS; ++i) {
+    const int64_t off = offsets[i], sz = sizes[i];
+    if (off < 0 || (off & 15) || sz < 64 || off + sz > image_size) { ret = OBGPU_INVALID_ARGUMENT; break; }
+    const int64_t padded = (sz + 15) & ~15ll;
+    const int64_t limit = i + 1 < n_blocks ? offsets[i + 1] : image_size;
+    if (image_on_device && off + padded > limit) {
+      ctx->err = "blocks of a device-resident image must be padded to 16 bytes";
+      ret = OBGPU_INVALID_ARGUMENT;
+      break;
+    }
+    const uint8_t *p = host + off;
+    const int16_t magic = (int16_t)rd16h(p), version = (int16_t)rd16h(p + 2);
+    const uint32_t header_size = rd32h(p + 4);
+    const uint16_t ncol = rd16h(p + 10), nkey = rd16h(p + 12);
+    const uint32_t rows = rd32h(p + 16);
+    const uint8_t rst = p[20];
+    const uint32_t row_data_off = rd32h(p + 24);
+    // ObMicroBlockHeader::is_valid (ob_micro_block_header.cpp:53-61) + get_micro_metas bounds
+    if (magic != obf::MICRO_BLOCK_HEADER_MAGIC || version < 1 || version > 3 || ncol < nkey || rst >= obf::MAX_ROW_STORE) {
+      ctx->err = "invalid micro block header";
+      ret = OBGPU_INVALID_DATA;
+      break;
+    }
+    if (rst != obf::ENCODING_ROW_STORE && rst != obf::SELECTIVE_ENCODING_ROW_STORE) {
+      ctx->err = "row store type not handled by the PAX device path";
+      ret = OBGPU_NOT_SUPPORTED;
+      break;
+    }
+    if (header_size < 64 || (int64_t)header_size + 16ll * ncol > sz || row_data_off > sz || rows == 0) {
+      ret = OBGPU_INVALID_DATA;
+      break;
+    }
+    if (rows > 65535u) {
+      ctx->err = "more than 65535 rows in one micro block";
+      ret = OBGPU_NOT_SUPPORTED;
+      break;
+    }
+    b->row_count[(size_t)i] = rows;
+    b->col_count[(size_t)i] = ncol;
+    b->bm_word_off[(size_t)i] = words;
+    words += (rows + 31) / 32;
+    b->total_rows += rows;
+    b->max_block_bytes = std::max<uint32_t>(b->max_block_bytes, (uint32_t)padded);
+    b->max_rows = std::max(b->max_rows, rows);
+    b->max_cols = std::max<uint32_t>(b->max_cols, ncol);
+    if (b->col_max_dict.size() < ncol) b->col_max_dict.resize(ncol, 0);
+    if (b->col_types.size() < ncol) b->col_types.resize(ncol, 0);
+    // dictionary sizes of DICT / RLE columns (sizes the shared-memory predicate bitsets)
+    const uint32_t meta_off = header_size + 16u * ncol;
+    for (uint32_t c = 0; c < ncol; ++c) {
+      const uint8_t *ch = p + header_size + 16u * c;
+      const int8_t type = (int8_t)ch[1];
+      const uint32_t coff = rd32h(ch + 8), clen = rd32h(ch + 12);
+      if (b->col_types[c] == 0) b->col_types[c] = ch[3];
+      else if (b->col_types[c] != ch[3]) b->col_types[c] = 0xff;
+      uint32_t dm = 0;
+      if (type == obf::COL_DICT) dm = meta_off + coff;
+      else if (type == obf::COL_RLE) {
+        if ((int64_t)meta_off + coff + 10 > sz) { ret = OBGPU_INVALID_DATA; break; }
+        dm = meta_off + coff + rd32h(p + meta_off + coff + 6);
+      } else continue;
+      if ((int64_t)dm + 9 > sz || (int64_t)meta_off + coff + clen > sz) { ret = OBGPU_INVALID_DATA; break; }
+      const uint32_t cnt = rd32h(p + dm + 2);
+      b->col_max_dict[c] = std::max(b->col_max_dict[c], cnt + 2);
+    }
+  }
+  b->bm_word_off[(size_t)n_blocks] = words;
+  if (ret == OBGPU_SUCCESS && (int)b->max_block_bytes + 16 > ctx->max_smem_optin - 8192) {
+    ctx->err = "micro block too large for one shared-memory page";
+    ret = OBGPU_NOT_SUPPORTED;
+  }
+  if (ret != OBGPU_SUCCESS) {
+    delete b;
+    return ret;
+  }
+  // device tables
+  const size_t tb = (size_t)n_blocks * (8 + 4) + ((size_t)n_blocks + 1) * 8 + 64;
+  cudaError_t e = cudaMallocAsync(&b->d_tables, tb, ctx->stream);
+  if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); delete b; return OBGPU_ALLOCATE_MEMORY_FAILED; }
+  uint8_t *dt = (uint8_t *)b->d_tables;
+  b->d_blk_off = (uint64_t *)dt;
+  b->d_bm_word_off = (int64_t *)(dt + (size_t)n_blocks * 8);
+  b->d_blk_size = (uint32_t *)(dt + (size_t)n_blocks * 8 + ((size_t)n_blocks + 1) * 8);
+  std::vector<uint8_t> stage(tb);
+  {
+    uint64_t *o = (uint64_t *)stage.data();
+    int64_t *w = (int64_t *)(stage.data() + (size_t)n_blocks * 8);
+    uint32_t *s = (uint32_t *)(stage.data() + (size_t)n_blocks * 8 + ((size_t)n_blocks + 1) * 8);
+    for (int32_t i = 0; i < n_blocks; ++i) { o[i] = (uint64_t)offsets[i]; s[i] = (uint32_t)sizes[i]; }
+    memcpy(w, b->bm_word_off.data(), ((size_t)n_blocks + 1) * 8);
+  }
+  e = cudaMemcpyAsync(b->d_tables, stage.data(), tb, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) {
+    if (image_on_device) {
+      b->d_image = (const uint8_t *)image;
+    } else {
+      void *di = nullptr;
+      e = cudaMallocAsync(&di, (size_t)image_size + 64, ctx->stream);
+      if (e == cudaSuccess) {
+        b->d_image = (const uint8_t *)di;
+        b->own_image = true;
+        e = cudaMemsetAsync((uint8_t *)di + image_size, 0, 64, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(di, image, (size_t)image_size, cudaMemcpyHostToDevice, ctx->stream);
+      }
+    }
+  }
+  // `stage` is pageable: the copy above is staged synchronously by the runtime before returning
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) {
+    ctx->err = cudaGetErrorString(e);
+    obgpu_batch_close(b);
+    return e == cudaErrorMemoryAllocation ? OBGPU_ALLOCATE_MEMORY_FAILED : OBGPU_ERR_SYS;
+  }
+  *out = b;
+  return OBGPU_SUCCESS;
+}
+
+void obgpu_batch_close(obgpu_batch *b) {
+  if (!b) return;
+  cudaSetDevice(b->ctx->device);
+  if (b->d_tables) cudaFreeAsync(b->d_tables, b->ctx->stream);
+  if (b->own_image && b->d_image) cudaFreeAsync((void *)b->d_image, b->ctx->stream);
+  delete b;
+}
+
+int obgpu_batch_block_info(const obgpu_batch *b, int32_t block, int64_t *row_count, int32_t *column_count) {
+  if (!b || block < 0 || block >= b->n_blocks) return OBGPU_INVALID_ARGUMENT;
+  if (row_count) *row_count = b->row_count[(size_t)block];
+  if (column_count) *column_count = b->col_count[(size_t)block];
+  return OBGPU_SUCCESS;
+}
+
+int obgpu_batch_total_rows(const obgpu_batch *b, int64_t *total_rows) {
+  if (!b || !total_rows) return OBGPU_INVALID_ARGUMENT;
+  *total_rows = b->total_rows;
+  return OBGPU_SUCCESS;
+}
+
+}  // extern "C"
+
+// ---- building the kernel parameter block ---------------------------------------------------------
+static int used_index(ScanParams &p, int32_t col) {
+  for (int i = 0; i < p.n_used; ++i)
+    if (p.used_col[i] == col) return i;
+  if (p.n_used >= kMaxUsedCols) return -1;
+  p.used_col[p.n_used] = col;
+  return p.n_used++;
+}
+
+// Flattens / validates the filter; resolves NULL constants the way
+// ObMicroBlockDecoder::filter_pushdown_filter does (ob_micro_block_decoder.cpp:1713-1715).
+static int build_filter(obgpu_ctx *ctx, const obgpu_batch *b, const obgpu_filter *f, ScanParams &p) {
+  p.n_nodes = 0;
+  p.n_slots = 0;
+  p.bitset_words = 0;
+  p.simple_shape = 0;
+  if (!f || f->n_nodes == 0) return OBGPU_SUCCESS;
+  if (!f->nodes || f->n_nodes < 0 || f->n_nodes > kMaxNodes) {
+    ctx->err = "filter tree too large for the device path";
+    return f && f->n_nodes > kMaxNodes ? OBGPU_NOT_SUPPORTED : OBGPU_INVALID_ARGUMENT;
+  }
+  int n_params = 0;
+  uint32_t heap = 0;
+  int depth = 0;
+  for (int i = 0; i < f->n_nodes; ++i) {
+    const obgpu_filter_node &src = f->nodes[i];
+    FilterNodeDev nd{};
+    nd.kind = (int8_t)src.kind;
+    nd.slot = -1;
+    if (src.kind == OBGPU_NODE_WHITE) {
+      if (src.op < 0 || src.op >= OBGPU_WHITE_OP_MAX || src.col < 0) return OBGPU_INVALID_ARGUMENT;
+      const int np = src.n_params;
+      if ((src.op <= OBGPU_WHITE_OP_NE && np != 1) || (src.op == OBGPU_WHITE_OP_BT && np != 2) ||
+          (src.op == OBGPU_WHITE_OP_IN && np < 1) || (src.op >= OBGPU_WHITE_OP_NU && np != 0))
+        return OBGPU_INVALID_ARGUMENT;
+      if (np > 0 && (!f->params || src.param_begin < 0 || src.param_begin + np > f->n_params))
+        return OBGPU_INVALID_ARGUMENT;
+      const int ui = used_index(p, src.col);
+      if (ui < 0) return OBGPU_NOT_SUPPORTED;
+      nd.used_idx = (int16_t)ui;
+      nd.op = (int16_t)src.op;
+      nd.param_begin = (int16_t)n_params;
+      int kept = 0;
+      bool null_param = false;
+      for (int k = 0; k < np; ++k) {
+        const obgpu_filter_param &sp = f->params[src.param_begin + k];
+        if (sp.is_null) {
+          if (src.op == OBGPU_WHITE_OP_IN) continue;  // NULLs never match inside an IN list
+          null_param = true;
+          continue;
+        }
+        if (n_params >= kMaxParams) return OBGPU_NOT_SUPPORTED;
+        ParamDev pd{};
+        pd.i64 = sp.i64;
+        pd.len = sp.len;
+        pd.heap_off = heap;
+        if (sp.ptr && sp.len > 0) {
+          if (heap + sp.len > (uint32_t)kParamHeap) return OBGPU_NOT_SUPPORTED;
+          memcpy(p.param_heap + heap, sp.ptr, sp.len);
+          heap += sp.len;
+        }
+        p.params[n_params++] = pd;
+        ++kept;
+      }
+      nd.n_params = (int16_t)kept;
+      if (null_param || (src.op == OBGPU_WHITE_OP_IN && kept == 0)) nd.op = OP_FALSE;
+      if (nd.op != OP_FALSE && (size_t)src.col < b->col_max_dict.size() && b->col_max_dict[(size_t)src.col] > 0) {
+        if (p.n_slots >= 127) return OBGPU_NOT_SUPPORTED;
+        nd.slot = (int8_t)p.n_slots++;
+        p.bitset_words = std::max<int32_t>(p.bitset_words, (int32_t)((b->col_max_dict[(size_t)src.col] + 31) / 32));
+      }
+      ++depth;
+    } else if (src.kind == OBGPU_NODE_AND || src.kind == OBGPU_NODE_OR) {
+      if (src.n_children < 2 || src.n_children > 31 || src.n_children > depth) return OBGPU_INVALID_ARGUMENT;
+      nd.n_children = (int16_t)src.n_children;
+      depth -= src.n_children - 1;
+    } else {
+      return OBGPU_INVALID_ARGUMENT;
+    }
+    if (depth > 31) return OBGPU_NOT_SUPPORTED;
+    p.nodes[p.n_nodes++] = nd;
+  }
+  if (depth != 1) return OBGPU_INVALID_ARGUMENT;
+  if (p.n_nodes >= 3) {
+    const FilterNodeDev &root = p.nodes[p.n_nodes - 1];
+    bool leaves = root.kind != NODE_WHITE && root.n_children == p.n_nodes - 1;
+    for (int i = 0; leaves && i < p.n_nodes - 1; ++i) leaves = p.nodes[i].kind == NODE_WHITE;
+    if (leaves) p.simple_shape = root.kind == NODE_AND ? 1 : 2;
+  }
+  return OBGPU_SUCCESS;
+}
+
+static void layout_smem(const obgpu_batch *b, ScanParams &p, bool need_sel) {
+  uint32_t off = (b->max_block_bytes + 16u + 127u) & ~127u;
+  const uint32_t rows_cap = need_sel ? std::max<uint32_t>(b->max_rows, 32u) : 0u;
+  const uint32_t words_cap = (rows_cap + 31u) / 32u;
+  p.rows_cap = need_sel ? rows_cap : 65535u;
+  p.smem_sel = off;   off += (rows_cap * 2u + 15u) & ~15u;
+  p.smem_bm = off;    off += (words_cap * 4u + 15u) & ~15u;
+  p.smem_wpre = off;  off += (words_cap * 4u + 15u) & ~15u;
+  p.smem_bitset = off; off += ((uint32_t)p.n_slots * (uint32_t)p.bitset_words * 4u + 15u) & ~15u;
+  p.smem_desc = off;  off += (uint32_t)sizeof(ColDesc) * (uint32_t)std::max(p.n_used, 1);
+  p.smem_total = (off + 15u) & ~15u;
+}
+
+static int check_status(obgpu_ctx *ctx, int status) {
+  if (status & ST_CORRUPT) { ctx->err = "corrupt micro block seen on device"; return OBGPU_INVALID_DATA; }
+  if (status & ST_UNSUPPORTED) { ctx->err = "column encoding / type not handled by the device path"; return OBGPU_NOT_SUPPORTED; }
+  if (status & ST_OVERFLOW) { ctx->err = "result capacity exceeded"; return OBGPU_BUF_NOT_ENOUGH; }
+  return OBGPU_SUCCESS;
+}
+
+extern "C" {
+
+int obgpu_scan(obgpu_batch *b, const obgpu_scan_spec *spec, obgpu_result **out) {
+  if (!b || !spec || !out) return OBGPU_INVALID_ARGUMENT;
+  obgpu_ctx *ctx = b->ctx;
+  if (spec->n_proj < 0 || spec->n_proj > kMaxProj || (spec->n_proj > 0 && !spec->proj_cols))
+    return spec->n_proj > kMaxProj ? OBGPU_NOT_SUPPORTED : OBGPU_INVALID_ARGUMENT;
+  cudaSetDevice(ctx->device);
+  ScanParams p;
+  memset(&p, 0, sizeof(p));
+  int ret = build_filter(ctx, b, spec->filter, p);
+  if (ret != OBGPU_SUCCESS) return ret;
+  obgpu_result *r = new (std::nothrow) obgpu_result();
+  if (!r) return OBGPU_ALLOCATE_MEMORY_FAILED;
+  r->batch = b;
+  r->ctx = ctx;
+  r->n_proj = spec->n_proj;
+  r->cap = spec->max_selected_rows > 0 ? std::min<int64_t>(spec->max_selected_rows, b->total_rows) : b->total_rows;
+  // column types were captured at open time (an SSTable has one schema; 0xff = blocks disagree)
+  for (int c = 0; c < spec->n_proj; ++c) {
+    const int32_t col = spec->proj_cols[c];
+    if (col < 0 || (uint32_t)col >= b->max_cols) { delete r; return OBGPU_INVALID_ARGUMENT; }
+    const int ui = used_index(p, col);
+    if (ui < 0) { delete r; return OBGPU_NOT_SUPPORTED; }
+    p.proj_used[c] = (int16_t)ui;
+  }
+  p.n_proj = spec->n_proj;
+  p.want_row_ids = spec->want_row_ids ? 1 : 0;
+  p.string_base = spec->string_base;
+  layout_smem(b, p, true);
+  if ((int)p.smem_total > ctx->max_smem_optin) {
+    ctx->err = "scan working set exceeds shared memory";
+    delete r;
+    return OBGPU_NOT_SUPPORTED;
+  }
+  // ---- result arena: [zeroed region | data] ---------------------------------------------------------
+  const int32_t n = b->n_blocks;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+  const size_t o_state = take((size_t)n * 8);
+  const size_t o_misc = take(256 + kMaxProj * 4);  // ticket, status, has_null
+  size_t o_nulls[kMaxProj];
+  const size_t null_bytes = (size_t)((r->cap + 63) / 64) * 8;
+  for (int c = 0; c < spec->n_proj; ++c) o_nulls[c] = take(null_bytes);
+  const size_t zero_bytes = off;
+  const size_t o_sel = take(((size_t)n + 1) * 8);
+  const size_t o_bm = take((size_t)b->bm_word_off[(size_t)n] * 4 + 4);
+  const size_t o_rid = spec->want_row_ids ? take((size_t)r->cap * 4) : 0;
+  size_t o_data[kMaxProj], o_lens[kMaxProj];
+  for (int c = 0; c < spec->n_proj; ++c) {
+    const int t = b->col_types[(size_t)spec->proj_cols[c]];
+    o_data[c] = 0;
+    o_lens[c] = 0;
+    const int sc = obf::store_class_of((uint8_t)t);
+    if (sc == 0) { ctx->err = "projected column type not handled by the device path"; delete r; return OBGPU_NOT_SUPPORTED; }
+    r->cols[c].obj_type = t;
+    r->cols[c].is_string = sc == 5;
+    r->cols[c].elem_len = sc == 5 ? 8 : obf::datum_len_of((uint8_t)t);
+    o_data[c] = take((size_t)r->cap * (size_t)r->cols[c].elem_len);
+    if (sc == 5) o_lens[c] = take((size_t)r->cap * 4);
+  }
+  r->arena_bytes = off;
+  cudaError_t e = cudaMallocAsync(&r->arena, r->arena_bytes, ctx->stream);
+  if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); delete r; return OBGPU_ALLOCATE_MEMORY_FAILED; }
+  uint8_t *a = (uint8_t *)r->arena;
+  e = cudaMemsetAsync(a, 0, zero_bytes, ctx->stream);
+  if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); obgpu_result_free(r); return OBGPU_ERR_SYS; }
+  p.image = b->d_image;
+  p.blk_off = b->d_blk_off;
+  p.blk_size = b->d_blk_size;
+  p.bm_word_off = b->d_bm_word_off;
+  p.n_blocks = n;
+  p.tile_state = (unsigned long long *)(a + o_state);
+  p.ticket = (int32_t *)(a + o_misc);
+  p.status = (int32_t *)(a + o_misc + 64);
+  p.has_null = (int32_t *)(a + o_misc + 128);
+  p.sel_offset = (int64_t *)(a + o_sel);
+  p.bitmap_words = (uint32_t *)(a + o_bm);
+  p.row_ids = spec->want_row_ids ? (int32_t *)(a + o_rid) : nullptr;
+  p.out_cap = r->cap;
+  for (int c = 0; c < spec->n_proj; ++c) {
+    r->cols[c].data = a + o_data[c];
+    r->cols[c].lens = r->cols[c].is_string ? (int32_t *)(a + o_lens[c]) : nullptr;
+    r->cols[c].nulls = (uint32_t *)(a + o_nulls[c]);
+    p.out_data[c] = r->cols[c].data;
+    p.out_lens[c] = r->cols[c].lens;
+    p.out_nulls[c] = r->cols[c].nulls;
+  }
+  r->d_has_null = p.has_null;
+  r->d_status = p.status;
+  r->d_sel_offset = p.sel_offset;
+  r->d_bitmap = p.bitmap_words;
+  r->d_row_ids = p.row_ids;
+  obgpu_scan_kernel<<<n, kThreads, p.smem_total, ctx->stream>>>(p);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); obgpu_result_free(r); return OBGPU_ERR_SYS; }
+  ctx->launches++;
+  *out = r;
+  return OBGPU_SUCCESS;
+}
+
+void obgpu_result_free(obgpu_result *r) {
+  if (!r) return;
+  cudaSetDevice(r->ctx->device);
+  if (r->arena) cudaFreeAsync(r->arena, r->ctx->stream);
+  delete r;
+}
+
+int obgpu_result_info_get(obgpu_result *r, obgpu_result_info *info) {
+  if (!r || !info) return OBGPU_INVALID_ARGUMENT;
+  obgpu_ctx *ctx = r->ctx;
+  if (!r->info_valid) {
+    cudaSetDevice(ctx->device);
+    int64_t *hp = (int64_t *)ctx->h_pinned;
+    int32_t *hs = (int32_t *)(hp + 1);
+    int32_t *hn = hs + 1;
+    CUDA_TRY(ctx, cudaMemcpyAsync(hp, r->d_sel_offset + r->batch->n_blocks, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(hs, r->d_status, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(hn, r->d_has_null, kMaxProj * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    r->info.total_rows = r->batch->total_rows;
+    r->info.selected_rows = *hp;
+    r->info.n_blocks = r->batch->n_blocks;
+    r->info.n_proj = r->n_proj;
+    r->status = *hs;
+    memcpy(r->has_null, hn, sizeof(r->has_null));
+    r->info_valid = true;
+  }
+  *info = r->info;
+  return check_status(ctx, r->status);
+}
+
+int obgpu_result_col_get(obgpu_result *r, int32_t i, obgpu_result_col *col) {
+  if (!r || !col || i < 0 || i >= r->n_proj) return OBGPU_INVALID_ARGUMENT;
+  col->data = r->cols[i].data;
+  col->aux = r->cols[i].lens;
+  col->nulls = (uint64_t *)r->cols[i].nulls;
+  col->elem_len = r->cols[i].elem_len;
+  col->is_string = r->cols[i].is_string;
+  col->has_null = r->info_valid ? r->has_null[i] : 0;
+  col->obj_type = r->cols[i].obj_type;
+  return OBGPU_SUCCESS;
+}
+
+int obgpu_result_block_tables(obgpu_result *r, const int64_t **sel_offset_dev, const uint32_t **bitmap_words_dev,
+                              const int64_t **bitmap_word_offset_dev, const int32_t **row_ids_dev) {
+  if (!r) return OBGPU_INVALID_ARGUMENT;
+  if (sel_offset_dev) *sel_offset_dev = r->d_sel_offset;
+  if (bitmap_words_dev) *bitmap_words_dev = r->d_bitmap;
+  if (bitmap_word_offset_dev) *bitmap_word_offset_dev = r->batch->d_bm_word_off;
+  if (row_ids_dev) *row_ids_dev = r->d_row_ids;
+  return OBGPU_SUCCESS;
+}
+
+int obgpu_result_fetch_col(obgpu_result *r, int32_t i, int64_t row_begin, int64_t row_count, void *host_data,
+                           void *host_aux, uint64_t *host_nulls) {
+  if (!r || i < 0 || i >= r->n_proj || row_begin < 0 || row_count < 0 || row_begin + row_count > r->cap)
+    return OBGPU_INVALID_ARGUMENT;
+  obgpu_ctx *ctx = r->ctx;
+  cudaSetDevice(ctx->device);
+  const ResultCol &c = r->cols[i];
+  if (row_count == 0) return OBGPU_SUCCESS;
+  if (host_data)
+    CUDA_TRY(ctx, cudaMemcpyAsync(host_data, (uint8_t *)c.data + row_begin * c.elem_len, (size_t)row_count * c.elem_len,
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+  if (host_aux && c.lens)
+    CUDA_TRY(ctx, cudaMemcpyAsync(host_aux, c.lens + row_begin, (size_t)row_count * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  std::vector<uint64_t> tmp;
+  const int64_t w0 = row_begin / 64, w1 = (row_begin + row_count + 63) / 64;
+  const int sh = (int)(row_begin % 64);
+  if (host_nulls) {
+    if (sh == 0) {
+      CUDA_TRY(ctx, cudaMemcpyAsync(host_nulls, (uint64_t *)c.nulls + w0, (size_t)(w1 - w0) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    } else {
+      tmp.resize((size_t)(w1 - w0) + 1, 0);
+      CUDA_TRY(ctx, cudaMemcpyAsync(tmp.data(), (uint64_t *)c.nulls + w0, (size_t)(w1 - w0) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+  }
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (host_nulls) {
+    const int64_t ow = (row_count + 63) / 64;
+    if (sh != 0)
+      for (int64_t k = 0; k < ow; ++k) host_nulls[k] = (tmp[(size_t)k] >> sh) | (tmp[(size_t)k + 1] << (64 - sh));
+    if (row_count % 64) host_nulls[ow - 1] &= (1ull << (row_count % 64)) - 1ull;
+  }
+  return OBGPU_SUCCESS;
+}
+
+int obgpu_result_fetch_sel_offsets(obgpu_result *r, int64_t *host_sel_offset) {
+  if (!r || !host_sel_offset) return OBGPU_INVALID_ARGUMENT;
+  obgpu_ctx *ctx = r->ctx;
+  cudaSetDevice(ctx->device);
+  CUDA_TRY(ctx, cudaMemcpyAsync(host_sel_offset, r->d_sel_offset, ((size_t)r->batch->n_blocks + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return OBGPU_SUCCESS;
+}
+
+int obgpu_result_fetch_row_ids(obgpu_result *r, int64_t row_begin, int64_t row_count, int32_t *host_row_ids) {
+  if (!r || !host_row_ids || !r->d_row_ids || row_begin < 0 || row_count < 0 || row_begin + row_count > r->cap)
+    return OBGPU_INVALID_ARGUMENT;
+  obgpu_ctx *ctx = r->ctx;
+  cudaSetDevice(ctx->device);
+  if (row_count == 0) return OBGPU_SUCCESS;
+  CUDA_TRY(ctx, cudaMemcpyAsync(host_row_ids, r->d_row_ids + row_begin, (size_t)row_count * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return OBGPU_SUCCESS;
+}
+
+int obgpu_result_fetch_bitmap(obgpu_result *r, int32_t block, int64_t start, int64_t count, uint8_t *host_bitmap_bytes) {
+  if (!r || !host_bitmap_bytes || block < 0 || block >= r->batch->n_blocks || start < 0 || count < 0 ||
+      start + count > (int64_t)r->batch->row_count[(size_t)block])
+    return OBGPU_INVALID_ARGUMENT;
+  obgpu_ctx *ctx = r->ctx;
+  cudaSetDevice(ctx->device);
+  const int64_t w0 = r->batch->bm_word_off[(size_t)block], nw = r->batch->bm_word_off[(size_t)block + 1] - w0;
+  std::vector<uint32_t> words((size_t)nw);
+  CUDA_TRY(ctx, cudaMemcpyAsync(words.data(), r->d_bitmap + w0, (size_t)nw * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int64_t i = 0; i < count; ++i) {
+    const int64_t row = start + i;
+    host_bitmap_bytes[i] = (words[(size_t)(row >> 5)] >> (row & 31)) & 1u;
+  }
+  return OBGPU_SUCCESS;
+}
+
+}  // extern "C"
+
+// =================================================================================================
+// Reference-granularity entry points (one block, one call). Same device code, one-CTA kernels.
+// =================================================================================================
+namespace {
+
+struct TempDev {
+  obgpu_ctx *ctx;
+  void *p = nullptr;
+  explicit TempDev(obgpu_ctx *c) : ctx(c) {}
+  cudaError_t alloc(size_t bytes) { return cudaMallocAsync(&p, bytes ? bytes : 16, ctx->stream); }
+  ~TempDev() { if (p) cudaFreeAsync(p, ctx->stream); }
+};
+
+int run_filter_block(obgpu_batch *b, int32_t block, const obgpu_filter *f, int64_t start, int64_t count,
+                     uint8_t *result_bitmap) {
+  if (!b || !f || !result_bitmap || block < 0 || block >= b->n_blocks || start < 0 || count < 0 ||
+      start + count > (int64_t)b->row_count[(size_t)block])
+    return OBGPU_INVALID_ARGUMENT;
+  obgpu_ctx *ctx = b->ctx;
+  cudaSetDevice(ctx->device);
+  ScanParams p;
+  memset(&p, 0, sizeof(p));
+  int ret = build_filter(ctx, b, f, p);
+  if (ret != OBGPU_SUCCESS) return ret;
+  if (p.n_nodes == 0) return OBGPU_INVALID_ARGUMENT;
+  if (count == 0) return OBGPU_SUCCESS;
+  layout_smem(b, p, false);
+  if ((int)p.smem_total > ctx->max_smem_optin) return OBGPU_NOT_SUPPORTED;
+  TempDev tmp(ctx);
+  CUDA_TRY(ctx, tmp.alloc((size_t)count + 64));
+  uint8_t *d_bytes = (uint8_t *)tmp.p + 64;
+  CUDA_TRY(ctx, cudaMemsetAsync(tmp.p, 0, 64, ctx->stream));
+  p.image = b->d_image;
+  p.blk_off = b->d_blk_off;
+  p.blk_size = b->d_blk_size;
+  p.bm_word_off = b->d_bm_word_off;
+  p.n_blocks = b->n_blocks;
+  p.status = (int32_t *)tmp.p;
+  obgpu_filter_block_kernel<<<1, kThreads, p.smem_total, ctx->stream>>>(p, block, start, count, d_bytes);
+  CUDA_TRY(ctx, cudaGetLastError());
+  ctx->launches++;
+  int32_t *hs = (int32_t *)ctx->h_pinned;
+  CUDA_TRY(ctx, cudaMemcpyAsync(hs, tmp.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(result_bitmap, d_bytes, (size_t)count, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return check_status(ctx, *hs);
+}
+
+int run_project_block(obgpu_batch *b, int32_t block, int32_t col, const int32_t *row_ids, int64_t row_cap,
+                      int64_t vec_offset, uint64_t string_base, void *data, int32_t elem_len, int32_t *lens,
+                      uint64_t *nulls, int32_t *has_null, bool want_string) {
+  if (!b || !row_ids || !data || block < 0 || block >= b->n_blocks || row_cap < 0 || vec_offset < 0 || col < 0)
+    return OBGPU_INVALID_ARGUMENT;
+  if (want_string && !lens) return OBGPU_INVALID_ARGUMENT;
+  if (!want_string && elem_len != 8 && elem_len != 4 && elem_len != 1) return OBGPU_INVALID_ARGUMENT;
+  if (row_cap == 0) return OBGPU_SUCCESS;
+  obgpu_ctx *ctx = b->ctx;
+  cudaSetDevice(ctx->device);
+  ScanParams p;
+  memset(&p, 0, sizeof(p));
+  p.n_used = 1;
+  p.used_col[0] = col;
+  layout_smem(b, p, false);
+  if ((int)p.smem_total > ctx->max_smem_optin) return OBGPU_NOT_SUPPORTED;
+  const size_t el = want_string ? 8 : (size_t)elem_len;
+  const int64_t total = vec_offset + row_cap;
+  const size_t null_words32 = (size_t)((total + 63) / 64) * 2;
+  size_t off = 256;
+  const size_t o_rid = off; off += ((size_t)row_cap * 4 + 255) & ~(size_t)255;
+  const size_t o_nulls = off; off += (null_words32 * 4 + 255) & ~(size_t)255;
+  const size_t o_data = off; off += ((size_t)total * el + 255) & ~(size_t)255;
+  const size_t o_lens = off; off += want_string ? (((size_t)total * 4 + 255) & ~(size_t)255) : 0;
+  TempDev tmp(ctx);
+  CUDA_TRY(ctx, tmp.alloc(off));
+  uint8_t *a = (uint8_t *)tmp.p;
+  CUDA_TRY(ctx, cudaMemsetAsync(a, 0, o_data, ctx->stream));  // status, has_null, row ids, nulls
+  CUDA_TRY(ctx, cudaMemcpyAsync(a + o_rid, row_ids, (size_t)row_cap * 4, cudaMemcpyHostToDevice, ctx->stream));
+  // the caller's vector keeps whatever it held in NULL slots / outside the window: seed the device
+  // image with it so that the copy back is a pure overlay (reference leaves NULL slots unwritten)
+  CUDA_TRY(ctx, cudaMemcpyAsync(a + o_data + (size_t)vec_offset * el, (uint8_t *)data + (size_t)vec_offset * el,
+                                (size_t)row_cap * el, cudaMemcpyHostToDevice, ctx->stream));
+  if (want_string)
+    CUDA_TRY(ctx, cudaMemcpyAsync(a + o_lens + (size_t)vec_offset * 4, lens + vec_offset, (size_t)row_cap * 4,
+                                  cudaMemcpyHostToDevice, ctx->stream));
+  p.image = b->d_image;
+  p.blk_off = b->d_blk_off;
+  p.blk_size = b->d_blk_size;
+  p.n_blocks = b->n_blocks;
+  p.status = (int32_t *)a;
+  p.has_null = (int32_t *)(a + 64);
+  p.string_base = string_base;
+  obgpu_project_block_kernel<<<1, kThreads, p.smem_total, ctx->stream>>>(
+      p, block, (const int32_t *)(a + o_rid), row_cap, vec_offset, a + o_data,
+      want_string ? (int32_t *)(a + o_lens) : nullptr, (uint32_t *)(a + o_nulls), (int32_t)el);
+  CUDA_TRY(ctx, cudaGetLastError());
+  ctx->launches++;
+  int32_t *hs = (int32_t *)ctx->h_pinned;
+  CUDA_TRY(ctx, cudaMemcpyAsync(hs, a, 128 + 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync((uint8_t *)data + (size_t)vec_offset * el, a + o_data + (size_t)vec_offset * el,
+                                (size_t)row_cap * el, cudaMemcpyDeviceToHost, ctx->stream));
+  if (want_string)
+    CUDA_TRY(ctx, cudaMemcpyAsync(lens + vec_offset, a + o_lens + (size_t)vec_offset * 4, (size_t)row_cap * 4,
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+  std::vector<uint64_t> hnulls(null_words32 / 2);
+  CUDA_TRY(ctx, cudaMemcpyAsync(hnulls.data(), a + o_nulls, null_words32 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  const int st = check_status(ctx, hs[0]);
+  if (st != OBGPU_SUCCESS) return st;
+  if (nulls)
+    for (size_t k = 0; k < hnulls.size(); ++k) nulls[k] |= hnulls[k];  // ObBitVector::set semantics
+  if (has_null && hs[16]) *has_null = 1;
+  return OBGPU_SUCCESS;
+}
+
+}  // namespace
+
+extern "C" {
+
+int obgpu_filter_white(obgpu_batch *batch, int32_t block, int32_t col, int32_t op, const obgpu_filter_param *params,
+                       int32_t n_params, int64_t start, int64_t count, uint8_t *result_bitmap) {
+  obgpu_filter_node nd{};
+  nd.kind = OBGPU_NODE_WHITE;
+  nd.op = op;
+  nd.col = col;
+  nd.param_begin = 0;
+  nd.n_params = n_params;
+  obgpu_filter f{&nd, 1, params, n_params};
+  return run_filter_block(batch, block, &f, start, count, result_bitmap);
+}
+
+int obgpu_filter_tree(obgpu_batch *batch, int32_t block, const obgpu_filter *filter, int64_t start, int64_t count,
+                      uint8_t *result_bitmap) {
+  return run_filter_block(batch, block, filter, start, count, result_bitmap);
+}
+
+int obgpu_bitmap_to_row_ids(obgpu_ctx *ctx, const uint8_t *bitmap, int64_t bitmap_size, int64_t *from, int64_t to,
+                            int64_t limit, int64_t id_offset, int32_t *row_ids, int64_t *row_count) {
+  // argument checks of ObBitmap::get_row_ids (ob_bitmap.cpp:547-552)
+  if (!ctx || !bitmap || !from || !row_ids || !row_count) return OBGPU_INVALID_ARGUMENT;
+  if (*from < 0 || to > bitmap_size || to < *from || limit <= 0 || *from < id_offset) return OBGPU_INVALID_ARGUMENT;
+  cudaSetDevice(ctx->device);
+  const int64_t span = to - *from;
+  if (span == 0) { *row_count = 0; return OBGPU_SUCCESS; }
+  const int64_t out_n = std::min(limit, span);
+  TempDev tmp(ctx);
+  const size_t o_bytes = 64, o_ids = o_bytes + (((size_t)span + 255) & ~(size_t)255);
+  CUDA_TRY(ctx, tmp.alloc(o_ids + (size_t)out_n * 4));
+  uint8_t *a = (uint8_t *)tmp.p;
+  CUDA_TRY(ctx, cudaMemcpyAsync(a + o_bytes, bitmap + *from, (size_t)span, cudaMemcpyHostToDevice, ctx->stream));
+  // device bitmap is re-based to *from: ids are (i + *from) - id_offset
+  obgpu_bitmap_row_ids_kernel<<<1, kThreads, 0, ctx->stream>>>(a + o_bytes, 0, span, limit, id_offset - *from,
+                                                               (int32_t *)(a + o_ids), (int64_t *)a);
+  CUDA_TRY(ctx, cudaGetLastError());
+  ctx->launches++;
+  int64_t *hc = (int64_t *)ctx->h_pinned;
+  CUDA_TRY(ctx, cudaMemcpyAsync(hc, a, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(row_ids, a + o_ids, (size_t)out_n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  const int64_t n = *hc;
+  *row_count = n;
+  if (n >= limit) *from = row_ids[limit - 1] + id_offset + 1;
+  else *from = to;
+  return OBGPU_SUCCESS;
+}
+
+int obgpu_project_fixed(obgpu_batch *batch, int32_t block, int32_t col, const int32_t *row_ids, int64_t row_cap,
+                        int64_t vec_offset, void *data, int32_t elem_len, uint64_t *nulls, int32_t *has_null) {
+  return run_project_block(batch, block, col, row_ids, row_cap, vec_offset, 0, data, elem_len, nullptr, nulls,
+                           has_null, false);
+}
+
+int obgpu_project_discrete(obgpu_batch *batch, int32_t block, int32_t col, const int32_t *row_ids, int64_t row_cap,
+                           int64_t vec_offset, uint64_t string_base, uint64_t *ptrs, int32_t *lens, uint64_t *nulls,
+                           int32_t *has_null) {
+  return run_project_block(batch, block, col, row_ids, row_cap, vec_offset, string_base, ptrs, 8, lens, nulls,
+                           has_null, true);
+}
+
+}  // extern "C"

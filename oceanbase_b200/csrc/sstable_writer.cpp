@@ -1,0 +1,827 @@
+// Host-side PAX ("ENCODING_ROW_STORE") micro-block writer.
+//
+// Produces reference-format micro-blocks for a forced per-column encoding, following the byte
+// layout the reference's encoder emits (this file is a fresh implementation written against that
+// layout, not a translation of the encoder's control flow):
+//   block assembly      encoding/ob_micro_block_encoder.cpp:499-721 (build_block,
+//                       store_encoding_meta_and_fix_cols), :724-931 (set_row_data_pos, fill_row_data)
+//   fixed column store  encoding/ob_icolumn_encoder.h:122-275 (calc_fix_data_size, store_fix_bits,
+//                       fill_column_store): [ext bits][bit-packed values] as ONE bit stream, then
+//                       byte-aligned fixed-width values
+//   RAW                 encoding/ob_raw_encoder.cpp:96-188 (width choice), :271-291
+//   DICT                encoding/ob_dict_encoder.cpp:84-133,187-276,380-400 (sorted dict, refs)
+//   RLE                 encoding/ob_rle_encoder.cpp:68-120,137-196 (run starts + refs + dict)
+//   INTEGER_BASE_DIFF   encoding/ob_integer_base_diff_encoder.cpp:154-245,267-287
+//   width rules         encoding/ob_encoding_util.cpp:37-97 (get_packing_size, get_int_size,
+//                       get_byte_packed_int_size)
+//   header finalisation blocksstable/ob_imicro_block_writer.cpp:169-204, ob_micro_block_header.cpp:203-233
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/obgpu_scan.h"
+#include "ob_format.h"
+
+namespace {
+
+using namespace obf;
+
+// ---- width rules -------------------------------------------------------------------------------
+int bit_width_of(uint64_t v) { return v == 0 ? 1 : 64 - __builtin_clzll(v); }
+
+// Returns size in bits when *bit_packing, else in bytes.
+int64_t packing_size(bool *bit_packing, uint64_t v, bool enable_bit_packing) {
+  int64_t size = 0;
+  if (enable_bit_packing) {
+    const int64_t bit_size = bit_width_of(v);
+    size = bit_size / 8;
+    const int64_t ext = bit_size % 8;
+    if (ext == 0) {
+      *bit_packing = false;
+    } else if (8 - ext < size / 2 + 1) {
+      size++;
+      *bit_packing = false;
+    } else {
+      *bit_packing = true;
+      size = bit_size;
+    }
+  } else {
+    *bit_packing = false;
+    size = v <= 0xffull ? 1 : v <= 0xffffull ? 2 : v <= 0xffffffffull ? 4 : 8;
+  }
+  return size;
+}
+int64_t int_size_bytes(uint64_t v) { return (bit_width_of(v) + 7) / 8; }
+int64_t byte_packed_int_size(uint64_t v) {
+  return v <= 0xffull ? 1 : v <= 0xffffull ? 2 : v <= 0xffffffffull ? 4 : 8;
+}
+
+// ---- LSB-first bit writer over a zeroed buffer -----------------------------------------------
+inline void put_bits(uint8_t *buf, int64_t pos, int len, uint64_t v) {
+  int64_t done = 0;
+  while (done < len) {
+    const int64_t byte = (pos + done) >> 3;
+    const int off = (pos + done) & 7;
+    const int take = (int)std::min<int64_t>(len - done, 8 - off);
+    buf[byte] |= (uint8_t)(((v >> done) & ((1u << take) - 1u)) << off);
+    done += take;
+  }
+}
+
+struct Buf {
+  std::vector<uint8_t> d;
+  size_t size() const { return d.size(); }
+  uint8_t *grow(size_t n) {
+    const size_t o = d.size();
+    d.resize(o + n, 0);
+    return d.data() + o;
+  }
+};
+
+struct StrRef {
+  const char *p;
+  int64_t len;
+};
+inline int str_cmp(const StrRef &a, const StrRef &b) {
+  const int64_t m = std::min(a.len, b.len);
+  const int c = m > 0 ? memcmp(a.p, b.p, (size_t)m) : 0;
+  if (c != 0) return c;
+  return a.len < b.len ? -1 : (a.len > b.len ? 1 : 0);
+}
+struct StrHash {
+  size_t operator()(const StrRef &s) const {
+    uint64_t h = 1469598103934665603ull;
+    for (int64_t i = 0; i < s.len; ++i) h = (h ^ (uint8_t)s.p[i]) * 1099511628211ull;
+    return (size_t)h;
+  }
+};
+struct StrEq {
+  bool operator()(const StrRef &a, const StrRef &b) const {
+    return a.len == b.len && (a.len == 0 || memcmp(a.p, b.p, (size_t)a.len) == 0);
+  }
+};
+
+struct ColCtx {
+  const obgpu_col_input *in;
+  int sc;  // store class 1 int / 2 uint / 5 string
+  int64_t row_begin, nrows;
+  int64_t null_cnt = 0;
+  bool enable_bp = true;
+  bool is_null(int64_t r) const { return in->is_null && in->is_null[row_begin + r]; }
+  int64_t ival(int64_t r) const { return in->i64[row_begin + r]; }
+  StrRef sval(int64_t r) const {
+    const int64_t a = in->str_off[row_begin + r], b = in->str_off[row_begin + r + 1];
+    return StrRef{in->str_heap + a, b - a};
+  }
+  // value image the reference stores: datum.get_uint64() & INTEGER_MASK_TABLE[type_store_size]
+  uint64_t uval(int64_t r) const {
+    const int ts = type_store_size((uint8_t)in->obj_type);
+    return (uint64_t)ival(r) & low_mask(ts * 8);
+  }
+};
+
+// What a column contributes to the block.
+struct ColOut {
+  ColumnHeader hdr{};
+  bool is_var = false;          // var-length cells live in the row data
+  bool need_ext_in_row = false; // var column with NULLs: ext bits inside each row
+};
+
+// Fixed column store: [ext bits][bit packed] then byte aligned fixed values.
+//   bp_len > 0  : value_of(row) packed bp_len bits;  fix_len > 0 : fix_len bytes per row.
+template <typename ValueOf>
+void fill_column_store(Buf &meta, const ColCtx &c, bool need_ext, int ext_bit, int bp_len,
+                       int fix_len, bool include_null_cells, ValueOf value_of) {
+  const int64_t n = c.nrows;
+  int64_t bits = 0;
+  if (need_ext) bits += (int64_t)ext_bit * n;
+  bits += (int64_t)bp_len * n;
+  const int64_t bits_size = (bits + 7) / 8;
+  uint8_t *buf = meta.grow((size_t)(bits_size + (int64_t)fix_len * n));
+  int64_t pos = 0;
+  if (need_ext) {
+    for (int64_t r = 0; r < n; ++r) {
+      if (c.is_null(r)) put_bits(buf, pos, ext_bit, STORED_NULL);
+      pos += ext_bit;
+    }
+  }
+  if (bp_len > 0) {
+    for (int64_t r = 0; r < n; ++r) {
+      if (include_null_cells || !c.is_null(r)) put_bits(buf, pos, bp_len, value_of(r) & low_mask(bp_len));
+      pos += bp_len;
+    }
+  }
+  if (fix_len > 0) {
+    uint8_t *p = buf + bits_size;
+    for (int64_t r = 0; r < n; ++r) {
+      if (include_null_cells || !c.is_null(r)) {
+        const uint64_t v = value_of(r);
+        memcpy(p, &v, (size_t)std::min(fix_len, 8));
+      }
+      p += fix_len;
+    }
+  }
+}
+
+// ---- dictionary builders ---------------------------------------------------------------------
+struct IntDict {
+  std::vector<uint64_t> values;  // dict order
+  std::vector<uint32_t> refs;    // per row (null -> count)
+  uint64_t max_integer = 0;
+};
+
+void build_int_dict(const ColCtx &c, bool sorted, IntDict &d) {
+  std::unordered_map<uint64_t, uint32_t> first;
+  first.reserve((size_t)std::min<int64_t>(c.nrows, 1 << 16));
+  d.refs.resize((size_t)c.nrows);
+  for (int64_t r = 0; r < c.nrows; ++r) {
+    if (c.is_null(r)) continue;
+    const uint64_t v = c.uval(r);
+    auto it = first.find(v);
+    if (it == first.end()) {
+      first.emplace(v, (uint32_t)d.values.size());
+      d.values.push_back(v);
+      d.max_integer = std::max(d.max_integer, v);
+    }
+  }
+  if (sorted) {
+    const uint8_t t = (uint8_t)c.in->obj_type;
+    const int ts = type_store_size(t);
+    if (c.sc == 1) {
+      const uint64_t sign = 1ull << (ts * 8 - 1);
+      std::sort(d.values.begin(), d.values.end(),
+                [sign](uint64_t a, uint64_t b) { return (a ^ sign) < (b ^ sign); });
+    } else {
+      std::sort(d.values.begin(), d.values.end());
+    }
+    for (uint32_t i = 0; i < d.values.size(); ++i) first[d.values[i]] = i;
+  }
+  const uint32_t cnt = (uint32_t)d.values.size();
+  for (int64_t r = 0; r < c.nrows; ++r) d.refs[(size_t)r] = c.is_null(r) ? cnt : first[c.uval(r)];
+}
+
+struct StrDict {
+  std::vector<StrRef> values;
+  std::vector<uint32_t> refs;
+  int64_t var_data_size = 0;  // sum of distinct lengths
+  int64_t fix_len = -1;       // >= 0 when every distinct value has the same length
+};
+
+void build_str_dict(const ColCtx &c, bool sorted, StrDict &d) {
+  std::unordered_map<StrRef, uint32_t, StrHash, StrEq> first;
+  d.refs.resize((size_t)c.nrows);
+  bool var = false;
+  for (int64_t r = 0; r < c.nrows; ++r) {
+    if (c.is_null(r)) continue;
+    const StrRef s = c.sval(r);
+    if (first.find(s) == first.end()) {
+      first.emplace(s, (uint32_t)d.values.size());
+      d.values.push_back(s);
+      d.var_data_size += s.len;
+      if (!var) {
+        if (d.fix_len < 0) d.fix_len = s.len;
+        else if (d.fix_len != s.len) { d.fix_len = -1; var = true; }
+      }
+    }
+  }
+  if (sorted) {
+    std::sort(d.values.begin(), d.values.end(),
+              [](const StrRef &a, const StrRef &b) { return str_cmp(a, b) < 0; });
+    for (uint32_t i = 0; i < d.values.size(); ++i) first[d.values[i]] = i;
+  }
+  const uint32_t cnt = (uint32_t)d.values.size();
+  for (int64_t r = 0; r < c.nrows; ++r) d.refs[(size_t)r] = c.is_null(r) ? cnt : first[c.sval(r)];
+}
+
+// Writes ObDictMetaHeader + payload; returns pointer offset of the header inside meta.
+size_t store_int_dict_meta(Buf &meta, const ColCtx &c, const IntDict &d, bool sorted) {
+  const int64_t data_size = c.enable_bp ? int_size_bytes(d.max_integer) : byte_packed_int_size(d.max_integer);
+  const size_t at = meta.size();
+  uint8_t *p = meta.grow(sizeof(DictMetaHeader) + (size_t)data_size * d.values.size());
+  DictMetaHeader h{};
+  h.count_ = (uint32_t)d.values.size();
+  h.data_size_ = (uint16_t)data_size;
+  h.attr_ = DICT_FIX_LENGTH | (sorted ? DICT_IS_SORTED : 0);
+  memcpy(p, &h, sizeof(h));
+  p += sizeof(h);
+  for (uint64_t v : d.values) {
+    memcpy(p, &v, (size_t)data_size);
+    p += data_size;
+  }
+  return at;
+}
+
+size_t store_str_dict_meta(Buf &meta, const StrDict &d) {
+  const size_t at = meta.size();
+  const size_t cnt = d.values.size();
+  DictMetaHeader h{};
+  h.count_ = (uint32_t)cnt;
+  const bool var = d.fix_len < 0 || d.fix_len > 0xffff;
+  if (!var) {
+    uint8_t *p = meta.grow(sizeof(h) + (size_t)d.fix_len * cnt);
+    h.data_size_ = (uint16_t)d.fix_len;
+    h.attr_ = DICT_FIX_LENGTH | DICT_IS_SORTED;  // need_sort_ => sorted attr on the fixed path
+    memcpy(p, &h, sizeof(h));
+    p += sizeof(h);
+    for (const StrRef &s : d.values) {
+      memcpy(p, s.p, (size_t)s.len);
+      p += s.len;
+    }
+  } else {
+    const int idx_byte = d.var_data_size <= 0xff ? 1 : (d.var_data_size <= 0xffff ? 2 : 4);
+    const size_t idx_bytes = cnt > 0 ? (cnt - 1) * (size_t)idx_byte : 0;
+    uint8_t *p = meta.grow(sizeof(h) + idx_bytes + (size_t)d.var_data_size);
+    h.data_size_ = (uint16_t)idx_byte;  // index_byte_
+    h.attr_ = 0;                        // var dict of strings: stored sorted, attr not set
+    memcpy(p, &h, sizeof(h));
+    uint8_t *idx = p + sizeof(h);
+    uint8_t *data = idx + idx_bytes;
+    int64_t off = 0;
+    for (size_t i = 0; i < cnt; ++i) {
+      if (i > 0) {
+        const uint64_t o = (uint64_t)off;
+        memcpy(idx + (i - 1) * (size_t)idx_byte, &o, (size_t)idx_byte);
+      }
+      memcpy(data + off, d.values[i].p, (size_t)d.values[i].len);
+      off += d.values[i].len;
+    }
+  }
+  return at;
+}
+
+struct BlockBuilder {
+  const obgpu_col_input *cols;
+  int32_t ncol;
+  int32_t rowkey_cnt;
+  int64_t row_begin, nrows;
+  std::vector<ColCtx> ctx;
+  std::vector<ColOut> out;
+  Buf meta;
+  int ext_bit = 0;
+
+  int encode_raw(int i);
+  int encode_dict(int i);
+  int encode_rle(int i);
+  int encode_base_diff(int i);
+  int build(std::vector<uint8_t> &block);
+};
+
+int BlockBuilder::encode_raw(int i) {
+  ColCtx &c = ctx[i];
+  ColOut &o = out[i];
+  o.hdr.type_ = COL_RAW;
+  const bool has_null = c.null_cnt > 0;
+  if (c.sc == 1 || c.sc == 2) {
+    uint64_t max_integer = 0;
+    for (int64_t r = 0; r < nrows; ++r)
+      if (!c.is_null(r)) max_integer = std::max(max_integer, c.uval(r));
+    bool bp = false;
+    const int64_t size = packing_size(&bp, max_integer, c.enable_bp);
+    // The reference turns the column into a var-stored one when NULLs dominate
+    // (ob_raw_encoder.cpp:106-110,150-155); integer var store is outside this writer's scope.
+    if (bp ? size * c.null_cnt > nrows * 2 * 8 : size * c.null_cnt > nrows * 2) return OBGPU_NOT_SUPPORTED;
+    o.hdr.attr_ |= ATTR_FIX_LENGTH;
+    if (has_null) o.hdr.attr_ |= ATTR_HAS_EXTEND_VALUE;
+    if (bp) o.hdr.attr_ |= ATTR_BIT_PACKING;
+    o.hdr.offset_ = (uint32_t)meta.size();
+    o.hdr.length_ = (uint32_t)size;
+    fill_column_store(meta, c, has_null, ext_bit, bp ? (int)size : 0, bp ? 0 : (int)size, false,
+                      [&](int64_t r) { return c.uval(r); });
+    return OBGPU_SUCCESS;
+  }
+  // string class
+  int64_t fix_len = -1;
+  bool var = false;
+  for (int64_t r = 0; r < nrows && !var; ++r) {
+    if (c.is_null(r)) continue;
+    const int64_t l = c.sval(r).len;
+    if (fix_len < 0) fix_len = l;
+    else if (fix_len != l) var = true;
+  }
+  if (!var && fix_len >= 0 && fix_len * c.null_cnt > nrows * 2) var = true;
+  if (fix_len < 0) var = true;  // all NULL
+  if (var || fix_len == 0) {
+    o.is_var = true;
+    o.need_ext_in_row = has_null;
+    if (has_null) o.hdr.attr_ |= ATTR_HAS_EXTEND_VALUE;
+    // offset_/length_ are set when the row data layout is fixed (set_data_pos)
+    return OBGPU_SUCCESS;
+  }
+  o.hdr.attr_ |= ATTR_FIX_LENGTH;
+  if (has_null) o.hdr.attr_ |= ATTR_HAS_EXTEND_VALUE;
+  o.hdr.offset_ = (uint32_t)meta.size();
+  o.hdr.length_ = (uint32_t)fix_len;
+  {
+    const int64_t bits_size = has_null ? ((int64_t)ext_bit * nrows + 7) / 8 : 0;
+    uint8_t *buf = meta.grow((size_t)(bits_size + fix_len * nrows));
+    if (has_null)
+      for (int64_t r = 0; r < nrows; ++r)
+        if (c.is_null(r)) put_bits(buf, r * ext_bit, ext_bit, STORED_NULL);
+    uint8_t *p = buf + bits_size;
+    for (int64_t r = 0; r < nrows; ++r, p += fix_len)
+      if (!c.is_null(r)) memcpy(p, c.sval(r).p, (size_t)fix_len);
+  }
+  return OBGPU_SUCCESS;
+}
+
+int BlockBuilder::encode_dict(int i) {
+  ColCtx &c = ctx[i];
+  ColOut &o = out[i];
+  o.hdr.type_ = COL_DICT;
+  const size_t meta_at = meta.size();
+  std::vector<uint32_t> *refs = nullptr;
+  IntDict idict;
+  StrDict sdict;
+  uint32_t cnt = 0;
+  if (c.sc == 5) {
+    build_str_dict(c, /*sorted=*/true, sdict);
+    store_str_dict_meta(meta, sdict);
+    refs = &sdict.refs;
+    cnt = (uint32_t)sdict.values.size();
+  } else {
+    build_int_dict(c, /*sorted=*/true, idict);
+    store_int_dict_meta(meta, c, idict, true);
+    refs = &idict.refs;
+    cnt = (uint32_t)idict.values.size();
+  }
+  if (cnt == 0) return OBGPU_NOT_SUPPORTED;  // all-NULL column: the reference picks CONST
+  const uint64_t max_ref = c.null_cnt > 0 ? cnt : cnt - 1;
+  bool bp = false;
+  const int64_t size = packing_size(&bp, max_ref, c.enable_bp);
+  o.hdr.attr_ |= ATTR_FIX_LENGTH;
+  if (bp) o.hdr.attr_ |= ATTR_BIT_PACKING;
+  o.hdr.offset_ = (uint32_t)meta_at;
+  o.hdr.length_ = (uint32_t)(meta.size() - meta_at);
+  reinterpret_cast<DictMetaHeader *>(meta.d.data() + meta_at)->row_ref_size_ = (uint8_t)size;
+  const std::vector<uint32_t> &rf = *refs;
+  fill_column_store(meta, c, false, ext_bit, bp ? (int)size : 0, bp ? 0 : (int)size, true,
+                    [&](int64_t r) { return (uint64_t)rf[(size_t)r]; });
+  return OBGPU_SUCCESS;
+}
+
+int BlockBuilder::encode_rle(int i) {
+  ColCtx &c = ctx[i];
+  ColOut &o = out[i];
+  o.hdr.type_ = COL_RLE;
+  IntDict idict;
+  StrDict sdict;
+  const std::vector<uint32_t> *refs;
+  uint32_t cnt;
+  if (c.sc == 5) {
+    build_str_dict(c, false, sdict);
+    refs = &sdict.refs;
+    cnt = (uint32_t)sdict.values.size();
+  } else {
+    build_int_dict(c, false, idict);
+    refs = &idict.refs;
+    cnt = (uint32_t)idict.values.size();
+  }
+  if (cnt == 0) return OBGPU_NOT_SUPPORTED;
+  std::vector<uint32_t> run_row, run_ref;
+  for (int64_t r = 0; r < nrows; ++r) {
+    if (r == 0 || (*refs)[(size_t)r] != (*refs)[(size_t)r - 1]) {
+      run_row.push_back((uint32_t)r);
+      run_ref.push_back((*refs)[(size_t)r]);
+    }
+  }
+  const uint64_t max_ref = c.null_cnt > 0 ? cnt : cnt - 1;
+  const int row_id_byte = (int)byte_packed_int_size(run_row.back());
+  const int ref_byte = (int)byte_packed_int_size(max_ref);
+  const size_t runs = run_row.size();
+  // ObRLEDecoder keeps count * row_id_byte in an int16 (ob_rle_decoder.h:193): stay inside it.
+  if ((int64_t)runs * row_id_byte > 32767) return OBGPU_NOT_SUPPORTED;
+  const size_t meta_at = meta.size();
+  const size_t head = sizeof(RLEMetaHeader) + runs * (size_t)(row_id_byte + ref_byte);
+  uint8_t *p = meta.grow(head);
+  RLEMetaHeader h{};
+  h.attr_ = (uint8_t)((row_id_byte & 7) | ((ref_byte & 7) << 3));
+  h.count_ = (uint32_t)runs;
+  h.offset_ = (uint32_t)head;
+  memcpy(p, &h, sizeof(h));
+  uint8_t *rid = p + sizeof(h);
+  uint8_t *rrf = rid + runs * (size_t)row_id_byte;
+  for (size_t k = 0; k < runs; ++k) {
+    memcpy(rid + k * (size_t)row_id_byte, &run_row[k], (size_t)row_id_byte);
+    memcpy(rrf + k * (size_t)ref_byte, &run_ref[k], (size_t)ref_byte);
+  }
+  if (c.sc == 5) store_str_dict_meta(meta, sdict);
+  else store_int_dict_meta(meta, c, idict, false);
+  if (c.sc == 5 && !(sdict.fix_len < 0 || sdict.fix_len > 0xffff)) {
+    // unsorted fixed-length string dict: clear the sorted attr set by the shared helper
+    reinterpret_cast<DictMetaHeader *>(meta.d.data() + meta_at + head)->attr_ = DICT_FIX_LENGTH;
+  }
+  o.hdr.attr_ = 0;
+  o.hdr.offset_ = (uint32_t)meta_at;
+  o.hdr.length_ = (uint32_t)(meta.size() - meta_at);
+  return OBGPU_SUCCESS;
+}
+
+int BlockBuilder::encode_base_diff(int i) {
+  ColCtx &c = ctx[i];
+  ColOut &o = out[i];
+  if (c.sc != 1 && c.sc != 2) return OBGPU_INVALID_ARGUMENT;
+  const uint8_t t = (uint8_t)c.in->obj_type;
+  const int ts = type_store_size(t);
+  bool any = false;
+  int64_t smin = INT64_MAX, smax = INT64_MIN;
+  uint64_t umin = UINT64_MAX, umax = 0;
+  auto to_signed = [&](uint64_t v) {
+    const uint64_t rev = ~low_mask(ts * 8);
+    if (rev != 0 && (v & (rev >> 1))) v |= rev;
+    return (int64_t)v;
+  };
+  for (int64_t r = 0; r < nrows; ++r) {
+    if (c.is_null(r)) continue;
+    any = true;
+    if (c.sc == 1) {
+      const int64_t v = to_signed(c.uval(r));
+      smin = std::min(smin, v);
+      smax = std::max(smax, v);
+    } else {
+      const uint64_t v = c.uval(r);
+      umin = std::min(umin, v);
+      umax = std::max(umax, v);
+    }
+  }
+  const uint64_t delta = !any ? 0 : (c.sc == 1 ? (uint64_t)smax - (uint64_t)smin : umax - umin);
+  if (delta == 0) return encode_raw(i);  // "not suitable for integer base diff" -> RAW
+  const uint64_t base = c.sc == 1 ? (uint64_t)smin : umin;
+  bool bp = false;
+  const int64_t size = packing_size(&bp, delta, true);
+  o.hdr.type_ = COL_INTEGER_BASE_DIFF;
+  o.hdr.attr_ |= ATTR_FIX_LENGTH;
+  if (bp) o.hdr.attr_ |= ATTR_BIT_PACKING;
+  const bool has_null = c.null_cnt > 0;
+  if (has_null) o.hdr.attr_ |= ATTR_HAS_EXTEND_VALUE;
+  const size_t meta_at = meta.size();
+  uint8_t *p = meta.grow(sizeof(IntegerBaseDiffHeader) + (size_t)ts);
+  IntegerBaseDiffHeader h{0, (uint8_t)size};
+  memcpy(p, &h, sizeof(h));
+  memcpy(p + sizeof(h), &base, (size_t)ts);
+  o.hdr.offset_ = (uint32_t)meta_at;
+  o.hdr.length_ = (uint32_t)(meta.size() - meta_at);
+  fill_column_store(meta, c, has_null, ext_bit, bp ? (int)size : 0, bp ? 0 : (int)size, false,
+                    [&](int64_t r) {
+                      return c.sc == 1 ? (uint64_t)to_signed(c.uval(r)) - base : c.uval(r) - base;
+                    });
+  return OBGPU_SUCCESS;
+}
+
+int BlockBuilder::build(std::vector<uint8_t> &block) {
+  if (ncol <= 0 || nrows <= 0 || nrows > 0x7fffffff || rowkey_cnt < 0 || rowkey_cnt > ncol)
+    return OBGPU_INVALID_ARGUMENT;
+  ctx.resize((size_t)ncol);
+  out.resize((size_t)ncol);
+  int64_t original = 0;
+  for (int i = 0; i < ncol; ++i) {
+    ColCtx &c = ctx[(size_t)i];
+    c.in = &cols[i];
+    c.sc = store_class_of((uint8_t)cols[i].obj_type);
+    c.row_begin = row_begin;
+    c.nrows = nrows;
+    c.enable_bp = !cols[i].byte_packing_only;
+    if (c.sc == 0) return OBGPU_NOT_SUPPORTED;
+    if ((c.sc == 5 && (!cols[i].str_heap || !cols[i].str_off)) || (c.sc != 5 && !cols[i].i64))
+      return OBGPU_INVALID_ARGUMENT;
+    for (int64_t r = 0; r < nrows; ++r) {
+      if (c.is_null(r)) c.null_cnt++;
+      else original += c.sc == 5 ? c.sval(r).len : datum_len_of((uint8_t)cols[i].obj_type);
+    }
+    if (c.null_cnt > 0) ext_bit = 1;  // ob_micro_block_encoder.cpp:507-517 (no NOP in major SSTables)
+  }
+  for (int i = 0; i < ncol; ++i) {
+    out[(size_t)i].hdr.obj_type_ = (uint8_t)cols[i].obj_type;
+    int ret;
+    switch (cols[i].encoding) {
+      case OBGPU_ENC_RAW: ret = encode_raw(i); break;
+      case OBGPU_ENC_DICT: ret = encode_dict(i); break;
+      case OBGPU_ENC_RLE: ret = encode_rle(i); break;
+      case OBGPU_ENC_INTEGER_BASE_DIFF: ret = encode_base_diff(i); break;
+      default: ret = OBGPU_NOT_SUPPORTED;
+    }
+    if (ret != OBGPU_SUCCESS) return ret;
+  }
+  // ---- row data: var-stored columns (set_row_data_pos / fill_row_data) ------------------------
+  std::vector<int> var_cols;
+  int64_t ext_bits_in_row = 0;
+  for (int i = 0; i < ncol; ++i) {
+    if (!out[(size_t)i].is_var) continue;
+    var_cols.push_back(i);
+    if (out[(size_t)i].need_ext_in_row) {
+      out[(size_t)i].hdr.extend_value_index_ = (uint32_t)ext_bits_in_row;
+      ext_bits_in_row += ext_bit;
+    }
+  }
+  const int64_t fix_data_size = (ext_bits_in_row + 7) / 8;
+  for (size_t k = 0; k < var_cols.size(); ++k) {
+    ColumnHeader &h = out[(size_t)var_cols[k]].hdr;
+    h.offset_ = (uint32_t)fix_data_size;  // row_offset_
+    h.length_ = (uint32_t)k;              // index among the var columns
+  }
+  if (!var_cols.empty()) out[(size_t)var_cols.back()].hdr.attr_ |= ATTR_LAST_VAR_FIELD;
+
+  const uint32_t header_size = MICRO_HEADER_FIXED_SIZE;
+  const size_t col_hdr_size = sizeof(ColumnHeader) * (size_t)ncol;
+  const size_t meta_off = header_size + col_hdr_size;
+  const size_t row_data_off = meta_off + meta.size();
+  Buf rows;
+  std::vector<uint64_t> row_index;
+  if (!var_cols.empty()) {
+    const size_t nv = var_cols.size();
+    row_index.push_back(0);
+    std::vector<int64_t> lens(nv);
+    for (int64_t r = 0; r < nrows; ++r) {
+      int64_t var_size = 0;
+      int col_idx_byte = 0;
+      for (size_t k = 0; k < nv; ++k) {
+        const ColCtx &c = ctx[(size_t)var_cols[k]];
+        lens[k] = c.is_null(r) ? 0 : c.sval(r).len;
+        if (k > 0 && k == nv - 1) col_idx_byte = var_size <= 0xff ? 1 : (var_size <= 0xffff ? 2 : 4);
+        var_size += lens[k];
+      }
+      const int64_t row_size = fix_data_size + var_size + (col_idx_byte > 0 ? 1 : 0) +
+                               (int64_t)col_idx_byte * (int64_t)(nv - 1);
+      uint8_t *data = rows.grow((size_t)row_size);
+      uint8_t *var = data + fix_data_size;
+      uint8_t *idx = nullptr;
+      if (col_idx_byte > 0) {
+        *var = (uint8_t)col_idx_byte;
+        idx = var + 1;
+        var += 1 + (size_t)col_idx_byte * (nv - 1);
+      }
+      int64_t off = 0;
+      for (size_t k = 0; k < nv; ++k) {
+        const ColCtx &c = ctx[(size_t)var_cols[k]];
+        if (k > 0) {
+          const uint64_t o = (uint64_t)off;
+          memcpy(idx + (k - 1) * (size_t)col_idx_byte, &o, (size_t)col_idx_byte);
+        }
+        if (c.is_null(r)) {
+          put_bits(data, out[(size_t)var_cols[k]].hdr.extend_value_index_, ext_bit, STORED_NULL);
+        } else if (lens[k] > 0) {
+          memcpy(var + off, c.sval(r).p, (size_t)lens[k]);
+        }
+        off += lens[k];
+      }
+      row_index.push_back((uint64_t)rows.size());
+    }
+  }
+  int row_index_byte = 0;
+  if (!var_cols.empty()) row_index_byte = row_index.back() > 0xffff ? 4 : 2;
+  const size_t total = row_data_off + rows.size() + row_index.size() * (size_t)row_index_byte;
+  block.assign(total, 0);
+  uint8_t *b = block.data();
+  for (int i = 0; i < ncol; ++i)
+    memcpy(b + header_size + sizeof(ColumnHeader) * (size_t)i, &out[(size_t)i].hdr, sizeof(ColumnHeader));
+  if (meta.size()) memcpy(b + meta_off, meta.d.data(), meta.size());
+  if (rows.size()) memcpy(b + row_data_off, rows.d.data(), rows.size());
+  for (size_t k = 0; k < row_index.size(); ++k)
+    memcpy(b + row_data_off + rows.size() + k * (size_t)row_index_byte, &row_index[k], (size_t)row_index_byte);
+
+  MicroBlockHeader h{};
+  h.magic_ = MICRO_BLOCK_HEADER_MAGIC;
+  h.version_ = MICRO_BLOCK_HEADER_VERSION;
+  h.header_size_ = header_size;
+  h.column_count_ = (uint16_t)ncol;
+  h.rowkey_column_count_ = (uint16_t)rowkey_cnt;
+  h.flag16_ = (uint16_t)(1u << 2);  // all_lob_in_row_ = 1, no column checksum
+  h.row_count_ = (uint32_t)nrows;
+  h.row_store_type_ = ENCODING_ROW_STORE;
+  h.opt_ = (uint8_t)((row_index_byte & 7) | ((ext_bit & 7) << 3));
+  h.opt2_ = (uint16_t)var_cols.size();
+  h.row_data_offset_ = (uint32_t)row_data_off;
+  h.original_length_ = (int32_t)std::min<int64_t>(original, INT32_MAX);
+  h.max_merged_trans_version_ = 0;
+  h.data_length_ = (int32_t)(total - header_size);
+  h.data_zlength_ = h.data_length_;
+  h.data_checksum_ = 0;
+  h.column_checksums_ptr_ = 0;
+  // payload checksum: ob_crc64_sse42 == CRC-32C (Castagnoli) with seed 0 and no final xor
+  {
+    uint64_t crc = 0;
+    const uint8_t *p = b + header_size;
+    size_t len = total - header_size;
+    static uint32_t tab[256];
+    static std::atomic<int> tab_ready{0};
+    if (!tab_ready.load(std::memory_order_acquire)) {
+      uint32_t t[256];
+      for (uint32_t n = 0; n < 256; ++n) {
+        uint32_t cc = n;
+        for (int k = 0; k < 8; ++k) cc = (cc & 1) ? 0x82f63b78u ^ (cc >> 1) : cc >> 1;
+        t[n] = cc;
+      }
+      memcpy(tab, t, sizeof(t));
+      tab_ready.store(1, std::memory_order_release);
+    }
+    uint32_t c32 = (uint32_t)crc;
+    for (size_t k = 0; k < len; ++k) c32 = tab[(c32 ^ p[k]) & 0xff] ^ (c32 >> 8);
+    h.data_checksum_ = (int64_t)(uint64_t)c32;
+  }
+  // header checksum: ob_micro_block_header.cpp:203-233
+  {
+    int16_t cs = 0;
+    auto f64 = [&](int64_t v) { for (int k = 0; k < 4; ++k) cs = (int16_t)(cs ^ ((v >> (k * 16)) & 0xFFFF)); };
+    auto f32 = [&](int32_t v) { for (int k = 0; k < 2; ++k) cs = (int16_t)(cs ^ ((v >> (k * 16)) & 0xFFFF)); };
+    cs = (int16_t)(cs ^ h.magic_);
+    cs = (int16_t)(cs ^ h.version_);
+    cs = (int16_t)(cs ^ (int16_t)h.row_store_type_);
+    cs = (int16_t)(cs ^ (int16_t)h.opt_);
+    f32(h.column_count_);
+    f32(h.rowkey_column_count_);
+    f32(h.flag16_ & 1);
+    f32(h.opt2_);
+    f64(h.header_size_);
+    f64(h.row_count_);
+    f64(h.row_data_offset_);
+    f64(h.original_length_);
+    f64(h.max_merged_trans_version_);
+    f64(h.data_length_);
+    f64(h.data_zlength_);
+    f64(h.data_checksum_);
+    h.header_checksum_ = cs;
+  }
+  memcpy(b, &h, sizeof(h));
+  return OBGPU_SUCCESS;
+}
+
+int encode_one(const obgpu_col_input *cols, int32_t ncol, int32_t rowkey_cnt, int64_t row_begin,
+               int64_t nrows, std::vector<uint8_t> &block) {
+  BlockBuilder bb;
+  bb.cols = cols;
+  bb.ncol = ncol;
+  bb.rowkey_cnt = rowkey_cnt;
+  bb.row_begin = row_begin;
+  bb.nrows = nrows;
+  return bb.build(block);
+}
+
+}  // namespace
+
+extern "C" {
+
+int64_t obgpu_writer_block_bound(const obgpu_col_input *cols, int32_t n_cols, int64_t row_begin,
+                                 int64_t nrows) {
+  if (!cols || n_cols <= 0 || nrows <= 0) return -1;
+  int64_t b = 64 + 16 * (int64_t)n_cols + 64;
+  for (int i = 0; i < n_cols; ++i) {
+    if (store_class_of((uint8_t)cols[i].obj_type) == 5) {
+      if (!cols[i].str_off) return -1;
+      const int64_t bytes = cols[i].str_off[row_begin + nrows] - cols[i].str_off[row_begin];
+      b += 2 * bytes + nrows * 16 + 64;
+    } else {
+      b += nrows * 21 + 64;
+    }
+  }
+  return b;
+}
+
+int obgpu_writer_encode_block(const obgpu_col_input *cols, int32_t n_cols, int32_t rowkey_col_cnt,
+                              int64_t row_begin, int64_t nrows, void *out, int64_t out_cap,
+                              int64_t *out_size) {
+  if (!cols || !out_size) return OBGPU_INVALID_ARGUMENT;
+  std::vector<uint8_t> block;
+  const int ret = encode_one(cols, n_cols, rowkey_col_cnt, row_begin, nrows, block);
+  if (ret != OBGPU_SUCCESS) return ret;
+  *out_size = (int64_t)block.size();
+  if (!out) return OBGPU_SUCCESS;
+  if ((int64_t)block.size() > out_cap) return OBGPU_BUF_NOT_ENOUGH;
+  memcpy(out, block.data(), block.size());
+  return OBGPU_SUCCESS;
+}
+
+struct obgpu_table_image {
+  std::vector<std::vector<uint8_t>> blocks;
+  std::vector<int64_t> offs;
+  int64_t image_size = 0;
+  int32_t align = 16;
+  int nt = 1;
+};
+
+int obgpu_writer_encode_table(const obgpu_col_input *cols, int32_t n_cols, int32_t rowkey_col_cnt,
+                              int64_t total_rows, int64_t rows_per_block, int32_t align,
+                              int32_t n_threads, obgpu_table_image **out) {
+  if (!cols || total_rows <= 0 || rows_per_block <= 0 || !out) return OBGPU_INVALID_ARGUMENT;
+  if (align < 16 || (align & (align - 1)) != 0) return OBGPU_INVALID_ARGUMENT;
+  const int64_t nb64 = (total_rows + rows_per_block - 1) / rows_per_block;
+  if (nb64 > INT32_MAX) return OBGPU_SIZE_OVERFLOW;
+  const int32_t nb = (int32_t)nb64;
+  obgpu_table_image *img = new (std::nothrow) obgpu_table_image();
+  if (!img) return OBGPU_ALLOCATE_MEMORY_FAILED;
+  img->blocks.resize((size_t)nb);
+  int nt = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+  nt = std::max(1, std::min(nt, nb));
+  img->nt = nt;
+  img->align = align;
+  std::atomic<int32_t> next{0};
+  std::atomic<int> err{OBGPU_SUCCESS};
+  auto work = [&]() {
+    for (;;) {
+      const int32_t b = next.fetch_add(1);
+      if (b >= nb || err.load() != OBGPU_SUCCESS) break;
+      const int64_t rb = (int64_t)b * rows_per_block;
+      const int64_t n = std::min(rows_per_block, total_rows - rb);
+      const int r = encode_one(cols, n_cols, rowkey_col_cnt, rb, n, img->blocks[(size_t)b]);
+      if (r != OBGPU_SUCCESS) err.store(r);
+    }
+  };
+  std::vector<std::thread> th;
+  for (int t = 1; t < nt; ++t) th.emplace_back(work);
+  work();
+  for (auto &t : th) t.join();
+  if (err.load() != OBGPU_SUCCESS) {
+    delete img;
+    return err.load();
+  }
+  int64_t pos = 0;
+  img->offs.resize((size_t)nb);
+  for (int32_t b = 0; b < nb; ++b) {
+    img->offs[(size_t)b] = pos;
+    pos += ((int64_t)img->blocks[(size_t)b].size() + align - 1) / align * align;
+  }
+  img->image_size = pos;
+  *out = img;
+  return OBGPU_SUCCESS;
+}
+
+int obgpu_table_image_info(const obgpu_table_image *img, int64_t *image_size, int32_t *n_blocks) {
+  if (!img) return OBGPU_INVALID_ARGUMENT;
+  if (image_size) *image_size = img->image_size;
+  if (n_blocks) *n_blocks = (int32_t)img->blocks.size();
+  return OBGPU_SUCCESS;
+}
+
+int obgpu_table_image_export(const obgpu_table_image *img, void *image, int64_t image_cap,
+                             int64_t *offsets, int64_t *sizes, int32_t tables_cap) {
+  if (!img || !image || !offsets || !sizes) return OBGPU_INVALID_ARGUMENT;
+  const int32_t nb = (int32_t)img->blocks.size();
+  if (image_cap < img->image_size || tables_cap < nb) return OBGPU_BUF_NOT_ENOUGH;
+  const size_t align = (size_t)img->align;
+  std::atomic<int32_t> nx{0};
+  auto copy = [&]() {
+    for (;;) {
+      const int32_t b = nx.fetch_add(1);
+      if (b >= nb) break;
+      uint8_t *dst = (uint8_t *)image + img->offs[(size_t)b];
+      const size_t sz = img->blocks[(size_t)b].size();
+      memcpy(dst, img->blocks[(size_t)b].data(), sz);
+      const size_t padded = (sz + align - 1) / align * align;
+      if (padded > sz) memset(dst + sz, 0, padded - sz);
+      offsets[b] = img->offs[(size_t)b];
+      sizes[b] = (int64_t)sz;
+    }
+  };
+  std::vector<std::thread> th2;
+  for (int t = 1; t < img->nt; ++t) th2.emplace_back(copy);
+  copy();
+  for (auto &t : th2) t.join();
+  return OBGPU_SUCCESS;
+}
+
+void obgpu_table_image_free(obgpu_table_image *img) { delete img; }
+
+}  // extern "C"

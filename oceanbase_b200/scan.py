@@ -1,0 +1,299 @@
+"""Host-side mirror of the scan operator surface over the C-ABI.
+
+Names follow the reference: a *white filter* is sql::ObWhiteFilterExecutor (one column, one
+ObWhiteFilterOperatorType, constants); And / Or are the logic nodes of the
+ObPushdownFilterExecutor tree (sql/engine/basic/ob_pushdown_filter.h:690-934); a PageBatch is what
+ObSSTableRowScanner feeds block by block to ObIMicroBlockReader::init; ScanResult holds what
+ObMicroBlockDecoder::get_rows would have written into the ObExpr vectors, dense over the batch.
+"""
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Union
+
+import numpy as np
+
+from . import capi
+from .capi import lib, check
+
+
+# ---- filter tree ---------------------------------------------------------------------------------
+@dataclass
+class White:
+    col: int
+    op: int
+    params: Sequence = ()     # ints, bytes, or None (NULL constant)
+
+
+@dataclass
+class And:
+    children: Sequence
+
+
+@dataclass
+class Or:
+    children: Sequence
+
+
+FilterExpr = Union[White, And, Or]
+
+
+def flatten_filter(expr: Optional[FilterExpr], node_cls=capi.FilterNode, param_cls=capi.FilterParam,
+                   filter_cls=capi.Filter):
+    """Post-order flattening (root last). Returns (filter_struct, keepalive) or (None, None)."""
+    if expr is None:
+        return None, None
+    nodes, params, keep = [], [], []
+
+    def visit(e):
+        if isinstance(e, White):
+            nd = node_cls()
+            nd.kind, nd.op, nd.col = capi.NODE_WHITE, e.op, e.col
+            nd.param_begin, nd.n_params, nd.n_children = len(params), len(e.params), 0
+            for v in e.params:
+                p = param_cls()
+                if v is None:
+                    p.is_null = 1
+                elif isinstance(v, (bytes, bytearray)):
+                    b = bytes(v)
+                    keep.append(b)
+                    p.ptr, p.len = b, len(b)
+                else:
+                    iv = int(v)
+                    if iv >= 1 << 63:
+                        iv -= 1 << 64
+                    p.i64 = iv
+                params.append(p)
+            nodes.append(nd)
+        else:
+            for c in e.children:
+                visit(c)
+            nd = node_cls()
+            nd.kind = capi.NODE_AND if isinstance(e, And) else capi.NODE_OR
+            nd.n_children = len(e.children)
+            nodes.append(nd)
+
+    visit(expr)
+    node_arr = (node_cls * len(nodes))(*nodes)
+    param_arr = (param_cls * max(len(params), 1))(*params)
+    f = filter_cls()
+    f.nodes, f.n_nodes = node_arr, len(nodes)
+    f.params, f.n_params = param_arr, len(params)
+    return f, (node_arr, param_arr, keep)
+
+
+# ---- context / batch / result ----------------------------------------------------------------------
+class ScanContext:
+    """obgpu_ctx: one per worker thread (device + stream)."""
+
+    def __init__(self, device: int = 0, stream: Optional[int] = None):
+        self._h = C.c_void_p()
+        code = lib.obgpu_ctx_create(device, C.byref(self._h))
+        if code != capi.OB_SUCCESS:
+            raise capi.ObGpuError(code, "obgpu_ctx_create", "no usable CUDA device; there is no CPU fallback")
+        self.device = device
+        if stream is not None:
+            self.set_stream(stream)
+
+    def set_stream(self, cuda_stream_ptr: Optional[int]):
+        check(lib.obgpu_ctx_set_stream(self._h, C.c_void_p(cuda_stream_ptr or 0)), "obgpu_ctx_set_stream", self._h)
+
+    def synchronize(self):
+        check(lib.obgpu_ctx_synchronize(self._h), "obgpu_ctx_synchronize", self._h)
+
+    @property
+    def launch_count(self) -> int:
+        return lib.obgpu_ctx_launch_count(self._h)
+
+    def last_error(self) -> str:
+        return (lib.obgpu_ctx_last_error(self._h) or b"").decode()
+
+    def open_batch(self, table, device_image_ptr: Optional[int] = None) -> "PageBatch":
+        return PageBatch(self, table, device_image_ptr)
+
+    def bitmap_to_row_ids(self, bitmap: np.ndarray, start: int, to: int, limit: int, id_offset: int = 0):
+        """common::ObBitmap::get_row_ids. Returns (row_ids, next_from)."""
+        bm = np.ascontiguousarray(bitmap, dtype=np.uint8)
+        out = np.zeros(max(min(limit, max(to - start, 0)), 1), dtype=np.int32)
+        frm, cnt = C.c_int64(start), C.c_int64(0)
+        check(lib.obgpu_bitmap_to_row_ids(self._h, bm.ctypes.data, bm.size, C.byref(frm), to, limit, id_offset,
+                                          out.ctypes.data, C.byref(cnt)), "obgpu_bitmap_to_row_ids", self._h)
+        return out[:cnt.value].copy(), frm.value
+
+    def close(self):
+        if self._h:
+            lib.obgpu_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class PageBatch:
+    """obgpu_batch: N micro-blocks resident in HBM."""
+
+    def __init__(self, ctx: ScanContext, table, device_image_ptr: Optional[int] = None):
+        self.ctx = ctx
+        self.table = table
+        self._h = C.c_void_p()
+        img = table.image
+        offs = np.ascontiguousarray(table.offsets, dtype=np.int64)
+        sizes = np.ascontiguousarray(table.sizes, dtype=np.int64)
+        if device_image_ptr is None:
+            code = lib.obgpu_batch_open(ctx._h, img.ctypes.data, img.size, offs.ctypes.data, sizes.ctypes.data,
+                                        len(offs), 0, None, C.byref(self._h))
+        else:
+            code = lib.obgpu_batch_open(ctx._h, C.c_void_p(device_image_ptr), img.size, offs.ctypes.data,
+                                        sizes.ctypes.data, len(offs), 1, img.ctypes.data, C.byref(self._h))
+        check(code, "obgpu_batch_open", ctx._h)
+        self.n_blocks = len(offs)
+        tr = C.c_int64(0)
+        check(lib.obgpu_batch_total_rows(self._h, C.byref(tr)), "obgpu_batch_total_rows", ctx._h)
+        self.total_rows = tr.value
+
+    def block_info(self, i):
+        rc, cc = C.c_int64(0), C.c_int32(0)
+        check(lib.obgpu_batch_block_info(self._h, i, C.byref(rc), C.byref(cc)), "obgpu_batch_block_info", self.ctx._h)
+        return rc.value, cc.value
+
+    def scan(self, filter: Optional[FilterExpr], proj_cols: Sequence[int], want_row_ids=False, string_base=0,
+             max_selected_rows=0) -> "ScanResult":
+        f, keep = flatten_filter(filter)
+        proj = (C.c_int32 * max(len(proj_cols), 1))(*proj_cols)
+        spec = capi.ScanSpec()
+        spec.filter = C.pointer(f) if f is not None else None
+        spec.proj_cols, spec.n_proj = proj, len(proj_cols)
+        spec.want_row_ids = 1 if want_row_ids else 0
+        spec.string_base = string_base
+        spec.max_selected_rows = max_selected_rows
+        h = C.c_void_p()
+        check(lib.obgpu_scan(self._h, C.byref(spec), C.byref(h)), "obgpu_scan", self.ctx._h)
+        return ScanResult(self, h, len(proj_cols))
+
+    # ---- reference-granularity calls -------------------------------------------------------------
+    def filter_white(self, block, col, op, params=(), start=0, count=None) -> np.ndarray:
+        f, keep = flatten_filter(White(col, op, params))
+        return self.filter_tree(block, None, start, count, _flat=f)
+
+    def filter_tree(self, block, expr, start=0, count=None, _flat=None) -> np.ndarray:
+        f = _flat
+        if f is None:
+            f, keep = flatten_filter(expr)
+        if count is None:
+            count = self.block_info(block)[0] - start
+        out = np.zeros(max(count, 1), dtype=np.uint8)
+        check(lib.obgpu_filter_tree(self._h, block, C.byref(f), start, count, out.ctypes.data), "obgpu_filter_tree",
+              self.ctx._h)
+        return out[:count]
+
+    def project_fixed(self, block, col, row_ids, elem_len=8, vec_offset=0, data=None, nulls=None):
+        rid = np.ascontiguousarray(row_ids, dtype=np.int32)
+        total = vec_offset + len(rid)
+        if data is None:
+            data = np.zeros(total * elem_len, dtype=np.uint8)
+        if nulls is None:
+            nulls = np.zeros((total + 63) // 64, dtype=np.uint64)
+        hn = C.c_int32(0)
+        check(lib.obgpu_project_fixed(self._h, block, col, rid.ctypes.data, len(rid), vec_offset, data.ctypes.data,
+                                      elem_len, nulls.ctypes.data, C.byref(hn)), "obgpu_project_fixed", self.ctx._h)
+        return data, nulls, hn.value
+
+    def project_discrete(self, block, col, row_ids, string_base=0, vec_offset=0):
+        rid = np.ascontiguousarray(row_ids, dtype=np.int32)
+        total = vec_offset + len(rid)
+        ptrs = np.zeros(total, dtype=np.uint64)
+        lens = np.zeros(total, dtype=np.int32)
+        nulls = np.zeros((total + 63) // 64, dtype=np.uint64)
+        hn = C.c_int32(0)
+        check(lib.obgpu_project_discrete(self._h, block, col, rid.ctypes.data, len(rid), vec_offset, string_base,
+                                         ptrs.ctypes.data, lens.ctypes.data, nulls.ctypes.data, C.byref(hn)),
+              "obgpu_project_discrete", self.ctx._h)
+        return ptrs, lens, nulls, hn.value
+
+    def close(self):
+        if self._h:
+            lib.obgpu_batch_close(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class ScanResult:
+    """obgpu_result: device-resident dense output of one fused scan."""
+
+    def __init__(self, batch: PageBatch, handle, n_proj):
+        self.batch = batch
+        self._h = handle
+        self.n_proj = n_proj
+        self._info = None
+
+    def info(self) -> capi.ResultInfo:
+        """Synchronises and returns totals; raises ObGpuError (e.g. OB_BUF_NOT_ENOUGH, OB_NOT_SUPPORTED)."""
+        if self._info is None:
+            info = capi.ResultInfo()
+            code = lib.obgpu_result_info_get(self._h, C.byref(info))
+            self._info = info
+            check(code, "obgpu_scan (device status)", self.batch.ctx._h)
+        return self._info
+
+    @property
+    def selected_rows(self) -> int:
+        return self.info().selected_rows
+
+    def col(self, i) -> capi.ResultCol:
+        c = capi.ResultCol()
+        check(lib.obgpu_result_col_get(self._h, i, C.byref(c)), "obgpu_result_col_get", self.batch.ctx._h)
+        return c
+
+    def fetch_col(self, i, row_begin=0, row_count=None, out=None, out_aux=None, out_nulls=None):
+        """Device->host copy of column i. Returns (data, aux(lens) or None, nulls words)."""
+        c = self.col(i)
+        if row_count is None:
+            row_count = self.selected_rows - row_begin
+        dt = {8: np.uint64, 4: np.uint32, 1: np.uint8}[c.elem_len]
+        data = np.zeros(max(row_count, 1), dtype=dt) if out is None else out
+        aux = (np.zeros(max(row_count, 1), dtype=np.int32) if out_aux is None else out_aux) if c.is_string else None
+        nulls = np.zeros(max((row_count + 63) // 64, 1), dtype=np.uint64) if out_nulls is None else out_nulls
+        check(lib.obgpu_result_fetch_col(self._h, i, row_begin, row_count, data.ctypes.data,
+                                         aux.ctypes.data if aux is not None else None, nulls.ctypes.data),
+              "obgpu_result_fetch_col", self.batch.ctx._h)
+        return data[:row_count], (aux[:row_count] if aux is not None else None), nulls[:(row_count + 63) // 64]
+
+    def fetch_sel_offsets(self) -> np.ndarray:
+        out = np.zeros(self.batch.n_blocks + 1, dtype=np.int64)
+        check(lib.obgpu_result_fetch_sel_offsets(self._h, out.ctypes.data), "obgpu_result_fetch_sel_offsets",
+              self.batch.ctx._h)
+        return out
+
+    def fetch_row_ids(self, row_begin=0, row_count=None) -> np.ndarray:
+        if row_count is None:
+            row_count = self.selected_rows - row_begin
+        out = np.zeros(max(row_count, 1), dtype=np.int32)
+        check(lib.obgpu_result_fetch_row_ids(self._h, row_begin, row_count, out.ctypes.data),
+              "obgpu_result_fetch_row_ids", self.batch.ctx._h)
+        return out[:row_count]
+
+    def fetch_bitmap(self, block, start=0, count=None) -> np.ndarray:
+        if count is None:
+            count = self.batch.block_info(block)[0] - start
+        out = np.zeros(max(count, 1), dtype=np.uint8)
+        check(lib.obgpu_result_fetch_bitmap(self._h, block, start, count, out.ctypes.data),
+              "obgpu_result_fetch_bitmap", self.batch.ctx._h)
+        return out[:count]
+
+    def free(self):
+        if self._h:
+            lib.obgpu_result_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass

@@ -1,0 +1,129 @@
+"""Synthetic SSTable construction on top of the host micro-block writer
+(oceanbase_b200/csrc/sstable_writer.cpp; reference: ObMicroBlockEncoder::build_block,
+encoding/ob_micro_block_encoder.cpp:561-721)."""
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import capi
+from .capi import lib, check
+
+
+@dataclass
+class Column:
+    """One column of the table to encode.
+
+    values: int64 ndarray for integer classes, or a sequence of bytes for string classes
+    (alternatively pass str_heap / str_off directly for big string columns)."""
+    obj_type: int
+    encoding: int
+    values: object = None
+    nulls: Optional[np.ndarray] = None
+    byte_packing_only: bool = False
+    str_heap: Optional[np.ndarray] = None
+    str_off: Optional[np.ndarray] = None
+    _keep: list = field(default_factory=list, repr=False)
+
+    def is_string(self):
+        return self.obj_type in (capi.OBJ_VARCHAR, capi.OBJ_CHAR)
+
+    def to_input(self) -> capi.ColInput:
+        ci = capi.ColInput()
+        ci.obj_type = self.obj_type
+        ci.encoding = self.encoding
+        ci.byte_packing_only = 1 if self.byte_packing_only else 0
+        if self.is_string():
+            if self.str_heap is None:
+                vals = [b"" if v is None else bytes(v) for v in self.values]
+                lens = np.fromiter((len(v) for v in vals), dtype=np.int64, count=len(vals))
+                off = np.zeros(len(vals) + 1, dtype=np.int64)
+                np.cumsum(lens, out=off[1:])
+                heap = np.frombuffer(b"".join(vals) + b"\0", dtype=np.uint8).copy()
+                self.str_heap, self.str_off = heap, off
+            heap = np.ascontiguousarray(self.str_heap, dtype=np.uint8)
+            off = np.ascontiguousarray(self.str_off, dtype=np.int64)
+            self._keep += [heap, off]
+            ci.str_heap = heap.ctypes.data
+            ci.str_off = off.ctypes.data
+        else:
+            v = np.ascontiguousarray(self.values, dtype=np.int64)
+            self._keep.append(v)
+            ci.i64 = v.ctypes.data
+        if self.nulls is not None:
+            n = np.ascontiguousarray(self.nulls, dtype=np.uint8)
+            self._keep.append(n)
+            ci.is_null = n.ctypes.data
+        return ci
+
+    def nrows(self):
+        if self.is_string():
+            return (len(self.str_off) - 1) if self.str_off is not None else len(self.values)
+        return len(self.values)
+
+
+@dataclass
+class TableImage:
+    """Packed image of consecutive micro-blocks (the 'block cache' view the scan consumes)."""
+    image: np.ndarray          # uint8
+    offsets: np.ndarray        # int64 [n_blocks]
+    sizes: np.ndarray          # int64 [n_blocks]
+    total_rows: int
+    n_cols: int
+
+    @property
+    def n_blocks(self):
+        return len(self.offsets)
+
+    def block(self, i) -> np.ndarray:
+        return self.image[self.offsets[i]:self.offsets[i] + self.sizes[i]]
+
+    @staticmethod
+    def concat(parts: Sequence["TableImage"]) -> "TableImage":
+        offs, pos = [], 0
+        for p in parts:
+            offs.append(p.offsets + pos)
+            pos += len(p.image)
+        return TableImage(np.concatenate([p.image for p in parts]), np.concatenate(offs),
+                          np.concatenate([p.sizes for p in parts]), sum(p.total_rows for p in parts),
+                          parts[0].n_cols)
+
+
+def _inputs(cols: List[Column]):
+    arr = (capi.ColInput * len(cols))()
+    for i, c in enumerate(cols):
+        arr[i] = c.to_input()
+    return arr
+
+
+def encode_block(cols: List[Column], row_begin=0, nrows=None, rowkey_cnt=0) -> np.ndarray:
+    n = cols[0].nrows() - row_begin if nrows is None else nrows
+    arr = _inputs(cols)
+    size = C.c_int64(0)
+    check(lib.obgpu_writer_encode_block(arr, len(cols), rowkey_cnt, row_begin, n, None, 0, C.byref(size)),
+          "obgpu_writer_encode_block(size)")
+    out = np.zeros(size.value, dtype=np.uint8)
+    check(lib.obgpu_writer_encode_block(arr, len(cols), rowkey_cnt, row_begin, n, out.ctypes.data, out.size,
+                                        C.byref(size)), "obgpu_writer_encode_block")
+    return out
+
+
+def encode_table(cols: List[Column], rows_per_block: int, rowkey_cnt=0, align=128, n_threads=0,
+                 out: Optional[np.ndarray] = None) -> TableImage:
+    total = cols[0].nrows()
+    arr = _inputs(cols)
+    h = C.c_void_p()
+    check(lib.obgpu_writer_encode_table(arr, len(cols), rowkey_cnt, total, rows_per_block, align, n_threads,
+                                        C.byref(h)), "obgpu_writer_encode_table")
+    try:
+        size, nb = C.c_int64(0), C.c_int32(0)
+        check(lib.obgpu_table_image_info(h, C.byref(size), C.byref(nb)), "obgpu_table_image_info")
+        image = np.empty(size.value, dtype=np.uint8) if out is None else out[:size.value]
+        offsets = np.zeros(nb.value, dtype=np.int64)
+        sizes = np.zeros(nb.value, dtype=np.int64)
+        check(lib.obgpu_table_image_export(h, image.ctypes.data, image.size, offsets.ctypes.data,
+                                           sizes.ctypes.data, nb.value), "obgpu_table_image_export")
+    finally:
+        lib.obgpu_table_image_free(h)
+    return TableImage(image, offsets, sizes, total, len(cols))

@@ -1,0 +1,155 @@
+"""Seeded synthetic SSTables of the BASELINE.json configs.
+
+Every column is generated from SplitMix64(seed, column) so any slice of a table can be regenerated
+independently (ranks generate their own shard without communication). Compressor none, PAX
+ENCODING_ROW_STORE blocks produced by the host writer.
+"""
+from dataclasses import dataclass
+from typing import List, Optional
+
+import numpy as np
+
+from . import capi
+from .scan import White, And
+from .sstable import Column, TableImage, encode_table
+
+_M64 = (1 << 64) - 1
+
+
+def splitmix64(seed: int, start: int, n: int) -> np.ndarray:
+    """n SplitMix64 outputs for counters start .. start+n-1 (stateless form: hash of seed+ctr*gamma)."""
+    with np.errstate(over="ignore"):
+        idx = np.arange(start + 1, start + n + 1, dtype=np.uint64)
+        z = np.uint64(seed & _M64) + idx * np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return z ^ (z >> np.uint64(31))
+
+
+def _col_seed(seed, col):
+    return (seed * 0x100000001B3 + col * 0x9E3779B1 + 12345) & _M64
+
+
+@dataclass
+class Workload:
+    table: TableImage
+    filter: object
+    proj: List[int]
+    proj_is_string: List[bool]
+    proj_elem_len: List[int]
+    name: str
+    rows_per_block: int
+    # algorithmic bytes per input row: B_in = encoded bytes, B_out = dense output
+    def alg_bytes(self, selected_rows: int) -> int:
+        out_per_row = sum(12 if s else l for s, l in zip(self.proj_is_string, self.proj_elem_len))
+        bitmap = (self.table.total_rows + 7) // 8
+        return int(self.table.sizes.sum()) + selected_rows * out_per_row + bitmap
+
+
+# ---- config 1: 4 x INT64, RAW fixed 8 B, no filter -------------------------------------------------
+def make_config1(rows=1_000_000, rows_per_block=500, seed=1, row_start=0) -> Workload:
+    cols = []
+    for c in range(4):
+        v = splitmix64(_col_seed(seed, c), row_start, rows).view(np.int64)
+        cols.append(Column(capi.OBJ_INT, capi.ENC_RAW, v))
+    table = encode_table(cols, rows_per_block)
+    return Workload(table, None, [0, 1, 2, 3], [False] * 4, [8] * 4, "cfg1: 4xINT64 RAW, no filter", rows_per_block)
+
+
+# ---- config 2: 8 x INT64, base-diff PK + 3 RLE + 4 bit-packed RAW, one range predicate ---------------
+def _rle_column(seed, start, n, dict_bits=8, mean_run=64):
+    """Runs with geometric length (mean `mean_run`) over a 2^dict_bits value dictionary. Run
+    boundaries are a pure function of the row index so shards line up."""
+    h = splitmix64(seed, start, n)
+    # a row starts a new run with probability 1/mean_run
+    boundary = (h % np.uint64(mean_run)) == 0
+    if n:
+        boundary[0] = True
+    run_id = np.cumsum(boundary) - 1
+    starts = np.flatnonzero(boundary)
+    # value of a run: hash of the absolute row index of its first row
+    run_vals = splitmix64(seed ^ 0xABCDEF, 0, 1)[0] ^ splitmix64(seed + 17, 0, 1)[0]
+    hv = splitmix64(seed + 99, start, n)[starts]
+    vals = (hv ^ run_vals) & np.uint64((1 << dict_bits) - 1)
+    # spread dictionary values over a wide integer range so the dict stores multi-byte values
+    wide = (vals.astype(np.int64) * 1_000_003 + 7)
+    return wide[run_id]
+
+
+def make_config2_like(rows=100_000, rows_per_block=1400, seed=2, shape="bt", row_start=0,
+                      n_threads=0, out=None) -> Workload:
+    s = lambda c: _col_seed(seed, c)
+    inc = (splitmix64(s(0), row_start, rows) % np.uint64(700)).astype(np.int64) + 1
+    # sorted PK: shard-independent base (expected increment 350.5 per row) + local cumsum
+    pk = np.cumsum(inc) + np.int64(row_start) * 351 + np.int64(1_000_000_007)
+    cols = [Column(capi.OBJ_INT, capi.ENC_INTEGER_BASE_DIFF, pk)]
+    for c in (1, 2, 3):
+        cols.append(Column(capi.OBJ_INT, capi.ENC_RLE, _rle_column(s(c), row_start, rows)))
+    for c, w in zip((4, 5, 6, 7), (7, 13, 21, 33)):
+        v = (splitmix64(s(c), row_start, rows) & np.uint64((1 << w) - 1)).astype(np.int64)
+        cols.append(Column(capi.OBJ_INT, capi.ENC_RAW, v))
+    table = encode_table(cols, rows_per_block, rowkey_cnt=1, n_threads=n_threads, out=out)
+    if shape == "bt":
+        flt = White(4, capi.WHITE_OP_BT, (32, 63))                      # 32/128 = 25 %
+    else:
+        flt = And([White(4, capi.WHITE_OP_GE, (32,)), White(4, capi.WHITE_OP_LE, (63,))])
+    return Workload(table, flt, list(range(8)), [False] * 8, [8] * 8,
+                    f"cfg2: 8xINT64 base-diff PK + 3 RLE + 4 bit-packed RAW, range predicate ({shape}) 25%",
+                    rows_per_block)
+
+
+# ---- config 3: 8 INT64 DICT + 8 VARCHAR DICT, 3-predicate AND ~10 % --------------------------------
+def _zipf_ranks(seed, start, n, card, a=1.1):
+    """Zipf(a) ranks in [0, card) by inverse CDF over a precomputed table."""
+    w = 1.0 / np.power(np.arange(1, card + 1, dtype=np.float64), a)
+    cdf = np.cumsum(w)
+    cdf /= cdf[-1]
+    u = (splitmix64(seed, start, n) >> np.uint64(11)).astype(np.float64) / float(1 << 53)
+    return np.searchsorted(cdf, u, side="left").astype(np.int64)
+
+
+def _string_dict(seed, card, min_len=8, max_len=32):
+    h = splitmix64(seed, 0, card)
+    lens = (h % np.uint64(max_len - min_len + 1)).astype(np.int64) + min_len
+    off = np.zeros(card + 1, dtype=np.int64)
+    np.cumsum(lens, out=off[1:])
+    raw = splitmix64(seed + 1, 0, int(off[-1]))
+    heap = (raw % np.uint64(26)).astype(np.uint8) + ord("a")
+    return heap, off
+
+
+def make_config3_like(rows=100_000, rows_per_block=1100, seed=3, row_start=0, n_threads=0, out=None) -> Workload:
+    s = lambda c: _col_seed(seed, c)
+    int_cards = [16, 64, 256, 4096, 16, 1024, 65536, 200]
+    cols = []
+    for c, card in enumerate(int_cards):
+        r = _zipf_ranks(s(c), row_start, rows, card)
+        # dictionary value of rank k: wide multi-byte integers, shard independent
+        vals = (splitmix64(s(c) + 5, 0, card) >> np.uint64(20)).astype(np.int64)
+        if c == 3:
+            vals = np.arange(card, dtype=np.int64) * 1000  # ordered domain for the `<` predicate
+        cols.append(Column(capi.OBJ_INT, capi.ENC_DICT, vals[r]))
+    str_dicts = []
+    for c in range(8, 16):
+        card = 1024
+        heap, off = _string_dict(s(c) + 3, card)
+        r = _zipf_ranks(s(c), row_start, rows, card)
+        lens = off[1:] - off[:-1]
+        rl = lens[r]
+        roff = np.zeros(rows + 1, dtype=np.int64)
+        np.cumsum(rl, out=roff[1:])
+        # gather bytes: index arithmetic without a python loop
+        idx = np.repeat(off[:-1][r] - roff[:-1], rl) + np.arange(roff[-1], dtype=np.int64)
+        cols.append(Column(capi.OBJ_VARCHAR, capi.ENC_DICT, None, str_heap=heap[idx], str_off=roff))
+        str_dicts.append((heap, off))
+    table = encode_table(cols, rows_per_block, n_threads=n_threads, out=out)
+    # c0 = k  (Zipf rank 0 of 16: ~30 %), c3 < v, s1 IN (5 strings): tuned to ~10 % combined
+    c0_vals = (splitmix64(s(0) + 5, 0, 16) >> np.uint64(20)).astype(np.int64)
+    heap9, off9 = str_dicts[1]
+    in_list = tuple(bytes(heap9[off9[k]:off9[k + 1]]) for k in (0, 1, 2, 3, 5))
+    flt = And([White(0, capi.WHITE_OP_EQ, (int(c0_vals[0]),)),
+               White(3, capi.WHITE_OP_LT, (2_000_000,)),
+               White(9, capi.WHITE_OP_IN, in_list)])
+    proj = [1, 2, 5, 6, 8, 10]
+    return Workload(table, flt, proj, [False] * 4 + [True] * 2, [8] * 4 + [8] * 2,
+                    "cfg3: 8 INT64 DICT + 8 VARCHAR DICT, 3-predicate AND", rows_per_block)

@@ -1,0 +1,975 @@
+/*
+ * ob_oracle.c -- CPU oracle (TEST INFRASTRUCTURE, see ob_oracle.h).
+ *
+ * Restates, in plain C, the reference's decode/filter/projection algorithm for PAX
+ * ("ENCODING_ROW_STORE") micro-blocks.  Reference = /root/reference/src/storage/blocksstable
+ * unless another root is given.  Nothing here is shared with the product code under
+ * oceanbase_b200/: the layout constants are restated independently from the same spec.
+ */
+#include "ob_oracle.h"
+
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ---- layout constants (ob_micro_block_header.h:97-153, ob_block_sstable_struct.h:201-264) ---- */
+enum { T_RAW = 0, T_DICT = 1, T_RLE = 2, T_CONST = 3, T_BASE_DIFF = 4 };
+enum { A_FIX = 0x1, A_EXT = 0x2, A_BITPACK = 0x4, A_LASTVAR = 0x8 };
+enum { EXT_NOT = 0, EXT_NULL = 1, EXT_NOPE = 2 };
+#define MAGIC 1005
+
+static inline uint16_t rd16(const uint8_t *p) { uint16_t v; memcpy(&v, p, 2); return v; }
+static inline uint32_t rd32(const uint8_t *p) { uint32_t v; memcpy(&v, p, 4); return v; }
+static inline uint64_t rd64(const uint8_t *p) { uint64_t v; memcpy(&v, p, 8); return v; }
+static inline uint64_t rd_len(const uint8_t *p, int len) {
+  uint64_t v = 0;
+  memcpy(&v, p, (size_t)len);
+  return v;
+}
+
+/* INTEGER_MASK_TABLE, encoding/ob_encoding_util.cpp:32-35 */
+static const uint64_t INT_MASK[9] = {0x0ull, 0xffull, 0xffffull, 0xffffffull, 0xffffffffull,
+                                     0xffffffffffull, 0xffffffffffffull, 0xffffffffffffffull,
+                                     0xffffffffffffffffull};
+
+/* store class / sizes, encoding/ob_encoding_util.h:59-195; datum map share/datum/ob_datum.cpp:22-92 */
+static int obj_store_class(uint8_t t) { /* 1 ObIntSC, 2 ObUIntSC, 5 ObStringSC, 0 other */
+  if ((t >= 1 && t <= 5) || t == 17 || t == 18 || t == 19 || t == 20) return 1;
+  if ((t >= 6 && t <= 10) || t == 21) return 2;
+  if (t == 22 || t == 23) return 5;
+  return 0;
+}
+static int obj_is_int_tc(uint8_t t) { return t >= 1 && t <= 5; } /* ObIntTC only */
+static int obj_signed_cmp(uint8_t t) { return obj_store_class(t) == 1; }
+static int obj_type_size(uint8_t t) {
+  switch (t) {
+    case 1: case 6: case 21: return 1;
+    case 2: case 7: return 2;
+    case 3: case 4: case 8: case 9: case 19: return 4;
+    case 5: case 10: case 17: case 18: case 20: return 8;
+    default: return -1;
+  }
+}
+static int obj_datum_len(uint8_t t) { return t == 21 ? 1 : (t == 19 ? 4 : 8); }
+static uint64_t obj_integer_mask(uint8_t t) {
+  /* ~INTEGER_MASK_TABLE[type_store_size] for ObIntTC, else 0 (ob_dict_decoder.cpp:198-203) */
+  return obj_is_int_tc(t) ? ~INT_MASK[obj_type_size(t)] : 0;
+}
+
+/* =============================================================================================
+ * Bit stream: LSB-first, byte granular (encoding/ob_bit_stream.h:169-187 get; :215-283 fast paths)
+ * ============================================================================================= */
+uint64_t ora_bs_get(const uint8_t *buf, int64_t offset, int64_t cnt) {
+  int64_t index = offset, done = 0;
+  uint64_t v = 0;
+  while (done < cnt) {
+    const int64_t word_off = index % 8;
+    const int64_t bit = (cnt - done) < (8 - word_off) ? (cnt - done) : (8 - word_off);
+    const uint64_t wv = (uint8_t)(((1u << bit) - 1u) & (buf[index / 8] >> word_off));
+    v |= wv << done;
+    done += bit;
+    index += bit;
+  }
+  return v;
+}
+
+/* get<PACKED_LEN_LESS_THAN_10 / _26 / DEFAULT> selected by width (get_unpack_func, :285-296) */
+uint64_t ora_bs_get_fast(const uint8_t *buf, int64_t offset, int64_t cnt, int64_t bs_len) {
+  if (cnt < 10) {
+    const int64_t byte_offset = offset >> 3, bit_offset = offset & 7;
+    if (offset >= bs_len - 8 && bit_offset + cnt <= 8) {
+      const uint8_t mask = (uint8_t)((1 << cnt) - 1);
+      return (uint64_t)((uint8_t)(buf[byte_offset] >> bit_offset) & mask);
+    } else {
+      const uint16_t mask = (uint16_t)((1 << cnt) - 1);
+      uint16_t v = rd16(buf + byte_offset);
+      v = (uint16_t)(v >> bit_offset);
+      return (uint64_t)(v & mask);
+    }
+  } else if (cnt < 26) {
+    if (offset >= bs_len - 24) return ora_bs_get(buf, offset, cnt);
+    const int64_t byte_offset = offset >> 3, bit_offset = offset & 7;
+    const uint32_t mask = (uint32_t)((1u << cnt) - 1u);
+    uint32_t v = rd32(buf + byte_offset);
+    v >>= bit_offset;
+    return (uint64_t)(v & mask);
+  }
+  return ora_bs_get(buf, offset, cnt);
+}
+
+/* ObBitStream::set (:147-167): OR bits into a zeroed buffer */
+void ora_bs_set(uint8_t *buf, int64_t offset, int64_t cnt, uint64_t value) {
+  int64_t index = offset, done = 0;
+  while (done < cnt) {
+    const int64_t word_off = index % 8;
+    const int64_t bit = (cnt - done) < (8 - word_off) ? (cnt - done) : (8 - word_off);
+    buf[index / 8] |= (uint8_t)((((1u << bit) - 1u) & (value >> done)) << word_off);
+    done += bit;
+    index += bit;
+  }
+}
+
+/* =============================================================================================
+ * Block init: ObIEncodeBlockReader::get_micro_metas (encoding/ob_micro_block_decoder.cpp:363-388),
+ * ObMicroBlockDecoder::do_init (:1268-1322), ObMicroBlockHeader::is_valid (header.cpp:53-61)
+ * ============================================================================================= */
+int ora_block_init(ora_block *b, const void *buf, int64_t size) {
+  if (!b || !buf || size < 64) return ORA_INVALID_ARGUMENT;
+  const uint8_t *p = (const uint8_t *)buf;
+  memset(b, 0, sizeof(*b));
+  const int16_t magic = (int16_t)rd16(p), version = (int16_t)rd16(p + 2);
+  b->buf = p;
+  b->size = size;
+  b->header_size = rd32(p + 4);
+  b->column_count = rd16(p + 10);
+  b->rowkey_column_count = rd16(p + 12);
+  b->row_count = rd32(p + 16);
+  const uint8_t row_store_type = p[20], opt = p[21];
+  b->row_index_byte = opt & 7;
+  b->extend_value_bit = (opt >> 3) & 7;
+  b->var_column_count = rd16(p + 22);
+  b->row_data_offset = rd32(p + 24);
+  if (magic != MAGIC || version < 1 || version > 3 || b->column_count < b->rowkey_column_count)
+    return ORA_INVALID_DATA;
+  if (row_store_type != 1 && row_store_type != 2) return ORA_NOT_SUPPORTED; /* PAX only */
+  if ((int64_t)b->header_size + 16ll * b->column_count > size || b->row_data_offset > size)
+    return ORA_INVALID_ARGUMENT;
+  b->col_headers = p + b->header_size;
+  b->meta = b->col_headers + 16u * b->column_count;
+  b->row_data = p + b->row_data_offset;
+  b->row_data_len = size - b->row_data_offset;
+  return ORA_SUCCESS;
+}
+
+/* crc32c, seed 0, no final xor == ob_crc64_sse42 (lib/checksum/ob_crc64.cpp:423-449) */
+static uint32_t crc32c_tab[256];
+static int crc32c_ready = 0;
+static uint64_t crc64_sse42(uint64_t crc, const uint8_t *p, int64_t len) {
+  if (!crc32c_ready) {
+    for (uint32_t n = 0; n < 256; n++) {
+      uint32_t c = n;
+      for (int k = 0; k < 8; k++) c = (c & 1) ? 0x82f63b78u ^ (c >> 1) : c >> 1;
+      crc32c_tab[n] = c;
+    }
+    crc32c_ready = 1;
+  }
+  uint32_t c = (uint32_t)crc;
+  for (int64_t i = 0; i < len; i++) c = crc32c_tab[(c ^ p[i]) & 0xff] ^ (c >> 8);
+  return c;
+}
+
+static void fmt_i64(int64_t v, int16_t *cs) { for (int i = 0; i < 4; i++) *cs = (int16_t)(*cs ^ ((v >> (i * 16)) & 0xFFFF)); }
+static void fmt_i32(int32_t v, int16_t *cs) { for (int i = 0; i < 2; i++) *cs = (int16_t)(*cs ^ ((v >> (i * 16)) & 0xFFFF)); }
+
+/* check_header_checksum / check_payload_checksum (ob_micro_block_header.cpp:236-285) */
+int ora_block_verify_checksums(const ora_block *b) {
+  const uint8_t *p = b->buf;
+  int16_t cs = 0;
+  cs = (int16_t)(cs ^ (int16_t)rd16(p));      /* magic */
+  cs = (int16_t)(cs ^ (int16_t)rd16(p + 2));  /* version */
+  cs = (int16_t)(cs ^ (int16_t)rd16(p + 8));  /* header_checksum */
+  cs = (int16_t)(cs ^ (int16_t)p[20]);        /* row_store_type */
+  cs = (int16_t)(cs ^ (int16_t)p[21]);        /* opt */
+  fmt_i32(b->column_count, &cs);
+  fmt_i32(b->rowkey_column_count, &cs);
+  fmt_i32(rd16(p + 14) & 1, &cs);
+  fmt_i32(rd16(p + 22), &cs);
+  fmt_i64(b->header_size, &cs);
+  fmt_i64(b->row_count, &cs);
+  fmt_i64(b->row_data_offset, &cs);
+  fmt_i64((int32_t)rd32(p + 28), &cs);
+  fmt_i64((int64_t)rd64(p + 32), &cs);
+  fmt_i64((int32_t)rd32(p + 40), &cs);
+  fmt_i64((int32_t)rd32(p + 44), &cs);
+  fmt_i64((int64_t)rd64(p + 48), &cs);
+  if (cs != 0) return ORA_INVALID_DATA;
+  const int32_t zlen = (int32_t)rd32(p + 44);
+  if (zlen != b->size - b->header_size) return ORA_INVALID_DATA;
+  if (crc64_sse42(0, p + b->header_size, zlen) != rd64(p + 48)) return ORA_INVALID_DATA;
+  return ORA_SUCCESS;
+}
+
+/* ---- column header view --------------------------------------------------------------------- */
+typedef struct col_hdr {
+  int8_t type, attr;
+  uint8_t obj_type;
+  uint32_t ext_index, offset, length;
+} col_hdr;
+
+static int get_col(const ora_block *b, int32_t col, col_hdr *h) {
+  if (col < 0 || col >= b->column_count) return ORA_INVALID_ARGUMENT;
+  const uint8_t *p = b->col_headers + 16 * col;
+  if (p[0] != 0) return ORA_INVALID_DATA;
+  h->type = (int8_t)p[1];
+  h->attr = (int8_t)p[2];
+  h->obj_type = p[3];
+  h->ext_index = rd32(p + 4);
+  h->offset = rd32(p + 8);
+  h->length = rd32(p + 12);
+  return ORA_SUCCESS;
+}
+
+/* load_data_to_datum for ObIntSC / ObUIntSC (encoding/ob_encoding_util.h:491-519) */
+static void load_int(uint8_t obj_type, const uint8_t *cell, int64_t cell_len, ora_datum *d) {
+  uint64_t value = rd_len(cell, (int)cell_len);
+  const uint64_t mask = obj_integer_mask(obj_type);
+  if (mask != 0 && (value & (mask >> 1))) value |= mask;
+  d->len = (uint32_t)obj_datum_len(obj_type);
+  d->ival = d->len >= 8 ? value : (value & INT_MASK[d->len]);
+  d->ptr = 0;
+  d->is_null = 0;
+}
+static void set_int(uint8_t obj_type, uint64_t value, ora_datum *d) { /* MEMCPY(datum.ptr_, &v, datum_len) */
+  d->len = (uint32_t)obj_datum_len(obj_type);
+  d->ival = d->len >= 8 ? value : (value & INT_MASK[d->len]);
+  d->ptr = 0;
+  d->is_null = 0;
+}
+static void set_null(ora_datum *d) { d->is_null = 1; d->len = 0; d->ptr = 0; d->ival = 0; }
+
+/* ---- row index (encoding/ob_row_index.h:100-140) -------------------------------------------- */
+static int locate_row(const ora_block *b, int64_t row, const uint8_t **data, int64_t *len) {
+  if (b->row_index_byte > 0) {
+    const int ib = b->row_index_byte;
+    const uint8_t *idx = b->row_data + b->row_data_len - (int64_t)ib * (b->row_count + 1);
+    const uint64_t off = rd_len(idx + row * ib, ib);
+    *data = b->row_data + off;
+    *len = (int64_t)(rd_len(idx + (row + 1) * ib, ib) - off);
+  } else {
+    const int64_t row_size = b->row_count ? b->row_data_len / b->row_count : 0;
+    *data = b->row_data + row * row_size;
+    *len = row_size;
+  }
+  return ORA_SUCCESS;
+}
+
+/* locate_cell_data for a var-stored column (encoding/ob_icolumn_decoder.h:463-527,
+ * ob_raw_decoder.cpp:29-125): row = [ext bits][col_idx_byte][idx x (nvar-1)][cells] */
+static void locate_var_cell(const ora_block *b, const col_hdr *h, const uint8_t *row, int64_t row_len,
+                            const uint8_t **cell, int64_t *cell_len) {
+  const int64_t header_off = h->offset; /* row_offset_: bytes of ext bits */
+  const int64_t k = h->length;          /* index among var columns */
+  const int last = (h->attr & A_LASTVAR) != 0;
+  if (b->var_column_count == 1) {
+    *cell = row + header_off;
+    *cell_len = row_len - header_off;
+    return;
+  }
+  const uint8_t *var = row + header_off;
+  const int ib = (int8_t)*var;
+  var += 1;
+  const uint8_t *idx = var;
+  var += (int64_t)ib * (b->var_column_count - 1);
+  const int64_t col_off = k == 0 ? 0 : (int64_t)rd_len(idx + (k - 1) * ib, ib);
+  if (last) *cell_len = row_len - col_off - (var - row);
+  else *cell_len = (int64_t)rd_len(idx + k * ib, ib) - col_off;
+  *cell = var + col_off;
+}
+
+/* =============================================================================================
+ * Dict (encoding/ob_dict_decoder.cpp:191-314)
+ * ============================================================================================= */
+typedef struct dict_view {
+  const uint8_t *hdr; /* ObDictMetaHeader */
+  uint32_t count;
+  uint8_t row_ref_size, attr;
+  uint16_t data_size; /* or index_byte */
+  const uint8_t *payload, *var_data;
+  int64_t meta_length; /* bytes from hdr to end of dict payload */
+} dict_view;
+
+static void dict_init(dict_view *d, const uint8_t *hdr, int64_t meta_length) {
+  d->hdr = hdr;
+  d->row_ref_size = hdr[1];
+  d->count = rd32(hdr + 2);
+  d->data_size = rd16(hdr + 6);
+  d->attr = hdr[8];
+  d->payload = hdr + 9;
+  d->meta_length = meta_length;
+  d->var_data = (d->attr & 1) ? 0 : d->payload + (int64_t)(d->count ? d->count - 1 : 0) * d->data_size;
+}
+
+/* ObDictDecoder::decode(obj_type, datum, ref, meta_length) (:243-314) */
+static int dict_decode(const dict_view *d, uint8_t obj_type, int64_t ref, ora_datum *out) {
+  const int64_t count = d->count;
+  if (ref >= count || count == 0) {
+    if (ref == count || count == 0) { set_null(out); return ORA_SUCCESS; }
+    if (ref == count + 1) { set_null(out); out->is_null = 2; return ORA_SUCCESS; } /* NOP */
+    return ORA_ERR_UNEXPECTED;
+  }
+  const uint8_t *cell;
+  int64_t cell_len;
+  if (d->attr & 1) {
+    cell = d->payload + ref * d->data_size;
+    cell_len = d->data_size;
+  } else {
+    const int ib = d->data_size;
+    const int64_t offset = ref == 0 ? 0 : (int64_t)rd_len(d->payload + (ref - 1) * ib, ib);
+    cell = d->var_data + offset;
+    if (ref == count - 1) cell_len = (d->hdr + d->meta_length) - cell;
+    else cell_len = (int64_t)rd_len(d->payload + ref * ib, ib) - offset;
+  }
+  if (obj_store_class(obj_type) == 5) {
+    out->ptr = cell;
+    out->len = (uint32_t)cell_len;
+    out->is_null = 0;
+    out->ival = 0;
+  } else {
+    load_int(obj_type, cell, cell_len, out);
+  }
+  return ORA_SUCCESS;
+}
+
+/* =============================================================================================
+ * Per-column decoder state
+ * ============================================================================================= */
+typedef struct col_dec {
+  col_hdr h;
+  int sc;
+  const uint8_t *meta; /* block meta + h.offset */
+  dict_view dict;      /* DICT / RLE */
+  /* RLE (ob_rle_decoder.h:179-207) */
+  uint32_t rle_count;
+  int rle_row_id_byte, rle_ref_byte;
+  const uint8_t *rle_row_ids, *rle_refs;
+  /* BASE_DIFF (ob_integer_base_diff_decoder.h:140-170) */
+  uint64_t base;
+  uint8_t diff_len;
+} col_dec;
+
+static int col_dec_init(const ora_block *b, int32_t col, col_dec *c) {
+  int ret = get_col(b, col, &c->h);
+  if (ret) return ret;
+  c->sc = obj_store_class(c->h.obj_type);
+  if (c->sc == 0) return ORA_NOT_SUPPORTED;
+  c->meta = b->meta + c->h.offset;
+  switch (c->h.type) {
+    case T_RAW: break;
+    case T_DICT: dict_init(&c->dict, c->meta, c->h.length); break;
+    case T_RLE: {
+      const uint8_t *m = c->meta;
+      c->rle_row_id_byte = m[1] & 7;
+      c->rle_ref_byte = (m[1] >> 3) & 7;
+      c->rle_count = rd32(m + 2);
+      const uint32_t dict_off = rd32(m + 6);
+      c->rle_row_ids = m + 10;
+      /* ref_offset_ is an int16 in the reference (ob_rle_decoder.h:193) */
+      c->rle_refs = c->rle_row_ids + (int16_t)(c->rle_count * c->rle_row_id_byte);
+      dict_init(&c->dict, m + dict_off, (int64_t)c->h.length - dict_off);
+      break;
+    }
+    case T_BASE_DIFF: {
+      if (c->sc != 1 && c->sc != 2) return ORA_ERR_UNEXPECTED;
+      const int store_size = obj_type_size(c->h.obj_type);
+      c->diff_len = c->meta[1];
+      c->base = rd_len(c->meta + 2, store_size);
+      const uint64_t mask = ~INT_MASK[store_size];
+      if (c->sc == 1 && mask != 0 && (c->base & (mask >> 1))) c->base |= mask;
+      break;
+    }
+    default: return ORA_NOT_SUPPORTED;
+  }
+  return ORA_SUCCESS;
+}
+
+/* upper_bound over the RLE run-start array (ObIntArrayFuncTable::upper_bound_) */
+static int64_t rle_upper_bound(const col_dec *c, int64_t row) {
+  int64_t lo = 0, hi = c->rle_count;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) / 2;
+    if ((int64_t)rd_len(c->rle_row_ids + mid * c->rle_row_id_byte, c->rle_row_id_byte) <= row) lo = mid + 1;
+    else hi = mid;
+  }
+  return lo;
+}
+static int64_t rle_ref_at(const col_dec *c, int64_t pos) {
+  return (int64_t)rd_len(c->rle_refs + pos * c->rle_ref_byte, c->rle_ref_byte);
+}
+
+/* dict column: ref of a row (ob_dict_decoder.cpp:229-241) */
+static int64_t dict_row_ref(const ora_block *b, const col_dec *c, int64_t row) {
+  const uint8_t *col_data = c->meta + c->h.length;
+  const int rs = c->dict.row_ref_size;
+  if (c->h.attr & A_BITPACK) return (int64_t)ora_bs_get(col_data, row * rs, rs);
+  (void)b;
+  return (int64_t)rd_len(col_data + row * rs, rs);
+}
+
+/* ext value of a fixed/bit-packed column row; column data starts at col_data */
+static uint64_t fixed_ext(const ora_block *b, const col_dec *c, const uint8_t *col_data, int64_t row) {
+  if (!(c->h.attr & A_EXT)) return EXT_NOT;
+  return ora_bs_get(col_data, row * b->extend_value_bit, b->extend_value_bit);
+}
+
+/* One cell: ObRawDecoder::decode (ob_raw_decoder.cpp:243-326), ObDictDecoder::decode (:214-241),
+ * ObRLEDecoder::decode (ob_rle_decoder.cpp:25-49), ObIntegerBaseDiffDecoder::decode (:25-82) */
+static int decode_cell(const ora_block *b, const col_dec *c, int64_t row, ora_datum *out) {
+  switch (c->h.type) {
+    case T_RAW: {
+      const uint8_t *col_data = c->meta;
+      const int fixed = (c->h.attr & A_FIX) != 0, bp = (c->h.attr & A_BITPACK) != 0;
+      uint64_t ext = EXT_NOT;
+      int64_t data_offset = 0;
+      const uint8_t *row_data = 0;
+      int64_t row_len = 0;
+      if (c->h.attr & A_EXT) {
+        if (fixed || bp) {
+          data_offset = (int64_t)b->row_count * b->extend_value_bit;
+          ext = ora_bs_get(col_data, row * b->extend_value_bit, b->extend_value_bit);
+        } else {
+          locate_row(b, row, &row_data, &row_len);
+          ext = ora_bs_get(row_data, c->h.ext_index, b->extend_value_bit);
+        }
+      }
+      if (ext != EXT_NOT) { set_null(out); if (ext == EXT_NOPE) out->is_null = 2; return ORA_SUCCESS; }
+      if (bp) {
+        set_int(c->h.obj_type, ora_bs_get(col_data, data_offset + row * c->h.length, c->h.length), out);
+        return ORA_SUCCESS;
+      }
+      const uint8_t *cell;
+      int64_t cell_len;
+      if (fixed) {
+        data_offset = (data_offset + 7) / 8;
+        cell = col_data + data_offset + row * (int64_t)c->h.length;
+        cell_len = c->h.length;
+      } else {
+        if (!row_data) locate_row(b, row, &row_data, &row_len);
+        locate_var_cell(b, &c->h, row_data, row_len, &cell, &cell_len);
+      }
+      if (c->sc == 5) { out->ptr = cell; out->len = (uint32_t)cell_len; out->is_null = 0; out->ival = 0; }
+      else load_int(c->h.obj_type, cell, cell_len, out);
+      return ORA_SUCCESS;
+    }
+    case T_DICT:
+      return dict_decode(&c->dict, c->h.obj_type, dict_row_ref(b, c, row), out);
+    case T_RLE: {
+      const int64_t pos = rle_upper_bound(c, row);
+      return dict_decode(&c->dict, c->h.obj_type, rle_ref_at(c, pos - 1), out);
+    }
+    case T_BASE_DIFF: {
+      const uint8_t *col_data = c->meta + c->h.length;
+      int64_t data_offset = 0;
+      uint64_t ext = EXT_NOT;
+      if (c->h.attr & A_EXT) {
+        data_offset = (int64_t)b->row_count * b->extend_value_bit;
+        ext = ora_bs_get(col_data, row * b->extend_value_bit, b->extend_value_bit);
+      }
+      if (ext != EXT_NOT) { set_null(out); if (ext == EXT_NOPE) out->is_null = 2; return ORA_SUCCESS; }
+      uint64_t v;
+      if (c->h.attr & A_BITPACK) {
+        v = ora_bs_get(col_data, data_offset + row * c->diff_len, c->diff_len);
+      } else {
+        data_offset = (data_offset + 7) / 8;
+        v = rd_len(col_data + data_offset + row * c->diff_len, c->diff_len);
+      }
+      set_int(c->h.obj_type, v + c->base, out);
+      return ORA_SUCCESS;
+    }
+    default: return ORA_NOT_SUPPORTED;
+  }
+}
+
+int ora_decode_cell(const ora_block *b, int32_t col, int64_t row, ora_datum *out) {
+  if (!b || !out || row < 0 || row >= b->row_count) return ORA_INVALID_ARGUMENT;
+  col_dec c;
+  const int ret = col_dec_init(b, col, &c);
+  if (ret) return ret;
+  return decode_cell(b, &c, row, out);
+}
+
+/* =============================================================================================
+ * Batch projection: ObMicroBlockDecoder::get_rows -> decode_vector
+ * (encoding/ob_micro_block_decoder.cpp:2473-2544; ob_raw_decoder.cpp:530-701;
+ *  ob_dict_decoder.cpp:473-541; ob_rle_decoder.cpp:528-583 monotone cursor)
+ * ============================================================================================= */
+static inline void bitvec_set(uint64_t *words, int64_t idx) { words[idx / 64] |= 1ull << (idx % 64); }
+
+/* RLE monotone cursor (extract_ref_and_null_count): refs for ascending row ids with a minimum of
+ * binary searches */
+typedef struct rle_cursor { int64_t pos, next_row; int64_t cur_ref; } rle_cursor;
+static void rle_cursor_init(const col_dec *c, rle_cursor *k) {
+  k->pos = 0;
+  k->next_row = (int64_t)rd_len(c->rle_row_ids, c->rle_row_id_byte);
+  k->cur_ref = rle_ref_at(c, 0);
+}
+static int64_t rle_cursor_ref(const col_dec *c, rle_cursor *k, int64_t row) {
+  const int64_t n = c->rle_count;
+  if (k->pos == n || row < k->next_row) {
+  } else if (row == k->next_row) {
+    ++k->pos;
+    if (k->pos < n) k->next_row = (int64_t)rd_len(c->rle_row_ids + k->pos * c->rle_row_id_byte, c->rle_row_id_byte);
+    k->cur_ref = rle_ref_at(c, k->pos - 1);
+  } else {
+    k->pos = rle_upper_bound(c, row);
+    if (k->pos < n) k->next_row = (int64_t)rd_len(c->rle_row_ids + k->pos * c->rle_row_id_byte, c->rle_row_id_byte);
+    k->cur_ref = rle_ref_at(c, k->pos - 1);
+  }
+  return k->cur_ref;
+}
+
+static int batch_decode(const ora_block *b, const col_dec *c, const int32_t *row_ids, int64_t row_cap,
+                        ora_datum *datums) {
+  if (c->h.type == T_RLE && row_cap > 0) {
+    /* rows ascending (forward scan) */
+    rle_cursor k;
+    rle_cursor_init(c, &k);
+    for (int64_t i = 0; i < row_cap; ++i) {
+      const int ret = dict_decode(&c->dict, c->h.obj_type, rle_cursor_ref(c, &k, row_ids[i]), &datums[i]);
+      if (ret) return ret;
+    }
+    return ORA_SUCCESS;
+  }
+  if (c->h.type == T_RAW && (c->h.attr & A_BITPACK)) {
+    /* decode_vector_bitpacked: fast unpack paths by width */
+    const uint8_t *col_data = c->meta;
+    const int64_t bs_len = (int64_t)c->h.length * b->row_count;
+    const int64_t data_offset = (c->h.attr & A_EXT) ? (int64_t)b->row_count * b->extend_value_bit : 0;
+    for (int64_t i = 0; i < row_cap; ++i) {
+      const int64_t row = row_ids[i];
+      if ((c->h.attr & A_EXT) && fixed_ext(b, c, col_data, row) != EXT_NOT) { set_null(&datums[i]); continue; }
+      set_int(c->h.obj_type, ora_bs_get_fast(col_data, data_offset + row * c->h.length, c->h.length, bs_len), &datums[i]);
+    }
+    return ORA_SUCCESS;
+  }
+  for (int64_t i = 0; i < row_cap; ++i) {
+    const int ret = decode_cell(b, c, row_ids[i], &datums[i]);
+    if (ret) return ret;
+  }
+  return ORA_SUCCESS;
+}
+
+#define ORA_MAX_BATCH 4096
+
+int ora_get_rows_fixed(const ora_block *b, int32_t col, const int32_t *row_ids, int64_t row_cap,
+                       int64_t vec_offset, void *data, int32_t elem_len, uint64_t *nulls,
+                       int32_t *has_null) {
+  if (!b || !row_ids || !data || row_cap < 0) return ORA_INVALID_ARGUMENT;
+  col_dec c;
+  int ret = col_dec_init(b, col, &c);
+  if (ret) return ret;
+  if (c.sc == 5 || elem_len != obj_datum_len(c.h.obj_type)) return ORA_INVALID_ARGUMENT;
+  ora_datum tmp[256];
+  for (int64_t done = 0; done < row_cap; done += 256) {
+    const int64_t n = row_cap - done < 256 ? row_cap - done : 256;
+    if ((ret = batch_decode(b, &c, row_ids + done, n, tmp))) return ret;
+    for (int64_t i = 0; i < n; ++i) {
+      const int64_t at = vec_offset + done + i;
+      if (tmp[i].is_null) { /* payload slot left unwritten (ob_vector_decode_util.h:726-734) */
+        if (nulls) bitvec_set(nulls, at);
+        if (has_null) *has_null = 1;
+      } else {
+        memcpy((uint8_t *)data + at * elem_len, &tmp[i].ival, (size_t)elem_len);
+      }
+    }
+  }
+  return ORA_SUCCESS;
+}
+
+int ora_get_rows_discrete(const ora_block *b, int32_t col, const int32_t *row_ids, int64_t row_cap,
+                          int64_t vec_offset, const uint8_t **ptrs, int32_t *lens, uint64_t *nulls,
+                          int32_t *has_null) {
+  if (!b || !row_ids || !ptrs || !lens || row_cap < 0) return ORA_INVALID_ARGUMENT;
+  col_dec c;
+  int ret = col_dec_init(b, col, &c);
+  if (ret) return ret;
+  if (c.sc != 5) return ORA_INVALID_ARGUMENT;
+  ora_datum tmp[256];
+  for (int64_t done = 0; done < row_cap; done += 256) {
+    const int64_t n = row_cap - done < 256 ? row_cap - done : 256;
+    if ((ret = batch_decode(b, &c, row_ids + done, n, tmp))) return ret;
+    for (int64_t i = 0; i < n; ++i) {
+      const int64_t at = vec_offset + done + i;
+      if (tmp[i].is_null) {
+        if (nulls) bitvec_set(nulls, at);
+        if (has_null) *has_null = 1;
+      } else {
+        ptrs[at] = tmp[i].ptr;
+        lens[at] = (int32_t)tmp[i].len;
+      }
+    }
+  }
+  return ORA_SUCCESS;
+}
+
+/* =============================================================================================
+ * White filters.  NULL never matches a comparison; NE excludes NULL; only NU / NN see NULL
+ * (ob_raw_decoder.cpp:703-706, ob_dict_decoder.cpp:1005-1012).  A NULL constant yields all-false
+ * unless the op is NU / NN (ob_micro_block_decoder.cpp:1713-1715).
+ * ============================================================================================= */
+static int cmp_datum_param(const ora_datum *d, uint8_t obj_type, int sc, const ora_param *p) {
+  if (sc == 5) {
+    const uint32_t m = d->len < p->len ? d->len : p->len;
+    const int c = m ? memcmp(d->ptr, p->ptr, m) : 0;
+    if (c) return c < 0 ? -1 : 1;
+    return d->len < p->len ? -1 : (d->len > p->len ? 1 : 0);
+  }
+  if (obj_signed_cmp(obj_type)) {
+    /* datum value of a 4-byte map type (date) is a signed 32-bit image */
+    int64_t a = (int64_t)d->ival;
+    if (d->len == 4) a = (int32_t)(uint32_t)d->ival;
+    const int64_t c = p->i64;
+    return a < c ? -1 : (a > c ? 1 : 0);
+  }
+  const uint64_t a = d->ival, c = (uint64_t)p->i64;
+  return a < c ? -1 : (a > c ? 1 : 0);
+}
+
+/* get_filter_cmp_ret_func: result of a compare -> predicate truth */
+static int cmp_to_bool(int op, int c) {
+  switch (op) {
+    case ORA_OP_EQ: return c == 0;
+    case ORA_OP_LE: return c <= 0;
+    case ORA_OP_LT: return c < 0;
+    case ORA_OP_GE: return c >= 0;
+    case ORA_OP_GT: return c > 0;
+    case ORA_OP_NE: return c != 0;
+    default: return 0;
+  }
+}
+
+/* predicate over one non-null datum */
+static int eval_pred(const ora_datum *d, uint8_t obj_type, int sc, int op, const ora_param *params, int32_t n) {
+  switch (op) {
+    case ORA_OP_BT:
+      return cmp_datum_param(d, obj_type, sc, &params[0]) >= 0 && cmp_datum_param(d, obj_type, sc, &params[1]) <= 0;
+    case ORA_OP_IN:
+      for (int32_t i = 0; i < n; ++i)
+        if (!params[i].is_null && cmp_datum_param(d, obj_type, sc, &params[i]) == 0) return 1;
+      return 0;
+    default:
+      return cmp_to_bool(op, cmp_datum_param(d, obj_type, sc, &params[0]));
+  }
+}
+
+static int params_contain_null(int op, const ora_param *params, int32_t n) {
+  if (op == ORA_OP_IN) return 0; /* IN list NULLs are skipped by the IN set build */
+  for (int32_t i = 0; i < n; ++i) if (params[i].is_null) return 1;
+  return 0;
+}
+
+int ora_filter_white(const ora_block *b, int32_t col, int32_t op, const ora_param *params,
+                     int32_t n_params, int64_t start, int64_t count, uint8_t *bitmap) {
+  if (!b || !bitmap || start < 0 || count < 0 || start + count > b->row_count || op < 0 || op >= ORA_OP_MAX)
+    return ORA_INVALID_ARGUMENT;
+  if ((op <= ORA_OP_NE && n_params != 1) || (op == ORA_OP_BT && n_params != 2) || (op == ORA_OP_IN && n_params < 1))
+    return ORA_INVALID_ARGUMENT;
+  col_dec c;
+  int ret = col_dec_init(b, col, &c);
+  if (ret) return ret;
+  memset(bitmap, 0, (size_t)count);
+  if (op != ORA_OP_NU && op != ORA_OP_NN && params_contain_null(op, params, n_params)) return ORA_SUCCESS;
+  ora_datum d;
+  if (c.h.type == T_DICT || c.h.type == T_RLE) {
+    /* predicate over the dictionary -> ref bitset -> scan refs
+     * (ob_dict_decoder.cpp:931-1017 eq/ne, :1061-1222 cmp, :1387-1487 set_res_with_bitset;
+     *  RLE: ob_rle_decoder.cpp:233-520 walks the runs) */
+    const uint32_t cnt = c.dict.count;
+    uint8_t *hit = (uint8_t *)calloc((size_t)cnt + 2, 1);
+    if (!hit) return ORA_ERR_UNEXPECTED;
+    if (op == ORA_OP_NU) hit[cnt] = 1;
+    else if (op == ORA_OP_NN) { memset(hit, 1, cnt); }
+    else {
+      for (uint32_t r = 0; r < cnt; ++r) {
+        if ((ret = dict_decode(&c.dict, c.h.obj_type, r, &d))) { free(hit); return ret; }
+        hit[r] = (uint8_t)eval_pred(&d, c.h.obj_type, c.sc, op, params, n_params);
+      }
+    }
+    if (c.h.type == T_DICT) {
+      for (int64_t i = 0; i < count; ++i) {
+        int64_t ref = dict_row_ref(b, &c, start + i);
+        if (ref > cnt + 1) { free(hit); return ORA_ERR_UNEXPECTED; }
+        bitmap[i] = hit[ref];
+      }
+    } else {
+      const int64_t n = c.rle_count;
+      for (int64_t k = rle_upper_bound(&c, start) - 1; k < n; ++k) {
+        const int64_t rs = (int64_t)rd_len(c.rle_row_ids + k * c.rle_row_id_byte, c.rle_row_id_byte);
+        const int64_t re = k + 1 < n ? (int64_t)rd_len(c.rle_row_ids + (k + 1) * c.rle_row_id_byte, c.rle_row_id_byte) : b->row_count;
+        if (rs >= start + count) break;
+        const int64_t ref = rle_ref_at(&c, k);
+        if (ref > cnt + 1) { free(hit); return ORA_ERR_UNEXPECTED; }
+        if (!hit[ref]) continue;
+        const int64_t lo = rs < start ? start : rs, hi = re > start + count ? start + count : re;
+        for (int64_t r = lo; r < hi; ++r) bitmap[r - start] = 1;
+      }
+    }
+    free(hit);
+    return ORA_SUCCESS;
+  }
+  /* RAW / INTEGER_BASE_DIFF: null bitmap first, then the operator (ob_raw_decoder.cpp:707-794,
+   * traverse_all_data :1141-1253; fast typed compare loops :1338-1382 give the same bits) */
+  if (c.h.type == T_RAW && (c.h.attr & A_FIX) && !(c.h.attr & (A_EXT | A_BITPACK)) && c.sc != 5 &&
+      op <= ORA_OP_NE && (c.h.length == 1 || c.h.length == 2 || c.h.length == 4 || c.h.length == 8) &&
+      obj_type_size(c.h.obj_type) == (int)c.h.length) {
+    /* fast_binary_comparison_operator shape: typed loop over the raw array */
+    const uint8_t *col_data = c.meta;
+    const int sgn = obj_signed_cmp(c.h.obj_type);
+    for (int64_t i = 0; i < count; ++i) {
+      const uint64_t raw = rd_len(col_data + (start + i) * c.h.length, (int)c.h.length);
+      int cr;
+      if (sgn) {
+        int64_t a;
+        switch (c.h.length) { case 1: a = (int8_t)raw; break; case 2: a = (int16_t)raw; break;
+                              case 4: a = (int32_t)raw; break; default: a = (int64_t)raw; }
+        cr = a < params[0].i64 ? -1 : (a > params[0].i64 ? 1 : 0);
+      } else {
+        const uint64_t cc = (uint64_t)params[0].i64;
+        cr = raw < cc ? -1 : (raw > cc ? 1 : 0);
+      }
+      bitmap[i] = (uint8_t)cmp_to_bool(op, cr);
+    }
+    return ORA_SUCCESS;
+  }
+  for (int64_t i = 0; i < count; ++i) {
+    if ((ret = decode_cell(b, &c, start + i, &d))) return ret;
+    if (op == ORA_OP_NU) bitmap[i] = d.is_null == 1;
+    else if (op == ORA_OP_NN) bitmap[i] = d.is_null != 1;
+    else bitmap[i] = d.is_null ? 0 : (uint8_t)eval_pred(&d, c.h.obj_type, c.sc, op, params, n_params);
+  }
+  return ORA_SUCCESS;
+}
+
+/* ObPushdownFilterExecutor::execute (sql/engine/basic/ob_pushdown_filter.cpp:1551-1624): logic
+ * nodes start all-true (AND) / all-false (OR), bit_and / bit_or each child, early-out when the
+ * accumulated bitmap is all-false / all-true. Post-order node array, root last. */
+static int exec_node(const ora_block *b, const ora_filter *f, int32_t idx, int64_t start, int64_t count,
+                     uint8_t *result, int32_t *first_node) {
+  const ora_node *nd = &f->nodes[idx];
+  if (nd->kind == ORA_NODE_WHITE) {
+    *first_node = idx;
+    if (nd->param_begin < 0 || nd->param_begin + nd->n_params > f->n_params) return ORA_INVALID_ARGUMENT;
+    return ora_filter_white(b, nd->col, nd->op, f->params + nd->param_begin, nd->n_params, start, count, result);
+  }
+  if (nd->n_children < 2) return ORA_ERR_UNEXPECTED;
+  /* children are the n_children subtrees ending right before idx, in order */
+  int32_t roots[64];
+  if (nd->n_children > 64) return ORA_NOT_SUPPORTED;
+  int32_t cur = idx - 1;
+  uint8_t *tmp = (uint8_t *)malloc((size_t)(count > 0 ? count : 1));
+  if (!tmp) return ORA_ERR_UNEXPECTED;
+  /* find subtree roots right-to-left */
+  for (int32_t k = nd->n_children - 1; k >= 0; --k) {
+    if (cur < 0) { free(tmp); return ORA_INVALID_ARGUMENT; }
+    roots[k] = cur;
+    /* skip the subtree rooted at cur */
+    int32_t need = 1;
+    while (need > 0) {
+      if (cur < 0) { free(tmp); return ORA_INVALID_ARGUMENT; }
+      const ora_node *x = &f->nodes[cur];
+      need += (x->kind == ORA_NODE_WHITE ? 0 : x->n_children) - 1;
+      --cur;
+    }
+  }
+  *first_node = cur + 1;
+  const int is_and = nd->kind == ORA_NODE_AND;
+  memset(result, is_and ? 1 : 0, (size_t)count);
+  int ret = ORA_SUCCESS;
+  for (int32_t k = 0; k < nd->n_children && ret == ORA_SUCCESS; ++k) {
+    int32_t dummy;
+    ret = exec_node(b, f, roots[k], start, count, tmp, &dummy);
+    if (ret) break;
+    int64_t ones = 0;
+    if (is_and) { for (int64_t i = 0; i < count; ++i) { result[i] &= tmp[i]; ones += result[i]; } if (ones == 0) break; }
+    else { for (int64_t i = 0; i < count; ++i) { result[i] |= tmp[i]; ones += result[i]; } if (ones == count) break; }
+  }
+  free(tmp);
+  return ret;
+}
+
+int ora_filter_tree(const ora_block *b, const ora_filter *f, int64_t start, int64_t count, uint8_t *bitmap) {
+  if (!b || !f || !f->nodes || f->n_nodes <= 0 || !bitmap) return ORA_INVALID_ARGUMENT;
+  int32_t first = 0;
+  const int ret = exec_node(b, f, f->n_nodes - 1, start, count, bitmap, &first);
+  if (ret) return ret;
+  return first == 0 ? ORA_SUCCESS : ORA_INVALID_ARGUMENT;
+}
+
+/* =============================================================================================
+ * ObBitmap::get_row_ids (lib/container/ob_bitmap.cpp:300-333, :540-561), popcnt (:475)
+ * ============================================================================================= */
+int ora_bitmap_get_row_ids(const uint8_t *data, int64_t valid_bytes, int32_t *row_ids, int64_t *row_count,
+                           int64_t *from, int64_t to, int64_t limit, int64_t id_offset) {
+  if (!data || !row_ids || !row_count || !from) return ORA_INVALID_ARGUMENT;
+  if (*from < 0 || to > valid_bytes || to < *from || limit <= 0 || *from < id_offset) return ORA_INVALID_ARGUMENT;
+  const uint8_t *pos = data + *from, *end_pos = data + to;
+  int64_t n = 0;
+  while (n < limit && pos < end_pos) {
+    if (*pos) row_ids[n++] = (int32_t)(pos - data - id_offset);
+    ++pos;
+  }
+  if (n >= limit) {
+    *from = row_ids[limit - 1] + id_offset + 1;
+    n = limit;
+  } else {
+    *from = to;
+  }
+  *row_count = n;
+  return ORA_SUCCESS;
+}
+
+int64_t ora_bitmap_popcnt(const uint8_t *bitmap, int64_t n) {
+  int64_t c = 0;
+  for (int64_t i = 0; i < n; ++i) c += bitmap[i] != 0;
+  return c;
+}
+
+/* =============================================================================================
+ * Whole path: per block  apply_filter -> ObBitmap ; then batches of batch_size:
+ * ObBlockBatchedRowStore::get_row_ids -> ObMicroBlockDecoder::get_rows per projected column.
+ * ============================================================================================= */
+int ora_scan_blocks(const void *image, const int64_t *offsets, const int64_t *sizes, int32_t block_begin,
+                    int32_t block_end, const ora_filter *filter, const int32_t *proj_cols, int32_t n_proj,
+                    int32_t batch_size, int64_t out_row_begin, ora_scan_out *out, int64_t *total_rows,
+                    int64_t *selected) {
+  if (!image || !offsets || !sizes || !out || batch_size <= 0 || batch_size > ORA_MAX_BATCH) return ORA_INVALID_ARGUMENT;
+  int64_t nsel = out_row_begin, nrows = 0;
+  uint8_t *bitmap = 0;
+  int64_t bitmap_cap = 0;
+  int32_t row_ids[ORA_MAX_BATCH];
+  int ret = ORA_SUCCESS;
+  if (out->sel_offset) out->sel_offset[block_begin] = out_row_begin;
+  for (int32_t bi = block_begin; bi < block_end && ret == ORA_SUCCESS; ++bi) {
+    ora_block b;
+    const uint8_t *bbuf = (const uint8_t *)image + offsets[bi];
+    if ((ret = ora_block_init(&b, bbuf, sizes[bi]))) break;
+    const int64_t rc = b.row_count;
+    nrows += rc;
+    if (rc > bitmap_cap) {
+      free(bitmap);
+      bitmap_cap = rc + 1024;
+      bitmap = (uint8_t *)malloc((size_t)bitmap_cap);
+      if (!bitmap) { ret = ORA_ERR_UNEXPECTED; break; }
+    }
+    if (filter && filter->n_nodes > 0) {
+      if ((ret = ora_filter_tree(&b, filter, 0, rc, bitmap))) break;
+    } else {
+      memset(bitmap, 1, (size_t)rc);
+    }
+    int64_t from = 0;
+    while (from < rc && ret == ORA_SUCCESS) {
+      int64_t cnt = 0;
+      if ((ret = ora_bitmap_get_row_ids(bitmap, rc, row_ids, &cnt, &from, rc, batch_size, 0))) break;
+      if (cnt == 0) continue;
+      if (nsel + cnt > out->cap_rows) { ret = ORA_BUF_NOT_ENOUGH; break; }
+      if (out->row_ids) memcpy(out->row_ids + nsel, row_ids, (size_t)cnt * 4);
+      for (int32_t p = 0; p < n_proj && ret == ORA_SUCCESS; ++p) {
+        col_hdr h;
+        if ((ret = get_col(&b, proj_cols[p], &h))) break;
+        if (obj_store_class(h.obj_type) == 5) {
+          if (!out->data || !out->data[p]) continue;
+          const uint8_t *ptrs[ORA_MAX_BATCH];
+          int32_t lens[ORA_MAX_BATCH];
+          uint64_t nulls[ORA_MAX_BATCH / 64 + 1];
+          memset(nulls, 0, sizeof(nulls));
+          memset(ptrs, 0, sizeof(ptrs[0]) * (size_t)cnt);
+          memset(lens, 0, sizeof(lens[0]) * (size_t)cnt);
+          int32_t hn = 0;
+          if ((ret = ora_get_rows_discrete(&b, proj_cols[p], row_ids, cnt, 0, ptrs, lens, nulls, &hn))) break;
+          uint64_t *dp = (uint64_t *)out->data[p];
+          for (int64_t i = 0; i < cnt; ++i) {
+            const int isnull = (nulls[i / 64] >> (i % 64)) & 1;
+            dp[nsel + i] = isnull ? 0 : out->string_base + (uint64_t)(ptrs[i] - (const uint8_t *)image);
+            if (out->lens && out->lens[p]) out->lens[p][nsel + i] = isnull ? 0 : lens[i];
+            if (isnull && out->nulls && out->nulls[p]) bitvec_set(out->nulls[p], nsel + i);
+          }
+          if (hn && out->has_null) out->has_null[p] = 1;
+        } else {
+          if (!out->data || !out->data[p]) continue;
+          int32_t hn = 0;
+          if ((ret = ora_get_rows_fixed(&b, proj_cols[p], row_ids, cnt, nsel, out->data[p], obj_datum_len(h.obj_type),
+                                        out->nulls ? out->nulls[p] : 0, &hn))) break;
+          if (hn && out->has_null) out->has_null[p] = 1;
+        }
+      }
+      nsel += cnt;
+    }
+    if (out->sel_offset) out->sel_offset[bi + 1] = nsel;
+  }
+  free(bitmap);
+  if (total_rows) *total_rows = nrows;
+  if (selected) *selected = nsel - out_row_begin;
+  return ret;
+}
+
+/* ---- multi-threaded timing harness ----------------------------------------------------------- */
+typedef struct mt_arg {
+  const void *image; const int64_t *offsets, *sizes; int32_t b0, b1;
+  const ora_filter *filter; const int32_t *proj; int32_t n_proj, batch;
+  int64_t rows, sel; uint64_t checksum; int ret;
+} mt_arg;
+
+static void *mt_worker(void *vp) {
+  mt_arg *a = (mt_arg *)vp;
+  a->rows = a->sel = 0; a->checksum = 0; a->ret = ORA_SUCCESS;
+  uint8_t *bitmap = 0; int64_t bitmap_cap = 0;
+  int32_t row_ids[ORA_MAX_BATCH];
+  uint64_t vals[ORA_MAX_BATCH];
+  const uint8_t *ptrs[ORA_MAX_BATCH];
+  int32_t lens[ORA_MAX_BATCH];
+  uint64_t nulls[ORA_MAX_BATCH / 64 + 1];
+  for (int32_t bi = a->b0; bi < a->b1 && a->ret == ORA_SUCCESS; ++bi) {
+    ora_block b;
+    if ((a->ret = ora_block_init(&b, (const uint8_t *)a->image + a->offsets[bi], a->sizes[bi]))) break;
+    const int64_t rc = b.row_count;
+    a->rows += rc;
+    if (rc > bitmap_cap) { free(bitmap); bitmap_cap = rc + 1024; bitmap = (uint8_t *)malloc((size_t)bitmap_cap); }
+    if (a->filter && a->filter->n_nodes > 0) { if ((a->ret = ora_filter_tree(&b, a->filter, 0, rc, bitmap))) break; }
+    else memset(bitmap, 1, (size_t)rc);
+    int64_t from = 0;
+    while (from < rc && a->ret == ORA_SUCCESS) {
+      int64_t cnt = 0;
+      if ((a->ret = ora_bitmap_get_row_ids(bitmap, rc, row_ids, &cnt, &from, rc, a->batch, 0))) break;
+      if (!cnt) continue;
+      for (int32_t p = 0; p < a->n_proj && a->ret == ORA_SUCCESS; ++p) {
+        col_hdr h;
+        if ((a->ret = get_col(&b, a->proj[p], &h))) break;
+        int32_t hn = 0;
+        memset(nulls, 0, sizeof(uint64_t) * (size_t)(cnt / 64 + 1));
+        if (obj_store_class(h.obj_type) == 5) {
+          if ((a->ret = ora_get_rows_discrete(&b, a->proj[p], row_ids, cnt, 0, ptrs, lens, nulls, &hn))) break;
+          for (int64_t i = 0; i < cnt; ++i) if (!((nulls[i / 64] >> (i % 64)) & 1)) a->checksum += (uint64_t)lens[i] + ptrs[i][0];
+        } else {
+          const int el = obj_datum_len(h.obj_type);
+          memset(vals, 0, sizeof(uint64_t) * (size_t)cnt);
+          if ((a->ret = ora_get_rows_fixed(&b, a->proj[p], row_ids, cnt, 0, vals, el, nulls, &hn))) break;
+          if (el == 8) for (int64_t i = 0; i < cnt; ++i) a->checksum += vals[i];
+          else for (int64_t i = 0; i < cnt; ++i) a->checksum += rd_len((const uint8_t *)vals + i * el, el);
+        }
+      }
+      a->sel += cnt;
+    }
+  }
+  free(bitmap);
+  return 0;
+}
+
+int ora_scan_blocks_mt(const void *image, const int64_t *offsets, const int64_t *sizes, int32_t n_blocks,
+                       const ora_filter *filter, const int32_t *proj_cols, int32_t n_proj, int32_t batch_size,
+                       int32_t n_threads, int64_t *total_rows, int64_t *selected, uint64_t *checksum) {
+  if (!image || n_blocks <= 0 || n_threads <= 0 || batch_size <= 0 || batch_size > ORA_MAX_BATCH) return ORA_INVALID_ARGUMENT;
+  if (n_threads > n_blocks) n_threads = n_blocks;
+  mt_arg *args = (mt_arg *)calloc((size_t)n_threads, sizeof(mt_arg));
+  pthread_t *th = (pthread_t *)calloc((size_t)n_threads, sizeof(pthread_t));
+  if (!args || !th) { free(args); free(th); return ORA_ERR_UNEXPECTED; }
+  for (int32_t t = 0; t < n_threads; ++t) {
+    args[t].image = image; args[t].offsets = offsets; args[t].sizes = sizes;
+    args[t].b0 = (int32_t)((int64_t)n_blocks * t / n_threads);
+    args[t].b1 = (int32_t)((int64_t)n_blocks * (t + 1) / n_threads);
+    args[t].filter = filter; args[t].proj = proj_cols; args[t].n_proj = n_proj; args[t].batch = batch_size;
+    if (t > 0) pthread_create(&th[t], 0, mt_worker, &args[t]);
+  }
+  mt_worker(&args[0]);
+  int ret = args[0].ret;
+  int64_t rows = args[0].rows, sel = args[0].sel;
+  uint64_t cs = args[0].checksum;
+  for (int32_t t = 1; t < n_threads; ++t) {
+    pthread_join(th[t], 0);
+    if (args[t].ret && !ret) ret = args[t].ret;
+    rows += args[t].rows; sel += args[t].sel; cs += args[t].checksum;
+  }
+  free(args); free(th);
+  if (total_rows) *total_rows = rows;
+  if (selected) *selected = sel;
+  if (checksum) *checksum = cs;
+  return ret;
+}

@@ -1,0 +1,143 @@
+/*
+ * ob_oracle.h -- CPU oracle for the columnar-scan hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  This is a plain-C restatement of the reference's (OceanBase 4.6.0.0)
+ * CPU algorithm for PAX micro-block decode, pushed-down white filters, ObBitmap row-id extraction
+ * and batch projection.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs may build, load or call it; the product (libobgpu_scan.so) never does.
+ *
+ * Pinning status: the bit-stream primitives are checked against the reference's own
+ * ObBitStream compiled from /root/reference (oracle/_ref, see Makefile + tests/test_ref_pin.py)
+ * and against the reference's known-answer tests (unittest/.../test_bit_stream.cpp:151-200);
+ * filter semantics are checked against the popcount expectations of
+ * unittest/.../test_raw_decoder.cpp:774-1200 re-expressed in tests/test_oracle_filter_kat.py.
+ * The reference ships no byte-level golden micro-blocks, so whole-block decode is
+ * pinned by construction (layout restated from the encoder) and by the independent GPU decoder.
+ *
+ * Each function cites the reference file:line it follows.
+ */
+#ifndef OB_ORACLE_H_
+#define OB_ORACLE_H_
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORA_SUCCESS 0
+#define ORA_INVALID_ARGUMENT (-4002)
+#define ORA_NOT_SUPPORTED (-4007)
+#define ORA_ERR_UNEXPECTED (-4016)
+#define ORA_BUF_NOT_ENOUGH (-4024)
+#define ORA_INVALID_DATA (-4070)
+
+enum { ORA_OP_EQ = 0, ORA_OP_LE, ORA_OP_LT, ORA_OP_GE, ORA_OP_GT, ORA_OP_NE, ORA_OP_BT, ORA_OP_IN,
+       ORA_OP_NU, ORA_OP_NN, ORA_OP_MAX };
+enum { ORA_NODE_WHITE = 0, ORA_NODE_AND = 1, ORA_NODE_OR = 2 };
+
+typedef struct ora_param {
+  int64_t i64;
+  const char *ptr;
+  uint32_t len;
+  int32_t is_null;
+} ora_param;
+
+typedef struct ora_node {
+  int32_t kind, op, col, param_begin, n_params, n_children;
+} ora_node;
+
+typedef struct ora_filter {
+  const ora_node *nodes;
+  int32_t n_nodes;
+  const ora_param *params;
+  int32_t n_params;
+} ora_filter;
+
+/* One decoded cell (ObDatum restated: ptr_/len_/null_). Integers are materialised in ival. */
+typedef struct ora_datum {
+  const uint8_t *ptr; /* strings: points into the block buffer */
+  uint32_t len;       /* datum length: 8/4/1 for integer classes, byte length for strings */
+  int32_t is_null;
+  uint64_t ival;      /* integer classes: value image (len low bytes are significant) */
+} ora_datum;
+
+/* Parsed view of one micro-block (ObMicroBlockDecoder::do_init). */
+typedef struct ora_block {
+  const uint8_t *buf;
+  int64_t size;
+  uint32_t header_size, row_count, row_data_offset;
+  uint16_t column_count, rowkey_column_count, var_column_count;
+  uint8_t row_index_byte, extend_value_bit;
+  const uint8_t *col_headers; /* column_count x 16 bytes */
+  const uint8_t *meta;        /* encoding meta start: column offsets are relative to it */
+  const uint8_t *row_data;
+  int64_t row_data_len;
+} ora_block;
+
+/* ---- bit stream (encoding/ob_bit_stream.h:169-283) -------------------------------------------- */
+uint64_t ora_bs_get(const uint8_t *buf, int64_t offset, int64_t cnt);
+uint64_t ora_bs_get_fast(const uint8_t *buf, int64_t offset, int64_t cnt, int64_t bs_len);
+void ora_bs_set(uint8_t *buf, int64_t offset, int64_t cnt, uint64_t value);
+
+/* ---- block ------------------------------------------------------------------------------------ */
+int ora_block_init(ora_block *blk, const void *buf, int64_t size);
+/* data checksum / header checksum verification (ob_micro_block_header.cpp:236-285) */
+int ora_block_verify_checksums(const ora_block *blk);
+int ora_decode_cell(const ora_block *blk, int32_t col, int64_t row, ora_datum *out);
+
+/* ObMicroBlockDecoder::get_rows into VEC_FIXED (data, nulls as ObBitVector words). */
+int ora_get_rows_fixed(const ora_block *blk, int32_t col, const int32_t *row_ids, int64_t row_cap,
+                       int64_t vec_offset, void *data, int32_t elem_len, uint64_t *nulls,
+                       int32_t *has_null);
+/* ... into VEC_DISCRETE (ptrs into the block buffer, lens). */
+int ora_get_rows_discrete(const ora_block *blk, int32_t col, const int32_t *row_ids,
+                          int64_t row_cap, int64_t vec_offset, const uint8_t **ptrs, int32_t *lens,
+                          uint64_t *nulls, int32_t *has_null);
+
+/* ---- filters ---------------------------------------------------------------------------------- */
+int ora_filter_white(const ora_block *blk, int32_t col, int32_t op, const ora_param *params,
+                     int32_t n_params, int64_t start, int64_t count, uint8_t *bitmap);
+int ora_filter_tree(const ora_block *blk, const ora_filter *filter, int64_t start, int64_t count,
+                    uint8_t *bitmap);
+
+/* ---- ObBitmap (lib/container/ob_bitmap.cpp) ---------------------------------------------------- */
+int ora_bitmap_get_row_ids(const uint8_t *bitmap, int64_t valid_bytes, int32_t *row_ids,
+                           int64_t *row_count, int64_t *from, int64_t to, int64_t limit,
+                           int64_t id_offset);
+int64_t ora_bitmap_popcnt(const uint8_t *bitmap, int64_t n);
+
+/* ---- whole-path scan (reference control structure) ----------------------------- */
+typedef struct ora_scan_out {
+  /* per projected column, dense over selected rows; any pointer may be NULL to skip storing */
+  void **data;          /* n_proj: int columns elem_len-byte values; string columns uint64 ptrs */
+  int32_t **lens;       /* n_proj: string columns lens (NULL entries for int columns) */
+  uint64_t **nulls;     /* n_proj: ObBitVector words */
+  int32_t *has_null;    /* n_proj */
+  int32_t *row_ids;     /* block-relative row ids of selected rows (optional) */
+  int64_t *sel_offset;  /* n_blocks + 1 (optional) */
+  int64_t cap_rows;     /* capacity of the dense arrays in rows */
+  uint64_t string_base; /* ptr value = string_base + (cell address - image) */
+} ora_scan_out;
+
+/* Scans blocks [block_begin, block_end) of the image with the reference's control structure:
+ * per block filter -> ObBitmap -> get_row_ids(limit = batch_size) -> per column get_rows.
+ * Dense output starts at out_row_begin. Returns selected row count in *selected. */
+int ora_scan_blocks(const void *image, const int64_t *offsets, const int64_t *sizes,
+                    int32_t block_begin, int32_t block_end, const ora_filter *filter,
+                    const int32_t *proj_cols, int32_t n_proj, int32_t batch_size,
+                    int64_t out_row_begin, ora_scan_out *out, int64_t *total_rows,
+                    int64_t *selected);
+
+/* Multi-threaded timing harness for the CPU baseline: blocks sharded contiguously over n_threads
+ * threads, each thread projecting into its own scratch (sized batch_size) -- i.e. the work of the
+ * scan without materialising one dense result. Returns rows scanned / selected and a checksum of
+ * every projected value so the work cannot be optimised away. */
+int ora_scan_blocks_mt(const void *image, const int64_t *offsets, const int64_t *sizes,
+                       int32_t n_blocks, const ora_filter *filter, const int32_t *proj_cols,
+                       int32_t n_proj, int32_t batch_size, int32_t n_threads, int64_t *total_rows,
+                       int64_t *selected, uint64_t *checksum);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

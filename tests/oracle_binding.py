@@ -1,0 +1,249 @@
+"""ctypes binding of the CPU oracle (oracle/libob_oracle.so). TEST INFRASTRUCTURE: only tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+ORACLE_LIB = os.path.join(ORACLE_DIR, "libob_oracle.so")
+REF_LIB = os.path.join(ORACLE_DIR, "_ref", "libref_bitstream.so")
+
+
+def build_oracle():
+    src = [os.path.join(ORACLE_DIR, f) for f in ("ob_oracle.c", "ob_oracle.h", "Makefile")]
+    stale = (not os.path.exists(ORACLE_LIB)) or any(os.path.getmtime(s) > os.path.getmtime(ORACLE_LIB) for s in src)
+    if stale:
+        subprocess.run(["make", "-C", ORACLE_DIR, "-s", "all"], check=True, capture_output=True)
+    elif os.path.isdir("/root/reference") and not os.path.exists(REF_LIB):
+        subprocess.run(["make", "-C", ORACLE_DIR, "-s", "ref"], check=True, capture_output=True)
+    return ORACLE_LIB
+
+
+class OraParam(C.Structure):
+    _fields_ = [("i64", C.c_int64), ("ptr", C.c_char_p), ("len", C.c_uint32), ("is_null", C.c_int32)]
+
+
+class OraNode(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("op", C.c_int32), ("col", C.c_int32), ("param_begin", C.c_int32),
+                ("n_params", C.c_int32), ("n_children", C.c_int32)]
+
+
+class OraFilter(C.Structure):
+    _fields_ = [("nodes", C.POINTER(OraNode)), ("n_nodes", C.c_int32), ("params", C.POINTER(OraParam)),
+                ("n_params", C.c_int32)]
+
+
+class OraDatum(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("len", C.c_uint32), ("is_null", C.c_int32), ("ival", C.c_uint64)]
+
+
+class OraBlock(C.Structure):
+    _fields_ = [("buf", C.c_void_p), ("size", C.c_int64), ("header_size", C.c_uint32), ("row_count", C.c_uint32),
+                ("row_data_offset", C.c_uint32), ("column_count", C.c_uint16), ("rowkey_column_count", C.c_uint16),
+                ("var_column_count", C.c_uint16), ("row_index_byte", C.c_uint8), ("extend_value_bit", C.c_uint8),
+                ("col_headers", C.c_void_p), ("meta", C.c_void_p), ("row_data", C.c_void_p),
+                ("row_data_len", C.c_int64)]
+
+
+class OraScanOut(C.Structure):
+    _fields_ = [("data", C.POINTER(C.c_void_p)), ("lens", C.POINTER(C.c_void_p)), ("nulls", C.POINTER(C.c_void_p)),
+                ("has_null", C.c_void_p), ("row_ids", C.c_void_p), ("sel_offset", C.c_void_p),
+                ("cap_rows", C.c_int64), ("string_base", C.c_uint64)]
+
+
+_lib = None
+
+
+def oracle():
+    global _lib
+    if _lib is None:
+        build_oracle()
+        L = C.CDLL(ORACLE_LIB)
+        vp, i32, i64, u64 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64
+        P = C.POINTER
+        L.ora_bs_get.restype = u64
+        L.ora_bs_get.argtypes = [vp, i64, i64]
+        L.ora_bs_get_fast.restype = u64
+        L.ora_bs_get_fast.argtypes = [vp, i64, i64, i64]
+        L.ora_bs_set.restype = None
+        L.ora_bs_set.argtypes = [vp, i64, i64, u64]
+        L.ora_block_init.argtypes = [P(OraBlock), vp, i64]
+        L.ora_block_verify_checksums.argtypes = [P(OraBlock)]
+        L.ora_decode_cell.argtypes = [P(OraBlock), i32, i64, P(OraDatum)]
+        L.ora_get_rows_fixed.argtypes = [P(OraBlock), i32, vp, i64, i64, vp, i32, vp, P(i32)]
+        L.ora_get_rows_discrete.argtypes = [P(OraBlock), i32, vp, i64, i64, vp, vp, vp, P(i32)]
+        L.ora_filter_white.argtypes = [P(OraBlock), i32, i32, P(OraParam), i32, i64, i64, vp]
+        L.ora_filter_tree.argtypes = [P(OraBlock), P(OraFilter), i64, i64, vp]
+        L.ora_bitmap_get_row_ids.argtypes = [vp, i64, vp, P(i64), P(i64), i64, i64, i64]
+        L.ora_bitmap_popcnt.restype = i64
+        L.ora_bitmap_popcnt.argtypes = [vp, i64]
+        L.ora_scan_blocks.argtypes = [vp, vp, vp, i32, i32, P(OraFilter), vp, i32, i32, i64, P(OraScanOut), P(i64),
+                                      P(i64)]
+        L.ora_scan_blocks_mt.argtypes = [vp, vp, vp, i32, P(OraFilter), vp, i32, i32, i32, P(i64), P(i64), P(u64)]
+        _lib = L
+    return _lib
+
+
+def ref_bitstream():
+    """The REAL reference ObBitStream (oracle/_ref), or None when it was never built."""
+    if not os.path.exists(REF_LIB):
+        return None
+    L = C.CDLL(REF_LIB)
+    L.ref_bs_get.restype = C.c_uint64
+    L.ref_bs_get.argtypes = [C.c_void_p, C.c_int64, C.c_int64]
+    L.ref_bs_get_unpack.restype = C.c_uint64
+    L.ref_bs_get_unpack.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64]
+    L.ref_bs_memory_safe_set.restype = None
+    L.ref_bs_memory_safe_set.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_uint64]
+    L.ref_bs_set.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64]
+    L.ref_bs_get_mask.restype = C.c_uint64
+    L.ref_bs_get_mask.argtypes = [C.c_int64]
+    return L
+
+
+def ora_check(code, what):
+    if code != 0:
+        raise RuntimeError(f"oracle {what} failed: {code}")
+
+
+class Block:
+    """One parsed micro-block view for the oracle."""
+
+    def __init__(self, buf: np.ndarray):
+        self.buf = np.ascontiguousarray(buf, dtype=np.uint8)
+        self.b = OraBlock()
+        ora_check(oracle().ora_block_init(C.byref(self.b), self.buf.ctypes.data, self.buf.size), "ora_block_init")
+        self.row_count = self.b.row_count
+        self.column_count = self.b.column_count
+
+    def verify_checksums(self):
+        return oracle().ora_block_verify_checksums(C.byref(self.b))
+
+    def cell(self, col, row):
+        d = OraDatum()
+        ora_check(oracle().ora_decode_cell(C.byref(self.b), col, row, C.byref(d)), "ora_decode_cell")
+        if d.is_null:
+            return None
+        if d.ptr:
+            off = d.ptr - self.buf.ctypes.data
+            return bytes(self.buf[off:off + d.len])
+        if d.len and d.ival == 0 and False:
+            return 0
+        return d.ival if d.len else b""
+
+    def cell_raw(self, col, row):
+        d = OraDatum()
+        ora_check(oracle().ora_decode_cell(C.byref(self.b), col, row, C.byref(d)), "ora_decode_cell")
+        return d
+
+    def get_rows_fixed(self, col, row_ids, elem_len=8, vec_offset=0, data=None, nulls=None):
+        rid = np.ascontiguousarray(row_ids, dtype=np.int32)
+        total = vec_offset + len(rid)
+        if data is None:
+            data = np.zeros(total * elem_len, dtype=np.uint8)
+        if nulls is None:
+            nulls = np.zeros((total + 63) // 64, dtype=np.uint64)
+        hn = C.c_int32(0)
+        ora_check(oracle().ora_get_rows_fixed(C.byref(self.b), col, rid.ctypes.data, len(rid), vec_offset,
+                                              data.ctypes.data, elem_len, nulls.ctypes.data, C.byref(hn)),
+                  "ora_get_rows_fixed")
+        return data, nulls, hn.value
+
+    def get_rows_discrete(self, col, row_ids, vec_offset=0):
+        rid = np.ascontiguousarray(row_ids, dtype=np.int32)
+        total = vec_offset + len(rid)
+        ptrs = np.zeros(total, dtype=np.uint64)
+        lens = np.zeros(total, dtype=np.int32)
+        nulls = np.zeros((total + 63) // 64, dtype=np.uint64)
+        hn = C.c_int32(0)
+        ora_check(oracle().ora_get_rows_discrete(C.byref(self.b), col, rid.ctypes.data, len(rid), vec_offset,
+                                                 ptrs.ctypes.data, lens.ctypes.data, nulls.ctypes.data, C.byref(hn)),
+                  "ora_get_rows_discrete")
+        # pointers -> offsets inside the block buffer
+        offs = np.where(ptrs != 0, ptrs - np.uint64(self.buf.ctypes.data), 0).astype(np.uint64)
+        return offs, lens, nulls, hn.value
+
+    def filter_tree(self, expr, start=0, count=None):
+        from oceanbase_b200.scan import flatten_filter
+        f, keep = flatten_filter(expr, OraNode, OraParam, OraFilter)
+        if count is None:
+            count = self.row_count - start
+        out = np.zeros(max(count, 1), dtype=np.uint8)
+        ora_check(oracle().ora_filter_tree(C.byref(self.b), C.byref(f), start, count, out.ctypes.data),
+                  "ora_filter_tree")
+        return out[:count]
+
+
+def bitmap_get_row_ids(bitmap, start, to, limit, id_offset=0):
+    bm = np.ascontiguousarray(bitmap, dtype=np.uint8)
+    out = np.zeros(max(limit, 1), dtype=np.int32)
+    frm, cnt = C.c_int64(start), C.c_int64(0)
+    code = oracle().ora_bitmap_get_row_ids(bm.ctypes.data, bm.size, out.ctypes.data, C.byref(cnt), C.byref(frm), to,
+                                           limit, id_offset)
+    ora_check(code, "ora_bitmap_get_row_ids")
+    return out[:cnt.value].copy(), frm.value
+
+
+def scan_table(table, filter_expr, proj_cols, proj_is_string, proj_elem_len, batch_size=256, want_row_ids=True,
+               string_base=0):
+    """Full-path oracle scan of a TableImage. Returns dict with dense outputs."""
+    from oceanbase_b200.scan import flatten_filter
+    L = oracle()
+    f, keep = flatten_filter(filter_expr, OraNode, OraParam, OraFilter)
+    n_proj = len(proj_cols)
+    cap = table.total_rows
+    datas, lens, nulls = [], [], []
+    for i in range(n_proj):
+        if proj_is_string[i]:
+            datas.append(np.zeros(max(cap, 1), dtype=np.uint64))
+            lens.append(np.zeros(max(cap, 1), dtype=np.int32))
+        else:
+            dt = {8: np.uint64, 4: np.uint32, 1: np.uint8}[proj_elem_len[i]]
+            datas.append(np.zeros(max(cap, 1), dtype=dt))
+            lens.append(None)
+        nulls.append(np.zeros(max((cap + 63) // 64, 1), dtype=np.uint64))
+    has_null = np.zeros(max(n_proj, 1), dtype=np.int32)
+    row_ids = np.zeros(max(cap, 1), dtype=np.int32)
+    sel_off = np.zeros(table.n_blocks + 1, dtype=np.int64)
+    out = OraScanOut()
+    da = (C.c_void_p * max(n_proj, 1))(*[d.ctypes.data for d in datas])
+    la = (C.c_void_p * max(n_proj, 1))(*[(l.ctypes.data if l is not None else None) for l in lens])
+    na = (C.c_void_p * max(n_proj, 1))(*[n.ctypes.data for n in nulls])
+    out.data, out.lens, out.nulls = da, la, na
+    out.has_null = has_null.ctypes.data
+    out.row_ids = row_ids.ctypes.data if want_row_ids else None
+    out.sel_offset = sel_off.ctypes.data
+    out.cap_rows = cap
+    out.string_base = string_base
+    proj = np.ascontiguousarray(proj_cols, dtype=np.int32)
+    total, sel = C.c_int64(0), C.c_int64(0)
+    offs = np.ascontiguousarray(table.offsets, dtype=np.int64)
+    sizes = np.ascontiguousarray(table.sizes, dtype=np.int64)
+    code = L.ora_scan_blocks(table.image.ctypes.data, offs.ctypes.data, sizes.ctypes.data, 0, table.n_blocks,
+                             C.byref(f) if f is not None else None, proj.ctypes.data, n_proj, batch_size, 0,
+                             C.byref(out), C.byref(total), C.byref(sel))
+    ora_check(code, "ora_scan_blocks")
+    n = sel.value
+    return {"total_rows": total.value, "selected": n, "data": [d[:n] for d in datas],
+            "lens": [(l[:n] if l is not None else None) for l in lens],
+            "nulls": [x[:(n + 63) // 64] for x in nulls], "has_null": has_null[:n_proj].copy(),
+            "row_ids": row_ids[:n], "sel_offset": sel_off}
+
+
+def scan_table_mt(table, filter_expr, proj_cols, batch_size=256, n_threads=1, block_limit=None):
+    from oceanbase_b200.scan import flatten_filter
+    L = oracle()
+    f, keep = flatten_filter(filter_expr, OraNode, OraParam, OraFilter)
+    proj = np.ascontiguousarray(proj_cols, dtype=np.int32)
+    offs = np.ascontiguousarray(table.offsets, dtype=np.int64)
+    sizes = np.ascontiguousarray(table.sizes, dtype=np.int64)
+    nb = table.n_blocks if block_limit is None else min(block_limit, table.n_blocks)
+    total, sel, cs = C.c_int64(0), C.c_int64(0), C.c_uint64(0)
+    code = L.ora_scan_blocks_mt(table.image.ctypes.data, offs.ctypes.data, sizes.ctypes.data, nb,
+                                C.byref(f) if f is not None else None, proj.ctypes.data, len(proj_cols), batch_size,
+                                n_threads, C.byref(total), C.byref(sel), C.byref(cs))
+    ora_check(code, "ora_scan_blocks_mt")
+    return total.value, sel.value, cs.value
