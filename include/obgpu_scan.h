@@ -93,6 +93,11 @@ int obgpu_ctx_synchronize(obgpu_ctx *ctx);
 const char *obgpu_ctx_last_error(const obgpu_ctx *ctx);
 /* Number of kernels this ctx has launched so far (bench.py's gpu_launches). */
 int64_t obgpu_ctx_launch_count(const obgpu_ctx *ctx);
+/* Kernel timing: when enabled, a CUDA event pair is recorded on the ctx stream around every
+ * obgpu_scan kernel launch; obgpu_ctx_kernel_times synchronises and returns the durations (ms) of
+ * the most recent launches, oldest first (ring of 256). */
+int obgpu_ctx_set_profiling(obgpu_ctx *ctx, int32_t enable);
+int obgpu_ctx_kernel_times(obgpu_ctx *ctx, float *ms, int32_t cap, int32_t *n);
 
 /* =============================================================================================
  * Page batch = what ObSSTableRowScanner::open_cur_data_block hands to the reader one block at a

@@ -74,6 +74,8 @@ def declared_signatures():
         "obgpu_ctx_synchronize": (C.c_int, [vp]),
         "obgpu_ctx_last_error": (C.c_char_p, [vp]),
         "obgpu_ctx_launch_count": (i64, [vp]),
+        "obgpu_ctx_set_profiling": (C.c_int, [vp, i32]),
+        "obgpu_ctx_kernel_times": (C.c_int, [vp, vp, i32, P(i32)]),
         "obgpu_batch_open": (C.c_int, [vp, vp, i64, vp, vp, i32, i32, vp, P(vp)]),
         "obgpu_batch_close": (None, [vp]),
         "obgpu_batch_block_info": (C.c_int, [vp, i32, P(i64), P(i32)]),

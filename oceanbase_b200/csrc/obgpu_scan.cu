@@ -665,6 +665,11 @@ struct obgpu_ctx {
   int64_t launches = 0;
   int max_smem_optin = 0;
   int *h_pinned = nullptr;  // small pinned staging (status, totals)
+  // optional kernel timing: ring of CUDA event pairs recorded around each scan kernel launch
+  bool profiling = false;
+  static constexpr int kProfRing = 256;
+  cudaEvent_t ev0[kProfRing] = {nullptr}, ev1[kProfRing] = {nullptr};
+  int64_t prof_count = 0;
 };
 
 struct obgpu_batch {
@@ -746,9 +751,22 @@ int obgpu_ctx_create(int device, obgpu_ctx **out) {
     uint64_t thr = UINT64_MAX;
     cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
   }
-  cudaFuncSetAttribute(obgpu_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin);
-  cudaFuncSetAttribute(obgpu_filter_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin);
-  cudaFuncSetAttribute(obgpu_project_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin);
+  // opt in to the full shared-memory carve-out (dynamic limit = opt-in max - static usage)
+  auto opt_in = [&](const void *fn) {
+    cudaFuncAttributes fa{};
+    if (cudaFuncGetAttributes(&fa, fn) != cudaSuccess) return false;
+    return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                c->max_smem_optin - (int)fa.sharedSizeBytes) == cudaSuccess;
+  };
+  const bool ok = opt_in((const void *)obgpu_scan_kernel) && opt_in((const void *)obgpu_filter_block_kernel) &&
+                  opt_in((const void *)obgpu_project_block_kernel);
+  cudaGetLastError();  // do not leave a stale (non-sticky) error for later launch checks
+  if (!ok) {
+    g_last_global_err = "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed: not an sm_100a device?";
+    obgpu_ctx_destroy(c);
+    return OBGPU_ERR_SYS;
+  }
+  c->max_smem_optin -= 1024;  // head-room for the kernels' static shared memory
   *out = c;
   return OBGPU_SUCCESS;
 }
@@ -759,6 +777,10 @@ void obgpu_ctx_destroy(obgpu_ctx *ctx) {
   cudaStreamSynchronize(ctx->stream);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+  for (int i = 0; i < obgpu_ctx::kProfRing; ++i) {
+    if (ctx->ev0[i]) cudaEventDestroy(ctx->ev0[i]);
+    if (ctx->ev1[i]) cudaEventDestroy(ctx->ev1[i]);
+  }
   delete ctx;
 }
 
@@ -779,6 +801,34 @@ const char *obgpu_ctx_last_error(const obgpu_ctx *ctx) {
 }
 
 int64_t obgpu_ctx_launch_count(const obgpu_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int obgpu_ctx_set_profiling(obgpu_ctx *ctx, int32_t enable) {
+  if (!ctx) return OBGPU_INVALID_ARGUMENT;
+  cudaSetDevice(ctx->device);
+  if (enable && !ctx->ev0[0]) {
+    for (int i = 0; i < obgpu_ctx::kProfRing; ++i) {
+      CUDA_TRY(ctx, cudaEventCreate(&ctx->ev0[i]));
+      CUDA_TRY(ctx, cudaEventCreate(&ctx->ev1[i]));
+    }
+  }
+  ctx->profiling = enable != 0;
+  ctx->prof_count = 0;
+  return OBGPU_SUCCESS;
+}
+
+int obgpu_ctx_kernel_times(obgpu_ctx *ctx, float *ms, int32_t cap, int32_t *n) {
+  if (!ctx || !ms || !n || cap < 0) return OBGPU_INVALID_ARGUMENT;
+  cudaSetDevice(ctx->device);
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  const int64_t have = std::min<int64_t>(ctx->prof_count, obgpu_ctx::kProfRing);
+  const int64_t take = std::min<int64_t>(have, cap);
+  for (int64_t k = 0; k < take; ++k) {
+    const int64_t idx = (ctx->prof_count - take + k) % obgpu_ctx::kProfRing;
+    CUDA_TRY(ctx, cudaEventElapsedTime(&ms[k], ctx->ev0[idx], ctx->ev1[idx]));
+  }
+  *n = (int32_t)take;
+  return OBGPU_SUCCESS;
+}
 
 // ---- batch ------------------------------------------------------------------------------------
 static uint32_t rd32h(const uint8_t *p) { uint32_t v; memcpy(&v, p, 4); return v; }
@@ -1152,8 +1202,14 @@ int obgpu_scan(obgpu_batch *b, const obgpu_scan_spec *spec, obgpu_result **out) 
   r->d_sel_offset = p.sel_offset;
   r->d_bitmap = p.bitmap_words;
   r->d_row_ids = p.row_ids;
+  const int pslot = (int)(ctx->prof_count % obgpu_ctx::kProfRing);
+  if (ctx->profiling) cudaEventRecord(ctx->ev0[pslot], ctx->stream);
   obgpu_scan_kernel<<<n, kThreads, p.smem_total, ctx->stream>>>(p);
   e = cudaGetLastError();
+  if (ctx->profiling) {
+    cudaEventRecord(ctx->ev1[pslot], ctx->stream);
+    ctx->prof_count++;
+  }
   if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); obgpu_result_free(r); return OBGPU_ERR_SYS; }
   ctx->launches++;
   *out = r;

@@ -104,6 +104,16 @@ class ScanContext:
     def launch_count(self) -> int:
         return lib.obgpu_ctx_launch_count(self._h)
 
+    def set_profiling(self, enable: bool = True):
+        check(lib.obgpu_ctx_set_profiling(self._h, 1 if enable else 0), "obgpu_ctx_set_profiling", self._h)
+
+    def kernel_times_ms(self, last_n: int = 256) -> np.ndarray:
+        ms = np.zeros(max(last_n, 1), dtype=np.float32)
+        n = C.c_int32(0)
+        check(lib.obgpu_ctx_kernel_times(self._h, ms.ctypes.data, last_n, C.byref(n)), "obgpu_ctx_kernel_times",
+              self._h)
+        return ms[:n.value].copy()
+
     def last_error(self) -> str:
         return (lib.obgpu_ctx_last_error(self._h) or b"").decode()
 
