@@ -38,12 +38,17 @@ using namespace obdev;
 // =================================================================================================
 struct FilterNodeDev {
   int8_t kind;
-  int8_t slot;       // dictionary-bitset slot of a leaf (-1: none)
-  int16_t used_idx;  // leaf: index into ScanParams::used_col
+  int8_t slot;        // dictionary-bitset slot of a leaf (-1: none)
+  int8_t range_ok;    // leaf: integer compare reducible to one range test on the 64-bit image
+  int8_t negate;      // leaf: NE = NOT(range) for non-NULL rows
+  int16_t used_idx;   // leaf: index into ScanParams::used_col
   int16_t op;
   int16_t param_begin;
   int16_t n_params;
   int16_t n_children;
+  int16_t pad;
+  uint64_t lo;        // range test: (uint64)(v - lo) <= span
+  uint64_t span;
 };
 
 struct ParamDev {
@@ -62,13 +67,16 @@ struct ScanParams {
   int32_t n_blocks;
   int32_t n_used;
   int32_t used_col[kMaxUsedCols];
+  int8_t used_rle_slot[kMaxUsedCols];  // run-table slot of a used column (-1: never RLE)
   int32_t n_nodes;
-  int32_t simple_shape;       // 1: root is AND over leaves only, 2: OR over leaves only, 0: generic
+  int32_t simple_shape;       // 1: single leaf or AND over leaves only, 2: OR over leaves only, 0: generic
   FilterNodeDev nodes[kMaxNodes];
   ParamDev params[kMaxParams];
   uint8_t param_heap[kParamHeap];
   int32_t n_slots;
   int32_t bitset_words;       // words per slot
+  int32_t n_rle_slots;
+  int32_t rle_runs_cap;       // run-table capacity (runs) per slot
   int32_t n_proj;
   int32_t want_row_ids;
   int16_t proj_used[kMaxProj];
@@ -85,8 +93,9 @@ struct ScanParams {
   int32_t *status;
   int64_t out_cap;
   // shared-memory layout (bytes from the dynamic smem base)
-  uint32_t smem_sel, smem_bm, smem_wpre, smem_bitset, smem_desc, smem_total;
-  uint32_t rows_cap;
+  uint32_t smem_sel, smem_bm, smem_wpre, smem_bitset, smem_rle, smem_desc, smem_total;
+  uint32_t rle_slot_bytes;    // bytes per run-table slot: starts[(cap + 2)] + g2run[words_cap]
+  uint32_t rows_cap, words_cap;
 };
 
 // =================================================================================================
@@ -139,12 +148,14 @@ constexpr unsigned long long kTilePrefix = 2ull << 62;
 constexpr unsigned long long kTileValueMask = (1ull << 62) - 1ull;
 
 // Decoupled look-back executed by one warp. Returns the exclusive prefix of `cnt` over tiles.
-__device__ __forceinline__ int64_t lookback(unsigned long long *state, int tile, int64_t cnt, int lane) {
+// `publish_own`: this warp also publishes the tile's aggregate first (otherwise the caller did).
+__device__ __forceinline__ int64_t lookback(unsigned long long *state, int tile, int64_t cnt, int lane,
+                                            bool publish_own = true) {
   if (tile == 0) {
-    if (lane == 0) st_release(&state[0], kTilePrefix | (unsigned long long)cnt);
+    if (lane == 0 && publish_own) st_release(&state[0], kTilePrefix | (unsigned long long)cnt);
     return 0;
   }
-  if (lane == 0) st_release(&state[tile], kTileAgg | (unsigned long long)cnt);
+  if (lane == 0 && publish_own) st_release(&state[tile], kTileAgg | (unsigned long long)cnt);
   int64_t excl = 0;
   int idx = tile - 1;
   for (;;) {
@@ -173,6 +184,7 @@ __device__ __forceinline__ int64_t lookback(unsigned long long *state, int tile,
 __device__ __forceinline__ bool int_pred(const ScanParams &p, const FilterNodeDev &nd, const ColDesc &d,
                                          uint64_t v) {
   const int64_t a = cmp_image(d, v);
+  if (nd.range_ok) return (((uint64_t)a - nd.lo) <= nd.span) != (nd.negate != 0);
   const bool sgn = d.sc == 1;
   auto cmp3 = [&](int64_t c) -> int {
     if (sgn) return a < c ? -1 : (a > c ? 1 : 0);
@@ -207,49 +219,59 @@ __device__ __forceinline__ bool str_pred(const ScanParams &p, const FilterNodeDe
   return false;
 }
 
-__device__ __forceinline__ bool eval_leaf(const ScanParams &p, const BlockView &b, const ColDesc *descs,
-                                          const uint32_t *bitsets, const FilterNodeDev &nd, uint32_t row) {
+struct BlockCtx {
+  BlockView b;
+  const ColDesc *descs;
+  const uint32_t *bitsets;
+  const uint8_t *rle_base;   // run-table scratch
+  uint32_t rle_slot_bytes, rle_starts_bytes;
+  __device__ __forceinline__ RleTable rle_table(int slot) const {
+    RleTable t;
+    t.starts = reinterpret_cast<const uint16_t *>(rle_base + (uint32_t)slot * rle_slot_bytes);
+    t.g2run = reinterpret_cast<const uint16_t *>(rle_base + (uint32_t)slot * rle_slot_bytes + rle_starts_bytes);
+    return t;
+  }
+};
+
+// generic per-row leaf (any codec, any type)
+__device__ __forceinline__ bool eval_leaf(const ScanParams &p, const BlockCtx &c, const FilterNodeDev &nd,
+                                          uint32_t row) {
   const int op = nd.op;
   if (op == OP_FALSE) return false;
   if (op == OP_TRUE) return true;
-  const ColDesc &d = descs[nd.used_idx];
-  if (d.type == COL_DICT || d.type == COL_RLE) {
-    uint32_t ref = ref_of(b.s, d, row);
+  const ColDesc &d = c.descs[nd.used_idx];
+  RleTable rt{};
+  const RleTable *rtp = nullptr;
+  if (d.kind == K_RLE && d.rle_slot >= 0) {
+    rt = c.rle_table(d.rle_slot);
+    rtp = &rt;
+  }
+  if (d.kind == K_DICT || d.kind == K_RLE) {
+    uint32_t ref = ref_of(c.b.s, d, rtp, row);
     if (ref > d.dict_count + 1) ref = d.dict_count + 1;
-    return (bitsets[nd.slot * p.bitset_words + (ref >> 5)] >> (ref & 31)) & 1u;
+    return (c.bitsets[nd.slot * p.bitset_words + (ref >> 5)] >> (ref & 31)) & 1u;
   }
   bool is_null;
   if (d.sc == 5) {
     uint32_t cell, len;
-    str_cell(b, d, row, cell, len, is_null);
+    str_cell(c.b, d, rtp, row, cell, len, is_null);
     if (op == OP_NU) return is_null;
     if (op == OP_NN) return !is_null;
-    return !is_null && str_pred(p, nd, b.s, cell, len);
+    return !is_null && str_pred(p, nd, c.b.s, cell, len);
   }
-  const uint64_t v = int_cell(b, d, row, is_null);
+  const uint64_t v = int_cell(c.b, d, rtp, row, is_null);
   if (op == OP_NU) return is_null;
   if (op == OP_NN) return !is_null;
   return !is_null && int_pred(p, nd, d, v);
 }
 
-__device__ __forceinline__ bool eval_tree(const ScanParams &p, const BlockView &b, const ColDesc *descs,
-                                          const uint32_t *bitsets, uint32_t row) {
-  if (p.simple_shape == 1) {
-    for (int i = 0; i < p.n_nodes - 1; ++i)
-      if (!eval_leaf(p, b, descs, bitsets, p.nodes[i], row)) return false;
-    return true;
-  }
-  if (p.simple_shape == 2) {
-    for (int i = 0; i < p.n_nodes - 1; ++i)
-      if (eval_leaf(p, b, descs, bitsets, p.nodes[i], row)) return true;
-    return false;
-  }
+__device__ __forceinline__ bool eval_tree(const ScanParams &p, const BlockCtx &c, uint32_t row) {
   uint32_t stack = 0;
   for (int i = 0; i < p.n_nodes; ++i) {
     const FilterNodeDev &nd = p.nodes[i];
     bool r;
     if (nd.kind == NODE_WHITE) {
-      r = eval_leaf(p, b, descs, bitsets, nd, row);
+      r = eval_leaf(p, c, nd, row);
     } else {
       const uint32_t m = (1u << nd.n_children) - 1u;
       const uint32_t top = stack & m;
@@ -287,6 +309,82 @@ __device__ __forceinline__ void build_dict_bitset(const ScanParams &p, const Blo
   }
 }
 
+// One leaf evaluated column-at-a-time over the ballot words owned by this warp (g = warp, warp+8,
+// ...). `and_mode`: bm[g] &= leaf, skipping groups that are already all-false; else bm[g] |= leaf
+// for groups that are not yet all-true (the reference's can_skip_filter / early-out, per 32 rows).
+__device__ __forceinline__ void leaf_over_words(const ScanParams &p, const BlockCtx &c, const FilterNodeDev &nd,
+                                                uint32_t *bm, uint32_t rows, uint32_t nwords, bool and_mode,
+                                                int warp, int lane) {
+  const ColDesc &d = c.descs[nd.used_idx];
+  const uint8_t *s = c.b.s;
+  const int op = nd.op;
+  auto valid_mask = [&](uint32_t g) -> uint32_t {
+    const uint32_t rem = rows - g * 32u;
+    return rem >= 32u ? 0xffffffffu : ((1u << rem) - 1u);
+  };
+  // ---- fast path A: integer range test on a K_BITS column without NULLs ------------------------------
+  if (d.kind == K_BITS && nd.range_ok && d.elem_len == 8 && d.ext_bit == 0) {
+    const uint32_t val_bit = d.val_bit, stride = d.stride, width = d.width;
+    const uint64_t lo = nd.lo - d.base, span = nd.span;  // (v + base - lo) <= span
+    const bool neg = nd.negate != 0, fix = d.sign_fix != 0;
+    const uint64_t mask = d.int_mask;
+    for (uint32_t g = (uint32_t)warp; g < nwords; g += kWarps) {
+      const uint32_t cur = bm[g], vm = valid_mask(g);
+      if (and_mode ? cur == 0u : cur == vm) continue;
+      const uint32_t row = g * 32u + (uint32_t)lane;
+      uint64_t v = width <= 32 ? (uint64_t)ld_bits32(s, val_bit + row * stride, width)
+                               : ld_bits(s, val_bit + row * stride, width);
+      if (fix) v = sign_fix(mask, v);
+      const bool pr = ((v - lo) <= span) != neg;
+      const uint32_t w = __ballot_sync(0xffffffffu, pr) & vm;
+      if (lane == 0) bm[g] = and_mode ? (cur & w) : (cur | w);
+    }
+    return;
+  }
+  // ---- fast path B: dictionary-coded column through the predicate bitset ----------------------------
+  if ((d.kind == K_DICT || (d.kind == K_RLE && d.rle_slot >= 0)) && op != OP_FALSE && op != OP_TRUE) {
+    const uint32_t *bits = c.bitsets + nd.slot * p.bitset_words;
+    const uint32_t cntp1 = d.dict_count + 1;
+    if (d.kind == K_DICT) {
+      const uint32_t val_bit = d.val_bit, stride = d.stride, width = d.width;
+      for (uint32_t g = (uint32_t)warp; g < nwords; g += kWarps) {
+        const uint32_t cur = bm[g], vm = valid_mask(g);
+        if (and_mode ? cur == 0u : cur == vm) continue;
+        const uint32_t row = g * 32u + (uint32_t)lane;
+        uint32_t ref = ld_bits32(s, val_bit + row * stride, width);
+        ref = ref < cntp1 ? ref : cntp1;
+        const bool pr = (bits[ref >> 5] >> (ref & 31)) & 1u;
+        const uint32_t w = __ballot_sync(0xffffffffu, pr) & vm;
+        if (lane == 0) bm[g] = and_mode ? (cur & w) : (cur | w);
+      }
+    } else {
+      const RleTable rt = c.rle_table(d.rle_slot);
+      const uint32_t refs_bit = d.rle_refs_bit, ref_bits = d.rle_ref_bits;
+      for (uint32_t g = (uint32_t)warp; g < nwords; g += kWarps) {
+        const uint32_t cur = bm[g], vm = valid_mask(g);
+        if (and_mode ? cur == 0u : cur == vm) continue;
+        uint32_t row = g * 32u + (uint32_t)lane;
+        row = row < rows ? row : rows - 1u;
+        uint32_t ref = ld_bits32(s, refs_bit + rle_run_of(rt, row) * ref_bits, ref_bits);
+        ref = ref < cntp1 ? ref : cntp1;
+        const bool pr = (bits[ref >> 5] >> (ref & 31)) & 1u;
+        const uint32_t w = __ballot_sync(0xffffffffu, pr) & vm;
+        if (lane == 0) bm[g] = and_mode ? (cur & w) : (cur | w);
+      }
+    }
+    return;
+  }
+  // ---- generic leaf ----------------------------------------------------------------------------------
+  for (uint32_t g = (uint32_t)warp; g < nwords; g += kWarps) {
+    const uint32_t cur = bm[g], vm = valid_mask(g);
+    if (and_mode ? cur == 0u : cur == vm) continue;
+    const uint32_t row = g * 32u + (uint32_t)lane;
+    const bool pr = row < rows && eval_leaf(p, c, nd, row);
+    const uint32_t w = __ballot_sync(0xffffffffu, pr) & vm;
+    if (lane == 0) bm[g] = and_mode ? (cur & w) : (cur | w);
+  }
+}
+
 // =================================================================================================
 // Block-wide helpers
 // =================================================================================================
@@ -301,17 +399,190 @@ __device__ __forceinline__ void load_block(uint8_t *smem, const uint8_t *src, ui
   mbar_wait(bar, parity);
 }
 
+extern __shared__ __align__(128) uint8_t g_smem[];
+
+// Parses the staged block and builds descriptors + RLE run tables. Returns false (uniformly) when the
+// block cannot be handled; *corrupt tells why. Must be called by all threads.
+__device__ __forceinline__ bool prepare_block(const ScanParams &p, uint8_t *sblk, uint32_t size, BlockView *s_view,
+                                              ColDesc *descs, uint8_t *rle_base, BlockCtx &c, bool &corrupt) {
+  const int tid = threadIdx.x;
+  (void)s_view;
+  // every thread parses the 64-byte header itself (a handful of shared-memory loads): no barrier
+  parse_block(sblk, size, c.b);
+  if (c.b.ok && c.b.row_count > p.rows_cap) c.b.ok = 0;
+  corrupt = !c.b.ok;
+  bool my_bad = false;
+  if (c.b.ok && tid < p.n_used) {
+    ColDesc d;
+    build_col_desc(c.b, p.used_col[tid], d);
+    d.rle_slot = d.kind == K_RLE ? p.used_rle_slot[tid] : (int8_t)-1;
+    if (d.kind == K_RLE && d.rle_slot >= 0 && d.rle_count > (uint32_t)p.rle_runs_cap) d.ok = 0;
+    descs[tid] = d;
+    my_bad = !d.ok;
+  }
+  const bool bad = __syncthreads_or(my_bad || !c.b.ok) != 0;
+  c.descs = descs;
+  c.rle_base = rle_base;
+  c.rle_slot_bytes = p.rle_slot_bytes;
+  c.rle_starts_bytes = ((uint32_t)p.rle_runs_cap + 2u) * 2u;
+  if (bad) return false;
+  // RLE run tables
+  if (p.n_rle_slots > 0) {
+    const uint32_t nwords = (c.b.row_count + 31u) >> 5;
+    bool any = false;
+    for (int i = 0; i < p.n_used; ++i) {
+      const ColDesc &d = descs[i];
+      if (d.kind != K_RLE || d.rle_slot < 0) continue;
+      any = true;
+      uint16_t *starts = reinterpret_cast<uint16_t *>(rle_base + (uint32_t)d.rle_slot * p.rle_slot_bytes);
+      for (uint32_t k = (uint32_t)tid; k <= d.rle_count; k += kThreads)
+        starts[k] = k < d.rle_count
+                        ? (uint16_t)ld_bits32(sblk, d.rle_row_ids_bit + k * d.rle_row_id_bits, d.rle_row_id_bits)
+                        : (uint16_t)0xFFFF;
+    }
+    if (any) {
+      __syncthreads();
+      for (int i = 0; i < p.n_used; ++i) {
+        const ColDesc &d = descs[i];
+        if (d.kind != K_RLE || d.rle_slot < 0) continue;
+        const uint16_t *starts = reinterpret_cast<const uint16_t *>(rle_base + (uint32_t)d.rle_slot * p.rle_slot_bytes);
+        uint16_t *g2run = reinterpret_cast<uint16_t *>(rle_base + (uint32_t)d.rle_slot * p.rle_slot_bytes +
+                                                       c.rle_starts_bytes);
+        for (uint32_t g = (uint32_t)tid; g < nwords; g += kThreads) {
+          const uint32_t row = g * 32u;
+          uint32_t lo = 0, hi = d.rle_count;  // upper_bound(starts, row)
+          while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (starts[mid] <= row) lo = mid + 1; else hi = mid;
+          }
+          g2run[g] = (uint16_t)(lo > 0 ? lo - 1 : 0);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  return true;
+}
+
+// =================================================================================================
+// Projection of one integer column over the selected rows (column-at-a-time, specialised)
+// =================================================================================================
+template <typename OutT>
+__device__ __forceinline__ void project_int_col(const ScanParams &p, const BlockCtx &c, const ColDesc &d, int pc,
+                                                const uint16_t *sel, uint32_t cnt, int64_t base_row) {
+  const uint8_t *s = c.b.s;
+  OutT *out = reinterpret_cast<OutT *>(p.out_data[pc]) + base_row;
+  const int tid = threadIdx.x;
+  bool saw_null = false;
+  auto mark_null = [&](uint32_t j) {
+    const int64_t o = base_row + (int64_t)j;
+    atomicOr(&p.out_nulls[pc][o >> 5], 1u << (o & 31));
+    saw_null = true;
+  };
+  if (d.kind == K_BITS) {
+    const uint32_t val_bit = d.val_bit, stride = d.stride, width = d.width;
+    const uint64_t add = d.base, mask = d.int_mask;
+    const bool fix = d.sign_fix != 0;
+    if (d.ext_bit == 0) {
+      if (width <= 32) {
+        for (uint32_t j = (uint32_t)tid; j < cnt; j += kThreads) {
+          uint64_t v = (uint64_t)ld_bits32(s, val_bit + (uint32_t)sel[j] * stride, width) + add;
+          if (fix) v = sign_fix(mask, v);
+          out[j] = (OutT)v;
+        }
+      } else {
+        for (uint32_t j = (uint32_t)tid; j < cnt; j += kThreads) {
+          uint64_t v = ld_bits(s, val_bit + (uint32_t)sel[j] * stride, width) + add;
+          if (fix) v = sign_fix(mask, v);
+          out[j] = (OutT)v;
+        }
+      }
+    } else {
+      const uint32_t ext_off = d.ext_bit_off, eb = d.ext_bit;
+      for (uint32_t j = (uint32_t)tid; j < cnt; j += kThreads) {
+        const uint32_t row = sel[j];
+        if (ld_bits32(s, ext_off + row * eb, eb) != STORED_NOT_EXT) {
+          out[j] = (OutT)0;
+          mark_null(j);
+          continue;
+        }
+        uint64_t v = ld_bits(s, val_bit + row * stride, width) + add;
+        if (fix) v = sign_fix(mask, v);
+        out[j] = (OutT)v;
+      }
+    }
+  } else {  // K_DICT / K_RLE
+    const uint32_t dcount = d.dict_count, dbits = d.dict_data_size * 8u, dpay = d.dict_payload * 8u;
+    const uint64_t mask = d.int_mask;
+    const bool fix = d.sign_fix != 0;
+    if (d.kind == K_DICT) {
+      const uint32_t val_bit = d.val_bit, stride = d.stride, width = d.width;
+      for (uint32_t j = (uint32_t)tid; j < cnt; j += kThreads) {
+        const uint32_t ref = ld_bits32(s, val_bit + (uint32_t)sel[j] * stride, width);
+        if (ref >= dcount) {
+          out[j] = (OutT)0;
+          mark_null(j);
+          continue;
+        }
+        uint64_t v = ld_bits(s, dpay + ref * dbits, dbits);
+        if (fix) v = sign_fix(mask, v);
+        out[j] = (OutT)v;
+      }
+    } else {
+      const RleTable rt = c.rle_table(d.rle_slot);
+      const uint32_t refs_bit = d.rle_refs_bit, ref_bits = d.rle_ref_bits;
+      for (uint32_t j = (uint32_t)tid; j < cnt; j += kThreads) {
+        const uint32_t ref = ld_bits32(s, refs_bit + rle_run_of(rt, sel[j]) * ref_bits, ref_bits);
+        if (ref >= dcount) {
+          out[j] = (OutT)0;
+          mark_null(j);
+          continue;
+        }
+        uint64_t v = ld_bits(s, dpay + ref * dbits, dbits);
+        if (fix) v = sign_fix(mask, v);
+        out[j] = (OutT)v;
+      }
+    }
+  }
+  if (saw_null) p.has_null[pc] = 1;
+}
+
+__device__ __forceinline__ void project_str_col(const ScanParams &p, const BlockCtx &c, const ColDesc &d, int pc,
+                                                const uint16_t *sel, uint32_t cnt, int64_t base_row,
+                                                uint64_t blk_addr) {
+  uint64_t *optr = reinterpret_cast<uint64_t *>(p.out_data[pc]) + base_row;
+  int32_t *olen = p.out_lens[pc] + base_row;
+  RleTable rt{};
+  const RleTable *rtp = nullptr;
+  if (d.kind == K_RLE && d.rle_slot >= 0) {
+    rt = c.rle_table(d.rle_slot);
+    rtp = &rt;
+  }
+  bool saw_null = false;
+  for (uint32_t j = (uint32_t)threadIdx.x; j < cnt; j += kThreads) {
+    uint32_t cell, len;
+    bool is_null;
+    str_cell(c.b, d, rtp, sel[j], cell, len, is_null);
+    optr[j] = is_null ? 0ull : blk_addr + cell;
+    olen[j] = is_null ? 0 : (int32_t)len;
+    if (is_null) {
+      const int64_t o = base_row + (int64_t)j;
+      atomicOr(&p.out_nulls[pc][o >> 5], 1u << (o & 31));
+      saw_null = true;
+    }
+  }
+  if (saw_null) p.has_null[pc] = 1;
+}
+
 // =================================================================================================
 // Fused scan kernel: one CTA per micro-block (logical order by ticket)
 // =================================================================================================
-extern __shared__ __align__(128) uint8_t g_smem[];
-
 __global__ void __launch_bounds__(kThreads) obgpu_scan_kernel(const __grid_constant__ ScanParams p) {
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ int s_tile;
-  __shared__ uint32_t s_warp_sum[kWarps];
   __shared__ long long s_base;
   __shared__ uint32_t s_cnt;
+  __shared__ uint32_t s_scan[kWarps];
   __shared__ BlockView s_view;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -335,29 +606,13 @@ __global__ void __launch_bounds__(kThreads) obgpu_scan_kernel(const __grid_const
   const uint32_t size = p.blk_size[tile];
   load_block(sblk, p.image + p.blk_off[tile], (size + 15u) & ~15u, &s_bar, 0);
 
-  // ---- 2. parse header, build column descriptors ------------------------------------------------
-  if (tid == 0) {
-    BlockView v;
-    parse_block(sblk, size, v);
-    if (v.ok && v.row_count > p.rows_cap) v.ok = 0;
-    s_view = v;
-  }
-  __syncthreads();
-  BlockView b = s_view;
-  b.s = sblk;
-  bool bad = !b.ok;
-  if (!bad && tid < p.n_used) {
-    ColDesc d;
-    build_col_desc(b, p.used_col[tid], d);
-    descs[tid] = d;
-  }
-  __syncthreads();
-  if (!bad) {
-    for (int i = 0; i < p.n_used; ++i) bad |= !descs[i].ok;
-  }
-  if (bad) {
+  // ---- 2. parse header, build column descriptors and RLE run tables -----------------------------
+  BlockCtx c;
+  c.bitsets = bitsets;
+  bool corrupt;
+  if (!prepare_block(p, sblk, size, &s_view, descs, g_smem + p.smem_rle, c, corrupt)) {
     // Unsupported / corrupt block: publish a zero count so later tiles are not blocked, flag it.
-    if (tid == 0) atomicOr(p.status, b.ok ? ST_UNSUPPORTED : ST_CORRUPT);
+    if (tid == 0) atomicOr(p.status, corrupt ? ST_CORRUPT : ST_UNSUPPORTED);
     if (warp == 0) {
       const int64_t excl = lookback(p.tile_state, tile, 0, lane);
       if (lane == 0) {
@@ -367,7 +622,7 @@ __global__ void __launch_bounds__(kThreads) obgpu_scan_kernel(const __grid_const
     }
     return;
   }
-  const uint32_t rows = b.row_count;
+  const uint32_t rows = c.b.row_count;
   const uint32_t nwords = (rows + 31u) >> 5;
 
   // ---- 3. predicate over dictionaries ------------------------------------------------------------
@@ -376,37 +631,51 @@ __global__ void __launch_bounds__(kThreads) obgpu_scan_kernel(const __grid_const
       const FilterNodeDev &nd = p.nodes[i];
       if (nd.kind != NODE_WHITE || nd.slot < 0) continue;
       const ColDesc &d = descs[nd.used_idx];
-      if (d.type == COL_DICT || d.type == COL_RLE)
-        build_dict_bitset(p, b, d, nd, bitsets + nd.slot * p.bitset_words, warp, lane);
+      if (d.kind == K_DICT || d.kind == K_RLE)
+        build_dict_bitset(p, c.b, d, nd, bitsets + nd.slot * p.bitset_words, warp, lane);
     }
     __syncthreads();
   }
 
   // ---- 4. filter -> ballot words (the packed selection bitmap) ------------------------------------
-  uint32_t *gbm = p.bitmap_words + p.bm_word_off[tile];
-  uint32_t my_cnt = 0;
-  for (uint32_t g = (uint32_t)warp; g < nwords; g += kWarps) {
-    const uint32_t row = g * 32u + (uint32_t)lane;
-    bool pr = row < rows;
-    if (pr && p.n_nodes > 0) pr = eval_tree(p, b, descs, bitsets, row);
-    const uint32_t word = __ballot_sync(0xffffffffu, pr);
-    if (lane == 0) {
-      bm[g] = word;
-      gbm[g] = word;
-      my_cnt += __popc(word);
+  // Each warp owns the words g = warp, warp + 8, ...: no block barrier between leaves.
+  if (p.simple_shape != 0) {
+    const bool and_mode = p.simple_shape == 1;
+    if (lane == 0)
+      for (uint32_t g = (uint32_t)warp; g < nwords; g += kWarps) {
+        const uint32_t rem = rows - g * 32u;
+        bm[g] = and_mode ? (rem >= 32u ? 0xffffffffu : ((1u << rem) - 1u)) : 0u;
+      }
+    __syncwarp();
+    const int n_leaves = p.n_nodes == 1 ? 1 : p.n_nodes - 1;
+    for (int i = 0; i < n_leaves; ++i) {
+      leaf_over_words(p, c, p.nodes[i], bm, rows, nwords, and_mode, warp, lane);
+      __syncwarp();
+    }
+  } else {
+    for (uint32_t g = (uint32_t)warp; g < nwords; g += kWarps) {
+      const uint32_t row = g * 32u + (uint32_t)lane;
+      bool pr = row < rows;
+      if (pr && p.n_nodes > 0) pr = eval_tree(p, c, row);
+      const uint32_t word = __ballot_sync(0xffffffffu, pr);
+      if (lane == 0) bm[g] = word;
     }
   }
-  if (lane == 0) s_warp_sum[warp] = my_cnt;
   __syncthreads();
 
-  // ---- 5. exclusive prefix of popcounts over words; total ----------------------------------------
+  // ---- 5. exclusive prefix of popcounts over words; total; publish the bitmap ----------------------
   {
+    uint32_t *gbm = p.bitmap_words + p.bm_word_off[tile];
     const uint32_t per = (nwords + kThreads - 1) / kThreads;
     const uint32_t w0 = (uint32_t)tid * per;
     uint32_t local = 0;
     for (uint32_t k = 0; k < per; ++k) {
       const uint32_t w = w0 + k;
-      if (w < nwords) local += __popc(bm[w]);
+      if (w < nwords) {
+        const uint32_t word = bm[w];
+        gbm[w] = word;
+        local += __popc(word);
+      }
     }
     uint32_t inc = local;
 #pragma unroll
@@ -414,11 +683,11 @@ __global__ void __launch_bounds__(kThreads) obgpu_scan_kernel(const __grid_const
       const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
       if (lane >= o) inc += t;
     }
-    __shared__ uint32_t s_scan[kWarps];
     if (lane == 31) s_scan[warp] = inc;
     __syncthreads();
     uint32_t warp_off = 0;
-    for (int k = 0; k < warp; ++k) warp_off += s_scan[k];
+#pragma unroll
+    for (int k = 0; k < kWarps; ++k) warp_off += k < warp ? s_scan[k] : 0u;
     uint32_t run = warp_off + inc - local;
     for (uint32_t k = 0; k < per; ++k) {
       const uint32_t w = w0 + k;
@@ -427,14 +696,18 @@ __global__ void __launch_bounds__(kThreads) obgpu_scan_kernel(const __grid_const
         run += __popc(bm[w]);
       }
     }
-    if (tid == kThreads - 1) s_cnt = run;
+    if (tid == kThreads - 1) {
+      s_cnt = run;
+      // publish this block's count as early as possible: successors' look-backs only need this
+      st_release(&p.tile_state[tile], (tile == 0 ? kTilePrefix : kTileAgg) | (unsigned long long)run);
+    }
   }
   __syncthreads();
   const uint32_t cnt = s_cnt;
 
   // ---- 6. look-back (warp 0) overlapped with building the selected-row list (other warps) --------
   if (warp == 0) {
-    const int64_t excl = lookback(p.tile_state, tile, (int64_t)cnt, lane);
+    const int64_t excl = lookback(p.tile_state, tile, (int64_t)cnt, lane, /*publish_own=*/false);
     if (lane == 0) {
       s_base = excl;
       p.sel_offset[tile] = excl;
@@ -453,45 +726,24 @@ __global__ void __launch_bounds__(kThreads) obgpu_scan_kernel(const __grid_const
     return;
   }
 
-  // ---- 7. projection ------------------------------------------------------------------------------
+  // ---- 7. projection, one column at a time -----------------------------------------------------------
+  if (p.want_row_ids) {
+    int32_t *rid = p.row_ids + base;
+    for (uint32_t j = (uint32_t)tid; j < cnt; j += kThreads) rid[j] = (int32_t)sel[j];
+  }
   const uint64_t blk_addr = p.string_base + p.blk_off[tile];
-  for (uint32_t j = (uint32_t)tid; j < cnt; j += kThreads) {
-    const uint32_t row = sel[j];
-    const int64_t o = base + (int64_t)j;
-    if (p.want_row_ids) p.row_ids[o] = (int32_t)row;
-    for (int c = 0; c < p.n_proj; ++c) {
-      const ColDesc &d = descs[p.proj_used[c]];
-      bool is_null;
-      if (d.sc == 5) {
-        uint32_t cell, len;
-        str_cell(b, d, row, cell, len, is_null);
-        reinterpret_cast<uint64_t *>(p.out_data[c])[o] = is_null ? 0ull : blk_addr + cell;
-        p.out_lens[c][o] = is_null ? 0 : (int32_t)len;
-      } else {
-        const uint64_t v = int_cell(b, d, row, is_null);
-        const uint64_t vv = is_null ? 0ull : v;
-        if (d.elem_len == 8) reinterpret_cast<uint64_t *>(p.out_data[c])[o] = vv;
-        else if (d.elem_len == 4) reinterpret_cast<uint32_t *>(p.out_data[c])[o] = (uint32_t)vv;
-        else reinterpret_cast<uint8_t *>(p.out_data[c])[o] = (uint8_t)vv;
-      }
-      if (is_null) {
-        atomicOr(&p.out_nulls[c][o >> 5], 1u << (o & 31));
-        p.has_null[c] = 1;
-      }
-    }
+  for (int pc = 0; pc < p.n_proj; ++pc) {
+    const ColDesc &d = descs[p.proj_used[pc]];
+    if (d.sc == 5) project_str_col(p, c, d, pc, sel, cnt, base, blk_addr);
+    else if (d.elem_len == 8) project_int_col<uint64_t>(p, c, d, pc, sel, cnt, base);
+    else if (d.elem_len == 4) project_int_col<uint32_t>(p, c, d, pc, sel, cnt, base);
+    else project_int_col<uint8_t>(p, c, d, pc, sel, cnt, base);
   }
 }
 
 // =================================================================================================
 // Single-block kernels for the reference-granularity entry points
 // =================================================================================================
-struct BlockOpParams {
-  const uint8_t *image;
-  uint64_t blk_off;
-  uint32_t blk_size;
-  int32_t *status;
-};
-
 // ObBitmap byte image of a filter tree over rows [start, start + count) of one block.
 __global__ void __launch_bounds__(kThreads) obgpu_filter_block_kernel(const __grid_constant__ ScanParams p,
                                                                       int tile, int64_t start, int64_t count,
@@ -509,37 +761,28 @@ __global__ void __launch_bounds__(kThreads) obgpu_filter_block_kernel(const __gr
   __syncthreads();
   const uint32_t size = p.blk_size[tile];
   load_block(sblk, p.image + p.blk_off[tile], (size + 15u) & ~15u, &s_bar, 0);
-  if (tid == 0) {
-    BlockView v;
-    parse_block(sblk, size, v);
-    s_view = v;
+  BlockCtx c;
+  c.bitsets = bitsets;
+  bool corrupt;
+  bool ok = prepare_block(p, sblk, size, &s_view, descs, g_smem + p.smem_rle, c, corrupt);
+  if (ok && (start < 0 || start + count > (int64_t)c.b.row_count)) {
+    ok = false;
+    corrupt = true;
   }
-  __syncthreads();
-  BlockView b = s_view;
-  b.s = sblk;
-  bool bad = !b.ok || start < 0 || start + count > (int64_t)b.row_count;
-  if (!bad && tid < p.n_used) {
-    ColDesc d;
-    build_col_desc(b, p.used_col[tid], d);
-    descs[tid] = d;
-  }
-  __syncthreads();
-  if (!bad)
-    for (int i = 0; i < p.n_used; ++i) bad |= !descs[i].ok;
-  if (bad) {
-    if (tid == 0) atomicOr(p.status, b.ok ? ST_UNSUPPORTED : ST_CORRUPT);
+  if (!ok) {
+    if (tid == 0) atomicOr(p.status, corrupt ? ST_CORRUPT : ST_UNSUPPORTED);
     return;
   }
   for (int i = 0; i < p.n_nodes; ++i) {
     const FilterNodeDev &nd = p.nodes[i];
     if (nd.kind != NODE_WHITE || nd.slot < 0) continue;
     const ColDesc &d = descs[nd.used_idx];
-    if (d.type == COL_DICT || d.type == COL_RLE)
-      build_dict_bitset(p, b, d, nd, bitsets + nd.slot * p.bitset_words, warp, lane);
+    if (d.kind == K_DICT || d.kind == K_RLE)
+      build_dict_bitset(p, c.b, d, nd, bitsets + nd.slot * p.bitset_words, warp, lane);
   }
   __syncthreads();
   for (int64_t i = tid; i < count; i += kThreads)
-    out_bytes[i] = eval_tree(p, b, descs, bitsets, (uint32_t)(start + i)) ? 1 : 0;
+    out_bytes[i] = eval_tree(p, c, (uint32_t)(start + i)) ? 1 : 0;
 }
 
 // decode_vector of one column for caller-supplied row ids (ObVectorDecodeCtx shape).
@@ -558,21 +801,11 @@ __global__ void __launch_bounds__(kThreads) obgpu_project_block_kernel(
   __syncthreads();
   const uint32_t size = p.blk_size[tile];
   load_block(sblk, p.image + p.blk_off[tile], (size + 15u) & ~15u, &s_bar, 0);
-  if (tid == 0) {
-    BlockView v;
-    parse_block(sblk, size, v);
-    s_view = v;
-    if (v.ok) {
-      ColDesc d;
-      build_col_desc(v, p.used_col[0], d);
-      descs[0] = d;
-    }
-  }
-  __syncthreads();
-  BlockView b = s_view;
-  b.s = sblk;
-  if (!b.ok || !descs[0].ok) {
-    if (tid == 0) atomicOr(p.status, b.ok ? ST_UNSUPPORTED : ST_CORRUPT);
+  BlockCtx c;
+  c.bitsets = nullptr;
+  bool corrupt;
+  if (!prepare_block(p, sblk, size, &s_view, descs, g_smem + p.smem_rle, c, corrupt)) {
+    if (tid == 0) atomicOr(p.status, corrupt ? ST_CORRUPT : ST_UNSUPPORTED);
     return;
   }
   const ColDesc &d = descs[0];
@@ -580,10 +813,16 @@ __global__ void __launch_bounds__(kThreads) obgpu_project_block_kernel(
     if (tid == 0) atomicOr(p.status, ST_UNSUPPORTED);
     return;
   }
+  RleTable rt{};
+  const RleTable *rtp = nullptr;
+  if (d.kind == K_RLE && d.rle_slot >= 0) {
+    rt = c.rle_table(d.rle_slot);
+    rtp = &rt;
+  }
   const uint64_t blk_addr = p.string_base + p.blk_off[tile];
   for (int64_t i = tid; i < row_cap; i += kThreads) {
     const int32_t r = row_ids[i];
-    if (r < 0 || (uint32_t)r >= b.row_count) {
+    if (r < 0 || (uint32_t)r >= c.b.row_count) {
       atomicOr(p.status, ST_CORRUPT);
       continue;
     }
@@ -591,13 +830,13 @@ __global__ void __launch_bounds__(kThreads) obgpu_project_block_kernel(
     bool is_null;
     if (d.sc == 5) {
       uint32_t cell, len;
-      str_cell(b, d, (uint32_t)r, cell, len, is_null);
+      str_cell(c.b, d, rtp, (uint32_t)r, cell, len, is_null);
       if (!is_null) {
         reinterpret_cast<uint64_t *>(data)[o] = blk_addr + cell;
         lens[o] = (int32_t)len;
       }
     } else {
-      const uint64_t v = int_cell(b, d, (uint32_t)r, is_null);
+      const uint64_t v = int_cell(c.b, d, rtp, (uint32_t)r, is_null);
       if (!is_null) {
         if (elem_len == 8) reinterpret_cast<uint64_t *>(data)[o] = v;
         else if (elem_len == 4) reinterpret_cast<uint32_t *>(data)[o] = (uint32_t)v;
@@ -686,6 +925,7 @@ struct obgpu_batch {
   uint32_t max_block_bytes = 0, max_rows = 0, max_cols = 0;
   std::vector<uint32_t> col_max_dict;  // per store index: max dict count + 2 over blocks
   std::vector<uint8_t> col_types;      // per store index: ObObjType (0xff: differs between blocks)
+  std::vector<uint32_t> col_max_rle;   // per store index: max RLE run count over blocks (0: never RLE)
   // device tables (one allocation)
   void *d_tables = nullptr;
   uint64_t *d_blk_off = nullptr;
@@ -904,6 +1144,7 @@ int obgpu_batch_open(obgpu_ctx *ctx, const void *image, int64_t image_size, cons
     b->max_cols = std::max<uint32_t>(b->max_cols, ncol);
     if (b->col_max_dict.size() < ncol) b->col_max_dict.resize(ncol, 0);
     if (b->col_types.size() < ncol) b->col_types.resize(ncol, 0);
+    if (b->col_max_rle.size() < ncol) b->col_max_rle.resize(ncol, 0);
     // dictionary sizes of DICT / RLE columns (sizes the shared-memory predicate bitsets)
     const uint32_t meta_off = header_size + 16u * ncol;
     for (uint32_t c = 0; c < ncol; ++c) {
@@ -917,6 +1158,7 @@ int obgpu_batch_open(obgpu_ctx *ctx, const void *image, int64_t image_size, cons
       else if (type == obf::COL_RLE) {
         if ((int64_t)meta_off + coff + 10 > sz) { ret = OBGPU_INVALID_DATA; break; }
         dm = meta_off + coff + rd32h(p + meta_off + coff + 6);
+        b->col_max_rle[c] = std::max(b->col_max_rle[c], rd32h(p + meta_off + coff + 2));
       } else continue;
       if ((int64_t)dm + 9 > sz || (int64_t)meta_off + coff + clen > sz) { ret = OBGPU_INVALID_DATA; break; }
       const uint32_t cnt = rd32h(p + dm + 2);
@@ -1063,6 +1305,36 @@ static int build_filter(obgpu_ctx *ctx, const obgpu_batch *b, const obgpu_filter
       }
       nd.n_params = (int16_t)kept;
       if (null_param || (src.op == OBGPU_WHITE_OP_IN && kept == 0)) nd.op = OP_FALSE;
+      // integer compares on 8-byte datum types reduce to one unsigned range test on the value image
+      {
+        const uint8_t t = (size_t)src.col < b->col_types.size() ? b->col_types[(size_t)src.col] : 0xff;
+        const int sc = t == 0xff ? 0 : obf::store_class_of(t);
+        if (nd.op != OP_FALSE && (sc == 1 || sc == 2) && obf::datum_len_of(t) == 8 && src.op <= OBGPU_WHITE_OP_BT) {
+          const bool sg = sc == 1;
+          const uint64_t MIN = sg ? (uint64_t)INT64_MIN : 0ull, MAX = sg ? (uint64_t)INT64_MAX : ~0ull;
+          auto less = [&](uint64_t x, uint64_t y) { return sg ? (int64_t)x < (int64_t)y : x < y; };
+          const uint64_t c0 = (uint64_t)p.params[nd.param_begin].i64;
+          uint64_t lo = MIN, hi = MAX;
+          bool empty = false;
+          switch (src.op) {
+            case OBGPU_WHITE_OP_EQ: case OBGPU_WHITE_OP_NE: lo = hi = c0; break;
+            case OBGPU_WHITE_OP_LE: hi = c0; break;
+            case OBGPU_WHITE_OP_LT: if (c0 == MIN) empty = true; else hi = c0 - 1; break;
+            case OBGPU_WHITE_OP_GE: lo = c0; break;
+            case OBGPU_WHITE_OP_GT: if (c0 == MAX) empty = true; else lo = c0 + 1; break;
+            case OBGPU_WHITE_OP_BT: lo = c0; hi = (uint64_t)p.params[nd.param_begin + 1].i64; if (less(hi, lo)) empty = true; break;
+            default: break;
+          }
+          if (empty) {
+            nd.op = OP_FALSE;
+          } else {
+            nd.range_ok = 1;
+            nd.negate = src.op == OBGPU_WHITE_OP_NE;
+            nd.lo = lo;
+            nd.span = hi - lo;
+          }
+        }
+      }
       if (nd.op != OP_FALSE && (size_t)src.col < b->col_max_dict.size() && b->col_max_dict[(size_t)src.col] > 0) {
         if (p.n_slots >= 127) return OBGPU_NOT_SUPPORTED;
         nd.slot = (int8_t)p.n_slots++;
@@ -1080,6 +1352,7 @@ static int build_filter(obgpu_ctx *ctx, const obgpu_batch *b, const obgpu_filter
     p.nodes[p.n_nodes++] = nd;
   }
   if (depth != 1) return OBGPU_INVALID_ARGUMENT;
+  if (p.n_nodes == 1) p.simple_shape = 1;  // single leaf == AND over one leaf
   if (p.n_nodes >= 3) {
     const FilterNodeDev &root = p.nodes[p.n_nodes - 1];
     bool leaves = root.kind != NODE_WHITE && root.n_children == p.n_nodes - 1;
@@ -1090,14 +1363,28 @@ static int build_filter(obgpu_ctx *ctx, const obgpu_batch *b, const obgpu_filter
 }
 
 static void layout_smem(const obgpu_batch *b, ScanParams &p, bool need_sel) {
+  // run-table slots for used columns that are RLE-coded in some block
+  p.n_rle_slots = 0;
+  p.rle_runs_cap = 0;
+  for (int i = 0; i < kMaxUsedCols; ++i) p.used_rle_slot[i] = -1;
+  for (int i = 0; i < p.n_used; ++i) {
+    const size_t col = (size_t)p.used_col[i];
+    if (col < b->col_max_rle.size() && b->col_max_rle[col] > 0) {
+      p.used_rle_slot[i] = (int8_t)p.n_rle_slots++;
+      p.rle_runs_cap = std::max<int32_t>(p.rle_runs_cap, (int32_t)std::min<uint32_t>(b->col_max_rle[col], 65535u));
+    }
+  }
   uint32_t off = (b->max_block_bytes + 16u + 127u) & ~127u;
-  const uint32_t rows_cap = need_sel ? std::max<uint32_t>(b->max_rows, 32u) : 0u;
+  const uint32_t rows_cap = std::max<uint32_t>(b->max_rows, 32u);
   const uint32_t words_cap = (rows_cap + 31u) / 32u;
-  p.rows_cap = need_sel ? rows_cap : 65535u;
-  p.smem_sel = off;   off += (rows_cap * 2u + 15u) & ~15u;
-  p.smem_bm = off;    off += (words_cap * 4u + 15u) & ~15u;
-  p.smem_wpre = off;  off += (words_cap * 4u + 15u) & ~15u;
+  p.rows_cap = rows_cap;
+  p.words_cap = words_cap;
+  p.smem_sel = off;   off += need_sel ? ((rows_cap * 2u + 15u) & ~15u) : 0u;
+  p.smem_bm = off;    off += need_sel ? ((words_cap * 4u + 15u) & ~15u) : 0u;
+  p.smem_wpre = off;  off += need_sel ? ((words_cap * 4u + 15u) & ~15u) : 0u;
   p.smem_bitset = off; off += ((uint32_t)p.n_slots * (uint32_t)p.bitset_words * 4u + 15u) & ~15u;
+  p.rle_slot_bytes = p.n_rle_slots > 0 ? ((((uint32_t)p.rle_runs_cap + 2u) * 2u + words_cap * 2u + 15u) & ~15u) : 0u;
+  p.smem_rle = off;   off += (uint32_t)p.n_rle_slots * p.rle_slot_bytes;
   p.smem_desc = off;  off += (uint32_t)sizeof(ColDesc) * (uint32_t)std::max(p.n_used, 1);
   p.smem_total = (off + 15u) & ~15u;
 }

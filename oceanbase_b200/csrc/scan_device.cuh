@@ -2,7 +2,9 @@
 //
 // A micro-block (one "page", ~16 KiB) is staged into shared memory by one TMA bulk copy; every
 // primitive below reads the block image out of shared memory with 32-bit aligned loads and
-// funnel shifts (the on-disk layout is byte/bit granular, see ob_format.h).
+// funnel shifts. All addressing is bit-granular (byte-aligned fields are the 8*n-bit special
+// case), which gives one uniform load path for bit-packed values, byte-packed values, dictionary
+// references and dictionary entries.
 //
 // Reference loops these replace (file:line in /root/reference/src/storage/blocksstable):
 //   K1 bit unpack        encoding/ob_bit_stream.h:169-283
@@ -26,7 +28,7 @@ constexpr int kMaxUsedCols = 24;   // distinct columns referenced by one scan (f
 constexpr int kMaxNodes = 16;      // filter tree nodes
 constexpr int kMaxParams = 48;     // filter constants
 constexpr int kMaxProj = 24;       // projected columns
-constexpr int kThreads = 256;      // threads per CTA (8 warps)
+constexpr int kThreads = 128;      // threads per CTA (4 warps): many small CTAs per SM hide the per-block latency chain
 constexpr int kWarps = kThreads / 32;
 
 // status bits written by kernels
@@ -37,69 +39,76 @@ enum : int { OP_EQ = 0, OP_LE, OP_LT, OP_GE, OP_GT, OP_NE, OP_BT, OP_IN, OP_NU, 
              OP_FALSE = 100, OP_TRUE = 101 };
 enum : int { NODE_WHITE = 0, NODE_AND = 1, NODE_OR = 2 };
 
-// ---- unaligned loads from the shared-memory block image ---------------------------------------
+// ---- loads from the shared-memory block image ---------------------------------------------------
 // `s` is 16-byte aligned and has >= 16 readable bytes of slack after the block.
 __device__ __forceinline__ uint32_t ld32(const uint8_t *s, uint32_t word_byte_off) {
   return *reinterpret_cast<const uint32_t *>(s + word_byte_off);
 }
 
-// n bytes (1..8) at byte offset off, zero extended
-__device__ __forceinline__ uint64_t ld_bytes(const uint8_t *s, uint32_t off, uint32_t n) {
-  const uint32_t a = off & ~3u;
-  const uint32_t sh = (off & 3u) * 8u;
-  const uint32_t w0 = ld32(s, a), w1 = ld32(s, a + 4);
-  const uint32_t lo = __funnelshift_r(w0, w1, sh);
-  if (n <= 4) return (uint64_t)(n == 4 ? lo : (lo & ((1u << (n * 8u)) - 1u)));
-  const uint32_t w2 = ld32(s, a + 8);
-  const uint32_t hi = __funnelshift_r(w1, w2, sh);
-  const uint64_t v = ((uint64_t)hi << 32) | lo;
-  return n == 8 ? v : (v & ((1ull << (n * 8u)) - 1ull));
+// w bits (1..32) at absolute bit offset (LSB-first stream, ObBitStream::get)
+__device__ __forceinline__ uint32_t ld_bits32(const uint8_t *s, uint32_t bit_off, uint32_t w) {
+  const uint32_t a = (bit_off >> 5) << 2, sh = bit_off & 31u;
+  const uint32_t lo = __funnelshift_r(ld32(s, a), ld32(s, a + 4), sh);
+  return lo & (0xffffffffu >> (32u - w));
 }
 
-// w bits (1..64) at absolute bit offset bit_off (LSB-first stream, ObBitStream::get)
+// w bits (1..64)
 __device__ __forceinline__ uint64_t ld_bits(const uint8_t *s, uint32_t bit_off, uint32_t w) {
-  const uint32_t byte = bit_off >> 3;
-  const uint32_t a = byte & ~3u;
-  const uint32_t sh = ((byte & 3u) << 3) + (bit_off & 7u);  // 0..31
+  const uint32_t a = (bit_off >> 5) << 2, sh = bit_off & 31u;
   const uint32_t w0 = ld32(s, a), w1 = ld32(s, a + 4);
   const uint32_t lo = __funnelshift_r(w0, w1, sh);
-  if (w <= 32) return (uint64_t)(w == 32 ? lo : (lo & ((1u << w) - 1u)));
-  const uint32_t w2 = ld32(s, a + 8);
-  const uint32_t hi = __funnelshift_r(w1, w2, sh);
-  const uint64_t v = ((uint64_t)hi << 32) | lo;
-  return w == 64 ? v : (v & ((1ull << w) - 1ull));
+  if (w <= 32) return (uint64_t)(lo & (0xffffffffu >> (32u - w)));
+  const uint32_t hi = __funnelshift_r(w1, ld32(s, a + 8), sh);
+  return (((uint64_t)hi << 32) | lo) & (~0ull >> (64u - w));
+}
+
+// n bytes (1..8) at byte offset off, zero extended
+__device__ __forceinline__ uint64_t ld_bytes(const uint8_t *s, uint32_t off, uint32_t n) {
+  return ld_bits(s, off * 8u, n * 8u);
 }
 
 // ---- per-column decode descriptor, built once per block per referenced column -----------------
+enum ColKind : uint8_t {
+  K_NONE = 0,
+  K_BITS,     // value = ld_bits(val_bit + row * stride, width) [+ base] : RAW fixed/bit-packed, BASE_DIFF
+  K_DICT,     // ref   = ld_bits32(val_bit + row * stride, width), then dictionary
+  K_RLE,      // ref   = refs[run_of(row)], then dictionary
+  K_VARSTR,   // RAW var-length string in the row data
+  K_FIXSTR,   // RAW fixed-length string
+};
+
 struct ColDesc {
+  uint8_t kind;        // ColKind
   uint8_t type;        // ColType
   uint8_t attr;        // ColAttr
   uint8_t obj_type;
   uint8_t sc;          // 1 signed int class, 2 unsigned int class, 5 string
   uint8_t elem_len;    // datum length of integer classes (8 / 4 / 1)
-  uint8_t width;       // RAW / BASE_DIFF: bits (bit-packed) or bytes; DICT: row_ref_size
   uint8_t ext_bit;     // extend_value_bit if the column stores ext bits, else 0
   uint8_t ok;          // 0 => unsupported encoding / type for the device path
-  uint32_t data_off;   // block offset of the column data (ext bits start here)
-  uint32_t val_off;    // bit offset (bit-packed) or byte offset (fixed bytes) of value 0
-  uint64_t base;       // BASE_DIFF base
-  uint64_t int_mask;   // sign-extension mask (~INTEGER_MASK_TABLE[type_store_size] for ObIntTC)
-  // dictionary (DICT / RLE)
-  uint32_t dict_payload;   // block offset of dict payload (after the 9-byte meta header)
-  uint32_t dict_var;       // block offset of var data (var dict)
-  uint32_t dict_end;       // block offset one past the dict meta (last var cell ends here)
-  uint32_t dict_count;
-  uint16_t dict_data_size; // fixed: bytes per entry; var: index_byte
+  uint8_t width;       // value / ref width in bits
+  uint8_t sign_fix;    // apply the ObIntTC sign-extension mask after the load
   uint8_t dict_fixed;
-  uint8_t var_is_last;     // RAW var: LAST_VAR_FIELD
+  uint8_t var_is_last; // RAW var: LAST_VAR_FIELD
+  uint32_t stride;     // bits between consecutive rows' values / refs
+  uint32_t val_bit;    // bit offset of value / ref 0
+  uint32_t ext_bit_off;// bit offset of ext value 0
+  uint64_t base;       // BASE_DIFF base
+  uint64_t int_mask;   // ~INTEGER_MASK_TABLE[type_store_size] for ObIntTC, else 0
+  // dictionary (DICT / RLE)
+  uint32_t dict_payload;   // block byte offset of the dict payload (after the 9-byte meta header)
+  uint32_t dict_var;       // block byte offset of var data (var dict)
+  uint32_t dict_end;       // block byte offset one past the dict meta (last var cell ends here)
+  uint32_t dict_count;
+  uint32_t dict_data_size; // fixed: bytes per entry (also RAW fixed string length); var: index_byte
   // RLE
   uint32_t rle_count;
-  uint32_t rle_row_ids;    // block offset
-  uint32_t rle_refs;       // block offset
-  uint8_t rle_row_id_byte, rle_ref_byte;
+  uint32_t rle_refs_bit;   // bit offset of ref 0
+  uint32_t rle_row_ids_bit;
+  uint8_t rle_row_id_bits, rle_ref_bits;
+  uint8_t var_ext_in_row;  // RAW var: ext bits inside each row at bit ext_index
+  int8_t rle_slot;         // run-table scratch slot (-1: none)
   // RAW var-length cells in the row data
-  uint8_t var_in_row;      // 1 => cell lives in the row data
-  uint8_t var_ext_in_row;  // ext bits inside each row at bit ext_index
   uint32_t var_header_off; // bytes of per-row ext bits (row_offset_)
   uint32_t var_k;          // index among the var columns
   uint32_t ext_index;
@@ -136,7 +145,7 @@ __device__ __forceinline__ void parse_block(const uint8_t *s, uint32_t size, Blo
   b.meta_off = b.header_size + 16u * b.column_count;
   b.ok = magic == MICRO_BLOCK_HEADER_MAGIC && version >= 1 && version <= 3 &&
          (row_store_type == ENCODING_ROW_STORE || row_store_type == SELECTIVE_ENCODING_ROW_STORE) &&
-         b.meta_off <= size && b.row_data_off <= size && b.header_size >= 64;
+         b.meta_off <= size && b.row_data_off <= size && b.header_size >= 64 && b.row_count > 0;
   b.row_index_off = 0;
   if (b.ok && b.row_index_byte > 0) {
     const uint32_t need = (uint32_t)b.row_index_byte * (b.row_count + 1);
@@ -149,6 +158,7 @@ __device__ __forceinline__ void parse_block(const uint8_t *s, uint32_t size, Blo
 __device__ __forceinline__ void build_col_desc(const BlockView &b, int col, ColDesc &d) {
   const uint8_t *s = b.s;
   d = ColDesc{};
+  d.rle_slot = -1;
   if (col < 0 || (uint32_t)col >= b.column_count) return;
   const uint32_t ch = b.header_size + 16u * (uint32_t)col;
   const uint32_t w0 = ld32(s, ch);
@@ -170,24 +180,35 @@ __device__ __forceinline__ void build_col_desc(const BlockView &b, int col, ColD
     case COL_RAW: {
       if (fixed || bp) {
         if (meta > b.size) return;
-        d.data_off = meta;
         d.ext_bit = has_ext ? b.ext_bit : 0;
+        d.ext_bit_off = meta * 8u;
         const uint32_t ext_bits = (uint32_t)d.ext_bit * b.row_count;
-        d.width = (uint8_t)length;
         if (bp) {
-          if (length == 0 || length > 64) return;
-          d.val_off = meta * 8u + ext_bits;
+          if (sc == 5 || length == 0 || length > 64) return;
+          d.kind = K_BITS;
+          d.width = (uint8_t)length;
+          d.stride = length;
+          d.val_bit = meta * 8u + ext_bits;
         } else {
-          if (length == 0 || (sc != 5 && length > 8)) return;
-          d.val_off = meta + (ext_bits + 7u) / 8u;
-          if (sc == 5) d.width = 0;  // fixed-length string: byte length kept in dict_data_size
-          d.dict_data_size = (uint16_t)length;
-          if (sc == 5 && length > 0xffff) return;
+          const uint32_t data = meta + (ext_bits + 7u) / 8u;
+          if (sc == 5) {
+            if (length == 0 || length > 0xffff) return;
+            d.kind = K_FIXSTR;
+            d.dict_data_size = length;
+            d.val_bit = data;  // byte offset of cell 0
+          } else {
+            if (length == 0 || length > 8) return;
+            d.kind = K_BITS;
+            d.width = (uint8_t)(length * 8u);
+            d.stride = length * 8u;
+            d.val_bit = data * 8u;
+            d.sign_fix = d.int_mask != 0;
+          }
         }
       } else {
         if (sc != 5) return;  // integer var store is not produced for the supported shapes
         if (b.row_index_byte == 0) return;
-        d.var_in_row = 1;
+        d.kind = K_VARSTR;
         d.var_ext_in_row = has_ext;
         d.ext_bit = has_ext ? b.ext_bit : 0;
         d.var_header_off = offset;
@@ -200,19 +221,27 @@ __device__ __forceinline__ void build_col_desc(const BlockView &b, int col, ColD
     case COL_INTEGER_BASE_DIFF: {
       if (sc == 5 || meta + length > b.size) return;
       const int ts = type_store_size(d.obj_type);
-      d.width = s[meta + 1];
-      if (d.width == 0 || d.width > 64) return;
+      const uint32_t dl = s[meta + 1];
+      if (dl == 0) return;
       uint64_t base = ld_bytes(s, meta + 2, (uint32_t)ts);
       const uint64_t mask = ~low_mask((uint32_t)ts * 8u);
       if (sc == 1 && mask != 0 && (base & (mask >> 1))) base |= mask;
       d.base = base;
-      d.data_off = meta + length;
+      const uint32_t data = meta + length;
       d.ext_bit = has_ext ? b.ext_bit : 0;
+      d.ext_bit_off = data * 8u;
       const uint32_t ext_bits = (uint32_t)d.ext_bit * b.row_count;
-      if (bp) d.val_off = d.data_off * 8u + ext_bits;
-      else {
-        if (d.width > 8) return;
-        d.val_off = d.data_off + (ext_bits + 7u) / 8u;
+      d.kind = K_BITS;
+      if (bp) {
+        if (dl > 64) return;
+        d.width = (uint8_t)dl;
+        d.stride = dl;
+        d.val_bit = data * 8u + ext_bits;
+      } else {
+        if (dl > 8) return;
+        d.width = (uint8_t)(dl * 8u);
+        d.stride = dl * 8u;
+        d.val_bit = (data + (ext_bits + 7u) / 8u) * 8u;
       }
       d.ok = 1;
       return;
@@ -224,22 +253,26 @@ __device__ __forceinline__ void build_col_desc(const BlockView &b, int col, ColD
       if (d.type == COL_RLE) {
         if (meta + 10 > b.size) return;
         const uint8_t a = s[meta + 1];
-        d.rle_row_id_byte = a & 7;
-        d.rle_ref_byte = (a >> 3) & 7;
+        const uint32_t rib = a & 7, rfb = (a >> 3) & 7;
         d.rle_count = (uint32_t)ld_bytes(s, meta + 2, 4);
         const uint32_t doff = (uint32_t)ld_bytes(s, meta + 6, 4);
-        d.rle_row_ids = meta + 10;
-        d.rle_refs = d.rle_row_ids + d.rle_count * d.rle_row_id_byte;
-        if (d.rle_count == 0 || d.rle_row_id_byte == 0 || d.rle_ref_byte == 0 || doff > length) return;
+        if (d.rle_count == 0 || rib == 0 || rfb == 0 || rib > 4 || rfb > 4 || doff > length) return;
         // the reference keeps count*row_id_byte in an int16 (ob_rle_decoder.h:193)
-        if (d.rle_count * d.rle_row_id_byte > 32767u) return;
+        if (d.rle_count * rib > 32767u) return;
+        d.rle_row_id_bits = (uint8_t)(rib * 8u);
+        d.rle_ref_bits = (uint8_t)(rfb * 8u);
+        d.rle_row_ids_bit = (meta + 10u) * 8u;
+        d.rle_refs_bit = (meta + 10u + d.rle_count * rib) * 8u;
         dm = meta + doff;
         dict_len = length - doff;
+        d.kind = K_RLE;
+      } else {
+        d.kind = K_DICT;
       }
       if (dm + 9 > b.size || dm + dict_len > b.size) return;
-      d.width = s[dm + 1];  // row_ref_size
+      const uint32_t ref_size = s[dm + 1];  // row_ref_size
       d.dict_count = (uint32_t)ld_bytes(s, dm + 2, 4);
-      d.dict_data_size = (uint16_t)ld_bytes(s, dm + 6, 2);
+      d.dict_data_size = (uint32_t)ld_bytes(s, dm + 6, 2);
       const uint8_t dattr = s[dm + 8];
       d.dict_fixed = dattr & DICT_FIX_LENGTH;
       d.dict_payload = dm + 9;
@@ -251,15 +284,19 @@ __device__ __forceinline__ void build_col_desc(const BlockView &b, int col, ColD
       } else if (sc != 5 && (d.dict_data_size == 0 || d.dict_data_size > 8)) {
         return;
       }
+      d.sign_fix = d.int_mask != 0;
       if (d.type == COL_DICT) {
-        d.data_off = meta + length;  // refs follow the dict meta
+        const uint32_t data = meta + length;  // refs follow the dict meta
         if (bp) {
-          if (d.width == 0 || d.width > 32) return;
-          d.val_off = d.data_off * 8u;
+          if (ref_size == 0 || ref_size > 32) return;
+          d.width = (uint8_t)ref_size;
+          d.stride = ref_size;
         } else {
-          if (d.width == 0 || d.width > 4) return;
-          d.val_off = d.data_off;
+          if (ref_size == 0 || ref_size > 4) return;
+          d.width = (uint8_t)(ref_size * 8u);
+          d.stride = ref_size * 8u;
         }
+        d.val_bit = data * 8u;
       }
       d.ok = 1;
       return;
@@ -269,33 +306,50 @@ __device__ __forceinline__ void build_col_desc(const BlockView &b, int col, ColD
   }
 }
 
-// ---- row -> dictionary reference -------------------------------------------------------------
-__device__ __forceinline__ uint32_t rle_ref_of(const uint8_t *s, const ColDesc &d, uint32_t row) {
-  // upper_bound over the run starts, then refs[pos - 1]
+// ---- RLE run table (per block, per RLE column, in shared memory) -------------------------------
+// starts[k] = first row of run k (k < count), starts[count] = 0xFFFF sentinel;
+// g2run[g]  = run containing row 32 * g. Built cooperatively by the whole CTA.
+struct RleTable {
+  const uint16_t *starts;
+  const uint16_t *g2run;
+};
+
+__device__ __forceinline__ uint32_t rle_run_of(const RleTable &t, uint32_t row) {
+  uint32_t k = t.g2run[row >> 5];
+  while (t.starts[k + 1] <= row) ++k;
+  return k;
+}
+
+__device__ __forceinline__ uint32_t rle_ref_slow(const uint8_t *s, const ColDesc &d, uint32_t row) {
+  // upper_bound over the run starts, then refs[pos - 1] (no table: one-off lookups)
   uint32_t lo = 0, hi = d.rle_count;
   while (lo < hi) {
     const uint32_t mid = (lo + hi) >> 1;
-    const uint32_t v = (uint32_t)ld_bytes(s, d.rle_row_ids + mid * d.rle_row_id_byte, d.rle_row_id_byte);
+    const uint32_t v = ld_bits32(s, d.rle_row_ids_bit + mid * d.rle_row_id_bits, d.rle_row_id_bits);
     if (v <= row) lo = mid + 1; else hi = mid;
   }
   const uint32_t pos = lo > 0 ? lo - 1 : 0;
-  return (uint32_t)ld_bytes(s, d.rle_refs + pos * d.rle_ref_byte, d.rle_ref_byte);
+  return ld_bits32(s, d.rle_refs_bit + pos * d.rle_ref_bits, d.rle_ref_bits);
 }
 
-__device__ __forceinline__ uint32_t ref_of(const uint8_t *s, const ColDesc &d, uint32_t row) {
-  if (d.type == COL_RLE) return rle_ref_of(s, d, row);
-  if (d.attr & ATTR_BIT_PACKING) return (uint32_t)ld_bits(s, d.val_off + row * d.width, d.width);
-  return (uint32_t)ld_bytes(s, d.val_off + row * d.width, d.width);
+// row -> dictionary reference (DICT / RLE). `rt` may be null for RLE (slow path).
+__device__ __forceinline__ uint32_t ref_of(const uint8_t *s, const ColDesc &d, const RleTable *rt, uint32_t row) {
+  if (d.kind == K_RLE) {
+    if (rt == nullptr) return rle_ref_slow(s, d, row);
+    return ld_bits32(s, d.rle_refs_bit + rle_run_of(*rt, row) * d.rle_ref_bits, d.rle_ref_bits);
+  }
+  return ld_bits32(s, d.val_bit + row * d.stride, d.width);
 }
 
-__device__ __forceinline__ uint64_t sign_fix(const ColDesc &d, uint64_t v) {
+__device__ __forceinline__ uint64_t sign_fix(uint64_t int_mask, uint64_t v) {
   // load_data_to_datum: if (mask && (v & (mask >> 1))) v |= mask   (ob_encoding_util.h:505-509)
-  if (d.int_mask != 0 && (v & (d.int_mask >> 1))) v |= d.int_mask;
+  if (int_mask != 0 && (v & (int_mask >> 1))) v |= int_mask;
   return v;
 }
 
 __device__ __forceinline__ uint64_t dict_int(const uint8_t *s, const ColDesc &d, uint32_t ref) {
-  return sign_fix(d, ld_bytes(s, d.dict_payload + ref * d.dict_data_size, d.dict_data_size));
+  const uint64_t v = ld_bits(s, (d.dict_payload + ref * d.dict_data_size) * 8u, d.dict_data_size * 8u);
+  return d.sign_fix ? sign_fix(d.int_mask, v) : v;
 }
 
 // dictionary string cell -> (block offset, length)
@@ -313,29 +367,24 @@ __device__ __forceinline__ void dict_str(const uint8_t *s, const ColDesc &d, uin
                                 : (uint32_t)ld_bytes(s, d.dict_payload + ref * ib, ib) - off;
 }
 
-// ---- integer-class cell ------------------------------------------------------------------------
+// ---- integer-class cell (generic path) -----------------------------------------------------------
 // Returns the 64-bit value image the reference would MEMCPY into the datum (low elem_len bytes
 // significant); is_null set for NULL (and NOP) cells.
-__device__ __forceinline__ uint64_t int_cell(const BlockView &b, const ColDesc &d, uint32_t row,
-                                             bool &is_null) {
+__device__ __forceinline__ uint64_t int_cell(const BlockView &b, const ColDesc &d, const RleTable *rt,
+                                             uint32_t row, bool &is_null) {
   const uint8_t *s = b.s;
   is_null = false;
-  if (d.type == COL_DICT || d.type == COL_RLE) {
-    const uint32_t ref = ref_of(s, d, row);
+  if (d.kind == K_DICT || d.kind == K_RLE) {
+    const uint32_t ref = ref_of(s, d, rt, row);
     if (ref >= d.dict_count) { is_null = true; return 0; }
     return dict_int(s, d, ref);
   }
-  if (d.ext_bit) {
-    if (ld_bits(s, d.data_off * 8u + row * d.ext_bit, d.ext_bit) != STORED_NOT_EXT) {
-      is_null = true;
-      return 0;
-    }
+  if (d.ext_bit && ld_bits32(s, d.ext_bit_off + row * d.ext_bit, d.ext_bit) != STORED_NOT_EXT) {
+    is_null = true;
+    return 0;
   }
-  uint64_t v;
-  if (d.attr & ATTR_BIT_PACKING) v = ld_bits(s, d.val_off + row * d.width, d.width);
-  else v = ld_bytes(s, d.val_off + row * d.width, d.width);
-  if (d.type == COL_INTEGER_BASE_DIFF) return v + d.base;
-  return (d.attr & ATTR_BIT_PACKING) ? v : sign_fix(d, v);
+  const uint64_t v = ld_bits(s, d.val_bit + row * d.stride, d.width) + d.base;
+  return d.sign_fix ? sign_fix(d.int_mask, v) : v;
 }
 
 // value used for comparisons: sign-extended from the datum length for signed classes
@@ -346,25 +395,25 @@ __device__ __forceinline__ int64_t cmp_image(const ColDesc &d, uint64_t v) {
 }
 
 // ---- string-class cell -------------------------------------------------------------------------
-__device__ __forceinline__ void str_cell(const BlockView &b, const ColDesc &d, uint32_t row,
+__device__ __forceinline__ void str_cell(const BlockView &b, const ColDesc &d, const RleTable *rt, uint32_t row,
                                          uint32_t &cell, uint32_t &len, bool &is_null) {
   const uint8_t *s = b.s;
   is_null = false;
   cell = 0;
   len = 0;
-  if (d.type == COL_DICT || d.type == COL_RLE) {
-    const uint32_t ref = ref_of(s, d, row);
+  if (d.kind == K_DICT || d.kind == K_RLE) {
+    const uint32_t ref = ref_of(s, d, rt, row);
     if (ref >= d.dict_count) { is_null = true; return; }
     dict_str(s, d, ref, cell, len);
     return;
   }
-  if (!d.var_in_row) {  // RAW fixed-length string
-    if (d.ext_bit && ld_bits(s, d.data_off * 8u + row * d.ext_bit, d.ext_bit) != STORED_NOT_EXT) {
+  if (d.kind == K_FIXSTR) {
+    if (d.ext_bit && ld_bits32(s, d.ext_bit_off + row * d.ext_bit, d.ext_bit) != STORED_NOT_EXT) {
       is_null = true;
       return;
     }
     len = d.dict_data_size;
-    cell = d.val_off + row * len;
+    cell = d.val_bit + row * len;
     return;
   }
   // RAW var-length: row = [ext bits][col_idx_byte][idx x (nvar-1)][cells]
@@ -373,7 +422,7 @@ __device__ __forceinline__ void str_cell(const BlockView &b, const ColDesc &d, u
   const uint32_t re = (uint32_t)ld_bytes(s, b.row_index_off + (row + 1) * rib, rib);
   const uint32_t rowp = b.row_data_off + ro;
   const uint32_t row_len = re - ro;
-  if (d.var_ext_in_row && ld_bits(s, rowp * 8u + d.ext_index, d.ext_bit) != STORED_NOT_EXT) {
+  if (d.var_ext_in_row && ld_bits32(s, rowp * 8u + d.ext_index, d.ext_bit) != STORED_NOT_EXT) {
     is_null = true;
     return;
   }
@@ -391,7 +440,7 @@ __device__ __forceinline__ void str_cell(const BlockView &b, const ColDesc &d, u
   cell = var + col_off;
 }
 
-// memcmp-then-length order of a shared-memory cell against a global-memory constant
+// memcmp-then-length order of a shared-memory cell against a constant
 __device__ __forceinline__ int str_cmp(const uint8_t *s, uint32_t cell, uint32_t len,
                                        const uint8_t *c, uint32_t clen) {
   const uint32_t m = len < clen ? len : clen;
