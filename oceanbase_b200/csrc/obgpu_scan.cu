@@ -22,6 +22,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -59,6 +60,12 @@ struct ParamDev {
 
 constexpr int kParamHeap = 768;
 
+// Persistent scan kernel geometry: one producer warp (TMA ring) + kConsumerWarps consumer warps.
+constexpr int kConsumerWarps = 4;
+constexpr int kConsumers = kConsumerWarps * 32;
+constexpr int kScanThreads = kConsumers + 32;
+constexpr int kStages = 3;
+
 struct ScanParams {
   const uint8_t *image;
   const uint64_t *blk_off;    // [n_blocks] byte offset of block i in image
@@ -92,14 +99,22 @@ struct ScanParams {
   int32_t *ticket;
   int32_t *status;
   int64_t out_cap;
-  // shared-memory layout (bytes from the dynamic smem base)
-  uint32_t smem_sel, smem_bm, smem_wpre, smem_bitset, smem_rle, smem_desc, smem_total;
+  // ---- shared-memory layout (bytes from the dynamic smem base) -------------------------------------
+  // single-block kernels: [block][bitsets][rle tables][descs]
+  // scan kernel:          [stage 0..kStages-1][bitsets][scratch 0][scratch 1], scratch = sel|bm|wpre|rle|descs
+  uint32_t stage_bytes;       // scan kernel: bytes per stage buffer
+  uint32_t smem_bitset;
+  uint32_t smem_rle, smem_desc;            // single-block kernels
+  uint32_t smem_scratch, scratch_bytes;    // scan kernel
+  uint32_t off_sel, off_bm, off_wpre, off_rle, off_desc;  // inside one scratch
+  uint32_t smem_total;
   uint32_t rle_slot_bytes;    // bytes per run-table slot: starts[(cap + 2)] + g2run[words_cap]
   uint32_t rows_cap, words_cap;
+  int32_t debug_flags;        // bit0: experiment -- skip the look-back (non-dense output at row offsets)
 };
 
 // =================================================================================================
-// PTX helpers: mbarrier + TMA bulk copy, acquire/release descriptor access
+// PTX helpers: mbarrier + TMA bulk copy, acquire/release descriptor access, named barriers
 // =================================================================================================
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -113,6 +128,9 @@ __device__ __forceinline__ void fence_barrier_init() {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
   asm volatile(
@@ -141,6 +159,37 @@ __device__ __forceinline__ unsigned long long ld_acquire(const unsigned long lon
 }
 __device__ __forceinline__ void st_release(unsigned long long *p, unsigned long long v) {
   asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// A team of threads cooperating on one block: either the whole CTA (bar 0) or the consumer warps
+// of the persistent kernel (named barrier 1).
+struct Team {
+  int tid, nthreads, warp, nwarps, lane, bar_id;
+  __device__ __forceinline__ void sync() const {
+    if (bar_id == 0) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nthreads) : "memory");
+  }
+  __device__ __forceinline__ bool sync_or(bool pred) const {
+    if (bar_id == 0) return __syncthreads_or(pred) != 0;
+    int r;
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %1, 0;\n\tbar.red.or.pred q, %2, %3, p;\n\tselp.b32 %0, 1, 0, q;\n\t}"
+        : "=r"(r)
+        : "r"((int)pred), "r"(bar_id), "r"(nthreads)
+        : "memory");
+    return r != 0;
+  }
+};
+
+__device__ __forceinline__ Team cta_team() {
+  Team t;
+  t.tid = threadIdx.x;
+  t.nthreads = kThreads;
+  t.warp = threadIdx.x >> 5;
+  t.nwarps = kWarps;
+  t.lane = threadIdx.x & 31;
+  t.bar_id = 0;
+  return t;
 }
 
 constexpr unsigned long long kTileAgg = 1ull << 62;
@@ -219,8 +268,10 @@ __device__ __forceinline__ bool str_pred(const ScanParams &p, const FilterNodeDe
   return false;
 }
 
+// Everything a team needs to know about the block it is working on.
 struct BlockCtx {
   BlockView b;
+  uint32_t sbit;             // bit offset of the staged block inside g_smem (fast-path loads)
   const ColDesc *descs;
   const uint32_t *bitsets;
   const uint8_t *rle_base;   // run-table scratch
@@ -285,11 +336,11 @@ __device__ __forceinline__ bool eval_tree(const ScanParams &p, const BlockCtx &c
 
 // Predicate over the dictionary of a DICT / RLE column -> bitset over refs (bit count = NULL ref).
 __device__ __forceinline__ void build_dict_bitset(const ScanParams &p, const BlockView &b, const ColDesc &d,
-                                                  const FilterNodeDev &nd, uint32_t *bits, int warp, int lane) {
+                                                  const FilterNodeDev &nd, uint32_t *bits, const Team &t) {
   const uint32_t n = d.dict_count + 2;
   const int op = nd.op;
-  for (uint32_t base = (uint32_t)warp * 32u; base < n; base += kWarps * 32u) {
-    const uint32_t idx = base + (uint32_t)lane;
+  for (uint32_t base = (uint32_t)t.warp * 32u; base < n; base += (uint32_t)t.nwarps * 32u) {
+    const uint32_t idx = base + (uint32_t)t.lane;
     bool r = false;
     if (idx < d.dict_count) {
       if (op == OP_NN) r = true;
@@ -305,39 +356,78 @@ __device__ __forceinline__ void build_dict_bitset(const ScanParams &p, const Blo
       r = op == OP_NU;
     }
     const uint32_t word = __ballot_sync(0xffffffffu, r);
-    if (lane == 0) bits[base >> 5] = word;
+    if (t.lane == 0) bits[base >> 5] = word;
   }
 }
 
-// One leaf evaluated column-at-a-time over the ballot words owned by this warp (g = warp, warp+8,
+__device__ __forceinline__ uint32_t valid_mask_of(uint32_t rows, uint32_t g) {
+  const uint32_t rem = rows - g * 32u;
+  return rem >= 32u ? 0xffffffffu : ((1u << rem) - 1u);
+}
+
+// Range test over a K_BITS column without NULLs / sign fix: the hot filter loop.
+//   MODE 0: first leaf (bm[g] = leaf), 1: AND into bm with early-out, 2: OR into bm with early-out
+template <bool WIDE, int MODE>
+__device__ __forceinline__ void filter_bits_range(const BlockCtx &c, const ColDesc &d, const FilterNodeDev &nd,
+                                                  uint32_t *bm, uint32_t rows, uint32_t nwords, const Team &t) {
+  const uint32_t stride = d.stride, width = d.width;
+  const uint64_t lo = nd.lo - d.base, span = nd.span;  // (v + base - lo) <= span
+  const bool neg = nd.negate != 0;
+  const uint32_t nfull = rows >> 5;
+  const uint32_t step = (uint32_t)t.nwarps * 32u * stride;
+  uint32_t bit = c.sbit + d.val_bit + ((uint32_t)t.warp * 32u + (uint32_t)t.lane) * stride;
+  uint32_t g = (uint32_t)t.warp;
+  for (; g < nfull; g += (uint32_t)t.nwarps, bit += step) {
+    uint32_t cur = 0;
+    if (MODE != 0) {
+      cur = bm[g];
+      if (MODE == 1 ? cur == 0u : cur == 0xffffffffu) continue;
+    }
+    const uint64_t v = WIDE ? sbits(bit, width) : (uint64_t)sbits32(bit, width);
+    const uint32_t w = __ballot_sync(0xffffffffu, ((v - lo) <= span) != neg);
+    if (t.lane == 0) bm[g] = MODE == 0 ? w : (MODE == 1 ? (cur & w) : (cur | w));
+  }
+  if (g < nwords) {  // ragged tail group
+    const uint32_t vm = valid_mask_of(rows, g);
+    const uint32_t cur = MODE == 0 ? 0u : bm[g];
+    const uint64_t v = WIDE ? sbits(bit, width) : (uint64_t)sbits32(bit, width);
+    const uint32_t w = __ballot_sync(0xffffffffu, ((v - lo) <= span) != neg) & vm;
+    if (t.lane == 0) bm[g] = MODE == 0 ? w : (MODE == 1 ? (cur & w) : (cur | w));
+  }
+}
+
+__device__ __forceinline__ bool leaf_is_bits_range(const ColDesc &d, const FilterNodeDev &nd) {
+  return d.kind == K_BITS && nd.range_ok && d.elem_len == 8 && d.ext_bit == 0 && !d.sign_fix;
+}
+
+// First leaf of an AND / OR list: writes bm directly (no initialisation pass) when it is a plain
+// range test. Returns false if the caller has to initialise bm and run the leaf generically.
+__device__ __forceinline__ bool leaf_first_fast(const ScanParams &p, const BlockCtx &c, const FilterNodeDev &nd,
+                                                uint32_t *bm, uint32_t rows, uint32_t nwords, const Team &t) {
+  if (nd.kind != NODE_WHITE) return false;
+  const ColDesc &d = c.descs[nd.used_idx];
+  if (!leaf_is_bits_range(d, nd)) return false;
+  if (d.width <= 32) filter_bits_range<false, 0>(c, d, nd, bm, rows, nwords, t);
+  else filter_bits_range<true, 0>(c, d, nd, bm, rows, nwords, t);
+  return true;
+}
+
+// One leaf evaluated column-at-a-time over the ballot words owned by this warp (g = warp, warp+n,
 // ...). `and_mode`: bm[g] &= leaf, skipping groups that are already all-false; else bm[g] |= leaf
 // for groups that are not yet all-true (the reference's can_skip_filter / early-out, per 32 rows).
 __device__ __forceinline__ void leaf_over_words(const ScanParams &p, const BlockCtx &c, const FilterNodeDev &nd,
                                                 uint32_t *bm, uint32_t rows, uint32_t nwords, bool and_mode,
-                                                int warp, int lane) {
+                                                const Team &t) {
   const ColDesc &d = c.descs[nd.used_idx];
-  const uint8_t *s = c.b.s;
   const int op = nd.op;
-  auto valid_mask = [&](uint32_t g) -> uint32_t {
-    const uint32_t rem = rows - g * 32u;
-    return rem >= 32u ? 0xffffffffu : ((1u << rem) - 1u);
-  };
   // ---- fast path A: integer range test on a K_BITS column without NULLs ------------------------------
-  if (d.kind == K_BITS && nd.range_ok && d.elem_len == 8 && d.ext_bit == 0) {
-    const uint32_t val_bit = d.val_bit, stride = d.stride, width = d.width;
-    const uint64_t lo = nd.lo - d.base, span = nd.span;  // (v + base - lo) <= span
-    const bool neg = nd.negate != 0, fix = d.sign_fix != 0;
-    const uint64_t mask = d.int_mask;
-    for (uint32_t g = (uint32_t)warp; g < nwords; g += kWarps) {
-      const uint32_t cur = bm[g], vm = valid_mask(g);
-      if (and_mode ? cur == 0u : cur == vm) continue;
-      const uint32_t row = g * 32u + (uint32_t)lane;
-      uint64_t v = width <= 32 ? (uint64_t)ld_bits32(s, val_bit + row * stride, width)
-                               : ld_bits(s, val_bit + row * stride, width);
-      if (fix) v = sign_fix(mask, v);
-      const bool pr = ((v - lo) <= span) != neg;
-      const uint32_t w = __ballot_sync(0xffffffffu, pr) & vm;
-      if (lane == 0) bm[g] = and_mode ? (cur & w) : (cur | w);
+  if (leaf_is_bits_range(d, nd)) {
+    if (d.width <= 32) {
+      if (and_mode) filter_bits_range<false, 1>(c, d, nd, bm, rows, nwords, t);
+      else filter_bits_range<false, 2>(c, d, nd, bm, rows, nwords, t);
+    } else {
+      if (and_mode) filter_bits_range<true, 1>(c, d, nd, bm, rows, nwords, t);
+      else filter_bits_range<true, 2>(c, d, nd, bm, rows, nwords, t);
     }
     return;
   }
@@ -346,49 +436,49 @@ __device__ __forceinline__ void leaf_over_words(const ScanParams &p, const Block
     const uint32_t *bits = c.bitsets + nd.slot * p.bitset_words;
     const uint32_t cntp1 = d.dict_count + 1;
     if (d.kind == K_DICT) {
-      const uint32_t val_bit = d.val_bit, stride = d.stride, width = d.width;
-      for (uint32_t g = (uint32_t)warp; g < nwords; g += kWarps) {
-        const uint32_t cur = bm[g], vm = valid_mask(g);
+      const uint32_t val_bit = c.sbit + d.val_bit, stride = d.stride, width = d.width;
+      for (uint32_t g = (uint32_t)t.warp; g < nwords; g += (uint32_t)t.nwarps) {
+        const uint32_t cur = bm[g], vm = valid_mask_of(rows, g);
         if (and_mode ? cur == 0u : cur == vm) continue;
-        const uint32_t row = g * 32u + (uint32_t)lane;
-        uint32_t ref = ld_bits32(s, val_bit + row * stride, width);
+        const uint32_t row = g * 32u + (uint32_t)t.lane;
+        uint32_t ref = sbits32(val_bit + row * stride, width);
         ref = ref < cntp1 ? ref : cntp1;
         const bool pr = (bits[ref >> 5] >> (ref & 31)) & 1u;
         const uint32_t w = __ballot_sync(0xffffffffu, pr) & vm;
-        if (lane == 0) bm[g] = and_mode ? (cur & w) : (cur | w);
+        if (t.lane == 0) bm[g] = and_mode ? (cur & w) : (cur | w);
       }
     } else {
       const RleTable rt = c.rle_table(d.rle_slot);
-      const uint32_t refs_bit = d.rle_refs_bit, ref_bits = d.rle_ref_bits;
-      for (uint32_t g = (uint32_t)warp; g < nwords; g += kWarps) {
-        const uint32_t cur = bm[g], vm = valid_mask(g);
+      const uint32_t refs_bit = c.sbit + d.rle_refs_bit, ref_bits = d.rle_ref_bits;
+      for (uint32_t g = (uint32_t)t.warp; g < nwords; g += (uint32_t)t.nwarps) {
+        const uint32_t cur = bm[g], vm = valid_mask_of(rows, g);
         if (and_mode ? cur == 0u : cur == vm) continue;
-        uint32_t row = g * 32u + (uint32_t)lane;
+        uint32_t row = g * 32u + (uint32_t)t.lane;
         row = row < rows ? row : rows - 1u;
-        uint32_t ref = ld_bits32(s, refs_bit + rle_run_of(rt, row) * ref_bits, ref_bits);
+        uint32_t ref = sbits32(refs_bit + rle_run_of(rt, row) * ref_bits, ref_bits);
         ref = ref < cntp1 ? ref : cntp1;
         const bool pr = (bits[ref >> 5] >> (ref & 31)) & 1u;
         const uint32_t w = __ballot_sync(0xffffffffu, pr) & vm;
-        if (lane == 0) bm[g] = and_mode ? (cur & w) : (cur | w);
+        if (t.lane == 0) bm[g] = and_mode ? (cur & w) : (cur | w);
       }
     }
     return;
   }
   // ---- generic leaf ----------------------------------------------------------------------------------
-  for (uint32_t g = (uint32_t)warp; g < nwords; g += kWarps) {
-    const uint32_t cur = bm[g], vm = valid_mask(g);
+  for (uint32_t g = (uint32_t)t.warp; g < nwords; g += (uint32_t)t.nwarps) {
+    const uint32_t cur = bm[g], vm = valid_mask_of(rows, g);
     if (and_mode ? cur == 0u : cur == vm) continue;
-    const uint32_t row = g * 32u + (uint32_t)lane;
+    const uint32_t row = g * 32u + (uint32_t)t.lane;
     const bool pr = row < rows && eval_leaf(p, c, nd, row);
     const uint32_t w = __ballot_sync(0xffffffffu, pr) & vm;
-    if (lane == 0) bm[g] = and_mode ? (cur & w) : (cur | w);
+    if (t.lane == 0) bm[g] = and_mode ? (cur & w) : (cur | w);
   }
 }
 
 // =================================================================================================
 // Block-wide helpers
 // =================================================================================================
-// Loads block `tile` into shared memory with one TMA bulk transaction; all threads return once the
+// Loads a block into shared memory with one TMA bulk transaction; all threads return once the
 // bytes have landed. `bar` must have been initialised by thread 0 (count 1) before the call.
 __device__ __forceinline__ void load_block(uint8_t *smem, const uint8_t *src, uint32_t bytes16, uint64_t *bar,
                                            uint32_t parity) {
@@ -399,28 +489,29 @@ __device__ __forceinline__ void load_block(uint8_t *smem, const uint8_t *src, ui
   mbar_wait(bar, parity);
 }
 
-extern __shared__ __align__(128) uint8_t g_smem[];
-
-// Parses the staged block and builds descriptors + RLE run tables. Returns false (uniformly) when the
-// block cannot be handled; *corrupt tells why. Must be called by all threads.
-__device__ __forceinline__ bool prepare_block(const ScanParams &p, uint8_t *sblk, uint32_t size, BlockView *s_view,
-                                              ColDesc *descs, uint8_t *rle_base, BlockCtx &c, bool &corrupt) {
-  const int tid = threadIdx.x;
-  (void)s_view;
+// Parses the staged block (at g_smem + soff) and builds descriptors + RLE run tables. Returns false
+// (uniformly over the team) when the block cannot be handled; *corrupt tells why.
+__device__ __forceinline__ bool prepare_block(const ScanParams &p, uint32_t soff, uint32_t size, ColDesc *descs,
+                                              uint8_t *rle_base, const Team &t, BlockCtx &c, bool &corrupt) {
+  const uint8_t *sblk = g_smem + soff;
   // every thread parses the 64-byte header itself (a handful of shared-memory loads): no barrier
   parse_block(sblk, size, c.b);
   if (c.b.ok && c.b.row_count > p.rows_cap) c.b.ok = 0;
+  c.sbit = (smem_u32(g_smem) + soff) * 8u;
   corrupt = !c.b.ok;
   bool my_bad = false;
-  if (c.b.ok && tid < p.n_used) {
+  // descriptors are built by the LAST threads of the team (the first warp may still be busy with
+  // the previous tile's look-back in the persistent kernel)
+  const int di = t.nthreads - 1 - t.tid;
+  if (c.b.ok && di < p.n_used) {
     ColDesc d;
-    build_col_desc(c.b, p.used_col[tid], d);
-    d.rle_slot = d.kind == K_RLE ? p.used_rle_slot[tid] : (int8_t)-1;
+    build_col_desc(c.b, p.used_col[di], d);
+    d.rle_slot = d.kind == K_RLE ? p.used_rle_slot[di] : (int8_t)-1;
     if (d.kind == K_RLE && d.rle_slot >= 0 && d.rle_count > (uint32_t)p.rle_runs_cap) d.ok = 0;
-    descs[tid] = d;
+    descs[di] = d;
     my_bad = !d.ok;
   }
-  const bool bad = __syncthreads_or(my_bad || !c.b.ok) != 0;
+  const bool bad = t.sync_or(my_bad || !c.b.ok);
   c.descs = descs;
   c.rle_base = rle_base;
   c.rle_slot_bytes = p.rle_slot_bytes;
@@ -431,24 +522,26 @@ __device__ __forceinline__ bool prepare_block(const ScanParams &p, uint8_t *sblk
     const uint32_t nwords = (c.b.row_count + 31u) >> 5;
     bool any = false;
     for (int i = 0; i < p.n_used; ++i) {
+      if (p.used_rle_slot[i] < 0) continue;
       const ColDesc &d = descs[i];
-      if (d.kind != K_RLE || d.rle_slot < 0) continue;
+      if (d.kind != K_RLE) continue;
       any = true;
       uint16_t *starts = reinterpret_cast<uint16_t *>(rle_base + (uint32_t)d.rle_slot * p.rle_slot_bytes);
-      for (uint32_t k = (uint32_t)tid; k <= d.rle_count; k += kThreads)
+      for (uint32_t k = (uint32_t)t.tid; k <= d.rle_count; k += (uint32_t)t.nthreads)
         starts[k] = k < d.rle_count
                         ? (uint16_t)ld_bits32(sblk, d.rle_row_ids_bit + k * d.rle_row_id_bits, d.rle_row_id_bits)
                         : (uint16_t)0xFFFF;
     }
     if (any) {
-      __syncthreads();
+      t.sync();
       for (int i = 0; i < p.n_used; ++i) {
+        if (p.used_rle_slot[i] < 0) continue;
         const ColDesc &d = descs[i];
-        if (d.kind != K_RLE || d.rle_slot < 0) continue;
+        if (d.kind != K_RLE) continue;
         const uint16_t *starts = reinterpret_cast<const uint16_t *>(rle_base + (uint32_t)d.rle_slot * p.rle_slot_bytes);
         uint16_t *g2run = reinterpret_cast<uint16_t *>(rle_base + (uint32_t)d.rle_slot * p.rle_slot_bytes +
                                                        c.rle_starts_bytes);
-        for (uint32_t g = (uint32_t)tid; g < nwords; g += kThreads) {
+        for (uint32_t g = (uint32_t)t.tid; g < nwords; g += (uint32_t)t.nthreads) {
           const uint32_t row = g * 32u;
           uint32_t lo = 0, hi = d.rle_count;  // upper_bound(starts, row)
           while (lo < hi) {
@@ -459,20 +552,19 @@ __device__ __forceinline__ bool prepare_block(const ScanParams &p, uint8_t *sblk
         }
       }
     }
-    __syncthreads();
+    t.sync();
   }
   return true;
 }
 
 // =================================================================================================
-// Projection of one integer column over the selected rows (column-at-a-time, specialised)
+// Projection of one column over the selected rows (column-at-a-time, specialised)
 // =================================================================================================
 template <typename OutT>
 __device__ __forceinline__ void project_int_col(const ScanParams &p, const BlockCtx &c, const ColDesc &d, int pc,
-                                                const uint16_t *sel, uint32_t cnt, int64_t base_row) {
-  const uint8_t *s = c.b.s;
+                                                const uint16_t *sel, uint32_t cnt, int64_t base_row, const Team &t) {
   OutT *out = reinterpret_cast<OutT *>(p.out_data[pc]) + base_row;
-  const int tid = threadIdx.x;
+  const uint32_t tid = (uint32_t)t.tid, nt = (uint32_t)t.nthreads;
   bool saw_null = false;
   auto mark_null = [&](uint32_t j) {
     const int64_t o = base_row + (int64_t)j;
@@ -480,67 +572,68 @@ __device__ __forceinline__ void project_int_col(const ScanParams &p, const Block
     saw_null = true;
   };
   if (d.kind == K_BITS) {
-    const uint32_t val_bit = d.val_bit, stride = d.stride, width = d.width;
+    const uint32_t val_bit = c.sbit + d.val_bit, stride = d.stride, width = d.width;
     const uint64_t add = d.base, mask = d.int_mask;
     const bool fix = d.sign_fix != 0;
-    if (d.ext_bit == 0) {
+    if (d.ext_bit == 0 && !fix) {
       if (width <= 32) {
-        for (uint32_t j = (uint32_t)tid; j < cnt; j += kThreads) {
-          uint64_t v = (uint64_t)ld_bits32(s, val_bit + (uint32_t)sel[j] * stride, width) + add;
-          if (fix) v = sign_fix(mask, v);
-          out[j] = (OutT)v;
-        }
+        for (uint32_t j = tid; j < cnt; j += nt)
+          out[j] = (OutT)((uint64_t)sbits32(val_bit + (uint32_t)sel[j] * stride, width) + add);
       } else {
-        for (uint32_t j = (uint32_t)tid; j < cnt; j += kThreads) {
-          uint64_t v = ld_bits(s, val_bit + (uint32_t)sel[j] * stride, width) + add;
-          if (fix) v = sign_fix(mask, v);
-          out[j] = (OutT)v;
-        }
+        for (uint32_t j = tid; j < cnt; j += nt)
+          out[j] = (OutT)(sbits(val_bit + (uint32_t)sel[j] * stride, width) + add);
       }
     } else {
-      const uint32_t ext_off = d.ext_bit_off, eb = d.ext_bit;
-      for (uint32_t j = (uint32_t)tid; j < cnt; j += kThreads) {
+      const uint32_t ext_off = c.sbit + d.ext_bit_off, eb = d.ext_bit;
+      for (uint32_t j = tid; j < cnt; j += nt) {
         const uint32_t row = sel[j];
-        if (ld_bits32(s, ext_off + row * eb, eb) != STORED_NOT_EXT) {
+        if (eb && sbits32(ext_off + row * eb, eb) != STORED_NOT_EXT) {
           out[j] = (OutT)0;
           mark_null(j);
           continue;
         }
-        uint64_t v = ld_bits(s, val_bit + row * stride, width) + add;
+        uint64_t v = sbits(val_bit + row * stride, width) + add;
         if (fix) v = sign_fix(mask, v);
         out[j] = (OutT)v;
       }
     }
   } else {  // K_DICT / K_RLE
-    const uint32_t dcount = d.dict_count, dbits = d.dict_data_size * 8u, dpay = d.dict_payload * 8u;
+    const uint32_t dcount = d.dict_count, dbits = d.dict_data_size * 8u, dpay = c.sbit + d.dict_payload * 8u;
     const uint64_t mask = d.int_mask;
     const bool fix = d.sign_fix != 0;
     if (d.kind == K_DICT) {
-      const uint32_t val_bit = d.val_bit, stride = d.stride, width = d.width;
-      for (uint32_t j = (uint32_t)tid; j < cnt; j += kThreads) {
-        const uint32_t ref = ld_bits32(s, val_bit + (uint32_t)sel[j] * stride, width);
+      const uint32_t val_bit = c.sbit + d.val_bit, stride = d.stride, width = d.width;
+      for (uint32_t j = tid; j < cnt; j += nt) {
+        const uint32_t ref = sbits32(val_bit + (uint32_t)sel[j] * stride, width);
         if (ref >= dcount) {
           out[j] = (OutT)0;
           mark_null(j);
           continue;
         }
-        uint64_t v = ld_bits(s, dpay + ref * dbits, dbits);
+        uint64_t v = sbits(dpay + ref * dbits, dbits);
+        if (fix) v = sign_fix(mask, v);
+        out[j] = (OutT)v;
+      }
+    } else if (d.rle_slot >= 0) {
+      const RleTable rt = c.rle_table(d.rle_slot);
+      const uint32_t refs_bit = c.sbit + d.rle_refs_bit, ref_bits = d.rle_ref_bits;
+      for (uint32_t j = tid; j < cnt; j += nt) {
+        const uint32_t ref = sbits32(refs_bit + rle_run_of(rt, sel[j]) * ref_bits, ref_bits);
+        if (ref >= dcount) {
+          out[j] = (OutT)0;
+          mark_null(j);
+          continue;
+        }
+        uint64_t v = sbits(dpay + ref * dbits, dbits);
         if (fix) v = sign_fix(mask, v);
         out[j] = (OutT)v;
       }
     } else {
-      const RleTable rt = c.rle_table(d.rle_slot);
-      const uint32_t refs_bit = d.rle_refs_bit, ref_bits = d.rle_ref_bits;
-      for (uint32_t j = (uint32_t)tid; j < cnt; j += kThreads) {
-        const uint32_t ref = ld_bits32(s, refs_bit + rle_run_of(rt, sel[j]) * ref_bits, ref_bits);
-        if (ref >= dcount) {
-          out[j] = (OutT)0;
-          mark_null(j);
-          continue;
-        }
-        uint64_t v = ld_bits(s, dpay + ref * dbits, dbits);
-        if (fix) v = sign_fix(mask, v);
-        out[j] = (OutT)v;
+      for (uint32_t j = tid; j < cnt; j += nt) {
+        bool is_null;
+        const uint64_t v = int_cell(c.b, d, nullptr, sel[j], is_null);
+        out[j] = (OutT)(is_null ? 0ull : v);
+        if (is_null) mark_null(j);
       }
     }
   }
@@ -549,7 +642,7 @@ __device__ __forceinline__ void project_int_col(const ScanParams &p, const Block
 
 __device__ __forceinline__ void project_str_col(const ScanParams &p, const BlockCtx &c, const ColDesc &d, int pc,
                                                 const uint16_t *sel, uint32_t cnt, int64_t base_row,
-                                                uint64_t blk_addr) {
+                                                uint64_t blk_addr, const Team &t) {
   uint64_t *optr = reinterpret_cast<uint64_t *>(p.out_data[pc]) + base_row;
   int32_t *olen = p.out_lens[pc] + base_row;
   RleTable rt{};
@@ -559,7 +652,7 @@ __device__ __forceinline__ void project_str_col(const ScanParams &p, const Block
     rtp = &rt;
   }
   bool saw_null = false;
-  for (uint32_t j = (uint32_t)threadIdx.x; j < cnt; j += kThreads) {
+  for (uint32_t j = (uint32_t)t.tid; j < cnt; j += (uint32_t)t.nthreads) {
     uint32_t cell, len;
     bool is_null;
     str_cell(c.b, d, rtp, sel[j], cell, len, is_null);
@@ -575,23 +668,29 @@ __device__ __forceinline__ void project_str_col(const ScanParams &p, const Block
 }
 
 // =================================================================================================
-// Fused scan kernel: one CTA per micro-block (logical order by ticket)
+// Fused scan kernel: one CTA (4 warps) per micro-block, logical block order by ticket.
+//
+// The kernel is instruction-issue bound on ~16 KiB pages, so everything that is not data-parallel
+// over rows runs in ONE warp (descriptors, RLE run tables, look-back) while the other warps wait at
+// a barrier (waiting warps cost no issue slots; ~10 co-resident CTAs per SM fill them), and the
+// per-row loops are templated down to the minimum instruction count.
 // =================================================================================================
 __global__ void __launch_bounds__(kThreads) obgpu_scan_kernel(const __grid_constant__ ScanParams p) {
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ int s_tile;
+  __shared__ int s_bad;  // 0 ok, 1 unsupported, 2 corrupt
   __shared__ long long s_base;
   __shared__ uint32_t s_cnt;
   __shared__ uint32_t s_scan[kWarps];
-  __shared__ BlockView s_view;
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  uint8_t *sblk = g_smem;
-  uint16_t *sel = reinterpret_cast<uint16_t *>(g_smem + p.smem_sel);
-  uint32_t *bm = reinterpret_cast<uint32_t *>(g_smem + p.smem_bm);
-  uint32_t *wpre = reinterpret_cast<uint32_t *>(g_smem + p.smem_wpre);
+  const Team t = cta_team();
+  const int tid = t.tid, lane = t.lane, warp = t.warp;
+  uint8_t *scr = g_smem + p.smem_scratch;
+  uint16_t *sel = reinterpret_cast<uint16_t *>(scr + p.off_sel);
+  uint32_t *bm = reinterpret_cast<uint32_t *>(scr + p.off_bm);
+  uint32_t *wpre = reinterpret_cast<uint32_t *>(scr + p.off_wpre);
+  ColDesc *descs = reinterpret_cast<ColDesc *>(scr + p.off_desc);
   uint32_t *bitsets = reinterpret_cast<uint32_t *>(g_smem + p.smem_bitset);
-  ColDesc *descs = reinterpret_cast<ColDesc *>(g_smem + p.smem_desc);
 
   if (tid == 0) {
     s_tile = atomicAdd(p.ticket, 1);
@@ -604,15 +703,61 @@ __global__ void __launch_bounds__(kThreads) obgpu_scan_kernel(const __grid_const
 
   // ---- 1. stage the block ----------------------------------------------------------------------
   const uint32_t size = p.blk_size[tile];
-  load_block(sblk, p.image + p.blk_off[tile], (size + 15u) & ~15u, &s_bar, 0);
+  load_block(g_smem, p.image + p.blk_off[tile], (size + 15u) & ~15u, &s_bar, 0);
 
-  // ---- 2. parse header, build column descriptors and RLE run tables -----------------------------
+  // ---- 2. descriptors + RLE run tables: warp 0 only ------------------------------------------------
   BlockCtx c;
   c.bitsets = bitsets;
-  bool corrupt;
-  if (!prepare_block(p, sblk, size, &s_view, descs, g_smem + p.smem_rle, c, corrupt)) {
+  parse_block(g_smem, size, c.b);
+  if (c.b.ok && c.b.row_count > p.rows_cap) c.b.ok = 0;
+  c.sbit = smem_u32(g_smem) * 8u;
+  c.descs = descs;
+  c.rle_base = scr + p.off_rle;
+  c.rle_slot_bytes = p.rle_slot_bytes;
+  c.rle_starts_bytes = ((uint32_t)p.rle_runs_cap + 2u) * 2u;
+  const uint32_t rows = c.b.row_count;
+  const uint32_t nwords = (rows + 31u) >> 5;
+  if (warp == 0) {
+    bool my_bad = false;
+    if (c.b.ok && lane < p.n_used) {
+      ColDesc d;
+      build_col_desc(c.b, p.used_col[lane], d);
+      d.rle_slot = d.kind == K_RLE ? p.used_rle_slot[lane] : (int8_t)-1;
+      if (d.kind == K_RLE && d.rle_slot >= 0 && d.rle_count > (uint32_t)p.rle_runs_cap) d.ok = 0;
+      descs[lane] = d;
+      my_bad = !d.ok;
+    }
+    const bool bad = __any_sync(0xffffffffu, my_bad) || !c.b.ok;
+    if (lane == 0) s_bad = !c.b.ok ? 2 : (bad ? 1 : 0);
+    __syncwarp();
+    if (!bad && p.n_rle_slots > 0) {
+      for (int i = 0; i < p.n_used; ++i) {
+        if (p.used_rle_slot[i] < 0) continue;
+        const ColDesc &d = descs[i];
+        if (d.kind != K_RLE) continue;
+        uint16_t *starts = reinterpret_cast<uint16_t *>(scr + p.off_rle + (uint32_t)d.rle_slot * p.rle_slot_bytes);
+        uint16_t *g2run = reinterpret_cast<uint16_t *>(scr + p.off_rle + (uint32_t)d.rle_slot * p.rle_slot_bytes +
+                                                       c.rle_starts_bytes);
+        const uint32_t rbit = c.sbit + d.rle_row_ids_bit, rw = d.rle_row_id_bits, n = d.rle_count;
+        for (uint32_t k = (uint32_t)lane; k <= n; k += 32u)
+          starts[k] = k < n ? (uint16_t)sbits32(rbit + k * rw, rw) : (uint16_t)0xFFFF;
+        __syncwarp();
+        for (uint32_t g = (uint32_t)lane; g < nwords; g += 32u) {
+          const uint32_t row = g * 32u;
+          uint32_t lo = 0, hi = n;  // upper_bound(starts, row)
+          while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (starts[mid] <= row) lo = mid + 1; else hi = mid;
+          }
+          g2run[g] = (uint16_t)(lo > 0 ? lo - 1 : 0);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (s_bad) {
     // Unsupported / corrupt block: publish a zero count so later tiles are not blocked, flag it.
-    if (tid == 0) atomicOr(p.status, corrupt ? ST_CORRUPT : ST_UNSUPPORTED);
+    if (tid == 0) atomicOr(p.status, s_bad == 2 ? ST_CORRUPT : ST_UNSUPPORTED);
     if (warp == 0) {
       const int64_t excl = lookback(p.tile_state, tile, 0, lane);
       if (lane == 0) {
@@ -622,8 +767,6 @@ __global__ void __launch_bounds__(kThreads) obgpu_scan_kernel(const __grid_const
     }
     return;
   }
-  const uint32_t rows = c.b.row_count;
-  const uint32_t nwords = (rows + 31u) >> 5;
 
   // ---- 3. predicate over dictionaries ------------------------------------------------------------
   if (p.n_slots > 0) {
@@ -632,24 +775,26 @@ __global__ void __launch_bounds__(kThreads) obgpu_scan_kernel(const __grid_const
       if (nd.kind != NODE_WHITE || nd.slot < 0) continue;
       const ColDesc &d = descs[nd.used_idx];
       if (d.kind == K_DICT || d.kind == K_RLE)
-        build_dict_bitset(p, c.b, d, nd, bitsets + nd.slot * p.bitset_words, warp, lane);
+        build_dict_bitset(p, c.b, d, nd, bitsets + nd.slot * p.bitset_words, t);
     }
     __syncthreads();
   }
 
   // ---- 4. filter -> ballot words (the packed selection bitmap) ------------------------------------
-  // Each warp owns the words g = warp, warp + 8, ...: no block barrier between leaves.
+  // Each warp owns the words g = warp, warp + 4, ...: no block barrier between leaves.
   if (p.simple_shape != 0) {
     const bool and_mode = p.simple_shape == 1;
-    if (lane == 0)
-      for (uint32_t g = (uint32_t)warp; g < nwords; g += kWarps) {
-        const uint32_t rem = rows - g * 32u;
-        bm[g] = and_mode ? (rem >= 32u ? 0xffffffffu : ((1u << rem) - 1u)) : 0u;
-      }
-    __syncwarp();
     const int n_leaves = p.n_nodes == 1 ? 1 : p.n_nodes - 1;
-    for (int i = 0; i < n_leaves; ++i) {
-      leaf_over_words(p, c, p.nodes[i], bm, rows, nwords, and_mode, warp, lane);
+    int first = 0;
+    if (!leaf_first_fast(p, c, p.nodes[0], bm, rows, nwords, t)) {
+      if (lane == 0)
+        for (uint32_t g = (uint32_t)warp; g < nwords; g += kWarps) bm[g] = and_mode ? valid_mask_of(rows, g) : 0u;
+    } else {
+      first = 1;
+    }
+    __syncwarp();
+    for (int i = first; i < n_leaves; ++i) {
+      leaf_over_words(p, c, p.nodes[i], bm, rows, nwords, and_mode, t);
       __syncwarp();
     }
   } else {
@@ -663,60 +808,58 @@ __global__ void __launch_bounds__(kThreads) obgpu_scan_kernel(const __grid_const
   }
   __syncthreads();
 
-  // ---- 5. exclusive prefix of popcounts over words; total; publish the bitmap ----------------------
+  // ---- 5. exclusive prefix of popcounts over words; total; publish bitmap + count ---------------------
   {
     uint32_t *gbm = p.bitmap_words + p.bm_word_off[tile];
-    const uint32_t per = (nwords + kThreads - 1) / kThreads;
-    const uint32_t w0 = (uint32_t)tid * per;
-    uint32_t local = 0;
-    for (uint32_t k = 0; k < per; ++k) {
-      const uint32_t w = w0 + k;
-      if (w < nwords) {
-        const uint32_t word = bm[w];
-        gbm[w] = word;
-        local += __popc(word);
-      }
-    }
-    uint32_t inc = local;
+    uint32_t run_total = 0;
+    for (uint32_t base_w = 0; base_w < nwords; base_w += kThreads) {  // one pass for <= 4096 rows
+      const uint32_t w = base_w + (uint32_t)tid;
+      const uint32_t word = w < nwords ? bm[w] : 0u;
+      if (w < nwords) gbm[w] = word;
+      const uint32_t local = __popc(word);
+      uint32_t inc = local;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-      if (lane >= o) inc += t;
-    }
-    if (lane == 31) s_scan[warp] = inc;
-    __syncthreads();
-    uint32_t warp_off = 0;
-#pragma unroll
-    for (int k = 0; k < kWarps; ++k) warp_off += k < warp ? s_scan[k] : 0u;
-    uint32_t run = warp_off + inc - local;
-    for (uint32_t k = 0; k < per; ++k) {
-      const uint32_t w = w0 + k;
-      if (w < nwords) {
-        wpre[w] = run;
-        run += __popc(bm[w]);
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += u;
       }
+      if (lane == 31) s_scan[warp] = inc;
+      __syncthreads();
+      uint32_t warp_off = run_total, total = run_total;
+#pragma unroll
+      for (int k = 0; k < kWarps; ++k) {
+        const uint32_t v = s_scan[k];
+        warp_off += k < warp ? v : 0u;
+        total += v;
+      }
+      if (w < nwords) wpre[w] = warp_off + inc - local;
+      run_total = total;
+      __syncthreads();
     }
-    if (tid == kThreads - 1) {
-      s_cnt = run;
+    if (tid == 0) {
+      s_cnt = run_total;
       // publish this block's count as early as possible: successors' look-backs only need this
-      st_release(&p.tile_state[tile], (tile == 0 ? kTilePrefix : kTileAgg) | (unsigned long long)run);
+      st_release(&p.tile_state[tile], (tile == 0 ? kTilePrefix : kTileAgg) | (unsigned long long)run_total);
     }
+    __syncthreads();
   }
-  __syncthreads();
   const uint32_t cnt = s_cnt;
 
-  // ---- 6. look-back (warp 0) overlapped with building the selected-row list (other warps) --------
+  // ---- 6. look-back (warp 0) overlapped with building the selected-row list (warps 1..3) ----------
   if (warp == 0) {
-    const int64_t excl = lookback(p.tile_state, tile, (int64_t)cnt, lane, /*publish_own=*/false);
+    int64_t excl;
+    if (p.debug_flags & 1) excl = p.bm_word_off[tile] * 32;
+    else excl = lookback(p.tile_state, tile, (int64_t)cnt, lane, /*publish_own=*/false);
     if (lane == 0) {
       s_base = excl;
       p.sel_offset[tile] = excl;
       if (tile == p.n_blocks - 1) p.sel_offset[p.n_blocks] = excl + (int64_t)cnt;
     }
-  }
-  for (uint32_t g = (uint32_t)warp; g < nwords; g += kWarps) {
-    const uint32_t word = bm[g];
-    if ((word >> lane) & 1u) sel[wpre[g] + __popc(word & ((1u << lane) - 1u))] = (uint16_t)(g * 32u + lane);
+  } else {
+    for (uint32_t g = (uint32_t)warp - 1u; g < nwords; g += kWarps - 1) {
+      const uint32_t word = bm[g];
+      if ((word >> lane) & 1u) sel[wpre[g] + __popc(word & ((1u << lane) - 1u))] = (uint16_t)(g * 32u + lane);
+    }
   }
   __syncthreads();
   const int64_t base = s_base;
@@ -734,43 +877,41 @@ __global__ void __launch_bounds__(kThreads) obgpu_scan_kernel(const __grid_const
   const uint64_t blk_addr = p.string_base + p.blk_off[tile];
   for (int pc = 0; pc < p.n_proj; ++pc) {
     const ColDesc &d = descs[p.proj_used[pc]];
-    if (d.sc == 5) project_str_col(p, c, d, pc, sel, cnt, base, blk_addr);
-    else if (d.elem_len == 8) project_int_col<uint64_t>(p, c, d, pc, sel, cnt, base);
-    else if (d.elem_len == 4) project_int_col<uint32_t>(p, c, d, pc, sel, cnt, base);
-    else project_int_col<uint8_t>(p, c, d, pc, sel, cnt, base);
+    if (d.sc == 5) project_str_col(p, c, d, pc, sel, cnt, base, blk_addr, t);
+    else if (d.elem_len == 8) project_int_col<uint64_t>(p, c, d, pc, sel, cnt, base, t);
+    else if (d.elem_len == 4) project_int_col<uint32_t>(p, c, d, pc, sel, cnt, base, t);
+    else project_int_col<uint8_t>(p, c, d, pc, sel, cnt, base, t);
   }
 }
 
 // =================================================================================================
-// Single-block kernels for the reference-granularity entry points
+// Single-block kernels for the reference-granularity entry points (one CTA, kThreads threads)
 // =================================================================================================
 // ObBitmap byte image of a filter tree over rows [start, start + count) of one block.
 __global__ void __launch_bounds__(kThreads) obgpu_filter_block_kernel(const __grid_constant__ ScanParams p,
                                                                       int tile, int64_t start, int64_t count,
                                                                       uint8_t *out_bytes) {
   __shared__ __align__(8) uint64_t s_bar;
-  __shared__ BlockView s_view;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  uint8_t *sblk = g_smem;
+  const Team t = cta_team();
   uint32_t *bitsets = reinterpret_cast<uint32_t *>(g_smem + p.smem_bitset);
   ColDesc *descs = reinterpret_cast<ColDesc *>(g_smem + p.smem_desc);
-  if (tid == 0) {
+  if (t.tid == 0) {
     mbar_init(&s_bar, 1);
     fence_barrier_init();
   }
   __syncthreads();
   const uint32_t size = p.blk_size[tile];
-  load_block(sblk, p.image + p.blk_off[tile], (size + 15u) & ~15u, &s_bar, 0);
+  load_block(g_smem, p.image + p.blk_off[tile], (size + 15u) & ~15u, &s_bar, 0);
   BlockCtx c;
   c.bitsets = bitsets;
   bool corrupt;
-  bool ok = prepare_block(p, sblk, size, &s_view, descs, g_smem + p.smem_rle, c, corrupt);
+  bool ok = prepare_block(p, 0, size, descs, g_smem + p.smem_rle, t, c, corrupt);
   if (ok && (start < 0 || start + count > (int64_t)c.b.row_count)) {
     ok = false;
     corrupt = true;
   }
   if (!ok) {
-    if (tid == 0) atomicOr(p.status, corrupt ? ST_CORRUPT : ST_UNSUPPORTED);
+    if (t.tid == 0) atomicOr(p.status, corrupt ? ST_CORRUPT : ST_UNSUPPORTED);
     return;
   }
   for (int i = 0; i < p.n_nodes; ++i) {
@@ -778,10 +919,10 @@ __global__ void __launch_bounds__(kThreads) obgpu_filter_block_kernel(const __gr
     if (nd.kind != NODE_WHITE || nd.slot < 0) continue;
     const ColDesc &d = descs[nd.used_idx];
     if (d.kind == K_DICT || d.kind == K_RLE)
-      build_dict_bitset(p, c.b, d, nd, bitsets + nd.slot * p.bitset_words, warp, lane);
+      build_dict_bitset(p, c.b, d, nd, bitsets + nd.slot * p.bitset_words, t);
   }
   __syncthreads();
-  for (int64_t i = tid; i < count; i += kThreads)
+  for (int64_t i = t.tid; i < count; i += kThreads)
     out_bytes[i] = eval_tree(p, c, (uint32_t)(start + i)) ? 1 : 0;
 }
 
@@ -790,27 +931,25 @@ __global__ void __launch_bounds__(kThreads) obgpu_project_block_kernel(
     const __grid_constant__ ScanParams p, int tile, const int32_t *row_ids, int64_t row_cap, int64_t vec_offset,
     void *data, int32_t *lens, uint32_t *nulls, int32_t elem_len) {
   __shared__ __align__(8) uint64_t s_bar;
-  __shared__ BlockView s_view;
-  const int tid = threadIdx.x;
-  uint8_t *sblk = g_smem;
+  const Team t = cta_team();
   ColDesc *descs = reinterpret_cast<ColDesc *>(g_smem + p.smem_desc);
-  if (tid == 0) {
+  if (t.tid == 0) {
     mbar_init(&s_bar, 1);
     fence_barrier_init();
   }
   __syncthreads();
   const uint32_t size = p.blk_size[tile];
-  load_block(sblk, p.image + p.blk_off[tile], (size + 15u) & ~15u, &s_bar, 0);
+  load_block(g_smem, p.image + p.blk_off[tile], (size + 15u) & ~15u, &s_bar, 0);
   BlockCtx c;
   c.bitsets = nullptr;
   bool corrupt;
-  if (!prepare_block(p, sblk, size, &s_view, descs, g_smem + p.smem_rle, c, corrupt)) {
-    if (tid == 0) atomicOr(p.status, corrupt ? ST_CORRUPT : ST_UNSUPPORTED);
+  if (!prepare_block(p, 0, size, descs, g_smem + p.smem_rle, t, c, corrupt)) {
+    if (t.tid == 0) atomicOr(p.status, corrupt ? ST_CORRUPT : ST_UNSUPPORTED);
     return;
   }
   const ColDesc &d = descs[0];
   if ((d.sc == 5) != (lens != nullptr) || (d.sc != 5 && d.elem_len != elem_len)) {
-    if (tid == 0) atomicOr(p.status, ST_UNSUPPORTED);
+    if (t.tid == 0) atomicOr(p.status, ST_UNSUPPORTED);
     return;
   }
   RleTable rt{};
@@ -820,7 +959,7 @@ __global__ void __launch_bounds__(kThreads) obgpu_project_block_kernel(
     rtp = &rt;
   }
   const uint64_t blk_addr = p.string_base + p.blk_off[tile];
-  for (int64_t i = tid; i < row_cap; i += kThreads) {
+  for (int64_t i = t.tid; i < row_cap; i += kThreads) {
     const int32_t r = row_ids[i];
     if (r < 0 || (uint32_t)r >= c.b.row_count) {
       atomicOr(p.status, ST_CORRUPT);
@@ -903,6 +1042,7 @@ struct obgpu_ctx {
   std::string err;
   int64_t launches = 0;
   int max_smem_optin = 0;
+  int sm_count = 0;
   int *h_pinned = nullptr;  // small pinned staging (status, totals)
   // optional kernel timing: ring of CUDA event pairs recorded around each scan kernel launch
   bool profiling = false;
@@ -984,6 +1124,7 @@ int obgpu_ctx_create(int device, obgpu_ctx **out) {
   }
   c->stream = c->own_stream;
   cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
   cudaMallocHost(&c->h_pinned, 4096);
   // keep freed result arenas in the stream-ordered pool: steady-state scans do no cudaMalloc
   cudaMemPool_t pool;
@@ -1362,8 +1503,8 @@ static int build_filter(obgpu_ctx *ctx, const obgpu_batch *b, const obgpu_filter
   return OBGPU_SUCCESS;
 }
 
-static void layout_smem(const obgpu_batch *b, ScanParams &p, bool need_sel) {
-  // run-table slots for used columns that are RLE-coded in some block
+// run-table slots for used columns that are RLE-coded in some block
+static void assign_rle_slots(const obgpu_batch *b, ScanParams &p) {
   p.n_rle_slots = 0;
   p.rle_runs_cap = 0;
   for (int i = 0; i < kMaxUsedCols; ++i) p.used_rle_slot[i] = -1;
@@ -1374,19 +1515,37 @@ static void layout_smem(const obgpu_batch *b, ScanParams &p, bool need_sel) {
       p.rle_runs_cap = std::max<int32_t>(p.rle_runs_cap, (int32_t)std::min<uint32_t>(b->col_max_rle[col], 65535u));
     }
   }
-  uint32_t off = (b->max_block_bytes + 16u + 127u) & ~127u;
   const uint32_t rows_cap = std::max<uint32_t>(b->max_rows, 32u);
-  const uint32_t words_cap = (rows_cap + 31u) / 32u;
   p.rows_cap = rows_cap;
-  p.words_cap = words_cap;
-  p.smem_sel = off;   off += need_sel ? ((rows_cap * 2u + 15u) & ~15u) : 0u;
-  p.smem_bm = off;    off += need_sel ? ((words_cap * 4u + 15u) & ~15u) : 0u;
-  p.smem_wpre = off;  off += need_sel ? ((words_cap * 4u + 15u) & ~15u) : 0u;
+  p.words_cap = (rows_cap + 31u) / 32u;
+  p.rle_slot_bytes = p.n_rle_slots > 0 ? ((((uint32_t)p.rle_runs_cap + 2u) * 2u + p.words_cap * 2u + 15u) & ~15u) : 0u;
+}
+
+// single-block kernels: [block][bitsets][rle tables][descs]
+static void layout_smem(const obgpu_batch *b, ScanParams &p, bool /*need_sel*/) {
+  assign_rle_slots(b, p);
+  uint32_t off = (b->max_block_bytes + 16u + 127u) & ~127u;
   p.smem_bitset = off; off += ((uint32_t)p.n_slots * (uint32_t)p.bitset_words * 4u + 15u) & ~15u;
-  p.rle_slot_bytes = p.n_rle_slots > 0 ? ((((uint32_t)p.rle_runs_cap + 2u) * 2u + words_cap * 2u + 15u) & ~15u) : 0u;
   p.smem_rle = off;   off += (uint32_t)p.n_rle_slots * p.rle_slot_bytes;
   p.smem_desc = off;  off += (uint32_t)sizeof(ColDesc) * (uint32_t)std::max(p.n_used, 1);
   p.smem_total = (off + 15u) & ~15u;
+}
+
+// persistent scan kernel: [stage x kStages][bitsets][scratch x 2], scratch = sel|bm|wpre|rle|descs
+static void layout_smem_scan(const obgpu_batch *b, ScanParams &p) {
+  assign_rle_slots(b, p);
+  p.stage_bytes = (b->max_block_bytes + 16u + 127u) & ~127u;
+  uint32_t off = p.stage_bytes;
+  p.smem_bitset = off; off += ((uint32_t)p.n_slots * (uint32_t)p.bitset_words * 4u + 15u) & ~15u;
+  uint32_t s = 0;
+  p.off_sel = s;  s += (p.rows_cap * 2u + 15u) & ~15u;
+  p.off_bm = s;   s += (p.words_cap * 4u + 15u) & ~15u;
+  p.off_wpre = s; s += (p.words_cap * 4u + 15u) & ~15u;
+  p.off_rle = s;  s += (uint32_t)p.n_rle_slots * p.rle_slot_bytes;
+  p.off_desc = s; s += ((uint32_t)sizeof(ColDesc) * (uint32_t)std::max(p.n_used, 1) + 15u) & ~15u;
+  p.scratch_bytes = (s + 127u) & ~127u;
+  p.smem_scratch = (off + 127u) & ~127u;
+  p.smem_total = p.smem_scratch + p.scratch_bytes;
 }
 
 static int check_status(obgpu_ctx *ctx, int status) {
@@ -1424,8 +1583,9 @@ int obgpu_scan(obgpu_batch *b, const obgpu_scan_spec *spec, obgpu_result **out) 
   }
   p.n_proj = spec->n_proj;
   p.want_row_ids = spec->want_row_ids ? 1 : 0;
+  if (const char *dbg = getenv("OBGPU_DEBUG_FLAGS")) p.debug_flags = atoi(dbg);
   p.string_base = spec->string_base;
-  layout_smem(b, p, true);
+  layout_smem_scan(b, p);
   if ((int)p.smem_total > ctx->max_smem_optin) {
     ctx->err = "scan working set exceeds shared memory";
     delete r;

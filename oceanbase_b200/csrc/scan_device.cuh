@@ -62,6 +62,27 @@ __device__ __forceinline__ uint64_t ld_bits(const uint8_t *s, uint32_t bit_off, 
   return (((uint64_t)hi << 32) | lo) & (~0ull >> (64u - w));
 }
 
+// Same loads on shared-window addresses (bit offset = 8 * 32-bit shared address): explicit
+// ld.shared keeps the compiler from re-deriving the generic->shared base inside hot loops.
+extern __shared__ __align__(128) uint8_t g_smem[];
+__device__ __forceinline__ uint32_t sld32(uint32_t saddr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ uint32_t sbits32(uint32_t bit_off, uint32_t w) {
+  const uint32_t a = (bit_off >> 5) << 2, sh = bit_off & 31u;
+  return __funnelshift_r(sld32(a), sld32(a + 4), sh) & (0xffffffffu >> (32u - w));
+}
+__device__ __forceinline__ uint64_t sbits(uint32_t bit_off, uint32_t w) {
+  const uint32_t a = (bit_off >> 5) << 2, sh = bit_off & 31u;
+  const uint32_t w0 = sld32(a), w1 = sld32(a + 4);
+  const uint32_t lo = __funnelshift_r(w0, w1, sh);
+  if (w <= 32) return (uint64_t)(lo & (0xffffffffu >> (32u - w)));
+  const uint32_t hi = __funnelshift_r(w1, sld32(a + 8), sh);
+  return (((uint64_t)hi << 32) | lo) & (~0ull >> (64u - w));
+}
+
 // n bytes (1..8) at byte offset off, zero extended
 __device__ __forceinline__ uint64_t ld_bytes(const uint8_t *s, uint32_t off, uint32_t n) {
   return ld_bits(s, off * 8u, n * 8u);

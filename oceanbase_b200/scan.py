@@ -224,7 +224,8 @@ class PageBatch:
 
     def close(self):
         if self._h:
-            lib.obgpu_batch_close(self._h)
+            if self.ctx._h:  # the C ctx owns the stream: never touch a batch after its ctx is gone
+                lib.obgpu_batch_close(self._h)
             self._h = C.c_void_p()
 
     def __del__(self):
@@ -299,7 +300,8 @@ class ScanResult:
 
     def free(self):
         if self._h:
-            lib.obgpu_result_free(self._h)
+            if self.batch.ctx._h:
+                lib.obgpu_result_free(self._h)
             self._h = C.c_void_p()
 
     def __del__(self):
