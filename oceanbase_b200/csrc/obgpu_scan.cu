@@ -60,11 +60,6 @@ struct ParamDev {
 
 constexpr int kParamHeap = 768;
 
-// Persistent scan kernel geometry: one producer warp (TMA ring) + kConsumerWarps consumer warps.
-constexpr int kConsumerWarps = 4;
-constexpr int kConsumers = kConsumerWarps * 32;
-constexpr int kScanThreads = kConsumers + 32;
-constexpr int kStages = 3;
 
 struct ScanParams {
   const uint8_t *image;
@@ -72,8 +67,14 @@ struct ScanParams {
   const uint32_t *blk_size;   // [n_blocks] exact block size
   const int64_t *bm_word_off; // [n_blocks + 1] prefix of ceil(rows / 32)
   int32_t n_blocks;
+  const ColDesc *plans;       // [n_blocks][max_cols] decode plans built once at batch open (index kernel)
+  const uint32_t *rows;       // [n_blocks] row counts (0: corrupt block)
+  uint32_t *counts;           // [n_blocks] selected rows per block (count kernel)
+  int32_t max_cols;
   int32_t n_used;
   int32_t used_col[kMaxUsedCols];
+  uint8_t used_in_filter[kMaxUsedCols];
+  uint8_t used_in_proj[kMaxUsedCols];
   int8_t used_rle_slot[kMaxUsedCols];  // run-table slot of a used column (-1: never RLE)
   int32_t n_nodes;
   int32_t simple_shape;       // 1: single leaf or AND over leaves only, 2: OR over leaves only, 0: generic
@@ -105,7 +106,8 @@ struct ScanParams {
   uint32_t stage_bytes;       // scan kernel: bytes per stage buffer
   uint32_t smem_bitset;
   uint32_t smem_rle, smem_desc;            // single-block kernels
-  uint32_t smem_scratch, scratch_bytes;    // scan kernel
+  uint32_t smem_scratch, scratch_bytes;    // project kernel
+  uint32_t cw_desc, cw_bm, cw_bitset, cw_bytes;  // count kernel: per-warp region = descs | bm | bitsets
   uint32_t off_sel, off_bm, off_wpre, off_rle, off_desc;  // inside one scratch
   uint32_t smem_total;
   uint32_t rle_slot_bytes;    // bytes per run-table slot: starts[(cap + 2)] + g2run[words_cap]
@@ -167,6 +169,7 @@ struct Team {
   int tid, nthreads, warp, nwarps, lane, bar_id;
   __device__ __forceinline__ void sync() const {
     if (bar_id == 0) __syncthreads();
+    else if (bar_id < 0) __syncwarp();  // a single warp working on its own block
     else asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nthreads) : "memory");
   }
   __device__ __forceinline__ bool sync_or(bool pred) const {
@@ -271,7 +274,7 @@ __device__ __forceinline__ bool str_pred(const ScanParams &p, const FilterNodeDe
 // Everything a team needs to know about the block it is working on.
 struct BlockCtx {
   BlockView b;
-  uint32_t sbit;             // bit offset of the staged block inside g_smem (fast-path loads)
+  uint32_t sbit;             // 8 * shared-window address of the staged block (fast-path loads)
   const ColDesc *descs;
   const uint32_t *bitsets;
   const uint8_t *rle_base;   // run-table scratch
@@ -367,7 +370,8 @@ __device__ __forceinline__ uint32_t valid_mask_of(uint32_t rows, uint32_t g) {
 
 // Range test over a K_BITS column without NULLs / sign fix: the hot filter loop.
 //   MODE 0: first leaf (bm[g] = leaf), 1: AND into bm with early-out, 2: OR into bm with early-out
-template <bool WIDE, int MODE>
+//   G: the block is read straight from global memory (count kernel) instead of shared memory
+template <bool WIDE, int MODE, bool G>
 __device__ __forceinline__ void filter_bits_range(const BlockCtx &c, const ColDesc &d, const FilterNodeDev &nd,
                                                   uint32_t *bm, uint32_t rows, uint32_t nwords, const Team &t) {
   const uint32_t stride = d.stride, width = d.width;
@@ -375,22 +379,27 @@ __device__ __forceinline__ void filter_bits_range(const BlockCtx &c, const ColDe
   const bool neg = nd.negate != 0;
   const uint32_t nfull = rows >> 5;
   const uint32_t step = (uint32_t)t.nwarps * 32u * stride;
-  uint32_t bit = c.sbit + d.val_bit + ((uint32_t)t.warp * 32u + (uint32_t)t.lane) * stride;
+  const uint8_t *gs = c.b.s;
+  uint32_t bit = (G ? 0u : c.sbit) + d.val_bit + ((uint32_t)t.warp * 32u + (uint32_t)t.lane) * stride;
   uint32_t g = (uint32_t)t.warp;
+  auto load = [&](uint32_t bo) -> uint64_t {
+    if (G) return WIDE ? ld_bits(gs, bo, width) : (uint64_t)ld_bits32(gs, bo, width);
+    return WIDE ? sbits(bo, width) : (uint64_t)sbits32(bo, width);
+  };
   for (; g < nfull; g += (uint32_t)t.nwarps, bit += step) {
     uint32_t cur = 0;
     if (MODE != 0) {
       cur = bm[g];
       if (MODE == 1 ? cur == 0u : cur == 0xffffffffu) continue;
     }
-    const uint64_t v = WIDE ? sbits(bit, width) : (uint64_t)sbits32(bit, width);
+    const uint64_t v = load(bit);
     const uint32_t w = __ballot_sync(0xffffffffu, ((v - lo) <= span) != neg);
     if (t.lane == 0) bm[g] = MODE == 0 ? w : (MODE == 1 ? (cur & w) : (cur | w));
   }
   if (g < nwords) {  // ragged tail group
     const uint32_t vm = valid_mask_of(rows, g);
     const uint32_t cur = MODE == 0 ? 0u : bm[g];
-    const uint64_t v = WIDE ? sbits(bit, width) : (uint64_t)sbits32(bit, width);
+    const uint64_t v = load(bit);
     const uint32_t w = __ballot_sync(0xffffffffu, ((v - lo) <= span) != neg) & vm;
     if (t.lane == 0) bm[g] = MODE == 0 ? w : (MODE == 1 ? (cur & w) : (cur | w));
   }
@@ -402,19 +411,21 @@ __device__ __forceinline__ bool leaf_is_bits_range(const ColDesc &d, const Filte
 
 // First leaf of an AND / OR list: writes bm directly (no initialisation pass) when it is a plain
 // range test. Returns false if the caller has to initialise bm and run the leaf generically.
+template <bool G>
 __device__ __forceinline__ bool leaf_first_fast(const ScanParams &p, const BlockCtx &c, const FilterNodeDev &nd,
                                                 uint32_t *bm, uint32_t rows, uint32_t nwords, const Team &t) {
   if (nd.kind != NODE_WHITE) return false;
   const ColDesc &d = c.descs[nd.used_idx];
   if (!leaf_is_bits_range(d, nd)) return false;
-  if (d.width <= 32) filter_bits_range<false, 0>(c, d, nd, bm, rows, nwords, t);
-  else filter_bits_range<true, 0>(c, d, nd, bm, rows, nwords, t);
+  if (d.width <= 32) filter_bits_range<false, 0, G>(c, d, nd, bm, rows, nwords, t);
+  else filter_bits_range<true, 0, G>(c, d, nd, bm, rows, nwords, t);
   return true;
 }
 
 // One leaf evaluated column-at-a-time over the ballot words owned by this warp (g = warp, warp+n,
 // ...). `and_mode`: bm[g] &= leaf, skipping groups that are already all-false; else bm[g] |= leaf
 // for groups that are not yet all-true (the reference's can_skip_filter / early-out, per 32 rows).
+template <bool G>
 __device__ __forceinline__ void leaf_over_words(const ScanParams &p, const BlockCtx &c, const FilterNodeDev &nd,
                                                 uint32_t *bm, uint32_t rows, uint32_t nwords, bool and_mode,
                                                 const Team &t) {
@@ -423,48 +434,33 @@ __device__ __forceinline__ void leaf_over_words(const ScanParams &p, const Block
   // ---- fast path A: integer range test on a K_BITS column without NULLs ------------------------------
   if (leaf_is_bits_range(d, nd)) {
     if (d.width <= 32) {
-      if (and_mode) filter_bits_range<false, 1>(c, d, nd, bm, rows, nwords, t);
-      else filter_bits_range<false, 2>(c, d, nd, bm, rows, nwords, t);
+      if (and_mode) filter_bits_range<false, 1, G>(c, d, nd, bm, rows, nwords, t);
+      else filter_bits_range<false, 2, G>(c, d, nd, bm, rows, nwords, t);
     } else {
-      if (and_mode) filter_bits_range<true, 1>(c, d, nd, bm, rows, nwords, t);
-      else filter_bits_range<true, 2>(c, d, nd, bm, rows, nwords, t);
+      if (and_mode) filter_bits_range<true, 1, G>(c, d, nd, bm, rows, nwords, t);
+      else filter_bits_range<true, 2, G>(c, d, nd, bm, rows, nwords, t);
     }
     return;
   }
-  // ---- fast path B: dictionary-coded column through the predicate bitset ----------------------------
-  if ((d.kind == K_DICT || (d.kind == K_RLE && d.rle_slot >= 0)) && op != OP_FALSE && op != OP_TRUE) {
+  // ---- fast path B: DICT column through the predicate bitset ------------------------------------------
+  if (d.kind == K_DICT && op != OP_FALSE && op != OP_TRUE) {
     const uint32_t *bits = c.bitsets + nd.slot * p.bitset_words;
     const uint32_t cntp1 = d.dict_count + 1;
-    if (d.kind == K_DICT) {
-      const uint32_t val_bit = c.sbit + d.val_bit, stride = d.stride, width = d.width;
-      for (uint32_t g = (uint32_t)t.warp; g < nwords; g += (uint32_t)t.nwarps) {
-        const uint32_t cur = bm[g], vm = valid_mask_of(rows, g);
-        if (and_mode ? cur == 0u : cur == vm) continue;
-        const uint32_t row = g * 32u + (uint32_t)t.lane;
-        uint32_t ref = sbits32(val_bit + row * stride, width);
-        ref = ref < cntp1 ? ref : cntp1;
-        const bool pr = (bits[ref >> 5] >> (ref & 31)) & 1u;
-        const uint32_t w = __ballot_sync(0xffffffffu, pr) & vm;
-        if (t.lane == 0) bm[g] = and_mode ? (cur & w) : (cur | w);
-      }
-    } else {
-      const RleTable rt = c.rle_table(d.rle_slot);
-      const uint32_t refs_bit = c.sbit + d.rle_refs_bit, ref_bits = d.rle_ref_bits;
-      for (uint32_t g = (uint32_t)t.warp; g < nwords; g += (uint32_t)t.nwarps) {
-        const uint32_t cur = bm[g], vm = valid_mask_of(rows, g);
-        if (and_mode ? cur == 0u : cur == vm) continue;
-        uint32_t row = g * 32u + (uint32_t)t.lane;
-        row = row < rows ? row : rows - 1u;
-        uint32_t ref = sbits32(refs_bit + rle_run_of(rt, row) * ref_bits, ref_bits);
-        ref = ref < cntp1 ? ref : cntp1;
-        const bool pr = (bits[ref >> 5] >> (ref & 31)) & 1u;
-        const uint32_t w = __ballot_sync(0xffffffffu, pr) & vm;
-        if (t.lane == 0) bm[g] = and_mode ? (cur & w) : (cur | w);
-      }
+    const uint32_t val_bit = (G ? 0u : c.sbit) + d.val_bit, stride = d.stride, width = d.width;
+    const uint8_t *gs = c.b.s;
+    for (uint32_t g = (uint32_t)t.warp; g < nwords; g += (uint32_t)t.nwarps) {
+      const uint32_t cur = bm[g], vm = valid_mask_of(rows, g);
+      if (and_mode ? cur == 0u : cur == vm) continue;
+      const uint32_t row = g * 32u + (uint32_t)t.lane;
+      uint32_t ref = G ? ld_bits32(gs, val_bit + row * stride, width) : sbits32(val_bit + row * stride, width);
+      ref = ref < cntp1 ? ref : cntp1;
+      const bool pr = (bits[ref >> 5] >> (ref & 31)) & 1u;
+      const uint32_t w = __ballot_sync(0xffffffffu, pr) & vm;
+      if (t.lane == 0) bm[g] = and_mode ? (cur & w) : (cur | w);
     }
     return;
   }
-  // ---- generic leaf ----------------------------------------------------------------------------------
+  // ---- generic leaf (RLE via the predicate bitset + run lookup, strings, NULL-able columns, ...) ----
   for (uint32_t g = (uint32_t)t.warp; g < nwords; g += (uint32_t)t.nwarps) {
     const uint32_t cur = bm[g], vm = valid_mask_of(rows, g);
     if (and_mode ? cur == 0u : cur == vm) continue;
@@ -560,7 +556,8 @@ __device__ __forceinline__ bool prepare_block(const ScanParams &p, uint32_t soff
 // =================================================================================================
 // Projection of one column over the selected rows (column-at-a-time, specialised)
 // =================================================================================================
-template <typename OutT>
+#define ROW(j) (IDENT ? (uint32_t)(j) : (uint32_t)sel[j])
+template <typename OutT, bool IDENT>
 __device__ __forceinline__ void project_int_col(const ScanParams &p, const BlockCtx &c, const ColDesc &d, int pc,
                                                 const uint16_t *sel, uint32_t cnt, int64_t base_row, const Team &t) {
   OutT *out = reinterpret_cast<OutT *>(p.out_data[pc]) + base_row;
@@ -578,15 +575,15 @@ __device__ __forceinline__ void project_int_col(const ScanParams &p, const Block
     if (d.ext_bit == 0 && !fix) {
       if (width <= 32) {
         for (uint32_t j = tid; j < cnt; j += nt)
-          out[j] = (OutT)((uint64_t)sbits32(val_bit + (uint32_t)sel[j] * stride, width) + add);
+          out[j] = (OutT)((uint64_t)sbits32(val_bit + ROW(j) * stride, width) + add);
       } else {
         for (uint32_t j = tid; j < cnt; j += nt)
-          out[j] = (OutT)(sbits(val_bit + (uint32_t)sel[j] * stride, width) + add);
+          out[j] = (OutT)(sbits(val_bit + ROW(j) * stride, width) + add);
       }
     } else {
       const uint32_t ext_off = c.sbit + d.ext_bit_off, eb = d.ext_bit;
       for (uint32_t j = tid; j < cnt; j += nt) {
-        const uint32_t row = sel[j];
+        const uint32_t row = ROW(j);
         if (eb && sbits32(ext_off + row * eb, eb) != STORED_NOT_EXT) {
           out[j] = (OutT)0;
           mark_null(j);
@@ -604,7 +601,7 @@ __device__ __forceinline__ void project_int_col(const ScanParams &p, const Block
     if (d.kind == K_DICT) {
       const uint32_t val_bit = c.sbit + d.val_bit, stride = d.stride, width = d.width;
       for (uint32_t j = tid; j < cnt; j += nt) {
-        const uint32_t ref = sbits32(val_bit + (uint32_t)sel[j] * stride, width);
+        const uint32_t ref = sbits32(val_bit + ROW(j) * stride, width);
         if (ref >= dcount) {
           out[j] = (OutT)0;
           mark_null(j);
@@ -618,7 +615,7 @@ __device__ __forceinline__ void project_int_col(const ScanParams &p, const Block
       const RleTable rt = c.rle_table(d.rle_slot);
       const uint32_t refs_bit = c.sbit + d.rle_refs_bit, ref_bits = d.rle_ref_bits;
       for (uint32_t j = tid; j < cnt; j += nt) {
-        const uint32_t ref = sbits32(refs_bit + rle_run_of(rt, sel[j]) * ref_bits, ref_bits);
+        const uint32_t ref = sbits32(refs_bit + rle_run_of(rt, ROW(j)) * ref_bits, ref_bits);
         if (ref >= dcount) {
           out[j] = (OutT)0;
           mark_null(j);
@@ -631,7 +628,7 @@ __device__ __forceinline__ void project_int_col(const ScanParams &p, const Block
     } else {
       for (uint32_t j = tid; j < cnt; j += nt) {
         bool is_null;
-        const uint64_t v = int_cell(c.b, d, nullptr, sel[j], is_null);
+        const uint64_t v = int_cell(c.b, d, nullptr, ROW(j), is_null);
         out[j] = (OutT)(is_null ? 0ull : v);
         if (is_null) mark_null(j);
       }
@@ -640,6 +637,7 @@ __device__ __forceinline__ void project_int_col(const ScanParams &p, const Block
   if (saw_null) p.has_null[pc] = 1;
 }
 
+template <bool IDENT>
 __device__ __forceinline__ void project_str_col(const ScanParams &p, const BlockCtx &c, const ColDesc &d, int pc,
                                                 const uint16_t *sel, uint32_t cnt, int64_t base_row,
                                                 uint64_t blk_addr, const Team &t) {
@@ -655,7 +653,7 @@ __device__ __forceinline__ void project_str_col(const ScanParams &p, const Block
   for (uint32_t j = (uint32_t)t.tid; j < cnt; j += (uint32_t)t.nthreads) {
     uint32_t cell, len;
     bool is_null;
-    str_cell(c.b, d, rtp, sel[j], cell, len, is_null);
+    str_cell(c.b, d, rtp, ROW(j), cell, len, is_null);
     optr[j] = is_null ? 0ull : blk_addr + cell;
     olen[j] = is_null ? 0 : (int32_t)len;
     if (is_null) {
@@ -667,108 +665,72 @@ __device__ __forceinline__ void project_str_col(const ScanParams &p, const Block
   if (saw_null) p.has_null[pc] = 1;
 }
 
+#undef ROW
+
 // =================================================================================================
-// Fused scan kernel: one CTA (4 warps) per micro-block, logical block order by ticket.
-//
-// The kernel is instruction-issue bound on ~16 KiB pages, so everything that is not data-parallel
-// over rows runs in ONE warp (descriptors, RLE run tables, look-back) while the other warps wait at
-// a barrier (waiting warps cost no issue slots; ~10 co-resident CTAs per SM fill them), and the
-// per-row loops are templated down to the minimum instruction count.
+// Index kernel (batch open): one thread per (block, column) parses the block straight from HBM and
+// stores the column's decode plan. The scan kernels never parse headers; the reference keeps the
+// same kind of cached decoder state beside a block in its block cache (ObBlockCachedDecoderHeader,
+// blocksstable/ob_micro_block_cache.cpp:1345-1363).
 // =================================================================================================
-__global__ void __launch_bounds__(kThreads) obgpu_scan_kernel(const __grid_constant__ ScanParams p) {
-  __shared__ __align__(8) uint64_t s_bar;
-  __shared__ int s_tile;
-  __shared__ int s_bad;  // 0 ok, 1 unsupported, 2 corrupt
-  __shared__ long long s_base;
-  __shared__ uint32_t s_cnt;
-  __shared__ uint32_t s_scan[kWarps];
+__global__ void __launch_bounds__(256) obgpu_index_kernel(const uint8_t *image, const uint64_t *blk_off,
+                                                          const uint32_t *blk_size, int n_blocks, int max_cols,
+                                                          ColDesc *plans, uint32_t *rows) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)n_blocks * max_cols) return;
+  const int block = (int)(i / max_cols), col = (int)(i % max_cols);
+  BlockView b;
+  parse_block(image + blk_off[block], blk_size[block], b);
+  ColDesc d{};
+  d.rle_slot = -1;
+  if (b.ok) build_col_desc(b, col, d);
+  plans[i] = d;
+  if (col == 0) rows[block] = b.ok ? b.row_count : 0u;
+}
 
-  const Team t = cta_team();
-  const int tid = t.tid, lane = t.lane, warp = t.warp;
-  uint8_t *scr = g_smem + p.smem_scratch;
-  uint16_t *sel = reinterpret_cast<uint16_t *>(scr + p.off_sel);
-  uint32_t *bm = reinterpret_cast<uint32_t *>(scr + p.off_bm);
-  uint32_t *wpre = reinterpret_cast<uint32_t *>(scr + p.off_wpre);
-  ColDesc *descs = reinterpret_cast<ColDesc *>(scr + p.off_desc);
-  uint32_t *bitsets = reinterpret_cast<uint32_t *>(g_smem + p.smem_bitset);
+// =================================================================================================
+// Count kernel: ONE WARP per micro-block evaluates the filter reading only the filter columns,
+// straight from global memory (coalesced: 32 consecutive rows of a bit-packed column are one or two
+// sectors), writes the packed selection bitmap and the block's selected-row count. No staging, no
+// CTA barriers, no inter-block dependency.
+// =================================================================================================
+__global__ void __launch_bounds__(kThreads) obgpu_count_kernel(const __grid_constant__ ScanParams p) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int block = blockIdx.x * kWarps + warp;
+  if (block >= p.n_blocks) return;
+  uint8_t *wr = g_smem + (uint32_t)warp * p.cw_bytes;
+  ColDesc *descs = reinterpret_cast<ColDesc *>(wr + p.cw_desc);
+  uint32_t *bm = reinterpret_cast<uint32_t *>(wr + p.cw_bm);
+  uint32_t *bitsets = reinterpret_cast<uint32_t *>(wr + p.cw_bitset);
+  Team t;
+  t.tid = lane; t.nthreads = 32; t.warp = 0; t.nwarps = 1; t.lane = lane; t.bar_id = -1;
 
-  if (tid == 0) {
-    s_tile = atomicAdd(p.ticket, 1);
-    mbar_init(&s_bar, 1);
-    fence_barrier_init();
+  const uint32_t rows = p.rows[block];
+  uint32_t *gbm = p.bitmap_words + p.bm_word_off[block];
+  bool bad = rows == 0;
+  if (!bad && lane < p.n_used && p.used_in_filter[lane]) {
+    const ColDesc d = p.plans[(int64_t)block * p.max_cols + p.used_col[lane]];
+    descs[lane] = d;  // rle_slot stays -1: RLE filter columns use the run binary search here
+    bad = !d.ok;
   }
-  __syncthreads();
-  const int tile = s_tile;
-  if (tile >= p.n_blocks) return;
-
-  // ---- 1. stage the block ----------------------------------------------------------------------
-  const uint32_t size = p.blk_size[tile];
-  load_block(g_smem, p.image + p.blk_off[tile], (size + 15u) & ~15u, &s_bar, 0);
-
-  // ---- 2. descriptors + RLE run tables: warp 0 only ------------------------------------------------
-  BlockCtx c;
-  c.bitsets = bitsets;
-  parse_block(g_smem, size, c.b);
-  if (c.b.ok && c.b.row_count > p.rows_cap) c.b.ok = 0;
-  c.sbit = smem_u32(g_smem) * 8u;
-  c.descs = descs;
-  c.rle_base = scr + p.off_rle;
-  c.rle_slot_bytes = p.rle_slot_bytes;
-  c.rle_starts_bytes = ((uint32_t)p.rle_runs_cap + 2u) * 2u;
-  const uint32_t rows = c.b.row_count;
-  const uint32_t nwords = (rows + 31u) >> 5;
-  if (warp == 0) {
-    bool my_bad = false;
-    if (c.b.ok && lane < p.n_used) {
-      ColDesc d;
-      build_col_desc(c.b, p.used_col[lane], d);
-      d.rle_slot = d.kind == K_RLE ? p.used_rle_slot[lane] : (int8_t)-1;
-      if (d.kind == K_RLE && d.rle_slot >= 0 && d.rle_count > (uint32_t)p.rle_runs_cap) d.ok = 0;
-      descs[lane] = d;
-      my_bad = !d.ok;
-    }
-    const bool bad = __any_sync(0xffffffffu, my_bad) || !c.b.ok;
-    if (lane == 0) s_bad = !c.b.ok ? 2 : (bad ? 1 : 0);
-    __syncwarp();
-    if (!bad && p.n_rle_slots > 0) {
-      for (int i = 0; i < p.n_used; ++i) {
-        if (p.used_rle_slot[i] < 0) continue;
-        const ColDesc &d = descs[i];
-        if (d.kind != K_RLE) continue;
-        uint16_t *starts = reinterpret_cast<uint16_t *>(scr + p.off_rle + (uint32_t)d.rle_slot * p.rle_slot_bytes);
-        uint16_t *g2run = reinterpret_cast<uint16_t *>(scr + p.off_rle + (uint32_t)d.rle_slot * p.rle_slot_bytes +
-                                                       c.rle_starts_bytes);
-        const uint32_t rbit = c.sbit + d.rle_row_ids_bit, rw = d.rle_row_id_bits, n = d.rle_count;
-        for (uint32_t k = (uint32_t)lane; k <= n; k += 32u)
-          starts[k] = k < n ? (uint16_t)sbits32(rbit + k * rw, rw) : (uint16_t)0xFFFF;
-        __syncwarp();
-        for (uint32_t g = (uint32_t)lane; g < nwords; g += 32u) {
-          const uint32_t row = g * 32u;
-          uint32_t lo = 0, hi = n;  // upper_bound(starts, row)
-          while (lo < hi) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (starts[mid] <= row) lo = mid + 1; else hi = mid;
-          }
-          g2run[g] = (uint16_t)(lo > 0 ? lo - 1 : 0);
-        }
-      }
-    }
-  }
-  __syncthreads();
-  if (s_bad) {
-    // Unsupported / corrupt block: publish a zero count so later tiles are not blocked, flag it.
-    if (tid == 0) atomicOr(p.status, s_bad == 2 ? ST_CORRUPT : ST_UNSUPPORTED);
-    if (warp == 0) {
-      const int64_t excl = lookback(p.tile_state, tile, 0, lane);
-      if (lane == 0) {
-        p.sel_offset[tile] = excl;
-        if (tile == p.n_blocks - 1) p.sel_offset[p.n_blocks] = excl;
-      }
+  const bool any_bad = __any_sync(0xffffffffu, bad);
+  if (any_bad) {
+    if (lane == 0) {
+      atomicOr(p.status, rows == 0 ? ST_CORRUPT : ST_UNSUPPORTED);
+      p.counts[block] = 0;
     }
     return;
   }
-
-  // ---- 3. predicate over dictionaries ------------------------------------------------------------
+  BlockCtx c;
+  parse_block(p.image + p.blk_off[block], p.blk_size[block], c.b);
+  c.sbit = 0;
+  c.descs = descs;
+  c.bitsets = bitsets;
+  c.rle_base = nullptr;
+  c.rle_slot_bytes = 0;
+  c.rle_starts_bytes = 0;
+  const uint32_t nwords = (rows + 31u) >> 5;
+  __syncwarp();
   if (p.n_slots > 0) {
     for (int i = 0; i < p.n_nodes; ++i) {
       const FilterNodeDev &nd = p.nodes[i];
@@ -777,45 +739,143 @@ __global__ void __launch_bounds__(kThreads) obgpu_scan_kernel(const __grid_const
       if (d.kind == K_DICT || d.kind == K_RLE)
         build_dict_bitset(p, c.b, d, nd, bitsets + nd.slot * p.bitset_words, t);
     }
-    __syncthreads();
+    __syncwarp();
   }
-
-  // ---- 4. filter -> ballot words (the packed selection bitmap) ------------------------------------
-  // Each warp owns the words g = warp, warp + 4, ...: no block barrier between leaves.
+  uint32_t cnt = 0;
   if (p.simple_shape != 0) {
     const bool and_mode = p.simple_shape == 1;
     const int n_leaves = p.n_nodes == 1 ? 1 : p.n_nodes - 1;
     int first = 0;
-    if (!leaf_first_fast(p, c, p.nodes[0], bm, rows, nwords, t)) {
-      if (lane == 0)
-        for (uint32_t g = (uint32_t)warp; g < nwords; g += kWarps) bm[g] = and_mode ? valid_mask_of(rows, g) : 0u;
+    if (!leaf_first_fast<true>(p, c, p.nodes[0], bm, rows, nwords, t)) {
+      for (uint32_t g = (uint32_t)lane; g < nwords; g += 32u) bm[g] = and_mode ? valid_mask_of(rows, g) : 0u;
     } else {
       first = 1;
     }
     __syncwarp();
     for (int i = first; i < n_leaves; ++i) {
-      leaf_over_words(p, c, p.nodes[i], bm, rows, nwords, and_mode, t);
+      leaf_over_words<true>(p, c, p.nodes[i], bm, rows, nwords, and_mode, t);
       __syncwarp();
     }
+    for (uint32_t g = (uint32_t)lane; g < nwords; g += 32u) {
+      const uint32_t w = bm[g];
+      gbm[g] = w;
+      cnt += __popc(w);
+    }
   } else {
-    for (uint32_t g = (uint32_t)warp; g < nwords; g += kWarps) {
+    for (uint32_t g = 0; g < nwords; ++g) {
       const uint32_t row = g * 32u + (uint32_t)lane;
-      bool pr = row < rows;
-      if (pr && p.n_nodes > 0) pr = eval_tree(p, c, row);
-      const uint32_t word = __ballot_sync(0xffffffffu, pr);
-      if (lane == 0) bm[g] = word;
+      const bool pr = row < rows && eval_tree(p, c, row);
+      const uint32_t w = __ballot_sync(0xffffffffu, pr);
+      if (lane == 0) {
+        gbm[g] = w;
+        cnt += __popc(w);
+      }
     }
   }
-  __syncthreads();
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if (lane == 0) p.counts[block] = cnt;
+}
 
-  // ---- 5. exclusive prefix of popcounts over words; total; publish bitmap + count ---------------------
-  {
-    uint32_t *gbm = p.bitmap_words + p.bm_word_off[tile];
+// =================================================================================================
+// Prefix kernel: exclusive scan of the per-block counts -> sel_offset[n + 1] (one CTA).
+// =================================================================================================
+__global__ void __launch_bounds__(1024) obgpu_prefix_kernel(const uint32_t *counts, int n, int64_t *sel_offset) {
+  __shared__ long long s_warp[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int per = (n + 1023) / 1024;
+  const int lo = tid * per, hi = min(n, lo + per);
+  long long sum = 0;
+  for (int i = lo; i < hi; ++i) sum += counts[i];
+  long long inc = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const long long u = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += u;
+  }
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    long long v = s_warp[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const long long u = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += u;
+    }
+    s_warp[lane] = v;
+  }
+  __syncthreads();
+  long long run = (warp > 0 ? s_warp[warp - 1] : 0) + inc - sum;
+  for (int i = lo; i < hi; ++i) {
+    sel_offset[i] = run;
+    run += counts[i];
+  }
+  if (tid == 1023) sel_offset[n] = s_warp[31];
+}
+
+// =================================================================================================
+// Project kernel: one CTA (4 warps) per micro-block with at least one selected row. TMA stages the
+// block; warp 0 fetches the plans of the projected columns and builds RLE run tables while the
+// other warps turn the block's bitmap words into the ascending selected-row list; then
+// column-at-a-time projection with coalesced stores at the dense offset given by the prefix.
+// =================================================================================================
+__global__ void __launch_bounds__(kThreads) obgpu_project_kernel(const __grid_constant__ ScanParams p) {
+  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ int s_bad;
+  __shared__ uint32_t s_scan[kWarps];
+
+  const Team t = cta_team();
+  const int tid = t.tid, lane = t.lane, warp = t.warp;
+  const int tile = blockIdx.x;
+  uint8_t *scr = g_smem + p.smem_scratch;
+  uint16_t *sel = reinterpret_cast<uint16_t *>(scr + p.off_sel);
+  uint32_t *bm = reinterpret_cast<uint32_t *>(scr + p.off_bm);
+  uint32_t *wpre = reinterpret_cast<uint32_t *>(scr + p.off_wpre);
+  ColDesc *descs = reinterpret_cast<ColDesc *>(scr + p.off_desc);
+
+  const int64_t base = p.sel_offset[tile];
+  const uint32_t cnt = (uint32_t)(p.sel_offset[tile + 1] - base);
+  const uint32_t rows = p.rows[tile];
+  if (rows == 0) {
+    if (tid == 0) atomicOr(p.status, ST_CORRUPT);
+    return;
+  }
+  if (cnt == 0) return;
+  if (base + (int64_t)cnt > p.out_cap) {
+    if (tid == 0) atomicOr(p.status, ST_OVERFLOW);
+    return;
+  }
+  // ---- stage the block ------------------------------------------------------------------------------
+  const uint32_t size = p.blk_size[tile];
+  if (tid == 0) {
+    mbar_init(&s_bar, 1);
+    fence_barrier_init();
+    mbar_expect_tx(&s_bar, (size + 15u) & ~15u);
+    tma_bulk_g2s(g_smem, p.image + p.blk_off[tile], (size + 15u) & ~15u, &s_bar);
+    s_bad = 0;
+  }
+  __syncthreads();  // barrier object + s_bad initialised before anyone waits on / writes them
+  const uint32_t nwords = (rows + 31u) >> 5;
+  const bool all_rows = cnt == rows;
+  // ---- warp 0: plans of the projected columns; others: bitmap words -> popcount prefix -----------------
+  if (warp == 0) {
+    bool my_bad = false;
+    if (lane < p.n_used && p.used_in_proj[lane]) {
+      ColDesc d = p.plans[(int64_t)tile * p.max_cols + p.used_col[lane]];
+      d.rle_slot = d.kind == K_RLE ? p.used_rle_slot[lane] : (int8_t)-1;
+      if (d.kind == K_RLE && d.rle_slot >= 0 && d.rle_count > (uint32_t)p.rle_runs_cap) d.ok = 0;
+      descs[lane] = d;
+      my_bad = !d.ok;
+    }
+    if (__any_sync(0xffffffffu, my_bad) && lane == 0) s_bad = 1;
+  }
+  if (!all_rows) {
+    const uint32_t *gbm = p.bitmap_words + p.bm_word_off[tile];
     uint32_t run_total = 0;
     for (uint32_t base_w = 0; base_w < nwords; base_w += kThreads) {  // one pass for <= 4096 rows
       const uint32_t w = base_w + (uint32_t)tid;
-      const uint32_t word = w < nwords ? bm[w] : 0u;
-      if (w < nwords) gbm[w] = word;
+      const uint32_t word = w < nwords ? gbm[w] : 0u;
+      if (w < nwords) bm[w] = word;
       const uint32_t local = __popc(word);
       uint32_t inc = local;
 #pragma unroll
@@ -836,51 +896,72 @@ __global__ void __launch_bounds__(kThreads) obgpu_scan_kernel(const __grid_const
       run_total = total;
       __syncthreads();
     }
-    if (tid == 0) {
-      s_cnt = run_total;
-      // publish this block's count as early as possible: successors' look-backs only need this
-      st_release(&p.tile_state[tile], (tile == 0 ? kTilePrefix : kTileAgg) | (unsigned long long)run_total);
-    }
-    __syncthreads();
-  }
-  const uint32_t cnt = s_cnt;
-
-  // ---- 6. look-back (warp 0) overlapped with building the selected-row list (warps 1..3) ----------
-  if (warp == 0) {
-    int64_t excl;
-    if (p.debug_flags & 1) excl = p.bm_word_off[tile] * 32;
-    else excl = lookback(p.tile_state, tile, (int64_t)cnt, lane, /*publish_own=*/false);
-    if (lane == 0) {
-      s_base = excl;
-      p.sel_offset[tile] = excl;
-      if (tile == p.n_blocks - 1) p.sel_offset[p.n_blocks] = excl + (int64_t)cnt;
-    }
-  } else {
-    for (uint32_t g = (uint32_t)warp - 1u; g < nwords; g += kWarps - 1) {
+    // selected-row list (ascending)
+    for (uint32_t g = (uint32_t)warp; g < nwords; g += kWarps) {
       const uint32_t word = bm[g];
       if ((word >> lane) & 1u) sel[wpre[g] + __popc(word & ((1u << lane) - 1u))] = (uint16_t)(g * 32u + lane);
     }
   }
+  // ---- block landed: RLE run tables (warp 0) -------------------------------------------------------------
+  mbar_wait(&s_bar, 0);
+  BlockCtx c;
+  parse_block(g_smem, size, c.b);
+  c.sbit = smem_u32(g_smem) * 8u;
+  c.descs = descs;
+  c.bitsets = nullptr;
+  c.rle_base = scr + p.off_rle;
+  c.rle_slot_bytes = p.rle_slot_bytes;
+  c.rle_starts_bytes = ((uint32_t)p.rle_runs_cap + 2u) * 2u;
+  if (warp == 0 && p.n_rle_slots > 0) {
+    __syncwarp();
+    for (int i = 0; i < p.n_used; ++i) {
+      if (p.used_rle_slot[i] < 0 || !p.used_in_proj[i]) continue;
+      const ColDesc &d = descs[i];
+      if (d.kind != K_RLE || !d.ok) continue;
+      uint16_t *starts = reinterpret_cast<uint16_t *>(scr + p.off_rle + (uint32_t)d.rle_slot * p.rle_slot_bytes);
+      uint16_t *g2run = reinterpret_cast<uint16_t *>(scr + p.off_rle + (uint32_t)d.rle_slot * p.rle_slot_bytes +
+                                                     c.rle_starts_bytes);
+      const uint32_t rbit = c.sbit + d.rle_row_ids_bit, rw = d.rle_row_id_bits, n = d.rle_count;
+      for (uint32_t k = (uint32_t)lane; k <= n; k += 32u)
+        starts[k] = k < n ? (uint16_t)sbits32(rbit + k * rw, rw) : (uint16_t)0xFFFF;
+      __syncwarp();
+      for (uint32_t g = (uint32_t)lane; g < nwords; g += 32u) {
+        const uint32_t row = g * 32u;
+        uint32_t lo = 0, hi = n;  // upper_bound(starts, row)
+        while (lo < hi) {
+          const uint32_t mid = (lo + hi) >> 1;
+          if (starts[mid] <= row) lo = mid + 1; else hi = mid;
+        }
+        g2run[g] = (uint16_t)(lo > 0 ? lo - 1 : 0);
+      }
+    }
+  }
   __syncthreads();
-  const int64_t base = s_base;
-  if (cnt == 0 || p.n_proj + p.want_row_ids == 0) return;
-  if (base + (int64_t)cnt > p.out_cap) {
-    if (tid == 0) atomicOr(p.status, ST_OVERFLOW);
+  if (s_bad || !c.b.ok) {
+    if (tid == 0) atomicOr(p.status, c.b.ok ? ST_UNSUPPORTED : ST_CORRUPT);
     return;
   }
 
-  // ---- 7. projection, one column at a time -----------------------------------------------------------
+  // ---- projection, one column at a time -----------------------------------------------------------
   if (p.want_row_ids) {
     int32_t *rid = p.row_ids + base;
-    for (uint32_t j = (uint32_t)tid; j < cnt; j += kThreads) rid[j] = (int32_t)sel[j];
+    if (all_rows) for (uint32_t j = (uint32_t)tid; j < cnt; j += kThreads) rid[j] = (int32_t)j;
+    else for (uint32_t j = (uint32_t)tid; j < cnt; j += kThreads) rid[j] = (int32_t)sel[j];
   }
   const uint64_t blk_addr = p.string_base + p.blk_off[tile];
   for (int pc = 0; pc < p.n_proj; ++pc) {
     const ColDesc &d = descs[p.proj_used[pc]];
-    if (d.sc == 5) project_str_col(p, c, d, pc, sel, cnt, base, blk_addr, t);
-    else if (d.elem_len == 8) project_int_col<uint64_t>(p, c, d, pc, sel, cnt, base, t);
-    else if (d.elem_len == 4) project_int_col<uint32_t>(p, c, d, pc, sel, cnt, base, t);
-    else project_int_col<uint8_t>(p, c, d, pc, sel, cnt, base, t);
+    if (all_rows) {
+      if (d.sc == 5) project_str_col<true>(p, c, d, pc, sel, cnt, base, blk_addr, t);
+      else if (d.elem_len == 8) project_int_col<uint64_t, true>(p, c, d, pc, sel, cnt, base, t);
+      else if (d.elem_len == 4) project_int_col<uint32_t, true>(p, c, d, pc, sel, cnt, base, t);
+      else project_int_col<uint8_t, true>(p, c, d, pc, sel, cnt, base, t);
+    } else {
+      if (d.sc == 5) project_str_col<false>(p, c, d, pc, sel, cnt, base, blk_addr, t);
+      else if (d.elem_len == 8) project_int_col<uint64_t, false>(p, c, d, pc, sel, cnt, base, t);
+      else if (d.elem_len == 4) project_int_col<uint32_t, false>(p, c, d, pc, sel, cnt, base, t);
+      else project_int_col<uint8_t, false>(p, c, d, pc, sel, cnt, base, t);
+    }
   }
 }
 
@@ -1071,6 +1152,9 @@ struct obgpu_batch {
   uint64_t *d_blk_off = nullptr;
   uint32_t *d_blk_size = nullptr;
   int64_t *d_bm_word_off = nullptr;
+  // decode plans + row counts built by the index kernel at open
+  ColDesc *d_plans = nullptr;
+  uint32_t *d_rows = nullptr;
 };
 
 struct ResultCol {
@@ -1096,6 +1180,7 @@ struct obgpu_result {
   int32_t *d_row_ids = nullptr;
   int64_t cap = 0;
   bool info_valid = false;
+  bool no_filter = false;
   obgpu_result_info info{};
   int32_t has_null[kMaxProj] = {0};
   int32_t status = 0;
@@ -1139,8 +1224,8 @@ int obgpu_ctx_create(int device, obgpu_ctx **out) {
     return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 c->max_smem_optin - (int)fa.sharedSizeBytes) == cudaSuccess;
   };
-  const bool ok = opt_in((const void *)obgpu_scan_kernel) && opt_in((const void *)obgpu_filter_block_kernel) &&
-                  opt_in((const void *)obgpu_project_block_kernel);
+  const bool ok = opt_in((const void *)obgpu_count_kernel) && opt_in((const void *)obgpu_project_kernel) &&
+                  opt_in((const void *)obgpu_filter_block_kernel) && opt_in((const void *)obgpu_project_block_kernel);
   cudaGetLastError();  // do not leave a stale (non-sticky) error for later launch checks
   if (!ok) {
     g_last_global_err = "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed: not an sm_100a device?";
@@ -1346,6 +1431,26 @@ int obgpu_batch_open(obgpu_ctx *ctx, const void *image, int64_t image_size, cons
       }
     }
   }
+  // decode plans: one thread per (block, column)
+  if (e == cudaSuccess && b->max_cols > 128) {
+    ctx->err = "more than 128 columns in a micro block";
+    obgpu_batch_close(b);
+    return OBGPU_NOT_SUPPORTED;
+  }
+  if (e == cudaSuccess) {
+    const size_t plan_bytes = (size_t)n_blocks * b->max_cols * sizeof(ColDesc);
+    void *dp = nullptr;
+    e = cudaMallocAsync(&dp, plan_bytes + (size_t)n_blocks * 4 + 64, ctx->stream);
+    if (e == cudaSuccess) {
+      b->d_plans = (ColDesc *)dp;
+      b->d_rows = (uint32_t *)((uint8_t *)dp + plan_bytes);
+      const int64_t nthreads = (int64_t)n_blocks * b->max_cols;
+      obgpu_index_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, ctx->stream>>>(
+          b->d_image, b->d_blk_off, b->d_blk_size, n_blocks, (int)b->max_cols, b->d_plans, b->d_rows);
+      e = cudaGetLastError();
+      ctx->launches++;
+    }
+  }
   // `stage` is pageable: the copy above is staged synchronously by the runtime before returning
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   if (e != cudaSuccess) {
@@ -1361,6 +1466,7 @@ void obgpu_batch_close(obgpu_batch *b) {
   if (!b) return;
   cudaSetDevice(b->ctx->device);
   if (b->d_tables) cudaFreeAsync(b->d_tables, b->ctx->stream);
+  if (b->d_plans) cudaFreeAsync(b->d_plans, b->ctx->stream);
   if (b->own_image && b->d_image) cudaFreeAsync((void *)b->d_image, b->ctx->stream);
   delete b;
 }
@@ -1419,6 +1525,8 @@ static int build_filter(obgpu_ctx *ctx, const obgpu_batch *b, const obgpu_filter
         return OBGPU_INVALID_ARGUMENT;
       const int ui = used_index(p, src.col);
       if (ui < 0) return OBGPU_NOT_SUPPORTED;
+      if ((uint32_t)src.col >= b->max_cols) return OBGPU_INVALID_ARGUMENT;
+      p.used_in_filter[ui] = 1;
       nd.used_idx = (int16_t)ui;
       nd.op = (int16_t)src.op;
       nd.param_begin = (int16_t)n_params;
@@ -1546,6 +1654,12 @@ static void layout_smem_scan(const obgpu_batch *b, ScanParams &p) {
   p.scratch_bytes = (s + 127u) & ~127u;
   p.smem_scratch = (off + 127u) & ~127u;
   p.smem_total = p.smem_scratch + p.scratch_bytes;
+  // count kernel, per warp: descs | bm | bitsets
+  uint32_t w = 0;
+  p.cw_desc = w;   w += ((uint32_t)sizeof(ColDesc) * (uint32_t)std::max(p.n_used, 1) + 15u) & ~15u;
+  p.cw_bm = w;     w += (p.words_cap * 4u + 15u) & ~15u;
+  p.cw_bitset = w; w += ((uint32_t)p.n_slots * (uint32_t)p.bitset_words * 4u + 15u) & ~15u;
+  p.cw_bytes = (w + 127u) & ~127u;
 }
 
 static int check_status(obgpu_ctx *ctx, int status) {
@@ -1579,6 +1693,7 @@ int obgpu_scan(obgpu_batch *b, const obgpu_scan_spec *spec, obgpu_result **out) 
     if (col < 0 || (uint32_t)col >= b->max_cols) { delete r; return OBGPU_INVALID_ARGUMENT; }
     const int ui = used_index(p, col);
     if (ui < 0) { delete r; return OBGPU_NOT_SUPPORTED; }
+    p.used_in_proj[ui] = 1;
     p.proj_used[c] = (int16_t)ui;
   }
   p.n_proj = spec->n_proj;
@@ -1595,12 +1710,12 @@ int obgpu_scan(obgpu_batch *b, const obgpu_scan_spec *spec, obgpu_result **out) 
   const int32_t n = b->n_blocks;
   size_t off = 0;
   auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
-  const size_t o_state = take((size_t)n * 8);
-  const size_t o_misc = take(256 + kMaxProj * 4);  // ticket, status, has_null
+  const size_t o_misc = take(256 + kMaxProj * 4);  // status, has_null
   size_t o_nulls[kMaxProj];
   const size_t null_bytes = (size_t)((r->cap + 63) / 64) * 8;
   for (int c = 0; c < spec->n_proj; ++c) o_nulls[c] = take(null_bytes);
   const size_t zero_bytes = off;
+  const size_t o_counts = take((size_t)n * 4);
   const size_t o_sel = take(((size_t)n + 1) * 8);
   const size_t o_bm = take((size_t)b->bm_word_off[(size_t)n] * 4 + 4);
   const size_t o_rid = spec->want_row_ids ? take((size_t)r->cap * 4) : 0;
@@ -1628,8 +1743,12 @@ int obgpu_scan(obgpu_batch *b, const obgpu_scan_spec *spec, obgpu_result **out) 
   p.blk_size = b->d_blk_size;
   p.bm_word_off = b->d_bm_word_off;
   p.n_blocks = n;
-  p.tile_state = (unsigned long long *)(a + o_state);
-  p.ticket = (int32_t *)(a + o_misc);
+  p.plans = b->d_plans;
+  p.rows = b->d_rows;
+  p.max_cols = (int32_t)b->max_cols;
+  p.counts = (uint32_t *)(a + o_counts);
+  p.tile_state = nullptr;
+  p.ticket = nullptr;
   p.status = (int32_t *)(a + o_misc + 64);
   p.has_null = (int32_t *)(a + o_misc + 128);
   p.sel_offset = (int64_t *)(a + o_sel);
@@ -1649,16 +1768,32 @@ int obgpu_scan(obgpu_batch *b, const obgpu_scan_spec *spec, obgpu_result **out) 
   r->d_sel_offset = p.sel_offset;
   r->d_bitmap = p.bitmap_words;
   r->d_row_ids = p.row_ids;
+  r->no_filter = p.n_nodes == 0;
+  // ---- launches: count (filter) -> prefix -> project ------------------------------------------------
   const int pslot = (int)(ctx->prof_count % obgpu_ctx::kProfRing);
   if (ctx->profiling) cudaEventRecord(ctx->ev0[pslot], ctx->stream);
-  obgpu_scan_kernel<<<n, kThreads, p.smem_total, ctx->stream>>>(p);
+  if (p.n_nodes > 0) {
+    const uint32_t cw_total = p.cw_bytes * (uint32_t)kWarps;
+    if ((int)cw_total > ctx->max_smem_optin) {
+      ctx->err = "filter working set exceeds shared memory";
+      obgpu_result_free(r);
+      return OBGPU_NOT_SUPPORTED;
+    }
+    obgpu_count_kernel<<<(n + kWarps - 1) / kWarps, kThreads, cw_total, ctx->stream>>>(p);
+    ctx->launches++;
+  }
+  obgpu_prefix_kernel<<<1, 1024, 0, ctx->stream>>>(p.n_nodes > 0 ? p.counts : b->d_rows, n, p.sel_offset);
+  ctx->launches++;
+  if (p.n_proj + p.want_row_ids > 0) {
+    obgpu_project_kernel<<<n, kThreads, p.smem_total, ctx->stream>>>(p);
+    ctx->launches++;
+  }
   e = cudaGetLastError();
   if (ctx->profiling) {
     cudaEventRecord(ctx->ev1[pslot], ctx->stream);
     ctx->prof_count++;
   }
   if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); obgpu_result_free(r); return OBGPU_ERR_SYS; }
-  ctx->launches++;
   *out = r;
   return OBGPU_SUCCESS;
 }
@@ -1776,6 +1911,10 @@ int obgpu_result_fetch_bitmap(obgpu_result *r, int32_t block, int64_t start, int
     return OBGPU_INVALID_ARGUMENT;
   obgpu_ctx *ctx = r->ctx;
   cudaSetDevice(ctx->device);
+  if (r->no_filter) {  // no predicate: every row is selected, the count kernel did not run
+    memset(host_bitmap_bytes, 1, (size_t)count);
+    return OBGPU_SUCCESS;
+  }
   const int64_t w0 = r->batch->bm_word_off[(size_t)block], nw = r->batch->bm_word_off[(size_t)block + 1] - w0;
   std::vector<uint32_t> words((size_t)nw);
   CUDA_TRY(ctx, cudaMemcpyAsync(words.data(), r->d_bitmap + w0, (size_t)nw * 4, cudaMemcpyDeviceToHost, ctx->stream));
