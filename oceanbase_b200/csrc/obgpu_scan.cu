@@ -108,6 +108,7 @@ struct ScanParams {
   uint32_t smem_rle, smem_desc;            // single-block kernels
   uint32_t smem_scratch, scratch_bytes;    // project kernel
   uint32_t cw_desc, cw_bm, cw_bitset, cw_bytes;  // count kernel: per-warp region = descs | bm | bitsets
+  uint32_t pw_rle, pw_bytes;  // project kernel: per-warp region at off_desc = ColDesc | RLE run table
   uint32_t off_sel, off_bm, off_wpre, off_rle, off_desc;  // inside one scratch
   uint32_t smem_total;
   uint32_t rle_slot_bytes;    // bytes per run-table slot: starts[(cap + 2)] + g2run[words_cap]
@@ -778,60 +779,90 @@ __global__ void __launch_bounds__(kThreads) obgpu_count_kernel(const __grid_cons
 }
 
 // =================================================================================================
-// Prefix kernel: exclusive scan of the per-block counts -> sel_offset[n + 1] (one CTA).
+// Prefix kernels: exclusive scan of the per-block counts -> sel_offset[n + 1].
+//   pass 1: every CTA scans a 2048-element chunk (coalesced) and writes its total;
+//   pass 2: every CTA adds the sum of the preceding chunk totals to its chunk.
 // =================================================================================================
-__global__ void __launch_bounds__(1024) obgpu_prefix_kernel(const uint32_t *counts, int n, int64_t *sel_offset) {
-  __shared__ long long s_warp[32];
+constexpr int kPrefixChunk = 2048;
+__global__ void __launch_bounds__(256) obgpu_prefix_local_kernel(const uint32_t *counts, int n, int64_t *sel_offset,
+                                                                 unsigned long long *chunk_total) {
+  __shared__ unsigned long long s_warp[8];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int per = (n + 1023) / 1024;
-  const int lo = tid * per, hi = min(n, lo + per);
-  long long sum = 0;
-  for (int i = lo; i < hi; ++i) sum += counts[i];
-  long long inc = sum;
+  const int base = blockIdx.x * kPrefixChunk + tid * 8;
+  uint32_t v[8];
+  unsigned long long sum = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    v[k] = base + k < n ? counts[base + k] : 0u;
+    sum += v[k];
+  }
+  unsigned long long inc = sum;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
-    const long long u = __shfl_up_sync(0xffffffffu, inc, o);
+    const unsigned long long u = __shfl_up_sync(0xffffffffu, inc, o);
     if (lane >= o) inc += u;
   }
   if (lane == 31) s_warp[warp] = inc;
   __syncthreads();
-  if (warp == 0) {
-    long long v = s_warp[lane];
+  unsigned long long woff = 0, total = 0;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const long long u = __shfl_up_sync(0xffffffffu, v, o);
-      if (lane >= o) v += u;
-    }
-    s_warp[lane] = v;
+  for (int k = 0; k < 8; ++k) {
+    woff += k < warp ? s_warp[k] : 0ull;
+    total += s_warp[k];
+  }
+  unsigned long long run = woff + inc - sum;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    if (base + k < n) sel_offset[base + k] = (int64_t)run;
+    run += v[k];
+  }
+  if (tid == 0) chunk_total[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(256) obgpu_prefix_fix_kernel(int n, int n_chunks, int64_t *sel_offset,
+                                                               const unsigned long long *chunk_total) {
+  __shared__ unsigned long long s_off;
+  const int tid = threadIdx.x, lane = tid & 31;
+  if (tid < 32) {
+    unsigned long long acc = 0;
+    const int upto = blockIdx.x < n_chunks ? blockIdx.x : n_chunks;
+    for (int k = lane; k < upto; k += 32) acc += chunk_total[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) s_off = acc;
   }
   __syncthreads();
-  long long run = (warp > 0 ? s_warp[warp - 1] : 0) + inc - sum;
-  for (int i = lo; i < hi; ++i) {
-    sel_offset[i] = run;
-    run += counts[i];
+  const unsigned long long off = s_off;
+  if (blockIdx.x == n_chunks) {  // extra CTA: total
+    if (tid == 0) sel_offset[n] = (int64_t)off;
+    return;
   }
-  if (tid == 1023) sel_offset[n] = s_warp[31];
+  const int base = blockIdx.x * kPrefixChunk + tid * 8;
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    if (base + k < n) sel_offset[base + k] += (int64_t)off;
 }
 
 // =================================================================================================
 // Project kernel: one CTA (4 warps) per micro-block with at least one selected row. TMA stages the
-// block; warp 0 fetches the plans of the projected columns and builds RLE run tables while the
-// other warps turn the block's bitmap words into the ascending selected-row list; then
-// column-at-a-time projection with coalesced stores at the dense offset given by the prefix.
+// block while all warps turn the block's bitmap words into the ascending selected-row list. Then
+// the projected COLUMNS are distributed over the warps (dynamic queue): a warp fetches the column's
+// plan, builds its RLE run table if needed (warp-private scratch, no CTA barrier) and decodes every
+// selected row of that column with coalesced stores at the dense offset given by the prefix.
+// Per-column setup is thus paid by one warp instead of four, and a warp runs ~cnt/32 iterations per
+// column instead of ~cnt/128.
 // =================================================================================================
 __global__ void __launch_bounds__(kThreads) obgpu_project_kernel(const __grid_constant__ ScanParams p) {
   __shared__ __align__(8) uint64_t s_bar;
-  __shared__ int s_bad;
+  __shared__ int s_next;
   __shared__ uint32_t s_scan[kWarps];
 
-  const Team t = cta_team();
-  const int tid = t.tid, lane = t.lane, warp = t.warp;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tile = blockIdx.x;
   uint8_t *scr = g_smem + p.smem_scratch;
   uint16_t *sel = reinterpret_cast<uint16_t *>(scr + p.off_sel);
   uint32_t *bm = reinterpret_cast<uint32_t *>(scr + p.off_bm);
   uint32_t *wpre = reinterpret_cast<uint32_t *>(scr + p.off_wpre);
-  ColDesc *descs = reinterpret_cast<ColDesc *>(scr + p.off_desc);
 
   const int64_t base = p.sel_offset[tile];
   const uint32_t cnt = (uint32_t)(p.sel_offset[tile + 1] - base);
@@ -852,23 +883,12 @@ __global__ void __launch_bounds__(kThreads) obgpu_project_kernel(const __grid_co
     fence_barrier_init();
     mbar_expect_tx(&s_bar, (size + 15u) & ~15u);
     tma_bulk_g2s(g_smem, p.image + p.blk_off[tile], (size + 15u) & ~15u, &s_bar);
-    s_bad = 0;
+    s_next = 0;
   }
-  __syncthreads();  // barrier object + s_bad initialised before anyone waits on / writes them
+  __syncthreads();  // barrier object + queue initialised before anyone uses them
   const uint32_t nwords = (rows + 31u) >> 5;
   const bool all_rows = cnt == rows;
-  // ---- warp 0: plans of the projected columns; others: bitmap words -> popcount prefix -----------------
-  if (warp == 0) {
-    bool my_bad = false;
-    if (lane < p.n_used && p.used_in_proj[lane]) {
-      ColDesc d = p.plans[(int64_t)tile * p.max_cols + p.used_col[lane]];
-      d.rle_slot = d.kind == K_RLE ? p.used_rle_slot[lane] : (int8_t)-1;
-      if (d.kind == K_RLE && d.rle_slot >= 0 && d.rle_count > (uint32_t)p.rle_runs_cap) d.ok = 0;
-      descs[lane] = d;
-      my_bad = !d.ok;
-    }
-    if (__any_sync(0xffffffffu, my_bad) && lane == 0) s_bad = 1;
-  }
+  // ---- bitmap words -> popcount prefix -> ascending selected-row list (overlaps the TMA) ------------------
   if (!all_rows) {
     const uint32_t *gbm = p.bitmap_words + p.bm_word_off[tile];
     uint32_t run_total = 0;
@@ -896,31 +916,64 @@ __global__ void __launch_bounds__(kThreads) obgpu_project_kernel(const __grid_co
       run_total = total;
       __syncthreads();
     }
-    // selected-row list (ascending)
     for (uint32_t g = (uint32_t)warp; g < nwords; g += kWarps) {
       const uint32_t word = bm[g];
       if ((word >> lane) & 1u) sel[wpre[g] + __popc(word & ((1u << lane) - 1u))] = (uint16_t)(g * 32u + lane);
     }
+    __syncthreads();
   }
-  // ---- block landed: RLE run tables (warp 0) -------------------------------------------------------------
+  // ---- block landed ---------------------------------------------------------------------------------------
   mbar_wait(&s_bar, 0);
   BlockCtx c;
   parse_block(g_smem, size, c.b);
+  if (!c.b.ok) {
+    if (tid == 0) atomicOr(p.status, ST_CORRUPT);
+    return;
+  }
   c.sbit = smem_u32(g_smem) * 8u;
-  c.descs = descs;
   c.bitsets = nullptr;
-  c.rle_base = scr + p.off_rle;
-  c.rle_slot_bytes = p.rle_slot_bytes;
+  // warp-private scratch: [ColDesc][RLE run table]
+  uint8_t *wscr = scr + p.off_desc + (uint32_t)warp * p.pw_bytes;
+  ColDesc *wdesc = reinterpret_cast<ColDesc *>(wscr);
+  c.descs = wdesc;
+  c.rle_base = wscr + p.pw_rle;
+  c.rle_slot_bytes = 0;  // one table per warp: slot 0
   c.rle_starts_bytes = ((uint32_t)p.rle_runs_cap + 2u) * 2u;
-  if (warp == 0 && p.n_rle_slots > 0) {
-    __syncwarp();
-    for (int i = 0; i < p.n_used; ++i) {
-      if (p.used_rle_slot[i] < 0 || !p.used_in_proj[i]) continue;
-      const ColDesc &d = descs[i];
-      if (d.kind != K_RLE || !d.ok) continue;
-      uint16_t *starts = reinterpret_cast<uint16_t *>(scr + p.off_rle + (uint32_t)d.rle_slot * p.rle_slot_bytes);
-      uint16_t *g2run = reinterpret_cast<uint16_t *>(scr + p.off_rle + (uint32_t)d.rle_slot * p.rle_slot_bytes +
-                                                     c.rle_starts_bytes);
+
+  if (p.want_row_ids) {
+    int32_t *rid = p.row_ids + base;
+    if (all_rows) for (uint32_t j = (uint32_t)tid; j < cnt; j += kThreads) rid[j] = (int32_t)j;
+    else for (uint32_t j = (uint32_t)tid; j < cnt; j += kThreads) rid[j] = (int32_t)sel[j];
+  }
+  const uint64_t blk_addr = p.string_base + p.blk_off[tile];
+  Team t;  // one warp per column
+  t.tid = lane; t.nthreads = 32; t.warp = 0; t.nwarps = 1; t.lane = lane; t.bar_id = -1;
+  for (;;) {
+    int pc = 0;
+    if (lane == 0) pc = atomicAdd(&s_next, 1);
+    pc = __shfl_sync(0xffffffffu, pc, 0);
+    if (pc >= p.n_proj) break;
+    // plan of this column: 6 lanes x 16 bytes
+    {
+      const uint4 *src = reinterpret_cast<const uint4 *>(p.plans + (int64_t)tile * p.max_cols + p.used_col[p.proj_used[pc]]);
+      if (lane < (int)(sizeof(ColDesc) / 16)) reinterpret_cast<uint4 *>(wdesc)[lane] = src[lane];
+      __syncwarp();
+    }
+    const ColDesc &d = *wdesc;
+    if (!d.ok) {
+      if (lane == 0) atomicOr(p.status, ST_UNSUPPORTED);
+      __syncwarp();
+      continue;
+    }
+    if (d.kind == K_RLE) {
+      if (d.rle_count > (uint32_t)p.rle_runs_cap) {
+        if (lane == 0) atomicOr(p.status, ST_UNSUPPORTED);
+        __syncwarp();
+        continue;
+      }
+      if (lane == 0) wdesc->rle_slot = 0;
+      uint16_t *starts = reinterpret_cast<uint16_t *>(wscr + p.pw_rle);
+      uint16_t *g2run = reinterpret_cast<uint16_t *>(wscr + p.pw_rle + c.rle_starts_bytes);
       const uint32_t rbit = c.sbit + d.rle_row_ids_bit, rw = d.rle_row_id_bits, n = d.rle_count;
       for (uint32_t k = (uint32_t)lane; k <= n; k += 32u)
         starts[k] = k < n ? (uint16_t)sbits32(rbit + k * rw, rw) : (uint16_t)0xFFFF;
@@ -934,23 +987,8 @@ __global__ void __launch_bounds__(kThreads) obgpu_project_kernel(const __grid_co
         }
         g2run[g] = (uint16_t)(lo > 0 ? lo - 1 : 0);
       }
+      __syncwarp();
     }
-  }
-  __syncthreads();
-  if (s_bad || !c.b.ok) {
-    if (tid == 0) atomicOr(p.status, c.b.ok ? ST_UNSUPPORTED : ST_CORRUPT);
-    return;
-  }
-
-  // ---- projection, one column at a time -----------------------------------------------------------
-  if (p.want_row_ids) {
-    int32_t *rid = p.row_ids + base;
-    if (all_rows) for (uint32_t j = (uint32_t)tid; j < cnt; j += kThreads) rid[j] = (int32_t)j;
-    else for (uint32_t j = (uint32_t)tid; j < cnt; j += kThreads) rid[j] = (int32_t)sel[j];
-  }
-  const uint64_t blk_addr = p.string_base + p.blk_off[tile];
-  for (int pc = 0; pc < p.n_proj; ++pc) {
-    const ColDesc &d = descs[p.proj_used[pc]];
     if (all_rows) {
       if (d.sc == 5) project_str_col<true>(p, c, d, pc, sel, cnt, base, blk_addr, t);
       else if (d.elem_len == 8) project_int_col<uint64_t, true>(p, c, d, pc, sel, cnt, base, t);
@@ -962,6 +1000,7 @@ __global__ void __launch_bounds__(kThreads) obgpu_project_kernel(const __grid_co
       else if (d.elem_len == 4) project_int_col<uint32_t, false>(p, c, d, pc, sel, cnt, base, t);
       else project_int_col<uint8_t, false>(p, c, d, pc, sel, cnt, base, t);
     }
+    __syncwarp();
   }
 }
 
@@ -1649,8 +1688,10 @@ static void layout_smem_scan(const obgpu_batch *b, ScanParams &p) {
   p.off_sel = s;  s += (p.rows_cap * 2u + 15u) & ~15u;
   p.off_bm = s;   s += (p.words_cap * 4u + 15u) & ~15u;
   p.off_wpre = s; s += (p.words_cap * 4u + 15u) & ~15u;
-  p.off_rle = s;  s += (uint32_t)p.n_rle_slots * p.rle_slot_bytes;
-  p.off_desc = s; s += ((uint32_t)sizeof(ColDesc) * (uint32_t)std::max(p.n_used, 1) + 15u) & ~15u;
+  p.off_rle = s;
+  p.pw_rle = ((uint32_t)sizeof(ColDesc) + 15u) & ~15u;
+  p.pw_bytes = (p.pw_rle + (p.n_rle_slots > 0 ? (((uint32_t)p.rle_runs_cap + 2u) * 2u + p.words_cap * 2u) : 0u) + 15u) & ~15u;
+  p.off_desc = s; s += p.pw_bytes * (uint32_t)kWarps;
   p.scratch_bytes = (s + 127u) & ~127u;
   p.smem_scratch = (off + 127u) & ~127u;
   p.smem_total = p.smem_scratch + p.scratch_bytes;
@@ -1716,6 +1757,7 @@ int obgpu_scan(obgpu_batch *b, const obgpu_scan_spec *spec, obgpu_result **out) 
   for (int c = 0; c < spec->n_proj; ++c) o_nulls[c] = take(null_bytes);
   const size_t zero_bytes = off;
   const size_t o_counts = take((size_t)n * 4);
+  const size_t o_chunk = take(((size_t)n / kPrefixChunk + 2) * 8);
   const size_t o_sel = take(((size_t)n + 1) * 8);
   const size_t o_bm = take((size_t)b->bm_word_off[(size_t)n] * 4 + 4);
   const size_t o_rid = spec->want_row_ids ? take((size_t)r->cap * 4) : 0;
@@ -1782,8 +1824,13 @@ int obgpu_scan(obgpu_batch *b, const obgpu_scan_spec *spec, obgpu_result **out) 
     obgpu_count_kernel<<<(n + kWarps - 1) / kWarps, kThreads, cw_total, ctx->stream>>>(p);
     ctx->launches++;
   }
-  obgpu_prefix_kernel<<<1, 1024, 0, ctx->stream>>>(p.n_nodes > 0 ? p.counts : b->d_rows, n, p.sel_offset);
-  ctx->launches++;
+  {
+    const int n_chunks = (n + kPrefixChunk - 1) / kPrefixChunk;
+    const uint32_t *cnts = p.n_nodes > 0 ? p.counts : b->d_rows;
+    obgpu_prefix_local_kernel<<<n_chunks, 256, 0, ctx->stream>>>(cnts, n, p.sel_offset, (unsigned long long *)(a + o_chunk));
+    obgpu_prefix_fix_kernel<<<n_chunks + 1, 256, 0, ctx->stream>>>(n, n_chunks, p.sel_offset, (const unsigned long long *)(a + o_chunk));
+    ctx->launches += 2;
+  }
   if (p.n_proj + p.want_row_ids > 0) {
     obgpu_project_kernel<<<n, kThreads, p.smem_total, ctx->stream>>>(p);
     ctx->launches++;

@@ -98,7 +98,7 @@ enum ColKind : uint8_t {
   K_FIXSTR,   // RAW fixed-length string
 };
 
-struct ColDesc {
+struct alignas(16) ColDesc {
   uint8_t kind;        // ColKind
   uint8_t type;        // ColType
   uint8_t attr;        // ColAttr
