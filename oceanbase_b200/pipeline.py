@@ -1,0 +1,109 @@
+"""Host-buffer scan pipeline: H2D of page batch i+1, kernels of batch i and D2H of batch i-1 overlap.
+
+A table that lives in host memory (the block cache) is cut into page batches of consecutive
+micro-blocks; `n_workers` worker threads, each with its own obgpu_ctx (= its own CUDA stream), pull
+batches from a queue and run open (H2D + index) -> scan -> fetch (D2H) through the public C-ABI.
+ctypes releases the GIL inside every C call, so the copies of different batches run concurrently in
+both PCIe directions while the kernels (sub-millisecond) slot in between. Results are delivered per
+batch in block order (dense inside a batch), which is how a block-at-a-time consumer such as
+ObSSTableRowScanner drains them.
+"""
+import threading
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from .scan import ScanContext
+from .sstable import TableImage
+
+
+@dataclass
+class BatchOutput:
+    block_begin: int
+    block_end: int
+    total_rows: int
+    selected_rows: int
+    cols: List[np.ndarray]           # per projected column: payload (uint64 / uint32 / uint8)
+    lens: List[Optional[np.ndarray]]  # string columns: int32 lens
+    nulls: List[np.ndarray]
+    has_null: List[int]
+
+
+def split_table(table: TableImage, blocks_per_batch: int) -> List[TableImage]:
+    parts = []
+    n = table.n_blocks
+    for b0 in range(0, n, blocks_per_batch):
+        b1 = min(n, b0 + blocks_per_batch)
+        lo = int(table.offsets[b0])
+        hi = int(table.offsets[b1]) if b1 < n else int(table.image.size)
+        parts.append(TableImage(table.image[lo:hi], table.offsets[b0:b1] - lo, table.sizes[b0:b1], 0, table.n_cols))
+    return parts
+
+
+class HostScanPipeline:
+    """Reusable pipeline (contexts, streams and pinned output buffers are created once)."""
+
+    def __init__(self, device: int, n_workers: int = 3):
+        self.device = device
+        self.ctxs = [ScanContext(device) for _ in range(n_workers)]
+
+    def close(self):
+        for c in self.ctxs:
+            c.close()
+        self.ctxs = []
+
+    def scan(self, table: TableImage, filter, proj: Sequence[int], blocks_per_batch: int, selectivity_hint: float,
+             out_buffers: Optional[List[List[np.ndarray]]] = None, string_base: int = 0) -> List[BatchOutput]:
+        parts = split_table(table, blocks_per_batch)
+        outs: List[Optional[BatchOutput]] = [None] * len(parts)
+        errors = []
+        lock = threading.Lock()
+        next_idx = [0]
+
+        def worker(ctx: ScanContext):
+            try:
+                while True:
+                    with lock:
+                        i = next_idx[0]
+                        next_idx[0] += 1
+                    if i >= len(parts):
+                        return
+                    part = parts[i]
+                    batch = ctx.open_batch(part)                      # H2D + index kernel
+                    cap = int(batch.total_rows * selectivity_hint) + 1024
+                    res = batch.scan(filter, proj, string_base=string_base, max_selected_rows=min(cap, batch.total_rows))
+                    try:
+                        n = res.selected_rows                         # sync + status
+                    except Exception as e:                             # capacity overflow: exact re-run
+                        from .capi import ObGpuError, OB_BUF_NOT_ENOUGH
+                        if isinstance(e, ObGpuError) and e.code == OB_BUF_NOT_ENOUGH:
+                            need = res._info.selected_rows
+                            res.free()
+                            res = batch.scan(filter, proj, string_base=string_base, max_selected_rows=need)
+                            n = res.selected_rows
+                        else:
+                            raise
+                    cols, lens, nulls, hn = [], [], [], []
+                    for c in range(len(proj)):
+                        ob = out_buffers[i][c] if out_buffers is not None else None
+                        d, l, nl = res.fetch_col(c, 0, n, out=ob)     # D2H
+                        cols.append(d)
+                        lens.append(l)
+                        nulls.append(nl)
+                        hn.append(res.col(c).has_null)
+                    outs[i] = BatchOutput(i * blocks_per_batch, i * blocks_per_batch + part.n_blocks, batch.total_rows,
+                                          n, cols, lens, nulls, hn)
+                    res.free()
+                    batch.close()
+            except Exception as e:  # pragma: no cover
+                errors.append(e)
+
+        threads = [threading.Thread(target=worker, args=(c,)) for c in self.ctxs]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
+        return outs
