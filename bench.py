@@ -54,21 +54,23 @@ def build_workload(rows, row_start, seed, chunk_rows=4_000_000, pinned=False, n_
 
     with ThreadPoolExecutor(workers) as ex:
         parts = list(ex.map(gen, starts))
-    w0 = parts[0]
-    total = sum(len(p.table.image) for p in parts)
-    if pinned:
-        import torch
-        buf = torch.empty(total, dtype=torch.uint8, pin_memory=True)
-        image = buf.numpy()
-    else:
-        buf = None
-        image = np.empty(total, dtype=np.uint8)
-    offs, pos = [], 0
-    for p in parts:
-        n = len(p.table.image)
-        image[pos:pos + n] = p.table.image
-        offs.append(p.table.offsets + pos)
-        pos += n
+        w0 = parts[0]
+        sizes = [len(p.table.image) for p in parts]
+        total = sum(sizes)
+        if pinned:
+            import torch
+            buf = torch.empty(total, dtype=torch.uint8, pin_memory=True)
+            image = buf.numpy()
+        else:
+            buf = None
+            image = np.empty(total, dtype=np.uint8)
+        pos = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+
+        def place(i):  # parallel first touch: pages spread over the NUMA nodes of the copying threads
+            image[pos[i]:pos[i + 1]] = parts[i].table.image
+            return parts[i].table.offsets + pos[i]
+
+        offs = list(ex.map(place, range(len(parts))))
     table = TableImage(image, np.concatenate(offs), np.concatenate([p.table.sizes for p in parts]),
                        sum(p.table.total_rows for p in parts), w0.table.n_cols)
     w0.table = table

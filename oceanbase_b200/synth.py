@@ -79,9 +79,10 @@ def _rle_column(seed, start, n, dict_bits=8, mean_run=64):
 def make_config2_like(rows=100_000, rows_per_block=1400, seed=2, shape="bt", row_start=0,
                       n_threads=0, out=None) -> Workload:
     s = lambda c: _col_seed(seed, c)
-    inc = (splitmix64(s(0), row_start, rows) % np.uint64(700)).astype(np.int64) + 1
-    # sorted PK: shard-independent base (expected increment 350.5 per row) + local cumsum
-    pk = np.cumsum(inc) + np.int64(row_start) * 351 + np.int64(1_000_000_007)
+    # sorted PK as a pure function of the absolute row index (shards / chunks line up, strictly
+    # increasing: consecutive rows differ by 351 + (j' - j) with j, j' in [0, 351))
+    jitter = (splitmix64(s(0), row_start, rows) % np.uint64(351)).astype(np.int64)
+    pk = np.int64(1_000_000_007) + (np.arange(row_start, row_start + rows, dtype=np.int64)) * 351 + jitter
     cols = [Column(capi.OBJ_INT, capi.ENC_INTEGER_BASE_DIFF, pk)]
     for c in (1, 2, 3):
         cols.append(Column(capi.OBJ_INT, capi.ENC_RLE, _rle_column(s(c), row_start, rows)))
