@@ -1,0 +1,252 @@
+// See ob_gpu_micro_block_decoder.h. Host glue only: every data-parallel step happens in
+// libobgpu_scan.so (sm_100a kernels); this file never decodes a cell itself.
+#include "ob_gpu_micro_block_decoder.h"
+
+#include <algorithm>
+#include <cstring>
+
+namespace oceanbase {
+using namespace common;
+namespace blocksstable {
+
+ObGpuScanRuntime::ObGpuScanRuntime(int device) {
+  if (obgpu_ctx_create(device, &ctx_) != OBGPU_SUCCESS) ctx_ = nullptr;
+}
+ObGpuScanRuntime::~ObGpuScanRuntime() {
+  if (ctx_) obgpu_ctx_destroy(ctx_);
+}
+
+// ---- ObGpuMicroBlockDecoder ------------------------------------------------------------------------
+void ObGpuMicroBlockDecoder::reset() {
+  if (batch_) obgpu_batch_close(batch_);
+  batch_ = nullptr;
+  row_count_ = column_count_ = 0;
+}
+
+int ObGpuMicroBlockDecoder::init(const ObMicroBlockData &block_data) {
+  if (!rt_.is_valid()) return OB_NOT_INIT;
+  if (block_data.get_buf() == nullptr || block_data.get_buf_size() <= 0) return OB_INVALID_ARGUMENT;
+  reset();  // can be init twice
+  const int64_t size = block_data.get_buf_size();
+  padded_.assign((size_t)((size + 15) & ~15ll) + 64, 0);
+  memcpy(padded_.data(), block_data.get_buf(), (size_t)size);
+  host_buf_ = block_data.get_buf();
+  const int64_t off = 0;
+  int ret = obgpu_batch_open(rt_.ctx(), padded_.data(), (int64_t)padded_.size(), &off, &size, 1, 0, nullptr, &batch_);
+  if (ret != OBGPU_SUCCESS) return ret;
+  int32_t cols = 0;
+  ret = obgpu_batch_block_info(batch_, 0, &row_count_, &cols);
+  column_count_ = cols;
+  return ret;
+}
+
+int ObGpuMicroBlockDecoder::get_row_count(int64_t &row_count) const {
+  if (!batch_) return OB_NOT_INIT;
+  row_count = row_count_;
+  return OB_SUCCESS;
+}
+
+int ObGpuMicroBlockDecoder::get_column_count(int64_t &column_count) const {
+  if (!batch_) return OB_NOT_INIT;
+  column_count = column_count_;
+  return OB_SUCCESS;
+}
+
+static void to_params(const sql::ObWhiteFilterExecutor &filter, std::vector<obgpu_filter_param> &params) {
+  for (const ObDatum &d : filter.get_datums()) {
+    obgpu_filter_param p{};
+    p.is_null = d.is_null() ? 1 : 0;
+    if (!d.is_null()) {
+      p.i64 = d.get_int();
+      p.ptr = d.ptr_;
+      p.len = d.len_;
+    }
+    params.push_back(p);
+  }
+}
+
+int ObGpuMicroBlockDecoder::filter_pushdown_filter(const sql::ObPushdownFilterExecutor *parent,
+                                                   sql::ObWhiteFilterExecutor &filter,
+                                                   const sql::PushdownFilterInfo &pd_filter_info,
+                                                   ObBitmap &result_bitmap) {
+  (void)parent;  // can_skip_filter is an optimisation of the CPU path; the result bitmap is the same
+  if (!batch_) return OB_NOT_INIT;
+  if (pd_filter_info.start_ < 0 || pd_filter_info.start_ + pd_filter_info.count_ > row_count_ ||
+      result_bitmap.size() != pd_filter_info.count_)
+    return OB_INVALID_ARGUMENT;
+  std::vector<obgpu_filter_param> params;
+  to_params(filter, params);
+  return obgpu_filter_white(batch_, 0, filter.get_col_offset(), (int32_t)filter.get_op_type(), params.data(),
+                            (int32_t)params.size(), pd_filter_info.start_, pd_filter_info.count_,
+                            result_bitmap.get_data());
+}
+
+int ObGpuMicroBlockDecoder::get_rows(const int32_t col, const int32_t *row_ids, const int64_t row_cap,
+                                     const int64_t vec_offset, ObFixedLengthVector &vec) {
+  if (!batch_) return OB_NOT_INIT;
+  if ((int64_t)vec.data_.size() < (vec_offset + row_cap) * vec.len_) return OB_BUF_NOT_ENOUGH;
+  int32_t has_null = 0;
+  const int ret = obgpu_project_fixed(batch_, 0, col, row_ids, row_cap, vec_offset, vec.data_.data(), vec.len_,
+                                      vec.nulls_.data(), &has_null);
+  if (has_null) vec.has_null_ = true;
+  return ret;
+}
+
+int ObGpuMicroBlockDecoder::get_rows(const int32_t col, const int32_t *row_ids, const int64_t row_cap,
+                                     const int64_t vec_offset, ObDiscreteVector &vec) {
+  if (!batch_) return OB_NOT_INIT;
+  if ((int64_t)vec.ptrs_.size() < vec_offset + row_cap) return OB_BUF_NOT_ENOUGH;
+  int32_t has_null = 0;
+  // string pointers land in the CALLER's block buffer (zero-copy like the reference, rule 8c.6)
+  const int ret = obgpu_project_discrete(batch_, 0, col, row_ids, row_cap, vec_offset, (uint64_t)(uintptr_t)host_buf_,
+                                         reinterpret_cast<uint64_t *>(vec.ptrs_.data()), vec.lens_.data(),
+                                         vec.nulls_.data(), &has_null);
+  if (has_null) vec.has_null_ = true;
+  return ret;
+}
+
+// ---- ObPushdownFilterExecutor::execute ----------------------------------------------------------------
+int execute_pushdown_filter(sql::ObPushdownFilterExecutor *filter, sql::ObPushdownFilterExecutor *parent,
+                            const sql::PushdownFilterInfo &pd, ObGpuMicroBlockDecoder &decoder) {
+  int ret = OB_SUCCESS;
+  ObBitmap *result = nullptr;
+  if (filter == nullptr || pd.start_ < 0 || pd.count_ <= 0) return OB_INVALID_ARGUMENT;
+  if ((ret = filter->init_bitmap(pd.count_, result)) != OB_SUCCESS) return ret;
+  if (filter->is_filter_node()) {
+    result->reuse(false);
+    return decoder.filter_pushdown_filter(parent, *static_cast<sql::ObWhiteFilterExecutor *>(filter), pd, *result);
+  }
+  if (filter->get_child_count() < 2) return OB_ERR_UNEXPECTED;
+  sql::ObPushdownFilterExecutor **children = filter->get_childs();
+  for (uint32_t i = 0; ret == OB_SUCCESS && i < filter->get_child_count(); ++i) {
+    if ((ret = execute_pushdown_filter(children[i], filter, pd, decoder)) != OB_SUCCESS) break;
+    const ObBitmap *child = children[i]->get_result();
+    if (filter->is_logic_and_node()) {
+      if ((ret = result->bit_and(*child)) == OB_SUCCESS && result->is_all_false()) break;
+    } else {
+      if ((ret = result->bit_or(*child)) == OB_SUCCESS && result->is_all_true()) break;
+    }
+  }
+  return ret;
+}
+
+// ---- ObGpuSSTableBatchScanner -------------------------------------------------------------------------
+void ObGpuSSTableBatchScanner::reset() {
+  if (result_) obgpu_result_free(result_);
+  if (batch_) obgpu_batch_close(batch_);
+  result_ = nullptr;
+  batch_ = nullptr;
+  cur_block_ = 0;
+  cur_row_ = 0;
+  selected_ = 0;
+}
+
+int ObGpuSSTableBatchScanner::flatten(sql::ObPushdownFilterExecutor *f, std::vector<obgpu_filter_node> &nodes,
+                                      std::vector<obgpu_filter_param> &params) {
+  obgpu_filter_node nd{};
+  if (f->is_filter_node()) {
+    auto *w = static_cast<sql::ObWhiteFilterExecutor *>(f);
+    nd.kind = OBGPU_NODE_WHITE;
+    nd.op = (int32_t)w->get_op_type();
+    nd.col = w->get_col_offset();
+    nd.param_begin = (int32_t)params.size();
+    to_params(*w, params);
+    nd.n_params = (int32_t)params.size() - nd.param_begin;
+  } else {
+    for (uint32_t i = 0; i < f->get_child_count(); ++i) {
+      const int ret = flatten(f->get_childs()[i], nodes, params);
+      if (ret != OB_SUCCESS) return ret;
+    }
+    nd.kind = f->is_logic_and_node() ? OBGPU_NODE_AND : OBGPU_NODE_OR;
+    nd.n_children = (int32_t)f->get_child_count();
+  }
+  nodes.push_back(nd);
+  return OB_SUCCESS;
+}
+
+int ObGpuSSTableBatchScanner::init(const void *image, int64_t image_size, const int64_t *offsets, const int64_t *sizes,
+                                   int32_t n_blocks, sql::ObPushdownFilterExecutor *filter,
+                                   const std::vector<int32_t> &proj, int64_t batch_size) {
+  if (!rt_.is_valid()) return OB_NOT_INIT;
+  if (batch_size <= 0) return OB_INVALID_ARGUMENT;
+  reset();
+  image_ = static_cast<const char *>(image);
+  n_blocks_ = n_blocks;
+  batch_size_ = batch_size;
+  proj_ = proj;
+  int ret = obgpu_batch_open(rt_.ctx(), image, image_size, offsets, sizes, n_blocks, 0, nullptr, &batch_);
+  if (ret != OBGPU_SUCCESS) return ret;
+  std::vector<obgpu_filter_node> nodes;
+  std::vector<obgpu_filter_param> params;
+  obgpu_filter flt{};
+  if (filter) {
+    if ((ret = flatten(filter, nodes, params)) != OB_SUCCESS) return ret;
+    flt.nodes = nodes.data();
+    flt.n_nodes = (int32_t)nodes.size();
+    flt.params = params.data();
+    flt.n_params = (int32_t)params.size();
+  }
+  obgpu_scan_spec spec{};
+  spec.filter = filter ? &flt : nullptr;
+  spec.proj_cols = proj_.data();
+  spec.n_proj = (int32_t)proj_.size();
+  spec.want_row_ids = 1;
+  spec.string_base = (uint64_t)(uintptr_t)image;
+  spec.max_selected_rows = 0;
+  if ((ret = obgpu_scan(batch_, &spec, &result_)) != OBGPU_SUCCESS) return ret;
+  obgpu_result_info info{};
+  if ((ret = obgpu_result_info_get(result_, &info)) != OBGPU_SUCCESS) return ret;
+  selected_ = info.selected_rows;
+  sel_offset_.assign((size_t)n_blocks + 1, 0);
+  if ((ret = obgpu_result_fetch_sel_offsets(result_, sel_offset_.data())) != OBGPU_SUCCESS) return ret;
+  cols_.resize(proj_.size());
+  for (size_t c = 0; c < proj_.size(); ++c)
+    if ((ret = obgpu_result_col_get(result_, (int32_t)c, &cols_[c])) != OBGPU_SUCCESS) return ret;
+  return OB_SUCCESS;
+}
+
+int ObGpuSSTableBatchScanner::get_next_rows(Batch &out) {
+  if (!result_) return OB_NOT_INIT;
+  // skip blocks without (remaining) selected rows
+  while (cur_block_ < n_blocks_ && cur_row_ >= sel_offset_[(size_t)cur_block_ + 1]) ++cur_block_;
+  if (cur_block_ >= n_blocks_) return OB_ITER_END;
+  const int64_t end = sel_offset_[(size_t)cur_block_ + 1];
+  const int64_t n = std::min<int64_t>(batch_size_, end - cur_row_);
+  out.block_idx = cur_block_;
+  out.count = n;
+  out.row_ids.resize((size_t)n);
+  int ret = obgpu_result_fetch_row_ids(result_, cur_row_, n, out.row_ids.data());
+  const size_t np = proj_.size();
+  out.ints.assign(np, {});
+  out.str_ptrs.assign(np, {});
+  out.str_lens.assign(np, {});
+  out.is_null.assign(np, {});
+  std::vector<uint64_t> nulls((size_t)(n + 63) / 64 + 1);
+  for (size_t c = 0; ret == OBGPU_SUCCESS && c < np; ++c) {
+    out.is_null[c].assign((size_t)n, 0);
+    if (cols_[c].is_string) {
+      std::vector<uint64_t> ptrs((size_t)n);
+      out.str_lens[c].resize((size_t)n);
+      ret = obgpu_result_fetch_col(result_, (int32_t)c, cur_row_, n, ptrs.data(), out.str_lens[c].data(), nulls.data());
+      out.str_ptrs[c].resize((size_t)n);
+      for (int64_t i = 0; i < n; ++i) out.str_ptrs[c][(size_t)i] = reinterpret_cast<const char *>((uintptr_t)ptrs[(size_t)i]);
+    } else {
+      const int el = cols_[c].elem_len;
+      std::vector<char> raw((size_t)n * el);
+      ret = obgpu_result_fetch_col(result_, (int32_t)c, cur_row_, n, raw.data(), nullptr, nulls.data());
+      out.ints[c].resize((size_t)n);
+      for (int64_t i = 0; i < n; ++i) {
+        int64_t v = 0;
+        memcpy(&v, raw.data() + i * el, (size_t)el);
+        if (el == 4) v = (int32_t)v;
+        out.ints[c][(size_t)i] = v;
+      }
+    }
+    for (int64_t i = 0; i < n; ++i) out.is_null[c][(size_t)i] = (nulls[(size_t)i / 64] >> (i % 64)) & 1;
+  }
+  cur_row_ += n;
+  return ret;
+}
+
+}  // namespace blocksstable
+}  // namespace oceanbase

@@ -1,0 +1,258 @@
+// C++ host adapter over the C-ABI (include/obgpu_scan.h), mirroring the reference's reader surface
+// for the scan path: same class / method names, argument meaning and error behaviour as
+//   blocksstable::ObIMicroBlockReader / ObIMicroBlockDecoder   (ob_imicro_block_reader.h:295-614,
+//                                                               encoding/ob_imicro_block_decoder.h:27-73)
+//   sql::ObPushdownFilterExecutor / ObWhiteFilterExecutor      (sql/engine/basic/ob_pushdown_filter.h:690-1259)
+//   common::ObBitmap                                           (deps/oblib/src/lib/container/ob_bitmap.h:64-171)
+//   storage::ObIStoreRowIterator::get_next_rows                (access/ob_store_row_iterator.h:34-185)
+// The reference headers do not compile outside its clang-17 build, so the few value
+// types the interface needs are restated here in the same namespaces with the same member names;
+// inside the reference tree the adapter derives from the real classes instead.
+#pragma once
+#include <stdint.h>
+
+#include <algorithm>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+extern "C" {
+#include "../../include/obgpu_scan.h"
+}
+
+namespace oceanbase {
+namespace common {
+
+constexpr int OB_SUCCESS = 0;
+constexpr int OB_INVALID_ARGUMENT = -4002;
+constexpr int OB_NOT_INIT = -4006;
+constexpr int OB_NOT_SUPPORTED = -4007;
+constexpr int OB_ITER_END = -4008;
+constexpr int OB_ERR_UNEXPECTED = -4016;
+constexpr int OB_BUF_NOT_ENOUGH = -4024;
+
+// Byte-per-row selection vector (0x00 / 0x01), the subset of common::ObBitmap the path uses.
+class ObBitmap {
+public:
+  int init(const int64_t valid_bytes, const bool is_all_true = false) {
+    data_.assign((size_t)valid_bytes, is_all_true ? 1 : 0);
+    return OB_SUCCESS;
+  }
+  void reuse(const bool is_all_true = false) { std::fill(data_.begin(), data_.end(), is_all_true ? 1 : 0); }
+  int64_t size() const { return (int64_t)data_.size(); }
+  uint8_t *get_data() { return data_.data(); }
+  const uint8_t *get_data() const { return data_.data(); }
+  bool test(const int64_t pos) const { return data_[(size_t)pos] != 0; }
+  uint64_t popcnt() const { uint64_t c = 0; for (uint8_t b : data_) c += b; return c; }
+  bool is_all_false() const { return popcnt() == 0; }
+  bool is_all_true() const { return popcnt() == data_.size(); }
+  int bit_and(const ObBitmap &r) {
+    if (r.size() != size()) return OB_INVALID_ARGUMENT;
+    for (size_t i = 0; i < data_.size(); ++i) data_[i] &= r.data_[i];
+    return OB_SUCCESS;
+  }
+  int bit_or(const ObBitmap &r) {
+    if (r.size() != size()) return OB_INVALID_ARGUMENT;
+    for (size_t i = 0; i < data_.size(); ++i) data_[i] |= r.data_[i];
+    return OB_SUCCESS;
+  }
+  int bit_not() { for (uint8_t &b : data_) b ^= 1; return OB_SUCCESS; }
+private:
+  std::vector<uint8_t> data_;
+};
+
+// share/datum/ob_datum.h:109-177 (ptr_ + {len_:29, flag_:2, null_:1}); the scan path only needs
+// value / NULL of filter constants and decoded cells.
+struct ObDatum {
+  const char *ptr_ = nullptr;
+  uint32_t len_ = 0;
+  bool null_ = false;
+  int64_t int_ = 0;  // integer classes: value
+  bool is_null() const { return null_; }
+  void set_null() { null_ = true; len_ = 0; ptr_ = nullptr; }
+  void set_int(int64_t v) { null_ = false; int_ = v; len_ = 8; ptr_ = reinterpret_cast<const char *>(&int_); }
+  void set_string(const char *p, uint32_t l) { null_ = false; ptr_ = p; len_ = l; }
+  int64_t get_int() const { return int_; }
+};
+
+}  // namespace common
+
+namespace sql {
+
+enum ObWhiteFilterOperatorType {  // ob_pushdown_filter.h:388-401
+  WHITE_OP_EQ = 0, WHITE_OP_LE, WHITE_OP_LT, WHITE_OP_GE, WHITE_OP_GT, WHITE_OP_NE, WHITE_OP_BT,
+  WHITE_OP_IN, WHITE_OP_NU, WHITE_OP_NN, WHITE_OP_MAX
+};
+
+struct PushdownFilterInfo {  // ob_pushdown_filter.h (start_/count_ window of one micro block)
+  int64_t start_ = 0;
+  int64_t count_ = 0;
+};
+
+enum PushdownExecutorType { WHITE_FILTER_EXECUTOR, AND_FILTER_EXECUTOR, OR_FILTER_EXECUTOR };
+
+class ObPushdownFilterExecutor {
+public:
+  explicit ObPushdownFilterExecutor(PushdownExecutorType t) : type_(t) {}
+  virtual ~ObPushdownFilterExecutor() = default;
+  bool is_filter_node() const { return type_ == WHITE_FILTER_EXECUTOR; }
+  bool is_logic_and_node() const { return type_ == AND_FILTER_EXECUTOR; }
+  bool is_logic_or_node() const { return type_ == OR_FILTER_EXECUTOR; }
+  uint32_t get_child_count() const { return (uint32_t)childs_.size(); }
+  ObPushdownFilterExecutor **get_childs() { return childs_.data(); }
+  void add_child(ObPushdownFilterExecutor *c) { childs_.push_back(c); }
+  common::ObBitmap *get_result() { return &filter_bitmap_; }
+  int init_bitmap(const int64_t row_count, common::ObBitmap *&bitmap) {
+    bitmap = &filter_bitmap_;
+    return filter_bitmap_.init(row_count, is_logic_and_node());
+  }
+protected:
+  PushdownExecutorType type_;
+  std::vector<ObPushdownFilterExecutor *> childs_;
+  common::ObBitmap filter_bitmap_;
+};
+
+class ObWhiteFilterExecutor : public ObPushdownFilterExecutor {
+public:
+  ObWhiteFilterExecutor(int32_t col_offset, ObWhiteFilterOperatorType op)
+      : ObPushdownFilterExecutor(WHITE_FILTER_EXECUTOR), col_offset_(col_offset), op_type_(op) {}
+  ObWhiteFilterOperatorType get_op_type() const { return op_type_; }
+  int32_t get_col_offset() const { return col_offset_; }  // get_col_offsets(is_pd_to_cg).at(0)
+  const std::vector<common::ObDatum> &get_datums() const { return datum_params_; }
+  std::vector<common::ObDatum> &get_datums() { return datum_params_; }
+  bool null_param_contained() const {
+    for (const auto &d : datum_params_) if (d.is_null()) return true;
+    return false;
+  }
+private:
+  int32_t col_offset_;
+  ObWhiteFilterOperatorType op_type_;
+  std::vector<common::ObDatum> datum_params_;
+};
+
+class ObAndFilterExecutor : public ObPushdownFilterExecutor {
+public:
+  ObAndFilterExecutor() : ObPushdownFilterExecutor(AND_FILTER_EXECUTOR) {}
+};
+class ObOrFilterExecutor : public ObPushdownFilterExecutor {
+public:
+  ObOrFilterExecutor() : ObPushdownFilterExecutor(OR_FILTER_EXECUTOR) {}
+};
+
+}  // namespace sql
+
+namespace blocksstable {
+
+struct ObMicroBlockData {  // blocksstable/ob_micro_block_info.h (buf_/size_ of a decompressed block)
+  const char *buf_ = nullptr;
+  int64_t size_ = 0;
+  const char *get_buf() const { return buf_; }
+  int64_t get_buf_size() const { return size_; }
+};
+
+// The vectors ObMicroBlockDecoder::get_rows fills (share/vector): VEC_FIXED and VEC_DISCRETE.
+struct ObFixedLengthVector {
+  int32_t len_ = 8;
+  std::vector<char> data_;
+  std::vector<uint64_t> nulls_;  // sql::ObBitVector words
+  bool has_null_ = false;
+  void reserve_rows(int64_t n) { data_.assign((size_t)n * len_, 0); nulls_.assign((size_t)(n + 63) / 64, 0); has_null_ = false; }
+  bool is_null(int64_t i) const { return (nulls_[(size_t)i / 64] >> (i % 64)) & 1; }
+  int64_t get_int(int64_t i) const { int64_t v = 0; memcpy(&v, data_.data() + i * len_, (size_t)len_); return v; }
+};
+struct ObDiscreteVector {
+  std::vector<char *> ptrs_;
+  std::vector<int32_t> lens_;
+  std::vector<uint64_t> nulls_;
+  bool has_null_ = false;
+  void reserve_rows(int64_t n) { ptrs_.assign((size_t)n, nullptr); lens_.assign((size_t)n, 0); nulls_.assign((size_t)(n + 63) / 64, 0); has_null_ = false; }
+  bool is_null(int64_t i) const { return (nulls_[(size_t)i / 64] >> (i % 64)) & 1; }
+};
+
+// Per worker thread: device + stream (obgpu_ctx).
+class ObGpuScanRuntime {
+public:
+  explicit ObGpuScanRuntime(int device = 0);
+  ~ObGpuScanRuntime();
+  bool is_valid() const { return ctx_ != nullptr; }
+  obgpu_ctx *ctx() { return ctx_; }
+  const char *last_error() const { return obgpu_ctx_last_error(ctx_); }
+private:
+  obgpu_ctx *ctx_ = nullptr;
+};
+
+// ObIMicroBlockDecoder over ONE micro block (reference granularity).
+class ObGpuMicroBlockDecoder {
+public:
+  explicit ObGpuMicroBlockDecoder(ObGpuScanRuntime &rt) : rt_(rt) {}
+  ~ObGpuMicroBlockDecoder() { reset(); }
+  // ObIMicroBlockReader::init -- re-entrant ("can be init twice")
+  int init(const ObMicroBlockData &block_data);
+  void reset();
+  int get_row_count(int64_t &row_count) const;
+  int get_column_count(int64_t &column_count) const;
+  // ObIMicroBlockDecoder::filter_pushdown_filter(parent, white filter, pd_filter_info, result_bitmap)
+  int filter_pushdown_filter(const sql::ObPushdownFilterExecutor *parent, sql::ObWhiteFilterExecutor &filter,
+                             const sql::PushdownFilterInfo &pd_filter_info, common::ObBitmap &result_bitmap);
+  // ObMicroBlockDecoder::get_rows (rich format): one call per projected column kind
+  int get_rows(const int32_t col, const int32_t *row_ids, const int64_t row_cap, const int64_t vec_offset,
+               ObFixedLengthVector &vec);
+  int get_rows(const int32_t col, const int32_t *row_ids, const int64_t row_cap, const int64_t vec_offset,
+               ObDiscreteVector &vec);
+  obgpu_batch *batch() { return batch_; }
+private:
+  ObGpuScanRuntime &rt_;
+  obgpu_batch *batch_ = nullptr;
+  std::vector<char> padded_;  // block copy padded to the 16-byte TMA granularity
+  const char *host_buf_ = nullptr;
+  int64_t row_count_ = 0, column_count_ = 0;
+};
+
+// ObPushdownFilterExecutor::execute (ob_pushdown_filter.cpp:1551-1624) driving the decoder leaf by
+// leaf with bit_and / bit_or and the reference's early-outs.
+int execute_pushdown_filter(sql::ObPushdownFilterExecutor *filter, sql::ObPushdownFilterExecutor *parent,
+                            const sql::PushdownFilterInfo &pd_filter_info, ObGpuMicroBlockDecoder &decoder);
+
+// Page-batch scanner with the ObIStoreRowIterator batch contract: open many micro blocks, one fused
+// device scan, then get_next_rows() hands out <= batch_size rows at a time, block by block, rows
+// ascending, OB_ITER_END after the last row (access/ob_store_row_iterator.h, ob_sstable_row_scanner.cpp:553).
+class ObGpuSSTableBatchScanner {
+public:
+  explicit ObGpuSSTableBatchScanner(ObGpuScanRuntime &rt) : rt_(rt) {}
+  ~ObGpuSSTableBatchScanner() { reset(); }
+  // image: consecutive micro blocks (16-byte aligned starts); filter may be null; proj: column store idxs
+  int init(const void *image, int64_t image_size, const int64_t *offsets, const int64_t *sizes, int32_t n_blocks,
+           sql::ObPushdownFilterExecutor *filter, const std::vector<int32_t> &proj, int64_t batch_size = 256);
+  void reset();
+  // Next batch: count rows of block `block_idx`, row ids ascending. Integer columns are returned as
+  // int64 values + null flags (per projected column), string columns as (ptr into image, len).
+  struct Batch {
+    int32_t block_idx = -1;
+    int64_t count = 0;
+    std::vector<int32_t> row_ids;
+    std::vector<std::vector<int64_t>> ints;          // [proj][count] (integer columns)
+    std::vector<std::vector<const char *>> str_ptrs; // [proj][count] (string columns)
+    std::vector<std::vector<int32_t>> str_lens;
+    std::vector<std::vector<uint8_t>> is_null;       // [proj][count]
+  };
+  int get_next_rows(Batch &batch);
+  int64_t total_selected() const { return selected_; }
+private:
+  int flatten(sql::ObPushdownFilterExecutor *f, std::vector<obgpu_filter_node> &nodes,
+              std::vector<obgpu_filter_param> &params);
+  ObGpuScanRuntime &rt_;
+  obgpu_batch *batch_ = nullptr;
+  obgpu_result *result_ = nullptr;
+  const char *image_ = nullptr;
+  int32_t n_blocks_ = 0;
+  int64_t batch_size_ = 256, selected_ = 0;
+  std::vector<int32_t> proj_;
+  std::vector<int64_t> sel_offset_;
+  std::vector<obgpu_result_col> cols_;
+  int32_t cur_block_ = 0;
+  int64_t cur_row_ = 0;  // dense row cursor
+};
+
+}  // namespace blocksstable
+}  // namespace oceanbase

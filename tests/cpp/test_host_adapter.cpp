@@ -1,0 +1,296 @@
+// C++ parity test of the host adapter (oceanbase_b200/host), written in the shape of the reference's
+// own decoder tests: unittest/storage/blocksstable/encoding/test_raw_decoder.cpp:774-1200 (filter
+// popcounts over [seedA .. | seedB x 10 | NULL x 10] blocks, whole block and pd_filter_info windows)
+// and test_micro_block_decoder.cpp:155-189 (every cell decodes back). The oracle
+// (oracle/libob_oracle.so) is the checker; the adapter runs on the GPU through the C-ABI.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../oceanbase_b200/host/ob_gpu_micro_block_decoder.h"
+extern "C" {
+#include "../../oracle/ob_oracle.h"
+}
+
+using namespace oceanbase;
+using namespace oceanbase::common;
+using namespace oceanbase::blocksstable;
+
+static int g_fail = 0;
+#define ASSERT_EQ(a, b)                                                                           \
+  do {                                                                                            \
+    const long long va__ = (long long)(a), vb__ = (long long)(b);                                 \
+    if (va__ != vb__) {                                                                           \
+      printf("FAIL %s:%d  %s = %lld, expected %lld\n", __FILE__, __LINE__, #a, va__, vb__);       \
+      ++g_fail;                                                                                   \
+    }                                                                                             \
+  } while (0)
+
+static const int64_t ROW_CNT = 64;
+
+struct Rows {
+  std::vector<int64_t> ints;
+  std::vector<std::string> strs;
+  std::vector<uint8_t> nulls;
+};
+
+static int64_t seed_int(int64_t seed) { return seed * 1000 + 7; }
+static std::string seed_str(int64_t seed) { char b[32]; snprintf(b, sizeof(b), "seed-%04lld", (long long)seed); return b; }
+
+static std::vector<uint8_t> build_block(const Rows &r, int enc_int, int enc_str) {
+  const int64_t n = (int64_t)r.ints.size();
+  std::vector<int64_t> pad(n);
+  std::iota(pad.begin(), pad.end(), 0);
+  std::string heap;
+  std::vector<int64_t> off(n + 1, 0);
+  for (int64_t i = 0; i < n; ++i) { heap += r.strs[i]; off[i + 1] = (int64_t)heap.size(); }
+  heap.push_back('\0');
+  obgpu_col_input cols[3];
+  memset(cols, 0, sizeof(cols));
+  cols[0].obj_type = OBGPU_OBJ_INT; cols[0].encoding = OBGPU_ENC_RAW; cols[0].i64 = pad.data();
+  cols[1].obj_type = OBGPU_OBJ_INT; cols[1].encoding = enc_int; cols[1].i64 = r.ints.data(); cols[1].is_null = r.nulls.data();
+  cols[2].obj_type = OBGPU_OBJ_VARCHAR; cols[2].encoding = enc_str; cols[2].str_heap = heap.data(); cols[2].str_off = off.data();
+  cols[2].is_null = r.nulls.data();
+  int64_t size = 0;
+  if (obgpu_writer_encode_block(cols, 3, 1, 0, n, nullptr, 0, &size) != 0) { printf("encode failed\n"); exit(2); }
+  std::vector<uint8_t> blk((size_t)size);
+  obgpu_writer_encode_block(cols, 3, 1, 0, n, blk.data(), size, &size);
+  return blk;
+}
+
+static Rows layout(std::initializer_list<std::pair<int64_t, int64_t>> parts) {  // (seed or -1 = NULL, count)
+  Rows r;
+  for (auto &p : parts)
+    for (int64_t i = 0; i < p.second; ++i) {
+      r.nulls.push_back(p.first < 0);
+      r.ints.push_back(seed_int(p.first < 0 ? 0 : p.first));
+      r.strs.push_back(seed_str(p.first < 0 ? 0 : p.first));
+    }
+  return r;
+}
+
+static int64_t pushdown_popcnt(ObGpuMicroBlockDecoder &dec, int col, sql::ObWhiteFilterOperatorType op,
+                               std::vector<int64_t> seeds, bool str, int64_t start, int64_t count) {
+  sql::ObWhiteFilterExecutor filter(col, op);
+  std::vector<std::string> keep;
+  keep.reserve(seeds.size());
+  for (int64_t s : seeds) {
+    ObDatum d;
+    if (str) { keep.push_back(seed_str(s)); d.set_string(keep.back().data(), (uint32_t)keep.back().size()); }
+    else d.set_int(seed_int(s));
+    filter.get_datums().push_back(d);
+  }
+  sql::PushdownFilterInfo pd;
+  pd.start_ = start;
+  pd.count_ = count;
+  ObBitmap bm;
+  bm.init(count);
+  ASSERT_EQ(OB_SUCCESS, dec.filter_pushdown_filter(nullptr, filter, pd, bm));
+  return (int64_t)bm.popcnt();
+}
+
+static void test_filter_pushdown(ObGpuScanRuntime &rt) {
+  const int encs[][2] = {{OBGPU_ENC_RAW, OBGPU_ENC_RAW}, {OBGPU_ENC_DICT, OBGPU_ENC_DICT},
+                         {OBGPU_ENC_RLE, OBGPU_ENC_RLE}, {OBGPU_ENC_INTEGER_BASE_DIFF, OBGPU_ENC_DICT}};
+  for (auto &e : encs) {
+    for (int str = 0; str < 2; ++str) {
+      const int col = str ? 2 : 1;
+      {  // filter_pushdown_all_eq_ne: [seed1 x N-20 | seed2 x 10 | NULL x 10]
+        std::vector<uint8_t> blk = build_block(layout({{0xF, ROW_CNT - 20}, {0x0, 10}, {-1, 10}}), e[0], e[1]);
+        ObGpuMicroBlockDecoder dec(rt);
+        ObMicroBlockData data{(const char *)blk.data(), (int64_t)blk.size()};
+        ASSERT_EQ(OB_SUCCESS, dec.init(data));
+        int64_t rc = 0;
+        ASSERT_EQ(OB_SUCCESS, dec.get_row_count(rc));
+        ASSERT_EQ(ROW_CNT, rc);
+        ASSERT_EQ(ROW_CNT - 20, pushdown_popcnt(dec, col, sql::WHITE_OP_EQ, {0xF}, str, 0, ROW_CNT));
+        ASSERT_EQ(25, pushdown_popcnt(dec, col, sql::WHITE_OP_EQ, {0xF}, str, ROW_CNT - 45, 30));
+        ASSERT_EQ(10, pushdown_popcnt(dec, col, sql::WHITE_OP_NE, {0xF}, str, 0, ROW_CNT));
+        ASSERT_EQ(5, pushdown_popcnt(dec, col, sql::WHITE_OP_NE, {0xF}, str, ROW_CNT - 45, 30));
+        ASSERT_EQ(OB_SUCCESS, dec.init(data));  // can be init twice
+      }
+      {  // filter_push_down_gt_lt_ge_le: [seed0 x N-30 | seed1 x 10 | seed2 x 10 | NULL x 10]
+        std::vector<uint8_t> blk = build_block(layout({{0, ROW_CNT - 30}, {1, 10}, {2, 10}, {-1, 10}}), e[0], e[1]);
+        ObGpuMicroBlockDecoder dec(rt);
+        ObMicroBlockData data{(const char *)blk.data(), (int64_t)blk.size()};
+        ASSERT_EQ(OB_SUCCESS, dec.init(data));
+        ASSERT_EQ(10, pushdown_popcnt(dec, col, sql::WHITE_OP_GT, {1}, str, 0, ROW_CNT));
+        ASSERT_EQ(5, pushdown_popcnt(dec, col, sql::WHITE_OP_GT, {1}, str, ROW_CNT - 45, 30));
+        ASSERT_EQ(ROW_CNT - 30, pushdown_popcnt(dec, col, sql::WHITE_OP_LT, {1}, str, 0, ROW_CNT));
+        ASSERT_EQ(15, pushdown_popcnt(dec, col, sql::WHITE_OP_LT, {1}, str, ROW_CNT - 45, 30));
+        ASSERT_EQ(20, pushdown_popcnt(dec, col, sql::WHITE_OP_GE, {1}, str, 0, ROW_CNT));
+        ASSERT_EQ(15, pushdown_popcnt(dec, col, sql::WHITE_OP_GE, {1}, str, ROW_CNT - 45, 30));
+        ASSERT_EQ(ROW_CNT - 20, pushdown_popcnt(dec, col, sql::WHITE_OP_LE, {1}, str, 0, ROW_CNT));
+        ASSERT_EQ(25, pushdown_popcnt(dec, col, sql::WHITE_OP_LE, {1}, str, ROW_CNT - 45, 30));
+      }
+      {  // filter_push_down_bt / in / nu / nn
+        std::vector<uint8_t> blk = build_block(layout({{0, ROW_CNT - 40}, {1, 10}, {2, 10}, {3, 10}, {-1, 10}}), e[0], e[1]);
+        ObGpuMicroBlockDecoder dec(rt);
+        ObMicroBlockData data{(const char *)blk.data(), (int64_t)blk.size()};
+        ASSERT_EQ(OB_SUCCESS, dec.init(data));
+        ASSERT_EQ(ROW_CNT - 20, pushdown_popcnt(dec, col, sql::WHITE_OP_BT, {0, 2}, str, 0, ROW_CNT));
+        ASSERT_EQ(0, pushdown_popcnt(dec, col, sql::WHITE_OP_BT, {2, 0}, str, 0, ROW_CNT));
+        ASSERT_EQ(20, pushdown_popcnt(dec, col, sql::WHITE_OP_IN, {1, 2, 5}, str, 0, ROW_CNT));
+        ASSERT_EQ(15, pushdown_popcnt(dec, col, sql::WHITE_OP_IN, {1, 2, 5}, str, ROW_CNT - 35, 30));
+        ASSERT_EQ(0, pushdown_popcnt(dec, col, sql::WHITE_OP_IN, {5, 5, 5}, str, 0, ROW_CNT));
+        ASSERT_EQ(10, pushdown_popcnt(dec, col, sql::WHITE_OP_NU, {}, str, 0, ROW_CNT));
+        ASSERT_EQ(5, pushdown_popcnt(dec, col, sql::WHITE_OP_NU, {}, str, ROW_CNT - 35, 30));
+        ASSERT_EQ(ROW_CNT - 10, pushdown_popcnt(dec, col, sql::WHITE_OP_NN, {}, str, 0, ROW_CNT));
+        ASSERT_EQ(25, pushdown_popcnt(dec, col, sql::WHITE_OP_NN, {}, str, ROW_CNT - 35, 30));
+      }
+    }
+  }
+}
+
+static void test_get_rows_vs_oracle(ObGpuScanRuntime &rt) {
+  // batch decode into VEC_FIXED / VEC_DISCRETE == oracle's get_rows, incl. vec_offset and NULLs
+  Rows r = layout({{3, 20}, {-1, 5}, {9, 30}, {-1, 2}, {1, 7}});
+  for (size_t i = 0; i < r.ints.size(); ++i) { r.ints[i] += (int64_t)i * 13; r.strs[i] += std::to_string(i % 7); }
+  std::vector<uint8_t> blk = build_block(r, OBGPU_ENC_RAW, OBGPU_ENC_DICT);
+  ObGpuMicroBlockDecoder dec(rt);
+  ObMicroBlockData data{(const char *)blk.data(), (int64_t)blk.size()};
+  ASSERT_EQ(OB_SUCCESS, dec.init(data));
+  ora_block ob;
+  ASSERT_EQ(0, ora_block_init(&ob, blk.data(), (int64_t)blk.size()));
+  std::vector<int32_t> row_ids;
+  for (int32_t i = 1; i < (int32_t)r.ints.size(); i += 2) row_ids.push_back(i);
+  const int64_t cap = (int64_t)row_ids.size(), voff = 3;
+  ObFixedLengthVector fv;
+  fv.len_ = 8;
+  fv.reserve_rows(voff + cap);
+  ASSERT_EQ(OB_SUCCESS, dec.get_rows(1, row_ids.data(), cap, voff, fv));
+  std::vector<uint64_t> ev((size_t)(voff + cap), 0), en((size_t)(voff + cap + 63) / 64, 0);
+  int32_t ehn = 0;
+  ASSERT_EQ(0, ora_get_rows_fixed(&ob, 1, row_ids.data(), cap, voff, ev.data(), 8, en.data(), &ehn));
+  ASSERT_EQ(ehn, (int)fv.has_null_);
+  for (int64_t i = 0; i < voff + cap; ++i) {
+    ASSERT_EQ((en[(size_t)i / 64] >> (i % 64)) & 1, (int)fv.is_null(i));
+    if (!fv.is_null(i)) ASSERT_EQ((int64_t)ev[(size_t)i], fv.get_int(i));
+  }
+  ObDiscreteVector dv;
+  dv.reserve_rows(voff + cap);
+  ASSERT_EQ(OB_SUCCESS, dec.get_rows(2, row_ids.data(), cap, voff, dv));
+  for (int64_t i = 0; i < cap; ++i) {
+    const int32_t row = row_ids[(size_t)i];
+    ASSERT_EQ((int)r.nulls[(size_t)row], (int)dv.is_null(voff + i));
+    if (!r.nulls[(size_t)row]) {
+      ASSERT_EQ((int64_t)r.strs[(size_t)row].size(), dv.lens_[(size_t)(voff + i)]);
+      // zero-copy: the pointer lands inside the caller's block buffer
+      const char *p = dv.ptrs_[(size_t)(voff + i)];
+      ASSERT_EQ(1, p >= (const char *)blk.data() && p < (const char *)blk.data() + blk.size());
+      ASSERT_EQ(0, memcmp(p, r.strs[(size_t)row].data(), r.strs[(size_t)row].size()));
+    }
+  }
+}
+
+static void test_filter_tree_and_batch_scanner(ObGpuScanRuntime &rt) {
+  // a small SSTable: 20 000 rows in blocks of 777; AND(OR(a < 100, a >= 900), s = 'k3') ; project a, s
+  const int64_t n = 20000, rpb = 777;
+  std::vector<int64_t> a(n), b(n);
+  std::string heap;
+  std::vector<int64_t> off(n + 1, 0);
+  std::vector<uint8_t> nulls(n, 0);
+  uint64_t x = 88172645463325252ull;
+  for (int64_t i = 0; i < n; ++i) {
+    x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+    a[i] = (int64_t)(x % 1000);
+    b[i] = i;
+    nulls[i] = (x >> 20) % 17 == 0;
+    heap += "k" + std::to_string((x >> 32) % 8);
+    off[i + 1] = (int64_t)heap.size();
+  }
+  heap.push_back('\0');
+  obgpu_col_input cols[3];
+  memset(cols, 0, sizeof(cols));
+  cols[0].obj_type = OBGPU_OBJ_INT; cols[0].encoding = OBGPU_ENC_INTEGER_BASE_DIFF; cols[0].i64 = b.data();
+  cols[1].obj_type = OBGPU_OBJ_INT; cols[1].encoding = OBGPU_ENC_RAW; cols[1].i64 = a.data(); cols[1].is_null = nulls.data();
+  cols[2].obj_type = OBGPU_OBJ_VARCHAR; cols[2].encoding = OBGPU_ENC_DICT; cols[2].str_heap = heap.data(); cols[2].str_off = off.data();
+  obgpu_table_image *img = nullptr;
+  ASSERT_EQ(0, obgpu_writer_encode_table(cols, 3, 1, n, rpb, 128, 2, &img));
+  int64_t image_size = 0;
+  int32_t nb = 0;
+  obgpu_table_image_info(img, &image_size, &nb);
+  std::vector<uint8_t> image((size_t)image_size + 64, 0);
+  std::vector<int64_t> offs((size_t)nb), sizes((size_t)nb);
+  ASSERT_EQ(0, obgpu_table_image_export(img, image.data(), image_size, offs.data(), sizes.data(), nb));
+  obgpu_table_image_free(img);
+
+  sql::ObWhiteFilterExecutor lt(1, sql::WHITE_OP_LT), ge(1, sql::WHITE_OP_GE), eq(2, sql::WHITE_OP_EQ);
+  ObDatum d;
+  d.set_int(100); lt.get_datums().push_back(d);
+  d.set_int(900); ge.get_datums().push_back(d);
+  ObDatum ds; ds.set_string("k3", 2); eq.get_datums().push_back(ds);
+  sql::ObOrFilterExecutor orf; orf.add_child(&lt); orf.add_child(&ge);
+  sql::ObAndFilterExecutor andf; andf.add_child(&orf); andf.add_child(&eq);
+
+  // (1) per-block tree execution through ObPushdownFilterExecutor::execute semantics
+  int64_t expect_total = 0;
+  for (int32_t blk = 0; blk < nb; blk += 7) {
+    ObGpuMicroBlockDecoder dec(rt);
+    ObMicroBlockData data{(const char *)image.data() + offs[(size_t)blk], sizes[(size_t)blk]};
+    ASSERT_EQ(OB_SUCCESS, dec.init(data));
+    int64_t rc = 0;
+    dec.get_row_count(rc);
+    sql::PushdownFilterInfo pd;
+    pd.start_ = 0; pd.count_ = rc;
+    ASSERT_EQ(OB_SUCCESS, execute_pushdown_filter(&andf, nullptr, pd, dec));
+    int64_t exp = 0;
+    for (int64_t i = 0; i < rc; ++i) {
+      const int64_t g = (int64_t)blk * rpb + i;
+      const bool m = !nulls[(size_t)g] && (a[(size_t)g] < 100 || a[(size_t)g] >= 900) &&
+                     heap.compare((size_t)off[(size_t)g], (size_t)(off[(size_t)g + 1] - off[(size_t)g]), "k3") == 0;
+      exp += m;
+      ASSERT_EQ((int)m, (int)andf.get_result()->test(i));
+    }
+    ASSERT_EQ(exp, (int64_t)andf.get_result()->popcnt());
+    expect_total += exp;
+  }
+  // (2) page-batch scanner: get_next_rows until OB_ITER_END == brute force over the generator
+  ObGpuSSTableBatchScanner scanner(rt);
+  ASSERT_EQ(OB_SUCCESS, scanner.init(image.data(), image_size, offs.data(), sizes.data(), nb, &andf, {1, 2, 0}, 256));
+  ObGpuSSTableBatchScanner::Batch batch;
+  int64_t seen = 0, g_expect = 0, last_block = -1, last_row = -1;
+  int ret;
+  while ((ret = scanner.get_next_rows(batch)) == OB_SUCCESS) {
+    ASSERT_EQ(1, batch.count > 0 && batch.count <= 256);
+    for (int64_t i = 0; i < batch.count; ++i) {
+      const int64_t row = batch.row_ids[(size_t)i];
+      // order: blocks ascending, rows ascending inside a block
+      ASSERT_EQ(1, batch.block_idx > last_block || (batch.block_idx == last_block && row > last_row));
+      last_block = batch.block_idx; last_row = row;
+      const int64_t g = (int64_t)batch.block_idx * rpb + row;
+      // advance the brute-force cursor to the next matching row: must be exactly g
+      while (g_expect < n && !( !nulls[(size_t)g_expect] && (a[(size_t)g_expect] < 100 || a[(size_t)g_expect] >= 900) &&
+             heap.compare((size_t)off[(size_t)g_expect], (size_t)(off[(size_t)g_expect + 1] - off[(size_t)g_expect]), "k3") == 0)) ++g_expect;
+      ASSERT_EQ(g_expect, g);
+      ++g_expect;
+      ASSERT_EQ(0, (int)batch.is_null[0][(size_t)i]);
+      ASSERT_EQ(a[(size_t)g], batch.ints[0][(size_t)i]);
+      ASSERT_EQ(2, batch.str_lens[1][(size_t)i]);
+      ASSERT_EQ(0, memcmp(batch.str_ptrs[1][(size_t)i], "k3", 2));
+      ASSERT_EQ(b[(size_t)g], batch.ints[2][(size_t)i]);
+    }
+    seen += batch.count;
+  }
+  ASSERT_EQ(OB_ITER_END, ret);
+  ASSERT_EQ(scanner.total_selected(), seen);
+  ASSERT_EQ(OB_ITER_END, scanner.get_next_rows(batch));
+  (void)expect_total;
+}
+
+int main() {
+  ObGpuScanRuntime rt(0);
+  if (!rt.is_valid()) {
+    printf("no CUDA device: the adapter has no CPU fallback (expected on a CPU-only box)\n");
+    return 77;
+  }
+  test_filter_pushdown(rt);
+  test_get_rows_vs_oracle(rt);
+  test_filter_tree_and_batch_scanner(rt);
+  if (g_fail) { printf("%d assertion(s) failed\n", g_fail); return 1; }
+  printf("host adapter tests passed\n");
+  return 0;
+}
