@@ -131,6 +131,17 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_traffic(rows):
+    """DRAM bytes per scan from the committed ncu capture (profiles/r1_traffic.json), when it was taken at
+    the same row count; otherwise null."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            t = json.load(f)
+        return int(t["total"]) if int(t["rows"]) == int(rows) else None
+    except Exception:
+        return None
+
+
 def cpu_reference_leg(w, steps, warmup, n_threads, sample_blocks):
     """Times the oracle port of the reference CPU path (tests/oracle_binding.py) on a bounded
     sample of the workload: first `sample_blocks` micro-blocks, all host threads."""
@@ -333,8 +344,8 @@ def run_ours(args):
                        "l2_policy": "input image (1.2 GB) larger than L2 (126 MB); no flush needed",
                        "gen_seconds": round(t_gen, 1)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "alg_bytes_per_launch": alg_bytes,
-                         "kernel_ms": kern_mean, "kernel": "obgpu_scan_kernel"},
+                         "traffic": measured_traffic(table.total_rows), "peak_source": peak_src, "alg_bytes_per_launch": alg_bytes,
+                         "kernel_ms": kern_mean, "kernel": "one scan = obgpu_count_kernel + obgpu_prefix_*_kernel + obgpu_project_kernel (project ~85%)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_ms, "steps": e2e_steps, "page_batches": len(parts), "streams": 3,
                     "timing": "host wall clock around the pipelined public API call (3 streams)"},
