@@ -107,8 +107,8 @@ struct ScanParams {
   uint32_t smem_bitset;
   uint32_t smem_rle, smem_desc;            // single-block kernels
   uint32_t smem_scratch, scratch_bytes;    // project kernel
-  uint32_t cw_desc, cw_bm, cw_bitset, cw_bytes;  // count kernel: per-warp region = descs | bm | bitsets
-  uint32_t pw_rle, pw_bytes;  // project kernel: per-warp region at off_desc = ColDesc | RLE run table
+  uint32_t cw_desc, cw_bm, cw_bitset, cw_stage, cw_stage_bytes, cw_bytes;  // count kernel, per-warp: descs | bm | bitsets | stage
+  uint32_t pw_rle, pw_rvals, pw_bytes;  // project kernel, per-warp region at off_desc: ColDesc | run values (u64) | RLE run table
   uint32_t off_sel, off_bm, off_wpre, off_rle, off_desc;  // inside one scratch
   uint32_t smem_total;
   uint32_t rle_slot_bytes;    // bytes per run-table slot: starts[(cap + 2)] + g2run[words_cap]
@@ -676,7 +676,7 @@ __device__ __forceinline__ void project_str_col(const ScanParams &p, const Block
 // =================================================================================================
 __global__ void __launch_bounds__(256) obgpu_index_kernel(const uint8_t *image, const uint64_t *blk_off,
                                                           const uint32_t *blk_size, int n_blocks, int max_cols,
-                                                          ColDesc *plans, uint32_t *rows) {
+                                                          ColDesc *plans, uint32_t *rows, uint32_t *col_span) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)n_blocks * max_cols) return;
   const int block = (int)(i / max_cols), col = (int)(i % max_cols);
@@ -687,6 +687,12 @@ __global__ void __launch_bounds__(256) obgpu_index_kernel(const uint8_t *image, 
   if (b.ok) build_col_desc(b, col, d);
   plans[i] = d;
   if (col == 0) rows[block] = b.ok ? b.row_count : 0u;
+  if (d.ok && (d.kind == K_BITS || d.kind == K_DICT)) {
+    // bytes of the value / ref array from the enclosing 16-byte boundary (count kernel staging buffer)
+    const uint32_t lo = (d.val_bit >> 3) & ~15u;
+    const uint32_t hi = ((d.val_bit + b.row_count * d.stride + 7u) >> 3) + 16u;
+    atomicMax(&col_span[col], (hi - lo + 15u) & ~15u);
+  }
 }
 
 // =================================================================================================
@@ -746,15 +752,54 @@ __global__ void __launch_bounds__(kThreads) obgpu_count_kernel(const __grid_cons
   if (p.simple_shape != 0) {
     const bool and_mode = p.simple_shape == 1;
     const int n_leaves = p.n_nodes == 1 ? 1 : p.n_nodes - 1;
-    int first = 0;
-    if (!leaf_first_fast<true>(p, c, p.nodes[0], bm, rows, nwords, t)) {
-      for (uint32_t g = (uint32_t)lane; g < nwords; g += 32u) bm[g] = and_mode ? valid_mask_of(rows, g) : 0u;
-    } else {
-      first = 1;
-    }
-    __syncwarp();
-    for (int i = first; i < n_leaves; ++i) {
-      leaf_over_words<true>(p, c, p.nodes[i], bm, rows, nwords, and_mode, t);
+    uint8_t *stage = wr + p.cw_stage;
+    const uint8_t *gblk = p.image + p.blk_off[block];
+    bool inited = false;
+    for (int i = 0; i < n_leaves; ++i) {
+      const FilterNodeDev &nd = p.nodes[i];
+      const ColDesc &d = descs[nd.used_idx];
+      // stage the leaf column's value / ref array: every lane pulls 16-byte pieces, all loads in flight
+      bool staged = false;
+      BlockCtx cs = c;
+      if (p.cw_stage_bytes > 0 && nd.op != OP_FALSE && nd.op != OP_TRUE && (d.kind == K_BITS || d.kind == K_DICT)) {
+        const uint32_t lo = (d.val_bit >> 3) & ~15u;
+        const uint32_t nbytes = ((((d.val_bit + rows * d.stride + 7u) >> 3) + 16u) - lo + 15u) & ~15u;
+        if (nbytes <= p.cw_stage_bytes) {
+          const uint4 *src = reinterpret_cast<const uint4 *>(gblk + lo);
+          uint4 *dst = reinterpret_cast<uint4 *>(stage);
+          const uint32_t n16 = nbytes >> 4;
+          __syncwarp();
+          for (uint32_t k = (uint32_t)lane; k < n16; k += 128u) {
+            uint4 v0 = src[k], v1{}, v2{}, v3{};
+            if (k + 32u < n16) v1 = src[k + 32u];
+            if (k + 64u < n16) v2 = src[k + 64u];
+            if (k + 96u < n16) v3 = src[k + 96u];
+            dst[k] = v0;
+            if (k + 32u < n16) dst[k + 32u] = v1;
+            if (k + 64u < n16) dst[k + 64u] = v2;
+            if (k + 96u < n16) dst[k + 96u] = v3;
+          }
+          __syncwarp();
+          cs.sbit = (smem_u32(stage) - lo) * 8u;
+          staged = true;
+        }
+      }
+      if (i == 0) {
+        const bool fast = staged ? leaf_first_fast<false>(p, cs, nd, bm, rows, nwords, t)
+                                 : leaf_first_fast<true>(p, c, nd, bm, rows, nwords, t);
+        if (fast) {
+          inited = true;
+          __syncwarp();
+          continue;
+        }
+      }
+      if (!inited) {
+        for (uint32_t g = (uint32_t)lane; g < nwords; g += 32u) bm[g] = and_mode ? valid_mask_of(rows, g) : 0u;
+        inited = true;
+        __syncwarp();
+      }
+      if (staged) leaf_over_words<false>(p, cs, nd, bm, rows, nwords, and_mode, t);
+      else leaf_over_words<true>(p, c, nd, bm, rows, nwords, and_mode, t);
       __syncwarp();
     }
     for (uint32_t g = (uint32_t)lane; g < nwords; g += 32u) {
@@ -988,6 +1033,33 @@ __global__ void __launch_bounds__(kThreads) obgpu_project_kernel(const __grid_co
         g2run[g] = (uint16_t)(lo > 0 ? lo - 1 : 0);
       }
       __syncwarp();
+      if (d.sc != 5 && d.elem_len == 8) {
+        // integer RLE column: decode each RUN once (value of run k), rows then only look up their run
+        uint64_t *rvals = reinterpret_cast<uint64_t *>(wscr + p.pw_rvals);
+        const uint32_t refs_bit = c.sbit + d.rle_refs_bit, ref_bits = d.rle_ref_bits;
+        const uint32_t dcount = d.dict_count, dbits = d.dict_data_size * 8u, dpay = c.sbit + d.dict_payload * 8u;
+        bool null_run = false;
+        for (uint32_t k = (uint32_t)lane; k < n; k += 32u) {
+          const uint32_t ref = sbits32(refs_bit + k * ref_bits, ref_bits);
+          uint64_t v = 0;
+          if (ref >= dcount) null_run = true;
+          else {
+            v = sbits(dpay + ref * dbits, dbits);
+            if (d.sign_fix) v = sign_fix(d.int_mask, v);
+          }
+          rvals[k] = v;
+        }
+        const bool any_null = __any_sync(0xffffffffu, null_run);
+        __syncwarp();
+        if (!any_null) {
+          uint64_t *out = reinterpret_cast<uint64_t *>(p.out_data[pc]) + base;
+          const RleTable rt = c.rle_table(0);
+          if (all_rows) for (uint32_t j = (uint32_t)lane; j < cnt; j += 32u) out[j] = rvals[rle_run_of(rt, j)];
+          else for (uint32_t j = (uint32_t)lane; j < cnt; j += 32u) out[j] = rvals[rle_run_of(rt, sel[j])];
+          __syncwarp();
+          continue;
+        }
+      }
     }
     if (all_rows) {
       if (d.sc == 5) project_str_col<true>(p, c, d, pc, sel, cnt, base, blk_addr, t);
@@ -1194,6 +1266,7 @@ struct obgpu_batch {
   // decode plans + row counts built by the index kernel at open
   ColDesc *d_plans = nullptr;
   uint32_t *d_rows = nullptr;
+  std::vector<uint32_t> col_span;      // per store index: max staged bytes of the value / ref array
 };
 
 struct ResultCol {
@@ -1479,15 +1552,21 @@ int obgpu_batch_open(obgpu_ctx *ctx, const void *image, int64_t image_size, cons
   if (e == cudaSuccess) {
     const size_t plan_bytes = (size_t)n_blocks * b->max_cols * sizeof(ColDesc);
     void *dp = nullptr;
-    e = cudaMallocAsync(&dp, plan_bytes + (size_t)n_blocks * 4 + 64, ctx->stream);
+    const size_t rows_bytes = ((size_t)n_blocks * 4 + 63) & ~(size_t)63;
+    e = cudaMallocAsync(&dp, plan_bytes + rows_bytes + (size_t)b->max_cols * 4 + 64, ctx->stream);
     if (e == cudaSuccess) {
       b->d_plans = (ColDesc *)dp;
       b->d_rows = (uint32_t *)((uint8_t *)dp + plan_bytes);
+      uint32_t *d_span = (uint32_t *)((uint8_t *)dp + plan_bytes + rows_bytes);
+      e = cudaMemsetAsync(d_span, 0, (size_t)b->max_cols * 4, ctx->stream);
       const int64_t nthreads = (int64_t)n_blocks * b->max_cols;
       obgpu_index_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, ctx->stream>>>(
-          b->d_image, b->d_blk_off, b->d_blk_size, n_blocks, (int)b->max_cols, b->d_plans, b->d_rows);
-      e = cudaGetLastError();
+          b->d_image, b->d_blk_off, b->d_blk_size, n_blocks, (int)b->max_cols, b->d_plans, b->d_rows, d_span);
+      if (e == cudaSuccess) e = cudaGetLastError();
       ctx->launches++;
+      b->col_span.assign(b->max_cols, 0);
+      if (e == cudaSuccess)
+        e = cudaMemcpyAsync(b->col_span.data(), d_span, (size_t)b->max_cols * 4, cudaMemcpyDeviceToHost, ctx->stream);
     }
   }
   // `stage` is pageable: the copy above is staged synchronously by the runtime before returning
@@ -1689,7 +1768,8 @@ static void layout_smem_scan(const obgpu_batch *b, ScanParams &p) {
   p.off_bm = s;   s += (p.words_cap * 4u + 15u) & ~15u;
   p.off_wpre = s; s += (p.words_cap * 4u + 15u) & ~15u;
   p.off_rle = s;
-  p.pw_rle = ((uint32_t)sizeof(ColDesc) + 15u) & ~15u;
+  p.pw_rvals = ((uint32_t)sizeof(ColDesc) + 15u) & ~15u;
+  p.pw_rle = p.pw_rvals + (p.n_rle_slots > 0 ? (((uint32_t)p.rle_runs_cap + 2u) * 8u) : 0u);
   p.pw_bytes = (p.pw_rle + (p.n_rle_slots > 0 ? (((uint32_t)p.rle_runs_cap + 2u) * 2u + p.words_cap * 2u) : 0u) + 15u) & ~15u;
   p.off_desc = s; s += p.pw_bytes * (uint32_t)kWarps;
   p.scratch_bytes = (s + 127u) & ~127u;
@@ -1700,6 +1780,13 @@ static void layout_smem_scan(const obgpu_batch *b, ScanParams &p) {
   p.cw_desc = w;   w += ((uint32_t)sizeof(ColDesc) * (uint32_t)std::max(p.n_used, 1) + 15u) & ~15u;
   p.cw_bm = w;     w += (p.words_cap * 4u + 15u) & ~15u;
   p.cw_bitset = w; w += ((uint32_t)p.n_slots * (uint32_t)p.bitset_words * 4u + 15u) & ~15u;
+  // staging buffer for the filter columns' value / ref arrays (coalesced 16-byte loads); skipped
+  // when a column's span would blow the per-warp budget (then the kernel reads global directly)
+  uint32_t span = 0;
+  for (int i = 0; i < p.n_used; ++i)
+    if (p.used_in_filter[i] && (size_t)p.used_col[i] < b->col_span.size()) span = std::max(span, b->col_span[(size_t)p.used_col[i]]);
+  p.cw_stage_bytes = span > 0 && span <= 12288u ? span + 32u : 0u;
+  p.cw_stage = (w + 15u) & ~15u; w = p.cw_stage + p.cw_stage_bytes;
   p.cw_bytes = (w + 127u) & ~127u;
 }
 
