@@ -106,6 +106,7 @@ static_assert(sizeof(ColumnHeader) == 16, "column header must be 16 bytes");
 static_assert(sizeof(DictMetaHeader) == 9, "dict meta header must be 9 bytes");
 static_assert(sizeof(RLEMetaHeader) == 10, "rle meta header must be 10 bytes");
 static_assert(sizeof(IntegerBaseDiffHeader) == 2, "base diff header must be 2 bytes");
+static_assert(sizeof(ConstMetaHeader) == 6, "const meta header must be 6 bytes");
 
 // ObColumnHeader::Type  ob_block_sstable_struct.h:203-216
 enum ColType : int8_t {

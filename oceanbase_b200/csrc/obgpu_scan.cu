@@ -301,7 +301,7 @@ __device__ __forceinline__ bool eval_leaf(const ScanParams &p, const BlockCtx &c
     rt = c.rle_table(d.rle_slot);
     rtp = &rt;
   }
-  if (d.kind == K_DICT || d.kind == K_RLE) {
+  if (is_dict_kind(d)) {
     uint32_t ref = ref_of(c.b.s, d, rtp, row);
     if (ref > d.dict_count + 1) ref = d.dict_count + 1;
     return (c.bitsets[nd.slot * p.bitset_words + (ref >> 5)] >> (ref & 31)) & 1u;
@@ -743,7 +743,7 @@ __global__ void __launch_bounds__(kThreads) obgpu_count_kernel(const __grid_cons
       const FilterNodeDev &nd = p.nodes[i];
       if (nd.kind != NODE_WHITE || nd.slot < 0) continue;
       const ColDesc &d = descs[nd.used_idx];
-      if (d.kind == K_DICT || d.kind == K_RLE)
+      if (is_dict_kind(d))
         build_dict_bitset(p, c.b, d, nd, bitsets + nd.slot * p.bitset_words, t);
     }
     __syncwarp();
@@ -1110,7 +1110,7 @@ __global__ void __launch_bounds__(kThreads) obgpu_filter_block_kernel(const __gr
     const FilterNodeDev &nd = p.nodes[i];
     if (nd.kind != NODE_WHITE || nd.slot < 0) continue;
     const ColDesc &d = descs[nd.used_idx];
-    if (d.kind == K_DICT || d.kind == K_RLE)
+    if (is_dict_kind(d))
       build_dict_bitset(p, c.b, d, nd, bitsets + nd.slot * p.bitset_words, t);
   }
   __syncthreads();
@@ -1497,6 +1497,14 @@ int obgpu_batch_open(obgpu_ctx *ctx, const void *image, int64_t image_size, cons
         if ((int64_t)meta_off + coff + 10 > sz) { ret = OBGPU_INVALID_DATA; break; }
         dm = meta_off + coff + rd32h(p + meta_off + coff + 6);
         b->col_max_rle[c] = std::max(b->col_max_rle[c], rd32h(p + meta_off + coff + 2));
+      } else if (type == obf::COL_CONST) {
+        if ((int64_t)meta_off + coff + 6 > sz) { ret = OBGPU_INVALID_DATA; break; }
+        const uint8_t *cm = p + meta_off + coff;
+        if (cm[1] == 0) {  // no exceptions: read as a one-entry dictionary
+          b->col_max_dict[c] = std::max(b->col_max_dict[c], 3u);
+          continue;
+        }
+        dm = meta_off + coff + (uint32_t)(cm[4] | (cm[5] << 8));
       } else continue;
       if ((int64_t)dm + 9 > sz || (int64_t)meta_off + coff + clen > sz) { ret = OBGPU_INVALID_DATA; break; }
       const uint32_t cnt = rd32h(p + dm + 2);

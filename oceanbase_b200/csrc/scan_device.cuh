@@ -96,6 +96,7 @@ enum ColKind : uint8_t {
   K_RLE,      // ref   = refs[run_of(row)], then dictionary
   K_VARSTR,   // RAW var-length string in the row data
   K_FIXSTR,   // RAW fixed-length string
+  K_CONST,    // ref   = exception ref if the row is in the exception list, else const_ref; then dictionary
 };
 
 struct alignas(16) ColDesc {
@@ -133,7 +134,14 @@ struct alignas(16) ColDesc {
   uint32_t var_header_off; // bytes of per-row ext bits (row_offset_)
   uint32_t var_k;          // index among the var columns
   uint32_t ext_index;
+  // CONST: exception list in rle_count / rle_row_ids_bit / rle_row_id_bits / rle_refs_bit (8-bit refs)
+  uint32_t const_ref;
 };
+static_assert(sizeof(ColDesc) == 96, "ColDesc layout is shared by the index kernel and the scan kernels");
+
+__device__ __forceinline__ bool is_dict_kind(const ColDesc &d) {
+  return d.kind == K_DICT || d.kind == K_RLE || d.kind == K_CONST;
+}
 
 struct BlockView {
   const uint8_t *s;        // shared-memory image
@@ -322,8 +330,54 @@ __device__ __forceinline__ void build_col_desc(const BlockView &b, int col, ColD
       d.ok = 1;
       return;
     }
+    case COL_CONST: {
+      // ObConstDecoder (ob_const_decoder.cpp:25-137): header {version, count, const_ref, row_id_byte:3,
+      // offset u16}; count == 0: value image after the header (const_ref 0) or NULL / NOP (1 / 2);
+      // count > 0: [count x u8 ref][count x row_id_byte row ids][dict meta at offset]
+      if (length < 6 || meta + length > b.size || s[meta] != 0) return;
+      const uint32_t count = s[meta + 1], cref = s[meta + 2], rib = s[meta + 3] & 7u;
+      const uint32_t doff = (uint32_t)ld_bytes(s, meta + 4, 2);
+      d.kind = K_CONST;
+      d.sign_fix = d.int_mask != 0;
+      d.dict_fixed = 1;
+      if (count == 0) {
+        if (cref > 2) return;
+        if (cref == 0) {  // a one-entry dictionary whose payload is the stored value
+          d.dict_count = 1;
+          d.dict_data_size = length - 6u;
+          d.dict_payload = meta + 6u;
+          d.dict_end = meta + length;
+          if (sc != 5 && d.dict_data_size != (uint32_t)type_store_size(d.obj_type)) return;
+        }  // else dict_count = 0: ref 0 >= count reads as NULL
+        d.ok = 1;
+        return;
+      }
+      if (rib != 1 && rib != 2 && rib != 4) return;
+      if (doff < 6u + count * (rib + 1u) || doff + 9u > length) return;
+      d.rle_count = count;
+      d.const_ref = cref;
+      d.rle_ref_bits = 8;
+      d.rle_row_id_bits = (uint8_t)(rib * 8u);
+      d.rle_refs_bit = (meta + 6u) * 8u;
+      d.rle_row_ids_bit = (meta + 6u + count) * 8u;
+      const uint32_t dm = meta + doff;
+      d.dict_count = (uint32_t)ld_bytes(s, dm + 2, 4);
+      d.dict_data_size = (uint32_t)ld_bytes(s, dm + 6, 2);
+      d.dict_fixed = s[dm + 8] & DICT_FIX_LENGTH;
+      d.dict_payload = dm + 9;
+      d.dict_end = meta + length;
+      if (!d.dict_fixed) {
+        if (d.dict_data_size != 1 && d.dict_data_size != 2 && d.dict_data_size != 4) return;
+        d.dict_var = d.dict_payload + (d.dict_count ? d.dict_count - 1 : 0) * d.dict_data_size;
+        if (sc != 5) return;
+      } else if (sc != 5 && (d.dict_data_size == 0 || d.dict_data_size > 8)) {
+        return;
+      }
+      d.ok = 1;
+      return;
+    }
     default:
-      return;  // CONST / STRING_DIFF / HEX / PREFIX / span columns: caller falls back
+      return;  // STRING_DIFF / HEX / PREFIX / span columns: caller falls back
   }
 }
 
@@ -358,6 +412,18 @@ __device__ __forceinline__ uint32_t ref_of(const uint8_t *s, const ColDesc &d, c
   if (d.kind == K_RLE) {
     if (rt == nullptr) return rle_ref_slow(s, d, row);
     return ld_bits32(s, d.rle_refs_bit + rle_run_of(*rt, row) * d.rle_ref_bits, d.rle_ref_bits);
+  }
+  if (d.kind == K_CONST) {
+    // lower_bound over the (sorted, <= 255) exception row ids (ob_const_decoder.cpp:93-121)
+    uint32_t lo = 0, hi = d.rle_count;
+    while (lo < hi) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (ld_bits32(s, d.rle_row_ids_bit + mid * d.rle_row_id_bits, d.rle_row_id_bits) < row) lo = mid + 1;
+      else hi = mid;
+    }
+    if (lo < d.rle_count && ld_bits32(s, d.rle_row_ids_bit + lo * d.rle_row_id_bits, d.rle_row_id_bits) == row)
+      return s[(d.rle_refs_bit >> 3) + lo];
+    return d.const_ref;
   }
   return ld_bits32(s, d.val_bit + row * d.stride, d.width);
 }
@@ -395,7 +461,7 @@ __device__ __forceinline__ uint64_t int_cell(const BlockView &b, const ColDesc &
                                              uint32_t row, bool &is_null) {
   const uint8_t *s = b.s;
   is_null = false;
-  if (d.kind == K_DICT || d.kind == K_RLE) {
+  if (is_dict_kind(d)) {
     const uint32_t ref = ref_of(s, d, rt, row);
     if (ref >= d.dict_count) { is_null = true; return 0; }
     return dict_int(s, d, ref);
@@ -422,7 +488,7 @@ __device__ __forceinline__ void str_cell(const BlockView &b, const ColDesc &d, c
   is_null = false;
   cell = 0;
   len = 0;
-  if (d.kind == K_DICT || d.kind == K_RLE) {
+  if (is_dict_kind(d)) {
     const uint32_t ref = ref_of(s, d, rt, row);
     if (ref >= d.dict_count) { is_null = true; return; }
     dict_str(s, d, ref, cell, len);

@@ -308,6 +308,7 @@ struct BlockBuilder {
   int encode_dict(int i);
   int encode_rle(int i);
   int encode_base_diff(int i);
+  int encode_const(int i);
   int build(std::vector<uint8_t> &block);
 };
 
@@ -461,6 +462,86 @@ int BlockBuilder::encode_rle(int i) {
   return OBGPU_SUCCESS;
 }
 
+// CONST: one dominant value (or NULL) + at most 32 exception rows
+// (ob_const_encoder.cpp:58-131 traverse / suitability, :154-196 no-exception meta, :296-356 meta with
+// exceptions: [header][count x u8 ref][count x row_id_byte row ids][sorted dict meta]).
+int BlockBuilder::encode_const(int i) {
+  ColCtx &c = ctx[i];
+  ColOut &o = out[i];
+  o.hdr.type_ = COL_CONST;
+  o.hdr.attr_ = 0;  // need_data_store_ = false, no ext bits: NULL is a dict ref
+  IntDict idict;
+  StrDict sdict;
+  const std::vector<uint32_t> *refs;
+  uint32_t cnt;
+  if (c.sc == 5) {
+    build_str_dict(c, true, sdict);
+    refs = &sdict.refs;
+    cnt = (uint32_t)sdict.values.size();
+  } else {
+    build_int_dict(c, true, idict);
+    refs = &idict.refs;
+    cnt = (uint32_t)idict.values.size();
+  }
+  // the constant: most frequent ref; NULL (ref == cnt) wins only when strictly more frequent
+  std::vector<int64_t> freq((size_t)cnt + 1, 0);
+  for (int64_t r = 0; r < nrows; ++r) freq[(*refs)[(size_t)r]]++;
+  uint32_t const_ref = 0;
+  int64_t max_cnt = 0;
+  for (uint32_t k = 0; k <= cnt; ++k)
+    if (freq[k] > max_cnt) { max_cnt = freq[k]; const_ref = k; }
+  const int64_t exceptions = nrows - max_cnt;
+  if (exceptions > 32 || exceptions > std::max<int64_t>(nrows * 10 / 100, 1)) return OBGPU_NOT_SUPPORTED;
+  const size_t meta_at = meta.size();
+  ConstMetaHeader h{};
+  if (exceptions == 0) {
+    h.offset_ = (uint16_t)sizeof(ConstMetaHeader);
+    if (cnt == 0) {  // every row NULL
+      h.const_ref_ = 1;
+      memcpy(meta.grow(sizeof(h)), &h, sizeof(h));
+    } else if (c.sc == 5) {
+      const StrRef &v = sdict.values[0];
+      uint8_t *p = meta.grow(sizeof(h) + (size_t)v.len);
+      memcpy(p, &h, sizeof(h));
+      memcpy(p + sizeof(h), v.p, (size_t)v.len);
+    } else {
+      const int ts = type_store_size((uint8_t)c.in->obj_type);
+      uint8_t *p = meta.grow(sizeof(h) + (size_t)ts);
+      memcpy(p, &h, sizeof(h));
+      memcpy(p + sizeof(h), &idict.values[0], (size_t)ts);
+    }
+  } else {
+    if (cnt + 1 > 255) return OBGPU_NOT_SUPPORTED;
+    int64_t max_row_id = 0;
+    for (int64_t r = nrows - 1; r >= 0; --r)
+      if ((*refs)[(size_t)r] != const_ref) { max_row_id = r; break; }
+    const int row_id_byte = (int)byte_packed_int_size((uint64_t)max_row_id);
+    const size_t head = sizeof(h) + (size_t)exceptions * (size_t)(row_id_byte + 1);
+    if (head > 0xffff) return OBGPU_NOT_SUPPORTED;
+    h.count_ = (uint8_t)exceptions;
+    h.const_ref_ = (uint8_t)const_ref;
+    h.row_id_byte_ = (uint8_t)(row_id_byte & 7);
+    h.offset_ = (uint16_t)head;
+    uint8_t *p = meta.grow(head);
+    memcpy(p, &h, sizeof(h));
+    uint8_t *rf = p + sizeof(h), *rid = rf + exceptions;
+    int64_t k = 0;
+    for (int64_t r = 0; r < nrows; ++r) {
+      const uint32_t ref = (*refs)[(size_t)r];
+      if (ref == const_ref) continue;
+      rf[k] = (uint8_t)ref;
+      const uint32_t r32 = (uint32_t)r;
+      memcpy(rid + k * row_id_byte, &r32, (size_t)row_id_byte);
+      ++k;
+    }
+    if (c.sc == 5) store_str_dict_meta(meta, sdict);
+    else store_int_dict_meta(meta, c, idict, true);
+  }
+  o.hdr.offset_ = (uint32_t)meta_at;
+  o.hdr.length_ = (uint32_t)(meta.size() - meta_at);
+  return OBGPU_SUCCESS;
+}
+
 int BlockBuilder::encode_base_diff(int i) {
   ColCtx &c = ctx[i];
   ColOut &o = out[i];
@@ -542,6 +623,7 @@ int BlockBuilder::build(std::vector<uint8_t> &block) {
       case OBGPU_ENC_DICT: ret = encode_dict(i); break;
       case OBGPU_ENC_RLE: ret = encode_rle(i); break;
       case OBGPU_ENC_INTEGER_BASE_DIFF: ret = encode_base_diff(i); break;
+      case OBGPU_ENC_CONST: ret = encode_const(i); break;
       default: ret = OBGPU_NOT_SUPPORTED;
     }
     if (ret != OBGPU_SUCCESS) return ret;

@@ -335,6 +335,14 @@ typedef struct col_dec {
   /* BASE_DIFF (ob_integer_base_diff_decoder.h:140-170) */
   uint64_t base;
   uint8_t diff_len;
+  /* CONST (ob_const_encoder.h:28-50, ob_const_decoder.cpp:60-137) */
+  uint32_t const_count;       /* exception rows */
+  uint8_t const_ref;          /* dict ref of the constant (no dict: 0 value, 1 NULL, 2 NOP) */
+  int const_row_id_byte;
+  const uint8_t *const_refs;  /* count x uint8 */
+  const uint8_t *const_row_ids;
+  const uint8_t *const_value; /* count == 0 && ref == 0: value image after the header */
+  int64_t const_value_len;
 } col_dec;
 
 static int col_dec_init(const ora_block *b, int32_t col, col_dec *c) {
@@ -367,9 +375,38 @@ static int col_dec_init(const ora_block *b, int32_t col, col_dec *c) {
       if (c->sc == 1 && mask != 0 && (c->base & (mask >> 1))) c->base |= mask;
       break;
     }
+    case T_CONST: {
+      const uint8_t *m = c->meta; /* version, count, const_ref, attr(row_id_byte:3), offset u16 */
+      if (m[0] != 0) return ORA_ERR_UNEXPECTED;
+      c->const_count = m[1];
+      c->const_ref = m[2];
+      c->const_row_id_byte = m[3] & 7;
+      const uint32_t dict_off = rd16(m + 4);
+      c->const_refs = m + 6;
+      c->const_row_ids = m + 6 + c->const_count;
+      c->const_value = m + 6;
+      c->const_value_len = (int64_t)c->h.length - 6;
+      if (c->const_count > 0) dict_init(&c->dict, m + dict_off, (int64_t)c->h.length - dict_off);
+      break;
+    }
     default: return ORA_NOT_SUPPORTED;
   }
   return ORA_SUCCESS;
+}
+
+/* CONST: ref of a row = exception ref if the row is in the sorted exception list, else the
+ * constant's ref (ObConstDecoder::decode, ob_const_decoder.cpp:93-121: lower_bound over row ids) */
+static int64_t const_row_ref(const col_dec *c, int64_t row) {
+  int64_t lo = 0, hi = c->const_count;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) / 2;
+    if ((int64_t)rd_len(c->const_row_ids + mid * c->const_row_id_byte, c->const_row_id_byte) < row) lo = mid + 1;
+    else hi = mid;
+  }
+  if (lo < c->const_count &&
+      (int64_t)rd_len(c->const_row_ids + lo * c->const_row_id_byte, c->const_row_id_byte) == row)
+    return c->const_refs[lo];
+  return c->const_ref;
 }
 
 /* upper_bound over the RLE run-start array (ObIntArrayFuncTable::upper_bound_) */
@@ -445,6 +482,20 @@ static int decode_cell(const ora_block *b, const col_dec *c, int64_t row, ora_da
     case T_RLE: {
       const int64_t pos = rle_upper_bound(c, row);
       return dict_decode(&c->dict, c->h.obj_type, rle_ref_at(c, pos - 1), out);
+    }
+    case T_CONST: {
+      if (c->const_count == 0) { /* decode_without_dict (ob_const_decoder.cpp:25-58) */
+        if (c->const_ref == 0) {
+          if (c->sc == 5) { out->ptr = c->const_value; out->len = (uint32_t)c->const_value_len; out->is_null = 0; out->ival = 0; }
+          else load_int(c->h.obj_type, c->const_value, c->const_value_len, out);
+          return ORA_SUCCESS;
+        }
+        if (c->const_ref > 2) return ORA_ERR_UNEXPECTED;
+        set_null(out);
+        if (c->const_ref == 2) out->is_null = 2;
+        return ORA_SUCCESS;
+      }
+      return dict_decode(&c->dict, c->h.obj_type, const_row_ref(c, row), out);
     }
     case T_BASE_DIFF: {
       const uint8_t *col_data = c->meta + c->h.length;
@@ -892,8 +943,10 @@ int ora_scan_blocks(const void *image, const int64_t *offsets, const int64_t *si
 }
 
 /* ---- multi-threaded timing harness ----------------------------------------------------------- */
+#define MT_CHUNK 32
 typedef struct mt_arg {
   const void *image; const int64_t *offsets, *sizes; int32_t b0, b1;
+  int32_t *next_block; int32_t n_blocks; /* shared work queue: chunks of MT_CHUNK blocks, claimed atomically */
   const ora_filter *filter; const int32_t *proj; int32_t n_proj, batch;
   int64_t rows, sel; uint64_t checksum; int ret;
 } mt_arg;
@@ -907,7 +960,14 @@ static void *mt_worker(void *vp) {
   const uint8_t *ptrs[ORA_MAX_BATCH];
   int32_t lens[ORA_MAX_BATCH];
   uint64_t nulls[ORA_MAX_BATCH / 64 + 1];
-  for (int32_t bi = a->b0; bi < a->b1 && a->ret == ORA_SUCCESS; ++bi) {
+  for (;;) {
+    if (a->ret != ORA_SUCCESS) break;
+    if (a->b0 >= a->b1) { /* claim the next chunk (blocks of one thread stay contiguous, like a PX granule) */
+      a->b0 = __atomic_fetch_add(a->next_block, MT_CHUNK, __ATOMIC_RELAXED);
+      if (a->b0 >= a->n_blocks || a->ret != ORA_SUCCESS) break;
+      a->b1 = a->b0 + MT_CHUNK < a->n_blocks ? a->b0 + MT_CHUNK : a->n_blocks;
+    }
+    const int32_t bi = a->b0++;
     ora_block b;
     if ((a->ret = ora_block_init(&b, (const uint8_t *)a->image + a->offsets[bi], a->sizes[bi]))) break;
     const int64_t rc = b.row_count;
@@ -951,10 +1011,10 @@ int ora_scan_blocks_mt(const void *image, const int64_t *offsets, const int64_t 
   mt_arg *args = (mt_arg *)calloc((size_t)n_threads, sizeof(mt_arg));
   pthread_t *th = (pthread_t *)calloc((size_t)n_threads, sizeof(pthread_t));
   if (!args || !th) { free(args); free(th); return ORA_ERR_UNEXPECTED; }
+  int32_t next_block = 0;
   for (int32_t t = 0; t < n_threads; ++t) {
     args[t].image = image; args[t].offsets = offsets; args[t].sizes = sizes;
-    args[t].b0 = (int32_t)((int64_t)n_blocks * t / n_threads);
-    args[t].b1 = (int32_t)((int64_t)n_blocks * (t + 1) / n_threads);
+    args[t].b0 = args[t].b1 = 0; args[t].next_block = &next_block; args[t].n_blocks = n_blocks;
     args[t].filter = filter; args[t].proj = proj_cols; args[t].n_proj = n_proj; args[t].batch = batch_size;
     if (t > 0) pthread_create(&th[t], 0, mt_worker, &args[t]);
   }

@@ -12,11 +12,34 @@ ORACLE_LIB = os.path.join(ORACLE_DIR, "libob_oracle.so")
 REF_LIB = os.path.join(ORACLE_DIR, "_ref", "libref_bitstream.so")
 
 
+def _cpu_stamp():
+    """-march=native code must run where it was compiled: identify the host by its cpu flags."""
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("flags"):
+                    import hashlib
+                    return hashlib.sha1(line.encode()).hexdigest()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def build_oracle():
     src = [os.path.join(ORACLE_DIR, f) for f in ("ob_oracle.c", "ob_oracle.h", "Makefile")]
-    stale = (not os.path.exists(ORACLE_LIB)) or any(os.path.getmtime(s) > os.path.getmtime(ORACLE_LIB) for s in src)
+    stamp_file = os.path.join(ORACLE_DIR, ".built_on")
+    stamp = _cpu_stamp()
+    try:
+        with open(stamp_file) as f:
+            same_host = f.read().strip() == stamp
+    except OSError:
+        same_host = False
+    stale = (not os.path.exists(ORACLE_LIB)) or not same_host or \
+        any(os.path.getmtime(s) > os.path.getmtime(ORACLE_LIB) for s in src)
     if stale:
-        subprocess.run(["make", "-C", ORACLE_DIR, "-s", "all"], check=True, capture_output=True)
+        subprocess.run(["make", "-B", "-C", ORACLE_DIR, "-s", "all"], check=True, capture_output=True)
+        with open(stamp_file, "w") as f:
+            f.write(stamp + "\n")
     elif os.path.isdir("/root/reference") and not os.path.exists(REF_LIB):
         subprocess.run(["make", "-C", ORACLE_DIR, "-s", "ref"], check=True, capture_output=True)
     return ORACLE_LIB

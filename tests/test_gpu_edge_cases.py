@@ -112,7 +112,7 @@ def test_unsupported_encoding_reports_not_supported(ob, ctx):
     block = ob.encode_block([ob.Column(ob.OBJ_INT, ob.ENC_RAW, v), ob.Column(ob.OBJ_INT, ob.ENC_RAW, v)])
     block = block.copy()
     hs = ora.Block(block).b.header_size
-    block[hs + 16 + 1] = 3  # column 1 pretends to be CONST: not handled by the device path
+    block[hs + 16 + 1] = 5  # column 1 pretends to be STRING_DIFF: not handled by the device path
     table = ob.TableImage(np.concatenate([block, np.zeros(256, dtype=np.uint8)]), np.array([0], dtype=np.int64),
                           np.array([len(block)], dtype=np.int64), 100, 2)
     batch = ctx.open_batch(table)
