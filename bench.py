@@ -62,12 +62,14 @@ def host_cpus():
     return max(1, n)
 
 
-def build_workload(rows, row_start, seed, chunk_rows=4_000_000, pinned=False, n_threads=0):
-    """Config-2 table of `rows` rows generated in chunks (bounded host memory), packed into one
-    image (optionally pinned host memory = the host-side block cache)."""
+def build_workload(rows, row_start, seed, chunk_rows=4_000_000, pinned=False, n_threads=0, maker=None,
+                   rows_per_block=1400):
+    """Config-2 table (or `maker`'s) of `rows` rows generated in chunks (bounded host memory), packed
+    into one image (optionally pinned host memory = the host-side block cache)."""
     from concurrent.futures import ThreadPoolExecutor
     from oceanbase_b200.synth import make_config2_like
     from oceanbase_b200.sstable import TableImage
+    maker = maker or make_config2_like
 
     starts = list(range(0, rows, chunk_rows))
     ncpu = host_cpus()
@@ -76,7 +78,7 @@ def build_workload(rows, row_start, seed, chunk_rows=4_000_000, pinned=False, n_
 
     def gen(s):
         n = min(chunk_rows, rows - s)
-        return make_config2_like(rows=n, rows_per_block=1400, seed=seed, row_start=row_start + s, n_threads=per)
+        return maker(rows=n, rows_per_block=rows_per_block, seed=seed, row_start=row_start + s, n_threads=per)
 
     with ThreadPoolExecutor(workers) as ex:
         parts = list(ex.map(gen, starts))

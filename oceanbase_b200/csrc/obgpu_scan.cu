@@ -69,6 +69,7 @@ struct ScanParams {
   int32_t n_blocks;
   const ColDesc *plans;       // [n_blocks][max_cols] decode plans built once at batch open (index kernel)
   const uint32_t *rows;       // [n_blocks] row counts (0: corrupt block)
+  const BlockRec *recs;       // [n_blocks] addressing + header fields (index kernel)
   uint32_t *counts;           // [n_blocks] selected rows per block (count kernel)
   int32_t max_cols;
   int32_t n_used;
@@ -108,10 +109,11 @@ struct ScanParams {
   uint32_t smem_rle, smem_desc;            // single-block kernels
   uint32_t smem_scratch, scratch_bytes;    // project kernel
   uint32_t cw_desc, cw_bm, cw_bitset, cw_stage, cw_stage_bytes, cw_bytes;  // count kernel, per-warp: descs | bm | bitsets | stage
-  uint32_t pw_rle, pw_rvals, pw_bytes;  // project kernel, per-warp region at off_desc: ColDesc | run values (u64) | RLE run table
+  uint32_t pw_rle, pw_rvals, pw_bytes;  // project kernel, per-warp region at off_desc: run values (u64) | RLE run table
+  uint32_t off_plans;                   // project kernel: the block's n_proj decode plans (ColDesc), prefetched
   uint32_t off_sel, off_bm, off_wpre, off_rle, off_desc;  // inside one scratch
   uint32_t smem_total;
-  uint32_t rle_slot_bytes;    // bytes per run-table slot: starts[(cap + 2)] + g2run[words_cap]
+  uint32_t rle_slot_bytes;    // bytes per run-table slot: mask[words_cap] (u32) + pre[words_cap] (u16)
   uint32_t rows_cap, words_cap;
   int32_t debug_flags;        // bit0: experiment -- skip the look-back (non-dense output at row offsets)
 };
@@ -279,11 +281,11 @@ struct BlockCtx {
   const ColDesc *descs;
   const uint32_t *bitsets;
   const uint8_t *rle_base;   // run-table scratch
-  uint32_t rle_slot_bytes, rle_starts_bytes;
+  uint32_t rle_slot_bytes, rle_starts_bytes;  // slot stride; offset of pre[] inside a slot (= 4 * words_cap)
   __device__ __forceinline__ RleTable rle_table(int slot) const {
     RleTable t;
-    t.starts = reinterpret_cast<const uint16_t *>(rle_base + (uint32_t)slot * rle_slot_bytes);
-    t.g2run = reinterpret_cast<const uint16_t *>(rle_base + (uint32_t)slot * rle_slot_bytes + rle_starts_bytes);
+    t.mask = reinterpret_cast<const uint32_t *>(rle_base + (uint32_t)slot * rle_slot_bytes);
+    t.pre = reinterpret_cast<const uint16_t *>(rle_base + (uint32_t)slot * rle_slot_bytes + rle_starts_bytes);
     return t;
   }
 };
@@ -486,6 +488,35 @@ __device__ __forceinline__ void load_block(uint8_t *smem, const uint8_t *src, ui
   mbar_wait(bar, parity);
 }
 
+// Builds the run table of RLE column d (see RleTable) with the whole team.
+__device__ __forceinline__ void rle_table_build(const uint8_t *s, const ColDesc &d, uint32_t rows, uint32_t *mask,
+                                                uint16_t *pre, const Team &t) {
+  const uint32_t nwords = (rows + 31u) >> 5;
+  for (uint32_t g = (uint32_t)t.tid; g < nwords; g += (uint32_t)t.nthreads) mask[g] = 0u;
+  t.sync();
+  for (uint32_t k = (uint32_t)t.tid; k < d.rle_count; k += (uint32_t)t.nthreads) {
+    const uint32_t start = ld_bits32(s, d.rle_row_ids_bit + k * d.rle_row_id_bits, d.rle_row_id_bits);
+    if (start < rows) atomicOr(&mask[start >> 5], 1u << (start & 31u));
+  }
+  t.sync();
+  if (t.tid < 32) {
+    uint32_t carry = 0;
+    for (uint32_t base = 0; base < nwords; base += 32u) {
+      const uint32_t g = base + (uint32_t)t.tid;
+      const uint32_t c = g < nwords ? (uint32_t)__popc(mask[g]) : 0u;
+      uint32_t inc = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+        if ((t.tid & 31) >= o) inc += u;
+      }
+      if (g < nwords) pre[g] = (uint16_t)(carry + inc - c);
+      carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+  }
+  t.sync();
+}
+
 // Parses the staged block (at g_smem + soff) and builds descriptors + RLE run tables. Returns false
 // (uniformly over the team) when the block cannot be handled; *corrupt tells why.
 __device__ __forceinline__ bool prepare_block(const ScanParams &p, uint32_t soff, uint32_t size, ColDesc *descs,
@@ -512,44 +543,18 @@ __device__ __forceinline__ bool prepare_block(const ScanParams &p, uint32_t soff
   c.descs = descs;
   c.rle_base = rle_base;
   c.rle_slot_bytes = p.rle_slot_bytes;
-  c.rle_starts_bytes = ((uint32_t)p.rle_runs_cap + 2u) * 2u;
+  c.rle_starts_bytes = p.words_cap * 4u;
   if (bad) return false;
   // RLE run tables
   if (p.n_rle_slots > 0) {
-    const uint32_t nwords = (c.b.row_count + 31u) >> 5;
-    bool any = false;
     for (int i = 0; i < p.n_used; ++i) {
       if (p.used_rle_slot[i] < 0) continue;
       const ColDesc &d = descs[i];
       if (d.kind != K_RLE) continue;
-      any = true;
-      uint16_t *starts = reinterpret_cast<uint16_t *>(rle_base + (uint32_t)d.rle_slot * p.rle_slot_bytes);
-      for (uint32_t k = (uint32_t)t.tid; k <= d.rle_count; k += (uint32_t)t.nthreads)
-        starts[k] = k < d.rle_count
-                        ? (uint16_t)ld_bits32(sblk, d.rle_row_ids_bit + k * d.rle_row_id_bits, d.rle_row_id_bits)
-                        : (uint16_t)0xFFFF;
+      uint8_t *slot = rle_base + (uint32_t)d.rle_slot * p.rle_slot_bytes;
+      rle_table_build(sblk, d, c.b.row_count, reinterpret_cast<uint32_t *>(slot),
+                      reinterpret_cast<uint16_t *>(slot + c.rle_starts_bytes), t);
     }
-    if (any) {
-      t.sync();
-      for (int i = 0; i < p.n_used; ++i) {
-        if (p.used_rle_slot[i] < 0) continue;
-        const ColDesc &d = descs[i];
-        if (d.kind != K_RLE) continue;
-        const uint16_t *starts = reinterpret_cast<const uint16_t *>(rle_base + (uint32_t)d.rle_slot * p.rle_slot_bytes);
-        uint16_t *g2run = reinterpret_cast<uint16_t *>(rle_base + (uint32_t)d.rle_slot * p.rle_slot_bytes +
-                                                       c.rle_starts_bytes);
-        for (uint32_t g = (uint32_t)t.tid; g < nwords; g += (uint32_t)t.nthreads) {
-          const uint32_t row = g * 32u;
-          uint32_t lo = 0, hi = d.rle_count;  // upper_bound(starts, row)
-          while (lo < hi) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (starts[mid] <= row) lo = mid + 1; else hi = mid;
-          }
-          g2run[g] = (uint16_t)(lo > 0 ? lo - 1 : 0);
-        }
-      }
-    }
-    t.sync();
   }
   return true;
 }
@@ -675,8 +680,9 @@ __device__ __forceinline__ void project_str_col(const ScanParams &p, const Block
 // blocksstable/ob_micro_block_cache.cpp:1345-1363).
 // =================================================================================================
 __global__ void __launch_bounds__(256) obgpu_index_kernel(const uint8_t *image, const uint64_t *blk_off,
-                                                          const uint32_t *blk_size, int n_blocks, int max_cols,
-                                                          ColDesc *plans, uint32_t *rows, uint32_t *col_span) {
+                                                          const uint32_t *blk_size, const int64_t *bm_word_off,
+                                                          int n_blocks, int max_cols, ColDesc *plans, uint32_t *rows,
+                                                          BlockRec *recs, uint32_t *col_span) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)n_blocks * max_cols) return;
   const int block = (int)(i / max_cols), col = (int)(i % max_cols);
@@ -686,7 +692,22 @@ __global__ void __launch_bounds__(256) obgpu_index_kernel(const uint8_t *image, 
   d.rle_slot = -1;
   if (b.ok) build_col_desc(b, col, d);
   plans[i] = d;
-  if (col == 0) rows[block] = b.ok ? b.row_count : 0u;
+  if (col == 0) {
+    rows[block] = b.ok ? b.row_count : 0u;
+    BlockRec r{};
+    r.off = blk_off[block];
+    r.bm_word_off = bm_word_off[block];
+    r.size = blk_size[block];
+    r.rows = b.ok ? b.row_count : 0u;
+    r.row_data_off = b.row_data_off;
+    r.row_index_off = b.row_index_off;
+    r.header_size = b.header_size;
+    r.column_count = (uint16_t)b.column_count;
+    r.var_col_cnt = b.var_col_cnt;
+    r.row_index_byte = b.row_index_byte;
+    r.ext_bit = b.ext_bit;
+    recs[block] = r;
+  }
   if (d.ok && (d.kind == K_BITS || d.kind == K_DICT)) {
     // bytes of the value / ref array from the enclosing 16-byte boundary (count kernel staging buffer)
     const uint32_t lo = (d.val_bit >> 3) & ~15u;
@@ -712,13 +733,14 @@ __global__ void __launch_bounds__(kThreads) obgpu_count_kernel(const __grid_cons
   Team t;
   t.tid = lane; t.nthreads = 32; t.warp = 0; t.nwarps = 1; t.lane = lane; t.bar_id = -1;
 
-  const uint32_t rows = p.rows[block];
-  uint32_t *gbm = p.bitmap_words + p.bm_word_off[block];
+  const BlockRec rec = p.recs[block];
+  const uint32_t rows = rec.rows;
+  uint32_t *gbm = p.bitmap_words + rec.bm_word_off;
   bool bad = rows == 0;
-  if (!bad && lane < p.n_used && p.used_in_filter[lane]) {
+  if (lane < p.n_used && p.used_in_filter[lane]) {
     const ColDesc d = p.plans[(int64_t)block * p.max_cols + p.used_col[lane]];
     descs[lane] = d;  // rle_slot stays -1: RLE filter columns use the run binary search here
-    bad = !d.ok;
+    bad = bad || !d.ok;
   }
   const bool any_bad = __any_sync(0xffffffffu, bad);
   if (any_bad) {
@@ -729,7 +751,8 @@ __global__ void __launch_bounds__(kThreads) obgpu_count_kernel(const __grid_cons
     return;
   }
   BlockCtx c;
-  parse_block(p.image + p.blk_off[block], p.blk_size[block], c.b);
+  const uint8_t *gblk = p.image + rec.off;
+  view_from_rec(rec, gblk, c.b);
   c.sbit = 0;
   c.descs = descs;
   c.bitsets = bitsets;
@@ -753,7 +776,6 @@ __global__ void __launch_bounds__(kThreads) obgpu_count_kernel(const __grid_cons
     const bool and_mode = p.simple_shape == 1;
     const int n_leaves = p.n_nodes == 1 ? 1 : p.n_nodes - 1;
     uint8_t *stage = wr + p.cw_stage;
-    const uint8_t *gblk = p.image + p.blk_off[block];
     bool inited = false;
     for (int i = 0; i < n_leaves; ++i) {
       const FilterNodeDev &nd = p.nodes[i];
@@ -909,9 +931,11 @@ __global__ void __launch_bounds__(kThreads) obgpu_project_kernel(const __grid_co
   uint32_t *bm = reinterpret_cast<uint32_t *>(scr + p.off_bm);
   uint32_t *wpre = reinterpret_cast<uint32_t *>(scr + p.off_wpre);
 
+  // one round trip: block record + the two prefix entries (independent loads)
+  const BlockRec rec = p.recs[tile];
   const int64_t base = p.sel_offset[tile];
   const uint32_t cnt = (uint32_t)(p.sel_offset[tile + 1] - base);
-  const uint32_t rows = p.rows[tile];
+  const uint32_t rows = rec.rows;
   if (rows == 0) {
     if (tid == 0) atomicOr(p.status, ST_CORRUPT);
     return;
@@ -921,25 +945,40 @@ __global__ void __launch_bounds__(kThreads) obgpu_project_kernel(const __grid_co
     if (tid == 0) atomicOr(p.status, ST_OVERFLOW);
     return;
   }
-  // ---- stage the block ------------------------------------------------------------------------------
-  const uint32_t size = p.blk_size[tile];
+  // ---- second round trip, all in flight together: TMA of the block, the block's decode plans, the
+  // first bitmap words ----------------------------------------------------------------------------------
+  const uint32_t size = rec.size;
   if (tid == 0) {
     mbar_init(&s_bar, 1);
     fence_barrier_init();
     mbar_expect_tx(&s_bar, (size + 15u) & ~15u);
-    tma_bulk_g2s(g_smem, p.image + p.blk_off[tile], (size + 15u) & ~15u, &s_bar);
+    tma_bulk_g2s(g_smem, p.image + rec.off, (size + 15u) & ~15u, &s_bar);
     s_next = 0;
   }
-  __syncthreads();  // barrier object + queue initialised before anyone uses them
-  const uint32_t nwords = (rows + 31u) >> 5;
+  ColDesc *plans_s = reinterpret_cast<ColDesc *>(scr + p.off_plans);
+  constexpr int kPieces = (int)(sizeof(ColDesc) / 16);
+  const int npieces = p.n_proj * kPieces;
+  uint4 pv0{}, pv1{};
+  {
+    const ColDesc *gp = p.plans + (int64_t)tile * p.max_cols;
+    if (tid < npieces)
+      pv0 = reinterpret_cast<const uint4 *>(gp + p.used_col[p.proj_used[tid / kPieces]])[tid % kPieces];
+    if (tid + kThreads < npieces)
+      pv1 = reinterpret_cast<const uint4 *>(gp + p.used_col[p.proj_used[(tid + kThreads) / kPieces]])[(tid + kThreads) % kPieces];
+  }
+  const uint32_t *gbm = p.bitmap_words + rec.bm_word_off;
   const bool all_rows = cnt == rows;
+  const uint32_t nwords = (rows + 31u) >> 5;
+  const uint32_t word0 = (!all_rows && (uint32_t)tid < nwords) ? gbm[tid] : 0u;
+  if (tid < npieces) reinterpret_cast<uint4 *>(plans_s)[tid] = pv0;
+  if (tid + kThreads < npieces) reinterpret_cast<uint4 *>(plans_s)[tid + kThreads] = pv1;
+  __syncthreads();  // barrier object, queue and plans initialised before anyone uses them
   // ---- bitmap words -> popcount prefix -> ascending selected-row list (overlaps the TMA) ------------------
   if (!all_rows) {
-    const uint32_t *gbm = p.bitmap_words + p.bm_word_off[tile];
     uint32_t run_total = 0;
     for (uint32_t base_w = 0; base_w < nwords; base_w += kThreads) {  // one pass for <= 4096 rows
       const uint32_t w = base_w + (uint32_t)tid;
-      const uint32_t word = w < nwords ? gbm[w] : 0u;
+      const uint32_t word = base_w == 0 ? word0 : (w < nwords ? gbm[w] : 0u);
       if (w < nwords) bm[w] = word;
       const uint32_t local = __popc(word);
       uint32_t inc = local;
@@ -970,20 +1009,15 @@ __global__ void __launch_bounds__(kThreads) obgpu_project_kernel(const __grid_co
   // ---- block landed ---------------------------------------------------------------------------------------
   mbar_wait(&s_bar, 0);
   BlockCtx c;
-  parse_block(g_smem, size, c.b);
-  if (!c.b.ok) {
-    if (tid == 0) atomicOr(p.status, ST_CORRUPT);
-    return;
-  }
+  view_from_rec(rec, g_smem, c.b);
   c.sbit = smem_u32(g_smem) * 8u;
   c.bitsets = nullptr;
-  // warp-private scratch: [ColDesc][RLE run table]
+  // warp-private scratch: [run values][RLE run table]
   uint8_t *wscr = scr + p.off_desc + (uint32_t)warp * p.pw_bytes;
-  ColDesc *wdesc = reinterpret_cast<ColDesc *>(wscr);
-  c.descs = wdesc;
+  c.descs = plans_s;
   c.rle_base = wscr + p.pw_rle;
   c.rle_slot_bytes = 0;  // one table per warp: slot 0
-  c.rle_starts_bytes = ((uint32_t)p.rle_runs_cap + 2u) * 2u;
+  c.rle_starts_bytes = p.words_cap * 4u;
 
   if (p.want_row_ids) {
     int32_t *rid = p.row_ids + base;
@@ -998,12 +1032,7 @@ __global__ void __launch_bounds__(kThreads) obgpu_project_kernel(const __grid_co
     if (lane == 0) pc = atomicAdd(&s_next, 1);
     pc = __shfl_sync(0xffffffffu, pc, 0);
     if (pc >= p.n_proj) break;
-    // plan of this column: 6 lanes x 16 bytes
-    {
-      const uint4 *src = reinterpret_cast<const uint4 *>(p.plans + (int64_t)tile * p.max_cols + p.used_col[p.proj_used[pc]]);
-      if (lane < (int)(sizeof(ColDesc) / 16)) reinterpret_cast<uint4 *>(wdesc)[lane] = src[lane];
-      __syncwarp();
-    }
+    ColDesc *wdesc = plans_s + pc;  // this column's plan: only this warp touches it
     const ColDesc &d = *wdesc;
     if (!d.ok) {
       if (lane == 0) atomicOr(p.status, ST_UNSUPPORTED);
@@ -1017,22 +1046,9 @@ __global__ void __launch_bounds__(kThreads) obgpu_project_kernel(const __grid_co
         continue;
       }
       if (lane == 0) wdesc->rle_slot = 0;
-      uint16_t *starts = reinterpret_cast<uint16_t *>(wscr + p.pw_rle);
-      uint16_t *g2run = reinterpret_cast<uint16_t *>(wscr + p.pw_rle + c.rle_starts_bytes);
-      const uint32_t rbit = c.sbit + d.rle_row_ids_bit, rw = d.rle_row_id_bits, n = d.rle_count;
-      for (uint32_t k = (uint32_t)lane; k <= n; k += 32u)
-        starts[k] = k < n ? (uint16_t)sbits32(rbit + k * rw, rw) : (uint16_t)0xFFFF;
-      __syncwarp();
-      for (uint32_t g = (uint32_t)lane; g < nwords; g += 32u) {
-        const uint32_t row = g * 32u;
-        uint32_t lo = 0, hi = n;  // upper_bound(starts, row)
-        while (lo < hi) {
-          const uint32_t mid = (lo + hi) >> 1;
-          if (starts[mid] <= row) lo = mid + 1; else hi = mid;
-        }
-        g2run[g] = (uint16_t)(lo > 0 ? lo - 1 : 0);
-      }
-      __syncwarp();
+      rle_table_build(g_smem, d, rows, reinterpret_cast<uint32_t *>(wscr + p.pw_rle),
+                      reinterpret_cast<uint16_t *>(wscr + p.pw_rle + c.rle_starts_bytes), t);
+      const uint32_t n = d.rle_count;
       if (d.sc != 5 && d.elem_len == 8) {
         // integer RLE column: decode each RUN once (value of run k), rows then only look up their run
         uint64_t *rvals = reinterpret_cast<uint64_t *>(wscr + p.pw_rvals);
@@ -1266,6 +1282,7 @@ struct obgpu_batch {
   // decode plans + row counts built by the index kernel at open
   ColDesc *d_plans = nullptr;
   uint32_t *d_rows = nullptr;
+  BlockRec *d_recs = nullptr;
   std::vector<uint32_t> col_span;      // per store index: max staged bytes of the value / ref array
 };
 
@@ -1561,15 +1578,18 @@ int obgpu_batch_open(obgpu_ctx *ctx, const void *image, int64_t image_size, cons
     const size_t plan_bytes = (size_t)n_blocks * b->max_cols * sizeof(ColDesc);
     void *dp = nullptr;
     const size_t rows_bytes = ((size_t)n_blocks * 4 + 63) & ~(size_t)63;
-    e = cudaMallocAsync(&dp, plan_bytes + rows_bytes + (size_t)b->max_cols * 4 + 64, ctx->stream);
+    const size_t rec_bytes = (size_t)n_blocks * sizeof(BlockRec);
+    e = cudaMallocAsync(&dp, plan_bytes + rows_bytes + rec_bytes + (size_t)b->max_cols * 4 + 64, ctx->stream);
     if (e == cudaSuccess) {
       b->d_plans = (ColDesc *)dp;
       b->d_rows = (uint32_t *)((uint8_t *)dp + plan_bytes);
-      uint32_t *d_span = (uint32_t *)((uint8_t *)dp + plan_bytes + rows_bytes);
+      b->d_recs = (BlockRec *)((uint8_t *)dp + plan_bytes + rows_bytes);
+      uint32_t *d_span = (uint32_t *)((uint8_t *)dp + plan_bytes + rows_bytes + rec_bytes);
       e = cudaMemsetAsync(d_span, 0, (size_t)b->max_cols * 4, ctx->stream);
       const int64_t nthreads = (int64_t)n_blocks * b->max_cols;
       obgpu_index_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, ctx->stream>>>(
-          b->d_image, b->d_blk_off, b->d_blk_size, n_blocks, (int)b->max_cols, b->d_plans, b->d_rows, d_span);
+          b->d_image, b->d_blk_off, b->d_blk_size, b->d_bm_word_off, n_blocks, (int)b->max_cols, b->d_plans,
+          b->d_rows, b->d_recs, d_span);
       if (e == cudaSuccess) e = cudaGetLastError();
       ctx->launches++;
       b->col_span.assign(b->max_cols, 0);
@@ -1752,7 +1772,7 @@ static void assign_rle_slots(const obgpu_batch *b, ScanParams &p) {
   const uint32_t rows_cap = std::max<uint32_t>(b->max_rows, 32u);
   p.rows_cap = rows_cap;
   p.words_cap = (rows_cap + 31u) / 32u;
-  p.rle_slot_bytes = p.n_rle_slots > 0 ? ((((uint32_t)p.rle_runs_cap + 2u) * 2u + p.words_cap * 2u + 15u) & ~15u) : 0u;
+  p.rle_slot_bytes = p.n_rle_slots > 0 ? ((p.words_cap * 6u + 15u) & ~15u) : 0u;
 }
 
 // single-block kernels: [block][bitsets][rle tables][descs]
@@ -1776,10 +1796,11 @@ static void layout_smem_scan(const obgpu_batch *b, ScanParams &p) {
   p.off_bm = s;   s += (p.words_cap * 4u + 15u) & ~15u;
   p.off_wpre = s; s += (p.words_cap * 4u + 15u) & ~15u;
   p.off_rle = s;
-  p.pw_rvals = ((uint32_t)sizeof(ColDesc) + 15u) & ~15u;
+  p.pw_rvals = 0;
   p.pw_rle = p.pw_rvals + (p.n_rle_slots > 0 ? (((uint32_t)p.rle_runs_cap + 2u) * 8u) : 0u);
-  p.pw_bytes = (p.pw_rle + (p.n_rle_slots > 0 ? (((uint32_t)p.rle_runs_cap + 2u) * 2u + p.words_cap * 2u) : 0u) + 15u) & ~15u;
+  p.pw_bytes = (p.pw_rle + (p.n_rle_slots > 0 ? p.words_cap * 6u : 0u) + 15u) & ~15u;
   p.off_desc = s; s += p.pw_bytes * (uint32_t)kWarps;
+  p.off_plans = s; s += (uint32_t)sizeof(ColDesc) * (uint32_t)std::max(p.n_proj, 1);
   p.scratch_bytes = (s + 127u) & ~127u;
   p.smem_scratch = (off + 127u) & ~127u;
   p.smem_total = p.smem_scratch + p.scratch_bytes;
@@ -1882,6 +1903,7 @@ int obgpu_scan(obgpu_batch *b, const obgpu_scan_spec *spec, obgpu_result **out) 
   p.n_blocks = n;
   p.plans = b->d_plans;
   p.rows = b->d_rows;
+  p.recs = b->d_recs;
   p.max_cols = (int32_t)b->max_cols;
   p.counts = (uint32_t *)(a + o_counts);
   p.tile_state = nullptr;

@@ -157,6 +157,39 @@ struct BlockView {
   uint8_t ok;
 };
 
+// Per-block record written once at batch open by the index kernel: everything the scan kernels
+// need to address a block and rebuild its BlockView with ONE dependent-free 48-byte load (instead
+// of a chain of table lookups followed by a header parse).
+struct alignas(16) BlockRec {
+  uint64_t off;           // byte offset of the block in the image
+  int64_t bm_word_off;    // first word of the block in the packed selection bitmap
+  uint32_t size;
+  uint32_t rows;          // 0: header rejected
+  uint32_t row_data_off;
+  uint32_t row_index_off;
+  uint32_t header_size;
+  uint16_t column_count;
+  uint16_t var_col_cnt;
+  uint8_t row_index_byte, ext_bit;
+  uint8_t pad[6];
+};
+static_assert(sizeof(BlockRec) == 48, "BlockRec is loaded as three 16-byte pieces");
+
+__device__ __forceinline__ void view_from_rec(const BlockRec &r, const uint8_t *s, BlockView &b) {
+  b.s = s;
+  b.size = r.size;
+  b.row_count = r.rows;
+  b.header_size = r.header_size;
+  b.column_count = r.column_count;
+  b.meta_off = r.header_size + 16u * r.column_count;
+  b.row_data_off = r.row_data_off;
+  b.row_index_off = r.row_index_off;
+  b.row_index_byte = r.row_index_byte;
+  b.ext_bit = r.ext_bit;
+  b.var_col_cnt = r.var_col_cnt;
+  b.ok = r.rows > 0;
+}
+
 __device__ __forceinline__ void parse_block(const uint8_t *s, uint32_t size, BlockView &b) {
   b.s = s;
   b.size = size;
@@ -382,17 +415,17 @@ __device__ __forceinline__ void build_col_desc(const BlockView &b, int col, ColD
 }
 
 // ---- RLE run table (per block, per RLE column, in shared memory) -------------------------------
-// starts[k] = first row of run k (k < count), starts[count] = 0xFFFF sentinel;
-// g2run[g]  = run containing row 32 * g. Built cooperatively by the whole CTA.
+// mask: one bit per row, set where a run starts; pre[g]: number of run starts before row 32 * g.
+// run(row) = rank of row among the run starts - 1: two loads + popc, no search, no divergence.
 struct RleTable {
-  const uint16_t *starts;
-  const uint16_t *g2run;
+  const uint32_t *mask;
+  const uint16_t *pre;
 };
 
 __device__ __forceinline__ uint32_t rle_run_of(const RleTable &t, uint32_t row) {
-  uint32_t k = t.g2run[row >> 5];
-  while (t.starts[k + 1] <= row) ++k;
-  return k;
+  const uint32_t w = row >> 5;
+  const uint32_t r = (uint32_t)t.pre[w] + (uint32_t)__popc(t.mask[w] & (0xffffffffu >> (31u - (row & 31u))));
+  return r ? r - 1u : 0u;
 }
 
 __device__ __forceinline__ uint32_t rle_ref_slow(const uint8_t *s, const ColDesc &d, uint32_t row) {
