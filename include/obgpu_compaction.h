@@ -1,0 +1,82 @@
+/* obgpu_compaction.h -- C-ABI of the B200-native major-compaction merge.
+ *
+ * Drop-in boundary for the reference's partition merger
+ *   compaction/ob_partition_merger.cpp:678-829   ObPartitionMajorMerger::merge_partition
+ *   compaction/ob_partition_rows_merger.cpp:815  ObPartitionMergeHelper::find_rowkey_minimum_iters
+ *   compaction/ob_partition_merge_fuser.cpp:106  ObMergeFuser::fuse_row (+ :284 end_fuse_row)
+ *   storage/ob_row_fuse.cpp:191-275              ObRowFuse::fuse_row (NOP fill, delete stops the fuse)
+ *   compaction/ob_partition_merger.cpp:648-676   inner_process (delete rows are dropped in a major merge)
+ * K sorted runs (one per table of the merge, table index ascending = older -> newer) are merged by
+ * rowkey; rows with the same rowkey are fused newest first; the result is the ordered row stream the
+ * reference hands to ObMacroBlockWriter::append_row. The runs arrive as decoded column arrays in HBM
+ * (obgpu_batch_decode_column turns an opened page batch into them), so the same entry point serves a
+ * single GPU and the range-partitioned multi-GPU merge (each rank merges the slices it received).
+ *
+ * Same conventions as obgpu_scan.h: int OB codes, no exceptions, caller-owned outputs. */
+#ifndef OBGPU_COMPACTION_H_
+#define OBGPU_COMPACTION_H_
+
+#include "obgpu_scan.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* blocksstable::ObDmlFlag (storage/blocksstable/ob_datum_row.h) */
+enum {
+  OBGPU_DF_NOT_EXIST = 0,
+  OBGPU_DF_LOCK = 1,
+  OBGPU_DF_UPDATE = 2,
+  OBGPU_DF_INSERT = 3,
+  OBGPU_DF_DELETE = 4
+};
+
+#define OBGPU_MERGE_MAX_RUNS 64
+#define OBGPU_MERGE_MAX_COLS 64
+
+/* All cells of integer-class column `col` of an opened batch, in row order, into caller-owned DEVICE
+ * buffers of total_rows entries: value image (what the reference would MEMCPY into the datum, 0 for
+ * ext cells) and ext (0 value, 1 NULL, 2 NOP -- ObStoredExtValue). Runs on the ctx stream. */
+int obgpu_batch_decode_column(obgpu_batch *batch, int32_t col, int64_t *dev_vals, uint8_t *dev_ext);
+
+/* One sorted run, decoded, resident in HBM (all pointers are device pointers; the vals / ext
+ * pointer ARRAYS themselves live in host memory). Rowkey: one INT64 column, ascending, unique
+ * inside the run. */
+typedef struct obgpu_merge_run {
+  int64_t n;
+  const int64_t *key;
+  const uint8_t *flag;         /* ObDmlFlag per row; NULL: every row DF_INSERT                  */
+  const int64_t *const *vals;  /* [n_cols] value arrays                                           */
+  const uint8_t *const *ext;   /* [n_cols] 0 value, 1 NULL, 2 NOP                                 */
+} obgpu_merge_run;
+
+typedef struct obgpu_merge_result obgpu_merge_result;
+
+/* runs[0] is the oldest table, runs[n_runs - 1] the newest. default_vals / default_null: the
+ * default row that fills cells still NOP after the fuse (ObMajorPartitionMergeFuser::end_fuse_row);
+ * NULL pointers mean "every default is NULL". */
+int obgpu_merge_decoded(obgpu_ctx *ctx, const obgpu_merge_run *runs, int32_t n_runs, int32_t n_cols,
+                        const int64_t *default_vals, const uint8_t *default_null,
+                        obgpu_merge_result **out);
+void obgpu_merge_result_free(obgpu_merge_result *res);
+
+typedef struct obgpu_merge_info {
+  int64_t in_rows;          /* rows of all runs                                              */
+  int64_t out_rows;         /* rows of the merged stream                                     */
+  int64_t dropped_deletes;  /* rowkeys whose fused row is a delete                           */
+  int64_t fused_rows;       /* output rows fused from more than one run                      */
+} obgpu_merge_info;
+/* Synchronises the ctx stream and reads back the totals. */
+int obgpu_merge_result_info(obgpu_merge_result *res, obgpu_merge_info *info);
+/* Device pointers of the merged stream (valid until obgpu_merge_result_free): rowkeys [out_rows],
+ * and per column values [out_rows] + null bytes (1 => NULL) [out_rows]. */
+int obgpu_merge_result_cols(obgpu_merge_result *res, const int64_t **key_dev,
+                            const int64_t *const **vals_dev, const uint8_t *const **null_dev);
+/* Device -> host copy of rows [row_begin, row_begin + row_count) of column `col` (-1: the rowkey). */
+int obgpu_merge_result_fetch(obgpu_merge_result *res, int32_t col, int64_t row_begin,
+                             int64_t row_count, int64_t *host_vals, uint8_t *host_null);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OBGPU_COMPACTION_H_ */

@@ -261,7 +261,7 @@ typedef struct obgpu_col_input {
   int32_t obj_type;        /* OBGPU_OBJ_*                                                      */
   int32_t encoding;        /* OBGPU_ENC_*                                                      */
   const int64_t *i64;      /* integer classes: value per row                                   */
-  const uint8_t *is_null;  /* optional: 1 => NULL                                              */
+  const uint8_t *is_null;  /* optional: 1 => NULL, 2 => NOP (cell absent in an incremental row)       */
   const char *str_heap;    /* string classes: bytes                                            */
   const int64_t *str_off;  /*   nrows + 1 offsets into str_heap                                */
   int32_t byte_packing_only; /* 1 => ObMicroBlockEncoderOpt.enable_bit_packing_ == false       */

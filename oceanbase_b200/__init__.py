@@ -11,6 +11,7 @@ from .capi import (  # noqa: F401
     WHITE_OP_IN, WHITE_OP_NU, WHITE_OP_NN,
     ENC_RAW, ENC_DICT, ENC_RLE, ENC_CONST, ENC_INTEGER_BASE_DIFF,
     OBJ_INT, OBJ_INT32, OBJ_UINT64, OBJ_VARCHAR, OBJ_DATE, OBJ_TINYINT, OBJ_SMALLINT, OBJ_UINT32,
+    DF_NOT_EXIST, DF_LOCK, DF_UPDATE, DF_INSERT, DF_DELETE,
 )
 from .sstable import Column, TableImage, encode_table, encode_block  # noqa: F401
 from .scan import (  # noqa: F401

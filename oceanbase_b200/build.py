@@ -7,7 +7,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB = os.path.join(CSRC, "libobgpu_scan.so")
 SOURCES = ["obgpu_scan.cu", "sstable_writer.cpp"]
-HEADERS = ["ob_format.h", "scan_device.cuh", os.path.join("..", "..", "include", "obgpu_scan.h")]
+HEADERS = ["ob_format.h", "scan_device.cuh", "merge_kernels.cuh", os.path.join("..", "..", "include", "obgpu_scan.h"),
+           os.path.join("..", "..", "include", "obgpu_compaction.h")]
 
 
 def nvcc_path():

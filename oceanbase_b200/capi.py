@@ -63,8 +63,22 @@ class ColInput(C.Structure):
                 ("reserved", C.c_int32)]
 
 
+DF_NOT_EXIST, DF_LOCK, DF_UPDATE, DF_INSERT, DF_DELETE = range(5)  # blocksstable::ObDmlFlag
+
+
+class MergeRun(C.Structure):
+    _fields_ = [("n", C.c_int64), ("key", C.c_void_p), ("flag", C.c_void_p), ("vals", C.POINTER(C.c_void_p)),
+                ("ext", C.POINTER(C.c_void_p))]
+
+
+class MergeInfo(C.Structure):
+    _fields_ = [("in_rows", C.c_int64), ("out_rows", C.c_int64), ("dropped_deletes", C.c_int64),
+                ("fused_rows", C.c_int64)]
+
+
 def declared_signatures():
-    """name -> (restype, argtypes) for every symbol include/obgpu_scan.h declares."""
+    """name -> (restype, argtypes) for every symbol include/obgpu_scan.h and include/obgpu_compaction.h
+    declare."""
     vp, i32, i64, u64 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64
     P = C.POINTER
     return {
@@ -101,6 +115,13 @@ def declared_signatures():
         "obgpu_table_image_export": (C.c_int, [vp, vp, i64, vp, vp, i32]),
         "obgpu_table_image_free": (None, [vp]),
         "obgpu_version": (C.c_char_p, []),
+        # include/obgpu_compaction.h
+        "obgpu_batch_decode_column": (C.c_int, [vp, i32, vp, vp]),
+        "obgpu_merge_decoded": (C.c_int, [vp, P(MergeRun), i32, i32, vp, vp, P(vp)]),
+        "obgpu_merge_result_free": (None, [vp]),
+        "obgpu_merge_result_info": (C.c_int, [vp, P(MergeInfo)]),
+        "obgpu_merge_result_cols": (C.c_int, [vp, P(vp), P(P(vp)), P(P(vp))]),
+        "obgpu_merge_result_fetch": (C.c_int, [vp, i32, i64, i64, vp, vp]),
     }
 
 

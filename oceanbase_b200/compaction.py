@@ -1,0 +1,265 @@
+"""Major-compaction merge: host mirror of include/obgpu_compaction.h plus the multi-GPU driver.
+
+Reference: ObPartitionMajorMerger::merge_partition (compaction/ob_partition_merger.cpp:678-829) merges
+the tables of a tablet by rowkey and fuses rows of one rowkey newest first; parallel merge cuts the
+rowkey space into ranges at macro-block boundaries (ObParallelMergeCtx,
+compaction/ob_partition_parallel_merge_ctx.cpp:187-424) and merges every range independently, the
+outputs being concatenated in range order. The multi-GPU driver below does the same with one range
+per rank: sample rowkeys -> all_gather -> pick world-1 splitters -> every rank sends the slice of each
+run it owns to the rank owning that range (the one exchange step of the path, NCCL over NVLink) ->
+local K-way merge on the device -> rank order is global rowkey order.
+
+torch is used for device memory and torch.distributed only; the merge itself is libobgpu_scan.so.
+"""
+import ctypes as C
+from dataclasses import dataclass
+from typing import Callable, Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import capi
+from .capi import lib, check
+
+
+@dataclass
+class DecodedRun:
+    """One sorted run as dense column tensors (device tensors for the GPU path)."""
+    key: object                    # int64 [n]
+    flag: Optional[object]         # uint8 [n] ObDmlFlag, or None = every row DF_INSERT
+    vals: List[object]             # n_cols x int64 [n]
+    ext: List[object]              # n_cols x uint8 [n]  (0 value, 1 NULL, 2 NOP)
+
+    @property
+    def n(self):
+        return int(self.key.shape[0])
+
+    def slice(self, lo, hi):
+        return DecodedRun(self.key[lo:hi], None if self.flag is None else self.flag[lo:hi],
+                          [v[lo:hi] for v in self.vals], [e[lo:hi] for e in self.ext])
+
+
+def decode_run(ctx, table, key_col: int, flag_col: Optional[int], cols: Sequence[int], device=None,
+               device_image_ptr: Optional[int] = None) -> DecodedRun:
+    """Opens `table` as a page batch on ctx and decodes rowkey, flag and payload columns into torch
+    tensors on the ctx device (obgpu_batch_decode_column)."""
+    import torch
+    device = device or torch.device("cuda", torch.cuda.current_device())
+    batch = ctx.open_batch(table, device_image_ptr=device_image_ptr)
+    n = batch.total_rows
+
+    def dec(col):
+        v = torch.empty(n, dtype=torch.int64, device=device)
+        e = torch.empty(n, dtype=torch.uint8, device=device)
+        check(lib.obgpu_batch_decode_column(batch._h, col, v.data_ptr(), e.data_ptr()), "obgpu_batch_decode_column", ctx._h)
+        return v, e
+
+    key, key_ext = dec(key_col)
+    flag = None
+    if flag_col is not None:
+        fv, _ = dec(flag_col)
+        flag = fv.to(torch.uint8)
+    vals, ext = [], []
+    for c in cols:
+        v, e = dec(c)
+        vals.append(v)
+        ext.append(e)
+    batch.close()
+    if bool((key_ext != 0).any()):
+        raise capi.ObGpuError(capi.OB_INVALID_DATA, "decode_run", "rowkey column holds NULL / NOP cells")
+    return DecodedRun(key, flag, vals, ext)
+
+
+class MergeResult:
+    def __init__(self, ctx, handle, n_cols, keep):
+        self.ctx, self._h, self.n_cols, self._keep = ctx, handle, n_cols, keep
+
+    def info(self) -> capi.MergeInfo:
+        info = capi.MergeInfo()
+        check(lib.obgpu_merge_result_info(self._h, C.byref(info)), "obgpu_merge_result_info", self.ctx._h)
+        return info
+
+    def fetch(self, col: int, row_begin=0, row_count=None):
+        """(values int64, null bytes) of output column `col` (-1: rowkey) on the host."""
+        n = self.info().out_rows
+        if row_count is None:
+            row_count = n - row_begin
+        v = np.empty(row_count, dtype=np.int64)
+        nl = np.empty(row_count, dtype=np.uint8)
+        check(lib.obgpu_merge_result_fetch(self._h, col, row_begin, row_count, v.ctypes.data, nl.ctypes.data),
+              "obgpu_merge_result_fetch", self.ctx._h)
+        return v, nl
+
+    def free(self):
+        if self._h and self.ctx._h:
+            lib.obgpu_merge_result_free(self._h)
+        self._h = C.c_void_p()
+        self._keep = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def merge_decoded(ctx, runs: Sequence[DecodedRun], default_vals=None, default_null=None) -> MergeResult:
+    """obgpu_merge_decoded over device-resident runs (runs[0] oldest ... runs[-1] newest)."""
+    n_cols = len(runs[0].vals)
+    arr = (capi.MergeRun * len(runs))()
+    keep = []
+    for i, r in enumerate(runs):
+        assert len(r.vals) == n_cols and len(r.ext) == n_cols
+        vp = (C.c_void_p * max(n_cols, 1))(*[v.data_ptr() for v in r.vals])
+        ep = (C.c_void_p * max(n_cols, 1))(*[e.data_ptr() for e in r.ext])
+        keep += [vp, ep, r]
+        arr[i].n = r.n
+        arr[i].key = r.key.data_ptr()
+        arr[i].flag = r.flag.data_ptr() if r.flag is not None else None
+        arr[i].vals = vp
+        arr[i].ext = ep
+    dv = dn = None
+    if default_vals is not None:
+        dv = np.ascontiguousarray(default_vals, dtype=np.int64)
+    if default_null is not None:
+        dn = np.ascontiguousarray(default_null, dtype=np.uint8)
+    h = C.c_void_p()
+    check(lib.obgpu_merge_decoded(ctx._h, arr, len(runs), n_cols, dv.ctypes.data if dv is not None else None,
+                                  dn.ctypes.data if dn is not None else None, C.byref(h)), "obgpu_merge_decoded", ctx._h)
+    return MergeResult(ctx, h, n_cols, keep)
+
+
+# ---- multi-GPU: range partition + one exchange step ----------------------------------------------------
+def choose_splitters(candidates, world: int):
+    """world-1 splitters at the quantiles of the gathered rowkey samples (sorted, duplicates kept)."""
+    import torch
+    c, _ = torch.sort(candidates)
+    if world <= 1 or c.numel() == 0:
+        return c[:0]
+    idx = (torch.arange(1, world, device=c.device, dtype=torch.int64) * c.numel()) // world
+    return c[idx.clamp(max=c.numel() - 1)]
+
+
+def _pack(run: DecodedRun, lo: int, hi: int):
+    """One contiguous byte buffer per (run, destination): int64 sections first (alignment), then bytes."""
+    import torch
+    n = hi - lo
+    n_cols = len(run.vals)
+    buf = torch.empty(n * (8 * (1 + n_cols) + 1 + n_cols), dtype=torch.uint8, device=run.key.device)
+    i64 = buf[:8 * n * (1 + n_cols)].view(torch.int64)
+    i64[:n] = run.key[lo:hi]
+    for c in range(n_cols):
+        i64[(1 + c) * n:(2 + c) * n] = run.vals[c][lo:hi]
+    b = buf[8 * n * (1 + n_cols):]
+    if run.flag is None:
+        b[:n] = capi.DF_INSERT
+    else:
+        b[:n] = run.flag[lo:hi]
+    for c in range(n_cols):
+        b[(1 + c) * n:(2 + c) * n] = run.ext[c][lo:hi]
+    return buf
+
+
+def _unpack(buf, n: int, n_cols: int) -> DecodedRun:
+    import torch
+    i64 = buf[:8 * n * (1 + n_cols)].view(torch.int64)
+    b = buf[8 * n * (1 + n_cols):]
+    return DecodedRun(i64[:n], b[:n], [i64[(1 + c) * n:(2 + c) * n] for c in range(n_cols)],
+                      [b[(1 + c) * n:(2 + c) * n] for c in range(n_cols)])
+
+
+def distributed_major_merge(local_runs: Dict[int, DecodedRun], n_runs_total: int, n_cols: int,
+                            merge_fn: Callable[[List[DecodedRun]], object], group=None, samples_per_run: int = 1024):
+    """Range-partitioned merge over the ranks of `group`.
+
+    local_runs: run index -> DecodedRun for the runs this rank holds (every run index in
+    [0, n_runs_total) is held by exactly one rank). merge_fn merges a list of DecodedRun ordered oldest
+    -> newest and returns whatever the caller wants back (the GPU path passes merge_decoded).
+    Returns (merge_fn result for this rank's rowkey range, splitters, received row counts)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    some = next(iter(local_runs.values())) if local_runs else None
+    device = some.key.device if some is not None else torch.device("cpu")
+    # 1. candidates: evenly spaced rowkeys of every local run; padded with the maximum so that the gather is rectangular
+    per_rank_slots = samples_per_run * n_runs_total
+    cand = torch.full((per_rank_slots,), torch.iinfo(torch.int64).max, dtype=torch.int64, device=device)
+    valid = torch.zeros((), dtype=torch.int64, device=device)
+    at = 0
+    for q in sorted(local_runs):
+        r = local_runs[q]
+        if r.n == 0:
+            continue
+        k = min(samples_per_run, r.n)
+        idx = (torch.arange(k, device=device, dtype=torch.int64) * r.n) // k
+        cand[at:at + k] = r.key[idx]
+        at += k
+    valid += at
+    if world > 1:
+        gathered = [torch.empty_like(cand) for _ in range(world)]
+        dist.all_gather(gathered, cand, group=group)
+        counts = [torch.empty_like(valid) for _ in range(world)]
+        dist.all_gather(counts, valid, group=group)
+        allc = torch.cat([g[:int(c)] for g, c in zip(gathered, counts)])
+    else:
+        allc = cand[:at]
+    splitters = choose_splitters(allc, world)
+    # 2. slice boundaries of every local run, row-count matrix [run, destination]
+    bounds = {}
+    cnt = torch.zeros((n_runs_total, world), dtype=torch.int64, device=device)
+    for q, r in local_runs.items():
+        b = torch.searchsorted(r.key.contiguous(), splitters, right=False) if world > 1 else splitters.new_zeros(0)
+        b = [0] + [int(x) for x in b.tolist()] + [r.n]
+        bounds[q] = b
+        cnt[q] = torch.tensor([b[j + 1] - b[j] for j in range(world)], dtype=torch.int64, device=device)
+    owner = torch.full((n_runs_total,), -1, dtype=torch.int64, device=device)
+    for q in local_runs:
+        owner[q] = rank
+    if world > 1:
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM, group=group)      # every row of cnt is filled by exactly one rank
+        dist.all_reduce(owner, op=dist.ReduceOp.MAX, group=group)
+    cnt_h = cnt.cpu().numpy()
+    owner_h = owner.cpu().numpy()
+    if (owner_h < 0).any():
+        raise ValueError("every run index must be held by exactly one rank")
+    # 3. the exchange: one packed buffer per (run, destination)
+    recv = {}
+    ops, keep = [], []
+    row_bytes = 8 * (1 + n_cols) + 1 + n_cols
+    for q in range(n_runs_total):
+        o = int(owner_h[q])
+        if o == rank:
+            b = bounds[q]
+            for j in range(world):
+                n = b[j + 1] - b[j]
+                if j == rank:
+                    recv[q] = local_runs[q].slice(b[j], b[j + 1])
+                elif n > 0:
+                    buf = _pack(local_runs[q], b[j], b[j + 1])
+                    keep.append(buf)
+                    ops.append(dist.P2POp(dist.isend, buf, j if group is None else dist.get_global_rank(group, j), group))
+        else:
+            n = int(cnt_h[q][rank])
+            if n > 0:
+                buf = torch.empty(n * row_bytes, dtype=torch.uint8, device=device)
+                recv[q] = (buf, n)
+                ops.append(dist.P2POp(dist.irecv, buf, o if group is None else dist.get_global_rank(group, o), group))
+            else:
+                recv[q] = None
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    runs = []
+    for q in range(n_runs_total):
+        x = recv.get(q)
+        if x is None:
+            z = torch.zeros(0, dtype=torch.int64, device=device)
+            zb = torch.zeros(0, dtype=torch.uint8, device=device)
+            runs.append(DecodedRun(z, zb, [z] * n_cols, [zb] * n_cols))
+        elif isinstance(x, tuple):
+            runs.append(_unpack(x[0], x[1], n_cols))
+        else:
+            runs.append(x)
+    if device.type == "cuda":
+        torch.cuda.current_stream(device).synchronize()  # the merge runs on the ctx stream
+    return merge_fn(runs), splitters, cnt_h[:, rank].copy()

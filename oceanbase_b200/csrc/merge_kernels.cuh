@@ -1,0 +1,552 @@
+// merge_kernels.cuh -- major-compaction merge on the device (included at the end of obgpu_scan.cu:
+// it uses the batch / ctx internals and the prefix kernels of the scan).
+//
+// Reference path (include/obgpu_compaction.h has the file:line list): a loser tree pops the run
+// heads in (rowkey ascending, newer table first) order, rows of one rowkey are fused newest first,
+// delete rows are dropped. Here:
+//   1. the K sorted runs are merged PAIRWISE with merge-path tiles (ceil(log2 K) passes over
+//      (rowkey, source) pairs, ties resolved "newer run first"), which yields exactly the pop order
+//      of the loser tree;
+//   2. group heads (first element of a rowkey) decide emit / drop from the newest existing row;
+//   3. an exclusive scan of the emit flags gives the dense output index;
+//   4. every emitting head fuses its group column by column (first non-NOP cell newest -> oldest,
+//      stopping at a delete row, defaults for what stays NOP) and writes the output row.
+// HBM-bound: (rowkey, source) pairs are read and written once per pass (16 B per row per pass),
+// payload cells are gathered once.
+#pragma once
+
+namespace mrg {
+
+constexpr int kTile = 2048;     // outputs per CTA in a merge pass
+constexpr int kThreads = 256;
+constexpr int kVT = kTile / kThreads;
+constexpr int kSrcShift = 40;   // source = run << 40 | row index inside the run
+constexpr int kFuseTile = 1024;
+
+struct Pair {        // one 2-way merge of a pass: A = [a0, a1), B = [b0, b1) of the input arrays
+  int64_t a0, a1, b0, b1, out0;
+  int64_t tile0;     // first tile of this pair in the pass's grid
+};
+
+struct RunsDev {
+  const int64_t *const *key;    // [K]
+  const uint8_t *const *flag;   // [K] (entries may be null)
+  const int64_t *const *vals;   // [K * n_cols]
+  const uint8_t *const *ext;    // [K * n_cols]
+  int32_t n_runs, n_cols;
+};
+
+__global__ void __launch_bounds__(256) init_kernel(const int64_t *key, int64_t n, uint64_t run, int64_t *kout,
+                                                   uint64_t *sout) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    kout[i] = key[i];
+    sout[i] = (run << kSrcShift) | (uint64_t)i;
+  }
+}
+
+// number of A elements among the first d outputs of merge(A, B), B first on equal keys
+__device__ __forceinline__ int64_t merge_path_g(const int64_t *a, int64_t na, const int64_t *b, int64_t nb, int64_t d) {
+  int64_t lo = d > nb ? d - nb : 0, hi = d < na ? d : na;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (a[mid] < b[d - 1 - mid]) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+__device__ __forceinline__ int merge_path_s(const int64_t *a, int na, const int64_t *b, int nb, int d) {
+  int lo = d > nb ? d - nb : 0, hi = d < na ? d : na;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (a[mid] < b[d - 1 - mid]) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(kThreads) pass_kernel(const int64_t *__restrict__ kin, const uint64_t *__restrict__ sin,
+                                                        int64_t *__restrict__ kout, uint64_t *__restrict__ sout,
+                                                        const Pair *__restrict__ pairs, int n_pairs) {
+  __shared__ int64_t s_key[kTile];
+  __shared__ uint64_t s_src[kTile];
+  __shared__ int64_t s_split[2];
+  const int tid = threadIdx.x;
+  int p = 0;
+  while (p + 1 < n_pairs && pairs[p + 1].tile0 <= (int64_t)blockIdx.x) ++p;
+  const Pair pr = pairs[p];
+  const int64_t na = pr.a1 - pr.a0, nb = pr.b1 - pr.b0;
+  const int64_t d0 = ((int64_t)blockIdx.x - pr.tile0) * kTile;
+  const int64_t d1 = d0 + kTile < na + nb ? d0 + kTile : na + nb;
+  const int64_t *A = kin + pr.a0, *B = kin + pr.b0;
+  if (tid < 2) s_split[tid] = merge_path_g(A, na, B, nb, tid == 0 ? d0 : d1);
+  __syncthreads();
+  const int64_t i0 = s_split[0], i1 = s_split[1];
+  const int64_t j0 = d0 - i0, j1 = d1 - i1;
+  const int ca = (int)(i1 - i0), cb = (int)(j1 - j0), total = ca + cb;
+  // stage: A part at [0, ca), B part at [ca, ca + cb)
+  for (int k = tid; k < total; k += kThreads) {
+    const int64_t g = k < ca ? pr.a0 + i0 + k : pr.b0 + j0 + (k - ca);
+    s_key[k] = kin[g];
+    s_src[k] = sin[g];
+  }
+  __syncthreads();
+  // per-thread merge of kVT consecutive outputs
+  const int od0 = tid * kVT < total ? tid * kVT : total;
+  const int od1 = od0 + kVT < total ? od0 + kVT : total;
+  int ia = merge_path_s(s_key, ca, s_key + ca, cb, od0);
+  int ib = od0 - ia;
+  int64_t rk[kVT];
+  uint64_t rs[kVT];
+#pragma unroll
+  for (int k = 0; k < kVT; ++k) {
+    if (od0 + k < od1) {
+      const bool take_b = ib < cb && (ia >= ca || s_key[ca + ib] <= s_key[ia]);
+      const int at = take_b ? ca + ib : ia;
+      rk[k] = s_key[at];
+      rs[k] = s_src[at];
+      if (take_b) ++ib; else ++ia;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < kVT; ++k) {
+    if (od0 + k < od1) {
+      s_key[od0 + k] = rk[k];
+      s_src[od0 + k] = rs[k];
+    }
+  }
+  __syncthreads();
+  for (int k = tid; k < total; k += kThreads) {
+    kout[pr.out0 + d0 + k] = s_key[k];
+    sout[pr.out0 + d0 + k] = s_src[k];
+  }
+}
+
+__device__ __forceinline__ int flag_of(const RunsDev &r, uint64_t src) {
+  const int run = (int)(src >> kSrcShift);
+  const uint8_t *f = r.flag[run];
+  return f ? (int)f[src & ((1ull << kSrcShift) - 1)] : OBGPU_DF_INSERT;
+}
+
+// Per element: is it the head of its rowkey group, and does the group emit a row? (decided by the
+// newest row that exists: delete -> dropped, insert / update -> emitted.) Writes emit[i] and the
+// number of emitting heads of the tile.
+__global__ void __launch_bounds__(256) head_kernel(const int64_t *__restrict__ keys, const uint64_t *__restrict__ src, int64_t n,
+                                                   RunsDev runs, uint8_t *__restrict__ emit, uint32_t *__restrict__ tile_count,
+                                                   unsigned long long *__restrict__ stats, int *__restrict__ status) {
+  __shared__ uint32_t s_cnt;
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
+  uint32_t mine = 0;
+  for (int k = 0; k < kFuseTile / 256; ++k) {
+    const int64_t i = (int64_t)blockIdx.x * kFuseTile + k * 256 + threadIdx.x;
+    if (i >= n) break;
+    const int64_t key = keys[i];
+    uint8_t e = 0;
+    if (i == 0 || keys[i - 1] != key) {
+      bool decided = false;
+      for (int64_t j = i; j < n && keys[j] == key && !decided; ++j) {
+        const int f = flag_of(runs, src[j]);
+        if (f == OBGPU_DF_NOT_EXIST) continue;
+        decided = true;
+        if (f == OBGPU_DF_DELETE) atomicAdd(&stats[0], 1ull);
+        else if (f == OBGPU_DF_INSERT || f == OBGPU_DF_UPDATE) e = 1;
+        else atomicOr(status, ST_CORRUPT);
+      }
+    }
+    emit[i] = e;
+    mine += e;
+  }
+  atomicAdd(&s_cnt, mine);
+  __syncthreads();
+  if (threadIdx.x == 0) tile_count[blockIdx.x] = s_cnt;
+}
+
+// Emitting heads fuse their group and write the output row at tile_off[tile] + rank inside the tile.
+__global__ void __launch_bounds__(256) fuse_kernel(const int64_t *__restrict__ keys, const uint64_t *__restrict__ src, int64_t n,
+                                                   RunsDev runs, const uint8_t *__restrict__ emit,
+                                                   const int64_t *__restrict__ tile_off, const int64_t *__restrict__ default_vals,
+                                                   const uint8_t *__restrict__ default_null, int64_t *__restrict__ out_key,
+                                                   int64_t *const *__restrict__ out_vals, uint8_t *const *__restrict__ out_null,
+                                                   unsigned long long *__restrict__ stats) {
+  __shared__ uint32_t s_warp[8];
+  __shared__ uint32_t s_base;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_base = 0;
+  __syncthreads();
+  const int64_t base_out = tile_off[blockIdx.x];
+  for (int k = 0; k < kFuseTile / 256; ++k) {
+    const int64_t i = (int64_t)blockIdx.x * kFuseTile + k * 256 + tid;
+    const uint32_t e = i < n ? emit[i] : 0u;
+    // rank among the emitting heads of this 256-element slice
+    const uint32_t bal = __ballot_sync(0xffffffffu, e != 0);
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    uint32_t woff = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      woff += w < warp ? s_warp[w] : 0u;
+      tot += s_warp[w];
+    }
+    const uint32_t rank = s_base + woff + __popc(bal & ((1u << lane) - 1u));
+    __syncthreads();
+    if (tid == 0) s_base += tot;
+    if (e) {
+      const int64_t o = base_out + rank;
+      const int64_t key = keys[i];
+      out_key[o] = key;
+      // rows of the group, newest first; the fuse stops at a delete row (final_result)
+      int64_t jend = i;
+      int rows = 0;
+      for (int64_t j = i; j < n && keys[j] == key; ++j) {
+        const int f = flag_of(runs, src[j]);
+        if (f == OBGPU_DF_DELETE) break;
+        jend = j + 1;
+        if (f != OBGPU_DF_NOT_EXIST) ++rows;
+      }
+      const uint64_t idx_mask = (1ull << kSrcShift) - 1;
+      for (int c = 0; c < runs.n_cols; ++c) {
+        int64_t v = 0;
+        uint8_t st = 2;  // NOP until a cell is found
+        for (int64_t j = i; j < jend && st == 2; ++j) {
+          const uint64_t s = src[j];
+          if (flag_of(runs, s) == OBGPU_DF_NOT_EXIST) continue;
+          const int run = (int)(s >> kSrcShift);
+          const int64_t at = (int64_t)(s & idx_mask);
+          const uint8_t x = runs.ext[run * runs.n_cols + c][at];
+          if (x != 2) {
+            st = x;
+            v = x ? 0 : runs.vals[run * runs.n_cols + c][at];
+          }
+        }
+        if (st == 2) {  // ObMajorPartitionMergeFuser::end_fuse_row: default row
+          const bool dn = default_null ? default_null[c] != 0 : true;
+          st = dn ? 1 : 0;
+          v = dn ? 0 : (default_vals ? default_vals[c] : 0);
+        }
+        out_vals[c][o] = v;
+        out_null[c][o] = st;
+      }
+      if (rows > 1) atomicAdd(&stats[1], 1ull);
+    }
+    __syncthreads();
+  }
+}
+
+// ---- run decode: every cell of one integer column of a batch -> (value, ext) ---------------------
+__global__ void __launch_bounds__(128) decode_col_kernel(const uint8_t *__restrict__ image, const BlockRec *__restrict__ recs,
+                                                         const ColDesc *__restrict__ plans, int max_cols, int col,
+                                                         const int64_t *__restrict__ row_start, int64_t *__restrict__ vals,
+                                                         uint8_t *__restrict__ ext, int *__restrict__ status) {
+  __shared__ ColDesc s_d;
+  const int block = blockIdx.x;
+  const BlockRec rec = recs[block];
+  if (threadIdx.x < (int)(sizeof(ColDesc) / 16))
+    reinterpret_cast<uint4 *>(&s_d)[threadIdx.x] =
+        reinterpret_cast<const uint4 *>(plans + (int64_t)block * max_cols + col)[threadIdx.x];
+  __syncthreads();
+  const ColDesc &d = s_d;
+  if (rec.rows == 0 || !d.ok || d.sc == 5) {
+    if (threadIdx.x == 0) atomicOr(status, rec.rows == 0 ? ST_CORRUPT : ST_UNSUPPORTED);
+    return;
+  }
+  BlockView b;
+  const uint8_t *s = image + rec.off;
+  view_from_rec(rec, s, b);
+  int64_t *ov = vals + row_start[block];
+  uint8_t *oe = ext + row_start[block];
+  for (uint32_t row = threadIdx.x; row < rec.rows; row += blockDim.x) {
+    uint64_t v = 0;
+    uint8_t e = 0;
+    if (is_dict_kind(d)) {
+      const uint32_t ref = ref_of(s, d, nullptr, row);
+      if (ref >= d.dict_count) e = ref == d.dict_count ? 1 : 2;
+      else v = dict_int(s, d, ref);
+    } else {
+      if (d.ext_bit) {
+        const uint32_t x = ld_bits32(s, d.ext_bit_off + row * d.ext_bit, d.ext_bit);
+        e = x == STORED_NOT_EXT ? 0 : (x == STORED_NULL ? 1 : 2);
+      }
+      if (!e) {
+        v = ld_bits(s, d.val_bit + row * d.stride, d.width) + d.base;
+        if (d.sign_fix) v = sign_fix(d.int_mask, v);
+      }
+    }
+    if (d.elem_len == 4) v &= 0xffffffffull;
+    else if (d.elem_len == 1) v &= 0xffull;
+    ov[row] = (int64_t)v;
+    oe[row] = e;
+  }
+}
+
+}  // namespace mrg
+
+struct obgpu_merge_result {
+  obgpu_ctx *ctx = nullptr;
+  void *arena = nullptr;      // pair buffers, emit flags, tables, outputs
+  int32_t n_cols = 0;
+  int64_t in_rows = 0;
+  int64_t *d_out_key = nullptr;
+  std::vector<int64_t *> out_vals;
+  std::vector<uint8_t *> out_null;
+  int64_t *d_tile_off = nullptr;  // n_tiles + 1
+  int64_t n_tiles = 0;
+  unsigned long long *d_stats = nullptr;
+  int *d_status = nullptr;
+  bool info_valid = false;
+  obgpu_merge_info info{};
+  std::vector<const int64_t *> vals_view;
+  std::vector<const uint8_t *> null_view;
+};
+
+extern "C" {
+
+int obgpu_batch_decode_column(obgpu_batch *b, int32_t col, int64_t *dev_vals, uint8_t *dev_ext) {
+  if (!b || !dev_vals || !dev_ext || col < 0 || (uint32_t)col >= b->max_cols) return OBGPU_INVALID_ARGUMENT;
+  obgpu_ctx *ctx = b->ctx;
+  cudaSetDevice(ctx->device);
+  const int n = b->n_blocks;
+  std::vector<int64_t> start((size_t)n + 1, 0);
+  for (int i = 0; i < n; ++i) start[(size_t)i + 1] = start[(size_t)i] + b->row_count[(size_t)i];
+  void *d = nullptr;
+  cudaError_t e = cudaMallocAsync(&d, ((size_t)n + 1) * 8 + 64, ctx->stream);
+  if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return OBGPU_ALLOCATE_MEMORY_FAILED; }
+  int64_t *d_start = (int64_t *)d;
+  int *d_status = (int *)((uint8_t *)d + ((size_t)n + 1) * 8);
+  cudaMemsetAsync(d_status, 0, 4, ctx->stream);
+  cudaMemcpyAsync(d_start, start.data(), ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream);
+  mrg::decode_col_kernel<<<n, 128, 0, ctx->stream>>>(b->d_image, b->d_recs, b->d_plans, (int)b->max_cols, col, d_start,
+                                                     dev_vals, dev_ext, d_status);
+  ctx->launches++;
+  int status = 0;
+  cudaMemcpyAsync(&status, d_status, 4, cudaMemcpyDeviceToHost, ctx->stream);
+  e = cudaStreamSynchronize(ctx->stream);  // `start` is pageable host memory: wait before it goes away
+  cudaFreeAsync(d, ctx->stream);
+  if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return OBGPU_ERR_SYS; }
+  return check_status(ctx, status);
+}
+
+int obgpu_merge_decoded(obgpu_ctx *ctx, const obgpu_merge_run *runs, int32_t n_runs, int32_t n_cols,
+                        const int64_t *default_vals, const uint8_t *default_null, obgpu_merge_result **out) {
+  if (!ctx || !runs || !out || n_runs <= 0 || n_runs > OBGPU_MERGE_MAX_RUNS || n_cols < 0 || n_cols > OBGPU_MERGE_MAX_COLS)
+    return OBGPU_INVALID_ARGUMENT;
+  int64_t N = 0;
+  for (int r = 0; r < n_runs; ++r) {
+    if (runs[r].n < 0 || runs[r].n >= (1ll << mrg::kSrcShift) || (runs[r].n > 0 && !runs[r].key)) return OBGPU_INVALID_ARGUMENT;
+    if (n_cols > 0 && runs[r].n > 0 && (!runs[r].vals || !runs[r].ext)) return OBGPU_INVALID_ARGUMENT;
+    N += runs[r].n;
+  }
+  cudaSetDevice(ctx->device);
+  obgpu_merge_result *res = new (std::nothrow) obgpu_merge_result();
+  if (!res) return OBGPU_ALLOCATE_MEMORY_FAILED;
+  res->ctx = ctx;
+  res->n_cols = n_cols;
+  res->in_rows = N;
+  const int64_t n_tiles = (N + mrg::kFuseTile - 1) / mrg::kFuseTile;
+  res->n_tiles = n_tiles;
+  // ---- arena -----------------------------------------------------------------------------------------
+  auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  size_t o = 0;
+  const size_t o_k0 = o; o += al((size_t)N * 8);
+  const size_t o_s0 = o; o += al((size_t)N * 8);
+  const size_t o_k1 = o; o += al((size_t)N * 8);
+  const size_t o_s1 = o; o += al((size_t)N * 8);
+  const size_t o_emit = o; o += al((size_t)N);
+  const size_t o_cnt = o; o += al(((size_t)n_tiles + 1) * 4);
+  const size_t o_off = o; o += al(((size_t)n_tiles + 2) * 8);
+  const size_t n_chunks = (size_t)((n_tiles + kPrefixChunk - 1) / kPrefixChunk);
+  const size_t o_chunk = o; o += al((n_chunks + 1) * 8);
+  const size_t o_stats = o; o += al(64);
+  const size_t tbl_entries = (size_t)n_runs * 2 + (size_t)n_runs * n_cols * 2 + (size_t)n_cols * 2;
+  const size_t o_tbl = o; o += al(tbl_entries * 8);
+  const size_t o_def = o; o += al((size_t)n_cols * 9 + 16);
+  const size_t o_pairs = o; o += al(sizeof(mrg::Pair) * (size_t)(n_runs + 1) * 8);
+  const size_t o_okey = o; o += al((size_t)N * 8);
+  std::vector<size_t> o_ov((size_t)n_cols), o_on((size_t)n_cols);
+  for (int c = 0; c < n_cols; ++c) { o_ov[(size_t)c] = o; o += al((size_t)N * 8); }
+  for (int c = 0; c < n_cols; ++c) { o_on[(size_t)c] = o; o += al((size_t)N); }
+  cudaError_t e = cudaMallocAsync(&res->arena, o + 256, ctx->stream);
+  if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); delete res; return OBGPU_ALLOCATE_MEMORY_FAILED; }
+  uint8_t *a = (uint8_t *)res->arena;
+  int64_t *k0 = (int64_t *)(a + o_k0), *k1 = (int64_t *)(a + o_k1);
+  uint64_t *s0 = (uint64_t *)(a + o_s0), *s1 = (uint64_t *)(a + o_s1);
+  uint8_t *emit = a + o_emit;
+  uint32_t *tile_cnt = (uint32_t *)(a + o_cnt);
+  res->d_tile_off = (int64_t *)(a + o_off);
+  res->d_stats = (unsigned long long *)(a + o_stats);
+  res->d_status = (int *)(a + o_stats + 32);
+  res->d_out_key = (int64_t *)(a + o_okey);
+  cudaMemsetAsync(a + o_stats, 0, 64, ctx->stream);
+  // ---- pointer tables (host -> device) ------------------------------------------------------------------
+  std::vector<uint64_t> tbl(tbl_entries, 0);
+  size_t t = 0;
+  const size_t t_key = t; for (int r = 0; r < n_runs; ++r) tbl[t++] = (uint64_t)runs[r].key;
+  const size_t t_flag = t; for (int r = 0; r < n_runs; ++r) tbl[t++] = (uint64_t)runs[r].flag;
+  const size_t t_vals = t;
+  for (int r = 0; r < n_runs; ++r) for (int c = 0; c < n_cols; ++c) tbl[t++] = runs[r].n > 0 ? (uint64_t)runs[r].vals[c] : 0;
+  const size_t t_ext = t;
+  for (int r = 0; r < n_runs; ++r) for (int c = 0; c < n_cols; ++c) tbl[t++] = runs[r].n > 0 ? (uint64_t)runs[r].ext[c] : 0;
+  const size_t t_ov = t;
+  for (int c = 0; c < n_cols; ++c) { res->out_vals.push_back((int64_t *)(a + o_ov[(size_t)c])); tbl[t++] = (uint64_t)res->out_vals.back(); }
+  const size_t t_on = t;
+  for (int c = 0; c < n_cols; ++c) { res->out_null.push_back(a + o_on[(size_t)c]); tbl[t++] = (uint64_t)res->out_null.back(); }
+  uint64_t *d_tbl = (uint64_t *)(a + o_tbl);
+  // defaults: [n_cols] int64 then [n_cols] bytes
+  std::vector<uint8_t> defs((size_t)n_cols * 9 + 16, 0);
+  for (int c = 0; c < n_cols; ++c) {
+    const int64_t v = default_vals ? default_vals[c] : 0;
+    memcpy(defs.data() + (size_t)c * 8, &v, 8);
+    defs[(size_t)n_cols * 8 + (size_t)c] = default_null ? default_null[c] : 1;
+  }
+  // merge passes (host plan)
+  struct Seg { int64_t begin, end; };
+  std::vector<Seg> segs;
+  {
+    int64_t at = 0;
+    for (int r = 0; r < n_runs; ++r) { segs.push_back({at, at + runs[r].n}); at += runs[r].n; }
+  }
+  std::vector<std::vector<mrg::Pair>> passes;
+  {
+    std::vector<Seg> cur = segs;
+    while (cur.size() > 1) {
+      std::vector<mrg::Pair> ps;
+      std::vector<Seg> next;
+      int64_t tile0 = 0;
+      for (size_t i = 0; i < cur.size(); i += 2) {
+        mrg::Pair p{};
+        p.a0 = cur[i].begin; p.a1 = cur[i].end;   // A = older group
+        if (i + 1 < cur.size()) { p.b0 = cur[i + 1].begin; p.b1 = cur[i + 1].end; }
+        else { p.b0 = p.b1 = cur[i].end; }
+        p.out0 = p.a0;
+        p.tile0 = tile0;
+        const int64_t tot = (p.a1 - p.a0) + (p.b1 - p.b0);
+        tile0 += (tot + mrg::kTile - 1) / mrg::kTile;
+        ps.push_back(p);
+        next.push_back({p.a0, p.a0 + tot});
+      }
+      mrg::Pair sentinel{};
+      sentinel.tile0 = tile0;
+      ps.push_back(sentinel);
+      passes.push_back(ps);
+      cur = next;
+    }
+  }
+  std::vector<mrg::Pair> all_pairs;
+  std::vector<size_t> pass_at;
+  for (auto &ps : passes) { pass_at.push_back(all_pairs.size()); all_pairs.insert(all_pairs.end(), ps.begin(), ps.end()); }
+  // one pinned-free upload: tables, defaults, pairs are small pageable buffers -> synchronous staging is fine
+  cudaMemcpyAsync(d_tbl, tbl.data(), tbl_entries * 8, cudaMemcpyHostToDevice, ctx->stream);
+  cudaMemcpyAsync(a + o_def, defs.data(), defs.size(), cudaMemcpyHostToDevice, ctx->stream);
+  if (!all_pairs.empty())
+    cudaMemcpyAsync(a + o_pairs, all_pairs.data(), all_pairs.size() * sizeof(mrg::Pair), cudaMemcpyHostToDevice, ctx->stream);
+  e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); obgpu_merge_result_free(res); return OBGPU_ERR_SYS; }
+  // ---- launches ----------------------------------------------------------------------------------------------
+  for (int r = 0; r < n_runs; ++r) {
+    if (runs[r].n == 0) continue;
+    mrg::init_kernel<<<(unsigned)((runs[r].n + 255) / 256), 256, 0, ctx->stream>>>(runs[r].key, runs[r].n, (uint64_t)r,
+                                                                                 k0 + segs[(size_t)r].begin, s0 + segs[(size_t)r].begin);
+    ctx->launches++;
+  }
+  int64_t *kin = k0, *kout = k1;
+  uint64_t *sin = s0, *sout = s1;
+  for (size_t ps = 0; ps < passes.size(); ++ps) {
+    const int n_pairs = (int)passes[ps].size() - 1;
+    const int64_t tiles = passes[ps].back().tile0;
+    if (tiles > 0) {
+      mrg::pass_kernel<<<(unsigned)tiles, mrg::kThreads, 0, ctx->stream>>>(
+          kin, sin, kout, sout, (const mrg::Pair *)(a + o_pairs) + pass_at[ps], n_pairs);
+      ctx->launches++;
+    }
+    std::swap(kin, kout);
+    std::swap(sin, sout);
+  }
+  mrg::RunsDev rd;
+  rd.key = (const int64_t *const *)(d_tbl + t_key);
+  rd.flag = (const uint8_t *const *)(d_tbl + t_flag);
+  rd.vals = (const int64_t *const *)(d_tbl + t_vals);
+  rd.ext = (const uint8_t *const *)(d_tbl + t_ext);
+  rd.n_runs = n_runs;
+  rd.n_cols = n_cols;
+  if (N > 0) {
+    mrg::head_kernel<<<(unsigned)n_tiles, 256, 0, ctx->stream>>>(kin, sin, N, rd, emit, tile_cnt, res->d_stats, res->d_status);
+    const int nc = (int)n_chunks;
+    obgpu_prefix_local_kernel<<<nc, 256, 0, ctx->stream>>>(tile_cnt, (int)n_tiles, res->d_tile_off,
+                                                          (unsigned long long *)(a + o_chunk));
+    obgpu_prefix_fix_kernel<<<nc + 1, 256, 0, ctx->stream>>>((int)n_tiles, nc, res->d_tile_off,
+                                                            (const unsigned long long *)(a + o_chunk));
+    mrg::fuse_kernel<<<(unsigned)n_tiles, 256, 0, ctx->stream>>>(
+        kin, sin, N, rd, emit, res->d_tile_off, (const int64_t *)(a + o_def), (const uint8_t *)(a + o_def + (size_t)n_cols * 8),
+        res->d_out_key, (int64_t *const *)(d_tbl + t_ov), (uint8_t *const *)(d_tbl + t_on), res->d_stats);
+    ctx->launches += 4;
+  } else {
+    cudaMemsetAsync(res->d_tile_off, 0, 16, ctx->stream);
+  }
+  e = cudaGetLastError();
+  if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); obgpu_merge_result_free(res); return OBGPU_ERR_SYS; }
+  for (int c = 0; c < n_cols; ++c) { res->vals_view.push_back(res->out_vals[(size_t)c]); res->null_view.push_back(res->out_null[(size_t)c]); }
+  *out = res;
+  return OBGPU_SUCCESS;
+}
+
+void obgpu_merge_result_free(obgpu_merge_result *res) {
+  if (!res) return;
+  cudaSetDevice(res->ctx->device);
+  if (res->arena) cudaFreeAsync(res->arena, res->ctx->stream);
+  delete res;
+}
+
+int obgpu_merge_result_info(obgpu_merge_result *res, obgpu_merge_info *info) {
+  if (!res || !info) return OBGPU_INVALID_ARGUMENT;
+  obgpu_ctx *ctx = res->ctx;
+  cudaSetDevice(ctx->device);
+  if (!res->info_valid) {
+    unsigned long long st[2] = {0, 0};
+    int64_t total = 0;
+    int status = 0;
+    cudaMemcpyAsync(st, res->d_stats, 16, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaMemcpyAsync(&status, res->d_status, 4, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaMemcpyAsync(&total, res->d_tile_off + res->n_tiles, 8, cudaMemcpyDeviceToHost, ctx->stream);
+    const cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return OBGPU_ERR_SYS; }
+    const int ret = check_status(ctx, status);
+    if (ret != OBGPU_SUCCESS) return ret;
+    res->info.in_rows = res->in_rows;
+    res->info.out_rows = res->in_rows > 0 ? total : 0;
+    res->info.dropped_deletes = (int64_t)st[0];
+    res->info.fused_rows = (int64_t)st[1];
+    res->info_valid = true;
+  }
+  *info = res->info;
+  return OBGPU_SUCCESS;
+}
+
+int obgpu_merge_result_cols(obgpu_merge_result *res, const int64_t **key_dev, const int64_t *const **vals_dev,
+                            const uint8_t *const **null_dev) {
+  if (!res) return OBGPU_INVALID_ARGUMENT;
+  if (key_dev) *key_dev = res->d_out_key;
+  if (vals_dev) *vals_dev = res->vals_view.data();
+  if (null_dev) *null_dev = res->null_view.data();
+  return OBGPU_SUCCESS;
+}
+
+int obgpu_merge_result_fetch(obgpu_merge_result *res, int32_t col, int64_t row_begin, int64_t row_count,
+                             int64_t *host_vals, uint8_t *host_null) {
+  if (!res || col < -1 || col >= res->n_cols || row_begin < 0 || row_count < 0) return OBGPU_INVALID_ARGUMENT;
+  obgpu_merge_info info;
+  const int ret = obgpu_merge_result_info(res, &info);
+  if (ret != OBGPU_SUCCESS) return ret;
+  if (row_begin + row_count > info.out_rows) return OBGPU_INVALID_ARGUMENT;
+  obgpu_ctx *ctx = res->ctx;
+  if (row_count == 0) return OBGPU_SUCCESS;
+  const int64_t *src = col < 0 ? res->d_out_key : res->out_vals[(size_t)col];
+  if (host_vals) cudaMemcpyAsync(host_vals, src + row_begin, (size_t)row_count * 8, cudaMemcpyDeviceToHost, ctx->stream);
+  if (host_null) {
+    if (col < 0) memset(host_null, 0, (size_t)row_count);
+    else cudaMemcpyAsync(host_null, res->out_null[(size_t)col] + row_begin, (size_t)row_count, cudaMemcpyDeviceToHost, ctx->stream);
+  }
+  const cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return OBGPU_ERR_SYS; }
+  return OBGPU_SUCCESS;
+}
+
+}  // extern "C"

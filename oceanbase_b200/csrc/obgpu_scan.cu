@@ -111,6 +111,7 @@ struct ScanParams {
   uint32_t cw_desc, cw_bm, cw_bitset, cw_stage, cw_stage_bytes, cw_bytes;  // count kernel, per-warp: descs | bm | bitsets | stage
   uint32_t pw_rle, pw_rvals, pw_bytes;  // project kernel, per-warp region at off_desc: run values (u64) | RLE run table
   uint32_t off_plans;                   // project kernel: the block's n_proj decode plans (ColDesc), prefetched
+  int32_t compact;                      // project kernel stages only the projected columns' regions (packed)
   uint32_t off_sel, off_bm, off_wpre, off_rle, off_desc;  // inside one scratch
   uint32_t smem_total;
   uint32_t rle_slot_bytes;    // bytes per run-table slot: mask[words_cap] (u32) + pre[words_cap] (u16)
@@ -708,11 +709,10 @@ __global__ void __launch_bounds__(256) obgpu_index_kernel(const uint8_t *image, 
     r.ext_bit = b.ext_bit;
     recs[block] = r;
   }
-  if (d.ok && (d.kind == K_BITS || d.kind == K_DICT)) {
-    // bytes of the value / ref array from the enclosing 16-byte boundary (count kernel staging buffer)
-    const uint32_t lo = (d.val_bit >> 3) & ~15u;
-    const uint32_t hi = ((d.val_bit + b.row_count * d.stride + 7u) >> 3) + 16u;
-    atomicMax(&col_span[col], (hi - lo + 15u) & ~15u);
+  if (d.ok) {
+    // bytes of the column's region (count kernel staging buffer, project kernel column staging)
+    uint32_t lo, hi;
+    if (col_region(d, b, lo, hi)) atomicMax(&col_span[col], hi - lo);
   }
 }
 
@@ -761,7 +761,7 @@ __global__ void __launch_bounds__(kThreads) obgpu_count_kernel(const __grid_cons
   c.rle_starts_bytes = 0;
   const uint32_t nwords = (rows + 31u) >> 5;
   __syncwarp();
-  if (p.n_slots > 0) {
+  if (p.n_slots > 0 && p.simple_shape == 0) {
     for (int i = 0; i < p.n_nodes; ++i) {
       const FilterNodeDev &nd = p.nodes[i];
       if (nd.kind != NODE_WHITE || nd.slot < 0) continue;
@@ -777,19 +777,20 @@ __global__ void __launch_bounds__(kThreads) obgpu_count_kernel(const __grid_cons
     const int n_leaves = p.n_nodes == 1 ? 1 : p.n_nodes - 1;
     uint8_t *stage = wr + p.cw_stage;
     bool inited = false;
+    int staged_idx = -1;  // used-column index currently held by the staging buffer
+    BlockCtx cs = c;
     for (int i = 0; i < n_leaves; ++i) {
       const FilterNodeDev &nd = p.nodes[i];
       const ColDesc &d = descs[nd.used_idx];
-      // stage the leaf column's value / ref array: every lane pulls 16-byte pieces, all loads in flight
-      bool staged = false;
-      BlockCtx cs = c;
-      if (p.cw_stage_bytes > 0 && nd.op != OP_FALSE && nd.op != OP_TRUE && (d.kind == K_BITS || d.kind == K_DICT)) {
-        const uint32_t lo = (d.val_bit >> 3) & ~15u;
-        const uint32_t nbytes = ((((d.val_bit + rows * d.stride + 7u) >> 3) + 16u) - lo + 15u) & ~15u;
-        if (nbytes <= p.cw_stage_bytes) {
+      // stage the leaf column's region (ext bits, values / refs, run arrays, dictionary): every lane
+      // pulls 16-byte pieces, 4 loads in flight per lane; all later reads hit shared memory
+      bool staged = staged_idx == nd.used_idx;
+      if (!staged && p.cw_stage_bytes > 0 && nd.op != OP_FALSE && nd.op != OP_TRUE) {
+        uint32_t lo, hi;
+        if (col_region(d, c.b, lo, hi) && hi - lo <= p.cw_stage_bytes && hi > lo) {
           const uint4 *src = reinterpret_cast<const uint4 *>(gblk + lo);
           uint4 *dst = reinterpret_cast<uint4 *>(stage);
-          const uint32_t n16 = nbytes >> 4;
+          const uint32_t n16 = (hi - lo) >> 4;
           __syncwarp();
           for (uint32_t k = (uint32_t)lane; k < n16; k += 128u) {
             uint4 v0 = src[k], v1{}, v2{}, v3{};
@@ -802,9 +803,17 @@ __global__ void __launch_bounds__(kThreads) obgpu_count_kernel(const __grid_cons
             if (k + 96u < n16) dst[k + 96u] = v3;
           }
           __syncwarp();
+          cs.b.s = stage - lo;  // block-relative offsets inside [lo, hi) now resolve to shared memory
           cs.sbit = (smem_u32(stage) - lo) * 8u;
           staged = true;
+          staged_idx = nd.used_idx;
+        } else {
+          staged_idx = -1;
         }
+      }
+      if (nd.slot >= 0 && is_dict_kind(d)) {
+        build_dict_bitset(p, staged ? cs.b : c.b, d, nd, bitsets + nd.slot * p.bitset_words, t);
+        __syncwarp();
       }
       if (i == 0) {
         const bool fast = staged ? leaf_first_fast<false>(p, cs, nd, bm, rows, nwords, t)
@@ -823,6 +832,14 @@ __global__ void __launch_bounds__(kThreads) obgpu_count_kernel(const __grid_cons
       if (staged) leaf_over_words<false>(p, cs, nd, bm, rows, nwords, and_mode, t);
       else leaf_over_words<true>(p, c, nd, bm, rows, nwords, and_mode, t);
       __syncwarp();
+      if (i + 1 < n_leaves) {
+        // the reference's early-out (ob_pushdown_filter.cpp:1603-1615): AND stops once the bitmap is
+        // all-false, OR once it is all-true
+        bool undecided = false;
+        for (uint32_t g = (uint32_t)lane; g < nwords; g += 32u)
+          undecided = undecided || (and_mode ? bm[g] != 0u : bm[g] != valid_mask_of(rows, g));
+        if (!__any_sync(0xffffffffu, undecided)) break;
+      }
     }
     for (uint32_t g = (uint32_t)lane; g < nwords; g += 32u) {
       const uint32_t w = bm[g];
@@ -923,6 +940,7 @@ __global__ void __launch_bounds__(kThreads) obgpu_project_kernel(const __grid_co
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ int s_next;
   __shared__ uint32_t s_scan[kWarps];
+  __shared__ int32_t s_delta[kMaxProj];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tile = blockIdx.x;
@@ -951,8 +969,10 @@ __global__ void __launch_bounds__(kThreads) obgpu_project_kernel(const __grid_co
   if (tid == 0) {
     mbar_init(&s_bar, 1);
     fence_barrier_init();
-    mbar_expect_tx(&s_bar, (size + 15u) & ~15u);
-    tma_bulk_g2s(g_smem, p.image + rec.off, (size + 15u) & ~15u, &s_bar);
+    if (!p.compact) {
+      mbar_expect_tx(&s_bar, (size + 15u) & ~15u);
+      tma_bulk_g2s(g_smem, p.image + rec.off, (size + 15u) & ~15u, &s_bar);
+    }
     s_next = 0;
   }
   ColDesc *plans_s = reinterpret_cast<ColDesc *>(scr + p.off_plans);
@@ -973,6 +993,41 @@ __global__ void __launch_bounds__(kThreads) obgpu_project_kernel(const __grid_co
   if (tid < npieces) reinterpret_cast<uint4 *>(plans_s)[tid] = pv0;
   if (tid + kThreads < npieces) reinterpret_cast<uint4 *>(plans_s)[tid + kThreads] = pv1;
   __syncthreads();  // barrier object, queue and plans initialised before anyone uses them
+  BlockCtx c;
+  view_from_rec(rec, g_smem, c.b);
+  if (p.compact) {
+    // Only the projected columns' regions are staged, packed back to back: lane pc of warp 0 issues
+    // the bulk copy of column pc; s_delta[pc] = (offset in shared memory) - (offset in the block), so
+    // block-relative addressing keeps working once the base is shifted by it.
+    if (warp == 0) {
+      uint32_t lo = 0, hi = 0;
+      bool ok = false, var = false;
+      if (lane < p.n_proj) {
+        const ColDesc &d = plans_s[lane];
+        ok = d.ok && col_region(d, c.b, lo, hi) && hi > lo;
+        var = ok && d.kind == K_VARSTR;
+      }
+      // RAW var-length columns share one copy of the row data
+      const uint32_t vmask = __ballot_sync(0xffffffffu, var);
+      const int vfirst = __ffs(vmask) - 1;
+      const bool dup = var && lane != vfirst;
+      const uint32_t bytes = ok && !dup ? hi - lo : 0u;
+      uint32_t inc = bytes;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += u;
+      }
+      uint32_t so = inc - bytes;
+      const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+      const uint32_t vso = __shfl_sync(0xffffffffu, so, vfirst < 0 ? 0 : vfirst);
+      if (dup) so = vso;
+      if (lane < p.n_proj) s_delta[lane] = (int32_t)so - (int32_t)lo;
+      if (lane == 0) mbar_expect_tx(&s_bar, total);
+      __syncwarp();
+      if (bytes) tma_bulk_g2s(g_smem + so, p.image + rec.off + lo, bytes, &s_bar);
+    }
+  }
   // ---- bitmap words -> popcount prefix -> ascending selected-row list (overlaps the TMA) ------------------
   if (!all_rows) {
     uint32_t run_total = 0;
@@ -1008,8 +1063,6 @@ __global__ void __launch_bounds__(kThreads) obgpu_project_kernel(const __grid_co
   }
   // ---- block landed ---------------------------------------------------------------------------------------
   mbar_wait(&s_bar, 0);
-  BlockCtx c;
-  view_from_rec(rec, g_smem, c.b);
   c.sbit = smem_u32(g_smem) * 8u;
   c.bitsets = nullptr;
   // warp-private scratch: [run values][RLE run table]
@@ -1024,7 +1077,7 @@ __global__ void __launch_bounds__(kThreads) obgpu_project_kernel(const __grid_co
     if (all_rows) for (uint32_t j = (uint32_t)tid; j < cnt; j += kThreads) rid[j] = (int32_t)j;
     else for (uint32_t j = (uint32_t)tid; j < cnt; j += kThreads) rid[j] = (int32_t)sel[j];
   }
-  const uint64_t blk_addr = p.string_base + p.blk_off[tile];
+  const uint64_t blk_addr = p.string_base + rec.off;
   Team t;  // one warp per column
   t.tid = lane; t.nthreads = 32; t.warp = 0; t.nwarps = 1; t.lane = lane; t.bar_id = -1;
   for (;;) {
@@ -1034,6 +1087,11 @@ __global__ void __launch_bounds__(kThreads) obgpu_project_kernel(const __grid_co
     if (pc >= p.n_proj) break;
     ColDesc *wdesc = plans_s + pc;  // this column's plan: only this warp touches it
     const ColDesc &d = *wdesc;
+    if (p.compact) {  // rebase onto this column's staged region
+      const int32_t delta = s_delta[pc];
+      c.b.s = g_smem + delta;
+      c.sbit = (smem_u32(g_smem) + (uint32_t)delta) * 8u;
+    }
     if (!d.ok) {
       if (lane == 0) atomicOr(p.status, ST_UNSUPPORTED);
       __syncwarp();
@@ -1046,7 +1104,7 @@ __global__ void __launch_bounds__(kThreads) obgpu_project_kernel(const __grid_co
         continue;
       }
       if (lane == 0) wdesc->rle_slot = 0;
-      rle_table_build(g_smem, d, rows, reinterpret_cast<uint32_t *>(wscr + p.pw_rle),
+      rle_table_build(c.b.s, d, rows, reinterpret_cast<uint32_t *>(wscr + p.pw_rle),
                       reinterpret_cast<uint16_t *>(wscr + p.pw_rle + c.rle_starts_bytes), t);
       const uint32_t n = d.rle_count;
       if (d.sc != 5 && d.elem_len == 8) {
@@ -1789,6 +1847,27 @@ static void layout_smem(const obgpu_batch *b, ScanParams &p, bool /*need_sel*/) 
 static void layout_smem_scan(const obgpu_batch *b, ScanParams &p) {
   assign_rle_slots(b, p);
   p.stage_bytes = (b->max_block_bytes + 16u + 127u) & ~127u;
+  {
+    // stage only the projected columns when that is clearly less than the whole block (upper bound:
+    // per-column maximum region over the batch's blocks)
+    uint64_t sum = 0;
+    bool known = p.n_proj > 0;
+    for (int i = 0; i < p.n_proj && known; ++i) {
+      const size_t col = (size_t)p.used_col[p.proj_used[i]];
+      if (col >= b->col_span.size()) known = false;
+      else sum += b->col_span[col];
+    }
+    p.compact = 0;
+    if (known && sum * 4 <= (uint64_t)p.stage_bytes * 3) {
+      p.compact = 1;
+      p.stage_bytes = ((uint32_t)sum + 127u) & ~127u;
+    }
+    if (const char *e = getenv("OBGPU_PROJECT_COMPACT")) {  // testing knob: force either mode
+      const int want = atoi(e);
+      if (want == 0) { p.compact = 0; p.stage_bytes = (b->max_block_bytes + 16u + 127u) & ~127u; }
+      else if (known && want == 1) { p.compact = 1; p.stage_bytes = ((uint32_t)sum + 127u) & ~127u; }
+    }
+  }
   uint32_t off = p.stage_bytes;
   p.smem_bitset = off; off += ((uint32_t)p.n_slots * (uint32_t)p.bitset_words * 4u + 15u) & ~15u;
   uint32_t s = 0;
@@ -1809,12 +1888,15 @@ static void layout_smem_scan(const obgpu_batch *b, ScanParams &p) {
   p.cw_desc = w;   w += ((uint32_t)sizeof(ColDesc) * (uint32_t)std::max(p.n_used, 1) + 15u) & ~15u;
   p.cw_bm = w;     w += (p.words_cap * 4u + 15u) & ~15u;
   p.cw_bitset = w; w += ((uint32_t)p.n_slots * (uint32_t)p.bitset_words * 4u + 15u) & ~15u;
-  // staging buffer for the filter columns' value / ref arrays (coalesced 16-byte loads); skipped
-  // when a column's span would blow the per-warp budget (then the kernel reads global directly)
+  // staging buffer for one filter column's region at a time (coalesced 16-byte loads); a column whose
+  // region exceeds the per-warp budget is read from global memory directly
   uint32_t span = 0;
-  for (int i = 0; i < p.n_used; ++i)
-    if (p.used_in_filter[i] && (size_t)p.used_col[i] < b->col_span.size()) span = std::max(span, b->col_span[(size_t)p.used_col[i]]);
-  p.cw_stage_bytes = span > 0 && span <= 12288u ? span + 32u : 0u;
+  for (int i = 0; i < p.n_used; ++i) {
+    if (!p.used_in_filter[i] || (size_t)p.used_col[i] >= b->col_span.size()) continue;
+    const uint32_t sp = b->col_span[(size_t)p.used_col[i]];
+    if (sp <= 24576u) span = std::max(span, sp);  // larger columns are read from global memory
+  }
+  p.cw_stage_bytes = span;
   p.cw_stage = (w + 15u) & ~15u; w = p.cw_stage + p.cw_stage_bytes;
   p.cw_bytes = (w + 127u) & ~127u;
 }
@@ -2271,3 +2353,7 @@ int obgpu_project_discrete(obgpu_batch *batch, int32_t block, int32_t col, const
 }
 
 }  // extern "C"
+
+// ---- major-compaction merge (include/obgpu_compaction.h) -----------------------------------------
+#include "../../include/obgpu_compaction.h"
+#include "merge_kernels.cuh"

@@ -414,6 +414,48 @@ __device__ __forceinline__ void build_col_desc(const BlockView &b, int col, ColD
   }
 }
 
+// Byte range [lo, hi) of the block that a scan of column d touches (lo 16-byte aligned, hi padded by
+// 16 for the funnel-shift over-read). Everything a fixed / bit-packed / DICT / RLE / CONST column
+// needs -- ext bits, values or refs, run arrays, dictionary -- lies inside its column region; RAW
+// var-length strings need the row data + row index instead.
+__device__ __forceinline__ bool col_region(const ColDesc &d, const BlockView &bv, uint32_t &lo, uint32_t &hi) {
+  const uint32_t rows = bv.row_count;
+  uint32_t a, b;
+  switch (d.kind) {
+    case K_VARSTR:  // cells live in the row data, addressed through the row index at the block tail
+      a = bv.row_data_off;
+      b = bv.size;
+      break;
+    case K_BITS:
+      a = (d.ext_bit ? (d.ext_bit_off < d.val_bit ? d.ext_bit_off : d.val_bit) : d.val_bit) >> 3;
+      b = (d.val_bit + rows * d.stride + 7u) >> 3;
+      break;
+    case K_FIXSTR:
+      a = d.ext_bit ? d.ext_bit_off >> 3 : d.val_bit;
+      b = d.val_bit + rows * d.dict_data_size;
+      break;
+    case K_DICT:
+      a = d.dict_payload;
+      b = (d.val_bit + rows * d.stride + 7u) >> 3;
+      if (b < d.dict_end) b = d.dict_end;
+      break;
+    case K_RLE:
+      a = d.rle_row_ids_bit >> 3;
+      b = d.dict_end;
+      break;
+    case K_CONST:
+      a = d.rle_count ? d.rle_refs_bit >> 3 : d.dict_payload;
+      b = d.dict_end;
+      if (d.dict_count == 0 && d.rle_count == 0) { a = 0; b = 0; }
+      break;
+    default:
+      return false;
+  }
+  lo = a & ~15u;
+  hi = ((b + 16u + 15u) & ~15u);
+  return true;
+}
+
 // ---- RLE run table (per block, per RLE column, in shared memory) -------------------------------
 // mask: one bit per row, set where a run starts; pre[g]: number of run starts before row 32 * g.
 // run(row) = rank of row among the run starts - 1: two loads + popc, no search, no divergence.

@@ -112,7 +112,11 @@ struct ColCtx {
   int64_t row_begin, nrows;
   int64_t null_cnt = 0;
   bool enable_bp = true;
+  // is_null[] : 0 value, 1 NULL, 2 NOP (ObStoredExtValue, ob_encoding_util.h:279-285); "null" below
+  // means "stored as an extend value"
   bool is_null(int64_t r) const { return in->is_null && in->is_null[row_begin + r]; }
+  uint64_t ext_val(int64_t r) const { return in->is_null[row_begin + r] == 2 ? STORED_NOPE : STORED_NULL; }
+  int64_t nope_cnt = 0;
   int64_t ival(int64_t r) const { return in->i64[row_begin + r]; }
   StrRef sval(int64_t r) const {
     const int64_t a = in->str_off[row_begin + r], b = in->str_off[row_begin + r + 1];
@@ -146,7 +150,7 @@ void fill_column_store(Buf &meta, const ColCtx &c, bool need_ext, int ext_bit, i
   int64_t pos = 0;
   if (need_ext) {
     for (int64_t r = 0; r < n; ++r) {
-      if (c.is_null(r)) put_bits(buf, pos, ext_bit, STORED_NULL);
+      if (c.is_null(r)) put_bits(buf, pos, ext_bit, c.ext_val(r));
       pos += ext_bit;
     }
   }
@@ -202,7 +206,8 @@ void build_int_dict(const ColCtx &c, bool sorted, IntDict &d) {
     for (uint32_t i = 0; i < d.values.size(); ++i) first[d.values[i]] = i;
   }
   const uint32_t cnt = (uint32_t)d.values.size();
-  for (int64_t r = 0; r < c.nrows; ++r) d.refs[(size_t)r] = c.is_null(r) ? cnt : first[c.uval(r)];
+  for (int64_t r = 0; r < c.nrows; ++r)
+    d.refs[(size_t)r] = c.is_null(r) ? (c.ext_val(r) == STORED_NOPE ? cnt + 1 : cnt) : first[c.uval(r)];
 }
 
 struct StrDict {
@@ -235,7 +240,8 @@ void build_str_dict(const ColCtx &c, bool sorted, StrDict &d) {
     for (uint32_t i = 0; i < d.values.size(); ++i) first[d.values[i]] = i;
   }
   const uint32_t cnt = (uint32_t)d.values.size();
-  for (int64_t r = 0; r < c.nrows; ++r) d.refs[(size_t)r] = c.is_null(r) ? cnt : first[c.sval(r)];
+  for (int64_t r = 0; r < c.nrows; ++r)
+    d.refs[(size_t)r] = c.is_null(r) ? (c.ext_val(r) == STORED_NOPE ? cnt + 1 : cnt) : first[c.sval(r)];
 }
 
 // Writes ObDictMetaHeader + payload; returns pointer offset of the header inside meta.
@@ -362,7 +368,7 @@ int BlockBuilder::encode_raw(int i) {
     uint8_t *buf = meta.grow((size_t)(bits_size + fix_len * nrows));
     if (has_null)
       for (int64_t r = 0; r < nrows; ++r)
-        if (c.is_null(r)) put_bits(buf, r * ext_bit, ext_bit, STORED_NULL);
+        if (c.is_null(r)) put_bits(buf, r * ext_bit, ext_bit, c.ext_val(r));
     uint8_t *p = buf + bits_size;
     for (int64_t r = 0; r < nrows; ++r, p += fix_len)
       if (!c.is_null(r)) memcpy(p, c.sval(r).p, (size_t)fix_len);
@@ -391,7 +397,7 @@ int BlockBuilder::encode_dict(int i) {
     cnt = (uint32_t)idict.values.size();
   }
   if (cnt == 0) return OBGPU_NOT_SUPPORTED;  // all-NULL column: the reference picks CONST
-  const uint64_t max_ref = c.null_cnt > 0 ? cnt : cnt - 1;
+  const uint64_t max_ref = c.nope_cnt > 0 ? cnt + 1 : (c.null_cnt > 0 ? cnt : cnt - 1);
   bool bp = false;
   const int64_t size = packing_size(&bp, max_ref, c.enable_bp);
   o.hdr.attr_ |= ATTR_FIX_LENGTH;
@@ -430,7 +436,7 @@ int BlockBuilder::encode_rle(int i) {
       run_ref.push_back((*refs)[(size_t)r]);
     }
   }
-  const uint64_t max_ref = c.null_cnt > 0 ? cnt : cnt - 1;
+  const uint64_t max_ref = c.nope_cnt > 0 ? cnt + 1 : (c.null_cnt > 0 ? cnt : cnt - 1);
   const int row_id_byte = (int)byte_packed_int_size(run_row.back());
   const int ref_byte = (int)byte_packed_int_size(max_ref);
   const size_t runs = run_row.size();
@@ -470,6 +476,7 @@ int BlockBuilder::encode_const(int i) {
   ColOut &o = out[i];
   o.hdr.type_ = COL_CONST;
   o.hdr.attr_ = 0;  // need_data_store_ = false, no ext bits: NULL is a dict ref
+  if (c.nope_cnt > 0) return OBGPU_NOT_SUPPORTED;  // NOP cells only arise in incremental runs: RAW / DICT / RLE
   IntDict idict;
   StrDict sdict;
   const std::vector<uint32_t> *refs;
@@ -610,10 +617,12 @@ int BlockBuilder::build(std::vector<uint8_t> &block) {
     if ((c.sc == 5 && (!cols[i].str_heap || !cols[i].str_off)) || (c.sc != 5 && !cols[i].i64))
       return OBGPU_INVALID_ARGUMENT;
     for (int64_t r = 0; r < nrows; ++r) {
-      if (c.is_null(r)) c.null_cnt++;
+      if (c.is_null(r)) { c.null_cnt++; if (c.ext_val(r) == STORED_NOPE) c.nope_cnt++; }
       else original += c.sc == 5 ? c.sval(r).len : datum_len_of((uint8_t)cols[i].obj_type);
     }
-    if (c.null_cnt > 0) ext_bit = 1;  // ob_micro_block_encoder.cpp:507-517 (no NOP in major SSTables)
+    // ob_micro_block_encoder.cpp:507-517: 1 bit when only NULLs occur, 2 bits once any column has a NOP
+    if (c.null_cnt > 0 && ext_bit < 1) ext_bit = 1;
+    if (c.nope_cnt > 0) ext_bit = 2;
   }
   for (int i = 0; i < ncol; ++i) {
     out[(size_t)i].hdr.obj_type_ = (uint8_t)cols[i].obj_type;
@@ -684,7 +693,7 @@ int BlockBuilder::build(std::vector<uint8_t> &block) {
           memcpy(idx + (k - 1) * (size_t)col_idx_byte, &o, (size_t)col_idx_byte);
         }
         if (c.is_null(r)) {
-          put_bits(data, out[(size_t)var_cols[k]].hdr.extend_value_index_, ext_bit, STORED_NULL);
+          put_bits(data, out[(size_t)var_cols[k]].hdr.extend_value_index_, ext_bit, c.ext_val(r));
         } else if (lens[k] > 0) {
           memcpy(var + off, c.sval(r).p, (size_t)lens[k]);
         }

@@ -154,3 +154,57 @@ def make_config3_like(rows=100_000, rows_per_block=1100, seed=3, row_start=0, n_
     proj = [1, 2, 5, 6, 8, 10]
     return Workload(table, flt, proj, [False] * 4 + [True] * 2, [8] * 4 + [8] * 2,
                     "cfg3: 8 INT64 DICT + 8 VARCHAR DICT, 3-predicate AND", rows_per_block)
+
+
+# ---- config 5: K sorted runs with overlapping rowkey ranges (major compaction input) -----------------
+def make_config5_runs(n_runs=8, window=100_000, seed=5, rows_per_block=1400, dup_pct=10, delete_pct=2,
+                      nop_pct=50, null_pct=5, n_threads=0, encode=True):
+    """Run r (0 = oldest table) covers rowkey indexes [r * window / 2, r * window / 2 + window): adjacent runs
+    overlap by 50 %. A rowkey index lives in one covering run (its home, chosen by hash); dup_pct % of the
+    indexes are present in EVERY covering run (newer copies are DF_UPDATE rows whose payload cells are NOP
+    with probability nop_pct %), delete_pct % of the rows of runs >= 1 are DF_DELETE rows (payload NOP).
+    Columns of a run's SSTable: 0 rowkey INT64 (INTEGER_BASE_DIFF), 1 ObDmlFlag (TINYINT RAW), 2..4 payload
+    INT64 (RAW, NULL / NOP as ext values). Returns a list of dicts: key, flag, vals[3], ext[3] (numpy) and
+    `table` (TableImage) when encode."""
+    runs = []
+    for r in range(n_runs):
+        lo = r * (window // 2)
+        i = np.arange(lo, lo + window, dtype=np.int64)
+        h = splitmix64(_col_seed(seed, 100), int(lo), window)           # pure function of the rowkey index
+        # covering runs of index i: those r' with r' * window/2 <= i < r' * window/2 + window
+        first_cov = np.maximum((i - window) // (window // 2) + 1, 0)
+        last_cov = np.minimum(i // (window // 2), n_runs - 1)
+        ncov = (last_cov - first_cov + 1).astype(np.uint64)
+        home = first_cov + (h % ncov).astype(np.int64)
+        dup = ((h >> np.uint64(20)) % np.uint64(100)) < np.uint64(dup_pct)
+        present = (home == r) | dup
+        idx = i[present]
+        hh = h[present]
+        key = np.int64(1_000_003) + idx * 5 + (hh % np.uint64(5)).astype(np.int64)
+        n = len(key)
+        newer_copy = dup[present] & (first_cov[present] < r)            # an older covering run holds this key too
+        hr = splitmix64(_col_seed(seed, 200 + r), int(lo), window)[present]
+        flag = np.full(n, capi.DF_INSERT, dtype=np.uint8)
+        flag[newer_copy] = capi.DF_UPDATE
+        is_del = (r >= 1) & (((hr >> np.uint64(8)) % np.uint64(100)) < np.uint64(delete_pct))
+        flag[is_del] = capi.DF_DELETE
+        vals, ext = [], []
+        for c in range(3):
+            hv = splitmix64(_col_seed(seed, 300 + 10 * r + c), int(lo), window)[present]
+            v = (hv >> np.uint64(24)).astype(np.int64)
+            e = np.zeros(n, dtype=np.uint8)
+            e[((hv % np.uint64(100)) < np.uint64(null_pct))] = 1
+            e[newer_copy & (((hv >> np.uint64(7)) % np.uint64(100)) < np.uint64(nop_pct))] = 2
+            e[flag == capi.DF_DELETE] = 2
+            v[e != 0] = 0
+            vals.append(v)
+            ext.append(e)
+        run = {"key": key, "flag": flag, "vals": vals, "ext": ext}
+        if encode:
+            cols = [Column(capi.OBJ_INT, capi.ENC_INTEGER_BASE_DIFF, key),
+                    Column(capi.OBJ_TINYINT, capi.ENC_RAW, flag.astype(np.int64))]
+            for c in range(3):
+                cols.append(Column(capi.OBJ_INT, capi.ENC_RAW, vals[c], nulls=ext[c] if ext[c].any() else None))
+            run["table"] = encode_table(cols, rows_per_block, rowkey_cnt=1, n_threads=n_threads)
+        runs.append(run)
+    return runs

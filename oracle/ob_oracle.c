@@ -1033,3 +1033,124 @@ int ora_scan_blocks_mt(const void *image, const int64_t *offsets, const int64_t 
   if (checksum) *checksum = cs;
   return ret;
 }
+
+/* =============================================================================================
+ * Major compaction merge
+ * ============================================================================================= */
+int ora_decode_column_ext(const void *image, const int64_t *offsets, const int64_t *sizes, int32_t n_blocks,
+                          int32_t col, int64_t *vals, uint8_t *ext, int64_t cap, int64_t *rows) {
+  if (!image || !offsets || !sizes || !vals || !ext) return ORA_INVALID_ARGUMENT;
+  int64_t n = 0;
+  for (int32_t bi = 0; bi < n_blocks; ++bi) {
+    ora_block b;
+    int ret = ora_block_init(&b, (const uint8_t *)image + offsets[bi], sizes[bi]);
+    if (ret) return ret;
+    col_dec c;
+    if ((ret = col_dec_init(&b, col, &c))) return ret;
+    if (c.sc == 5) return ORA_NOT_SUPPORTED;
+    if (n + b.row_count > cap) return ORA_BUF_NOT_ENOUGH;
+    for (int64_t r = 0; r < b.row_count; ++r) {
+      ora_datum d;
+      if ((ret = decode_cell(&b, &c, r, &d))) return ret;
+      vals[n] = d.is_null ? 0 : (int64_t)d.ival;
+      ext[n] = (uint8_t)d.is_null;
+      ++n;
+    }
+  }
+  if (rows) *rows = n;
+  return ORA_SUCCESS;
+}
+
+/* The reference keeps the run heads in a loser tree (ObPartitionMajorRowsMerger); any priority
+ * structure that pops (rowkey ascending, newer table first among equal rowkeys) gives the same
+ * sequence. A binary heap over (key, -run) is used here. */
+typedef struct mrg_head { int64_t key; int32_t run; } mrg_head;
+static int mrg_less(const mrg_head *a, const mrg_head *b) {
+  if (a->key != b->key) return a->key < b->key;
+  return a->run > b->run; /* newer table first */
+}
+static void mrg_sift_down(mrg_head *h, int32_t n, int32_t i) {
+  for (;;) {
+    int32_t l = 2 * i + 1, r = l + 1, m = i;
+    if (l < n && mrg_less(&h[l], &h[m])) m = l;
+    if (r < n && mrg_less(&h[r], &h[m])) m = r;
+    if (m == i) return;
+    const mrg_head t = h[i]; h[i] = h[m]; h[m] = t;
+    i = m;
+  }
+}
+
+int ora_major_merge(const ora_merge_run *runs, int32_t n_runs, int32_t n_cols, const int64_t *default_vals,
+                    const uint8_t *default_null, int64_t out_cap, int64_t *out_key, int64_t *const *out_vals,
+                    uint8_t *const *out_null, int64_t *out_rows, int64_t *stats) {
+  if (!runs || n_runs <= 0 || n_runs > 64 || n_cols < 0 || n_cols > 64 || !out_key || !out_rows) return ORA_INVALID_ARGUMENT;
+  mrg_head heap[64];
+  int64_t pos[64];
+  int32_t hn = 0;
+  for (int32_t r = 0; r < n_runs; ++r) {
+    pos[r] = 0;
+    if (runs[r].n > 0) { heap[hn].key = runs[r].key[0]; heap[hn].run = r; ++hn; }
+  }
+  for (int32_t i = hn / 2 - 1; i >= 0; --i) mrg_sift_down(heap, hn, i);
+  int64_t nout = 0, dropped = 0, fused = 0;
+  while (hn > 0) {
+    /* find_rowkey_minimum_iters: every iter whose current rowkey equals the minimum, newest first */
+    const int64_t key = heap[0].key;
+    int32_t iters[64];
+    int32_t ni = 0;
+    while (hn > 0 && heap[0].key == key) {
+      iters[ni++] = heap[0].run;
+      const int32_t r = heap[0].run;
+      ++pos[r];
+      if (pos[r] < runs[r].n) {
+        if (runs[r].key[pos[r]] <= key) return ORA_INVALID_DATA; /* run not strictly ascending */
+        heap[0].key = runs[r].key[pos[r]];
+      } else {
+        heap[0] = heap[--hn];
+      }
+      mrg_sift_down(heap, hn, 0);
+    }
+    /* fuse_row: newest first */
+    int64_t rv[64];
+    uint8_t rs[64];     /* 0 value, 1 NULL, 2 NOP (still open) */
+    int result_delete = 0, first = 1, left = 0;
+    for (int32_t k = 0; k < ni; ++k) {
+      const ora_merge_run *run = &runs[iters[k]];
+      const int64_t at = pos[iters[k]] - 1;
+      const int flag = run->flag ? run->flag[at] : ORA_DF_INSERT;
+      if (flag == ORA_DF_NOT_EXIST) continue;                 /* former.row_flag_.is_not_exist(): nothing */
+      if (flag != ORA_DF_DELETE && flag != ORA_DF_INSERT && flag != ORA_DF_UPDATE) return ORA_INVALID_ARGUMENT;
+      if (flag == ORA_DF_DELETE) {
+        if (first) result_delete = 1;                         /* result flag = delete */
+        break;                                                /* final_result = true */
+      }
+      left = 0;
+      for (int32_t c = 0; c < n_cols; ++c) {
+        if (!first && rs[c] != 2) continue;                   /* only the open NOP positions */
+        const uint8_t e = run->ext[c][at];
+        if (first || e != 2) { rv[c] = e ? 0 : run->vals[c][at]; rs[c] = e; }
+        if (e == 2) ++left;
+      }
+      first = 0;
+      if (left == 0) break;                                   /* final_result */
+    }
+    if (first && !result_delete) continue;                    /* only not-exist rows: no output */
+    if (result_delete) { ++dropped; continue; }               /* inner_process drops delete rows */
+    /* end_fuse_row: open NOPs take the default row */
+    for (int32_t c = 0; c < n_cols; ++c) {
+      if (rs[c] == 2) {
+        const int dn = default_null ? default_null[c] : 1;
+        rs[c] = dn ? 1 : 0;
+        rv[c] = dn ? 0 : (default_vals ? default_vals[c] : 0);
+      }
+    }
+    if (nout >= out_cap) return ORA_BUF_NOT_ENOUGH;
+    out_key[nout] = key;
+    for (int32_t c = 0; c < n_cols; ++c) { out_vals[c][nout] = rv[c]; out_null[c][nout] = rs[c]; }
+    if (ni > 1) ++fused;
+    ++nout;
+  }
+  *out_rows = nout;
+  if (stats) { stats[0] = dropped; stats[1] = fused; }
+  return ORA_SUCCESS;
+}

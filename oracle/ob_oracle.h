@@ -137,6 +137,33 @@ int ora_scan_blocks_mt(const void *image, const int64_t *offsets, const int64_t 
                        int32_t n_proj, int32_t batch_size, int32_t n_threads, int64_t *total_rows,
                        int64_t *selected, uint64_t *checksum);
 
+/* ---- major compaction merge (compaction/ob_partition_merger.cpp:678-829 merge_partition ->
+ * ObPartitionMergeHelper::find_rowkey_minimum_iters (ob_partition_rows_merger.cpp:815-857) ->
+ * ObMergeFuser::fuse_row (ob_partition_merge_fuser.cpp:106-142) -> ObRowFuse::fuse_row
+ * (storage/ob_row_fuse.cpp:191-275) -> ObMajorPartitionMergeFuser::end_fuse_row (:284-322) ->
+ * ObPartitionMajorMerger::inner_process (:648-676, delete rows dropped)). ---------------------- */
+/* all cells of column `col` of a table, in row order: value image + ext (0 value, 1 NULL, 2 NOP) */
+int ora_decode_column_ext(const void *image, const int64_t *offsets, const int64_t *sizes, int32_t n_blocks,
+                          int32_t col, int64_t *vals, uint8_t *ext, int64_t cap, int64_t *rows);
+#define ORA_DF_NOT_EXIST 0
+#define ORA_DF_LOCK 1
+#define ORA_DF_UPDATE 2
+#define ORA_DF_INSERT 3
+#define ORA_DF_DELETE 4
+typedef struct ora_merge_run {       /* one sorted run (rowkey ascending, unique inside the run) */
+  int64_t n;
+  const int64_t *key;                /* INT64 rowkey */
+  const uint8_t *flag;               /* ObDmlFlag per row; NULL: every row DF_INSERT */
+  const int64_t *const *vals;        /* [n_cols][n] */
+  const uint8_t *const *ext;         /* [n_cols][n]: 0 value, 1 NULL, 2 NOP */
+} ora_merge_run;
+/* runs[0] is the OLDEST table, runs[n_runs - 1] the newest (iters are fused newest first).
+ * out_null[c][i]: 1 => NULL. stats[0] = keys dropped because the fused row is a delete,
+ * stats[1] = output rows fused from more than one run. */
+int ora_major_merge(const ora_merge_run *runs, int32_t n_runs, int32_t n_cols, const int64_t *default_vals,
+                    const uint8_t *default_null, int64_t out_cap, int64_t *out_key, int64_t *const *out_vals,
+                    uint8_t *const *out_null, int64_t *out_rows, int64_t *stats);
+
 #ifdef __cplusplus
 }
 #endif

@@ -80,6 +80,11 @@ class OraScanOut(C.Structure):
 _lib = None
 
 
+class OraMergeRun(C.Structure):
+    _fields_ = [("n", C.c_int64), ("key", C.c_void_p), ("flag", C.c_void_p), ("vals", C.POINTER(C.c_void_p)),
+                ("ext", C.POINTER(C.c_void_p))]
+
+
 def oracle():
     global _lib
     if _lib is None:
@@ -106,6 +111,8 @@ def oracle():
         L.ora_scan_blocks.argtypes = [vp, vp, vp, i32, i32, P(OraFilter), vp, i32, i32, i64, P(OraScanOut), P(i64),
                                       P(i64)]
         L.ora_scan_blocks_mt.argtypes = [vp, vp, vp, i32, P(OraFilter), vp, i32, i32, i32, P(i64), P(i64), P(u64)]
+        L.ora_decode_column_ext.argtypes = [vp, vp, vp, i32, i32, vp, vp, i64, P(i64)]
+        L.ora_major_merge.argtypes = [P(OraMergeRun), i32, i32, vp, vp, i64, vp, P(vp), P(vp), P(i64), P(i64)]
         _lib = L
     return _lib
 
@@ -270,3 +277,55 @@ def scan_table_mt(table, filter_expr, proj_cols, batch_size=256, n_threads=1, bl
                                 n_threads, C.byref(total), C.byref(sel), C.byref(cs))
     ora_check(code, "ora_scan_blocks_mt")
     return total.value, sel.value, cs.value
+
+
+# ---- major compaction merge -------------------------------------------------------------------------
+def decode_column_ext(table, col):
+    """(values int64, ext uint8) of every cell of integer column `col`, by the oracle's block decoder."""
+    n = int(table.total_rows)
+    vals = np.zeros(n, dtype=np.int64)
+    ext = np.zeros(n, dtype=np.uint8)
+    offs = np.ascontiguousarray(table.offsets, dtype=np.int64)
+    sizes = np.ascontiguousarray(table.sizes, dtype=np.int64)
+    rows = C.c_int64(0)
+    ora_check(oracle().ora_decode_column_ext(table.image.ctypes.data, offs.ctypes.data, sizes.ctypes.data, len(offs), col,
+                                             vals.ctypes.data, ext.ctypes.data, n, C.byref(rows)), "ora_decode_column_ext")
+    assert rows.value == n
+    return vals, ext
+
+
+def major_merge(runs, n_cols, default_vals=None, default_null=None):
+    """runs: list (oldest -> newest) of dicts {key, flag (or None), vals [n_cols], ext [n_cols]} of numpy
+    arrays. Returns dict(key, vals, null, dropped, fused)."""
+    arr = (OraMergeRun * len(runs))()
+    keep = []
+    total = 0
+    for i, r in enumerate(runs):
+        key = np.ascontiguousarray(r["key"], dtype=np.int64)
+        flag = None if r.get("flag") is None else np.ascontiguousarray(r["flag"], dtype=np.uint8)
+        vals = [np.ascontiguousarray(v, dtype=np.int64) for v in r["vals"]]
+        ext = [np.ascontiguousarray(e, dtype=np.uint8) for e in r["ext"]]
+        vp = (C.c_void_p * max(n_cols, 1))(*[v.ctypes.data for v in vals])
+        ep = (C.c_void_p * max(n_cols, 1))(*[e.ctypes.data for e in ext])
+        keep += [key, flag, vals, ext, vp, ep]
+        arr[i].n = len(key)
+        arr[i].key = key.ctypes.data
+        arr[i].flag = flag.ctypes.data if flag is not None else None
+        arr[i].vals = vp
+        arr[i].ext = ep
+        total += len(key)
+    out_key = np.zeros(max(total, 1), dtype=np.int64)
+    out_vals = [np.zeros(max(total, 1), dtype=np.int64) for _ in range(n_cols)]
+    out_null = [np.zeros(max(total, 1), dtype=np.uint8) for _ in range(n_cols)]
+    ovp = (C.c_void_p * max(n_cols, 1))(*[v.ctypes.data for v in out_vals])
+    onp = (C.c_void_p * max(n_cols, 1))(*[v.ctypes.data for v in out_null])
+    dv = None if default_vals is None else np.ascontiguousarray(default_vals, dtype=np.int64)
+    dn = None if default_null is None else np.ascontiguousarray(default_null, dtype=np.uint8)
+    rows = C.c_int64(0)
+    stats = (C.c_int64 * 2)()
+    ora_check(oracle().ora_major_merge(arr, len(runs), n_cols, dv.ctypes.data if dv is not None else None,
+                                       dn.ctypes.data if dn is not None else None, total, out_key.ctypes.data, ovp, onp,
+                                       C.byref(rows), stats), "ora_major_merge")
+    n = rows.value
+    return {"key": out_key[:n], "vals": [v[:n] for v in out_vals], "null": [v[:n] for v in out_null],
+            "dropped": stats[0], "fused": stats[1]}

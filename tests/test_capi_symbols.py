@@ -1,5 +1,5 @@
-"""The C-ABI library loads on a CPU-only box and exports every symbol include/obgpu_scan.h
-declares (no compute calls without a GPU); the product fails loudly without a device."""
+"""The C-ABI library loads on a CPU-only box and exports every symbol include/*.h
+declare (no compute calls without a GPU); the product fails loudly without a device."""
 import ctypes
 import os
 import re
@@ -10,9 +10,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def declared_in_header():
-    text = open(os.path.join(ROOT, "include", "obgpu_scan.h")).read()
-    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(obgpu_[a-z0-9_]+)\s*\(", text)))
+    names = set()
+    for h in sorted(os.listdir(os.path.join(ROOT, "include"))):
+        if not h.endswith(".h"):
+            continue
+        text = open(os.path.join(ROOT, "include", h)).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        names |= set(re.findall(r"\b(obgpu_[a-z0-9_]+)\s*\(", text))
+    return sorted(names)
 
 
 def test_library_exports_every_declared_symbol():

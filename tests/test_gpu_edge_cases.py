@@ -157,3 +157,13 @@ def test_many_small_blocks_lookback_chain(ob, ctx):
     table = ob.encode_table(cols, 10)
     flt = ob.White(0, ob.WHITE_OP_LT, (37,))
     assert_scan_matches(ctx, W(table, flt, [1], [False], [8]))
+
+
+@pytest.mark.parametrize("compact", ["0", "1"])
+@pytest.mark.parametrize("proj", [[0, 3, 8, 11], [8, 9, 10, 11], [12], list(range(13))])
+def test_projection_staging_modes(ob, ctx, compact, proj, monkeypatch):
+    # whole-block TMA vs packed per-column regions (several RAW var-length columns share the row data)
+    monkeypatch.setenv("OBGPU_PROJECT_COMPACT", compact)
+    table, _ = _mixed_table(ob, 12_000, 640, 5)
+    flt = ob.White(1, ob.WHITE_OP_LT, (700,))
+    assert_scan_matches(ctx, W(table, flt, proj, [IS_STR[i] for i in proj], [ELEM[i] for i in proj]))
