@@ -128,6 +128,21 @@ def merge_decoded(ctx, runs: Sequence[DecodedRun], default_vals=None, default_nu
     return MergeResult(ctx, h, n_cols, keep)
 
 
+def write_merged_sstable(res: MergeResult, rows_per_block: int = 1400, payload_encoding=None, n_threads: int = 0):
+    """The merged row stream as a new major SSTable shard (ObMacroBlockWriter::append_row ->
+    ObMicroBlockEncoder::build_block in the reference, blocksstable/ob_macro_block_writer.cpp:837): rowkey
+    INTEGER_BASE_DIFF, payload RAW unless told otherwise; every row DF_INSERT, so no flag column and no NOP.
+    The encoder runs on the host (it does in the reference too); the block bytes are reference-format."""
+    from .sstable import Column, encode_table
+    key, _ = res.fetch(-1)
+    cols = [Column(capi.OBJ_INT, capi.ENC_INTEGER_BASE_DIFF, key)]
+    for c in range(res.n_cols):
+        v, nl = res.fetch(c)
+        enc = capi.ENC_RAW if payload_encoding is None else payload_encoding[c]
+        cols.append(Column(capi.OBJ_INT, enc, v, nulls=nl if nl.any() else None))
+    return encode_table(cols, rows_per_block, rowkey_cnt=1, n_threads=n_threads)
+
+
 # ---- multi-GPU: range partition + one exchange step ----------------------------------------------------
 def choose_splitters(candidates, world: int):
     """world-1 splitters at the quantiles of the gathered rowkey samples (sorted, duplicates kept)."""

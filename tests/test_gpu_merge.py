@@ -113,3 +113,27 @@ def test_every_key_in_every_run(ob, env):
     res = merge_decoded(ctx, [to_dev(torch, r) for r in runs], [1, 2, 3, 4], [0, 0, 1, 0])
     assert_merge_equal(res, ora.major_merge(runs, 4, [1, 2, 3, 4], [0, 0, 1, 0]), 4)
     res.free()
+
+
+def test_merged_stream_written_as_sstable_scans_back(ob, env):
+    # compaction output -> reference-format blocks -> the scan path reads them back bit-exactly
+    from oceanbase_b200.compaction import decode_run, merge_decoded, write_merged_sstable
+    from oceanbase_b200.synth import make_config5_runs
+    ctx, torch = env
+    runs = make_config5_runs(n_runs=4, window=25000, seed=41)
+    dec = [decode_run(ctx, r["table"], 0, 1, [2, 3, 4]) for r in runs]
+    res = merge_decoded(ctx, dec)
+    want = ora.major_merge(runs, 3)
+    table = write_merged_sstable(res, rows_per_block=1000)
+    assert table.total_rows == len(want["key"])
+    k, e = ora.decode_column_ext(table, 0)
+    assert np.array_equal(k, want["key"]) and not e.any()
+    for c in range(3):
+        v, e = ora.decode_column_ext(table, 1 + c)
+        assert np.array_equal(e, want["null"][c]) and np.array_equal(v, want["vals"][c])
+    d2 = decode_run(ctx, table, 0, None, [1, 2, 3])
+    torch.cuda.synchronize()
+    assert np.array_equal(d2.key.cpu().numpy(), want["key"])
+    for c in range(3):
+        assert np.array_equal(d2.ext[c].cpu().numpy(), want["null"][c])
+    res.free()
