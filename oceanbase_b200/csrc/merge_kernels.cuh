@@ -196,12 +196,14 @@ __global__ void __launch_bounds__(256) fuse_kernel(const int64_t *__restrict__ k
       out_key[o] = key;
       // rows of the group, newest first; the fuse stops at a delete row (final_result)
       int64_t jend = i;
-      int rows = 0;
+      int group = 0;        // iters sharing this rowkey (minimum_iters_.count())
+      bool open = true;     // no delete row met yet
       for (int64_t j = i; j < n && keys[j] == key; ++j) {
-        const int f = flag_of(runs, src[j]);
-        if (f == OBGPU_DF_DELETE) break;
-        jend = j + 1;
-        if (f != OBGPU_DF_NOT_EXIST) ++rows;
+        ++group;
+        if (open) {
+          if (flag_of(runs, src[j]) == OBGPU_DF_DELETE) open = false;
+          else jend = j + 1;
+        }
       }
       const uint64_t idx_mask = (1ull << kSrcShift) - 1;
       for (int c = 0; c < runs.n_cols; ++c) {
@@ -226,7 +228,7 @@ __global__ void __launch_bounds__(256) fuse_kernel(const int64_t *__restrict__ k
         out_vals[c][o] = v;
         out_null[c][o] = st;
       }
-      if (rows > 1) atomicAdd(&stats[1], 1ull);
+      if (group > 1) atomicAdd(&stats[1], 1ull);
     }
     __syncthreads();
   }
@@ -305,22 +307,17 @@ int obgpu_batch_decode_column(obgpu_batch *b, int32_t col, int64_t *dev_vals, ui
   obgpu_ctx *ctx = b->ctx;
   cudaSetDevice(ctx->device);
   const int n = b->n_blocks;
-  std::vector<int64_t> start((size_t)n + 1, 0);
-  for (int i = 0; i < n; ++i) start[(size_t)i + 1] = start[(size_t)i] + b->row_count[(size_t)i];
-  void *d = nullptr;
-  cudaError_t e = cudaMallocAsync(&d, ((size_t)n + 1) * 8 + 64, ctx->stream);
+  int *d_status = nullptr;
+  cudaError_t e = cudaMallocAsync((void **)&d_status, 64, ctx->stream);
   if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return OBGPU_ALLOCATE_MEMORY_FAILED; }
-  int64_t *d_start = (int64_t *)d;
-  int *d_status = (int *)((uint8_t *)d + ((size_t)n + 1) * 8);
   cudaMemsetAsync(d_status, 0, 4, ctx->stream);
-  cudaMemcpyAsync(d_start, start.data(), ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream);
-  mrg::decode_col_kernel<<<n, 128, 0, ctx->stream>>>(b->d_image, b->d_recs, b->d_plans, (int)b->max_cols, col, d_start,
+  mrg::decode_col_kernel<<<n, 128, 0, ctx->stream>>>(b->d_image, b->d_recs, b->d_plans, (int)b->max_cols, col, b->d_row_start,
                                                      dev_vals, dev_ext, d_status);
   ctx->launches++;
   int status = 0;
   cudaMemcpyAsync(&status, d_status, 4, cudaMemcpyDeviceToHost, ctx->stream);
-  e = cudaStreamSynchronize(ctx->stream);  // `start` is pageable host memory: wait before it goes away
-  cudaFreeAsync(d, ctx->stream);
+  e = cudaStreamSynchronize(ctx->stream);
+  cudaFreeAsync(d_status, ctx->stream);
   if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return OBGPU_ERR_SYS; }
   return check_status(ctx, status);
 }

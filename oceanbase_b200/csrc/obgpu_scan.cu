@@ -265,13 +265,18 @@ __device__ __forceinline__ bool str_pred(const ScanParams &p, const FilterNodeDe
     return str_cmp(s, cell, len, p.param_heap + pp.heap_off, pp.len);
   };
   const int op = nd.op;
+  if (op == OP_EQ || op == OP_NE || op == OP_IN) {
+    // equality tests: length and the first 8 bytes decide almost every pair without a byte loop
+    const uint64_t pre = len ? ld_bits(s, cell * 8u, (len < 8u ? len : 8u) * 8u) : 0ull;
+    bool hit = false;
+    for (int k = 0; k < nd.n_params && !hit; ++k) {
+      const ParamDev &pp = p.params[nd.param_begin + k];
+      hit = pp.len == len && (uint64_t)pp.i64 == pre && (len <= 8u || cmp3(k) == 0);
+    }
+    return hit != (op == OP_NE);
+  }
   if (op <= OP_NE) return cmp_to_bool(op, cmp3(0));
   if (op == OP_BT) return cmp3(0) >= 0 && cmp3(1) <= 0;
-  if (op == OP_IN) {
-    for (int i = 0; i < nd.n_params; ++i)
-      if (cmp3(i) == 0) return true;
-    return false;
-  }
   return false;
 }
 
@@ -1337,6 +1342,7 @@ struct obgpu_batch {
   uint64_t *d_blk_off = nullptr;
   uint32_t *d_blk_size = nullptr;
   int64_t *d_bm_word_off = nullptr;
+  int64_t *d_row_start = nullptr;  // n + 1: first row of each block (dense row order of the batch)
   // decode plans + row counts built by the index kernel at open
   ColDesc *d_plans = nullptr;
   uint32_t *d_rows = nullptr;
@@ -1596,7 +1602,8 @@ int obgpu_batch_open(obgpu_ctx *ctx, const void *image, int64_t image_size, cons
     return ret;
   }
   // device tables
-  const size_t tb = (size_t)n_blocks * (8 + 4) + ((size_t)n_blocks + 1) * 8 + 64;
+  const size_t tb_rs = (((size_t)n_blocks * (8 + 4) + ((size_t)n_blocks + 1) * 8) + 15) & ~(size_t)15;  // row_start follows
+  const size_t tb = tb_rs + ((size_t)n_blocks + 1) * 8 + 64;
   cudaError_t e = cudaMallocAsync(&b->d_tables, tb, ctx->stream);
   if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); delete b; return OBGPU_ALLOCATE_MEMORY_FAILED; }
   uint8_t *dt = (uint8_t *)b->d_tables;
@@ -1610,7 +1617,11 @@ int obgpu_batch_open(obgpu_ctx *ctx, const void *image, int64_t image_size, cons
     uint32_t *s = (uint32_t *)(stage.data() + (size_t)n_blocks * 8 + ((size_t)n_blocks + 1) * 8);
     for (int32_t i = 0; i < n_blocks; ++i) { o[i] = (uint64_t)offsets[i]; s[i] = (uint32_t)sizes[i]; }
     memcpy(w, b->bm_word_off.data(), ((size_t)n_blocks + 1) * 8);
+    int64_t *rs = (int64_t *)(stage.data() + tb_rs);  // first row of every block in the batch's row order
+    rs[0] = 0;
+    for (int32_t i = 0; i < n_blocks; ++i) rs[i + 1] = rs[i] + b->row_count[(size_t)i];
   }
+  b->d_row_start = (int64_t *)(dt + tb_rs);
   e = cudaMemcpyAsync(b->d_tables, stage.data(), tb, cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess) {
     if (image_on_device) {
@@ -1752,6 +1763,12 @@ static int build_filter(obgpu_ctx *ctx, const obgpu_batch *b, const obgpu_filter
           if (heap + sp.len > (uint32_t)kParamHeap) return OBGPU_NOT_SUPPORTED;
           memcpy(p.param_heap + heap, sp.ptr, sp.len);
           heap += sp.len;
+        }
+        if ((size_t)src.col < b->col_types.size() && obf::store_class_of(b->col_types[(size_t)src.col]) == 5) {
+          // string constant: i64 carries the first min(len, 8) bytes (little endian) for the equality prefilter
+          uint64_t pre = 0;
+          if (sp.ptr) memcpy(&pre, sp.ptr, std::min<uint32_t>(sp.len, 8u));
+          pd.i64 = (int64_t)pre;
         }
         p.params[n_params++] = pd;
         ++kept;
