@@ -303,20 +303,22 @@ def run_ours(args):
     from oceanbase_b200.pipeline import HostScanPipeline, split_table
     bpb = max(1, table.n_blocks // args.e2e_batches)
     parts = split_table(table, bpb)
-    out_host, out_np = [], []
+    out_host, out_np, null_np = [], [], []
     for part in parts:
         rows_part = int(part.n_blocks) * 1400
         capp = int(rows_part * 0.30) + 2048
         bufs = [torch.empty(capp, dtype=torch.int64, pin_memory=True) for _ in w.proj]
-        out_host.append(bufs)
+        nbufs = [torch.zeros((capp + 63) // 64, dtype=torch.int64, pin_memory=True) for _ in w.proj]
+        out_host.append(bufs + nbufs)
         out_np.append([t.numpy().view(np.uint64) for t in bufs])
-    pipe = HostScanPipeline(local, n_workers=3)
+        null_np.append([t.numpy().view(np.uint64) for t in nbufs])
+    pipe = HostScanPipeline(local, n_workers=args.e2e_workers)
     h2d = table.image.size
     d2h = 0
 
     def e2e_step():
         nonlocal d2h
-        outs = pipe.scan(table, w.filter, w.proj, bpb, 0.30, out_buffers=out_np)
+        outs = pipe.scan(table, w.filter, w.proj, bpb, 0.30, out_buffers=out_np, null_buffers=null_np)
         n = sum(o.selected_rows for o in outs)
         d2h = n * 8 * len(w.proj)
         return n
@@ -377,8 +379,8 @@ def run_ours(args):
                          "traffic": measured_traffic(table.total_rows), "peak_source": peak_src, "alg_bytes_per_launch": alg_bytes,
                          "kernel_ms": kern_mean, "kernel": "one scan = obgpu_count_kernel + obgpu_prefix_*_kernel + obgpu_project_kernel (project ~85%)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": e2e_ms, "steps": e2e_steps, "page_batches": len(parts), "streams": 3,
-                    "timing": "host wall clock around the pipelined public API call (3 streams)"},
+                    "ms_per_step": e2e_ms, "steps": e2e_steps, "page_batches": len(parts), "streams": args.e2e_workers,
+                    "timing": f"host wall clock around the pipelined public API call ({args.e2e_workers} streams)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "gbs_decoded_equiv": total_rows_all * 8 * 8 / (step_ms * 1e-3) / 1e9,
@@ -405,6 +407,7 @@ def main():
     ap.add_argument("--cpu-sample-rows", type=int, default=16_000_000)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--e2e-batches", type=int, default=12, help="page batches per e2e step (pipeline depth)")
+    ap.add_argument("--e2e-workers", type=int, default=3, help="host worker threads = CUDA streams of the e2e pipeline")
     ap.add_argument("--seed", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -64,7 +64,9 @@ enum {
   OBGPU_ENC_DICT = 1,
   OBGPU_ENC_RLE = 2,
   OBGPU_ENC_CONST = 3,
-  OBGPU_ENC_INTEGER_BASE_DIFF = 4
+  OBGPU_ENC_INTEGER_BASE_DIFF = 4,
+  /* writer only: columns of a CS_ENCODING_ROW_STORE block (ObCSColumnHeader::Type) */
+  OBGPU_ENC_CS_INTEGER = 16
 };
 
 /* ---- ObObjType values the path accepts (common/object/ob_obj_type.h) ------------------------ */
@@ -216,12 +218,36 @@ int obgpu_result_block_tables(obgpu_result *res, const int64_t **sel_offset_dev,
  * that bit 0 is row_begin. */
 int obgpu_result_fetch_col(obgpu_result *res, int32_t i, int64_t row_begin, int64_t row_count,
                            void *host_data, void *host_aux, uint64_t *host_nulls);
+/* Same for several columns with ONE stream synchronisation (all copies are enqueued first): cols[k]
+ * goes to host_data[k] / host_aux[k] / host_nulls[k]; any of the three arrays (or entries) may be NULL. */
+int obgpu_result_fetch_cols(obgpu_result *res, int32_t n_cols, const int32_t *cols, int64_t row_begin,
+                            int64_t row_count, void *const *host_data, void *const *host_aux,
+                            uint64_t *const *host_nulls);
 int obgpu_result_fetch_sel_offsets(obgpu_result *res, int64_t *host_sel_offset /* n_blocks+1 */);
 int obgpu_result_fetch_row_ids(obgpu_result *res, int64_t row_begin, int64_t row_count,
                                int32_t *host_row_ids);
 /* common::ObBitmap image (one byte 0x00/0x01 per row) of block b, rows [start, start+count). */
 int obgpu_result_fetch_bitmap(obgpu_result *res, int32_t block, int64_t start, int64_t count,
                               uint8_t *host_bitmap_bytes);
+
+/* Pushed-down aggregates over the selected rows of a scan (the reference folds them batch by batch in
+ * ObAggregatedStoreVec / ObPushdownAggregateVec, access/ob_aggregated_store_vec.h:143,
+ * access/ob_pushdown_aggregate_vec.cpp): computed on the device from the dense projected columns,
+ * exact integer arithmetic. NULL rows are skipped (a product is NULL when either side is).
+ *   COUNT       : out[0] = rows where col_a is not NULL
+ *   SUM         : out[0..1] = 128-bit two's-complement sum of col_a (low, high word)
+ *   SUM_PRODUCT : out[0..1] = 128-bit sum of col_a * col_b (each product taken in 128 bits)
+ *   MIN / MAX   : out[0] = extreme of col_a in the column's own (signed / unsigned) order,
+ *                 out[1] = 1 when at least one non-NULL row exists
+ * col_a / col_b index the projection list of the scan (integer-class columns). */
+enum {
+  OBGPU_AGG_COUNT = 0,
+  OBGPU_AGG_SUM = 1,
+  OBGPU_AGG_SUM_PRODUCT = 2,
+  OBGPU_AGG_MIN = 3,
+  OBGPU_AGG_MAX = 4
+};
+int obgpu_result_aggregate(obgpu_result *res, int32_t kind, int32_t col_a, int32_t col_b, int64_t out[2]);
 
 /* =============================================================================================
  * Reference-granularity calls (one micro-block, one leaf, one <=batch-size projection). They run

@@ -16,6 +16,7 @@ OB_INVALID_DATA = -4070
 (WHITE_OP_EQ, WHITE_OP_LE, WHITE_OP_LT, WHITE_OP_GE, WHITE_OP_GT, WHITE_OP_NE, WHITE_OP_BT,
  WHITE_OP_IN, WHITE_OP_NU, WHITE_OP_NN) = range(10)
 ENC_RAW, ENC_DICT, ENC_RLE, ENC_CONST, ENC_INTEGER_BASE_DIFF = range(5)
+ENC_CS_INTEGER = 16  # column of a CS_ENCODING_ROW_STORE block
 OBJ_TINYINT, OBJ_SMALLINT, OBJ_MEDIUMINT, OBJ_INT32, OBJ_INT = 1, 2, 3, 4, 5
 OBJ_UTINYINT, OBJ_USMALLINT, OBJ_UMEDIUMINT, OBJ_UINT32, OBJ_UINT64 = 6, 7, 8, 9, 10
 OBJ_DATETIME, OBJ_TIMESTAMP, OBJ_DATE, OBJ_TIME, OBJ_YEAR, OBJ_VARCHAR, OBJ_CHAR = 17, 18, 19, 20, 21, 22, 23
@@ -63,6 +64,7 @@ class ColInput(C.Structure):
                 ("reserved", C.c_int32)]
 
 
+AGG_COUNT, AGG_SUM, AGG_SUM_PRODUCT, AGG_MIN, AGG_MAX = range(5)
 DF_NOT_EXIST, DF_LOCK, DF_UPDATE, DF_INSERT, DF_DELETE = range(5)  # blocksstable::ObDmlFlag
 
 
@@ -100,6 +102,8 @@ def declared_signatures():
         "obgpu_result_col_get": (C.c_int, [vp, i32, P(ResultCol)]),
         "obgpu_result_block_tables": (C.c_int, [vp, P(vp), P(vp), P(vp), P(vp)]),
         "obgpu_result_fetch_col": (C.c_int, [vp, i32, i64, i64, vp, vp, vp]),
+        "obgpu_result_fetch_cols": (C.c_int, [vp, i32, vp, i64, i64, vp, vp, vp]),
+        "obgpu_result_aggregate": (C.c_int, [vp, i32, i32, i32, vp]),
         "obgpu_result_fetch_sel_offsets": (C.c_int, [vp, vp]),
         "obgpu_result_fetch_row_ids": (C.c_int, [vp, i64, i64, vp]),
         "obgpu_result_fetch_bitmap": (C.c_int, [vp, i32, i64, i64, vp]),

@@ -265,12 +265,16 @@ __global__ void __launch_bounds__(128) decode_col_kernel(const uint8_t *__restri
       else v = dict_int(s, d, ref);
     } else {
       if (d.ext_bit) {
-        const uint32_t x = ld_bits32(s, d.ext_bit_off + row * d.ext_bit, d.ext_bit);
+        const uint32_t x = ld_bits32(s, d.ext_bit_off + ext_row(d, row) * d.ext_bit, d.ext_bit);
         e = x == STORED_NOT_EXT ? 0 : (x == STORED_NULL ? 1 : 2);
       }
       if (!e) {
-        v = ld_bits(s, d.val_bit + row * d.stride, d.width) + d.base;
-        if (d.sign_fix) v = sign_fix(d.int_mask, v);
+        const uint64_t raw = ld_bits(s, d.val_bit + row * d.stride, d.width);
+        if (null_replaced_on(d) && raw == null_replaced_raw(d)) e = 1;
+        else {
+          v = raw + d.base;
+          if (d.sign_fix) v = sign_fix(d.int_mask, v);
+        }
       }
     }
     if (d.elem_len == 4) v &= 0xffffffffull;

@@ -99,7 +99,44 @@ struct ConstMetaHeader {
   uint8_t row_id_byte_;
   uint16_t offset_;      // dict meta offset (when count_ > 0)
 };
+// ---- CS_ENCODING_ROW_STORE (column-store encoding) ---------------------------------------------
+// cs_encoding/ob_column_encoding_struct.h:142-181
+struct AllColumnHeader {
+  uint8_t version_;
+  uint8_t attrs_;                    // IS_FULL_TRANSFORMED 0x1 (memory only), IS_ALL_STRING_COMPRESSED 0x2
+  uint32_t all_string_data_length_;
+  uint32_t stream_offsets_length_;
+  uint16_t stream_count_;
+};
+// cs_encoding/ob_column_encoding_struct.h:31-139
+struct CSColumnHeader {
+  uint8_t version_;
+  uint8_t type_;                     // CSColType
+  uint8_t attrs_;                    // CSColAttr
+  uint8_t obj_type_;
+};
+// cs_encoding/ob_column_encoding_struct.h:183-221
+struct DictEncodingMeta {
+  uint8_t version_;
+  uint8_t attrs_;                    // IS_SORTED 0x1, HAS_NULL 0x2, CONST_ENCODING_REF 0x4
+  uint32_t distinct_val_cnt_;
+  uint32_t ref_row_cnt_;
+};
 #pragma pack(pop)
+
+static_assert(sizeof(AllColumnHeader) == 12, "all column header must be 12 bytes");
+static_assert(sizeof(CSColumnHeader) == 4, "cs column header must be 4 bytes");
+static_assert(sizeof(DictEncodingMeta) == 10, "dict encoding meta must be 10 bytes");
+
+enum CSColType : uint8_t { CS_INTEGER = 0, CS_STRING = 1, CS_INT_DICT = 2, CS_STR_DICT = 3, CS_SEMISTRUCT = 4, CS_MAX_TYPE = 5 };
+enum CSColAttr : uint8_t { CS_IS_FIXED_LENGTH = 0x01, CS_HAS_NULL_OR_NOP_BITMAP = 0x02, CS_OUT_ROW = 0x04,
+                           CS_HAS_NOP_BITMAP = 0x08, CS_HAS_NOP = 0x10 };
+// ObIntegerStreamMeta (cs_encoding/ob_stream_encoding_struct.h:108-290), serialized as
+//   version u8, attr u8, type u8, width u8, [vi64 base], [vi64 null_replaced], [u8 decimal width], (v2:) u8 pfor type
+enum IntStreamAttr : uint8_t { IS_USE_BASE = 0x1, IS_REPLACE_NULL_VALUE = 0x2, IS_DECIMAL_INT = 0x4 };
+enum IntStreamType : uint8_t { IS_RAW = 1 };   // the other codecs need the CPU transformer (not handled)
+constexpr uint8_t INTEGER_STREAM_META_V2 = 1;
+constexpr uint8_t COMPRESSOR_NONE = 1;         // common::ObCompressorType::NONE_COMPRESSOR
 
 static_assert(sizeof(MicroBlockHeader) == 64, "micro header must be 64 bytes");
 static_assert(sizeof(ColumnHeader) == 16, "column header must be 16 bytes");

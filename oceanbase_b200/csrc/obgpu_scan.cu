@@ -415,7 +415,7 @@ __device__ __forceinline__ void filter_bits_range(const BlockCtx &c, const ColDe
 }
 
 __device__ __forceinline__ bool leaf_is_bits_range(const ColDesc &d, const FilterNodeDev &nd) {
-  return d.kind == K_BITS && nd.range_ok && d.elem_len == 8 && d.ext_bit == 0 && !d.sign_fix;
+  return d.kind == K_BITS && nd.range_ok && d.elem_len == 8 && d.ext_bit == 0 && !d.sign_fix && !d.var_is_last;
 }
 
 // First leaf of an AND / OR list: writes bm directly (no initialisation pass) when it is a plain
@@ -584,7 +584,7 @@ __device__ __forceinline__ void project_int_col(const ScanParams &p, const Block
     const uint32_t val_bit = c.sbit + d.val_bit, stride = d.stride, width = d.width;
     const uint64_t add = d.base, mask = d.int_mask;
     const bool fix = d.sign_fix != 0;
-    if (d.ext_bit == 0 && !fix) {
+    if (d.ext_bit == 0 && !fix && !d.var_is_last) {
       if (width <= 32) {
         for (uint32_t j = tid; j < cnt; j += nt)
           out[j] = (OutT)((uint64_t)sbits32(val_bit + ROW(j) * stride, width) + add);
@@ -593,15 +593,23 @@ __device__ __forceinline__ void project_int_col(const ScanParams &p, const Block
           out[j] = (OutT)(sbits(val_bit + ROW(j) * stride, width) + add);
       }
     } else {
-      const uint32_t ext_off = c.sbit + d.ext_bit_off, eb = d.ext_bit;
+      const uint32_t ext_off = c.sbit + d.ext_bit_off, eb = d.ext_bit, exor = d.var_ext_in_row;
+      const bool repl = d.var_is_last != 0;
+      const uint64_t repl_raw = null_replaced_raw(d);
       for (uint32_t j = tid; j < cnt; j += nt) {
         const uint32_t row = ROW(j);
-        if (eb && sbits32(ext_off + row * eb, eb) != STORED_NOT_EXT) {
+        if (eb && sbits32(ext_off + (row ^ exor) * eb, eb) != STORED_NOT_EXT) {
           out[j] = (OutT)0;
           mark_null(j);
           continue;
         }
-        uint64_t v = sbits(val_bit + row * stride, width) + add;
+        const uint64_t raw = sbits(val_bit + row * stride, width);
+        if (repl && raw == repl_raw) {
+          out[j] = (OutT)0;
+          mark_null(j);
+          continue;
+        }
+        uint64_t v = raw + add;
         if (fix) v = sign_fix(mask, v);
         out[j] = (OutT)v;
       }
@@ -712,6 +720,7 @@ __global__ void __launch_bounds__(256) obgpu_index_kernel(const uint8_t *image, 
     r.var_col_cnt = b.var_col_cnt;
     r.row_index_byte = b.row_index_byte;
     r.ext_bit = b.ext_bit;
+    r.pad[0] = b.is_cs;
     recs[block] = r;
   }
   if (d.ok) {
@@ -1539,12 +1548,14 @@ int obgpu_batch_open(obgpu_ctx *ctx, const void *image, int64_t image_size, cons
       ret = OBGPU_INVALID_DATA;
       break;
     }
-    if (rst != obf::ENCODING_ROW_STORE && rst != obf::SELECTIVE_ENCODING_ROW_STORE) {
-      ctx->err = "row store type not handled by the PAX device path";
+    const bool is_cs = rst == obf::CS_ENCODING_ROW_STORE;
+    if (rst != obf::ENCODING_ROW_STORE && rst != obf::SELECTIVE_ENCODING_ROW_STORE && !is_cs) {
+      ctx->err = "row store type not handled by the device path";
       ret = OBGPU_NOT_SUPPORTED;
       break;
     }
-    if (header_size < 64 || (int64_t)header_size + 16ll * ncol > sz || row_data_off > sz || rows == 0) {
+    if (header_size < 64 || (int64_t)header_size + (is_cs ? 12ll + 4ll * ncol : 16ll * ncol) > sz || (!is_cs && row_data_off > sz) ||
+        rows == 0) {
       ret = OBGPU_INVALID_DATA;
       break;
     }
@@ -1566,6 +1577,14 @@ int obgpu_batch_open(obgpu_ctx *ctx, const void *image, int64_t image_size, cons
     if (b->col_max_rle.size() < ncol) b->col_max_rle.resize(ncol, 0);
     // dictionary sizes of DICT / RLE columns (sizes the shared-memory predicate bitsets)
     const uint32_t meta_off = header_size + 16u * ncol;
+    if (is_cs) {  // ObCSColumnHeader x ncol after the 12-byte ObAllColumnHeader: version, type, attrs, obj_type
+      for (uint32_t c = 0; c < ncol; ++c) {
+        const uint8_t t = p[header_size + 12u + 4u * c + 3];
+        if (b->col_types[c] == 0) b->col_types[c] = t;
+        else if (b->col_types[c] != t) b->col_types[c] = 0xff;
+      }
+      continue;
+    }
     for (uint32_t c = 0; c < ncol; ++c) {
       const uint8_t *ch = p + header_size + 16u * c;
       const int8_t type = (int8_t)ch[1];
@@ -1918,6 +1937,105 @@ static void layout_smem_scan(const obgpu_batch *b, ScanParams &p) {
   p.cw_bytes = (w + 127u) & ~127u;
 }
 
+
+// ---- pushed-down aggregates over the dense projected columns ------------------------------------------
+struct AggAcc {
+  unsigned long long lo, hi;   // SUM: 128-bit; MIN / MAX: lo = value, hi = seen; COUNT: lo
+};
+__device__ __forceinline__ void add128(unsigned long long &lo, unsigned long long &hi, unsigned long long alo,
+                                       unsigned long long ahi) {
+  const unsigned long long nlo = lo + alo;
+  hi += ahi + (nlo < lo ? 1ull : 0ull);
+  lo = nlo;
+}
+template <typename T>
+__device__ __forceinline__ long long agg_load(const void *data, int64_t i, bool sgn) {
+  const T v = reinterpret_cast<const T *>(data)[i];
+  return sgn ? (long long)(typename std::make_signed<T>::type)v : (long long)(unsigned long long)v;
+}
+__device__ __forceinline__ long long agg_value(const void *data, int elem_len, bool sgn, int64_t i) {
+  if (elem_len == 8) return (long long)reinterpret_cast<const unsigned long long *>(data)[i];
+  if (elem_len == 4) return agg_load<uint32_t>(data, i, sgn);
+  return agg_load<uint8_t>(data, i, sgn);
+}
+__global__ void __launch_bounds__(256) obgpu_aggregate_kernel(int kind, const void *a, const uint32_t *a_nulls, int a_len, int a_sgn,
+                                                              const void *b, const uint32_t *b_nulls, int b_len, int b_sgn,
+                                                              const int64_t *n_rows_ptr, unsigned long long *out) {
+  __shared__ unsigned long long s_lo[8], s_hi[8];
+  const int64_t n = *n_rows_ptr;
+  unsigned long long lo = 0, hi = 0;
+  const bool is_min = kind == OBGPU_AGG_MIN, is_max = kind == OBGPU_AGG_MAX;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    if ((a_nulls[i >> 5] >> (i & 31)) & 1u) continue;
+    if (kind == OBGPU_AGG_SUM_PRODUCT && ((b_nulls[i >> 5] >> (i & 31)) & 1u)) continue;
+    const long long va = agg_value(a, a_len, a_sgn != 0, i);
+    if (kind == OBGPU_AGG_COUNT) { ++lo; continue; }
+    if (kind == OBGPU_AGG_SUM) {
+      // 8-byte unsigned columns are zero-extended, everything else sign-extended into 128 bits
+      const bool neg = (a_sgn || a_len < 8) ? va < 0 : false;
+      add128(lo, hi, (unsigned long long)va, neg ? ~0ull : 0ull);
+      continue;
+    }
+    if (kind == OBGPU_AGG_SUM_PRODUCT) {
+      const long long vb = agg_value(b, b_len, b_sgn != 0, i);
+      const __int128 pa = (a_sgn || a_len < 8) ? (__int128)va : (__int128)(unsigned long long)va;
+      const __int128 pb = (b_sgn || b_len < 8) ? (__int128)vb : (__int128)(unsigned long long)vb;
+      const unsigned __int128 pr = (unsigned __int128)(pa * pb);
+      add128(lo, hi, (unsigned long long)pr, (unsigned long long)(pr >> 64));
+      continue;
+    }
+    // MIN / MAX in the column's own order
+    bool better;
+    if (!hi) better = true;
+    else if (a_sgn || a_len < 8) better = is_min ? va < (long long)lo : va > (long long)lo;
+    else better = is_min ? (unsigned long long)va < lo : (unsigned long long)va > lo;
+    if (better) { lo = (unsigned long long)va; hi = 1; }
+  }
+  // block reduction, then one atomic merge per CTA
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long olo = __shfl_xor_sync(0xffffffffu, lo, o), ohi = __shfl_xor_sync(0xffffffffu, hi, o);
+    if (is_min || is_max) {
+      bool take = false;
+      if (ohi) {
+        if (!hi) take = true;
+        else if (a_sgn || a_len < 8) take = is_min ? (long long)olo < (long long)lo : (long long)olo > (long long)lo;
+        else take = is_min ? olo < lo : olo > lo;
+      }
+      if (take) { lo = olo; hi = 1; }
+    } else {
+      add128(lo, hi, olo, ohi);
+    }
+  }
+  if (lane == 0) { s_lo[warp] = lo; s_hi[warp] = hi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
+      if (is_min || is_max) {
+        bool take = false;
+        if (s_hi[w]) {
+          if (!hi) take = true;
+          else if (a_sgn || a_len < 8) take = is_min ? (long long)s_lo[w] < (long long)lo : (long long)s_lo[w] > (long long)lo;
+          else take = is_min ? s_lo[w] < lo : s_lo[w] > lo;
+        }
+        if (take) { lo = s_lo[w]; hi = 1; }
+      } else {
+        add128(lo, hi, s_lo[w], s_hi[w]);
+      }
+    }
+    if (is_min || is_max) {
+      if (hi) {  // out[0]: order-preserving unsigned key (sign bit flipped for signed columns), out[1]: seen
+        const unsigned long long key = (a_sgn || a_len < 8) ? lo ^ (1ull << 63) : lo;
+        if (is_min) atomicMin(&out[0], key); else atomicMax(&out[0], key);
+        atomicOr(&out[1], 1ull);
+      }
+    } else {
+      const unsigned long long prev = atomicAdd(&out[0], lo);
+      atomicAdd(&out[1], hi + ((prev + lo) < prev ? 1ull : 0ull));
+    }
+  }
+}
+
 static int check_status(obgpu_ctx *ctx, int status) {
   if (status & ST_CORRUPT) { ctx->err = "corrupt micro block seen on device"; return OBGPU_INVALID_DATA; }
   if (status & ST_UNSUPPORTED) { ctx->err = "column encoding / type not handled by the device path"; return OBGPU_NOT_SUPPORTED; }
@@ -2114,38 +2232,93 @@ int obgpu_result_block_tables(obgpu_result *r, const int64_t **sel_offset_dev, c
   return OBGPU_SUCCESS;
 }
 
-int obgpu_result_fetch_col(obgpu_result *r, int32_t i, int64_t row_begin, int64_t row_count, void *host_data,
-                           void *host_aux, uint64_t *host_nulls) {
-  if (!r || i < 0 || i >= r->n_proj || row_begin < 0 || row_count < 0 || row_begin + row_count > r->cap)
-    return OBGPU_INVALID_ARGUMENT;
+int obgpu_result_aggregate(obgpu_result *r, int32_t kind, int32_t col_a, int32_t col_b, int64_t out[2]) {
+  if (!r || !out || kind < OBGPU_AGG_COUNT || kind > OBGPU_AGG_MAX || col_a < 0 || col_a >= r->n_proj) return OBGPU_INVALID_ARGUMENT;
+  if (kind == OBGPU_AGG_SUM_PRODUCT && (col_b < 0 || col_b >= r->n_proj)) return OBGPU_INVALID_ARGUMENT;
+  const ResultCol &a = r->cols[col_a];
+  const ResultCol &b = r->cols[kind == OBGPU_AGG_SUM_PRODUCT ? col_b : col_a];
+  if (a.is_string || b.is_string) return OBGPU_NOT_SUPPORTED;
   obgpu_ctx *ctx = r->ctx;
   cudaSetDevice(ctx->device);
-  const ResultCol &c = r->cols[i];
-  if (row_count == 0) return OBGPU_SUCCESS;
-  if (host_data)
-    CUDA_TRY(ctx, cudaMemcpyAsync(host_data, (uint8_t *)c.data + row_begin * c.elem_len, (size_t)row_count * c.elem_len,
-                                  cudaMemcpyDeviceToHost, ctx->stream));
-  if (host_aux && c.lens)
-    CUDA_TRY(ctx, cudaMemcpyAsync(host_aux, c.lens + row_begin, (size_t)row_count * 4, cudaMemcpyDeviceToHost, ctx->stream));
-  std::vector<uint64_t> tmp;
+  unsigned long long *d_out = nullptr;
+  CUDA_TRY(ctx, cudaMallocAsync((void **)&d_out, 32, ctx->stream));
+  CUDA_TRY(ctx, cudaMemsetAsync(d_out, 0, 32, ctx->stream));
+  if (kind == OBGPU_AGG_MIN) CUDA_TRY(ctx, cudaMemsetAsync(d_out, 0xff, 8, ctx->stream));
+  const int a_sgn = obf::store_class_of((uint8_t)a.obj_type) == 1, b_sgn = obf::store_class_of((uint8_t)b.obj_type) == 1;
+  // number of selected rows: last entry of the prefix (device resident: no host round trip before the launch)
+  obgpu_aggregate_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(kind, a.data, a.nulls, a.elem_len, a_sgn, b.data, b.nulls, b.elem_len,
+                                                                    b_sgn, r->d_sel_offset + r->batch->n_blocks, d_out);
+  ctx->launches++;
+  unsigned long long h[2] = {0, 0};
+  CUDA_TRY(ctx, cudaMemcpyAsync(h, d_out, 16, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  cudaFreeAsync(d_out, ctx->stream);
+  int status = 0;
+  {
+    obgpu_result_info info;
+    const int ret = obgpu_result_info_get(r, &info);  // surfaces overflow / unsupported of the scan itself
+    if (ret != OBGPU_SUCCESS) return ret;
+  }
+  (void)status;
+  if ((kind == OBGPU_AGG_MIN || kind == OBGPU_AGG_MAX) && (a_sgn || a.elem_len < 8)) h[0] ^= 1ull << 63;
+  out[0] = (int64_t)h[0];
+  out[1] = (int64_t)h[1];
+  return OBGPU_SUCCESS;
+}
+
+int obgpu_result_fetch_cols(obgpu_result *r, int32_t n_cols, const int32_t *cols, int64_t row_begin, int64_t row_count,
+                            void *const *host_data, void *const *host_aux, uint64_t *const *host_nulls) {
+  if (!r || n_cols < 0 || (n_cols > 0 && !cols) || row_begin < 0 || row_count < 0 || row_begin + row_count > r->cap)
+    return OBGPU_INVALID_ARGUMENT;
+  for (int32_t k = 0; k < n_cols; ++k)
+    if (cols[k] < 0 || cols[k] >= r->n_proj) return OBGPU_INVALID_ARGUMENT;
+  obgpu_ctx *ctx = r->ctx;
+  cudaSetDevice(ctx->device);
+  if (row_count == 0 || n_cols == 0) return OBGPU_SUCCESS;
   const int64_t w0 = row_begin / 64, w1 = (row_begin + row_count + 63) / 64;
   const int sh = (int)(row_begin % 64);
-  if (host_nulls) {
-    if (sh == 0) {
-      CUDA_TRY(ctx, cudaMemcpyAsync(host_nulls, (uint64_t *)c.nulls + w0, (size_t)(w1 - w0) * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    } else {
-      tmp.resize((size_t)(w1 - w0) + 1, 0);
-      CUDA_TRY(ctx, cudaMemcpyAsync(tmp.data(), (uint64_t *)c.nulls + w0, (size_t)(w1 - w0) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  std::vector<std::vector<uint64_t>> tmp((size_t)n_cols);
+  // every copy is enqueued before the single synchronisation
+  for (int32_t k = 0; k < n_cols; ++k) {
+    const ResultCol &c = r->cols[cols[k]];
+    void *hd = host_data ? host_data[k] : nullptr;
+    void *ha = host_aux ? host_aux[k] : nullptr;
+    uint64_t *hn = host_nulls ? host_nulls[k] : nullptr;
+    if (hd)
+      CUDA_TRY(ctx, cudaMemcpyAsync(hd, (uint8_t *)c.data + row_begin * c.elem_len, (size_t)row_count * c.elem_len,
+                                    cudaMemcpyDeviceToHost, ctx->stream));
+    if (ha && c.lens)
+      CUDA_TRY(ctx, cudaMemcpyAsync(ha, c.lens + row_begin, (size_t)row_count * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (hn) {
+      if (sh == 0) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(hn, (uint64_t *)c.nulls + w0, (size_t)(w1 - w0) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+      } else {
+        tmp[(size_t)k].resize((size_t)(w1 - w0) + 1, 0);
+        CUDA_TRY(ctx, cudaMemcpyAsync(tmp[(size_t)k].data(), (uint64_t *)c.nulls + w0, (size_t)(w1 - w0) * 8,
+                                      cudaMemcpyDeviceToHost, ctx->stream));
+      }
     }
   }
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-  if (host_nulls) {
-    const int64_t ow = (row_count + 63) / 64;
-    if (sh != 0)
-      for (int64_t k = 0; k < ow; ++k) host_nulls[k] = (tmp[(size_t)k] >> sh) | (tmp[(size_t)k + 1] << (64 - sh));
-    if (row_count % 64) host_nulls[ow - 1] &= (1ull << (row_count % 64)) - 1ull;
+  const int64_t ow = (row_count + 63) / 64;
+  for (int32_t k = 0; k < n_cols; ++k) {
+    uint64_t *hn = host_nulls ? host_nulls[k] : nullptr;
+    if (!hn) continue;
+    if (sh != 0) {
+      const std::vector<uint64_t> &t = tmp[(size_t)k];
+      for (int64_t j = 0; j < ow; ++j) hn[j] = (t[(size_t)j] >> sh) | (t[(size_t)j + 1] << (64 - sh));
+    }
+    if (row_count % 64) hn[ow - 1] &= (1ull << (row_count % 64)) - 1ull;
   }
   return OBGPU_SUCCESS;
+}
+
+int obgpu_result_fetch_col(obgpu_result *r, int32_t i, int64_t row_begin, int64_t row_count, void *host_data,
+                           void *host_aux, uint64_t *host_nulls) {
+  if (!r || i < 0 || i >= r->n_proj) return OBGPU_INVALID_ARGUMENT;
+  void *hd[1] = {host_data}, *ha[1] = {host_aux};
+  uint64_t *hn[1] = {host_nulls};
+  return obgpu_result_fetch_cols(r, 1, &i, row_begin, row_count, hd, ha, hn);
 }
 
 int obgpu_result_fetch_sel_offsets(obgpu_result *r, int64_t *host_sel_offset) {

@@ -139,6 +139,17 @@ struct alignas(16) ColDesc {
 };
 static_assert(sizeof(ColDesc) == 96, "ColDesc layout is shared by the index kernel and the scan kernels");
 
+// K_BITS columns of CS_ENCODING_ROW_STORE blocks reuse the (otherwise RAW-var-only) fields:
+//   var_ext_in_row -> XOR applied to the row index of an ext lookup (7: the CS null bitmap is MSB-first
+//                     per byte, so bit `row` of it is bit `row ^ 7` of an LSB-first stream; 0 for PAX)
+//   var_is_last    -> 1: NULL is a replaced value (ObIntegerStreamMeta REPLACE_NULL_VALUE)
+//   var_header_off / var_k -> low / high half of the raw value that stands for NULL (null_replaced - base)
+__device__ __forceinline__ uint32_t ext_row(const ColDesc &d, uint32_t row) { return row ^ (uint32_t)d.var_ext_in_row; }
+__device__ __forceinline__ bool null_replaced_on(const ColDesc &d) { return d.kind == K_BITS && d.var_is_last != 0; }
+__device__ __forceinline__ uint64_t null_replaced_raw(const ColDesc &d) {
+  return ((uint64_t)d.var_k << 32) | (uint64_t)d.var_header_off;
+}
+
 __device__ __forceinline__ bool is_dict_kind(const ColDesc &d) {
   return d.kind == K_DICT || d.kind == K_RLE || d.kind == K_CONST;
 }
@@ -155,6 +166,11 @@ struct BlockView {
   uint8_t row_index_byte, ext_bit;
   uint16_t var_col_cnt;
   uint8_t ok;
+  uint8_t is_cs;           // CS_ENCODING_ROW_STORE block: the fields below replace the PAX ones
+  uint16_t cs_stream_count;
+  uint32_t cs_first_stream_begin;  // header + ObAllColumnHeader + ObCSColumnHeader x ncol
+  uint32_t cs_off_data;            // block offset of the stream end offsets array
+  uint32_t cs_off_width;           // bytes per stream end offset
 };
 
 // Per-block record written once at batch open by the index kernel: everything the scan kernels
@@ -188,6 +204,72 @@ __device__ __forceinline__ void view_from_rec(const BlockRec &r, const uint8_t *
   b.ext_bit = r.ext_bit;
   b.var_col_cnt = r.var_col_cnt;
   b.ok = r.rows > 0;
+  b.is_cs = r.pad[0];   // the scan kernels work from the plans: the CS stream tables are not needed again
+  b.cs_stream_count = 0;
+  b.cs_first_stream_begin = b.cs_off_data = b.cs_off_width = 0;
+}
+
+// ObIntegerStreamMeta, serialized (cs_encoding/ob_stream_encoding_struct.cpp:27-77)
+struct IntStreamMeta {
+  uint32_t width;      // bytes
+  uint32_t meta_len;
+  uint64_t base, null_replaced;
+  uint8_t use_base, replace_null, ok;
+};
+__device__ __forceinline__ bool rd_vi64(const uint8_t *s, uint32_t &pos, uint32_t end, uint64_t &v) {
+  uint64_t r = 0;
+  int shift = 0;
+  while (pos < end && shift <= 63) {
+    const uint8_t c = s[pos++];
+    r |= (uint64_t)(c & 0x7f) << shift;
+    if (!(c & 0x80)) { v = r; return true; }
+    shift += 7;
+  }
+  return false;
+}
+__device__ __forceinline__ void parse_int_stream_meta(const uint8_t *s, uint32_t at, uint32_t end, IntStreamMeta &m) {
+  m = IntStreamMeta{};
+  if (at + 4u > end) return;
+  const uint8_t version = s[at], attr = s[at + 1], type = s[at + 2], wtag = s[at + 3];
+  uint32_t pos = at + 4u;
+  m.use_base = attr & IS_USE_BASE;
+  m.replace_null = (attr & IS_REPLACE_NULL_VALUE) != 0;
+  if (m.use_base && !rd_vi64(s, pos, end, m.base)) return;
+  if (m.replace_null && !rd_vi64(s, pos, end, m.null_replaced)) return;
+  if (attr & IS_DECIMAL_INT) return;
+  if (version > 0) { if (pos >= end) return; ++pos; }
+  if (wtag > 3 || type != IS_RAW) return;   // the other stream codecs need the CPU transformer
+  m.width = 1u << wtag;
+  m.meta_len = pos - at;
+  m.ok = 1;
+}
+
+// CS block: ObCSMicroBlockTransformer::init / decode_stream_offsets_ (ob_cs_micro_block_transformer.cpp:106-202)
+__device__ __forceinline__ void parse_cs_block(const uint8_t *s, uint32_t size, int16_t magic, int16_t version, BlockView &b) {
+  b.is_cs = 1;
+  b.ok = 0;
+  b.row_index_off = 0;
+  b.row_index_byte = b.ext_bit = 0;
+  b.var_col_cnt = 0;
+  b.row_data_off = size;
+  if (magic != MICRO_BLOCK_HEADER_MAGIC || version < 1 || version > 3 || b.header_size < 64 || b.row_count == 0) return;
+  const uint32_t ah = b.header_size;
+  b.meta_off = ah + 12u + 4u * b.column_count;   // ObAllColumnHeader + ObCSColumnHeader x ncol
+  if (b.meta_off > size) return;
+  if (s[ah] != 0 || (s[ah + 1] & 0x3)) return;  // transformed / compressed string data: not handled
+  const uint32_t offsets_len = (uint32_t)ld_bytes(s, ah + 6, 4);
+  b.cs_stream_count = (uint16_t)ld_bytes(s, ah + 10, 2);
+  b.cs_first_stream_begin = b.meta_off;
+  if (offsets_len > size - b.meta_off) return;
+  if (b.cs_stream_count > 0) {
+    IntStreamMeta m;
+    parse_int_stream_meta(s, size - offsets_len, size, m);
+    if (!m.ok || m.use_base || m.width > 4) return;
+    if (m.meta_len + m.width * b.cs_stream_count != offsets_len) return;
+    b.cs_off_data = size - offsets_len + m.meta_len;
+    b.cs_off_width = m.width;
+  }
+  b.ok = 1;
 }
 
 __device__ __forceinline__ void parse_block(const uint8_t *s, uint32_t size, BlockView &b) {
@@ -205,6 +287,13 @@ __device__ __forceinline__ void parse_block(const uint8_t *s, uint32_t size, Blo
   b.ext_bit = (opt >> 3) & 7;
   b.row_data_off = ld32(s, 24);
   b.meta_off = b.header_size + 16u * b.column_count;
+  b.is_cs = 0;
+  b.cs_stream_count = 0;
+  b.cs_first_stream_begin = b.cs_off_data = b.cs_off_width = 0;
+  if (row_store_type == CS_ENCODING_ROW_STORE) {
+    parse_cs_block(s, size, magic, version, b);
+    return;
+  }
   b.ok = magic == MICRO_BLOCK_HEADER_MAGIC && version >= 1 && version <= 3 &&
          (row_store_type == ENCODING_ROW_STORE || row_store_type == SELECTIVE_ENCODING_ROW_STORE) &&
          b.meta_off <= size && b.row_data_off <= size && b.header_size >= 64 && b.row_count > 0;
@@ -216,12 +305,92 @@ __device__ __forceinline__ void parse_block(const uint8_t *s, uint32_t size, Blo
   }
 }
 
+// CS INTEGER column -> K_BITS plan. Walks the column headers like
+// ObCSMicroBlockTransformer::build_original_transform_desc_ (ob_cs_micro_block_transformer.cpp:216-380)
+// to find the column's meta and first stream; value = raw + base (ConvertUintToDatum_T,
+// ob_integer_stream_decoder.cpp:37-350); NULL by MSB-first bitmap or by replaced value.
+__device__ __forceinline__ void build_cs_col_desc(const BlockView &b, int col, ColDesc &d) {
+  const uint8_t *s = b.s;
+  const uint32_t bitmap_bytes = (b.row_count + 7u) >> 3;
+  const uint32_t hdrs = b.header_size + 12u;
+  uint32_t pos = b.cs_first_stream_begin;
+  int stream_idx = -1;
+  for (int i = 0; i <= col; ++i) {
+    const uint32_t w = ld32(s, hdrs + 4u * (uint32_t)i);
+    const uint32_t type = (w >> 8) & 0xff, attrs = (w >> 16) & 0xff;
+    if ((w & 0xff) != 0) return;
+    int n_streams;
+    uint32_t meta_len = 0;
+    if (type == CS_INTEGER) {
+      n_streams = 1;
+      meta_len = ((attrs & CS_HAS_NULL_OR_NOP_BITMAP) ? bitmap_bytes : 0u) + ((attrs & CS_HAS_NOP_BITMAP) ? bitmap_bytes : 0u);
+    } else if (type == CS_STRING) {
+      n_streams = (attrs & CS_IS_FIXED_LENGTH) ? 1 : 2;
+    } else if (type == CS_INT_DICT || type == CS_STR_DICT) {
+      if (pos + 10u > b.size) return;
+      const uint32_t distinct = (uint32_t)ld_bytes(s, pos + 2, 4);
+      meta_len = 10u + ((attrs & CS_HAS_NOP_BITMAP) ? bitmap_bytes : 0u);
+      n_streams = distinct == 0 ? 0 : (type == CS_INT_DICT ? 2 : ((attrs & CS_IS_FIXED_LENGTH) ? 2 : 3));
+    } else {
+      return;
+    }
+    if (i == col) {
+      d.type = (uint8_t)(100 + type);
+      d.attr = (uint8_t)attrs;
+      d.obj_type = (uint8_t)(w >> 24);
+      const int sc = store_class_of(d.obj_type);
+      if (type != CS_INTEGER || (sc != 1 && sc != 2)) return;
+      if (attrs & (CS_HAS_NOP_BITMAP | CS_HAS_NOP | CS_OUT_ROW)) return;
+      if (stream_idx + 1 >= (int)b.cs_stream_count) return;
+      const uint32_t end = (uint32_t)ld_bytes(s, b.cs_off_data + (uint32_t)(stream_idx + 1) * b.cs_off_width, b.cs_off_width);
+      if (end > b.size || pos + meta_len > end) return;
+      IntStreamMeta m;
+      parse_int_stream_meta(s, pos + meta_len, end, m);
+      if (!m.ok) return;
+      const uint32_t data = pos + meta_len + m.meta_len;
+      if (data + m.width * b.row_count != end) return;
+      d.sc = (uint8_t)sc;
+      d.elem_len = (uint8_t)datum_len_of(d.obj_type);
+      d.int_mask = 0;
+      d.kind = K_BITS;
+      d.width = (uint8_t)(m.width * 8u);
+      d.stride = m.width * 8u;
+      d.val_bit = data * 8u;
+      d.base = m.use_base ? m.base : 0;
+      d.sign_fix = 0;
+      if (attrs & CS_HAS_NULL_OR_NOP_BITMAP) {
+        d.ext_bit = 1;
+        d.ext_bit_off = pos * 8u;
+        d.var_ext_in_row = 7;   // MSB-first bitmap (see ext_row)
+      } else if (m.replace_null) {
+        uint64_t raw = m.null_replaced - d.base;
+        if (m.width < 8) raw &= low_mask(m.width * 8u);
+        d.var_is_last = 1;
+        d.var_header_off = (uint32_t)raw;
+        d.var_k = (uint32_t)(raw >> 32);
+      }
+      d.ok = 1;
+      return;
+    }
+    if (n_streams == 0) pos += meta_len;
+    else {
+      stream_idx += n_streams;
+      if (stream_idx >= (int)b.cs_stream_count) return;
+      pos = (uint32_t)ld_bytes(s, b.cs_off_data + (uint32_t)stream_idx * b.cs_off_width, b.cs_off_width);
+    }
+  }
+}
+
 // Builds the descriptor of column `col`. Mirrors the decoder init of each codec.
 __device__ __forceinline__ void build_col_desc(const BlockView &b, int col, ColDesc &d) {
   const uint8_t *s = b.s;
   d = ColDesc{};
   d.rle_slot = -1;
   if (col < 0 || (uint32_t)col >= b.column_count) return;
+  if (b.is_cs) {
+    build_cs_col_desc(b, col, d);
+    return;
+  }
   const uint32_t ch = b.header_size + 16u * (uint32_t)col;
   const uint32_t w0 = ld32(s, ch);
   if ((w0 & 0xff) != 0) return;  // version
@@ -541,11 +710,16 @@ __device__ __forceinline__ uint64_t int_cell(const BlockView &b, const ColDesc &
     if (ref >= d.dict_count) { is_null = true; return 0; }
     return dict_int(s, d, ref);
   }
-  if (d.ext_bit && ld_bits32(s, d.ext_bit_off + row * d.ext_bit, d.ext_bit) != STORED_NOT_EXT) {
+  if (d.ext_bit && ld_bits32(s, d.ext_bit_off + ext_row(d, row) * d.ext_bit, d.ext_bit) != STORED_NOT_EXT) {
     is_null = true;
     return 0;
   }
-  const uint64_t v = ld_bits(s, d.val_bit + row * d.stride, d.width) + d.base;
+  const uint64_t raw = ld_bits(s, d.val_bit + row * d.stride, d.width);
+  if (null_replaced_on(d) && raw == null_replaced_raw(d)) {
+    is_null = true;
+    return 0;
+  }
+  const uint64_t v = raw + d.base;
   return d.sign_fix ? sign_fix(d.int_mask, v) : v;
 }
 

@@ -300,6 +300,77 @@ size_t store_str_dict_meta(Buf &meta, const StrDict &d) {
   return at;
 }
 
+// Fills the 64-byte micro block header in front of the finished payload: CRC-32C payload checksum
+// (ob_crc64_sse42, seed 0, no final xor) and the 16-bit header checksum (ob_micro_block_header.cpp:193-224).
+void finish_header(std::vector<uint8_t> &block, uint32_t header_size, int32_t ncol, int32_t rowkey_cnt, int64_t nrows,
+                   uint8_t row_store_type, uint8_t opt, uint16_t opt2, uint32_t row_offset, int64_t original) {
+  uint8_t *b = block.data();
+  const size_t total = block.size();
+  MicroBlockHeader h{};
+  h.magic_ = MICRO_BLOCK_HEADER_MAGIC;
+  h.version_ = MICRO_BLOCK_HEADER_VERSION;
+  h.header_size_ = header_size;
+  h.column_count_ = (uint16_t)ncol;
+  h.rowkey_column_count_ = (uint16_t)rowkey_cnt;
+  h.flag16_ = (uint16_t)(1u << 2);  // all_lob_in_row_ = 1, no column checksum
+  h.row_count_ = (uint32_t)nrows;
+  h.row_store_type_ = row_store_type;
+  h.opt_ = opt;
+  h.opt2_ = opt2;
+  h.row_data_offset_ = row_offset;
+  h.original_length_ = (int32_t)std::min<int64_t>(original, INT32_MAX);
+  h.max_merged_trans_version_ = 0;
+  h.data_length_ = (int32_t)(total - header_size);
+  h.data_zlength_ = h.data_length_;
+  h.data_checksum_ = 0;
+  h.column_checksums_ptr_ = 0;
+  // payload checksum: ob_crc64_sse42 == CRC-32C (Castagnoli) with seed 0 and no final xor
+  {
+    uint64_t crc = 0;
+    const uint8_t *p = b + header_size;
+    size_t len = total - header_size;
+    static uint32_t tab[256];
+    static std::atomic<int> tab_ready{0};
+    if (!tab_ready.load(std::memory_order_acquire)) {
+      uint32_t t[256];
+      for (uint32_t n = 0; n < 256; ++n) {
+        uint32_t cc = n;
+        for (int k = 0; k < 8; ++k) cc = (cc & 1) ? 0x82f63b78u ^ (cc >> 1) : cc >> 1;
+        t[n] = cc;
+      }
+      memcpy(tab, t, sizeof(t));
+      tab_ready.store(1, std::memory_order_release);
+    }
+    uint32_t c32 = (uint32_t)crc;
+    for (size_t k = 0; k < len; ++k) c32 = tab[(c32 ^ p[k]) & 0xff] ^ (c32 >> 8);
+    h.data_checksum_ = (int64_t)(uint64_t)c32;
+  }
+  // header checksum: ob_micro_block_header.cpp:203-233
+  {
+    int16_t cs = 0;
+    auto f64 = [&](int64_t v) { for (int k = 0; k < 4; ++k) cs = (int16_t)(cs ^ ((v >> (k * 16)) & 0xFFFF)); };
+    auto f32 = [&](int32_t v) { for (int k = 0; k < 2; ++k) cs = (int16_t)(cs ^ ((v >> (k * 16)) & 0xFFFF)); };
+    cs = (int16_t)(cs ^ h.magic_);
+    cs = (int16_t)(cs ^ h.version_);
+    cs = (int16_t)(cs ^ (int16_t)h.row_store_type_);
+    cs = (int16_t)(cs ^ (int16_t)h.opt_);
+    f32(h.column_count_);
+    f32(h.rowkey_column_count_);
+    f32(h.flag16_ & 1);
+    f32(h.opt2_);
+    f64(h.header_size_);
+    f64(h.row_count_);
+    f64(h.row_data_offset_);
+    f64(h.original_length_);
+    f64(h.max_merged_trans_version_);
+    f64(h.data_length_);
+    f64(h.data_zlength_);
+    f64(h.data_checksum_);
+    h.header_checksum_ = cs;
+  }
+  memcpy(b, &h, sizeof(h));
+}
+
 struct BlockBuilder {
   const obgpu_col_input *cols;
   int32_t ncol;
@@ -315,6 +386,7 @@ struct BlockBuilder {
   int encode_rle(int i);
   int encode_base_diff(int i);
   int encode_const(int i);
+  int build_cs(std::vector<uint8_t> &block, int64_t original);
   int build(std::vector<uint8_t> &block);
 };
 
@@ -624,6 +696,12 @@ int BlockBuilder::build(std::vector<uint8_t> &block) {
     if (c.null_cnt > 0 && ext_bit < 1) ext_bit = 1;
     if (c.nope_cnt > 0) ext_bit = 2;
   }
+  {
+    int n_cs = 0;
+    for (int i = 0; i < ncol; ++i) n_cs += cols[i].encoding >= OBGPU_ENC_CS_INTEGER;
+    if (n_cs == ncol) return build_cs(block, original);
+    if (n_cs != 0) return OBGPU_INVALID_ARGUMENT;  // one row store type per block
+  }
   for (int i = 0; i < ncol; ++i) {
     out[(size_t)i].hdr.obj_type_ = (uint8_t)cols[i].obj_type;
     int ret;
@@ -714,69 +792,146 @@ int BlockBuilder::build(std::vector<uint8_t> &block) {
   for (size_t k = 0; k < row_index.size(); ++k)
     memcpy(b + row_data_off + rows.size() + k * (size_t)row_index_byte, &row_index[k], (size_t)row_index_byte);
 
-  MicroBlockHeader h{};
-  h.magic_ = MICRO_BLOCK_HEADER_MAGIC;
-  h.version_ = MICRO_BLOCK_HEADER_VERSION;
-  h.header_size_ = header_size;
-  h.column_count_ = (uint16_t)ncol;
-  h.rowkey_column_count_ = (uint16_t)rowkey_cnt;
-  h.flag16_ = (uint16_t)(1u << 2);  // all_lob_in_row_ = 1, no column checksum
-  h.row_count_ = (uint32_t)nrows;
-  h.row_store_type_ = ENCODING_ROW_STORE;
-  h.opt_ = (uint8_t)((row_index_byte & 7) | ((ext_bit & 7) << 3));
-  h.opt2_ = (uint16_t)var_cols.size();
-  h.row_data_offset_ = (uint32_t)row_data_off;
-  h.original_length_ = (int32_t)std::min<int64_t>(original, INT32_MAX);
-  h.max_merged_trans_version_ = 0;
-  h.data_length_ = (int32_t)(total - header_size);
-  h.data_zlength_ = h.data_length_;
-  h.data_checksum_ = 0;
-  h.column_checksums_ptr_ = 0;
-  // payload checksum: ob_crc64_sse42 == CRC-32C (Castagnoli) with seed 0 and no final xor
-  {
-    uint64_t crc = 0;
-    const uint8_t *p = b + header_size;
-    size_t len = total - header_size;
-    static uint32_t tab[256];
-    static std::atomic<int> tab_ready{0};
-    if (!tab_ready.load(std::memory_order_acquire)) {
-      uint32_t t[256];
-      for (uint32_t n = 0; n < 256; ++n) {
-        uint32_t cc = n;
-        for (int k = 0; k < 8; ++k) cc = (cc & 1) ? 0x82f63b78u ^ (cc >> 1) : cc >> 1;
-        t[n] = cc;
-      }
-      memcpy(tab, t, sizeof(t));
-      tab_ready.store(1, std::memory_order_release);
+  finish_header(block, header_size, ncol, rowkey_cnt, nrows, ENCODING_ROW_STORE,
+                (uint8_t)((row_index_byte & 7) | ((ext_bit & 7) << 3)), (uint16_t)var_cols.size(), (uint32_t)row_data_off,
+                original);
+  return OBGPU_SUCCESS;
+}
+
+// ---- CS_ENCODING_ROW_STORE block (ObMicroBlockCSEncoder::build_block, cs_encoding/ob_micro_block_cs_encoder.cpp:1394):
+//   [header][ObAllColumnHeader][ObCSColumnHeader x ncol][per column: meta (null bitmap) + integer streams]
+//   [all string data (none here)][stream offsets = one more integer stream]
+// Integer streams are written RAW (serialized ObIntegerStreamMeta + width-byte array); the width / base / null
+// replacement rules follow ObIntegerColumnEncoder::build_signed_stream_meta_ / build_unsigned_encoder_ctx_
+// (cs_encoding/ob_integer_column_encoder.cpp:177-287) and ObIntegerStreamEncoderCtx::build_*_stream_meta
+// (ob_stream_encoding_struct.cpp:101-190). Stream end offsets are relative to the block start.
+static void put_vi64(Buf &b, uint64_t v) {  // serialization::encode_vi64
+  while (v > 0x7f) { *b.grow(1) = (uint8_t)(v | 0x80); v >>= 7; }
+  *b.grow(1) = (uint8_t)(v & 0x7f);
+}
+static uint8_t width_tag(int bytes) { return bytes == 1 ? 0 : (bytes == 2 ? 1 : (bytes == 4 ? 2 : 3)); }
+
+struct IntStreamPlan {
+  int width = 1;
+  bool use_base = false, replace_null = false;
+  uint64_t base = 0, null_replaced = 0;
+};
+static void put_stream_meta(Buf &b, const IntStreamPlan &sp) {
+  uint8_t *p = b.grow(4);
+  p[0] = INTEGER_STREAM_META_V2;
+  p[1] = (uint8_t)((sp.use_base ? IS_USE_BASE : 0) | (sp.replace_null ? IS_REPLACE_NULL_VALUE : 0));
+  p[2] = IS_RAW;
+  p[3] = width_tag(sp.width);
+  if (sp.use_base) put_vi64(b, sp.base);
+  if (sp.replace_null) put_vi64(b, sp.null_replaced);
+  *b.grow(1) = 1;  // pfor_packing_type_: CPU_ARCH_INDEPENDANT_SCALAR
+}
+
+int BlockBuilder::build_cs(std::vector<uint8_t> &block, int64_t original) {
+  const uint32_t header_size = (uint32_t)sizeof(MicroBlockHeader);
+  Buf body;  // everything after the micro header
+  body.grow(sizeof(AllColumnHeader) + sizeof(CSColumnHeader) * (size_t)ncol);
+  std::vector<CSColumnHeader> chdr((size_t)ncol);
+  std::vector<uint32_t> stream_end;  // relative to the block start
+  const size_t bitmap_bytes = (size_t)((nrows + 7) / 8);
+  for (int i = 0; i < ncol; ++i) {
+    ColCtx &c = ctx[(size_t)i];
+    CSColumnHeader &ch = chdr[(size_t)i];
+    ch = CSColumnHeader{};
+    ch.obj_type_ = (uint8_t)cols[i].obj_type;
+    if (cols[i].encoding != OBGPU_ENC_CS_INTEGER || (c.sc != 1 && c.sc != 2)) return OBGPU_NOT_SUPPORTED;
+    if (c.nope_cnt > 0) return OBGPU_NOT_SUPPORTED;
+    ch.type_ = CS_INTEGER;
+    const int ts = type_store_size((uint8_t)cols[i].obj_type);
+    const uint64_t mask = low_mask(ts * 8);
+    const bool sgn = c.sc == 1;
+    // value range over the non-null cells, in the column's own domain
+    bool any = false;
+    int64_t smin = 0, smax = 0;
+    uint64_t umin = 0, umax = 0;
+    for (int64_t r = 0; r < nrows; ++r) {
+      if (c.is_null(r)) continue;
+      const int64_t sv = c.ival(r);
+      const uint64_t uv = (uint64_t)sv & mask;
+      if (!any) { smin = smax = sv; umin = umax = uv; any = true; }
+      else { smin = std::min(smin, sv); smax = std::max(smax, sv); umin = std::min(umin, uv); umax = std::max(umax, uv); }
     }
-    uint32_t c32 = (uint32_t)crc;
-    for (size_t k = 0; k < len; ++k) c32 = tab[(c32 ^ p[k]) & 0xff] ^ (c32 >> 8);
-    h.data_checksum_ = (int64_t)(uint64_t)c32;
+    IntStreamPlan sp;
+    bool bitmap = false;
+    if (sgn) {
+      const uint64_t rmask = ~mask;
+      const int64_t type_min = rmask == 0 ? INT64_MIN : (int64_t)(rmask | (rmask >> 1));
+      const int64_t type_max = (int64_t)(mask >> 1);
+      int64_t nmin = smin, nmax = smax;
+      if (c.null_cnt > 0) {
+        if (!any) { nmin = nmax = 0; }
+        if (nmin == 0) {
+          if (nmax != type_max) { nmax = nmax + 1; sp.replace_null = true; sp.null_replaced = (uint64_t)nmax; }
+          else { nmin = -1; sp.replace_null = true; sp.null_replaced = (uint64_t)nmin; }
+        } else if (nmin == type_min) {
+          if (nmax != type_max) { nmax = nmax + 1; sp.replace_null = true; sp.null_replaced = (uint64_t)nmax; }
+          else bitmap = true;
+        } else {
+          nmin = nmin - 1; sp.replace_null = true; sp.null_replaced = (uint64_t)nmin;
+        }
+      }
+      if (nmin < 0) {
+        sp.use_base = true;
+        sp.base = (uint64_t)nmin;
+        sp.width = (int)byte_packed_int_size((uint64_t)nmax - (uint64_t)nmin);
+      } else {
+        sp.width = (int)byte_packed_int_size((uint64_t)nmax);
+      }
+    } else {
+      uint64_t nmin = umin, nmax = umax;
+      if (c.null_cnt > 0) {
+        if (!any) { nmin = nmax = 0; }
+        if (nmin == 0) {
+          if (nmax != mask) { nmax = nmax + 1; sp.replace_null = true; sp.null_replaced = nmax; }
+          else bitmap = true;
+        } else {
+          nmin = nmin - 1; sp.replace_null = true; sp.null_replaced = nmin;
+        }
+      }
+      sp.width = (int)byte_packed_int_size(nmax);
+    }
+    if (bitmap) {
+      ch.attrs_ |= CS_HAS_NULL_OR_NOP_BITMAP;
+      uint8_t *bm = body.grow(bitmap_bytes);
+      memset(bm, 0, bitmap_bytes);
+      for (int64_t r = 0; r < nrows; ++r)
+        if (c.is_null(r)) bm[r / 8] |= (uint8_t)(1u << (7 - r % 8));  // MSB first (ob_icolumn_cs_encoder.cpp:100-123)
+    }
+    put_stream_meta(body, sp);
+    uint8_t *data = body.grow((size_t)sp.width * (size_t)nrows);
+    for (int64_t r = 0; r < nrows; ++r) {
+      uint64_t v;
+      if (c.is_null(r)) v = sp.replace_null ? sp.null_replaced - sp.base : 0;
+      else v = (sgn ? (uint64_t)c.ival(r) : ((uint64_t)c.ival(r) & mask)) - sp.base;
+      memcpy(data + (size_t)r * (size_t)sp.width, &v, (size_t)sp.width);
+    }
+    stream_end.push_back(header_size + (uint32_t)body.size());
   }
-  // header checksum: ob_micro_block_header.cpp:203-233
+  // stream offsets: an integer stream without base (ObMicroBlockCSEncoder::store_stream_offsets_, :1312-1372)
+  const size_t offsets_at = body.size();
   {
-    int16_t cs = 0;
-    auto f64 = [&](int64_t v) { for (int k = 0; k < 4; ++k) cs = (int16_t)(cs ^ ((v >> (k * 16)) & 0xFFFF)); };
-    auto f32 = [&](int32_t v) { for (int k = 0; k < 2; ++k) cs = (int16_t)(cs ^ ((v >> (k * 16)) & 0xFFFF)); };
-    cs = (int16_t)(cs ^ h.magic_);
-    cs = (int16_t)(cs ^ h.version_);
-    cs = (int16_t)(cs ^ (int16_t)h.row_store_type_);
-    cs = (int16_t)(cs ^ (int16_t)h.opt_);
-    f32(h.column_count_);
-    f32(h.rowkey_column_count_);
-    f32(h.flag16_ & 1);
-    f32(h.opt2_);
-    f64(h.header_size_);
-    f64(h.row_count_);
-    f64(h.row_data_offset_);
-    f64(h.original_length_);
-    f64(h.max_merged_trans_version_);
-    f64(h.data_length_);
-    f64(h.data_zlength_);
-    f64(h.data_checksum_);
-    h.header_checksum_ = cs;
+    IntStreamPlan sp;
+    sp.width = (int)byte_packed_int_size(stream_end.back());
+    if (sp.width > 4) return OBGPU_NOT_SUPPORTED;
+    put_stream_meta(body, sp);
+    uint8_t *data = body.grow((size_t)sp.width * stream_end.size());
+    for (size_t k = 0; k < stream_end.size(); ++k) memcpy(data + k * (size_t)sp.width, &stream_end[k], (size_t)sp.width);
   }
-  memcpy(b, &h, sizeof(h));
+  AllColumnHeader ah{};
+  ah.all_string_data_length_ = 0;
+  ah.stream_offsets_length_ = (uint32_t)(body.size() - offsets_at);
+  ah.stream_count_ = (uint16_t)stream_end.size();
+  memcpy(body.d.data(), &ah, sizeof(ah));
+  memcpy(body.d.data() + sizeof(ah), chdr.data(), sizeof(CSColumnHeader) * (size_t)ncol);
+  block.assign(header_size + body.size(), 0);
+  memcpy(block.data() + header_size, body.d.data(), body.size());
+  // opt_: single_version_rows_ etc. = 0; opt2_: compressor_type_ = NONE, has_row_header_ = 0
+  finish_header(block, header_size, ncol, rowkey_cnt, nrows, CS_ENCODING_ROW_STORE, 0, (uint16_t)COMPRESSOR_NONE, 0, original);
   return OBGPU_SUCCESS;
 }
 

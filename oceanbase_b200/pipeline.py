@@ -54,7 +54,8 @@ class HostScanPipeline:
         self.ctxs = []
 
     def scan(self, table: TableImage, filter, proj: Sequence[int], blocks_per_batch: int, selectivity_hint: float,
-             out_buffers: Optional[List[List[np.ndarray]]] = None, string_base: int = 0) -> List[BatchOutput]:
+             out_buffers: Optional[List[List[np.ndarray]]] = None, string_base: int = 0,
+             null_buffers: Optional[List[List[np.ndarray]]] = None) -> List[BatchOutput]:
         parts = split_table(table, blocks_per_batch)
         outs: List[Optional[BatchOutput]] = [None] * len(parts)
         errors = []
@@ -85,13 +86,22 @@ class HostScanPipeline:
                         else:
                             raise
                     cols, lens, nulls, hn = [], [], [], []
-                    for c in range(len(proj)):
-                        ob = out_buffers[i][c] if out_buffers is not None else None
-                        d, l, nl = res.fetch_col(c, 0, n, out=ob)     # D2H
-                        cols.append(d)
-                        lens.append(l)
-                        nulls.append(nl)
-                        hn.append(res.col(c).has_null)
+                    is_str = [res.col(c).is_string for c in range(len(proj))]
+                    if not any(is_str):
+                        # one synchronisation for the whole batch: every column's D2H is enqueued first
+                        cols, nulls = res.fetch_cols(list(range(len(proj))), 0, n,
+                                                     outs=out_buffers[i] if out_buffers is not None else None,
+                                                     out_nulls=null_buffers[i] if null_buffers is not None else None)
+                        lens = [None] * len(proj)
+                        hn = [res.col(c).has_null for c in range(len(proj))]
+                    else:
+                        for c in range(len(proj)):
+                            ob = out_buffers[i][c] if out_buffers is not None else None
+                            d, l, nl = res.fetch_col(c, 0, n, out=ob)     # D2H
+                            cols.append(d)
+                            lens.append(l)
+                            nulls.append(nl)
+                            hn.append(res.col(c).has_null)
                     outs[i] = BatchOutput(i * blocks_per_batch, i * blocks_per_batch + part.n_blocks, batch.total_rows,
                                           n, cols, lens, nulls, hn)
                     res.free()

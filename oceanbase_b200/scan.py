@@ -276,6 +276,42 @@ class ScanResult:
               "obgpu_result_fetch_col", self.batch.ctx._h)
         return data[:row_count], (aux[:row_count] if aux is not None else None), nulls[:(row_count + 63) // 64]
 
+    def fetch_cols(self, idxs, row_begin=0, row_count=None, outs=None, out_nulls=None):
+        """Several integer-class columns with one synchronisation (obgpu_result_fetch_cols). Returns
+        ([data], [nulls words]); outs / out_nulls: optional preallocated (pinned) arrays per column."""
+        if row_count is None:
+            row_count = self.selected_rows - row_begin
+        n = len(idxs)
+        cols = [self.col(i) for i in idxs]
+        datas, nulls = [], []
+        for k, c in enumerate(cols):
+            if c.is_string:
+                raise ValueError("fetch_cols handles integer-class columns; use fetch_col for strings")
+            dt = {8: np.uint64, 4: np.uint32, 1: np.uint8}[c.elem_len]
+            datas.append(np.empty(max(row_count, 1), dtype=dt) if outs is None else outs[k])
+            nulls.append(np.zeros(max((row_count + 63) // 64, 1), dtype=np.uint64) if out_nulls is None else out_nulls[k])
+        ci = (C.c_int32 * max(n, 1))(*idxs)
+        hd = (C.c_void_p * max(n, 1))(*[d.ctypes.data for d in datas])
+        hn = (C.c_void_p * max(n, 1))(*[x.ctypes.data for x in nulls])
+        check(lib.obgpu_result_fetch_cols(self._h, n, ci, row_begin, row_count, hd, None, hn), "obgpu_result_fetch_cols",
+              self.batch.ctx._h)
+        return [d[:row_count] for d in datas], [x[:(row_count + 63) // 64] for x in nulls]
+
+    def aggregate(self, kind: int, col_a: int, col_b: int = -1):
+        """Pushed-down aggregate over the selected rows (obgpu_result_aggregate). SUM / SUM_PRODUCT return a
+        Python int (128-bit exact), COUNT an int, MIN / MAX an int or None when every row is NULL."""
+        out = (C.c_int64 * 2)()
+        check(lib.obgpu_result_aggregate(self._h, kind, col_a, col_b, out), "obgpu_result_aggregate", self.batch.ctx._h)
+        lo, hi = int(out[0]), int(out[1])
+        if kind in (capi.AGG_SUM, capi.AGG_SUM_PRODUCT):
+            return (hi << 64) | (lo & ((1 << 64) - 1))
+        if kind in (capi.AGG_MIN, capi.AGG_MAX):
+            if not hi:
+                return None
+            return lo if self.col(col_a).obj_type not in (capi.OBJ_UINT64, capi.OBJ_UINT32, capi.OBJ_UTINYINT,
+                                                          capi.OBJ_USMALLINT, capi.OBJ_UMEDIUMINT) else lo & ((1 << 64) - 1)
+        return lo
+
     def fetch_sel_offsets(self) -> np.ndarray:
         out = np.zeros(self.batch.n_blocks + 1, dtype=np.int64)
         check(lib.obgpu_result_fetch_sel_offsets(self._h, out.ctypes.data), "obgpu_result_fetch_sel_offsets",

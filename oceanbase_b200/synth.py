@@ -208,3 +208,28 @@ def make_config5_runs(n_runs=8, window=100_000, seed=5, rows_per_block=1400, dup
             run["table"] = encode_table(cols, rows_per_block, rowkey_cnt=1, n_threads=n_threads)
         runs.append(run)
     return runs
+
+
+# ---- config 4: TPC-H lineitem columns of Q6 as a CS_ENCODING_ROW_STORE column group -----------------
+Q6_DATE_LO, Q6_DATE_HI = 8766, 9131        # 1994-01-01 <= l_shipdate < 1995-01-01 (days since 1970-01-01)
+
+
+def make_config4_like(rows=100_000, rows_per_block=2000, seed=4, row_start=0, n_threads=0) -> Workload:
+    """dbgen-shaped value domains (TPC-H spec 4.2.3): l_shipdate uniform in [1992-01-02, 1998-12-01], l_discount
+    0.00..0.10 (stored x100), l_quantity 1..50, l_extendedprice = quantity x part retail price (90 000..200 000
+    cents, stored as decimal-int cents). Columns: 0 l_shipdate (DATE), 1 l_discount, 2 l_quantity,
+    3 l_extendedprice, all CS INTEGER. Filter = Q6, projection = (l_extendedprice, l_discount)."""
+    s = lambda c: _col_seed(seed, c)
+    shipdate = (splitmix64(s(0), row_start, rows) % np.uint64(2526)).astype(np.int64) + 8036
+    discount = (splitmix64(s(1), row_start, rows) % np.uint64(11)).astype(np.int64)
+    quantity = (splitmix64(s(2), row_start, rows) % np.uint64(50)).astype(np.int64) + 1
+    retail = (splitmix64(s(3), row_start, rows) % np.uint64(110_001)).astype(np.int64) + 90_000
+    price = quantity * retail
+    cols = [Column(capi.OBJ_DATE, capi.ENC_CS_INTEGER, shipdate), Column(capi.OBJ_INT, capi.ENC_CS_INTEGER, discount),
+            Column(capi.OBJ_INT, capi.ENC_CS_INTEGER, quantity), Column(capi.OBJ_INT, capi.ENC_CS_INTEGER, price)]
+    table = encode_table(cols, rows_per_block, n_threads=n_threads)
+    flt = And([White(0, capi.WHITE_OP_GE, (Q6_DATE_LO,)), White(0, capi.WHITE_OP_LT, (Q6_DATE_HI,)),
+               White(1, capi.WHITE_OP_BT, (5, 7)), White(2, capi.WHITE_OP_LT, (24,))])
+    return Workload(table, flt, [3, 1], [False, False], [8, 8],
+                    "cfg4: TPC-H lineitem Q6 columns as a CS column group (4 CS INTEGER columns), Q6 predicate, SUM(price*discount)",
+                    rows_per_block)

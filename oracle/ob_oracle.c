@@ -13,7 +13,7 @@
 #include <string.h>
 
 /* ---- layout constants (ob_micro_block_header.h:97-153, ob_block_sstable_struct.h:201-264) ---- */
-enum { T_RAW = 0, T_DICT = 1, T_RLE = 2, T_CONST = 3, T_BASE_DIFF = 4 };
+enum { T_RAW = 0, T_DICT = 1, T_RLE = 2, T_CONST = 3, T_BASE_DIFF = 4, T_CS_INTEGER = 100 /* CS block, ObCSColumnHeader::INTEGER */ };
 enum { A_FIX = 0x1, A_EXT = 0x2, A_BITPACK = 0x4, A_LASTVAR = 0x8 };
 enum { EXT_NOT = 0, EXT_NULL = 1, EXT_NOPE = 2 };
 #define MAGIC 1005
@@ -113,6 +113,72 @@ void ora_bs_set(uint8_t *buf, int64_t offset, int64_t cnt, uint64_t value) {
  * Block init: ObIEncodeBlockReader::get_micro_metas (encoding/ob_micro_block_decoder.cpp:363-388),
  * ObMicroBlockDecoder::do_init (:1268-1322), ObMicroBlockHeader::is_valid (header.cpp:53-61)
  * ============================================================================================= */
+/* ---- CS blocks: ObIntegerStreamMeta (de)serialization (ob_stream_encoding_struct.cpp:27-77) ------ */
+typedef struct int_stream_meta {
+  uint8_t version, attr, type, width_tag;
+  uint64_t base, null_replaced;
+  int width;       /* bytes */
+  int64_t meta_len;
+} int_stream_meta;
+
+static int rd_vi64(const uint8_t *p, int64_t len, int64_t *pos, uint64_t *v) { /* serialization::decode_vi64 */
+  uint64_t r = 0;
+  int shift = 0;
+  while (*pos < len) {
+    const uint8_t c = p[(*pos)++];
+    r |= (uint64_t)(c & 0x7f) << shift;
+    if (!(c & 0x80)) { *v = r; return ORA_SUCCESS; }
+    shift += 7;
+    if (shift > 63) return ORA_INVALID_DATA;
+  }
+  return ORA_INVALID_DATA;
+}
+
+static int parse_int_stream_meta(const uint8_t *p, int64_t len, int_stream_meta *m) {
+  static const int widths[4] = {1, 2, 4, 8};
+  if (len < 4) return ORA_INVALID_DATA;
+  int64_t pos = 4;
+  m->version = p[0]; m->attr = p[1]; m->type = p[2]; m->width_tag = p[3];
+  m->base = 0; m->null_replaced = 0;
+  int ret = ORA_SUCCESS;
+  if ((m->attr & 0x1) && (ret = rd_vi64(p, len, &pos, &m->base))) return ret;
+  if ((m->attr & 0x2) && (ret = rd_vi64(p, len, &pos, &m->null_replaced))) return ret;
+  if (m->attr & 0x4) return ORA_NOT_SUPPORTED;                 /* decimal int */
+  if (m->version > 0) { if (pos >= len) return ORA_INVALID_DATA; ++pos; } /* pfor_packing_type_ */
+  if (m->width_tag > 3) return ORA_NOT_SUPPORTED;
+  if (m->type != 1) return ORA_NOT_SUPPORTED;                  /* only RAW streams: the other codecs need the transformer */
+  m->width = widths[m->width_tag];
+  m->meta_len = pos;
+  return ORA_SUCCESS;
+}
+
+/* ObCSMicroBlockTransformer::init + decode_stream_offsets_ (ob_cs_micro_block_transformer.cpp:106-202) */
+static int cs_block_init(ora_block *b) {
+  const uint8_t *p = b->buf;
+  const int64_t payload_len = b->size - b->header_size;
+  if (payload_len < 12 + 4ll * b->column_count) return ORA_INVALID_DATA;
+  const uint8_t *ah = p + b->header_size;          /* ObAllColumnHeader: version, attrs, u32 string len, u32 offsets len, u16 streams */
+  if (ah[0] != 0 || (ah[1] & 0x1)) return ORA_INVALID_DATA;
+  if (ah[1] & 0x2) return ORA_NOT_SUPPORTED;       /* compressed string data */
+  const uint32_t all_string_len = rd32(ah + 2), offsets_len = rd32(ah + 6);
+  b->cs_stream_count = rd16(ah + 10);
+  b->cs_col_headers = ah + 12;
+  b->cs_first_stream_begin = b->header_size + 12u + 4u * b->column_count;
+  if ((int64_t)offsets_len + all_string_len > payload_len) return ORA_INVALID_DATA;
+  b->cs_all_string_offset = (uint32_t)(b->size - offsets_len - all_string_len);
+  if (b->cs_stream_count > 0) {
+    const uint8_t *so = p + b->size - offsets_len;
+    int_stream_meta m;
+    int ret = parse_int_stream_meta(so, offsets_len, &m);
+    if (ret) return ret;
+    if ((m.attr & 0x1) || m.width > 4) return ORA_ERR_UNEXPECTED; /* "stream offsets encoding must has no base" */
+    if (m.meta_len + (int64_t)m.width * b->cs_stream_count != offsets_len) return ORA_INVALID_DATA;
+    b->cs_off_data = so + m.meta_len;
+    b->cs_off_width = (uint8_t)m.width;
+  }
+  return ORA_SUCCESS;
+}
+
 int ora_block_init(ora_block *b, const void *buf, int64_t size) {
   if (!b || !buf || size < 64) return ORA_INVALID_ARGUMENT;
   const uint8_t *p = (const uint8_t *)buf;
@@ -131,7 +197,9 @@ int ora_block_init(ora_block *b, const void *buf, int64_t size) {
   b->row_data_offset = rd32(p + 24);
   if (magic != MAGIC || version < 1 || version > 3 || b->column_count < b->rowkey_column_count)
     return ORA_INVALID_DATA;
-  if (row_store_type != 1 && row_store_type != 2) return ORA_NOT_SUPPORTED; /* PAX only */
+  b->row_store_type = row_store_type;
+  if (row_store_type == 3) return cs_block_init(b);
+  if (row_store_type != 1 && row_store_type != 2) return ORA_NOT_SUPPORTED;
   if ((int64_t)b->header_size + 16ll * b->column_count > size || b->row_data_offset > size)
     return ORA_INVALID_ARGUMENT;
   b->col_headers = p + b->header_size;
@@ -198,6 +266,15 @@ typedef struct col_hdr {
 
 static int get_col(const ora_block *b, int32_t col, col_hdr *h) {
   if (col < 0 || col >= b->column_count) return ORA_INVALID_ARGUMENT;
+  if (b->row_store_type == 3) { /* ObCSColumnHeader: version, type, attrs, obj_type */
+    const uint8_t *c = b->cs_col_headers + 4 * col;
+    if (c[0] != 0) return ORA_INVALID_DATA;
+    h->type = (int8_t)(c[1] == 0 ? T_CS_INTEGER : 127);
+    h->attr = (int8_t)c[2];
+    h->obj_type = c[3];
+    h->ext_index = h->offset = h->length = 0;
+    return ORA_SUCCESS;
+  }
   const uint8_t *p = b->col_headers + 16 * col;
   if (p[0] != 0) return ORA_INVALID_DATA;
   h->type = (int8_t)p[1];
@@ -343,7 +420,73 @@ typedef struct col_dec {
   const uint8_t *const_row_ids;
   const uint8_t *const_value; /* count == 0 && ref == 0: value image after the header */
   int64_t const_value_len;
+  /* CS INTEGER column (cs_encoding/ob_integer_column_decoder.cpp:26-110) */
+  const uint8_t *cs_null_bitmap, *cs_nop_bitmap; /* MSB-first per byte, or NULL */
+  const uint8_t *cs_data;
+  int cs_width;
+  int cs_replace_null;
+  uint64_t cs_base, cs_null_raw;                 /* null_replaced_value - base */
 } col_dec;
+
+static uint32_t cs_stream_end(const ora_block *b, int32_t idx) {
+  return (uint32_t)rd_len(b->cs_off_data + (int64_t)idx * b->cs_off_width, b->cs_off_width);
+}
+
+/* Walks the column headers like ObCSMicroBlockTransformer::build_original_transform_desc_
+ * (ob_cs_micro_block_transformer.cpp:216-380) to find column `col`'s meta position and first stream. */
+static int cs_int_col_init(const ora_block *b, int32_t col, col_dec *c) {
+  const int64_t bitmap_bytes = ((int64_t)b->row_count + 7) / 8;
+  uint32_t pos = b->cs_first_stream_begin;   /* absolute offset where the current column's meta starts */
+  int32_t stream_idx = -1;
+  for (int32_t i = 0; i <= col; ++i) {
+    const uint8_t *h = b->cs_col_headers + 4 * i;
+    const uint8_t type = h[1], attrs = h[2];
+    int32_t n_streams = 0;
+    int64_t meta_len = 0;
+    if (type == 0) {                         /* INTEGER */
+      n_streams = 1;
+      meta_len = ((attrs & 0x02) ? bitmap_bytes : 0) + ((attrs & 0x08) ? bitmap_bytes : 0);
+    } else if (type == 1) {                  /* STRING: bytes stream (+ offsets stream when not fixed length) */
+      n_streams = (attrs & 0x01) ? 1 : 2;
+    } else if (type == 2 || type == 3) {     /* INT_DICT / STR_DICT */
+      if ((int64_t)pos + 10 > b->size) return ORA_INVALID_DATA;
+      const uint32_t distinct = rd32(b->buf + pos + 2);
+      meta_len = 10 + ((attrs & 0x08) ? bitmap_bytes : 0);
+      if (distinct == 0) n_streams = 0;
+      else if (type == 2) n_streams = 2;
+      else n_streams = (attrs & 0x01) ? 2 : 3;
+    } else {
+      return ORA_NOT_SUPPORTED;
+    }
+    if (i == col) {
+      if (type != 0) return ORA_NOT_SUPPORTED;
+      if (stream_idx + 1 >= b->cs_stream_count) return ORA_INVALID_DATA;
+      const uint32_t end = cs_stream_end(b, stream_idx + 1);
+      const uint8_t *meta = b->buf + pos;
+      if ((int64_t)pos + meta_len > end || end > b->size) return ORA_INVALID_DATA;
+      c->cs_null_bitmap = (attrs & 0x02) ? meta : 0;
+      c->cs_nop_bitmap = (attrs & 0x08) ? meta + ((attrs & 0x02) ? bitmap_bytes : 0) : 0;
+      int_stream_meta m;
+      const int ret = parse_int_stream_meta(meta + meta_len, (int64_t)end - pos - meta_len, &m);
+      if (ret) return ret;
+      if (pos + meta_len + m.meta_len + (int64_t)m.width * b->row_count != end) return ORA_INVALID_DATA;
+      c->cs_data = meta + meta_len + m.meta_len;
+      c->cs_width = m.width;
+      c->cs_base = (m.attr & 0x1) ? m.base : 0;
+      c->cs_replace_null = (m.attr & 0x2) != 0 && !c->cs_null_bitmap;
+      c->cs_null_raw = m.null_replaced - c->cs_base;
+      if (c->cs_width < 8) c->cs_null_raw &= INT_MASK[c->cs_width];
+      return ORA_SUCCESS;
+    }
+    if (n_streams == 0) pos += (uint32_t)meta_len;
+    else {
+      stream_idx += n_streams;
+      if (stream_idx >= b->cs_stream_count) return ORA_INVALID_DATA;
+      pos = cs_stream_end(b, stream_idx);
+    }
+  }
+  return ORA_ERR_UNEXPECTED;
+}
 
 static int col_dec_init(const ora_block *b, int32_t col, col_dec *c) {
   int ret = get_col(b, col, &c->h);
@@ -375,6 +518,7 @@ static int col_dec_init(const ora_block *b, int32_t col, col_dec *c) {
       if (c->sc == 1 && mask != 0 && (c->base & (mask >> 1))) c->base |= mask;
       break;
     }
+    case T_CS_INTEGER: return cs_int_col_init(b, col, c);
     case T_CONST: {
       const uint8_t *m = c->meta; /* version, count, const_ref, attr(row_id_byte:3), offset u16 */
       if (m[0] != 0) return ORA_ERR_UNEXPECTED;
@@ -482,6 +626,17 @@ static int decode_cell(const ora_block *b, const col_dec *c, int64_t row, ora_da
     case T_RLE: {
       const int64_t pos = rle_upper_bound(c, row);
       return dict_decode(&c->dict, c->h.obj_type, rle_ref_at(c, pos - 1), out);
+    }
+    case T_CS_INTEGER: { /* ConvertUintToDatum_T (ob_integer_stream_decoder.cpp:37-350): value = raw + base */
+      if (c->cs_null_bitmap && ((c->cs_null_bitmap[row / 8] >> (7 - row % 8)) & 1)) {
+        set_null(out);
+        if (c->cs_nop_bitmap && ((c->cs_nop_bitmap[row / 8] >> (7 - row % 8)) & 1)) out->is_null = 2;
+        return ORA_SUCCESS;
+      }
+      const uint64_t raw = rd_len(c->cs_data + row * c->cs_width, c->cs_width);
+      if (c->cs_replace_null && raw == c->cs_null_raw) { set_null(out); return ORA_SUCCESS; }
+      set_int(c->h.obj_type, raw + c->cs_base, out);
+      return ORA_SUCCESS;
     }
     case T_CONST: {
       if (c->const_count == 0) { /* decode_without_dict (ob_const_decoder.cpp:25-58) */

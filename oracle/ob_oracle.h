@@ -72,6 +72,14 @@ typedef struct ora_block {
   const uint8_t *meta;        /* encoding meta start: column offsets are relative to it */
   const uint8_t *row_data;
   int64_t row_data_len;
+  /* CS_ENCODING_ROW_STORE blocks (cs_encoding/ob_cs_micro_block_transformer.cpp:106-143) */
+  uint8_t row_store_type;          /* 1 / 2 PAX, 3 CS */
+  uint8_t cs_off_width;            /* bytes per stream end offset */
+  uint16_t cs_stream_count;
+  const uint8_t *cs_col_headers;   /* column_count x 4 bytes (ObCSColumnHeader) */
+  const uint8_t *cs_off_data;      /* stream end offsets, relative to the block start */
+  uint32_t cs_first_stream_begin;  /* header + ObAllColumnHeader + column headers */
+  uint32_t cs_all_string_offset;
 } ora_block;
 
 /* ---- bit stream (encoding/ob_bit_stream.h:169-283) -------------------------------------------- */

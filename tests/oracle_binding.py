@@ -68,7 +68,10 @@ class OraBlock(C.Structure):
                 ("row_data_offset", C.c_uint32), ("column_count", C.c_uint16), ("rowkey_column_count", C.c_uint16),
                 ("var_column_count", C.c_uint16), ("row_index_byte", C.c_uint8), ("extend_value_bit", C.c_uint8),
                 ("col_headers", C.c_void_p), ("meta", C.c_void_p), ("row_data", C.c_void_p),
-                ("row_data_len", C.c_int64)]
+                ("row_data_len", C.c_int64),
+                ("row_store_type", C.c_uint8), ("cs_off_width", C.c_uint8), ("cs_stream_count", C.c_uint16),
+                ("cs_col_headers", C.c_void_p), ("cs_off_data", C.c_void_p), ("cs_first_stream_begin", C.c_uint32),
+                ("cs_all_string_offset", C.c_uint32)]
 
 
 class OraScanOut(C.Structure):

@@ -1,0 +1,112 @@
+"""CS_ENCODING_ROW_STORE blocks (column-store encoding), INTEGER columns with RAW integer streams:
+writer -> oracle round trips over every ObIntegerStreamMeta shape the encoder rules produce
+(cs_encoding/ob_integer_column_encoder.cpp:177-287: no base / base for negative minima, NULL as a
+replaced value below the minimum or above the maximum, NULL bitmap when the type's value range is
+exhausted; widths 1/2/4/8), the block framing (ObAllColumnHeader, ObCSColumnHeader, stream end
+offsets relative to the block start) and the white-filter semantics on top of it."""
+import numpy as np
+import pytest
+
+import oceanbase_b200 as ob
+import oracle_binding as ora
+from oceanbase_b200 import White
+
+RNG = np.random.default_rng(77)
+I64_MIN, I64_MAX = -(1 << 63), (1 << 63) - 1
+
+SHAPES = {
+    # name: (obj_type, values, expect meta: (width bytes, use_base, null mode with NULLs present))
+    "u8_from_zero": (ob.OBJ_INT, lambda n: RNG.integers(0, 200, size=n), (1, False, "replace_max_plus_1")),
+    "u16_positive_min": (ob.OBJ_INT, lambda n: RNG.integers(300, 60000, size=n), (2, False, "replace_min_minus_1")),
+    "negative_small": (ob.OBJ_INT, lambda n: RNG.integers(-100, 100, size=n), (1, True, "replace_min_minus_1")),
+    "negative_wide": (ob.OBJ_INT, lambda n: RNG.integers(-(1 << 40), 1 << 40, size=n), (8, True, "replace_min_minus_1")),
+    "full_range": (ob.OBJ_INT, lambda n: np.concatenate([[I64_MIN, I64_MAX], RNG.integers(-5, 5, size=n - 2)]), (8, True, "bitmap")),
+    "int32_full": (ob.OBJ_INT32, lambda n: np.concatenate([[-(1 << 31), (1 << 31) - 1], RNG.integers(-9, 9, size=n - 2)]), (4, True, "bitmap")),
+    "uint32_from_zero_to_max": (ob.OBJ_UINT32, lambda n: np.concatenate([[0, (1 << 32) - 1], RNG.integers(0, 9, size=n - 2)]), (4, False, "bitmap")),
+    "uint64_big": (ob.OBJ_UINT64, lambda n: RNG.integers(1 << 40, 1 << 62, size=n), (8, False, "replace_min_minus_1")),
+    "date": (ob.OBJ_DATE, lambda n: RNG.integers(8036, 10562, size=n), (2, False, "replace_min_minus_1")),
+    "tinyint_neg": (ob.OBJ_TINYINT, lambda n: RNG.integers(-128, 127, size=n), (1, True, "replace_max_plus_1")),
+}
+
+
+def stream_meta_of(block, blk, col):
+    """Parses the column's serialized ObIntegerStreamMeta straight from the bytes (single-stream INTEGER columns)."""
+    hs, ncol = blk.b.header_size, blk.column_count
+    first = hs + 12 + 4 * ncol
+    ah = block[hs:hs + 12]
+    offsets_len = int(ah[6:10].view(np.uint32)[0])
+    so = block[len(block) - offsets_len:]
+    ow = 1 << int(so[3])
+    ends = so[5:].view({1: np.uint8, 2: np.uint16, 4: np.uint32}[ow])
+    pos = first if col == 0 else int(ends[col - 1])
+    attrs = int(block[hs + 12 + 4 * col + 2])
+    if attrs & 0x02:
+        pos += (blk.row_count + 7) // 8
+    m = block[pos:]
+    return dict(version=int(m[0]), attr=int(m[1]), type=int(m[2]), width=1 << int(m[3]), has_bitmap=bool(attrs & 0x02),
+                end=int(ends[col]))
+
+
+@pytest.mark.parametrize("shape", sorted(SHAPES))
+@pytest.mark.parametrize("with_nulls", [False, True])
+def test_cs_integer_roundtrip(shape, with_nulls):
+    obj_type, gen, (width, use_base, null_mode) = SHAPES[shape]
+    n = 500
+    v = gen(n).astype(np.int64) if obj_type != ob.OBJ_UINT64 else gen(n).astype(np.uint64).view(np.int64)
+    nulls = (RNG.random(n) < 0.15).astype(np.uint8) if with_nulls else None
+    if nulls is not None:
+        nulls[:2] = 0  # keep the extreme values of the "full range" shapes
+    pad = np.arange(n, dtype=np.int64)
+    block = ob.encode_block([ob.Column(ob.OBJ_INT, ob.ENC_CS_INTEGER, pad), ob.Column(obj_type, ob.ENC_CS_INTEGER, v, nulls=nulls)])
+    blk = ora.Block(block)
+    assert blk.verify_checksums() == 0
+    assert blk.b.row_store_type == 3 and blk.b.cs_stream_count == 2
+    m = stream_meta_of(block, blk, 1)
+    assert m["version"] == 1 and m["type"] == 1            # V2 meta, RAW stream
+    assert bool(m["attr"] & 1) == use_base, m
+    if with_nulls:
+        assert m["has_bitmap"] == (null_mode == "bitmap")
+        assert bool(m["attr"] & 2) == (null_mode != "bitmap")
+    else:
+        assert not m["has_bitmap"] and not (m["attr"] & 2)
+        assert m["width"] == width
+    for r in range(n):
+        d = blk.cell_raw(1, r)
+        if nulls is not None and nulls[r]:
+            assert d.is_null == 1
+            continue
+        assert d.is_null == 0
+        if obj_type == ob.OBJ_DATE:
+            assert d.len == 4 and np.int32(np.uint32(d.ival)) == v[r]
+        elif obj_type in (ob.OBJ_UINT32, ob.OBJ_UINT64):
+            assert d.len == 8 and d.ival == int(np.uint64(v[r]))
+        else:
+            assert d.len == 8 and np.int64(np.uint64(d.ival)) == v[r]
+    assert [blk.cell(0, r) for r in range(0, n, 37)] == list(range(0, n, 37))
+
+
+def test_cs_white_filters_match_pax():
+    # the same values stored as PAX RAW and as CS INTEGER give the same bitmaps for every operator
+    n = 64
+    v = np.array([7] * 34 + [1007] * 10 + [2007] * 10 + [0] * 10, dtype=np.int64)
+    nulls = np.array([0] * 54 + [1] * 10, dtype=np.uint8)
+    pad = np.arange(n, dtype=np.int64)
+    pax = ora.Block(ob.encode_block([ob.Column(ob.OBJ_INT, ob.ENC_RAW, pad), ob.Column(ob.OBJ_INT, ob.ENC_RAW, v, nulls=nulls)]))
+    cs = ora.Block(ob.encode_block([ob.Column(ob.OBJ_INT, ob.ENC_CS_INTEGER, pad), ob.Column(ob.OBJ_INT, ob.ENC_CS_INTEGER, v, nulls=nulls)]))
+    plist = [(ob.WHITE_OP_EQ, (1007,)), (ob.WHITE_OP_NE, (1007,)), (ob.WHITE_OP_LT, (2007,)), (ob.WHITE_OP_LE, (7,)),
+             (ob.WHITE_OP_GT, (7,)), (ob.WHITE_OP_GE, (2007,)), (ob.WHITE_OP_BT, (8, 2007)), (ob.WHITE_OP_IN, (7, 2007, 5)),
+             (ob.WHITE_OP_NU, ()), (ob.WHITE_OP_NN, ()), (ob.WHITE_OP_EQ, (None,))]
+    for op, params in plist:
+        for start, count in ((0, None), (19, 30)):
+            a = pax.filter_tree(White(1, op, params), start, count)
+            b = cs.filter_tree(White(1, op, params), start, count)
+            assert np.array_equal(a, b), (op, params)
+    # reference popcounts (test_raw_decoder.cpp:862-980 layout re-used by the cs decoder tests): GT seed1 -> 10
+    assert int(cs.filter_tree(White(1, ob.WHITE_OP_GT, (1007,))).sum()) == 10
+    assert int(cs.filter_tree(White(1, ob.WHITE_OP_NU, ())).sum()) == 10
+
+
+def test_mixed_row_store_types_in_one_block_are_rejected():
+    v = np.arange(10, dtype=np.int64)
+    with pytest.raises(ob.ObGpuError):
+        ob.encode_block([ob.Column(ob.OBJ_INT, ob.ENC_RAW, v), ob.Column(ob.OBJ_INT, ob.ENC_CS_INTEGER, v)])

@@ -1,0 +1,119 @@
+"""CS_ENCODING_ROW_STORE blocks on the device path vs the oracle: every ObIntegerStreamMeta shape through the
+whole-table scan (filter + projection), the per-block entry points, and the Q6 shape of BASELINE config 4 with
+the pushed-down SUM(l_extendedprice * l_discount) checked exactly against Python integers."""
+import numpy as np
+import pytest
+
+import oracle_binding as ora
+from test_gpu_scan import assert_scan_matches
+from test_cs_encoding_kat import SHAPES
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ob():
+    import oceanbase_b200
+    return oceanbase_b200
+
+
+@pytest.fixture(scope="module")
+def ctx(ob):
+    c = ob.ScanContext(0)
+    yield c
+    c.close()
+
+
+class W:
+    def __init__(self, table, flt, proj, is_str, elem):
+        self.table, self.filter, self.proj, self.proj_is_string, self.proj_elem_len = table, flt, proj, is_str, elem
+
+
+@pytest.mark.parametrize("shape", sorted(SHAPES))
+@pytest.mark.parametrize("with_nulls", [False, True])
+def test_cs_integer_columns_scan(ob, ctx, shape, with_nulls):
+    obj_type, gen, _ = SHAPES[shape]
+    rng = np.random.default_rng(3)
+    n = 7000
+    v = gen(n).astype(np.int64) if obj_type != ob.OBJ_UINT64 else gen(n).astype(np.uint64).view(np.int64)
+    nulls = (rng.random(n) < 0.15).astype(np.uint8) if with_nulls else None
+    sel = rng.integers(0, 1000, size=n, dtype=np.int64)
+    table = ob.encode_table([ob.Column(ob.OBJ_INT, ob.ENC_CS_INTEGER, sel), ob.Column(obj_type, ob.ENC_CS_INTEGER, v, nulls=nulls)], 900)
+    elem = 4 if obj_type == ob.OBJ_DATE else 8
+    mid = int(np.median(v)) if obj_type != ob.OBJ_UINT64 else int(np.median(v.view(np.uint64)))
+    for flt in (None, ob.White(0, ob.WHITE_OP_LT, (300,)), ob.White(1, ob.WHITE_OP_GE, (mid,)),
+                ob.And([ob.White(0, ob.WHITE_OP_GE, (100,)), ob.White(1, ob.WHITE_OP_LT, (mid,))]),
+                ob.Or([ob.White(1, ob.WHITE_OP_NU, ()), ob.White(0, ob.WHITE_OP_EQ, (5,))])):
+        assert_scan_matches(ctx, W(table, flt, [0, 1], [False, False], [8, elem]))
+
+
+def test_cs_block_entry_points(ob, ctx):
+    n = 300
+    rng = np.random.default_rng(8)
+    v = rng.integers(-1000, 1000, size=n, dtype=np.int64)
+    nulls = (rng.random(n) < 0.2).astype(np.uint8)
+    block = ob.encode_block([ob.Column(ob.OBJ_INT, ob.ENC_CS_INTEGER, np.arange(n, dtype=np.int64)),
+                             ob.Column(ob.OBJ_INT, ob.ENC_CS_INTEGER, v, nulls=nulls)])
+    blk = ora.Block(block)
+    table = ob.TableImage(np.concatenate([block, np.zeros((-len(block)) % 128 + 128, dtype=np.uint8)]),
+                          np.array([0], dtype=np.int64), np.array([len(block)], dtype=np.int64), 0, 0)
+    batch = ctx.open_batch(table)
+    for op, params in ((ob.WHITE_OP_LT, (0,)), (ob.WHITE_OP_BT, (-10, 500)), (ob.WHITE_OP_NU, ()), (ob.WHITE_OP_NE, (int(v[3]),))):
+        for start, count in ((0, None), (17, 200)):
+            assert np.array_equal(batch.filter_white(0, 1, op, params, start, count),
+                                  blk.filter_tree(ob.White(1, op, params), start, count))
+    rid = np.arange(0, n, 3, dtype=np.int32)
+    ed, en, ehn = blk.get_rows_fixed(1, rid, 8, 4)
+    gd, gn, ghn = batch.project_fixed(0, 1, rid, 8, 4)
+    assert np.array_equal(gd, ed) and np.array_equal(gn, en) and ghn == ehn
+    batch.close()
+
+
+def test_q6_scan_and_pushdown_sum(ob, ctx):
+    from oceanbase_b200.synth import make_config4_like
+    w = make_config4_like(rows=400_000, rows_per_block=2000, seed=4)
+    n = assert_scan_matches(ctx, w)
+    assert 0.012 < n / w.table.total_rows < 0.026          # Q6 selects ~1.9 %
+    batch = ctx.open_batch(w.table)
+    res = batch.scan(w.filter, w.proj)
+    want = ora.scan_table(w.table, w.filter, w.proj, w.proj_is_string, w.proj_elem_len)
+    price = want["data"][0].view(np.int64)[:n]
+    disc = want["data"][1].view(np.int64)[:n]
+    exact = sum(int(a) * int(b) for a, b in zip(price.tolist(), disc.tolist()))
+    assert res.aggregate(ob.AGG_SUM_PRODUCT, 0, 1) == exact
+    assert res.aggregate(ob.AGG_SUM, 0) == int(price.astype(object).sum())
+    assert res.aggregate(ob.AGG_COUNT, 1) == n
+    assert res.aggregate(ob.AGG_MIN, 0) == int(price.min()) and res.aggregate(ob.AGG_MAX, 0) == int(price.max())
+    res.free()
+    batch.close()
+
+
+def test_aggregates_with_nulls_and_wide_values(ob, ctx):
+    rng = np.random.default_rng(12)
+    n = 50_000
+    a = rng.integers(-(1 << 62), 1 << 62, size=n, dtype=np.int64)
+    b = rng.integers(-(1 << 62), 1 << 62, size=n, dtype=np.int64)
+    na = (rng.random(n) < 0.1).astype(np.uint8)
+    nb = (rng.random(n) < 0.1).astype(np.uint8)
+    u = rng.integers(0, 1 << 63, size=n, dtype=np.int64) * 2 + 1          # uint64 values above 2^63
+    table = ob.encode_table([ob.Column(ob.OBJ_INT, ob.ENC_RAW, a, nulls=na), ob.Column(ob.OBJ_INT, ob.ENC_RAW, b, nulls=nb),
+                             ob.Column(ob.OBJ_UINT64, ob.ENC_RAW, u)], 1000)
+    batch = ctx.open_batch(table)
+    res = batch.scan(None, [0, 1, 2])
+    ok = (na == 0)
+    both = ok & (nb == 0)
+    M = 1 << 128
+    exact_sum = sum(int(x) for x in a[ok].tolist())
+    exact_prod = sum(int(x) * int(y) for x, y in zip(a[both].tolist(), b[both].tolist()))
+    assert res.aggregate(ob.AGG_SUM, 0) % M == exact_sum % M               # 128-bit two's complement
+    assert res.aggregate(ob.AGG_SUM_PRODUCT, 0, 1) % M == exact_prod % M
+    assert res.aggregate(ob.AGG_COUNT, 0) == int(ok.sum())
+    assert res.aggregate(ob.AGG_MIN, 0) == int(a[ok].min()) and res.aggregate(ob.AGG_MAX, 0) == int(a[ok].max())
+    uu = u.view(np.uint64)
+    assert res.aggregate(ob.AGG_SUM, 2) == sum(int(x) for x in uu.tolist())
+    assert res.aggregate(ob.AGG_MAX, 2) == int(uu.max()) and res.aggregate(ob.AGG_MIN, 2) == int(uu.min())
+    res.free()
+    none = batch.scan(ob.White(0, ob.WHITE_OP_NU, ()), [0])
+    assert none.aggregate(ob.AGG_MIN, 0) is None and none.aggregate(ob.AGG_COUNT, 0) == 0 and none.aggregate(ob.AGG_SUM, 0) == 0
+    none.free()
+    batch.close()
