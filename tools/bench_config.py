@@ -1,0 +1,133 @@
+"""Config 3 (BASELINE.json configs[2]) on the device path: 16-column dictionary-encoded SSTable
+(8 INT64 DICT + 8 VARCHAR DICT), 3-predicate AND ~10 %, 4 INT64 + 2 VARCHAR projected, device
+resident, one shard per rank (weak scaling, no collective). A seeded segment of --rows rows is
+generated once and tiled --tile times (the 1 B-row table of the config would take hours to generate
+on the box's 16-CPU quota; every tile is larger than L2, so tiling does not change the memory
+behaviour). Prints one JSON line like bench.py (value, roofline, kernel split); not the round's
+bench line."""
+import argparse, json, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import bench
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--rows", type=int, default=8_000_000)
+    ap.add_argument("--tile", type=int, default=4)
+    ap.add_argument("--rows-per-block", type=int, default=1100)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--cpu-blocks", type=int, default=2000)
+    ap.add_argument("--config", type=int, default=3, choices=[3, 4], help="3: dict-encoded 16-column table; 4: TPC-H Q6 on a CS column group")
+    args = ap.parse_args()
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as g
+    rank, world, local = bench.env_int("RANK", 0), bench.env_int("WORLD_SIZE", 1), bench.env_int("LOCAL_RANK", 0)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if rank == 0:
+        g.build()
+    if world > 1:
+        dist.barrier()
+    import oceanbase_b200 as ob
+    from oceanbase_b200.synth import make_config3_like, make_config4_like
+    from oceanbase_b200.sstable import TableImage
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    t0 = time.perf_counter()
+    is_q6 = args.config == 4
+    if is_q6 and args.rows_per_block == 1100:
+        args.rows_per_block = 2000
+    w, _ = bench.build_workload(args.rows, rank * args.rows, args.config, chunk_rows=4_000_000 if is_q6 else 1_000_000,
+                                maker=make_config4_like if is_q6 else make_config3_like,
+                                rows_per_block=args.rows_per_block, n_threads=max(1, bench.host_cpus() // world))
+    seg = w.table
+    seg_bytes = seg.image.size
+    image = np.tile(seg.image, args.tile)
+    offs = np.concatenate([seg.offsets + k * seg_bytes for k in range(args.tile)])
+    table = TableImage(image, offs, np.tile(seg.sizes, args.tile), seg.total_rows * args.tile, seg.n_cols)
+    w.table = table
+    t_gen = time.perf_counter() - t0
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    ctx = ob.ScanContext(local, stream=stream.cuda_stream)
+    ctx.set_profiling(True)
+    d_image = torch.empty(image.size + 64, dtype=torch.uint8, device=dev)
+    d_image[:image.size].copy_(torch.from_numpy(image))
+    d_image[image.size:].zero_()
+    torch.cuda.synchronize()
+    batch = ctx.open_batch(table, device_image_ptr=d_image.data_ptr())
+    cap = int(table.total_rows * (0.03 if is_q6 else 0.15))
+    agg = None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        r = batch.scan(w.filter, w.proj, max_selected_rows=cap)
+        r.info()
+        if is_q6:
+            agg = r.aggregate(ob.AGG_SUM_PRODUCT, 0, 1)
+        r.free()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    last = None
+    for _ in range(args.steps):
+        if last is not None:
+            last.free()
+        last = batch.scan(w.filter, w.proj, max_selected_rows=cap)
+        if is_q6:
+            agg = last.aggregate(ob.AGG_SUM_PRODUCT, 0, 1)   # pushed-down SUM(l_extendedprice * l_discount), syncs
+    ev1.record(stream)
+    barrier()
+    step_ms = ev0.elapsed_time(ev1) / args.steps
+    info = last.info()
+    selected = info.selected_rows
+    kern_ms = float(np.mean(ctx.kernel_times_ms(args.steps)))
+    last.free()
+    if world > 1:
+        t = torch.tensor([step_ms, kern_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        step_ms, kern_ms = t.tolist()
+        tot = torch.tensor([table.total_rows, selected], device=dev, dtype=torch.int64)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        rows_all, sel_all = tot.tolist()
+    else:
+        rows_all, sel_all = table.total_rows, selected
+    if rank == 0:
+        peak, src = bench.measured_peak_gbs()
+        alg = w.alg_bytes(selected)
+        line = {"metric": bench.METRIC, "value": rows_all / (step_ms * 1e-3), "unit": bench.UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "scaling": "weak",
+                "dtype": "int64/bytes", "data": "synthetic",
+                "config": {"workload": w.name, "rows_per_gpu": table.total_rows, "segment_rows": seg.total_rows,
+                           "tile": args.tile, "rows_per_block": args.rows_per_block, "micro_blocks_per_gpu": table.n_blocks,
+                           "encoded_bytes_per_gpu": int(table.sizes.sum()), "bytes_per_row_in": float(table.sizes.sum()) / table.total_rows,
+                           "selectivity": selected / table.total_rows, "gen_seconds": round(t_gen, 1)},
+                "roofline": {"bound": "hbm", "achieved": alg / (kern_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                             "frac": alg / (kern_ms * 1e-3) / 1e9 / peak, "alg_bytes_per_launch": alg, "kernel_ms": kern_ms,
+                             "peak_source": src}}
+        if is_q6:
+            line["q6_revenue_x10000"] = str(agg)
+        if world == 1 and args.cpu_blocks > 0:
+            ncpu = bench.host_cpus()
+            rates, crow, csel = bench.cpu_reference_leg(w, 2, 1, ncpu, min(args.cpu_blocks, table.n_blocks))
+            line["cpu_baseline"] = {"value": crow / float(np.mean([d for _, d in rates])), "unit": bench.UNIT, "cores": ncpu,
+                                    "kind": "port", "sample": f"first {crow} rows, 2 timed passes"}
+        print(json.dumps(line))
+    batch.close()
+    ctx.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
