@@ -66,7 +66,8 @@ enum {
   OBGPU_ENC_CONST = 3,
   OBGPU_ENC_INTEGER_BASE_DIFF = 4,
   /* writer only: columns of a CS_ENCODING_ROW_STORE block (ObCSColumnHeader::Type) */
-  OBGPU_ENC_CS_INTEGER = 16
+  OBGPU_ENC_CS_INTEGER = 16,
+  OBGPU_ENC_CS_INT_DICT = 17
 };
 
 /* ---- ObObjType values the path accepts (common/object/ob_obj_type.h) ------------------------ */

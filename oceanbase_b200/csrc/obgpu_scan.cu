@@ -81,7 +81,7 @@ struct ScanParams {
   int32_t simple_shape;       // 1: single leaf or AND over leaves only, 2: OR over leaves only, 0: generic
   FilterNodeDev nodes[kMaxNodes];
   ParamDev params[kMaxParams];
-  uint8_t param_heap[kParamHeap];
+  alignas(8) uint8_t param_heap[kParamHeap];  // string constants, each 8-byte aligned and padded
   int32_t n_slots;
   int32_t bitset_words;       // words per slot
   int32_t n_rle_slots;
@@ -616,7 +616,7 @@ __device__ __forceinline__ void project_int_col(const ScanParams &p, const Block
     }
   } else {  // K_DICT / K_RLE
     const uint32_t dcount = d.dict_count, dbits = d.dict_data_size * 8u, dpay = c.sbit + d.dict_payload * 8u;
-    const uint64_t mask = d.int_mask;
+    const uint64_t mask = d.int_mask, dbase = d.base;
     const bool fix = d.sign_fix != 0;
     if (d.kind == K_DICT) {
       const uint32_t val_bit = c.sbit + d.val_bit, stride = d.stride, width = d.width;
@@ -627,7 +627,7 @@ __device__ __forceinline__ void project_int_col(const ScanParams &p, const Block
           mark_null(j);
           continue;
         }
-        uint64_t v = sbits(dpay + ref * dbits, dbits);
+        uint64_t v = sbits(dpay + ref * dbits, dbits) + dbase;
         if (fix) v = sign_fix(mask, v);
         out[j] = (OutT)v;
       }
@@ -727,6 +727,8 @@ __global__ void __launch_bounds__(256) obgpu_index_kernel(const uint8_t *image, 
     // bytes of the column's region (count kernel staging buffer, project kernel column staging)
     uint32_t lo, hi;
     if (col_region(d, b, lo, hi)) atomicMax(&col_span[col], hi - lo);
+    // dictionary size (predicate bitset words) of dictionary-coded columns: col_span[max_cols + col]
+    if (is_dict_kind(d)) atomicMax(&col_span[max_cols + col], d.dict_count + 2u);
   }
 }
 
@@ -1667,26 +1669,32 @@ int obgpu_batch_open(obgpu_ctx *ctx, const void *image, int64_t image_size, cons
     void *dp = nullptr;
     const size_t rows_bytes = ((size_t)n_blocks * 4 + 63) & ~(size_t)63;
     const size_t rec_bytes = (size_t)n_blocks * sizeof(BlockRec);
-    e = cudaMallocAsync(&dp, plan_bytes + rows_bytes + rec_bytes + (size_t)b->max_cols * 4 + 64, ctx->stream);
+    e = cudaMallocAsync(&dp, plan_bytes + rows_bytes + rec_bytes + (size_t)b->max_cols * 8 + 64, ctx->stream);
     if (e == cudaSuccess) {
       b->d_plans = (ColDesc *)dp;
       b->d_rows = (uint32_t *)((uint8_t *)dp + plan_bytes);
       b->d_recs = (BlockRec *)((uint8_t *)dp + plan_bytes + rows_bytes);
       uint32_t *d_span = (uint32_t *)((uint8_t *)dp + plan_bytes + rows_bytes + rec_bytes);
-      e = cudaMemsetAsync(d_span, 0, (size_t)b->max_cols * 4, ctx->stream);
+      e = cudaMemsetAsync(d_span, 0, (size_t)b->max_cols * 8, ctx->stream);
       const int64_t nthreads = (int64_t)n_blocks * b->max_cols;
       obgpu_index_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, ctx->stream>>>(
           b->d_image, b->d_blk_off, b->d_blk_size, b->d_bm_word_off, n_blocks, (int)b->max_cols, b->d_plans,
           b->d_rows, b->d_recs, d_span);
       if (e == cudaSuccess) e = cudaGetLastError();
       ctx->launches++;
-      b->col_span.assign(b->max_cols, 0);
+      b->col_span.assign((size_t)b->max_cols * 2, 0);  // [spans][dictionary sizes]
       if (e == cudaSuccess)
-        e = cudaMemcpyAsync(b->col_span.data(), d_span, (size_t)b->max_cols * 4, cudaMemcpyDeviceToHost, ctx->stream);
+        e = cudaMemcpyAsync(b->col_span.data(), d_span, (size_t)b->max_cols * 8, cudaMemcpyDeviceToHost, ctx->stream);
     }
   }
   // `stage` is pageable: the copy above is staged synchronously by the runtime before returning
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e == cudaSuccess && b->col_span.size() == (size_t)b->max_cols * 2) {
+    // dictionary sizes seen by the index kernel (covers CS blocks, whose stream tables the host does not walk)
+    for (uint32_t c = 0; c < b->max_cols; ++c)
+      b->col_max_dict[c] = std::max(b->col_max_dict[c], b->col_span[(size_t)b->max_cols + c]);
+    b->col_span.resize(b->max_cols);
+  }
   if (e != cudaSuccess) {
     ctx->err = cudaGetErrorString(e);
     obgpu_batch_close(b);
@@ -1779,9 +1787,11 @@ static int build_filter(obgpu_ctx *ctx, const obgpu_batch *b, const obgpu_filter
         pd.len = sp.len;
         pd.heap_off = heap;
         if (sp.ptr && sp.len > 0) {
-          if (heap + sp.len > (uint32_t)kParamHeap) return OBGPU_NOT_SUPPORTED;
+          // constants start 8-byte aligned and are padded to 8 bytes: str_cmp reads them in 64-bit words
+          const uint32_t padded = (sp.len + 7u) & ~7u;
+          if (heap + padded > (uint32_t)kParamHeap) return OBGPU_NOT_SUPPORTED;
           memcpy(p.param_heap + heap, sp.ptr, sp.len);
-          heap += sp.len;
+          heap += padded;
         }
         if ((size_t)src.col < b->col_types.size() && obf::store_class_of(b->col_types[(size_t)src.col]) == 5) {
           // string constant: i64 carries the first min(len, 8) bytes (little endian) for the equality prefilter

@@ -339,7 +339,48 @@ __device__ __forceinline__ void build_cs_col_desc(const BlockView &b, int col, C
       d.attr = (uint8_t)attrs;
       d.obj_type = (uint8_t)(w >> 24);
       const int sc = store_class_of(d.obj_type);
-      if (type != CS_INTEGER || (sc != 1 && sc != 2)) return;
+      if ((type != CS_INTEGER && type != CS_INT_DICT) || (sc != 1 && sc != 2)) return;
+      if (type == CS_INT_DICT) {
+        // [ObDictEncodingMeta 10 B][dict value stream][ref stream] -> K_DICT plan (ref == distinct count: NULL,
+        // value = dict[ref] + base, ob_int_dict_column_decoder.cpp:25-60)
+        if (attrs & (CS_HAS_NOP_BITMAP | CS_HAS_NOP | CS_OUT_ROW)) return;
+        if (s[pos] != 0 || (s[pos + 1] & 0x4)) return;   // const-encoded refs: not handled
+        const uint32_t distinct = (uint32_t)ld_bytes(s, pos + 2, 4);
+        d.sc = (uint8_t)sc;
+        d.elem_len = (uint8_t)datum_len_of(d.obj_type);
+        d.int_mask = 0;
+        d.sign_fix = 0;
+        d.dict_fixed = 1;
+        if (distinct == 0) {  // every row NULL: a CONST plan with an empty dictionary reads no memory
+          d.kind = K_CONST;
+          d.ok = 1;
+          return;
+        }
+        if (stream_idx + 2 >= (int)b.cs_stream_count) return;
+        const uint32_t end0 = (uint32_t)ld_bytes(s, b.cs_off_data + (uint32_t)(stream_idx + 1) * b.cs_off_width, b.cs_off_width);
+        const uint32_t end1 = (uint32_t)ld_bytes(s, b.cs_off_data + (uint32_t)(stream_idx + 2) * b.cs_off_width, b.cs_off_width);
+        if (pos + meta_len > end0 || end0 > end1 || end1 > b.size) return;
+        IntStreamMeta m;
+        parse_int_stream_meta(s, pos + meta_len, end0, m);
+        if (!m.ok || m.replace_null) return;
+        const uint32_t dict = pos + meta_len + m.meta_len;
+        if (dict + m.width * distinct != end0) return;
+        d.kind = K_DICT;
+        d.dict_count = distinct;
+        d.dict_data_size = m.width;
+        d.dict_payload = dict;
+        d.dict_end = end0;
+        d.base = m.use_base ? m.base : 0;
+        parse_int_stream_meta(s, end0, end1, m);
+        if (!m.ok || m.use_base || m.replace_null || m.width > 4) return;
+        const uint32_t refs = end0 + m.meta_len;
+        if (refs + m.width * b.row_count != end1) return;
+        d.width = (uint8_t)(m.width * 8u);
+        d.stride = m.width * 8u;
+        d.val_bit = refs * 8u;
+        d.ok = 1;
+        return;
+      }
       if (attrs & (CS_HAS_NOP_BITMAP | CS_HAS_NOP | CS_OUT_ROW)) return;
       if (stream_idx + 1 >= (int)b.cs_stream_count) return;
       const uint32_t end = (uint32_t)ld_bytes(s, b.cs_off_data + (uint32_t)(stream_idx + 1) * b.cs_off_width, b.cs_off_width);
@@ -679,8 +720,8 @@ __device__ __forceinline__ uint64_t sign_fix(uint64_t int_mask, uint64_t v) {
 }
 
 __device__ __forceinline__ uint64_t dict_int(const uint8_t *s, const ColDesc &d, uint32_t ref) {
-  const uint64_t v = ld_bits(s, (d.dict_payload + ref * d.dict_data_size) * 8u, d.dict_data_size * 8u);
-  return d.sign_fix ? sign_fix(d.int_mask, v) : v;
+  const uint64_t v = ld_bits(s, (d.dict_payload + ref * d.dict_data_size) * 8u, d.dict_data_size * 8u) + d.base;
+  return d.sign_fix ? sign_fix(d.int_mask, v) : v;   // base: CS INT_DICT value streams (0 for PAX dictionaries)
 }
 
 // dictionary string cell -> (block offset, length)
@@ -776,13 +817,19 @@ __device__ __forceinline__ void str_cell(const BlockView &b, const ColDesc &d, c
   cell = var + col_off;
 }
 
-// memcmp-then-length order of a shared-memory cell against a constant
+// memcmp-then-length order of a cell against a constant, 8 bytes per step. `c` is 8-byte aligned and
+// readable up to the next multiple of 8 past clen (the host pads the constant heap).
 __device__ __forceinline__ int str_cmp(const uint8_t *s, uint32_t cell, uint32_t len,
                                        const uint8_t *c, uint32_t clen) {
   const uint32_t m = len < clen ? len : clen;
-  for (uint32_t i = 0; i < m; ++i) {
-    const int a = s[cell + i], bb = c[i];
-    if (a != bb) return a < bb ? -1 : 1;
+  for (uint32_t i = 0; i < m; i += 8u) {
+    const uint32_t nb = m - i < 8u ? m - i : 8u;
+    const uint64_t a = ld_bits(s, (cell + i) * 8u, nb * 8u);   // little endian: first byte in the low bits
+    const uint64_t b = *reinterpret_cast<const uint64_t *>(c + i) & (~0ull >> (64u - nb * 8u));
+    if (a != b) {
+      const int k = (__ffsll((long long)(a ^ b)) - 1) & ~7;      // first differing byte
+      return ((a >> k) & 0xffull) < ((b >> k) & 0xffull) ? -1 : 1;
+    }
   }
   return len < clen ? -1 : (len > clen ? 1 : 0);
 }

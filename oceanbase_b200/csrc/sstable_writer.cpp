@@ -839,8 +839,62 @@ int BlockBuilder::build_cs(std::vector<uint8_t> &block, int64_t original) {
     CSColumnHeader &ch = chdr[(size_t)i];
     ch = CSColumnHeader{};
     ch.obj_type_ = (uint8_t)cols[i].obj_type;
-    if (cols[i].encoding != OBGPU_ENC_CS_INTEGER || (c.sc != 1 && c.sc != 2)) return OBGPU_NOT_SUPPORTED;
+    if ((cols[i].encoding != OBGPU_ENC_CS_INTEGER && cols[i].encoding != OBGPU_ENC_CS_INT_DICT) || (c.sc != 1 && c.sc != 2))
+      return OBGPU_NOT_SUPPORTED;
     if (c.nope_cnt > 0) return OBGPU_NOT_SUPPORTED;
+    if (cols[i].encoding == OBGPU_ENC_CS_INT_DICT) {
+      // ObIntDictColumnEncoder: [ObDictEncodingMeta][dict values: integer stream][refs: integer stream];
+      // ref == distinct_val_cnt is NULL; an all-NULL column has the meta only (no streams)
+      ch.type_ = CS_INT_DICT;
+      const int ts = type_store_size((uint8_t)cols[i].obj_type);
+      const uint64_t mask = low_mask(ts * 8);
+      const bool sgn = c.sc == 1;
+      std::vector<int64_t> vals;
+      vals.reserve((size_t)nrows);
+      for (int64_t r = 0; r < nrows; ++r)
+        if (!c.is_null(r)) vals.push_back(sgn ? c.ival(r) : (int64_t)((uint64_t)c.ival(r) & mask));
+      if (sgn) std::sort(vals.begin(), vals.end());
+      else std::sort(vals.begin(), vals.end(), [](int64_t a, int64_t b) { return (uint64_t)a < (uint64_t)b; });
+      vals.erase(std::unique(vals.begin(), vals.end()), vals.end());
+      DictEncodingMeta dm{};
+      dm.attrs_ = (uint8_t)(0x1 | (c.null_cnt > 0 ? 0x2 : 0));  // IS_SORTED | HAS_NULL
+      dm.distinct_val_cnt_ = (uint32_t)vals.size();
+      dm.ref_row_cnt_ = (uint32_t)nrows;
+      memcpy(body.grow(sizeof(dm)), &dm, sizeof(dm));
+      if (vals.empty()) continue;
+      IntStreamPlan dp;
+      if (sgn && vals.front() < 0) {
+        dp.use_base = true;
+        dp.base = (uint64_t)vals.front();
+        dp.width = (int)byte_packed_int_size((uint64_t)vals.back() - (uint64_t)vals.front());
+      } else {
+        dp.width = (int)byte_packed_int_size((uint64_t)vals.back());
+      }
+      put_stream_meta(body, dp);
+      uint8_t *dd = body.grow((size_t)dp.width * vals.size());
+      for (size_t k = 0; k < vals.size(); ++k) {
+        const uint64_t v = (uint64_t)vals[k] - dp.base;
+        memcpy(dd + k * (size_t)dp.width, &v, (size_t)dp.width);
+      }
+      stream_end.push_back(header_size + (uint32_t)body.size());
+      IntStreamPlan rp;
+      rp.width = (int)byte_packed_int_size(c.null_cnt > 0 ? vals.size() : vals.size() - 1);
+      put_stream_meta(body, rp);
+      uint8_t *rd = body.grow((size_t)rp.width * (size_t)nrows);
+      for (int64_t r = 0; r < nrows; ++r) {
+        uint64_t ref;
+        if (c.is_null(r)) ref = vals.size();
+        else {
+          const int64_t v = sgn ? c.ival(r) : (int64_t)((uint64_t)c.ival(r) & mask);
+          ref = sgn ? (uint64_t)(std::lower_bound(vals.begin(), vals.end(), v) - vals.begin())
+                    : (uint64_t)(std::lower_bound(vals.begin(), vals.end(), v,
+                                                  [](int64_t a, int64_t b) { return (uint64_t)a < (uint64_t)b; }) - vals.begin());
+        }
+        memcpy(rd + (size_t)r * (size_t)rp.width, &ref, (size_t)rp.width);
+      }
+      stream_end.push_back(header_size + (uint32_t)body.size());
+      continue;
+    }
     ch.type_ = CS_INTEGER;
     const int ts = type_store_size((uint8_t)cols[i].obj_type);
     const uint64_t mask = low_mask(ts * 8);
@@ -914,7 +968,7 @@ int BlockBuilder::build_cs(std::vector<uint8_t> &block, int64_t original) {
   }
   // stream offsets: an integer stream without base (ObMicroBlockCSEncoder::store_stream_offsets_, :1312-1372)
   const size_t offsets_at = body.size();
-  {
+  if (!stream_end.empty()) {
     IntStreamPlan sp;
     sp.width = (int)byte_packed_int_size(stream_end.back());
     if (sp.width > 4) return OBGPU_NOT_SUPPORTED;

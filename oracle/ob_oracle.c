@@ -13,7 +13,7 @@
 #include <string.h>
 
 /* ---- layout constants (ob_micro_block_header.h:97-153, ob_block_sstable_struct.h:201-264) ---- */
-enum { T_RAW = 0, T_DICT = 1, T_RLE = 2, T_CONST = 3, T_BASE_DIFF = 4, T_CS_INTEGER = 100 /* CS block, ObCSColumnHeader::INTEGER */ };
+enum { T_RAW = 0, T_DICT = 1, T_RLE = 2, T_CONST = 3, T_BASE_DIFF = 4, T_CS_INTEGER = 100, T_CS_INT_DICT = 102 /* CS block: 100 + ObCSColumnHeader::Type */ };
 enum { A_FIX = 0x1, A_EXT = 0x2, A_BITPACK = 0x4, A_LASTVAR = 0x8 };
 enum { EXT_NOT = 0, EXT_NULL = 1, EXT_NOPE = 2 };
 #define MAGIC 1005
@@ -269,7 +269,7 @@ static int get_col(const ora_block *b, int32_t col, col_hdr *h) {
   if (b->row_store_type == 3) { /* ObCSColumnHeader: version, type, attrs, obj_type */
     const uint8_t *c = b->cs_col_headers + 4 * col;
     if (c[0] != 0) return ORA_INVALID_DATA;
-    h->type = (int8_t)(c[1] == 0 ? T_CS_INTEGER : 127);
+    h->type = (int8_t)(c[1] == 0 ? T_CS_INTEGER : (c[1] == 2 ? T_CS_INT_DICT : 127));
     h->attr = (int8_t)c[2];
     h->obj_type = c[3];
     h->ext_index = h->offset = h->length = 0;
@@ -426,6 +426,11 @@ typedef struct col_dec {
   int cs_width;
   int cs_replace_null;
   uint64_t cs_base, cs_null_raw;                 /* null_replaced_value - base */
+  /* CS INT_DICT column (cs_encoding/ob_int_dict_column_decoder.cpp:25-60): cs_data / cs_width / cs_base describe
+   * the dictionary value stream */
+  uint32_t cs_distinct;
+  const uint8_t *cs_ref_data;
+  int cs_ref_width;
 } col_dec;
 
 static uint32_t cs_stream_end(const ora_block *b, int32_t idx) {
@@ -459,6 +464,27 @@ static int cs_int_col_init(const ora_block *b, int32_t col, col_dec *c) {
       return ORA_NOT_SUPPORTED;
     }
     if (i == col) {
+      if (type == 2) { /* INT_DICT: [ObDictEncodingMeta 10 B][dict value stream][ref stream] */
+        const uint8_t *dm = b->buf + pos;
+        if (dm[0] != 0 || (dm[1] & 0x4) || (attrs & 0x08)) return ORA_NOT_SUPPORTED; /* const-encoded refs / nop bitmap */
+        c->cs_distinct = rd32(dm + 2);
+        if (c->cs_distinct == 0) return ORA_SUCCESS;        /* every row NULL */
+        if (stream_idx + 2 >= b->cs_stream_count) return ORA_INVALID_DATA;
+        const uint32_t end0 = cs_stream_end(b, stream_idx + 1), end1 = cs_stream_end(b, stream_idx + 2);
+        if ((int64_t)pos + meta_len > end0 || end0 > end1 || end1 > b->size) return ORA_INVALID_DATA;
+        int_stream_meta m;
+        int ret = parse_int_stream_meta(dm + meta_len, (int64_t)end0 - pos - meta_len, &m);
+        if (ret) return ret;
+        if (pos + meta_len + m.meta_len + (int64_t)m.width * c->cs_distinct != end0) return ORA_INVALID_DATA;
+        c->cs_data = dm + meta_len + m.meta_len;
+        c->cs_width = m.width;
+        c->cs_base = (m.attr & 0x1) ? m.base : 0;
+        if ((ret = parse_int_stream_meta(b->buf + end0, (int64_t)end1 - end0, &m))) return ret;
+        if ((m.attr & 0x3) || end0 + m.meta_len + (int64_t)m.width * b->row_count != end1) return ORA_INVALID_DATA;
+        c->cs_ref_data = b->buf + end0 + m.meta_len;
+        c->cs_ref_width = m.width;
+        return ORA_SUCCESS;
+      }
       if (type != 0) return ORA_NOT_SUPPORTED;
       if (stream_idx + 1 >= b->cs_stream_count) return ORA_INVALID_DATA;
       const uint32_t end = cs_stream_end(b, stream_idx + 1);
@@ -518,7 +544,8 @@ static int col_dec_init(const ora_block *b, int32_t col, col_dec *c) {
       if (c->sc == 1 && mask != 0 && (c->base & (mask >> 1))) c->base |= mask;
       break;
     }
-    case T_CS_INTEGER: return cs_int_col_init(b, col, c);
+    case T_CS_INTEGER:
+    case T_CS_INT_DICT: return cs_int_col_init(b, col, c);
     case T_CONST: {
       const uint8_t *m = c->meta; /* version, count, const_ref, attr(row_id_byte:3), offset u16 */
       if (m[0] != 0) return ORA_ERR_UNEXPECTED;
@@ -636,6 +663,14 @@ static int decode_cell(const ora_block *b, const col_dec *c, int64_t row, ora_da
       const uint64_t raw = rd_len(c->cs_data + row * c->cs_width, c->cs_width);
       if (c->cs_replace_null && raw == c->cs_null_raw) { set_null(out); return ORA_SUCCESS; }
       set_int(c->h.obj_type, raw + c->cs_base, out);
+      return ORA_SUCCESS;
+    }
+    case T_CS_INT_DICT: { /* ObIntDictColumnDecoder::decode: ref == distinct_val_cnt is NULL, value = dict[ref] + base */
+      if (c->cs_distinct == 0) { set_null(out); return ORA_SUCCESS; }
+      const uint64_t ref = rd_len(c->cs_ref_data + row * c->cs_ref_width, c->cs_ref_width);
+      if (ref == c->cs_distinct) { set_null(out); return ORA_SUCCESS; }
+      if (ref > c->cs_distinct) return ORA_ERR_UNEXPECTED;
+      set_int(c->h.obj_type, rd_len(c->cs_data + ref * c->cs_width, c->cs_width) + c->cs_base, out);
       return ORA_SUCCESS;
     }
     case T_CONST: {

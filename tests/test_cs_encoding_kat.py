@@ -110,3 +110,44 @@ def test_mixed_row_store_types_in_one_block_are_rejected():
     v = np.arange(10, dtype=np.int64)
     with pytest.raises(ob.ObGpuError):
         ob.encode_block([ob.Column(ob.OBJ_INT, ob.ENC_RAW, v), ob.Column(ob.OBJ_INT, ob.ENC_CS_INTEGER, v)])
+
+
+@pytest.mark.parametrize("obj_type,lo,hi", [(ob.OBJ_INT, -50, 50), (ob.OBJ_INT, 0, 70000), (ob.OBJ_UINT64, 1 << 40, (1 << 40) + 300),
+                                            (ob.OBJ_DATE, 8000, 8100), (ob.OBJ_INT32, -(1 << 31), -(1 << 31) + 200)])
+@pytest.mark.parametrize("with_nulls", [False, True])
+def test_cs_int_dict_roundtrip(obj_type, lo, hi, with_nulls):
+    # ObIntDictColumnDecoder::decode (cs_encoding/ob_int_dict_column_decoder.cpp:25-60): ref == distinct count is NULL
+    n = 600
+    v = RNG.integers(lo, hi, size=n).astype(np.int64)
+    nulls = (RNG.random(n) < 0.2).astype(np.uint8) if with_nulls else None
+    block = ob.encode_block([ob.Column(ob.OBJ_INT, ob.ENC_CS_INTEGER, np.arange(n, dtype=np.int64)),
+                             ob.Column(obj_type, ob.ENC_CS_INT_DICT, v, nulls=nulls),
+                             ob.Column(ob.OBJ_INT, ob.ENC_CS_INTEGER, v)])
+    blk = ora.Block(block)
+    assert blk.verify_checksums() == 0 and blk.b.cs_stream_count == 4
+    hs = blk.b.header_size
+    assert int(block[hs + 12 + 4 + 1]) == 2                      # ObCSColumnHeader::INT_DICT
+    for r in range(n):
+        d = blk.cell_raw(1, r)
+        if nulls is not None and nulls[r]:
+            assert d.is_null == 1
+        elif obj_type == ob.OBJ_DATE:
+            assert d.is_null == 0 and d.len == 4 and np.int32(np.uint32(d.ival)) == v[r]
+        else:
+            assert d.is_null == 0 and np.int64(np.uint64(d.ival)) == v[r]
+    assert [blk.cell(2, r) for r in range(0, n, 41)] == [int(np.uint64(x)) for x in v[::41]]   # column after the dict column
+    mid = int(np.median(v))
+    pax = ora.Block(ob.encode_block([ob.Column(ob.OBJ_INT, ob.ENC_RAW, np.arange(n, dtype=np.int64)),
+                                     ob.Column(obj_type, ob.ENC_DICT, v, nulls=nulls)]))
+    for op, params in ((ob.WHITE_OP_LT, (mid,)), (ob.WHITE_OP_IN, (int(v[0]), int(v[1]), mid)), (ob.WHITE_OP_NU, ()), (ob.WHITE_OP_NE, (mid,))):
+        assert np.array_equal(blk.filter_tree(White(1, op, params)), pax.filter_tree(White(1, op, params)))
+
+
+def test_cs_int_dict_all_null_column_has_no_streams():
+    n = 100
+    block = ob.encode_block([ob.Column(ob.OBJ_INT, ob.ENC_CS_INT_DICT, np.zeros(n, dtype=np.int64), nulls=np.ones(n, dtype=np.uint8)),
+                             ob.Column(ob.OBJ_INT, ob.ENC_CS_INTEGER, np.arange(n, dtype=np.int64))])
+    blk = ora.Block(block)
+    assert blk.b.cs_stream_count == 1
+    assert all(blk.cell(0, r) is None for r in range(n))
+    assert [blk.cell(1, r) for r in range(n)] == list(range(n))

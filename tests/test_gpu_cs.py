@@ -117,3 +117,22 @@ def test_aggregates_with_nulls_and_wide_values(ob, ctx):
     assert none.aggregate(ob.AGG_MIN, 0) is None and none.aggregate(ob.AGG_COUNT, 0) == 0 and none.aggregate(ob.AGG_SUM, 0) == 0
     none.free()
     batch.close()
+
+
+@pytest.mark.parametrize("with_nulls", [False, True])
+def test_cs_int_dict_columns_scan(ob, ctx, with_nulls):
+    rng = np.random.default_rng(21)
+    n = 9000
+    a = rng.integers(-40, 40, size=n, dtype=np.int64) * 1000
+    b = rng.integers(8000, 8200, size=n, dtype=np.int64)
+    na = (rng.random(n) < 0.2).astype(np.uint8) if with_nulls else None
+    allnull = np.ones(n, dtype=np.uint8)
+    table = ob.encode_table([ob.Column(ob.OBJ_INT, ob.ENC_CS_INT_DICT, a, nulls=na),
+                             ob.Column(ob.OBJ_DATE, ob.ENC_CS_INT_DICT, b),
+                             ob.Column(ob.OBJ_INT, ob.ENC_CS_INTEGER, rng.integers(0, 1 << 40, size=n, dtype=np.int64)),
+                             ob.Column(ob.OBJ_INT, ob.ENC_CS_INT_DICT, np.zeros(n, dtype=np.int64), nulls=allnull)], 1100)
+    flts = [None, ob.White(0, ob.WHITE_OP_GE, (0,)), ob.White(1, ob.WHITE_OP_IN, (8001, 8100, 9999)),
+            ob.And([ob.White(0, ob.WHITE_OP_NE, (5000,)), ob.White(1, ob.WHITE_OP_BT, (8050, 8150)), ob.White(2, ob.WHITE_OP_LT, (1 << 39,))]),
+            ob.Or([ob.White(0, ob.WHITE_OP_NU, ()), ob.White(3, ob.WHITE_OP_NN, ())])]
+    for flt in flts:
+        assert_scan_matches(ctx, W(table, flt, [0, 1, 2, 3], [False] * 4, [8, 4, 8, 8]))
