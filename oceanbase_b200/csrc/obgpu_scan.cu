@@ -405,10 +405,10 @@ __device__ __forceinline__ void filter_bits_range(const BlockCtx &c, const ColDe
     const uint32_t w = __ballot_sync(0xffffffffu, ((v - lo) <= span) != neg);
     if (t.lane == 0) bm[g] = MODE == 0 ? w : (MODE == 1 ? (cur & w) : (cur | w));
   }
-  if (g < nwords) {  // ragged tail group
+  if (g < nwords) {  // ragged tail group: lanes past the last row must not touch memory
     const uint32_t vm = valid_mask_of(rows, g);
     const uint32_t cur = MODE == 0 ? 0u : bm[g];
-    const uint64_t v = load(bit);
+    const uint64_t v = g * 32u + (uint32_t)t.lane < rows ? load(bit) : 0ull;
     const uint32_t w = __ballot_sync(0xffffffffu, ((v - lo) <= span) != neg) & vm;
     if (t.lane == 0) bm[g] = MODE == 0 ? w : (MODE == 1 ? (cur & w) : (cur | w));
   }
@@ -461,7 +461,8 @@ __device__ __forceinline__ void leaf_over_words(const ScanParams &p, const Block
       const uint32_t cur = bm[g], vm = valid_mask_of(rows, g);
       if (and_mode ? cur == 0u : cur == vm) continue;
       const uint32_t row = g * 32u + (uint32_t)t.lane;
-      uint32_t ref = G ? ld_bits32(gs, val_bit + row * stride, width) : sbits32(val_bit + row * stride, width);
+      uint32_t ref = cntp1;  // lanes past the last row must not touch memory (masked by vm anyway)
+      if (row < rows) ref = G ? ld_bits32(gs, val_bit + row * stride, width) : sbits32(val_bit + row * stride, width);
       ref = ref < cntp1 ? ref : cntp1;
       const bool pr = (bits[ref >> 5] >> (ref & 31)) & 1u;
       const uint32_t w = __ballot_sync(0xffffffffu, pr) & vm;
