@@ -38,6 +38,9 @@ enum {
  * buffers of total_rows entries: value image (what the reference would MEMCPY into the datum, 0 for
  * ext cells) and ext (0 value, 1 NULL, 2 NOP -- ObStoredExtValue). Runs on the ctx stream. */
 int obgpu_batch_decode_column(obgpu_batch *batch, int32_t col, int64_t *dev_vals, uint8_t *dev_ext);
+/* Up to 16 columns with one launch and one synchronisation (each block image is read once). */
+int obgpu_batch_decode_columns(obgpu_batch *batch, int32_t n_cols, const int32_t *cols,
+                               int64_t *const *dev_vals, uint8_t *const *dev_ext);
 
 /* One sorted run, decoded, resident in HBM (all pointers are device pointers; the vals / ext
  * pointer ARRAYS themselves live in host memory). Rowkey: one INT64 column, ascending, unique

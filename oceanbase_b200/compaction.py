@@ -47,22 +47,22 @@ def decode_run(ctx, table, key_col: int, flag_col: Optional[int], cols: Sequence
     batch = ctx.open_batch(table, device_image_ptr=device_image_ptr)
     n = batch.total_rows
 
-    def dec(col):
-        v = torch.empty(n, dtype=torch.int64, device=device)
-        e = torch.empty(n, dtype=torch.uint8, device=device)
-        check(lib.obgpu_batch_decode_column(batch._h, col, v.data_ptr(), e.data_ptr()), "obgpu_batch_decode_column", ctx._h)
-        return v, e
-
-    key, key_ext = dec(key_col)
+    all_cols = [key_col] + ([flag_col] if flag_col is not None else []) + list(cols)
+    vs = [torch.empty(n, dtype=torch.int64, device=device) for _ in all_cols]
+    es = [torch.empty(n, dtype=torch.uint8, device=device) for _ in all_cols]
+    for k in range(0, len(all_cols), 16):   # one launch per 16 columns: every block image is read once
+        sub = all_cols[k:k + 16]
+        ci = (C.c_int32 * len(sub))(*sub)
+        vp = (C.c_void_p * len(sub))(*[v.data_ptr() for v in vs[k:k + 16]])
+        ep = (C.c_void_p * len(sub))(*[e.data_ptr() for e in es[k:k + 16]])
+        check(lib.obgpu_batch_decode_columns(batch._h, len(sub), ci, vp, ep), "obgpu_batch_decode_columns", ctx._h)
+    key, key_ext = vs[0], es[0]
     flag = None
+    at = 1
     if flag_col is not None:
-        fv, _ = dec(flag_col)
-        flag = fv.to(torch.uint8)
-    vals, ext = [], []
-    for c in cols:
-        v, e = dec(c)
-        vals.append(v)
-        ext.append(e)
+        flag = vs[1].to(torch.uint8)
+        at = 2
+    vals, ext = vs[at:], es[at:]
     batch.close()
     if bool((key_ext != 0).any()):
         raise capi.ObGpuError(capi.OB_INVALID_DATA, "decode_run", "rowkey column holds NULL / NOP cells")

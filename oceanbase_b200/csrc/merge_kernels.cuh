@@ -234,53 +234,72 @@ __global__ void __launch_bounds__(256) fuse_kernel(const int64_t *__restrict__ k
   }
 }
 
-// ---- run decode: every cell of one integer column of a batch -> (value, ext) ---------------------
-__global__ void __launch_bounds__(128) decode_col_kernel(const uint8_t *__restrict__ image, const BlockRec *__restrict__ recs,
-                                                         const ColDesc *__restrict__ plans, int max_cols, int col,
-                                                         const int64_t *__restrict__ row_start, int64_t *__restrict__ vals,
-                                                         uint8_t *__restrict__ ext, int *__restrict__ status) {
-  __shared__ ColDesc s_d;
+// ---- run decode: every cell of up to kMaxDecodeCols integer columns of a batch -> (value, ext) ---------
+constexpr int kMaxDecodeCols = 16;
+struct DecodeCols {
+  int32_t n;
+  int32_t col[kMaxDecodeCols];
+  int64_t *vals[kMaxDecodeCols];
+  uint8_t *ext[kMaxDecodeCols];
+};
+
+__global__ void __launch_bounds__(128) decode_cols_kernel(const uint8_t *__restrict__ image, const BlockRec *__restrict__ recs,
+                                                          const ColDesc *__restrict__ plans, int max_cols,
+                                                          const __grid_constant__ DecodeCols dc,
+                                                          const int64_t *__restrict__ row_start, int *__restrict__ status) {
+  __shared__ ColDesc s_d[kMaxDecodeCols];
   const int block = blockIdx.x;
   const BlockRec rec = recs[block];
-  if (threadIdx.x < (int)(sizeof(ColDesc) / 16))
-    reinterpret_cast<uint4 *>(&s_d)[threadIdx.x] =
-        reinterpret_cast<const uint4 *>(plans + (int64_t)block * max_cols + col)[threadIdx.x];
+  constexpr int kPieces = (int)(sizeof(ColDesc) / 16);
+  for (int k = threadIdx.x; k < dc.n * kPieces; k += blockDim.x)
+    reinterpret_cast<uint4 *>(s_d)[k] =
+        reinterpret_cast<const uint4 *>(plans + (int64_t)block * max_cols + dc.col[k / kPieces])[k % kPieces];
   __syncthreads();
-  const ColDesc &d = s_d;
-  if (rec.rows == 0 || !d.ok || d.sc == 5) {
-    if (threadIdx.x == 0) atomicOr(status, rec.rows == 0 ? ST_CORRUPT : ST_UNSUPPORTED);
+  if (rec.rows == 0) {
+    if (threadIdx.x == 0) atomicOr(status, ST_CORRUPT);
     return;
   }
   BlockView b;
   const uint8_t *s = image + rec.off;
   view_from_rec(rec, s, b);
-  int64_t *ov = vals + row_start[block];
-  uint8_t *oe = ext + row_start[block];
-  for (uint32_t row = threadIdx.x; row < rec.rows; row += blockDim.x) {
-    uint64_t v = 0;
-    uint8_t e = 0;
-    if (is_dict_kind(d)) {
-      const uint32_t ref = ref_of(s, d, nullptr, row);
-      if (ref >= d.dict_count) e = ref == d.dict_count ? 1 : 2;
-      else v = dict_int(s, d, ref);
-    } else {
-      if (d.ext_bit) {
-        const uint32_t x = ld_bits32(s, d.ext_bit_off + ext_row(d, row) * d.ext_bit, d.ext_bit);
-        e = x == STORED_NOT_EXT ? 0 : (x == STORED_NULL ? 1 : 2);
-      }
-      if (!e) {
-        const uint64_t raw = ld_bits(s, d.val_bit + row * d.stride, d.width);
-        if (null_replaced_on(d) && raw == null_replaced_raw(d)) e = 1;
-        else {
-          v = raw + d.base;
-          if (d.sign_fix) v = sign_fix(d.int_mask, v);
+  const int64_t row0 = row_start[block];
+  for (int c = 0; c < dc.n; ++c) {
+    const ColDesc &d = s_d[c];
+    if (!d.ok || d.sc == 5) {
+      if (threadIdx.x == 0) atomicOr(status, ST_UNSUPPORTED);
+      continue;
+    }
+    int64_t *ov = dc.vals[c] + row0;
+    uint8_t *oe = dc.ext[c] + row0;
+    const bool plain = d.kind == K_BITS && d.ext_bit == 0 && !d.var_is_last && !d.sign_fix && d.elem_len == 8;
+    for (uint32_t row = threadIdx.x; row < rec.rows; row += blockDim.x) {
+      uint64_t v = 0;
+      uint8_t e = 0;
+      if (plain) {
+        v = ld_bits(s, d.val_bit + row * d.stride, d.width) + d.base;
+      } else if (is_dict_kind(d)) {
+        const uint32_t ref = ref_of(s, d, nullptr, row);
+        if (ref >= d.dict_count) e = ref == d.dict_count ? 1 : 2;
+        else v = dict_int(s, d, ref);
+      } else {
+        if (d.ext_bit) {
+          const uint32_t x = ld_bits32(s, d.ext_bit_off + ext_row(d, row) * d.ext_bit, d.ext_bit);
+          e = x == STORED_NOT_EXT ? 0 : (x == STORED_NULL ? 1 : 2);
+        }
+        if (!e) {
+          const uint64_t raw = ld_bits(s, d.val_bit + row * d.stride, d.width);
+          if (null_replaced_on(d) && raw == null_replaced_raw(d)) e = 1;
+          else {
+            v = raw + d.base;
+            if (d.sign_fix) v = sign_fix(d.int_mask, v);
+          }
         }
       }
+      if (d.elem_len == 4) v &= 0xffffffffull;
+      else if (d.elem_len == 1) v &= 0xffull;
+      ov[row] = (int64_t)v;
+      oe[row] = e;
     }
-    if (d.elem_len == 4) v &= 0xffffffffull;
-    else if (d.elem_len == 1) v &= 0xffull;
-    ov[row] = (int64_t)v;
-    oe[row] = e;
   }
 }
 
@@ -306,17 +325,25 @@ struct obgpu_merge_result {
 
 extern "C" {
 
-int obgpu_batch_decode_column(obgpu_batch *b, int32_t col, int64_t *dev_vals, uint8_t *dev_ext) {
-  if (!b || !dev_vals || !dev_ext || col < 0 || (uint32_t)col >= b->max_cols) return OBGPU_INVALID_ARGUMENT;
+int obgpu_batch_decode_columns(obgpu_batch *b, int32_t n_cols, const int32_t *cols, int64_t *const *dev_vals,
+                               uint8_t *const *dev_ext) {
+  if (!b || n_cols <= 0 || n_cols > mrg::kMaxDecodeCols || !cols || !dev_vals || !dev_ext) return OBGPU_INVALID_ARGUMENT;
+  mrg::DecodeCols dc{};
+  dc.n = n_cols;
+  for (int i = 0; i < n_cols; ++i) {
+    if (cols[i] < 0 || (uint32_t)cols[i] >= b->max_cols || !dev_vals[i] || !dev_ext[i]) return OBGPU_INVALID_ARGUMENT;
+    dc.col[i] = cols[i];
+    dc.vals[i] = dev_vals[i];
+    dc.ext[i] = dev_ext[i];
+  }
   obgpu_ctx *ctx = b->ctx;
   cudaSetDevice(ctx->device);
-  const int n = b->n_blocks;
   int *d_status = nullptr;
   cudaError_t e = cudaMallocAsync((void **)&d_status, 64, ctx->stream);
   if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return OBGPU_ALLOCATE_MEMORY_FAILED; }
   cudaMemsetAsync(d_status, 0, 4, ctx->stream);
-  mrg::decode_col_kernel<<<n, 128, 0, ctx->stream>>>(b->d_image, b->d_recs, b->d_plans, (int)b->max_cols, col, b->d_row_start,
-                                                     dev_vals, dev_ext, d_status);
+  mrg::decode_cols_kernel<<<b->n_blocks, 128, 0, ctx->stream>>>(b->d_image, b->d_recs, b->d_plans, (int)b->max_cols, dc,
+                                                                b->d_row_start, d_status);
   ctx->launches++;
   int status = 0;
   cudaMemcpyAsync(&status, d_status, 4, cudaMemcpyDeviceToHost, ctx->stream);
@@ -324,6 +351,10 @@ int obgpu_batch_decode_column(obgpu_batch *b, int32_t col, int64_t *dev_vals, ui
   cudaFreeAsync(d_status, ctx->stream);
   if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return OBGPU_ERR_SYS; }
   return check_status(ctx, status);
+}
+
+int obgpu_batch_decode_column(obgpu_batch *b, int32_t col, int64_t *dev_vals, uint8_t *dev_ext) {
+  return obgpu_batch_decode_columns(b, 1, &col, &dev_vals, &dev_ext);
 }
 
 int obgpu_merge_decoded(obgpu_ctx *ctx, const obgpu_merge_run *runs, int32_t n_runs, int32_t n_cols,
