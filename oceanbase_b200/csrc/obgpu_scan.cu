@@ -380,11 +380,15 @@ __device__ __forceinline__ uint32_t valid_mask_of(uint32_t rows, uint32_t g) {
 // Range test over a K_BITS column without NULLs / sign fix: the hot filter loop.
 //   MODE 0: first leaf (bm[g] = leaf), 1: AND into bm with early-out, 2: OR into bm with early-out
 //   G: the block is read straight from global memory (count kernel) instead of shared memory
-template <bool WIDE, int MODE, bool G>
+//   NARROW: datum narrower than 8 bytes (date, year, ...): the compare image is the low elem_len bytes of
+//   value + base, sign-extended for signed classes (cmp_image) -- done with and / xor / sub on the lane
+template <bool WIDE, int MODE, bool G, bool NARROW>
 __device__ __forceinline__ void filter_bits_range(const BlockCtx &c, const ColDesc &d, const FilterNodeDev &nd,
                                                   uint32_t *bm, uint32_t rows, uint32_t nwords, const Team &t) {
   const uint32_t stride = d.stride, width = d.width;
-  const uint64_t lo = nd.lo - d.base, span = nd.span;  // (v + base - lo) <= span
+  const uint64_t lo = NARROW ? nd.lo : nd.lo - d.base, span = nd.span;  // (v + base - lo) <= span
+  const uint64_t nbase = d.base, nmask = d.elem_len == 4 ? 0xffffffffull : 0xffull;
+  const uint64_t nsign = (d.elem_len == 4 && d.sc == 1) ? 0x80000000ull : 0ull;
   const bool neg = nd.negate != 0;
   const uint32_t nfull = rows >> 5;
   const uint32_t step = (uint32_t)t.nwarps * 32u * stride;
@@ -392,8 +396,11 @@ __device__ __forceinline__ void filter_bits_range(const BlockCtx &c, const ColDe
   uint32_t bit = (G ? 0u : c.sbit) + d.val_bit + ((uint32_t)t.warp * 32u + (uint32_t)t.lane) * stride;
   uint32_t g = (uint32_t)t.warp;
   auto load = [&](uint32_t bo) -> uint64_t {
-    if (G) return WIDE ? ld_bits(gs, bo, width) : (uint64_t)ld_bits32(gs, bo, width);
-    return WIDE ? sbits(bo, width) : (uint64_t)sbits32(bo, width);
+    uint64_t v;
+    if (G) v = WIDE ? ld_bits(gs, bo, width) : (uint64_t)ld_bits32(gs, bo, width);
+    else v = WIDE ? sbits(bo, width) : (uint64_t)sbits32(bo, width);
+    if (NARROW) v = ((((v + nbase) & nmask) ^ nsign) - nsign);
+    return v;
   };
   for (; g < nfull; g += (uint32_t)t.nwarps, bit += step) {
     uint32_t cur = 0;
@@ -415,7 +422,7 @@ __device__ __forceinline__ void filter_bits_range(const BlockCtx &c, const ColDe
 }
 
 __device__ __forceinline__ bool leaf_is_bits_range(const ColDesc &d, const FilterNodeDev &nd) {
-  return d.kind == K_BITS && nd.range_ok && d.elem_len == 8 && d.ext_bit == 0 && !d.sign_fix && !d.var_is_last;
+  return d.kind == K_BITS && nd.range_ok && d.ext_bit == 0 && !d.sign_fix && !d.var_is_last;
 }
 
 // First leaf of an AND / OR list: writes bm directly (no initialisation pass) when it is a plain
@@ -426,8 +433,11 @@ __device__ __forceinline__ bool leaf_first_fast(const ScanParams &p, const Block
   if (nd.kind != NODE_WHITE) return false;
   const ColDesc &d = c.descs[nd.used_idx];
   if (!leaf_is_bits_range(d, nd)) return false;
-  if (d.width <= 32) filter_bits_range<false, 0, G>(c, d, nd, bm, rows, nwords, t);
-  else filter_bits_range<true, 0, G>(c, d, nd, bm, rows, nwords, t);
+  if (d.elem_len != 8) {
+    if (d.width <= 32) filter_bits_range<false, 0, G, true>(c, d, nd, bm, rows, nwords, t);
+    else filter_bits_range<true, 0, G, true>(c, d, nd, bm, rows, nwords, t);
+  } else if (d.width <= 32) filter_bits_range<false, 0, G, false>(c, d, nd, bm, rows, nwords, t);
+  else filter_bits_range<true, 0, G, false>(c, d, nd, bm, rows, nwords, t);
   return true;
 }
 
@@ -442,12 +452,20 @@ __device__ __forceinline__ void leaf_over_words(const ScanParams &p, const Block
   const int op = nd.op;
   // ---- fast path A: integer range test on a K_BITS column without NULLs ------------------------------
   if (leaf_is_bits_range(d, nd)) {
-    if (d.width <= 32) {
-      if (and_mode) filter_bits_range<false, 1, G>(c, d, nd, bm, rows, nwords, t);
-      else filter_bits_range<false, 2, G>(c, d, nd, bm, rows, nwords, t);
+    if (d.elem_len != 8) {
+      if (d.width <= 32) {
+        if (and_mode) filter_bits_range<false, 1, G, true>(c, d, nd, bm, rows, nwords, t);
+        else filter_bits_range<false, 2, G, true>(c, d, nd, bm, rows, nwords, t);
+      } else {
+        if (and_mode) filter_bits_range<true, 1, G, true>(c, d, nd, bm, rows, nwords, t);
+        else filter_bits_range<true, 2, G, true>(c, d, nd, bm, rows, nwords, t);
+      }
+    } else if (d.width <= 32) {
+      if (and_mode) filter_bits_range<false, 1, G, false>(c, d, nd, bm, rows, nwords, t);
+      else filter_bits_range<false, 2, G, false>(c, d, nd, bm, rows, nwords, t);
     } else {
-      if (and_mode) filter_bits_range<true, 1, G>(c, d, nd, bm, rows, nwords, t);
-      else filter_bits_range<true, 2, G>(c, d, nd, bm, rows, nwords, t);
+      if (and_mode) filter_bits_range<true, 1, G, false>(c, d, nd, bm, rows, nwords, t);
+      else filter_bits_range<true, 2, G, false>(c, d, nd, bm, rows, nwords, t);
     }
     return;
   }
@@ -653,6 +671,25 @@ __device__ __forceinline__ void project_int_col(const ScanParams &p, const Block
         out[j] = (OutT)(is_null ? 0ull : v);
         if (is_null) mark_null(j);
       }
+    }
+  }
+  if (saw_null) p.has_null[pc] = 1;
+}
+
+// Same projection through generic loads on the block in global memory (sparse selections).
+template <typename OutT>
+__device__ __forceinline__ void project_int_col_global(const ScanParams &p, const BlockCtx &c, const ColDesc &d, int pc,
+                                                       const uint16_t *sel, uint32_t cnt, int64_t base_row, const Team &t) {
+  OutT *out = reinterpret_cast<OutT *>(p.out_data[pc]) + base_row;
+  bool saw_null = false;
+  for (uint32_t j = (uint32_t)t.tid; j < cnt; j += (uint32_t)t.nthreads) {
+    bool is_null;
+    const uint64_t v = int_cell(c.b, d, nullptr, (uint32_t)sel[j], is_null);
+    out[j] = (OutT)(is_null ? 0ull : v);
+    if (is_null) {
+      const int64_t o = base_row + (int64_t)j;
+      atomicOr(&p.out_nulls[pc][o >> 5], 1u << (o & 31));
+      saw_null = true;
     }
   }
   if (saw_null) p.has_null[pc] = 1;
@@ -983,10 +1020,13 @@ __global__ void __launch_bounds__(kThreads) obgpu_project_kernel(const __grid_co
   // ---- second round trip, all in flight together: TMA of the block, the block's decode plans, the
   // first bitmap words ----------------------------------------------------------------------------------
   const uint32_t size = rec.size;
+  // Few selected rows: staging the block would move far more bytes than the cells that are read. Such a
+  // block is decoded straight from global memory (generic loads, a handful of sectors per column).
+  const bool sparse = (uint64_t)cnt * 16u <= rows;
   if (tid == 0) {
     mbar_init(&s_bar, 1);
     fence_barrier_init();
-    if (!p.compact) {
+    if (!p.compact && !sparse) {
       mbar_expect_tx(&s_bar, (size + 15u) & ~15u);
       tma_bulk_g2s(g_smem, p.image + rec.off, (size + 15u) & ~15u, &s_bar);
     }
@@ -1011,8 +1051,8 @@ __global__ void __launch_bounds__(kThreads) obgpu_project_kernel(const __grid_co
   if (tid + kThreads < npieces) reinterpret_cast<uint4 *>(plans_s)[tid + kThreads] = pv1;
   __syncthreads();  // barrier object, queue and plans initialised before anyone uses them
   BlockCtx c;
-  view_from_rec(rec, g_smem, c.b);
-  if (p.compact) {
+  view_from_rec(rec, sparse ? p.image + rec.off : g_smem, c.b);
+  if (p.compact && !sparse) {
     // Only the projected columns' regions are staged, packed back to back: lane pc of warp 0 issues
     // the bulk copy of column pc; s_delta[pc] = (offset in shared memory) - (offset in the block), so
     // block-relative addressing keeps working once the base is shifted by it.
@@ -1079,7 +1119,7 @@ __global__ void __launch_bounds__(kThreads) obgpu_project_kernel(const __grid_co
     __syncthreads();
   }
   // ---- block landed ---------------------------------------------------------------------------------------
-  mbar_wait(&s_bar, 0);
+  if (!sparse) mbar_wait(&s_bar, 0);
   c.sbit = smem_u32(g_smem) * 8u;
   c.bitsets = nullptr;
   // warp-private scratch: [run values][RLE run table]
@@ -1104,6 +1144,21 @@ __global__ void __launch_bounds__(kThreads) obgpu_project_kernel(const __grid_co
     if (pc >= p.n_proj) break;
     ColDesc *wdesc = plans_s + pc;  // this column's plan: only this warp touches it
     const ColDesc &d = *wdesc;
+    if (sparse) {
+      if (!d.ok) {
+        if (lane == 0) atomicOr(p.status, ST_UNSUPPORTED);
+      } else if (d.sc == 5) {
+        project_str_col<false>(p, c, d, pc, sel, cnt, base, blk_addr, t);
+      } else if (d.elem_len == 8) {
+        project_int_col_global<uint64_t>(p, c, d, pc, sel, cnt, base, t);
+      } else if (d.elem_len == 4) {
+        project_int_col_global<uint32_t>(p, c, d, pc, sel, cnt, base, t);
+      } else {
+        project_int_col_global<uint8_t>(p, c, d, pc, sel, cnt, base, t);
+      }
+      __syncwarp();
+      continue;
+    }
     if (p.compact) {  // rebase onto this column's staged region
       const int32_t delta = s_delta[pc];
       c.b.s = g_smem + delta;
@@ -1805,11 +1860,12 @@ static int build_filter(obgpu_ctx *ctx, const obgpu_batch *b, const obgpu_filter
       }
       nd.n_params = (int16_t)kept;
       if (null_param || (src.op == OBGPU_WHITE_OP_IN && kept == 0)) nd.op = OP_FALSE;
-      // integer compares on 8-byte datum types reduce to one unsigned range test on the value image
+      // integer compares reduce to one unsigned range test on the compare image (cmp_image: the datum's low
+      // bytes, sign-extended for signed classes)
       {
         const uint8_t t = (size_t)src.col < b->col_types.size() ? b->col_types[(size_t)src.col] : 0xff;
         const int sc = t == 0xff ? 0 : obf::store_class_of(t);
-        if (nd.op != OP_FALSE && (sc == 1 || sc == 2) && obf::datum_len_of(t) == 8 && src.op <= OBGPU_WHITE_OP_BT) {
+        if (nd.op != OP_FALSE && (sc == 1 || sc == 2) && src.op <= OBGPU_WHITE_OP_BT) {
           const bool sg = sc == 1;
           const uint64_t MIN = sg ? (uint64_t)INT64_MIN : 0ull, MAX = sg ? (uint64_t)INT64_MAX : ~0ull;
           auto less = [&](uint64_t x, uint64_t y) { return sg ? (int64_t)x < (int64_t)y : x < y; };
@@ -1858,6 +1914,34 @@ static int build_filter(obgpu_ctx *ctx, const obgpu_batch *b, const obgpu_filter
     bool leaves = root.kind != NODE_WHITE && root.n_children == p.n_nodes - 1;
     for (int i = 0; leaves && i < p.n_nodes - 1; ++i) leaves = p.nodes[i].kind == NODE_WHITE;
     if (leaves) p.simple_shape = root.kind == NODE_AND ? 1 : 2;
+  }
+  // AND over leaves: range tests on the same column collapse into one (a SQL BETWEEN arrives as >= and <=
+  // leaves under an AND node, sql/engine/basic/ob_pushdown_filter.cpp:212-262). Same rows selected.
+  if (p.simple_shape == 1 && p.n_nodes >= 3) {
+    int n_leaves = p.n_nodes - 1;
+    for (int i = 0; i < n_leaves; ++i) {
+      FilterNodeDev &a = p.nodes[i];
+      if (!a.range_ok || a.negate || a.op == OP_FALSE) continue;
+      const uint8_t t = (size_t)p.used_col[a.used_idx] < b->col_types.size() ? b->col_types[(size_t)p.used_col[a.used_idx]] : 0xff;
+      const bool sg = t != 0xff && obf::store_class_of(t) == 1;
+      auto less = [&](uint64_t x, uint64_t y) { return sg ? (int64_t)x < (int64_t)y : x < y; };
+      for (int j = i + 1; j < n_leaves;) {
+        const FilterNodeDev &c = p.nodes[j];
+        if (c.used_idx != a.used_idx || !c.range_ok || c.negate || c.op == OP_FALSE) { ++j; continue; }
+        uint64_t lo = a.lo, hi = a.lo + a.span;
+        const uint64_t clo = c.lo, chi = c.lo + c.span;
+        if (less(lo, clo)) lo = clo;
+        if (less(chi, hi)) hi = chi;
+        if (less(hi, lo)) { a.op = OP_FALSE; a.range_ok = 0; }
+        else { a.lo = lo; a.span = hi - lo; a.op = OP_BT; }  // op is informational once range_ok is set
+        for (int k = j; k + 1 < p.n_nodes; ++k) p.nodes[k] = p.nodes[k + 1];
+        --p.n_nodes;
+        --n_leaves;
+        if (a.op == OP_FALSE) break;
+      }
+    }
+    if (n_leaves == 1) p.n_nodes = 1;            // a single leaf needs no AND node
+    else p.nodes[p.n_nodes - 1].n_children = (int16_t)n_leaves;
   }
   return OBGPU_SUCCESS;
 }
