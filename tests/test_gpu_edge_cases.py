@@ -167,3 +167,11 @@ def test_projection_staging_modes(ob, ctx, compact, proj, monkeypatch):
     table, _ = _mixed_table(ob, 12_000, 640, 5)
     flt = ob.White(1, ob.WHITE_OP_LT, (700,))
     assert_scan_matches(ctx, W(table, flt, proj, [IS_STR[i] for i in proj], [ELEM[i] for i in proj]))
+
+
+@pytest.mark.parametrize("limit", [0, 3, 60, 200])
+def test_sparse_selection_decodes_from_global_memory(ob, ctx, limit):
+    # <= 1/16 of a block selected: the projection skips the shared-memory staging (every codec, NULLs, strings)
+    table, _ = _mixed_table(ob, 15_000, 750, 9)
+    flt = ob.White(1, ob.WHITE_OP_LT, (limit,))
+    assert_scan_matches(ctx, W(table, flt, PROJ, IS_STR, ELEM))
