@@ -425,6 +425,89 @@ __device__ __forceinline__ bool leaf_is_bits_range(const ColDesc &d, const Filte
   return d.kind == K_BITS && nd.range_ok && d.ext_bit == 0 && !d.sign_fix && !d.var_is_last;
 }
 
+
+// ---- byte-aligned columns: one LANE per 32 rows, SIMD-in-register compares ----------------------------
+// For value arrays of whole bytes (every CS integer stream, PAX byte-packed columns) a lane owns a whole
+// bitmap word: it reads its 32 values as 32-bit words from the staged column (funnel-shifted to the value
+// alignment), tests 4 (or 2) values per instruction with the per-byte (halfword) video instructions and
+// packs the compare masks into its own bitmap word. No ballot, ~50 warp instructions per 1024 rows.
+// The range lo..hi is first moved into the raw (value - base) domain with 128-bit arithmetic.
+struct RawRange { uint32_t lo, span; bool none; };
+__device__ __forceinline__ RawRange raw_range_of(const ColDesc &d, const FilterNodeDev &nd, uint32_t bytes) {
+  const bool sg = d.sc == 1;
+  const uint64_t hi64 = nd.lo + nd.span;
+  const __int128 lo = sg ? (__int128)(int64_t)nd.lo : (__int128)nd.lo;
+  const __int128 hi = sg ? (__int128)(int64_t)hi64 : (__int128)hi64;
+  const __int128 base = sg ? (__int128)(int64_t)d.base : (__int128)d.base;
+  const __int128 vmax = ((__int128)1 << (bytes * 8u)) - 1;
+  __int128 l = lo - base, h = hi - base;
+  RawRange r;
+  r.none = h < 0 || l > vmax || l > h;
+  if (l < 0) l = 0;
+  if (h > vmax) h = vmax;
+  r.lo = (uint32_t)l;
+  r.span = r.none ? 0u : (uint32_t)(h - l);
+  return r;
+}
+// may the raw-domain test stand in for the compare image of this column? (narrow signed datums: only when
+// base + raw cannot leave the datum's range, which valid data never does)
+__device__ __forceinline__ bool simd_domain_ok(const ColDesc &d, uint32_t bytes) {
+  if (d.elem_len == 8) return true;
+  if (d.elem_len == 4 && d.sc == 1) {
+    const int64_t b = (int64_t)d.base, top = b + (int64_t)((1ull << (bytes * 8u)) - 1ull);
+    return b >= (int64_t)INT32_MIN && top <= (int64_t)INT32_MAX;
+  }
+  return false;
+}
+__device__ __forceinline__ bool leaf_is_bytes_simd(const ColDesc &d, const FilterNodeDev &nd) {
+  return d.kind == K_BITS && nd.range_ok && d.ext_bit == 0 && !d.sign_fix && !d.var_is_last && d.stride == d.width &&
+         (d.width == 8 || d.width == 16) && (d.val_bit & 7u) == 0 && simd_domain_ok(d, d.width >> 3);
+}
+template <int BYTES, int MODE>
+__device__ __forceinline__ void filter_bytes_simd(const BlockCtx &c, const ColDesc &d, const FilterNodeDev &nd, uint32_t *bm,
+                                                  uint32_t rows, uint32_t nwords, const Team &t) {
+  const RawRange rr = raw_range_of(d, nd, BYTES);
+  const bool neg = nd.negate != 0;
+  const uint32_t lo4 = BYTES == 1 ? rr.lo * 0x01010101u : rr.lo * 0x00010001u;
+  const uint32_t sp4 = BYTES == 1 ? rr.span * 0x01010101u : rr.span * 0x00010001u;
+  const uint32_t vbyte = (c.sbit + d.val_bit) >> 3;  // shared-window byte address of value 0
+  constexpr uint32_t kWordsPerGroup = 8u * BYTES;     // 32-bit words holding 32 values
+  for (uint32_t g = (uint32_t)t.tid; g < nwords; g += (uint32_t)t.nthreads) {
+    uint32_t cur = 0;
+    if (MODE != 0) {
+      cur = bm[g];
+      if (MODE == 1 ? cur == 0u : cur == 0xffffffffu) continue;
+    }
+    const uint32_t vm = valid_mask_of(rows, g);
+    uint32_t m = 0;
+    if (!rr.none) {
+      const uint32_t nvalid = rows - g * 32u < 32u ? rows - g * 32u : 32u;
+      const uint32_t kmax = (nvalid * BYTES + 3u) >> 2;  // words that hold valid rows: never read past the column
+      const uint32_t first = vbyte + g * 32u * BYTES;
+      const uint32_t a = first & ~3u, sh = (first & 3u) * 8u;
+      uint32_t w0 = sld32(a);
+#pragma unroll
+      for (uint32_t k = 0; k < kWordsPerGroup; ++k) {
+        if (k < kmax) {
+          const uint32_t w1 = sld32(a + 4u * k + 4u);
+          const uint32_t v = __funnelshift_r(w0, w1, sh);
+          w0 = w1;
+          if (BYTES == 1) {
+            const uint32_t hit = __vcmpleu4(__vsub4(v, lo4), sp4) & 0x01010101u;
+            m |= (((hit * 0x01020408u) >> 24) & 0xfu) << (4u * k);
+          } else {
+            const uint32_t hit = __vcmpleu2(__vsub2(v, lo4), sp4) & 0x00010001u;
+            m |= ((hit | (hit >> 15)) & 0x3u) << (2u * k);
+          }
+        }
+      }
+    }
+    if (neg) m = ~m;
+    m &= vm;
+    bm[g] = MODE == 0 ? m : (MODE == 1 ? (cur & m) : (cur | m));
+  }
+}
+
 // First leaf of an AND / OR list: writes bm directly (no initialisation pass) when it is a plain
 // range test. Returns false if the caller has to initialise bm and run the leaf generically.
 template <bool G>
@@ -433,6 +516,11 @@ __device__ __forceinline__ bool leaf_first_fast(const ScanParams &p, const Block
   if (nd.kind != NODE_WHITE) return false;
   const ColDesc &d = c.descs[nd.used_idx];
   if (!leaf_is_bits_range(d, nd)) return false;
+  if (!G && leaf_is_bytes_simd(d, nd)) {
+    if (d.width == 8) filter_bytes_simd<1, 0>(c, d, nd, bm, rows, nwords, t);
+    else filter_bytes_simd<2, 0>(c, d, nd, bm, rows, nwords, t);
+    return true;
+  }
   if (d.elem_len != 8) {
     if (d.width <= 32) filter_bits_range<false, 0, G, true>(c, d, nd, bm, rows, nwords, t);
     else filter_bits_range<true, 0, G, true>(c, d, nd, bm, rows, nwords, t);
@@ -452,6 +540,16 @@ __device__ __forceinline__ void leaf_over_words(const ScanParams &p, const Block
   const int op = nd.op;
   // ---- fast path A: integer range test on a K_BITS column without NULLs ------------------------------
   if (leaf_is_bits_range(d, nd)) {
+    if (!G && leaf_is_bytes_simd(d, nd)) {
+      if (d.width == 8) {
+        if (and_mode) filter_bytes_simd<1, 1>(c, d, nd, bm, rows, nwords, t);
+        else filter_bytes_simd<1, 2>(c, d, nd, bm, rows, nwords, t);
+      } else {
+        if (and_mode) filter_bytes_simd<2, 1>(c, d, nd, bm, rows, nwords, t);
+        else filter_bytes_simd<2, 2>(c, d, nd, bm, rows, nwords, t);
+      }
+      return;
+    }
     if (d.elem_len != 8) {
       if (d.width <= 32) {
         if (and_mode) filter_bits_range<false, 1, G, true>(c, d, nd, bm, rows, nwords, t);
