@@ -112,6 +112,7 @@ struct ScanParams {
   uint32_t pw_rle, pw_rvals, pw_bytes;  // project kernel, per-warp region at off_desc: run values (u64) | RLE run table
   uint32_t off_plans;                   // project kernel: the block's n_proj decode plans (ColDesc), prefetched
   int32_t compact;                      // project kernel stages only the projected columns' regions (packed)
+  int32_t sparse_split;                 // selectivity hint <= 1/16: sparse blocks go to the warp-per-block kernel
   uint32_t off_sel, off_bm, off_wpre, off_rle, off_desc;  // inside one scratch
   uint32_t smem_total;
   uint32_t rle_slot_bytes;    // bytes per run-table slot: mask[words_cap] (u32) + pre[words_cap] (u16)
@@ -1121,6 +1122,7 @@ __global__ void __launch_bounds__(kThreads) obgpu_project_kernel(const __grid_co
   // Few selected rows: staging the block would move far more bytes than the cells that are read. Such a
   // block is decoded straight from global memory (generic loads, a handful of sectors per column).
   const bool sparse = (uint64_t)cnt * 16u <= rows;
+  if (sparse && p.sparse_split) return;  // obgpu_project_sparse_kernel owns this block
   if (tid == 0) {
     mbar_init(&s_bar, 1);
     fence_barrier_init();
@@ -1317,6 +1319,88 @@ __global__ void __launch_bounds__(kThreads) obgpu_project_kernel(const __grid_co
       else project_int_col<uint8_t, false>(p, c, d, pc, sel, cnt, base, t);
     }
     __syncwarp();
+  }
+}
+
+// =================================================================================================
+// Sparse projection: ONE WARP per micro-block whose selection is at most 1/16 of its rows (launched next to
+// obgpu_project_kernel when the caller's selectivity hint says most blocks will be sparse). No staging, no
+// CTA barriers: bitmap words -> selected-row list (warp scan), then every projected column is decoded for the
+// few selected rows with generic loads from global memory. Four times as many blocks in flight per CTA slot.
+// =================================================================================================
+__global__ void __launch_bounds__(kThreads) obgpu_project_sparse_kernel(const __grid_constant__ ScanParams p) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int tile = blockIdx.x * kWarps + warp;
+  if (tile >= p.n_blocks) return;
+  const BlockRec rec = p.recs[tile];
+  const int64_t base = p.sel_offset[tile];
+  const uint32_t cnt = (uint32_t)(p.sel_offset[tile + 1] - base);
+  const uint32_t rows = rec.rows;
+  if (rows == 0 || cnt == 0 || (uint64_t)cnt * 16u > rows) return;  // dense / empty / corrupt: the CTA kernel's job
+  if (base + (int64_t)cnt > p.out_cap) {
+    if (lane == 0) atomicOr(p.status, ST_OVERFLOW);
+    return;
+  }
+  const uint32_t sel_cap = p.rows_cap / 16u + 32u;
+  uint8_t *wr = g_smem + (uint32_t)warp * (((sel_cap * 2u + 15u) & ~15u) + (uint32_t)sizeof(ColDesc));
+  uint16_t *sel = reinterpret_cast<uint16_t *>(wr);
+  ColDesc *wdesc = reinterpret_cast<ColDesc *>(wr + ((sel_cap * 2u + 15u) & ~15u));
+  // bitmap words -> ascending selected-row list
+  const uint32_t *gbm = p.bitmap_words + rec.bm_word_off;
+  const uint32_t nwords = (rows + 31u) >> 5;
+  uint32_t running = 0;
+  for (uint32_t base_w = 0; base_w < nwords; base_w += 32u) {
+    const uint32_t w = base_w + (uint32_t)lane;
+    uint32_t word = w < nwords ? gbm[w] : 0u;
+    const uint32_t local = __popc(word);
+    uint32_t inc = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += u;
+    }
+    uint32_t at = running + inc - local;
+    while (word) {
+      const uint32_t bit = (uint32_t)__ffs((int)word) - 1u;
+      sel[at++] = (uint16_t)(w * 32u + bit);
+      word &= word - 1u;
+    }
+    running += __shfl_sync(0xffffffffu, inc, 31);
+  }
+  __syncwarp();
+  if (p.want_row_ids) {
+    int32_t *rid = p.row_ids + base;
+    for (uint32_t j = (uint32_t)lane; j < cnt; j += 32u) rid[j] = (int32_t)sel[j];
+  }
+  BlockCtx c;
+  view_from_rec(rec, p.image + rec.off, c.b);
+  c.sbit = 0;
+  c.bitsets = nullptr;
+  c.descs = wdesc;
+  c.rle_base = nullptr;
+  c.rle_slot_bytes = c.rle_starts_bytes = 0;
+  const uint64_t blk_addr = p.string_base + rec.off;
+  Team t;
+  t.tid = lane; t.nthreads = 32; t.warp = 0; t.nwarps = 1; t.lane = lane; t.bar_id = -1;
+  for (int pc = 0; pc < p.n_proj; ++pc) {
+    __syncwarp();
+    {
+      const uint4 *src = reinterpret_cast<const uint4 *>(p.plans + (int64_t)tile * p.max_cols + p.used_col[p.proj_used[pc]]);
+      if (lane < (int)(sizeof(ColDesc) / 16)) reinterpret_cast<uint4 *>(wdesc)[lane] = src[lane];
+    }
+    __syncwarp();
+    const ColDesc &d = *wdesc;
+    if (!d.ok) {
+      if (lane == 0) atomicOr(p.status, ST_UNSUPPORTED);
+    } else if (d.sc == 5) {
+      project_str_col<false>(p, c, d, pc, sel, cnt, base, blk_addr, t);
+    } else if (d.elem_len == 8) {
+      project_int_col_global<uint64_t>(p, c, d, pc, sel, cnt, base, t);
+    } else if (d.elem_len == 4) {
+      project_int_col_global<uint32_t>(p, c, d, pc, sel, cnt, base, t);
+    } else {
+      project_int_col_global<uint8_t>(p, c, d, pc, sel, cnt, base, t);
+    }
   }
 }
 
@@ -2267,6 +2351,10 @@ int obgpu_scan(obgpu_batch *b, const obgpu_scan_spec *spec, obgpu_result **out) 
   p.want_row_ids = spec->want_row_ids ? 1 : 0;
   if (const char *dbg = getenv("OBGPU_DEBUG_FLAGS")) p.debug_flags = atoi(dbg);
   p.string_base = spec->string_base;
+  // the caller's selectivity estimate (max_selected_rows): when it says at most 1/16 of the rows survive, most
+  // blocks will be sparse and the warp-per-block kernel takes them
+  p.sparse_split = (p.n_nodes > 0 && r->cap * 16 <= b->total_rows) ? 1 : 0;
+  if (const char *e = getenv("OBGPU_SPARSE_SPLIT")) p.sparse_split = atoi(e) ? (p.n_nodes > 0 ? 1 : 0) : 0;  // testing knob
   layout_smem_scan(b, p);
   if ((int)p.smem_total > ctx->max_smem_optin) {
     ctx->err = "scan working set exceeds shared memory";
@@ -2361,6 +2449,11 @@ int obgpu_scan(obgpu_batch *b, const obgpu_scan_spec *spec, obgpu_result **out) 
   if (p.n_proj + p.want_row_ids > 0) {
     obgpu_project_kernel<<<n, kThreads, p.smem_total, ctx->stream>>>(p);
     ctx->launches++;
+    if (p.sparse_split) {
+      const uint32_t per_warp = (((p.rows_cap / 16u + 32u) * 2u + 15u) & ~15u) + (uint32_t)sizeof(ColDesc);
+      obgpu_project_sparse_kernel<<<(n + kWarps - 1) / kWarps, kThreads, per_warp * (uint32_t)kWarps, ctx->stream>>>(p);
+      ctx->launches++;
+    }
   }
   e = cudaGetLastError();
   if (ctx->profiling) {

@@ -170,8 +170,11 @@ def test_projection_staging_modes(ob, ctx, compact, proj, monkeypatch):
 
 
 @pytest.mark.parametrize("limit", [0, 3, 60, 200])
-def test_sparse_selection_decodes_from_global_memory(ob, ctx, limit):
-    # <= 1/16 of a block selected: the projection skips the shared-memory staging (every codec, NULLs, strings)
+@pytest.mark.parametrize("split", ["0", "1"])
+def test_sparse_selection_decodes_from_global_memory(ob, ctx, limit, split, monkeypatch):
+    # <= 1/16 of a block selected: the projection skips the shared-memory staging (every codec, NULLs, strings);
+    # split = 1 routes those blocks to the warp-per-block kernel (what a low selectivity hint does)
+    monkeypatch.setenv("OBGPU_SPARSE_SPLIT", split)
     table, _ = _mixed_table(ob, 15_000, 750, 9)
     flt = ob.White(1, ob.WHITE_OP_LT, (limit,))
     assert_scan_matches(ctx, W(table, flt, PROJ, IS_STR, ELEM))
