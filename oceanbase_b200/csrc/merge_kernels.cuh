@@ -63,12 +63,24 @@ __device__ __forceinline__ int merge_path_s(const int64_t *a, int na, const int6
   return lo;
 }
 
+// Merge-path partition: one THREAD per tile start diagonal (all binary searches of a pass in flight together,
+// instead of every merge CTA waiting on its own two searches). split[t] = A elements before tile t.
+__global__ void __launch_bounds__(256) partition_kernel(const int64_t *__restrict__ kin, const Pair *__restrict__ pairs, int n_pairs,
+                                                        int64_t n_tiles, int64_t *__restrict__ split) {
+  const int64_t tile = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tile >= n_tiles) return;
+  int p = 0;
+  while (p + 1 < n_pairs && pairs[p + 1].tile0 <= tile) ++p;
+  const Pair pr = pairs[p];
+  split[tile] = merge_path_g(kin + pr.a0, pr.a1 - pr.a0, kin + pr.b0, pr.b1 - pr.b0, (tile - pr.tile0) * kTile);
+}
+
 __global__ void __launch_bounds__(kThreads) pass_kernel(const int64_t *__restrict__ kin, const uint64_t *__restrict__ sin,
                                                         int64_t *__restrict__ kout, uint64_t *__restrict__ sout,
-                                                        const Pair *__restrict__ pairs, int n_pairs) {
+                                                        const Pair *__restrict__ pairs, int n_pairs,
+                                                        const int64_t *__restrict__ split) {
   __shared__ int64_t s_key[kTile];
   __shared__ uint64_t s_src[kTile];
-  __shared__ int64_t s_split[2];
   const int tid = threadIdx.x;
   int p = 0;
   while (p + 1 < n_pairs && pairs[p + 1].tile0 <= (int64_t)blockIdx.x) ++p;
@@ -76,10 +88,9 @@ __global__ void __launch_bounds__(kThreads) pass_kernel(const int64_t *__restric
   const int64_t na = pr.a1 - pr.a0, nb = pr.b1 - pr.b0;
   const int64_t d0 = ((int64_t)blockIdx.x - pr.tile0) * kTile;
   const int64_t d1 = d0 + kTile < na + nb ? d0 + kTile : na + nb;
-  const int64_t *A = kin + pr.a0, *B = kin + pr.b0;
-  if (tid < 2) s_split[tid] = merge_path_g(A, na, B, nb, tid == 0 ? d0 : d1);
-  __syncthreads();
-  const int64_t i0 = s_split[0], i1 = s_split[1];
+  // this tile's end split is the next tile's start split, unless the tile closes its pair
+  const int64_t i0 = split[blockIdx.x];
+  const int64_t i1 = d1 == na + nb ? na : split[blockIdx.x + 1];
   const int64_t j0 = d0 - i0, j1 = d1 - i1;
   const int ca = (int)(i1 - i0), cb = (int)(j1 - j0), total = ca + cb;
   // stage: A part at [0, ca), B part at [ca, ca + cb)
@@ -392,6 +403,8 @@ int obgpu_merge_decoded(obgpu_ctx *ctx, const obgpu_merge_run *runs, int32_t n_r
   const size_t o_tbl = o; o += al(tbl_entries * 8);
   const size_t o_def = o; o += al((size_t)n_cols * 9 + 16);
   const size_t o_pairs = o; o += al(sizeof(mrg::Pair) * (size_t)(n_runs + 1) * 8);
+  const size_t max_tiles = (size_t)(N / mrg::kTile) + (size_t)n_runs + 2;
+  const size_t o_split = o; o += al((max_tiles + 1) * 8);
   const size_t o_okey = o; o += al((size_t)N * 8);
   std::vector<size_t> o_ov((size_t)n_cols), o_on((size_t)n_cols);
   for (int c = 0; c < n_cols; ++c) { o_ov[(size_t)c] = o; o += al((size_t)N * 8); }
@@ -485,9 +498,12 @@ int obgpu_merge_decoded(obgpu_ctx *ctx, const obgpu_merge_run *runs, int32_t n_r
     const int n_pairs = (int)passes[ps].size() - 1;
     const int64_t tiles = passes[ps].back().tile0;
     if (tiles > 0) {
+      int64_t *split = (int64_t *)(a + o_split);
+      mrg::partition_kernel<<<(unsigned)((tiles + 255) / 256), 256, 0, ctx->stream>>>(
+          kin, (const mrg::Pair *)(a + o_pairs) + pass_at[ps], n_pairs, tiles, split);
       mrg::pass_kernel<<<(unsigned)tiles, mrg::kThreads, 0, ctx->stream>>>(
-          kin, sin, kout, sout, (const mrg::Pair *)(a + o_pairs) + pass_at[ps], n_pairs);
-      ctx->launches++;
+          kin, sin, kout, sout, (const mrg::Pair *)(a + o_pairs) + pass_at[ps], n_pairs, split);
+      ctx->launches += 2;
     }
     std::swap(kin, kout);
     std::swap(sin, sout);
