@@ -63,6 +63,14 @@ int obgpu_merge_decoded(obgpu_ctx *ctx, const obgpu_merge_run *runs, int32_t n_r
                         obgpu_merge_result **out);
 void obgpu_merge_result_free(obgpu_merge_result *res);
 
+/* The whole merge of one range from opened page batches (one per table, oldest first): decodes rowkey_col,
+ * flag_col (-1: every row DF_INSERT) and the payload columns of every run into temporary device arrays and
+ * calls obgpu_merge_decoded. This is the call the C++ adapter (oceanbase_b200/host/ob_gpu_partition_merger.h)
+ * makes from ObPartitionMajorMerger::merge_partition. All batches must belong to `ctx`. */
+int obgpu_merge_runs(obgpu_ctx *ctx, obgpu_batch *const *runs, int32_t n_runs, int32_t rowkey_col,
+                     int32_t flag_col, const int32_t *cols, int32_t n_cols, const int64_t *default_vals,
+                     const uint8_t *default_null, obgpu_merge_result **out);
+
 typedef struct obgpu_merge_info {
   int64_t in_rows;          /* rows of all runs                                              */
   int64_t out_rows;         /* rows of the merged stream                                     */

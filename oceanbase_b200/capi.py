@@ -123,6 +123,7 @@ def declared_signatures():
         "obgpu_batch_decode_column": (C.c_int, [vp, i32, vp, vp]),
         "obgpu_batch_decode_columns": (C.c_int, [vp, i32, vp, vp, vp]),
         "obgpu_merge_decoded": (C.c_int, [vp, P(MergeRun), i32, i32, vp, vp, P(vp)]),
+        "obgpu_merge_runs": (C.c_int, [vp, P(vp), i32, i32, i32, vp, i32, vp, vp, P(vp)]),
         "obgpu_merge_result_free": (None, [vp]),
         "obgpu_merge_result_info": (C.c_int, [vp, P(MergeInfo)]),
         "obgpu_merge_result_cols": (C.c_int, [vp, P(vp), P(P(vp)), P(P(vp))]),

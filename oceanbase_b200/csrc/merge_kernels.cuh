@@ -314,6 +314,11 @@ __global__ void __launch_bounds__(128) decode_cols_kernel(const uint8_t *__restr
   }
 }
 
+__global__ void __launch_bounds__(256) narrow_flag_kernel(const int64_t *__restrict__ v, int64_t n, uint8_t *__restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (uint8_t)v[i];
+}
+
 }  // namespace mrg
 
 struct obgpu_merge_result {
@@ -534,6 +539,71 @@ int obgpu_merge_decoded(obgpu_ctx *ctx, const obgpu_merge_run *runs, int32_t n_r
   for (int c = 0; c < n_cols; ++c) { res->vals_view.push_back(res->out_vals[(size_t)c]); res->null_view.push_back(res->out_null[(size_t)c]); }
   *out = res;
   return OBGPU_SUCCESS;
+}
+
+int obgpu_merge_runs(obgpu_ctx *ctx, obgpu_batch *const *batches, int32_t n_runs, int32_t rowkey_col, int32_t flag_col,
+                     const int32_t *cols, int32_t n_cols, const int64_t *default_vals, const uint8_t *default_null,
+                     obgpu_merge_result **out) {
+  if (!ctx || !batches || !out || n_runs <= 0 || n_runs > OBGPU_MERGE_MAX_RUNS || n_cols < 0 ||
+      n_cols + 2 > mrg::kMaxDecodeCols || (n_cols > 0 && !cols))
+    return OBGPU_INVALID_ARGUMENT;
+  for (int r = 0; r < n_runs; ++r)
+    if (!batches[r] || batches[r]->ctx != ctx) return OBGPU_INVALID_ARGUMENT;
+  cudaSetDevice(ctx->device);
+  std::vector<void *> temps;
+  auto release = [&]() { for (void *t : temps) cudaFreeAsync(t, ctx->stream); };
+  std::vector<obgpu_merge_run> runs((size_t)n_runs);
+  std::vector<std::vector<const int64_t *>> vals((size_t)n_runs);
+  std::vector<std::vector<const uint8_t *>> exts((size_t)n_runs);
+  int ret = OBGPU_SUCCESS;
+  for (int r = 0; r < n_runs && ret == OBGPU_SUCCESS; ++r) {
+    obgpu_batch *b = batches[r];
+    const int64_t n = b->total_rows;
+    const int n_dec = 1 + (flag_col >= 0 ? 1 : 0) + n_cols;
+    // one allocation per run: n_dec value arrays, n_dec ext arrays, the narrowed flag bytes
+    void *buf = nullptr;
+    const size_t per = ((size_t)n * 8 + 255) & ~(size_t)255, per_e = ((size_t)n + 255) & ~(size_t)255;
+    cudaError_t e = cudaMallocAsync(&buf, (per + per_e) * (size_t)n_dec + per_e + 256, ctx->stream);
+    if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); ret = OBGPU_ALLOCATE_MEMORY_FAILED; break; }
+    temps.push_back(buf);
+    uint8_t *base = (uint8_t *)buf;
+    int32_t dcols[mrg::kMaxDecodeCols];
+    int64_t *dv[mrg::kMaxDecodeCols];
+    uint8_t *de[mrg::kMaxDecodeCols];
+    int k = 0;
+    dcols[k++] = rowkey_col;
+    if (flag_col >= 0) dcols[k++] = flag_col;
+    for (int c = 0; c < n_cols; ++c) dcols[k++] = cols[c];
+    for (int i = 0; i < n_dec; ++i) {
+      dv[i] = (int64_t *)(base + per * (size_t)i);
+      de[i] = base + per * (size_t)n_dec + per_e * (size_t)i;
+    }
+    uint8_t *flag8 = base + (per + per_e) * (size_t)n_dec;
+    if (n > 0) ret = obgpu_batch_decode_columns(b, n_dec, dcols, dv, de);
+    if (ret != OBGPU_SUCCESS) break;
+    obgpu_merge_run &run = runs[(size_t)r];
+    run.n = n;
+    run.key = dv[0];
+    run.flag = nullptr;
+    int at = 1;
+    if (flag_col >= 0) {
+      if (n > 0) {
+        mrg::narrow_flag_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(dv[1], n, flag8);
+        ctx->launches++;
+      }
+      run.flag = flag8;
+      at = 2;
+    }
+    for (int c = 0; c < n_cols; ++c) {
+      vals[(size_t)r].push_back(dv[at + c]);
+      exts[(size_t)r].push_back(de[at + c]);
+    }
+    run.vals = vals[(size_t)r].data();
+    run.ext = exts[(size_t)r].data();
+  }
+  if (ret == OBGPU_SUCCESS) ret = obgpu_merge_decoded(ctx, runs.data(), n_runs, n_cols, default_vals, default_null, out);
+  release();  // stream-ordered: the merge kernels were enqueued before these frees
+  return ret;
 }
 
 void obgpu_merge_result_free(obgpu_merge_result *res) {

@@ -26,6 +26,7 @@ namespace common {
 
 constexpr int OB_SUCCESS = 0;
 constexpr int OB_INVALID_ARGUMENT = -4002;
+constexpr int OB_INIT_TWICE = -4005;
 constexpr int OB_NOT_INIT = -4006;
 constexpr int OB_NOT_SUPPORTED = -4007;
 constexpr int OB_ITER_END = -4008;

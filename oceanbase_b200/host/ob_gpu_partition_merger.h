@@ -1,0 +1,77 @@
+// ob_gpu_partition_merger.h -- host-side (C++) adapter for the major-compaction merge, written the way a
+// maintainer would add it next to compaction/ob_partition_merger.h: the names and call order mirror
+// ObPartitionMajorMerger (merge_partition -> rows handed to the macro block writer), the work goes through
+// the C-ABI in include/obgpu_compaction.h. Stand-ins for reference types are minimal and local.
+#ifndef OB_GPU_PARTITION_MERGER_H_
+#define OB_GPU_PARTITION_MERGER_H_
+
+#include <cstdint>
+#include <vector>
+
+extern "C" {
+#include "../../include/obgpu_compaction.h"
+}
+#include "ob_gpu_micro_block_decoder.h"
+
+namespace oceanbase {
+namespace compaction {
+
+// One table of the merge (ObTablesHandleArray entry): the encoded micro blocks of the merge range.
+struct ObGpuMergeTable {
+  const void *image_ = nullptr;
+  int64_t image_size_ = 0;
+  const int64_t *offsets_ = nullptr;
+  const int64_t *sizes_ = nullptr;
+  int32_t block_count_ = 0;
+};
+
+// Column roles inside the tables' row layout (ObStaticMergeParam / ObTableReadInfo would provide them).
+struct ObGpuMergeSchema {
+  int32_t rowkey_col_ = 0;
+  int32_t flag_col_ = -1;               // column holding the ObDmlFlag image, -1: every row DF_INSERT
+  std::vector<int32_t> payload_cols_;
+  std::vector<int64_t> default_vals_;   // default row (ObMajorPartitionMergeFuser::default_row_)
+  std::vector<uint8_t> default_null_;   // empty: every default is NULL
+};
+
+// Window of the merged row stream, what ObPartitionMajorMerger::process hands to
+// ObMacroBlockWriter::append_row row by row (here: column arrays for append_batch).
+struct ObGpuMergedRows {
+  int64_t row_count_ = 0;
+  std::vector<int64_t> rowkeys_;
+  std::vector<std::vector<int64_t>> values_;   // [payload column][row]
+  std::vector<std::vector<uint8_t>> nulls_;    // 1 => NULL
+};
+
+class ObGpuPartitionMajorMerger {
+public:
+  ObGpuPartitionMajorMerger() = default;
+  ~ObGpuPartitionMajorMerger();
+  ObGpuPartitionMajorMerger(const ObGpuPartitionMajorMerger &) = delete;
+  ObGpuPartitionMajorMerger &operator=(const ObGpuPartitionMajorMerger &) = delete;
+
+  // tables oldest -> newest (tables_handle order); returns OB_NOT_SUPPORTED when no device is usable so that
+  // the caller keeps the CPU merger.
+  int init(int device, const std::vector<ObGpuMergeTable> &tables, const ObGpuMergeSchema &schema);
+  // ObPartitionMajorMerger::merge_partition: runs the whole merge of the range on the device.
+  int merge_partition();
+  int64_t get_output_row_count() const { return info_.out_rows; }
+  int64_t get_dropped_delete_count() const { return info_.dropped_deletes; }
+  int64_t get_fused_row_count() const { return info_.fused_rows; }
+  // Next window of at most max_rows merged rows in rowkey order; OB_ITER_END after the last one.
+  int get_next_rows(int64_t max_rows, ObGpuMergedRows &rows);
+  void reset();
+
+private:
+  obgpu_ctx *ctx_ = nullptr;
+  std::vector<obgpu_batch *> batches_;
+  ObGpuMergeSchema schema_;
+  obgpu_merge_result *result_ = nullptr;
+  obgpu_merge_info info_{};
+  int64_t cursor_ = 0;
+  bool merged_ = false;
+};
+
+}  // namespace compaction
+}  // namespace oceanbase
+#endif

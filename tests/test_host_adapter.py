@@ -31,3 +31,21 @@ def test_adapter_parity_on_gpu():
     r = subprocess.run([BIN], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
     assert "host adapter tests passed" in r.stdout
+
+
+MERGER_BIN = os.path.join(ROOT, "tests", "cpp", "test_partition_merger")
+
+
+def test_partition_merger_builds_and_refuses_without_device():
+    assert os.path.exists(MERGER_BIN)
+    if _has_gpu():
+        pytest.skip("device present: covered by the gpu test")
+    r = subprocess.run([MERGER_BIN], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 77, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_partition_merger_parity_on_gpu():
+    r = subprocess.run([MERGER_BIN], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
+    assert "partition merger tests passed" in r.stdout
