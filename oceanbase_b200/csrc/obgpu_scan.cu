@@ -1,15 +1,17 @@
-// libobgpu_scan.so -- fused micro-block scan kernels (sm_100a) and the C-ABI around them.
+// libobgpu_scan.so -- micro-block scan kernels (sm_100a) and the C-ABI around them.
 //
-// One launch processes a whole page batch (thousands of ~16 KiB micro-blocks):
-//   CTA  <- ticket (atomic)                  : logical block index in scan order
-//   TMA bulk copy (cp.async.bulk + mbarrier) : block image HBM -> shared memory, one transaction
-//   filter      : white-filter tree per row, predicate-on-dictionary for DICT/RLE columns,
-//                 warp ballot -> packed selection bitmap (K4/K6/K9/K14)
-//   compaction  : popcount prefix over ballot words -> ascending selected-row list
-//   look-back   : decoupled look-back over per-block counts -> dense output offset (single pass,
-//                 the block image is read from HBM exactly once)
-//   projection  : decode selected rows of each projected column straight from shared memory,
-//                 coalesced 8-byte stores into the dense VEC_FIXED / VEC_DISCRETE buffers (K1-K8)
+// A page batch (thousands of ~16 KiB micro-blocks, PAX or CS format) is scanned by
+//   index   (once, at batch open): one thread per (block, column) -> 96-byte decode plan + block record
+//   count   : one warp per block; filter columns staged with coalesced 16-byte loads; white-filter tree,
+//             predicate-on-dictionary for dictionary-coded columns, warp ballot / SIMD-in-register
+//             compares -> packed selection bitmap + per-block count (K4/K6/K9/K14)
+//   prefix  : exclusive scan of the counts -> dense output offset of every block
+//   project : one CTA per block; TMA bulk copy (cp.async.bulk + mbarrier) of the block or of the projected
+//             column regions into shared memory; bitmap -> ascending selected-row list; columns
+//             distributed over the warps, coalesced 8-byte stores into the dense VEC_FIXED /
+//             VEC_DISCRETE buffers (K1-K8); sparse selections are decoded straight from global memory
+//   aggregate (optional): COUNT / SUM / SUM(a*b) / MIN / MAX over the dense columns, 128-bit exact
+// and merge_kernels.cuh (included at the end) holds the major-compaction merge.
 //
 // Reference control flow this replaces (per block, per <=256-row batch, per column virtual calls):
 //   ObIMicroBlockRowScanner::apply_filter        blocksstable/ob_micro_block_row_scanner.cpp:361,927
@@ -97,8 +99,6 @@ struct ScanParams {
   uint32_t *bitmap_words;
   int64_t *sel_offset;        // [n_blocks + 1]
   int32_t *row_ids;
-  unsigned long long *tile_state;
-  int32_t *ticket;
   int32_t *status;
   int64_t out_cap;
   // ---- shared-memory layout (bytes from the dynamic smem base) -------------------------------------
@@ -117,7 +117,6 @@ struct ScanParams {
   uint32_t smem_total;
   uint32_t rle_slot_bytes;    // bytes per run-table slot: mask[words_cap] (u32) + pre[words_cap] (u16)
   uint32_t rows_cap, words_cap;
-  int32_t debug_flags;        // bit0: experiment -- skip the look-back (non-dense output at row offsets)
 };
 
 // =================================================================================================
@@ -159,17 +158,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
-__device__ __forceinline__ unsigned long long ld_acquire(const unsigned long long *p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release(unsigned long long *p, unsigned long long v) {
-  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
 
-// A team of threads cooperating on one block: either the whole CTA (bar 0) or the consumer warps
-// of the persistent kernel (named barrier 1).
+// A team of threads cooperating on one block: the whole CTA (bar 0), a single warp (bar < 0) or a
+// subset of warps on a named barrier (bar > 0).
 struct Team {
   int tid, nthreads, warp, nwarps, lane, bar_id;
   __device__ __forceinline__ void sync() const {
@@ -198,41 +189,6 @@ __device__ __forceinline__ Team cta_team() {
   t.lane = threadIdx.x & 31;
   t.bar_id = 0;
   return t;
-}
-
-constexpr unsigned long long kTileAgg = 1ull << 62;
-constexpr unsigned long long kTilePrefix = 2ull << 62;
-constexpr unsigned long long kTileValueMask = (1ull << 62) - 1ull;
-
-// Decoupled look-back executed by one warp. Returns the exclusive prefix of `cnt` over tiles.
-// `publish_own`: this warp also publishes the tile's aggregate first (otherwise the caller did).
-__device__ __forceinline__ int64_t lookback(unsigned long long *state, int tile, int64_t cnt, int lane,
-                                            bool publish_own = true) {
-  if (tile == 0) {
-    if (lane == 0 && publish_own) st_release(&state[0], kTilePrefix | (unsigned long long)cnt);
-    return 0;
-  }
-  if (lane == 0 && publish_own) st_release(&state[tile], kTileAgg | (unsigned long long)cnt);
-  int64_t excl = 0;
-  int idx = tile - 1;
-  for (;;) {
-    const int my = idx - lane;
-    unsigned long long s = kTilePrefix;  // tiles before 0 behave as an empty inclusive prefix
-    if (my >= 0) {
-      do { s = ld_acquire(&state[my]); } while ((s >> 62) == 0);
-    }
-    const bool is_prefix = (s >> 62) == 2;
-    const unsigned pmask = __ballot_sync(0xffffffffu, is_prefix);
-    const int first = __ffs(pmask) - 1;  // nearest predecessor holding an inclusive prefix
-    int64_t v = (pmask == 0 || lane <= first) ? (int64_t)(s & kTileValueMask) : 0;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    excl += v;
-    if (pmask) break;
-    idx -= 32;
-  }
-  if (lane == 0) st_release(&state[tile], kTilePrefix | (unsigned long long)(excl + cnt));
-  return excl;
 }
 
 // =================================================================================================
@@ -652,8 +608,7 @@ __device__ __forceinline__ bool prepare_block(const ScanParams &p, uint32_t soff
   c.sbit = (smem_u32(g_smem) + soff) * 8u;
   corrupt = !c.b.ok;
   bool my_bad = false;
-  // descriptors are built by the LAST threads of the team (the first warp may still be busy with
-  // the previous tile's look-back in the persistent kernel)
+  // descriptors are built by the last threads of the team
   const int di = t.nthreads - 1 - t.tid;
   if (c.b.ok && di < p.n_used) {
     ColDesc d;
@@ -2156,7 +2111,8 @@ static void layout_smem(const obgpu_batch *b, ScanParams &p, bool /*need_sel*/) 
   p.smem_total = (off + 15u) & ~15u;
 }
 
-// persistent scan kernel: [stage x kStages][bitsets][scratch x 2], scratch = sel|bm|wpre|rle|descs
+// project kernel: [staged block or packed column regions][bitsets][scratch = sel|bm|wpre|per-warp rle|plans];
+// count kernel: per warp descs | bm | bitsets | staging buffer
 static void layout_smem_scan(const obgpu_batch *b, ScanParams &p) {
   assign_rle_slots(b, p);
   p.stage_bytes = (b->max_block_bytes + 16u + 127u) & ~127u;
@@ -2349,7 +2305,6 @@ int obgpu_scan(obgpu_batch *b, const obgpu_scan_spec *spec, obgpu_result **out) 
   }
   p.n_proj = spec->n_proj;
   p.want_row_ids = spec->want_row_ids ? 1 : 0;
-  if (const char *dbg = getenv("OBGPU_DEBUG_FLAGS")) p.debug_flags = atoi(dbg);
   p.string_base = spec->string_base;
   // the caller's selectivity estimate (max_selected_rows): when it says at most 1/16 of the rows survive, most
   // blocks will be sparse and the warp-per-block kernel takes them
@@ -2404,8 +2359,6 @@ int obgpu_scan(obgpu_batch *b, const obgpu_scan_spec *spec, obgpu_result **out) 
   p.recs = b->d_recs;
   p.max_cols = (int32_t)b->max_cols;
   p.counts = (uint32_t *)(a + o_counts);
-  p.tile_state = nullptr;
-  p.ticket = nullptr;
   p.status = (int32_t *)(a + o_misc + 64);
   p.has_null = (int32_t *)(a + o_misc + 128);
   p.sel_offset = (int64_t *)(a + o_sel);
