@@ -113,6 +113,7 @@ struct ScanParams {
   uint32_t off_plans;                   // project kernel: the block's n_proj decode plans (ColDesc), prefetched
   int32_t compact;                      // project kernel stages only the projected columns' regions (packed)
   int32_t sparse_split;                 // selectivity hint <= 1/16: sparse blocks go to the warp-per-block kernel
+  int32_t no_stage;                     // blocks do not fit shared memory: every block is decoded from global memory
   uint32_t off_sel, off_bm, off_wpre, off_rle, off_desc;  // inside one scratch
   uint32_t smem_total;
   uint32_t rle_slot_bytes;    // bytes per run-table slot: mask[words_cap] (u32) + pre[words_cap] (u16)
@@ -1076,8 +1077,9 @@ __global__ void __launch_bounds__(kThreads) obgpu_project_kernel(const __grid_co
   const uint32_t size = rec.size;
   // Few selected rows: staging the block would move far more bytes than the cells that are read. Such a
   // block is decoded straight from global memory (generic loads, a handful of sectors per column).
-  const bool sparse = (uint64_t)cnt * 16u <= rows;
-  if (sparse && p.sparse_split) return;  // obgpu_project_sparse_kernel owns this block
+  const bool few = (uint64_t)cnt * 16u <= rows;
+  if (few && p.sparse_split) return;     // obgpu_project_sparse_kernel owns this block
+  const bool sparse = few || p.no_stage != 0;
   if (tid == 0) {
     mbar_init(&s_bar, 1);
     fence_barrier_init();
@@ -1171,6 +1173,10 @@ __global__ void __launch_bounds__(kThreads) obgpu_project_kernel(const __grid_co
       const uint32_t word = bm[g];
       if ((word >> lane) & 1u) sel[wpre[g] + __popc(word & ((1u << lane) - 1u))] = (uint16_t)(g * 32u + lane);
     }
+    __syncthreads();
+  }
+  if (all_rows && sparse) {  // unstaged block with every row selected: the global path walks an identity list
+    for (uint32_t j = (uint32_t)tid; j < cnt; j += kThreads) sel[j] = (uint16_t)j;
     __syncthreads();
   }
   // ---- block landed ---------------------------------------------------------------------------------------
@@ -1807,10 +1813,8 @@ int obgpu_batch_open(obgpu_ctx *ctx, const void *image, int64_t image_size, cons
     }
   }
   b->bm_word_off[(size_t)n_blocks] = words;
-  if (ret == OBGPU_SUCCESS && (int)b->max_block_bytes + 16 > ctx->max_smem_optin - 8192) {
-    ctx->err = "micro block too large for one shared-memory page";
-    ret = OBGPU_NOT_SUPPORTED;
-  }
+  // blocks larger than a shared-memory page are fine for the batch scan (columns are then decoded straight
+  // from global memory); only the one-block entry points need the block to fit
   if (ret != OBGPU_SUCCESS) {
     delete b;
     return ret;
@@ -2113,8 +2117,9 @@ static void layout_smem(const obgpu_batch *b, ScanParams &p, bool /*need_sel*/) 
 
 // project kernel: [staged block or packed column regions][bitsets][scratch = sel|bm|wpre|per-warp rle|plans];
 // count kernel: per warp descs | bm | bitsets | staging buffer
-static void layout_smem_scan(const obgpu_batch *b, ScanParams &p) {
+static void layout_smem_scan(const obgpu_batch *b, ScanParams &p, int max_smem) {
   assign_rle_slots(b, p);
+  p.no_stage = 0;
   p.stage_bytes = (b->max_block_bytes + 16u + 127u) & ~127u;
   {
     // stage only the projected columns when that is clearly less than the whole block (upper bound:
@@ -2152,6 +2157,15 @@ static void layout_smem_scan(const obgpu_batch *b, ScanParams &p) {
   p.scratch_bytes = (s + 127u) & ~127u;
   p.smem_scratch = (off + 127u) & ~127u;
   p.smem_total = p.smem_scratch + p.scratch_bytes;
+  if ((int)p.smem_total > max_smem && p.stage_bytes > 0) {
+    // the blocks (or the projected column regions) do not fit next to the scratch: no staging at all
+    p.no_stage = 1;
+    p.compact = 0;
+    p.smem_bitset -= p.stage_bytes;
+    p.stage_bytes = 0;
+    p.smem_scratch = ((p.smem_bitset + (((uint32_t)p.n_slots * (uint32_t)p.bitset_words * 4u + 15u) & ~15u)) + 127u) & ~127u;
+    p.smem_total = p.smem_scratch + p.scratch_bytes;
+  }
   // count kernel, per warp: descs | bm | bitsets
   uint32_t w = 0;
   p.cw_desc = w;   w += ((uint32_t)sizeof(ColDesc) * (uint32_t)std::max(p.n_used, 1) + 15u) & ~15u;
@@ -2310,7 +2324,7 @@ int obgpu_scan(obgpu_batch *b, const obgpu_scan_spec *spec, obgpu_result **out) 
   // blocks will be sparse and the warp-per-block kernel takes them
   p.sparse_split = (p.n_nodes > 0 && r->cap * 16 <= b->total_rows) ? 1 : 0;
   if (const char *e = getenv("OBGPU_SPARSE_SPLIT")) p.sparse_split = atoi(e) ? (p.n_nodes > 0 ? 1 : 0) : 0;  // testing knob
-  layout_smem_scan(b, p);
+  layout_smem_scan(b, p, ctx->max_smem_optin);
   if ((int)p.smem_total > ctx->max_smem_optin) {
     ctx->err = "scan working set exceeds shared memory";
     delete r;

@@ -97,7 +97,7 @@ def test_empty_and_full_selection_and_no_projection(ob, ctx):
     batch.close()
 
 
-@pytest.mark.parametrize("rows,rpb", [(1, 1), (33, 32), (40000, 40000), (70001, 35000), (257, 1)])
+@pytest.mark.parametrize("rows,rpb", [(1, 1), (33, 32), (40000, 40000), (70001, 35000), (257, 1), (65535, 65535), (131070, 65535)])
 def test_block_shapes(ob, ctx, rows, rpb):
     rng = np.random.default_rng(rows)
     cols = [ob.Column(ob.OBJ_INT, ob.ENC_RAW, rng.integers(0, 1 << 9, size=rows, dtype=np.int64)),
@@ -178,3 +178,13 @@ def test_sparse_selection_decodes_from_global_memory(ob, ctx, limit, split, monk
     table, _ = _mixed_table(ob, 15_000, 750, 9)
     flt = ob.White(1, ob.WHITE_OP_LT, (limit,))
     assert_scan_matches(ctx, W(table, flt, PROJ, IS_STR, ELEM))
+
+
+def test_blocks_larger_than_shared_memory(ob, ctx):
+    # ~1 MB micro blocks (the reference allows up to 1 MB): nothing is staged, every column is decoded from
+    # global memory; filters on bit-packed, dictionary and string columns, NULLs, all rows / some rows / few rows
+    table, _ = _mixed_table(ob, 60_000, 30_000, 13)
+    assert int(table.sizes.max()) > 400_000
+    for flt in (None, ob.White(1, ob.WHITE_OP_LT, (900,)), ob.White(1, ob.WHITE_OP_LT, (20,)),
+                ob.And([ob.White(2, ob.WHITE_OP_GE, (0,)), ob.White(9, ob.WHITE_OP_NN, ())])):
+        assert_scan_matches(ctx, W(table, flt, PROJ, IS_STR, ELEM))
