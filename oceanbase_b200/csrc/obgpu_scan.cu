@@ -2158,12 +2158,17 @@ static void layout_smem_scan(const obgpu_batch *b, ScanParams &p, int max_smem) 
   p.smem_scratch = (off + 127u) & ~127u;
   p.smem_total = p.smem_scratch + p.scratch_bytes;
   if ((int)p.smem_total > max_smem && p.stage_bytes > 0) {
-    // the blocks (or the projected column regions) do not fit next to the scratch: no staging at all
+    // the blocks (or the projected column regions) do not fit next to the scratch: no staging at all, and
+    // no per-warp run tables either (the global path looks runs up by binary search)
     p.no_stage = 1;
     p.compact = 0;
-    p.smem_bitset -= p.stage_bytes;
     p.stage_bytes = 0;
-    p.smem_scratch = ((p.smem_bitset + (((uint32_t)p.n_slots * (uint32_t)p.bitset_words * 4u + 15u) & ~15u)) + 127u) & ~127u;
+    p.smem_bitset = 0;
+    p.pw_rle = p.pw_bytes = 0;
+    uint32_t s2 = p.off_desc;          // sel | bm | wpre stay where they are
+    p.off_plans = s2; s2 += (uint32_t)sizeof(ColDesc) * (uint32_t)std::max(p.n_proj, 1);
+    p.scratch_bytes = (s2 + 127u) & ~127u;
+    p.smem_scratch = ((((uint32_t)p.n_slots * (uint32_t)p.bitset_words * 4u + 15u) & ~15u) + 127u) & ~127u;
     p.smem_total = p.smem_scratch + p.scratch_bytes;
   }
   // count kernel, per warp: descs | bm | bitsets
