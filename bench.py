@@ -62,6 +62,32 @@ def host_cpus():
     return max(1, n)
 
 
+def bind_to_gpu_numa_node(local):
+    """Pin this process (and the threads / first-touched pages it creates from now on) to the CPUs of the
+    NUMA node the GPU hangs off, so that the pinned host image and result buffers sit next to the PCIe root
+    the copies go through. Returns the node number or None when it cannot be determined."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def build_workload(rows, row_start, seed, chunk_rows=4_000_000, pinned=False, n_threads=0, maker=None,
                    rows_per_block=1400):
     """Config-2 table (or `maker`'s) of `rows` rows generated in chunks (bounded host memory), packed
@@ -235,6 +261,7 @@ def run_ours(args):
 
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_node = None if args.no_numa_bind else bind_to_gpu_numa_node(local)
     rows = args.rows
     t_gen = time.perf_counter()
     w, pinned_buf = build_workload(rows, rank * rows, args.seed, pinned=True,
@@ -374,7 +401,7 @@ def run_ours(args):
                        "micro_blocks_per_gpu": table.n_blocks, "encoded_bytes_per_gpu": int(table.sizes.sum()),
                        "selectivity": selected / table.total_rows, "parallelism": f"shard{world}",
                        "l2_policy": "input image (1.2 GB) larger than L2 (126 MB); no flush needed",
-                       "gen_seconds": round(t_gen, 1)},
+                       "gen_seconds": round(t_gen, 1), "host_numa_node": numa_node},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": measured_traffic(table.total_rows), "peak_source": peak_src, "alg_bytes_per_launch": alg_bytes,
                          "kernel_ms": kern_mean, "kernel": "one scan = obgpu_count_kernel + obgpu_prefix_*_kernel + obgpu_project_kernel (project ~85%)"},
@@ -410,6 +437,7 @@ def main():
     ap.add_argument("--e2e-workers", type=int, default=3, help="host worker threads = CUDA streams of the e2e pipeline")
     ap.add_argument("--seed", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the process to the GPU's NUMA node")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
