@@ -2,7 +2,8 @@
  * ob_oracle.c -- CPU oracle (TEST INFRASTRUCTURE, see ob_oracle.h).
  *
  * Restates, in plain C, the reference's decode/filter/projection algorithm for PAX
- * ("ENCODING_ROW_STORE") micro-blocks.  Reference = /root/reference/src/storage/blocksstable
+ * ("ENCODING_ROW_STORE") and CS ("CS_ENCODING_ROW_STORE", integer columns) micro-blocks and the
+ * major-compaction merge.  Reference = /root/reference/src/storage/blocksstable
  * unless another root is given.  Nothing here is shared with the product code under
  * oceanbase_b200/: the layout constants are restated independently from the same spec.
  */

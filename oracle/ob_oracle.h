@@ -2,15 +2,19 @@
  * ob_oracle.h -- CPU oracle for the columnar-scan hot path.
  *
  * TEST INFRASTRUCTURE ONLY.  This is a plain-C restatement of the reference's (OceanBase 4.6.0.0)
- * CPU algorithm for PAX micro-block decode, pushed-down white filters, ObBitmap row-id extraction
- * and batch projection.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * CPU algorithm for PAX and CS micro-block decode, pushed-down white filters, ObBitmap row-id
+ * extraction, batch projection and the major-compaction merge (row fuse).  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
  * --impl reference legs may build, load or call it; the product (libobgpu_scan.so) never does.
  *
  * Pinning status: the bit-stream primitives are checked against the reference's own
- * ObBitStream compiled from /root/reference (oracle/_ref, see Makefile + tests/test_ref_pin.py)
+ * ObBitStream compiled from /root/reference (oracle/_ref, see Makefile + tests/test_bitstream_kat.py)
  * and against the reference's known-answer tests (unittest/.../test_bit_stream.cpp:151-200);
  * filter semantics are checked against the popcount expectations of
- * unittest/.../test_raw_decoder.cpp:774-1200 re-expressed in tests/test_oracle_filter_kat.py.
+ * unittest/.../test_raw_decoder.cpp:774-1200 (tests/test_oracle_filter_kat.py) and
+ * test_const_decoder.cpp:111-770 (tests/test_const_kat.py); the row fuse of the compaction merge
+ * against unittest/storage/test_row_fuse.cpp:118-227 (tests/test_major_merge_kat.py). CS blocks:
+ * restatement only (no reference vectors for the block framing) -- parity unpinned for them beyond
+ * the shared filter expectations.
  * The reference ships no byte-level golden micro-blocks, so whole-block decode is
  * pinned by construction (layout restated from the encoder) and by the independent GPU decoder.
  *
