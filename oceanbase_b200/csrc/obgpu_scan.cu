@@ -114,6 +114,7 @@ struct ScanParams {
   int32_t compact;                      // project kernel stages only the projected columns' regions (packed)
   int32_t sparse_split;                 // selectivity hint <= 1/16: sparse blocks go to the warp-per-block kernel
   int32_t no_stage;                     // blocks do not fit shared memory: every block is decoded from global memory
+  int32_t proj_tiles;                   // blocks walked by one CTA of the project kernel (1, or 8 with the sparse split)
   uint32_t off_sel, off_bm, off_wpre, off_rle, off_desc;  // inside one scratch
   uint32_t smem_total;
   uint32_t rle_slot_bytes;    // bytes per run-table slot: mask[words_cap] (u32) + pre[words_cap] (u16)
@@ -131,6 +132,9 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
 }
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_inval(uint64_t *bar) {
+  asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
@@ -1045,6 +1049,7 @@ __global__ void __launch_bounds__(256) obgpu_prefix_fix_kernel(int n, int n_chun
 // Per-column setup is thus paid by one warp instead of four, and a warp runs ~cnt/32 iterations per
 // column instead of ~cnt/128.
 // =================================================================================================
+template <bool MULTI>
 __global__ void __launch_bounds__(kThreads) obgpu_project_kernel(const __grid_constant__ ScanParams p) {
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ int s_next;
@@ -1052,234 +1057,247 @@ __global__ void __launch_bounds__(kThreads) obgpu_project_kernel(const __grid_co
   __shared__ int32_t s_delta[kMaxProj];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int tile = blockIdx.x;
   uint8_t *scr = g_smem + p.smem_scratch;
   uint16_t *sel = reinterpret_cast<uint16_t *>(scr + p.off_sel);
   uint32_t *bm = reinterpret_cast<uint32_t *>(scr + p.off_bm);
   uint32_t *wpre = reinterpret_cast<uint32_t *>(scr + p.off_wpre);
+  // One block per CTA normally; with the sparse split most blocks belong to the warp-per-block kernel, so a CTA
+  // walks p.proj_tiles consecutive blocks and only works on the dense ones (far fewer CTAs to launch and retire).
+  // Blocks are visited last-to-first: the count kernel has just walked the batch front to back, so the
+  // filter-column bytes of the LAST blocks are the ones still sitting in L2.
+  bool used_bar = false;
+  const int ntiles = MULTI ? p.proj_tiles : 1;  // MULTI = false: the loop and its bookkeeping compile away
+  for (int it = 0; it < ntiles; ++it) {
+    const int lin = (int)blockIdx.x * ntiles + it;
+    if (lin >= p.n_blocks) break;
+    const int tile = p.n_blocks - 1 - lin;
+    if (used_bar) __syncthreads();  // everyone is done with the shared state of the previous block
 
-  // one round trip: block record + the two prefix entries (independent loads)
-  const BlockRec rec = p.recs[tile];
-  const int64_t base = p.sel_offset[tile];
-  const uint32_t cnt = (uint32_t)(p.sel_offset[tile + 1] - base);
-  const uint32_t rows = rec.rows;
-  if (rows == 0) {
-    if (tid == 0) atomicOr(p.status, ST_CORRUPT);
-    return;
-  }
-  if (cnt == 0) return;
-  if (base + (int64_t)cnt > p.out_cap) {
-    if (tid == 0) atomicOr(p.status, ST_OVERFLOW);
-    return;
-  }
-  // ---- second round trip, all in flight together: TMA of the block, the block's decode plans, the
-  // first bitmap words ----------------------------------------------------------------------------------
-  const uint32_t size = rec.size;
-  // Few selected rows: staging the block would move far more bytes than the cells that are read. Such a
-  // block is decoded straight from global memory (generic loads, a handful of sectors per column).
-  const bool few = (uint64_t)cnt * 16u <= rows;
-  if (few && p.sparse_split) return;     // obgpu_project_sparse_kernel owns this block
-  const bool sparse = few || p.no_stage != 0;
-  if (tid == 0) {
-    mbar_init(&s_bar, 1);
-    fence_barrier_init();
-    if (!p.compact && !sparse) {
-      mbar_expect_tx(&s_bar, (size + 15u) & ~15u);
-      tma_bulk_g2s(g_smem, p.image + rec.off, (size + 15u) & ~15u, &s_bar);
+    // one round trip: block record + the two prefix entries (independent loads)
+    const BlockRec rec = p.recs[tile];
+    const int64_t base = p.sel_offset[tile];
+    const uint32_t cnt = (uint32_t)(p.sel_offset[tile + 1] - base);
+    const uint32_t rows = rec.rows;
+    if (rows == 0) {
+      if (tid == 0) atomicOr(p.status, ST_CORRUPT);
+      continue;
     }
-    s_next = 0;
-  }
-  ColDesc *plans_s = reinterpret_cast<ColDesc *>(scr + p.off_plans);
-  constexpr int kPieces = (int)(sizeof(ColDesc) / 16);
-  const int npieces = p.n_proj * kPieces;
-  uint4 pv0{}, pv1{};
-  {
-    const ColDesc *gp = p.plans + (int64_t)tile * p.max_cols;
-    if (tid < npieces)
-      pv0 = reinterpret_cast<const uint4 *>(gp + p.used_col[p.proj_used[tid / kPieces]])[tid % kPieces];
-    if (tid + kThreads < npieces)
-      pv1 = reinterpret_cast<const uint4 *>(gp + p.used_col[p.proj_used[(tid + kThreads) / kPieces]])[(tid + kThreads) % kPieces];
-  }
-  const uint32_t *gbm = p.bitmap_words + rec.bm_word_off;
-  const bool all_rows = cnt == rows;
-  const uint32_t nwords = (rows + 31u) >> 5;
-  const uint32_t word0 = (!all_rows && (uint32_t)tid < nwords) ? gbm[tid] : 0u;
-  if (tid < npieces) reinterpret_cast<uint4 *>(plans_s)[tid] = pv0;
-  if (tid + kThreads < npieces) reinterpret_cast<uint4 *>(plans_s)[tid + kThreads] = pv1;
-  __syncthreads();  // barrier object, queue and plans initialised before anyone uses them
-  BlockCtx c;
-  view_from_rec(rec, sparse ? p.image + rec.off : g_smem, c.b);
-  if (p.compact && !sparse) {
-    // Only the projected columns' regions are staged, packed back to back: lane pc of warp 0 issues
-    // the bulk copy of column pc; s_delta[pc] = (offset in shared memory) - (offset in the block), so
-    // block-relative addressing keeps working once the base is shifted by it.
-    if (warp == 0) {
-      uint32_t lo = 0, hi = 0;
-      bool ok = false, var = false;
-      if (lane < p.n_proj) {
-        const ColDesc &d = plans_s[lane];
-        ok = d.ok && col_region(d, c.b, lo, hi) && hi > lo;
-        var = ok && d.kind == K_VARSTR;
-      }
-      // RAW var-length columns share one copy of the row data
-      const uint32_t vmask = __ballot_sync(0xffffffffu, var);
-      const int vfirst = __ffs(vmask) - 1;
-      const bool dup = var && lane != vfirst;
-      const uint32_t bytes = ok && !dup ? hi - lo : 0u;
-      uint32_t inc = bytes;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += u;
-      }
-      uint32_t so = inc - bytes;
-      const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
-      const uint32_t vso = __shfl_sync(0xffffffffu, so, vfirst < 0 ? 0 : vfirst);
-      if (dup) so = vso;
-      if (lane < p.n_proj) s_delta[lane] = (int32_t)so - (int32_t)lo;
-      if (lane == 0) mbar_expect_tx(&s_bar, total);
-      __syncwarp();
-      if (bytes) tma_bulk_g2s(g_smem + so, p.image + rec.off + lo, bytes, &s_bar);
+    if (cnt == 0) continue;
+    if (base + (int64_t)cnt > p.out_cap) {
+      if (tid == 0) atomicOr(p.status, ST_OVERFLOW);
+      continue;
     }
-  }
-  // ---- bitmap words -> popcount prefix -> ascending selected-row list (overlaps the TMA) ------------------
-  if (!all_rows) {
-    uint32_t run_total = 0;
-    for (uint32_t base_w = 0; base_w < nwords; base_w += kThreads) {  // one pass for <= 4096 rows
-      const uint32_t w = base_w + (uint32_t)tid;
-      const uint32_t word = base_w == 0 ? word0 : (w < nwords ? gbm[w] : 0u);
-      if (w < nwords) bm[w] = word;
-      const uint32_t local = __popc(word);
-      uint32_t inc = local;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += u;
+    // ---- second round trip, all in flight together: TMA of the block, the block's decode plans, the
+    // first bitmap words ----------------------------------------------------------------------------------
+    const uint32_t size = rec.size;
+    // Few selected rows: staging the block would move far more bytes than the cells that are read. Such a
+    // block is decoded straight from global memory (generic loads, a handful of sectors per column).
+    const bool few = (uint64_t)cnt * 16u <= rows;
+    if (few && p.sparse_split) continue;   // obgpu_project_sparse_kernel owns this block
+    const bool sparse = few || p.no_stage != 0;
+    if (tid == 0) {
+      if (used_bar) mbar_inval(&s_bar);  // a block handled earlier by this CTA left the barrier initialised
+      mbar_init(&s_bar, 1);
+      fence_barrier_init();
+      if (!p.compact && !sparse) {
+        mbar_expect_tx(&s_bar, (size + 15u) & ~15u);
+        tma_bulk_g2s(g_smem, p.image + rec.off, (size + 15u) & ~15u, &s_bar);
       }
-      if (lane == 31) s_scan[warp] = inc;
+      s_next = 0;
+    }
+    ColDesc *plans_s = reinterpret_cast<ColDesc *>(scr + p.off_plans);
+    constexpr int kPieces = (int)(sizeof(ColDesc) / 16);
+    const int npieces = p.n_proj * kPieces;
+    uint4 pv0{}, pv1{};
+    {
+      const ColDesc *gp = p.plans + (int64_t)tile * p.max_cols;
+      if (tid < npieces)
+        pv0 = reinterpret_cast<const uint4 *>(gp + p.used_col[p.proj_used[tid / kPieces]])[tid % kPieces];
+      if (tid + kThreads < npieces)
+        pv1 = reinterpret_cast<const uint4 *>(gp + p.used_col[p.proj_used[(tid + kThreads) / kPieces]])[(tid + kThreads) % kPieces];
+    }
+    const uint32_t *gbm = p.bitmap_words + rec.bm_word_off;
+    const bool all_rows = cnt == rows;
+    const uint32_t nwords = (rows + 31u) >> 5;
+    const uint32_t word0 = (!all_rows && (uint32_t)tid < nwords) ? gbm[tid] : 0u;
+    if (tid < npieces) reinterpret_cast<uint4 *>(plans_s)[tid] = pv0;
+    if (tid + kThreads < npieces) reinterpret_cast<uint4 *>(plans_s)[tid + kThreads] = pv1;
+    __syncthreads();  // barrier object, queue and plans initialised before anyone uses them
+    BlockCtx c;
+    view_from_rec(rec, sparse ? p.image + rec.off : g_smem, c.b);
+    if (p.compact && !sparse) {
+      // Only the projected columns' regions are staged, packed back to back: lane pc of warp 0 issues
+      // the bulk copy of column pc; s_delta[pc] = (offset in shared memory) - (offset in the block), so
+      // block-relative addressing keeps working once the base is shifted by it.
+      if (warp == 0) {
+        uint32_t lo = 0, hi = 0;
+        bool ok = false, var = false;
+        if (lane < p.n_proj) {
+          const ColDesc &d = plans_s[lane];
+          ok = d.ok && col_region(d, c.b, lo, hi) && hi > lo;
+          var = ok && d.kind == K_VARSTR;
+        }
+        // RAW var-length columns share one copy of the row data
+        const uint32_t vmask = __ballot_sync(0xffffffffu, var);
+        const int vfirst = __ffs(vmask) - 1;
+        const bool dup = var && lane != vfirst;
+        const uint32_t bytes = ok && !dup ? hi - lo : 0u;
+        uint32_t inc = bytes;
+  #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += u;
+        }
+        uint32_t so = inc - bytes;
+        const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+        const uint32_t vso = __shfl_sync(0xffffffffu, so, vfirst < 0 ? 0 : vfirst);
+        if (dup) so = vso;
+        if (lane < p.n_proj) s_delta[lane] = (int32_t)so - (int32_t)lo;
+        if (lane == 0) mbar_expect_tx(&s_bar, total);
+        __syncwarp();
+        if (bytes) tma_bulk_g2s(g_smem + so, p.image + rec.off + lo, bytes, &s_bar);
+      }
+    }
+    // ---- bitmap words -> popcount prefix -> ascending selected-row list (overlaps the TMA) ------------------
+    if (!all_rows) {
+      uint32_t run_total = 0;
+      for (uint32_t base_w = 0; base_w < nwords; base_w += kThreads) {  // one pass for <= 4096 rows
+        const uint32_t w = base_w + (uint32_t)tid;
+        const uint32_t word = base_w == 0 ? word0 : (w < nwords ? gbm[w] : 0u);
+        if (w < nwords) bm[w] = word;
+        const uint32_t local = __popc(word);
+        uint32_t inc = local;
+  #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += u;
+        }
+        if (lane == 31) s_scan[warp] = inc;
+        __syncthreads();
+        uint32_t warp_off = run_total, total = run_total;
+  #pragma unroll
+        for (int k = 0; k < kWarps; ++k) {
+          const uint32_t v = s_scan[k];
+          warp_off += k < warp ? v : 0u;
+          total += v;
+        }
+        if (w < nwords) wpre[w] = warp_off + inc - local;
+        run_total = total;
+        __syncthreads();
+      }
+      for (uint32_t g = (uint32_t)warp; g < nwords; g += kWarps) {
+        const uint32_t word = bm[g];
+        if ((word >> lane) & 1u) sel[wpre[g] + __popc(word & ((1u << lane) - 1u))] = (uint16_t)(g * 32u + lane);
+      }
       __syncthreads();
-      uint32_t warp_off = run_total, total = run_total;
-#pragma unroll
-      for (int k = 0; k < kWarps; ++k) {
-        const uint32_t v = s_scan[k];
-        warp_off += k < warp ? v : 0u;
-        total += v;
-      }
-      if (w < nwords) wpre[w] = warp_off + inc - local;
-      run_total = total;
+    }
+    if (all_rows && sparse) {  // unstaged block with every row selected: the global path walks an identity list
+      for (uint32_t j = (uint32_t)tid; j < cnt; j += kThreads) sel[j] = (uint16_t)j;
       __syncthreads();
     }
-    for (uint32_t g = (uint32_t)warp; g < nwords; g += kWarps) {
-      const uint32_t word = bm[g];
-      if ((word >> lane) & 1u) sel[wpre[g] + __popc(word & ((1u << lane) - 1u))] = (uint16_t)(g * 32u + lane);
-    }
-    __syncthreads();
-  }
-  if (all_rows && sparse) {  // unstaged block with every row selected: the global path walks an identity list
-    for (uint32_t j = (uint32_t)tid; j < cnt; j += kThreads) sel[j] = (uint16_t)j;
-    __syncthreads();
-  }
-  // ---- block landed ---------------------------------------------------------------------------------------
-  if (!sparse) mbar_wait(&s_bar, 0);
-  c.sbit = smem_u32(g_smem) * 8u;
-  c.bitsets = nullptr;
-  // warp-private scratch: [run values][RLE run table]
-  uint8_t *wscr = scr + p.off_desc + (uint32_t)warp * p.pw_bytes;
-  c.descs = plans_s;
-  c.rle_base = wscr + p.pw_rle;
-  c.rle_slot_bytes = 0;  // one table per warp: slot 0
-  c.rle_starts_bytes = p.words_cap * 4u;
+    // ---- block landed ---------------------------------------------------------------------------------------
+    if (!sparse) mbar_wait(&s_bar, 0);
+    c.sbit = smem_u32(g_smem) * 8u;
+    c.bitsets = nullptr;
+    // warp-private scratch: [run values][RLE run table]
+    uint8_t *wscr = scr + p.off_desc + (uint32_t)warp * p.pw_bytes;
+    c.descs = plans_s;
+    c.rle_base = wscr + p.pw_rle;
+    c.rle_slot_bytes = 0;  // one table per warp: slot 0
+    c.rle_starts_bytes = p.words_cap * 4u;
 
-  if (p.want_row_ids) {
-    int32_t *rid = p.row_ids + base;
-    if (all_rows) for (uint32_t j = (uint32_t)tid; j < cnt; j += kThreads) rid[j] = (int32_t)j;
-    else for (uint32_t j = (uint32_t)tid; j < cnt; j += kThreads) rid[j] = (int32_t)sel[j];
-  }
-  const uint64_t blk_addr = p.string_base + rec.off;
-  Team t;  // one warp per column
-  t.tid = lane; t.nthreads = 32; t.warp = 0; t.nwarps = 1; t.lane = lane; t.bar_id = -1;
-  for (;;) {
-    int pc = 0;
-    if (lane == 0) pc = atomicAdd(&s_next, 1);
-    pc = __shfl_sync(0xffffffffu, pc, 0);
-    if (pc >= p.n_proj) break;
-    ColDesc *wdesc = plans_s + pc;  // this column's plan: only this warp touches it
-    const ColDesc &d = *wdesc;
-    if (sparse) {
+    if (p.want_row_ids) {
+      int32_t *rid = p.row_ids + base;
+      if (all_rows) for (uint32_t j = (uint32_t)tid; j < cnt; j += kThreads) rid[j] = (int32_t)j;
+      else for (uint32_t j = (uint32_t)tid; j < cnt; j += kThreads) rid[j] = (int32_t)sel[j];
+    }
+    const uint64_t blk_addr = p.string_base + rec.off;
+    Team t;  // one warp per column
+    t.tid = lane; t.nthreads = 32; t.warp = 0; t.nwarps = 1; t.lane = lane; t.bar_id = -1;
+    for (;;) {
+      int pc = 0;
+      if (lane == 0) pc = atomicAdd(&s_next, 1);
+      pc = __shfl_sync(0xffffffffu, pc, 0);
+      if (pc >= p.n_proj) break;
+      ColDesc *wdesc = plans_s + pc;  // this column's plan: only this warp touches it
+      const ColDesc &d = *wdesc;
+      if (sparse) {
+        if (!d.ok) {
+          if (lane == 0) atomicOr(p.status, ST_UNSUPPORTED);
+        } else if (d.sc == 5) {
+          project_str_col<false>(p, c, d, pc, sel, cnt, base, blk_addr, t);
+        } else if (d.elem_len == 8) {
+          project_int_col_global<uint64_t>(p, c, d, pc, sel, cnt, base, t);
+        } else if (d.elem_len == 4) {
+          project_int_col_global<uint32_t>(p, c, d, pc, sel, cnt, base, t);
+        } else {
+          project_int_col_global<uint8_t>(p, c, d, pc, sel, cnt, base, t);
+        }
+        __syncwarp();
+        continue;
+      }
+      if (p.compact) {  // rebase onto this column's staged region
+        const int32_t delta = s_delta[pc];
+        c.b.s = g_smem + delta;
+        c.sbit = (smem_u32(g_smem) + (uint32_t)delta) * 8u;
+      }
       if (!d.ok) {
-        if (lane == 0) atomicOr(p.status, ST_UNSUPPORTED);
-      } else if (d.sc == 5) {
-        project_str_col<false>(p, c, d, pc, sel, cnt, base, blk_addr, t);
-      } else if (d.elem_len == 8) {
-        project_int_col_global<uint64_t>(p, c, d, pc, sel, cnt, base, t);
-      } else if (d.elem_len == 4) {
-        project_int_col_global<uint32_t>(p, c, d, pc, sel, cnt, base, t);
-      } else {
-        project_int_col_global<uint8_t>(p, c, d, pc, sel, cnt, base, t);
-      }
-      __syncwarp();
-      continue;
-    }
-    if (p.compact) {  // rebase onto this column's staged region
-      const int32_t delta = s_delta[pc];
-      c.b.s = g_smem + delta;
-      c.sbit = (smem_u32(g_smem) + (uint32_t)delta) * 8u;
-    }
-    if (!d.ok) {
-      if (lane == 0) atomicOr(p.status, ST_UNSUPPORTED);
-      __syncwarp();
-      continue;
-    }
-    if (d.kind == K_RLE) {
-      if (d.rle_count > (uint32_t)p.rle_runs_cap) {
         if (lane == 0) atomicOr(p.status, ST_UNSUPPORTED);
         __syncwarp();
         continue;
       }
-      if (lane == 0) wdesc->rle_slot = 0;
-      rle_table_build(c.b.s, d, rows, reinterpret_cast<uint32_t *>(wscr + p.pw_rle),
-                      reinterpret_cast<uint16_t *>(wscr + p.pw_rle + c.rle_starts_bytes), t);
-      const uint32_t n = d.rle_count;
-      if (d.sc != 5 && d.elem_len == 8) {
-        // integer RLE column: decode each RUN once (value of run k), rows then only look up their run
-        uint64_t *rvals = reinterpret_cast<uint64_t *>(wscr + p.pw_rvals);
-        const uint32_t refs_bit = c.sbit + d.rle_refs_bit, ref_bits = d.rle_ref_bits;
-        const uint32_t dcount = d.dict_count, dbits = d.dict_data_size * 8u, dpay = c.sbit + d.dict_payload * 8u;
-        bool null_run = false;
-        for (uint32_t k = (uint32_t)lane; k < n; k += 32u) {
-          const uint32_t ref = sbits32(refs_bit + k * ref_bits, ref_bits);
-          uint64_t v = 0;
-          if (ref >= dcount) null_run = true;
-          else {
-            v = sbits(dpay + ref * dbits, dbits);
-            if (d.sign_fix) v = sign_fix(d.int_mask, v);
-          }
-          rvals[k] = v;
-        }
-        const bool any_null = __any_sync(0xffffffffu, null_run);
-        __syncwarp();
-        if (!any_null) {
-          uint64_t *out = reinterpret_cast<uint64_t *>(p.out_data[pc]) + base;
-          const RleTable rt = c.rle_table(0);
-          if (all_rows) for (uint32_t j = (uint32_t)lane; j < cnt; j += 32u) out[j] = rvals[rle_run_of(rt, j)];
-          else for (uint32_t j = (uint32_t)lane; j < cnt; j += 32u) out[j] = rvals[rle_run_of(rt, sel[j])];
+      if (d.kind == K_RLE) {
+        if (d.rle_count > (uint32_t)p.rle_runs_cap) {
+          if (lane == 0) atomicOr(p.status, ST_UNSUPPORTED);
           __syncwarp();
           continue;
         }
+        if (lane == 0) wdesc->rle_slot = 0;
+        rle_table_build(c.b.s, d, rows, reinterpret_cast<uint32_t *>(wscr + p.pw_rle),
+                        reinterpret_cast<uint16_t *>(wscr + p.pw_rle + c.rle_starts_bytes), t);
+        const uint32_t n = d.rle_count;
+        if (d.sc != 5 && d.elem_len == 8) {
+          // integer RLE column: decode each RUN once (value of run k), rows then only look up their run
+          uint64_t *rvals = reinterpret_cast<uint64_t *>(wscr + p.pw_rvals);
+          const uint32_t refs_bit = c.sbit + d.rle_refs_bit, ref_bits = d.rle_ref_bits;
+          const uint32_t dcount = d.dict_count, dbits = d.dict_data_size * 8u, dpay = c.sbit + d.dict_payload * 8u;
+          bool null_run = false;
+          for (uint32_t k = (uint32_t)lane; k < n; k += 32u) {
+            const uint32_t ref = sbits32(refs_bit + k * ref_bits, ref_bits);
+            uint64_t v = 0;
+            if (ref >= dcount) null_run = true;
+            else {
+              v = sbits(dpay + ref * dbits, dbits);
+              if (d.sign_fix) v = sign_fix(d.int_mask, v);
+            }
+            rvals[k] = v;
+          }
+          const bool any_null = __any_sync(0xffffffffu, null_run);
+          __syncwarp();
+          if (!any_null) {
+            uint64_t *out = reinterpret_cast<uint64_t *>(p.out_data[pc]) + base;
+            const RleTable rt = c.rle_table(0);
+            if (all_rows) for (uint32_t j = (uint32_t)lane; j < cnt; j += 32u) out[j] = rvals[rle_run_of(rt, j)];
+            else for (uint32_t j = (uint32_t)lane; j < cnt; j += 32u) out[j] = rvals[rle_run_of(rt, sel[j])];
+            __syncwarp();
+            continue;
+          }
+        }
       }
+      if (all_rows) {
+        if (d.sc == 5) project_str_col<true>(p, c, d, pc, sel, cnt, base, blk_addr, t);
+        else if (d.elem_len == 8) project_int_col<uint64_t, true>(p, c, d, pc, sel, cnt, base, t);
+        else if (d.elem_len == 4) project_int_col<uint32_t, true>(p, c, d, pc, sel, cnt, base, t);
+        else project_int_col<uint8_t, true>(p, c, d, pc, sel, cnt, base, t);
+      } else {
+        if (d.sc == 5) project_str_col<false>(p, c, d, pc, sel, cnt, base, blk_addr, t);
+        else if (d.elem_len == 8) project_int_col<uint64_t, false>(p, c, d, pc, sel, cnt, base, t);
+        else if (d.elem_len == 4) project_int_col<uint32_t, false>(p, c, d, pc, sel, cnt, base, t);
+        else project_int_col<uint8_t, false>(p, c, d, pc, sel, cnt, base, t);
+      }
+      __syncwarp();
     }
-    if (all_rows) {
-      if (d.sc == 5) project_str_col<true>(p, c, d, pc, sel, cnt, base, blk_addr, t);
-      else if (d.elem_len == 8) project_int_col<uint64_t, true>(p, c, d, pc, sel, cnt, base, t);
-      else if (d.elem_len == 4) project_int_col<uint32_t, true>(p, c, d, pc, sel, cnt, base, t);
-      else project_int_col<uint8_t, true>(p, c, d, pc, sel, cnt, base, t);
-    } else {
-      if (d.sc == 5) project_str_col<false>(p, c, d, pc, sel, cnt, base, blk_addr, t);
-      else if (d.elem_len == 8) project_int_col<uint64_t, false>(p, c, d, pc, sel, cnt, base, t);
-      else if (d.elem_len == 4) project_int_col<uint32_t, false>(p, c, d, pc, sel, cnt, base, t);
-      else project_int_col<uint8_t, false>(p, c, d, pc, sel, cnt, base, t);
-    }
-    __syncwarp();
+    used_bar = true;
   }
 }
 
@@ -1627,7 +1645,7 @@ int obgpu_ctx_create(int device, obgpu_ctx **out) {
     return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 c->max_smem_optin - (int)fa.sharedSizeBytes) == cudaSuccess;
   };
-  const bool ok = opt_in((const void *)obgpu_count_kernel) && opt_in((const void *)obgpu_project_kernel) &&
+  const bool ok = opt_in((const void *)obgpu_count_kernel) && opt_in((const void *)obgpu_project_kernel<false>) && opt_in((const void *)obgpu_project_kernel<true>) &&
                   opt_in((const void *)obgpu_filter_block_kernel) && opt_in((const void *)obgpu_project_block_kernel);
   cudaGetLastError();  // do not leave a stale (non-sticky) error for later launch checks
   if (!ok) {
@@ -2419,7 +2437,9 @@ int obgpu_scan(obgpu_batch *b, const obgpu_scan_spec *spec, obgpu_result **out) 
     ctx->launches += 2;
   }
   if (p.n_proj + p.want_row_ids > 0) {
-    obgpu_project_kernel<<<n, kThreads, p.smem_total, ctx->stream>>>(p);
+    p.proj_tiles = p.sparse_split ? 8 : 1;
+    if (p.sparse_split) obgpu_project_kernel<true><<<(n + p.proj_tiles - 1) / p.proj_tiles, kThreads, p.smem_total, ctx->stream>>>(p);
+    else obgpu_project_kernel<false><<<n, kThreads, p.smem_total, ctx->stream>>>(p);
     ctx->launches++;
     if (p.sparse_split) {
       const uint32_t per_warp = (((p.rows_cap / 16u + 32u) * 2u + 15u) & ~15u) + (uint32_t)sizeof(ColDesc);
