@@ -535,16 +535,27 @@ __device__ __forceinline__ void leaf_over_words(const ScanParams &p, const Block
     const uint32_t cntp1 = d.dict_count + 1;
     const uint32_t val_bit = (G ? 0u : c.sbit) + d.val_bit, stride = d.stride, width = d.width;
     const uint8_t *gs = c.b.s;
-    for (uint32_t g = (uint32_t)t.warp; g < nwords; g += (uint32_t)t.nwarps) {
-      const uint32_t cur = bm[g], vm = valid_mask_of(rows, g);
-      if (and_mode ? cur == 0u : cur == vm) continue;
-      const uint32_t row = g * 32u + (uint32_t)t.lane;
-      uint32_t ref = cntp1;  // lanes past the last row must not touch memory (masked by vm anyway)
-      if (row < rows) ref = G ? ld_bits32(gs, val_bit + row * stride, width) : sbits32(val_bit + row * stride, width);
+    const uint32_t nfull = rows >> 5;
+    uint32_t g = (uint32_t)t.warp;
+    uint32_t bit = val_bit + ((uint32_t)t.warp * 32u + (uint32_t)t.lane) * stride;
+    const uint32_t step = (uint32_t)t.nwarps * 32u * stride;
+    for (; g < nfull; g += (uint32_t)t.nwarps, bit += step) {  // full words: no row bound, no valid mask
+      const uint32_t cur = bm[g];
+      if (and_mode ? cur == 0u : cur == 0xffffffffu) continue;
+      uint32_t ref = G ? ld_bits32(gs, bit, width) : sbits32(bit, width);
       ref = ref < cntp1 ? ref : cntp1;
-      const bool pr = (bits[ref >> 5] >> (ref & 31)) & 1u;
-      const uint32_t w = __ballot_sync(0xffffffffu, pr) & vm;
+      const uint32_t w = __ballot_sync(0xffffffffu, (bits[ref >> 5] >> (ref & 31)) & 1u);
       if (t.lane == 0) bm[g] = and_mode ? (cur & w) : (cur | w);
+    }
+    if (g < nwords) {  // ragged tail: lanes past the last row must not touch memory
+      const uint32_t cur = bm[g], vm = valid_mask_of(rows, g);
+      if (!(and_mode ? cur == 0u : cur == vm)) {
+        uint32_t ref = cntp1;
+        if (g * 32u + (uint32_t)t.lane < rows) ref = G ? ld_bits32(gs, bit, width) : sbits32(bit, width);
+        ref = ref < cntp1 ? ref : cntp1;
+        const uint32_t w = __ballot_sync(0xffffffffu, (bits[ref >> 5] >> (ref & 31)) & 1u) & vm;
+        if (t.lane == 0) bm[g] = and_mode ? (cur & w) : (cur | w);
+      }
     }
     return;
   }
