@@ -2542,13 +2542,11 @@ int obgpu_result_aggregate(obgpu_result *r, int32_t kind, int32_t col_a, int32_t
   CUDA_TRY(ctx, cudaMemcpyAsync(h, d_out, 16, cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   cudaFreeAsync(d_out, ctx->stream);
-  int status = 0;
   {
     obgpu_result_info info;
     const int ret = obgpu_result_info_get(r, &info);  // surfaces overflow / unsupported of the scan itself
     if (ret != OBGPU_SUCCESS) return ret;
   }
-  (void)status;
   if ((kind == OBGPU_AGG_MIN || kind == OBGPU_AGG_MAX) && (a_sgn || a.elem_len < 8)) h[0] ^= 1ull << 63;
   out[0] = (int64_t)h[0];
   out[1] = (int64_t)h[1];
