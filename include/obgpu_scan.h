@@ -67,7 +67,9 @@ enum {
   OBGPU_ENC_INTEGER_BASE_DIFF = 4,
   /* writer only: columns of a CS_ENCODING_ROW_STORE block (ObCSColumnHeader::Type) */
   OBGPU_ENC_CS_INTEGER = 16,
-  OBGPU_ENC_CS_INT_DICT = 17
+  OBGPU_ENC_CS_INT_DICT = 17,
+  OBGPU_ENC_CS_STRING = 18,
+  OBGPU_ENC_CS_STR_DICT = 19
 };
 
 /* ---- ObObjType values the path accepts (common/object/ob_obj_type.h) ------------------------ */

@@ -827,21 +827,152 @@ static void put_stream_meta(Buf &b, const IntStreamPlan &sp) {
   *b.grow(1) = 1;  // pfor_packing_type_: CPU_ARCH_INDEPENDANT_SCALAR
 }
 
+// ObStringStreamMeta, serialized: version u8, attr u8 (USE_ZERO_LEN_AS_NULL 0x1, IS_FIXED_LEN_STRING 0x2),
+// vi32 uncompressed_len, [vi32 fixed_str_len] (cs_encoding/ob_stream_encoding_struct.cpp:255-268)
+static void put_string_stream_meta(Buf &b, bool zero_len_null, int64_t fixed_len, uint32_t uncompressed_len) {
+  uint8_t *p = b.grow(2);
+  p[0] = 0;
+  p[1] = (uint8_t)((zero_len_null ? 0x1 : 0) | (fixed_len >= 0 ? 0x2 : 0));
+  put_vi64(b, uncompressed_len);
+  if (fixed_len >= 0) put_vi64(b, (uint64_t)fixed_len);
+}
+static void put_raw_stream(Buf &body, const std::vector<uint64_t> &vals, uint64_t max_value) {
+  IntStreamPlan sp;
+  sp.width = (int)byte_packed_int_size(max_value);
+  put_stream_meta(body, sp);
+  uint8_t *d = body.grow((size_t)sp.width * vals.size());
+  for (size_t k = 0; k < vals.size(); ++k) memcpy(d + k * (size_t)sp.width, &vals[k], (size_t)sp.width);
+}
+
+// ObStringColumnEncoder::do_init_ (cs_encoding/ob_string_column_encoder.cpp:59-139) decides fixed length / NULL
+// bitmap / zero-length-as-NULL; the bytes go to the block's all-string-data area, the column keeps the
+// serialized string stream meta and, for variable length, one END offset per row.
+static int cs_string_column(const ColCtx &c, CSColumnHeader &ch, Buf &body, Buf &all_string, std::vector<uint32_t> &stream_end,
+                            uint32_t header_size) {
+  const int64_t n = c.nrows;
+  ch.type_ = CS_STRING;
+  bool has_zero = false;
+  int64_t fix = -1, var_size = 0;
+  bool var = false;
+  for (int64_t r = 0; r < n; ++r) {
+    if (c.is_null(r)) continue;
+    const int64_t l = c.sval(r).len;
+    var_size += l;
+    has_zero = has_zero || l == 0;
+    if (fix < 0 && !var) fix = l;
+    else if (fix != l) { var = true; fix = -1; }
+  }
+  if (var) fix = -1;
+  bool bitmap = false, zero_null = false;
+  int64_t fixed_len = -1;
+  if (c.null_cnt > 0) {
+    if (has_zero) {
+      bitmap = true;
+      if (fix >= 0) fixed_len = fix;
+    } else if (fix >= 0) {
+      const int64_t pad = fix * c.null_cnt, bm = (n + 7) / 8;
+      const int64_t off_arr = n * byte_packed_int_size((uint64_t)var_size);
+      if (pad + bm < off_arr) { fixed_len = fix; bitmap = true; }
+      else zero_null = true;
+    } else {
+      zero_null = true;
+    }
+  } else if (fix >= 0) {
+    fixed_len = fix;
+  }
+  if (fixed_len >= 0) ch.attrs_ |= CS_IS_FIXED_LENGTH;
+  if (bitmap) {
+    ch.attrs_ |= CS_HAS_NULL_OR_NOP_BITMAP;
+    uint8_t *bmp = body.grow((size_t)((n + 7) / 8));
+    memset(bmp, 0, (size_t)((n + 7) / 8));
+    for (int64_t r = 0; r < n; ++r)
+      if (c.is_null(r)) bmp[r / 8] |= (uint8_t)(1u << (7 - r % 8));
+  }
+  const uint64_t total = fixed_len >= 0 ? (uint64_t)fixed_len * (uint64_t)n : (uint64_t)var_size;
+  if (total > 0xffffffffull) return OBGPU_NOT_SUPPORTED;
+  put_string_stream_meta(body, zero_null, fixed_len, (uint32_t)total);
+  stream_end.push_back(header_size + (uint32_t)body.size());
+  std::vector<uint64_t> ends;
+  uint64_t pos = 0;
+  uint8_t *dst = all_string.grow((size_t)total);
+  for (int64_t r = 0; r < n; ++r) {
+    if (c.is_null(r)) {
+      if (fixed_len >= 0) { memset(dst + pos, 0, (size_t)fixed_len); pos += (uint64_t)fixed_len; }
+    } else {
+      const StrRef v = c.sval(r);
+      memcpy(dst + pos, v.p, (size_t)v.len);
+      pos += (uint64_t)v.len;
+    }
+    if (fixed_len < 0) ends.push_back(pos);
+  }
+  if (fixed_len < 0) {
+    put_raw_stream(body, ends, total);
+    stream_end.push_back(header_size + (uint32_t)body.size());
+  }
+  return OBGPU_SUCCESS;
+}
+
+// String dictionary column: [ObDictEncodingMeta][dict bytes: string stream (+ END offsets when variable)][refs];
+// ref == distinct_val_cnt is NULL (cs_encoding/ob_dict_column_decoder.cpp:158-326).
+static int cs_str_dict_column(const ColCtx &c, CSColumnHeader &ch, Buf &body, Buf &all_string, std::vector<uint32_t> &stream_end,
+                              uint32_t header_size) {
+  const int64_t n = c.nrows;
+  ch.type_ = CS_STR_DICT;
+  StrDict d;
+  build_str_dict(c, true, d);
+  DictEncodingMeta dm{};
+  dm.attrs_ = (uint8_t)(0x1 | (c.null_cnt > 0 ? 0x2 : 0));
+  dm.distinct_val_cnt_ = (uint32_t)d.values.size();
+  dm.ref_row_cnt_ = (uint32_t)n;
+  memcpy(body.grow(sizeof(dm)), &dm, sizeof(dm));
+  if (d.values.empty()) return OBGPU_SUCCESS;
+  const bool fixed = d.fix_len >= 0;
+  if (fixed) ch.attrs_ |= CS_IS_FIXED_LENGTH;
+  const uint64_t total = (uint64_t)d.var_data_size;
+  put_string_stream_meta(body, false, fixed ? d.fix_len : -1, (uint32_t)total);
+  stream_end.push_back(header_size + (uint32_t)body.size());
+  uint8_t *dst = all_string.grow((size_t)total);
+  std::vector<uint64_t> ends;
+  uint64_t pos = 0;
+  for (const StrRef &v : d.values) {
+    memcpy(dst + pos, v.p, (size_t)v.len);
+    pos += (uint64_t)v.len;
+    ends.push_back(pos);
+  }
+  if (!fixed) {
+    put_raw_stream(body, ends, total);
+    stream_end.push_back(header_size + (uint32_t)body.size());
+  }
+  std::vector<uint64_t> refs((size_t)n);
+  for (int64_t r = 0; r < n; ++r) refs[(size_t)r] = d.refs[(size_t)r];
+  put_raw_stream(body, refs, c.null_cnt > 0 ? d.values.size() : d.values.size() - 1);
+  stream_end.push_back(header_size + (uint32_t)body.size());
+  return OBGPU_SUCCESS;
+}
+
 int BlockBuilder::build_cs(std::vector<uint8_t> &block, int64_t original) {
   const uint32_t header_size = (uint32_t)sizeof(MicroBlockHeader);
   Buf body;  // everything after the micro header
   body.grow(sizeof(AllColumnHeader) + sizeof(CSColumnHeader) * (size_t)ncol);
   std::vector<CSColumnHeader> chdr((size_t)ncol);
   std::vector<uint32_t> stream_end;  // relative to the block start
+  Buf all_string;                    // bytes of every string stream, in stream order (store_all_string_data_)
   const size_t bitmap_bytes = (size_t)((nrows + 7) / 8);
   for (int i = 0; i < ncol; ++i) {
     ColCtx &c = ctx[(size_t)i];
     CSColumnHeader &ch = chdr[(size_t)i];
     ch = CSColumnHeader{};
     ch.obj_type_ = (uint8_t)cols[i].obj_type;
+    if (c.nope_cnt > 0) return OBGPU_NOT_SUPPORTED;
+    if (cols[i].encoding == OBGPU_ENC_CS_STRING || cols[i].encoding == OBGPU_ENC_CS_STR_DICT) {
+      if (c.sc != 5) return OBGPU_NOT_SUPPORTED;
+      const int ret = cols[i].encoding == OBGPU_ENC_CS_STRING ? cs_string_column(c, ch, body, all_string, stream_end, header_size)
+                                                              : cs_str_dict_column(c, ch, body, all_string, stream_end, header_size);
+      if (ret != OBGPU_SUCCESS) return ret;
+      continue;
+    }
     if ((cols[i].encoding != OBGPU_ENC_CS_INTEGER && cols[i].encoding != OBGPU_ENC_CS_INT_DICT) || (c.sc != 1 && c.sc != 2))
       return OBGPU_NOT_SUPPORTED;
-    if (c.nope_cnt > 0) return OBGPU_NOT_SUPPORTED;
     if (cols[i].encoding == OBGPU_ENC_CS_INT_DICT) {
       // ObIntDictColumnEncoder: [ObDictEncodingMeta][dict values: integer stream][refs: integer stream];
       // ref == distinct_val_cnt is NULL; an all-NULL column has the meta only (no streams)
@@ -966,7 +1097,9 @@ int BlockBuilder::build_cs(std::vector<uint8_t> &block, int64_t original) {
     }
     stream_end.push_back(header_size + (uint32_t)body.size());
   }
-  // stream offsets: an integer stream without base (ObMicroBlockCSEncoder::store_stream_offsets_, :1312-1372)
+  // all string data (uncompressed: compressor none), then the stream offsets: an integer stream without base
+  // (ObMicroBlockCSEncoder::store_all_string_data_ :1254-1309, store_stream_offsets_ :1312-1372)
+  if (all_string.size()) memcpy(body.grow(all_string.size()), all_string.d.data(), all_string.size());
   const size_t offsets_at = body.size();
   if (!stream_end.empty()) {
     IntStreamPlan sp;
@@ -977,7 +1110,7 @@ int BlockBuilder::build_cs(std::vector<uint8_t> &block, int64_t original) {
     for (size_t k = 0; k < stream_end.size(); ++k) memcpy(data + k * (size_t)sp.width, &stream_end[k], (size_t)sp.width);
   }
   AllColumnHeader ah{};
-  ah.all_string_data_length_ = 0;
+  ah.all_string_data_length_ = (uint32_t)all_string.size();
   ah.stream_offsets_length_ = (uint32_t)(body.size() - offsets_at);
   ah.stream_count_ = (uint16_t)stream_end.size();
   memcpy(body.d.data(), &ah, sizeof(ah));
