@@ -326,6 +326,7 @@ __device__ __forceinline__ void build_cs_col_desc(const BlockView &b, int col, C
       meta_len = ((attrs & CS_HAS_NULL_OR_NOP_BITMAP) ? bitmap_bytes : 0u) + ((attrs & CS_HAS_NOP_BITMAP) ? bitmap_bytes : 0u);
     } else if (type == CS_STRING) {
       n_streams = (attrs & CS_IS_FIXED_LENGTH) ? 1 : 2;
+      meta_len = ((attrs & CS_HAS_NULL_OR_NOP_BITMAP) ? bitmap_bytes : 0u) + ((attrs & CS_HAS_NOP_BITMAP) ? bitmap_bytes : 0u);
     } else if (type == CS_INT_DICT || type == CS_STR_DICT) {
       if (pos + 10u > b.size) return;
       const uint32_t distinct = (uint32_t)ld_bytes(s, pos + 2, 4);

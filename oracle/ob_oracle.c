@@ -14,7 +14,7 @@
 #include <string.h>
 
 /* ---- layout constants (ob_micro_block_header.h:97-153, ob_block_sstable_struct.h:201-264) ---- */
-enum { T_RAW = 0, T_DICT = 1, T_RLE = 2, T_CONST = 3, T_BASE_DIFF = 4, T_CS_INTEGER = 100, T_CS_INT_DICT = 102 /* CS block: 100 + ObCSColumnHeader::Type */ };
+enum { T_RAW = 0, T_DICT = 1, T_RLE = 2, T_CONST = 3, T_BASE_DIFF = 4, T_CS_INTEGER = 100, T_CS_STRING = 101, T_CS_INT_DICT = 102, T_CS_STR_DICT = 103 /* CS block: 100 + ObCSColumnHeader::Type */ };
 enum { A_FIX = 0x1, A_EXT = 0x2, A_BITPACK = 0x4, A_LASTVAR = 0x8 };
 enum { EXT_NOT = 0, EXT_NULL = 1, EXT_NOPE = 2 };
 #define MAGIC 1005
@@ -270,7 +270,7 @@ static int get_col(const ora_block *b, int32_t col, col_hdr *h) {
   if (b->row_store_type == 3) { /* ObCSColumnHeader: version, type, attrs, obj_type */
     const uint8_t *c = b->cs_col_headers + 4 * col;
     if (c[0] != 0) return ORA_INVALID_DATA;
-    h->type = (int8_t)(c[1] == 0 ? T_CS_INTEGER : (c[1] == 2 ? T_CS_INT_DICT : 127));
+    h->type = (int8_t)(c[1] <= 3 ? 100 + c[1] : 127);
     h->attr = (int8_t)c[2];
     h->obj_type = c[3];
     h->ext_index = h->offset = h->length = 0;
@@ -432,7 +432,30 @@ typedef struct col_dec {
   uint32_t cs_distinct;
   const uint8_t *cs_ref_data;
   int cs_ref_width;
+  /* CS STRING / STR_DICT (cs_encoding/ob_string_stream_decoder.cpp:79-82, ob_dict_column_decoder.cpp): bytes in the
+   * block's all-string-data area, END offsets (cs_off_*) unless fixed length */
+  const uint8_t *cs_str;           /* first byte of this column's string stream */
+  int64_t cs_fixed_len;            /* >= 0: fixed length strings */
+  const uint8_t *cs_off;           /* END offsets: one per row (STRING) or per dictionary entry (STR_DICT) */
+  int cs_off_w;
+  int cs_zero_len_null;
 } col_dec;
+
+/* ObStringStreamMeta, serialized (ob_stream_encoding_struct.cpp:255-283) */
+typedef struct str_stream_meta { uint8_t attr; uint32_t uncompressed_len, fixed_len; int64_t meta_len; } str_stream_meta;
+static int parse_str_stream_meta(const uint8_t *p, int64_t len, str_stream_meta *m) {
+  if (len < 3 || p[0] != 0) return ORA_INVALID_DATA;
+  int64_t pos = 2;
+  uint64_t v = 0;
+  m->attr = p[1];
+  int ret = rd_vi64(p, len, &pos, &v);
+  if (ret) return ret;
+  m->uncompressed_len = (uint32_t)v;
+  m->fixed_len = 0;
+  if (m->attr & 0x2) { if ((ret = rd_vi64(p, len, &pos, &v))) return ret; m->fixed_len = (uint32_t)v; }
+  m->meta_len = pos;
+  return ORA_SUCCESS;
+}
 
 static uint32_t cs_stream_end(const ora_block *b, int32_t idx) {
   return (uint32_t)rd_len(b->cs_off_data + (int64_t)idx * b->cs_off_width, b->cs_off_width);
@@ -444,6 +467,7 @@ static int cs_int_col_init(const ora_block *b, int32_t col, col_dec *c) {
   const int64_t bitmap_bytes = ((int64_t)b->row_count + 7) / 8;
   uint32_t pos = b->cs_first_stream_begin;   /* absolute offset where the current column's meta starts */
   int32_t stream_idx = -1;
+  uint32_t str_at = b->cs_all_string_offset; /* running position inside the all-string-data area (stream order) */
   for (int32_t i = 0; i <= col; ++i) {
     const uint8_t *h = b->cs_col_headers + 4 * i;
     const uint8_t type = h[1], attrs = h[2];
@@ -454,6 +478,7 @@ static int cs_int_col_init(const ora_block *b, int32_t col, col_dec *c) {
       meta_len = ((attrs & 0x02) ? bitmap_bytes : 0) + ((attrs & 0x08) ? bitmap_bytes : 0);
     } else if (type == 1) {                  /* STRING: bytes stream (+ offsets stream when not fixed length) */
       n_streams = (attrs & 0x01) ? 1 : 2;
+      meta_len = ((attrs & 0x02) ? bitmap_bytes : 0) + ((attrs & 0x08) ? bitmap_bytes : 0);
     } else if (type == 2 || type == 3) {     /* INT_DICT / STR_DICT */
       if ((int64_t)pos + 10 > b->size) return ORA_INVALID_DATA;
       const uint32_t distinct = rd32(b->buf + pos + 2);
@@ -464,7 +489,62 @@ static int cs_int_col_init(const ora_block *b, int32_t col, col_dec *c) {
     } else {
       return ORA_NOT_SUPPORTED;
     }
+    if ((type == 1 || type == 3) && n_streams > 0) { /* this column owns one string stream: first stream after the meta */
+      if (stream_idx + 1 >= b->cs_stream_count) return ORA_INVALID_DATA;
+      const uint32_t send = cs_stream_end(b, stream_idx + 1);
+      if ((int64_t)pos + meta_len > send || send > b->size) return ORA_INVALID_DATA;
+      str_stream_meta sm;
+      const int ret = parse_str_stream_meta(b->buf + pos + meta_len, (int64_t)send - pos - meta_len, &sm);
+      if (ret) return ret;
+      if (i == col) {
+        c->cs_str = b->buf + str_at;
+        c->cs_fixed_len = (sm.attr & 0x2) ? (int64_t)sm.fixed_len : -1;
+        c->cs_zero_len_null = (sm.attr & 0x1) != 0;
+        if ((int64_t)str_at + sm.uncompressed_len > b->size) return ORA_INVALID_DATA;
+        const int32_t s_off = stream_idx + 2;   /* END offsets stream (variable length only) */
+        if (type == 1) {
+          if (attrs & 0x08) return ORA_NOT_SUPPORTED;
+          c->cs_null_bitmap = (attrs & 0x02) ? b->buf + pos : 0;
+          if (c->cs_fixed_len < 0) {
+            int_stream_meta m;
+            const uint32_t oend = cs_stream_end(b, s_off);
+            int r2 = parse_int_stream_meta(b->buf + send, (int64_t)oend - send, &m);
+            if (r2) return r2;
+            if ((m.attr & 0x3) || send + m.meta_len + (int64_t)m.width * b->row_count != oend) return ORA_INVALID_DATA;
+            c->cs_off = b->buf + send + m.meta_len;
+            c->cs_off_w = m.width;
+          }
+          return ORA_SUCCESS;
+        }
+        /* STR_DICT: [dict meta][string stream][END offsets x distinct (variable)][refs x rows] */
+        const uint8_t *dm = b->buf + pos;
+        if (dm[0] != 0 || (dm[1] & 0x4) || (attrs & 0x08)) return ORA_NOT_SUPPORTED;
+        c->cs_distinct = rd32(dm + 2);
+        uint32_t at = send;
+        int32_t si = s_off;
+        int_stream_meta m;
+        if (c->cs_fixed_len < 0) {
+          const uint32_t oend = cs_stream_end(b, si);
+          int r2 = parse_int_stream_meta(b->buf + at, (int64_t)oend - at, &m);
+          if (r2) return r2;
+          if ((m.attr & 0x3) || at + m.meta_len + (int64_t)m.width * c->cs_distinct != oend) return ORA_INVALID_DATA;
+          c->cs_off = b->buf + at + m.meta_len;
+          c->cs_off_w = m.width;
+          at = oend;
+          ++si;
+        }
+        const uint32_t rend = cs_stream_end(b, si);
+        int r3 = parse_int_stream_meta(b->buf + at, (int64_t)rend - at, &m);
+        if (r3) return r3;
+        if ((m.attr & 0x3) || at + m.meta_len + (int64_t)m.width * b->row_count != rend) return ORA_INVALID_DATA;
+        c->cs_ref_data = b->buf + at + m.meta_len;
+        c->cs_ref_width = m.width;
+        return ORA_SUCCESS;
+      }
+      str_at += sm.uncompressed_len;
+    }
     if (i == col) {
+      if (type == 3) { c->cs_distinct = 0; return ORA_SUCCESS; }   /* STR_DICT without streams: every row NULL */
       if (type == 2) { /* INT_DICT: [ObDictEncodingMeta 10 B][dict value stream][ref stream] */
         const uint8_t *dm = b->buf + pos;
         if (dm[0] != 0 || (dm[1] & 0x4) || (attrs & 0x08)) return ORA_NOT_SUPPORTED; /* const-encoded refs / nop bitmap */
@@ -546,7 +626,9 @@ static int col_dec_init(const ora_block *b, int32_t col, col_dec *c) {
       break;
     }
     case T_CS_INTEGER:
-    case T_CS_INT_DICT: return cs_int_col_init(b, col, c);
+    case T_CS_STRING:
+    case T_CS_INT_DICT:
+    case T_CS_STR_DICT: return cs_int_col_init(b, col, c);
     case T_CONST: {
       const uint8_t *m = c->meta; /* version, count, const_ref, attr(row_id_byte:3), offset u16 */
       if (m[0] != 0) return ORA_ERR_UNEXPECTED;
@@ -664,6 +746,28 @@ static int decode_cell(const ora_block *b, const col_dec *c, int64_t row, ora_da
       const uint64_t raw = rd_len(c->cs_data + row * c->cs_width, c->cs_width);
       if (c->cs_replace_null && raw == c->cs_null_raw) { set_null(out); return ORA_SUCCESS; }
       set_int(c->h.obj_type, raw + c->cs_base, out);
+      return ORA_SUCCESS;
+    }
+    case T_CS_STRING:
+    case T_CS_STR_DICT: {
+      int64_t idx = row;
+      if (c->h.type == T_CS_STR_DICT) {
+        if (c->cs_distinct == 0) { set_null(out); return ORA_SUCCESS; }
+        idx = (int64_t)rd_len(c->cs_ref_data + row * c->cs_ref_width, c->cs_ref_width);
+        if (idx == c->cs_distinct) { set_null(out); return ORA_SUCCESS; }
+        if (idx > c->cs_distinct) return ORA_ERR_UNEXPECTED;
+      } else if (c->cs_null_bitmap && ((c->cs_null_bitmap[row / 8] >> (7 - row % 8)) & 1)) {
+        set_null(out);
+        return ORA_SUCCESS;
+      }
+      int64_t start, len;
+      if (c->cs_fixed_len >= 0) { start = idx * c->cs_fixed_len; len = c->cs_fixed_len; }
+      else {
+        start = idx ? (int64_t)rd_len(c->cs_off + (idx - 1) * c->cs_off_w, c->cs_off_w) : 0;
+        len = (int64_t)rd_len(c->cs_off + idx * c->cs_off_w, c->cs_off_w) - start;
+      }
+      if (c->h.type == T_CS_STRING && c->cs_zero_len_null && len == 0) { set_null(out); return ORA_SUCCESS; }
+      out->ptr = c->cs_str + start; out->len = (uint32_t)len; out->is_null = 0; out->ival = 0;
       return ORA_SUCCESS;
     }
     case T_CS_INT_DICT: { /* ObIntDictColumnDecoder::decode: ref == distinct_val_cnt is NULL, value = dict[ref] + base */

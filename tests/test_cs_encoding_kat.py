@@ -151,3 +151,54 @@ def test_cs_int_dict_all_null_column_has_no_streams():
     assert blk.b.cs_stream_count == 1
     assert all(blk.cell(0, r) is None for r in range(n))
     assert [blk.cell(1, r) for r in range(n)] == list(range(n))
+
+
+def _strings(rng, n, minl, maxl, card):
+    d = [bytes(rng.integers(97, 123, size=int(rng.integers(minl, maxl + 1)), dtype=np.uint8)) for _ in range(card)]
+    return [d[i] for i in rng.integers(0, card, size=n)]
+
+
+STR_SHAPES = {
+    # name: (generator, ObCSColumnHeader attrs expected for (no NULLs, some NULLs) with the STRING encoding)
+    "var": (lambda rng, n: _strings(rng, n, 1, 12, 50), (0x00, 0x00)),                  # NULL as zero length
+    "var_with_empty": (lambda rng, n: [b"" if i % 7 == 0 else x for i, x in enumerate(_strings(rng, n, 1, 9, 40))], (0x00, 0x02)),
+    "fixed": (lambda rng, n: _strings(rng, n, 5, 5, 30), (0x01, None)),                # bitmap vs offsets by size
+    "all_empty": (lambda rng, n: [b""] * n, (0x01, 0x03)),
+}
+
+
+@pytest.mark.parametrize("shape", sorted(STR_SHAPES))
+@pytest.mark.parametrize("null_frac", [0.0, 0.2, 1.0])
+@pytest.mark.parametrize("enc", ["string", "str_dict"])
+def test_cs_string_roundtrip(shape, null_frac, enc):
+    # ObStringColumnEncoder::do_init_ (cs_encoding/ob_string_column_encoder.cpp:44-99): fixed length, NULL as a zero
+    # length value or a NULL bitmap; ObStrDictColumnEncoder: [dict meta][string stream (+offsets)][ref stream];
+    # every string stream's bytes live in the block's all-string-data area (ob_micro_block_cs_encoder.cpp store_all_string_data_)
+    rng = np.random.default_rng(5)
+    n = 400
+    gen, (attrs_plain, attrs_nulls) = STR_SHAPES[shape]
+    v = gen(rng, n)
+    nulls = (rng.random(n) < null_frac).astype(np.uint8) if null_frac else None
+    e = ob.ENC_CS_STRING if enc == "string" else ob.ENC_CS_STR_DICT
+    block = ob.encode_block([ob.Column(ob.OBJ_VARCHAR, e, v, nulls=nulls),
+                             ob.Column(ob.OBJ_INT, ob.ENC_CS_INTEGER, np.arange(n, dtype=np.int64)),
+                             ob.Column(ob.OBJ_VARCHAR, ob.ENC_CS_STRING, v[::-1])])
+    blk = ora.Block(block)
+    assert blk.verify_checksums() == 0
+    hs = blk.b.header_size
+    assert int(block[hs + 12 + 1]) == (1 if enc == "string" else 3)       # ObCSColumnHeader::STRING / STR_DICT
+    if enc == "string" and 0.0 < null_frac < 1.0:
+        if attrs_nulls is not None:
+            assert int(block[hs + 12 + 2]) == attrs_nulls
+    elif enc == "string" and null_frac == 0.0:
+        assert int(block[hs + 12 + 2]) == attrs_plain
+    exp = [None if (nulls is not None and nulls[r]) else v[r] for r in range(n)]
+    assert [blk.cell(0, r) for r in range(n)] == exp
+    assert [blk.cell(2, r) for r in range(n)] == v[::-1]
+    assert [blk.cell(1, r) for r in range(0, n, 50)] == list(range(0, n, 50))
+    # white filters agree with the PAX RAW encoding of the same cells
+    pax = ora.Block(ob.encode_block([ob.Column(ob.OBJ_VARCHAR, ob.ENC_RAW, v, nulls=nulls)]))
+    probe = v[3]
+    for op, params in ((ob.WHITE_OP_EQ, (probe,)), (ob.WHITE_OP_LT, (probe,)), (ob.WHITE_OP_GE, (b"m",)), (ob.WHITE_OP_NU, ()),
+                       (ob.WHITE_OP_IN, (probe, v[9], b"zzzz")), (ob.WHITE_OP_NE, (probe,)), (ob.WHITE_OP_BT, (b"c", b"t"))):
+        assert np.array_equal(blk.filter_tree(White(0, op, params)), pax.filter_tree(White(0, op, params))), (op, params)
