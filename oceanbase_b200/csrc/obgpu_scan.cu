@@ -835,6 +835,7 @@ __global__ void __launch_bounds__(256) obgpu_index_kernel(const uint8_t *image, 
     // bytes of the column's region (count kernel staging buffer, project kernel column staging)
     uint32_t lo, hi;
     if (col_region(d, b, lo, hi)) atomicMax(&col_span[col], hi - lo);
+    else atomicMax(&col_span[col], 0xffffffffu);   // no single region (CS string bytes): whole-block staging only
     // dictionary size (predicate bitset words) of dictionary-coded columns: col_span[max_cols + col]
     if (is_dict_kind(d)) atomicMax(&col_span[max_cols + col], d.dict_count + 2u);
   }

@@ -97,6 +97,7 @@ enum ColKind : uint8_t {
   K_VARSTR,   // RAW var-length string in the row data
   K_FIXSTR,   // RAW fixed-length string
   K_CONST,    // ref   = exception ref if the row is in the exception list, else const_ref; then dictionary
+  K_CSSTR,    // CS STRING, variable length: END offset per row (dict_payload, dict_data_size bytes each), bytes at dict_var
 };
 
 struct alignas(16) ColDesc {
@@ -149,6 +150,11 @@ __device__ __forceinline__ bool null_replaced_on(const ColDesc &d) { return d.ki
 __device__ __forceinline__ uint64_t null_replaced_raw(const ColDesc &d) {
   return ((uint64_t)d.var_k << 32) | (uint64_t)d.var_header_off;
 }
+
+// CS string columns (STRING / STR_DICT) keep their bytes in the block's all-string-data area, outside the
+// column's own meta + streams: no single region covers them (see col_region). K_CSSTR / CS K_FIXSTR use
+// var_ext_in_row like K_BITS (MSB-first NULL bitmap) and var_is_last = 1 for "a zero-length value is NULL".
+__device__ __forceinline__ bool cs_bytes_outside(const ColDesc &d) { return d.type == 101 || d.type == 103; }
 
 __device__ __forceinline__ bool is_dict_kind(const ColDesc &d) {
   return d.kind == K_DICT || d.kind == K_RLE || d.kind == K_CONST;
@@ -244,6 +250,28 @@ __device__ __forceinline__ void parse_int_stream_meta(const uint8_t *s, uint32_t
   m.ok = 1;
 }
 
+// ObStringStreamMeta, serialized (ob_stream_encoding_struct.cpp:255-283): version, attr (1 zero length is NULL,
+// 2 fixed length), vi32 uncompressed_len, [vi32 fixed_len]
+struct StrStreamMeta {
+  uint32_t uncompressed_len, fixed_len;
+  uint8_t zero_len_null, fixed, ok;
+};
+__device__ __forceinline__ void parse_str_stream_meta(const uint8_t *s, uint32_t at, uint32_t end, StrStreamMeta &m) {
+  m = StrStreamMeta{};
+  if (at + 3u > end || s[at] != 0) return;
+  uint32_t pos = at + 2u;
+  uint64_t v = 0;
+  m.zero_len_null = s[at + 1] & 0x1;
+  m.fixed = (s[at + 1] & 0x2) != 0;
+  if (!rd_vi64(s, pos, end, v) || v > 0xffffffffull) return;
+  m.uncompressed_len = (uint32_t)v;
+  if (m.fixed) {
+    if (!rd_vi64(s, pos, end, v) || v > 0xffffull) return;
+    m.fixed_len = (uint32_t)v;
+  }
+  m.ok = 1;
+}
+
 // CS block: ObCSMicroBlockTransformer::init / decode_stream_offsets_ (ob_cs_micro_block_transformer.cpp:106-202)
 __device__ __forceinline__ void parse_cs_block(const uint8_t *s, uint32_t size, int16_t magic, int16_t version, BlockView &b) {
   b.is_cs = 1;
@@ -257,10 +285,12 @@ __device__ __forceinline__ void parse_cs_block(const uint8_t *s, uint32_t size, 
   b.meta_off = ah + 12u + 4u * b.column_count;   // ObAllColumnHeader + ObCSColumnHeader x ncol
   if (b.meta_off > size) return;
   if (s[ah] != 0 || (s[ah + 1] & 0x3)) return;  // transformed / compressed string data: not handled
+  const uint32_t all_string_len = (uint32_t)ld_bytes(s, ah + 2, 4);
   const uint32_t offsets_len = (uint32_t)ld_bytes(s, ah + 6, 4);
   b.cs_stream_count = (uint16_t)ld_bytes(s, ah + 10, 2);
   b.cs_first_stream_begin = b.meta_off;
-  if (offsets_len > size - b.meta_off) return;
+  if (offsets_len > size - b.meta_off || all_string_len > size - b.meta_off - offsets_len) return;
+  b.row_data_off = size - offsets_len - all_string_len;   // CS: start of the all-string-data area
   if (b.cs_stream_count > 0) {
     IntStreamMeta m;
     parse_int_stream_meta(s, size - offsets_len, size, m);
@@ -305,6 +335,88 @@ __device__ __forceinline__ void parse_block(const uint8_t *s, uint32_t size, Blo
   }
 }
 
+// CS STRING / STR_DICT column (cs_encoding/ob_string_column_decoder.cpp, ob_dict_column_decoder.cpp:158-326).
+// pos: the column's meta (NULL bitmap or ObDictEncodingMeta), str_at: its bytes in the all-string-data area,
+// send: end of the string stream (= start of the next stream of this column), next_stream: index of that stream.
+__device__ __forceinline__ void build_cs_str_col_desc(const BlockView &b, uint32_t w, uint32_t pos, uint32_t str_at, uint32_t send,
+                                                      int next_stream, const StrStreamMeta &sm, ColDesc &d) {
+  const uint8_t *s = b.s;
+  const uint32_t type = (w >> 8) & 0xff, attrs = (w >> 16) & 0xff;
+  d.type = (uint8_t)(100 + type);
+  d.attr = (uint8_t)attrs;
+  d.obj_type = (uint8_t)(w >> 24);
+  if (store_class_of(d.obj_type) != 5 || (attrs & (CS_HAS_NOP_BITMAP | CS_HAS_NOP | CS_OUT_ROW))) return;
+  d.sc = 5;
+  if (sm.fixed != ((attrs & CS_IS_FIXED_LENGTH) != 0)) return;
+  const uint32_t count = type == CS_STRING ? b.row_count : (uint32_t)ld_bytes(s, pos + 2, 4);
+  uint32_t at = send;
+  uint32_t off_data = 0, off_w = 0;
+  if (sm.fixed) {
+    if ((uint64_t)sm.fixed_len * count != sm.uncompressed_len) return;
+  } else {  // END offset per value: RAW integer stream, no base
+    if (next_stream >= (int)b.cs_stream_count) return;
+    const uint32_t oend = (uint32_t)ld_bytes(s, b.cs_off_data + (uint32_t)next_stream * b.cs_off_width, b.cs_off_width);
+    if (oend < at || oend > b.size) return;
+    IntStreamMeta m;
+    parse_int_stream_meta(s, at, oend, m);
+    if (!m.ok || m.use_base || m.replace_null || m.width > 4) return;
+    if (at + m.meta_len + m.width * count != oend) return;
+    off_data = at + m.meta_len;
+    off_w = m.width;
+    at = oend;
+    ++next_stream;
+  }
+  if (type == CS_STRING) {
+    if (attrs & CS_HAS_NULL_OR_NOP_BITMAP) {
+      d.ext_bit = 1;
+      d.ext_bit_off = pos * 8u;
+      d.var_ext_in_row = 7;
+    }
+    d.var_is_last = sm.zero_len_null;
+    if (sm.fixed) {
+      d.kind = K_FIXSTR;
+      d.dict_data_size = sm.fixed_len;
+      d.val_bit = str_at;
+    } else {
+      d.kind = K_CSSTR;
+      d.dict_count = count;
+      d.dict_payload = off_data;
+      d.dict_data_size = off_w;
+      d.dict_var = str_at;
+      d.dict_end = str_at + sm.uncompressed_len;
+    }
+    d.ok = 1;
+    return;
+  }
+  // STR_DICT: [ObDictEncodingMeta][string stream meta][END offsets x distinct (variable)][refs x rows]
+  if (s[pos] != 0 || (s[pos + 1] & 0x4)) return;   // const-encoded refs: not handled
+  if (next_stream >= (int)b.cs_stream_count) return;
+  const uint32_t rend = (uint32_t)ld_bytes(s, b.cs_off_data + (uint32_t)next_stream * b.cs_off_width, b.cs_off_width);
+  if (rend < at || rend > b.size) return;
+  IntStreamMeta m;
+  parse_int_stream_meta(s, at, rend, m);
+  if (!m.ok || m.use_base || m.replace_null || m.width > 4) return;
+  if (at + m.meta_len + m.width * b.row_count != rend) return;
+  d.kind = K_DICT;
+  d.dict_count = count;
+  d.width = (uint8_t)(m.width * 8u);
+  d.stride = m.width * 8u;
+  d.val_bit = (at + m.meta_len) * 8u;
+  if (sm.fixed) {
+    d.dict_fixed = 1;
+    d.dict_data_size = sm.fixed_len;
+    d.dict_payload = str_at;
+    d.dict_end = str_at + sm.uncompressed_len;
+  } else {
+    d.dict_fixed = 0;
+    d.dict_payload = off_data;
+    d.dict_data_size = off_w;
+    d.dict_var = str_at;
+    d.dict_end = str_at + sm.uncompressed_len;
+  }
+  d.ok = 1;
+}
+
 // CS INTEGER column -> K_BITS plan. Walks the column headers like
 // ObCSMicroBlockTransformer::build_original_transform_desc_ (ob_cs_micro_block_transformer.cpp:216-380)
 // to find the column's meta and first stream; value = raw + base (ConvertUintToDatum_T,
@@ -314,6 +426,7 @@ __device__ __forceinline__ void build_cs_col_desc(const BlockView &b, int col, C
   const uint32_t bitmap_bytes = (b.row_count + 7u) >> 3;
   const uint32_t hdrs = b.header_size + 12u;
   uint32_t pos = b.cs_first_stream_begin;
+  uint32_t str_at = b.row_data_off;   // running position inside the all-string-data area
   int stream_idx = -1;
   for (int i = 0; i <= col; ++i) {
     const uint32_t w = ld32(s, hdrs + 4u * (uint32_t)i);
@@ -335,11 +448,32 @@ __device__ __forceinline__ void build_cs_col_desc(const BlockView &b, int col, C
     } else {
       return;
     }
+    if ((type == CS_STRING || type == CS_STR_DICT) && n_streams > 0) {
+      // the column's first stream is its string stream: the meta stays here, the bytes are the next
+      // uncompressed_len bytes of the all-string-data area (stream order)
+      if (stream_idx + 1 >= (int)b.cs_stream_count) return;
+      const uint32_t send = (uint32_t)ld_bytes(s, b.cs_off_data + (uint32_t)(stream_idx + 1) * b.cs_off_width, b.cs_off_width);
+      if (pos + meta_len > send || send > b.size) return;
+      StrStreamMeta sm;
+      parse_str_stream_meta(s, pos + meta_len, send, sm);
+      if (!sm.ok || sm.uncompressed_len > b.size - str_at) return;
+      if (i == col) {
+        build_cs_str_col_desc(b, w, pos, str_at, send, stream_idx + 2, sm, d);
+        return;
+      }
+      str_at += sm.uncompressed_len;
+    }
     if (i == col) {
       d.type = (uint8_t)(100 + type);
       d.attr = (uint8_t)attrs;
       d.obj_type = (uint8_t)(w >> 24);
       const int sc = store_class_of(d.obj_type);
+      if (type == CS_STR_DICT && sc == 5 && !(attrs & (CS_HAS_NOP_BITMAP | CS_HAS_NOP | CS_OUT_ROW))) {
+        d.sc = 5;                     // no streams: every row NULL (CONST plan with an empty dictionary)
+        d.kind = K_CONST;
+        d.ok = 1;
+        return;
+      }
       if ((type != CS_INTEGER && type != CS_INT_DICT) || (sc != 1 && sc != 2)) return;
       if (type == CS_INT_DICT) {
         // [ObDictEncodingMeta 10 B][dict value stream][ref stream] -> K_DICT plan (ref == distinct count: NULL,
@@ -632,6 +766,7 @@ __device__ __forceinline__ void build_col_desc(const BlockView &b, int col, ColD
 __device__ __forceinline__ bool col_region(const ColDesc &d, const BlockView &bv, uint32_t &lo, uint32_t &hi) {
   const uint32_t rows = bv.row_count;
   uint32_t a, b;
+  if (cs_bytes_outside(d) && d.kind != K_CONST) return false;   // meta here, bytes in the all-string-data area
   switch (d.kind) {
     case K_VARSTR:  // cells live in the row data, addressed through the row index at the block tail
       a = bv.row_data_off;
@@ -786,12 +921,24 @@ __device__ __forceinline__ void str_cell(const BlockView &b, const ColDesc &d, c
     return;
   }
   if (d.kind == K_FIXSTR) {
-    if (d.ext_bit && ld_bits32(s, d.ext_bit_off + row * d.ext_bit, d.ext_bit) != STORED_NOT_EXT) {
+    if (d.ext_bit && ld_bits32(s, d.ext_bit_off + ext_row(d, row) * d.ext_bit, d.ext_bit) != STORED_NOT_EXT) {
       is_null = true;
       return;
     }
     len = d.dict_data_size;
     cell = d.val_bit + row * len;
+    return;
+  }
+  if (d.kind == K_CSSTR) {  // END offset per row; NULL by bitmap or as a zero-length value
+    if (d.ext_bit && ld_bits32(s, d.ext_bit_off + ext_row(d, row) * d.ext_bit, d.ext_bit) != STORED_NOT_EXT) {
+      is_null = true;
+      return;
+    }
+    const uint32_t ib = d.dict_data_size;
+    const uint32_t off = row == 0 ? 0u : (uint32_t)ld_bytes(s, d.dict_payload + (row - 1) * ib, ib);
+    cell = d.dict_var + off;
+    len = (uint32_t)ld_bytes(s, d.dict_payload + row * ib, ib) - off;
+    if (d.var_is_last && len == 0) is_null = true;
     return;
   }
   // RAW var-length: row = [ext bits][col_idx_byte][idx x (nvar-1)][cells]

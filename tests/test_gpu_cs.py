@@ -136,3 +136,55 @@ def test_cs_int_dict_columns_scan(ob, ctx, with_nulls):
             ob.Or([ob.White(0, ob.WHITE_OP_NU, ()), ob.White(3, ob.WHITE_OP_NN, ())])]
     for flt in flts:
         assert_scan_matches(ctx, W(table, flt, [0, 1, 2, 3], [False] * 4, [8, 4, 8, 8]))
+
+
+@pytest.mark.parametrize("shape", ["var", "var_with_empty", "fixed", "all_empty"])
+@pytest.mark.parametrize("null_frac", [0.0, 0.2, 1.0])
+def test_cs_string_columns_scan(ob, ctx, shape, null_frac):
+    # STRING (fixed / END offsets, NULL bitmap / zero length) and STR_DICT columns: bytes in the all-string-data area
+    from test_cs_encoding_kat import STR_SHAPES
+    rng = np.random.default_rng(31)
+    n = 6000
+    v = STR_SHAPES[shape][0](rng, n)
+    nulls = (rng.random(n) < null_frac).astype(np.uint8) if null_frac else None
+    k = rng.integers(0, 1000, size=n, dtype=np.int64)
+    table = ob.encode_table([ob.Column(ob.OBJ_VARCHAR, ob.ENC_CS_STRING, v, nulls=nulls),
+                             ob.Column(ob.OBJ_INT, ob.ENC_CS_INTEGER, k),
+                             ob.Column(ob.OBJ_VARCHAR, ob.ENC_CS_STR_DICT, v, nulls=nulls),
+                             ob.Column(ob.OBJ_VARCHAR, ob.ENC_CS_STRING, v[::-1])], 800)
+    probe = v[5]
+    flts = [None, ob.White(0, ob.WHITE_OP_GE, (b"m",)), ob.White(2, ob.WHITE_OP_LT, (probe,)),
+            ob.And([ob.White(1, ob.WHITE_OP_LT, (500,)), ob.White(2, ob.WHITE_OP_IN, (probe, v[77], b"zz")), ob.White(3, ob.WHITE_OP_NE, (probe,))]),
+            ob.Or([ob.White(0, ob.WHITE_OP_NU, ()), ob.White(2, ob.WHITE_OP_EQ, (probe,)), ob.White(3, ob.WHITE_OP_BT, (b"c", b"f"))])]
+    for flt in flts:
+        assert_scan_matches(ctx, W(table, flt, [0, 1, 2, 3], [True, False, True, True], [8, 8, 8, 8]))
+    assert_scan_matches(ctx, W(table, ob.White(1, ob.WHITE_OP_LT, (20,)), [2, 0], [True, True], [8, 8]))   # sparse selection
+
+
+def test_cs_string_block_entry_points_and_bytes(ob, ctx):
+    from test_cs_encoding_kat import _strings
+    rng = np.random.default_rng(32)
+    n = 500
+    v = _strings(rng, n, 0, 14, 45)
+    nulls = (rng.random(n) < 0.25).astype(np.uint8)
+    block = ob.encode_block([ob.Column(ob.OBJ_VARCHAR, ob.ENC_CS_STRING, v, nulls=nulls),
+                             ob.Column(ob.OBJ_VARCHAR, ob.ENC_CS_STR_DICT, v, nulls=nulls)])
+    blk = ora.Block(block)
+    image = np.concatenate([block, np.zeros((-len(block)) % 128 + 128, dtype=np.uint8)])
+    table = ob.TableImage(image, np.array([0], dtype=np.int64), np.array([len(block)], dtype=np.int64), 0, 0)
+    batch = ctx.open_batch(table)
+    for col in (0, 1):
+        for op, params in ((ob.WHITE_OP_LE, (v[1],)), (ob.WHITE_OP_NU, ()), (ob.WHITE_OP_IN, (v[2], v[3])), (ob.WHITE_OP_NE, (v[4],))):
+            assert np.array_equal(batch.filter_white(0, col, op, params, 0, None), blk.filter_tree(ob.White(col, op, params)))
+    base = 0x20_0000_0000
+    res = batch.scan(None, [0, 1], string_base=base)
+    for c in (0, 1):
+        data, lens, nl = res.fetch_col(c)
+        for r in range(n):
+            is_null = (int(nl[r >> 6]) >> (r & 63)) & 1
+            assert bool(is_null) == bool(nulls[r])
+            if not is_null:
+                off = int(data[r]) - base
+                assert bytes(image[off:off + int(lens[r])]) == v[r]
+    res.free()
+    batch.close()
