@@ -329,7 +329,7 @@ def run_ours(args):
     # page batches; open (H2D + index) -> scan -> fetch (D2H) of different batches overlap on 3 streams.
     from oceanbase_b200.pipeline import HostScanPipeline, split_table
     bpb = max(1, table.n_blocks // args.e2e_batches)
-    parts = split_table(table, bpb)
+    parts = split_table(table, bpb, args.e2e_ramp)
     out_host, out_np, null_np = [], [], []
     for part in parts:
         rows_part = int(part.n_blocks) * 1400
@@ -345,7 +345,7 @@ def run_ours(args):
 
     def e2e_step():
         nonlocal d2h
-        outs = pipe.scan(table, w.filter, w.proj, bpb, 0.30, out_buffers=out_np, null_buffers=null_np)
+        outs = pipe.scan(table, w.filter, w.proj, bpb, 0.30, out_buffers=out_np, null_buffers=null_np, ramp=args.e2e_ramp)
         n = sum(o.selected_rows for o in outs)
         d2h = n * 8 * len(w.proj)
         return n
@@ -434,6 +434,7 @@ def main():
     ap.add_argument("--cpu-sample-rows", type=int, default=16_000_000)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--e2e-batches", type=int, default=12, help="page batches per e2e step (pipeline depth)")
+    ap.add_argument("--e2e-ramp", type=int, default=2, help="the first N page batches are 1/2^N .. 1/2 of a full one")
     ap.add_argument("--e2e-workers", type=int, default=3, help="host worker threads = CUDA streams of the e2e pipeline")
     ap.add_argument("--seed", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")

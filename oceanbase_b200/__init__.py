@@ -13,8 +13,12 @@ from .capi import (  # noqa: F401
     OBJ_INT, OBJ_INT32, OBJ_UINT64, OBJ_VARCHAR, OBJ_DATE, OBJ_TINYINT, OBJ_SMALLINT, OBJ_UINT32,
     DF_NOT_EXIST, DF_LOCK, DF_UPDATE, DF_INSERT, DF_DELETE,
     AGG_COUNT, AGG_SUM, AGG_SUM_PRODUCT, AGG_MIN, AGG_MAX,
+    SK_IDX_MIN, SK_IDX_MAX, SK_IDX_NULL_COUNT, SK_IDX_SUM,
+    BOOL_MASK_UNCERTAIN, BOOL_MASK_ALWAYS_TRUE, BOOL_MASK_ALWAYS_FALSE,
 )
-from .sstable import Column, TableImage, encode_table, encode_block  # noqa: F401
+from .sstable import (  # noqa: F401
+    Column, TableImage, encode_table, encode_block, agg_row_write, block_agg_row, table_agg_rows,
+)
 from .scan import (  # noqa: F401
     White, And, Or, ScanContext, PageBatch, ScanResult, flatten_filter,
 )

@@ -64,6 +64,13 @@ class ColInput(C.Structure):
                 ("reserved", C.c_int32)]
 
 
+class AggCell(C.Structure):
+    _fields_ = [("col_idx", C.c_uint32), ("col_type", C.c_uint8), ("is_null", C.c_uint8), ("is_prefix", C.c_uint8),
+                ("reserved", C.c_uint8), ("len", C.c_int32), ("data", C.c_void_p)]
+
+
+SK_IDX_MIN, SK_IDX_MAX, SK_IDX_NULL_COUNT, SK_IDX_SUM = range(4)           # blocksstable::ObSkipIndexColType
+BOOL_MASK_UNCERTAIN, BOOL_MASK_ALWAYS_TRUE, BOOL_MASK_ALWAYS_FALSE = range(3)  # sql::ObBoolMaskType
 AGG_COUNT, AGG_SUM, AGG_SUM_PRODUCT, AGG_MIN, AGG_MAX = range(5)
 DF_NOT_EXIST, DF_LOCK, DF_UPDATE, DF_INSERT, DF_DELETE = range(5)  # blocksstable::ObDmlFlag
 
@@ -79,8 +86,8 @@ class MergeInfo(C.Structure):
 
 
 def declared_signatures():
-    """name -> (restype, argtypes) for every symbol include/obgpu_scan.h and include/obgpu_compaction.h
-    declare."""
+    """name -> (restype, argtypes) for every symbol include/obgpu_scan.h, include/obgpu_compaction.h and
+    include/obgpu_skip_index.h declare."""
     vp, i32, i64, u64 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64
     P = C.POINTER
     return {
@@ -128,6 +135,13 @@ def declared_signatures():
         "obgpu_merge_result_info": (C.c_int, [vp, P(MergeInfo)]),
         "obgpu_merge_result_cols": (C.c_int, [vp, P(vp), P(P(vp)), P(P(vp))]),
         "obgpu_merge_result_fetch": (C.c_int, [vp, i32, i64, i64, vp, vp]),
+        # include/obgpu_skip_index.h
+        "obgpu_agg_row_write": (C.c_int, [P(AggCell), i32, i32, vp, i64, P(i64)]),
+        "obgpu_writer_block_agg_row": (C.c_int, [P(ColInput), i32, vp, i32, i64, i64, vp, i64, P(i64)]),
+        "obgpu_writer_table_agg_rows": (C.c_int, [P(ColInput), i32, vp, i32, i64, i64, vp, i64, vp, P(i64)]),
+        "obgpu_batch_set_agg_rows": (C.c_int, [vp, vp, vp]),
+        "obgpu_batch_skip_index_filter": (C.c_int, [vp, P(Filter), vp]),
+        "obgpu_result_skip_info": (C.c_int, [vp, P(i64), P(i64)]),
     }
 
 

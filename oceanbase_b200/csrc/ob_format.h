@@ -227,6 +227,15 @@ OBF_HD int type_store_size(uint8_t t) {
   }
 }
 
+// ---- skip index aggregate row (index_block/ob_agg_row_struct.h:27-66) -----------------------------------------
+struct AggRowHeader {
+  int16_t version_;      // 1, 2 (prefix bitmap per cell), 3 (revised max prefix)
+  int16_t length_;       // bytes of the whole row
+  int16_t agg_col_cnt_;  // aggregated columns (cells)
+  uint16_t pack_;        // agg_col_idx_size:6 | agg_col_idx_off_size:3 | cell_off_size:3 | bitmap_size:4 (== 1)
+};
+static_assert(sizeof(AggRowHeader) == 8, "ObAggRowHeader is 8 bytes");
+
 // Datum length of an integer-class obj type: 4 for the 4-byte map types, 1 for year, else 8
 // (ObDatum::get_obj_datum_map_type, share/datum/ob_datum.h; get_uint_data_datum_len).
 OBF_HD int datum_len_of(uint8_t t) {

@@ -31,6 +31,7 @@
 #include <vector>
 
 #include "../../include/obgpu_scan.h"
+#include "../../include/obgpu_skip_index.h"
 #include "ob_format.h"
 #include "scan_device.cuh"
 
@@ -101,6 +102,10 @@ struct ScanParams {
   int32_t *row_ids;
   int32_t *status;
   int64_t out_cap;
+  // skip index verdicts (nullptr: no aggregate rows attached): per block 0 uncertain / 1 always true / 2 always false,
+  // and the same per (block, filter node)
+  const uint8_t *blk_const;
+  const uint8_t *leaf_const;
   // ---- shared-memory layout (bytes from the dynamic smem base) -------------------------------------
   // single-block kernels: [block][bitsets][rle tables][descs]
   // scan kernel:          [stage 0..kStages-1][bitsets][scratch 0][scratch 1], scratch = sel|bm|wpre|rle|descs
@@ -861,6 +866,16 @@ __global__ void __launch_bounds__(kThreads) obgpu_count_kernel(const __grid_cons
   const BlockRec rec = p.recs[block];
   const uint32_t rows = rec.rows;
   uint32_t *gbm = p.bitmap_words + rec.bm_word_off;
+  if (p.blk_const != nullptr && rows != 0) {
+    // the skip index decided this block (ObMicroIndexInfo::is_filter_always_false / _true): it is not read
+    const uint8_t verdict = p.blk_const[block];
+    if (verdict != 0) {
+      const uint32_t nw = (rows + 31u) >> 5;
+      for (uint32_t g = (uint32_t)lane; g < nw; g += 32u) gbm[g] = verdict == 1 ? valid_mask_of(rows, g) : 0u;
+      if (lane == 0) p.counts[block] = verdict == 1 ? rows : 0u;
+      return;
+    }
+  }
   bool bad = rows == 0;
   if (lane < p.n_used && p.used_in_filter[lane]) {
     const ColDesc d = p.plans[(int64_t)block * p.max_cols + p.used_col[lane]];
@@ -907,6 +922,8 @@ __global__ void __launch_bounds__(kThreads) obgpu_count_kernel(const __grid_cons
     for (int i = 0; i < n_leaves; ++i) {
       const FilterNodeDev &nd = p.nodes[i];
       const ColDesc &d = descs[nd.used_idx];
+      // a leaf the skip index found constant on this (undecided) block is the neutral element of the AND / OR
+      if (p.leaf_const != nullptr && p.leaf_const[(int64_t)block * p.n_nodes + i] != 0) continue;
       // stage the leaf column's region (ext bits, values / refs, run arrays, dictionary): every lane
       // pulls 16-byte pieces, 4 loads in flight per lane; all later reads hit shared memory
       bool staged = staged_idx == nd.used_idx;
@@ -965,6 +982,10 @@ __global__ void __launch_bounds__(kThreads) obgpu_count_kernel(const __grid_cons
           undecided = undecided || (and_mode ? bm[g] != 0u : bm[g] != valid_mask_of(rows, g));
         if (!__any_sync(0xffffffffu, undecided)) break;
       }
+    }
+    if (!inited) {  // every leaf was constant (cannot happen for an undecided block; kept for safety)
+      for (uint32_t g = (uint32_t)lane; g < nwords; g += 32u) bm[g] = and_mode ? valid_mask_of(rows, g) : 0u;
+      __syncwarp();
     }
     for (uint32_t g = (uint32_t)lane; g < nwords; g += 32u) {
       const uint32_t w = bm[g];
@@ -1546,6 +1567,8 @@ __global__ void __launch_bounds__(kThreads) obgpu_bitmap_row_ids_kernel(const ui
     }                                                                                             \
   } while (0)
 
+#include "skip_index.cuh"
+
 struct obgpu_ctx {
   int device = 0;
   cudaStream_t own_stream = nullptr;
@@ -1588,6 +1611,9 @@ struct obgpu_batch {
   uint32_t *d_rows = nullptr;
   BlockRec *d_recs = nullptr;
   std::vector<uint32_t> col_span;      // per store index: max staged bytes of the value / ref array
+  // skip index: serialized aggregate rows of the blocks (obgpu_batch_set_agg_rows), [d_agg_off[b], d_agg_off[b + 1])
+  uint8_t *d_agg = nullptr;
+  int64_t *d_agg_off = nullptr;
 };
 
 struct ResultCol {
@@ -1614,6 +1640,8 @@ struct obgpu_result {
   int64_t cap = 0;
   bool info_valid = false;
   bool no_filter = false;
+  unsigned long long *d_skip_counters = nullptr;  // [always-false blocks, always-true blocks]
+  int64_t skip_false = 0, skip_true = 0;
   obgpu_result_info info{};
   int32_t has_null[kMaxProj] = {0};
   int32_t status = 0;
@@ -1936,6 +1964,8 @@ void obgpu_batch_close(obgpu_batch *b) {
   cudaSetDevice(b->ctx->device);
   if (b->d_tables) cudaFreeAsync(b->d_tables, b->ctx->stream);
   if (b->d_plans) cudaFreeAsync(b->d_plans, b->ctx->stream);
+  if (b->d_agg) cudaFreeAsync(b->d_agg, b->ctx->stream);
+  if (b->d_agg_off) cudaFreeAsync(b->d_agg_off, b->ctx->stream);
   if (b->own_image && b->d_image) cudaFreeAsync((void *)b->d_image, b->ctx->stream);
   delete b;
 }
@@ -2379,6 +2409,9 @@ int obgpu_scan(obgpu_batch *b, const obgpu_scan_spec *spec, obgpu_result **out) 
   const size_t o_sel = take(((size_t)n + 1) * 8);
   const size_t o_bm = take((size_t)b->bm_word_off[(size_t)n] * 4 + 4);
   const size_t o_rid = spec->want_row_ids ? take((size_t)r->cap * 4) : 0;
+  const bool use_skip = b->d_agg != nullptr && p.n_nodes > 0;
+  const size_t o_blk_const = use_skip ? take((size_t)n) : 0;
+  const size_t o_leaf_const = use_skip ? take((size_t)n * (size_t)p.n_nodes) : 0;
   size_t o_data[kMaxProj], o_lens[kMaxProj];
   for (int c = 0; c < spec->n_proj; ++c) {
     const int t = b->col_types[(size_t)spec->proj_cols[c]];
@@ -2428,9 +2461,17 @@ int obgpu_scan(obgpu_batch *b, const obgpu_scan_spec *spec, obgpu_result **out) 
   r->d_bitmap = p.bitmap_words;
   r->d_row_ids = p.row_ids;
   r->no_filter = p.n_nodes == 0;
-  // ---- launches: count (filter) -> prefix -> project ------------------------------------------------
+  r->d_skip_counters = (unsigned long long *)(a + o_misc + 16);
+  // ---- launches: [skip index ->] count (filter) -> prefix -> project --------------------------------
   const int pslot = (int)(ctx->prof_count % obgpu_ctx::kProfRing);
   if (ctx->profiling) cudaEventRecord(ctx->ev0[pslot], ctx->stream);
+  if (use_skip) {
+    skipidx::skip_index_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(p, b->d_agg, b->d_agg_off, a + o_blk_const,
+                                                                        a + o_leaf_const, r->d_skip_counters);
+    ctx->launches++;
+    p.blk_const = a + o_blk_const;
+    p.leaf_const = a + o_leaf_const;
+  }
   if (p.n_nodes > 0) {
     const uint32_t cw_total = p.cw_bytes * (uint32_t)kWarps;
     if ((int)cw_total > ctx->max_smem_optin) {
@@ -2469,6 +2510,73 @@ int obgpu_scan(obgpu_batch *b, const obgpu_scan_spec *spec, obgpu_result **out) 
   return OBGPU_SUCCESS;
 }
 
+int obgpu_batch_set_agg_rows(obgpu_batch *b, const void *agg_rows, const int64_t *agg_off) {
+  if (!b) return OBGPU_INVALID_ARGUMENT;
+  obgpu_ctx *ctx = b->ctx;
+  cudaSetDevice(ctx->device);
+  if (b->d_agg) { cudaFreeAsync(b->d_agg, ctx->stream); b->d_agg = nullptr; }
+  if (b->d_agg_off) { cudaFreeAsync(b->d_agg_off, ctx->stream); b->d_agg_off = nullptr; }
+  if (!agg_rows && !agg_off) return OBGPU_SUCCESS;   // detach
+  if (!agg_rows || !agg_off) return OBGPU_INVALID_ARGUMENT;
+  const int32_t n = b->n_blocks;
+  if (agg_off[0] < 0) return OBGPU_INVALID_ARGUMENT;
+  for (int32_t i = 0; i < n; ++i)
+    if (agg_off[i + 1] < agg_off[i] || agg_off[i + 1] - agg_off[i] > UINT16_MAX) return OBGPU_INVALID_ARGUMENT;
+  const int64_t lo = agg_off[0], bytes = agg_off[n] - lo;
+  // offsets are rebased to the copied range; the stream-ordered copies read the caller's buffers before returning
+  std::vector<int64_t> off((size_t)n + 1);
+  for (int32_t i = 0; i <= n; ++i) off[(size_t)i] = agg_off[i] - lo;
+  CUDA_TRY(ctx, cudaMallocAsync((void **)&b->d_agg, (size_t)bytes + 16, ctx->stream));
+  CUDA_TRY(ctx, cudaMallocAsync((void **)&b->d_agg_off, ((size_t)n + 1) * 8, ctx->stream));
+  if (bytes > 0)
+    CUDA_TRY(ctx, cudaMemcpyAsync(b->d_agg, (const uint8_t *)agg_rows + lo, (size_t)bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(b->d_agg_off, off.data(), ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return OBGPU_SUCCESS;
+}
+
+int obgpu_batch_skip_index_filter(obgpu_batch *b, const obgpu_filter *filter, uint8_t *block_mask) {
+  if (!b || !filter || !block_mask) return OBGPU_INVALID_ARGUMENT;
+  obgpu_ctx *ctx = b->ctx;
+  cudaSetDevice(ctx->device);
+  const int32_t n = b->n_blocks;
+  if (!b->d_agg) {  // no aggregate data: every block is uncertain (ObMicroIndexInfo::has_agg_data() false)
+    memset(block_mask, OBGPU_BOOL_MASK_UNCERTAIN, (size_t)n);
+    return OBGPU_SUCCESS;
+  }
+  ScanParams p;
+  memset(&p, 0, sizeof(p));
+  const int ret = build_filter(ctx, b, filter, p);
+  if (ret != OBGPU_SUCCESS) return ret;
+  if (p.n_nodes == 0) return OBGPU_INVALID_ARGUMENT;
+  p.n_blocks = n;
+  p.plans = b->d_plans;
+  p.rows = b->d_rows;
+  p.max_cols = (int32_t)b->max_cols;
+  uint8_t *verdicts = nullptr;   // [n block verdicts][n x n_nodes node verdicts]
+  CUDA_TRY(ctx, cudaMallocAsync((void **)&verdicts, (size_t)n * (size_t)(1 + p.n_nodes) + 16, ctx->stream));
+  skipidx::skip_index_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(p, b->d_agg, b->d_agg_off, verdicts, verdicts + n, nullptr);
+  ctx->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(block_mask, verdicts, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFreeAsync(verdicts, ctx->stream);
+  if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return OBGPU_ERR_SYS; }
+  return OBGPU_SUCCESS;
+}
+
+int obgpu_result_skip_info(obgpu_result *r, int64_t *always_false_blocks, int64_t *always_true_blocks) {
+  if (!r) return OBGPU_INVALID_ARGUMENT;
+  if (!r->info_valid) {
+    obgpu_result_info info;
+    const int ret = obgpu_result_info_get(r, &info);
+    if (ret != OBGPU_SUCCESS && ret != OBGPU_BUF_NOT_ENOUGH) return ret;
+  }
+  if (always_false_blocks) *always_false_blocks = r->skip_false;
+  if (always_true_blocks) *always_true_blocks = r->skip_true;
+  return OBGPU_SUCCESS;
+}
+
 void obgpu_result_free(obgpu_result *r) {
   if (!r) return;
   cudaSetDevice(r->ctx->device);
@@ -2487,7 +2595,11 @@ int obgpu_result_info_get(obgpu_result *r, obgpu_result_info *info) {
     CUDA_TRY(ctx, cudaMemcpyAsync(hp, r->d_sel_offset + r->batch->n_blocks, 8, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(hs, r->d_status, 4, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(hn, r->d_has_null, kMaxProj * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    unsigned long long *hk = (unsigned long long *)((uint8_t *)ctx->h_pinned + 1024);
+    CUDA_TRY(ctx, cudaMemcpyAsync(hk, r->d_skip_counters, 16, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    r->skip_false = (int64_t)hk[0];
+    r->skip_true = (int64_t)hk[1];
     r->info.total_rows = r->batch->total_rows;
     r->info.selected_rows = *hp;
     r->info.n_blocks = r->batch->n_blocks;

@@ -25,6 +25,7 @@
 #include <vector>
 
 #include "../../include/obgpu_scan.h"
+#include "../../include/obgpu_skip_index.h"
 #include "ob_format.h"
 
 namespace {
@@ -1133,6 +1134,172 @@ int encode_one(const obgpu_col_input *cols, int32_t ncol, int32_t rowkey_cnt, in
   return bb.build(block);
 }
 
+
+// ---- skip index: aggregate row (ObAggRowWriter, index_block/ob_agg_row_struct.cpp:49-300) ------------------
+// [ObAggRowHeader 8 B][col idx x cnt][cell offset x cnt] then one cell per aggregated column:
+// [type bitmap 1 B][prefix bitmap 1 B (version >= 2)][data offsets x (stored + 1)][data ...], offsets relative to
+// the cell start, the last one being the cell end; a column without a stored aggregate has the bitmaps only.
+struct AggCellIn {
+  uint32_t col_idx;
+  uint8_t col_type, is_null, is_prefix;
+  std::string data;
+};
+
+void put_le(uint8_t *p, uint64_t v, int bytes) { memcpy(p, &v, (size_t)bytes); }
+
+int write_agg_row(std::vector<AggCellIn> cells, int version, std::vector<uint8_t> &out) {
+  if (cells.empty() || version < 1 || version > 3) return OBGPU_INVALID_ARGUMENT;
+  for (const AggCellIn &c : cells)
+    if (c.col_type >= OBGPU_SK_IDX_MAX_COL_TYPE || c.col_idx >= (1u << 24)) return OBGPU_INVALID_ARGUMENT;
+  std::stable_sort(cells.begin(), cells.end(), [](const AggCellIn &a, const AggCellIn &b) {
+    return a.col_idx != b.col_idx ? a.col_idx < b.col_idx : a.col_type < b.col_type;
+  });
+  const bool store_prefix = version >= 2;
+  const int bitmaps = store_prefix ? 2 : 1;
+  int idx_size = 0;
+  for (uint32_t m = cells.back().col_idx;;) { ++idx_size; m >>= 8; if (m == 0) break; }
+  int cell_off_size = 1, idx_off_size = 1;
+  int64_t col_cnt = 0, data_size = 0, stored_total = 0;
+  const size_t n = cells.size();
+  for (size_t i = 0; i < n;) {
+    size_t e = i;
+    int64_t cell_size = 0, nop = 0;
+    while (e < n && cells[e].col_idx == cells[i].col_idx) {
+      if (cells[e].is_null) ++nop; else cell_size += (int64_t)cells[e].data.size();
+      ++e;
+    }
+    cell_size += bitmaps;
+    int64_t stored = (int64_t)(e - i) - nop;
+    if (stored > 0) ++stored;  // one more offset for the cell end
+    if (cell_off_size == 1 && cell_size + stored > UINT8_MAX) cell_off_size = 2;
+    ++col_cnt;
+    data_size += cell_size;
+    stored_total += stored;
+    i = e;
+  }
+  data_size += stored_total * cell_off_size;
+  int64_t header_size = (int64_t)sizeof(AggRowHeader) + col_cnt * idx_size + col_cnt * idx_off_size;
+  if (data_size + header_size > UINT8_MAX) {
+    idx_off_size = 2;
+    header_size = (int64_t)sizeof(AggRowHeader) + col_cnt * idx_size + col_cnt * idx_off_size;
+    if (data_size + header_size > UINT16_MAX) return OBGPU_NOT_SUPPORTED;
+  }
+  AggRowHeader h{};
+  h.version_ = (int16_t)version;
+  h.length_ = (int16_t)(data_size + header_size);
+  h.agg_col_cnt_ = (int16_t)col_cnt;
+  h.pack_ = (uint16_t)(idx_size | (idx_off_size << 6) | (cell_off_size << 9) | (1 << 12));
+  out.assign((size_t)(data_size + header_size), 0);
+  uint8_t *buf = out.data();
+  memcpy(buf, &h, sizeof(h));
+  uint8_t *idx_arr = buf + sizeof(h), *idx_off_arr = idx_arr + col_cnt * idx_size;
+  int64_t pos = header_size, k = 0;
+  for (size_t i = 0; i < n; ++k) {
+    size_t e = i;
+    int64_t nop = 0;
+    while (e < n && cells[e].col_idx == cells[i].col_idx) { nop += cells[e].is_null ? 1 : 0; ++e; }
+    put_le(idx_arr + k * idx_size, cells[i].col_idx, idx_size);
+    put_le(idx_off_arr + k * idx_off_size, (uint64_t)pos, idx_off_size);
+    const int64_t cell = pos;
+    uint8_t *bm = buf + pos;
+    pos += bitmaps;
+    int64_t stored = (int64_t)(e - i) - nop;
+    if (stored > 0) ++stored;
+    uint8_t *offs = buf + pos;
+    pos += stored * cell_off_size;
+    int64_t w = 0;
+    for (size_t j = i; j < e; ++j) {
+      const AggCellIn &c = cells[j];
+      if (c.is_null) continue;
+      bm[0] |= (uint8_t)(1u << c.col_type);
+      if (store_prefix && c.is_prefix && (c.col_type == OBGPU_SK_IDX_MIN || c.col_type == OBGPU_SK_IDX_MAX))
+        bm[1] |= (uint8_t)(1u << c.col_type);
+      put_le(offs + w * cell_off_size, (uint64_t)(pos - cell), cell_off_size);
+      memcpy(buf + pos, c.data.data(), c.data.size());
+      pos += (int64_t)c.data.size();
+      ++w;
+    }
+    if (stored > 0) put_le(offs + (stored - 1) * cell_off_size, (uint64_t)(pos - cell), cell_off_size);
+    i = e;
+  }
+  return pos == (int64_t)out.size() ? OBGPU_SUCCESS : OBGPU_ERR_UNEXPECTED;
+}
+
+// MIN / MAX / NULL_COUNT of one column over a row range (ObColMinAggregator / ObColMaxAggregator /
+// ObColNullCountAggregator, ob_index_block_aggregator.cpp): a NOP cell makes the column "not aggregated";
+// integer classes compare on the datum image, strings bytewise (binary collation), a string longer than 40 bytes
+// is kept as a 40-byte prefix with the prefix flag.
+void aggregate_column(const obgpu_col_input &in, uint32_t col_idx, int64_t row_begin, int64_t nrows,
+                      std::vector<AggCellIn> &cells) {
+  const int sc = store_class_of((uint8_t)in.obj_type);
+  int64_t null_cnt = 0;
+  bool any = false, nop = false;
+  AggCellIn mn{col_idx, OBGPU_SK_IDX_MIN, 1, 0, {}}, mx{col_idx, OBGPU_SK_IDX_MAX, 1, 0, {}};
+  AggCellIn nc{col_idx, OBGPU_SK_IDX_NULL_COUNT, 1, 0, {}};
+  if (sc == 5) {
+    StrRef lo{nullptr, 0}, hi{nullptr, 0};
+    for (int64_t r = row_begin; r < row_begin + nrows; ++r) {
+      if (in.is_null && in.is_null[r]) { nop = nop || in.is_null[r] == 2; ++null_cnt; continue; }
+      const StrRef v{in.str_heap + in.str_off[r], in.str_off[r + 1] - in.str_off[r]};
+      if (!any || str_cmp(v, lo) < 0) lo = v;
+      if (!any || str_cmp(v, hi) > 0) hi = v;
+      any = true;
+    }
+    if (any) {
+      const int64_t cap = OBGPU_SKIP_INDEX_MAX_COL_LENGTH;
+      mn.is_null = mx.is_null = 0;
+      mn.is_prefix = lo.len > cap;
+      mx.is_prefix = hi.len > cap;
+      mn.data.assign(lo.p, (size_t)std::min(lo.len, cap));
+      mx.data.assign(hi.p, (size_t)std::min(hi.len, cap));
+    }
+  } else {
+    const int dl = datum_len_of((uint8_t)in.obj_type);
+    auto image = [&](int64_t v) -> int64_t {  // compare image of the datum: low dl bytes, sign-extended for signed classes
+      if (dl == 4) return sc == 1 ? (int64_t)(int32_t)(uint32_t)v : (int64_t)(uint32_t)v;
+      if (dl == 1) return (int64_t)(uint8_t)v;
+      return v;
+    };
+    auto less = [&](int64_t a, int64_t b) { return (sc == 1 || dl < 8) ? a < b : (uint64_t)a < (uint64_t)b; };
+    int64_t lo = 0, hi = 0;
+    for (int64_t r = row_begin; r < row_begin + nrows; ++r) {
+      if (in.is_null && in.is_null[r]) { nop = nop || in.is_null[r] == 2; ++null_cnt; continue; }
+      const int64_t v = image(in.i64[r]);
+      if (!any || less(v, lo)) lo = v;
+      if (!any || less(hi, v)) hi = v;
+      any = true;
+    }
+    if (any) {
+      mn.is_null = mx.is_null = 0;
+      mn.data.assign((const char *)&lo, (size_t)dl);
+      mx.data.assign((const char *)&hi, (size_t)dl);
+    }
+  }
+  if (!nop) {
+    nc.is_null = 0;
+    nc.data.assign((const char *)&null_cnt, 8);
+  } else {
+    mn.is_null = mx.is_null = 1;
+  }
+  cells.push_back(mn);
+  cells.push_back(mx);
+  cells.push_back(nc);
+}
+
+int block_agg_row(const obgpu_col_input *cols, int32_t n_cols, const int32_t *agg_cols, int32_t n_agg_cols,
+                  int64_t row_begin, int64_t nrows, std::vector<uint8_t> &out) {
+  std::vector<AggCellIn> cells;
+  for (int32_t k = 0; k < n_agg_cols; ++k) {
+    const int32_t c = agg_cols[k];
+    if (c < 0 || c >= n_cols) return OBGPU_INVALID_ARGUMENT;
+    const int sc = store_class_of((uint8_t)cols[c].obj_type);
+    if (sc == 5 ? (!cols[c].str_off || !cols[c].str_heap) : !cols[c].i64) return OBGPU_INVALID_ARGUMENT;
+    if (sc != 1 && sc != 2 && sc != 5) return OBGPU_NOT_SUPPORTED;
+    aggregate_column(cols[c], (uint32_t)c, row_begin, nrows, cells);
+  }
+  return write_agg_row(std::move(cells), 3, out);
+}
+
 }  // namespace
 
 extern "C" {
@@ -1256,5 +1423,79 @@ int obgpu_table_image_export(const obgpu_table_image *img, void *image, int64_t 
 }
 
 void obgpu_table_image_free(obgpu_table_image *img) { delete img; }
+
+int obgpu_agg_row_write(const obgpu_agg_cell *cells, int32_t n_cells, int32_t version, void *out, int64_t out_cap,
+                        int64_t *out_size) {
+  if (!cells || n_cells <= 0 || !out_size) return OBGPU_INVALID_ARGUMENT;
+  std::vector<AggCellIn> in;
+  for (int32_t i = 0; i < n_cells; ++i) {
+    AggCellIn c{cells[i].col_idx, cells[i].col_type, cells[i].is_null, cells[i].is_prefix, {}};
+    if (!c.is_null) {
+      if (cells[i].len < 0 || (cells[i].len > 0 && !cells[i].data)) return OBGPU_INVALID_ARGUMENT;
+      c.data.assign((const char *)cells[i].data, (size_t)cells[i].len);
+    }
+    in.push_back(std::move(c));
+  }
+  std::vector<uint8_t> row;
+  const int ret = write_agg_row(std::move(in), version, row);
+  if (ret != OBGPU_SUCCESS) return ret;
+  *out_size = (int64_t)row.size();
+  if (!out) return OBGPU_SUCCESS;
+  if ((int64_t)row.size() > out_cap) return OBGPU_BUF_NOT_ENOUGH;
+  memcpy(out, row.data(), row.size());
+  return OBGPU_SUCCESS;
+}
+
+int obgpu_writer_block_agg_row(const obgpu_col_input *cols, int32_t n_cols, const int32_t *agg_cols, int32_t n_agg_cols,
+                               int64_t row_begin, int64_t nrows, void *out, int64_t out_cap, int64_t *out_size) {
+  if (!cols || !agg_cols || n_agg_cols <= 0 || nrows <= 0 || row_begin < 0 || !out_size) return OBGPU_INVALID_ARGUMENT;
+  std::vector<uint8_t> row;
+  const int ret = block_agg_row(cols, n_cols, agg_cols, n_agg_cols, row_begin, nrows, row);
+  if (ret != OBGPU_SUCCESS) return ret;
+  *out_size = (int64_t)row.size();
+  if (!out) return OBGPU_SUCCESS;
+  if ((int64_t)row.size() > out_cap) return OBGPU_BUF_NOT_ENOUGH;
+  memcpy(out, row.data(), row.size());
+  return OBGPU_SUCCESS;
+}
+
+int obgpu_writer_table_agg_rows(const obgpu_col_input *cols, int32_t n_cols, const int32_t *agg_cols, int32_t n_agg_cols,
+                                int64_t total_rows, int64_t rows_per_block, void *out, int64_t out_cap, int64_t *offsets,
+                                int64_t *out_size) {
+  if (!cols || !agg_cols || n_agg_cols <= 0 || total_rows <= 0 || rows_per_block <= 0 || !out_size) return OBGPU_INVALID_ARGUMENT;
+  const int64_t nb = (total_rows + rows_per_block - 1) / rows_per_block;
+  std::vector<std::vector<uint8_t>> rows((size_t)nb);
+  int nt = std::max(1, std::min<int>((int)std::thread::hardware_concurrency(), (int)std::min<int64_t>(nb, 64)));
+  std::atomic<int64_t> next{0};
+  std::atomic<int> err{OBGPU_SUCCESS};
+  auto work = [&]() {
+    for (;;) {
+      const int64_t b = next.fetch_add(1);
+      if (b >= nb || err.load() != OBGPU_SUCCESS) break;
+      const int64_t rb = b * rows_per_block;
+      const int r = block_agg_row(cols, n_cols, agg_cols, n_agg_cols, rb, std::min(rows_per_block, total_rows - rb), rows[(size_t)b]);
+      if (r != OBGPU_SUCCESS) err.store(r);
+    }
+  };
+  std::vector<std::thread> th;
+  for (int t = 1; t < nt; ++t) th.emplace_back(work);
+  work();
+  for (auto &t : th) t.join();
+  if (err.load() != OBGPU_SUCCESS) return err.load();
+  int64_t total = 0;
+  for (const auto &r : rows) total += (int64_t)r.size();
+  *out_size = total;
+  if (!out) return OBGPU_SUCCESS;
+  if (total > out_cap || !offsets) return OBGPU_BUF_NOT_ENOUGH;
+  int64_t pos = 0;
+  for (int64_t b = 0; b < nb; ++b) {
+    offsets[b] = pos;
+    memcpy((uint8_t *)out + pos, rows[(size_t)b].data(), rows[(size_t)b].size());
+    pos += (int64_t)rows[(size_t)b].size();
+  }
+  offsets[nb] = pos;
+  return OBGPU_SUCCESS;
+}
+
 
 }  // extern "C"

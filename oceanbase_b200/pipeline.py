@@ -30,11 +30,28 @@ class BatchOutput:
     has_null: List[int]
 
 
-def split_table(table: TableImage, blocks_per_batch: int) -> List[TableImage]:
+def batch_bounds(n_blocks: int, blocks_per_batch: int, ramp: int = 0) -> List[int]:
+    """Block index where every page batch starts (+ n_blocks at the end). ramp > 0: the first `ramp`
+    batches are 1/2^ramp, ..., 1/2 of a full batch, so that the first results start flowing back (D2H)
+    while most of the input is still on its way in."""
+    bounds, b0 = [0], 0
+    for k in range(ramp, 0, -1):
+        step = max(1, blocks_per_batch >> k)
+        if b0 + step >= n_blocks:
+            break
+        b0 += step
+        bounds.append(b0)
+    while b0 < n_blocks:
+        b0 = min(n_blocks, b0 + blocks_per_batch)
+        bounds.append(b0)
+    return bounds
+
+
+def split_table(table: TableImage, blocks_per_batch: int, ramp: int = 0) -> List[TableImage]:
     parts = []
     n = table.n_blocks
-    for b0 in range(0, n, blocks_per_batch):
-        b1 = min(n, b0 + blocks_per_batch)
+    bounds = batch_bounds(n, blocks_per_batch, ramp)
+    for b0, b1 in zip(bounds[:-1], bounds[1:]):
         lo = int(table.offsets[b0])
         hi = int(table.offsets[b1]) if b1 < n else int(table.image.size)
         parts.append(TableImage(table.image[lo:hi], table.offsets[b0:b1] - lo, table.sizes[b0:b1], 0, table.n_cols))
@@ -55,8 +72,9 @@ class HostScanPipeline:
 
     def scan(self, table: TableImage, filter, proj: Sequence[int], blocks_per_batch: int, selectivity_hint: float,
              out_buffers: Optional[List[List[np.ndarray]]] = None, string_base: int = 0,
-             null_buffers: Optional[List[List[np.ndarray]]] = None) -> List[BatchOutput]:
-        parts = split_table(table, blocks_per_batch)
+             null_buffers: Optional[List[List[np.ndarray]]] = None, ramp: int = 0) -> List[BatchOutput]:
+        parts = split_table(table, blocks_per_batch, ramp)
+        bounds = batch_bounds(table.n_blocks, blocks_per_batch, ramp)
         outs: List[Optional[BatchOutput]] = [None] * len(parts)
         errors = []
         lock = threading.Lock()
@@ -102,7 +120,7 @@ class HostScanPipeline:
                             lens.append(l)
                             nulls.append(nl)
                             hn.append(res.col(c).has_null)
-                    outs[i] = BatchOutput(i * blocks_per_batch, i * blocks_per_batch + part.n_blocks, batch.total_rows,
+                    outs[i] = BatchOutput(bounds[i], bounds[i + 1], batch.total_rows,
                                           n, cols, lens, nulls, hn)
                     res.free()
                     batch.close()

@@ -182,6 +182,27 @@ class PageBatch:
         check(lib.obgpu_scan(self._h, C.byref(spec), C.byref(h)), "obgpu_scan", self.ctx._h)
         return ScanResult(self, h, len(proj_cols))
 
+    # ---- skip index (include/obgpu_skip_index.h) ---------------------------------------------------
+    def set_agg_rows(self, agg_rows: Optional[np.ndarray], agg_off: Optional[np.ndarray] = None):
+        """Attach the blocks' serialized aggregate rows (block b: agg_rows[agg_off[b]:agg_off[b + 1]]); None detaches.
+        Scans of this batch then prune with them."""
+        if agg_rows is None:
+            check(lib.obgpu_batch_set_agg_rows(self._h, None, None), "obgpu_batch_set_agg_rows", self.ctx._h)
+            return
+        rows = np.ascontiguousarray(agg_rows, dtype=np.uint8)
+        off = np.ascontiguousarray(agg_off, dtype=np.int64)
+        assert len(off) == self.n_blocks + 1
+        check(lib.obgpu_batch_set_agg_rows(self._h, rows.ctypes.data, off.ctypes.data), "obgpu_batch_set_agg_rows",
+              self.ctx._h)
+
+    def skip_index_filter(self, expr: FilterExpr) -> np.ndarray:
+        """ObSSTableIndexFilter::check_range per block: uint8 verdicts (capi.BOOL_MASK_*)."""
+        f, keep = flatten_filter(expr)
+        out = np.zeros(max(self.n_blocks, 1), dtype=np.uint8)
+        check(lib.obgpu_batch_skip_index_filter(self._h, C.byref(f), out.ctypes.data), "obgpu_batch_skip_index_filter",
+              self.ctx._h)
+        return out[:self.n_blocks]
+
     # ---- reference-granularity calls -------------------------------------------------------------
     def filter_white(self, block, col, op, params=(), start=0, count=None) -> np.ndarray:
         f, keep = flatten_filter(White(col, op, params))
@@ -296,6 +317,12 @@ class ScanResult:
         check(lib.obgpu_result_fetch_cols(self._h, n, ci, row_begin, row_count, hd, None, hn), "obgpu_result_fetch_cols",
               self.batch.ctx._h)
         return [d[:row_count] for d in datas], [x[:(row_count + 63) // 64] for x in nulls]
+
+    def skip_info(self):
+        """(always-false blocks, always-true blocks) the skip index decided in this scan."""
+        f, t = C.c_int64(0), C.c_int64(0)
+        check(lib.obgpu_result_skip_info(self._h, C.byref(f), C.byref(t)), "obgpu_result_skip_info", self.batch.ctx._h)
+        return f.value, t.value
 
     def aggregate(self, kind: int, col_a: int, col_b: int = -1):
         """Pushed-down aggregate over the selected rows (obgpu_result_aggregate). SUM / SUM_PRODUCT return a

@@ -127,3 +127,55 @@ def encode_table(cols: List[Column], rows_per_block: int, rowkey_cnt=0, align=12
     finally:
         lib.obgpu_table_image_free(h)
     return TableImage(image, offsets, sizes, total, len(cols))
+
+
+# ---- skip index: aggregate rows (include/obgpu_skip_index.h) -------------------------------------------------
+def agg_row_write(cells, version: int = 3) -> np.ndarray:
+    """ObAggRowWriter: cells = [(col_idx, col_type, value)] with value None (not stored), bytes, or
+    (bytes, is_prefix)."""
+    arr = (capi.AggCell * len(cells))()
+    keep = []
+    for i, (col_idx, col_type, value) in enumerate(cells):
+        arr[i].col_idx, arr[i].col_type = col_idx, col_type
+        if value is None:
+            arr[i].is_null = 1
+            continue
+        data, prefix = value if isinstance(value, tuple) else (value, False)
+        buf = C.create_string_buffer(bytes(data), max(len(data), 1))
+        keep.append(buf)
+        arr[i].data, arr[i].len, arr[i].is_prefix = C.addressof(buf), len(data), 1 if prefix else 0
+    size = C.c_int64(0)
+    check(lib.obgpu_agg_row_write(arr, len(cells), version, None, 0, C.byref(size)), "obgpu_agg_row_write(size)")
+    out = np.zeros(size.value, dtype=np.uint8)
+    check(lib.obgpu_agg_row_write(arr, len(cells), version, out.ctypes.data, out.size, C.byref(size)), "obgpu_agg_row_write")
+    return out
+
+
+def block_agg_row(cols: List[Column], agg_cols: Sequence[int], row_begin=0, nrows=None) -> np.ndarray:
+    """MIN / MAX / NULL_COUNT of the listed columns over a row range, serialized (ObSkipIndexAggregator + ObAggRowWriter)."""
+    n = cols[0].nrows() - row_begin if nrows is None else nrows
+    arr = _inputs(cols)
+    ac = np.ascontiguousarray(agg_cols, dtype=np.int32)
+    size = C.c_int64(0)
+    check(lib.obgpu_writer_block_agg_row(arr, len(cols), ac.ctypes.data, len(ac), row_begin, n, None, 0, C.byref(size)),
+          "obgpu_writer_block_agg_row(size)")
+    out = np.zeros(size.value, dtype=np.uint8)
+    check(lib.obgpu_writer_block_agg_row(arr, len(cols), ac.ctypes.data, len(ac), row_begin, n, out.ctypes.data, out.size,
+                                         C.byref(size)), "obgpu_writer_block_agg_row")
+    return out
+
+
+def table_agg_rows(cols: List[Column], agg_cols: Sequence[int], rows_per_block: int):
+    """One aggregate row per block of encode_table's blocking: (bytes, offsets[n_blocks + 1])."""
+    total = cols[0].nrows()
+    arr = _inputs(cols)
+    ac = np.ascontiguousarray(agg_cols, dtype=np.int32)
+    nb = (total + rows_per_block - 1) // rows_per_block
+    size = C.c_int64(0)
+    check(lib.obgpu_writer_table_agg_rows(arr, len(cols), ac.ctypes.data, len(ac), total, rows_per_block, None, 0, None,
+                                          C.byref(size)), "obgpu_writer_table_agg_rows(size)")
+    out = np.zeros(max(size.value, 1), dtype=np.uint8)
+    offs = np.zeros(nb + 1, dtype=np.int64)
+    check(lib.obgpu_writer_table_agg_rows(arr, len(cols), ac.ctypes.data, len(ac), total, rows_per_block, out.ctypes.data,
+                                          out.size, offs.ctypes.data, C.byref(size)), "obgpu_writer_table_agg_rows")
+    return out[:size.value], offs

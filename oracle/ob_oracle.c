@@ -1449,3 +1449,274 @@ int ora_major_merge(const ora_merge_run *runs, int32_t n_runs, int32_t n_cols, c
   if (stats) { stats[0] = dropped; stats[1] = fused; }
   return ORA_SUCCESS;
 }
+
+/* =============================================================================================
+ * Skip index: aggregate row reader + min / max / null-count filter verdicts.
+ * ============================================================================================= */
+static uint64_t rd_le(const uint8_t *p, int bytes) {
+  uint64_t v = 0;
+  memcpy(&v, p, (size_t)bytes);
+  return v;
+}
+
+/* ObAggRowReader::init / binary_search_col / find_col / read_cell (ob_agg_row_struct.cpp:303-482) */
+int ora_agg_row_read(const void *buf_, int64_t size, uint32_t col_idx, int32_t col_type, const uint8_t **data,
+                     int32_t *len, int32_t *is_prefix) {
+  const uint8_t *buf = (const uint8_t *)buf_;
+  if (!buf || size < 8 || !data || !len || !is_prefix || col_type < 0 || col_type >= 6) return ORA_INVALID_ARGUMENT;
+  *data = 0;
+  *len = 0;
+  *is_prefix = 0;
+  const int16_t version = (int16_t)rd_le(buf, 2), cnt = (int16_t)rd_le(buf + 4, 2);
+  const uint16_t pack = (uint16_t)rd_le(buf + 6, 2);
+  const int idx_size = pack & 0x3f, idx_off_size = (pack >> 6) & 7, cell_off_size = (pack >> 9) & 7, bitmap_size = (pack >> 12) & 0xf;
+  if (version < 1 || version > 3 || cnt <= 0 || idx_size <= 0 || idx_off_size <= 0 || bitmap_size != 1) return ORA_INVALID_DATA;
+  if (idx_size > 4 || (idx_off_size != 1 && idx_off_size != 2) || (cell_off_size != 1 && cell_off_size != 2)) return ORA_INVALID_DATA;
+  const int64_t header_size = 8 + (int64_t)cnt * idx_size + (int64_t)cnt * idx_off_size;
+  if (size < header_size) return ORA_INVALID_DATA;
+  const uint8_t *idx_arr = buf + 8, *off_arr = idx_arr + (int64_t)cnt * idx_size;
+  int lo = 0, hi = cnt;                    /* lower_bound over the sorted column indexes */
+  while (lo < hi) {
+    const int mid = (lo + hi) / 2;
+    if (rd_le(idx_arr + (int64_t)mid * idx_size, idx_size) < col_idx) lo = mid + 1; else hi = mid;
+  }
+  if (lo >= cnt || rd_le(idx_arr + (int64_t)lo * idx_size, idx_size) != col_idx) return ORA_SUCCESS; /* not aggregated */
+  const int64_t pos = (int64_t)rd_le(off_arr + (int64_t)lo * idx_off_size, idx_off_size);
+  if (pos == 0) return ORA_SUCCESS;
+  const int bitmaps = version >= 2 ? 2 : 1;
+  if (pos + bitmaps > size) return ORA_INVALID_DATA;
+  const uint8_t *cell = buf + pos;
+  const uint32_t types = cell[0], mask = 1u << col_type;
+  if (!(types & mask)) return ORA_SUCCESS;
+  if (pos + bitmaps + cell_off_size > size) return ORA_INVALID_DATA;
+  int pre = 0;
+  for (uint32_t n = types & (mask - 1); n; n &= n - 1) ++pre;
+  const uint8_t *offs = cell + bitmaps;
+  if (pos + bitmaps + (int64_t)(pre + 2) * cell_off_size > size) return ORA_INVALID_DATA;
+  const int64_t a = (int64_t)rd_le(offs + (int64_t)pre * cell_off_size, cell_off_size);
+  const int64_t b = (int64_t)rd_le(offs + (int64_t)(pre + 1) * cell_off_size, cell_off_size);
+  if (b < a || pos + b > size) return ORA_INVALID_DATA;
+  *data = cell + a;
+  *len = (int32_t)(b - a);
+  if (version >= 2) *is_prefix = (cell[1] & mask) != 0;
+  return ORA_SUCCESS;
+}
+
+/* ObSkipIndexCmpRes */
+typedef struct sk_cmp { int cmp, certain; } sk_cmp;
+static int sk_gt(sk_cmp r) { return r.certain && r.cmp > 0; }
+static int sk_lt(sk_cmp r) { return r.certain && r.cmp < 0; }
+static int sk_le(sk_cmp r) { return r.certain && r.cmp <= 0; }
+static int sk_ge(sk_cmp r) { return r.certain && r.cmp >= 0; }
+static int sk_eq(sk_cmp r) { return r.certain && r.cmp == 0; }
+
+/* ObSkipIndexFilterExecutor::compare (:498-528) with compare_for_non_pad_charset (:476-496) and
+ * compare_with_prefix (:415-452) for a binary collation (one character = one byte). skip == NULL: the
+ * aggregate is missing, i.e. -infinity for a min and +infinity for a max. */
+static sk_cmp sk_compare(const ora_datum *skip, int compare_min, int is_prefix, uint8_t obj_type, int sc, const ora_param *f) {
+  sk_cmp r = {0, 0};
+  if (!skip) { r.certain = 1; r.cmp = compare_min ? -1 : 1; return r; }
+  r.cmp = cmp_datum_param(skip, obj_type, sc, f);
+  if (!is_prefix) { r.certain = 1; return r; }
+  if (r.cmp >= 0) { r.cmp = 1; r.certain = 1; return r; }
+  if (skip->len >= f->len) { r.certain = 1; return r; }
+  ora_param fp = *f;                       /* the constant cut to the prefix's length */
+  fp.len = skip->len;
+  const int c2 = cmp_datum_param(skip, obj_type, sc, &fp);
+  r.certain = c2 == r.cmp;                 /* c2 == 0: the prefix is a prefix of the constant -> uncertain */
+  return r;
+}
+
+static int sk_param_less(const ora_param *a, const ora_param *b, uint8_t obj_type, int sc) {
+  ora_datum d;
+  memset(&d, 0, sizeof(d));
+  d.ptr = (const uint8_t *)a->ptr;
+  d.len = sc == 5 ? a->len : 8;
+  d.ival = (uint64_t)a->i64;
+  return cmp_datum_param(&d, obj_type, sc, b) < 0;
+}
+
+int ora_skip_index_leaf(const void *agg, int64_t agg_size, int64_t row_count, int32_t col, uint8_t obj_type, int32_t op,
+                        const ora_param *params, int32_t n_params, int32_t *mask) {
+  if (!mask || op < 0 || op >= ORA_OP_MAX || col < 0) return ORA_INVALID_ARGUMENT;
+  *mask = ORA_MASK_UNCERTAIN;
+  const int sc = obj_store_class(obj_type);
+  if (sc != 1 && sc != 2 && sc != 5) return ORA_NOT_SUPPORTED;
+  /* is_cmp_op_with_null_ref_value (:163-164): a NULL constant (or an IN list left empty) never matches */
+  if (op != ORA_OP_NU && op != ORA_OP_NN) {
+    int null_ref = params_contain_null(op, params, n_params);
+    if (op == ORA_OP_IN) {
+      null_ref = 1;
+      for (int32_t i = 0; i < n_params; ++i) if (!params[i].is_null) null_ref = 0;
+    }
+    if (null_ref) { *mask = ORA_MASK_ALWAYS_FALSE; return ORA_SUCCESS; }
+  }
+  if (!agg || agg_size <= 0) return ORA_SUCCESS;    /* !has_agg_data(): nothing to decide with */
+  const uint8_t *p_nc = 0, *p_min = 0, *p_max = 0;
+  int32_t l_nc = 0, l_min = 0, l_max = 0, pre_nc = 0, min_prefix = 0, max_prefix = 0;
+  int ret = ora_agg_row_read(agg, agg_size, (uint32_t)col, 2, &p_nc, &l_nc, &pre_nc);
+  if (!ret) ret = ora_agg_row_read(agg, agg_size, (uint32_t)col, 0, &p_min, &l_min, &min_prefix);
+  if (!ret) ret = ora_agg_row_read(agg, agg_size, (uint32_t)col, 1, &p_max, &l_max, &max_prefix);
+  if (ret) return ret;
+  if (!p_nc && !p_min && !p_max) return ORA_SUCCESS;  /* ObMinMaxFilterParam::is_uncertain */
+  int64_t null_count = 0;
+  if (p_nc) {
+    if (l_nc != 8) return ORA_INVALID_DATA;
+    memcpy(&null_count, p_nc, 8);
+    if (null_count < 0 || null_count > row_count) return ORA_ERR_UNEXPECTED;
+  }
+  const int all_null = p_nc && null_count == row_count;
+  const int all_not_null = p_nc && null_count == 0;
+  const int has_null = p_nc ? (null_count > 0 && null_count < row_count) : 1;
+  const int min_max_null = !p_min && !p_max;
+  ora_datum dmin, dmax;
+  memset(&dmin, 0, sizeof(dmin));
+  memset(&dmax, 0, sizeof(dmax));
+  if (p_min) { dmin.ptr = p_min; dmin.len = (uint32_t)l_min; if (sc != 5) { if (l_min > 8) return ORA_INVALID_DATA; memcpy(&dmin.ival, p_min, (size_t)l_min); } }
+  if (p_max) { dmax.ptr = p_max; dmax.len = (uint32_t)l_max; if (sc != 5) { if (l_max > 8) return ORA_INVALID_DATA; memcpy(&dmax.ival, p_max, (size_t)l_max); } }
+  const ora_datum *mn = p_min ? &dmin : 0, *mx = p_max ? &dmax : 0;
+  int m = ORA_MASK_UNCERTAIN;
+#define CMP_MIN(f) sk_compare(mn, 1, min_prefix, obj_type, sc, (f))
+#define CMP_MAX(f) sk_compare(mx, 0, max_prefix, obj_type, sc, (f))
+  if (op == ORA_OP_NU) {
+    m = all_not_null ? ORA_MASK_ALWAYS_FALSE : (all_null ? ORA_MASK_ALWAYS_TRUE : ORA_MASK_UNCERTAIN);
+  } else if (op == ORA_OP_NN) {
+    m = all_null ? ORA_MASK_ALWAYS_FALSE : (all_not_null ? ORA_MASK_ALWAYS_TRUE : ORA_MASK_UNCERTAIN);
+  } else if (all_null) {
+    m = ORA_MASK_ALWAYS_FALSE;
+  } else if (min_max_null) {
+    m = ORA_MASK_UNCERTAIN;                /* the reference leaves the (reset) mask untouched here (:296-297) */
+  } else {
+    const ora_param *ref = &params[0];
+    sk_cmp a, b;
+    switch (op) {
+      case ORA_OP_EQ:
+        a = CMP_MIN(ref);
+        if (sk_gt(a)) { m = ORA_MASK_ALWAYS_FALSE; break; }
+        b = CMP_MAX(ref);
+        if (sk_lt(b)) m = ORA_MASK_ALWAYS_FALSE;
+        else if (sk_eq(a) && sk_eq(b)) m = ORA_MASK_ALWAYS_TRUE;
+        break;
+      case ORA_OP_NE:
+        a = CMP_MIN(ref);
+        if (sk_gt(a)) { m = ORA_MASK_ALWAYS_TRUE; break; }
+        b = CMP_MAX(ref);
+        if (sk_lt(b)) m = ORA_MASK_ALWAYS_TRUE;
+        else if (sk_eq(a) && sk_eq(b)) m = ORA_MASK_ALWAYS_FALSE;
+        break;
+      case ORA_OP_GT:
+        a = CMP_MIN(ref);
+        if (sk_gt(a)) { m = ORA_MASK_ALWAYS_TRUE; break; }
+        b = CMP_MAX(ref);
+        if (sk_le(b)) m = ORA_MASK_ALWAYS_FALSE;
+        break;
+      case ORA_OP_GE:
+        a = CMP_MIN(ref);
+        if (sk_ge(a)) { m = ORA_MASK_ALWAYS_TRUE; break; }
+        b = CMP_MAX(ref);
+        if (sk_lt(b)) m = ORA_MASK_ALWAYS_FALSE;
+        break;
+      case ORA_OP_LT:
+        a = CMP_MIN(ref);
+        if (sk_ge(a)) { m = ORA_MASK_ALWAYS_FALSE; break; }
+        b = CMP_MAX(ref);
+        if (sk_lt(b)) m = ORA_MASK_ALWAYS_TRUE;
+        break;
+      case ORA_OP_LE:
+        a = CMP_MIN(ref);
+        if (sk_gt(a)) { m = ORA_MASK_ALWAYS_FALSE; break; }
+        b = CMP_MAX(ref);
+        if (sk_le(b)) m = ORA_MASK_ALWAYS_TRUE;
+        break;
+      case ORA_OP_BT: {
+        const ora_param *left = &params[0], *right = &params[1];
+        a = CMP_MIN(right);
+        if (sk_gt(a)) { m = ORA_MASK_ALWAYS_FALSE; break; }
+        b = CMP_MAX(left);
+        if (sk_lt(b)) { m = ORA_MASK_ALWAYS_FALSE; break; }
+        if (sk_ge(CMP_MIN(left)) && sk_le(CMP_MAX(right))) m = ORA_MASK_ALWAYS_TRUE;
+        break;
+      }
+      case ORA_OP_IN: {
+        /* the executor keeps the non-NULL constants sorted and distinct (init_in_eval_datums) */
+        ora_param *sorted = (ora_param *)malloc(sizeof(ora_param) * (size_t)(n_params > 0 ? n_params : 1));
+        if (!sorted) return ORA_ERR_UNEXPECTED;
+        int32_t n = 0;
+        for (int32_t i = 0; i < n_params; ++i) if (!params[i].is_null) sorted[n++] = params[i];
+        for (int32_t i = 1; i < n; ++i) {            /* insertion sort: IN lists are short */
+          ora_param t = sorted[i];
+          int32_t j = i;
+          while (j > 0 && sk_param_less(&t, &sorted[j - 1], obj_type, sc)) { sorted[j] = sorted[j - 1]; --j; }
+          sorted[j] = t;
+        }
+        int32_t pos = 0, equal = 0;
+        if (mn) {
+          /* min prefix: upper_bound (first constant > min), else lower_bound (first constant >= min) */
+          while (pos < n) {
+            const int c = cmp_datum_param(mn, obj_type, sc, &sorted[pos]);   /* min vs constant */
+            if (min_prefix ? c >= 0 : c > 0) ++pos; else { equal = !min_prefix && c == 0; break; }
+          }
+        }
+        if (pos == n) {
+          m = ORA_MASK_ALWAYS_FALSE;
+        } else {
+          b = CMP_MAX(&sorted[pos]);
+          if (sk_gt(b)) m = ORA_MASK_UNCERTAIN;
+          else if (sk_lt(b)) m = ORA_MASK_ALWAYS_FALSE;
+          else if (equal) m = max_prefix ? ORA_MASK_UNCERTAIN : ORA_MASK_ALWAYS_TRUE;
+        }
+        free(sorted);
+        break;
+      }
+      default:
+        return ORA_NOT_SUPPORTED;
+    }
+  }
+#undef CMP_MIN
+#undef CMP_MAX
+  if (has_null && m == ORA_MASK_ALWAYS_TRUE) m = ORA_MASK_UNCERTAIN;
+  *mask = m;
+  return ORA_SUCCESS;
+}
+
+int ora_skip_index_filter(const void *agg, int64_t agg_size, int64_t row_count, const uint8_t *col_types, int32_t n_cols,
+                          const ora_filter *f, int32_t *mask) {
+  if (!f || !mask || !col_types || f->n_nodes <= 0 || f->n_nodes > 256) return ORA_INVALID_ARGUMENT;
+  int32_t stack[256];
+  int32_t sp = 0;
+  for (int32_t i = 0; i < f->n_nodes; ++i) {
+    const ora_node *nd = &f->nodes[i];
+    if (nd->kind == ORA_NODE_WHITE) {
+      if (nd->col < 0 || nd->col >= n_cols) return ORA_INVALID_ARGUMENT;
+      int32_t m = ORA_MASK_UNCERTAIN;
+      const int ret = ora_skip_index_leaf(agg, agg_size, row_count, nd->col, col_types[nd->col], nd->op,
+                                          f->params + nd->param_begin, nd->n_params, &m);
+      if (ret == ORA_NOT_SUPPORTED) m = ORA_MASK_UNCERTAIN;   /* no skip index for this column type */
+      else if (ret) return ret;
+      stack[sp++] = m;
+    } else {
+      if (nd->n_children < 1 || nd->n_children > sp) return ORA_INVALID_ARGUMENT;
+      /* ObBoolMask operator& / operator| (ob_pushdown_filter.h:133-158), left to right */
+      int32_t bm = stack[sp - nd->n_children];
+      for (int32_t k = 1; k < nd->n_children; ++k) {
+        const int32_t c = stack[sp - nd->n_children + k];
+        if (nd->kind == ORA_NODE_AND) {
+          if (c == ORA_MASK_ALWAYS_TRUE) { /* bm stays */ }
+          else if (bm == ORA_MASK_ALWAYS_TRUE) bm = c;
+          else if (c == ORA_MASK_ALWAYS_FALSE || bm == ORA_MASK_ALWAYS_FALSE) bm = ORA_MASK_ALWAYS_FALSE;
+          else bm = ORA_MASK_UNCERTAIN;
+        } else {
+          if (c == ORA_MASK_ALWAYS_FALSE) { /* bm stays */ }
+          else if (bm == ORA_MASK_ALWAYS_FALSE) bm = c;
+          else if (c == ORA_MASK_ALWAYS_TRUE || bm == ORA_MASK_ALWAYS_TRUE) bm = ORA_MASK_ALWAYS_TRUE;
+          else bm = ORA_MASK_UNCERTAIN;
+        }
+      }
+      sp -= nd->n_children;
+      stack[sp++] = bm;
+    }
+  }
+  if (sp != 1) return ORA_INVALID_ARGUMENT;
+  *mask = stack[0];
+  return ORA_SUCCESS;
+}

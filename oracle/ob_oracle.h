@@ -176,6 +176,22 @@ int ora_major_merge(const ora_merge_run *runs, int32_t n_runs, int32_t n_cols, c
                     const uint8_t *default_null, int64_t out_cap, int64_t *out_key, int64_t *const *out_vals,
                     uint8_t *const *out_null, int64_t *out_rows, int64_t *stats);
 
+/* ---- skip index (pre-aggregated min / max / null count per micro-block) ------------------------------------
+ * ObAggRowReader::read (index_block/ob_agg_row_struct.cpp:339-482): aggregate `col_type` (ObSkipIndexColType)
+ * of column `col_idx` inside a serialized aggregate row; *data == NULL when it is not stored (NULL datum). */
+int ora_agg_row_read(const void *buf, int64_t size, uint32_t col_idx, int32_t col_type, const uint8_t **data,
+                     int32_t *len, int32_t *is_prefix);
+/* ObBoolMaskType: verdict of a filter over a block */
+enum { ORA_MASK_UNCERTAIN = 0, ORA_MASK_ALWAYS_TRUE = 1, ORA_MASK_ALWAYS_FALSE = 2 };
+/* ObSkipIndexFilterExecutor::falsifiable_pushdown_filter -> filter_on_min_max for one white leaf
+ * (ob_skip_index_filter_executor.cpp:114-189, 250-396, 498-822); binary collation for strings. */
+int ora_skip_index_leaf(const void *agg, int64_t agg_size, int64_t row_count, int32_t col, uint8_t obj_type, int32_t op,
+                        const ora_param *params, int32_t n_params, int32_t *mask);
+/* ObSSTableIndexFilter::check_range: every leaf, then ObPushdownFilterExecutor::execute_skipping_filter
+ * (sql/engine/basic/ob_pushdown_filter.cpp:1707-1740). col_types[c] = obj type of column store index c. */
+int ora_skip_index_filter(const void *agg, int64_t agg_size, int64_t row_count, const uint8_t *col_types, int32_t n_cols,
+                          const ora_filter *filter, int32_t *mask);
+
 #ifdef __cplusplus
 }
 #endif

@@ -116,6 +116,8 @@ def oracle():
         L.ora_scan_blocks_mt.argtypes = [vp, vp, vp, i32, P(OraFilter), vp, i32, i32, i32, P(i64), P(i64), P(u64)]
         L.ora_decode_column_ext.argtypes = [vp, vp, vp, i32, i32, vp, vp, i64, P(i64)]
         L.ora_major_merge.argtypes = [P(OraMergeRun), i32, i32, vp, vp, i64, vp, P(vp), P(vp), P(i64), P(i64)]
+        L.ora_agg_row_read.argtypes = [vp, i64, C.c_uint32, i32, P(vp), P(i32), P(i32)]
+        L.ora_skip_index_filter.argtypes = [vp, i64, i64, vp, i32, P(OraFilter), P(i32)]
         _lib = L
     return _lib
 
@@ -332,3 +334,29 @@ def major_merge(runs, n_cols, default_vals=None, default_null=None):
     n = rows.value
     return {"key": out_key[:n], "vals": [v[:n] for v in out_vals], "null": [v[:n] for v in out_null],
             "dropped": stats[0], "fused": stats[1]}
+
+
+# ---- skip index -------------------------------------------------------------------------------------------
+def agg_row_read(row, col_idx, col_type):
+    """ObAggRowReader::read: (bytes or None, is_prefix)."""
+    buf = np.ascontiguousarray(row, dtype=np.uint8)
+    ptr, ln, pre = C.c_void_p(), C.c_int32(0), C.c_int32(0)
+    ora_check(oracle().ora_agg_row_read(buf.ctypes.data, buf.size, col_idx, col_type, C.byref(ptr), C.byref(ln),
+                                        C.byref(pre)), "ora_agg_row_read")
+    if not ptr.value:
+        return None, False
+    off = ptr.value - buf.ctypes.data
+    return bytes(buf[off:off + ln.value]), bool(pre.value)
+
+
+def skip_index_filter(row, row_count, col_types, expr):
+    """ObSSTableIndexFilter::check_range on one block's aggregate row: ORA_MASK_* (0 uncertain, 1 true, 2 false)."""
+    from oceanbase_b200.scan import flatten_filter
+    f, keep = flatten_filter(expr, OraNode, OraParam, OraFilter)
+    buf = np.ascontiguousarray(row, dtype=np.uint8) if row is not None and len(row) else None
+    types = np.ascontiguousarray(col_types, dtype=np.uint8)
+    mask = C.c_int32(0)
+    ora_check(oracle().ora_skip_index_filter(buf.ctypes.data if buf is not None else None, buf.size if buf is not None else 0,
+                                             row_count, types.ctypes.data, len(types), C.byref(f), C.byref(mask)),
+              "ora_skip_index_filter")
+    return mask.value

@@ -15,10 +15,12 @@ def ctx():
     c.close()
 
 
-def assert_scan_matches(ctx, w, want_row_ids=True, max_selected_rows=0):
+def assert_scan_matches(ctx, w, want_row_ids=True, max_selected_rows=0, agg=None):
     table = w.table
     base = 0x10_0000_0000  # arbitrary non-zero rebasing address for VEC_DISCRETE pointers
     batch = ctx.open_batch(table)
+    if agg is not None:     # (aggregate rows, offsets): the scan prunes with the skip index
+        batch.set_agg_rows(*agg)
     res = batch.scan(w.filter, w.proj, want_row_ids=want_row_ids, string_base=base,
                      max_selected_rows=max_selected_rows)
     want = ora.scan_table(table, w.filter, w.proj, w.proj_is_string, w.proj_elem_len, string_base=base)

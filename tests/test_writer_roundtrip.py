@@ -211,3 +211,12 @@ def test_table_image_alignment_and_headers():
         nxt = t.offsets[i + 1] if i + 1 < t.n_blocks else t.image.size
         assert not t.image[end:nxt].any()  # padding is zero
     assert rows == n
+
+
+def test_page_batch_bounds_with_ramp():
+    from oceanbase_b200.pipeline import batch_bounds
+    assert batch_bounds(100, 16) == [0, 16, 32, 48, 64, 80, 96, 100]
+    assert batch_bounds(100, 16, 2) == [0, 4, 12, 28, 44, 60, 76, 92, 100]
+    assert batch_bounds(5, 16, 2) == [0, 4, 5]
+    assert batch_bounds(3, 16, 3) == [0, 2, 3]
+    assert batch_bounds(1, 1, 2) == [0, 1]
