@@ -164,6 +164,14 @@ int ObGpuSSTableBatchScanner::flatten(sql::ObPushdownFilterExecutor *f, std::vec
   return OB_SUCCESS;
 }
 
+int ObGpuSSTableBatchScanner::set_index_infos(ObMicroIndexInfo *infos, int32_t n_blocks) {
+  if (batch_) return OB_INIT_TWICE;   // the aggregate rows travel with the batch: before init only
+  if ((infos == nullptr) != (n_blocks == 0) || n_blocks < 0) return OB_INVALID_ARGUMENT;
+  index_infos_ = infos;
+  n_index_infos_ = n_blocks;
+  return OB_SUCCESS;
+}
+
 int ObGpuSSTableBatchScanner::init(const void *image, int64_t image_size, const int64_t *offsets, const int64_t *sizes,
                                    int32_t n_blocks, sql::ObPushdownFilterExecutor *filter,
                                    const std::vector<int32_t> &proj, int64_t batch_size) {
@@ -186,6 +194,22 @@ int ObGpuSSTableBatchScanner::init(const void *image, int64_t image_size, const 
     flt.params = params.data();
     flt.n_params = (int32_t)params.size();
   }
+  const bool use_index = filter && index_infos_ != nullptr;
+  if (use_index) {
+    if (n_index_infos_ != n_blocks) return OB_INVALID_ARGUMENT;
+    std::vector<char> rows;
+    std::vector<int64_t> off((size_t)n_blocks + 1, 0);
+    for (int32_t b = 0; b < n_blocks; ++b) {
+      if (index_infos_[b].has_agg_data())
+        rows.insert(rows.end(), index_infos_[b].agg_row_buf_, index_infos_[b].agg_row_buf_ + index_infos_[b].agg_buf_size_);
+      off[(size_t)b + 1] = (int64_t)rows.size();
+    }
+    rows.push_back(0);
+    if ((ret = obgpu_batch_set_agg_rows(batch_, rows.data(), off.data())) != OBGPU_SUCCESS) return ret;
+    std::vector<uint8_t> verdicts((size_t)n_blocks, 0);
+    if ((ret = obgpu_batch_skip_index_filter(batch_, &flt, verdicts.data())) != OBGPU_SUCCESS) return ret;
+    for (int32_t b = 0; b < n_blocks; ++b) index_infos_[b].set_filter_constant_type(verdicts[(size_t)b]);
+  }
   obgpu_scan_spec spec{};
   spec.filter = filter ? &flt : nullptr;
   spec.proj_cols = proj_.data();
@@ -197,6 +221,7 @@ int ObGpuSSTableBatchScanner::init(const void *image, int64_t image_size, const 
   obgpu_result_info info{};
   if ((ret = obgpu_result_info_get(result_, &info)) != OBGPU_SUCCESS) return ret;
   selected_ = info.selected_rows;
+  if (use_index && (ret = obgpu_result_skip_info(result_, &skip_false_, &skip_true_)) != OBGPU_SUCCESS) return ret;
   sel_offset_.assign((size_t)n_blocks + 1, 0);
   if ((ret = obgpu_result_fetch_sel_offsets(result_, sel_offset_.data())) != OBGPU_SUCCESS) return ret;
   cols_.resize(proj_.size());

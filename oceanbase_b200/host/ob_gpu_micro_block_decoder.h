@@ -19,6 +19,7 @@
 
 extern "C" {
 #include "../../include/obgpu_scan.h"
+#include "../../include/obgpu_skip_index.h"
 }
 
 namespace oceanbase {
@@ -215,6 +216,19 @@ private:
 int execute_pushdown_filter(sql::ObPushdownFilterExecutor *filter, sql::ObPushdownFilterExecutor *parent,
                             const sql::PushdownFilterInfo &pd_filter_info, ObGpuMicroBlockDecoder &decoder);
 
+// The slice of blocksstable::ObMicroIndexInfo (index_block/ob_index_block_row_struct.h) the skip index needs: the
+// serialized aggregate row of the micro block's index row and the verdict check_range leaves on it.
+struct ObMicroIndexInfo {
+  const char *agg_row_buf_ = nullptr;
+  int64_t agg_buf_size_ = 0;
+  uint8_t filter_constant_type_ = OBGPU_BOOL_MASK_UNCERTAIN;   // sql::ObBoolMaskType
+  bool has_agg_data() const { return agg_row_buf_ != nullptr && agg_buf_size_ > 0; }
+  bool is_filter_always_false() const { return filter_constant_type_ == OBGPU_BOOL_MASK_ALWAYS_FALSE; }
+  bool is_filter_always_true() const { return filter_constant_type_ == OBGPU_BOOL_MASK_ALWAYS_TRUE; }
+  bool is_filter_uncertain() const { return filter_constant_type_ == OBGPU_BOOL_MASK_UNCERTAIN; }
+  void set_filter_constant_type(uint8_t t) { filter_constant_type_ = t; }
+};
+
 // Page-batch scanner with the ObIStoreRowIterator batch contract: open many micro blocks, one fused
 // device scan, then get_next_rows() hands out <= batch_size rows at a time, block by block, rows
 // ascending, OB_ITER_END after the last row (access/ob_store_row_iterator.h, ob_sstable_row_scanner.cpp:553).
@@ -226,6 +240,12 @@ public:
   int init(const void *image, int64_t image_size, const int64_t *offsets, const int64_t *sizes, int32_t n_blocks,
            sql::ObPushdownFilterExecutor *filter, const std::vector<int32_t> &proj, int64_t batch_size = 256);
   void reset();
+  // Skip index (storage::ObSSTableIndexFilter::check_range, access/ob_sstable_index_filter.cpp:56-108): hand over the
+  // micro blocks' index infos BEFORE init; the fused scan then prunes with their aggregate rows, and after init
+  // every info carries the verdict (set_filter_constant_type) of the whole pushed-down filter on its block.
+  int set_index_infos(ObMicroIndexInfo *infos, int32_t n_blocks);
+  int64_t skipped_blocks() const { return skip_false_; }       // always-false: never read
+  int64_t unfiltered_blocks() const { return skip_true_; }     // always-true: no filter evaluation
   // Next batch: count rows of block `block_idx`, row ids ascending. Integer columns are returned as
   // int64 values + null flags (per projected column), string columns as (ptr into image, len).
   struct Batch {
@@ -253,6 +273,9 @@ private:
   std::vector<obgpu_result_col> cols_;
   int32_t cur_block_ = 0;
   int64_t cur_row_ = 0;  // dense row cursor
+  ObMicroIndexInfo *index_infos_ = nullptr;
+  int32_t n_index_infos_ = 0;
+  int64_t skip_false_ = 0, skip_true_ = 0;
 };
 
 }  // namespace blocksstable

@@ -76,13 +76,17 @@ def _rle_column(seed, start, n, dict_bits=8, mean_run=64):
     return wide[run_id]
 
 
+def config2_pk(rows, seed, row_start=0):
+    """Sorted PK of the config-2 table as a pure function of the absolute row index (shards / chunks line up,
+    strictly increasing: consecutive rows differ by 351 + (j' - j) with j, j' in [0, 351))."""
+    jitter = (splitmix64(_col_seed(seed, 0), row_start, rows) % np.uint64(351)).astype(np.int64)
+    return np.int64(1_000_000_007) + (np.arange(row_start, row_start + rows, dtype=np.int64)) * 351 + jitter
+
+
 def make_config2_like(rows=100_000, rows_per_block=1400, seed=2, shape="bt", row_start=0,
                       n_threads=0, out=None) -> Workload:
     s = lambda c: _col_seed(seed, c)
-    # sorted PK as a pure function of the absolute row index (shards / chunks line up, strictly
-    # increasing: consecutive rows differ by 351 + (j' - j) with j, j' in [0, 351))
-    jitter = (splitmix64(s(0), row_start, rows) % np.uint64(351)).astype(np.int64)
-    pk = np.int64(1_000_000_007) + (np.arange(row_start, row_start + rows, dtype=np.int64)) * 351 + jitter
+    pk = config2_pk(rows, seed, row_start)
     cols = [Column(capi.OBJ_INT, capi.ENC_INTEGER_BASE_DIFF, pk)]
     for c in (1, 2, 3):
         cols.append(Column(capi.OBJ_INT, capi.ENC_RLE, _rle_column(s(c), row_start, rows)))

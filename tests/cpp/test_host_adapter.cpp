@@ -279,6 +279,48 @@ static void test_filter_tree_and_batch_scanner(ObGpuScanRuntime &rt) {
   ASSERT_EQ(scanner.total_selected(), seen);
   ASSERT_EQ(OB_ITER_END, scanner.get_next_rows(batch));
   (void)expect_total;
+
+  // (3) skip index: b (column 0) is the row number, so BETWEEN on it is decided by min / max for all but the two
+  // boundary blocks; same rows come back, the index infos carry the verdicts, pruned blocks are counted
+  int32_t agg_cols[1] = {0};
+  int64_t agg_size = 0;
+  std::vector<int64_t> agg_off((size_t)nb + 1);
+  ASSERT_EQ(0, obgpu_writer_table_agg_rows(cols, 3, agg_cols, 1, n, rpb, nullptr, 0, nullptr, &agg_size));
+  std::vector<char> agg((size_t)agg_size);
+  ASSERT_EQ(0, obgpu_writer_table_agg_rows(cols, 3, agg_cols, 1, n, rpb, agg.data(), agg_size, agg_off.data(), &agg_size));
+  std::vector<ObMicroIndexInfo> infos((size_t)nb);
+  for (int32_t i = 0; i < nb; ++i) {
+    infos[(size_t)i].agg_row_buf_ = agg.data() + agg_off[(size_t)i];
+    infos[(size_t)i].agg_buf_size_ = agg_off[(size_t)i + 1] - agg_off[(size_t)i];
+  }
+  const int64_t lo = 3 * rpb + 5, hi = 9 * rpb - 1;   // blocks 4..8 are inside, 3 partly, the rest outside
+  sql::ObWhiteFilterExecutor bt(0, sql::WHITE_OP_BT);
+  d.set_int(lo); bt.get_datums().push_back(d);
+  d.set_int(hi); bt.get_datums().push_back(d);
+  ObGpuSSTableBatchScanner pruned(rt);
+  ASSERT_EQ(OB_SUCCESS, pruned.set_index_infos(infos.data(), nb));
+  ASSERT_EQ(OB_SUCCESS, pruned.init(image.data(), image_size, offs.data(), sizes.data(), nb, &bt, {0, 1}, 256));
+  ASSERT_EQ(hi - lo + 1, pruned.total_selected());
+  ASSERT_EQ((int64_t)nb - 6, pruned.skipped_blocks());
+  ASSERT_EQ(5, pruned.unfiltered_blocks());
+  for (int32_t i = 0; i < nb; ++i) {
+    const bool inside = i >= 4 && i <= 8;
+    ASSERT_EQ(inside, infos[(size_t)i].is_filter_always_true());
+    ASSERT_EQ(i != 3 && !inside, infos[(size_t)i].is_filter_always_false());
+  }
+  int64_t next = lo;
+  while ((ret = pruned.get_next_rows(batch)) == OB_SUCCESS) {
+    for (int64_t i = 0; i < batch.count; ++i) {
+      ASSERT_EQ(next, batch.ints[0][(size_t)i]);
+      ASSERT_EQ(next, (int64_t)batch.block_idx * rpb + batch.row_ids[(size_t)i]);
+      if (!batch.is_null[1][(size_t)i]) ASSERT_EQ(a[(size_t)next], batch.ints[1][(size_t)i]);
+      ASSERT_EQ((int)nulls[(size_t)next], (int)batch.is_null[1][(size_t)i]);
+      ++next;
+    }
+  }
+  ASSERT_EQ(OB_ITER_END, ret);
+  ASSERT_EQ(hi + 1, next);
+  ASSERT_EQ(OB_INIT_TWICE, pruned.set_index_infos(infos.data(), nb));
 }
 
 int main() {

@@ -99,7 +99,7 @@ def test_block_verdicts_match_the_oracle(ob, ctx, long_strings):
 
 @pytest.mark.parametrize("long_strings", [False, True])
 def test_pruned_scans_return_the_same_rows(ob, ctx, long_strings):
-    t = make_table(ob, n=30_000, rpb=700, seed=6, long_strings=long_strings)
+    t = make_table(ob, n=40_000, rpb=700, seed=6, long_strings=long_strings)
     for flt in filters(ob, t):
         assert_scan_matches(ctx, W(t["table"], flt, [0, 1, 2, 3], [False, False, True, False], [8, 8, 8, 4]), agg=t["agg"])
 
@@ -140,7 +140,7 @@ def test_skip_info_and_unread_blocks(ob, ctx):
 
 
 def test_partial_and_missing_aggregate_rows(ob, ctx):
-    t = make_table(ob, n=12_000, rpb=600, seed=8)
+    t = make_table(ob, n=40_000, rpb=600, seed=8)
     rows, offs = t["agg"]
     # every second block loses its aggregate row (ObMicroIndexInfo::has_agg_data() false): uncertain there
     keep = np.arange(t["table"].n_blocks) % 2 == 0
