@@ -335,6 +335,25 @@ __device__ __forceinline__ void parse_block(const uint8_t *s, uint32_t size, Blo
   }
 }
 
+// Const-encoded dictionary refs (ObDictColumnEncoder::do_store_dict_ref_, cs_encoding/ob_dict_column_encoder.h:65-116;
+// ObConstEncodingRefDesc, ob_dict_column_decoder.h:73-95): the ref stream holds
+// [exception count][const ref][exception row ids x count][exception refs x count] instead of one ref per row.
+// It is the PAX CONST codec's shape: a K_CONST plan over the column's dictionary.
+__device__ __forceinline__ bool cs_const_ref_plan(const uint8_t *s, uint32_t data, uint32_t end, uint32_t width, uint32_t ref_cnt,
+                                                  uint32_t row_count, ColDesc &d) {
+  if (ref_cnt < 2 || data + width * ref_cnt != end) return false;
+  const uint32_t exc = (uint32_t)ld_bytes(s, data, width);
+  if (ref_cnt != 2u + 2u * exc || exc > row_count) return false;
+  d.kind = K_CONST;
+  d.const_ref = (uint32_t)ld_bytes(s, data + width, width);
+  d.rle_count = exc;
+  d.rle_row_id_bits = (uint8_t)(width * 8u);
+  d.rle_ref_bits = (uint8_t)(width * 8u);
+  d.rle_row_ids_bit = (data + 2u * width) * 8u;
+  d.rle_refs_bit = (data + 2u * width + exc * width) * 8u;
+  return true;
+}
+
 // CS STRING / STR_DICT column (cs_encoding/ob_string_column_decoder.cpp, ob_dict_column_decoder.cpp:158-326).
 // pos: the column's meta (NULL bitmap or ObDictEncodingMeta), str_at: its bytes in the all-string-data area,
 // send: end of the string stream (= start of the next stream of this column), next_stream: index of that stream.
@@ -389,19 +408,24 @@ __device__ __forceinline__ void build_cs_str_col_desc(const BlockView &b, uint32
     return;
   }
   // STR_DICT: [ObDictEncodingMeta][string stream meta][END offsets x distinct (variable)][refs x rows]
-  if (s[pos] != 0 || (s[pos + 1] & 0x4)) return;   // const-encoded refs: not handled
+  if (s[pos] != 0) return;
+  const bool const_refs = (s[pos + 1] & 0x4) != 0;   // ObDictEncodingMeta::CONST_ENCODING_REF
   if (next_stream >= (int)b.cs_stream_count) return;
   const uint32_t rend = (uint32_t)ld_bytes(s, b.cs_off_data + (uint32_t)next_stream * b.cs_off_width, b.cs_off_width);
   if (rend < at || rend > b.size) return;
   IntStreamMeta m;
   parse_int_stream_meta(s, at, rend, m);
   if (!m.ok || m.use_base || m.replace_null || m.width > 4) return;
-  if (at + m.meta_len + m.width * b.row_count != rend) return;
   d.kind = K_DICT;
   d.dict_count = count;
-  d.width = (uint8_t)(m.width * 8u);
-  d.stride = m.width * 8u;
-  d.val_bit = (at + m.meta_len) * 8u;
+  if (const_refs) {
+    if (!cs_const_ref_plan(s, at + m.meta_len, rend, m.width, (uint32_t)ld_bytes(s, pos + 6, 4), b.row_count, d)) return;
+  } else {
+    if (at + m.meta_len + m.width * b.row_count != rend) return;
+    d.width = (uint8_t)(m.width * 8u);
+    d.stride = m.width * 8u;
+    d.val_bit = (at + m.meta_len) * 8u;
+  }
   if (sm.fixed) {
     d.dict_fixed = 1;
     d.dict_data_size = sm.fixed_len;
@@ -479,7 +503,9 @@ __device__ __forceinline__ void build_cs_col_desc(const BlockView &b, int col, C
         // [ObDictEncodingMeta 10 B][dict value stream][ref stream] -> K_DICT plan (ref == distinct count: NULL,
         // value = dict[ref] + base, ob_int_dict_column_decoder.cpp:25-60)
         if (attrs & (CS_HAS_NOP_BITMAP | CS_HAS_NOP | CS_OUT_ROW)) return;
-        if (s[pos] != 0 || (s[pos + 1] & 0x4)) return;   // const-encoded refs: not handled
+        if (s[pos] != 0) return;
+        const bool const_refs = (s[pos + 1] & 0x4) != 0;   // ObDictEncodingMeta::CONST_ENCODING_REF
+        const uint32_t ref_cnt = (uint32_t)ld_bytes(s, pos + 6, 4);
         const uint32_t distinct = (uint32_t)ld_bytes(s, pos + 2, 4);
         d.sc = (uint8_t)sc;
         d.elem_len = (uint8_t)datum_len_of(d.obj_type);
@@ -509,10 +535,14 @@ __device__ __forceinline__ void build_cs_col_desc(const BlockView &b, int col, C
         parse_int_stream_meta(s, end0, end1, m);
         if (!m.ok || m.use_base || m.replace_null || m.width > 4) return;
         const uint32_t refs = end0 + m.meta_len;
-        if (refs + m.width * b.row_count != end1) return;
-        d.width = (uint8_t)(m.width * 8u);
-        d.stride = m.width * 8u;
-        d.val_bit = refs * 8u;
+        if (const_refs) {
+          if (!cs_const_ref_plan(s, refs, end1, m.width, ref_cnt, b.row_count, d)) return;
+        } else {
+          if (refs + m.width * b.row_count != end1) return;
+          d.width = (uint8_t)(m.width * 8u);
+          d.stride = m.width * 8u;
+          d.val_bit = refs * 8u;
+        }
         d.ok = 1;
         return;
       }
@@ -789,11 +819,21 @@ __device__ __forceinline__ bool col_region(const ColDesc &d, const BlockView &bv
       a = d.rle_row_ids_bit >> 3;
       b = d.dict_end;
       break;
-    case K_CONST:
-      a = d.rle_count ? d.rle_refs_bit >> 3 : d.dict_payload;
-      b = d.dict_end;
-      if (d.dict_count == 0 && d.rle_count == 0) { a = 0; b = 0; }
+    case K_CONST: {
+      // dictionary + exception lists (PAX: refs, row ids, dictionary in this order; CS: dictionary stream, then
+      // the ref stream holding row ids and refs)
+      a = 0xffffffffu;
+      b = 0;
+      if (d.dict_count) { a = d.dict_payload; b = d.dict_end; }
+      if (d.rle_count) {
+        const uint32_t r0 = d.rle_refs_bit >> 3, r1 = (d.rle_refs_bit + d.rle_count * d.rle_ref_bits + 7u) >> 3;
+        const uint32_t i0 = d.rle_row_ids_bit >> 3, i1 = (d.rle_row_ids_bit + d.rle_count * d.rle_row_id_bits + 7u) >> 3;
+        a = min(a, min(r0, i0));
+        b = max(b, max(r1, i1));
+      }
+      if (a > b) { a = 0; b = 0; }
       break;
+    }
     default:
       return false;
   }
@@ -843,7 +883,7 @@ __device__ __forceinline__ uint32_t ref_of(const uint8_t *s, const ColDesc &d, c
       else hi = mid;
     }
     if (lo < d.rle_count && ld_bits32(s, d.rle_row_ids_bit + lo * d.rle_row_id_bits, d.rle_row_id_bits) == row)
-      return s[(d.rle_refs_bit >> 3) + lo];
+      return ld_bits32(s, d.rle_refs_bit + lo * d.rle_ref_bits, d.rle_ref_bits);   // 8-bit refs in PAX CONST, stream width in CS
     return d.const_ref;
   }
   return ld_bits32(s, d.val_bit + row * d.stride, d.width);

@@ -913,6 +913,39 @@ static int cs_string_column(const ColCtx &c, CSColumnHeader &ch, Buf &body, Buf 
   return OBGPU_SUCCESS;
 }
 
+// Ref stream of a CS dictionary column (ObDictColumnEncoder::try_const_encoding_ref_ / do_store_dict_ref_,
+// cs_encoding/ob_dict_column_encoder.cpp:144-189, .h:65-116): when one ref (a value or NULL) covers all rows, or
+// all but <= 64 rows and fewer than 10 % of them, the stream holds [exception count][const ref][exception row
+// ids][exception refs] and the dict meta says CONST_ENCODING_REF with ref_row_cnt_ = 2 + 2 * exceptions.
+static void put_dict_ref_stream(Buf &body, size_t dm_at, const std::vector<uint64_t> &refs, uint64_t distinct, bool has_null) {
+  const int64_t n = (int64_t)refs.size();
+  const uint64_t max_ref = has_null ? distinct : distinct - 1;
+  std::vector<int64_t> freq((size_t)distinct + 1, 0);
+  for (uint64_t r : refs) ++freq[(size_t)r];
+  uint64_t const_ref = 0;
+  int64_t max_cnt = 0;
+  for (uint64_t k = 0; k < distinct; ++k)
+    if (freq[(size_t)k] > max_cnt) { max_cnt = freq[(size_t)k]; const_ref = k; }
+  if (freq[(size_t)distinct] > max_cnt) { max_cnt = freq[(size_t)distinct]; const_ref = distinct; }
+  const int64_t exc = n - max_cnt;
+  if (exc == 0 || (exc <= 64 && exc < n * 10 / 100)) {
+    std::vector<uint64_t> st;
+    st.push_back((uint64_t)exc);
+    st.push_back(const_ref);
+    uint64_t max_row = 0;
+    for (int64_t r = 0; r < n; ++r) if (refs[(size_t)r] != const_ref) { st.push_back((uint64_t)r); max_row = (uint64_t)r; }
+    for (int64_t r = 0; r < n; ++r) if (refs[(size_t)r] != const_ref) st.push_back(refs[(size_t)r]);
+    DictEncodingMeta dm;
+    memcpy(&dm, body.d.data() + dm_at, sizeof(dm));
+    dm.attrs_ |= 0x4;
+    dm.ref_row_cnt_ = (uint32_t)(2 + 2 * exc);
+    memcpy(body.d.data() + dm_at, &dm, sizeof(dm));
+    put_raw_stream(body, st, exc == 0 ? std::max<uint64_t>(0, const_ref) : std::max<uint64_t>(std::max<uint64_t>((uint64_t)exc, max_row), max_ref));
+    return;
+  }
+  put_raw_stream(body, refs, max_ref);
+}
+
 // String dictionary column: [ObDictEncodingMeta][dict bytes: string stream (+ END offsets when variable)][refs];
 // ref == distinct_val_cnt is NULL (cs_encoding/ob_dict_column_decoder.cpp:158-326).
 static int cs_str_dict_column(const ColCtx &c, CSColumnHeader &ch, Buf &body, Buf &all_string, std::vector<uint32_t> &stream_end,
@@ -925,6 +958,7 @@ static int cs_str_dict_column(const ColCtx &c, CSColumnHeader &ch, Buf &body, Bu
   dm.attrs_ = (uint8_t)(0x1 | (c.null_cnt > 0 ? 0x2 : 0));
   dm.distinct_val_cnt_ = (uint32_t)d.values.size();
   dm.ref_row_cnt_ = (uint32_t)n;
+  const size_t dm_at = body.size();
   memcpy(body.grow(sizeof(dm)), &dm, sizeof(dm));
   if (d.values.empty()) return OBGPU_SUCCESS;
   const bool fixed = d.fix_len >= 0;
@@ -946,7 +980,7 @@ static int cs_str_dict_column(const ColCtx &c, CSColumnHeader &ch, Buf &body, Bu
   }
   std::vector<uint64_t> refs((size_t)n);
   for (int64_t r = 0; r < n; ++r) refs[(size_t)r] = d.refs[(size_t)r];
-  put_raw_stream(body, refs, c.null_cnt > 0 ? d.values.size() : d.values.size() - 1);
+  put_dict_ref_stream(body, dm_at, refs, d.values.size(), c.null_cnt > 0);
   stream_end.push_back(header_size + (uint32_t)body.size());
   return OBGPU_SUCCESS;
 }
@@ -992,6 +1026,7 @@ int BlockBuilder::build_cs(std::vector<uint8_t> &block, int64_t original) {
       dm.attrs_ = (uint8_t)(0x1 | (c.null_cnt > 0 ? 0x2 : 0));  // IS_SORTED | HAS_NULL
       dm.distinct_val_cnt_ = (uint32_t)vals.size();
       dm.ref_row_cnt_ = (uint32_t)nrows;
+      const size_t dm_at = body.size();
       memcpy(body.grow(sizeof(dm)), &dm, sizeof(dm));
       if (vals.empty()) continue;
       IntStreamPlan dp;
@@ -1009,10 +1044,7 @@ int BlockBuilder::build_cs(std::vector<uint8_t> &block, int64_t original) {
         memcpy(dd + k * (size_t)dp.width, &v, (size_t)dp.width);
       }
       stream_end.push_back(header_size + (uint32_t)body.size());
-      IntStreamPlan rp;
-      rp.width = (int)byte_packed_int_size(c.null_cnt > 0 ? vals.size() : vals.size() - 1);
-      put_stream_meta(body, rp);
-      uint8_t *rd = body.grow((size_t)rp.width * (size_t)nrows);
+      std::vector<uint64_t> refs((size_t)nrows);
       for (int64_t r = 0; r < nrows; ++r) {
         uint64_t ref;
         if (c.is_null(r)) ref = vals.size();
@@ -1022,8 +1054,9 @@ int BlockBuilder::build_cs(std::vector<uint8_t> &block, int64_t original) {
                     : (uint64_t)(std::lower_bound(vals.begin(), vals.end(), v,
                                                   [](int64_t a, int64_t b) { return (uint64_t)a < (uint64_t)b; }) - vals.begin());
         }
-        memcpy(rd + (size_t)r * (size_t)rp.width, &ref, (size_t)rp.width);
+        refs[(size_t)r] = ref;
       }
+      put_dict_ref_stream(body, dm_at, refs, vals.size(), c.null_cnt > 0);
       stream_end.push_back(header_size + (uint32_t)body.size());
       continue;
     }

@@ -432,6 +432,8 @@ typedef struct col_dec {
   uint32_t cs_distinct;
   const uint8_t *cs_ref_data;
   int cs_ref_width;
+  int cs_const_refs;            /* ObDictEncodingMeta::CONST_ENCODING_REF: ref stream = [exception cnt][const ref][row ids][refs] */
+  uint32_t cs_ref_cnt;          /* elements of the ref stream (ref_row_cnt_) */
   /* CS STRING / STR_DICT (cs_encoding/ob_string_stream_decoder.cpp:79-82, ob_dict_column_decoder.cpp): bytes in the
    * block's all-string-data area, END offsets (cs_off_*) unless fixed length */
   const uint8_t *cs_str;           /* first byte of this column's string stream */
@@ -459,6 +461,30 @@ static int parse_str_stream_meta(const uint8_t *p, int64_t len, str_stream_meta 
 
 static uint32_t cs_stream_end(const ora_block *b, int32_t idx) {
   return (uint32_t)rd_len(b->cs_off_data + (int64_t)idx * b->cs_off_width, b->cs_off_width);
+}
+
+/* Const-encoded refs (ObConstEncodingRefDesc, cs_encoding/ob_dict_column_decoder.h:73-95; the per-row lookup of
+ * extract_ref_and_null_count_, ob_dict_column_decoder.cpp:199-261): the exception row ids are ascending, a row
+ * that is not listed has the const ref. */
+static int cs_check_const_refs(const ora_block *b, const col_dec *c) {
+  if (!c->cs_const_refs) return ORA_SUCCESS;
+  if (c->cs_ref_cnt < 2) return ORA_INVALID_DATA;
+  const uint64_t exc = rd_len(c->cs_ref_data, c->cs_ref_width);
+  if (c->cs_ref_cnt != 2 + 2 * exc || exc > b->row_count) return ORA_INVALID_DATA;
+  return ORA_SUCCESS;
+}
+static uint64_t cs_dict_ref(const col_dec *c, int64_t row) {
+  const int w = c->cs_ref_width;
+  if (!c->cs_const_refs) return rd_len(c->cs_ref_data + row * w, w);
+  const int64_t exc = (int64_t)rd_len(c->cs_ref_data, w);
+  const uint8_t *ids = c->cs_ref_data + 2 * w, *refs = ids + exc * w;
+  int64_t lo = 0, hi = exc;              /* lower_bound over the exception row ids */
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) / 2;
+    if ((int64_t)rd_len(ids + mid * w, w) < row) lo = mid + 1; else hi = mid;
+  }
+  if (lo < exc && (int64_t)rd_len(ids + lo * w, w) == row) return rd_len(refs + lo * w, w);
+  return rd_len(c->cs_ref_data + w, w);
 }
 
 /* Walks the column headers like ObCSMicroBlockTransformer::build_original_transform_desc_
@@ -518,8 +544,10 @@ static int cs_int_col_init(const ora_block *b, int32_t col, col_dec *c) {
         }
         /* STR_DICT: [dict meta][string stream][END offsets x distinct (variable)][refs x rows] */
         const uint8_t *dm = b->buf + pos;
-        if (dm[0] != 0 || (dm[1] & 0x4) || (attrs & 0x08)) return ORA_NOT_SUPPORTED;
+        if (dm[0] != 0 || (attrs & 0x08)) return ORA_NOT_SUPPORTED;
         c->cs_distinct = rd32(dm + 2);
+        c->cs_const_refs = (dm[1] & 0x4) != 0;
+        c->cs_ref_cnt = c->cs_const_refs ? rd32(dm + 6) : b->row_count;
         uint32_t at = send;
         int32_t si = s_off;
         int_stream_meta m;
@@ -536,10 +564,10 @@ static int cs_int_col_init(const ora_block *b, int32_t col, col_dec *c) {
         const uint32_t rend = cs_stream_end(b, si);
         int r3 = parse_int_stream_meta(b->buf + at, (int64_t)rend - at, &m);
         if (r3) return r3;
-        if ((m.attr & 0x3) || at + m.meta_len + (int64_t)m.width * b->row_count != rend) return ORA_INVALID_DATA;
+        if ((m.attr & 0x3) || at + m.meta_len + (int64_t)m.width * c->cs_ref_cnt != rend) return ORA_INVALID_DATA;
         c->cs_ref_data = b->buf + at + m.meta_len;
         c->cs_ref_width = m.width;
-        return ORA_SUCCESS;
+        return cs_check_const_refs(b, c);
       }
       str_at += sm.uncompressed_len;
     }
@@ -547,9 +575,11 @@ static int cs_int_col_init(const ora_block *b, int32_t col, col_dec *c) {
       if (type == 3) { c->cs_distinct = 0; return ORA_SUCCESS; }   /* STR_DICT without streams: every row NULL */
       if (type == 2) { /* INT_DICT: [ObDictEncodingMeta 10 B][dict value stream][ref stream] */
         const uint8_t *dm = b->buf + pos;
-        if (dm[0] != 0 || (dm[1] & 0x4) || (attrs & 0x08)) return ORA_NOT_SUPPORTED; /* const-encoded refs / nop bitmap */
+        if (dm[0] != 0 || (attrs & 0x08)) return ORA_NOT_SUPPORTED; /* nop bitmap */
         c->cs_distinct = rd32(dm + 2);
         if (c->cs_distinct == 0) return ORA_SUCCESS;        /* every row NULL */
+        c->cs_const_refs = (dm[1] & 0x4) != 0;
+        c->cs_ref_cnt = c->cs_const_refs ? rd32(dm + 6) : b->row_count;
         if (stream_idx + 2 >= b->cs_stream_count) return ORA_INVALID_DATA;
         const uint32_t end0 = cs_stream_end(b, stream_idx + 1), end1 = cs_stream_end(b, stream_idx + 2);
         if ((int64_t)pos + meta_len > end0 || end0 > end1 || end1 > b->size) return ORA_INVALID_DATA;
@@ -561,10 +591,10 @@ static int cs_int_col_init(const ora_block *b, int32_t col, col_dec *c) {
         c->cs_width = m.width;
         c->cs_base = (m.attr & 0x1) ? m.base : 0;
         if ((ret = parse_int_stream_meta(b->buf + end0, (int64_t)end1 - end0, &m))) return ret;
-        if ((m.attr & 0x3) || end0 + m.meta_len + (int64_t)m.width * b->row_count != end1) return ORA_INVALID_DATA;
+        if ((m.attr & 0x3) || end0 + m.meta_len + (int64_t)m.width * c->cs_ref_cnt != end1) return ORA_INVALID_DATA;
         c->cs_ref_data = b->buf + end0 + m.meta_len;
         c->cs_ref_width = m.width;
-        return ORA_SUCCESS;
+        return cs_check_const_refs(b, c);
       }
       if (type != 0) return ORA_NOT_SUPPORTED;
       if (stream_idx + 1 >= b->cs_stream_count) return ORA_INVALID_DATA;
@@ -753,7 +783,7 @@ static int decode_cell(const ora_block *b, const col_dec *c, int64_t row, ora_da
       int64_t idx = row;
       if (c->h.type == T_CS_STR_DICT) {
         if (c->cs_distinct == 0) { set_null(out); return ORA_SUCCESS; }
-        idx = (int64_t)rd_len(c->cs_ref_data + row * c->cs_ref_width, c->cs_ref_width);
+        idx = (int64_t)cs_dict_ref(c, row);
         if (idx == c->cs_distinct) { set_null(out); return ORA_SUCCESS; }
         if (idx > c->cs_distinct) return ORA_ERR_UNEXPECTED;
       } else if (c->cs_null_bitmap && ((c->cs_null_bitmap[row / 8] >> (7 - row % 8)) & 1)) {
@@ -772,7 +802,7 @@ static int decode_cell(const ora_block *b, const col_dec *c, int64_t row, ora_da
     }
     case T_CS_INT_DICT: { /* ObIntDictColumnDecoder::decode: ref == distinct_val_cnt is NULL, value = dict[ref] + base */
       if (c->cs_distinct == 0) { set_null(out); return ORA_SUCCESS; }
-      const uint64_t ref = rd_len(c->cs_ref_data + row * c->cs_ref_width, c->cs_ref_width);
+      const uint64_t ref = cs_dict_ref(c, row);
       if (ref == c->cs_distinct) { set_null(out); return ORA_SUCCESS; }
       if (ref > c->cs_distinct) return ORA_ERR_UNEXPECTED;
       set_int(c->h.obj_type, rd_len(c->cs_data + ref * c->cs_width, c->cs_width) + c->cs_base, out);

@@ -202,3 +202,58 @@ def test_cs_string_roundtrip(shape, null_frac, enc):
     for op, params in ((ob.WHITE_OP_EQ, (probe,)), (ob.WHITE_OP_LT, (probe,)), (ob.WHITE_OP_GE, (b"m",)), (ob.WHITE_OP_NU, ()),
                        (ob.WHITE_OP_IN, (probe, v[9], b"zzzz")), (ob.WHITE_OP_NE, (probe,)), (ob.WHITE_OP_BT, (b"c", b"t"))):
         assert np.array_equal(blk.filter_tree(White(0, op, params)), pax.filter_tree(White(0, op, params))), (op, params)
+
+
+@pytest.mark.parametrize("kind", ["int", "str"])
+@pytest.mark.parametrize("shape", ["one_value", "dominant_value", "dominant_null", "too_many_exceptions", "ten_percent"])
+def test_cs_dict_const_encoded_refs(kind, shape):
+    # ObDictColumnEncoder::try_const_encoding_ref_ (cs_encoding/ob_dict_column_encoder.cpp:144-189): one ref covering
+    # all rows, or all but <= 64 rows and < 10 % of them, turns the ref stream into
+    # [exception count][const ref][exception row ids][exception refs] (ob_dict_column_encoder.h:65-116)
+    rng = np.random.default_rng(23)
+    n = 1000
+    idx = np.zeros(n, dtype=np.int64)
+    nulls = None
+    exc = {"one_value": 0, "dominant_value": 40, "dominant_null": 30, "too_many_exceptions": 70, "ten_percent": 100}[shape]
+    if shape in ("too_many_exceptions", "ten_percent"):
+        n = 2000 if shape == "too_many_exceptions" else 1000    # 70 of 2000 (> 64), 100 of 1000 (not < 10 %)
+        idx = np.zeros(n, dtype=np.int64)
+    where = rng.choice(n, size=exc, replace=False)
+    idx[where] = rng.integers(1, 9, size=exc)
+    if shape == "dominant_null":
+        nulls = np.ones(n, dtype=np.uint8)
+        nulls[where] = 0
+    if kind == "int":
+        vals = (idx * 1000 - 3000).astype(np.int64)
+        col = ob.Column(ob.OBJ_INT, ob.ENC_CS_INT_DICT, vals, nulls=nulls)
+        expect = [None if (nulls is not None and nulls[r]) else int(np.uint64(vals[r])) for r in range(n)]
+    else:
+        words = [b"", b"alpha", b"be", b"gamma", b"delta!", b"e", b"zeta", b"eta", b"theta"]
+        vals = [words[i] for i in idx.tolist()]
+        col = ob.Column(ob.OBJ_VARCHAR, ob.ENC_CS_STR_DICT, vals, nulls=nulls)
+        expect = [None if (nulls is not None and nulls[r]) else vals[r] for r in range(n)]
+    block = ob.encode_block([ob.Column(ob.OBJ_INT, ob.ENC_CS_INTEGER, np.arange(n, dtype=np.int64)), col,
+                             ob.Column(ob.OBJ_INT, ob.ENC_CS_INTEGER, np.arange(n, dtype=np.int64) * 3)])
+    blk = ora.Block(block)
+    assert blk.verify_checksums() == 0
+    # ObDictEncodingMeta of column 1: right after column 0's stream
+    hs, ncol = blk.b.header_size, 3
+    ah = block[hs:hs + 12]
+    so = block[len(block) - int(ah[6:10].view(np.uint32)[0]):]
+    ends = so[5:].view({1: np.uint8, 2: np.uint16, 4: np.uint32}[1 << int(so[3])])
+    dm = block[int(ends[0]):int(ends[0]) + 10]
+    is_const = bool(dm[1] & 0x4)
+    assert is_const == (shape in ("one_value", "dominant_value", "dominant_null"))
+    ref_row_cnt = int(dm[6:10].view(np.uint32)[0])
+    assert ref_row_cnt == (2 + 2 * exc if is_const else n)
+    assert [blk.cell(1, r) for r in range(n)] == expect
+    assert [blk.cell(2, r) for r in range(0, n, 97)] == [3 * r for r in range(0, n, 97)]
+    probe = expect[int(where[0])] if exc and shape != "dominant_null" else (expect[0] if expect[0] is not None else expect[int(where[0])])
+    for op, params in ((ob.WHITE_OP_EQ, (probe,)), (ob.WHITE_OP_NE, (probe,)), (ob.WHITE_OP_NU, ()), (ob.WHITE_OP_GE, (probe,))):
+        if kind == "int":
+            params = tuple(int(np.int64(np.uint64(x))) for x in params)
+        bits = blk.filter_tree(White(1, op, params))
+        want = np.array([(e is None) if op == ob.WHITE_OP_NU else (e is not None and {ob.WHITE_OP_EQ: e == probe, ob.WHITE_OP_NE: e != probe,
+                         ob.WHITE_OP_GE: (np.int64(np.uint64(e)) >= np.int64(np.uint64(probe))) if kind == "int" else e >= probe}[op])
+                         for e in expect], dtype=np.uint8)
+        assert np.array_equal(bits, want), op

@@ -188,3 +188,30 @@ def test_cs_string_block_entry_points_and_bytes(ob, ctx):
                 assert bytes(image[off:off + int(lens[r])]) == v[r]
     res.free()
     batch.close()
+
+
+@pytest.mark.parametrize("kind", ["int", "str"])
+def test_cs_dict_const_encoded_refs_scan(ob, ctx, kind):
+    # a dominant value (or NULL) per block: the encoder's const-encoded ref stream -> K_CONST plan over the dictionary
+    rng = np.random.default_rng(41)
+    n = 12_000
+    idx = np.zeros(n, dtype=np.int64)
+    where = rng.choice(n, size=n // 40, replace=False)            # 2.5 % exceptions
+    idx[where] = rng.integers(1, 9, size=len(where))
+    nulls = np.zeros(n, dtype=np.uint8)
+    nulls[6000:] = 1                                              # second half: NULL is the const ref
+    nulls[where] = 0
+    idx[9000:9600] = 0                                            # one block with a single distinct ref (all NULL)
+    nulls[9000:9600] = 1
+    if kind == "int":
+        col = ob.Column(ob.OBJ_INT, ob.ENC_CS_INT_DICT, (idx * 1000 - 3000).astype(np.int64), nulls=nulls)
+        probe, is_str = 1000, False
+    else:
+        words = [b"", b"alpha", b"be", b"gamma", b"delta!", b"e", b"zeta", b"eta", b"theta"]
+        col = ob.Column(ob.OBJ_VARCHAR, ob.ENC_CS_STR_DICT, [words[i] for i in idx.tolist()], nulls=nulls)
+        probe, is_str = b"gamma", True
+    table = ob.encode_table([col, ob.Column(ob.OBJ_INT, ob.ENC_CS_INTEGER, np.arange(n, dtype=np.int64))], 600)
+    for flt in (None, ob.White(0, ob.WHITE_OP_EQ, (probe,)), ob.White(0, ob.WHITE_OP_NE, (probe,)), ob.White(0, ob.WHITE_OP_NU, ()),
+                ob.And([ob.White(0, ob.WHITE_OP_GE, (probe,)), ob.White(1, ob.WHITE_OP_LT, (8000,))]),
+                ob.Or([ob.White(0, ob.WHITE_OP_NN, ()), ob.White(1, ob.WHITE_OP_EQ, (9100,))])):
+        assert_scan_matches(ctx, W(table, flt, [0, 1], [is_str, False], [8, 8]))
