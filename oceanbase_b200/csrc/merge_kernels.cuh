@@ -524,9 +524,9 @@ int obgpu_merge_decoded(obgpu_ctx *ctx, const obgpu_merge_run *runs, int32_t n_r
     mrg::head_kernel<<<(unsigned)n_tiles, 256, 0, ctx->stream>>>(kin, sin, N, rd, emit, tile_cnt, res->d_stats, res->d_status);
     const int nc = (int)n_chunks;
     obgpu_prefix_local_kernel<<<nc, 256, 0, ctx->stream>>>(tile_cnt, (int)n_tiles, res->d_tile_off,
-                                                          (unsigned long long *)(a + o_chunk), nullptr);
+                                                          (unsigned long long *)(a + o_chunk));
     obgpu_prefix_fix_kernel<<<nc + 1, 256, 0, ctx->stream>>>((int)n_tiles, nc, res->d_tile_off,
-                                                            (const unsigned long long *)(a + o_chunk), nullptr, nullptr);
+                                                            (const unsigned long long *)(a + o_chunk));
     mrg::fuse_kernel<<<(unsigned)n_tiles, 256, 0, ctx->stream>>>(
         kin, sin, N, rd, emit, res->d_tile_off, (const int64_t *)(a + o_def), (const uint8_t *)(a + o_def + (size_t)n_cols * 8),
         res->d_out_key, (int64_t *const *)(d_tbl + t_ov), (uint8_t *const *)(d_tbl + t_on), res->d_stats);

@@ -70,7 +70,6 @@ struct ScanParams {
   const uint32_t *blk_size;   // [n_blocks] exact block size
   const int64_t *bm_word_off; // [n_blocks + 1] prefix of ceil(rows / 32)
   int32_t n_blocks;
-  int32_t blk_first, blk_count;  // blocks [blk_first, blk_first + blk_count) belong to this launch (a slice of the batch)
   const ColDesc *plans;       // [n_blocks][max_cols] decode plans built once at batch open (index kernel)
   const uint32_t *rows;       // [n_blocks] row counts (0: corrupt block)
   const BlockRec *recs;       // [n_blocks] addressing + header fields (index kernel)
@@ -855,9 +854,8 @@ __global__ void __launch_bounds__(256) obgpu_index_kernel(const uint8_t *image, 
 // =================================================================================================
 __global__ void __launch_bounds__(kThreads) obgpu_count_kernel(const __grid_constant__ ScanParams p) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int local = blockIdx.x * kWarps + warp;
-  if (local >= p.blk_count) return;
-  const int block = p.blk_first + local;
+  const int block = blockIdx.x * kWarps + warp;
+  if (block >= p.n_blocks) return;
   uint8_t *wr = g_smem + (uint32_t)warp * p.cw_bytes;
   ColDesc *descs = reinterpret_cast<ColDesc *>(wr + p.cw_desc);
   uint32_t *bm = reinterpret_cast<uint32_t *>(wr + p.cw_bm);
@@ -1016,10 +1014,8 @@ __global__ void __launch_bounds__(kThreads) obgpu_count_kernel(const __grid_cons
 //   pass 2: every CTA adds the sum of the preceding chunk totals to its chunk.
 // =================================================================================================
 constexpr int kPrefixChunk = 2048;
-// `base`: selected rows before the first element (a slice of the batch continues the previous slice's total);
-// nullptr = 0. The first chunk's entries are therefore final after pass 1.
 __global__ void __launch_bounds__(256) obgpu_prefix_local_kernel(const uint32_t *counts, int n, int64_t *sel_offset,
-                                                                 unsigned long long *chunk_total, const int64_t *base_ptr) {
+                                                                 unsigned long long *chunk_total) {
   __shared__ unsigned long long s_warp[8];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int base = blockIdx.x * kPrefixChunk + tid * 8;
@@ -1044,7 +1040,7 @@ __global__ void __launch_bounds__(256) obgpu_prefix_local_kernel(const uint32_t 
     woff += k < warp ? s_warp[k] : 0ull;
     total += s_warp[k];
   }
-  unsigned long long run = woff + inc - sum + (base_ptr ? (unsigned long long)*base_ptr : 0ull);
+  unsigned long long run = woff + inc - sum;
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     if (base + k < n) sel_offset[base + k] = (int64_t)run;
@@ -1054,8 +1050,7 @@ __global__ void __launch_bounds__(256) obgpu_prefix_local_kernel(const uint32_t 
 }
 
 __global__ void __launch_bounds__(256) obgpu_prefix_fix_kernel(int n, int n_chunks, int64_t *sel_offset,
-                                                               const unsigned long long *chunk_total, const int64_t *base_ptr,
-                                                               int64_t *total_out) {
+                                                               const unsigned long long *chunk_total) {
   __shared__ unsigned long long s_off;
   const int tid = threadIdx.x, lane = tid & 31;
   if (tid < 32) {
@@ -1068,12 +1063,8 @@ __global__ void __launch_bounds__(256) obgpu_prefix_fix_kernel(int n, int n_chun
   }
   __syncthreads();
   const unsigned long long off = s_off;
-  if (blockIdx.x == n_chunks) {  // extra CTA: total (the next slice's base)
-    if (tid == 0) {
-      const int64_t total = (int64_t)off + (base_ptr ? *base_ptr : 0);
-      sel_offset[n] = total;
-      if (total_out) *total_out = total;
-    }
+  if (blockIdx.x == n_chunks) {  // extra CTA: total
+    if (tid == 0) sel_offset[n] = (int64_t)off;
     return;
   }
   const int base = blockIdx.x * kPrefixChunk + tid * 8;
@@ -1111,8 +1102,8 @@ __global__ void __launch_bounds__(kThreads) obgpu_project_kernel(const __grid_co
   const int ntiles = MULTI ? p.proj_tiles : 1;  // MULTI = false: the loop and its bookkeeping compile away
   for (int it = 0; it < ntiles; ++it) {
     const int lin = (int)blockIdx.x * ntiles + it;
-    if (lin >= p.blk_count) break;
-    const int tile = p.blk_first + p.blk_count - 1 - lin;
+    if (lin >= p.n_blocks) break;
+    const int tile = p.n_blocks - 1 - lin;
     if (used_bar) __syncthreads();  // everyone is done with the shared state of the previous block
 
     // one round trip: block record + the two prefix entries (independent loads)
@@ -1351,9 +1342,8 @@ __global__ void __launch_bounds__(kThreads) obgpu_project_kernel(const __grid_co
 // =================================================================================================
 __global__ void __launch_bounds__(kThreads) obgpu_project_sparse_kernel(const __grid_constant__ ScanParams p) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int local = blockIdx.x * kWarps + warp;
-  if (local >= p.blk_count) return;
-  const int tile = p.blk_first + local;
+  const int tile = blockIdx.x * kWarps + warp;
+  if (tile >= p.n_blocks) return;
   const BlockRec rec = p.recs[tile];
   const int64_t base = p.sel_offset[tile];
   const uint32_t cnt = (uint32_t)(p.sel_offset[tile + 1] - base);
@@ -1593,10 +1583,6 @@ struct obgpu_ctx {
   static constexpr int kProfRing = 256;
   cudaEvent_t ev0[kProfRing] = {nullptr}, ev1[kProfRing] = {nullptr};
   int64_t prof_count = 0;
-  // sliced scans: the filter (count + prefix) of slice c + 1 runs on aux_stream while slice c is projected on `stream`
-  static constexpr int kMaxSlices = 8;
-  cudaStream_t aux_stream = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_slice[kMaxSlices] = {nullptr};
 };
 
 struct obgpu_batch {
@@ -1716,9 +1702,6 @@ void obgpu_ctx_destroy(obgpu_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  if (ctx->aux_stream) { cudaStreamSynchronize(ctx->aux_stream); cudaStreamDestroy(ctx->aux_stream); }
-  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
-  for (int i = 0; i < obgpu_ctx::kMaxSlices; ++i) if (ctx->ev_slice[i]) cudaEventDestroy(ctx->ev_slice[i]);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   for (int i = 0; i < obgpu_ctx::kProfRing; ++i) {
@@ -2374,16 +2357,6 @@ static int check_status(obgpu_ctx *ctx, int status) {
 
 extern "C" {
 
-static int ensure_aux_stream(obgpu_ctx *ctx) {
-  if (ctx->aux_stream) return OBGPU_SUCCESS;
-  if (cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking) != cudaSuccess) { ctx->aux_stream = nullptr; return OBGPU_ERR_SYS; }
-  bool ok = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess;
-  for (int i = 0; ok && i < obgpu_ctx::kMaxSlices; ++i)
-    ok = cudaEventCreateWithFlags(&ctx->ev_slice[i], cudaEventDisableTiming) == cudaSuccess;
-  if (!ok) { cudaGetLastError(); return OBGPU_ERR_SYS; }
-  return OBGPU_SUCCESS;
-}
-
 int obgpu_scan(obgpu_batch *b, const obgpu_scan_spec *spec, obgpu_result **out) {
   if (!b || !spec || !out) return OBGPU_INVALID_ARGUMENT;
   obgpu_ctx *ctx = b->ctx;
@@ -2432,7 +2405,7 @@ int obgpu_scan(obgpu_batch *b, const obgpu_scan_spec *spec, obgpu_result **out) 
   for (int c = 0; c < spec->n_proj; ++c) o_nulls[c] = take(null_bytes);
   const size_t zero_bytes = off;
   const size_t o_counts = take((size_t)n * 4);
-  const size_t o_chunk = take(((size_t)n / kPrefixChunk + 2 * (size_t)obgpu_ctx::kMaxSlices + 2) * 8);
+  const size_t o_chunk = take(((size_t)n / kPrefixChunk + 2) * 8);
   const size_t o_sel = take(((size_t)n + 1) * 8);
   const size_t o_bm = take((size_t)b->bm_word_off[(size_t)n] * 4 + 4);
   const size_t o_rid = spec->want_row_ids ? take((size_t)r->cap * 4) : 0;
@@ -2490,83 +2463,40 @@ int obgpu_scan(obgpu_batch *b, const obgpu_scan_spec *spec, obgpu_result **out) 
   r->no_filter = p.n_nodes == 0;
   r->d_skip_counters = (unsigned long long *)(a + o_misc + 16);
   // ---- launches: [skip index ->] count (filter) -> prefix -> project --------------------------------
-  // A large filtered batch is cut into slices: the filter side (count + prefix) of the slices runs back to back on the
-  // ctx's auxiliary stream, the projection of slice c starts on the ctx stream as soon as ITS prefix is there. The count
-  // kernel is latency-bound and the project kernel bandwidth-bound, so the count of the later slices hides under the
-  // projection of the earlier ones; a slice's filter column is also still in L2 when its projection re-reads it.
-  if (p.n_nodes > 0 && (int)(p.cw_bytes * (uint32_t)kWarps) > ctx->max_smem_optin) {
-    ctx->err = "filter working set exceeds shared memory";
-    obgpu_result_free(r);
-    return OBGPU_NOT_SUPPORTED;
-  }
   const int pslot = (int)(ctx->prof_count % obgpu_ctx::kProfRing);
   if (ctx->profiling) cudaEventRecord(ctx->ev0[pslot], ctx->stream);
-  int n_slices = 1;
-  int32_t bounds[obgpu_ctx::kMaxSlices + 1] = {0};
-  {
-    int want = (p.n_nodes > 0 && (p.n_proj + p.want_row_ids) > 0 && n >= 16384) ? 5 : 1;
-    if (const char *e2 = getenv("OBGPU_SCAN_SLICES")) want = std::max(1, std::min(atoi(e2), obgpu_ctx::kMaxSlices));  // testing knob
-    if (want > 1 && (p.n_nodes == 0 || n < want * 64)) want = 1;
-    if (want > 1 && ensure_aux_stream(ctx) != OBGPU_SUCCESS) want = 1;
-    n_slices = want;
-    // a short first slice (1/16 of the batch) so that the projection starts early; the rest in equal parts
-    for (int c = 1; c < n_slices; ++c) {
-      int64_t at = n / 16 + (int64_t)(n - n / 16) * (c - 1) / (n_slices - 1);
-      at = (at + 31) / 32 * 32;     // whole count CTAs and whole project tiles
-      bounds[c] = (int32_t)std::min<int64_t>(std::max<int64_t>(at, bounds[c - 1] + 32), n);
-    }
-    bounds[n_slices] = n;
-    for (int c = 1; c < n_slices; ++c)
-      if (bounds[c] >= n) { n_slices = c; bounds[c] = n; break; }
-  }
-  cudaStream_t fs = n_slices > 1 ? ctx->aux_stream : ctx->stream;   // stream of the filter side
-  if (n_slices > 1) {
-    cudaEventRecord(ctx->ev_fork, ctx->stream);       // arena allocated / zeroed, earlier work of the caller done
-    cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0);
-  }
   if (use_skip) {
-    skipidx::skip_index_kernel<<<(n + 127) / 128, 128, 0, fs>>>(p, b->d_agg, b->d_agg_off, a + o_blk_const,
-                                                                a + o_leaf_const, r->d_skip_counters);
+    skipidx::skip_index_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(p, b->d_agg, b->d_agg_off, a + o_blk_const,
+                                                                        a + o_leaf_const, r->d_skip_counters);
     ctx->launches++;
     p.blk_const = a + o_blk_const;
     p.leaf_const = a + o_leaf_const;
   }
-  unsigned long long *chunk_scratch = (unsigned long long *)(a + o_chunk);
-  int64_t *slice_total = (int64_t *)(a + o_misc + 32);   // [2]: running total handed from slice to slice (ping-pong)
-  size_t chunk_at = 0;
-  // filter side of every slice
-  for (int c = 0; c < n_slices; ++c) {
-    const int32_t b0 = bounds[c], cnt_blocks = bounds[c + 1] - bounds[c];
-    p.blk_first = b0;
-    p.blk_count = cnt_blocks;
-    if (p.n_nodes > 0) {
-      obgpu_count_kernel<<<(cnt_blocks + kWarps - 1) / kWarps, kThreads, p.cw_bytes * (uint32_t)kWarps, fs>>>(p);
-      ctx->launches++;
+  if (p.n_nodes > 0) {
+    const uint32_t cw_total = p.cw_bytes * (uint32_t)kWarps;
+    if ((int)cw_total > ctx->max_smem_optin) {
+      ctx->err = "filter working set exceeds shared memory";
+      obgpu_result_free(r);
+      return OBGPU_NOT_SUPPORTED;
     }
-    const int n_chunks = (cnt_blocks + kPrefixChunk - 1) / kPrefixChunk;
-    const uint32_t *cnts = (p.n_nodes > 0 ? p.counts : b->d_rows) + b0;
-    const int64_t *base_in = c > 0 ? slice_total + ((c - 1) & 1) : nullptr;
-    obgpu_prefix_local_kernel<<<n_chunks, 256, 0, fs>>>(cnts, cnt_blocks, p.sel_offset + b0, chunk_scratch + chunk_at, base_in);
-    obgpu_prefix_fix_kernel<<<n_chunks + 1, 256, 0, fs>>>(cnt_blocks, n_chunks, p.sel_offset + b0, chunk_scratch + chunk_at, base_in,
-                                                         slice_total + (c & 1));
-    ctx->launches += 2;
-    chunk_at += (size_t)n_chunks + 1;
-    if (n_slices > 1) cudaEventRecord(ctx->ev_slice[c], fs);
+    obgpu_count_kernel<<<(n + kWarps - 1) / kWarps, kThreads, cw_total, ctx->stream>>>(p);
+    ctx->launches++;
   }
-  // projection side
-  for (int c = 0; c < n_slices; ++c) {
-    const int32_t b0 = bounds[c], cnt_blocks = bounds[c + 1] - bounds[c];
-    if (n_slices > 1) cudaStreamWaitEvent(ctx->stream, ctx->ev_slice[c], 0);
-    if (p.n_proj + p.want_row_ids <= 0) continue;
-    p.blk_first = b0;
-    p.blk_count = cnt_blocks;
+  {
+    const int n_chunks = (n + kPrefixChunk - 1) / kPrefixChunk;
+    const uint32_t *cnts = p.n_nodes > 0 ? p.counts : b->d_rows;
+    obgpu_prefix_local_kernel<<<n_chunks, 256, 0, ctx->stream>>>(cnts, n, p.sel_offset, (unsigned long long *)(a + o_chunk));
+    obgpu_prefix_fix_kernel<<<n_chunks + 1, 256, 0, ctx->stream>>>(n, n_chunks, p.sel_offset, (const unsigned long long *)(a + o_chunk));
+    ctx->launches += 2;
+  }
+  if (p.n_proj + p.want_row_ids > 0) {
     p.proj_tiles = p.sparse_split ? 8 : 1;
-    if (p.sparse_split) obgpu_project_kernel<true><<<(cnt_blocks + p.proj_tiles - 1) / p.proj_tiles, kThreads, p.smem_total, ctx->stream>>>(p);
-    else obgpu_project_kernel<false><<<cnt_blocks, kThreads, p.smem_total, ctx->stream>>>(p);
+    if (p.sparse_split) obgpu_project_kernel<true><<<(n + p.proj_tiles - 1) / p.proj_tiles, kThreads, p.smem_total, ctx->stream>>>(p);
+    else obgpu_project_kernel<false><<<n, kThreads, p.smem_total, ctx->stream>>>(p);
     ctx->launches++;
     if (p.sparse_split) {
       const uint32_t per_warp = (((p.rows_cap / 16u + 32u) * 2u + 15u) & ~15u) + (uint32_t)sizeof(ColDesc);
-      obgpu_project_sparse_kernel<<<(cnt_blocks + kWarps - 1) / kWarps, kThreads, per_warp * (uint32_t)kWarps, ctx->stream>>>(p);
+      obgpu_project_sparse_kernel<<<(n + kWarps - 1) / kWarps, kThreads, per_warp * (uint32_t)kWarps, ctx->stream>>>(p);
       ctx->launches++;
     }
   }

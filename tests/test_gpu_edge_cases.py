@@ -188,34 +188,3 @@ def test_blocks_larger_than_shared_memory(ob, ctx):
     for flt in (None, ob.White(1, ob.WHITE_OP_LT, (900,)), ob.White(1, ob.WHITE_OP_LT, (20,)),
                 ob.And([ob.White(2, ob.WHITE_OP_GE, (0,)), ob.White(9, ob.WHITE_OP_NN, ())])):
         assert_scan_matches(ctx, W(table, flt, PROJ, IS_STR, ELEM))
-
-
-@pytest.mark.parametrize("slices", ["1", "2", "5", "8"])
-@pytest.mark.parametrize("shape", ["cfg2", "cfg3", "sparse", "skip_index"])
-def test_sliced_scan_pipeline(ob, ctx, slices, shape, monkeypatch):
-    # large filtered batches are cut into slices whose filter side runs on an auxiliary stream ahead of the
-    # projection (OBGPU_SCAN_SLICES forces the slicing on a small table): same rows, same order, same offsets
-    from oceanbase_b200.synth import make_config2_like, make_config3_like
-    monkeypatch.setenv("OBGPU_SCAN_SLICES", slices)
-    agg = None
-    kw = {}
-    if shape == "cfg2":
-        w = make_config2_like(rows=90_000, rows_per_block=130, seed=31)
-    elif shape == "cfg3":
-        w = make_config3_like(rows=60_000, rows_per_block=100, seed=32)
-    elif shape == "sparse":
-        w = make_config2_like(rows=90_000, rows_per_block=130, seed=33)
-        w.filter = ob.White(4, ob.WHITE_OP_EQ, (5,))          # 1/128 of the rows: the warp-per-block kernel
-        kw["max_selected_rows"] = 4000
-    else:
-        rng = np.random.default_rng(34)
-        n = 80_000
-        k = np.sort(rng.integers(0, 1 << 30, size=n, dtype=np.int64))
-        v = rng.integers(0, 100, size=n, dtype=np.int64)
-        cols = [ob.Column(ob.OBJ_INT, ob.ENC_INTEGER_BASE_DIFF, k), ob.Column(ob.OBJ_INT, ob.ENC_RAW, v)]
-        table = ob.encode_table(cols, 120)
-        agg = ob.table_agg_rows(cols, [0, 1], 120)
-        flt = ob.And([ob.White(0, ob.WHITE_OP_BT, (int(k[20_000]), int(k[50_000]))), ob.White(1, ob.WHITE_OP_LT, (50,))])
-        w = W(table, flt, [0, 1], [False, False], [8, 8])
-    for _ in range(3):                                         # back-to-back scans reuse the ctx's stream pair
-        assert_scan_matches(ctx, w, agg=agg, **kw)
