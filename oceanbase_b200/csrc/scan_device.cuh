@@ -643,8 +643,11 @@ __device__ __forceinline__ void build_col_desc(const BlockView &b, int col, ColD
           }
         }
       } else {
-        if (sc != 5) return;  // integer var store is not produced for the supported shapes
+        // var-stored cells in the row data: strings, and integer columns the encoder turned into var-stored ones
+        // because NULLs dominate (ObRawEncoder::traverse, ob_raw_encoder.cpp:106-110,150-155: a non-NULL cell
+        // holds the low fix_data_size_ bytes of the datum, a NULL cell nothing)
         if (b.row_index_byte == 0) return;
+        d.sign_fix = sc != 5 && d.int_mask != 0;
         d.kind = K_VARSTR;
         d.var_ext_in_row = has_ext;
         d.ext_bit = has_ext ? b.ext_bit : 0;
@@ -918,10 +921,20 @@ __device__ __forceinline__ void dict_str(const uint8_t *s, const ColDesc &d, uin
 // ---- integer-class cell (generic path) -----------------------------------------------------------
 // Returns the 64-bit value image the reference would MEMCPY into the datum (low elem_len bytes
 // significant); is_null set for NULL (and NOP) cells.
+__device__ __forceinline__ void str_cell(const BlockView &b, const ColDesc &d, const RleTable *rt, uint32_t row,
+                                         uint32_t &cell, uint32_t &len, bool &is_null);
+
 __device__ __forceinline__ uint64_t int_cell(const BlockView &b, const ColDesc &d, const RleTable *rt,
                                              uint32_t row, bool &is_null) {
   const uint8_t *s = b.s;
   is_null = false;
+  if (d.kind == K_VARSTR) {  // var-stored integer: the cell's bytes are the low bytes of the datum
+    uint32_t cell, len;
+    str_cell(b, d, rt, row, cell, len, is_null);
+    if (is_null) return 0;
+    const uint64_t v = len ? ld_bytes(s, cell, len < 8u ? len : 8u) : 0ull;
+    return d.sign_fix ? sign_fix(d.int_mask, v) : v;
+  }
   if (is_dict_kind(d)) {
     const uint32_t ref = ref_of(s, d, rt, row);
     if (ref >= d.dict_count) { is_null = true; return 0; }

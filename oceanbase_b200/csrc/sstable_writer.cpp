@@ -134,6 +134,7 @@ struct ColCtx {
 struct ColOut {
   ColumnHeader hdr{};
   bool is_var = false;          // var-length cells live in the row data
+  int var_int_size = 0;         // integer column turned into a var-stored one: bytes per non-NULL cell
   bool need_ext_in_row = false; // var column with NULLs: ext bits inside each row
 };
 
@@ -402,9 +403,17 @@ int BlockBuilder::encode_raw(int i) {
       if (!c.is_null(r)) max_integer = std::max(max_integer, c.uval(r));
     bool bp = false;
     const int64_t size = packing_size(&bp, max_integer, c.enable_bp);
-    // The reference turns the column into a var-stored one when NULLs dominate
-    // (ob_raw_encoder.cpp:106-110,150-155); integer var store is outside this writer's scope.
-    if (bp ? size * c.null_cnt > nrows * 2 * 8 : size * c.null_cnt > nrows * 2) return OBGPU_NOT_SUPPORTED;
+    // The reference turns the column into a var-stored one when NULLs dominate (ObRawEncoder::traverse,
+    // ob_raw_encoder.cpp:106-110,150-155): every non-NULL cell then takes fix_data_size_ bytes of the row data
+    // (size / 8 + 1 for a bit-packing width, else the byte width; get_var_length :194-234, store_data
+    // ob_raw_encoder.h:84-122), a NULL cell none.
+    if (bp ? size * c.null_cnt > nrows * 2 * 8 : size * c.null_cnt > nrows * 2) {
+      o.is_var = true;
+      o.var_int_size = (int)(bp ? size / 8 + 1 : size);
+      o.need_ext_in_row = has_null;
+      if (has_null) o.hdr.attr_ |= ATTR_HAS_EXTEND_VALUE;
+      return OBGPU_SUCCESS;
+    }
     o.hdr.attr_ |= ATTR_FIX_LENGTH;
     if (has_null) o.hdr.attr_ |= ATTR_HAS_EXTEND_VALUE;
     if (bp) o.hdr.attr_ |= ATTR_BIT_PACKING;
@@ -750,7 +759,8 @@ int BlockBuilder::build(std::vector<uint8_t> &block) {
       int col_idx_byte = 0;
       for (size_t k = 0; k < nv; ++k) {
         const ColCtx &c = ctx[(size_t)var_cols[k]];
-        lens[k] = c.is_null(r) ? 0 : c.sval(r).len;
+        const int vis = out[(size_t)var_cols[k]].var_int_size;
+        lens[k] = c.is_null(r) ? 0 : (vis > 0 ? (int64_t)vis : c.sval(r).len);
         if (k > 0 && k == nv - 1) col_idx_byte = var_size <= 0xff ? 1 : (var_size <= 0xffff ? 2 : 4);
         var_size += lens[k];
       }
@@ -773,6 +783,9 @@ int BlockBuilder::build(std::vector<uint8_t> &block) {
         }
         if (c.is_null(r)) {
           put_bits(data, out[(size_t)var_cols[k]].hdr.extend_value_index_, ext_bit, c.ext_val(r));
+        } else if (out[(size_t)var_cols[k]].var_int_size > 0) {
+          const uint64_t v = c.uval(r);   // low bytes of the datum (MEMCPY(buf, datum.ptr_, len))
+          memcpy(var + off, &v, (size_t)std::min<int64_t>(lens[k], 8));
         } else if (lens[k] > 0) {
           memcpy(var + off, c.sval(r).p, (size_t)lens[k]);
         }

@@ -188,3 +188,24 @@ def test_blocks_larger_than_shared_memory(ob, ctx):
     for flt in (None, ob.White(1, ob.WHITE_OP_LT, (900,)), ob.White(1, ob.WHITE_OP_LT, (20,)),
                 ob.And([ob.White(2, ob.WHITE_OP_GE, (0,)), ob.White(9, ob.WHITE_OP_NN, ())])):
         assert_scan_matches(ctx, W(table, flt, PROJ, IS_STR, ELEM))
+
+
+@pytest.mark.parametrize("obj_type,lo,hi,elem", [("OBJ_DATE", -30000, 30000, 4), ("OBJ_UINT32", 1065958239, 1065960342, 8),
+                                                  ("OBJ_INT", -5, 1 << 40, 8), ("OBJ_INT32", -100, 100, 8)])
+def test_var_stored_integer_columns(ob, ctx, obj_type, lo, hi, elem):
+    # NULL-dominated RAW integer columns live in the row data next to the var-length strings (ObRawEncoder::traverse)
+    t = getattr(ob, obj_type)
+    rng = np.random.default_rng(14)
+    n = 9000
+    v = rng.integers(lo, hi, size=n, dtype=np.int64)
+    nulls = (rng.random(n) < 0.7).astype(np.uint8)
+    s = [bytes(rng.integers(97, 123, size=int(rng.integers(0, 9)), dtype=np.uint8)) for _ in range(n)]
+    k = rng.integers(0, 1000, size=n, dtype=np.int64)
+    table = ob.encode_table([ob.Column(t, ob.ENC_RAW, v, nulls=nulls), ob.Column(ob.OBJ_VARCHAR, ob.ENC_RAW, s),
+                             ob.Column(t, ob.ENC_RAW, v[::-1].copy(), nulls=nulls), ob.Column(ob.OBJ_INT, ob.ENC_RAW, k)], 800)
+    assert not (table.block(0)[64 + 2] & 1)                                     # column 0 is var-stored
+    mid = int(np.median(v))
+    for flt in (None, ob.White(0, ob.WHITE_OP_GE, (mid,)), ob.White(2, ob.WHITE_OP_NU, ()), ob.White(3, ob.WHITE_OP_LT, (30,)),
+                ob.And([ob.White(0, ob.WHITE_OP_LT, (mid,)), ob.White(2, ob.WHITE_OP_NE, (int(v[5]),)), ob.White(3, ob.WHITE_OP_GE, (100,))]),
+                ob.Or([ob.White(0, ob.WHITE_OP_IN, (int(v[0]), int(v[1]), int(v[2]))), ob.White(1, ob.WHITE_OP_EQ, (s[9],))])):
+        assert_scan_matches(ctx, W(table, flt, [0, 1, 2, 3], [False, True, False, False], [elem, 8, elem, 8]))

@@ -141,7 +141,7 @@ def random_leaf(ob, rng, meta, n):
         key = (lambda z: z) if is_str or t != ob.OBJ_UINT64 else (lambda z: z % (1 << 64))
         params = (a, b) if key(a) <= key(b) or rng.integers(0, 5) == 0 else (b, a)
     elif op == ob.WHITE_OP_IN:
-        params = tuple(const() for _ in range(int(rng.integers(1, 6))))
+        params = tuple(const() for _ in range(int(rng.integers(1, 5))))
         if rng.integers(0, 6) == 0:
             params = params + (None,)
     else:
@@ -153,7 +153,7 @@ def random_filter(ob, rng, meta, n, depth=0):
     r = rng.integers(0, 10)
     if depth >= 2 or r < 4:
         return random_leaf(ob, rng, meta, n)
-    kids = [random_filter(ob, rng, meta, n, depth + 1) for _ in range(int(rng.integers(2, 5)))]
+    kids = [random_filter(ob, rng, meta, n, depth + 1) for _ in range(int(rng.integers(2, 4)))]   # <= 13 nodes, <= 45 constants
     return ob.And(kids) if r < 7 else ob.Or(kids)
 
 

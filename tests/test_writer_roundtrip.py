@@ -220,3 +220,38 @@ def test_page_batch_bounds_with_ramp():
     assert batch_bounds(5, 16, 2) == [0, 4, 5]
     assert batch_bounds(3, 16, 3) == [0, 2, 3]
     assert batch_bounds(1, 1, 2) == [0, 1]
+
+
+@pytest.mark.parametrize("obj_type,lo,hi,null_frac,expect_var", [
+    (ob.OBJ_DATE, -30000, 30000, 0.7, True), (ob.OBJ_UINT32, 1065958239, 1065960342, 0.6, True),
+    (ob.OBJ_INT, -5, 1 << 40, 0.5, True), (ob.OBJ_INT32, -100, 100, 0.7, True),
+    (ob.OBJ_INT, 0, 1000, 0.1, False), (ob.OBJ_TINYINT, -128, 127, 0.7, False)])
+def test_integer_column_turned_into_var_store(obj_type, lo, hi, null_frac, expect_var):
+    # ObRawEncoder::traverse (ob_raw_encoder.cpp:106-110,150-155): when NULLs dominate, a RAW integer column is stored in
+    # the row data, fix_data_size_ bytes per non-NULL cell and nothing per NULL cell (get_var_length :194-234)
+    rng = np.random.default_rng(3)
+    n = 3000
+    v = rng.integers(lo, hi, size=n, dtype=np.int64)
+    nulls = (rng.random(n) < null_frac).astype(np.uint8)
+    s = [b"x%d" % i + b"y" * (i % 3) for i in range(n)]
+    table = ob.encode_table([ob.Column(obj_type, ob.ENC_RAW, v, nulls=nulls), ob.Column(ob.OBJ_VARCHAR, ob.ENC_RAW, s),
+                             ob.Column(obj_type, ob.ENC_RAW, v[::-1].copy(), nulls=nulls)], 700)
+    for b in range(table.n_blocks):
+        raw = table.block(b)
+        blk = ora.Block(raw)
+        assert blk.verify_checksums() == 0
+        assert bool(raw[64 + 2] & 1) != expect_var               # ObColumnHeader FIX_LENGTH attribute of column 0
+        assert int(raw[22:24].view(np.uint16)[0]) == (3 if expect_var else 1)    # var_column_count_
+        for c, vals in ((0, v), (2, v[::-1])):
+            for r in range(0, blk.row_count, 7):
+                g = b * 700 + r
+                d = blk.cell_raw(c, r)
+                if nulls[g]:
+                    assert d.is_null == 1
+                elif obj_type in (ob.OBJ_DATE,):
+                    assert d.len == 4 and np.int32(np.uint32(d.ival)) == vals[g]
+                elif obj_type == ob.OBJ_UINT32:
+                    assert d.ival == vals[g]
+                else:
+                    assert d.is_null == 0 and np.int64(np.uint64(d.ival)) == vals[g]
+        assert [blk.cell(1, r) for r in range(0, blk.row_count, 50)] == [s[b * 700 + r] for r in range(0, blk.row_count, 50)]
