@@ -2188,7 +2188,7 @@ static void layout_smem_scan(const obgpu_batch *b, ScanParams &p, int max_smem) 
     bool known = p.n_proj > 0;
     for (int i = 0; i < p.n_proj && known; ++i) {
       const size_t col = (size_t)p.used_col[p.proj_used[i]];
-      if (col >= b->col_span.size()) known = false;
+      if (col >= b->col_span.size() || b->col_span[col] == 0xffffffffu) known = false;   // no single region (CS string bytes)
       else sum += b->col_span[col];
     }
     p.compact = 0;
