@@ -139,6 +139,7 @@ void ObGpuSSTableBatchScanner::reset() {
   cur_block_ = 0;
   cur_row_ = 0;
   selected_ = 0;
+  rev_started_ = false;
 }
 
 int ObGpuSSTableBatchScanner::flatten(sql::ObPushdownFilterExecutor *f, std::vector<obgpu_filter_node> &nodes,
@@ -232,15 +233,49 @@ int ObGpuSSTableBatchScanner::init(const void *image, int64_t image_size, const 
 
 int ObGpuSSTableBatchScanner::get_next_rows(Batch &out) {
   if (!result_) return OB_NOT_INIT;
+  if (reverse_) return get_next_rows_reverse(out);
   // skip blocks without (remaining) selected rows
   while (cur_block_ < n_blocks_ && cur_row_ >= sel_offset_[(size_t)cur_block_ + 1]) ++cur_block_;
   if (cur_block_ >= n_blocks_) return OB_ITER_END;
   const int64_t end = sel_offset_[(size_t)cur_block_ + 1];
   const int64_t n = std::min<int64_t>(batch_size_, end - cur_row_);
-  out.block_idx = cur_block_;
+  const int ret = fetch_window(cur_block_, cur_row_, n, out);
+  cur_row_ += n;
+  return ret;
+}
+
+// Reverse scan (ObIMicroBlockRowScanner with step_ == -1, blocksstable/ob_micro_block_row_scanner.cpp:167-260: blocks
+// last to first, rows descending): the dense result is walked from its end, every window is handed out reversed.
+int ObGpuSSTableBatchScanner::get_next_rows_reverse(Batch &out) {
+  if (!rev_started_) {
+    rev_started_ = true;
+    cur_block_ = n_blocks_ - 1;
+    cur_row_ = selected_;      // one past the next row to hand out
+  }
+  while (cur_block_ >= 0 && cur_row_ <= sel_offset_[(size_t)cur_block_]) --cur_block_;
+  if (cur_block_ < 0) return OB_ITER_END;
+  const int64_t begin = sel_offset_[(size_t)cur_block_];
+  const int64_t n = std::min<int64_t>(batch_size_, cur_row_ - begin);
+  const int ret = fetch_window(cur_block_, cur_row_ - n, n, out);
+  if (ret == OB_SUCCESS) {
+    std::reverse(out.row_ids.begin(), out.row_ids.end());
+    for (size_t c = 0; c < proj_.size(); ++c) {
+      std::reverse(out.ints[c].begin(), out.ints[c].end());
+      std::reverse(out.str_ptrs[c].begin(), out.str_ptrs[c].end());
+      std::reverse(out.str_lens[c].begin(), out.str_lens[c].end());
+      std::reverse(out.is_null[c].begin(), out.is_null[c].end());
+    }
+  }
+  cur_row_ -= n;
+  return ret;
+}
+
+// rows [row_begin, row_begin + n) of the dense result (all inside block `block`) -> Batch
+int ObGpuSSTableBatchScanner::fetch_window(int32_t block, int64_t row_begin, int64_t n, Batch &out) {
+  out.block_idx = block;
   out.count = n;
   out.row_ids.resize((size_t)n);
-  int ret = obgpu_result_fetch_row_ids(result_, cur_row_, n, out.row_ids.data());
+  int ret = obgpu_result_fetch_row_ids(result_, row_begin, n, out.row_ids.data());
   const size_t np = proj_.size();
   out.ints.assign(np, {});
   out.str_ptrs.assign(np, {});
@@ -252,13 +287,13 @@ int ObGpuSSTableBatchScanner::get_next_rows(Batch &out) {
     if (cols_[c].is_string) {
       std::vector<uint64_t> ptrs((size_t)n);
       out.str_lens[c].resize((size_t)n);
-      ret = obgpu_result_fetch_col(result_, (int32_t)c, cur_row_, n, ptrs.data(), out.str_lens[c].data(), nulls.data());
+      ret = obgpu_result_fetch_col(result_, (int32_t)c, row_begin, n, ptrs.data(), out.str_lens[c].data(), nulls.data());
       out.str_ptrs[c].resize((size_t)n);
       for (int64_t i = 0; i < n; ++i) out.str_ptrs[c][(size_t)i] = reinterpret_cast<const char *>((uintptr_t)ptrs[(size_t)i]);
     } else {
       const int el = cols_[c].elem_len;
       std::vector<char> raw((size_t)n * el);
-      ret = obgpu_result_fetch_col(result_, (int32_t)c, cur_row_, n, raw.data(), nullptr, nulls.data());
+      ret = obgpu_result_fetch_col(result_, (int32_t)c, row_begin, n, raw.data(), nullptr, nulls.data());
       out.ints[c].resize((size_t)n);
       for (int64_t i = 0; i < n; ++i) {
         int64_t v = 0;
@@ -269,7 +304,6 @@ int ObGpuSSTableBatchScanner::get_next_rows(Batch &out) {
     }
     for (int64_t i = 0; i < n; ++i) out.is_null[c][(size_t)i] = (nulls[(size_t)i / 64] >> (i % 64)) & 1;
   }
-  cur_row_ += n;
   return ret;
 }
 

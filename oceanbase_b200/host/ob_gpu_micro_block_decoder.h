@@ -244,6 +244,9 @@ public:
   // micro blocks' index infos BEFORE init; the fused scan then prunes with their aggregate rows, and after init
   // every info carries the verdict (set_filter_constant_type) of the whole pushed-down filter on its block.
   int set_index_infos(ObMicroIndexInfo *infos, int32_t n_blocks);
+  // Reverse scan (is_reverse_scan_ / step_ == -1 of the row scanners): call before the first get_next_rows; batches then
+  // come blocks last to first, rows descending inside a block.
+  void set_reverse_scan(bool reverse) { reverse_ = reverse; }
   int64_t skipped_blocks() const { return skip_false_; }       // always-false: never read
   int64_t unfiltered_blocks() const { return skip_true_; }     // always-true: no filter evaluation
   // Next batch: count rows of block `block_idx`, row ids ascending. Integer columns are returned as
@@ -262,6 +265,9 @@ public:
 private:
   int flatten(sql::ObPushdownFilterExecutor *f, std::vector<obgpu_filter_node> &nodes,
               std::vector<obgpu_filter_param> &params);
+  int fetch_window(int32_t block, int64_t row_begin, int64_t n, Batch &out);
+  int get_next_rows_reverse(Batch &out);
+  bool reverse_ = false, rev_started_ = false;
   ObGpuScanRuntime &rt_;
   obgpu_batch *batch_ = nullptr;
   obgpu_result *result_ = nullptr;

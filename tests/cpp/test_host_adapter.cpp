@@ -321,6 +321,25 @@ static void test_filter_tree_and_batch_scanner(ObGpuScanRuntime &rt) {
   ASSERT_EQ(OB_ITER_END, ret);
   ASSERT_EQ(hi + 1, next);
   ASSERT_EQ(OB_INIT_TWICE, pruned.set_index_infos(infos.data(), nb));
+
+  // (4) reverse scan: same rows, blocks last to first, rows descending, batches of at most 100
+  ObGpuSSTableBatchScanner rev(rt);
+  rev.set_reverse_scan(true);
+  ASSERT_EQ(OB_SUCCESS, rev.init(image.data(), image_size, offs.data(), sizes.data(), nb, &bt, {0, 2}, 100));
+  next = hi;
+  while ((ret = rev.get_next_rows(batch)) == OB_SUCCESS) {
+    ASSERT_EQ(1, batch.count > 0 && batch.count <= 100);
+    for (int64_t i = 0; i < batch.count; ++i) {
+      ASSERT_EQ(next, batch.ints[0][(size_t)i]);
+      ASSERT_EQ(next, (int64_t)batch.block_idx * rpb + batch.row_ids[(size_t)i]);
+      const std::string want = heap.substr((size_t)off[(size_t)next], (size_t)(off[(size_t)next + 1] - off[(size_t)next]));
+      ASSERT_EQ((int64_t)want.size(), (int64_t)batch.str_lens[1][(size_t)i]);
+      ASSERT_EQ(0, memcmp(batch.str_ptrs[1][(size_t)i], want.data(), want.size()));
+      --next;
+    }
+  }
+  ASSERT_EQ(OB_ITER_END, ret);
+  ASSERT_EQ(lo - 1, next);
 }
 
 int main() {
