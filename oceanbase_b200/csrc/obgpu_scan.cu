@@ -80,8 +80,6 @@ struct ScanParams {
   uint8_t used_in_filter[kMaxUsedCols];
   uint8_t used_in_proj[kMaxUsedCols];
   int8_t used_rle_slot[kMaxUsedCols];  // run-table slot of a used column (-1: never RLE)
-  int8_t filt_used[kMaxUsedCols];      // used-column indexes referenced by the filter (count kernel plan prefetch)
-  int32_t n_filt;
   int32_t n_nodes;
   int32_t simple_shape;       // 1: single leaf or AND over leaves only, 2: OR over leaves only, 0: generic
   FilterNodeDev nodes[kMaxNodes];
@@ -854,7 +852,7 @@ __global__ void __launch_bounds__(256) obgpu_index_kernel(const uint8_t *image, 
 // sectors), writes the packed selection bitmap and the block's selected-row count. No staging, no
 // CTA barriers, no inter-block dependency.
 // =================================================================================================
-__global__ void __launch_bounds__(kThreads, 9) obgpu_count_kernel(const __grid_constant__ ScanParams p) {
+__global__ void __launch_bounds__(kThreads) obgpu_count_kernel(const __grid_constant__ ScanParams p) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int block = blockIdx.x * kWarps + warp;
   if (block >= p.n_blocks) return;
@@ -865,21 +863,12 @@ __global__ void __launch_bounds__(kThreads, 9) obgpu_count_kernel(const __grid_c
   Team t;
   t.tid = lane; t.nthreads = 32; t.warp = 0; t.nwarps = 1; t.lane = lane; t.bar_id = -1;
 
-  // one round trip for everything that only depends on the block index: the filter columns' decode plans (16-byte
-  // pieces spread over the lanes), the block record and the skip-index verdict are in flight together
-  constexpr int kPieces = (int)(sizeof(ColDesc) / 16);
-  const int npieces = p.n_filt * kPieces;
-  const ColDesc *gplans = p.plans + (int64_t)block * p.max_cols;
-  uint4 pv0{}, pv1{};
-  if (lane < npieces) pv0 = reinterpret_cast<const uint4 *>(gplans + p.used_col[p.filt_used[lane / kPieces]])[lane % kPieces];
-  if (lane + 32 < npieces)
-    pv1 = reinterpret_cast<const uint4 *>(gplans + p.used_col[p.filt_used[(lane + 32) / kPieces]])[(lane + 32) % kPieces];
-  const uint8_t verdict = p.blk_const != nullptr ? p.blk_const[block] : (uint8_t)0;
   const BlockRec rec = p.recs[block];
   const uint32_t rows = rec.rows;
   uint32_t *gbm = p.bitmap_words + rec.bm_word_off;
-  if (rows != 0) {
+  if (p.blk_const != nullptr && rows != 0) {
     // the skip index decided this block (ObMicroIndexInfo::is_filter_always_false / _true): it is not read
+    const uint8_t verdict = p.blk_const[block];
     if (verdict != 0) {
       const uint32_t nw = (rows + 31u) >> 5;
       for (uint32_t g = (uint32_t)lane; g < nw; g += 32u) gbm[g] = verdict == 1 ? valid_mask_of(rows, g) : 0u;
@@ -887,15 +876,12 @@ __global__ void __launch_bounds__(kThreads, 9) obgpu_count_kernel(const __grid_c
       return;
     }
   }
-  // plans -> shared memory (rle_slot stays -1: RLE filter columns use the run binary search here)
-  if (lane < npieces) reinterpret_cast<uint4 *>(descs + p.filt_used[lane / kPieces])[lane % kPieces] = pv0;
-  if (lane + 32 < npieces) reinterpret_cast<uint4 *>(descs + p.filt_used[(lane + 32) / kPieces])[(lane + 32) % kPieces] = pv1;
-  for (int k = lane + 64; k < npieces; k += 32)   // more than 10 filter columns: rare
-    reinterpret_cast<uint4 *>(descs + p.filt_used[k / kPieces])[k % kPieces] =
-        reinterpret_cast<const uint4 *>(gplans + p.used_col[p.filt_used[k / kPieces]])[k % kPieces];
-  __syncwarp();
   bool bad = rows == 0;
-  if (lane < p.n_filt) bad = bad || !descs[p.filt_used[lane]].ok;
+  if (lane < p.n_used && p.used_in_filter[lane]) {
+    const ColDesc d = p.plans[(int64_t)block * p.max_cols + p.used_col[lane]];
+    descs[lane] = d;  // rle_slot stays -1: RLE filter columns use the run binary search here
+    bad = bad || !d.ok;
+  }
   const bool any_bad = __any_sync(0xffffffffu, bad);
   if (any_bad) {
     if (lane == 0) {
@@ -2158,9 +2144,6 @@ static int build_filter(obgpu_ctx *ctx, const obgpu_batch *b, const obgpu_filter
     if (n_leaves == 1) p.n_nodes = 1;            // a single leaf needs no AND node
     else p.nodes[p.n_nodes - 1].n_children = (int16_t)n_leaves;
   }
-  p.n_filt = 0;
-  for (int i = 0; i < p.n_used; ++i)
-    if (p.used_in_filter[i]) p.filt_used[p.n_filt++] = (int8_t)i;
   return OBGPU_SUCCESS;
 }
 
