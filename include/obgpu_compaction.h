@@ -34,13 +34,21 @@ enum {
 #define OBGPU_MERGE_MAX_RUNS 64
 #define OBGPU_MERGE_MAX_COLS 64
 
-/* All cells of integer-class column `col` of an opened batch, in row order, into caller-owned DEVICE
+/* All cells of column `col` (integer class, or string class as references -- see below) of an opened batch, in row order, into caller-owned DEVICE
  * buffers of total_rows entries: value image (what the reference would MEMCPY into the datum, 0 for
  * ext cells) and ext (0 value, 1 NULL, 2 NOP -- ObStoredExtValue). Runs on the ctx stream. */
 int obgpu_batch_decode_column(obgpu_batch *batch, int32_t col, int64_t *dev_vals, uint8_t *dev_ext);
 /* Up to 16 columns with one launch and one synchronisation (each block image is read once). */
 int obgpu_batch_decode_columns(obgpu_batch *batch, int32_t n_cols, const int32_t *cols,
                                int64_t *const *dev_vals, uint8_t *const *dev_ext);
+
+/* String-class columns: the "value image" of a cell is a REFERENCE into the run's page batch,
+ *     ref = (tag << 58) | (byte offset of the cell inside the batch image << 22) | length
+ * (tag < 64, offset < 2^36, length < 2^22; larger cells report OBGPU_NOT_SUPPORTED). The merge moves references like
+ * integer cells; obgpu_merge_result_fetch_strings turns them back into bytes. `string_tag` names the run the batch
+ * belongs to (obgpu_merge_runs uses the run index); obgpu_batch_decode_columns is the tag-0 form. */
+int obgpu_batch_decode_columns_tagged(obgpu_batch *batch, int32_t n_cols, const int32_t *cols, int32_t string_tag,
+                                      int64_t *const *dev_vals, uint8_t *const *dev_ext);
 
 /* One sorted run, decoded, resident in HBM (all pointers are device pointers; the vals / ext
  * pointer ARRAYS themselves live in host memory). Rowkey: one INT64 column, ascending, unique
@@ -86,6 +94,17 @@ int obgpu_merge_result_cols(obgpu_merge_result *res, const int64_t **key_dev,
 /* Device -> host copy of rows [row_begin, row_begin + row_count) of column `col` (-1: the rowkey). */
 int obgpu_merge_result_fetch(obgpu_merge_result *res, int32_t col, int64_t row_begin,
                              int64_t row_count, int64_t *host_vals, uint8_t *host_null);
+
+/* String columns of the merged stream (what ObMacroBlockWriter::append_row receives as ObString datums): cells
+ * [row_begin, row_begin + row_count) of column `col` are copied back to back into host_heap, row i occupying
+ * [host_off[i], host_off[i + 1]) (row_count + 1 offsets; a NULL cell is empty and flagged in host_null). *heap_bytes
+ * receives the bytes needed; OBGPU_BUF_NOT_ENOUGH when heap_cap is smaller (nothing copied). The page batches the
+ * references point into must still be open: obgpu_merge_runs records their images itself; after obgpu_merge_decoded
+ * the caller names them (index = string tag). */
+int obgpu_merge_result_set_string_images(obgpu_merge_result *res, const void *const *dev_images, int32_t n_images);
+int obgpu_merge_result_fetch_strings(obgpu_merge_result *res, int32_t col, int64_t row_begin, int64_t row_count,
+                                     void *host_heap, int64_t heap_cap, int64_t *host_off, uint8_t *host_null,
+                                     int64_t *heap_bytes);
 
 #ifdef __cplusplus
 }

@@ -89,6 +89,30 @@ class MergeResult:
               "obgpu_merge_result_fetch", self.ctx._h)
         return v, nl
 
+    def fetch_strings(self, col: int, row_begin=0, row_count=None):
+        """String column `col` of the merged stream: (heap bytes uint8, offsets int64 [rows + 1], null bytes)."""
+        n = self.info().out_rows
+        if row_count is None:
+            row_count = n - row_begin
+        off = np.zeros(row_count + 1, dtype=np.int64)
+        nl = np.zeros(max(row_count, 1), dtype=np.uint8)
+        need = C.c_int64(0)
+        code = lib.obgpu_merge_result_fetch_strings(self._h, col, row_begin, row_count, None, 0, off.ctypes.data,
+                                                    nl.ctypes.data, C.byref(need))
+        if code not in (capi.OB_SUCCESS, capi.OB_BUF_NOT_ENOUGH):
+            check(code, "obgpu_merge_result_fetch_strings(size)", self.ctx._h)
+        heap = np.zeros(max(need.value, 1), dtype=np.uint8)
+        if need.value > 0:
+            check(lib.obgpu_merge_result_fetch_strings(self._h, col, row_begin, row_count, heap.ctypes.data, heap.size,
+                                                       off.ctypes.data, nl.ctypes.data, C.byref(need)),
+                  "obgpu_merge_result_fetch_strings", self.ctx._h)
+        return heap[:need.value], off, nl[:row_count]
+
+    def set_string_images(self, device_ptrs: Sequence[int]):
+        arr = (C.c_void_p * max(len(device_ptrs), 1))(*device_ptrs)
+        check(lib.obgpu_merge_result_set_string_images(self._h, arr, len(device_ptrs)), "obgpu_merge_result_set_string_images",
+              self.ctx._h)
+
     def free(self):
         if self._h and self.ctx._h:
             lib.obgpu_merge_result_free(self._h)
@@ -128,7 +152,23 @@ def merge_decoded(ctx, runs: Sequence[DecodedRun], default_vals=None, default_nu
     return MergeResult(ctx, h, n_cols, keep)
 
 
-def write_merged_sstable(res: MergeResult, rows_per_block: int = 1400, payload_encoding=None, n_threads: int = 0):
+def merge_batches(ctx, batches, rowkey_col: int, flag_col: Optional[int], cols: Sequence[int], default_vals=None,
+                  default_null=None) -> MergeResult:
+    """obgpu_merge_runs: the whole merge of one range from opened page batches (oldest first). String payload columns
+    travel as references into the batches, which must stay open until the strings have been fetched."""
+    arr = (C.c_void_p * len(batches))(*[b._h for b in batches])
+    ci = (C.c_int32 * max(len(cols), 1))(*cols)
+    dv = np.ascontiguousarray(default_vals, dtype=np.int64) if default_vals is not None else None
+    dn = np.ascontiguousarray(default_null, dtype=np.uint8) if default_null is not None else None
+    h = C.c_void_p()
+    check(lib.obgpu_merge_runs(ctx._h, arr, len(batches), rowkey_col, -1 if flag_col is None else flag_col, ci, len(cols),
+                               dv.ctypes.data if dv is not None else None, dn.ctypes.data if dn is not None else None,
+                               C.byref(h)), "obgpu_merge_runs", ctx._h)
+    return MergeResult(ctx, h, len(cols), list(batches))
+
+
+def write_merged_sstable(res: MergeResult, rows_per_block: int = 1400, payload_encoding=None, n_threads: int = 0,
+                         string_cols: Sequence[int] = ()):
     """The merged row stream as a new major SSTable shard (ObMacroBlockWriter::append_row ->
     ObMicroBlockEncoder::build_block in the reference, blocksstable/ob_macro_block_writer.cpp:837): rowkey
     INTEGER_BASE_DIFF, payload RAW unless told otherwise; every row DF_INSERT, so no flag column and no NOP.
@@ -137,9 +177,13 @@ def write_merged_sstable(res: MergeResult, rows_per_block: int = 1400, payload_e
     key, _ = res.fetch(-1)
     cols = [Column(capi.OBJ_INT, capi.ENC_INTEGER_BASE_DIFF, key)]
     for c in range(res.n_cols):
-        v, nl = res.fetch(c)
         enc = capi.ENC_RAW if payload_encoding is None else payload_encoding[c]
-        cols.append(Column(capi.OBJ_INT, enc, v, nulls=nl if nl.any() else None))
+        if c in string_cols:
+            heap, off, nl = res.fetch_strings(c)
+            cols.append(Column(capi.OBJ_VARCHAR, enc, None, nulls=nl if nl.any() else None, str_heap=heap, str_off=off))
+        else:
+            v, nl = res.fetch(c)
+            cols.append(Column(capi.OBJ_INT, enc, v, nulls=nl if nl.any() else None))
     return encode_table(cols, rows_per_block, rowkey_cnt=1, n_threads=n_threads)
 
 

@@ -247,8 +247,15 @@ __global__ void __launch_bounds__(256) fuse_kernel(const int64_t *__restrict__ k
 
 // ---- run decode: every cell of up to kMaxDecodeCols integer columns of a batch -> (value, ext) ---------
 constexpr int kMaxDecodeCols = 16;
+// String-class cells are decoded to a REFERENCE into the run's page batch: (tag << 58) | (byte offset of the cell
+// inside the batch image << 22) | length. The merge moves these 64-bit images like integer cells; the tag (the
+// run index) tells after the merge which image a reference points into.
+constexpr int kRefTagShift = 58, kRefOffShift = 22;
+constexpr uint64_t kRefLenMask = (1ull << kRefOffShift) - 1, kRefOffMask = (1ull << (kRefTagShift - kRefOffShift)) - 1;
+
 struct DecodeCols {
   int32_t n;
+  uint32_t string_tag;
   int32_t col[kMaxDecodeCols];
   int64_t *vals[kMaxDecodeCols];
   uint8_t *ext[kMaxDecodeCols];
@@ -276,12 +283,49 @@ __global__ void __launch_bounds__(128) decode_cols_kernel(const uint8_t *__restr
   const int64_t row0 = row_start[block];
   for (int c = 0; c < dc.n; ++c) {
     const ColDesc &d = s_d[c];
-    if (!d.ok || d.sc == 5) {
+    if (!d.ok) {
       if (threadIdx.x == 0) atomicOr(status, ST_UNSUPPORTED);
       continue;
     }
     int64_t *ov = dc.vals[c] + row0;
     uint8_t *oe = dc.ext[c] + row0;
+    if (d.sc == 5 || d.kind == K_VARSTR) {
+      // strings -> references; var-stored integers -> value image; NULL / NOP from the stored ext value
+      for (uint32_t row = threadIdx.x; row < rec.rows; row += blockDim.x) {
+        uint64_t v = 0;
+        uint8_t e = 0;
+        bool is_null;
+        if (d.sc == 5) {
+          uint32_t cell, len;
+          str_cell(b, d, nullptr, row, cell, len, is_null);
+          if (!is_null) {
+            const uint64_t off = rec.off + (uint64_t)cell;
+            if (off > kRefOffMask || len > kRefLenMask) atomicOr(status, ST_UNSUPPORTED);
+            v = ((uint64_t)dc.string_tag << kRefTagShift) | (off << kRefOffShift) | (uint64_t)len;
+          }
+        } else {
+          v = int_cell(b, d, nullptr, row, is_null);
+          if (d.elem_len == 4) v &= 0xffffffffull;
+          else if (d.elem_len == 1) v &= 0xffull;
+        }
+        if (is_null) {
+          e = 1;
+          v = 0;
+          if (is_dict_kind(d)) {
+            if (ref_of(s, d, nullptr, row) > d.dict_count) e = 2;                     // ref == count + 1: NOP
+          } else if (d.kind == K_VARSTR && d.var_ext_in_row) {
+            const uint32_t rib = b.row_index_byte;
+            const uint32_t ro = (uint32_t)ld_bytes(s, b.row_index_off + row * rib, rib);
+            if (ld_bits32(s, (b.row_data_off + ro) * 8u + d.ext_index, d.ext_bit) == STORED_NOPE) e = 2;
+          } else if (d.kind == K_FIXSTR && d.ext_bit && !b.is_cs) {
+            if (ld_bits32(s, d.ext_bit_off + row * d.ext_bit, d.ext_bit) == STORED_NOPE) e = 2;
+          }
+        }
+        ov[row] = (int64_t)v;
+        oe[row] = e;
+      }
+      continue;
+    }
     const bool plain = d.kind == K_BITS && d.ext_bit == 0 && !d.var_is_last && !d.sign_fix && d.elem_len == 8;
     for (uint32_t row = threadIdx.x; row < rec.rows; row += blockDim.x) {
       uint64_t v = 0;
@@ -319,6 +363,32 @@ __global__ void __launch_bounds__(256) narrow_flag_kernel(const int64_t *__restr
   if (i < n) out[i] = (uint8_t)v[i];
 }
 
+// ---- merged string columns: references -> bytes -------------------------------------------------------------
+__global__ void __launch_bounds__(256) ref_len_kernel(const int64_t *__restrict__ refs, const uint8_t *__restrict__ nulls, int64_t n,
+                                                      uint32_t *__restrict__ lens) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) lens[i] = nulls[i] ? 0u : (uint32_t)((uint64_t)refs[i] & kRefLenMask);
+}
+// one warp per row: copies the cell from the image its tag names to heap[off[row] ..)
+__global__ void __launch_bounds__(256) ref_gather_kernel(const int64_t *__restrict__ refs, const uint8_t *__restrict__ nulls, int64_t n,
+                                                         const uint8_t *const *__restrict__ images, int n_images,
+                                                         const int64_t *__restrict__ off, uint8_t *__restrict__ heap,
+                                                         int *__restrict__ status) {
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= n || nulls[row]) return;
+  const uint64_t r = (uint64_t)refs[row];
+  const int tag = (int)(r >> kRefTagShift);
+  const uint32_t len = (uint32_t)(r & kRefLenMask);
+  if (tag >= n_images || images[tag] == nullptr) {
+    if (lane == 0) atomicOr(status, ST_CORRUPT);
+    return;
+  }
+  const uint8_t *src = images[tag] + ((r >> kRefOffShift) & kRefOffMask);
+  uint8_t *dst = heap + off[row];
+  for (uint32_t k = (uint32_t)lane; k < len; k += 32u) dst[k] = src[k];
+}
+
 }  // namespace mrg
 
 struct obgpu_merge_result {
@@ -337,15 +407,19 @@ struct obgpu_merge_result {
   obgpu_merge_info info{};
   std::vector<const int64_t *> vals_view;
   std::vector<const uint8_t *> null_view;
+  std::vector<const uint8_t *> string_images;   // tag -> device image the string references point into
 };
 
 extern "C" {
 
-int obgpu_batch_decode_columns(obgpu_batch *b, int32_t n_cols, const int32_t *cols, int64_t *const *dev_vals,
-                               uint8_t *const *dev_ext) {
-  if (!b || n_cols <= 0 || n_cols > mrg::kMaxDecodeCols || !cols || !dev_vals || !dev_ext) return OBGPU_INVALID_ARGUMENT;
+int obgpu_batch_decode_columns_tagged(obgpu_batch *b, int32_t n_cols, const int32_t *cols, int32_t string_tag,
+                                      int64_t *const *dev_vals, uint8_t *const *dev_ext) {
+  if (!b || n_cols <= 0 || n_cols > mrg::kMaxDecodeCols || !cols || !dev_vals || !dev_ext || string_tag < 0 ||
+      string_tag >= OBGPU_MERGE_MAX_RUNS)
+    return OBGPU_INVALID_ARGUMENT;
   mrg::DecodeCols dc{};
   dc.n = n_cols;
+  dc.string_tag = (uint32_t)string_tag;
   for (int i = 0; i < n_cols; ++i) {
     if (cols[i] < 0 || (uint32_t)cols[i] >= b->max_cols || !dev_vals[i] || !dev_ext[i]) return OBGPU_INVALID_ARGUMENT;
     dc.col[i] = cols[i];
@@ -367,6 +441,11 @@ int obgpu_batch_decode_columns(obgpu_batch *b, int32_t n_cols, const int32_t *co
   cudaFreeAsync(d_status, ctx->stream);
   if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return OBGPU_ERR_SYS; }
   return check_status(ctx, status);
+}
+
+int obgpu_batch_decode_columns(obgpu_batch *b, int32_t n_cols, const int32_t *cols, int64_t *const *dev_vals,
+                               uint8_t *const *dev_ext) {
+  return obgpu_batch_decode_columns_tagged(b, n_cols, cols, 0, dev_vals, dev_ext);
 }
 
 int obgpu_batch_decode_column(obgpu_batch *b, int32_t col, int64_t *dev_vals, uint8_t *dev_ext) {
@@ -579,7 +658,7 @@ int obgpu_merge_runs(obgpu_ctx *ctx, obgpu_batch *const *batches, int32_t n_runs
       de[i] = base + per * (size_t)n_dec + per_e * (size_t)i;
     }
     uint8_t *flag8 = base + (per + per_e) * (size_t)n_dec;
-    if (n > 0) ret = obgpu_batch_decode_columns(b, n_dec, dcols, dv, de);
+    if (n > 0) ret = obgpu_batch_decode_columns_tagged(b, n_dec, dcols, r, dv, de);
     if (ret != OBGPU_SUCCESS) break;
     obgpu_merge_run &run = runs[(size_t)r];
     run.n = n;
@@ -602,8 +681,73 @@ int obgpu_merge_runs(obgpu_ctx *ctx, obgpu_batch *const *batches, int32_t n_runs
     run.ext = exts[(size_t)r].data();
   }
   if (ret == OBGPU_SUCCESS) ret = obgpu_merge_decoded(ctx, runs.data(), n_runs, n_cols, default_vals, default_null, out);
+  if (ret == OBGPU_SUCCESS)   // string references of run r carry tag r and point into that batch's image
+    for (int r = 0; r < n_runs; ++r) (*out)->string_images.push_back(batches[r]->d_image);
   release();  // stream-ordered: the merge kernels were enqueued before these frees
   return ret;
+}
+
+int obgpu_merge_result_set_string_images(obgpu_merge_result *res, const void *const *dev_images, int32_t n_images) {
+  if (!res || n_images < 0 || n_images > OBGPU_MERGE_MAX_RUNS || (n_images > 0 && !dev_images)) return OBGPU_INVALID_ARGUMENT;
+  res->string_images.clear();
+  for (int i = 0; i < n_images; ++i) res->string_images.push_back((const uint8_t *)dev_images[i]);
+  return OBGPU_SUCCESS;
+}
+
+int obgpu_merge_result_fetch_strings(obgpu_merge_result *res, int32_t col, int64_t row_begin, int64_t row_count,
+                                     void *host_heap, int64_t heap_cap, int64_t *host_off, uint8_t *host_null,
+                                     int64_t *heap_bytes) {
+  if (!res || col < 0 || col >= res->n_cols || row_begin < 0 || row_count < 0 || !host_off || !heap_bytes) return OBGPU_INVALID_ARGUMENT;
+  obgpu_merge_info info;
+  int ret = obgpu_merge_result_info(res, &info);
+  if (ret != OBGPU_SUCCESS) return ret;
+  if (row_begin + row_count > info.out_rows) return OBGPU_INVALID_ARGUMENT;
+  obgpu_ctx *ctx = res->ctx;
+  cudaSetDevice(ctx->device);
+  host_off[0] = 0;
+  *heap_bytes = 0;
+  if (row_count == 0) return OBGPU_SUCCESS;
+  if (res->string_images.empty()) { ctx->err = "no page-batch images attached to the merge result"; return OBGPU_INVALID_ARGUMENT; }
+  const int64_t n = row_count;
+  const int n_chunks = (int)((n + kPrefixChunk - 1) / kPrefixChunk);
+  auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  const size_t o_len = 0, o_off = al((size_t)n * 4), o_chunk = o_off + al(((size_t)n + 1) * 8);
+  const size_t o_img = o_chunk + al(((size_t)n_chunks + 2) * 8), o_st = o_img + al(res->string_images.size() * 8);
+  uint8_t *tmp = nullptr;
+  CUDA_TRY(ctx, cudaMallocAsync((void **)&tmp, o_st + 256, ctx->stream));
+  const int64_t *refs = res->out_vals[(size_t)col] + row_begin;
+  const uint8_t *nulls = res->out_null[(size_t)col] + row_begin;
+  int64_t *d_off = (int64_t *)(tmp + o_off);
+  cudaMemsetAsync(tmp + o_st, 0, 4, ctx->stream);
+  cudaMemcpyAsync(tmp + o_img, res->string_images.data(), res->string_images.size() * 8, cudaMemcpyHostToDevice, ctx->stream);
+  mrg::ref_len_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(refs, nulls, n, (uint32_t *)(tmp + o_len));
+  obgpu_prefix_local_kernel<<<n_chunks, 256, 0, ctx->stream>>>((const uint32_t *)(tmp + o_len), (int)n, d_off,
+                                                              (unsigned long long *)(tmp + o_chunk));
+  obgpu_prefix_fix_kernel<<<n_chunks + 1, 256, 0, ctx->stream>>>((int)n, n_chunks, d_off, (const unsigned long long *)(tmp + o_chunk));
+  ctx->launches += 3;
+  cudaMemcpyAsync(host_off, d_off, ((size_t)n + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream);
+  if (host_null) cudaMemcpyAsync(host_null, nulls, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream);
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); cudaFreeAsync(tmp, ctx->stream); return OBGPU_ERR_SYS; }
+  const int64_t total = host_off[n];
+  *heap_bytes = total;
+  if (total > heap_cap || (total > 0 && !host_heap)) { cudaFreeAsync(tmp, ctx->stream); return OBGPU_BUF_NOT_ENOUGH; }
+  int status = 0;
+  if (total > 0) {
+    uint8_t *d_heap = nullptr;
+    e = cudaMallocAsync((void **)&d_heap, (size_t)total + 16, ctx->stream);
+    if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); cudaFreeAsync(tmp, ctx->stream); return OBGPU_ALLOCATE_MEMORY_FAILED; }
+    mrg::ref_gather_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, ctx->stream>>>(
+        refs, nulls, n, (const uint8_t *const *)(tmp + o_img), (int)res->string_images.size(), d_off, d_heap, (int *)(tmp + o_st));
+    ctx->launches++;
+    cudaMemcpyAsync(host_heap, d_heap, (size_t)total, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaMemcpyAsync(&status, tmp + o_st, 4, cudaMemcpyDeviceToHost, ctx->stream);
+    e = cudaStreamSynchronize(ctx->stream);
+    cudaFreeAsync(d_heap, ctx->stream);
+  }
+  cudaFreeAsync(tmp, ctx->stream);
+  if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return OBGPU_ERR_SYS; }
+  return check_status(ctx, status);
 }
 
 void obgpu_merge_result_free(obgpu_merge_result *res) {

@@ -137,3 +137,132 @@ def test_merged_stream_written_as_sstable_scans_back(ob, env):
     for c in range(3):
         assert np.array_equal(d2.ext[c].cpu().numpy(), want["null"][c])
     res.free()
+
+
+def _string_runs(ob, rng, n_runs, n_keys, cs):
+    """Runs with an INT64 rowkey, a DML flag, one INT64 and two VARCHAR payload columns (NULL and NOP cells)."""
+    words = [bytes(rng.integers(97, 123, size=int(rng.integers(0, 24)), dtype=np.uint8)) for _ in range(200)]
+    runs = []
+    for r in range(n_runs):
+        keys = np.sort(rng.choice(n_keys, size=int(n_keys * 0.45), replace=False)).astype(np.int64)
+        n = len(keys)
+        flag = np.where(rng.random(n) < 0.06, ob.DF_DELETE, ob.DF_INSERT if r == 0 else ob.DF_UPDATE).astype(np.int64)
+        iv = rng.integers(-1000, 1000, size=n, dtype=np.int64)
+        s1 = [words[i] for i in rng.integers(0, 200, size=n)]
+        s2 = [words[i] + b"#%d" % r for i in rng.integers(0, 200, size=n)]
+        ext = lambda: rng.choice([0, 0, 0, 1, 2] if r else [0, 0, 0, 1], size=n).astype(np.uint8)   # NOP only in increments
+        runs.append(dict(key=keys, flag=flag, iv=iv, s1=s1, s2=s2, e_iv=ext(), e_s1=ext(), e_s2=ext()))
+    return runs
+
+
+@pytest.mark.parametrize("block_format", ["pax", "cs"])
+def test_merge_with_string_payload_columns(env, ob, block_format):
+    # VARCHAR payload cells travel through the merge as references into their run's page batch and are materialised
+    # once, for the merged rows only (obgpu_merge_runs + obgpu_merge_result_fetch_strings)
+    from oceanbase_b200.compaction import merge_batches, write_merged_sstable
+    ctx, torch = env
+    rng = np.random.default_rng(77)
+    cs = block_format == "cs"
+    runs = _string_runs(ob, rng, 5, 30_000, cs)
+    batches = []
+    for r in runs:
+        if cs:   # CS blocks have no NOP: incremental cells that are NOP become NULL for this variant
+            for k in ("e_iv", "e_s1", "e_s2"):
+                r[k] = np.minimum(r[k], 1).astype(np.uint8)
+            enc_i, enc_s1, enc_s2 = ob.ENC_CS_INTEGER, ob.ENC_CS_STRING, ob.ENC_CS_STR_DICT
+        else:
+            enc_i, enc_s1, enc_s2 = ob.ENC_RAW, ob.ENC_RAW, ob.ENC_DICT
+        cols = [ob.Column(ob.OBJ_INT, ob.ENC_CS_INTEGER if cs else ob.ENC_INTEGER_BASE_DIFF, r["key"]),
+                ob.Column(ob.OBJ_INT, enc_i, r["flag"]),
+                ob.Column(ob.OBJ_INT, enc_i, r["iv"], nulls=r["e_iv"]),
+                ob.Column(ob.OBJ_VARCHAR, enc_s1, r["s1"], nulls=r["e_s1"]),
+                ob.Column(ob.OBJ_VARCHAR, enc_s2, r["s2"], nulls=r["e_s2"])]
+        batches.append(ctx.open_batch(ob.encode_table(cols, 900, rowkey_cnt=1)))
+    res = merge_batches(ctx, batches, 0, 1, [2, 3, 4])
+    # model: per rowkey the rows newest first; first non-NOP cell wins, a delete stops the fuse, delete first drops the key
+    rows = {}
+    for ri, r in enumerate(runs):
+        for i, k in enumerate(r["key"].tolist()):
+            rows.setdefault(k, []).append((ri, i))
+    exp_key, exp = [], [[], [], []]
+    for k in sorted(rows):
+        cells = [None, None, None]          # None = still NOP
+        first, deleted = True, False
+        for ri, i in sorted(rows[k], reverse=True):
+            r = runs[ri]
+            if r["flag"][i] == ob.DF_DELETE:
+                deleted = first
+                break
+            first = False
+            for c, (vals, ext) in enumerate(((r["iv"], r["e_iv"]), (r["s1"], r["e_s1"]), (r["s2"], r["e_s2"]))):
+                if cells[c] is None and ext[i] != 2:
+                    cells[c] = ("null",) if ext[i] == 1 else ("v", vals[i])
+        if deleted or first:
+            continue
+        exp_key.append(k)
+        for c in range(3):
+            exp[c].append(None if cells[c] in (None, ("null",)) else cells[c][1])   # open NOPs take the NULL default
+    assert res.info().out_rows == len(exp_key)
+    assert np.array_equal(res.fetch(-1)[0], np.array(exp_key, dtype=np.int64))
+    v, nl = res.fetch(0)
+    assert [None if z else int(x) for x, z in zip(v, nl)] == exp[0]
+    for c in (1, 2):
+        heap, off, nl = res.fetch_strings(c)
+        got = [None if nl[i] else bytes(heap[off[i]:off[i + 1]]) for i in range(len(exp_key))]
+        assert got == exp[c], f"string column {c}"
+        h2, o2, n2 = res.fetch_strings(c, 1000, 500)                 # a window
+        assert [None if n2[i] else bytes(h2[o2[i]:o2[i + 1]]) for i in range(500)] == exp[c][1000:1500]
+    # the merged stream as a new SSTable, read back through the oracle
+    out = write_merged_sstable(res, 1000, string_cols=(1, 2))
+    blk = ora.Block(out.block(3))
+    for r in range(0, blk.row_count, 37):
+        g = 3000 + r
+        assert blk.cell(0, r) == exp_key[g] % (1 << 64) and blk.cell(2, r) == exp[1][g] and blk.cell(3, r) == exp[2][g]
+    res.free()
+    for b in batches:
+        b.close()
+
+
+def test_decode_columns_tagged_and_named_images(env, ob):
+    # the two-step form: decode runs into caller-owned arrays (string cells = tagged references), merge_decoded, then name
+    # the images the tags stand for
+    import ctypes as C
+    from oceanbase_b200.capi import lib, check
+    from oceanbase_b200.compaction import DecodedRun, merge_decoded
+    ctx, torch = env
+    rng = np.random.default_rng(5)
+    runs, images, keep = [], [], []
+    for tag in range(3):
+        n = 4000
+        key = (np.arange(n, dtype=np.int64) * 3 + tag)                   # disjoint rowkeys: nothing fuses
+        s = [b"r%d-" % tag + bytes(rng.integers(97, 123, size=int(rng.integers(0, 9)), dtype=np.uint8)) for _ in range(n)]
+        nulls = (rng.random(n) < 0.1).astype(np.uint8)
+        table = ob.encode_table([ob.Column(ob.OBJ_INT, ob.ENC_INTEGER_BASE_DIFF, key), ob.Column(ob.OBJ_VARCHAR, ob.ENC_RAW, s, nulls=nulls)], 700)
+        d_img = torch.zeros(table.image.size + 64, dtype=torch.uint8, device="cuda")
+        d_img[:table.image.size].copy_(torch.from_numpy(table.image))
+        torch.cuda.synchronize()
+        batch = ctx.open_batch(table, device_image_ptr=d_img.data_ptr())
+        vs = [torch.empty(n, dtype=torch.int64, device="cuda") for _ in range(2)]
+        es = [torch.empty(n, dtype=torch.uint8, device="cuda") for _ in range(2)]
+        ci = (C.c_int32 * 2)(0, 1)
+        vp = (C.c_void_p * 2)(*[v.data_ptr() for v in vs])
+        ep = (C.c_void_p * 2)(*[e.data_ptr() for e in es])
+        check(lib.obgpu_batch_decode_columns_tagged(batch._h, 2, ci, tag, vp, ep), "obgpu_batch_decode_columns_tagged", ctx._h)
+        refs = vs[1].cpu().numpy().view(np.uint64)
+        live = nulls == 0
+        assert np.all((refs[live] >> np.uint64(58)) == tag) and np.all(refs[~live] == 0)
+        assert np.array_equal((refs[live] & np.uint64((1 << 22) - 1)).astype(np.int64), np.array([len(x) for x, z in zip(s, nulls) if not z]))
+        runs.append(DecodedRun(vs[0], None, [vs[1]], [es[1]]))
+        images.append(d_img.data_ptr())
+        keep += [d_img, batch, s, nulls]
+    res = merge_decoded(ctx, runs)
+    res.set_string_images(images)
+    heap, off, nl = res.fetch_strings(0)
+    k, _ = res.fetch(-1)
+    for i in range(0, len(k), 53):
+        tag, idx = int(k[i]) % 3, int(k[i]) // 3
+        s, nulls = keep[tag * 4 + 2], keep[tag * 4 + 3]
+        assert (None if nl[i] else bytes(heap[off[i]:off[i + 1]])) == (None if nulls[idx] else s[idx])
+    res.free()
+    for t in range(3):
+        keep[t * 4 + 1].close()
