@@ -27,7 +27,16 @@ def main():
     rpb = w.rows_per_block
     t0 = time.perf_counter()
     pk = config2_pk(args.rows, seed)
-    agg_rows, agg_off = ob.table_agg_rows([ob.Column(ob.OBJ_INT, ob.ENC_RAW, pk)], [0], rpb)
+    # build_workload encodes the table in chunks of 4 M rows (each ends with a short block): same blocking here
+    chunk = 4_000_000
+    parts, offs, pos = [], [np.zeros(1, dtype=np.int64)], 0
+    for s0 in range(0, args.rows, chunk):
+        r, o = ob.table_agg_rows([ob.Column(ob.OBJ_INT, ob.ENC_RAW, pk[s0:s0 + chunk])], [0], rpb)
+        parts.append(r)
+        offs.append(o[1:] + pos)
+        pos += int(o[-1])
+    agg_rows, agg_off = np.concatenate(parts), np.concatenate(offs)
+    assert len(agg_off) == table.n_blocks + 1
     t_agg = time.perf_counter() - t0
     lo_row = int(args.rows * (0.5 - args.frac / 2))
     hi_row = int(args.rows * (0.5 + args.frac / 2)) - 1
