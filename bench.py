@@ -387,10 +387,11 @@ def run_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             ncpu = host_cpus()
             sample_blocks = min(table.n_blocks, max(64, int(args.cpu_sample_rows // 1400)))
-            rates, crow, csel = cpu_reference_leg(w, 2, 1, ncpu, sample_blocks)
+            rates, crow, csel = cpu_reference_leg(w, 4, 1, ncpu, sample_blocks)
             mean_dt = float(np.mean([d for _, d in rates]))
             cpu = {"value": crow / mean_dt, "unit": UNIT, "cores": ncpu, "kind": "port",
-                   "sample": f"first {crow} rows ({sample_blocks} micro-blocks) of the same table, 2 timed passes, "
+                   "sample": f"first {crow} rows ({sample_blocks} micro-blocks) of the same table, 4 timed passes "
+                             f"({sum(d for _, d in rates) * ncpu:.0f} CPU-seconds), "
                              f"oracle port of the reference scan (batch {BATCH_ROWS}), {ncpu} threads = cgroup cpu quota "
                              f"({os.cpu_count()} logical CPUs visible)"}
         line = {
@@ -431,7 +432,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rows", type=int, default=100_000_000, help="rows per GPU (BASELINE configs[1]: 100 M)")
     ap.add_argument("--ref-rows", type=int, default=32_000_000, help="rows per step of the reference arm sample")
-    ap.add_argument("--cpu-sample-rows", type=int, default=16_000_000)
+    ap.add_argument("--cpu-sample-rows", type=int, default=100_000_000,
+                    help="rows of the workload the cpu_baseline leg scans per pass (4 timed passes: ~10-20 s of CPU work)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--e2e-batches", type=int, default=12, help="page batches per e2e step (pipeline depth)")
     ap.add_argument("--e2e-ramp", type=int, default=2, help="the first N page batches are 1/2^N .. 1/2 of a full one")
