@@ -33,6 +33,7 @@ enum {
 
 #define OBGPU_MERGE_MAX_RUNS 64
 #define OBGPU_MERGE_MAX_COLS 64
+#define OBGPU_MERGE_MAX_KEY_COLS 8
 
 /* All cells of column `col` (integer class, or string class as references -- see below) of an opened batch, in row order, into caller-owned DEVICE
  * buffers of total_rows entries: value image (what the reference would MEMCPY into the datum, 0 for
@@ -51,14 +52,18 @@ int obgpu_batch_decode_columns_tagged(obgpu_batch *batch, int32_t n_cols, const 
                                       int64_t *const *dev_vals, uint8_t *const *dev_ext);
 
 /* One sorted run, decoded, resident in HBM (all pointers are device pointers; the vals / ext
- * pointer ARRAYS themselves live in host memory). Rowkey: one INT64 column, ascending, unique
- * inside the run. */
+ * pointer ARRAYS themselves live in host memory). Rowkey: INT64 columns (`key`, plus
+ * `more_keys` for a composite rowkey), ascending, unique inside the run. */
 typedef struct obgpu_merge_run {
   int64_t n;
   const int64_t *key;
   const uint8_t *flag;         /* ObDmlFlag per row; NULL: every row DF_INSERT                  */
   const int64_t *const *vals;  /* [n_cols] value arrays                                           */
   const uint8_t *const *ext;   /* [n_cols] 0 value, 1 NULL, 2 NOP                                 */
+  /* composite rowkeys: the rowkey columns after the first (INT64 images, no NULLs), compared column by column
+   * after `key` like ObStorageDatumUtils does; the same count in every run, 0 for a single-column rowkey       */
+  const int64_t *const *more_keys;
+  int32_t n_more_keys;
 } obgpu_merge_run;
 
 typedef struct obgpu_merge_result obgpu_merge_result;
@@ -79,6 +84,11 @@ int obgpu_merge_runs(obgpu_ctx *ctx, obgpu_batch *const *runs, int32_t n_runs, i
                      int32_t flag_col, const int32_t *cols, int32_t n_cols, const int64_t *default_vals,
                      const uint8_t *default_null, obgpu_merge_result **out);
 
+/* Same with a composite rowkey: rowkey_cols[0 .. n_rowkey_cols) in comparison order (at most OBGPU_MERGE_MAX_KEY_COLS). */
+int obgpu_merge_runs_keys(obgpu_ctx *ctx, obgpu_batch *const *runs, int32_t n_runs, const int32_t *rowkey_cols,
+                          int32_t n_rowkey_cols, int32_t flag_col, const int32_t *cols, int32_t n_cols,
+                          const int64_t *default_vals, const uint8_t *default_null, obgpu_merge_result **out);
+
 typedef struct obgpu_merge_info {
   int64_t in_rows;          /* rows of all runs                                              */
   int64_t out_rows;         /* rows of the merged stream                                     */
@@ -91,7 +101,8 @@ int obgpu_merge_result_info(obgpu_merge_result *res, obgpu_merge_info *info);
  * and per column values [out_rows] + null bytes (1 => NULL) [out_rows]. */
 int obgpu_merge_result_cols(obgpu_merge_result *res, const int64_t **key_dev,
                             const int64_t *const **vals_dev, const uint8_t *const **null_dev);
-/* Device -> host copy of rows [row_begin, row_begin + row_count) of column `col` (-1: the rowkey). */
+/* Device -> host copy of rows [row_begin, row_begin + row_count) of column `col` (-1: the first rowkey column,
+ * -2, -3, ...: the following rowkey columns of a composite rowkey). */
 int obgpu_merge_result_fetch(obgpu_merge_result *res, int32_t col, int64_t row_begin,
                              int64_t row_count, int64_t *host_vals, uint8_t *host_null);
 

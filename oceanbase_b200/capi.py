@@ -77,7 +77,7 @@ DF_NOT_EXIST, DF_LOCK, DF_UPDATE, DF_INSERT, DF_DELETE = range(5)  # blocksstabl
 
 class MergeRun(C.Structure):
     _fields_ = [("n", C.c_int64), ("key", C.c_void_p), ("flag", C.c_void_p), ("vals", C.POINTER(C.c_void_p)),
-                ("ext", C.POINTER(C.c_void_p))]
+                ("ext", C.POINTER(C.c_void_p)), ("more_keys", C.POINTER(C.c_void_p)), ("n_more_keys", C.c_int32)]
 
 
 class MergeInfo(C.Structure):
@@ -134,6 +134,7 @@ def declared_signatures():
         "obgpu_merge_result_fetch_strings": (C.c_int, [vp, i32, i64, i64, vp, i64, vp, vp, P(i64)]),
         "obgpu_merge_decoded": (C.c_int, [vp, P(MergeRun), i32, i32, vp, vp, P(vp)]),
         "obgpu_merge_runs": (C.c_int, [vp, P(vp), i32, i32, i32, vp, i32, vp, vp, P(vp)]),
+        "obgpu_merge_runs_keys": (C.c_int, [vp, P(vp), i32, vp, i32, i32, vp, i32, vp, vp, P(vp)]),
         "obgpu_merge_result_free": (None, [vp]),
         "obgpu_merge_result_info": (C.c_int, [vp, P(MergeInfo)]),
         "obgpu_merge_result_cols": (C.c_int, [vp, P(vp), P(P(vp)), P(P(vp))]),

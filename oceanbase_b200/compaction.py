@@ -28,6 +28,7 @@ class DecodedRun:
     flag: Optional[object]         # uint8 [n] ObDmlFlag, or None = every row DF_INSERT
     vals: List[object]             # n_cols x int64 [n]
     ext: List[object]              # n_cols x uint8 [n]  (0 value, 1 NULL, 2 NOP)
+    more_keys: Optional[List[object]] = None   # rowkey columns after the first (composite rowkeys), int64 [n] each
 
     @property
     def n(self):
@@ -35,7 +36,8 @@ class DecodedRun:
 
     def slice(self, lo, hi):
         return DecodedRun(self.key[lo:hi], None if self.flag is None else self.flag[lo:hi],
-                          [v[lo:hi] for v in self.vals], [e[lo:hi] for e in self.ext])
+                          [v[lo:hi] for v in self.vals], [e[lo:hi] for e in self.ext],
+                          None if self.more_keys is None else [k[lo:hi] for k in self.more_keys])
 
 
 def decode_run(ctx, table, key_col: int, flag_col: Optional[int], cols: Sequence[int], device=None,
@@ -141,6 +143,11 @@ def merge_decoded(ctx, runs: Sequence[DecodedRun], default_vals=None, default_nu
         arr[i].flag = r.flag.data_ptr() if r.flag is not None else None
         arr[i].vals = vp
         arr[i].ext = ep
+        if r.more_keys:
+            mp = (C.c_void_p * len(r.more_keys))(*[k.data_ptr() for k in r.more_keys])
+            keep.append(mp)
+            arr[i].more_keys = mp
+            arr[i].n_more_keys = len(r.more_keys)
     dv = dn = None
     if default_vals is not None:
         dv = np.ascontiguousarray(default_vals, dtype=np.int64)
@@ -152,12 +159,23 @@ def merge_decoded(ctx, runs: Sequence[DecodedRun], default_vals=None, default_nu
     return MergeResult(ctx, h, n_cols, keep)
 
 
-def merge_batches(ctx, batches, rowkey_col: int, flag_col: Optional[int], cols: Sequence[int], default_vals=None,
+def merge_batches(ctx, batches, rowkey_col, flag_col: Optional[int], cols: Sequence[int], default_vals=None,
                   default_null=None) -> MergeResult:
-    """obgpu_merge_runs: the whole merge of one range from opened page batches (oldest first). String payload columns
-    travel as references into the batches, which must stay open until the strings have been fetched."""
+    """obgpu_merge_runs(_keys): the whole merge of one range from opened page batches (oldest first). rowkey_col: one
+    column index or the list of a composite rowkey. String payload columns travel as references into the batches, which
+    must stay open until the strings have been fetched."""
     arr = (C.c_void_p * len(batches))(*[b._h for b in batches])
     ci = (C.c_int32 * max(len(cols), 1))(*cols)
+    if not isinstance(rowkey_col, int):
+        keys = list(rowkey_col)
+        kc = (C.c_int32 * len(keys))(*keys)
+        dv = np.ascontiguousarray(default_vals, dtype=np.int64) if default_vals is not None else None
+        dn = np.ascontiguousarray(default_null, dtype=np.uint8) if default_null is not None else None
+        h = C.c_void_p()
+        check(lib.obgpu_merge_runs_keys(ctx._h, arr, len(batches), kc, len(keys), -1 if flag_col is None else flag_col, ci,
+                                        len(cols), dv.ctypes.data if dv is not None else None,
+                                        dn.ctypes.data if dn is not None else None, C.byref(h)), "obgpu_merge_runs_keys", ctx._h)
+        return MergeResult(ctx, h, len(cols), list(batches))
     dv = np.ascontiguousarray(default_vals, dtype=np.int64) if default_vals is not None else None
     dn = np.ascontiguousarray(default_null, dtype=np.uint8) if default_null is not None else None
     h = C.c_void_p()

@@ -33,8 +33,28 @@ struct RunsDev {
   const uint8_t *const *flag;   // [K] (entries may be null)
   const int64_t *const *vals;   // [K * n_cols]
   const uint8_t *const *ext;    // [K * n_cols]
-  int32_t n_runs, n_cols;
+  const int64_t *const *more;   // [K * n_more]: rowkey columns after the first (composite rowkeys)
+  int32_t n_runs, n_cols, n_more;
 };
+
+// Composite rowkeys: the merge passes carry the FIRST rowkey column next to the source; the remaining columns are
+// looked up through the source only when the first column ties (ObStorageDatumUtils compares column by column too).
+__device__ __forceinline__ int rest_cmp(const RunsDev &r, uint64_t sa, uint64_t sb) {
+  const uint64_t idx_mask = (1ull << kSrcShift) - 1;
+  const int ra = (int)(sa >> kSrcShift), rb = (int)(sb >> kSrcShift);
+  const int64_t ia = (int64_t)(sa & idx_mask), ib = (int64_t)(sb & idx_mask);
+  for (int c = 0; c < r.n_more; ++c) {
+    const int64_t a = r.more[ra * r.n_more + c][ia], b = r.more[rb * r.n_more + c][ib];
+    if (a != b) return a < b ? -1 : 1;
+  }
+  return 0;
+}
+__device__ __forceinline__ bool key_less(const RunsDev &r, int64_t ka, uint64_t sa, int64_t kb, uint64_t sb) {
+  return ka < kb || (ka == kb && r.n_more > 0 && rest_cmp(r, sa, sb) < 0);
+}
+__device__ __forceinline__ bool key_equal(const RunsDev &r, int64_t ka, uint64_t sa, int64_t kb, uint64_t sb) {
+  return ka == kb && (r.n_more == 0 || rest_cmp(r, sa, sb) == 0);
+}
 
 __global__ void __launch_bounds__(256) init_kernel(const int64_t *key, int64_t n, uint64_t run, int64_t *kout,
                                                    uint64_t *sout) {
@@ -46,37 +66,41 @@ __global__ void __launch_bounds__(256) init_kernel(const int64_t *key, int64_t n
 }
 
 // number of A elements among the first d outputs of merge(A, B), B first on equal keys
-__device__ __forceinline__ int64_t merge_path_g(const int64_t *a, int64_t na, const int64_t *b, int64_t nb, int64_t d) {
+__device__ __forceinline__ int64_t merge_path_g(const RunsDev &r, const int64_t *a, const uint64_t *sa, int64_t na,
+                                                const int64_t *b, const uint64_t *sb, int64_t nb, int64_t d) {
   int64_t lo = d > nb ? d - nb : 0, hi = d < na ? d : na;
   while (lo < hi) {
     const int64_t mid = (lo + hi) >> 1;
-    if (a[mid] < b[d - 1 - mid]) lo = mid + 1; else hi = mid;
+    if (key_less(r, a[mid], sa[mid], b[d - 1 - mid], sb[d - 1 - mid])) lo = mid + 1; else hi = mid;
   }
   return lo;
 }
-__device__ __forceinline__ int merge_path_s(const int64_t *a, int na, const int64_t *b, int nb, int d) {
+__device__ __forceinline__ int merge_path_s(const RunsDev &r, const int64_t *a, const uint64_t *sa, int na, const int64_t *b,
+                                            const uint64_t *sb, int nb, int d) {
   int lo = d > nb ? d - nb : 0, hi = d < na ? d : na;
   while (lo < hi) {
     const int mid = (lo + hi) >> 1;
-    if (a[mid] < b[d - 1 - mid]) lo = mid + 1; else hi = mid;
+    if (key_less(r, a[mid], sa[mid], b[d - 1 - mid], sb[d - 1 - mid])) lo = mid + 1; else hi = mid;
   }
   return lo;
 }
 
 // Merge-path partition: one THREAD per tile start diagonal (all binary searches of a pass in flight together,
 // instead of every merge CTA waiting on its own two searches). split[t] = A elements before tile t.
-__global__ void __launch_bounds__(256) partition_kernel(const int64_t *__restrict__ kin, const Pair *__restrict__ pairs, int n_pairs,
+__global__ void __launch_bounds__(256) partition_kernel(const int64_t *__restrict__ kin, const uint64_t *__restrict__ sin, RunsDev runs,
+                                                        const Pair *__restrict__ pairs, int n_pairs,
                                                         int64_t n_tiles, int64_t *__restrict__ split) {
   const int64_t tile = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (tile >= n_tiles) return;
   int p = 0;
   while (p + 1 < n_pairs && pairs[p + 1].tile0 <= tile) ++p;
   const Pair pr = pairs[p];
-  split[tile] = merge_path_g(kin + pr.a0, pr.a1 - pr.a0, kin + pr.b0, pr.b1 - pr.b0, (tile - pr.tile0) * kTile);
+  split[tile] = merge_path_g(runs, kin + pr.a0, sin + pr.a0, pr.a1 - pr.a0, kin + pr.b0, sin + pr.b0, pr.b1 - pr.b0,
+                             (tile - pr.tile0) * kTile);
 }
 
 __global__ void __launch_bounds__(kThreads) pass_kernel(const int64_t *__restrict__ kin, const uint64_t *__restrict__ sin,
-                                                        int64_t *__restrict__ kout, uint64_t *__restrict__ sout,
+                                                        int64_t *__restrict__ kout, uint64_t *__restrict__ sout, RunsDev runs,
                                                         const Pair *__restrict__ pairs, int n_pairs,
                                                         const int64_t *__restrict__ split) {
   __shared__ int64_t s_key[kTile];
@@ -103,14 +127,14 @@ __global__ void __launch_bounds__(kThreads) pass_kernel(const int64_t *__restric
   // per-thread merge of kVT consecutive outputs
   const int od0 = tid * kVT < total ? tid * kVT : total;
   const int od1 = od0 + kVT < total ? od0 + kVT : total;
-  int ia = merge_path_s(s_key, ca, s_key + ca, cb, od0);
+  int ia = merge_path_s(runs, s_key, s_src, ca, s_key + ca, s_src + ca, cb, od0);
   int ib = od0 - ia;
   int64_t rk[kVT];
   uint64_t rs[kVT];
 #pragma unroll
   for (int k = 0; k < kVT; ++k) {
     if (od0 + k < od1) {
-      const bool take_b = ib < cb && (ia >= ca || s_key[ca + ib] <= s_key[ia]);
+      const bool take_b = ib < cb && (ia >= ca || !key_less(runs, s_key[ia], s_src[ia], s_key[ca + ib], s_src[ca + ib]));
       const int at = take_b ? ca + ib : ia;
       rk[k] = s_key[at];
       rs[k] = s_src[at];
@@ -152,10 +176,11 @@ __global__ void __launch_bounds__(256) head_kernel(const int64_t *__restrict__ k
     const int64_t i = (int64_t)blockIdx.x * kFuseTile + k * 256 + threadIdx.x;
     if (i >= n) break;
     const int64_t key = keys[i];
+    const uint64_t ksrc = src[i];
     uint8_t e = 0;
-    if (i == 0 || keys[i - 1] != key) {
+    if (i == 0 || !key_equal(runs, keys[i - 1], src[i - 1], key, ksrc)) {
       bool decided = false;
-      for (int64_t j = i; j < n && keys[j] == key && !decided; ++j) {
+      for (int64_t j = i; j < n && key_equal(runs, keys[j], src[j], key, ksrc) && !decided; ++j) {
         const int f = flag_of(runs, src[j]);
         if (f == OBGPU_DF_NOT_EXIST) continue;
         decided = true;
@@ -178,7 +203,7 @@ __global__ void __launch_bounds__(256) fuse_kernel(const int64_t *__restrict__ k
                                                    const int64_t *__restrict__ tile_off, const int64_t *__restrict__ default_vals,
                                                    const uint8_t *__restrict__ default_null, int64_t *__restrict__ out_key,
                                                    int64_t *const *__restrict__ out_vals, uint8_t *const *__restrict__ out_null,
-                                                   unsigned long long *__restrict__ stats) {
+                                                   int64_t *const *__restrict__ out_more, unsigned long long *__restrict__ stats) {
   __shared__ uint32_t s_warp[8];
   __shared__ uint32_t s_base;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -204,12 +229,15 @@ __global__ void __launch_bounds__(256) fuse_kernel(const int64_t *__restrict__ k
     if (e) {
       const int64_t o = base_out + rank;
       const int64_t key = keys[i];
+      const uint64_t ksrc = src[i];
       out_key[o] = key;
+      for (int c = 0; c < runs.n_more; ++c)
+        out_more[c][o] = runs.more[(int)(ksrc >> kSrcShift) * runs.n_more + c][(int64_t)(ksrc & ((1ull << kSrcShift) - 1))];
       // rows of the group, newest first; the fuse stops at a delete row (final_result)
       int64_t jend = i;
       int group = 0;        // iters sharing this rowkey (minimum_iters_.count())
       bool open = true;     // no delete row met yet
-      for (int64_t j = i; j < n && keys[j] == key; ++j) {
+      for (int64_t j = i; j < n && key_equal(runs, keys[j], src[j], key, ksrc); ++j) {
         ++group;
         if (open) {
           if (flag_of(runs, src[j]) == OBGPU_DF_DELETE) open = false;
@@ -408,6 +436,7 @@ struct obgpu_merge_result {
   std::vector<const int64_t *> vals_view;
   std::vector<const uint8_t *> null_view;
   std::vector<const uint8_t *> string_images;   // tag -> device image the string references point into
+  std::vector<int64_t *> out_more;              // rowkey columns after the first
 };
 
 extern "C" {
@@ -457,7 +486,10 @@ int obgpu_merge_decoded(obgpu_ctx *ctx, const obgpu_merge_run *runs, int32_t n_r
   if (!ctx || !runs || !out || n_runs <= 0 || n_runs > OBGPU_MERGE_MAX_RUNS || n_cols < 0 || n_cols > OBGPU_MERGE_MAX_COLS)
     return OBGPU_INVALID_ARGUMENT;
   int64_t N = 0;
+  const int n_more = runs[0].n_more_keys;
+  if (n_more < 0 || n_more > OBGPU_MERGE_MAX_KEY_COLS - 1) return OBGPU_INVALID_ARGUMENT;
   for (int r = 0; r < n_runs; ++r) {
+    if (runs[r].n_more_keys != n_more || (n_more > 0 && runs[r].n > 0 && !runs[r].more_keys)) return OBGPU_INVALID_ARGUMENT;
     if (runs[r].n < 0 || runs[r].n >= (1ll << mrg::kSrcShift) || (runs[r].n > 0 && !runs[r].key)) return OBGPU_INVALID_ARGUMENT;
     if (n_cols > 0 && runs[r].n > 0 && (!runs[r].vals || !runs[r].ext)) return OBGPU_INVALID_ARGUMENT;
     N += runs[r].n;
@@ -483,7 +515,7 @@ int obgpu_merge_decoded(obgpu_ctx *ctx, const obgpu_merge_run *runs, int32_t n_r
   const size_t n_chunks = (size_t)((n_tiles + kPrefixChunk - 1) / kPrefixChunk);
   const size_t o_chunk = o; o += al((n_chunks + 1) * 8);
   const size_t o_stats = o; o += al(64);
-  const size_t tbl_entries = (size_t)n_runs * 2 + (size_t)n_runs * n_cols * 2 + (size_t)n_cols * 2;
+  const size_t tbl_entries = (size_t)n_runs * 2 + (size_t)n_runs * n_cols * 2 + (size_t)n_cols * 2 + (size_t)n_runs * n_more + (size_t)n_more;
   const size_t o_tbl = o; o += al(tbl_entries * 8);
   const size_t o_def = o; o += al((size_t)n_cols * 9 + 16);
   const size_t o_pairs = o; o += al(sizeof(mrg::Pair) * (size_t)(n_runs + 1) * 8);
@@ -493,6 +525,8 @@ int obgpu_merge_decoded(obgpu_ctx *ctx, const obgpu_merge_run *runs, int32_t n_r
   std::vector<size_t> o_ov((size_t)n_cols), o_on((size_t)n_cols);
   for (int c = 0; c < n_cols; ++c) { o_ov[(size_t)c] = o; o += al((size_t)N * 8); }
   for (int c = 0; c < n_cols; ++c) { o_on[(size_t)c] = o; o += al((size_t)N); }
+  std::vector<size_t> o_om((size_t)n_more);
+  for (int c = 0; c < n_more; ++c) { o_om[(size_t)c] = o; o += al((size_t)N * 8); }
   cudaError_t e = cudaMallocAsync(&res->arena, o + 256, ctx->stream);
   if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); delete res; return OBGPU_ALLOCATE_MEMORY_FAILED; }
   uint8_t *a = (uint8_t *)res->arena;
@@ -518,6 +552,10 @@ int obgpu_merge_decoded(obgpu_ctx *ctx, const obgpu_merge_run *runs, int32_t n_r
   for (int c = 0; c < n_cols; ++c) { res->out_vals.push_back((int64_t *)(a + o_ov[(size_t)c])); tbl[t++] = (uint64_t)res->out_vals.back(); }
   const size_t t_on = t;
   for (int c = 0; c < n_cols; ++c) { res->out_null.push_back(a + o_on[(size_t)c]); tbl[t++] = (uint64_t)res->out_null.back(); }
+  const size_t t_more = t;
+  for (int r = 0; r < n_runs; ++r) for (int c = 0; c < n_more; ++c) tbl[t++] = runs[r].n > 0 ? (uint64_t)runs[r].more_keys[c] : 0;
+  const size_t t_om = t;
+  for (int c = 0; c < n_more; ++c) { res->out_more.push_back((int64_t *)(a + o_om[(size_t)c])); tbl[t++] = (uint64_t)res->out_more.back(); }
   uint64_t *d_tbl = (uint64_t *)(a + o_tbl);
   // defaults: [n_cols] int64 then [n_cols] bytes
   std::vector<uint8_t> defs((size_t)n_cols * 9 + 16, 0);
@@ -576,6 +614,15 @@ int obgpu_merge_decoded(obgpu_ctx *ctx, const obgpu_merge_run *runs, int32_t n_r
                                                                                  k0 + segs[(size_t)r].begin, s0 + segs[(size_t)r].begin);
     ctx->launches++;
   }
+  mrg::RunsDev rd;
+  rd.key = (const int64_t *const *)(d_tbl + t_key);
+  rd.flag = (const uint8_t *const *)(d_tbl + t_flag);
+  rd.vals = (const int64_t *const *)(d_tbl + t_vals);
+  rd.ext = (const uint8_t *const *)(d_tbl + t_ext);
+  rd.more = (const int64_t *const *)(d_tbl + t_more);
+  rd.n_runs = n_runs;
+  rd.n_cols = n_cols;
+  rd.n_more = n_more;
   int64_t *kin = k0, *kout = k1;
   uint64_t *sin = s0, *sout = s1;
   for (size_t ps = 0; ps < passes.size(); ++ps) {
@@ -584,21 +631,14 @@ int obgpu_merge_decoded(obgpu_ctx *ctx, const obgpu_merge_run *runs, int32_t n_r
     if (tiles > 0) {
       int64_t *split = (int64_t *)(a + o_split);
       mrg::partition_kernel<<<(unsigned)((tiles + 255) / 256), 256, 0, ctx->stream>>>(
-          kin, (const mrg::Pair *)(a + o_pairs) + pass_at[ps], n_pairs, tiles, split);
+          kin, sin, rd, (const mrg::Pair *)(a + o_pairs) + pass_at[ps], n_pairs, tiles, split);
       mrg::pass_kernel<<<(unsigned)tiles, mrg::kThreads, 0, ctx->stream>>>(
-          kin, sin, kout, sout, (const mrg::Pair *)(a + o_pairs) + pass_at[ps], n_pairs, split);
+          kin, sin, kout, sout, rd, (const mrg::Pair *)(a + o_pairs) + pass_at[ps], n_pairs, split);
       ctx->launches += 2;
     }
     std::swap(kin, kout);
     std::swap(sin, sout);
   }
-  mrg::RunsDev rd;
-  rd.key = (const int64_t *const *)(d_tbl + t_key);
-  rd.flag = (const uint8_t *const *)(d_tbl + t_flag);
-  rd.vals = (const int64_t *const *)(d_tbl + t_vals);
-  rd.ext = (const uint8_t *const *)(d_tbl + t_ext);
-  rd.n_runs = n_runs;
-  rd.n_cols = n_cols;
   if (N > 0) {
     mrg::head_kernel<<<(unsigned)n_tiles, 256, 0, ctx->stream>>>(kin, sin, N, rd, emit, tile_cnt, res->d_stats, res->d_status);
     const int nc = (int)n_chunks;
@@ -608,7 +648,8 @@ int obgpu_merge_decoded(obgpu_ctx *ctx, const obgpu_merge_run *runs, int32_t n_r
                                                             (const unsigned long long *)(a + o_chunk));
     mrg::fuse_kernel<<<(unsigned)n_tiles, 256, 0, ctx->stream>>>(
         kin, sin, N, rd, emit, res->d_tile_off, (const int64_t *)(a + o_def), (const uint8_t *)(a + o_def + (size_t)n_cols * 8),
-        res->d_out_key, (int64_t *const *)(d_tbl + t_ov), (uint8_t *const *)(d_tbl + t_on), res->d_stats);
+        res->d_out_key, (int64_t *const *)(d_tbl + t_ov), (uint8_t *const *)(d_tbl + t_on), (int64_t *const *)(d_tbl + t_om),
+        res->d_stats);
     ctx->launches += 4;
   } else {
     cudaMemsetAsync(res->d_tile_off, 0, 16, ctx->stream);
@@ -623,9 +664,18 @@ int obgpu_merge_decoded(obgpu_ctx *ctx, const obgpu_merge_run *runs, int32_t n_r
 int obgpu_merge_runs(obgpu_ctx *ctx, obgpu_batch *const *batches, int32_t n_runs, int32_t rowkey_col, int32_t flag_col,
                      const int32_t *cols, int32_t n_cols, const int64_t *default_vals, const uint8_t *default_null,
                      obgpu_merge_result **out) {
-  if (!ctx || !batches || !out || n_runs <= 0 || n_runs > OBGPU_MERGE_MAX_RUNS || n_cols < 0 ||
-      n_cols + 2 > mrg::kMaxDecodeCols || (n_cols > 0 && !cols))
+  return obgpu_merge_runs_keys(ctx, batches, n_runs, &rowkey_col, 1, flag_col, cols, n_cols, default_vals, default_null, out);
+}
+
+int obgpu_merge_runs_keys(obgpu_ctx *ctx, obgpu_batch *const *batches, int32_t n_runs, const int32_t *rowkey_cols,
+                          int32_t n_rowkey_cols, int32_t flag_col, const int32_t *cols, int32_t n_cols,
+                          const int64_t *default_vals, const uint8_t *default_null, obgpu_merge_result **out) {
+  if (!ctx || !batches || !out || n_runs <= 0 || n_runs > OBGPU_MERGE_MAX_RUNS || n_cols < 0 || !rowkey_cols ||
+      n_rowkey_cols < 1 || n_rowkey_cols > OBGPU_MERGE_MAX_KEY_COLS ||
+      n_cols + 1 + n_rowkey_cols > mrg::kMaxDecodeCols || (n_cols > 0 && !cols))
     return OBGPU_INVALID_ARGUMENT;
+  const int n_more = n_rowkey_cols - 1;
+  std::vector<std::vector<const int64_t *>> mores((size_t)n_runs);
   for (int r = 0; r < n_runs; ++r)
     if (!batches[r] || batches[r]->ctx != ctx) return OBGPU_INVALID_ARGUMENT;
   cudaSetDevice(ctx->device);
@@ -638,7 +688,7 @@ int obgpu_merge_runs(obgpu_ctx *ctx, obgpu_batch *const *batches, int32_t n_runs
   for (int r = 0; r < n_runs && ret == OBGPU_SUCCESS; ++r) {
     obgpu_batch *b = batches[r];
     const int64_t n = b->total_rows;
-    const int n_dec = 1 + (flag_col >= 0 ? 1 : 0) + n_cols;
+    const int n_dec = n_rowkey_cols + (flag_col >= 0 ? 1 : 0) + n_cols;
     // one allocation per run: n_dec value arrays, n_dec ext arrays, the narrowed flag bytes
     void *buf = nullptr;
     const size_t per = ((size_t)n * 8 + 255) & ~(size_t)255, per_e = ((size_t)n + 255) & ~(size_t)255;
@@ -650,9 +700,10 @@ int obgpu_merge_runs(obgpu_ctx *ctx, obgpu_batch *const *batches, int32_t n_runs
     int64_t *dv[mrg::kMaxDecodeCols];
     uint8_t *de[mrg::kMaxDecodeCols];
     int k = 0;
-    dcols[k++] = rowkey_col;
+    dcols[k++] = rowkey_cols[0];
     if (flag_col >= 0) dcols[k++] = flag_col;
     for (int c = 0; c < n_cols; ++c) dcols[k++] = cols[c];
+    for (int c = 0; c < n_more; ++c) dcols[k++] = rowkey_cols[1 + c];   // remaining rowkey columns last
     for (int i = 0; i < n_dec; ++i) {
       dv[i] = (int64_t *)(base + per * (size_t)i);
       de[i] = base + per * (size_t)n_dec + per_e * (size_t)i;
@@ -679,6 +730,9 @@ int obgpu_merge_runs(obgpu_ctx *ctx, obgpu_batch *const *batches, int32_t n_runs
     }
     run.vals = vals[(size_t)r].data();
     run.ext = exts[(size_t)r].data();
+    for (int c = 0; c < n_more; ++c) mores[(size_t)r].push_back(dv[at + n_cols + c]);
+    run.more_keys = n_more > 0 ? mores[(size_t)r].data() : nullptr;
+    run.n_more_keys = n_more;
   }
   if (ret == OBGPU_SUCCESS) ret = obgpu_merge_decoded(ctx, runs.data(), n_runs, n_cols, default_vals, default_null, out);
   if (ret == OBGPU_SUCCESS)   // string references of run r carry tag r and point into that batch's image
@@ -793,14 +847,15 @@ int obgpu_merge_result_cols(obgpu_merge_result *res, const int64_t **key_dev, co
 
 int obgpu_merge_result_fetch(obgpu_merge_result *res, int32_t col, int64_t row_begin, int64_t row_count,
                              int64_t *host_vals, uint8_t *host_null) {
-  if (!res || col < -1 || col >= res->n_cols || row_begin < 0 || row_count < 0) return OBGPU_INVALID_ARGUMENT;
+  if (!res || col < -1 - (int32_t)res->out_more.size() || col >= res->n_cols || row_begin < 0 || row_count < 0)
+    return OBGPU_INVALID_ARGUMENT;
   obgpu_merge_info info;
   const int ret = obgpu_merge_result_info(res, &info);
   if (ret != OBGPU_SUCCESS) return ret;
   if (row_begin + row_count > info.out_rows) return OBGPU_INVALID_ARGUMENT;
   obgpu_ctx *ctx = res->ctx;
   if (row_count == 0) return OBGPU_SUCCESS;
-  const int64_t *src = col < 0 ? res->d_out_key : res->out_vals[(size_t)col];
+  const int64_t *src = col == -1 ? res->d_out_key : (col < -1 ? res->out_more[(size_t)(-col - 2)] : res->out_vals[(size_t)col]);
   if (host_vals) cudaMemcpyAsync(host_vals, src + row_begin, (size_t)row_count * 8, cudaMemcpyDeviceToHost, ctx->stream);
   if (host_null) {
     if (col < 0) memset(host_null, 0, (size_t)row_count);

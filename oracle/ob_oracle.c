@@ -1389,9 +1389,21 @@ int ora_decode_column_ext(const void *image, const int64_t *offsets, const int64
 /* The reference keeps the run heads in a loser tree (ObPartitionMajorRowsMerger); any priority
  * structure that pops (rowkey ascending, newer table first among equal rowkeys) gives the same
  * sequence. A binary heap over (key, -run) is used here. */
-typedef struct mrg_head { int64_t key; int32_t run; } mrg_head;
+typedef struct mrg_head { int64_t key; int32_t run; int64_t at; } mrg_head;
+static const ora_merge_run *g_mrg_runs;   /* the runs of the merge in progress (single-threaded test infrastructure) */
+/* rowkey order: column by column (ObStorageDatumUtils / ObPartitionMergeLoserTreeCmp::compare_rowkey) */
+static int mrg_key_cmp(const mrg_head *a, const mrg_head *b) {
+  if (a->key != b->key) return a->key < b->key ? -1 : 1;
+  const ora_merge_run *ra = &g_mrg_runs[a->run], *rb = &g_mrg_runs[b->run];
+  for (int32_t c = 0; c < ra->n_more_keys; ++c) {
+    const int64_t x = ra->more_keys[c][a->at], y = rb->more_keys[c][b->at];
+    if (x != y) return x < y ? -1 : 1;
+  }
+  return 0;
+}
 static int mrg_less(const mrg_head *a, const mrg_head *b) {
-  if (a->key != b->key) return a->key < b->key;
+  const int c = mrg_key_cmp(a, b);
+  if (c) return c < 0;
   return a->run > b->run; /* newer table first */
 }
 static void mrg_sift_down(mrg_head *h, int32_t n, int32_t i) {
@@ -1408,28 +1420,42 @@ static void mrg_sift_down(mrg_head *h, int32_t n, int32_t i) {
 int ora_major_merge(const ora_merge_run *runs, int32_t n_runs, int32_t n_cols, const int64_t *default_vals,
                     const uint8_t *default_null, int64_t out_cap, int64_t *out_key, int64_t *const *out_vals,
                     uint8_t *const *out_null, int64_t *out_rows, int64_t *stats) {
+  return ora_major_merge_keys(runs, n_runs, n_cols, default_vals, default_null, out_cap, out_key, 0, out_vals, out_null,
+                              out_rows, stats);
+}
+
+int ora_major_merge_keys(const ora_merge_run *runs, int32_t n_runs, int32_t n_cols, const int64_t *default_vals,
+                         const uint8_t *default_null, int64_t out_cap, int64_t *out_key, int64_t *const *out_more_keys,
+                         int64_t *const *out_vals, uint8_t *const *out_null, int64_t *out_rows, int64_t *stats) {
   if (!runs || n_runs <= 0 || n_runs > 64 || n_cols < 0 || n_cols > 64 || !out_key || !out_rows) return ORA_INVALID_ARGUMENT;
+  const int32_t n_more = runs[0].n_more_keys;
+  for (int32_t r = 0; r < n_runs; ++r)
+    if (runs[r].n_more_keys != n_more || (n_more > 0 && (!runs[r].more_keys || !out_more_keys))) return ORA_INVALID_ARGUMENT;
+  g_mrg_runs = runs;
   mrg_head heap[64];
   int64_t pos[64];
   int32_t hn = 0;
   for (int32_t r = 0; r < n_runs; ++r) {
     pos[r] = 0;
-    if (runs[r].n > 0) { heap[hn].key = runs[r].key[0]; heap[hn].run = r; ++hn; }
+    if (runs[r].n > 0) { heap[hn].key = runs[r].key[0]; heap[hn].run = r; heap[hn].at = 0; ++hn; }
   }
   for (int32_t i = hn / 2 - 1; i >= 0; --i) mrg_sift_down(heap, hn, i);
   int64_t nout = 0, dropped = 0, fused = 0;
   while (hn > 0) {
     /* find_rowkey_minimum_iters: every iter whose current rowkey equals the minimum, newest first */
     const int64_t key = heap[0].key;
+    const mrg_head min_head = heap[0];
     int32_t iters[64];
     int32_t ni = 0;
-    while (hn > 0 && heap[0].key == key) {
+    while (hn > 0 && mrg_key_cmp(&heap[0], &min_head) == 0) {
       iters[ni++] = heap[0].run;
       const int32_t r = heap[0].run;
       ++pos[r];
       if (pos[r] < runs[r].n) {
-        if (runs[r].key[pos[r]] <= key) return ORA_INVALID_DATA; /* run not strictly ascending */
-        heap[0].key = runs[r].key[pos[r]];
+        mrg_head nxt = {runs[r].key[pos[r]], r, pos[r]};
+        const mrg_head cur = {runs[r].key[pos[r] - 1], r, pos[r] - 1};
+        if (mrg_key_cmp(&nxt, &cur) <= 0) return ORA_INVALID_DATA; /* run not strictly ascending */
+        heap[0] = nxt;
       } else {
         heap[0] = heap[--hn];
       }
@@ -1471,6 +1497,7 @@ int ora_major_merge(const ora_merge_run *runs, int32_t n_runs, int32_t n_cols, c
     }
     if (nout >= out_cap) return ORA_BUF_NOT_ENOUGH;
     out_key[nout] = key;
+    for (int32_t c = 0; c < n_more; ++c) out_more_keys[c][nout] = runs[min_head.run].more_keys[c][min_head.at];
     for (int32_t c = 0; c < n_cols; ++c) { out_vals[c][nout] = rv[c]; out_null[c][nout] = rs[c]; }
     if (ni > 1) ++fused;
     ++nout;

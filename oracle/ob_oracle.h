@@ -168,6 +168,8 @@ typedef struct ora_merge_run {       /* one sorted run (rowkey ascending, unique
   const uint8_t *flag;               /* ObDmlFlag per row; NULL: every row DF_INSERT */
   const int64_t *const *vals;        /* [n_cols][n] */
   const uint8_t *const *ext;         /* [n_cols][n]: 0 value, 1 NULL, 2 NOP */
+  const int64_t *const *more_keys;   /* composite rowkey: the columns after `key`, [n_more_keys][n] */
+  int32_t n_more_keys;
 } ora_merge_run;
 /* runs[0] is the OLDEST table, runs[n_runs - 1] the newest (iters are fused newest first).
  * out_null[c][i]: 1 => NULL. stats[0] = keys dropped because the fused row is a delete,
@@ -175,6 +177,10 @@ typedef struct ora_merge_run {       /* one sorted run (rowkey ascending, unique
 int ora_major_merge(const ora_merge_run *runs, int32_t n_runs, int32_t n_cols, const int64_t *default_vals,
                     const uint8_t *default_null, int64_t out_cap, int64_t *out_key, int64_t *const *out_vals,
                     uint8_t *const *out_null, int64_t *out_rows, int64_t *stats);
+/* Same with the extra rowkey columns of a composite rowkey written to out_more_keys[n_more_keys][..]. */
+int ora_major_merge_keys(const ora_merge_run *runs, int32_t n_runs, int32_t n_cols, const int64_t *default_vals,
+                         const uint8_t *default_null, int64_t out_cap, int64_t *out_key, int64_t *const *out_more_keys,
+                         int64_t *const *out_vals, uint8_t *const *out_null, int64_t *out_rows, int64_t *stats);
 
 /* ---- skip index (pre-aggregated min / max / null count per micro-block) ------------------------------------
  * ObAggRowReader::read (index_block/ob_agg_row_struct.cpp:339-482): aggregate `col_type` (ObSkipIndexColType)

@@ -85,7 +85,7 @@ _lib = None
 
 class OraMergeRun(C.Structure):
     _fields_ = [("n", C.c_int64), ("key", C.c_void_p), ("flag", C.c_void_p), ("vals", C.POINTER(C.c_void_p)),
-                ("ext", C.POINTER(C.c_void_p))]
+                ("ext", C.POINTER(C.c_void_p)), ("more_keys", C.POINTER(C.c_void_p)), ("n_more_keys", C.c_int32)]
 
 
 def oracle():
@@ -116,6 +116,7 @@ def oracle():
         L.ora_scan_blocks_mt.argtypes = [vp, vp, vp, i32, P(OraFilter), vp, i32, i32, i32, P(i64), P(i64), P(u64)]
         L.ora_decode_column_ext.argtypes = [vp, vp, vp, i32, i32, vp, vp, i64, P(i64)]
         L.ora_major_merge.argtypes = [P(OraMergeRun), i32, i32, vp, vp, i64, vp, P(vp), P(vp), P(i64), P(i64)]
+        L.ora_major_merge_keys.argtypes = [P(OraMergeRun), i32, i32, vp, vp, i64, vp, P(vp), P(vp), P(vp), P(i64), P(i64)]
         L.ora_agg_row_read.argtypes = [vp, i64, C.c_uint32, i32, P(vp), P(i32), P(i32)]
         L.ora_skip_index_filter.argtypes = [vp, i64, i64, vp, i32, P(OraFilter), P(i32)]
         _lib = L
@@ -318,6 +319,12 @@ def major_merge(runs, n_cols, default_vals=None, default_null=None):
         arr[i].flag = flag.ctypes.data if flag is not None else None
         arr[i].vals = vp
         arr[i].ext = ep
+        more = [np.ascontiguousarray(k, dtype=np.int64) for k in (r.get("more_keys") or [])]
+        if more:
+            mp = (C.c_void_p * len(more))(*[k.ctypes.data for k in more])
+            keep += [more, mp]
+            arr[i].more_keys = mp
+            arr[i].n_more_keys = len(more)
         total += len(key)
     out_key = np.zeros(max(total, 1), dtype=np.int64)
     out_vals = [np.zeros(max(total, 1), dtype=np.int64) for _ in range(n_cols)]
@@ -328,12 +335,15 @@ def major_merge(runs, n_cols, default_vals=None, default_null=None):
     dn = None if default_null is None else np.ascontiguousarray(default_null, dtype=np.uint8)
     rows = C.c_int64(0)
     stats = (C.c_int64 * 2)()
-    ora_check(oracle().ora_major_merge(arr, len(runs), n_cols, dv.ctypes.data if dv is not None else None,
-                                       dn.ctypes.data if dn is not None else None, total, out_key.ctypes.data, ovp, onp,
-                                       C.byref(rows), stats), "ora_major_merge")
+    n_more = len(runs[0].get("more_keys") or [])
+    out_more = [np.zeros(max(total, 1), dtype=np.int64) for _ in range(n_more)]
+    omp = (C.c_void_p * max(n_more, 1))(*[v.ctypes.data for v in out_more])
+    ora_check(oracle().ora_major_merge_keys(arr, len(runs), n_cols, dv.ctypes.data if dv is not None else None,
+                                            dn.ctypes.data if dn is not None else None, total, out_key.ctypes.data, omp, ovp, onp,
+                                            C.byref(rows), stats), "ora_major_merge_keys")
     n = rows.value
-    return {"key": out_key[:n], "vals": [v[:n] for v in out_vals], "null": [v[:n] for v in out_null],
-            "dropped": stats[0], "fused": stats[1]}
+    return {"key": out_key[:n], "more_keys": [v[:n] for v in out_more], "vals": [v[:n] for v in out_vals],
+            "null": [v[:n] for v in out_null], "dropped": stats[0], "fused": stats[1]}
 
 
 # ---- skip index -------------------------------------------------------------------------------------------

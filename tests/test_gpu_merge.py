@@ -266,3 +266,50 @@ def test_decode_columns_tagged_and_named_images(env, ob):
     res.free()
     for t in range(3):
         keep[t * 4 + 1].close()
+
+
+@pytest.mark.parametrize("n_more", [1, 2, 3])
+def test_composite_rowkeys_on_device(env, n_more):
+    from test_major_merge_kat import composite_runs
+    from oceanbase_b200.compaction import DecodedRun, merge_decoded
+    ctx, torch = env
+    rng = np.random.default_rng(90 + n_more)
+    runs = composite_runs(rng, 7, 40_000, n_more)
+    t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).cuda()
+    dev = [DecodedRun(t(r["key"], np.int64), t(r["flag"], np.uint8), [t(r["vals"][0], np.int64)], [t(r["ext"][0], np.uint8)],
+                      [t(k, np.int64) for k in r["more_keys"]]) for r in runs]
+    res = merge_decoded(ctx, dev)
+    want = ora.major_merge(runs, 1)
+    assert_merge_equal(res, want, 1)
+    for c in range(n_more):
+        assert np.array_equal(res.fetch(-2 - c)[0], want["more_keys"][c]), f"rowkey column {1 + c}"
+    res.free()
+
+
+def test_composite_rowkeys_from_page_batches(env, ob):
+    # obgpu_merge_runs_keys: (tenant, order) rowkey decoded from the runs' SSTables, VARCHAR payload along
+    from test_major_merge_kat import composite_runs
+    from oceanbase_b200.compaction import merge_batches
+    ctx, torch = env
+    rng = np.random.default_rng(123)
+    runs = composite_runs(rng, 4, 30_000, 1)
+    batches = []
+    for ri, r in enumerate(runs):
+        n = len(r["key"])
+        r["s"] = [b"t%d-%d-%d" % (ri, int(a), int(b)) for a, b in zip(r["key"], r["more_keys"][0])]
+        cols = [ob.Column(ob.OBJ_INT, ob.ENC_RLE, r["key"]), ob.Column(ob.OBJ_INT, ob.ENC_RAW, r["more_keys"][0]),
+                ob.Column(ob.OBJ_INT, ob.ENC_RAW, r["flag"].astype(np.int64)),
+                ob.Column(ob.OBJ_INT, ob.ENC_RAW, r["vals"][0], nulls=r["ext"][0]), ob.Column(ob.OBJ_VARCHAR, ob.ENC_RAW, r["s"])]
+        batches.append(ctx.open_batch(ob.encode_table(cols, 800, rowkey_cnt=2)))
+    res = merge_batches(ctx, batches, [0, 1], 2, [3, 4])
+    want = ora.major_merge(runs, 1)
+    assert_merge_equal(res, want, 1)
+    assert np.array_equal(res.fetch(-2)[0], want["more_keys"][0])
+    heap, off, nl = res.fetch_strings(1)
+    k0, k1 = res.fetch(-1)[0], res.fetch(-2)[0]
+    for i in range(0, len(k0), 41):   # the newest existing row of the group wrote the string
+        s = bytes(heap[off[i]:off[i + 1]])
+        assert not nl[i] and s.startswith(b"t") and s.endswith(b"-%d-%d" % (int(k0[i]), int(k1[i])))
+    res.free()
+    for b in batches:
+        b.close()

@@ -135,3 +135,69 @@ def test_unsorted_run_is_rejected():
     r = {"key": np.array([5, 5, 9], dtype=np.int64), "flag": None, "vals": [], "ext": []}
     with pytest.raises(Exception):
         ora.major_merge([r], 0)
+
+
+def composite_runs(rng, n_runs, n_keys, n_more):
+    """Runs with a composite INT64 rowkey whose FIRST column ties a lot (so the later columns decide), one payload column."""
+    runs = []
+    universe = np.stack([rng.integers(0, 40, size=n_keys)] + [rng.integers(-5, 5, size=n_keys) for _ in range(n_more)], axis=1)
+    universe = np.unique(universe, axis=0)                                  # sorted lexicographically, distinct
+    for r in range(n_runs):
+        pick = np.sort(rng.choice(len(universe), size=int(len(universe) * 0.5), replace=False))
+        keys = universe[pick]
+        n = len(keys)
+        flag = np.where(rng.random(n) < 0.08, 4, 3 if r == 0 else 2).astype(np.uint8)
+        runs.append(dict(key=keys[:, 0].astype(np.int64), more_keys=[keys[:, 1 + c].astype(np.int64) for c in range(n_more)],
+                         flag=flag, vals=[rng.integers(0, 1000, size=n, dtype=np.int64)],
+                         ext=[rng.choice([0, 0, 1, 2] if r else [0, 0, 1], size=n).astype(np.uint8)]))
+    return runs
+
+
+def composite_model(runs, n_more):
+    rows = {}
+    for ri, r in enumerate(runs):
+        for i in range(len(r["key"])):
+            k = (int(r["key"][i]),) + tuple(int(r["more_keys"][c][i]) for c in range(n_more))
+            rows.setdefault(k, []).append((ri, i))
+    keys, vals, nulls, dropped, fused = [], [], [], 0, 0
+    for k in sorted(rows):
+        cell, first, deleted = None, True, False
+        for ri, i in sorted(rows[k], reverse=True):
+            r = runs[ri]
+            if r["flag"][i] == 4:
+                deleted = first
+                break
+            first = False
+            if cell is None and r["ext"][0][i] != 2:
+                cell = (int(r["ext"][0][i]), 0 if r["ext"][0][i] else int(r["vals"][0][i]))
+                break
+        if deleted:
+            dropped += 1
+            continue
+        if first:
+            continue
+        keys.append(k)
+        nulls.append(1 if cell is None else cell[0])
+        vals.append(0 if cell is None else cell[1])
+        fused += len(rows[k]) > 1
+    return keys, vals, nulls, dropped, fused
+
+
+@pytest.mark.parametrize("n_more", [1, 2, 3])
+def test_composite_rowkeys_in_the_oracle(n_more):
+    # rowkeys compare column by column (ObStorageDatumUtils); the first column alone does not separate the groups
+    rng = np.random.default_rng(60 + n_more)
+    runs = composite_runs(rng, 5, 3000, n_more)
+    got = ora.major_merge(runs, 1)
+    keys, vals, nulls, dropped, fused = composite_model(runs, n_more)
+    assert len(got["key"]) == len(keys) and got["dropped"] == dropped and got["fused"] == fused
+    assert [(int(got["key"][i]),) + tuple(int(got["more_keys"][c][i]) for c in range(n_more)) for i in range(len(keys))] == keys
+    assert got["null"][0].tolist() == nulls and got["vals"][0].tolist() == vals
+    # a run that is not strictly ascending in the composite order is refused
+    bad = composite_runs(rng, 2, 500, n_more)
+    bad[1]["more_keys"][0][1] = bad[1]["more_keys"][0][0]
+    bad[1]["key"][1] = bad[1]["key"][0]
+    for c in range(1, n_more):
+        bad[1]["more_keys"][c][1] = bad[1]["more_keys"][c][0]
+    with pytest.raises(RuntimeError):
+        ora.major_merge(bad, 1)
