@@ -662,6 +662,8 @@ __device__ __forceinline__ bool prepare_block(const ScanParams &p, uint32_t soff
 // =================================================================================================
 // Projection of one column over the selected rows (column-at-a-time, specialised)
 // =================================================================================================
+// Output vectors are written once and never read again by the scan: streaming stores (st.global.cs) keep them from
+// evicting the block bytes the count kernel has just pulled through L2.
 #define ROW(j) (IDENT ? (uint32_t)(j) : (uint32_t)sel[j])
 template <typename OutT, bool IDENT>
 __device__ __forceinline__ void project_int_col(const ScanParams &p, const BlockCtx &c, const ColDesc &d, int pc,
@@ -681,10 +683,10 @@ __device__ __forceinline__ void project_int_col(const ScanParams &p, const Block
     if (d.ext_bit == 0 && !fix && !d.var_is_last) {
       if (width <= 32) {
         for (uint32_t j = tid; j < cnt; j += nt)
-          out[j] = (OutT)((uint64_t)sbits32(val_bit + ROW(j) * stride, width) + add);
+          __stcs(&out[j], (OutT)((uint64_t)sbits32(val_bit + ROW(j) * stride, width) + add));
       } else {
         for (uint32_t j = tid; j < cnt; j += nt)
-          out[j] = (OutT)(sbits(val_bit + ROW(j) * stride, width) + add);
+          __stcs(&out[j], (OutT)(sbits(val_bit + ROW(j) * stride, width) + add));
       }
     } else {
       const uint32_t ext_off = c.sbit + d.ext_bit_off, eb = d.ext_bit, exor = d.var_ext_in_row;
@@ -693,19 +695,19 @@ __device__ __forceinline__ void project_int_col(const ScanParams &p, const Block
       for (uint32_t j = tid; j < cnt; j += nt) {
         const uint32_t row = ROW(j);
         if (eb && sbits32(ext_off + (row ^ exor) * eb, eb) != STORED_NOT_EXT) {
-          out[j] = (OutT)0;
+          __stcs(&out[j], (OutT)0);
           mark_null(j);
           continue;
         }
         const uint64_t raw = sbits(val_bit + row * stride, width);
         if (repl && raw == repl_raw) {
-          out[j] = (OutT)0;
+          __stcs(&out[j], (OutT)0);
           mark_null(j);
           continue;
         }
         uint64_t v = raw + add;
         if (fix) v = sign_fix(mask, v);
-        out[j] = (OutT)v;
+        __stcs(&out[j], (OutT)v);
       }
     }
   } else {  // K_DICT / K_RLE
@@ -717,13 +719,13 @@ __device__ __forceinline__ void project_int_col(const ScanParams &p, const Block
       for (uint32_t j = tid; j < cnt; j += nt) {
         const uint32_t ref = sbits32(val_bit + ROW(j) * stride, width);
         if (ref >= dcount) {
-          out[j] = (OutT)0;
+          __stcs(&out[j], (OutT)0);
           mark_null(j);
           continue;
         }
         uint64_t v = sbits(dpay + ref * dbits, dbits) + dbase;
         if (fix) v = sign_fix(mask, v);
-        out[j] = (OutT)v;
+        __stcs(&out[j], (OutT)v);
       }
     } else if (d.rle_slot >= 0) {
       const RleTable rt = c.rle_table(d.rle_slot);
@@ -731,19 +733,19 @@ __device__ __forceinline__ void project_int_col(const ScanParams &p, const Block
       for (uint32_t j = tid; j < cnt; j += nt) {
         const uint32_t ref = sbits32(refs_bit + rle_run_of(rt, ROW(j)) * ref_bits, ref_bits);
         if (ref >= dcount) {
-          out[j] = (OutT)0;
+          __stcs(&out[j], (OutT)0);
           mark_null(j);
           continue;
         }
         uint64_t v = sbits(dpay + ref * dbits, dbits);
         if (fix) v = sign_fix(mask, v);
-        out[j] = (OutT)v;
+        __stcs(&out[j], (OutT)v);
       }
     } else {
       for (uint32_t j = tid; j < cnt; j += nt) {
         bool is_null;
         const uint64_t v = int_cell(c.b, d, nullptr, ROW(j), is_null);
-        out[j] = (OutT)(is_null ? 0ull : v);
+        __stcs(&out[j], (OutT)(is_null ? 0ull : v));
         if (is_null) mark_null(j);
       }
     }
@@ -1310,8 +1312,8 @@ __global__ void __launch_bounds__(kThreads) obgpu_project_kernel(const __grid_co
           if (!any_null) {
             uint64_t *out = reinterpret_cast<uint64_t *>(p.out_data[pc]) + base;
             const RleTable rt = c.rle_table(0);
-            if (all_rows) for (uint32_t j = (uint32_t)lane; j < cnt; j += 32u) out[j] = rvals[rle_run_of(rt, j)];
-            else for (uint32_t j = (uint32_t)lane; j < cnt; j += 32u) out[j] = rvals[rle_run_of(rt, sel[j])];
+            if (all_rows) for (uint32_t j = (uint32_t)lane; j < cnt; j += 32u) __stcs(&out[j], rvals[rle_run_of(rt, j)]);
+            else for (uint32_t j = (uint32_t)lane; j < cnt; j += 32u) __stcs(&out[j], rvals[rle_run_of(rt, sel[j])]);
             __syncwarp();
             continue;
           }
