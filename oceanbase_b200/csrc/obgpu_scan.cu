@@ -762,7 +762,7 @@ __device__ __forceinline__ void project_int_col_global(const ScanParams &p, cons
   for (uint32_t j = (uint32_t)t.tid; j < cnt; j += (uint32_t)t.nthreads) {
     bool is_null;
     const uint64_t v = int_cell(c.b, d, nullptr, (uint32_t)sel[j], is_null);
-    out[j] = (OutT)(is_null ? 0ull : v);
+    __stcs(&out[j], (OutT)(is_null ? 0ull : v));
     if (is_null) {
       const int64_t o = base_row + (int64_t)j;
       atomicOr(&p.out_nulls[pc][o >> 5], 1u << (o & 31));
@@ -789,8 +789,8 @@ __device__ __forceinline__ void project_str_col(const ScanParams &p, const Block
     uint32_t cell, len;
     bool is_null;
     str_cell(c.b, d, rtp, ROW(j), cell, len, is_null);
-    optr[j] = is_null ? 0ull : blk_addr + cell;
-    olen[j] = is_null ? 0 : (int32_t)len;
+    __stcs(&optr[j], is_null ? 0ull : blk_addr + cell);
+    __stcs(&olen[j], is_null ? 0 : (int32_t)len);
     if (is_null) {
       const int64_t o = base_row + (int64_t)j;
       atomicOr(&p.out_nulls[pc][o >> 5], 1u << (o & 31));
