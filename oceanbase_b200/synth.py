@@ -83,16 +83,22 @@ def config2_pk(rows, seed, row_start=0):
     return np.int64(1_000_000_007) + (np.arange(row_start, row_start + rows, dtype=np.int64)) * 351 + jitter
 
 
+def config2_columns(rows, seed, row_start=0):
+    """The 8 INT64 columns of a config-2 chunk (the values the encoded table must decode back to)."""
+    s = lambda c: _col_seed(seed, c)
+    vals = [config2_pk(rows, seed, row_start)]
+    for c in (1, 2, 3):
+        vals.append(_rle_column(s(c), row_start, rows))
+    for c, w in zip((4, 5, 6, 7), (7, 13, 21, 33)):
+        vals.append((splitmix64(s(c), row_start, rows) & np.uint64((1 << w) - 1)).astype(np.int64))
+    return vals
+
+
 def make_config2_like(rows=100_000, rows_per_block=1400, seed=2, shape="bt", row_start=0,
                       n_threads=0, out=None) -> Workload:
-    s = lambda c: _col_seed(seed, c)
-    pk = config2_pk(rows, seed, row_start)
-    cols = [Column(capi.OBJ_INT, capi.ENC_INTEGER_BASE_DIFF, pk)]
-    for c in (1, 2, 3):
-        cols.append(Column(capi.OBJ_INT, capi.ENC_RLE, _rle_column(s(c), row_start, rows)))
-    for c, w in zip((4, 5, 6, 7), (7, 13, 21, 33)):
-        v = (splitmix64(s(c), row_start, rows) & np.uint64((1 << w) - 1)).astype(np.int64)
-        cols.append(Column(capi.OBJ_INT, capi.ENC_RAW, v))
+    vals = config2_columns(rows, seed, row_start)
+    encs = [capi.ENC_INTEGER_BASE_DIFF] + [capi.ENC_RLE] * 3 + [capi.ENC_RAW] * 4
+    cols = [Column(capi.OBJ_INT, e, v) for e, v in zip(encs, vals)]
     table = encode_table(cols, rows_per_block, rowkey_cnt=1, n_threads=n_threads, out=out)
     if shape == "bt":
         flt = White(4, capi.WHITE_OP_BT, (32, 63))                      # 32/128 = 25 %
