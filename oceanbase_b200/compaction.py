@@ -221,12 +221,16 @@ def _pack(run: DecodedRun, lo: int, hi: int):
     import torch
     n = hi - lo
     n_cols = len(run.vals)
-    buf = torch.empty(n * (8 * (1 + n_cols) + 1 + n_cols), dtype=torch.uint8, device=run.key.device)
-    i64 = buf[:8 * n * (1 + n_cols)].view(torch.int64)
+    more = run.more_keys or []
+    n64 = 1 + n_cols + len(more)               # rowkey, payload, then the remaining rowkey columns of a composite rowkey
+    buf = torch.empty(n * (8 * n64 + 1 + n_cols), dtype=torch.uint8, device=run.key.device)
+    i64 = buf[:8 * n * n64].view(torch.int64)
     i64[:n] = run.key[lo:hi]
     for c in range(n_cols):
         i64[(1 + c) * n:(2 + c) * n] = run.vals[c][lo:hi]
-    b = buf[8 * n * (1 + n_cols):]
+    for c, k in enumerate(more):
+        i64[(1 + n_cols + c) * n:(2 + n_cols + c) * n] = k[lo:hi]
+    b = buf[8 * n * n64:]
     if run.flag is None:
         b[:n] = capi.DF_INSERT
     else:
@@ -236,12 +240,14 @@ def _pack(run: DecodedRun, lo: int, hi: int):
     return buf
 
 
-def _unpack(buf, n: int, n_cols: int) -> DecodedRun:
+def _unpack(buf, n: int, n_cols: int, n_more: int = 0) -> DecodedRun:
     import torch
-    i64 = buf[:8 * n * (1 + n_cols)].view(torch.int64)
-    b = buf[8 * n * (1 + n_cols):]
+    n64 = 1 + n_cols + n_more
+    i64 = buf[:8 * n * n64].view(torch.int64)
+    b = buf[8 * n * n64:]
     return DecodedRun(i64[:n], b[:n], [i64[(1 + c) * n:(2 + c) * n] for c in range(n_cols)],
-                      [b[(1 + c) * n:(2 + c) * n] for c in range(n_cols)])
+                      [b[(1 + c) * n:(2 + c) * n] for c in range(n_cols)],
+                      [i64[(1 + n_cols + c) * n:(2 + n_cols + c) * n] for c in range(n_more)] if n_more else None)
 
 
 def distributed_major_merge(local_runs: Dict[int, DecodedRun], n_runs_total: int, n_cols: int,
@@ -302,7 +308,13 @@ def distributed_major_merge(local_runs: Dict[int, DecodedRun], n_runs_total: int
     # 3. the exchange: one packed buffer per (run, destination)
     recv = {}
     ops, keep = [], []
-    row_bytes = 8 * (1 + n_cols) + 1 + n_cols
+    # composite rowkeys: the partition looks at the first rowkey column only (rows that tie on it stay on one rank), the
+    # other rowkey columns travel like payload; every rank must agree on their number
+    n_more_t = torch.tensor([len(some.more_keys or []) if some is not None else 0], dtype=torch.int64, device=device)
+    if world > 1:
+        dist.all_reduce(n_more_t, op=dist.ReduceOp.MAX, group=group)
+    n_more = int(n_more_t.item())
+    row_bytes = 8 * (1 + n_cols + n_more) + 1 + n_cols
     for q in range(n_runs_total):
         o = int(owner_h[q])
         if o == rank:
@@ -332,9 +344,9 @@ def distributed_major_merge(local_runs: Dict[int, DecodedRun], n_runs_total: int
         if x is None:
             z = torch.zeros(0, dtype=torch.int64, device=device)
             zb = torch.zeros(0, dtype=torch.uint8, device=device)
-            runs.append(DecodedRun(z, zb, [z] * n_cols, [zb] * n_cols))
+            runs.append(DecodedRun(z, zb, [z] * n_cols, [zb] * n_cols, [z] * n_more if n_more else None))
         elif isinstance(x, tuple):
-            runs.append(_unpack(x[0], x[1], n_cols))
+            runs.append(_unpack(x[0], x[1], n_cols, n_more))
         else:
             runs.append(x)
     if device.type == "cuda":

@@ -76,3 +76,55 @@ def test_range_partitioned_merge_equals_single_process(world, n_runs):
     # all rows of one rowkey land on one rank
     for a, b in zip(got[:-1], got[1:]):
         assert a[1][-1] < b[1][0]
+
+
+def _worker_composite(rank, world, n_runs, port, out):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import oracle_binding as ora
+    from test_major_merge_kat import composite_runs
+    from oceanbase_b200.compaction import DecodedRun, distributed_major_merge
+    runs = composite_runs(np.random.default_rng(7), n_runs, 4000, 2)
+    t = torch.from_numpy
+    local = {q: DecodedRun(t(r["key"].copy()), t(r["flag"].copy()), [t(r["vals"][0].copy())], [t(r["ext"][0].copy())],
+                           [t(k.copy()) for k in r["more_keys"]]) for q, r in enumerate(runs) if q % world == rank}
+
+    def merge_fn(rs):
+        return ora.major_merge([{"key": r.key.numpy(), "flag": r.flag.numpy(), "vals": [r.vals[0].numpy()], "ext": [r.ext[0].numpy()],
+                                 "more_keys": [k.numpy() for k in r.more_keys]} for r in rs], 1)
+
+    m, _, _ = distributed_major_merge(local, n_runs, 1, merge_fn, samples_per_run=64)
+    out.put((rank, m["key"], m["more_keys"], m["vals"][0], m["null"][0]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_range_partitioned_merge_with_composite_rowkeys():
+    # the partition cuts on the first rowkey column only, so rows that tie on it stay on one rank; the other rowkey
+    # columns travel with the payload
+    import torch.multiprocessing as mp
+    sys.path.insert(0, ROOT)
+    import oracle_binding as ora
+    from test_major_merge_kat import composite_runs
+    world, n_runs = 2, 5
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_composite, args=(r, world, n_runs, 29677, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = sorted([q.get(timeout=240) for _ in range(world)], key=lambda x: x[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = ora.major_merge(composite_runs(np.random.default_rng(7), n_runs, 4000, 2), 1)
+    assert np.array_equal(np.concatenate([g[1] for g in got]), want["key"])
+    for c in range(2):
+        assert np.array_equal(np.concatenate([g[2][c] for g in got]), want["more_keys"][c])
+    assert np.array_equal(np.concatenate([g[3] for g in got]), want["vals"][0])
+    assert np.array_equal(np.concatenate([g[4] for g in got]), want["null"][0])
+    assert all(len(g[1]) > 0 for g in got) and got[0][1][-1] < got[1][1][0]
