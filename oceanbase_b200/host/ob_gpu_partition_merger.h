@@ -27,9 +27,11 @@ struct ObGpuMergeTable {
 
 // Column roles inside the tables' row layout (ObStaticMergeParam / ObTableReadInfo would provide them).
 struct ObGpuMergeSchema {
-  int32_t rowkey_col_ = 0;
+  int32_t rowkey_col_ = 0;              // first (or only) rowkey column
+  std::vector<int32_t> more_rowkey_cols_;  // the following columns of a composite rowkey, in comparison order
   int32_t flag_col_ = -1;               // column holding the ObDmlFlag image, -1: every row DF_INSERT
   std::vector<int32_t> payload_cols_;
+  std::vector<uint8_t> payload_is_string_;  // per payload column: 1 => VARCHAR / CHAR (empty: all integer class)
   std::vector<int64_t> default_vals_;   // default row (ObMajorPartitionMergeFuser::default_row_)
   std::vector<uint8_t> default_null_;   // empty: every default is NULL
 };
@@ -39,8 +41,12 @@ struct ObGpuMergeSchema {
 struct ObGpuMergedRows {
   int64_t row_count_ = 0;
   std::vector<int64_t> rowkeys_;
-  std::vector<std::vector<int64_t>> values_;   // [payload column][row]
+  std::vector<std::vector<int64_t>> more_rowkeys_;  // [extra rowkey column][row]
+  std::vector<std::vector<int64_t>> values_;   // [payload column][row] (integer class)
   std::vector<std::vector<uint8_t>> nulls_;    // 1 => NULL
+  // string payload columns: cell i of column c = heap_[c][offsets_[c][i] .. offsets_[c][i + 1])
+  std::vector<std::vector<char>> heap_;
+  std::vector<std::vector<int64_t>> offsets_;
 };
 
 class ObGpuPartitionMajorMerger {

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <string>
 #include <vector>
 
 #include "../../oceanbase_b200/host/ob_gpu_partition_merger.h"
@@ -196,6 +197,80 @@ int main() {
     ASSERT_EQ(rows.values_[1][0], 333);
     ASSERT_EQ(rows.nulls_[2][0], 1);
     ASSERT_EQ(merger.get_next_rows(16, rows), OB_ITER_END);
+  }
+  // ---- composite rowkey (tenant, order) + a VARCHAR payload column: three tables, every (tenant, order) in one or two of
+  // them; the newest table's string wins ---------------------------------------------------------------------------------
+  {
+    const int K = 3;
+    const int64_t tenants = 40, orders = 60;
+    struct SRun { std::vector<int64_t> k0, k1, flag; std::string heap; std::vector<int64_t> off; std::vector<uint8_t> image;
+                  std::vector<int64_t> offsets, sizes; };
+    std::vector<SRun> runs(K);
+    std::vector<std::string> expect((size_t)(tenants * orders));     // by (tenant, order): winning string ("" = absent)
+    for (int r = 0; r < K; ++r) {
+      SRun &run = runs[r];
+      run.off.push_back(0);
+      for (int64_t t = 0; t < tenants; ++t)
+        for (int64_t o = 0; o < orders; ++o) {
+          if (mix((uint64_t)(t * 1000 + o) * 31u + (uint64_t)r) % 3 == 0) continue;   // about two thirds of the keys per table
+          run.k0.push_back(t * 7 - 100);
+          run.k1.push_back(o - 30);
+          run.flag.push_back(r == 0 ? OBGPU_DF_INSERT : OBGPU_DF_UPDATE);
+          const std::string v = "t" + std::to_string(t) + "/o" + std::to_string(o) + "@" + std::to_string(r);
+          run.heap += v;
+          run.off.push_back((int64_t)run.heap.size());
+          expect[(size_t)(t * orders + o)] = v;                                       // later (newer) tables overwrite
+        }
+      run.heap.push_back('\0');
+      obgpu_col_input cols[4];
+      memset(cols, 0, sizeof(cols));
+      cols[0].obj_type = OBGPU_OBJ_INT; cols[0].encoding = OBGPU_ENC_RLE; cols[0].i64 = run.k0.data();
+      cols[1].obj_type = OBGPU_OBJ_INT; cols[1].encoding = OBGPU_ENC_RAW; cols[1].i64 = run.k1.data();
+      cols[2].obj_type = OBGPU_OBJ_TINYINT; cols[2].encoding = OBGPU_ENC_RAW; cols[2].i64 = run.flag.data();
+      cols[3].obj_type = OBGPU_OBJ_VARCHAR; cols[3].encoding = OBGPU_ENC_RAW; cols[3].str_heap = run.heap.data(); cols[3].str_off = run.off.data();
+      obgpu_table_image *img = nullptr;
+      ASSERT_EQ(obgpu_writer_encode_table(cols, 4, 2, (int64_t)run.k0.size(), 500, 128, 2, &img), 0);
+      int64_t size = 0; int32_t nb = 0;
+      obgpu_table_image_info(img, &size, &nb);
+      run.image.assign((size_t)size + 64, 0);
+      run.offsets.resize((size_t)nb); run.sizes.resize((size_t)nb);
+      obgpu_table_image_export(img, run.image.data(), size, run.offsets.data(), run.sizes.data(), nb);
+      obgpu_table_image_free(img);
+    }
+    std::vector<ObGpuMergeTable> tables;
+    for (SRun &r : runs) {
+      ObGpuMergeTable t;
+      t.image_ = r.image.data(); t.image_size_ = (int64_t)r.image.size() - 64;
+      t.offsets_ = r.offsets.data(); t.sizes_ = r.sizes.data(); t.block_count_ = (int32_t)r.offsets.size();
+      tables.push_back(t);
+    }
+    ObGpuMergeSchema schema;
+    schema.rowkey_col_ = 0; schema.more_rowkey_cols_ = {1}; schema.flag_col_ = 2;
+    schema.payload_cols_ = {3}; schema.payload_is_string_ = {1};
+    ObGpuPartitionMajorMerger merger;
+    ASSERT_EQ(merger.init(0, tables, schema), OB_SUCCESS);
+    ASSERT_EQ(merger.merge_partition(), OB_SUCCESS);
+    int64_t present = 0;
+    for (const std::string &e : expect) present += !e.empty();
+    ASSERT_EQ(merger.get_output_row_count(), present);
+    ObGpuMergedRows rows;
+    int64_t t = 0, o = -1, seen = 0;
+    int ret;
+    while ((ret = merger.get_next_rows(700, rows)) == OB_SUCCESS) {
+      for (int64_t i = 0; i < rows.row_count_; ++i) {
+        do { if (++o == orders) { o = 0; ++t; } } while (t < tenants && expect[(size_t)(t * orders + o)].empty());   // next present key
+        ASSERT_EQ(rows.rowkeys_[(size_t)i], t * 7 - 100);
+        ASSERT_EQ(rows.more_rowkeys_[0][(size_t)i], o - 30);
+        const std::string &want = expect[(size_t)(t * orders + o)];
+        const int64_t a = rows.offsets_[0][(size_t)i], b = rows.offsets_[0][(size_t)i + 1];
+        ASSERT_EQ(b - a, (int64_t)want.size());
+        ASSERT_EQ(memcmp(rows.heap_[0].data() + a, want.data(), want.size()), 0);
+        ASSERT_EQ((int)rows.nulls_[0][(size_t)i], 0);
+        ++seen;
+      }
+    }
+    ASSERT_EQ(ret, OB_ITER_END);
+    ASSERT_EQ(seen, present);
   }
   if (g_fail) { printf("%d failures\n", g_fail); return 1; }
   printf("partition merger tests passed\n");
