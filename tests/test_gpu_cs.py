@@ -215,3 +215,20 @@ def test_cs_dict_const_encoded_refs_scan(ob, ctx, kind):
                 ob.And([ob.White(0, ob.WHITE_OP_GE, (probe,)), ob.White(1, ob.WHITE_OP_LT, (8000,))]),
                 ob.Or([ob.White(0, ob.WHITE_OP_NN, ()), ob.White(1, ob.WHITE_OP_EQ, (9100,))])):
         assert_scan_matches(ctx, W(table, flt, [0, 1], [is_str, False], [8, 8]))
+
+
+@pytest.mark.parametrize("name", ["integer", "integer_nulls", "uint", "uint_nulls", "int_dict_const", "varchar", "varchar_nulls"])
+def test_reference_cs_filter_expectations_on_device(ob, ctx, name):
+    # the reference's own CS pd-filter unit-test datasets and expected counts (tests/test_cs_reference_filter_kat.py)
+    from test_cs_reference_filter_kat import DATASETS, OPS, build
+    for enc in DATASETS[name][1]:
+        block, cases = build(name, enc)
+        image = np.concatenate([block, np.zeros((-len(block)) % 128 + 128, dtype=np.uint8)])
+        table = ob.TableImage(image, np.array([0], dtype=np.int64), np.array([len(block)], dtype=np.int64), 0, 0)
+        batch = ctx.open_batch(table)
+        for op, params, expect in cases:
+            assert int(batch.filter_white(0, 1, OPS[op], params).sum()) == expect, (name, enc, op, params)
+            res = batch.scan(ob.White(1, OPS[op], params), [0])
+            assert res.selected_rows == expect
+            res.free()
+        batch.close()
