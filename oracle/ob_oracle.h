@@ -12,9 +12,13 @@
  * filter semantics are checked against the popcount expectations of
  * unittest/.../test_raw_decoder.cpp:774-1200 (tests/test_oracle_filter_kat.py) and
  * test_const_decoder.cpp:111-770 (tests/test_const_kat.py); the row fuse of the compaction merge
- * against unittest/storage/test_row_fuse.cpp:118-227 (tests/test_major_merge_kat.py). CS blocks:
- * restatement only (no reference vectors for the block framing) -- parity unpinned for them beyond
- * the shared filter expectations.
+ * against unittest/storage/test_row_fuse.cpp:118-227 (tests/test_major_merge_kat.py); the aggregate
+ * row and the skip-index verdicts against test_agg_row_struct.cpp:209-293 and
+ * test_skip_index_filter.cpp:405-1420 (tests/test_skip_index_kat.py). CS blocks: filter results are
+ * checked against the datasets and expected counts of the reference's CS pd-filter unit tests
+ * (cs_encoding/test_integer_pd_filter.cpp, test_int_dict_pd_filter.cpp, test_string_pd_filter.cpp;
+ * tests/test_cs_reference_filter_kat.py); the block framing itself has no reference vectors and is a
+ * restatement only -- byte-level CS parity is unpinned.
  * The reference ships no byte-level golden micro-blocks, so whole-block decode is
  * pinned by construction (layout restated from the encoder) and by the independent GPU decoder.
  *
