@@ -111,8 +111,10 @@ int obgpu_merge_result_fetch(obgpu_merge_result *res, int32_t col, int64_t row_b
  * [host_off[i], host_off[i + 1]) (row_count + 1 offsets; a NULL cell is empty and flagged in host_null). *heap_bytes
  * receives the bytes needed; OBGPU_BUF_NOT_ENOUGH when heap_cap is smaller (nothing copied). The page batches the
  * references point into must still be open: obgpu_merge_runs records their images itself; after obgpu_merge_decoded
- * the caller names them (index = string tag). */
-int obgpu_merge_result_set_string_images(obgpu_merge_result *res, const void *const *dev_images, int32_t n_images);
+ * the caller names them (index = string tag) with their sizes; a reference that does not lie inside its image reports
+ * OBGPU_INVALID_DATA instead of being followed. */
+int obgpu_merge_result_set_string_images(obgpu_merge_result *res, const void *const *dev_images, const int64_t *image_sizes,
+                                         int32_t n_images);
 int obgpu_merge_result_fetch_strings(obgpu_merge_result *res, int32_t col, int64_t row_begin, int64_t row_count,
                                      void *host_heap, int64_t heap_cap, int64_t *host_off, uint8_t *host_null,
                                      int64_t *heap_bytes);

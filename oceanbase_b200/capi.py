@@ -130,7 +130,7 @@ def declared_signatures():
         "obgpu_batch_decode_column": (C.c_int, [vp, i32, vp, vp]),
         "obgpu_batch_decode_columns": (C.c_int, [vp, i32, vp, vp, vp]),
         "obgpu_batch_decode_columns_tagged": (C.c_int, [vp, i32, vp, i32, vp, vp]),
-        "obgpu_merge_result_set_string_images": (C.c_int, [vp, vp, i32]),
+        "obgpu_merge_result_set_string_images": (C.c_int, [vp, vp, vp, i32]),
         "obgpu_merge_result_fetch_strings": (C.c_int, [vp, i32, i64, i64, vp, i64, vp, vp, P(i64)]),
         "obgpu_merge_decoded": (C.c_int, [vp, P(MergeRun), i32, i32, vp, vp, P(vp)]),
         "obgpu_merge_runs": (C.c_int, [vp, P(vp), i32, i32, i32, vp, i32, vp, vp, P(vp)]),

@@ -110,10 +110,11 @@ class MergeResult:
                   "obgpu_merge_result_fetch_strings", self.ctx._h)
         return heap[:need.value], off, nl[:row_count]
 
-    def set_string_images(self, device_ptrs: Sequence[int]):
+    def set_string_images(self, device_ptrs: Sequence[int], sizes: Sequence[int]):
         arr = (C.c_void_p * max(len(device_ptrs), 1))(*device_ptrs)
-        check(lib.obgpu_merge_result_set_string_images(self._h, arr, len(device_ptrs)), "obgpu_merge_result_set_string_images",
-              self.ctx._h)
+        sz = np.ascontiguousarray(sizes, dtype=np.int64)
+        check(lib.obgpu_merge_result_set_string_images(self._h, arr, sz.ctypes.data, len(device_ptrs)),
+              "obgpu_merge_result_set_string_images", self.ctx._h)
 
     def free(self):
         if self._h and self.ctx._h:

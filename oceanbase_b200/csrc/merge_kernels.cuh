@@ -399,7 +399,8 @@ __global__ void __launch_bounds__(256) ref_len_kernel(const int64_t *__restrict_
 }
 // one warp per row: copies the cell from the image its tag names to heap[off[row] ..)
 __global__ void __launch_bounds__(256) ref_gather_kernel(const int64_t *__restrict__ refs, const uint8_t *__restrict__ nulls, int64_t n,
-                                                         const uint8_t *const *__restrict__ images, int n_images,
+                                                         const uint8_t *const *__restrict__ images,
+                                                         const uint64_t *__restrict__ image_sizes, int n_images,
                                                          const int64_t *__restrict__ off, uint8_t *__restrict__ heap,
                                                          int *__restrict__ status) {
   const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -412,7 +413,12 @@ __global__ void __launch_bounds__(256) ref_gather_kernel(const int64_t *__restri
     if (lane == 0) atomicOr(status, ST_CORRUPT);
     return;
   }
-  const uint8_t *src = images[tag] + ((r >> kRefOffShift) & kRefOffMask);
+  const uint64_t at = (r >> kRefOffShift) & kRefOffMask;
+  if (at + len > image_sizes[tag]) {   // not a reference into that image (e.g. an integer column was asked for)
+    if (lane == 0) atomicOr(status, ST_CORRUPT);
+    return;
+  }
+  const uint8_t *src = images[tag] + at;
   uint8_t *dst = heap + off[row];
   for (uint32_t k = (uint32_t)lane; k < len; k += 32u) dst[k] = src[k];
 }
@@ -436,6 +442,8 @@ struct obgpu_merge_result {
   std::vector<const int64_t *> vals_view;
   std::vector<const uint8_t *> null_view;
   std::vector<const uint8_t *> string_images;   // tag -> device image the string references point into
+  std::vector<uint64_t> string_image_sizes;     // bytes of each image (bounds of a reference)
+  std::vector<uint8_t> col_is_string;           // known when the runs were decoded here (obgpu_merge_runs_keys)
   std::vector<int64_t *> out_more;              // rowkey columns after the first
 };
 
@@ -735,16 +743,32 @@ int obgpu_merge_runs_keys(obgpu_ctx *ctx, obgpu_batch *const *batches, int32_t n
     run.n_more_keys = n_more;
   }
   if (ret == OBGPU_SUCCESS) ret = obgpu_merge_decoded(ctx, runs.data(), n_runs, n_cols, default_vals, default_null, out);
-  if (ret == OBGPU_SUCCESS)   // string references of run r carry tag r and point into that batch's image
-    for (int r = 0; r < n_runs; ++r) (*out)->string_images.push_back(batches[r]->d_image);
+  if (ret == OBGPU_SUCCESS) {   // string references of run r carry tag r and point into that batch's image
+    for (int r = 0; r < n_runs; ++r) {
+      (*out)->string_images.push_back(batches[r]->d_image);
+      (*out)->string_image_sizes.push_back((uint64_t)batches[r]->image_size);
+    }
+    for (int c = 0; c < n_cols; ++c) {
+      const uint32_t col = (uint32_t)cols[c];
+      const uint8_t t = col < batches[0]->col_types.size() ? batches[0]->col_types[col] : 0xff;
+      (*out)->col_is_string.push_back(t != 0xff && obf::store_class_of(t) == 5);
+    }
+  }
   release();  // stream-ordered: the merge kernels were enqueued before these frees
   return ret;
 }
 
-int obgpu_merge_result_set_string_images(obgpu_merge_result *res, const void *const *dev_images, int32_t n_images) {
-  if (!res || n_images < 0 || n_images > OBGPU_MERGE_MAX_RUNS || (n_images > 0 && !dev_images)) return OBGPU_INVALID_ARGUMENT;
+int obgpu_merge_result_set_string_images(obgpu_merge_result *res, const void *const *dev_images, const int64_t *image_sizes,
+                                         int32_t n_images) {
+  if (!res || n_images < 0 || n_images > OBGPU_MERGE_MAX_RUNS || (n_images > 0 && (!dev_images || !image_sizes)))
+    return OBGPU_INVALID_ARGUMENT;
   res->string_images.clear();
-  for (int i = 0; i < n_images; ++i) res->string_images.push_back((const uint8_t *)dev_images[i]);
+  res->string_image_sizes.clear();
+  for (int i = 0; i < n_images; ++i) {
+    if (image_sizes[i] < 0) return OBGPU_INVALID_ARGUMENT;
+    res->string_images.push_back((const uint8_t *)dev_images[i]);
+    res->string_image_sizes.push_back((uint64_t)image_sizes[i]);
+  }
   return OBGPU_SUCCESS;
 }
 
@@ -762,11 +786,13 @@ int obgpu_merge_result_fetch_strings(obgpu_merge_result *res, int32_t col, int64
   *heap_bytes = 0;
   if (row_count == 0) return OBGPU_SUCCESS;
   if (res->string_images.empty()) { ctx->err = "no page-batch images attached to the merge result"; return OBGPU_INVALID_ARGUMENT; }
+  if (!res->col_is_string.empty() && !res->col_is_string[(size_t)col]) { ctx->err = "not a string column"; return OBGPU_INVALID_ARGUMENT; }
   const int64_t n = row_count;
   const int n_chunks = (int)((n + kPrefixChunk - 1) / kPrefixChunk);
   auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
   const size_t o_len = 0, o_off = al((size_t)n * 4), o_chunk = o_off + al(((size_t)n + 1) * 8);
-  const size_t o_img = o_chunk + al(((size_t)n_chunks + 2) * 8), o_st = o_img + al(res->string_images.size() * 8);
+  const size_t o_img = o_chunk + al(((size_t)n_chunks + 2) * 8), o_isz = o_img + al(res->string_images.size() * 8);
+  const size_t o_st = o_isz + al(res->string_image_sizes.size() * 8);
   uint8_t *tmp = nullptr;
   CUDA_TRY(ctx, cudaMallocAsync((void **)&tmp, o_st + 256, ctx->stream));
   const int64_t *refs = res->out_vals[(size_t)col] + row_begin;
@@ -774,6 +800,7 @@ int obgpu_merge_result_fetch_strings(obgpu_merge_result *res, int32_t col, int64
   int64_t *d_off = (int64_t *)(tmp + o_off);
   cudaMemsetAsync(tmp + o_st, 0, 4, ctx->stream);
   cudaMemcpyAsync(tmp + o_img, res->string_images.data(), res->string_images.size() * 8, cudaMemcpyHostToDevice, ctx->stream);
+  cudaMemcpyAsync(tmp + o_isz, res->string_image_sizes.data(), res->string_image_sizes.size() * 8, cudaMemcpyHostToDevice, ctx->stream);
   mrg::ref_len_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(refs, nulls, n, (uint32_t *)(tmp + o_len));
   obgpu_prefix_local_kernel<<<n_chunks, 256, 0, ctx->stream>>>((const uint32_t *)(tmp + o_len), (int)n, d_off,
                                                               (unsigned long long *)(tmp + o_chunk));
@@ -792,7 +819,8 @@ int obgpu_merge_result_fetch_strings(obgpu_merge_result *res, int32_t col, int64
     e = cudaMallocAsync((void **)&d_heap, (size_t)total + 16, ctx->stream);
     if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); cudaFreeAsync(tmp, ctx->stream); return OBGPU_ALLOCATE_MEMORY_FAILED; }
     mrg::ref_gather_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, ctx->stream>>>(
-        refs, nulls, n, (const uint8_t *const *)(tmp + o_img), (int)res->string_images.size(), d_off, d_heap, (int *)(tmp + o_st));
+        refs, nulls, n, (const uint8_t *const *)(tmp + o_img), (const uint64_t *)(tmp + o_isz), (int)res->string_images.size(), d_off,
+        d_heap, (int *)(tmp + o_st));
     ctx->launches++;
     cudaMemcpyAsync(host_heap, d_heap, (size_t)total, cudaMemcpyDeviceToHost, ctx->stream);
     cudaMemcpyAsync(&status, tmp + o_st, 4, cudaMemcpyDeviceToHost, ctx->stream);

@@ -206,6 +206,8 @@ def test_merge_with_string_payload_columns(env, ob, block_format):
     assert np.array_equal(res.fetch(-1)[0], np.array(exp_key, dtype=np.int64))
     v, nl = res.fetch(0)
     assert [None if z else int(x) for x, z in zip(v, nl)] == exp[0]
+    with pytest.raises(ob.ObGpuError):
+        res.fetch_strings(0)                                         # an integer column holds no references
     for c in (1, 2):
         heap, off, nl = res.fetch_strings(c)
         got = [None if nl[i] else bytes(heap[off[i]:off[i + 1]]) for i in range(len(exp_key))]
@@ -231,7 +233,7 @@ def test_decode_columns_tagged_and_named_images(env, ob):
     from oceanbase_b200.compaction import DecodedRun, merge_decoded
     ctx, torch = env
     rng = np.random.default_rng(5)
-    runs, images, keep = [], [], []
+    runs, images, sizes, keep = [], [], [], []
     for tag in range(3):
         n = 4000
         key = (np.arange(n, dtype=np.int64) * 3 + tag)                   # disjoint rowkeys: nothing fuses
@@ -254,9 +256,13 @@ def test_decode_columns_tagged_and_named_images(env, ob):
         assert np.array_equal((refs[live] & np.uint64((1 << 22) - 1)).astype(np.int64), np.array([len(x) for x, z in zip(s, nulls) if not z]))
         runs.append(DecodedRun(vs[0], None, [vs[1]], [es[1]]))
         images.append(d_img.data_ptr())
+        sizes.append(table.image.size)
         keep += [d_img, batch, s, nulls]
     res = merge_decoded(ctx, runs)
-    res.set_string_images(images)
+    res.set_string_images(images, [8] * 3)                      # images declared too small: references are refused, not followed
+    with pytest.raises(ob.ObGpuError):
+        res.fetch_strings(0)
+    res.set_string_images(images, sizes)
     heap, off, nl = res.fetch_strings(0)
     k, _ = res.fetch(-1)
     for i in range(0, len(k), 53):
