@@ -4,6 +4,7 @@ expected selected-row counts of
                                             test_integer_pd_filter.cpp:114-189  test_integer_decoder_uint_type
                                             test_int_dict_pd_filter.cpp:186-270 test_int_dict_const_decoder (const-encoded refs)
                                             test_string_pd_filter.cpp:25-123    test_string_decoder_filter_varchar
+                                            test_str_dict_pd_filter.cpp:276-372 test_var_string_dict_const_decoder (const-encoded refs)
 are rebuilt with this repo's CS writer and evaluated by the oracle (and, in tests/test_gpu_cs.py, by the device)."""
 import numpy as np
 import pytest
@@ -78,12 +79,30 @@ def string_dataset(has_null):
     return ob.OBJ_VARCHAR, v, nulls, cases
 
 
+def str_dict_const_dataset():
+    # test_str_dict_pd_filter.cpp:276-372 test_var_string_dict_const_decoder: one dominant string, 4 exceptions, one NULL
+    s = lambda idx, ln: bytes([ord("a") + idx]) * ln
+    v = [s(0, 50)] * 115 + [s(1, 50), s(2, 50), s(3, 50), s(4, 50), b""]
+    nulls = np.array([0] * 119 + [1], dtype=np.uint8)
+    cases = [("NU", (), 1), ("NN", (), 119)]
+    cases += [("EQ", (s(*r),), e) for r, e in zip(((0, 50), (1, 50), (0, 100)), (115, 1, 0))]
+    cases += [("NE", (s(*r),), e) for r, e in zip(((0, 50), (1, 50), (0, 100)), (4, 118, 119))]
+    cases += [("LT", (s(*r),), e) for r, e in zip(((0, 50), (0, 51), (2, 50)), (0, 115, 116))]
+    cases += [("LE", (s(*r),), e) for r, e in zip(((0, 50), (0, 51), (2, 50)), (115, 115, 117))]
+    cases += [("GT", (s(*r),), e) for r, e in zip(((0, 49), (0, 50), (2, 50)), (119, 4, 2))]
+    cases += [("GE", (s(*r),), e) for r, e in zip(((0, 49), (0, 50), (2, 50)), (119, 119, 3))]
+    cases += [("IN", tuple(s(*r) for r in ((0, 50), (0, 100), (1, 40), (2, 100), (3, 50))), 116)]
+    cases += [("BT", (s(*a), s(*b)), e) for (a, b), e in zip((((0, 10), (0, 49)), ((0, 10), (1, 50)), ((1, 50), (4, 50))), (0, 116, 4))]
+    return ob.OBJ_VARCHAR, v, nulls, cases
+
+
 DATASETS = {
     "integer": (lambda: integer_dataset(False), [ob.ENC_CS_INTEGER, ob.ENC_CS_INT_DICT, ob.ENC_RAW, ob.ENC_DICT]),
     "integer_nulls": (lambda: integer_dataset(True), [ob.ENC_CS_INTEGER, ob.ENC_CS_INT_DICT, ob.ENC_RAW, ob.ENC_DICT]),
     "uint": (lambda: uint_dataset(False), [ob.ENC_CS_INTEGER, ob.ENC_CS_INT_DICT]),
     "uint_nulls": (lambda: uint_dataset(True), [ob.ENC_CS_INTEGER, ob.ENC_CS_INT_DICT]),
     "int_dict_const": (const_dict_dataset, [ob.ENC_CS_INT_DICT, ob.ENC_CS_INTEGER]),
+    "str_dict_const": (str_dict_const_dataset, [ob.ENC_CS_STR_DICT, ob.ENC_CS_STRING, ob.ENC_DICT]),
     "varchar": (lambda: string_dataset(False), [ob.ENC_CS_STRING, ob.ENC_CS_STR_DICT, ob.ENC_RAW, ob.ENC_DICT]),
     "varchar_nulls": (lambda: string_dataset(True), [ob.ENC_CS_STRING, ob.ENC_CS_STR_DICT, ob.ENC_RAW, ob.ENC_DICT]),
 }

@@ -217,7 +217,7 @@ def test_cs_dict_const_encoded_refs_scan(ob, ctx, kind):
         assert_scan_matches(ctx, W(table, flt, [0, 1], [is_str, False], [8, 8]))
 
 
-@pytest.mark.parametrize("name", ["integer", "integer_nulls", "uint", "uint_nulls", "int_dict_const", "varchar", "varchar_nulls"])
+@pytest.mark.parametrize("name", ["integer", "integer_nulls", "uint", "uint_nulls", "int_dict_const", "str_dict_const", "varchar", "varchar_nulls"])
 def test_reference_cs_filter_expectations_on_device(ob, ctx, name):
     # the reference's own CS pd-filter unit-test datasets and expected counts (tests/test_cs_reference_filter_kat.py)
     from test_cs_reference_filter_kat import DATASETS, OPS, build
