@@ -72,9 +72,16 @@ class HostScanPipeline:
 
     def scan(self, table: TableImage, filter, proj: Sequence[int], blocks_per_batch: int, selectivity_hint: float,
              out_buffers: Optional[List[List[np.ndarray]]] = None, string_base: int = 0,
-             null_buffers: Optional[List[List[np.ndarray]]] = None, ramp: int = 0) -> List[BatchOutput]:
+             null_buffers: Optional[List[List[np.ndarray]]] = None, ramp: int = 0,
+             agg_rows: Optional[np.ndarray] = None, agg_off: Optional[np.ndarray] = None) -> List[BatchOutput]:
+        """agg_rows / agg_off: the micro-blocks' serialized aggregate rows (block b: agg_rows[agg_off[b]:agg_off[b + 1]]);
+        every page batch then carries its slice and the scan prunes with the skip index."""
         parts = split_table(table, blocks_per_batch, ramp)
         bounds = batch_bounds(table.n_blocks, blocks_per_batch, ramp)
+        if agg_rows is not None:
+            agg_rows = np.ascontiguousarray(agg_rows, dtype=np.uint8)
+            agg_off = np.ascontiguousarray(agg_off, dtype=np.int64)
+            assert len(agg_off) == table.n_blocks + 1
         outs: List[Optional[BatchOutput]] = [None] * len(parts)
         errors = []
         lock = threading.Lock()
@@ -90,6 +97,8 @@ class HostScanPipeline:
                         return
                     part = parts[i]
                     batch = ctx.open_batch(part)                      # H2D + index kernel
+                    if agg_rows is not None:                           # offsets keep their table-wide base: no copy
+                        batch.set_agg_rows(agg_rows, agg_off[bounds[i]:bounds[i + 1] + 1])
                     cap = int(batch.total_rows * selectivity_hint) + 1024
                     res = batch.scan(filter, proj, string_base=string_base, max_selected_rows=min(cap, batch.total_rows))
                     try:

@@ -37,3 +37,24 @@ def test_pipeline_with_ramped_batches():
         assert np.array_equal(np.concatenate([o.cols[c] for o in outs]), want["data"][c])
     bounds = batch_bounds(w.table.n_blocks, 16, 2)
     assert [o.block_begin for o in outs] == bounds[:-1] and [o.block_end for o in outs] == bounds[1:]
+
+
+def test_pipeline_with_skip_index():
+    # every page batch carries its slice of the aggregate rows: same rows as the unpruned oracle scan
+    import oceanbase_b200 as ob
+    from oceanbase_b200.pipeline import HostScanPipeline
+    rng = np.random.default_rng(3)
+    n = 90_000
+    k = np.sort(rng.integers(0, 1 << 30, size=n, dtype=np.int64))
+    v = rng.integers(0, 100, size=n, dtype=np.int64)
+    cols = [ob.Column(ob.OBJ_INT, ob.ENC_INTEGER_BASE_DIFF, k), ob.Column(ob.OBJ_INT, ob.ENC_RAW, v)]
+    table = ob.encode_table(cols, 700)
+    rows, offs = ob.table_agg_rows(cols, [0, 1], 700)
+    flt = ob.And([ob.White(0, ob.WHITE_OP_BT, (int(k[20_000]), int(k[45_000]))), ob.White(1, ob.WHITE_OP_LT, (60,))])
+    pipe = HostScanPipeline(0, n_workers=3)
+    outs = pipe.scan(table, flt, [0, 1], blocks_per_batch=11, selectivity_hint=0.3, ramp=2, agg_rows=rows, agg_off=offs)
+    pipe.close()
+    want = ora.scan_table(table, flt, [0, 1], [False, False], [8, 8])
+    assert sum(o.selected_rows for o in outs) == want["selected"]
+    for c in range(2):
+        assert np.array_equal(np.concatenate([o.cols[c] for o in outs]), want["data"][c])
