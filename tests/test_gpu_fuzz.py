@@ -35,7 +35,7 @@ def random_int_values(rng, n, obj_type, ob):
     if shape == 0:      # full range
         v = rng.integers(lo, hi, size=n, dtype=np.int64)
     elif shape == 1:    # narrow band somewhere in the range
-        w = int(rng.integers(1, 5000))
+        w = min(int(rng.integers(1, 5000)), hi - lo)      # stay inside the type's domain
         a = int(rng.integers(lo, max(lo + 1, hi - w)))
         v = rng.integers(a, a + w, size=n, dtype=np.int64)
     elif shape == 2:    # few distinct values
