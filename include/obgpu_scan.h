@@ -280,43 +280,6 @@ int obgpu_project_discrete(obgpu_batch *batch, int32_t block, int32_t col, const
                            int64_t row_cap, int64_t vec_offset, uint64_t string_base,
                            uint64_t *ptrs, int32_t *lens, uint64_t *nulls, int32_t *has_null);
 
-/* =============================================================================================
- * Writer: host-side PAX micro-block encoder producing reference-format blocks
- * (ObMicroBlockEncoder::build_block, encoding/ob_micro_block_encoder.cpp:561-721) for a forced
- * per-column encoding.  Used to build SSTables for tests / benchmarks and by the compaction
- * writer.  Column inputs are column-major arrays over the rows of the table.
- * ============================================================================================= */
-typedef struct obgpu_col_input {
-  int32_t obj_type;        /* OBGPU_OBJ_*                                                      */
-  int32_t encoding;        /* OBGPU_ENC_*                                                      */
-  const int64_t *i64;      /* integer classes: value per row                                   */
-  const uint8_t *is_null;  /* optional: 1 => NULL, 2 => NOP (cell absent in an incremental row)       */
-  const char *str_heap;    /* string classes: bytes                                            */
-  const int64_t *str_off;  /*   nrows + 1 offsets into str_heap                                */
-  int32_t byte_packing_only; /* 1 => ObMicroBlockEncoderOpt.enable_bit_packing_ == false       */
-  int32_t reserved;
-} obgpu_col_input;
-
-/* Upper bound of the encoded size of a block of nrows rows. */
-int64_t obgpu_writer_block_bound(const obgpu_col_input *cols, int32_t n_cols, int64_t row_begin,
-                                 int64_t nrows);
-/* Encode rows [row_begin, row_begin + nrows) into one micro-block. */
-int obgpu_writer_encode_block(const obgpu_col_input *cols, int32_t n_cols,
-                              int32_t rowkey_col_cnt, int64_t row_begin, int64_t nrows,
-                              void *out, int64_t out_cap, int64_t *out_size);
-/* Encode total_rows rows as consecutive blocks of rows_per_block rows (last one shorter). The
- * encoded blocks are held by the returned handle; export packs them into one image where block i
- * starts at offsets[i] (aligned to `align`, a power of two >= 16, padding zeroed) and is sizes[i]
- * bytes long. n_threads <= 0 uses all hardware threads. */
-typedef struct obgpu_table_image obgpu_table_image;
-int obgpu_writer_encode_table(const obgpu_col_input *cols, int32_t n_cols, int32_t rowkey_col_cnt,
-                              int64_t total_rows, int64_t rows_per_block, int32_t align,
-                              int32_t n_threads, obgpu_table_image **out);
-int obgpu_table_image_info(const obgpu_table_image *img, int64_t *image_size, int32_t *n_blocks);
-int obgpu_table_image_export(const obgpu_table_image *img, void *image, int64_t image_cap,
-                             int64_t *offsets, int64_t *sizes, int32_t tables_cap);
-void obgpu_table_image_free(obgpu_table_image *img);
-
 /* Library self-description (build id, arch) for logs. */
 const char *obgpu_version(void);
 

@@ -42,37 +42,6 @@ enum {
   OBGPU_BOOL_MASK_ALWAYS_FALSE = 2
 };
 
-#define OBGPU_SKIP_INDEX_MAX_COL_LENGTH 40 /* ObSkipIndexColMeta::MAX_SKIP_INDEX_COL_LENGTH */
-
-/* One aggregate of an aggregate row: (ObSkipIndexColMeta, ObStorageDatum, is_min_max_prefix). */
-typedef struct obgpu_agg_cell {
-  uint32_t col_idx;  /* column store index the aggregate refers to                      */
-  uint8_t col_type;  /* OBGPU_SK_IDX_*                                                  */
-  uint8_t is_null;   /* NULL / NOP datum: the aggregate is not stored                   */
-  uint8_t is_prefix; /* MIN / MAX of a string longer than 40 bytes: only a prefix kept  */
-  uint8_t reserved;
-  int32_t len;       /* datum length in bytes                                           */
-  const void *data;  /* datum bytes                                                     */
-} obgpu_agg_cell;
-
-/* ObAggRowWriter::init + write_agg_data (ob_agg_row_struct.cpp:49-300): serializes the cells (any order)
- * as one aggregate row. version: 1, 2 (prefix bitmap) or 3 (revised max prefix; the current one).
- * out == NULL: only *out_size is computed. */
-int obgpu_agg_row_write(const obgpu_agg_cell *cells, int32_t n_cells, int32_t version, void *out,
-                        int64_t out_cap, int64_t *out_size);
-
-/* ObSkipIndexAggregator over rows [row_begin, row_begin + nrows) of the writer's column inputs
- * (index_block/ob_index_block_aggregator.cpp): MIN / MAX / NULL_COUNT of every column listed in agg_cols,
- * serialized as one version-3 aggregate row. Strings longer than 40 bytes keep a 40-byte prefix. */
-int obgpu_writer_block_agg_row(const obgpu_col_input *cols, int32_t n_cols, const int32_t *agg_cols,
-                               int32_t n_agg_cols, int64_t row_begin, int64_t nrows, void *out,
-                               int64_t out_cap, int64_t *out_size);
-/* One aggregate row per block of obgpu_writer_encode_table's blocking: row b occupies
- * [offsets[b], offsets[b + 1]) of `out` (n_blocks + 1 offsets). out == NULL: only *out_size. */
-int obgpu_writer_table_agg_rows(const obgpu_col_input *cols, int32_t n_cols, const int32_t *agg_cols,
-                                int32_t n_agg_cols, int64_t total_rows, int64_t rows_per_block, void *out,
-                                int64_t out_cap, int64_t *offsets, int64_t *out_size);
-
 /* Attaches the aggregate rows of the batch's micro-blocks (host buffers; copied to the device on the ctx
  * stream): block b's row is agg_rows[agg_off[b] .. agg_off[b + 1]); an empty range means "no aggregate
  * data" (ObMicroIndexInfo::has_agg_data() false: every filter is uncertain on that block). From then on

@@ -1,14 +1,23 @@
-"""Builds libobgpu_scan.so in-tree (nvcc cross-compiles sm_100a without a GPU)."""
+"""Builds the in-tree shared libraries (nvcc cross-compiles sm_100a without a GPU):
+  libobgpu_scan.so   -- the product: CUDA kernels + C-ABI (include/obgpu_scan.h, obgpu_skip_index.h, obgpu_compaction.h)
+  libobgpu_writer.so -- plain C++ micro-block / aggregate-row writer (include/obgpu_writer.h); no CUDA, so the
+                        reference arm of bench.py and the CPU tests never map the product library to WRITE blocks.
+"""
 import os
 import shutil
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
+INC = os.path.join(_HERE, "..", "include")
 LIB = os.path.join(CSRC, "libobgpu_scan.so")
-SOURCES = ["obgpu_scan.cu", "sstable_writer.cpp"]
-HEADERS = ["ob_format.h", "scan_device.cuh", "merge_kernels.cuh", os.path.join("..", "..", "include", "obgpu_scan.h"),
-           os.path.join("..", "..", "include", "obgpu_compaction.h")]
+WRITER_LIB = os.path.join(CSRC, "libobgpu_writer.so")
+SOURCES = ["obgpu_scan.cu"]
+HEADERS = ["ob_format.h", "scan_device.cuh", "scan_small.cuh", "merge_kernels.cuh", "skip_index.cuh", "stream_codecs.cuh",
+           os.path.join(INC, "obgpu_scan.h"), os.path.join(INC, "obgpu_compaction.h"), os.path.join(INC, "obgpu_skip_index.h")]
+WRITER_SOURCES = ["sstable_writer.cpp"]
+WRITER_HEADERS = ["ob_format.h", os.path.join(INC, "obgpu_writer.h"), os.path.join(INC, "obgpu_scan.h"),
+                  os.path.join(INC, "obgpu_skip_index.h")]
 
 
 def nvcc_path():
@@ -18,15 +27,30 @@ def nvcc_path():
     raise RuntimeError("nvcc not found")
 
 
-def needs_build():
-    if not os.path.exists(LIB):
+def _stale(lib, deps):
+    if not os.path.exists(lib):
         return True
-    t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
+    t = os.path.getmtime(lib)
+    return any(os.path.exists(os.path.join(CSRC, f)) and os.path.getmtime(os.path.join(CSRC, f)) > t for f in deps)
+
+
+def needs_build():
+    return _stale(LIB, SOURCES + HEADERS) or _stale(WRITER_LIB, WRITER_SOURCES + WRITER_HEADERS)
+
+
+def build_writer(force=False):
+    if not force and not _stale(WRITER_LIB, WRITER_SOURCES + WRITER_HEADERS):
+        return WRITER_LIB
+    cmd = ["g++", "-std=c++17", "-O3", "-fPIC", "-shared", "-pthread", "-o", WRITER_LIB] + WRITER_SOURCES
+    r = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("g++ (writer) failed:\n" + r.stdout + r.stderr)
+    return WRITER_LIB
 
 
 def build(force=False, verbose=False):
-    if not force and not needs_build():
+    build_writer(force)
+    if not force and not _stale(LIB, SOURCES + HEADERS):
         return LIB
     cmd = [nvcc_path(), "-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
            "-Xcompiler", "-fPIC", "-shared", "-o", LIB] + SOURCES

@@ -5,6 +5,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 lib_path = os.path.join(_HERE, "csrc", "libobgpu_scan.so")
+writer_lib_path = os.path.join(_HERE, "csrc", "libobgpu_writer.so")
 
 OB_SUCCESS = 0
 OB_INVALID_ARGUMENT = -4002
@@ -85,9 +86,26 @@ class MergeInfo(C.Structure):
                 ("fused_rows", C.c_int64)]
 
 
+def writer_signatures():
+    """name -> (restype, argtypes) for every symbol include/obgpu_writer.h declares (libobgpu_writer.so)."""
+    vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
+    P = C.POINTER
+    return {
+        "obgpu_writer_block_bound": (i64, [P(ColInput), i32, i64, i64]),
+        "obgpu_writer_encode_block": (C.c_int, [P(ColInput), i32, i32, i64, i64, vp, i64, P(i64)]),
+        "obgpu_writer_encode_table": (C.c_int, [P(ColInput), i32, i32, i64, i64, i32, i32, P(vp)]),
+        "obgpu_table_image_info": (C.c_int, [vp, P(i64), P(i32)]),
+        "obgpu_table_image_export": (C.c_int, [vp, vp, i64, vp, vp, i32]),
+        "obgpu_table_image_free": (None, [vp]),
+        "obgpu_agg_row_write": (C.c_int, [P(AggCell), i32, i32, vp, i64, P(i64)]),
+        "obgpu_writer_block_agg_row": (C.c_int, [P(ColInput), i32, vp, i32, i64, i64, vp, i64, P(i64)]),
+        "obgpu_writer_table_agg_rows": (C.c_int, [P(ColInput), i32, vp, i32, i64, i64, vp, i64, vp, P(i64)]),
+    }
+
+
 def declared_signatures():
     """name -> (restype, argtypes) for every symbol include/obgpu_scan.h, include/obgpu_compaction.h and
-    include/obgpu_skip_index.h declare."""
+    include/obgpu_skip_index.h declare (libobgpu_scan.so)."""
     vp, i32, i64, u64 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64
     P = C.POINTER
     return {
@@ -119,12 +137,6 @@ def declared_signatures():
         "obgpu_bitmap_to_row_ids": (C.c_int, [vp, vp, i64, P(i64), i64, i64, i64, vp, P(i64)]),
         "obgpu_project_fixed": (C.c_int, [vp, i32, i32, vp, i64, i64, vp, i32, vp, P(i32)]),
         "obgpu_project_discrete": (C.c_int, [vp, i32, i32, vp, i64, i64, u64, vp, vp, vp, P(i32)]),
-        "obgpu_writer_block_bound": (i64, [P(ColInput), i32, i64, i64]),
-        "obgpu_writer_encode_block": (C.c_int, [P(ColInput), i32, i32, i64, i64, vp, i64, P(i64)]),
-        "obgpu_writer_encode_table": (C.c_int, [P(ColInput), i32, i32, i64, i64, i32, i32, P(vp)]),
-        "obgpu_table_image_info": (C.c_int, [vp, P(i64), P(i32)]),
-        "obgpu_table_image_export": (C.c_int, [vp, vp, i64, vp, vp, i32]),
-        "obgpu_table_image_free": (None, [vp]),
         "obgpu_version": (C.c_char_p, []),
         # include/obgpu_compaction.h
         "obgpu_batch_decode_column": (C.c_int, [vp, i32, vp, vp]),
@@ -140,36 +152,57 @@ def declared_signatures():
         "obgpu_merge_result_cols": (C.c_int, [vp, P(vp), P(P(vp)), P(P(vp))]),
         "obgpu_merge_result_fetch": (C.c_int, [vp, i32, i64, i64, vp, vp]),
         # include/obgpu_skip_index.h
-        "obgpu_agg_row_write": (C.c_int, [P(AggCell), i32, i32, vp, i64, P(i64)]),
-        "obgpu_writer_block_agg_row": (C.c_int, [P(ColInput), i32, vp, i32, i64, i64, vp, i64, P(i64)]),
-        "obgpu_writer_table_agg_rows": (C.c_int, [P(ColInput), i32, vp, i32, i64, i64, vp, i64, vp, P(i64)]),
         "obgpu_batch_set_agg_rows": (C.c_int, [vp, vp, vp]),
         "obgpu_batch_skip_index_filter": (C.c_int, [vp, P(Filter), vp]),
         "obgpu_result_skip_info": (C.c_int, [vp, P(i64), P(i64)]),
     }
 
 
-def _load():
-    if not os.path.exists(lib_path):
+def _load(path, signatures):
+    if not os.path.exists(path):
         raise ImportError(
-            f"{lib_path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(nvcc -gencode arch=compute_100a,code=sm_100a). oceanbase_b200 has no CPU fallback.")
-    L = C.CDLL(lib_path)
-    for name, (res, args) in declared_signatures().items():
+    L = C.CDLL(path)
+    for name, (res, args) in signatures.items():
         fn = getattr(L, name)  # AttributeError => the library does not export the declared ABI
         fn.restype = res
         fn.argtypes = args
     return L
 
 
-lib = _load()
+class _Libs:
+    """Symbol lookup over the two in-tree libraries: the writer entry points resolve to libobgpu_writer.so
+    (plain C++), everything else to the CUDA product library, which is only mapped on first use."""
+
+    def __init__(self):
+        self.writer = _load(writer_lib_path, writer_signatures())
+        self._scan = None
+        self._wnames = set(writer_signatures())
+
+    @property
+    def scan(self):
+        if self._scan is None:
+            self._scan = _load(lib_path, declared_signatures())
+        return self._scan
+
+    def __getattr__(self, name):
+        if name.startswith("obgpu_"):
+            return getattr(self.writer if name in self._wnames else self.scan, name)
+        raise AttributeError(name)
+
+
+if not os.path.exists(lib_path):   # the product fails loudly when its CUDA library is missing
+    _load(lib_path, {})
+lib = _Libs()
 
 
 def check(code, what, ctx=None):
     if code != OB_SUCCESS:
         detail = ""
         try:
-            detail = (lib.obgpu_ctx_last_error(ctx) or b"").decode()
+            if ctx is not None:   # writer calls have no ctx (and must not map the CUDA library)
+                detail = (lib.obgpu_ctx_last_error(ctx) or b"").decode()
         except Exception:  # pragma: no cover
             pass
         raise ObGpuError(code, what, detail)

@@ -24,8 +24,7 @@
 #include <unordered_map>
 #include <vector>
 
-#include "../../include/obgpu_scan.h"
-#include "../../include/obgpu_skip_index.h"
+#include "../../include/obgpu_writer.h"
 #include "ob_format.h"
 
 namespace {

@@ -12,6 +12,7 @@
 
 #include "../../oceanbase_b200/host/ob_gpu_micro_block_decoder.h"
 extern "C" {
+#include "../../include/obgpu_writer.h"
 #include "../../oracle/ob_oracle.h"
 }
 

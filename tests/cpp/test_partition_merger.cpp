@@ -11,6 +11,7 @@
 
 #include "../../oceanbase_b200/host/ob_gpu_partition_merger.h"
 extern "C" {
+#include "../../include/obgpu_writer.h"
 #include "../../oracle/ob_oracle.h"
 }
 

@@ -9,10 +9,13 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def declared_in_header():
+WRITER_HEADERS = ("obgpu_writer.h",)
+
+
+def declared_in_header(writer=False):
     names = set()
     for h in sorted(os.listdir(os.path.join(ROOT, "include"))):
-        if not h.endswith(".h"):
+        if not h.endswith(".h") or (h in WRITER_HEADERS) != writer:
             continue
         text = open(os.path.join(ROOT, "include", h)).read()
         text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
@@ -26,12 +29,25 @@ def test_library_exports_every_declared_symbol():
     names = declared_in_header()
     assert len(names) >= 30
     for n in names:
-        assert hasattr(L, n), f"{n} declared in include/obgpu_scan.h but not exported"
+        assert hasattr(L, n), f"{n} declared in include/*.h but not exported"
+    W = ctypes.CDLL(ob.capi.writer_lib_path)
+    wnames = declared_in_header(writer=True)
+    assert len(wnames) >= 9
+    for n in wnames:
+        assert hasattr(W, n), f"{n} declared in include/obgpu_writer.h but not exported by libobgpu_writer.so"
+        assert not hasattr(L, n), f"{n}: the writer must not live in the CUDA product library"
 
 
 def test_python_binding_covers_the_header():
     from oceanbase_b200 import capi
     assert sorted(capi.declared_signatures()) == declared_in_header()
+    assert sorted(capi.writer_signatures()) == declared_in_header(writer=True)
+
+
+def test_writer_library_has_no_cuda_dependency():
+    import oceanbase_b200 as ob
+    out = os.popen(f"ldd {ob.capi.writer_lib_path}").read()
+    assert "cuda" not in out.lower() and "obgpu_scan" not in out
 
 
 def test_no_cpu_fallback_without_device():
