@@ -192,9 +192,7 @@ class _Libs:
         raise AttributeError(name)
 
 
-if not os.path.exists(lib_path):   # the product fails loudly when its CUDA library is missing
-    _load(lib_path, {})
-lib = _Libs()
+lib = _Libs()   # the first product call raises ImportError when libobgpu_scan.so is missing: no CPU path exists
 
 
 def check(code, what, ctx=None):

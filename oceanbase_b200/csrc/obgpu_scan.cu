@@ -1773,6 +1773,10 @@ int obgpu_batch_open(obgpu_ctx *ctx, const void *image, int64_t image_size, cons
     ctx->err = "device-resident image needs a host header_view";
     return OBGPU_INVALID_ARGUMENT;
   }
+  if (image_on_device && ((uintptr_t)image & 15u) != 0) {
+    ctx->err = "device-resident image must be 16-byte aligned (TMA bulk copies)";
+    return OBGPU_INVALID_ARGUMENT;
+  }
   cudaSetDevice(ctx->device);
   obgpu_batch *b = new (std::nothrow) obgpu_batch();
   if (!b) return OBGPU_ALLOCATE_MEMORY_FAILED;
@@ -1852,11 +1856,11 @@ int obgpu_batch_open(obgpu_ctx *ctx, const void *image, int64_t image_size, cons
       const uint32_t coff = rd32h(ch + 8), clen = rd32h(ch + 12);
       if (b->col_types[c] == 0) b->col_types[c] = ch[3];
       else if (b->col_types[c] != ch[3]) b->col_types[c] = 0xff;
-      uint32_t dm = 0;
-      if (type == obf::COL_DICT) dm = meta_off + coff;
+      int64_t dm = 0;   // 64-bit: untrusted 32-bit fields must not wrap before the bounds checks
+      if (type == obf::COL_DICT) dm = (int64_t)meta_off + coff;
       else if (type == obf::COL_RLE) {
         if ((int64_t)meta_off + coff + 10 > sz) { ret = OBGPU_INVALID_DATA; break; }
-        dm = meta_off + coff + rd32h(p + meta_off + coff + 6);
+        dm = (int64_t)meta_off + coff + rd32h(p + meta_off + coff + 6);
         b->col_max_rle[c] = std::max(b->col_max_rle[c], rd32h(p + meta_off + coff + 2));
       } else if (type == obf::COL_CONST) {
         if ((int64_t)meta_off + coff + 6 > sz) { ret = OBGPU_INVALID_DATA; break; }
@@ -1865,9 +1869,9 @@ int obgpu_batch_open(obgpu_ctx *ctx, const void *image, int64_t image_size, cons
           b->col_max_dict[c] = std::max(b->col_max_dict[c], 3u);
           continue;
         }
-        dm = meta_off + coff + (uint32_t)(cm[4] | (cm[5] << 8));
+        dm = (int64_t)meta_off + coff + (int64_t)(cm[4] | (cm[5] << 8));
       } else continue;
-      if ((int64_t)dm + 9 > sz || (int64_t)meta_off + coff + clen > sz) { ret = OBGPU_INVALID_DATA; break; }
+      if (dm + 9 > sz || (int64_t)meta_off + coff + clen > sz) { ret = OBGPU_INVALID_DATA; break; }
       const uint32_t cnt = rd32h(p + dm + 2);
       b->col_max_dict[c] = std::max(b->col_max_dict[c], cnt + 2);
     }
@@ -2644,6 +2648,13 @@ int obgpu_result_aggregate(obgpu_result *r, int32_t kind, int32_t col_a, int32_t
   if (a.is_string || b.is_string) return OBGPU_NOT_SUPPORTED;
   obgpu_ctx *ctx = r->ctx;
   cudaSetDevice(ctx->device);
+  {
+    // the scan's own status first: after a capacity overflow sel_offset[n_blocks] exceeds the arena's row
+    // capacity and the dense columns hold gaps -- nothing may be read from them
+    obgpu_result_info info;
+    const int ret = obgpu_result_info_get(r, &info);
+    if (ret != OBGPU_SUCCESS) return ret;
+  }
   unsigned long long *d_out = nullptr;
   CUDA_TRY(ctx, cudaMallocAsync((void **)&d_out, 32, ctx->stream));
   CUDA_TRY(ctx, cudaMemsetAsync(d_out, 0, 32, ctx->stream));
@@ -2657,11 +2668,6 @@ int obgpu_result_aggregate(obgpu_result *r, int32_t kind, int32_t col_a, int32_t
   CUDA_TRY(ctx, cudaMemcpyAsync(h, d_out, 16, cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   cudaFreeAsync(d_out, ctx->stream);
-  {
-    obgpu_result_info info;
-    const int ret = obgpu_result_info_get(r, &info);  // surfaces overflow / unsupported of the scan itself
-    if (ret != OBGPU_SUCCESS) return ret;
-  }
   if ((kind == OBGPU_AGG_MIN || kind == OBGPU_AGG_MAX) && (a_sgn || a.elem_len < 8)) h[0] ^= 1ull << 63;
   out[0] = (int64_t)h[0];
   out[1] = (int64_t)h[1];

@@ -610,6 +610,7 @@ __device__ __forceinline__ void build_col_desc(const BlockView &b, int col, ColD
   d.sc = (uint8_t)sc;
   d.elem_len = (uint8_t)datum_len_of(d.obj_type);
   d.int_mask = integer_mask_of(d.obj_type);
+  if (offset > b.size || b.meta_off > b.size - offset) return;   // untrusted: no wrap-around in meta_off + offset
   const uint32_t meta = b.meta_off + offset;
   const bool has_ext = d.attr & ATTR_HAS_EXTEND_VALUE;
   const bool fixed = d.attr & ATTR_FIX_LENGTH, bp = d.attr & ATTR_BIT_PACKING;
@@ -696,7 +697,9 @@ __device__ __forceinline__ void build_col_desc(const BlockView &b, int col, ColD
         const uint32_t rib = a & 7, rfb = (a >> 3) & 7;
         d.rle_count = (uint32_t)ld_bytes(s, meta + 2, 4);
         const uint32_t doff = (uint32_t)ld_bytes(s, meta + 6, 4);
-        if (d.rle_count == 0 || rib == 0 || rfb == 0 || rib > 4 || rfb > 4 || doff > length) return;
+        if (d.rle_count == 0 || rib == 0 || rfb == 0 || rib > 4 || rfb > 4 || doff > length || length > b.size - meta) return;
+        // run-start ids and refs lie between the 10-byte header and the dictionary meta
+        if (10ull + (uint64_t)d.rle_count * (rib + rfb) > doff) return;
         // the reference keeps count*row_id_byte in an int16 (ob_rle_decoder.h:193)
         if (d.rle_count * rib > 32767u) return;
         d.rle_row_id_bits = (uint8_t)(rib * 8u);
@@ -764,7 +767,7 @@ __device__ __forceinline__ void build_col_desc(const BlockView &b, int col, ColD
         return;
       }
       if (rib != 1 && rib != 2 && rib != 4) return;
-      if (doff < 6u + count * (rib + 1u) || doff + 9u > length) return;
+      if (doff < 6u + count * (rib + 1u) || doff + 9u > length) return;   // exception refs + row ids end before the dict meta
       d.rle_count = count;
       d.const_ref = cref;
       d.rle_ref_bits = 8;

@@ -28,6 +28,7 @@ class BatchOutput:
     lens: List[Optional[np.ndarray]]  # string columns: int32 lens
     nulls: List[np.ndarray]
     has_null: List[int]
+    image_lo: int = 0                # byte offset of the batch's first block inside the caller's table image
 
 
 def batch_bounds(n_blocks: int, blocks_per_batch: int, ramp: int = 0) -> List[int]:
@@ -54,7 +55,9 @@ def split_table(table: TableImage, blocks_per_batch: int, ramp: int = 0) -> List
     for b0, b1 in zip(bounds[:-1], bounds[1:]):
         lo = int(table.offsets[b0])
         hi = int(table.offsets[b1]) if b1 < n else int(table.image.size)
-        parts.append(TableImage(table.image[lo:hi], table.offsets[b0:b1] - lo, table.sizes[b0:b1], 0, table.n_cols))
+        part = TableImage(table.image[lo:hi], table.offsets[b0:b1] - lo, table.sizes[b0:b1], 0, table.n_cols)
+        part.image_lo = lo   # byte offset of the part inside the caller's table image (string pointers are rebased by it)
+        parts.append(part)
     return parts
 
 
@@ -100,7 +103,10 @@ class HostScanPipeline:
                     if agg_rows is not None:                           # offsets keep their table-wide base: no copy
                         batch.set_agg_rows(agg_rows, agg_off[bounds[i]:bounds[i + 1] + 1])
                     cap = int(batch.total_rows * selectivity_hint) + 1024
-                    res = batch.scan(filter, proj, string_base=string_base, max_selected_rows=min(cap, batch.total_rows))
+                    # VEC_DISCRETE pointers must address the CALLER's table buffer: the part's block offsets were rebased by
+                    # image_lo, so the base moves up by the same amount
+                    sbase = string_base + part.image_lo
+                    res = batch.scan(filter, proj, string_base=sbase, max_selected_rows=min(cap, batch.total_rows))
                     try:
                         n = res.selected_rows                         # sync + status
                     except Exception as e:                             # capacity overflow: exact re-run
@@ -108,7 +114,7 @@ class HostScanPipeline:
                         if isinstance(e, ObGpuError) and e.code == OB_BUF_NOT_ENOUGH:
                             need = res._info.selected_rows
                             res.free()
-                            res = batch.scan(filter, proj, string_base=string_base, max_selected_rows=need)
+                            res = batch.scan(filter, proj, string_base=sbase, max_selected_rows=need)
                             n = res.selected_rows
                         else:
                             raise
@@ -130,7 +136,7 @@ class HostScanPipeline:
                             nulls.append(nl)
                             hn.append(res.col(c).has_null)
                     outs[i] = BatchOutput(bounds[i], bounds[i + 1], batch.total_rows,
-                                          n, cols, lens, nulls, hn)
+                                          n, cols, lens, nulls, hn, part.image_lo)
                     res.free()
                     batch.close()
             except Exception as e:  # pragma: no cover

@@ -71,6 +71,7 @@ class TableImage:
     sizes: np.ndarray          # int64 [n_blocks]
     total_rows: int
     n_cols: int
+    image_lo: int = 0          # set by pipeline.split_table: offset of this part inside the table it was cut from
 
     @property
     def n_blocks(self):

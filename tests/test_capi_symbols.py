@@ -7,6 +7,7 @@ import re
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.needs_product_lib
 
 
 WRITER_HEADERS = ("obgpu_writer.h",)
