@@ -1,14 +1,18 @@
 #!/usr/bin/env python
-"""bench.py -- columnar-scan hot path benchmark (contract: see task statement, section 4).
+"""bench.py -- columnar-scan hot path benchmark (contract: task statement section 4).
 
     python bench.py --gpus N --steps K --warmup W            # our B200 path
     python bench.py --impl reference --gpus N --steps K ...   # the reference CPU algorithm (oracle port)
 
-A "step" is one pass of the hot path (filter -> selection -> projection) over one page batch:
-BASELINE.json configs[1] -- 100 M rows x 8 INT64 columns (base-diff PK, 3 RLE, 4 bit-packed RAW),
-one pushed-down range predicate (25 %), all 8 columns projected -- per GPU (weak scaling: every
-rank scans its own 100 M-row shard, no data-path collective). The encoded image (~1.2 GB) is far
-larger than the 126 MB L2, so timed iterations never hit a warm cache.
+Headline workload = BASELINE.json configs[2] ("cfg3", the north-star target): a 1-billion-row, 16-column
+dictionary-encoded SSTable (8 INT64 DICT + 8 VARCHAR DICT, Zipf(1.1) over per-column dictionaries), micro-blocks
+cut at the reference's 16 KiB target, 3-predicate AND filter (~10 %), 4 INT64 + 2 VARCHAR columns projected.
+A "step" is one pass of the hot path (skip nothing: filter -> selection -> projection) over the whole table.
+The 1 B rows are split over the ranks (strong scaling: every rank scans 1 B / N rows, no data-path collective).
+A rank generates ONE seeded segment of its shard on the host (SplitMix64 columns, ~2 GB encoded) and tiles it in
+HBM (`config.tiles` physically distinct copies): generating 125 GB of blocks on the box's 16-CPU quota would take
+an hour, and every tile (2 GB) is far larger than L2 (126 MB), so timed iterations never see a warm cache.
+`secondary.cfg2` repeats the measurement on BASELINE.json configs[1] (100 M rows x 8 INT64 per GPU, weak).
 """
 import argparse
 import json
@@ -27,6 +31,8 @@ import numpy as np  # noqa: E402
 METRIC = "decoded+filtered rows/sec"
 UNIT = "rows/s"
 BATCH_ROWS = 256  # _rowsets_max_rows default (src/share/parameter/ob_parameter_seed.ipp:418)
+CFG3_NAME = ("cfg3: 1 B rows x 16 dict-encoded columns (8 INT64 DICT + 8 VARCHAR DICT), 16 KiB micro-blocks, "
+             "3-predicate AND ~10 %, 4 INT64 + 2 VARCHAR projected")
 
 
 def env_int(name, default):
@@ -62,17 +68,24 @@ def host_cpus():
     return max(1, n)
 
 
-def bind_to_gpu_numa_node(local):
-    """Pin this process (and the threads / first-touched pages it creates from now on) to the CPUs of the
-    NUMA node the GPU hangs off, so that the pinned host image and result buffers sit next to the PCIe root
-    the copies go through. Returns the node number or None when it cannot be determined."""
+def gpu_numa_node(local):
     try:
         import torch
         pr = torch.cuda.get_device_properties(local)
         bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
         with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
-            node = int(f.read().strip())
-        if node < 0:
+            return int(f.read().strip())
+    except Exception:
+        return None
+
+
+def bind_to_gpu_numa_node(local):
+    """Pin this process (and the threads / first-touched pages it creates from now on) to the CPUs of the
+    NUMA node the GPU hangs off, so that the pinned host image and result buffers sit next to the PCIe root
+    the copies go through. Returns the node number or None when it cannot be determined."""
+    try:
+        node = gpu_numa_node(local)
+        if node is None or node < 0:
             return None
         with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
             cpus = set()
@@ -89,14 +102,16 @@ def bind_to_gpu_numa_node(local):
 
 
 def build_workload(rows, row_start, seed, chunk_rows=4_000_000, pinned=False, n_threads=0, maker=None,
-                   rows_per_block=1400):
-    """Config-2 table (or `maker`'s) of `rows` rows generated in chunks (bounded host memory), packed
+                   rows_per_block=1400, align_chunks=False):
+    """Table of `rows` rows (config 2, or `maker`'s) generated in chunks (bounded host memory), packed
     into one image (optionally pinned host memory = the host-side block cache)."""
     from concurrent.futures import ThreadPoolExecutor
     from oceanbase_b200.synth import make_config2_like
     from oceanbase_b200.sstable import TableImage
     maker = maker or make_config2_like
 
+    if align_chunks:   # chunks end on block boundaries: no ragged block inside the table
+        chunk_rows = max(rows_per_block, chunk_rows // rows_per_block * rows_per_block)
     starts = list(range(0, rows, chunk_rows))
     ncpu = host_cpus()
     workers = max(1, min(8, ncpu // 4, len(starts)))
@@ -185,13 +200,13 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def measured_traffic(rows):
-    """DRAM bytes per scan from the committed ncu capture (profiles/r1_traffic.json), when it was taken at
-    the same row count; otherwise null."""
+def measured_traffic(name, rows):
+    """DRAM bytes per scan from the committed ncu capture (profiles/<name>), scaled by rows when the capture was
+    taken on a smaller tiling of the same segment (traffic per row is a property of the blocks); null if absent."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", name)) as f:
             t = json.load(f)
-        return int(t["total"]) if int(t["rows"]) == int(rows) else None
+        return int(round(float(t["total"]) * float(rows) / float(t["rows"])))
     except Exception:
         return None
 
@@ -212,29 +227,75 @@ def cpu_reference_leg(w, steps, warmup, n_threads, sample_blocks):
     return rates, rows, sel
 
 
+# ---- workloads -----------------------------------------------------------------------------------------------
+def cfg3_shape(args, world):
+    """(rows per GPU, tiles, segment rows): rows per GPU = total / world, cut into `tiles` copies of one segment."""
+    per_gpu = args.rows // max(world, 1)
+    tiles = max(1, -(-per_gpu // args.segment_rows))
+    seg = per_gpu // tiles
+    return seg * tiles, tiles, seg
+
+
+def cfg3_config(args, world, rpb, seg_rows, tiles, seg_table=None, selectivity=None, extra=None):
+    cfg = {"workload": CFG3_NAME, "rows": int(seg_rows) * tiles * world, "columns": 16,
+           "micro_block_target_bytes": 16384, "rows_per_block": int(rpb), "segment_rows": int(seg_rows),
+           "tiles_per_gpu": int(tiles), "seed": args.seed}
+    if seg_table is not None:
+        cfg["encoded_bytes_per_row"] = round(float(seg_table.sizes.sum()) / seg_table.total_rows, 3)
+        cfg["mean_block_bytes"] = round(float(seg_table.sizes.mean()), 1)
+    if selectivity is not None:
+        cfg["selectivity"] = selectivity
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+def make_cfg3_segment(args, rank, world, pinned):
+    from oceanbase_b200.synth import make_config3_like, rows_per_block_for_target
+    rpb = args.rows_per_block or rows_per_block_for_target(make_config3_like, seed=args.seed)
+    rows_gpu, tiles, seg_rows = cfg3_shape(args, world)
+    w, buf = build_workload(seg_rows, rank * rows_gpu, args.seed, chunk_rows=1_000_000, pinned=pinned,
+                            maker=make_config3_like, rows_per_block=rpb, align_chunks=True,
+                            n_threads=max(1, host_cpus() // max(1, min(world, 8))))
+    return w, buf, rpb, tiles, seg_rows
+
+
 def run_reference(args):
-    rank, world = env_int("RANK", 0), env_int("WORLD_SIZE", 1)
+    rank = env_int("RANK", 0)
+    world = env_int("WORLD_SIZE", 1)
     if rank != 0:
         return 0
     import __graft_entry__ as g
-    g.build()
+    g.build_cpu_side()
     ncpu = host_cpus()
-    sample_rows = args.ref_rows
-    w, _ = build_workload(sample_rows, 0, args.seed)
-    # one thread first to size the sample sensibly is unnecessary: the sample is fixed and stated
-    rates, rows, sel = cpu_reference_leg(w, args.steps, args.warmup, ncpu, None)
+    if args.workload == "cfg3":
+        # the same table definition as our arm; one step = one pass over a bounded sample (the first ref_rows rows of
+        # rank 0's segment) with every host thread
+        rows_gpu, tiles, seg_rows = cfg3_shape(args, world)
+        a2 = argparse.Namespace(**vars(args))
+        w, _, rpb, _, _ = make_cfg3_segment(a2, 0, world, pinned=False)
+        sample_blocks = max(1, min(w.table.n_blocks, args.ref_rows // rpb))
+        config = cfg3_config(args, world, rpb, seg_rows, tiles, w.table)
+        what = "the cfg3 table"
+    else:
+        w, _ = build_workload(args.ref_rows, 0, args.seed)
+        sample_blocks = None
+        config = {"workload": w.name, "rows_per_gpu": args.cfg2_rows, "columns": 8}
+        what = "the config-2 table"
+    rates, rows, sel = cpu_reference_leg(w, args.steps, args.warmup, ncpu, sample_blocks)
     best = max(r for r, _ in rates)
     mean_dt = float(np.mean([d for _, d in rates]))
     value = rows / mean_dt
+    config["selectivity"] = sel / max(rows, 1)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": mean_dt * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-        "config": {"workload": w.name, "rows_per_step": rows, "columns": 8, "batch_rows": BATCH_ROWS,
-                   "selectivity": sel / max(rows, 1)},
+        "scaling": "strong" if args.workload == "cfg3" else "weak", "vs_baseline": None, "dtype": "int64/bytes", "data": "synthetic",
+        "config": config,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": ncpu, "kind": "port",
-                         "sample": f"{rows} rows ({w.table.n_blocks} micro-blocks) of the config-2 table per step, "
-                                   f"oracle port of the reference scan, {ncpu} threads (cgroup cpu quota of the box; "
+                         "sample": f"{rows} rows ({sample_blocks or w.table.n_blocks} micro-blocks) of {what} per step "
+                                   f"(rate metric: the table is a repetition of such segments), "
+                                   f"oracle port of the reference scan (batch {BATCH_ROWS}), {ncpu} threads (cgroup cpu quota of the box; "
                                    f"{os.cpu_count()} logical CPUs visible), 32-block granules claimed dynamically",
                          "best": best},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -242,6 +303,95 @@ def run_reference(args):
     }
     print(json.dumps(line))
     return 0
+
+
+class DeviceRun:
+    """Device-resident measurement of one workload: K timed scans of one page batch."""
+
+    def __init__(self, ctx, stream, batch, w, cap, world, dist):
+        self.ctx, self.stream, self.batch, self.w, self.cap, self.world, self.dist = ctx, stream, batch, w, cap, world, dist
+
+    def barrier(self):
+        import torch
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def run(self, steps, warmup, local, rank):
+        import torch
+        batch, w, cap, ctx = self.batch, self.w, self.cap, self.ctx
+        for _ in range(warmup):
+            r = batch.scan(w.filter, w.proj, max_selected_rows=cap)
+            r.info()
+            r.free()
+        sampler = ClockSampler(local)
+        self.barrier()
+        if rank == 0:
+            sampler.start()
+            time.sleep(0.3)
+        launches0 = ctx.launch_count
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        ev0.record(self.stream)
+        last = None
+        for _ in range(steps):
+            if last is not None:
+                last.free()
+            last = batch.scan(w.filter, w.proj, max_selected_rows=cap)
+        ev1.record(self.stream)
+        self.barrier()
+        clocks = sampler.stop() if rank == 0 else None
+        launches = ctx.launch_count - launches0
+        step_ms = ev0.elapsed_time(ev1) / steps
+        info = last.info()  # raises on overflow / unsupported
+        kern_ms = float(np.mean(ctx.kernel_times_ms(min(steps, 256))))
+        last.free()
+        return step_ms, kern_ms, int(info.selected_rows), int(launches), clocks
+
+
+def e2e_run(local, table, w, rows_per_block, sel_hint, args, repeats, barrier):
+    """Host buffers in, host vectors out through the public host-buffer API; `repeats` passes over the host table
+    per step (the tiled table: every pass is a real H2D of the segment and a real D2H of its results)."""
+    import torch
+    from oceanbase_b200.pipeline import HostScanPipeline, split_table
+    bpb = max(1, table.n_blocks // args.e2e_batches)
+    parts = split_table(table, bpb, args.e2e_ramp)
+    out_np, null_np, keep = [], [], []
+    n_int = sum(1 for s in w.proj_is_string if not s)
+    all_int = n_int == len(w.proj)
+    for part in parts:
+        capp = int(int(part.n_blocks) * rows_per_block * sel_hint) + 2048
+        bufs = [torch.empty(capp, dtype=torch.int64, pin_memory=True) for _ in w.proj]
+        nbufs = [torch.zeros((capp + 63) // 64, dtype=torch.int64, pin_memory=True) for _ in w.proj]
+        keep.append(bufs + nbufs)
+        out_np.append([t.numpy().view(np.uint64) for t in bufs])
+        null_np.append([t.numpy().view(np.uint64) for t in nbufs])
+    pipe = HostScanPipeline(local, n_workers=args.e2e_workers)
+    d2h = [0]
+
+    def step():
+        total = 0
+        for _ in range(repeats):
+            outs = pipe.scan(table, w.filter, w.proj, bpb, sel_hint, out_buffers=out_np,
+                             null_buffers=null_np if all_int else None, ramp=args.e2e_ramp)
+            total += sum(o.selected_rows for o in outs)
+        d2h[0] = total * sum(12 if s else l for s, l in zip(w.proj_is_string, w.proj_elem_len))
+        return total
+
+    step() if repeats == 1 else pipe.scan(table, w.filter, w.proj, bpb, sel_hint, out_buffers=out_np,
+                                         null_buffers=null_np if all_int else None, ramp=args.e2e_ramp)
+    steps = max(1, args.e2e_steps)
+    barrier()
+    t0 = time.perf_counter()
+    n = 0
+    for _ in range(steps):
+        n = step()
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) * 1e3 / steps   # wall clock: every worker stream is drained per step
+    barrier()
+    launches = sum(c.launch_count for c in pipe.ctxs)
+    pipe.close()
+    return ms, n, int(table.image.size) * repeats, int(d2h[0]), len(parts), steps, int(launches)
 
 
 def run_ours(args):
@@ -258,165 +408,169 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
     import oceanbase_b200 as ob
+    from oceanbase_b200.sstable import TableImage
+    from oceanbase_b200.synth import referenced_bytes, filter_columns
 
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     numa_node = None if args.no_numa_bind else bind_to_gpu_numa_node(local)
-    rows = args.rows
-    t_gen = time.perf_counter()
-    w, pinned_buf = build_workload(rows, rank * rows, args.seed, pinned=True,
-                                   n_threads=max(1, host_cpus() // max(world, 1)))
-    t_gen = time.perf_counter() - t_gen
-    table = w.table
-
-    # a dedicated (non-default) torch stream: the ctx launches on it, torch.cuda.Event times it
-    stream = torch.cuda.Stream(device=dev)
+    if numa_node is None:
+        numa_node = gpu_numa_node(local)
+    stream = torch.cuda.Stream(device=dev)   # a dedicated (non-default) torch stream: the ctx launches on it
     torch.cuda.set_stream(stream)
-    assert stream.cuda_stream != 0
     ctx = ob.ScanContext(local, stream=stream.cuda_stream)
     ctx.set_profiling(True)
-    d_image = torch.empty(table.image.size + 64, dtype=torch.uint8, device=dev)
-    d_image[:table.image.size].copy_(pinned_buf, non_blocking=True)
-    d_image[table.image.size:].zero_()
-    torch.cuda.synchronize()
-    batch = ctx.open_batch(table, device_image_ptr=d_image.data_ptr())
-
-    # result capacity: optimizer-style selectivity estimate (25 %) with head-room; overflow is
-    # detected by the kernel and reported as OB_BUF_NOT_ENOUGH (checked below)
-    cap = int(table.total_rows * 0.30)
-
-    def step():
-        res = batch.scan(w.filter, w.proj, max_selected_rows=cap)
-        return res
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- value: device-resident input, K timed steps ------------------------------------------------
-    last = None
-    for _ in range(args.warmup):
-        r = step()
-        r.info()
-        r.free()
-    sampler = ClockSampler(local)
-    barrier()
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.3)
-    launches0 = ctx.launch_count
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record(stream)
-    for i in range(args.steps):
-        if last is not None:
-            last.free()
-        last = step()
-    ev1.record(stream)
-    barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    launches = ctx.launch_count - launches0
-    step_ms = ev0.elapsed_time(ev1) / args.steps
-    info = last.info()  # raises on overflow / unsupported
-    selected = info.selected_rows
-    kern_ms = ctx.kernel_times_ms(args.steps)
-    last.free()
-    last = None
-
-    # ---- e2e: host buffers in, host vectors out, copies inside the timed region ------------------------
-    # Public host-buffer API (oceanbase_b200.pipeline.HostScanPipeline): the pinned host image is cut into
-    # page batches; open (H2D + index) -> scan -> fetch (D2H) of different batches overlap on 3 streams.
-    from oceanbase_b200.pipeline import HostScanPipeline, split_table
-    bpb = max(1, table.n_blocks // args.e2e_batches)
-    parts = split_table(table, bpb, args.e2e_ramp)
-    out_host, out_np, null_np = [], [], []
-    for part in parts:
-        rows_part = int(part.n_blocks) * 1400
-        capp = int(rows_part * 0.30) + 2048
-        bufs = [torch.empty(capp, dtype=torch.int64, pin_memory=True) for _ in w.proj]
-        nbufs = [torch.zeros((capp + 63) // 64, dtype=torch.int64, pin_memory=True) for _ in w.proj]
-        out_host.append(bufs + nbufs)
-        out_np.append([t.numpy().view(np.uint64) for t in bufs])
-        null_np.append([t.numpy().view(np.uint64) for t in nbufs])
-    pipe = HostScanPipeline(local, n_workers=args.e2e_workers)
-    h2d = table.image.size
-    d2h = 0
-
-    def e2e_step():
-        nonlocal d2h
-        outs = pipe.scan(table, w.filter, w.proj, bpb, 0.30, out_buffers=out_np, null_buffers=null_np, ramp=args.e2e_ramp)
-        n = sum(o.selected_rows for o in outs)
-        d2h = n * 8 * len(w.proj)
-        return n
-
-    e2e_warm = max(1, min(args.warmup, 2))
-    e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    for _ in range(e2e_warm):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        n_e2e = e2e_step()
-    torch.cuda.synchronize()
-    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps  # wall clock: every worker stream is drained per step
-    barrier()
-    assert n_e2e == selected
-    e2e_launches = sum(c.launch_count for c in pipe.ctxs)
-    pipe.close()
-
-    # ---- max over ranks -----------------------------------------------------------------------------------
-    if world > 1:
-        t = torch.tensor([step_ms, e2e_ms, float(np.mean(kern_ms))], device=dev, dtype=torch.float64)
+    def allmax(vals):
+        if world == 1:
+            return list(vals)
+        t = torch.tensor(list(vals), device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        step_ms, e2e_ms, kern_mean = t.tolist()
-        tot = torch.tensor([table.total_rows, selected], device=dev, dtype=torch.int64)
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-        total_rows_all, selected_all = tot.tolist()
-    else:
-        kern_mean = float(np.mean(kern_ms))
-        total_rows_all, selected_all = table.total_rows, selected
+        return t.tolist()
 
+    def allsum(vals):
+        if world == 1:
+            return list(vals)
+        t = torch.tensor(list(vals), device=dev, dtype=torch.int64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return t.tolist()
+
+    peak, peak_src = measured_peak_gbs()
+    line = None
+    if args.workload == "cfg3":
+        t_gen = time.perf_counter()
+        w, pinned_buf, rpb, tiles, seg_rows = make_cfg3_segment(args, rank, world, pinned=True)
+        t_gen = time.perf_counter() - t_gen
+        seg = w.table
+        stride = (seg.image.size + 127) // 128 * 128
+        d_image = torch.empty(stride * tiles + 64, dtype=torch.uint8, device=dev)
+        d_image[stride * tiles:].zero_()
+        d_image[:seg.image.size].copy_(pinned_buf, non_blocking=True)
+        if stride > seg.image.size:
+            d_image[seg.image.size:stride].zero_()
+        for k in range(1, tiles):                       # physically distinct copies of the segment in HBM
+            d_image[k * stride:(k + 1) * stride].copy_(d_image[:stride], non_blocking=True)
+        torch.cuda.synchronize()
+        offs = (seg.offsets[None, :] + (np.arange(tiles, dtype=np.int64) * stride)[:, None]).reshape(-1)
+        table = TableImage(None, offs, np.tile(seg.sizes, tiles), seg.total_rows * tiles, seg.n_cols)
+        batch = ctx.open_batch(table, device_image_ptr=d_image.data_ptr(), host_view=False, image_size=stride * tiles)
+        cap = int(table.total_rows * 0.13)
+        run = DeviceRun(ctx, stream, batch, w, cap, world, dist)
+        step_ms, kern_ms, selected, launches, clocks = run.run(args.steps, args.warmup, local, rank)
+        batch.close()
+        del d_image
+        torch.cuda.empty_cache()
+        # e2e: the host segment goes through the host-buffer API `tiles` times per step (every pass a real H2D / D2H)
+        e2e_ms, n_e2e, h2d, d2h, n_parts, e2e_steps, e2e_launches = e2e_run(local, seg, w, rpb, 0.14, args,
+                                                                           tiles if not args.e2e_one_tile else 1, barrier)
+        e2e_rows = seg.total_rows * (tiles if not args.e2e_one_tile else 1)
+        step_ms, e2e_ms, kern_ms = allmax([step_ms, e2e_ms, kern_ms])
+        rows_all, sel_all, e2e_rows_all = allsum([table.total_rows, selected, e2e_rows])
+        if rank == 0:
+            used = sorted(set(w.proj) | set(filter_columns(w.filter)))
+            out_per_row = sum(12 if s else l for s, l in zip(w.proj_is_string, w.proj_elem_len))
+            b_in = referenced_bytes(seg, used) * tiles
+            alg = b_in + selected * out_per_row + (table.total_rows + 7) // 8
+            achieved = alg / (kern_ms * 1e-3) / 1e9
+            line = {
+                "metric": METRIC, "value": rows_all / (step_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "int64/bytes", "data": "synthetic",
+                "config": cfg3_config(args, world, rpb, seg_rows, tiles, seg, sel_all / rows_all, {
+                    "rows_per_gpu": table.total_rows, "micro_blocks_per_gpu": table.n_blocks,
+                    "encoded_bytes_per_gpu": int(seg.sizes.sum()) * tiles, "parallelism": f"shard{world}",
+                    "tiling": f"one seeded {seg.total_rows}-row segment per rank, generated on the host and copied {tiles}x into "
+                              f"HBM (physically distinct tiles, one page batch of {table.n_blocks} micro-blocks)",
+                    "l2_policy": "every tile (~2 GB) is larger than L2 (126 MB); no flush needed",
+                    "gen_seconds": round(t_gen, 1), "host_numa_node": numa_node}),
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": measured_traffic("r2_traffic_cfg3.json", table.total_rows), "peak_source": peak_src,
+                             "alg_bytes_per_launch": int(alg), "alg_bytes_in": int(b_in), "alg_bytes_out": int(selected * out_per_row),
+                             "alg_rule": "SURVEY 8d with staged regions: per block header + column headers + regions of the referenced "
+                                         "columns (3 filter + 6 projected) + selected x (4 x 8 B + 2 x 12 B) + bitmap",
+                             "kernel_ms": kern_ms,
+                             "kernel": "one scan = count + prefix + project kernels, CUDA events on the launching stream"},
+                "e2e": {"value": e2e_rows_all / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                        "ms_per_step": e2e_ms, "steps": e2e_steps, "rows_per_step": int(e2e_rows_all), "page_batches": n_parts,
+                        "streams": args.e2e_workers,
+                        "timing": f"host wall clock around the pipelined public API ({args.e2e_workers} streams); the pinned host "
+                                  f"segment is scanned {tiles if not args.e2e_one_tile else 1}x per step, every pass a real H2D + D2H"},
+                "gpu_launches": int(launches),
+                "clocks": clocks,
+                "gbs_decoded_equiv": rows_all * 16 * 8 / (step_ms * 1e-3) / 1e9,
+            }
+            if world == 1 and not args.no_cpu_baseline:
+                ncpu = host_cpus()
+                sample_blocks = max(1, min(seg.n_blocks, args.cpu_sample_rows // rpb))
+                passes = 6
+                rates, crow, csel = cpu_reference_leg(w, passes, 1, ncpu, sample_blocks)
+                mean_dt = float(np.mean([d for _, d in rates]))
+                line["cpu_baseline"] = {
+                    "value": crow / mean_dt, "unit": UNIT, "cores": ncpu, "kind": "port",
+                    "sample": f"first {crow} rows ({sample_blocks} micro-blocks) of the segment, {passes} timed passes "
+                              f"({sum(d for _, d in rates) * ncpu:.0f} CPU-seconds), oracle port of the reference scan "
+                              f"(batch {BATCH_ROWS}), {ncpu} threads = cgroup cpu quota ({os.cpu_count()} logical CPUs visible)"}
+        del w, pinned_buf, seg
+    # ---- configs[1] (cfg2): 100 M rows x 8 INT64 per GPU, weak scaling ----------------------------------------------
+    if args.workload == "cfg2" or not args.no_secondary:
+        rows = args.cfg2_rows
+        t_gen = time.perf_counter()
+        w, pinned_buf = build_workload(rows, rank * rows, 2, pinned=True, n_threads=max(1, host_cpus() // max(world, 1)))
+        t_gen = time.perf_counter() - t_gen
+        table = w.table
+        d_image = torch.empty(table.image.size + 64, dtype=torch.uint8, device=dev)
+        d_image[:table.image.size].copy_(pinned_buf, non_blocking=True)
+        d_image[table.image.size:].zero_()
+        torch.cuda.synchronize()
+        batch = ctx.open_batch(table, device_image_ptr=d_image.data_ptr())
+        run = DeviceRun(ctx, stream, batch, w, int(table.total_rows * 0.30), world, dist)
+        step_ms, kern_ms, selected, launches, clocks = run.run(args.steps, args.warmup, local, rank)
+        batch.close()
+        e2e_ms, n_e2e, h2d, d2h, n_parts, e2e_steps, e2e_launches = e2e_run(local, table, w, 1400, 0.30, args, 1, barrier)
+        assert n_e2e == selected
+        step_ms, e2e_ms, kern_ms = allmax([step_ms, e2e_ms, kern_ms])
+        rows_all, sel_all = allsum([table.total_rows, selected])
+        if rank == 0:
+            alg = w.alg_bytes(selected)
+            achieved = alg / (kern_ms * 1e-3) / 1e9
+            c2 = {
+                "metric": METRIC, "value": rows_all / (step_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+                "config": {"workload": w.name, "rows_per_gpu": table.total_rows, "columns": 8,
+                           "micro_blocks_per_gpu": table.n_blocks, "encoded_bytes_per_gpu": int(table.sizes.sum()),
+                           "selectivity": selected / table.total_rows, "parallelism": f"shard{world}",
+                           "l2_policy": "input image (1.2 GB) larger than L2 (126 MB); no flush needed",
+                           "gen_seconds": round(t_gen, 1), "host_numa_node": numa_node},
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": measured_traffic("r1_traffic.json", table.total_rows), "peak_source": peak_src,
+                             "alg_bytes_per_launch": alg, "kernel_ms": kern_ms,
+                             "alg_rule": "whole blocks are staged: full block bytes + selected x 64 B + bitmap"},
+                "e2e": {"value": rows_all / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                        "ms_per_step": e2e_ms, "steps": e2e_steps, "page_batches": n_parts, "streams": args.e2e_workers,
+                        "timing": f"host wall clock around the pipelined public API call ({args.e2e_workers} streams)"},
+                "gpu_launches": int(launches), "clocks": clocks,
+                "gbs_decoded_equiv": rows_all * 8 * 8 / (step_ms * 1e-3) / 1e9,
+            }
+            if world == 1 and not args.no_cpu_baseline and (args.workload == "cfg2"):
+                ncpu = host_cpus()
+                sample_blocks = min(table.n_blocks, max(64, int(args.cpu_sample_rows // 1400)))
+                rates, crow, csel = cpu_reference_leg(w, 4, 1, ncpu, sample_blocks)
+                mean_dt = float(np.mean([d for _, d in rates]))
+                c2["cpu_baseline"] = {"value": crow / mean_dt, "unit": UNIT, "cores": ncpu, "kind": "port",
+                                      "sample": f"first {crow} rows ({sample_blocks} micro-blocks) of the same table, 4 timed passes, "
+                                                f"oracle port of the reference scan (batch {BATCH_ROWS}), {ncpu} threads"}
+            if line is None:
+                line = c2
+            else:
+                line["secondary"] = {"cfg2": c2}
     if rank == 0:
-        peak, peak_src = measured_peak_gbs()
-        alg_bytes = w.alg_bytes(selected)  # per launch (this rank): B_in + B_out
-        achieved = alg_bytes / (kern_mean * 1e-3) / 1e9
-        value = total_rows_all / (step_ms * 1e-3)
-        e2e_value = total_rows_all / (e2e_ms * 1e-3)
-        cpu = None
-        if world == 1 and not args.no_cpu_baseline:
-            ncpu = host_cpus()
-            sample_blocks = min(table.n_blocks, max(64, int(args.cpu_sample_rows // 1400)))
-            rates, crow, csel = cpu_reference_leg(w, 4, 1, ncpu, sample_blocks)
-            mean_dt = float(np.mean([d for _, d in rates]))
-            cpu = {"value": crow / mean_dt, "unit": UNIT, "cores": ncpu, "kind": "port",
-                   "sample": f"first {crow} rows ({sample_blocks} micro-blocks) of the same table, 4 timed passes "
-                             f"({sum(d for _, d in rates) * ncpu:.0f} CPU-seconds), "
-                             f"oracle port of the reference scan (batch {BATCH_ROWS}), {ncpu} threads = cgroup cpu quota "
-                             f"({os.cpu_count()} logical CPUs visible)"}
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-            "config": {"workload": w.name, "rows_per_gpu": table.total_rows, "columns": 8,
-                       "micro_blocks_per_gpu": table.n_blocks, "encoded_bytes_per_gpu": int(table.sizes.sum()),
-                       "selectivity": selected / table.total_rows, "parallelism": f"shard{world}",
-                       "l2_policy": "input image (1.2 GB) larger than L2 (126 MB); no flush needed",
-                       "gen_seconds": round(t_gen, 1), "host_numa_node": numa_node},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": measured_traffic(table.total_rows), "peak_source": peak_src, "alg_bytes_per_launch": alg_bytes,
-                         "kernel_ms": kern_mean, "kernel": "one scan = obgpu_count_kernel + obgpu_prefix_*_kernel + obgpu_project_kernel (project ~85%)"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": e2e_ms, "steps": e2e_steps, "page_batches": len(parts), "streams": args.e2e_workers,
-                    "timing": f"host wall clock around the pipelined public API call ({args.e2e_workers} streams)"},
-            "gpu_launches": int(launches),
-            "clocks": clocks,
-            "gbs_decoded_equiv": total_rows_all * 8 * 8 / (step_ms * 1e-3) / 1e9,
-        }
-        if cpu is not None:
-            line["cpu_baseline"] = cpu
         print(json.dumps(line))
-    batch.close()
     ctx.close()
     if world > 1:
         dist.barrier()
@@ -430,16 +584,22 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--rows", type=int, default=100_000_000, help="rows per GPU (BASELINE configs[1]: 100 M)")
-    ap.add_argument("--ref-rows", type=int, default=32_000_000, help="rows per step of the reference arm sample")
-    ap.add_argument("--cpu-sample-rows", type=int, default=100_000_000,
-                    help="rows of the workload the cpu_baseline leg scans per pass (4 timed passes: ~10-20 s of CPU work)")
-    ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--e2e-batches", type=int, default=12, help="page batches per e2e step (pipeline depth)")
+    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg2"])
+    ap.add_argument("--rows", type=int, default=1_000_000_000, help="cfg3: rows of the whole table (split over the GPUs)")
+    ap.add_argument("--segment-rows", type=int, default=15_625_000, help="cfg3: rows of the generated segment (upper bound)")
+    ap.add_argument("--rows-per-block", type=int, default=0, help="cfg3: 0 = cut micro-blocks at the 16 KiB target")
+    ap.add_argument("--cfg2-rows", type=int, default=100_000_000, help="cfg2: rows per GPU (BASELINE configs[1]: 100 M)")
+    ap.add_argument("--ref-rows", type=int, default=16_000_000, help="rows per step of the reference arm's sample")
+    ap.add_argument("--cpu-sample-rows", type=int, default=16_000_000,
+                    help="rows of the workload the cpu_baseline leg scans per pass")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-one-tile", action="store_true", help="cfg3 e2e: one pass over the host segment per step instead of `tiles`")
+    ap.add_argument("--e2e-batches", type=int, default=12, help="page batches per e2e pass (pipeline depth)")
     ap.add_argument("--e2e-ramp", type=int, default=2, help="the first N page batches are 1/2^N .. 1/2 of a full one")
     ap.add_argument("--e2e-workers", type=int, default=3, help="host worker threads = CUDA streams of the e2e pipeline")
-    ap.add_argument("--seed", type=int, default=2)
+    ap.add_argument("--seed", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the cfg2 measurement")
     ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the process to the GPU's NUMA node")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

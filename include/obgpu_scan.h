@@ -118,6 +118,8 @@ int obgpu_ctx_kernel_times(obgpu_ctx *ctx, float *ms, int32_t cap, int32_t *n);
  * ObMicroBlockHeader::is_valid / get_micro_metas do (ob_micro_block_header.cpp:53-61,
  * encoding/ob_micro_block_decoder.cpp:363-388); `header_view` (optional, host memory, same
  * layout as image) lets the caller keep a host copy of a device-resident image for that parse.
+ * A device-resident image with header_view == NULL is validated by a header survey kernel on the
+ * device instead (same checks, one small device-to-host copy of the row / column counts).
  * ============================================================================================= */
 int obgpu_batch_open(obgpu_ctx *ctx, const void *image, int64_t image_size,
                      const int64_t *offsets, const int64_t *sizes, int32_t n_blocks,

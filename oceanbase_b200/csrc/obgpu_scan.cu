@@ -122,6 +122,15 @@ struct ScanParams {
   int32_t proj_tiles;                   // blocks walked by one CTA of the project kernel (1, or 8 with the sparse split)
   uint32_t off_sel, off_bm, off_wpre, off_rle, off_desc;  // inside one scratch
   uint32_t smem_total;
+  // ---- small-block pipelined kernels (scan_small.cuh): warp per block, cp.async rings ----------------------------
+  int32_t pipe_count, pipe_project;         // which of the two kernels this scan uses
+  int32_t pf_n;                             // filter columns = used columns [0, pf_n)
+  uint32_t pf_off[8], pf_span[8];           // count: offset / capacity of a filter column's region inside a region slot
+  uint32_t pc_meta_bytes, pc_region_bytes;  // count: bytes per meta / region slot
+  uint32_t pc_meta, pc_region, pc_bm, pc_bitset, pc_bytes;   // count: per-warp layout
+  uint32_t pp_off[kMaxProj], pp_span[kMaxProj];              // project: offset / capacity of a column's ranges in a region slot
+  uint32_t pp_meta_bytes, pp_region_bytes, pp_hdr_bytes, pp_bm_bytes;
+  uint32_t pp_meta, pp_region, pp_sel, pp_wscr, pp_bytes;    // project: per-warp layout
   uint32_t rle_slot_bytes;    // bytes per run-table slot: mask[words_cap] (u32) + pre[words_cap] (u16)
   uint32_t rows_cap, words_cap;
 };
@@ -313,11 +322,88 @@ __device__ __forceinline__ bool eval_tree(const ScanParams &p, const BlockCtx &c
   return stack & 1u;
 }
 
+// Number of leading dictionary indexes for which `pred` holds (pred is monotone over a sorted dictionary: true ...
+// true false ... false). Warp-cooperative 32-ary search: every round probes 32 evenly spaced entries, so a
+// 1 K-entry dictionary takes two rounds (the reference binary-searches, std::lower_bound / upper_bound over
+// ObDictDecoderIterator, encoding/ob_dict_decoder.cpp:967-988,1085-1176).
+template <typename Pred>
+__device__ __forceinline__ uint32_t warp_partition_point(uint32_t n, int lane, Pred pred) {
+  uint32_t lo = 0, hi = n;
+  while (lo < hi) {
+    const uint32_t step = (hi - lo + 31u) >> 5;
+    const uint32_t idx = lo + (uint32_t)lane * step;
+    const uint32_t k = __popc(__ballot_sync(0xffffffffu, idx < hi && pred(idx)));  // true probes form a prefix
+    if (k == 0) break;
+    const uint32_t last_true = lo + (k - 1u) * step;
+    lo = last_true + 1u;
+    hi = min(hi, last_true + step);
+  }
+  return lo;
+}
+
+__device__ __forceinline__ uint32_t range_word(uint32_t a, uint32_t b, uint32_t w) {   // bits of [a, b) that fall in word w
+  const uint32_t lo = w * 32u, s = a > lo ? a : lo, e = b < lo + 32u ? b : lo + 32u;
+  if (s >= e) return 0u;
+  const uint32_t len = e - s;
+  return (len == 32u ? 0xffffffffu : ((1u << len) - 1u)) << (s - lo);
+}
+
+// Sorted fixed-length dictionary (IS_SORTED): the matching refs of a comparison form one index interval [a, b),
+// found by searching the constants instead of evaluating every entry (fast_cmp_ref_and_set_res,
+// ob_dict_decoder.cpp:1426). Returns false when the leaf does not have that shape (IN lists, NU / NN, ...).
+__device__ __forceinline__ bool build_dict_bitset_sorted(const ScanParams &p, const BlockView &b, const ColDesc &d,
+                                                         const FilterNodeDev &nd, uint32_t *bits, const Team &t) {
+  const uint32_t n = d.dict_count;
+  const int op = nd.op;
+  uint32_t a = 0, e = 0;
+  bool neg = false;
+  if (d.sc != 5) {
+    if (!nd.range_ok) return false;
+    const bool sg = d.sc == 1;
+    const uint64_t lo = nd.lo, hi = nd.lo + nd.span;
+    auto lt = [&](uint64_t x, uint64_t y) { return sg ? (int64_t)x < (int64_t)y : x < y; };
+    a = warp_partition_point(n, t.lane, [&](uint32_t i) { return lt((uint64_t)cmp_image(d, dict_int(b.s, d, i)), lo); });
+    e = warp_partition_point(n, t.lane, [&](uint32_t i) { return !lt(hi, (uint64_t)cmp_image(d, dict_int(b.s, d, i))); });
+    neg = nd.negate != 0;
+  } else {
+    if (op > OP_BT) return false;
+    const uint32_t len = d.dict_data_size;
+    auto cmpk = [&](uint32_t i, int k) {
+      const ParamDev &pp = p.params[nd.param_begin + k];
+      return str_cmp(b.s, d.dict_payload + i * len, len, p.param_heap + pp.heap_off, pp.len);
+    };
+    const int k_hi = op == OP_BT ? 1 : 0;
+    const bool need_lb = op == OP_EQ || op == OP_NE || op == OP_GE || op == OP_BT || op == OP_LT;
+    const bool need_ub = op == OP_EQ || op == OP_NE || op == OP_LE || op == OP_BT || op == OP_GT;
+    uint32_t lb = 0, ub = 0;
+    if (need_lb) lb = warp_partition_point(n, t.lane, [&](uint32_t i) { return cmpk(i, 0) < 0; });       // first entry >= c0
+    if (need_ub) ub = warp_partition_point(n, t.lane, [&](uint32_t i) { return cmpk(i, k_hi) <= 0; });   // first entry > c (c1 for BT)
+    switch (op) {
+      case OP_EQ: a = lb; e = ub; break;
+      case OP_NE: a = lb; e = ub; neg = true; break;
+      case OP_LT: a = 0; e = lb; break;
+      case OP_LE: a = 0; e = ub; break;
+      case OP_GE: a = lb; e = n; break;
+      case OP_GT: a = ub; e = n; break;
+      default: a = lb; e = ub; break;   // BT
+    }
+  }
+  if (e < a) e = a;
+  const uint32_t nw = (n + 2u + 31u) >> 5;
+  for (uint32_t w = (uint32_t)t.warp * 32u + (uint32_t)t.lane; w < nw; w += (uint32_t)t.nwarps * 32u) {
+    uint32_t m = range_word(a, e, w);
+    if (neg) m = ~m & range_word(0, n, w);   // NE: every non-NULL ref outside the interval
+    bits[w] = m;                             // refs n (NULL) and n + 1 (NOP) never match a comparison
+  }
+  return true;
+}
+
 // Predicate over the dictionary of a DICT / RLE column -> bitset over refs (bit count = NULL ref).
 __device__ __forceinline__ void build_dict_bitset(const ScanParams &p, const BlockView &b, const ColDesc &d,
                                                   const FilterNodeDev &nd, uint32_t *bits, const Team &t) {
   const uint32_t n = d.dict_count + 2;
   const int op = nd.op;
+  if (d.dict_sorted && t.nwarps == 1 && op != OP_FALSE && op != OP_TRUE && build_dict_bitset_sorted(p, b, d, nd, bits, t)) return;
   for (uint32_t base = (uint32_t)t.warp * 32u; base < n; base += (uint32_t)t.nwarps * 32u) {
     const uint32_t idx = base + (uint32_t)t.lane;
     bool r = false;
@@ -802,6 +888,67 @@ __device__ __forceinline__ void project_str_col(const ScanParams &p, const Block
 
 #undef ROW
 
+// One projected column of one block decoded by ONE WARP from the staged image (c.b.s / c.sbit already point at the
+// column's staged bytes): RLE columns get their run table (and, for 8-byte integers, their run values) in the warp's
+// private scratch `wscr` first. Shared by the CTA-per-block and the warp-per-block projection kernels.
+__device__ __forceinline__ void project_column_staged(const ScanParams &p, BlockCtx &c, ColDesc *wdesc, int pc, const uint16_t *sel,
+                                                      uint32_t cnt, int64_t base, uint64_t blk_addr, bool all_rows, uint32_t rows,
+                                                      uint8_t *wscr, const Team &t) {
+  const int lane = t.lane;
+  const ColDesc &d = *wdesc;
+  if (!d.ok) {
+    if (lane == 0) atomicOr(p.status, ST_UNSUPPORTED);
+    return;
+  }
+  if (d.kind == K_RLE) {
+    if (d.rle_count > (uint32_t)p.rle_runs_cap) {
+      if (lane == 0) atomicOr(p.status, ST_UNSUPPORTED);
+      return;
+    }
+    if (lane == 0) wdesc->rle_slot = 0;
+    rle_table_build(c.b.s, d, rows, reinterpret_cast<uint32_t *>(wscr + p.pw_rle),
+                    reinterpret_cast<uint16_t *>(wscr + p.pw_rle + c.rle_starts_bytes), t);
+    const uint32_t n = d.rle_count;
+    if (d.sc != 5 && d.elem_len == 8) {
+      // integer RLE column: decode each RUN once (value of run k), rows then only look up their run
+      uint64_t *rvals = reinterpret_cast<uint64_t *>(wscr + p.pw_rvals);
+      const uint32_t refs_bit = c.sbit + d.rle_refs_bit, ref_bits = d.rle_ref_bits;
+      const uint32_t dcount = d.dict_count, dbits = d.dict_data_size * 8u, dpay = c.sbit + d.dict_payload * 8u;
+      bool null_run = false;
+      for (uint32_t k = (uint32_t)lane; k < n; k += 32u) {
+        const uint32_t ref = sbits32(refs_bit + k * ref_bits, ref_bits);
+        uint64_t v = 0;
+        if (ref >= dcount) null_run = true;
+        else {
+          v = sbits(dpay + ref * dbits, dbits);
+          if (d.sign_fix) v = sign_fix(d.int_mask, v);
+        }
+        rvals[k] = v;
+      }
+      const bool any_null = __any_sync(0xffffffffu, null_run);
+      __syncwarp();
+      if (!any_null) {
+        uint64_t *out = reinterpret_cast<uint64_t *>(p.out_data[pc]) + base;
+        const RleTable rt = c.rle_table(0);
+        if (all_rows) for (uint32_t j = (uint32_t)lane; j < cnt; j += 32u) __stcs(&out[j], rvals[rle_run_of(rt, j)]);
+        else for (uint32_t j = (uint32_t)lane; j < cnt; j += 32u) __stcs(&out[j], rvals[rle_run_of(rt, sel[j])]);
+        return;
+      }
+    }
+  }
+  if (all_rows) {
+    if (d.sc == 5) project_str_col<true>(p, c, d, pc, sel, cnt, base, blk_addr, t);
+    else if (d.elem_len == 8) project_int_col<uint64_t, true>(p, c, d, pc, sel, cnt, base, t);
+    else if (d.elem_len == 4) project_int_col<uint32_t, true>(p, c, d, pc, sel, cnt, base, t);
+    else project_int_col<uint8_t, true>(p, c, d, pc, sel, cnt, base, t);
+  } else {
+    if (d.sc == 5) project_str_col<false>(p, c, d, pc, sel, cnt, base, blk_addr, t);
+    else if (d.elem_len == 8) project_int_col<uint64_t, false>(p, c, d, pc, sel, cnt, base, t);
+    else if (d.elem_len == 4) project_int_col<uint32_t, false>(p, c, d, pc, sel, cnt, base, t);
+    else project_int_col<uint8_t, false>(p, c, d, pc, sel, cnt, base, t);
+  }
+}
+
 // =================================================================================================
 // Index kernel (batch open): one thread per (block, column) parses the block straight from HBM and
 // stores the column's decode plan. The scan kernels never parse headers; the reference keeps the
@@ -845,7 +992,52 @@ __global__ void __launch_bounds__(256) obgpu_index_kernel(const uint8_t *image, 
     else atomicMax(&col_span[col], 0xffffffffu);   // no single region (CS string bytes): whole-block staging only
     // dictionary size (predicate bitset words) of dictionary-coded columns: col_span[max_cols + col]
     if (is_dict_kind(d)) atomicMax(&col_span[max_cols + col], d.dict_count + 2u);
+    // bytes a projection of the column stages (scan_small.cuh: VARCHAR dictionaries without their string bytes)
+    atomicMax(&col_span[5 * max_cols + col], proj_ranges_bytes(d, b));
   }
+  if (b.ok && (uint32_t)col < b.column_count) {
+    // per-column facts the host keeps for a batch: ObObjType (min / max over the blocks: equal when the blocks
+    // agree) and the largest RLE run count (sizes the run tables)
+    const uint8_t *s = image + blk_off[block];
+    const uint32_t t = b.is_cs ? s[b.header_size + 12u + 4u * (uint32_t)col + 3u] : s[b.header_size + 16u * (uint32_t)col + 3u];
+    atomicMin(&col_span[2 * max_cols + col], t);
+    atomicMax(&col_span[3 * max_cols + col], t);
+    if (!b.is_cs && s[b.header_size + 16u * (uint32_t)col + 1u] == COL_RLE) {
+      const uint32_t off = ld32(s, b.header_size + 16u * (uint32_t)col + 8u);
+      if (off <= b.size && b.meta_off <= b.size - off && b.meta_off + off + 10u <= b.size)
+        atomicMax(&col_span[4 * max_cols + col], (uint32_t)ld_bytes(s, b.meta_off + off + 2u, 4));
+    }
+  }
+}
+
+// Header survey of a device-resident image opened without a host view: one thread per block parses the
+// 64-byte header (ObMicroBlockHeader::is_valid, ob_micro_block_header.cpp:53-61) and reports
+// {row count, column count, verdict}: 0 ok, 1 invalid data, 2 not handled by the device path.
+__global__ void __launch_bounds__(256) obgpu_survey_kernel(const uint8_t *image, const uint64_t *blk_off, const uint32_t *blk_size,
+                                                           int n_blocks, uint32_t *out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_blocks) return;
+  const uint8_t *s = image + blk_off[i];
+  const uint32_t size = blk_size[i];
+  const uint32_t w0 = ld32(s, 0);
+  const int16_t magic = (int16_t)(w0 & 0xffff), version = (int16_t)(w0 >> 16);
+  const uint32_t header_size = ld32(s, 4);
+  const uint32_t ncol = ld32(s, 8) >> 16, nkey = ld32(s, 12) & 0xffffu;
+  const uint32_t rows = ld32(s, 16);
+  const uint32_t rst = ld32(s, 20) & 0xffu;
+  const uint32_t row_data_off = ld32(s, 24);
+  uint32_t verdict = 0;
+  if (magic != MICRO_BLOCK_HEADER_MAGIC || version < 1 || version > 3 || ncol < nkey || rst >= MAX_ROW_STORE) verdict = 1;
+  else if (rst != ENCODING_ROW_STORE && rst != SELECTIVE_ENCODING_ROW_STORE && rst != CS_ENCODING_ROW_STORE) verdict = 2;
+  else {
+    const bool is_cs = rst == CS_ENCODING_ROW_STORE;
+    if (header_size < 64 || (uint64_t)header_size + (is_cs ? 12ull + 4ull * ncol : 16ull * ncol) > size ||
+        (!is_cs && row_data_off > size) || rows == 0)
+      verdict = 1;
+    else if (rows > 65535u) verdict = 2;
+  }
+  out[2 * i] = rows;
+  out[2 * i + 1] = ncol | (verdict << 16);
 }
 
 // =================================================================================================
@@ -1276,60 +1468,7 @@ __global__ void __launch_bounds__(kThreads) obgpu_project_kernel(const __grid_co
         c.b.s = g_smem + delta;
         c.sbit = (smem_u32(g_smem) + (uint32_t)delta) * 8u;
       }
-      if (!d.ok) {
-        if (lane == 0) atomicOr(p.status, ST_UNSUPPORTED);
-        __syncwarp();
-        continue;
-      }
-      if (d.kind == K_RLE) {
-        if (d.rle_count > (uint32_t)p.rle_runs_cap) {
-          if (lane == 0) atomicOr(p.status, ST_UNSUPPORTED);
-          __syncwarp();
-          continue;
-        }
-        if (lane == 0) wdesc->rle_slot = 0;
-        rle_table_build(c.b.s, d, rows, reinterpret_cast<uint32_t *>(wscr + p.pw_rle),
-                        reinterpret_cast<uint16_t *>(wscr + p.pw_rle + c.rle_starts_bytes), t);
-        const uint32_t n = d.rle_count;
-        if (d.sc != 5 && d.elem_len == 8) {
-          // integer RLE column: decode each RUN once (value of run k), rows then only look up their run
-          uint64_t *rvals = reinterpret_cast<uint64_t *>(wscr + p.pw_rvals);
-          const uint32_t refs_bit = c.sbit + d.rle_refs_bit, ref_bits = d.rle_ref_bits;
-          const uint32_t dcount = d.dict_count, dbits = d.dict_data_size * 8u, dpay = c.sbit + d.dict_payload * 8u;
-          bool null_run = false;
-          for (uint32_t k = (uint32_t)lane; k < n; k += 32u) {
-            const uint32_t ref = sbits32(refs_bit + k * ref_bits, ref_bits);
-            uint64_t v = 0;
-            if (ref >= dcount) null_run = true;
-            else {
-              v = sbits(dpay + ref * dbits, dbits);
-              if (d.sign_fix) v = sign_fix(d.int_mask, v);
-            }
-            rvals[k] = v;
-          }
-          const bool any_null = __any_sync(0xffffffffu, null_run);
-          __syncwarp();
-          if (!any_null) {
-            uint64_t *out = reinterpret_cast<uint64_t *>(p.out_data[pc]) + base;
-            const RleTable rt = c.rle_table(0);
-            if (all_rows) for (uint32_t j = (uint32_t)lane; j < cnt; j += 32u) __stcs(&out[j], rvals[rle_run_of(rt, j)]);
-            else for (uint32_t j = (uint32_t)lane; j < cnt; j += 32u) __stcs(&out[j], rvals[rle_run_of(rt, sel[j])]);
-            __syncwarp();
-            continue;
-          }
-        }
-      }
-      if (all_rows) {
-        if (d.sc == 5) project_str_col<true>(p, c, d, pc, sel, cnt, base, blk_addr, t);
-        else if (d.elem_len == 8) project_int_col<uint64_t, true>(p, c, d, pc, sel, cnt, base, t);
-        else if (d.elem_len == 4) project_int_col<uint32_t, true>(p, c, d, pc, sel, cnt, base, t);
-        else project_int_col<uint8_t, true>(p, c, d, pc, sel, cnt, base, t);
-      } else {
-        if (d.sc == 5) project_str_col<false>(p, c, d, pc, sel, cnt, base, blk_addr, t);
-        else if (d.elem_len == 8) project_int_col<uint64_t, false>(p, c, d, pc, sel, cnt, base, t);
-        else if (d.elem_len == 4) project_int_col<uint32_t, false>(p, c, d, pc, sel, cnt, base, t);
-        else project_int_col<uint8_t, false>(p, c, d, pc, sel, cnt, base, t);
-      }
+      project_column_staged(p, c, wdesc, pc, sel, cnt, base, blk_addr, all_rows, rows, wscr, t);
       __syncwarp();
     }
     used_bar = true;
@@ -1557,6 +1696,8 @@ __global__ void __launch_bounds__(kThreads) obgpu_bitmap_row_ids_kernel(const ui
   if (tid == 0) *out_count = s_running < limit ? s_running : limit;
 }
 
+#include "scan_small.cuh"
+
 // =================================================================================================
 // Host side
 // =================================================================================================
@@ -1613,6 +1754,7 @@ struct obgpu_batch {
   uint32_t *d_rows = nullptr;
   BlockRec *d_recs = nullptr;
   std::vector<uint32_t> col_span;      // per store index: max staged bytes of the value / ref array
+  std::vector<uint32_t> col_pspan;     // per store index: max bytes a projection stages (proj_ranges)
   // skip index: serialized aggregate rows of the blocks (obgpu_batch_set_agg_rows), [d_agg_off[b], d_agg_off[b + 1])
   uint8_t *d_agg = nullptr;
   int64_t *d_agg_off = nullptr;
@@ -1688,7 +1830,8 @@ int obgpu_ctx_create(int device, obgpu_ctx **out) {
                                 c->max_smem_optin - (int)fa.sharedSizeBytes) == cudaSuccess;
   };
   const bool ok = opt_in((const void *)obgpu_count_kernel) && opt_in((const void *)obgpu_project_kernel<false>) && opt_in((const void *)obgpu_project_kernel<true>) &&
-                  opt_in((const void *)obgpu_filter_block_kernel) && opt_in((const void *)obgpu_project_block_kernel);
+                  opt_in((const void *)obgpu_filter_block_kernel) && opt_in((const void *)obgpu_project_block_kernel) &&
+                  opt_in((const void *)obgpu_count_pipe_kernel) && opt_in((const void *)obgpu_project_pipe_kernel);
   cudaGetLastError();  // do not leave a stale (non-sticky) error for later launch checks
   if (!ok) {
     g_last_global_err = "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed: not an sm_100a device?";
@@ -1768,11 +1911,9 @@ int obgpu_batch_open(obgpu_ctx *ctx, const void *image, int64_t image_size, cons
                      obgpu_batch **out) {
   if (!ctx || !image || !offsets || !sizes || n_blocks <= 0 || !out || image_size <= 0)
     return OBGPU_INVALID_ARGUMENT;
+  // header facts come from a host view of the blocks when there is one; a device-resident image opened without
+  // a host view is surveyed on the device instead (obgpu_survey_kernel)
   const uint8_t *host = image_on_device ? (const uint8_t *)header_view : (const uint8_t *)image;
-  if (!host) {
-    ctx->err = "device-resident image needs a host header_view";
-    return OBGPU_INVALID_ARGUMENT;
-  }
   if (image_on_device && ((uintptr_t)image & 15u) != 0) {
     ctx->err = "device-resident image must be 16-byte aligned (TMA bulk copies)";
     return OBGPU_INVALID_ARGUMENT;
@@ -1789,10 +1930,9 @@ int obgpu_batch_open(obgpu_ctx *ctx, const void *image, int64_t image_size, cons
   b->col_count.resize((size_t)n_blocks);
   b->bm_word_off.resize((size_t)n_blocks + 1);
   int ret = OBGPU_SUCCESS;
-  int64_t words = 0;
-  for (int32_t i = 0; i < n_blocks && ret == OBGPU_SUCCESS; ++i) {
+  for (int32_t i = 0; i < n_blocks; ++i) {
     const int64_t off = offsets[i], sz = sizes[i];
-    if (off < 0 || (off & 15) || sz < 64 || off + sz > image_size) { ret = OBGPU_INVALID_ARGUMENT; break; }
+    if (off < 0 || (off & 15) || sz < 64 || sz > 0x7fffffffll || off + sz > image_size) { ret = OBGPU_INVALID_ARGUMENT; break; }
     const int64_t padded = (sz + 15) & ~15ll;
     const int64_t limit = i + 1 < n_blocks ? offsets[i + 1] : image_size;
     if (image_on_device && off + padded > limit) {
@@ -1800,90 +1940,10 @@ int obgpu_batch_open(obgpu_ctx *ctx, const void *image, int64_t image_size, cons
       ret = OBGPU_INVALID_ARGUMENT;
       break;
     }
-    const uint8_t *p = host + off;
-    const int16_t magic = (int16_t)rd16h(p), version = (int16_t)rd16h(p + 2);
-    const uint32_t header_size = rd32h(p + 4);
-    const uint16_t ncol = rd16h(p + 10), nkey = rd16h(p + 12);
-    const uint32_t rows = rd32h(p + 16);
-    const uint8_t rst = p[20];
-    const uint32_t row_data_off = rd32h(p + 24);
-    // ObMicroBlockHeader::is_valid (ob_micro_block_header.cpp:53-61) + get_micro_metas bounds
-    if (magic != obf::MICRO_BLOCK_HEADER_MAGIC || version < 1 || version > 3 || ncol < nkey || rst >= obf::MAX_ROW_STORE) {
-      ctx->err = "invalid micro block header";
-      ret = OBGPU_INVALID_DATA;
-      break;
-    }
-    const bool is_cs = rst == obf::CS_ENCODING_ROW_STORE;
-    if (rst != obf::ENCODING_ROW_STORE && rst != obf::SELECTIVE_ENCODING_ROW_STORE && !is_cs) {
-      ctx->err = "row store type not handled by the device path";
-      ret = OBGPU_NOT_SUPPORTED;
-      break;
-    }
-    if (header_size < 64 || (int64_t)header_size + (is_cs ? 12ll + 4ll * ncol : 16ll * ncol) > sz || (!is_cs && row_data_off > sz) ||
-        rows == 0) {
-      ret = OBGPU_INVALID_DATA;
-      break;
-    }
-    if (rows > 65535u) {
-      ctx->err = "more than 65535 rows in one micro block";
-      ret = OBGPU_NOT_SUPPORTED;
-      break;
-    }
-    b->row_count[(size_t)i] = rows;
-    b->col_count[(size_t)i] = ncol;
-    b->bm_word_off[(size_t)i] = words;
-    words += (rows + 31) / 32;
-    b->total_rows += rows;
     b->max_block_bytes = std::max<uint32_t>(b->max_block_bytes, (uint32_t)padded);
-    b->max_rows = std::max(b->max_rows, rows);
-    b->max_cols = std::max<uint32_t>(b->max_cols, ncol);
-    if (b->col_max_dict.size() < ncol) b->col_max_dict.resize(ncol, 0);
-    if (b->col_types.size() < ncol) b->col_types.resize(ncol, 0);
-    if (b->col_max_rle.size() < ncol) b->col_max_rle.resize(ncol, 0);
-    // dictionary sizes of DICT / RLE columns (sizes the shared-memory predicate bitsets)
-    const uint32_t meta_off = header_size + 16u * ncol;
-    if (is_cs) {  // ObCSColumnHeader x ncol after the 12-byte ObAllColumnHeader: version, type, attrs, obj_type
-      for (uint32_t c = 0; c < ncol; ++c) {
-        const uint8_t t = p[header_size + 12u + 4u * c + 3];
-        if (b->col_types[c] == 0) b->col_types[c] = t;
-        else if (b->col_types[c] != t) b->col_types[c] = 0xff;
-      }
-      continue;
-    }
-    for (uint32_t c = 0; c < ncol; ++c) {
-      const uint8_t *ch = p + header_size + 16u * c;
-      const int8_t type = (int8_t)ch[1];
-      const uint32_t coff = rd32h(ch + 8), clen = rd32h(ch + 12);
-      if (b->col_types[c] == 0) b->col_types[c] = ch[3];
-      else if (b->col_types[c] != ch[3]) b->col_types[c] = 0xff;
-      int64_t dm = 0;   // 64-bit: untrusted 32-bit fields must not wrap before the bounds checks
-      if (type == obf::COL_DICT) dm = (int64_t)meta_off + coff;
-      else if (type == obf::COL_RLE) {
-        if ((int64_t)meta_off + coff + 10 > sz) { ret = OBGPU_INVALID_DATA; break; }
-        dm = (int64_t)meta_off + coff + rd32h(p + meta_off + coff + 6);
-        b->col_max_rle[c] = std::max(b->col_max_rle[c], rd32h(p + meta_off + coff + 2));
-      } else if (type == obf::COL_CONST) {
-        if ((int64_t)meta_off + coff + 6 > sz) { ret = OBGPU_INVALID_DATA; break; }
-        const uint8_t *cm = p + meta_off + coff;
-        if (cm[1] == 0) {  // no exceptions: read as a one-entry dictionary
-          b->col_max_dict[c] = std::max(b->col_max_dict[c], 3u);
-          continue;
-        }
-        dm = (int64_t)meta_off + coff + (int64_t)(cm[4] | (cm[5] << 8));
-      } else continue;
-      if (dm + 9 > sz || (int64_t)meta_off + coff + clen > sz) { ret = OBGPU_INVALID_DATA; break; }
-      const uint32_t cnt = rd32h(p + dm + 2);
-      b->col_max_dict[c] = std::max(b->col_max_dict[c], cnt + 2);
-    }
   }
-  b->bm_word_off[(size_t)n_blocks] = words;
-  // blocks larger than a shared-memory page are fine for the batch scan (columns are then decoded straight
-  // from global memory); only the one-block entry points need the block to fit
-  if (ret != OBGPU_SUCCESS) {
-    delete b;
-    return ret;
-  }
-  // device tables
+  if (ret != OBGPU_SUCCESS) { delete b; return ret; }
+  // device tables: [blk_off u64 x n][bm_word_off i64 x (n + 1)][blk_size u32 x n] ... [row_start i64 x (n + 1)]
   const size_t tb_rs = (((size_t)n_blocks * (8 + 4) + ((size_t)n_blocks + 1) * 8) + 15) & ~(size_t)15;  // row_start follows
   const size_t tb = tb_rs + ((size_t)n_blocks + 1) * 8 + 64;
   cudaError_t e = cudaMallocAsync(&b->d_tables, tb, ctx->stream);
@@ -1892,18 +1952,107 @@ int obgpu_batch_open(obgpu_ctx *ctx, const void *image, int64_t image_size, cons
   b->d_blk_off = (uint64_t *)dt;
   b->d_bm_word_off = (int64_t *)(dt + (size_t)n_blocks * 8);
   b->d_blk_size = (uint32_t *)(dt + (size_t)n_blocks * 8 + ((size_t)n_blocks + 1) * 8);
+  b->d_row_start = (int64_t *)(dt + tb_rs);
   std::vector<uint8_t> stage(tb);
   {
     uint64_t *o = (uint64_t *)stage.data();
-    int64_t *w = (int64_t *)(stage.data() + (size_t)n_blocks * 8);
     uint32_t *s = (uint32_t *)(stage.data() + (size_t)n_blocks * 8 + ((size_t)n_blocks + 1) * 8);
     for (int32_t i = 0; i < n_blocks; ++i) { o[i] = (uint64_t)offsets[i]; s[i] = (uint32_t)sizes[i]; }
+  }
+  if (host) {
+    for (int32_t i = 0; i < n_blocks && ret == OBGPU_SUCCESS; ++i) {
+      const int64_t sz = sizes[i];
+      const uint8_t *p = host + offsets[i];
+      const int16_t magic = (int16_t)rd16h(p), version = (int16_t)rd16h(p + 2);
+      const uint32_t header_size = rd32h(p + 4);
+      const uint16_t ncol = rd16h(p + 10), nkey = rd16h(p + 12);
+      const uint32_t rows = rd32h(p + 16);
+      const uint8_t rst = p[20];
+      const uint32_t row_data_off = rd32h(p + 24);
+      // ObMicroBlockHeader::is_valid (ob_micro_block_header.cpp:53-61) + get_micro_metas bounds
+      if (magic != obf::MICRO_BLOCK_HEADER_MAGIC || version < 1 || version > 3 || ncol < nkey || rst >= obf::MAX_ROW_STORE) {
+        ctx->err = "invalid micro block header";
+        ret = OBGPU_INVALID_DATA;
+        break;
+      }
+      const bool is_cs = rst == obf::CS_ENCODING_ROW_STORE;
+      if (rst != obf::ENCODING_ROW_STORE && rst != obf::SELECTIVE_ENCODING_ROW_STORE && !is_cs) {
+        ctx->err = "row store type not handled by the device path";
+        ret = OBGPU_NOT_SUPPORTED;
+        break;
+      }
+      if (header_size < 64 || (int64_t)header_size + (is_cs ? 12ll + 4ll * ncol : 16ll * ncol) > sz || (!is_cs && row_data_off > sz) ||
+          rows == 0) {
+        ret = OBGPU_INVALID_DATA;
+        break;
+      }
+      if (rows > 65535u) {
+        ctx->err = "more than 65535 rows in one micro block";
+        ret = OBGPU_NOT_SUPPORTED;
+        break;
+      }
+      b->row_count[(size_t)i] = rows;
+      b->col_count[(size_t)i] = ncol;
+    }
+  } else {
+    if (!image_on_device) { ret = OBGPU_INVALID_ARGUMENT; }
+    uint32_t *d_sv = nullptr;
+    std::vector<uint32_t> sv((size_t)n_blocks * 2);
+    if (ret == OBGPU_SUCCESS) {
+      e = cudaMemcpyAsync(b->d_tables, stage.data(), tb_rs, cudaMemcpyHostToDevice, ctx->stream);
+      if (e == cudaSuccess) e = cudaMallocAsync((void **)&d_sv, (size_t)n_blocks * 8, ctx->stream);
+      if (e == cudaSuccess) {
+        obgpu_survey_kernel<<<(unsigned)((n_blocks + 255) / 256), 256, 0, ctx->stream>>>((const uint8_t *)image, b->d_blk_off, b->d_blk_size,
+                                                                                         n_blocks, d_sv);
+        ctx->launches++;
+        e = cudaGetLastError();
+      }
+      if (e == cudaSuccess) e = cudaMemcpyAsync(sv.data(), d_sv, (size_t)n_blocks * 8, cudaMemcpyDeviceToHost, ctx->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+      if (d_sv) cudaFreeAsync(d_sv, ctx->stream);
+      if (e != cudaSuccess) {
+        ctx->err = cudaGetErrorString(e);
+        obgpu_batch_close(b);
+        return e == cudaErrorMemoryAllocation ? OBGPU_ALLOCATE_MEMORY_FAILED : OBGPU_ERR_SYS;
+      }
+      for (int32_t i = 0; i < n_blocks; ++i) {
+        const uint32_t verdict = sv[(size_t)2 * i + 1] >> 16;
+        if (verdict != 0) {
+          ctx->err = verdict == 1 ? "invalid micro block header" : "micro block not handled by the device path";
+          ret = verdict == 1 ? OBGPU_INVALID_DATA : OBGPU_NOT_SUPPORTED;
+          break;
+        }
+        b->row_count[(size_t)i] = sv[(size_t)2 * i];
+        b->col_count[(size_t)i] = (int32_t)(sv[(size_t)2 * i + 1] & 0xffffu);
+      }
+    }
+  }
+  if (ret != OBGPU_SUCCESS) {
+    obgpu_batch_close(b);
+    return ret;
+  }
+  int64_t words = 0;
+  for (int32_t i = 0; i < n_blocks; ++i) {
+    const uint32_t rows = b->row_count[(size_t)i];
+    b->bm_word_off[(size_t)i] = words;
+    words += (rows + 31) / 32;
+    b->total_rows += rows;
+    b->max_rows = std::max(b->max_rows, rows);
+    b->max_cols = std::max<uint32_t>(b->max_cols, (uint32_t)b->col_count[(size_t)i]);
+  }
+  b->bm_word_off[(size_t)n_blocks] = words;
+  b->col_max_dict.assign(b->max_cols, 0);
+  b->col_types.assign(b->max_cols, 0);
+  b->col_max_rle.assign(b->max_cols, 0);
+  // blocks larger than a shared-memory page are fine for the batch scan (columns are then decoded straight
+  // from global memory); only the one-block entry points need the block to fit
+  {
+    int64_t *w = (int64_t *)(stage.data() + (size_t)n_blocks * 8);
     memcpy(w, b->bm_word_off.data(), ((size_t)n_blocks + 1) * 8);
     int64_t *rs = (int64_t *)(stage.data() + tb_rs);  // first row of every block in the batch's row order
     rs[0] = 0;
     for (int32_t i = 0; i < n_blocks; ++i) rs[i + 1] = rs[i] + b->row_count[(size_t)i];
   }
-  b->d_row_start = (int64_t *)(dt + tb_rs);
   e = cudaMemcpyAsync(b->d_tables, stage.data(), tb, cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess) {
     if (image_on_device) {
@@ -1930,31 +2079,38 @@ int obgpu_batch_open(obgpu_ctx *ctx, const void *image, int64_t image_size, cons
     void *dp = nullptr;
     const size_t rows_bytes = ((size_t)n_blocks * 4 + 63) & ~(size_t)63;
     const size_t rec_bytes = (size_t)n_blocks * sizeof(BlockRec);
-    e = cudaMallocAsync(&dp, plan_bytes + rows_bytes + rec_bytes + (size_t)b->max_cols * 8 + 64, ctx->stream);
+    e = cudaMallocAsync(&dp, plan_bytes + rows_bytes + rec_bytes + (size_t)b->max_cols * 24 + 64, ctx->stream);
     if (e == cudaSuccess) {
       b->d_plans = (ColDesc *)dp;
       b->d_rows = (uint32_t *)((uint8_t *)dp + plan_bytes);
       b->d_recs = (BlockRec *)((uint8_t *)dp + plan_bytes + rows_bytes);
       uint32_t *d_span = (uint32_t *)((uint8_t *)dp + plan_bytes + rows_bytes + rec_bytes);
-      e = cudaMemsetAsync(d_span, 0, (size_t)b->max_cols * 8, ctx->stream);
+      // per-column reductions of the index kernel: [region span][dictionary size][type min][type max][RLE runs][projection span]
+      e = cudaMemsetAsync(d_span, 0, (size_t)b->max_cols * 24, ctx->stream);
+      if (e == cudaSuccess) e = cudaMemsetAsync(d_span + 2 * (size_t)b->max_cols, 0xff, (size_t)b->max_cols * 4, ctx->stream);
       const int64_t nthreads = (int64_t)n_blocks * b->max_cols;
       obgpu_index_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, ctx->stream>>>(
           b->d_image, b->d_blk_off, b->d_blk_size, b->d_bm_word_off, n_blocks, (int)b->max_cols, b->d_plans,
           b->d_rows, b->d_recs, d_span);
       if (e == cudaSuccess) e = cudaGetLastError();
       ctx->launches++;
-      b->col_span.assign((size_t)b->max_cols * 2, 0);  // [spans][dictionary sizes]
+      b->col_span.assign((size_t)b->max_cols * 6, 0);
       if (e == cudaSuccess)
-        e = cudaMemcpyAsync(b->col_span.data(), d_span, (size_t)b->max_cols * 8, cudaMemcpyDeviceToHost, ctx->stream);
+        e = cudaMemcpyAsync(b->col_span.data(), d_span, (size_t)b->max_cols * 24, cudaMemcpyDeviceToHost, ctx->stream);
     }
   }
   // `stage` is pageable: the copy above is staged synchronously by the runtime before returning
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-  if (e == cudaSuccess && b->col_span.size() == (size_t)b->max_cols * 2) {
-    // dictionary sizes seen by the index kernel (covers CS blocks, whose stream tables the host does not walk)
-    for (uint32_t c = 0; c < b->max_cols; ++c)
-      b->col_max_dict[c] = std::max(b->col_max_dict[c], b->col_span[(size_t)b->max_cols + c]);
-    b->col_span.resize(b->max_cols);
+  if (e == cudaSuccess && b->col_span.size() == (size_t)b->max_cols * 6) {
+    const size_t mc = b->max_cols;
+    b->col_pspan.assign(b->col_span.begin() + 5 * mc, b->col_span.begin() + 6 * mc);
+    for (size_t c = 0; c < mc; ++c) {
+      b->col_max_dict[c] = b->col_span[mc + c];
+      const uint32_t tmin = b->col_span[2 * mc + c], tmax = b->col_span[3 * mc + c];
+      b->col_types[c] = tmin == 0xffffffffu ? 0 : (tmin == tmax ? (uint8_t)tmin : 0xff);   // 0xff: the blocks disagree
+      b->col_max_rle[c] = b->col_span[4 * mc + c];
+    }
+    b->col_span.resize(mc);
   }
   if (e != cudaSuccess) {
     ctx->err = cudaGetErrorString(e);
@@ -2256,6 +2412,74 @@ static void layout_smem_scan(const obgpu_batch *b, ScanParams &p, int max_smem) 
 }
 
 
+// Small-block pipelined kernels (scan_small.cuh): which of them this scan can use, and their per-warp layouts.
+static void layout_pipe(const obgpu_batch *b, ScanParams &p, int max_smem) {
+  p.pipe_count = p.pipe_project = 0;
+  bool want = b->max_rows <= 512;
+  if (const char *e = getenv("OBGPU_PIPE")) want = atoi(e) != 0;   // testing knob: force the path on / off
+  if (!want) return;
+  auto r16 = [](uint32_t v) { return (v + 15u) & ~15u; };
+  // ---- count: every filter column (= the first pf_n used columns) has a bounded region ----------------------
+  if (p.n_nodes > 0 && p.simple_shape != 0) {
+    int nf = 0;
+    bool ok = true;
+    while (nf < p.n_used && p.used_in_filter[nf]) ++nf;
+    for (int i = nf; i < p.n_used; ++i) ok = ok && !p.used_in_filter[i];
+    ok = ok && nf > 0 && nf <= 8;
+    uint32_t off = 0;
+    for (int i = 0; i < nf && ok; ++i) {
+      const size_t col = (size_t)p.used_col[i];
+      const uint32_t sp = col < b->col_span.size() ? b->col_span[col] : 0xffffffffu;
+      if (sp == 0xffffffffu || sp > 12288u) { ok = false; break; }
+      p.pf_off[i] = off;
+      p.pf_span[i] = r16(sp);
+      off += r16(sp);
+    }
+    if (ok) {
+      p.pf_n = nf;
+      p.pc_meta_bytes = 64u + (uint32_t)nf * (uint32_t)sizeof(ColDesc);
+      p.pc_region_bytes = 64u + off;
+      uint32_t w = 0;
+      p.pc_meta = w;   w += 3u * p.pc_meta_bytes;
+      p.pc_region = w; w += 2u * p.pc_region_bytes;
+      p.pc_bm = w;     w += r16(p.words_cap * 4u);
+      p.pc_bitset = w; w += r16((uint32_t)p.n_slots * (uint32_t)p.bitset_words * 4u);
+      p.pc_bytes = (w + 127u) & ~127u;
+      if (p.pc_bytes * (uint32_t)kWarps * 2u <= (uint32_t)max_smem) p.pipe_count = 1;   // at least two CTAs per SM
+    }
+  }
+  // ---- project ------------------------------------------------------------------------------------------------------
+  if (p.n_proj + p.want_row_ids > 0) {
+    bool ok = true;
+    uint32_t off = 0;
+    for (int i = 0; i < p.n_proj && ok; ++i) {
+      const size_t col = (size_t)p.used_col[p.proj_used[i]];
+      const uint32_t sp = col < b->col_pspan.size() ? b->col_pspan[col] : 0xffffffffu;
+      if (sp == 0xffffffffu || sp > 16384u) { ok = false; break; }
+      p.pp_off[i] = off;
+      p.pp_span[i] = r16(sp);
+      off += r16(sp);
+    }
+    if (ok) {
+      p.pp_meta_bytes = 64u + (uint32_t)std::max(p.n_proj, 1) * (uint32_t)sizeof(ColDesc);
+      p.pp_hdr_bytes = r16((2u * (uint32_t)kMaxProj + 1u) * 4u);
+      p.pp_bm_bytes = r16(p.words_cap * 4u);
+      p.pp_region_bytes = p.pp_hdr_bytes + p.pp_bm_bytes + off;
+      // warp-private RLE scratch: [run values][run table] (same shape as the CTA kernel's)
+      p.pw_rvals = 0;
+      p.pw_rle = p.n_rle_slots > 0 ? (((uint32_t)p.rle_runs_cap + 2u) * 8u) : 0u;
+      p.pw_bytes = r16(p.pw_rle + (p.n_rle_slots > 0 ? p.words_cap * 6u : 0u));
+      uint32_t w = 0;
+      p.pp_meta = w;   w += 3u * p.pp_meta_bytes;
+      p.pp_region = w; w += 2u * p.pp_region_bytes;
+      p.pp_sel = w;    w += r16(p.rows_cap * 2u);
+      p.pp_wscr = w;   w += p.pw_bytes;
+      p.pp_bytes = (w + 127u) & ~127u;
+      if (p.pp_bytes * (uint32_t)kWarps * 2u <= (uint32_t)max_smem) p.pipe_project = 1;
+    }
+  }
+}
+
 // ---- pushed-down aggregates over the dense projected columns ------------------------------------------
 struct AggAcc {
   unsigned long long lo, hi;   // SUM: 128-bit; MIN / MAX: lo = value, hi = seen; COUNT: lo
@@ -2396,7 +2620,8 @@ int obgpu_scan(obgpu_batch *b, const obgpu_scan_spec *spec, obgpu_result **out) 
   p.sparse_split = (p.n_nodes > 0 && r->cap * 16 <= b->total_rows) ? 1 : 0;
   if (const char *e = getenv("OBGPU_SPARSE_SPLIT")) p.sparse_split = atoi(e) ? (p.n_nodes > 0 ? 1 : 0) : 0;  // testing knob
   layout_smem_scan(b, p, ctx->max_smem_optin);
-  if ((int)p.smem_total > ctx->max_smem_optin) {
+  layout_pipe(b, p, ctx->max_smem_optin);
+  if ((int)p.smem_total > ctx->max_smem_optin && !p.pipe_project) {
     ctx->err = "scan working set exceeds shared memory";
     delete r;
     return OBGPU_NOT_SUPPORTED;
@@ -2485,7 +2710,15 @@ int obgpu_scan(obgpu_batch *b, const obgpu_scan_spec *spec, obgpu_result **out) 
       obgpu_result_free(r);
       return OBGPU_NOT_SUPPORTED;
     }
-    obgpu_count_kernel<<<(n + kWarps - 1) / kWarps, kThreads, cw_total, ctx->stream>>>(p);
+    if (p.pipe_count) {
+      const int smem = (int)(p.pc_bytes * (uint32_t)kWarps);
+      int occ = 1;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, obgpu_count_pipe_kernel, kThreads, smem);
+      const int grid = std::min((n + kWarps - 1) / kWarps, std::max(1, occ) * ctx->sm_count);
+      obgpu_count_pipe_kernel<<<grid, kThreads, smem, ctx->stream>>>(p);
+    } else {
+      obgpu_count_kernel<<<(n + kWarps - 1) / kWarps, kThreads, cw_total, ctx->stream>>>(p);
+    }
     ctx->launches++;
   }
   {
@@ -2497,10 +2730,16 @@ int obgpu_scan(obgpu_batch *b, const obgpu_scan_spec *spec, obgpu_result **out) 
   }
   if (p.n_proj + p.want_row_ids > 0) {
     p.proj_tiles = p.sparse_split ? 8 : 1;
-    if (p.sparse_split) obgpu_project_kernel<true><<<(n + p.proj_tiles - 1) / p.proj_tiles, kThreads, p.smem_total, ctx->stream>>>(p);
+    if (p.pipe_project) {
+      const int smem = (int)(p.pp_bytes * (uint32_t)kWarps);
+      int occ = 1;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, obgpu_project_pipe_kernel, kThreads, smem);
+      const int grid = std::min((n + kWarps - 1) / kWarps, std::max(1, occ) * ctx->sm_count);
+      obgpu_project_pipe_kernel<<<grid, kThreads, smem, ctx->stream>>>(p);
+    } else if (p.sparse_split) obgpu_project_kernel<true><<<(n + p.proj_tiles - 1) / p.proj_tiles, kThreads, p.smem_total, ctx->stream>>>(p);
     else obgpu_project_kernel<false><<<n, kThreads, p.smem_total, ctx->stream>>>(p);
     ctx->launches++;
-    if (p.sparse_split) {
+    if (p.sparse_split && !p.pipe_project) {
       const uint32_t per_warp = (((p.rows_cap / 16u + 32u) * 2u + 15u) & ~15u) + (uint32_t)sizeof(ColDesc);
       obgpu_project_sparse_kernel<<<(n + kWarps - 1) / kWarps, kThreads, per_warp * (uint32_t)kWarps, ctx->stream>>>(p);
       ctx->launches++;

@@ -137,6 +137,8 @@ struct alignas(16) ColDesc {
   uint32_t ext_index;
   // CONST: exception list in rle_count / rle_row_ids_bit / rle_row_id_bits / rle_refs_bit (8-bit refs)
   uint32_t const_ref;
+  uint8_t dict_sorted;     // ObDictMetaHeader::IS_SORTED on a fixed-length dictionary: entries ascend in the column's order
+  uint8_t pad_[3];
 };
 static_assert(sizeof(ColDesc) == 96, "ColDesc layout is shared by the index kernel and the scan kernels");
 
@@ -718,6 +720,7 @@ __device__ __forceinline__ void build_col_desc(const BlockView &b, int col, ColD
       d.dict_data_size = (uint32_t)ld_bytes(s, dm + 6, 2);
       const uint8_t dattr = s[dm + 8];
       d.dict_fixed = dattr & DICT_FIX_LENGTH;
+      d.dict_sorted = (dattr & DICT_IS_SORTED) && d.dict_fixed;
       d.dict_payload = dm + 9;
       d.dict_end = dm + dict_len;
       if (!d.dict_fixed) {
@@ -778,6 +781,7 @@ __device__ __forceinline__ void build_col_desc(const BlockView &b, int col, ColD
       d.dict_count = (uint32_t)ld_bytes(s, dm + 2, 4);
       d.dict_data_size = (uint32_t)ld_bytes(s, dm + 6, 2);
       d.dict_fixed = s[dm + 8] & DICT_FIX_LENGTH;
+      d.dict_sorted = (s[dm + 8] & DICT_IS_SORTED) && d.dict_fixed;
       d.dict_payload = dm + 9;
       d.dict_end = meta + length;
       if (!d.dict_fixed) {
@@ -846,6 +850,35 @@ __device__ __forceinline__ bool col_region(const ColDesc &d, const BlockView &bv
   lo = a & ~15u;
   hi = ((b + 16u + 15u) & ~15u);
   return true;
+}
+
+// Byte ranges of the block a PROJECTION of column d reads (r = {lo0, hi0, lo1, hi1}, 16-byte aligned, padded for the
+// funnel-shift over-read). Returns the number of ranges: 0 = no bounded range (the caller reports it), 1, or 2 for a
+// var-length string dictionary whose offset array and refs are staged without the string bytes between them.
+__device__ __forceinline__ int proj_ranges(const ColDesc &d, const BlockView &bv, uint32_t r[4]) {
+  if (d.kind == K_DICT && d.sc == 5) {
+    const uint32_t ref_lo = (d.val_bit >> 3) & ~15u;
+    const uint32_t ref_hi = (((d.val_bit + bv.row_count * d.stride + 7u) >> 3) + 16u + 15u) & ~15u;
+    if (d.dict_fixed) { r[0] = ref_lo; r[1] = ref_hi; return 1; }   // cell address is arithmetic: refs only
+    const uint32_t idx_lo = d.dict_payload & ~15u;
+    const uint32_t idx_hi = (d.dict_payload + d.dict_count * d.dict_data_size + 16u + 15u) & ~15u;
+    if (idx_hi < ref_lo) { r[0] = idx_lo; r[1] = idx_hi; r[2] = ref_lo; r[3] = ref_hi; return 2; }
+    if (ref_hi < idx_lo) { r[0] = ref_lo; r[1] = ref_hi; r[2] = idx_lo; r[3] = idx_hi; return 2; }
+    r[0] = min(idx_lo, ref_lo);
+    r[1] = max(idx_hi, ref_hi);
+    return 1;
+  }
+  uint32_t lo, hi;
+  if (!col_region(d, bv, lo, hi) || hi <= lo) return 0;
+  r[0] = lo;
+  r[1] = hi;
+  return 1;
+}
+__device__ __forceinline__ uint32_t proj_ranges_bytes(const ColDesc &d, const BlockView &bv) {
+  uint32_t r[4];
+  const int n = proj_ranges(d, bv, r);
+  if (n == 0) return 0xffffffffu;
+  return (r[1] - r[0]) + (n == 2 ? r[3] - r[2] : 0u);
 }
 
 // ---- RLE run table (per block, per RLE column, in shared memory) -------------------------------

@@ -1,0 +1,413 @@
+// Small micro-blocks (a 16 KiB block of a wide dictionary-coded table holds ~130 rows): per block there are only a
+// few hundred bytes to filter and a dozen rows to project, so a scan is bound by the per-block chain of dependent
+// global round trips (record -> plans -> column bytes), not by bandwidth. These two kernels keep ONE WARP per block
+// but run it as a software pipeline over the blocks it owns (persistent grid, blocks strided over the warps):
+//
+//     iteration b:   wait   regions(b), meta(b + 1)          (cp.async groups, issued one / two iterations ago)
+//                    issue  regions(b + 1)   <- needs meta(b + 1): block offset, decode plans -> column byte ranges
+//                    issue  meta(b + 2)      <- block record, decode plans (and the two prefix entries)
+//                    work   on block b from shared memory
+//
+// so a block's three round trips overlap the work on the two blocks before it. All copies are 16-byte cp.async
+// (LDGSTS: no registers, no mbarrier), completion is cp.async.wait_group + __syncwarp.
+//   obgpu_count_pipe_kernel   : stages every filter column's region of the block at once, then the same leaf loops
+//                               as obgpu_count_kernel (K4 / K6 / K9 / K14)
+//   obgpu_project_pipe_kernel : stages the block's bitmap words and the projected columns' byte ranges; a projected
+//                               VARCHAR dictionary column needs only its refs and its offset array (VEC_DISCRETE
+//                               output is pointers into the caller's block: the dictionary's bytes are never read)
+#pragma once
+
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void *g) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async8(uint32_t saddr, const void *g) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t saddr, const void *g) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+constexpr int kPipeMaxFilterCols = 8;
+
+// =================================================================================================
+// Count, pipelined. Per warp: meta ring (3 slots: block record + the filter columns' plans), region ring (2 slots:
+// header with the per-column deltas + the filter columns' regions), bitmap words, predicate bitsets.
+// =================================================================================================
+__global__ void __launch_bounds__(kThreads) obgpu_count_pipe_kernel(const __grid_constant__ ScanParams p) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nwarps_total = (int)gridDim.x * kWarps;
+  int blk = (int)blockIdx.x * kWarps + warp;
+  if (blk >= p.n_blocks) return;
+  uint8_t *wr = g_smem + (uint32_t)warp * p.pc_bytes;
+  uint8_t *meta0 = wr + p.pc_meta, *reg0 = wr + p.pc_region;
+  uint32_t *bm = reinterpret_cast<uint32_t *>(wr + p.pc_bm);
+  uint32_t *bitsets = reinterpret_cast<uint32_t *>(wr + p.pc_bitset);
+  const int nf = p.pf_n;
+  Team t;
+  t.tid = lane; t.nthreads = 32; t.warp = 0; t.nwarps = 1; t.lane = lane; t.bar_id = -1;
+
+  auto issue_meta = [&](int b, int slot) {
+    if (b >= p.n_blocks) return;
+    const uint32_t sa = smem_u32(meta0 + (uint32_t)slot * p.pc_meta_bytes);
+    const uint8_t *rec = reinterpret_cast<const uint8_t *>(p.recs + b);
+    const uint8_t *plans = reinterpret_cast<const uint8_t *>(p.plans + (int64_t)b * p.max_cols);
+    for (int q = lane; q < 3 + nf * 6; q += 32) {
+      if (q < 3) cp_async16(sa + (uint32_t)q * 16u, rec + q * 16);
+      else {
+        const int i = (q - 3) / 6, piece = (q - 3) % 6;
+        cp_async16(sa + 64u + (uint32_t)i * 96u + (uint32_t)piece * 16u, plans + (size_t)p.used_col[i] * sizeof(ColDesc) + piece * 16);
+      }
+    }
+  };
+  // region slot: [int32 delta[kPipeMaxFilterCols] | uint32 flags] (64 bytes) then the regions at p.pf_off[i]
+  auto issue_regions = [&](int b, int mslot, int rslot, uint32_t verdict) {
+    if (b >= p.n_blocks) return;
+    const uint8_t *m = meta0 + (uint32_t)mslot * p.pc_meta_bytes;
+    uint8_t *rs = reg0 + (uint32_t)rslot * p.pc_region_bytes;
+    const BlockRec &rec = *reinterpret_cast<const BlockRec *>(m);
+    const ColDesc *descs = reinterpret_cast<const ColDesc *>(m + 64);
+    int32_t *hdr = reinterpret_cast<int32_t *>(rs);
+    uint32_t lo = 0, hi = 0;
+    bool bad = false;
+    if (lane < nf && rec.rows != 0 && verdict == 0) {
+      BlockView bv;
+      view_from_rec(rec, nullptr, bv);
+      const ColDesc &d = descs[lane];
+      if (!d.ok || !col_region(d, bv, lo, hi) || hi - lo > p.pf_span[lane] || hi > ((rec.size + 15u) & ~15u) + 32u) { bad = true; lo = hi = 0; }
+      hdr[lane] = (int32_t)(64u + p.pf_off[lane]) - (int32_t)lo;
+    }
+    const uint32_t badmask = __ballot_sync(0xffffffffu, bad);
+    if (lane == 0) hdr[kPipeMaxFilterCols] = (int32_t)badmask;
+    const uint8_t *gblk = p.image + rec.off;
+    for (int i = 0; i < nf; ++i) {
+      const uint32_t l = __shfl_sync(0xffffffffu, lo, i), h = __shfl_sync(0xffffffffu, hi, i);
+      const uint32_t dst = smem_u32(rs) + 64u + p.pf_off[i];
+      for (uint32_t k = (uint32_t)lane * 16u; k < h - l; k += 512u) cp_async16(dst + k, gblk + l + k);
+    }
+  };
+
+  // prologue: meta(b0), then regions(b0) + meta(b1)
+  uint32_t v_cur = 0, v_next = 0, v_next2 = 0;   // skip-index verdicts, fetched two blocks ahead
+  if (p.blk_const != nullptr) {
+    v_cur = p.blk_const[blk];
+    if (blk + nwarps_total < p.n_blocks) v_next = p.blk_const[blk + nwarps_total];
+  }
+  issue_meta(blk, 0);
+  cp_async_commit();
+  cp_async_wait_all();
+  __syncwarp();
+  issue_regions(blk, 0, 0, v_cur);
+  cp_async_commit();
+  issue_meta(blk + nwarps_total, 1);
+  cp_async_commit();
+  int it = 0;
+  for (; blk < p.n_blocks; blk += nwarps_total, ++it) {
+    const int ms = it % 3, rsl = it & 1;
+    cp_async_wait_all();
+    __syncwarp();
+    const int b2 = blk + 2 * nwarps_total;
+    if (p.blk_const != nullptr && b2 < p.n_blocks) v_next2 = p.blk_const[b2];
+    issue_regions(blk + nwarps_total, (it + 1) % 3, rsl ^ 1, v_next);
+    cp_async_commit();
+    issue_meta(b2, (it + 2) % 3);
+    cp_async_commit();
+
+    // ---- block `blk` from shared memory -------------------------------------------------------------------------
+    const uint8_t *m = meta0 + (uint32_t)ms * p.pc_meta_bytes;
+    uint8_t *rs = reg0 + (uint32_t)rsl * p.pc_region_bytes;
+    const BlockRec rec = *reinterpret_cast<const BlockRec *>(m);
+    const ColDesc *descs = reinterpret_cast<const ColDesc *>(m + 64);
+    const int32_t *hdr = reinterpret_cast<const int32_t *>(rs);
+    const uint32_t rows = rec.rows;
+    uint32_t *gbm = p.bitmap_words + rec.bm_word_off;
+    const uint32_t nwords = (rows + 31u) >> 5;
+    const uint32_t verdict = v_cur;
+    v_cur = v_next;
+    v_next = v_next2;
+    if (verdict != 0 && rows != 0) {   // decided by the skip index: the block was not read
+      for (uint32_t g = (uint32_t)lane; g < nwords; g += 32u) gbm[g] = verdict == 1 ? valid_mask_of(rows, g) : 0u;
+      if (lane == 0) p.counts[blk] = verdict == 1 ? rows : 0u;
+      __syncwarp();
+      continue;
+    }
+    if (rows == 0 || hdr[kPipeMaxFilterCols] != 0) {
+      if (lane == 0) {
+        atomicOr(p.status, rows == 0 ? ST_CORRUPT : ST_UNSUPPORTED);
+        p.counts[blk] = 0;
+      }
+      __syncwarp();
+      continue;
+    }
+    BlockCtx c;
+    view_from_rec(rec, nullptr, c.b);
+    c.descs = descs;
+    c.bitsets = bitsets;
+    c.rle_base = nullptr;
+    c.rle_slot_bytes = c.rle_starts_bytes = 0;
+    const bool and_mode = p.simple_shape == 1;
+    const int n_leaves = p.n_nodes == 1 ? 1 : p.n_nodes - 1;
+    bool inited = false;
+    for (int i = 0; i < n_leaves; ++i) {
+      const FilterNodeDev &nd = p.nodes[i];
+      if (p.leaf_const != nullptr && p.leaf_const[(int64_t)blk * p.n_nodes + i] != 0) continue;
+      if (nd.op != OP_FALSE && nd.op != OP_TRUE) {   // block-relative offsets of this leaf's column resolve into its staged region
+        c.b.s = rs + hdr[nd.used_idx];
+        c.sbit = (smem_u32(rs) + (uint32_t)hdr[nd.used_idx]) * 8u;
+      }
+      const ColDesc &d = descs[nd.used_idx];
+      if (nd.slot >= 0 && is_dict_kind(d)) {
+        build_dict_bitset(p, c.b, d, nd, bitsets + nd.slot * p.bitset_words, t);
+        __syncwarp();
+      }
+      if (i == 0 && leaf_first_fast<false>(p, c, nd, bm, rows, nwords, t)) {
+        inited = true;
+        __syncwarp();
+        continue;
+      }
+      if (!inited) {
+        for (uint32_t g = (uint32_t)lane; g < nwords; g += 32u) bm[g] = and_mode ? valid_mask_of(rows, g) : 0u;
+        inited = true;
+        __syncwarp();
+      }
+      leaf_over_words<false>(p, c, nd, bm, rows, nwords, and_mode, t);
+      __syncwarp();
+      if (i + 1 < n_leaves) {   // early-out of the AND / OR (ob_pushdown_filter.cpp:1603-1615)
+        bool undecided = false;
+        for (uint32_t g = (uint32_t)lane; g < nwords; g += 32u)
+          undecided = undecided || (and_mode ? bm[g] != 0u : bm[g] != valid_mask_of(rows, g));
+        if (!__any_sync(0xffffffffu, undecided)) break;
+      }
+    }
+    if (!inited) {
+      for (uint32_t g = (uint32_t)lane; g < nwords; g += 32u) bm[g] = and_mode ? valid_mask_of(rows, g) : 0u;
+      __syncwarp();
+    }
+    uint32_t cnt = 0;
+    for (uint32_t g = (uint32_t)lane; g < nwords; g += 32u) {
+      const uint32_t w = bm[g];
+      gbm[g] = w;
+      cnt += __popc(w);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) p.counts[blk] = cnt;
+    __syncwarp();   // every lane is done with this iteration's slots before the next iteration refills them
+  }
+  cp_async_wait_all();
+}
+
+// =================================================================================================
+// Projection, pipelined. Meta slot: [record 48 | sel_offset pair 16 | plans n_proj x 96]; region slot:
+// [header: per column {delta0, delta1} + flags | bitmap words | column byte ranges at p.pp_off[pc]].
+// =================================================================================================
+#define ROW(j) (IDENT ? (uint32_t)(j) : (uint32_t)sel[j])
+template <bool IDENT>
+__device__ __forceinline__ void project_str_dict_shallow(const ScanParams &p, const ColDesc &d, int pc, const uint16_t *sel,
+                                                         uint32_t cnt, int64_t base_row, uint64_t blk_addr, uint32_t ref_sbit,
+                                                         uint32_t idx_sbit, int lane) {
+  uint64_t *optr = reinterpret_cast<uint64_t *>(p.out_data[pc]) + base_row;
+  int32_t *olen = p.out_lens[pc] + base_row;
+  const uint32_t vbit = ref_sbit + d.val_bit, stride = d.stride, width = d.width, dcount = d.dict_count;
+  const uint32_t ib8 = d.dict_data_size * 8u, ibit = idx_sbit + d.dict_payload * 8u, heap_len = d.dict_end - d.dict_var;
+  const bool fixed = d.dict_fixed != 0;
+  bool saw_null = false;
+  for (uint32_t j = (uint32_t)lane; j < cnt; j += 32u) {
+    const uint32_t ref = sbits32(vbit + ROW(j) * stride, width);
+    uint32_t cell = 0, len = 0;
+    const bool is_null = ref >= dcount;
+    if (!is_null) {
+      if (fixed) {
+        len = d.dict_data_size;
+        cell = d.dict_payload + ref * len;
+      } else {
+        const uint32_t off = ref == 0 ? 0u : sbits32(ibit + (ref - 1u) * ib8, ib8);
+        const uint32_t end = ref == dcount - 1u ? heap_len : sbits32(ibit + ref * ib8, ib8);
+        cell = d.dict_var + off;
+        len = end - off;
+      }
+    }
+    __stcs(&optr[j], is_null ? 0ull : blk_addr + cell);
+    __stcs(&olen[j], is_null ? 0 : (int32_t)len);
+    if (is_null) {
+      const int64_t o = base_row + (int64_t)j;
+      atomicOr(&p.out_nulls[pc][o >> 5], 1u << (o & 31));
+      saw_null = true;
+    }
+  }
+  if (saw_null) p.has_null[pc] = 1;
+}
+#undef ROW
+
+__global__ void __launch_bounds__(kThreads) obgpu_project_pipe_kernel(const __grid_constant__ ScanParams p) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nwarps_total = (int)gridDim.x * kWarps;
+  int blk = (int)blockIdx.x * kWarps + warp;
+  if (blk >= p.n_blocks) return;
+  uint8_t *wr = g_smem + (uint32_t)warp * p.pp_bytes;
+  uint8_t *meta0 = wr + p.pp_meta, *reg0 = wr + p.pp_region;
+  uint16_t *sel = reinterpret_cast<uint16_t *>(wr + p.pp_sel);
+  uint8_t *wscr = wr + p.pp_wscr;
+  const int np = p.n_proj;
+  const uint32_t hdr_bytes = p.pp_hdr_bytes, bm_bytes = p.pp_bm_bytes;
+  Team t;
+  t.tid = lane; t.nthreads = 32; t.warp = 0; t.nwarps = 1; t.lane = lane; t.bar_id = -1;
+
+  auto issue_meta = [&](int b, int slot) {
+    if (b >= p.n_blocks) return;
+    const uint32_t sa = smem_u32(meta0 + (uint32_t)slot * p.pp_meta_bytes);
+    const uint8_t *rec = reinterpret_cast<const uint8_t *>(p.recs + b);
+    const uint8_t *plans = reinterpret_cast<const uint8_t *>(p.plans + (int64_t)b * p.max_cols);
+    for (int q = lane; q < 5 + np * 6; q += 32) {
+      if (q < 3) cp_async16(sa + (uint32_t)q * 16u, rec + q * 16);
+      else if (q < 5) cp_async8(sa + 48u + (uint32_t)(q - 3) * 8u, p.sel_offset + b + (q - 3));
+      else {
+        const int i = (q - 5) / 6, piece = (q - 5) % 6;
+        cp_async16(sa + 64u + (uint32_t)i * 96u + (uint32_t)piece * 16u,
+                   plans + (size_t)p.used_col[p.proj_used[i]] * sizeof(ColDesc) + piece * 16);
+      }
+    }
+  };
+  // what a block needs beyond its meta: nothing (no selected row / overflow / corrupt), or bitmap words + column ranges
+  auto issue_regions = [&](int b, int mslot, int rslot) {
+    if (b >= p.n_blocks) return;
+    const uint8_t *m = meta0 + (uint32_t)mslot * p.pp_meta_bytes;
+    uint8_t *rs = reg0 + (uint32_t)rslot * p.pp_region_bytes;
+    const BlockRec &rec = *reinterpret_cast<const BlockRec *>(m);
+    const int64_t base = *reinterpret_cast<const int64_t *>(m + 48);
+    const uint32_t cnt = (uint32_t)(*reinterpret_cast<const int64_t *>(m + 56) - base);
+    const uint32_t rows = rec.rows;
+    if (rows == 0 || cnt == 0 || base + (int64_t)cnt > p.out_cap) return;
+    if (cnt != rows) {
+      const uint32_t nwords = (rows + 31u) >> 5;
+      const uint32_t *gbm = p.bitmap_words + rec.bm_word_off;
+      for (uint32_t g = (uint32_t)lane; g < nwords; g += 32u) cp_async4(smem_u32(rs) + hdr_bytes + g * 4u, gbm + g);
+    }
+    const ColDesc *plans = reinterpret_cast<const ColDesc *>(m + 64);
+    int32_t *hdr = reinterpret_cast<int32_t *>(rs);
+    uint32_t r[4] = {0, 0, 0, 0};
+    int nr = 0;
+    if (lane < np) {
+      BlockView bv;
+      view_from_rec(rec, nullptr, bv);
+      const ColDesc &d = plans[lane];
+      nr = d.ok ? proj_ranges(d, bv, r) : 0;
+      const uint32_t lim = ((rec.size + 15u) & ~15u) + 32u;
+      if (nr > 0 && ((r[1] - r[0]) + (nr == 2 ? r[3] - r[2] : 0u) > p.pp_span[lane] || r[1] > lim || (nr == 2 && r[3] > lim))) nr = 0;
+      if (nr == 0) r[0] = r[1] = r[2] = r[3] = 0;
+      const uint32_t o0 = hdr_bytes + bm_bytes + p.pp_off[lane], o1 = o0 + (r[1] - r[0]);
+      hdr[2 * lane] = (int32_t)o0 - (int32_t)r[0];
+      hdr[2 * lane + 1] = nr == 2 ? (int32_t)o1 - (int32_t)r[2] : (int32_t)o0 - (int32_t)r[0];
+    }
+    const uint32_t badmask = __ballot_sync(0xffffffffu, lane < np && nr == 0);
+    if (lane == 0) hdr[2 * kMaxProj] = (int32_t)badmask;
+    const uint8_t *gblk = p.image + rec.off;
+    for (int i = 0; i < np; ++i) {
+      const uint32_t l0 = __shfl_sync(0xffffffffu, r[0], i), h0 = __shfl_sync(0xffffffffu, r[1], i);
+      const uint32_t l1 = __shfl_sync(0xffffffffu, r[2], i), h1 = __shfl_sync(0xffffffffu, r[3], i);
+      const uint32_t dst = smem_u32(rs) + hdr_bytes + bm_bytes + p.pp_off[i];
+      for (uint32_t k = (uint32_t)lane * 16u; k < h0 - l0; k += 512u) cp_async16(dst + k, gblk + l0 + k);
+      for (uint32_t k = (uint32_t)lane * 16u; k < h1 - l1; k += 512u) cp_async16(dst + (h0 - l0) + k, gblk + l1 + k);
+    }
+  };
+
+  issue_meta(blk, 0);
+  cp_async_commit();
+  cp_async_wait_all();
+  __syncwarp();
+  issue_regions(blk, 0, 0);
+  cp_async_commit();
+  issue_meta(blk + nwarps_total, 1);
+  cp_async_commit();
+  int it = 0;
+  for (; blk < p.n_blocks; blk += nwarps_total, ++it) {
+    const int ms = it % 3, rsl = it & 1;
+    cp_async_wait_all();
+    __syncwarp();
+    issue_regions(blk + nwarps_total, (it + 1) % 3, rsl ^ 1);
+    cp_async_commit();
+    issue_meta(blk + 2 * nwarps_total, (it + 2) % 3);
+    cp_async_commit();
+
+    uint8_t *m = meta0 + (uint32_t)ms * p.pp_meta_bytes;
+    uint8_t *rs = reg0 + (uint32_t)rsl * p.pp_region_bytes;
+    const BlockRec rec = *reinterpret_cast<const BlockRec *>(m);
+    const int64_t base = *reinterpret_cast<const int64_t *>(m + 48);
+    const uint32_t cnt = (uint32_t)(*reinterpret_cast<const int64_t *>(m + 56) - base);
+    const uint32_t rows = rec.rows;
+    if (rows == 0 || cnt == 0 || base + (int64_t)cnt > p.out_cap) {
+      if (lane == 0 && rows == 0) atomicOr(p.status, ST_CORRUPT);
+      if (lane == 0 && rows != 0 && cnt != 0) atomicOr(p.status, ST_OVERFLOW);
+      __syncwarp();
+      continue;
+    }
+    ColDesc *plans = reinterpret_cast<ColDesc *>(m + 64);
+    const int32_t *hdr = reinterpret_cast<const int32_t *>(rs);
+    const uint32_t badmask = (uint32_t)hdr[2 * kMaxProj];
+    const bool all_rows = cnt == rows;
+    if (!all_rows) {
+      // bitmap words -> ascending selected-row list: lane g owns word g of each group of 32 words
+      const uint32_t *bmw = reinterpret_cast<const uint32_t *>(rs + hdr_bytes);
+      const uint32_t nwords = (rows + 31u) >> 5;
+      uint32_t running = 0;
+      for (uint32_t base_w = 0; base_w < nwords; base_w += 32u) {
+        const uint32_t w = base_w + (uint32_t)lane;
+        const uint32_t word = w < nwords ? bmw[w] : 0u;
+        const uint32_t local = __popc(word);
+        uint32_t inc = local;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += u;
+        }
+        const uint32_t excl = running + inc - local;
+        const uint32_t ng = min(32u, nwords - base_w);
+        for (uint32_t g = 0; g < ng; ++g) {   // every lane tests its own bit of word g: coalesced, divergence-free
+          const uint32_t wg = __shfl_sync(0xffffffffu, word, g), og = __shfl_sync(0xffffffffu, excl, g);
+          if ((wg >> lane) & 1u) sel[og + __popc(wg & ((1u << lane) - 1u))] = (uint16_t)((base_w + g) * 32u + (uint32_t)lane);
+        }
+        running += __shfl_sync(0xffffffffu, inc, 31);
+      }
+      __syncwarp();
+    }
+    if (p.want_row_ids) {
+      int32_t *rid = p.row_ids + base;
+      if (all_rows) for (uint32_t j = (uint32_t)lane; j < cnt; j += 32u) rid[j] = (int32_t)j;
+      else for (uint32_t j = (uint32_t)lane; j < cnt; j += 32u) rid[j] = (int32_t)sel[j];
+    }
+    BlockCtx c;
+    view_from_rec(rec, nullptr, c.b);
+    c.bitsets = nullptr;
+    c.descs = plans;
+    c.rle_base = wscr + p.pw_rle;
+    c.rle_slot_bytes = 0;
+    c.rle_starts_bytes = p.words_cap * 4u;
+    const uint64_t blk_addr = p.string_base + rec.off;
+    for (int pc = 0; pc < np; ++pc) {
+      ColDesc *wdesc = plans + pc;
+      if (!wdesc->ok || ((badmask >> pc) & 1u)) {
+        if (lane == 0) atomicOr(p.status, ST_UNSUPPORTED);
+        continue;
+      }
+      const int32_t d0 = hdr[2 * pc], d1 = hdr[2 * pc + 1];
+      if (wdesc->kind == K_DICT && wdesc->sc == 5) {
+        const uint32_t idx_sbit = (smem_u32(rs) + (uint32_t)d0) * 8u, ref_sbit = (smem_u32(rs) + (uint32_t)d1) * 8u;
+        // which delta belongs to the refs: with two ranges they are ordered by block offset (proj_ranges)
+        uint32_t rbit = ref_sbit, ibit = idx_sbit;
+        if (d0 == d1) rbit = ibit = idx_sbit;
+        else if ((wdesc->val_bit >> 3) < wdesc->dict_payload) { rbit = idx_sbit; ibit = ref_sbit; }
+        if (all_rows) project_str_dict_shallow<true>(p, *wdesc, pc, sel, cnt, base, blk_addr, rbit, ibit, lane);
+        else project_str_dict_shallow<false>(p, *wdesc, pc, sel, cnt, base, blk_addr, rbit, ibit, lane);
+        __syncwarp();
+        continue;
+      }
+      c.b.s = rs + d0;
+      c.sbit = (smem_u32(rs) + (uint32_t)d0) * 8u;
+      project_column_staged(p, c, wdesc, pc, sel, cnt, base, blk_addr, all_rows, rows, wscr, t);
+      __syncwarp();
+    }
+    __syncwarp();
+  }
+  cp_async_wait_all();
+}

@@ -117,8 +117,9 @@ class ScanContext:
     def last_error(self) -> str:
         return (lib.obgpu_ctx_last_error(self._h) or b"").decode()
 
-    def open_batch(self, table, device_image_ptr: Optional[int] = None) -> "PageBatch":
-        return PageBatch(self, table, device_image_ptr)
+    def open_batch(self, table, device_image_ptr: Optional[int] = None, host_view: bool = True,
+                   image_size: Optional[int] = None) -> "PageBatch":
+        return PageBatch(self, table, device_image_ptr, host_view, image_size)
 
     def bitmap_to_row_ids(self, bitmap: np.ndarray, start: int, to: int, limit: int, id_offset: int = 0):
         """common::ObBitmap::get_row_ids. Returns (row_ids, next_from)."""
@@ -144,7 +145,10 @@ class ScanContext:
 class PageBatch:
     """obgpu_batch: N micro-blocks resident in HBM."""
 
-    def __init__(self, ctx: ScanContext, table, device_image_ptr: Optional[int] = None):
+    def __init__(self, ctx: ScanContext, table, device_image_ptr: Optional[int] = None, host_view: bool = True,
+                 image_size: Optional[int] = None):
+        """host_view=False: a device-resident image is opened without a host copy of it (table.image may then be
+        None; the headers are surveyed on the device)."""
         self.ctx = ctx
         self.table = table
         self._h = C.c_void_p()
@@ -155,8 +159,10 @@ class PageBatch:
             code = lib.obgpu_batch_open(ctx._h, img.ctypes.data, img.size, offs.ctypes.data, sizes.ctypes.data,
                                         len(offs), 0, None, C.byref(self._h))
         else:
-            code = lib.obgpu_batch_open(ctx._h, C.c_void_p(device_image_ptr), img.size, offs.ctypes.data,
-                                        sizes.ctypes.data, len(offs), 1, img.ctypes.data, C.byref(self._h))
+            size = int(image_size) if image_size is not None else img.size
+            code = lib.obgpu_batch_open(ctx._h, C.c_void_p(device_image_ptr), size, offs.ctypes.data,
+                                        sizes.ctypes.data, len(offs), 1,
+                                        img.ctypes.data if (host_view and img is not None) else None, C.byref(self._h))
         check(code, "obgpu_batch_open", ctx._h)
         self.n_blocks = len(offs)
         tr = C.c_int64(0)

@@ -243,3 +243,76 @@ def make_config4_like(rows=100_000, rows_per_block=2000, seed=4, row_start=0, n_
     return Workload(table, flt, [3, 1], [False, False], [8, 8],
                     "cfg4: TPC-H lineitem Q6 columns as a CS column group (4 CS INTEGER columns), Q6 predicate, SUM(price*discount)",
                     rows_per_block)
+
+
+# ---- micro-block size target ------------------------------------------------------------------------------
+MICRO_BLOCK_TARGET = 16 << 10   # OB_DEFAULT_SSTABLE_BLOCK_SIZE (deps/oblib/src/lib/ob_define.h:1988)
+
+
+def rows_per_block_for_target(maker, target_bytes=MICRO_BLOCK_TARGET, sample_rows=40_000, seed=None, lo=16, hi=8192):
+    """Rows per micro-block at which `maker`'s table cuts blocks of (on average) at most `target_bytes` encoded
+    bytes. The reference's encoder cuts a block when the running size estimate reaches the limit and corrects the
+    estimate with the previous block's real / estimated ratio (ObMicroBlockEncoder::update_estimate_size_limit,
+    encoding/ob_micro_block_encoder.cpp:357-381), i.e. it converges on blocks of about the target size; the
+    synthetic tables have stationary columns, so a constant row count per block is that steady state. Found by
+    bisection on a seeded sample."""
+    kw = {} if seed is None else {"seed": seed}
+
+    def mean_block(rpb):
+        w = maker(rows=max(sample_rows, rpb * 8), rows_per_block=rpb, **kw)
+        n_full = max(1, w.table.n_blocks - 1)   # the ragged last block does not count
+        return float(w.table.sizes[:n_full].mean())
+
+    if mean_block(lo) > target_bytes:
+        return lo
+    while lo + 1 < hi:
+        mid = (lo + hi) // 2
+        if mean_block(mid) <= target_bytes:
+            lo = mid
+        else:
+            hi = mid
+    return lo
+
+
+def referenced_bytes(table: TableImage, cols) -> int:
+    """Bytes of the blocks' accessed regions for a scan that references `cols` (B_in): per PAX block
+    the 64-byte header + the column headers + the region [offset_c, offset_{c+1}) of the column area for every
+    referenced column (meta + values / refs + dictionary: exactly what the kernels stage). Blocks with var-stored
+    columns (row data) or CS blocks count whole."""
+    img, total = table.image, 0
+    cols = sorted(set(int(c) for c in cols))
+    offs = np.asarray(table.offsets, dtype=np.int64)
+    sizes = np.asarray(table.sizes, dtype=np.int64)
+    hdr = np.stack([img[offs + k] for k in range(28)], axis=1).astype(np.int64)
+    u16 = lambda a: hdr[:, a] | (hdr[:, a + 1] << 8)
+    u32 = lambda a: hdr[:, a] | (hdr[:, a + 1] << 8) | (hdr[:, a + 2] << 16) | (hdr[:, a + 3] << 24)
+    header_size, ncol, rst, var_cols, row_data_off = u32(4), u16(10), hdr[:, 20], u16(22), u32(24)
+    whole = (rst == 3) | (var_cols > 0)     # CS_ENCODING_ROW_STORE / var-stored columns: no per-column region
+    total += int(sizes[whole].sum())
+    sel = ~whole
+    if sel.any():
+        o, hs, nc, rdo = offs[sel], header_size[sel], ncol[sel], row_data_off[sel]
+        meta = hs + 16 * nc
+
+        def col_off(c):
+            b = o + hs + 16 * c + 8
+            return (img[b].astype(np.int64) | (img[b + 1].astype(np.int64) << 8) | (img[b + 2].astype(np.int64) << 16) |
+                    (img[b + 3].astype(np.int64) << 24))
+        total += int(meta.sum())
+        for c in cols:
+            start = col_off(c)
+            nxt = np.where(c + 1 < nc, col_off(np.minimum(c + 1, nc - 1)), rdo - meta)
+            total += int((nxt - start).sum())
+    return total
+
+
+def filter_columns(expr):
+    """Store indexes of the columns a filter tree references."""
+    if expr is None:
+        return []
+    if isinstance(expr, White):
+        return [expr.col]
+    out = []
+    for c in expr.children:
+        out += filter_columns(c)
+    return sorted(set(out))

@@ -10,6 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
 ORACLE_LIB = os.path.join(ORACLE_DIR, "libob_oracle.so")
 REF_LIB = os.path.join(ORACLE_DIR, "_ref", "libref_bitstream.so")
+REF_CODEC_LIB = os.path.join(ORACLE_DIR, "_ref", "libref_codec.so")
 
 
 def _cpu_stamp():
@@ -40,7 +41,7 @@ def build_oracle():
         subprocess.run(["make", "-B", "-C", ORACLE_DIR, "-s", "all"], check=True, capture_output=True)
         with open(stamp_file, "w") as f:
             f.write(stamp + "\n")
-    elif os.path.isdir("/root/reference") and not os.path.exists(REF_LIB):
+    elif os.path.isdir("/root/reference") and not (os.path.exists(REF_LIB) and os.path.exists(REF_CODEC_LIB)):
         subprocess.run(["make", "-C", ORACLE_DIR, "-s", "ref"], check=True, capture_output=True)
     return ORACLE_LIB
 

@@ -209,3 +209,37 @@ def test_var_stored_integer_columns(ob, ctx, obj_type, lo, hi, elem):
                 ob.And([ob.White(0, ob.WHITE_OP_LT, (mid,)), ob.White(2, ob.WHITE_OP_NE, (int(v[5]),)), ob.White(3, ob.WHITE_OP_GE, (100,))]),
                 ob.Or([ob.White(0, ob.WHITE_OP_IN, (int(v[0]), int(v[1]), int(v[2]))), ob.White(1, ob.WHITE_OP_EQ, (s[9],))])):
         assert_scan_matches(ctx, W(table, flt, [0, 1, 2, 3], [False, True, False, False], [elem, 8, elem, 8]))
+
+
+def test_device_image_without_host_view(ob, ctx):
+    """A device-resident image opened with header_view == NULL is surveyed on the device: same batch facts, same scan
+    result as the host-validated open; a corrupt header is still refused with OB_INVALID_DATA."""
+    import torch
+    table, _ = _mixed_table(ob, 5000, 700, seed=41)
+    d_img = torch.zeros(table.image.size + 64, dtype=torch.uint8, device="cuda")
+    d_img[:table.image.size].copy_(torch.from_numpy(table.image))
+    torch.cuda.synchronize()
+    flt = ob.And([ob.White(1, ob.WHITE_OP_LT, (1500,)), ob.White(9, ob.WHITE_OP_NN, ())])
+    a = ctx.open_batch(table, device_image_ptr=d_img.data_ptr())
+    b = ctx.open_batch(table, device_image_ptr=d_img.data_ptr(), host_view=False)
+    assert a.total_rows == b.total_rows == 5000
+    for i in (0, table.n_blocks - 1):
+        assert a.block_info(i) == b.block_info(i)
+    ra, rb = a.scan(flt, PROJ, want_row_ids=True), b.scan(flt, PROJ, want_row_ids=True)
+    assert ra.selected_rows == rb.selected_rows > 0
+    assert np.array_equal(ra.fetch_row_ids(), rb.fetch_row_ids())
+    for c in range(len(PROJ)):
+        da, la, na = ra.fetch_col(c)
+        db, lb, nb = rb.fetch_col(c)
+        assert np.array_equal(na, nb)
+        if IS_STR[c]:
+            assert np.array_equal(la, lb)
+        else:
+            assert np.array_equal(da, db)
+    ra.free(); rb.free(); a.close(); b.close()
+    bad = d_img.clone()
+    bad[int(table.offsets[1])] ^= 0x55     # magic of block 1
+    torch.cuda.synchronize()
+    with pytest.raises(ob.ObGpuError) as ei:
+        ctx.open_batch(table, device_image_ptr=bad.data_ptr(), host_view=False)
+    assert ei.value.code == ob.OB_INVALID_DATA
