@@ -30,6 +30,124 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 constexpr int kPipeMaxFilterCols = 8;
+constexpr uint32_t kCountHdrBytes = 64u + 16u * kPipeMaxFilterCols;   // count region slot: deltas + flags | range list | regions
+
+// Stages up to 32 byte ranges of a block with 16-byte cp.async. list[i] = {byte offset inside the block, shared
+// address, length (multiple of 16), -}; the warp is split into groups of S lanes, one group per range.
+__device__ __forceinline__ void stage_ranges(const uint8_t *gblk, const uint4 *list, uint32_t n_ranges, int lane) {
+  if (n_ranges == 0) return;
+  const uint32_t sh = n_ranges > 16u ? 0u : (n_ranges > 8u ? 1u : (n_ranges > 4u ? 2u : (n_ranges > 2u ? 3u : (n_ranges > 1u ? 4u : 5u))));
+  const uint32_t grp = (uint32_t)lane >> sh, sub = (uint32_t)lane & ((1u << sh) - 1u);
+  if (grp < n_ranges) {
+    const uint4 e = list[grp];
+    for (uint32_t k = sub * 16u; k < e.z; k += 16u << sh) cp_async16(e.y + k, gblk + e.x + k);
+  }
+}
+
+__device__ __forceinline__ uint32_t warp_sum_u32(uint32_t v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---- lean leaf pieces for blocks of at most 1024 rows (bitmap in registers, lane g owns word g) ----------------------
+// Range leaf over the fixed-width integer dictionary of a K_DICT column -> predicate bitset (bit count = NULL: never set).
+__device__ __forceinline__ void lean_bitset_int_range(const ColDesc &d, const FilterNodeDev &nd, uint32_t sbit, uint32_t *bits, int lane) {
+  const uint32_t n = d.dict_count, dbits = d.dict_data_size * 8u, dpay = sbit + d.dict_payload * 8u;
+  const uint64_t lo = nd.lo, span = nd.span, base = d.base, mask = d.int_mask;
+  const bool fix = d.sign_fix != 0, neg = nd.negate != 0;
+  const uint32_t el = d.elem_len, sc = d.sc;
+  for (uint32_t b0 = 0; b0 < n + 2u; b0 += 32u) {
+    const uint32_t idx = b0 + (uint32_t)lane;
+    bool r = false;
+    if (idx < n) {
+      uint64_t v = (dbits <= 32u ? (uint64_t)sbits32(dpay + idx * dbits, dbits) : sbits(dpay + idx * dbits, dbits)) + base;
+      if (fix) v = sign_fix(mask, v);
+      if (el == 4) v = sc == 1 ? (uint64_t)(int64_t)(int32_t)(uint32_t)v : (uint64_t)(uint32_t)v;
+      else if (el == 1) v = (uint64_t)(uint8_t)v;
+      r = ((v - lo) <= span) != neg;
+    }
+    const uint32_t word = __ballot_sync(0xffffffffu, r);
+    if (lane == 0) bits[b0 >> 5] = word;
+  }
+}
+
+// Rows of a K_DICT column against a predicate bitset over refs; returns the lane's updated bitmap word.
+__device__ __forceinline__ uint32_t lean_rows_bitset(const ColDesc &d, uint32_t sbit, const uint32_t *bits, uint32_t mybm, uint32_t myvalid,
+                                                     uint32_t nwords, uint32_t rows, bool and_mode, int lane) {
+  const uint32_t vbit = sbit + d.val_bit + (uint32_t)lane * d.stride, step = 32u * d.stride, width = d.width, cntp1 = d.dict_count + 1u;
+  for (uint32_t g = 0, bit = vbit; g < nwords; ++g, bit += step) {
+    const uint32_t cur = __shfl_sync(0xffffffffu, mybm, g), vm = __shfl_sync(0xffffffffu, myvalid, g);
+    if (and_mode ? cur == 0u : cur == vm) continue;
+    uint32_t ref = cntp1;
+    if (g * 32u + (uint32_t)lane < rows) ref = min(sbits32(bit, width), cntp1);
+    const uint32_t w = __ballot_sync(0xffffffffu, (bits[ref >> 5] >> (ref & 31u)) & 1u) & vm;
+    if ((uint32_t)lane == g) mybm = and_mode ? (cur & w) : (cur | w);
+  }
+  return mybm;
+}
+
+// AND leaf on a string K_DICT column when few rows are still alive: evaluate the leaf on the survivors' own
+// dictionary entries (one pass over <= alive rows) instead of on every dictionary entry.
+__device__ __forceinline__ uint32_t lean_survivor_str(const ScanParams &p, const FilterNodeDev &nd, const ColDesc &d, uint32_t sbit,
+                                                      const uint8_t *rs_generic, uint32_t mybm, uint32_t nwords, uint32_t alive,
+                                                      uint32_t *bm, int lane) {
+  // survivor list (ascending rows) in the spilled-bitmap scratch: uint16 rows after the 32 bitmap words
+  uint16_t *list = reinterpret_cast<uint16_t *>(bm + 32);
+  const uint32_t local = __popc(mybm);
+  uint32_t inc = local;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += u;
+  }
+  const uint32_t excl = inc - local;
+  for (uint32_t g = 0; g < nwords; ++g) {
+    const uint32_t wg = __shfl_sync(0xffffffffu, mybm, g), og = __shfl_sync(0xffffffffu, excl, g);
+    if ((wg >> lane) & 1u) list[og + __popc(wg & ((1u << lane) - 1u))] = (uint16_t)(g * 32u + (uint32_t)lane);
+  }
+  bm[lane] = mybm;
+  __syncwarp();
+  const uint32_t vbit = sbit + d.val_bit, stride = d.stride, width = d.width, dcount = d.dict_count;
+  const uint32_t ib8 = d.dict_data_size * 8u, ibit = sbit + d.dict_payload * 8u, heap_len = d.dict_end - d.dict_var;
+  const int op = nd.op;
+  const uint8_t *s = rs_generic;   // generic pointer for the (rare) full string compare
+  for (uint32_t j = (uint32_t)lane; j < alive; j += 32u) {
+    const uint32_t row = list[j];
+    const uint32_t ref = sbits32(vbit + row * stride, width);
+    bool pass;
+    if (ref >= dcount) pass = op == OP_NU;
+    else if (op == OP_NU) pass = false;
+    else if (op == OP_NN) pass = true;
+    else {
+      uint32_t cell, len;
+      if (d.dict_fixed) {
+        len = d.dict_data_size;
+        cell = d.dict_payload + ref * len;
+      } else {
+        const uint32_t off = ref == 0 ? 0u : sbits32(ibit + (ref - 1u) * ib8, ib8);
+        const uint32_t end = ref == dcount - 1u ? heap_len : sbits32(ibit + ref * ib8, ib8);
+        cell = d.dict_var + off;
+        len = end - off;
+      }
+      if (op == OP_EQ || op == OP_NE || op == OP_IN) {
+        const uint32_t pl = len < 8u ? len : 8u;
+        const uint64_t pre = pl ? sbits(sbit + cell * 8u, pl * 8u) : 0ull;
+        bool hit = false;
+        for (int k = 0; k < nd.n_params && !hit; ++k) {
+          const ParamDev &pp = p.params[nd.param_begin + k];
+          hit = pp.len == len && (uint64_t)pp.i64 == pre && (len <= 8u || str_cmp(s, cell, len, p.param_heap + pp.heap_off, pp.len) == 0);
+        }
+        pass = hit != (op == OP_NE);
+      } else {
+        pass = str_pred(p, nd, s, cell, len);
+      }
+    }
+    if (!pass) atomicAnd(&bm[row >> 5], ~(1u << (row & 31u)));
+  }
+  __syncwarp();
+  return (uint32_t)lane < nwords ? bm[lane] : 0u;
+}
 
 // =================================================================================================
 // Count, pipelined. Per warp: meta ring (3 slots: block record + the filter columns' plans), region ring (2 slots:
@@ -76,16 +194,15 @@ __global__ void __launch_bounds__(kThreads) obgpu_count_pipe_kernel(const __grid
       view_from_rec(rec, nullptr, bv);
       const ColDesc &d = descs[lane];
       if (!d.ok || !col_region(d, bv, lo, hi) || hi - lo > p.pf_span[lane] || hi > ((rec.size + 15u) & ~15u) + 32u) { bad = true; lo = hi = 0; }
-      hdr[lane] = (int32_t)(64u + p.pf_off[lane]) - (int32_t)lo;
+      hdr[lane] = (int32_t)(kCountHdrBytes + p.pf_off[lane]) - (int32_t)lo;
     }
     const uint32_t badmask = __ballot_sync(0xffffffffu, bad);
     if (lane == 0) hdr[kPipeMaxFilterCols] = (int32_t)badmask;
-    const uint8_t *gblk = p.image + rec.off;
-    for (int i = 0; i < nf; ++i) {
-      const uint32_t l = __shfl_sync(0xffffffffu, lo, i), h = __shfl_sync(0xffffffffu, hi, i);
-      const uint32_t dst = smem_u32(rs) + 64u + p.pf_off[i];
-      for (uint32_t k = (uint32_t)lane * 16u; k < h - l; k += 512u) cp_async16(dst + k, gblk + l + k);
-    }
+    uint4 *list = reinterpret_cast<uint4 *>(rs + 64);
+    const uint32_t have = __ballot_sync(0xffffffffu, hi > lo);
+    if (hi > lo) list[__popc(have & ((1u << lane) - 1u))] = make_uint4(lo, smem_u32(rs) + kCountHdrBytes + p.pf_off[lane], hi - lo, 0u);
+    __syncwarp();
+    stage_ranges(p.image + rec.off, list, (uint32_t)__popc(have), lane);
   };
 
   // prologue: meta(b0), then regions(b0) + meta(b1)
@@ -148,47 +265,97 @@ __global__ void __launch_bounds__(kThreads) obgpu_count_pipe_kernel(const __grid
     c.rle_slot_bytes = c.rle_starts_bytes = 0;
     const bool and_mode = p.simple_shape == 1;
     const int n_leaves = p.n_nodes == 1 ? 1 : p.n_nodes - 1;
-    bool inited = false;
-    for (int i = 0; i < n_leaves; ++i) {
-      const FilterNodeDev &nd = p.nodes[i];
-      if (p.leaf_const != nullptr && p.leaf_const[(int64_t)blk * p.n_nodes + i] != 0) continue;
-      if (nd.op != OP_FALSE && nd.op != OP_TRUE) {   // block-relative offsets of this leaf's column resolve into its staged region
-        c.b.s = rs + hdr[nd.used_idx];
-        c.sbit = (smem_u32(rs) + (uint32_t)hdr[nd.used_idx]) * 8u;
+    uint32_t cnt = 0;
+    if (nwords <= 32u) {
+      // ---- lean path: the block's bitmap lives in registers (lane g owns word g); dictionary-coded leaves run
+      // through explicit shared-memory loads, everything else through the generic leaf code on a spilled bitmap
+      const uint32_t myvalid = (uint32_t)lane < nwords ? valid_mask_of(rows, (uint32_t)lane) : 0u;
+      uint32_t mybm = and_mode ? myvalid : 0u;
+      for (int i = 0; i < n_leaves; ++i) {
+        const FilterNodeDev &nd = p.nodes[i];
+        if (p.leaf_const != nullptr && p.leaf_const[(int64_t)blk * p.n_nodes + i] != 0) continue;
+        const ColDesc &d = descs[nd.used_idx];
+        const uint32_t sbit = (smem_u32(rs) + (uint32_t)hdr[nd.used_idx]) * 8u;
+        if (d.kind == K_DICT && nd.slot >= 0 && nd.op != OP_FALSE && nd.op != OP_TRUE && d.width <= 32u) {
+          uint32_t *bits = bitsets + nd.slot * p.bitset_words;
+          const bool is_str = d.sc == 5;
+          if (is_str && and_mode) {
+            // few surviving rows and a larger dictionary: test the survivors' own entries instead of every entry
+            const uint32_t alive = warp_sum_u32(__popc(mybm));
+            if (alive * 2u <= d.dict_count) {
+              mybm = lean_survivor_str(p, nd, d, sbit, rs + hdr[nd.used_idx], mybm, nwords, alive, bm, lane);
+              continue;
+            }
+          }
+          if (!is_str && nd.range_ok) lean_bitset_int_range(d, nd, sbit, bits, lane);
+          else {
+            c.b.s = rs + hdr[nd.used_idx];
+            c.sbit = sbit;
+            build_dict_bitset(p, c.b, d, nd, bits, t);
+          }
+          __syncwarp();
+          mybm = lean_rows_bitset(d, sbit, bits, mybm, myvalid, nwords, rows, and_mode, lane);
+        } else {
+          bm[lane] = mybm;   // words_cap >= 32 words are reserved for the spilled bitmap
+          __syncwarp();
+          if (nd.op != OP_FALSE && nd.op != OP_TRUE) {
+            c.b.s = rs + hdr[nd.used_idx];
+            c.sbit = sbit;
+          }
+          if (nd.slot >= 0 && is_dict_kind(d)) {
+            build_dict_bitset(p, c.b, d, nd, bitsets + nd.slot * p.bitset_words, t);
+            __syncwarp();
+          }
+          leaf_over_words<false>(p, c, nd, bm, rows, nwords, and_mode, t);
+          __syncwarp();
+          mybm = (uint32_t)lane < nwords ? bm[lane] : 0u;
+        }
+        if (i + 1 < n_leaves && !__any_sync(0xffffffffu, and_mode ? mybm != 0u : mybm != myvalid)) break;   // early-out
       }
-      const ColDesc &d = descs[nd.used_idx];
-      if (nd.slot >= 0 && is_dict_kind(d)) {
-        build_dict_bitset(p, c.b, d, nd, bitsets + nd.slot * p.bitset_words, t);
+      if ((uint32_t)lane < nwords) gbm[lane] = mybm;
+      cnt = __popc(mybm);
+    } else {
+      bool inited = false;
+      for (int i = 0; i < n_leaves; ++i) {
+        const FilterNodeDev &nd = p.nodes[i];
+        if (p.leaf_const != nullptr && p.leaf_const[(int64_t)blk * p.n_nodes + i] != 0) continue;
+        if (nd.op != OP_FALSE && nd.op != OP_TRUE) {   // block-relative offsets of this leaf's column resolve into its staged region
+          c.b.s = rs + hdr[nd.used_idx];
+          c.sbit = (smem_u32(rs) + (uint32_t)hdr[nd.used_idx]) * 8u;
+        }
+        const ColDesc &d = descs[nd.used_idx];
+        if (nd.slot >= 0 && is_dict_kind(d)) {
+          build_dict_bitset(p, c.b, d, nd, bitsets + nd.slot * p.bitset_words, t);
+          __syncwarp();
+        }
+        if (i == 0 && leaf_first_fast<false>(p, c, nd, bm, rows, nwords, t)) {
+          inited = true;
+          __syncwarp();
+          continue;
+        }
+        if (!inited) {
+          for (uint32_t g = (uint32_t)lane; g < nwords; g += 32u) bm[g] = and_mode ? valid_mask_of(rows, g) : 0u;
+          inited = true;
+          __syncwarp();
+        }
+        leaf_over_words<false>(p, c, nd, bm, rows, nwords, and_mode, t);
         __syncwarp();
-      }
-      if (i == 0 && leaf_first_fast<false>(p, c, nd, bm, rows, nwords, t)) {
-        inited = true;
-        __syncwarp();
-        continue;
+        if (i + 1 < n_leaves) {   // early-out of the AND / OR (ob_pushdown_filter.cpp:1603-1615)
+          bool undecided = false;
+          for (uint32_t g = (uint32_t)lane; g < nwords; g += 32u)
+            undecided = undecided || (and_mode ? bm[g] != 0u : bm[g] != valid_mask_of(rows, g));
+          if (!__any_sync(0xffffffffu, undecided)) break;
+        }
       }
       if (!inited) {
         for (uint32_t g = (uint32_t)lane; g < nwords; g += 32u) bm[g] = and_mode ? valid_mask_of(rows, g) : 0u;
-        inited = true;
         __syncwarp();
       }
-      leaf_over_words<false>(p, c, nd, bm, rows, nwords, and_mode, t);
-      __syncwarp();
-      if (i + 1 < n_leaves) {   // early-out of the AND / OR (ob_pushdown_filter.cpp:1603-1615)
-        bool undecided = false;
-        for (uint32_t g = (uint32_t)lane; g < nwords; g += 32u)
-          undecided = undecided || (and_mode ? bm[g] != 0u : bm[g] != valid_mask_of(rows, g));
-        if (!__any_sync(0xffffffffu, undecided)) break;
+      for (uint32_t g = (uint32_t)lane; g < nwords; g += 32u) {
+        const uint32_t w = bm[g];
+        gbm[g] = w;
+        cnt += __popc(w);
       }
-    }
-    if (!inited) {
-      for (uint32_t g = (uint32_t)lane; g < nwords; g += 32u) bm[g] = and_mode ? valid_mask_of(rows, g) : 0u;
-      __syncwarp();
-    }
-    uint32_t cnt = 0;
-    for (uint32_t g = (uint32_t)lane; g < nwords; g += 32u) {
-      const uint32_t w = bm[g];
-      gbm[g] = w;
-      cnt += __popc(w);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
@@ -235,6 +402,30 @@ __device__ __forceinline__ void project_str_dict_shallow(const ScanParams &p, co
       atomicOr(&p.out_nulls[pc][o >> 5], 1u << (o & 31));
       saw_null = true;
     }
+  }
+  if (saw_null) p.has_null[pc] = 1;
+}
+template <bool IDENT>
+__device__ __forceinline__ void lean_project_dict_i64(const ScanParams &p, const ColDesc &d, int pc, const uint16_t *sel, uint32_t cnt,
+                                                      int64_t base_row, uint32_t sbit, int lane) {
+  uint64_t *out = reinterpret_cast<uint64_t *>(p.out_data[pc]) + base_row;
+  const uint32_t vbit = sbit + d.val_bit, stride = d.stride, width = d.width, dcount = d.dict_count;
+  const uint32_t dbits = d.dict_data_size * 8u, dpay = sbit + d.dict_payload * 8u;
+  const uint64_t dbase = d.base, mask = d.int_mask;
+  const bool fix = d.sign_fix != 0;
+  bool saw_null = false;
+  for (uint32_t j = (uint32_t)lane; j < cnt; j += 32u) {
+    const uint32_t ref = sbits32(vbit + ROW(j) * stride, width);
+    uint64_t v = 0;
+    if (ref >= dcount) {
+      const int64_t o = base_row + (int64_t)j;
+      atomicOr(&p.out_nulls[pc][o >> 5], 1u << (o & 31));
+      saw_null = true;
+    } else {
+      v = (dbits <= 32u ? (uint64_t)sbits32(dpay + ref * dbits, dbits) : sbits(dpay + ref * dbits, dbits)) + dbase;
+      if (fix) v = sign_fix(mask, v);
+    }
+    __stcs(&out[j], v);
   }
   if (saw_null) p.has_null[pc] = 1;
 }
@@ -302,14 +493,13 @@ __global__ void __launch_bounds__(kThreads) obgpu_project_pipe_kernel(const __gr
     }
     const uint32_t badmask = __ballot_sync(0xffffffffu, lane < np && nr == 0);
     if (lane == 0) hdr[2 * kMaxProj] = (int32_t)badmask;
-    const uint8_t *gblk = p.image + rec.off;
-    for (int i = 0; i < np; ++i) {
-      const uint32_t l0 = __shfl_sync(0xffffffffu, r[0], i), h0 = __shfl_sync(0xffffffffu, r[1], i);
-      const uint32_t l1 = __shfl_sync(0xffffffffu, r[2], i), h1 = __shfl_sync(0xffffffffu, r[3], i);
-      const uint32_t dst = smem_u32(rs) + hdr_bytes + bm_bytes + p.pp_off[i];
-      for (uint32_t k = (uint32_t)lane * 16u; k < h0 - l0; k += 512u) cp_async16(dst + k, gblk + l0 + k);
-      for (uint32_t k = (uint32_t)lane * 16u; k < h1 - l1; k += 512u) cp_async16(dst + (h0 - l0) + k, gblk + l1 + k);
-    }
+    uint4 *list = reinterpret_cast<uint4 *>(rs + p.pp_list);
+    const uint32_t m0 = __ballot_sync(0xffffffffu, nr >= 1), m1 = __ballot_sync(0xffffffffu, nr == 2);
+    const uint32_t below = (1u << lane) - 1u, dst0 = smem_u32(rs) + hdr_bytes + bm_bytes + (lane < np ? p.pp_off[lane] : 0u);
+    if (nr >= 1) list[__popc(m0 & below)] = make_uint4(r[0], dst0, r[1] - r[0], 0u);
+    if (nr == 2) list[__popc(m0) + __popc(m1 & below)] = make_uint4(r[2], dst0 + (r[1] - r[0]), r[3] - r[2], 0u);
+    __syncwarp();
+    stage_ranges(p.image + rec.off, list, (uint32_t)(__popc(m0) + __popc(m1)), lane);
   };
 
   issue_meta(blk, 0);
@@ -400,6 +590,12 @@ __global__ void __launch_bounds__(kThreads) obgpu_project_pipe_kernel(const __gr
         if (all_rows) project_str_dict_shallow<true>(p, *wdesc, pc, sel, cnt, base, blk_addr, rbit, ibit, lane);
         else project_str_dict_shallow<false>(p, *wdesc, pc, sel, cnt, base, blk_addr, rbit, ibit, lane);
         __syncwarp();
+        continue;
+      }
+      if (wdesc->kind == K_DICT && wdesc->elem_len == 8) {   // fixed-width integer dictionary -> 8-byte datums
+        const uint32_t sb = (smem_u32(rs) + (uint32_t)d0) * 8u;
+        if (all_rows) lean_project_dict_i64<true>(p, *wdesc, pc, sel, cnt, base, sb, lane);
+        else lean_project_dict_i64<false>(p, *wdesc, pc, sel, cnt, base, sb, lane);
         continue;
       }
       c.b.s = rs + d0;

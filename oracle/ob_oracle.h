@@ -205,4 +205,11 @@ int ora_skip_index_filter(const void *agg, int64_t agg_size, int64_t row_count, 
 #ifdef __cplusplus
 }
 #endif
+/* ---- integer stream codecs of CS blocks (ob_stream_codecs.c): ObIntegerStreamDecoder::decode_body -------------------
+ * type = ObIntegerStream::EncodingType (1 RAW, 2 DOUBLE_DELTA_ZIGZAG_RLE, 3 DOUBLE_DELTA_ZIGZAG_PFOR, 4 DELTA_ZIGZAG_RLE,
+ * 5 DELTA_ZIGZAG_PFOR, 6 SIMD_FIXEDPFOR, 8 XOR_FIXED_PFOR); decodes `count` values of width_bytes each from the
+ * codec's bytes (stream data WITHOUT the ObIntegerStreamMeta) into out[count]. */
+int ora_int_stream_decode(int32_t type, uint32_t width_bytes, const void *in, int64_t in_len, int64_t count, void *out,
+                          int64_t *consumed);
+
 #endif

@@ -49,6 +49,7 @@ int with_codec(int type, int uint_bytes, F f) {
   };
   switch (type) {
     case RAW: { ObSimpleBitPacking c; c.set_uint_packing_bits((uint8_t)(uint_bytes * 8)); return run(c); }
+    case 100: { ObSimpleBitPacking c; return run(c); }   // [b][n x b bits]: the remainder coder of the PFOR family
     case SIMD_FIXEDPFOR: { ObCompositeCodec<ObSIMDFixedPFor, ObSimpleBitPacking> c; return run(c); }
     case DOUBLE_DELTA_ZIGZAG_RLE: { ObDoubleDeltaZigzagRle c; return run(c); }
     case DOUBLE_DELTA_ZIGZAG_PFOR: { ObDoubleDeltaZigzagPFor c; return run(c); }

@@ -27,7 +27,7 @@ def _cpu_stamp():
 
 
 def build_oracle():
-    src = [os.path.join(ORACLE_DIR, f) for f in ("ob_oracle.c", "ob_oracle.h", "Makefile")]
+    src = [os.path.join(ORACLE_DIR, f) for f in ("ob_oracle.c", "ob_stream_codecs.c", "ob_oracle.h", "Makefile")]
     stamp_file = os.path.join(ORACLE_DIR, ".built_on")
     stamp = _cpu_stamp()
     try:
