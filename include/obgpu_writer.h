@@ -89,6 +89,16 @@ int obgpu_writer_table_agg_rows(const obgpu_col_input *cols, int32_t n_cols, con
                                 int32_t n_agg_cols, int64_t total_rows, int64_t rows_per_block, void *out,
                                 int64_t out_cap, int64_t *offsets, int64_t *out_size);
 
+/* Integer stream codecs of CS blocks (ObIntegerStream::EncodingType, cs_encoding/ob_stream_encoding_struct.h:64-76:
+ * 1 RAW, 2 DOUBLE_DELTA_ZIGZAG_RLE, 3 DOUBLE_DELTA_ZIGZAG_PFOR, 4 DELTA_ZIGZAG_RLE, 5 DELTA_ZIGZAG_PFOR, 6 SIMD_FIXEDPFOR,
+ * 8 XOR_FIXED_PFOR). The CS writer encodes its column streams with: mode 1 RAW (default); 0 the codec
+ * ObIntegerStreamEncoder::choose_stream_codec would detect (smallest on a sample, cs_encoding/ob_integer_stream_encoder.h:
+ * 195-400); 2..8 that codec wherever it is not larger than RAW. Process-wide setting. */
+int obgpu_writer_set_cs_stream_encoding(int32_t mode);
+/* The codec bytes alone (no ObIntegerStreamMeta) for count values of width_bytes (low bytes of vals[i]); type 0 =
+ * detect. out == NULL: only *out_len. Byte-exact with the reference encoders (ObCodec::encode). */
+int obgpu_writer_stream_encode(int32_t type, int32_t width_bytes, const uint64_t *vals, int64_t count, void *out,
+                               int64_t out_cap, int64_t *out_len);
 
 #ifdef __cplusplus
 }

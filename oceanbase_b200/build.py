@@ -16,7 +16,7 @@ SOURCES = ["obgpu_scan.cu"]
 HEADERS = ["ob_format.h", "scan_device.cuh", "scan_small.cuh", "merge_kernels.cuh", "skip_index.cuh", "stream_codecs.cuh",
            os.path.join(INC, "obgpu_scan.h"), os.path.join(INC, "obgpu_compaction.h"), os.path.join(INC, "obgpu_skip_index.h")]
 WRITER_SOURCES = ["sstable_writer.cpp"]
-WRITER_HEADERS = ["ob_format.h", os.path.join(INC, "obgpu_writer.h"), os.path.join(INC, "obgpu_scan.h"),
+WRITER_HEADERS = ["ob_format.h", "stream_codecs_host.h", os.path.join(INC, "obgpu_writer.h"), os.path.join(INC, "obgpu_scan.h"),
                   os.path.join(INC, "obgpu_skip_index.h")]
 
 

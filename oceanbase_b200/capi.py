@@ -100,6 +100,8 @@ def writer_signatures():
         "obgpu_agg_row_write": (C.c_int, [P(AggCell), i32, i32, vp, i64, P(i64)]),
         "obgpu_writer_block_agg_row": (C.c_int, [P(ColInput), i32, vp, i32, i64, i64, vp, i64, P(i64)]),
         "obgpu_writer_table_agg_rows": (C.c_int, [P(ColInput), i32, vp, i32, i64, i64, vp, i64, vp, P(i64)]),
+        "obgpu_writer_set_cs_stream_encoding": (C.c_int, [i32]),
+        "obgpu_writer_stream_encode": (C.c_int, [i32, i32, vp, i64, vp, i64, P(i64)]),
     }
 
 

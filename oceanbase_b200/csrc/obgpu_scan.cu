@@ -127,10 +127,10 @@ struct ScanParams {
   int32_t pf_n;                             // filter columns = used columns [0, pf_n)
   uint32_t pf_off[8], pf_span[8];           // count: offset / capacity of a filter column's region inside a region slot
   uint32_t pc_meta_bytes, pc_region_bytes;  // count: bytes per meta / region slot
-  uint32_t pc_meta, pc_region, pc_bm, pc_bitset, pc_bytes;   // count: per-warp layout
+  uint32_t pc_meta, pc_region, pc_bm, pc_bitset, pc_bar, pc_bytes;   // count: per-warp layout
   uint32_t pp_off[kMaxProj], pp_span[kMaxProj];              // project: offset / capacity of a column's ranges in a region slot
   uint32_t pp_meta_bytes, pp_region_bytes, pp_hdr_bytes, pp_bm_bytes, pp_list;
-  uint32_t pp_meta, pp_region, pp_sel, pp_wscr, pp_bytes;    // project: per-warp layout
+  uint32_t pp_meta, pp_region, pp_sel, pp_wscr, pp_bar, pp_bytes;    // project: per-warp layout
   uint32_t rle_slot_bytes;    // bytes per run-table slot: mask[words_cap] (u32) + pre[words_cap] (u16)
   uint32_t rows_cap, words_cap;
 };
@@ -2438,19 +2438,20 @@ static void layout_pipe(const obgpu_batch *b, ScanParams &p, int max_smem) {
     if (ok) {
       p.pf_n = nf;
       p.pc_meta_bytes = 64u + (uint32_t)nf * (uint32_t)sizeof(ColDesc);
-      p.pc_region_bytes = (64u + 16u * 8u) + off;   // kCountHdrBytes
+      p.pc_region_bytes = 64u + off;   // kCountHdrBytes
       uint32_t w = 0;
       p.pc_meta = w;   w += 3u * p.pc_meta_bytes;
       p.pc_region = w; w += 2u * p.pc_region_bytes;
       p.pc_bm = w;     w += r16(std::max(p.words_cap, 32u) * 4u) + r16(p.rows_cap * 2u);   // spilled bitmap + survivor list
       p.pc_bitset = w; w += r16((uint32_t)p.n_slots * (uint32_t)p.bitset_words * 4u);
+      p.pc_bar = w;    w += 16u;
       p.pc_bytes = ((w + 127u) & ~127u) + 128u;   // slack: ragged tail words read a few refs past the staged region
       if (p.pc_bytes * (uint32_t)kWarps * 2u <= (uint32_t)max_smem) p.pipe_count = 1;   // at least two CTAs per SM
     }
   }
   // ---- project ------------------------------------------------------------------------------------------------------
   if (p.n_proj + p.want_row_ids > 0) {
-    bool ok = p.n_proj <= 16;   // at most 32 byte ranges per block (stage_ranges)
+    bool ok = p.n_proj <= 32;   // one lane per projected column computes and issues its byte ranges
     uint32_t off = 0;
     for (int i = 0; i < p.n_proj && ok; ++i) {
       const size_t col = (size_t)p.used_col[p.proj_used[i]];
@@ -2462,8 +2463,8 @@ static void layout_pipe(const obgpu_batch *b, ScanParams &p, int max_smem) {
     }
     if (ok) {
       p.pp_meta_bytes = 64u + (uint32_t)std::max(p.n_proj, 1) * (uint32_t)sizeof(ColDesc);
-      p.pp_list = r16((2u * (uint32_t)kMaxProj + 1u) * 4u);
-      p.pp_hdr_bytes = p.pp_list + 32u * 16u;   // deltas + flags | range list
+      p.pp_list = 0;
+      p.pp_hdr_bytes = r16((2u * (uint32_t)kMaxProj + 1u) * 4u);   // deltas + flags
       p.pp_bm_bytes = r16(p.words_cap * 4u);
       p.pp_region_bytes = p.pp_hdr_bytes + p.pp_bm_bytes + off;
       // warp-private RLE scratch: [run values][run table] (same shape as the CTA kernel's)
@@ -2475,6 +2476,7 @@ static void layout_pipe(const obgpu_batch *b, ScanParams &p, int max_smem) {
       p.pp_region = w; w += 2u * p.pp_region_bytes;
       p.pp_sel = w;    w += r16(p.rows_cap * 2u);
       p.pp_wscr = w;   w += p.pw_bytes;
+      p.pp_bar = w;    w += 16u;
       p.pp_bytes = (w + 127u) & ~127u;
       if (p.pp_bytes * (uint32_t)kWarps * 2u <= (uint32_t)max_smem) p.pipe_project = 1;
     }

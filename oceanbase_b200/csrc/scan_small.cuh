@@ -30,19 +30,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 constexpr int kPipeMaxFilterCols = 8;
-constexpr uint32_t kCountHdrBytes = 64u + 16u * kPipeMaxFilterCols;   // count region slot: deltas + flags | range list | regions
-
-// Stages up to 32 byte ranges of a block with 16-byte cp.async. list[i] = {byte offset inside the block, shared
-// address, length (multiple of 16), -}; the warp is split into groups of S lanes, one group per range.
-__device__ __forceinline__ void stage_ranges(const uint8_t *gblk, const uint4 *list, uint32_t n_ranges, int lane) {
-  if (n_ranges == 0) return;
-  const uint32_t sh = n_ranges > 16u ? 0u : (n_ranges > 8u ? 1u : (n_ranges > 4u ? 2u : (n_ranges > 2u ? 3u : (n_ranges > 1u ? 4u : 5u))));
-  const uint32_t grp = (uint32_t)lane >> sh, sub = (uint32_t)lane & ((1u << sh) - 1u);
-  if (grp < n_ranges) {
-    const uint4 e = list[grp];
-    for (uint32_t k = sub * 16u; k < e.z; k += 16u << sh) cp_async16(e.y + k, gblk + e.x + k);
-  }
-}
+constexpr uint32_t kCountHdrBytes = 64u;   // count region slot: deltas + flags | regions
 
 __device__ __forceinline__ uint32_t warp_sum_u32(uint32_t v) {
 #pragma unroll
@@ -72,19 +60,56 @@ __device__ __forceinline__ void lean_bitset_int_range(const ColDesc &d, const Fi
   }
 }
 
-// Rows of a K_DICT column against a predicate bitset over refs; returns the lane's updated bitmap word.
-__device__ __forceinline__ uint32_t lean_rows_bitset(const ColDesc &d, uint32_t sbit, const uint32_t *bits, uint32_t mybm, uint32_t myvalid,
-                                                     uint32_t nwords, uint32_t rows, bool and_mode, int lane) {
-  const uint32_t vbit = sbit + d.val_bit + (uint32_t)lane * d.stride, step = 32u * d.stride, width = d.width, cntp1 = d.dict_count + 1u;
-  for (uint32_t g = 0, bit = vbit; g < nwords; ++g, bit += step) {
-    const uint32_t cur = __shfl_sync(0xffffffffu, mybm, g), vm = __shfl_sync(0xffffffffu, myvalid, g);
-    if (and_mode ? cur == 0u : cur == vm) continue;
-    uint32_t ref = cntp1;
-    if (g * 32u + (uint32_t)lane < rows) ref = min(sbits32(bit, width), cntp1);
-    const uint32_t w = __ballot_sync(0xffffffffu, (bits[ref >> 5] >> (ref & 31u)) & 1u) & vm;
-    if ((uint32_t)lane == g) mybm = and_mode ? (cur & w) : (cur | w);
+// Rows of a K_DICT column against a predicate over refs -- a bitset in shared memory (BITSET) or a ref interval
+// [a, e), complemented inside [0, count) when neg (sorted dictionary). Lane g collects word g; returns the lane's
+// updated bitmap word.
+template <bool BITSET>
+__device__ __forceinline__ uint32_t lean_rows(const ColDesc &d, uint32_t sbit, const uint32_t *bits, uint32_t a, uint32_t e, bool neg,
+                                              uint32_t mybm, uint32_t myvalid, uint32_t nwords, bool and_mode, int lane) {
+  const uint32_t step = 32u * d.stride, width = d.width, dcount = d.dict_count, cntp1 = dcount + 1u, span = e - a;
+  uint32_t bit = sbit + d.val_bit + (uint32_t)lane * d.stride, acc = 0;
+  for (uint32_t g = 0; g < nwords; ++g, bit += step) {
+    // lanes past the last row read a few refs beyond the column (inside the warp's shared memory): masked by myvalid
+    const uint32_t ref = sbits32(bit, width);
+    bool hit;
+    if (BITSET) {
+      const uint32_t rr = min(ref, cntp1);
+      hit = (bits[rr >> 5] >> (rr & 31u)) & 1u;
+    } else {
+      hit = ((ref - a) < span) != (neg && ref < dcount);
+    }
+    const uint32_t w = __ballot_sync(0xffffffffu, hit);
+    if ((uint32_t)lane == g) acc = w;
   }
-  return mybm;
+  acc &= myvalid;
+  return and_mode ? (mybm & acc) : (mybm | acc);
+}
+
+// Sorted fixed-width integer dictionary and a range leaf: the matching refs are [a, e) = [#entries below the range,
+// #entries not above it) (the reference binary-searches the bounds, ob_dict_decoder.cpp:967-988,1085-1176).
+__device__ __forceinline__ void lean_interval_sorted_int(const ColDesc &d, const FilterNodeDev &nd, uint32_t sbit, int lane,
+                                                         uint32_t &a, uint32_t &e) {
+  const uint32_t n = d.dict_count, dbits = d.dict_data_size * 8u, dpay = sbit + d.dict_payload * 8u;
+  const uint64_t lo = nd.lo, hi = nd.lo + nd.span, base = d.base, mask = d.int_mask;
+  const bool fix = d.sign_fix != 0, sg = d.sc == 1;
+  const uint32_t el = d.elem_len;
+  uint32_t below = 0, not_above = 0;
+  for (uint32_t b0 = 0; b0 < n; b0 += 32u) {
+    const uint32_t idx = b0 + (uint32_t)lane;
+    bool lt = false, le = false;
+    if (idx < n) {
+      uint64_t v = (dbits <= 32u ? (uint64_t)sbits32(dpay + idx * dbits, dbits) : sbits(dpay + idx * dbits, dbits)) + base;
+      if (fix) v = sign_fix(mask, v);
+      if (el == 4) v = sg ? (uint64_t)(int64_t)(int32_t)(uint32_t)v : (uint64_t)(uint32_t)v;
+      else if (el == 1) v = (uint64_t)(uint8_t)v;
+      lt = sg ? (int64_t)v < (int64_t)lo : v < lo;
+      le = sg ? (int64_t)v <= (int64_t)hi : v <= hi;
+    }
+    below += __popc(__ballot_sync(0xffffffffu, lt));
+    not_above += __popc(__ballot_sync(0xffffffffu, le));
+  }
+  a = below;
+  e = not_above < below ? below : not_above;
 }
 
 // AND leaf on a string K_DICT column when few rows are still alive: evaluate the leaf on the survivors' own
@@ -162,9 +187,16 @@ __global__ void __launch_bounds__(kThreads) obgpu_count_pipe_kernel(const __grid
   uint8_t *meta0 = wr + p.pc_meta, *reg0 = wr + p.pc_region;
   uint32_t *bm = reinterpret_cast<uint32_t *>(wr + p.pc_bm);
   uint32_t *bitsets = reinterpret_cast<uint32_t *>(wr + p.pc_bitset);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(wr + p.pc_bar);   // one mbarrier per region slot
   const int nf = p.pf_n;
   Team t;
   t.tid = lane; t.nthreads = 32; t.warp = 0; t.nwarps = 1; t.lane = lane; t.bar_id = -1;
+  if (lane == 0) {
+    mbar_init(bars, 1);
+    mbar_init(bars + 1, 1);
+    fence_barrier_init();
+  }
+  __syncwarp();
 
   auto issue_meta = [&](int b, int slot) {
     if (b >= p.n_blocks) return;
@@ -198,11 +230,12 @@ __global__ void __launch_bounds__(kThreads) obgpu_count_pipe_kernel(const __grid
     }
     const uint32_t badmask = __ballot_sync(0xffffffffu, bad);
     if (lane == 0) hdr[kPipeMaxFilterCols] = (int32_t)badmask;
-    uint4 *list = reinterpret_cast<uint4 *>(rs + 64);
-    const uint32_t have = __ballot_sync(0xffffffffu, hi > lo);
-    if (hi > lo) list[__popc(have & ((1u << lane) - 1u))] = make_uint4(lo, smem_u32(rs) + kCountHdrBytes + p.pf_off[lane], hi - lo, 0u);
+    // one bulk copy (TMA) per filter column, all completing on the slot's mbarrier
+    const uint32_t total = warp_sum_u32(hi - lo);
+    uint64_t *bar = bars + rslot;
+    if (lane == 0) mbar_expect_tx(bar, total);
     __syncwarp();
-    stage_ranges(p.image + rec.off, list, (uint32_t)__popc(have), lane);
+    if (hi > lo) tma_bulk_g2s(rs + kCountHdrBytes + p.pf_off[lane], p.image + rec.off + lo, hi - lo, bar);
   };
 
   // prologue: meta(b0), then regions(b0) + meta(b1)
@@ -223,6 +256,7 @@ __global__ void __launch_bounds__(kThreads) obgpu_count_pipe_kernel(const __grid
   for (; blk < p.n_blocks; blk += nwarps_total, ++it) {
     const int ms = it % 3, rsl = it & 1;
     cp_async_wait_all();
+    mbar_wait(bars + rsl, (uint32_t)(it >> 1) & 1u);
     __syncwarp();
     const int b2 = blk + 2 * nwarps_total;
     if (p.blk_const != nullptr && b2 < p.n_blocks) v_next2 = p.blk_const[b2];
@@ -282,10 +316,16 @@ __global__ void __launch_bounds__(kThreads) obgpu_count_pipe_kernel(const __grid
           if (is_str && and_mode) {
             // few surviving rows and a larger dictionary: test the survivors' own entries instead of every entry
             const uint32_t alive = warp_sum_u32(__popc(mybm));
-            if (alive * 2u <= d.dict_count) {
+            if (alive <= d.dict_count) {
               mybm = lean_survivor_str(p, nd, d, sbit, rs + hdr[nd.used_idx], mybm, nwords, alive, bm, lane);
               continue;
             }
+          }
+          if (!is_str && nd.range_ok && d.dict_sorted) {
+            uint32_t a, e;
+            lean_interval_sorted_int(d, nd, sbit, lane, a, e);
+            mybm = lean_rows<false>(d, sbit, nullptr, a, e, nd.negate != 0, mybm, myvalid, nwords, and_mode, lane);
+            goto leaf_done;
           }
           if (!is_str && nd.range_ok) lean_bitset_int_range(d, nd, sbit, bits, lane);
           else {
@@ -294,7 +334,7 @@ __global__ void __launch_bounds__(kThreads) obgpu_count_pipe_kernel(const __grid
             build_dict_bitset(p, c.b, d, nd, bits, t);
           }
           __syncwarp();
-          mybm = lean_rows_bitset(d, sbit, bits, mybm, myvalid, nwords, rows, and_mode, lane);
+          mybm = lean_rows<true>(d, sbit, bits, 0u, 0u, false, mybm, myvalid, nwords, and_mode, lane);
         } else {
           bm[lane] = mybm;   // words_cap >= 32 words are reserved for the spilled bitmap
           __syncwarp();
@@ -310,6 +350,7 @@ __global__ void __launch_bounds__(kThreads) obgpu_count_pipe_kernel(const __grid
           __syncwarp();
           mybm = (uint32_t)lane < nwords ? bm[lane] : 0u;
         }
+      leaf_done:
         if (i + 1 < n_leaves && !__any_sync(0xffffffffu, and_mode ? mybm != 0u : mybm != myvalid)) break;   // early-out
       }
       if ((uint32_t)lane < nwords) gbm[lane] = mybm;
@@ -440,6 +481,13 @@ __global__ void __launch_bounds__(kThreads) obgpu_project_pipe_kernel(const __gr
   uint8_t *meta0 = wr + p.pp_meta, *reg0 = wr + p.pp_region;
   uint16_t *sel = reinterpret_cast<uint16_t *>(wr + p.pp_sel);
   uint8_t *wscr = wr + p.pp_wscr;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(wr + p.pp_bar);   // one mbarrier per region slot
+  if (lane == 0) {
+    mbar_init(bars, 1);
+    mbar_init(bars + 1, 1);
+    fence_barrier_init();
+  }
+  __syncwarp();
   const int np = p.n_proj;
   const uint32_t hdr_bytes = p.pp_hdr_bytes, bm_bytes = p.pp_bm_bytes;
   Team t;
@@ -469,7 +517,10 @@ __global__ void __launch_bounds__(kThreads) obgpu_project_pipe_kernel(const __gr
     const int64_t base = *reinterpret_cast<const int64_t *>(m + 48);
     const uint32_t cnt = (uint32_t)(*reinterpret_cast<const int64_t *>(m + 56) - base);
     const uint32_t rows = rec.rows;
-    if (rows == 0 || cnt == 0 || base + (int64_t)cnt > p.out_cap) return;
+    if (rows == 0 || cnt == 0 || base + (int64_t)cnt > p.out_cap) {
+      if (lane == 0) mbar_expect_tx(bars + rslot, 0u);   // nothing to stage: the slot's phase still completes
+      return;
+    }
     if (cnt != rows) {
       const uint32_t nwords = (rows + 31u) >> 5;
       const uint32_t *gbm = p.bitmap_words + rec.bm_word_off;
@@ -493,13 +544,18 @@ __global__ void __launch_bounds__(kThreads) obgpu_project_pipe_kernel(const __gr
     }
     const uint32_t badmask = __ballot_sync(0xffffffffu, lane < np && nr == 0);
     if (lane == 0) hdr[2 * kMaxProj] = (int32_t)badmask;
-    uint4 *list = reinterpret_cast<uint4 *>(rs + p.pp_list);
-    const uint32_t m0 = __ballot_sync(0xffffffffu, nr >= 1), m1 = __ballot_sync(0xffffffffu, nr == 2);
-    const uint32_t below = (1u << lane) - 1u, dst0 = smem_u32(rs) + hdr_bytes + bm_bytes + (lane < np ? p.pp_off[lane] : 0u);
-    if (nr >= 1) list[__popc(m0 & below)] = make_uint4(r[0], dst0, r[1] - r[0], 0u);
-    if (nr == 2) list[__popc(m0) + __popc(m1 & below)] = make_uint4(r[2], dst0 + (r[1] - r[0]), r[3] - r[2], 0u);
+    // one bulk copy (TMA) per byte range, all completing on the slot's mbarrier
+    const uint32_t len0 = r[1] - r[0], len1 = nr == 2 ? r[3] - r[2] : 0u;
+    const uint32_t total = warp_sum_u32(len0 + len1);
+    uint64_t *bar = bars + rslot;
+    if (lane == 0) mbar_expect_tx(bar, total);
     __syncwarp();
-    stage_ranges(p.image + rec.off, list, (uint32_t)(__popc(m0) + __popc(m1)), lane);
+    if (lane < np && nr >= 1) {
+      uint8_t *dst0 = rs + hdr_bytes + bm_bytes + p.pp_off[lane];
+      const uint8_t *gblk = p.image + rec.off;
+      tma_bulk_g2s(dst0, gblk + r[0], len0, bar);
+      if (nr == 2) tma_bulk_g2s(dst0 + len0, gblk + r[2], len1, bar);
+    }
   };
 
   issue_meta(blk, 0);
@@ -514,6 +570,7 @@ __global__ void __launch_bounds__(kThreads) obgpu_project_pipe_kernel(const __gr
   for (; blk < p.n_blocks; blk += nwarps_total, ++it) {
     const int ms = it % 3, rsl = it & 1;
     cp_async_wait_all();
+    mbar_wait(bars + rsl, (uint32_t)(it >> 1) & 1u);
     __syncwarp();
     issue_regions(blk + nwarps_total, (it + 1) % 3, rsl ^ 1);
     cp_async_commit();

@@ -26,6 +26,7 @@
 
 #include "../../include/obgpu_writer.h"
 #include "ob_format.h"
+#include "stream_codecs_host.h"
 
 namespace {
 
@@ -829,11 +830,16 @@ struct IntStreamPlan {
   bool use_base = false, replace_null = false;
   uint64_t base = 0, null_replaced = 0;
 };
-static void put_stream_meta(Buf &b, const IntStreamPlan &sp) {
+// Stream codec choice for the integer streams of CS blocks (obgpu_writer_set_cs_stream_encoding): 1 = RAW (default),
+// 0 = detect per stream like ObIntegerStreamEncoder::choose_stream_codec, 2..8 = that ObIntegerStream::EncodingType
+// wherever it is not larger than RAW. The stream-offsets stream stays RAW.
+static std::atomic<int> g_cs_stream_mode{1};
+
+static void put_stream_meta(Buf &b, const IntStreamPlan &sp, int type = IS_RAW) {
   uint8_t *p = b.grow(4);
   p[0] = INTEGER_STREAM_META_V2;
   p[1] = (uint8_t)((sp.use_base ? IS_USE_BASE : 0) | (sp.replace_null ? IS_REPLACE_NULL_VALUE : 0));
-  p[2] = IS_RAW;
+  p[2] = (uint8_t)type;
   p[3] = width_tag(sp.width);
   if (sp.use_base) put_vi64(b, sp.base);
   if (sp.replace_null) put_vi64(b, sp.null_replaced);
@@ -849,12 +855,38 @@ static void put_string_stream_meta(Buf &b, bool zero_len_null, int64_t fixed_len
   put_vi64(b, uncompressed_len);
   if (fixed_len >= 0) put_vi64(b, (uint64_t)fixed_len);
 }
+// One integer stream: serialized ObIntegerStreamMeta + the codec's bytes for `vals` (already minus the base).
+// ObIntegerStreamEncoder::inner_encode (cs_encoding/ob_integer_stream_encoder.h:224-290): the chosen codec, RAW when
+// its output is larger than the raw array.
+static void emit_int_stream(Buf &body, const IntStreamPlan &sp, const std::vector<uint64_t> &vals, bool allow_codecs = true) {
+  const int mode = allow_codecs ? g_cs_stream_mode.load(std::memory_order_relaxed) : 1;
+  const uint32_t wb = (uint32_t)sp.width;
+  int type = obstream::T_RAW;
+  if (mode == 0) {
+    bool mono = true;
+    const uint64_t m = obstream::mask_of(wb);
+    for (size_t k = 1; k < vals.size() && mono; ++k) mono = (vals[k] & m) >= (vals[k - 1] & m);
+    type = obstream::detect(wb, vals.data(), vals.size(), mono);
+  } else if (mode >= 2 && mode <= 8 && mode != obstream::T_UNIVERSAL) {
+    type = mode;
+  }
+  std::vector<uint8_t> enc;
+  if (type != obstream::T_RAW) {
+    obstream::encode(type, wb, vals.data(), vals.size(), enc);
+    if (enc.size() > vals.size() * (size_t)wb) type = obstream::T_RAW;
+  }
+  put_stream_meta(body, sp, type);
+  if (type == obstream::T_RAW) {
+    uint8_t *d = body.grow((size_t)wb * vals.size());
+    for (size_t k = 0; k < vals.size(); ++k) memcpy(d + k * (size_t)wb, &vals[k], (size_t)wb);
+  } else if (!enc.empty()) {
+    memcpy(body.grow(enc.size()), enc.data(), enc.size());
+  }
+}
 static void put_raw_stream(Buf &body, const std::vector<uint64_t> &vals, uint64_t max_value) {
   IntStreamPlan sp;
   sp.width = (int)byte_packed_int_size(max_value);
-  put_stream_meta(body, sp);
-  uint8_t *d = body.grow((size_t)sp.width * vals.size());
-  for (size_t k = 0; k < vals.size(); ++k) memcpy(d + k * (size_t)sp.width, &vals[k], (size_t)sp.width);
+  emit_int_stream(body, sp, vals);
 }
 
 // ObStringColumnEncoder::do_init_ (cs_encoding/ob_string_column_encoder.cpp:59-139) decides fixed length / NULL
@@ -1049,11 +1081,10 @@ int BlockBuilder::build_cs(std::vector<uint8_t> &block, int64_t original) {
       } else {
         dp.width = (int)byte_packed_int_size((uint64_t)vals.back());
       }
-      put_stream_meta(body, dp);
-      uint8_t *dd = body.grow((size_t)dp.width * vals.size());
-      for (size_t k = 0; k < vals.size(); ++k) {
-        const uint64_t v = (uint64_t)vals[k] - dp.base;
-        memcpy(dd + k * (size_t)dp.width, &v, (size_t)dp.width);
+      {
+        std::vector<uint64_t> dv(vals.size());
+        for (size_t k = 0; k < vals.size(); ++k) dv[k] = (uint64_t)vals[k] - dp.base;
+        emit_int_stream(body, dp, dv);
       }
       stream_end.push_back(header_size + (uint32_t)body.size());
       std::vector<uint64_t> refs((size_t)nrows);
@@ -1133,13 +1164,13 @@ int BlockBuilder::build_cs(std::vector<uint8_t> &block, int64_t original) {
       for (int64_t r = 0; r < nrows; ++r)
         if (c.is_null(r)) bm[r / 8] |= (uint8_t)(1u << (7 - r % 8));  // MSB first (ob_icolumn_cs_encoder.cpp:100-123)
     }
-    put_stream_meta(body, sp);
-    uint8_t *data = body.grow((size_t)sp.width * (size_t)nrows);
-    for (int64_t r = 0; r < nrows; ++r) {
-      uint64_t v;
-      if (c.is_null(r)) v = sp.replace_null ? sp.null_replaced - sp.base : 0;
-      else v = (sgn ? (uint64_t)c.ival(r) : ((uint64_t)c.ival(r) & mask)) - sp.base;
-      memcpy(data + (size_t)r * (size_t)sp.width, &v, (size_t)sp.width);
+    {
+      std::vector<uint64_t> cv((size_t)nrows);
+      for (int64_t r = 0; r < nrows; ++r) {
+        if (c.is_null(r)) cv[(size_t)r] = sp.replace_null ? sp.null_replaced - sp.base : 0;
+        else cv[(size_t)r] = (sgn ? (uint64_t)c.ival(r) : ((uint64_t)c.ival(r) & mask)) - sp.base;
+      }
+      emit_int_stream(body, sp, cv);
     }
     stream_end.push_back(header_size + (uint32_t)body.size());
   }
@@ -1542,5 +1573,25 @@ int obgpu_writer_table_agg_rows(const obgpu_col_input *cols, int32_t n_cols, con
   return OBGPU_SUCCESS;
 }
 
+
+int obgpu_writer_set_cs_stream_encoding(int32_t mode) {
+  if (mode < 0 || mode > 8 || mode == obstream::T_UNIVERSAL) return OBGPU_INVALID_ARGUMENT;
+  g_cs_stream_mode.store(mode);
+  return OBGPU_SUCCESS;
+}
+
+int obgpu_writer_stream_encode(int32_t type, int32_t width_bytes, const uint64_t *vals, int64_t count, void *out, int64_t out_cap,
+                               int64_t *out_len) {
+  if (!vals || !out_len || count < 0 || (width_bytes != 1 && width_bytes != 2 && width_bytes != 4 && width_bytes != 8))
+    return OBGPU_INVALID_ARGUMENT;
+  std::vector<uint8_t> enc;
+  if (type == 0) type = obstream::detect((uint32_t)width_bytes, vals, (size_t)count, false);
+  if (!obstream::encode(type, (uint32_t)width_bytes, vals, (size_t)count, enc)) return OBGPU_NOT_SUPPORTED;
+  *out_len = (int64_t)enc.size();
+  if (!out) return OBGPU_SUCCESS;
+  if ((int64_t)enc.size() > out_cap) return OBGPU_BUF_NOT_ENOUGH;
+  if (!enc.empty()) memcpy(out, enc.data(), enc.size());
+  return OBGPU_SUCCESS;
+}
 
 }  // extern "C"

@@ -212,4 +212,8 @@ int ora_skip_index_filter(const void *agg, int64_t agg_size, int64_t row_count, 
 int ora_int_stream_decode(int32_t type, uint32_t width_bytes, const void *in, int64_t in_len, int64_t count, void *out,
                           int64_t *consumed);
 
+/* CS block -> the same block with every integer stream restated as RAW (what ObCSMicroBlockTransformer::full_transform
+ * achieves at cache fill, kept in the on-disk layout; see ob_stream_codecs.c). out == NULL: only *out_size. */
+int ora_cs_transform(const void *block, int64_t size, void *out, int64_t out_cap, int64_t *out_size);
+
 #endif

@@ -16,6 +16,7 @@
  */
 #include "ob_oracle.h"
 
+#include <stdlib.h>
 #include <string.h>
 
 /* ---- plain LSB-first bit reader over [p, end) ------------------------------------------------------------ */
@@ -211,4 +212,163 @@ int ora_int_stream_decode(int32_t type, uint32_t width_bytes, const void *in, in
     case 8: return dec_pfor_family(3, p, in_len, width_bytes, count, out, consumed);
     default: return ORA_NOT_SUPPORTED;   /* 7 UNIVERSAL_COMPRESS needs a general compressor (deps/3rd, absent) */
   }
+}
+
+/* =============================================================================================
+ * CS block -> the same block with every integer stream restated as RAW.
+ *
+ * The reference decodes non-RAW integer streams once, when a block enters the block cache
+ * (ObCSMicroBlockTransformer::full_transform, cs_encoding/ob_cs_micro_block_transformer.cpp:721-898 ->
+ * ObIntegerStreamDecoder::transform_to_raw_array, ob_integer_stream_decoder.cpp:398-431), into an in-memory
+ * image that also carries C++ structs (ObMicroBlockTransformDesc, decoder ctxs). Here the result is restated
+ * in the ON-DISK layout instead -- what ObMicroBlockCSEncoder::build_block would have written had every stream
+ * chosen RAW: [header][ObAllColumnHeader][ObCSColumnHeader x ncol][per column: meta + streams (ObIntegerStreamMeta
+ * with type RAW + width-byte array)][all string data][stream END offsets, RAW] -- so the RAW-only readers (this
+ * oracle's block decoder, the device kernels) run on it unchanged. The micro header is copied as is (its length /
+ * checksum fields keep describing the on-disk block, as in the reference's deep copy).
+ * ============================================================================================= */
+typedef struct xmeta { uint8_t version, attr, type, wtag; uint32_t width; int64_t meta_len; } xmeta;
+
+static uint32_t x_rd32(const uint8_t *p) { uint32_t v; memcpy(&v, p, 4); return v; }
+static uint16_t x_rd16(const uint8_t *p) { uint16_t v; memcpy(&v, p, 2); return v; }
+
+static int x_parse_meta(const uint8_t *p, int64_t len, xmeta *m) {   /* ObIntegerStreamMeta::deserialize */
+  if (len < 4) return ORA_INVALID_DATA;
+  int64_t pos = 4;
+  m->version = p[0]; m->attr = p[1]; m->type = p[2]; m->wtag = p[3];
+  for (int k = 0; k < 2; ++k) {
+    if (!(m->attr & (1 << k))) continue;
+    for (;;) {   /* vi64 */
+      if (pos >= len) return ORA_INVALID_DATA;
+      if (!(p[pos++] & 0x80)) break;
+    }
+  }
+  if (m->attr & 0x4) return ORA_NOT_SUPPORTED;   /* decimal int: precision fields follow */
+  if (m->version > 0) { if (pos >= len) return ORA_INVALID_DATA; ++pos; }
+  if (m->wtag > 3) return ORA_NOT_SUPPORTED;
+  m->width = 1u << m->wtag;
+  m->meta_len = pos;
+  return ORA_SUCCESS;
+}
+
+static uint32_t x_bytes_for(uint64_t v) { return v <= 0xff ? 1u : (v <= 0xffff ? 2u : (v <= 0xffffffffull ? 4u : 8u)); }
+
+int ora_cs_transform(const void *block, int64_t size, void *out, int64_t out_cap, int64_t *out_size) {
+  if (!block || size < 64 || !out_size) return ORA_INVALID_ARGUMENT;
+  const uint8_t *p = (const uint8_t *)block;
+  const uint32_t header_size = x_rd32(p + 4), ncol = x_rd16(p + 10), rows = x_rd32(p + 16);
+  if (p[20] != 3 /* CS_ENCODING_ROW_STORE */ || header_size < 64 || (int64_t)header_size + 12 + 4ll * ncol > size) return ORA_INVALID_ARGUMENT;
+  const uint8_t *ah = p + header_size;
+  if (ah[0] != 0 || (ah[1] & 0x3)) return ORA_NOT_SUPPORTED;
+  const uint32_t all_string_len = x_rd32(ah + 2), offsets_len = x_rd32(ah + 6), n_streams_total = x_rd16(ah + 10);
+  if ((int64_t)offsets_len + all_string_len > size - header_size) return ORA_INVALID_DATA;
+  const uint32_t str_begin = (uint32_t)(size - offsets_len - all_string_len);
+  /* stream END offsets (an integer stream of its own, any codec) */
+  uint64_t *ends = (uint64_t *)calloc(n_streams_total + 1u, sizeof(uint64_t));
+  uint64_t *new_ends = (uint64_t *)calloc(n_streams_total + 1u, sizeof(uint64_t));
+  if (!ends || !new_ends) { free(ends); free(new_ends); return ORA_ERR_UNEXPECTED; }
+  int ret = ORA_SUCCESS;
+  xmeta om;
+  memset(&om, 0, sizeof(om));
+  if (n_streams_total > 0) {
+    const uint8_t *so = p + size - offsets_len;
+    if ((ret = x_parse_meta(so, offsets_len, &om))) { free(ends); free(new_ends); return ret; }
+    uint8_t tmp[8 * 4096];
+    if ((om.attr & 0x3) || n_streams_total > 4096) { free(ends); free(new_ends); return ORA_NOT_SUPPORTED; }
+    if ((ret = ora_int_stream_decode(om.type, om.width, so + om.meta_len, offsets_len - om.meta_len, n_streams_total, tmp, 0))) { free(ends); free(new_ends); return ret; }
+    for (uint32_t k = 0; k < n_streams_total; ++k) {
+      uint64_t v = 0;
+      memcpy(&v, tmp + (size_t)k * om.width, om.width);
+      ends[k] = v;
+    }
+  }
+  /* output: worst case every stream grows to 8 bytes per value */
+  const int64_t cap_need = size + 16;   /* rechecked as we go */
+  (void)cap_need;
+  uint8_t *o = (uint8_t *)out;
+  int64_t opos = 0;
+#define X_PUT(src, n) do { const int64_t n__ = (int64_t)(n); if (o) { if (opos + n__ > out_cap) { ret = ORA_BUF_NOT_ENOUGH; goto done; } memcpy(o + opos, (src), (size_t)n__); } opos += n__; } while (0)
+  X_PUT(p, header_size + 12u + 4u * ncol);
+  {
+    const int64_t bitmap_bytes = ((int64_t)rows + 7) / 8;
+    uint32_t pos = header_size + 12u + 4u * ncol;
+    int32_t si = 0;   /* next stream index */
+    for (uint32_t c = 0; c < ncol && ret == ORA_SUCCESS; ++c) {
+      const uint8_t *h = ah + 12 + 4 * c;
+      const uint8_t type = h[1], attrs = h[2];
+      int64_t meta_len;
+      /* streams of this column: (is_string, count) in order */
+      int n_s = 0, is_str[3] = {0, 0, 0};
+      int64_t cnt[3] = {0, 0, 0};
+      if (type == 0) { meta_len = ((attrs & 0x02) ? bitmap_bytes : 0) + ((attrs & 0x08) ? bitmap_bytes : 0); n_s = 1; cnt[0] = rows; }
+      else if (type == 1) {
+        meta_len = ((attrs & 0x02) ? bitmap_bytes : 0) + ((attrs & 0x08) ? bitmap_bytes : 0);
+        is_str[0] = 1; n_s = 1;
+        if (!(attrs & 0x01)) { cnt[1] = rows; n_s = 2; }
+      } else if (type == 2 || type == 3) {
+        if ((int64_t)pos + 10 > size) { ret = ORA_INVALID_DATA; break; }
+        const uint8_t *dm = p + pos;
+        const uint32_t distinct = x_rd32(dm + 2);
+        const int64_t ref_cnt = (dm[1] & 0x4) ? (int64_t)x_rd32(dm + 6) : (int64_t)rows;
+        meta_len = 10 + ((attrs & 0x08) ? bitmap_bytes : 0);
+        if (distinct > 0) {
+          if (type == 2) { cnt[0] = distinct; cnt[1] = ref_cnt; n_s = 2; }
+          else if (attrs & 0x01) { is_str[0] = 1; cnt[1] = ref_cnt; n_s = 2; }
+          else { is_str[0] = 1; cnt[1] = distinct; cnt[2] = ref_cnt; n_s = 3; }
+        }
+      } else { ret = ORA_NOT_SUPPORTED; break; }
+      if ((int64_t)pos + meta_len > size) { ret = ORA_INVALID_DATA; break; }
+      X_PUT(p + pos, meta_len);
+      uint32_t at = pos + (uint32_t)meta_len;
+      for (int k = 0; k < n_s; ++k, ++si) {
+        if (si >= (int32_t)n_streams_total) { ret = ORA_INVALID_DATA; break; }
+        const uint32_t end = (uint32_t)ends[si];
+        if (end < at || end > (uint32_t)size) { ret = ORA_INVALID_DATA; break; }
+        if (is_str[k]) {
+          X_PUT(p + at, end - at);                 /* ObStringStreamMeta only: the bytes live in the all-string-data area */
+        } else {
+          xmeta m;
+          if ((ret = x_parse_meta(p + at, end - at, &m))) break;
+          if (o) {
+            if (opos + m.meta_len + cnt[k] * (int64_t)m.width > out_cap) { ret = ORA_BUF_NOT_ENOUGH; break; }
+            memcpy(o + opos, p + at, (size_t)m.meta_len);
+            o[opos + 2] = 1;                        /* ObIntegerStream::EncodingType::RAW */
+            int64_t used = 0;
+            ret = ora_int_stream_decode(m.type, m.width, p + at + m.meta_len, (int64_t)end - at - m.meta_len, cnt[k],
+                                        o + opos + m.meta_len, &used);
+            if (ret) break;
+            if (used != (int64_t)end - at - m.meta_len) { ret = ORA_INVALID_DATA; break; }
+          }
+          opos += m.meta_len + cnt[k] * (int64_t)m.width;
+        }
+        new_ends[si] = (uint64_t)opos;
+        at = end;
+      }
+      pos = n_s == 0 ? pos + (uint32_t)meta_len : (uint32_t)ends[si - 1];
+    }
+    if (ret == ORA_SUCCESS && si != (int32_t)n_streams_total) ret = ORA_INVALID_DATA;
+    if (ret == ORA_SUCCESS && pos != str_begin) ret = ORA_INVALID_DATA;
+  }
+  if (ret) goto done;
+  X_PUT(p + str_begin, all_string_len);
+  {
+    const int64_t off_at = opos;
+    if (n_streams_total > 0) {
+      const uint32_t w = x_bytes_for(new_ends[n_streams_total - 1]);
+      if (w > 4) { ret = ORA_NOT_SUPPORTED; goto done; }
+      uint8_t meta[8];
+      memcpy(meta, p + size - offsets_len, (size_t)om.meta_len);
+      meta[2] = 1;
+      meta[3] = (uint8_t)(w == 1 ? 0 : (w == 2 ? 1 : 2));
+      X_PUT(meta, om.meta_len);
+      for (uint32_t k = 0; k < n_streams_total; ++k) X_PUT(&new_ends[k], w);
+    }
+    if (o) { const uint32_t nl = (uint32_t)(opos - off_at); memcpy(o + header_size + 6, &nl, 4); }
+  }
+done:
+#undef X_PUT
+  free(ends);
+  free(new_ends);
+  *out_size = opos;
+  return ret;
 }

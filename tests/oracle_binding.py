@@ -146,6 +146,35 @@ def ora_check(code, what):
         raise RuntimeError(f"oracle {what} failed: {code}")
 
 
+def cs_transform(buf: np.ndarray) -> np.ndarray:
+    """CS block -> the same block with every integer stream restated as RAW (ora_cs_transform)."""
+    L = oracle()
+    L.ora_cs_transform.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
+    src = np.ascontiguousarray(buf, dtype=np.uint8)
+    n = C.c_int64(0)
+    ora_check(L.ora_cs_transform(src.ctypes.data, src.size, None, 0, C.byref(n)), "ora_cs_transform(size)")
+    out = np.zeros(n.value, dtype=np.uint8)
+    ora_check(L.ora_cs_transform(src.ctypes.data, src.size, out.ctypes.data, out.size, C.byref(n)), "ora_cs_transform")
+    return out[:n.value]
+
+
+def cs_transform_table(table):
+    """Every block of a CS table through cs_transform: a new TableImage (128-byte aligned blocks)."""
+    from oceanbase_b200.sstable import TableImage
+    parts, offs, sizes, pos = [], [], [], 0
+    for i in range(table.n_blocks):
+        t = cs_transform(table.block(i))
+        pad = (-len(t)) % 128
+        offs.append(pos)
+        sizes.append(len(t))
+        parts.append(t)
+        if pad:
+            parts.append(np.zeros(pad, dtype=np.uint8))
+        pos += len(t) + pad
+    return TableImage(np.concatenate(parts), np.array(offs, dtype=np.int64), np.array(sizes, dtype=np.int64), table.total_rows,
+                      table.n_cols)
+
+
 class Block:
     """One parsed micro-block view for the oracle."""
 

@@ -82,3 +82,22 @@ def test_oracle_decodes_reference_streams(t, ub):
         assert r == 0, (TYPES[t], ub, name, a.size, r)
         assert np.array_equal(got, a), (TYPES[t], ub, name, a.size)
         assert cons.value == used.value == enc.size, (TYPES[t], ub, name, a.size, cons.value, used.value, enc.size)
+
+
+@pytest.mark.parametrize("t", sorted(TYPES))
+@pytest.mark.parametrize("ub", sorted(WIDTHS))
+def test_writer_encoders_are_byte_exact(t, ub):
+    """The writer's stream encoders (oceanbase_b200/csrc/stream_codecs_host.h) produce the reference encoders' bytes."""
+    L = _ref()
+    from oceanbase_b200.capi import lib
+    dt = WIDTHS[ub]
+    rng = np.random.default_rng(77 * t + ub)
+    for name, a in datasets(dt, rng):
+        a = np.ascontiguousarray(a)
+        want = ref_encode(L, t, a)
+        v64 = np.ascontiguousarray(a.astype(np.uint64))
+        n = C.c_int64(0)
+        out = np.zeros(a.size * ub * 2 + 4096, dtype=np.uint8)
+        r = lib.obgpu_writer_stream_encode(t, ub, v64.ctypes.data, a.size, out.ctypes.data, out.size, C.byref(n))
+        assert r == 0
+        assert n.value == want.size and np.array_equal(out[:n.value], want), (TYPES[t], ub, name, a.size, n.value, want.size)
