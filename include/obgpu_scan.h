@@ -85,6 +85,15 @@ typedef struct obgpu_ctx obgpu_ctx;       /* per worker thread: device, stream, 
 typedef struct obgpu_batch obgpu_batch;   /* a page batch: N micro-blocks resident in HBM       */
 typedef struct obgpu_result obgpu_result; /* device-resident result of one fused scan           */
 
+/* common::ObDatum (share/datum/ob_datum.h:109-177): 12 packed bytes */
+#pragma pack(push, 1)
+typedef struct obgpu_datum {
+  uint64_t ptr;
+  uint32_t pack; /* len:29 | flag:2 | null:1 */
+} obgpu_datum;
+#pragma pack(pop)
+#define OBGPU_DATUM_NULL_BIT 0x80000000u
+
 /* =============================================================================================
  * Context
  * ============================================================================================= */
@@ -223,6 +232,12 @@ int obgpu_result_block_tables(obgpu_result *res, const int64_t **sel_offset_dev,
  * that bit 0 is row_begin. */
 int obgpu_result_fetch_col(obgpu_result *res, int32_t i, int64_t row_begin, int64_t row_count,
                            void *host_data, void *host_aux, uint64_t *host_nulls);
+/* Rows [row_begin, row_begin + row_count) of projected column i as ObDatum[] (datum format of the batch result):
+ * formatted on the device, one copy back. Integer classes: host_slots receives 8 bytes per row (value in the low
+ * datum-length bytes) and datum k points at host_slots + 8 k; strings: ptr / len as in obgpu_project_datums
+ * (host_slots may be NULL). */
+int obgpu_result_fetch_datums(obgpu_result *result, int32_t i, int64_t row_begin, int64_t row_count,
+                              obgpu_datum *host_datums, void *host_slots);
 /* Same for several columns with ONE stream synchronisation (all copies are enqueued first): cols[k]
  * goes to host_data[k] / host_aux[k] / host_nulls[k]; any of the three arrays (or entries) may be NULL. */
 int obgpu_result_fetch_cols(obgpu_result *res, int32_t n_cols, const int32_t *cols, int64_t row_begin,
@@ -281,6 +296,15 @@ int obgpu_project_fixed(obgpu_batch *batch, int32_t block, int32_t col, const in
 int obgpu_project_discrete(obgpu_batch *batch, int32_t block, int32_t col, const int32_t *row_ids,
                            int64_t row_cap, int64_t vec_offset, uint64_t string_base,
                            uint64_t *ptrs, int32_t *lens, uint64_t *nulls, int32_t *has_null);
+
+/* ---- datum format (ObMicroBlockDecoder::get_rows into ObDatum[], encoding/ob_micro_block_decoder.cpp:2100-2140,
+ * get_col_datums :2201-2237): common::ObDatum is 12 packed bytes -- 8-byte pointer + {len:29, flag:2, null:1}
+ * (share/datum/ob_datum.h:109-177). Integer classes: the caller's datums already point at their reserved 8-byte
+ * slots (the expression's datum buffer); the value is written THROUGH datum.ptr with the datum length of the type
+ * (8 / 4 / 1) like load_data_to_datum. Strings: ptr = string_base + offset of the cell in the caller's image, len set.
+ * NULL: ObDatum::set_null() (len 0, null 1; ptr untouched). */
+int obgpu_project_datums(obgpu_batch *batch, int32_t block, int32_t col, const int32_t *row_ids,
+                         int64_t row_cap, int64_t datum_offset, uint64_t string_base, obgpu_datum *datums);
 
 /* Library self-description (build id, arch) for logs. */
 const char *obgpu_version(void);

@@ -139,6 +139,8 @@ def declared_signatures():
         "obgpu_bitmap_to_row_ids": (C.c_int, [vp, vp, i64, P(i64), i64, i64, i64, vp, P(i64)]),
         "obgpu_project_fixed": (C.c_int, [vp, i32, i32, vp, i64, i64, vp, i32, vp, P(i32)]),
         "obgpu_project_discrete": (C.c_int, [vp, i32, i32, vp, i64, i64, u64, vp, vp, vp, P(i32)]),
+        "obgpu_project_datums": (C.c_int, [vp, i32, i32, vp, i64, i64, u64, vp]),
+        "obgpu_result_fetch_datums": (C.c_int, [vp, i32, i64, i64, vp, vp]),
         "obgpu_version": (C.c_char_p, []),
         # include/obgpu_compaction.h
         "obgpu_batch_decode_column": (C.c_int, [vp, i32, vp, vp]),

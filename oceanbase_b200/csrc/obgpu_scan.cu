@@ -63,6 +63,9 @@ struct ParamDev {
 
 constexpr int kParamHeap = 768;
 
+// layout of obcs::XformRec (stream_codecs.cuh), declared here for the kernel parameter block
+struct XformRecFwd { uint64_t orig_off; int64_t str_delta; };
+
 
 struct ScanParams {
   const uint8_t *image;
@@ -106,6 +109,8 @@ struct ScanParams {
   // and the same per (block, filter node)
   const uint8_t *blk_const;
   const uint8_t *leaf_const;
+  // blocks of a batch whose CS streams were restated as RAW at open (stream_codecs.cuh): where each block came from
+  const struct XformRecFwd *xf;
   // ---- shared-memory layout (bytes from the dynamic smem base) -------------------------------------
   // single-block kernels: [block][bitsets][rle tables][descs]
   // scan kernel:          [stage 0..kStages-1][bitsets][scratch 0][scratch 1], scratch = sel|bm|wpre|rle|descs
@@ -254,6 +259,16 @@ __device__ __forceinline__ bool str_pred(const ScanParams &p, const FilterNodeDe
   if (op <= OP_NE) return cmp_to_bool(op, cmp3(0));
   if (op == OP_BT) return cmp3(0) >= 0 && cmp3(1) <= 0;
   return false;
+}
+
+// Address the string cells of block `tile` are reported at: string_base + the block's offset in the CALLER's image.
+// In a batch restated at open (CS stream codecs) the block moved and its string area shifted: the record undoes both.
+__device__ __forceinline__ uint64_t block_string_addr(const ScanParams &p, int tile, uint64_t off) {
+  if (p.xf != nullptr) {
+    const XformRecFwd x = p.xf[tile];
+    return p.string_base + x.orig_off + (uint64_t)x.str_delta;
+  }
+  return p.string_base + off;
 }
 
 // Everything a team needs to know about the block it is working on.
@@ -1438,7 +1453,7 @@ __global__ void __launch_bounds__(kThreads) obgpu_project_kernel(const __grid_co
       if (all_rows) for (uint32_t j = (uint32_t)tid; j < cnt; j += kThreads) rid[j] = (int32_t)j;
       else for (uint32_t j = (uint32_t)tid; j < cnt; j += kThreads) rid[j] = (int32_t)sel[j];
     }
-    const uint64_t blk_addr = p.string_base + rec.off;
+    const uint64_t blk_addr = block_string_addr(p, tile, rec.off);
     Team t;  // one warp per column
     t.tid = lane; t.nthreads = 32; t.warp = 0; t.nwarps = 1; t.lane = lane; t.bar_id = -1;
     for (;;) {
@@ -1532,7 +1547,7 @@ __global__ void __launch_bounds__(kThreads) obgpu_project_sparse_kernel(const __
   c.descs = wdesc;
   c.rle_base = nullptr;
   c.rle_slot_bytes = c.rle_starts_bytes = 0;
-  const uint64_t blk_addr = p.string_base + rec.off;
+  const uint64_t blk_addr = block_string_addr(p, tile, rec.off);
   Team t;
   t.tid = lane; t.nthreads = 32; t.warp = 0; t.nwarps = 1; t.lane = lane; t.bar_id = -1;
   for (int pc = 0; pc < p.n_proj; ++pc) {
@@ -1631,7 +1646,7 @@ __global__ void __launch_bounds__(kThreads) obgpu_project_block_kernel(
     rt = c.rle_table(d.rle_slot);
     rtp = &rt;
   }
-  const uint64_t blk_addr = p.string_base + p.blk_off[tile];
+  const uint64_t blk_addr = block_string_addr(p, tile, p.blk_off[tile]);
   for (int64_t i = t.tid; i < row_cap; i += kThreads) {
     const int32_t r = row_ids[i];
     if (r < 0 || (uint32_t)r >= c.b.row_count) {
@@ -1697,6 +1712,7 @@ __global__ void __launch_bounds__(kThreads) obgpu_bitmap_row_ids_kernel(const ui
 }
 
 #include "scan_small.cuh"
+#include "stream_codecs.cuh"
 
 // =================================================================================================
 // Host side
@@ -1758,6 +1774,9 @@ struct obgpu_batch {
   // skip index: serialized aggregate rows of the blocks (obgpu_batch_set_agg_rows), [d_agg_off[b], d_agg_off[b + 1])
   uint8_t *d_agg = nullptr;
   int64_t *d_agg_off = nullptr;
+  // CS stream codecs: blocks restated as RAW at open (stream_codecs.cuh); nullptr when nothing had to be decoded
+  obcs::XformRec *d_xf = nullptr;
+  int64_t restated_blocks = 0, decoded_streams = 0;
 };
 
 struct ResultCol {
@@ -1903,6 +1922,104 @@ int obgpu_ctx_kernel_times(obgpu_ctx *ctx, float *ms, int32_t cap, int32_t *n) {
 }
 
 // ---- batch ------------------------------------------------------------------------------------
+// CS blocks with non-RAW integer streams -> a RAW restatement of the batch's image (stream_codecs.cuh), in place of
+// the caller's image for every later kernel. Runs on the ctx stream after the image is resident; synchronises.
+static int cs_restate_batch(obgpu_ctx *ctx, obgpu_batch *b) {
+  const int32_t n = b->n_blocks;
+  uint32_t *d_sv = nullptr;
+  std::vector<uint32_t> sv((size_t)n * 4);
+  CUDA_TRY(ctx, cudaMallocAsync((void **)&d_sv, (size_t)n * 16, ctx->stream));
+  obcs::cs_survey_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(b->d_image, b->d_blk_off, b->d_blk_size, n, d_sv);
+  ctx->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(sv.data(), d_sv, (size_t)n * 16, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFreeAsync(d_sv, ctx->stream);
+  if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return OBGPU_ERR_SYS; }
+  bool any = false;
+  for (int32_t i = 0; i < n; ++i) {
+    const uint32_t flags = sv[(size_t)4 * i + 2];
+    if (flags & obcs::XF_CORRUPT) { ctx->err = "corrupt CS micro block (stream layout)"; return OBGPU_INVALID_DATA; }
+    if (flags & obcs::XF_UNSUPPORTED) continue;   // the index kernel marks the plans of such blocks unsupported: scans say OB_NOT_SUPPORTED
+    any = any || (flags & obcs::XF_NONRAW);
+  }
+  if (!any) return OBGPU_SUCCESS;
+  // layout of the restated image and of the job / scratch tables
+  std::vector<uint64_t> tab((size_t)n * 3);   // [new_off][job_base][scratch_base]
+  std::vector<uint32_t> nsz((size_t)n);
+  uint64_t pos = 0, jobs = 0, scr = 0;
+  int64_t restated = 0;
+  for (int32_t i = 0; i < n; ++i) {
+    const bool bad = (sv[(size_t)4 * i + 2] & obcs::XF_UNSUPPORTED) != 0;
+    const uint32_t ns = bad ? (uint32_t)b->sizes[(size_t)i] : sv[(size_t)4 * i];
+    tab[(size_t)i] = pos;
+    tab[(size_t)n + i] = jobs;
+    tab[(size_t)2 * n + i] = scr;
+    nsz[(size_t)i] = ns;
+    pos += ((uint64_t)ns + 127) & ~127ull;
+    jobs += bad ? 0 : sv[(size_t)4 * i + 1];
+    scr += 4ull * sv[(size_t)4 * i + 3];
+    restated += (sv[(size_t)4 * i + 2] & obcs::XF_NONRAW) ? 1 : 0;
+  }
+  uint8_t *d_new = nullptr, *d_scr = nullptr;
+  uint64_t *d_tab = nullptr;
+  uint32_t *d_nsz = nullptr;
+  obcs::StreamJob *d_jobs = nullptr;
+  int *d_status = nullptr;
+  auto cleanup = [&]() {
+    if (d_scr) cudaFreeAsync(d_scr, ctx->stream);
+    if (d_tab) cudaFreeAsync(d_tab, ctx->stream);
+    if (d_nsz) cudaFreeAsync(d_nsz, ctx->stream);
+    if (d_jobs) cudaFreeAsync(d_jobs, ctx->stream);
+    if (d_status) cudaFreeAsync(d_status, ctx->stream);
+  };
+  e = cudaMallocAsync((void **)&d_new, (size_t)pos + 64, ctx->stream);
+  if (e == cudaSuccess) e = cudaMallocAsync((void **)&d_scr, (size_t)scr + 16, ctx->stream);
+  if (e == cudaSuccess) e = cudaMallocAsync((void **)&d_tab, (size_t)n * 24, ctx->stream);
+  if (e == cudaSuccess) e = cudaMallocAsync((void **)&d_nsz, (size_t)n * 4, ctx->stream);
+  if (e == cudaSuccess) e = cudaMallocAsync((void **)&d_jobs, (size_t)(jobs + 1) * sizeof(obcs::StreamJob), ctx->stream);
+  if (e == cudaSuccess) e = cudaMallocAsync((void **)&d_status, 16, ctx->stream);
+  if (e == cudaSuccess) e = cudaMallocAsync((void **)&b->d_xf, (size_t)n * sizeof(obcs::XformRec), ctx->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_status, 0, 16, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_new, 0, (size_t)pos + 64, ctx->stream);   // block padding and tail slack read as zero
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_tab, tab.data(), (size_t)n * 24, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_nsz, nsz.data(), (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) {
+    obcs::cs_rewrite_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(b->d_image, b->d_blk_off, b->d_blk_size, n, d_new, d_tab, d_nsz,
+                                                                              d_tab + n, d_jobs, d_scr, d_tab + 2 * (size_t)n, b->d_xf, d_status);
+    if (jobs > 0)
+      obcs::cs_decode_kernel<<<(unsigned)((jobs + 127) / 128), 128, 0, ctx->stream>>>(b->d_image, d_new, d_jobs, (int64_t)jobs, d_status);
+    ctx->launches += jobs > 0 ? 2 : 1;
+    e = cudaGetLastError();
+  }
+  int st = 0;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&st, d_status, 4, cudaMemcpyDeviceToHost, ctx->stream);
+  // the batch now lives in the restated image
+  if (e == cudaSuccess) e = cudaMemcpyAsync(b->d_blk_off, tab.data(), (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(b->d_blk_size, nsz.data(), (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cleanup();
+  if (e != cudaSuccess || st != 0) {
+    if (d_new) cudaFreeAsync(d_new, ctx->stream);
+    if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return e == cudaErrorMemoryAllocation ? OBGPU_ALLOCATE_MEMORY_FAILED : OBGPU_ERR_SYS; }
+    ctx->err = "CS integer stream does not decode (corrupt or unsupported codec)";
+    return (st & obcs::XF_CORRUPT) ? OBGPU_INVALID_DATA : OBGPU_NOT_SUPPORTED;
+  }
+  if (b->own_image && b->d_image) cudaFreeAsync((void *)b->d_image, ctx->stream);
+  b->d_image = d_new;
+  b->own_image = true;
+  b->image_size = (int64_t)pos;
+  b->max_block_bytes = 0;
+  for (int32_t i = 0; i < n; ++i) {
+    b->offsets[(size_t)i] = (int64_t)tab[(size_t)i];
+    b->sizes[(size_t)i] = nsz[(size_t)i];
+    b->max_block_bytes = std::max<uint32_t>(b->max_block_bytes, (nsz[(size_t)i] + 15u) & ~15u);
+  }
+  b->restated_blocks = restated;
+  b->decoded_streams = (int64_t)jobs;
+  return OBGPU_SUCCESS;
+}
+
 static uint32_t rd32h(const uint8_t *p) { uint32_t v; memcpy(&v, p, 4); return v; }
 static uint16_t rd16h(const uint8_t *p) { uint16_t v; memcpy(&v, p, 2); return v; }
 
@@ -1930,6 +2047,7 @@ int obgpu_batch_open(obgpu_ctx *ctx, const void *image, int64_t image_size, cons
   b->col_count.resize((size_t)n_blocks);
   b->bm_word_off.resize((size_t)n_blocks + 1);
   int ret = OBGPU_SUCCESS;
+  bool any_cs = false;
   for (int32_t i = 0; i < n_blocks; ++i) {
     const int64_t off = offsets[i], sz = sizes[i];
     if (off < 0 || (off & 15) || sz < 64 || sz > 0x7fffffffll || off + sz > image_size) { ret = OBGPU_INVALID_ARGUMENT; break; }
@@ -1993,8 +2111,10 @@ int obgpu_batch_open(obgpu_ctx *ctx, const void *image, int64_t image_size, cons
       }
       b->row_count[(size_t)i] = rows;
       b->col_count[(size_t)i] = ncol;
+      any_cs = any_cs || is_cs;
     }
   } else {
+    any_cs = true;   // no host view: the survey kernel of the restatement looks at every block's store type
     if (!image_on_device) { ret = OBGPU_INVALID_ARGUMENT; }
     uint32_t *d_sv = nullptr;
     std::vector<uint32_t> sv((size_t)n_blocks * 2);
@@ -2068,6 +2188,14 @@ int obgpu_batch_open(obgpu_ctx *ctx, const void *image, int64_t image_size, cons
       }
     }
   }
+  // CS blocks whose integer streams carry codecs are restated as RAW once, here (the reference's full_transform at cache fill)
+  if (e == cudaSuccess && any_cs) {
+    const int rret = cs_restate_batch(ctx, b);
+    if (rret != OBGPU_SUCCESS) {
+      obgpu_batch_close(b);
+      return rret;
+    }
+  }
   // decode plans: one thread per (block, column)
   if (e == cudaSuccess && b->max_cols > 128) {
     ctx->err = "more than 128 columns in a micro block";
@@ -2128,6 +2256,7 @@ void obgpu_batch_close(obgpu_batch *b) {
   if (b->d_plans) cudaFreeAsync(b->d_plans, b->ctx->stream);
   if (b->d_agg) cudaFreeAsync(b->d_agg, b->ctx->stream);
   if (b->d_agg_off) cudaFreeAsync(b->d_agg_off, b->ctx->stream);
+  if (b->d_xf) cudaFreeAsync(b->d_xf, b->ctx->stream);
   if (b->own_image && b->d_image) cudaFreeAsync((void *)b->d_image, b->ctx->stream);
   delete b;
 }
@@ -2581,6 +2710,43 @@ __global__ void __launch_bounds__(256) obgpu_aggregate_kernel(int kind, const vo
   }
 }
 
+// Dense result column -> ObDatum[] (12 packed bytes: ptr, {len:29, flag:2, null:1}) + 8-byte value slots for integers.
+__global__ void __launch_bounds__(256) obgpu_format_datums_kernel(const void *data, const int32_t *lens, const uint32_t *nulls, int elem_len,
+                                                                  int is_string, int64_t row_begin, int64_t n, uint64_t slot_base,
+                                                                  uint32_t *out12, uint64_t *slots) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int64_t i = row_begin + k;
+  const bool is_null = (nulls[i >> 5] >> (i & 31)) & 1u;
+  uint64_t ptr;
+  uint32_t pack;
+  if (is_string) {
+    ptr = is_null ? 0ull : reinterpret_cast<const uint64_t *>(data)[i];
+    pack = is_null ? 0x80000000u : ((uint32_t)lens[i] & 0x1fffffffu);
+  } else {
+    uint64_t v = 0;
+    if (!is_null) {
+      if (elem_len == 8) v = reinterpret_cast<const uint64_t *>(data)[i];
+      else if (elem_len == 4) v = reinterpret_cast<const uint32_t *>(data)[i];
+      else v = reinterpret_cast<const uint8_t *>(data)[i];
+    }
+    slots[k] = v;
+    ptr = slot_base + 8ull * (uint64_t)k;
+    pack = is_null ? 0x80000000u : (uint32_t)elem_len;
+  }
+  out12[3 * k] = (uint32_t)ptr;
+  out12[3 * k + 1] = (uint32_t)(ptr >> 32);
+  out12[3 * k + 2] = pack;
+}
+
+struct TempDevResult {
+  obgpu_ctx *ctx;
+  void *p = nullptr;
+  explicit TempDevResult(obgpu_ctx *c) : ctx(c) {}
+  cudaError_t alloc(size_t bytes) { return cudaMallocAsync(&p, bytes ? bytes : 16, ctx->stream); }
+  ~TempDevResult() { if (p) cudaFreeAsync(p, ctx->stream); }
+};
+
 static int check_status(obgpu_ctx *ctx, int status) {
   if (status & ST_CORRUPT) { ctx->err = "corrupt micro block seen on device"; return OBGPU_INVALID_DATA; }
   if (status & ST_UNSUPPORTED) { ctx->err = "column encoding / type not handled by the device path"; return OBGPU_NOT_SUPPORTED; }
@@ -2673,6 +2839,7 @@ int obgpu_scan(obgpu_batch *b, const obgpu_scan_spec *spec, obgpu_result **out) 
   p.plans = b->d_plans;
   p.rows = b->d_rows;
   p.recs = b->d_recs;
+  p.xf = reinterpret_cast<const XformRecFwd *>(b->d_xf);
   p.max_cols = (int32_t)b->max_cols;
   p.counts = (uint32_t *)(a + o_counts);
   p.status = (int32_t *)(a + o_misc + 64);
@@ -2971,6 +3138,30 @@ int obgpu_result_fetch_col(obgpu_result *r, int32_t i, int64_t row_begin, int64_
   return obgpu_result_fetch_cols(r, 1, &i, row_begin, row_count, hd, ha, hn);
 }
 
+int obgpu_result_fetch_datums(obgpu_result *r, int32_t i, int64_t row_begin, int64_t row_count, obgpu_datum *host_datums,
+                              void *host_slots) {
+  if (!r || i < 0 || i >= r->n_proj || row_begin < 0 || row_count < 0 || row_begin + row_count > r->cap || !host_datums)
+    return OBGPU_INVALID_ARGUMENT;
+  const ResultCol &c = r->cols[i];
+  if (!c.is_string && !host_slots) return OBGPU_INVALID_ARGUMENT;
+  obgpu_ctx *ctx = r->ctx;
+  cudaSetDevice(ctx->device);
+  if (row_count == 0) return OBGPU_SUCCESS;
+  TempDevResult tmp(ctx);
+  const size_t o_slots = ((size_t)row_count * 12 + 255) & ~(size_t)255;
+  CUDA_TRY(ctx, tmp.alloc(o_slots + (c.is_string ? 0 : (size_t)row_count * 8)));
+  uint8_t *d12 = (uint8_t *)tmp.p;
+  uint64_t *dslots = c.is_string ? nullptr : (uint64_t *)((uint8_t *)tmp.p + o_slots);
+  obgpu_format_datums_kernel<<<(unsigned)((row_count + 255) / 256), 256, 0, ctx->stream>>>(
+      c.data, c.lens, c.nulls, c.elem_len, c.is_string, row_begin, row_count, (uint64_t)(uintptr_t)host_slots, (uint32_t *)d12, dslots);
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  CUDA_TRY(ctx, cudaMemcpyAsync(host_datums, d12, (size_t)row_count * 12, cudaMemcpyDeviceToHost, ctx->stream));
+  if (dslots) CUDA_TRY(ctx, cudaMemcpyAsync(host_slots, dslots, (size_t)row_count * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return OBGPU_SUCCESS;
+}
+
 int obgpu_result_fetch_sel_offsets(obgpu_result *r, int64_t *host_sel_offset) {
   if (!r || !host_sel_offset) return OBGPU_INVALID_ARGUMENT;
   obgpu_ctx *ctx = r->ctx;
@@ -3105,6 +3296,7 @@ int run_project_block(obgpu_batch *b, int32_t block, int32_t col, const int32_t 
   p.status = (int32_t *)a;
   p.has_null = (int32_t *)(a + 64);
   p.string_base = string_base;
+  p.xf = reinterpret_cast<const XformRecFwd *>(b->d_xf);
   obgpu_project_block_kernel<<<1, kThreads, p.smem_total, ctx->stream>>>(
       p, block, (const int32_t *)(a + o_rid), row_cap, vec_offset, a + o_data,
       want_string ? (int32_t *)(a + o_lens) : nullptr, (uint32_t *)(a + o_nulls), (int32_t)el);
@@ -3190,6 +3382,36 @@ int obgpu_project_discrete(obgpu_batch *batch, int32_t block, int32_t col, const
                            int32_t *has_null) {
   return run_project_block(batch, block, col, row_ids, row_cap, vec_offset, string_base, ptrs, 8, lens, nulls,
                            has_null, true);
+}
+
+int obgpu_project_datums(obgpu_batch *batch, int32_t block, int32_t col, const int32_t *row_ids, int64_t row_cap, int64_t datum_offset,
+                         uint64_t string_base, obgpu_datum *datums) {
+  if (!batch || !datums || row_cap < 0 || datum_offset < 0 || col < 0 || (uint32_t)col >= batch->max_cols) return OBGPU_INVALID_ARGUMENT;
+  if (row_cap == 0) return OBGPU_SUCCESS;
+  const int sc = obf::store_class_of(batch->col_types[(size_t)col]);
+  if (sc == 0) return OBGPU_NOT_SUPPORTED;
+  const bool is_str = sc == 5;
+  const int el = is_str ? 8 : obf::datum_len_of(batch->col_types[(size_t)col]);
+  std::vector<uint64_t> data((size_t)row_cap, 0), nulls((size_t)(row_cap + 63) / 64, 0);
+  std::vector<int32_t> lens(is_str ? (size_t)row_cap : 0);
+  int32_t has_null = 0;
+  const int ret = run_project_block(batch, block, col, row_ids, row_cap, 0, string_base, data.data(), el, is_str ? lens.data() : nullptr,
+                                    nulls.data(), &has_null, is_str);
+  if (ret != OBGPU_SUCCESS) return ret;
+  obgpu_datum *out = datums + datum_offset;
+  for (int64_t i = 0; i < row_cap; ++i) {
+    if ((nulls[(size_t)i / 64] >> (i % 64)) & 1ull) { out[i].pack = OBGPU_DATUM_NULL_BIT; continue; }   // ObDatum::set_null()
+    if (is_str) {
+      out[i].ptr = data[(size_t)i];
+      out[i].pack = (uint32_t)lens[(size_t)i] & 0x1fffffffu;
+    } else {
+      // load_data_to_datum: MEMCPY through the datum's own pointer (the caller's reserved slot), then the length
+      if (out[i].ptr == 0) return OBGPU_INVALID_ARGUMENT;
+      memcpy(reinterpret_cast<void *>((uintptr_t)out[i].ptr), reinterpret_cast<const uint8_t *>(data.data()) + (size_t)i * (size_t)el, (size_t)el);
+      out[i].pack = (uint32_t)el;
+    }
+  }
+  return OBGPU_SUCCESS;
 }
 
 }  // extern "C"

@@ -112,6 +112,48 @@ __device__ __forceinline__ void lean_interval_sorted_int(const ColDesc &d, const
   e = not_above < below ? below : not_above;
 }
 
+// EQ / NE / IN leaf over the string dictionary of a K_DICT column -> predicate bitset. Every entry is screened by
+// (length, first 8 bytes) against the constants; only the (few) entries that pass compare their tails, 8 bytes at a
+// time, out of shared memory.
+__device__ __forceinline__ void lean_bitset_str_eq(const ScanParams &p, const FilterNodeDev &nd, const ColDesc &d, uint32_t sbit,
+                                                   uint32_t *bits, int lane) {
+  const uint32_t n = d.dict_count, ib8 = d.dict_data_size * 8u, ibit = sbit + d.dict_payload * 8u, heap_len = d.dict_end - d.dict_var;
+  const bool fixed = d.dict_fixed != 0, ne = nd.op == OP_NE;
+  for (uint32_t b0 = 0; b0 < n + 2u; b0 += 32u) {
+    const uint32_t idx = b0 + (uint32_t)lane;
+    bool r = false;
+    if (idx < n) {
+      uint32_t cell, len;
+      if (fixed) {
+        len = d.dict_data_size;
+        cell = d.dict_payload + idx * len;
+      } else {
+        const uint32_t off = idx == 0 ? 0u : sbits32(ibit + (idx - 1u) * ib8, ib8);
+        const uint32_t end = idx == n - 1u ? heap_len : sbits32(ibit + idx * ib8, ib8);
+        cell = d.dict_var + off;
+        len = end - off;
+      }
+      const uint32_t pl = len < 8u ? len : 8u;
+      const uint64_t pre = pl ? sbits(sbit + cell * 8u, pl * 8u) : 0ull;
+      for (int k = 0; k < nd.n_params && !r; ++k) {
+        const ParamDev &pp = p.params[nd.param_begin + k];
+        if (pp.len != len || (uint64_t)pp.i64 != pre) continue;
+        bool same = true;
+        for (uint32_t i = 8u; i < len && same; i += 8u) {
+          const uint32_t nb = len - i < 8u ? len - i : 8u;
+          const uint64_t a = sbits(sbit + (cell + i) * 8u, nb * 8u);
+          const uint64_t c = *reinterpret_cast<const uint64_t *>(p.param_heap + pp.heap_off + i) & (~0ull >> (64u - nb * 8u));
+          same = a == c;
+        }
+        r = same;
+      }
+      r = r != ne;
+    }
+    const uint32_t word = __ballot_sync(0xffffffffu, r);
+    if (lane == 0) bits[b0 >> 5] = word;
+  }
+}
+
 // AND leaf on a string K_DICT column when few rows are still alive: evaluate the leaf on the survivors' own
 // dictionary entries (one pass over <= alive rows) instead of on every dictionary entry.
 __device__ __forceinline__ uint32_t lean_survivor_str(const ScanParams &p, const FilterNodeDev &nd, const ColDesc &d, uint32_t sbit,
@@ -316,7 +358,7 @@ __global__ void __launch_bounds__(kThreads) obgpu_count_pipe_kernel(const __grid
           if (is_str && and_mode) {
             // few surviving rows and a larger dictionary: test the survivors' own entries instead of every entry
             const uint32_t alive = warp_sum_u32(__popc(mybm));
-            if (alive <= d.dict_count) {
+            if (alive * 4u <= d.dict_count) {
               mybm = lean_survivor_str(p, nd, d, sbit, rs + hdr[nd.used_idx], mybm, nwords, alive, bm, lane);
               continue;
             }
@@ -328,6 +370,7 @@ __global__ void __launch_bounds__(kThreads) obgpu_count_pipe_kernel(const __grid
             goto leaf_done;
           }
           if (!is_str && nd.range_ok) lean_bitset_int_range(d, nd, sbit, bits, lane);
+          else if (is_str && (nd.op == OP_EQ || nd.op == OP_NE || nd.op == OP_IN)) lean_bitset_str_eq(p, nd, d, sbit, bits, lane);
           else {
             c.b.s = rs + hdr[nd.used_idx];
             c.sbit = sbit;
@@ -630,7 +673,7 @@ __global__ void __launch_bounds__(kThreads) obgpu_project_pipe_kernel(const __gr
     c.rle_base = wscr + p.pw_rle;
     c.rle_slot_bytes = 0;
     c.rle_starts_bytes = p.words_cap * 4u;
-    const uint64_t blk_addr = p.string_base + rec.off;
+    const uint64_t blk_addr = block_string_addr(p, blk, rec.off);
     for (int pc = 0; pc < np; ++pc) {
       ColDesc *wdesc = plans + pc;
       if (!wdesc->ok || ((badmask >> pc) & 1u)) {

@@ -53,7 +53,7 @@ int ObGpuMicroBlockDecoder::get_column_count(int64_t &column_count) const {
 }
 
 static void to_params(const sql::ObWhiteFilterExecutor &filter, std::vector<obgpu_filter_param> &params) {
-  for (const ObDatum &d : filter.get_datums()) {
+  for (const ObStorageDatum &d : filter.get_datums()) {
     obgpu_filter_param p{};
     p.is_null = d.is_null() ? 1 : 0;
     if (!d.is_null()) {
@@ -103,6 +103,15 @@ int ObGpuMicroBlockDecoder::get_rows(const int32_t col, const int32_t *row_ids, 
                                          vec.nulls_.data(), &has_null);
   if (has_null) vec.has_null_ = true;
   return ret;
+}
+
+int ObGpuMicroBlockDecoder::get_rows(const int32_t col, const int32_t *row_ids, const int64_t row_cap, const int64_t datum_offset,
+                                     common::ObDatum *col_datums) {
+  if (!batch_) return OB_NOT_INIT;
+  if (!row_ids || !col_datums) return OB_INVALID_ARGUMENT;
+  // string datums point into the caller's block buffer (host_buf_), like the reference's shallow string datums
+  return obgpu_project_datums(batch_, 0, col, row_ids, row_cap, datum_offset, (uint64_t)(uintptr_t)host_buf_,
+                              reinterpret_cast<obgpu_datum *>(col_datums));
 }
 
 // ---- ObPushdownFilterExecutor::execute ----------------------------------------------------------------
@@ -231,8 +240,44 @@ int ObGpuSSTableBatchScanner::init(const void *image, int64_t image_size, const 
   return OB_SUCCESS;
 }
 
+// get_next_rows with the reference's per-batch LIMIT / OFFSET arithmetic (ObBlockBatchedRowStore::get_row_ids,
+// access/ob_block_batched_row_store.cpp:163-186): out_cnt_ counts the selected rows seen so far; a batch keeps rows
+// [start, end) where start skips what is left of the offset and end stops at offset + limit.
 int ObGpuSSTableBatchScanner::get_next_rows(Batch &out) {
   if (!result_) return OB_NOT_INIT;
+  for (;;) {
+    if (limit_end_) return OB_ITER_END;               // IterEndState::LIMIT_ITER_END
+    const int ret = next_window(out);
+    if (ret != OB_SUCCESS) return ret;
+    if (limit_offset_ == 0 && limit_ < 0) return OB_SUCCESS;
+    const int64_t row_count = out.count;
+    int64_t start = 0, end = row_count;
+    if (limit_offset_ > out_cnt_) start = std::min(limit_offset_ - out_cnt_, row_count);
+    if (limit_ >= 0 && out_cnt_ + row_count - limit_offset_ >= limit_) {
+      limit_end_ = true;
+      end = limit_ - out_cnt_ + limit_offset_;
+    }
+    out_cnt_ += end;
+    if (end < start) end = start;
+    trim(out, start, end);
+    if (out.count > 0) return OB_SUCCESS;
+  }
+}
+
+void ObGpuSSTableBatchScanner::trim(Batch &out, int64_t start, int64_t end) {
+  if (start == 0 && end == out.count) return;
+  auto cut = [&](auto &v) { if (!v.empty()) { v.erase(v.begin() + end, v.end()); v.erase(v.begin(), v.begin() + start); } };
+  cut(out.row_ids);
+  for (size_t c = 0; c < proj_.size(); ++c) {
+    cut(out.ints[c]);
+    cut(out.str_ptrs[c]);
+    cut(out.str_lens[c]);
+    cut(out.is_null[c]);
+  }
+  out.count = end - start;
+}
+
+int ObGpuSSTableBatchScanner::next_window(Batch &out) {
   if (reverse_) return get_next_rows_reverse(out);
   // skip blocks without (remaining) selected rows
   while (cur_block_ < n_blocks_ && cur_row_ >= sel_offset_[(size_t)cur_block_ + 1]) ++cur_block_;

@@ -64,9 +64,9 @@ private:
   std::vector<uint8_t> data_;
 };
 
-// share/datum/ob_datum.h:109-177 (ptr_ + {len_:29, flag_:2, null_:1}); the scan path only needs
-// value / NULL of filter constants and decoded cells.
-struct ObDatum {
+// blocksstable::ObStorageDatum (a datum with its own value buffer, storage/blocksstable/ob_datum_row.h): what a white
+// filter's constants are held in; the scan path only needs their value / NULL.
+struct ObStorageDatum {
   const char *ptr_ = nullptr;
   uint32_t len_ = 0;
   bool null_ = false;
@@ -78,6 +78,24 @@ struct ObDatum {
   int64_t get_int() const { return int_; }
 };
 
+// common::ObDatum (share/datum/ob_datum.h:109-197): 8-byte pointer + {len:29, flag:2, null:1}, 12 packed bytes. Same
+// layout as obgpu_datum, so an ObDatum array is handed to the C-ABI as is.
+struct ObDatum {
+  const char *ptr_ = nullptr;
+  union {
+    struct {
+      uint32_t len_ : 29;
+      uint32_t flag_ : 2;
+      uint32_t null_ : 1;
+    };
+    uint32_t pack_;
+  };
+  ObDatum() : pack_(0) {}
+  bool is_null() const { return null_ == 1; }
+  void set_null() { len_ = 0; null_ = 1; flag_ = 0; }
+  int64_t get_int() const { int64_t v = 0; memcpy(&v, ptr_, len_ < 8 ? len_ : 8); if (len_ == 4) v = (int32_t)v; return v; }
+} __attribute__((packed));
+static_assert(sizeof(ObDatum) == 12 && sizeof(ObDatum) == sizeof(obgpu_datum), "ObDatum is 12 packed bytes");
 }  // namespace common
 
 namespace sql {
@@ -121,8 +139,8 @@ public:
       : ObPushdownFilterExecutor(WHITE_FILTER_EXECUTOR), col_offset_(col_offset), op_type_(op) {}
   ObWhiteFilterOperatorType get_op_type() const { return op_type_; }
   int32_t get_col_offset() const { return col_offset_; }  // get_col_offsets(is_pd_to_cg).at(0)
-  const std::vector<common::ObDatum> &get_datums() const { return datum_params_; }
-  std::vector<common::ObDatum> &get_datums() { return datum_params_; }
+  const std::vector<common::ObStorageDatum> &get_datums() const { return datum_params_; }
+  std::vector<common::ObStorageDatum> &get_datums() { return datum_params_; }
   bool null_param_contained() const {
     for (const auto &d : datum_params_) if (d.is_null()) return true;
     return false;
@@ -130,7 +148,7 @@ public:
 private:
   int32_t col_offset_;
   ObWhiteFilterOperatorType op_type_;
-  std::vector<common::ObDatum> datum_params_;
+  std::vector<common::ObStorageDatum> datum_params_;
 };
 
 class ObAndFilterExecutor : public ObPushdownFilterExecutor {
@@ -202,6 +220,10 @@ public:
                ObFixedLengthVector &vec);
   int get_rows(const int32_t col, const int32_t *row_ids, const int64_t row_cap, const int64_t vec_offset,
                ObDiscreteVector &vec);
+  // ObMicroBlockDecoder::get_rows, datum format (get_col_datums, encoding/ob_micro_block_decoder.cpp:2100-2140,2201-2237):
+  // integer datums point at the caller's reserved slots and are written through, string datums point into the block
+  int get_rows(const int32_t col, const int32_t *row_ids, const int64_t row_cap, const int64_t datum_offset,
+               common::ObDatum *col_datums);
   obgpu_batch *batch() { return batch_; }
 private:
   ObGpuScanRuntime &rt_;
@@ -247,6 +269,10 @@ public:
   // Reverse scan (is_reverse_scan_ / step_ == -1 of the row scanners): call before the first get_next_rows; batches then
   // come blocks last to first, rows descending inside a block.
   void set_reverse_scan(bool reverse) { reverse_ = reverse; }
+  // LIMIT / OFFSET pushed down to the scan (ObTableAccessContext::limit_param_): every batch is trimmed the way
+  // ObBlockBatchedRowStore::get_row_ids does (access/ob_block_batched_row_store.cpp:163-186) -- the first `offset`
+  // selected rows are dropped, OB_ITER_END follows the batch that reaches `limit` (limit < 0: none).
+  void set_limit(int64_t offset, int64_t limit) { limit_offset_ = offset < 0 ? 0 : offset; limit_ = limit; out_cnt_ = 0; limit_end_ = false; }
   int64_t skipped_blocks() const { return skip_false_; }       // always-false: never read
   int64_t unfiltered_blocks() const { return skip_true_; }     // always-true: no filter evaluation
   // Next batch: count rows of block `block_idx`, row ids ascending. Integer columns are returned as
@@ -267,7 +293,11 @@ private:
               std::vector<obgpu_filter_param> &params);
   int fetch_window(int32_t block, int64_t row_begin, int64_t n, Batch &out);
   int get_next_rows_reverse(Batch &out);
+  int next_window(Batch &out);
+  void trim(Batch &out, int64_t start, int64_t end);
   bool reverse_ = false, rev_started_ = false;
+  int64_t limit_offset_ = 0, limit_ = -1, out_cnt_ = 0;
+  bool limit_end_ = false;
   ObGpuScanRuntime &rt_;
   obgpu_batch *batch_ = nullptr;
   obgpu_result *result_ = nullptr;

@@ -16,6 +16,11 @@ from . import capi
 from .capi import lib, check
 
 
+# common::ObDatum: 8-byte pointer + {len:29, flag:2, null:1}, 12 packed bytes (share/datum/ob_datum.h:109-177)
+DATUM_DTYPE = np.dtype([("ptr", "<u8"), ("pack", "<u4")], align=False)
+DATUM_NULL_BIT = 0x80000000
+
+
 # ---- filter tree ---------------------------------------------------------------------------------
 @dataclass
 class White:
@@ -302,6 +307,18 @@ class ScanResult:
                                          aux.ctypes.data if aux is not None else None, nulls.ctypes.data),
               "obgpu_result_fetch_col", self.batch.ctx._h)
         return data[:row_count], (aux[:row_count] if aux is not None else None), nulls[:(row_count + 63) // 64]
+
+    def fetch_datums(self, i, row_begin=0, row_count=None):
+        """Column i as ObDatum[] (datum format): (datums structured array, slots uint64 array or None for strings)."""
+        c = self.col(i)
+        if row_count is None:
+            row_count = self.selected_rows - row_begin
+        datums = np.zeros(max(row_count, 1), dtype=DATUM_DTYPE)
+        slots = None if c.is_string else np.zeros(max(row_count, 1), dtype=np.uint64)
+        check(lib.obgpu_result_fetch_datums(self._h, i, row_begin, row_count, datums.ctypes.data,
+                                            slots.ctypes.data if slots is not None else None), "obgpu_result_fetch_datums",
+              self.batch.ctx._h)
+        return datums[:row_count], (slots[:row_count] if slots is not None else None)
 
     def fetch_cols(self, idxs, row_begin=0, row_count=None, outs=None, out_nulls=None):
         """Several integer-class columns with one synchronisation (obgpu_result_fetch_cols). Returns

@@ -79,7 +79,7 @@ static int64_t pushdown_popcnt(ObGpuMicroBlockDecoder &dec, int col, sql::ObWhit
   std::vector<std::string> keep;
   keep.reserve(seeds.size());
   for (int64_t s : seeds) {
-    ObDatum d;
+    ObStorageDatum d;
     if (str) { keep.push_back(seed_str(s)); d.set_string(keep.back().data(), (uint32_t)keep.back().size()); }
     else d.set_int(seed_int(s));
     filter.get_datums().push_back(d);
@@ -185,6 +185,34 @@ static void test_get_rows_vs_oracle(ObGpuScanRuntime &rt) {
       ASSERT_EQ(0, memcmp(p, r.strs[(size_t)row].data(), r.strs[(size_t)row].size()));
     }
   }
+  // datum format (ObMicroBlockDecoder::get_rows into ObDatum[], ob_micro_block_decoder.cpp:2100-2140): integers are
+  // written through the datums' own pointers (the expression's reserved slots), strings point into the block
+  const int64_t doff = 2;
+  std::vector<int64_t> slots((size_t)(doff + cap), 0x5a5a5a5a5a5a5a5aLL);
+  std::vector<common::ObDatum> datums((size_t)(doff + cap));
+  for (size_t i = 0; i < datums.size(); ++i) datums[i].ptr_ = reinterpret_cast<const char *>(&slots[i]);
+  ASSERT_EQ(OB_SUCCESS, dec.get_rows(1, row_ids.data(), cap, doff, datums.data()));
+  for (int64_t i = 0; i < cap; ++i) {
+    const common::ObDatum &d = datums[(size_t)(doff + i)];
+    const bool is_null = (en[(size_t)(voff + i) / 64] >> ((voff + i) % 64)) & 1;
+    ASSERT_EQ((int)is_null, (int)d.is_null());
+    if (is_null) { ASSERT_EQ(0x5a5a5a5a5a5a5a5aLL, slots[(size_t)(doff + i)]); continue; }
+    ASSERT_EQ(8, (int)d.len_);
+    ASSERT_EQ(1, d.ptr_ == reinterpret_cast<const char *>(&slots[(size_t)(doff + i)]));
+    ASSERT_EQ((int64_t)ev[(size_t)(voff + i)], d.get_int());
+  }
+  ASSERT_EQ(0, (int)datums[0].pack_);
+  std::vector<common::ObDatum> sd((size_t)cap);
+  ASSERT_EQ(OB_SUCCESS, dec.get_rows(2, row_ids.data(), cap, 0, sd.data()));
+  for (int64_t i = 0; i < cap; ++i) {
+    const int32_t row = row_ids[(size_t)i];
+    ASSERT_EQ((int)r.nulls[(size_t)row], (int)sd[(size_t)i].is_null());
+    if (!r.nulls[(size_t)row]) {
+      ASSERT_EQ((int64_t)r.strs[(size_t)row].size(), (int64_t)sd[(size_t)i].len_);
+      ASSERT_EQ(1, sd[(size_t)i].ptr_ >= (const char *)blk.data() && sd[(size_t)i].ptr_ < (const char *)blk.data() + blk.size());
+      ASSERT_EQ(0, memcmp(sd[(size_t)i].ptr_, r.strs[(size_t)row].data(), r.strs[(size_t)row].size()));
+    }
+  }
 }
 
 static void test_filter_tree_and_batch_scanner(ObGpuScanRuntime &rt) {
@@ -220,10 +248,10 @@ static void test_filter_tree_and_batch_scanner(ObGpuScanRuntime &rt) {
   obgpu_table_image_free(img);
 
   sql::ObWhiteFilterExecutor lt(1, sql::WHITE_OP_LT), ge(1, sql::WHITE_OP_GE), eq(2, sql::WHITE_OP_EQ);
-  ObDatum d;
+  ObStorageDatum d;
   d.set_int(100); lt.get_datums().push_back(d);
   d.set_int(900); ge.get_datums().push_back(d);
-  ObDatum ds; ds.set_string("k3", 2); eq.get_datums().push_back(ds);
+  ObStorageDatum ds; ds.set_string("k3", 2); eq.get_datums().push_back(ds);
   sql::ObOrFilterExecutor orf; orf.add_child(&lt); orf.add_child(&ge);
   sql::ObAndFilterExecutor andf; andf.add_child(&orf); andf.add_child(&eq);
 
@@ -341,6 +369,27 @@ static void test_filter_tree_and_batch_scanner(ObGpuScanRuntime &rt) {
   }
   ASSERT_EQ(OB_ITER_END, ret);
   ASSERT_EQ(lo - 1, next);
+
+  // (5) LIMIT / OFFSET (ObBlockBatchedRowStore::get_row_ids, ob_block_batched_row_store.cpp:163-186): the first `offset`
+  // selected rows are dropped batch by batch, the scan ends with the batch that reaches `limit`
+  const int64_t cases[][2] = {{0, 10}, {7, 300}, {255, 2}, {256, 256}, {1000, -1}, {hi - lo + 5, 10}, {3, 0}, {0, hi - lo + 100}};
+  for (const auto &cs : cases) {
+    const int64_t offset = cs[0], limit = cs[1];
+    ObGpuSSTableBatchScanner lim(rt);
+    lim.set_limit(offset, limit);
+    ASSERT_EQ(OB_SUCCESS, lim.init(image.data(), image_size, offs.data(), sizes.data(), nb, &bt, {0}, 256));
+    const int64_t total = hi - lo + 1;
+    const int64_t first = std::min(offset, total), want_n = limit < 0 ? total - first : std::min(limit, total - first);
+    int64_t got = 0;
+    next = lo + first;
+    while ((ret = lim.get_next_rows(batch)) == OB_SUCCESS) {
+      ASSERT_EQ(1, batch.count > 0);
+      for (int64_t i = 0; i < batch.count; ++i) ASSERT_EQ(next++, batch.ints[0][(size_t)i]);
+      got += batch.count;
+    }
+    ASSERT_EQ(OB_ITER_END, ret);
+    ASSERT_EQ(want_n, got);
+  }
 }
 
 int main() {

@@ -146,6 +146,49 @@ def ora_check(code, what):
         raise RuntimeError(f"oracle {what} failed: {code}")
 
 
+def ora_flatten_filter(expr):
+    """The checker's own post-order flattening of a filter tree (root last) into the oracle's structs. The expression
+    objects are duck-typed (a leaf has .col / .op / .params, a logic node has .children and a class name of And / Or):
+    nothing of the product's filter code runs on the oracle's side."""
+    if expr is None:
+        return None, None
+    nodes, params, keep = [], [], []
+
+    def visit(e):
+        if hasattr(e, "children"):
+            for c in e.children:
+                visit(c)
+            nd = OraNode()
+            nd.kind = 1 if type(e).__name__ == "And" else 2     # ORA_NODE_AND / ORA_NODE_OR
+            nd.n_children = len(e.children)
+            nodes.append(nd)
+            return
+        nd = OraNode()
+        nd.kind, nd.op, nd.col = 0, int(e.op), int(e.col)
+        nd.param_begin, nd.n_params, nd.n_children = len(params), len(e.params), 0
+        for v in e.params:
+            p = OraParam()
+            if v is None:
+                p.is_null = 1
+            elif isinstance(v, (bytes, bytearray)):
+                b = bytes(v)
+                keep.append(b)
+                p.ptr, p.len = b, len(b)
+            else:
+                iv = int(v)
+                p.i64 = iv - (1 << 64) if iv >= 1 << 63 else iv
+            params.append(p)
+        nodes.append(nd)
+
+    visit(expr)
+    node_arr = (OraNode * len(nodes))(*nodes)
+    param_arr = (OraParam * max(len(params), 1))(*params)
+    f = OraFilter()
+    f.nodes, f.n_nodes = node_arr, len(nodes)
+    f.params, f.n_params = param_arr, len(params)
+    return f, (node_arr, param_arr, keep)
+
+
 def cs_transform(buf: np.ndarray) -> np.ndarray:
     """CS block -> the same block with every integer stream restated as RAW (ora_cs_transform)."""
     L = oracle()
@@ -233,8 +276,7 @@ class Block:
         return offs, lens, nulls, hn.value
 
     def filter_tree(self, expr, start=0, count=None):
-        from oceanbase_b200.scan import flatten_filter
-        f, keep = flatten_filter(expr, OraNode, OraParam, OraFilter)
+        f, keep = ora_flatten_filter(expr)
         if count is None:
             count = self.row_count - start
         out = np.zeros(max(count, 1), dtype=np.uint8)
@@ -256,9 +298,8 @@ def bitmap_get_row_ids(bitmap, start, to, limit, id_offset=0):
 def scan_table(table, filter_expr, proj_cols, proj_is_string, proj_elem_len, batch_size=256, want_row_ids=True,
                string_base=0):
     """Full-path oracle scan of a TableImage. Returns dict with dense outputs."""
-    from oceanbase_b200.scan import flatten_filter
     L = oracle()
-    f, keep = flatten_filter(filter_expr, OraNode, OraParam, OraFilter)
+    f, keep = ora_flatten_filter(filter_expr)
     n_proj = len(proj_cols)
     cap = table.total_rows
     datas, lens, nulls = [], [], []
@@ -300,9 +341,8 @@ def scan_table(table, filter_expr, proj_cols, proj_is_string, proj_elem_len, bat
 
 
 def scan_table_mt(table, filter_expr, proj_cols, batch_size=256, n_threads=1, block_limit=None):
-    from oceanbase_b200.scan import flatten_filter
     L = oracle()
-    f, keep = flatten_filter(filter_expr, OraNode, OraParam, OraFilter)
+    f, keep = ora_flatten_filter(filter_expr)
     proj = np.ascontiguousarray(proj_cols, dtype=np.int32)
     offs = np.ascontiguousarray(table.offsets, dtype=np.int64)
     sizes = np.ascontiguousarray(table.sizes, dtype=np.int64)
@@ -391,8 +431,7 @@ def agg_row_read(row, col_idx, col_type):
 
 def skip_index_filter(row, row_count, col_types, expr):
     """ObSSTableIndexFilter::check_range on one block's aggregate row: ORA_MASK_* (0 uncertain, 1 true, 2 false)."""
-    from oceanbase_b200.scan import flatten_filter
-    f, keep = flatten_filter(expr, OraNode, OraParam, OraFilter)
+    f, keep = ora_flatten_filter(expr)
     buf = np.ascontiguousarray(row, dtype=np.uint8) if row is not None and len(row) else None
     types = np.ascontiguousarray(col_types, dtype=np.uint8)
     mask = C.c_int32(0)

@@ -158,3 +158,68 @@ def test_project_fixed_and_discrete_with_vec_offset(ob, ctx):
             go = np.where(gp != 0, gp - np.uint64(1 << 40), 0)
             assert np.array_equal(go, eo)
         batch.close()
+
+
+def test_datum_format_get_rows(ob, ctx):
+    """ObMicroBlockDecoder::get_rows, datum format (ob_micro_block_decoder.cpp:2100-2140): 12-byte ObDatum per row; integers
+    are written through the datum's own pointer with the type's datum length, strings point into the caller's block,
+    NULL is set_null(). Checked against the oracle's vector output, per block and for a whole batch result."""
+    import ctypes as C
+    rng = np.random.default_rng(91)
+    n = 3000
+    strs = [bytes(rng.integers(97, 123, size=rng.integers(1, 12), dtype=np.uint8)) for _ in range(40)]
+    nl = (rng.random(n) < 0.2).astype(np.uint8)
+    cols = [ob.Column(ob.OBJ_INT, ob.ENC_DICT, rng.integers(-9, 9, size=n) * 10 ** 10, nulls=nl),
+            ob.Column(ob.OBJ_INT32, ob.ENC_RAW, rng.integers(-(1 << 31), 1 << 31, size=n), nulls=nl),
+            ob.Column(ob.OBJ_VARCHAR, ob.ENC_DICT, [strs[i] for i in rng.integers(0, 40, size=n)], nulls=nl)]
+    table = ob.encode_table(cols, 800)
+    batch = ctx.open_batch(table)
+    base = table.image.ctypes.data           # string datums address the caller's own buffer
+    blk = ora.Block(table.block(1))
+    rid = np.arange(1, blk.row_count, 2, dtype=np.int32)
+    for col, el in ((0, 8), (1, 4)):
+        slots = np.full(len(rid) + 3, 0x5a5a5a5a5a5a5a5a, dtype=np.uint64)
+        datums = np.zeros(len(rid) + 3, dtype=ob.DATUM_DTYPE)
+        datums["ptr"] = slots.ctypes.data + 8 * np.arange(len(rid) + 3, dtype=np.uint64)
+        batch.project_datums(1, col, rid, datums, datum_offset=3)
+        wd, wn, _ = blk.get_rows_fixed(col, rid, elem_len=el)
+        want = wd.view({8: np.uint64, 4: np.uint32}[el])
+        for i in range(len(rid)):
+            d = datums[3 + i]
+            isnull = bool((wn[i // 64] >> np.uint64(i % 64)) & np.uint64(1))
+            assert bool(d["pack"] & ob.DATUM_NULL_BIT) == isnull
+            if isnull:
+                assert d["pack"] == ob.DATUM_NULL_BIT and slots[3 + i] == 0x5a5a5a5a5a5a5a5a     # slot untouched
+            else:
+                assert d["pack"] == el and d["ptr"] == slots.ctypes.data + 8 * (3 + i)
+                assert (int(slots[3 + i]) & ((1 << (8 * el)) - 1)) == int(want[i])
+        assert np.all(datums["pack"][:3] == 0)
+    datums = np.zeros(len(rid), dtype=ob.DATUM_DTYPE)
+    batch.project_datums(1, 2, rid, datums, string_base=base + int(table.offsets[1]) - int(table.offsets[1]))
+    offs, lens, wn, _ = blk.get_rows_discrete(2, rid)
+    for i in range(len(rid)):
+        isnull = bool((wn[i // 64] >> np.uint64(i % 64)) & np.uint64(1))
+        assert bool(datums[i]["pack"] & ob.DATUM_NULL_BIT) == isnull
+        if not isnull:
+            assert datums[i]["pack"] == lens[i]
+            got = C.string_at(int(datums[i]["ptr"]), int(lens[i]))
+            assert got == bytes(blk.buf[int(offs[i]):int(offs[i]) + int(lens[i])])
+    # whole-batch result as datums
+    res = batch.scan(ob.White(1, ob.WHITE_OP_GT, (0,)), [0, 1, 2], string_base=base)
+    k = res.selected_rows
+    for c, el in ((0, 8), (1, 4)):
+        data, _, nulls = res.fetch_col(c)
+        datums, slots = res.fetch_datums(c)
+        isnull = ((nulls[np.arange(k) // 64] >> (np.arange(k) % 64).astype(np.uint64)) & np.uint64(1)).astype(bool)
+        assert np.array_equal((datums["pack"] & ob.DATUM_NULL_BIT) != 0, isnull)
+        assert np.all(datums["pack"][~isnull] == el)
+        assert np.array_equal(datums["ptr"], slots.ctypes.data + 8 * np.arange(k, dtype=np.uint64))
+        assert np.array_equal(slots[~isnull], data.astype(np.uint64)[~isnull])
+    data, lens, nulls = res.fetch_col(2)
+    datums, slots = res.fetch_datums(2)
+    isnull = ((nulls[np.arange(k) // 64] >> (np.arange(k) % 64).astype(np.uint64)) & np.uint64(1)).astype(bool)
+    assert slots is None and np.array_equal(datums["ptr"][~isnull], data[~isnull])
+    assert np.array_equal(datums["pack"][~isnull], lens[~isnull].astype(np.uint32))
+    assert np.all(datums["pack"][isnull] == ob.DATUM_NULL_BIT)
+    res.free()
+    batch.close()
