@@ -119,6 +119,32 @@ int obgpu_merge_result_fetch_strings(obgpu_merge_result *res, int32_t col, int64
                                      void *host_heap, int64_t heap_cap, int64_t *host_off, uint8_t *host_null,
                                      int64_t *heap_bytes);
 
+/* =============================================================================================
+ * Multi-GPU: the range-partitioned merge (one rowkey range per rank, ObParallelMergeCtx,
+ * compaction/ob_partition_parallel_merge_ctx.cpp:187-424). The exchange of run slices between the ranks is the one
+ * collective step of the whole path: sampled splitters through ncclAllGather, slices through grouped
+ * ncclSend / ncclRecv over NVLink, all enqueued on the ctx stream by the library (NCCL is bound with dlopen).
+ * ============================================================================================= */
+#define OBGPU_COMM_ID_BYTES 128
+typedef struct obgpu_comm obgpu_comm;
+/* Rank 0 makes the communicator id (ncclGetUniqueId) and hands its 128 bytes to every rank through the caller's own
+ * channel; then every rank calls obgpu_comm_create with the same id. One process per GPU. */
+int obgpu_comm_unique_id(void *id_out);
+int obgpu_comm_create(obgpu_ctx *ctx, const void *id, int32_t rank, int32_t world, obgpu_comm **out);
+void obgpu_comm_destroy(obgpu_comm *comm);
+/* Every run index in [0, n_runs_total) is held (decoded, in HBM) by exactly one rank: local_runs[q] is run
+ * run_index[q]. Collective over the communicator: splitters from samples_per_run evenly spaced rowkeys of every run,
+ * every rank receives the slices of its rowkey range and merges them (obgpu_merge_decoded); the concatenation of the
+ * ranks' results in rank order is the merged stream. Integer payload columns (string references are only valid on the
+ * device that decoded them). Composite rowkeys partition on the first rowkey column. The local runs' arrays must stay
+ * alive until the ctx stream has been synchronised (e.g. obgpu_merge_result_info). splitters_out: world - 1 values,
+ * recv_rows_out: rows of every run in this rank's range (both optional, host). */
+int obgpu_merge_decoded_distributed(obgpu_ctx *ctx, obgpu_comm *comm, const obgpu_merge_run *local_runs,
+                                    const int32_t *run_index, int32_t n_local, int32_t n_runs_total, int32_t n_cols,
+                                    int32_t n_more_keys, const int64_t *default_vals, const uint8_t *default_null,
+                                    int32_t samples_per_run, obgpu_merge_result **out, int64_t *splitters_out,
+                                    int64_t *recv_rows_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -24,6 +24,11 @@ OBJ_DATETIME, OBJ_TIMESTAMP, OBJ_DATE, OBJ_TIME, OBJ_YEAR, OBJ_VARCHAR, OBJ_CHAR
 NODE_WHITE, NODE_AND, NODE_OR = 0, 1, 2
 
 
+def datum_len_of(obj_type: int) -> int:
+    """Datum length of an integer-class ObObjType (ObDatum::get_obj_datum_map_type): year 1, date 4, else 8."""
+    return 1 if obj_type == OBJ_YEAR else (4 if obj_type == OBJ_DATE else 8)
+
+
 class ObGpuError(RuntimeError):
     def __init__(self, code, what, detail=""):
         self.code = code
@@ -57,6 +62,27 @@ class ResultInfo(C.Structure):
 class ResultCol(C.Structure):
     _fields_ = [("data", C.c_void_p), ("aux", C.c_void_p), ("nulls", C.c_void_p), ("elem_len", C.c_int32),
                 ("is_string", C.c_int32), ("has_null", C.c_int32), ("obj_type", C.c_int32)]
+
+
+class HostAgg(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("col_a", C.c_int32), ("col_b", C.c_int32)]
+
+
+class HostScanSpec(C.Structure):
+    _fields_ = [("image", C.c_void_p), ("image_size", C.c_int64), ("offsets", C.c_void_p), ("sizes", C.c_void_p),
+                ("n_blocks", C.c_int32), ("filter", C.POINTER(Filter)), ("proj_cols", C.POINTER(C.c_int32)), ("n_proj", C.c_int32),
+                ("blocks_per_batch", C.c_int32), ("ramp", C.c_int32), ("selectivity_hint", C.c_double), ("string_base", C.c_uint64),
+                ("agg_rows", C.c_void_p), ("agg_off", C.c_void_p), ("out_data", C.POINTER(C.c_void_p)),
+                ("out_lens", C.POINTER(C.c_void_p)), ("out_nulls", C.POINTER(C.c_void_p)), ("out_cap_rows", C.c_int64),
+                ("out_row_ids", C.c_void_p), ("out_block_begin", C.c_void_p), ("out_block_count", C.c_void_p),
+                ("no_row_output", C.c_int32), ("aggs", C.POINTER(HostAgg)), ("n_aggs", C.c_int32)]
+
+
+class HostScanResult(C.Structure):
+    _fields_ = [("total_rows", C.c_int64), ("selected_rows", C.c_int64), ("n_batches", C.c_int32),
+                ("batch_row_begin", C.c_void_p), ("batch_rows", C.c_void_p), ("batch_block_begin", C.c_void_p),
+                ("n_batches_cap", C.c_int32), ("agg_out", (C.c_int64 * 2) * 16), ("h2d_bytes", C.c_int64),
+                ("d2h_bytes", C.c_int64), ("kernel_launches", C.c_int64)]
 
 
 class ColInput(C.Structure):
@@ -119,6 +145,15 @@ def declared_signatures():
         "obgpu_ctx_launch_count": (i64, [vp]),
         "obgpu_ctx_set_profiling": (C.c_int, [vp, i32]),
         "obgpu_ctx_kernel_times": (C.c_int, [vp, vp, i32, P(i32)]),
+        "obgpu_comm_unique_id": (C.c_int, [vp]),
+        "obgpu_comm_create": (C.c_int, [vp, vp, i32, i32, P(vp)]),
+        "obgpu_comm_destroy": (None, [vp]),
+        "obgpu_merge_decoded_distributed": (C.c_int, [vp, vp, P(MergeRun), vp, i32, i32, i32, i32, vp, vp, i32, P(vp), vp, vp]),
+        "obgpu_pipeline_create": (C.c_int, [C.c_int, i32, P(vp)]),
+        "obgpu_pipeline_destroy": (None, [vp]),
+        "obgpu_pipeline_last_error": (C.c_char_p, [vp]),
+        "obgpu_pipeline_plan": (C.c_int, [P(HostScanSpec), P(i32), P(i64)]),
+        "obgpu_pipeline_scan": (C.c_int, [vp, P(HostScanSpec), P(HostScanResult)]),
         "obgpu_batch_open": (C.c_int, [vp, vp, i64, vp, vp, i32, i32, vp, P(vp)]),
         "obgpu_batch_close": (None, [vp]),
         "obgpu_batch_block_info": (C.c_int, [vp, i32, P(i64), P(i32)]),

@@ -160,6 +160,81 @@ def merge_decoded(ctx, runs: Sequence[DecodedRun], default_vals=None, default_nu
     return MergeResult(ctx, h, n_cols, keep)
 
 
+class Comm:
+    """obgpu_comm: NCCL communicator bound inside the library (one process per GPU). The 128-byte id comes from rank 0
+    (Comm.unique_id()) and reaches the other ranks through the caller's own channel -- torch.distributed here."""
+
+    def __init__(self, ctx, comm_id: bytes, rank: int, world: int):
+        self.ctx, self.rank, self.world = ctx, rank, world
+        self._h = C.c_void_p()
+        buf = C.create_string_buffer(bytes(comm_id), 128)
+        check(lib.obgpu_comm_create(ctx._h, buf, rank, world, C.byref(self._h)), "obgpu_comm_create", ctx._h)
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        check(lib.obgpu_comm_unique_id(buf), "obgpu_comm_unique_id")
+        return bytes(buf.raw)
+
+    @staticmethod
+    def from_torch_distributed(ctx, device=None, group=None) -> "Comm":
+        """Rank 0 makes the id, a broadcast hands it out."""
+        import torch
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        device = device or torch.device("cuda", torch.cuda.current_device())
+        t = torch.zeros(128, dtype=torch.uint8, device=device)
+        if rank == 0:
+            t.copy_(torch.frombuffer(bytearray(Comm.unique_id()), dtype=torch.uint8))
+        dist.broadcast(t, src=0 if group is None else dist.get_global_rank(group, 0), group=group)
+        return Comm(ctx, bytes(t.cpu().numpy().tobytes()), rank, world)
+
+    def close(self):
+        if self._h:
+            lib.obgpu_comm_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def merge_decoded_distributed(ctx, comm: Comm, local_runs: Dict[int, DecodedRun], n_runs_total: int, n_cols: int,
+                              n_more_keys: int = 0, default_vals=None, default_null=None, samples_per_run: int = 1024):
+    """obgpu_merge_decoded_distributed: the range-partitioned merge with the exchange inside the library (NCCL on the ctx
+    stream). Returns (MergeResult of this rank's rowkey range, splitters, rows received per run)."""
+    idx = sorted(local_runs)
+    arr = (capi.MergeRun * max(len(idx), 1))()
+    keep = []
+    for i, q in enumerate(idx):
+        r = local_runs[q]
+        vp = (C.c_void_p * max(n_cols, 1))(*[v.data_ptr() for v in r.vals])
+        ep = (C.c_void_p * max(n_cols, 1))(*[e.data_ptr() for e in r.ext])
+        keep += [vp, ep, r]
+        arr[i].n = r.n
+        arr[i].key = r.key.data_ptr()
+        arr[i].flag = r.flag.data_ptr() if r.flag is not None else None
+        arr[i].vals, arr[i].ext = vp, ep
+        if n_more_keys:
+            mp = (C.c_void_p * n_more_keys)(*[k.data_ptr() for k in r.more_keys])
+            keep.append(mp)
+            arr[i].more_keys = mp
+        arr[i].n_more_keys = n_more_keys
+    ri = (C.c_int32 * max(len(idx), 1))(*idx)
+    dv = np.ascontiguousarray(default_vals, dtype=np.int64) if default_vals is not None else None
+    dn = np.ascontiguousarray(default_null, dtype=np.uint8) if default_null is not None else None
+    split = np.zeros(max(comm.world - 1, 1), dtype=np.int64)
+    recv = np.zeros(n_runs_total, dtype=np.int64)
+    h = C.c_void_p()
+    check(lib.obgpu_merge_decoded_distributed(ctx._h, comm._h, arr, ri, len(idx), n_runs_total, n_cols, n_more_keys,
+                                              dv.ctypes.data if dv is not None else None,
+                                              dn.ctypes.data if dn is not None else None, samples_per_run, C.byref(h),
+                                              split.ctypes.data, recv.ctypes.data), "obgpu_merge_decoded_distributed", ctx._h)
+    return MergeResult(ctx, h, n_cols, keep), split[:comm.world - 1], recv
+
+
 def merge_batches(ctx, batches, rowkey_col, flag_col: Optional[int], cols: Sequence[int], default_vals=None,
                   default_null=None) -> MergeResult:
     """obgpu_merge_runs(_keys): the whole merge of one range from opened page batches (oldest first). rowkey_col: one

@@ -3419,3 +3419,7 @@ int obgpu_project_datums(obgpu_batch *batch, int32_t block, int32_t col, const i
 // ---- major-compaction merge (include/obgpu_compaction.h) -----------------------------------------
 #include "../../include/obgpu_compaction.h"
 #include "merge_kernels.cuh"
+#include "merge_exchange.cuh"
+
+// ---- host-buffer scan pipeline (include/obgpu_pipeline.h) ------------------------------------------------
+#include "host_pipeline.h"

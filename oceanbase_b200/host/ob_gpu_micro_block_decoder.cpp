@@ -143,6 +143,9 @@ int execute_pushdown_filter(sql::ObPushdownFilterExecutor *filter, sql::ObPushdo
 void ObGpuSSTableBatchScanner::reset() {
   if (result_) obgpu_result_free(result_);
   if (batch_) obgpu_batch_close(batch_);
+  if (pipe_) obgpu_pipeline_destroy(pipe_);
+  pipe_ = nullptr;
+  host_mode_ = false;
   result_ = nullptr;
   batch_ = nullptr;
   cur_block_ = 0;
@@ -192,8 +195,7 @@ int ObGpuSSTableBatchScanner::init(const void *image, int64_t image_size, const 
   n_blocks_ = n_blocks;
   batch_size_ = batch_size;
   proj_ = proj;
-  int ret = obgpu_batch_open(rt_.ctx(), image, image_size, offsets, sizes, n_blocks, 0, nullptr, &batch_);
-  if (ret != OBGPU_SUCCESS) return ret;
+  int ret = OB_SUCCESS;
   std::vector<obgpu_filter_node> nodes;
   std::vector<obgpu_filter_param> params;
   obgpu_filter flt{};
@@ -205,6 +207,79 @@ int ObGpuSSTableBatchScanner::init(const void *image, int64_t image_size, const 
     flt.n_params = (int32_t)params.size();
   }
   const bool use_index = filter && index_infos_ != nullptr;
+  if (pipe_streams_ > 0 && !use_index) {
+    // ---- pipelined open: every page batch's H2D, kernels and D2H overlap; the result ends up in host memory ----
+    if ((ret = obgpu_pipeline_create(0, pipe_streams_, &pipe_)) != OBGPU_SUCCESS) return ret;
+    obgpu_host_scan_spec hs{};
+    hs.image = image;
+    hs.image_size = image_size;
+    hs.offsets = offsets;
+    hs.sizes = sizes;
+    hs.n_blocks = n_blocks;
+    hs.filter = filter ? &flt : nullptr;
+    hs.proj_cols = proj_.data();
+    hs.n_proj = (int32_t)proj_.size();
+    hs.blocks_per_batch = pipe_bpb_;
+    hs.selectivity_hint = 1.0;                 // slices hold every row of their batch: no overflow handling needed
+    hs.string_base = (uint64_t)(uintptr_t)image;
+    int32_t nb = 0;
+    int64_t cap = 0;
+    if ((ret = obgpu_pipeline_plan(&hs, &nb, &cap)) != OBGPU_SUCCESS) return ret;
+    // column shapes from the first block's headers through a one-block batch (types are per SSTable)
+    {
+      obgpu_batch *probe = nullptr;
+      const int64_t zero = 0;
+      if ((ret = obgpu_batch_open(rt_.ctx(), (const char *)image + offsets[0], sizes[0], &zero, sizes, 1, 0, nullptr, &probe)) != OBGPU_SUCCESS) return ret;
+      obgpu_scan_spec ps{};
+      ps.proj_cols = proj_.data();
+      ps.n_proj = (int32_t)proj_.size();
+      ps.max_selected_rows = 1;
+      obgpu_result *pr = nullptr;
+      ret = obgpu_scan(probe, &ps, &pr);
+      cols_.resize(proj_.size());
+      for (size_t c = 0; ret == OBGPU_SUCCESS && c < proj_.size(); ++c) ret = obgpu_result_col_get(pr, (int32_t)c, &cols_[c]);
+      if (pr) obgpu_result_free(pr);
+      obgpu_batch_close(probe);
+      if (ret != OBGPU_SUCCESS) return ret;
+    }
+    const size_t np = proj_.size();
+    h_data_.assign(np, {});
+    h_lens_.assign(np, {});
+    h_nulls_.assign(np, {});
+    std::vector<void *> od(np);
+    std::vector<int32_t *> ol(np);
+    std::vector<uint64_t *> on(np);
+    for (size_t c = 0; c < np; ++c) {
+      h_data_[c].assign((size_t)cap * (cols_[c].is_string ? 8 : (size_t)cols_[c].elem_len) + 64, 0);
+      if (cols_[c].is_string) h_lens_[c].assign((size_t)cap + 16, 0);
+      h_nulls_[c].assign((size_t)cap / 64 + 2, 0);
+      od[c] = h_data_[c].data();
+      ol[c] = cols_[c].is_string ? h_lens_[c].data() : nullptr;
+      on[c] = h_nulls_[c].data();
+    }
+    h_row_ids_.assign((size_t)cap + 16, 0);
+    h_block_begin_.assign((size_t)n_blocks, 0);
+    std::vector<int64_t> block_count((size_t)n_blocks, 0), row_begin((size_t)nb + 1), rows((size_t)nb + 1);
+    hs.out_data = od.data();
+    hs.out_lens = ol.data();
+    hs.out_nulls = on.data();
+    hs.out_cap_rows = cap;
+    hs.out_row_ids = h_row_ids_.data();
+    hs.out_block_begin = h_block_begin_.data();
+    hs.out_block_count = block_count.data();
+    obgpu_host_scan_result hr{};
+    hr.batch_row_begin = row_begin.data();
+    hr.batch_rows = rows.data();
+    hr.n_batches_cap = nb;
+    if ((ret = obgpu_pipeline_scan(pipe_, &hs, &hr)) != OBGPU_SUCCESS) return ret;
+    selected_ = hr.selected_rows;
+    sel_offset_.assign((size_t)n_blocks + 1, 0);
+    for (int32_t b = 0; b < n_blocks; ++b) sel_offset_[(size_t)b + 1] = sel_offset_[(size_t)b] + block_count[(size_t)b];
+    host_mode_ = true;
+    return OB_SUCCESS;
+  }
+  ret = obgpu_batch_open(rt_.ctx(), image, image_size, offsets, sizes, n_blocks, 0, nullptr, &batch_);
+  if (ret != OBGPU_SUCCESS) return ret;
   if (use_index) {
     if (n_index_infos_ != n_blocks) return OB_INVALID_ARGUMENT;
     std::vector<char> rows;
@@ -244,7 +319,7 @@ int ObGpuSSTableBatchScanner::init(const void *image, int64_t image_size, const 
 // access/ob_block_batched_row_store.cpp:163-186): out_cnt_ counts the selected rows seen so far; a batch keeps rows
 // [start, end) where start skips what is left of the offset and end stops at offset + limit.
 int ObGpuSSTableBatchScanner::get_next_rows(Batch &out) {
-  if (!result_) return OB_NOT_INIT;
+  if (!result_ && !host_mode_) return OB_NOT_INIT;
   for (;;) {
     if (limit_end_) return OB_ITER_END;               // IterEndState::LIMIT_ITER_END
     const int ret = next_window(out);
@@ -320,6 +395,38 @@ int ObGpuSSTableBatchScanner::fetch_window(int32_t block, int64_t row_begin, int
   out.block_idx = block;
   out.count = n;
   out.row_ids.resize((size_t)n);
+  if (host_mode_) {   // the pipelined open left everything in host memory: a window is a handful of memcpys
+    const int64_t h0 = h_block_begin_[(size_t)block] + (row_begin - sel_offset_[(size_t)block]);
+    memcpy(out.row_ids.data(), h_row_ids_.data() + h0, (size_t)n * 4);
+    const size_t np = proj_.size();
+    out.ints.assign(np, {});
+    out.str_ptrs.assign(np, {});
+    out.str_lens.assign(np, {});
+    out.is_null.assign(np, {});
+    for (size_t c = 0; c < np; ++c) {
+      out.is_null[c].resize((size_t)n);
+      for (int64_t i = 0; i < n; ++i) out.is_null[c][(size_t)i] = (h_nulls_[c][(size_t)(h0 + i) / 64] >> ((h0 + i) % 64)) & 1;
+      if (cols_[c].is_string) {
+        out.str_ptrs[c].resize((size_t)n);
+        out.str_lens[c].assign(h_lens_[c].begin() + h0, h_lens_[c].begin() + h0 + n);
+        for (int64_t i = 0; i < n; ++i) {
+          uint64_t ptr;
+          memcpy(&ptr, h_data_[c].data() + (size_t)(h0 + i) * 8, 8);
+          out.str_ptrs[c][(size_t)i] = reinterpret_cast<const char *>((uintptr_t)ptr);
+        }
+      } else {
+        const int el = cols_[c].elem_len;
+        out.ints[c].resize((size_t)n);
+        for (int64_t i = 0; i < n; ++i) {
+          int64_t v = 0;
+          memcpy(&v, h_data_[c].data() + (size_t)(h0 + i) * (size_t)el, (size_t)el);
+          if (el == 4) v = (int32_t)v;
+          out.ints[c][(size_t)i] = v;
+        }
+      }
+    }
+    return OB_SUCCESS;
+  }
   int ret = obgpu_result_fetch_row_ids(result_, row_begin, n, out.row_ids.data());
   const size_t np = proj_.size();
   out.ints.assign(np, {});

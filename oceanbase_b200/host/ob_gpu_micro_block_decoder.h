@@ -19,6 +19,7 @@
 
 extern "C" {
 #include "../../include/obgpu_scan.h"
+#include "../../include/obgpu_pipeline.h"
 #include "../../include/obgpu_skip_index.h"
 }
 
@@ -269,6 +270,10 @@ public:
   // Reverse scan (is_reverse_scan_ / step_ == -1 of the row scanners): call before the first get_next_rows; batches then
   // come blocks last to first, rows descending inside a block.
   void set_reverse_scan(bool reverse) { reverse_ = reverse; }
+  // Pipelined open (include/obgpu_pipeline.h): init cuts the blocks into page batches and overlaps their host->device
+  // copies, kernels and device->host copies on n_streams streams; get_next_rows then serves every batch from host
+  // memory. Call before init. (With index infos attached the single-batch path is used: the verdicts come from it.)
+  void set_pipelined(int32_t n_streams, int32_t blocks_per_batch = 0) { pipe_streams_ = n_streams; pipe_bpb_ = blocks_per_batch; }
   // LIMIT / OFFSET pushed down to the scan (ObTableAccessContext::limit_param_): every batch is trimmed the way
   // ObBlockBatchedRowStore::get_row_ids does (access/ob_block_batched_row_store.cpp:163-186) -- the first `offset`
   // selected rows are dropped, OB_ITER_END follows the batch that reaches `limit` (limit < 0: none).
@@ -298,6 +303,15 @@ private:
   bool reverse_ = false, rev_started_ = false;
   int64_t limit_offset_ = 0, limit_ = -1, out_cnt_ = 0;
   bool limit_end_ = false;
+  // pipelined mode: the whole result lives in host memory
+  int32_t pipe_streams_ = 0, pipe_bpb_ = 0;
+  obgpu_pipeline *pipe_ = nullptr;
+  bool host_mode_ = false;
+  std::vector<std::vector<char>> h_data_;
+  std::vector<std::vector<int32_t>> h_lens_;
+  std::vector<std::vector<uint64_t>> h_nulls_;
+  std::vector<int32_t> h_row_ids_;
+  std::vector<int64_t> h_block_begin_;   // output row where a block's selected rows start
   ObGpuScanRuntime &rt_;
   obgpu_batch *batch_ = nullptr;
   obgpu_result *result_ = nullptr;

@@ -254,6 +254,14 @@ class PageBatch:
               "obgpu_project_discrete", self.ctx._h)
         return ptrs, lens, nulls, hn.value
 
+    def project_datums(self, block, col, row_ids, datums: np.ndarray, datum_offset=0, string_base=0):
+        """ObMicroBlockDecoder::get_rows, datum format: fills `datums` (structured array DATUM_DTYPE, 12 bytes each) from
+        datum_offset on. Integer datums must already point at their 8-byte slots."""
+        rid = np.ascontiguousarray(row_ids, dtype=np.int32)
+        check(lib.obgpu_project_datums(self._h, block, col, rid.ctypes.data, len(rid), datum_offset, string_base,
+                                       datums.ctypes.data), "obgpu_project_datums", self.ctx._h)
+        return datums
+
     def close(self):
         if self._h:
             if self.ctx._h:  # the C ctx owns the stream: never touch a batch after its ctx is gone

@@ -370,6 +370,30 @@ static void test_filter_tree_and_batch_scanner(ObGpuScanRuntime &rt) {
   ASSERT_EQ(OB_ITER_END, ret);
   ASSERT_EQ(lo - 1, next);
 
+  // (4b) pipelined open (obgpu_pipeline_scan underneath): same rows served from host memory, forward and reverse
+  for (int rev_mode = 0; rev_mode < 2; ++rev_mode) {
+    ObGpuSSTableBatchScanner pl(rt);
+    pl.set_pipelined(3, 4);
+    pl.set_reverse_scan(rev_mode == 1);
+    ASSERT_EQ(OB_SUCCESS, pl.init(image.data(), image_size, offs.data(), sizes.data(), nb, &bt, {0, 1, 2}, 100));
+    ASSERT_EQ(hi - lo + 1, pl.total_selected());
+    next = rev_mode ? hi : lo;
+    while ((ret = pl.get_next_rows(batch)) == OB_SUCCESS) {
+      for (int64_t i = 0; i < batch.count; ++i) {
+        ASSERT_EQ(next, batch.ints[0][(size_t)i]);
+        ASSERT_EQ(next, (int64_t)batch.block_idx * rpb + batch.row_ids[(size_t)i]);
+        ASSERT_EQ((int)nulls[(size_t)next], (int)batch.is_null[1][(size_t)i]);
+        if (!batch.is_null[1][(size_t)i]) ASSERT_EQ(a[(size_t)next], batch.ints[1][(size_t)i]);
+        const std::string want = heap.substr((size_t)off[(size_t)next], (size_t)(off[(size_t)next + 1] - off[(size_t)next]));
+        ASSERT_EQ((int64_t)want.size(), (int64_t)batch.str_lens[2][(size_t)i]);
+        ASSERT_EQ(0, memcmp(batch.str_ptrs[2][(size_t)i], want.data(), want.size()));
+        next += rev_mode ? -1 : 1;
+      }
+    }
+    ASSERT_EQ(OB_ITER_END, ret);
+    ASSERT_EQ(rev_mode ? lo - 1 : hi + 1, next);
+  }
+
   // (5) LIMIT / OFFSET (ObBlockBatchedRowStore::get_row_ids, ob_block_batched_row_store.cpp:163-186): the first `offset`
   // selected rows are dropped batch by batch, the scan ends with the batch that reaches `limit`
   const int64_t cases[][2] = {{0, 10}, {7, 300}, {255, 2}, {256, 256}, {1000, -1}, {hi - lo + 5, 10}, {3, 0}, {0, hi - lo + 100}};

@@ -13,11 +13,10 @@ def test_pipeline_matches_oracle():
     from oceanbase_b200.synth import make_config2_like
     w = make_config2_like(rows=120_000, rows_per_block=1400, seed=11)
     pipe = HostScanPipeline(0, n_workers=3)
-    outs = pipe.scan(w.table, w.filter, w.proj, blocks_per_batch=7, selectivity_hint=0.05)  # forces overflow re-runs
+    outs = pipe.scan(w.table, w.filter, w.proj, blocks_per_batch=7, selectivity_hint=0.05).batches  # forces overflow re-runs
     pipe.close()
     want = ora.scan_table(w.table, w.filter, w.proj, w.proj_is_string, w.proj_elem_len)
     assert sum(o.selected_rows for o in outs) == want["selected"]
-    assert sum(o.total_rows for o in outs) == w.table.total_rows
     for c in range(len(w.proj)):
         got = np.concatenate([o.cols[c] for o in outs])
         assert np.array_equal(got, want["data"][c])
@@ -29,7 +28,7 @@ def test_pipeline_with_ramped_batches():
     from oceanbase_b200.synth import make_config2_like
     w = make_config2_like(rows=120_000, rows_per_block=1400, seed=12)
     pipe = HostScanPipeline(0, n_workers=2)
-    outs = pipe.scan(w.table, w.filter, w.proj, blocks_per_batch=16, selectivity_hint=0.3, ramp=2)
+    outs = pipe.scan(w.table, w.filter, w.proj, blocks_per_batch=16, selectivity_hint=0.3, ramp=2).batches
     pipe.close()
     want = ora.scan_table(w.table, w.filter, w.proj, w.proj_is_string, w.proj_elem_len)
     assert sum(o.selected_rows for o in outs) == want["selected"]
@@ -52,9 +51,40 @@ def test_pipeline_with_skip_index():
     rows, offs = ob.table_agg_rows(cols, [0, 1], 700)
     flt = ob.And([ob.White(0, ob.WHITE_OP_BT, (int(k[20_000]), int(k[45_000]))), ob.White(1, ob.WHITE_OP_LT, (60,))])
     pipe = HostScanPipeline(0, n_workers=3)
-    outs = pipe.scan(table, flt, [0, 1], blocks_per_batch=11, selectivity_hint=0.3, ramp=2, agg_rows=rows, agg_off=offs)
+    outs = pipe.scan(table, flt, [0, 1], blocks_per_batch=11, selectivity_hint=0.3, ramp=2, agg_rows=rows, agg_off=offs).batches
     pipe.close()
     want = ora.scan_table(table, flt, [0, 1], [False, False], [8, 8])
     assert sum(o.selected_rows for o in outs) == want["selected"]
     for c in range(2):
         assert np.array_equal(np.concatenate([o.cols[c] for o in outs]), want["data"][c])
+
+
+def test_pipeline_strings_and_pushed_down_aggregates():
+    """VARCHAR columns come back as (pointer into the caller's image, length) per batch; aggregates are folded on the
+    device per page batch and summed in the library: with no_row_output only 16 bytes per aggregate and batch return."""
+    import oceanbase_b200 as ob
+    from oceanbase_b200.pipeline import HostScanPipeline
+    from oceanbase_b200.synth import make_config3_like
+    w = make_config3_like(rows=40_000, rows_per_block=133, seed=3)
+    base = w.table.image.ctypes.data
+    pipe = HostScanPipeline(0, n_workers=3)
+    out = pipe.scan(w.table, w.filter, w.proj, blocks_per_batch=40, selectivity_hint=0.14, ramp=2, string_base=base,
+                    proj_is_string=w.proj_is_string, proj_elem_len=w.proj_elem_len,
+                    aggs=[(ob.AGG_COUNT, 0, -1), (ob.AGG_SUM, 1, -1), (ob.AGG_MAX, 2, -1), (ob.AGG_SUM_PRODUCT, 0, 3)])
+    want = ora.scan_table(w.table, w.filter, w.proj, w.proj_is_string, w.proj_elem_len, string_base=base)
+    assert out.selected_rows == want["selected"] and out.total_rows == w.table.total_rows
+    for c in range(len(w.proj)):
+        got = np.concatenate([b.cols[c] for b in out.batches])
+        assert np.array_equal(got, want["data"][c]), c
+        if w.proj_is_string[c]:
+            assert np.array_equal(np.concatenate([b.lens[c] for b in out.batches]), want["lens"][c])
+    v = [want["data"][c].view(np.int64) for c in range(4)]
+    assert out.aggregates[0] == want["selected"]
+    assert out.aggregates[1] == int(sum(int(x) for x in v[1]))
+    assert out.aggregates[2] == int(v[2].max())
+    assert out.aggregates[3] == int(sum(int(a) * int(b) for a, b in zip(v[0], v[3])))
+    only = pipe.scan(w.table, w.filter, w.proj, blocks_per_batch=40, selectivity_hint=0.01, no_row_output=True,
+                     aggs=[(ob.AGG_SUM_PRODUCT, 0, 3)])
+    assert only.aggregates[0] == out.aggregates[3] and only.selected_rows == out.selected_rows
+    assert only.d2h_bytes == 16 * len(only.batches)
+    pipe.close()
