@@ -574,7 +574,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg2"])
+    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg2", "compaction"])
+    ap.add_argument("--compaction-window", type=int, default=4_000_000, help="compaction: rowkey indexes covered by one of the 8 runs")
+    ap.add_argument("--verify", action="store_true", help="compaction: compare the merged stream with the oracle (small sizes)")
     ap.add_argument("--rows", type=int, default=1_000_000_000, help="cfg3: rows of the whole table (split over the GPUs)")
     ap.add_argument("--segment-rows", type=int, default=15_625_000, help="cfg3: rows of the generated segment (upper bound)")
     ap.add_argument("--rows-per-block", type=int, default=0, help="cfg3: 0 = cut micro-blocks at the 16 KiB target")
@@ -594,6 +596,12 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
+    if args.workload == "compaction":
+        # BASELINE.json configs[4] (stand-in size): K-way major-compaction merge, range-partitioned over the GPUs
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_compaction
+        return bench_compaction.run(argparse.Namespace(runs=8, window=args.compaction_window, steps=args.steps, warmup=args.warmup,
+                                                      verify=args.verify, python_exchange=False))
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)

@@ -306,6 +306,55 @@ int obgpu_project_discrete(obgpu_batch *batch, int32_t block, int32_t col, const
 int obgpu_project_datums(obgpu_batch *batch, int32_t block, int32_t col, const int32_t *row_ids,
                          int64_t row_cap, int64_t datum_offset, uint64_t string_base, obgpu_datum *datums);
 
+/* =============================================================================================
+ * Dictionary surface of one micro-block (pushdown GROUP BY, black filter on one dictionary column).
+ * A column is "dictionary coded" in a block when its encoding is DICT / RLE / CONST (PAX) or INT_DICT / STR_DICT (CS);
+ * otherwise the calls return OBGPU_NOT_SUPPORTED, the condition under which the reference falls back too
+ * (ObIMicroBlockReader::can_apply_black, ob_micro_block_decoder.h:332-337; ObAggGroupByDecoder: group by needs
+ * ObDictDecoder, ob_pushdown_aggregate.cpp check_column_can_group_by).
+ * ============================================================================================= */
+/* Column `col` (store index) of the batch: its ObObjType as the column headers carry it (0xff when the blocks of the batch
+ * disagree) and the datum length of its class: 8 / 4 / 1 for integer classes, 0 for strings (the length is per cell). */
+int obgpu_batch_column_type(const obgpu_batch *batch, int32_t col, int32_t *obj_type, int32_t *datum_len);
+/* ObIMicroBlockReader::get_distinct_count(group_by_col, distinct_cnt) (ob_micro_block_decoder.cpp:2263-2278,
+ * ObDictDecoder::get_distinct_count ob_dict_decoder.cpp:1681-1686). */
+int obgpu_block_distinct_count(obgpu_batch *batch, int32_t block, int32_t col, int64_t *count);
+/* ObIMicroBlockReader::read_distinct (ob_micro_block_decoder.cpp:2280-2304; ObDictDecoder::batch_read_distinct
+ * ob_dict_decoder.cpp:1708-1790): entry i of the dictionary in dictionary order. Integer classes: vals[i] = value image
+ * (low datum-length bytes significant); strings: vals[i] = string_base + offset of the cell in the caller's image,
+ * lens[i] its length. *count is always set; OBGPU_BUF_NOT_ENOUGH when it exceeds cap. */
+int obgpu_block_read_distinct(obgpu_batch *batch, int32_t block, int32_t col, uint64_t string_base, uint64_t *vals,
+                              int32_t *lens, int64_t cap, int64_t *count);
+/* ObIMicroBlockReader::read_reference (ob_micro_block_decoder.cpp:2306-2330; ObDictDecoder::read_reference
+ * ob_dict_decoder.cpp:1792-1830): refs[i] = dictionary reference of row row_ids[i]; NULL rows give the distinct count
+ * (the reference's "ref == dict count means NULL"). */
+int obgpu_block_read_reference(obgpu_batch *batch, int32_t block, int32_t col, const int32_t *row_ids, int64_t row_cap,
+                               uint32_t *refs);
+/* ObMicroBlockDecoder::filter_black_filter_batch on a single dictionary column (ob_micro_block_decoder.cpp:1822-1859
+ * -> ObDictDecoder::pushdown_operator for ObBlackFilterExecutor): the caller evaluates its expression once per distinct
+ * value (obgpu_block_read_distinct) and passes the verdicts; rows [start, start + count) whose ref passes get
+ * result_bitmap[i] = 1, NULL rows get null_pass. n_entries must equal the block's distinct count. */
+int obgpu_filter_dict_pass(obgpu_batch *batch, int32_t block, int32_t col, const uint8_t *entry_pass, int64_t n_entries,
+                           int32_t null_pass, int64_t start, int64_t count, uint8_t *result_bitmap);
+/* Pushdown GROUP BY (ObIMicroBlockReader::get_group_by_aggregate_result, ob_micro_block_decoder.cpp:2332-2400;
+ * ObGroupByCell::eval_batch): rows are grouped by the ref of group_col (group g = dictionary entry g of the block,
+ * group == distinct count: the NULL group) and every aggregate is folded per group.
+ *   kind COUNT with col < 0: COUNT(*); COUNT(col): non-NULL rows; SUM / MIN / MAX as obgpu_result_aggregate.
+ * host_out is [n_aggs][groups][2] int64 (pairs as obgpu_result_aggregate's out[2]); cols are STORE indexes of
+ * integer-class columns. */
+typedef struct obgpu_group_agg {
+  int32_t kind; /* OBGPU_AGG_COUNT / SUM / MIN / MAX */
+  int32_t col;
+} obgpu_group_agg;
+/* one block, the rows of row_ids (the reference call shape); *n_groups = distinct count + 1 */
+int obgpu_block_group_by(obgpu_batch *batch, int32_t block, int32_t group_col, const obgpu_group_agg *aggs, int32_t n_aggs,
+                         const int32_t *row_ids, int64_t row_cap, int64_t *host_out, int64_t out_cap_groups,
+                         int64_t *n_groups);
+/* every block of a scan, the rows its filter selected, ONE launch: block b's groups are
+ * [host_group_off[b], host_group_off[b + 1]) of the group axis (host_group_off: n_blocks + 1 entries, may be NULL). */
+int obgpu_result_group_by(obgpu_result *res, int32_t group_col, const obgpu_group_agg *aggs, int32_t n_aggs,
+                          int64_t *host_group_off, int64_t *host_out, int64_t out_cap_groups, int64_t *total_groups);
+
 /* Library self-description (build id, arch) for logs. */
 const char *obgpu_version(void);
 

@@ -176,6 +176,13 @@ def declared_signatures():
         "obgpu_project_discrete": (C.c_int, [vp, i32, i32, vp, i64, i64, u64, vp, vp, vp, P(i32)]),
         "obgpu_project_datums": (C.c_int, [vp, i32, i32, vp, i64, i64, u64, vp]),
         "obgpu_result_fetch_datums": (C.c_int, [vp, i32, i64, i64, vp, vp]),
+        "obgpu_batch_column_type": (C.c_int, [vp, i32, P(i32), P(i32)]),
+        "obgpu_block_distinct_count": (C.c_int, [vp, i32, i32, P(i64)]),
+        "obgpu_block_read_distinct": (C.c_int, [vp, i32, i32, u64, vp, vp, i64, P(i64)]),
+        "obgpu_block_read_reference": (C.c_int, [vp, i32, i32, vp, i64, vp]),
+        "obgpu_filter_dict_pass": (C.c_int, [vp, i32, i32, vp, i64, i32, i64, i64, vp]),
+        "obgpu_block_group_by": (C.c_int, [vp, i32, i32, vp, i32, vp, i64, vp, i64, P(i64)]),
+        "obgpu_result_group_by": (C.c_int, [vp, i32, vp, i32, vp, vp, i64, P(i64)]),
         "obgpu_version": (C.c_char_p, []),
         # include/obgpu_compaction.h
         "obgpu_batch_decode_column": (C.c_int, [vp, i32, vp, vp]),

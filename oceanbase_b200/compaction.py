@@ -41,12 +41,14 @@ class DecodedRun:
 
 
 def decode_run(ctx, table, key_col: int, flag_col: Optional[int], cols: Sequence[int], device=None,
-               device_image_ptr: Optional[int] = None) -> DecodedRun:
-    """Opens `table` as a page batch on ctx and decodes rowkey, flag and payload columns into torch
-    tensors on the ctx device (obgpu_batch_decode_column)."""
+               device_image_ptr: Optional[int] = None, batch=None, check_rowkey: bool = True) -> DecodedRun:
+    """Opens `table` as a page batch on ctx (or takes an already open `batch`, which stays open) and decodes rowkey,
+    flag and payload columns into torch tensors on the ctx device (obgpu_batch_decode_column)."""
     import torch
     device = device or torch.device("cuda", torch.cuda.current_device())
-    batch = ctx.open_batch(table, device_image_ptr=device_image_ptr)
+    own = batch is None
+    if own:
+        batch = ctx.open_batch(table, device_image_ptr=device_image_ptr)
     n = batch.total_rows
 
     all_cols = [key_col] + ([flag_col] if flag_col is not None else []) + list(cols)
@@ -65,8 +67,9 @@ def decode_run(ctx, table, key_col: int, flag_col: Optional[int], cols: Sequence
         flag = vs[1].to(torch.uint8)
         at = 2
     vals, ext = vs[at:], es[at:]
-    batch.close()
-    if bool((key_ext != 0).any()):
+    if own:
+        batch.close()
+    if check_rowkey and bool((key_ext != 0).any()):
         raise capi.ObGpuError(capi.OB_INVALID_DATA, "decode_run", "rowkey column holds NULL / NOP cells")
     return DecodedRun(key, flag, vals, ext)
 

@@ -3416,6 +3416,9 @@ int obgpu_project_datums(obgpu_batch *batch, int32_t block, int32_t col, const i
 
 }  // extern "C"
 
+// ---- dictionary surface: distinct values, references, black filter on one dictionary column, GROUP BY ----
+#include "dict_ops.cuh"
+
 // ---- major-compaction merge (include/obgpu_compaction.h) -----------------------------------------
 #include "../../include/obgpu_compaction.h"
 #include "merge_kernels.cuh"

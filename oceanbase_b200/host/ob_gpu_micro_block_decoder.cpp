@@ -114,6 +114,81 @@ int ObGpuMicroBlockDecoder::get_rows(const int32_t col, const int32_t *row_ids, 
                               reinterpret_cast<obgpu_datum *>(col_datums));
 }
 
+// ---- dictionary surface ----------------------------------------------------------------------------------
+int ObGpuMicroBlockDecoder::get_distinct_count(const int32_t group_by_col, int64_t &distinct_cnt) const {
+  if (!batch_) return OB_NOT_INIT;
+  return obgpu_block_distinct_count(batch_, 0, group_by_col, &distinct_cnt);
+}
+
+int ObGpuMicroBlockDecoder::read_distinct(const int32_t group_by_col, common::ObDatum *datums, const int64_t cap,
+                                          int64_t &distinct_cnt) const {
+  if (!batch_) return OB_NOT_INIT;
+  if (!datums || cap < 0) return OB_INVALID_ARGUMENT;
+  int ret = obgpu_block_distinct_count(batch_, 0, group_by_col, &distinct_cnt);
+  if (ret != OB_SUCCESS) return ret;
+  if (distinct_cnt > cap) return OB_BUF_NOT_ENOUGH;
+  std::vector<uint64_t> vals((size_t)distinct_cnt + 1);
+  std::vector<int32_t> lens((size_t)distinct_cnt + 1, -1);
+  ret = obgpu_block_read_distinct(batch_, 0, group_by_col, (uint64_t)(uintptr_t)host_buf_, vals.data(), lens.data(), distinct_cnt,
+                                  &distinct_cnt);
+  if (ret != OB_SUCCESS) return ret;
+  int32_t el = 0;
+  if ((ret = obgpu_batch_column_type(batch_, group_by_col, nullptr, &el)) != OB_SUCCESS) return ret;
+  for (int64_t i = 0; i < distinct_cnt; ++i) {
+    ObDatum &d = datums[i];
+    if (el == 0) {   // string: shallow datum into the block
+      d.ptr_ = reinterpret_cast<const char *>((uintptr_t)vals[(size_t)i]);
+      d.pack_ = (uint32_t)lens[(size_t)i] & 0x1fffffffu;
+    } else {
+      if (d.ptr_ == nullptr) return OB_INVALID_ARGUMENT;
+      memcpy(const_cast<char *>(d.ptr_), &vals[(size_t)i], (size_t)el);
+      d.pack_ = (uint32_t)el;
+    }
+  }
+  return OB_SUCCESS;
+}
+
+int ObGpuMicroBlockDecoder::read_reference(const int32_t group_by_col, const int32_t *row_ids, const int64_t row_cap,
+                                           uint32_t *refs) const {
+  if (!batch_) return OB_NOT_INIT;
+  return obgpu_block_read_reference(batch_, 0, group_by_col, row_ids, row_cap, refs);
+}
+
+int ObGpuMicroBlockDecoder::filter_black_filter_batch(const sql::ObPushdownFilterExecutor *parent, sql::ObBlackFilterExecutor &filter,
+                                                      const sql::PushdownFilterInfo &pd_filter_info, ObBitmap &result_bitmap,
+                                                      bool &filter_applied) {
+  (void)parent;
+  filter_applied = false;
+  if (!batch_) return OB_NOT_INIT;
+  if (pd_filter_info.start_ < 0 || pd_filter_info.start_ + pd_filter_info.count_ > row_count_ ||
+      result_bitmap.size() != pd_filter_info.count_)
+    return OB_INVALID_ARGUMENT;
+  if (filter.get_col_offsets().size() != 1) return OB_SUCCESS;
+  const int32_t col = filter.get_col_offsets()[0];
+  int64_t cnt = 0;
+  int ret = obgpu_block_distinct_count(batch_, 0, col, &cnt);
+  if (ret == OB_NOT_SUPPORTED) return OB_SUCCESS;   // not dictionary coded: the caller's row-wise path
+  if (ret != OB_SUCCESS) return ret;
+  std::vector<uint64_t> slots((size_t)cnt + 1);
+  std::vector<ObDatum> datums((size_t)cnt + 1);
+  for (int64_t i = 0; i <= cnt; ++i) datums[(size_t)i].ptr_ = reinterpret_cast<const char *>(&slots[(size_t)i]);
+  if ((ret = read_distinct(col, datums.data(), cnt, cnt)) != OB_SUCCESS) return ret;
+  std::vector<uint8_t> pass((size_t)cnt + 1, 0);
+  for (int64_t i = 0; i < cnt; ++i) {
+    bool filtered = false;
+    if ((ret = filter.filter(datums[(size_t)i], filtered)) != OB_SUCCESS) return ret;
+    pass[(size_t)i] = filtered ? 0 : 1;
+  }
+  ObDatum null_datum;
+  null_datum.set_null();
+  bool null_filtered = false;
+  if ((ret = filter.filter(null_datum, null_filtered)) != OB_SUCCESS) return ret;
+  ret = obgpu_filter_dict_pass(batch_, 0, col, pass.data(), cnt, null_filtered ? 0 : 1, pd_filter_info.start_, pd_filter_info.count_,
+                               result_bitmap.get_data());
+  if (ret == OB_SUCCESS) filter_applied = true;
+  return ret;
+}
+
 // ---- ObPushdownFilterExecutor::execute ----------------------------------------------------------------
 int execute_pushdown_filter(sql::ObPushdownFilterExecutor *filter, sql::ObPushdownFilterExecutor *parent,
                             const sql::PushdownFilterInfo &pd, ObGpuMicroBlockDecoder &decoder) {

@@ -111,7 +111,7 @@ struct PushdownFilterInfo {  // ob_pushdown_filter.h (start_/count_ window of on
   int64_t count_ = 0;
 };
 
-enum PushdownExecutorType { WHITE_FILTER_EXECUTOR, AND_FILTER_EXECUTOR, OR_FILTER_EXECUTOR };
+enum PushdownExecutorType { WHITE_FILTER_EXECUTOR, AND_FILTER_EXECUTOR, OR_FILTER_EXECUTOR, BLACK_FILTER_EXECUTOR };
 
 class ObPushdownFilterExecutor {
 public:
@@ -150,6 +150,19 @@ private:
   int32_t col_offset_;
   ObWhiteFilterOperatorType op_type_;
   std::vector<common::ObStorageDatum> datum_params_;
+};
+
+// sql::ObBlackFilterExecutor (ob_pushdown_filter.h): an arbitrary SQL expression over the filter's columns. Only its
+// owner can evaluate it, one datum at a time: filter(datum, filtered) as ObBlackFilterExecutor::filter(ObStorageDatum &,
+// skip_bit, bool &filtered) (ob_pushdown_filter.cpp:2579-2582); filtered == true drops the row.
+class ObBlackFilterExecutor : public ObPushdownFilterExecutor {
+public:
+  explicit ObBlackFilterExecutor(std::vector<int32_t> col_offsets)
+      : ObPushdownFilterExecutor(BLACK_FILTER_EXECUTOR), col_offsets_(std::move(col_offsets)) {}
+  const std::vector<int32_t> &get_col_offsets() const { return col_offsets_; }
+  virtual int filter(const common::ObDatum &datum, bool &filtered) = 0;
+private:
+  std::vector<int32_t> col_offsets_;
 };
 
 class ObAndFilterExecutor : public ObPushdownFilterExecutor {
@@ -225,6 +238,19 @@ public:
   // integer datums point at the caller's reserved slots and are written through, string datums point into the block
   int get_rows(const int32_t col, const int32_t *row_ids, const int64_t row_cap, const int64_t datum_offset,
                common::ObDatum *col_datums);
+  // ObMicroBlockDecoder::filter_black_filter_batch (encoding/ob_micro_block_decoder.cpp:1822-1859): a black filter over ONE
+  // dictionary-coded column is evaluated once per distinct value, rows test their ref on the device. filter_applied
+  // stays false (bitmap untouched) when the filter has several columns or the column is not dictionary coded here: the
+  // caller then falls back to its row-wise path, as in the reference.
+  int filter_black_filter_batch(const sql::ObPushdownFilterExecutor *parent, sql::ObBlackFilterExecutor &filter,
+                                const sql::PushdownFilterInfo &pd_filter_info, common::ObBitmap &result_bitmap,
+                                bool &filter_applied);
+  // Pushdown GROUP BY surface (encoding/ob_micro_block_decoder.cpp:2263-2330): distinct values in dictionary order
+  // (integer datums are written through their reserved slots like get_rows; strings point into the block) and the ref of
+  // every listed row; a NULL row's ref is the distinct count.
+  int get_distinct_count(const int32_t group_by_col, int64_t &distinct_cnt) const;
+  int read_distinct(const int32_t group_by_col, common::ObDatum *datums, const int64_t cap, int64_t &distinct_cnt) const;
+  int read_reference(const int32_t group_by_col, const int32_t *row_ids, const int64_t row_cap, uint32_t *refs) const;
   obgpu_batch *batch() { return batch_; }
 private:
   ObGpuScanRuntime &rt_;

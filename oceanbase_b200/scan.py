@@ -262,6 +262,55 @@ class PageBatch:
                                        datums.ctypes.data), "obgpu_project_datums", self.ctx._h)
         return datums
 
+    # ---- dictionary surface (pushdown GROUP BY, black filter on one dictionary column) ----
+    def distinct_count(self, block, col) -> int:
+        """ObIMicroBlockReader::get_distinct_count."""
+        n = C.c_int64(0)
+        check(lib.obgpu_block_distinct_count(self._h, block, col, C.byref(n)), "obgpu_block_distinct_count", self.ctx._h)
+        return n.value
+
+    def read_distinct(self, block, col, string_base=0):
+        """ObIMicroBlockReader::read_distinct: (vals uint64, lens int32) in dictionary order; strings: vals are addresses
+        string_base + offset in the caller's image."""
+        n = self.distinct_count(block, col)
+        vals = np.zeros(max(n, 1), dtype=np.uint64)
+        lens = np.zeros(max(n, 1), dtype=np.int32)
+        got = C.c_int64(0)
+        check(lib.obgpu_block_read_distinct(self._h, block, col, string_base, vals.ctypes.data, lens.ctypes.data, n, C.byref(got)),
+              "obgpu_block_read_distinct", self.ctx._h)
+        return vals[:n], lens[:n]
+
+    def read_reference(self, block, col, row_ids) -> np.ndarray:
+        """ObIMicroBlockReader::read_reference: ref per listed row, the distinct count for NULL rows."""
+        rid = np.ascontiguousarray(row_ids, dtype=np.int32)
+        refs = np.zeros(max(len(rid), 1), dtype=np.uint32)
+        check(lib.obgpu_block_read_reference(self._h, block, col, rid.ctypes.data, len(rid), refs.ctypes.data),
+              "obgpu_block_read_reference", self.ctx._h)
+        return refs[:len(rid)]
+
+    def filter_dict_pass(self, block, col, entry_pass, null_pass=False, start=0, count=None) -> np.ndarray:
+        """Black filter on one dictionary column: verdict per distinct value -> ObBitmap bytes of rows [start, start + count)."""
+        ep = np.ascontiguousarray(entry_pass, dtype=np.uint8)
+        if count is None:
+            count = self.block_info(block)[0] - start
+        out = np.zeros(max(count, 1), dtype=np.uint8)
+        check(lib.obgpu_filter_dict_pass(self._h, block, col, ep.ctypes.data if len(ep) else None, len(ep), int(bool(null_pass)),
+                                         start, count, out.ctypes.data), "obgpu_filter_dict_pass", self.ctx._h)
+        return out[:count]
+
+    def group_by(self, block, group_col, aggs, row_ids):
+        """Pushdown GROUP BY on one block: aggs = [(kind, store col or -1)]; returns int64 [n_aggs][groups][2]
+        (groups = distinct count + 1, the last one is the NULL group)."""
+        rid = np.ascontiguousarray(row_ids, dtype=np.int32)
+        g = self.distinct_count(block, group_col) + 1
+        spec = np.array([(k, c) for k, c in aggs], dtype=np.int32).reshape(-1, 2)
+        out = np.zeros((len(aggs), g, 2), dtype=np.int64)
+        n = C.c_int64(0)
+        check(lib.obgpu_block_group_by(self._h, block, group_col, spec.ctypes.data, len(aggs), rid.ctypes.data, len(rid),
+                                       out.ctypes.data, g, C.byref(n)), "obgpu_block_group_by", self.ctx._h)
+        assert n.value == g
+        return out
+
     def close(self):
         if self._h:
             if self.ctx._h:  # the C ctx owns the stream: never touch a batch after its ctx is gone
@@ -315,6 +364,22 @@ class ScanResult:
                                          aux.ctypes.data if aux is not None else None, nulls.ctypes.data),
               "obgpu_result_fetch_col", self.batch.ctx._h)
         return data[:row_count], (aux[:row_count] if aux is not None else None), nulls[:(row_count + 63) // 64]
+
+    def group_by(self, group_col, aggs):
+        """GROUP BY over every block of the scan, the rows the filter selected (one launch): returns (group_off int64
+        [n_blocks + 1], out int64 [n_aggs][total groups][2]); block b's groups are its dictionary entries + the NULL group."""
+        nb = self.batch.n_blocks
+        goff = np.zeros(nb + 1, dtype=np.int64)
+        spec = np.array([(k, c) for k, c in aggs], dtype=np.int32).reshape(-1, 2)
+        total = C.c_int64(0)
+        dummy = np.zeros((len(aggs), 1, 2), dtype=np.int64)
+        rc = lib.obgpu_result_group_by(self._h, group_col, spec.ctypes.data, len(aggs), goff.ctypes.data, dummy.ctypes.data, 0, C.byref(total))
+        if rc != capi.OB_BUF_NOT_ENOUGH:
+            check(rc, "obgpu_result_group_by", self.batch.ctx._h)
+        out = np.zeros((len(aggs), max(total.value, 1), 2), dtype=np.int64)
+        check(lib.obgpu_result_group_by(self._h, group_col, spec.ctypes.data, len(aggs), goff.ctypes.data, out.ctypes.data,
+                                        max(total.value, 1), C.byref(total)), "obgpu_result_group_by", self.batch.ctx._h)
+        return goff, out[:, :total.value]
 
     def fetch_datums(self, i, row_begin=0, row_count=None):
         """Column i as ObDatum[] (datum format): (datums structured array, slots uint64 array or None for strings)."""

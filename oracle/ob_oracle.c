@@ -854,6 +854,81 @@ int ora_decode_cell(const ora_block *b, int32_t col, int64_t row, ora_datum *out
 }
 
 /* =============================================================================================
+ * Dictionary surface (pushdown GROUP BY / black filter on a dictionary column):
+ * ObDictDecoder::get_distinct_count / read_distinct / read_reference (encoding/ob_dict_decoder.cpp:1681-1830),
+ * ObDictColumnDecoder (cs_encoding/ob_dict_column_decoder.cpp: get_distinct_count, read_distinct, read_reference).
+ * A CONST column without exceptions (ObConstDecoder::get_distinct_count / read_distinct / read_reference,
+ * ob_const_decoder.cpp:966-1019): one distinct value = the stored constant, every ref 0; an all-NULL / all-NOP one has
+ * only the NULL group, which this surface numbers like everywhere else (ref == distinct count, here 0).
+ * ============================================================================================= */
+static int dict_col(const col_dec *c, int64_t *count) {
+  switch (c->h.type) {
+    case T_DICT: case T_RLE: *count = c->dict.count; return ORA_SUCCESS;
+    case T_CONST: *count = c->const_count == 0 ? (c->const_ref == 0 ? 1 : 0) : c->dict.count; return ORA_SUCCESS;
+    case T_CS_INT_DICT: case T_CS_STR_DICT: *count = c->cs_distinct; return ORA_SUCCESS;
+    default: return ORA_NOT_SUPPORTED;
+  }
+}
+
+int ora_dict_count(const ora_block *b, int32_t col, int64_t *count) {
+  if (!b || !count) return ORA_INVALID_ARGUMENT;
+  col_dec c;
+  const int ret = col_dec_init(b, col, &c);
+  return ret ? ret : dict_col(&c, count);
+}
+
+/* entry `ref` of the dictionary, decoded like a cell */
+int ora_dict_entry(const ora_block *b, int32_t col, int64_t ref, ora_datum *out) {
+  if (!b || !out) return ORA_INVALID_ARGUMENT;
+  col_dec c;
+  int64_t count;
+  int ret = col_dec_init(b, col, &c);
+  if (!ret) ret = dict_col(&c, &count);
+  if (ret) return ret;
+  if (ref < 0 || ref >= count) return ORA_INVALID_ARGUMENT;
+  if (c.h.type == T_CONST && c.const_count == 0) return decode_cell(b, &c, 0, out);
+  if (c.h.type == T_CS_INT_DICT) {
+    set_int(c.h.obj_type, rd_len(c.cs_data + ref * c.cs_width, c.cs_width) + c.cs_base, out);
+    return ORA_SUCCESS;
+  }
+  if (c.h.type == T_CS_STR_DICT) {
+    int64_t start, len;
+    if (c.cs_fixed_len >= 0) { start = ref * c.cs_fixed_len; len = c.cs_fixed_len; }
+    else {
+      start = ref ? (int64_t)rd_len(c.cs_off + (ref - 1) * c.cs_off_w, c.cs_off_w) : 0;
+      len = (int64_t)rd_len(c.cs_off + ref * c.cs_off_w, c.cs_off_w) - start;
+    }
+    out->ptr = c.cs_str + start; out->len = (uint32_t)len; out->is_null = 0; out->ival = 0;
+    return ORA_SUCCESS;
+  }
+  return dict_decode(&c.dict, c.h.obj_type, ref, out);
+}
+
+/* ref of every listed row; NULL and NOP rows report the distinct count (read_reference's NULL group) */
+int ora_dict_refs(const ora_block *b, int32_t col, const int32_t *row_ids, int64_t row_cap, uint32_t *refs) {
+  if (!b || !row_ids || !refs) return ORA_INVALID_ARGUMENT;
+  col_dec c;
+  int64_t count;
+  int ret = col_dec_init(b, col, &c);
+  if (!ret) ret = dict_col(&c, &count);
+  if (ret) return ret;
+  for (int64_t i = 0; i < row_cap; ++i) {
+    const int64_t row = row_ids[i];
+    if (row < 0 || row >= b->row_count) return ORA_INVALID_ARGUMENT;
+    int64_t ref;
+    switch (c.h.type) {
+      case T_DICT: ref = dict_row_ref(b, &c, row); break;
+      case T_RLE: ref = rle_ref_at(&c, rle_upper_bound(&c, row) - 1); break;
+      case T_CONST: ref = c.const_count == 0 ? 0 : const_row_ref(&c, row); break;
+      default: ref = count ? (int64_t)cs_dict_ref(&c, row) : 0; break;
+    }
+    if (ref > count + 1) return ORA_ERR_UNEXPECTED;
+    refs[i] = (uint32_t)(ref < count ? ref : count);
+  }
+  return ORA_SUCCESS;
+}
+
+/* =============================================================================================
  * Batch projection: ObMicroBlockDecoder::get_rows -> decode_vector
  * (encoding/ob_micro_block_decoder.cpp:2473-2544; ob_raw_decoder.cpp:530-701;
  *  ob_dict_decoder.cpp:473-541; ob_rle_decoder.cpp:528-583 monotone cursor)

@@ -100,6 +100,11 @@ int ora_block_init(ora_block *blk, const void *buf, int64_t size);
 /* data checksum / header checksum verification (ob_micro_block_header.cpp:236-285) */
 int ora_block_verify_checksums(const ora_block *blk);
 int ora_decode_cell(const ora_block *blk, int32_t col, int64_t row, ora_datum *out);
+/* dictionary surface of a dictionary-coded column (DICT / RLE / CONST with exceptions / CS INT_DICT / STR_DICT):
+ * distinct count, entry `ref` decoded like a cell, refs of rows (NULL / NOP rows: the distinct count) */
+int ora_dict_count(const ora_block *blk, int32_t col, int64_t *count);
+int ora_dict_entry(const ora_block *blk, int32_t col, int64_t ref, ora_datum *out);
+int ora_dict_refs(const ora_block *blk, int32_t col, const int32_t *row_ids, int64_t row_cap, uint32_t *refs);
 
 /* ObMicroBlockDecoder::get_rows into VEC_FIXED (data, nulls as ObBitVector words). */
 int ora_get_rows_fixed(const ora_block *blk, int32_t col, const int32_t *row_ids, int64_t row_cap,

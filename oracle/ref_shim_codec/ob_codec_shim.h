@@ -16,7 +16,6 @@
 #define OB_LIKELY(x) __builtin_expect(!!(x), 1)
 #define OB_UNLIKELY(x) __builtin_expect(!!(x), 0)
 #define OB_ISNULL(p) (OB_UNLIKELY(nullptr == (p)))
-#define OB_NOT_NULL(p) (OB_LIKELY(nullptr != (p)))
 #define OB_SUCC(x) (OB_LIKELY(::oceanbase::common::OB_SUCCESS == (ret = (x))))
 #define OB_FAIL(x) (OB_UNLIKELY(::oceanbase::common::OB_SUCCESS != (ret = (x))))
 #define FAILEDx(x) (OB_SUCC(ret) && OB_FAIL(x))
@@ -42,6 +41,11 @@
 #define UNUSED(x) ((void)(x))
 #define UNUSEDx(...)
 #define OB_ASSERT(x) ((void)0)
+#define IS_INIT (is_inited_)
+#define IS_NOT_INIT (!is_inited_)
+#define KPHEX_(x, y) 0
+#define KPHEX(x, y) 0
+#define OB_NOT_NULL(p) (OB_LIKELY(nullptr != (p)))
 #define ob_abort() abort()
 #ifndef CACHE_ALIGN_SIZE
 #define CACHE_ALIGN_SIZE 64
@@ -68,6 +72,10 @@ namespace oceanbase {
 namespace common {
 constexpr int OB_SUCCESS = 0;
 constexpr int OB_INVALID_ARGUMENT = -4002;
+constexpr int OB_ERROR_OUT_OF_RANGE = -4175;
+constexpr int OB_INIT_TWICE = -4005;
+constexpr int OB_ERROR = -4000;
+constexpr int OB_ITER_END = -4008;
 constexpr int OB_NOT_INIT = -4006;
 constexpr int OB_NOT_SUPPORTED = -4007;
 constexpr int OB_ALLOCATE_MEMORY_FAILED = -4013;

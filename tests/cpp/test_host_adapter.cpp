@@ -416,6 +416,81 @@ static void test_filter_tree_and_batch_scanner(ObGpuScanRuntime &rt) {
   }
 }
 
+// Black filter on one dictionary column + the group-by surface (test_dict_decoder.cpp's batch black-filter / group-by
+// cases in shape): the expression is only known to the caller, here "value % 2000 == 7 or NULL" / "string ends in an odd digit".
+struct OddSeedFilter : public sql::ObBlackFilterExecutor {
+  bool str_;
+  int calls_ = 0;
+  OddSeedFilter(int32_t col, bool str) : sql::ObBlackFilterExecutor({col}), str_(str) {}
+  int filter(const common::ObDatum &d, bool &filtered) override {
+    ++calls_;
+    if (d.is_null()) { filtered = false; return OB_SUCCESS; }          // NULL rows pass (IS NULL OR ...)
+    if (str_) filtered = ((d.ptr_[d.len_ - 1] - '0') & 1) == 0;
+    else filtered = ((d.get_int() / 1000) & 1) == 0;
+    return OB_SUCCESS;
+  }
+};
+
+static void test_black_filter_and_group_by_surface(ObGpuScanRuntime &rt) {
+  const int encs[] = {OBGPU_ENC_DICT, OBGPU_ENC_RLE};
+  for (int enc : encs) {
+    // [seed0 x 24 | seed1 x 10 | seed2 x 10 | seed3 x 10 | NULL x 10]
+    std::vector<uint8_t> blk = build_block(layout({{0, ROW_CNT - 40}, {1, 10}, {2, 10}, {3, 10}, {-1, 10}}), enc, enc);
+    ObGpuMicroBlockDecoder dec(rt);
+    ObMicroBlockData data{(const char *)blk.data(), (int64_t)blk.size()};
+    ASSERT_EQ(OB_SUCCESS, dec.init(data));
+    for (int str = 0; str < 2; ++str) {
+      const int col = str ? 2 : 1;
+      int64_t cnt = 0;
+      ASSERT_EQ(OB_SUCCESS, dec.get_distinct_count(col, cnt));
+      ASSERT_EQ(4, cnt);
+      std::vector<uint64_t> slots(4);
+      std::vector<ObDatum> dist(4);
+      for (int i = 0; i < 4; ++i) dist[i].ptr_ = (const char *)&slots[i];
+      ASSERT_EQ(OB_SUCCESS, dec.read_distinct(col, dist.data(), 4, cnt));
+      for (int i = 0; i < 4; ++i) {   // the writer's dictionaries are sorted: entry i is seed i
+        if (str) ASSERT_EQ(0, memcmp(dist[i].ptr_, seed_str(i).data(), dist[i].len_) + (int)(dist[i].len_ != seed_str(i).size()));
+        else ASSERT_EQ(seed_int(i), dist[i].get_int());
+      }
+      ASSERT_EQ(OB_BUF_NOT_ENOUGH, dec.read_distinct(col, dist.data(), 3, cnt));
+      std::vector<int32_t> rid = {0, 23, 24, 33, 34, 44, 53, 54, 63};
+      std::vector<uint32_t> refs(rid.size());
+      ASSERT_EQ(OB_SUCCESS, dec.read_reference(col, rid.data(), (int64_t)rid.size(), refs.data()));
+      const uint32_t want_refs[] = {0, 0, 1, 1, 2, 3, 3, 4, 4};
+      for (size_t i = 0; i < rid.size(); ++i) ASSERT_EQ(want_refs[i], refs[i]);
+      // black filter: seeds 1 and 3 pass (10 + 10 rows) + the 10 NULL rows
+      OddSeedFilter f(col, str != 0);
+      sql::PushdownFilterInfo pd;
+      pd.start_ = 0; pd.count_ = ROW_CNT;
+      ObBitmap bm;
+      bm.init(ROW_CNT);
+      bool applied = false;
+      ASSERT_EQ(OB_SUCCESS, dec.filter_black_filter_batch(nullptr, f, pd, bm, applied));
+      ASSERT_EQ(1, applied);
+      ASSERT_EQ(30, bm.popcnt());
+      ASSERT_EQ(5, f.calls_);   // once per distinct value + once for NULL, not once per row
+      for (int64_t r = 0; r < ROW_CNT; ++r) ASSERT_EQ((r >= 24 && r < 34) || r >= 44, bm.test(r));
+      pd.start_ = ROW_CNT - 35; pd.count_ = 30;   // rows 29..58
+      ObBitmap win;
+      win.init(30);
+      ASSERT_EQ(OB_SUCCESS, dec.filter_black_filter_batch(nullptr, f, pd, win, applied));
+      ASSERT_EQ(5 + 10 + 5, win.popcnt());
+    }
+    // column 0 is RAW: not applied, bitmap untouched, no error (the caller keeps its row-wise path)
+    OddSeedFilter f0(0, false);
+    sql::PushdownFilterInfo pd;
+    pd.start_ = 0; pd.count_ = ROW_CNT;
+    ObBitmap bm;
+    bm.init(ROW_CNT);
+    bool applied = true;
+    ASSERT_EQ(OB_SUCCESS, dec.filter_black_filter_batch(nullptr, f0, pd, bm, applied));
+    ASSERT_EQ(0, applied);
+    ASSERT_EQ(0, bm.popcnt());
+    int64_t cnt = 0;
+    ASSERT_EQ(OB_NOT_SUPPORTED, dec.get_distinct_count(0, cnt));
+  }
+}
+
 int main() {
   ObGpuScanRuntime rt(0);
   if (!rt.is_valid()) {
@@ -425,6 +500,7 @@ int main() {
   test_filter_pushdown(rt);
   test_get_rows_vs_oracle(rt);
   test_filter_tree_and_batch_scanner(rt);
+  test_black_filter_and_group_by_surface(rt);
   if (g_fail) { printf("%d assertion(s) failed\n", g_fail); return 1; }
   printf("host adapter tests passed\n");
   return 0;

@@ -11,6 +11,7 @@ ORACLE_DIR = os.path.join(ROOT, "oracle")
 ORACLE_LIB = os.path.join(ORACLE_DIR, "libob_oracle.so")
 REF_LIB = os.path.join(ORACLE_DIR, "_ref", "libref_bitstream.so")
 REF_CODEC_LIB = os.path.join(ORACLE_DIR, "_ref", "libref_codec.so")
+REF_BITMAP_LIB = os.path.join(ORACLE_DIR, "_ref", "libref_bitmap.so")
 
 
 def _cpu_stamp():
@@ -41,7 +42,7 @@ def build_oracle():
         subprocess.run(["make", "-B", "-C", ORACLE_DIR, "-s", "all"], check=True, capture_output=True)
         with open(stamp_file, "w") as f:
             f.write(stamp + "\n")
-    elif os.path.isdir("/root/reference") and not (os.path.exists(REF_LIB) and os.path.exists(REF_CODEC_LIB)):
+    elif os.path.isdir("/root/reference") and not (os.path.exists(REF_LIB) and os.path.exists(REF_CODEC_LIB) and os.path.exists(REF_BITMAP_LIB)):
         subprocess.run(["make", "-C", ORACLE_DIR, "-s", "ref"], check=True, capture_output=True)
     return ORACLE_LIB
 
@@ -105,6 +106,9 @@ def oracle():
         L.ora_block_init.argtypes = [P(OraBlock), vp, i64]
         L.ora_block_verify_checksums.argtypes = [P(OraBlock)]
         L.ora_decode_cell.argtypes = [P(OraBlock), i32, i64, P(OraDatum)]
+        L.ora_dict_count.argtypes = [P(OraBlock), i32, P(i64)]
+        L.ora_dict_entry.argtypes = [P(OraBlock), i32, i64, P(OraDatum)]
+        L.ora_dict_refs.argtypes = [P(OraBlock), i32, C.c_void_p, i64, C.c_void_p]
         L.ora_get_rows_fixed.argtypes = [P(OraBlock), i32, vp, i64, i64, vp, i32, vp, P(i32)]
         L.ora_get_rows_discrete.argtypes = [P(OraBlock), i32, vp, i64, i64, vp, vp, vp, P(i32)]
         L.ora_filter_white.argtypes = [P(OraBlock), i32, i32, P(OraParam), i32, i64, i64, vp]
@@ -242,6 +246,27 @@ class Block:
         if d.len and d.ival == 0 and False:
             return 0
         return d.ival if d.len else b""
+
+    # dictionary surface
+    def dict_count(self, col):
+        n = C.c_int64(0)
+        ora_check(oracle().ora_dict_count(C.byref(self.b), col, C.byref(n)), "ora_dict_count")
+        return n.value
+
+    def dict_entry(self, col, ref):
+        """bytes for strings, int (64-bit image) for integer classes"""
+        d = OraDatum()
+        ora_check(oracle().ora_dict_entry(C.byref(self.b), col, ref, C.byref(d)), "ora_dict_entry")
+        if d.ptr:
+            off = d.ptr - self.buf.ctypes.data
+            return bytes(self.buf[off:off + d.len]), off
+        return (d.ival if d.len else b""), None
+
+    def dict_refs(self, col, row_ids):
+        rid = np.ascontiguousarray(row_ids, dtype=np.int32)
+        refs = np.zeros(max(len(rid), 1), dtype=np.uint32)
+        ora_check(oracle().ora_dict_refs(C.byref(self.b), col, rid.ctypes.data, len(rid), refs.ctypes.data), "ora_dict_refs")
+        return refs[:len(rid)]
 
     def cell_raw(self, col, row):
         d = OraDatum()

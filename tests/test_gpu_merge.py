@@ -319,3 +319,20 @@ def test_composite_rowkeys_from_page_batches(env, ob):
     res.free()
     for b in batches:
         b.close()
+
+
+def test_distributed_entry_on_one_rank(ob, env):
+    """obgpu_merge_decoded_distributed with a one-rank communicator (NCCL bound inside the library): no splitters, every
+    run stays local, the result is the plain merge. The multi-rank exchange is exercised by tools/bench_compaction.py
+    --verify under torchrun (gpurun --gpus N)."""
+    from oceanbase_b200.compaction import Comm, merge_decoded_distributed
+    from oceanbase_b200.synth import make_config5_runs
+    ctx, torch = env
+    runs = make_config5_runs(n_runs=5, window=30_000, seed=9, encode=False)
+    comm = Comm(ctx, Comm.unique_id(), 0, 1)
+    dec = {q: to_dev(torch, runs[q]) for q in range(5)}
+    res, split, recv = merge_decoded_distributed(ctx, comm, dec, 5, 3)
+    assert len(split) == 0 and list(recv) == [len(r["key"]) for r in runs]
+    assert_merge_equal(res, ora.major_merge(runs, 3), 3)
+    res.free()
+    comm.close()

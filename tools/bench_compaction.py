@@ -18,7 +18,12 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--verify", action="store_true", help="compare the merged stream with the oracle (small sizes)")
+    ap.add_argument("--python-exchange", action="store_true", help="round-1 path: torch.distributed exchange driven from Python")
     args = ap.parse_args()
+    return run(args)
+
+
+def run(args):
     import torch
     import torch.distributed as dist
     import __graft_entry__ as g
@@ -32,7 +37,7 @@ def main():
         dist.barrier()
     import oceanbase_b200 as ob
     from oceanbase_b200.synth import make_config5_runs
-    from oceanbase_b200.compaction import decode_run, merge_decoded, distributed_major_merge
+    from oceanbase_b200.compaction import decode_run, merge_decoded, distributed_major_merge, merge_decoded_distributed, Comm
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     stream = torch.cuda.Stream(device=dev)
@@ -52,6 +57,11 @@ def main():
         d[tb.image.size:].zero_()
         images[q] = d
     torch.cuda.synchronize()
+    # page batches stay open across steps (the block cache); the communicator is made once
+    batches = {q: ctx.open_batch(runs[q]["table"], device_image_ptr=images[q].data_ptr()) for q in mine}
+    comm = None
+    if world > 1 and not getattr(args, "python_exchange", False):
+        comm = Comm.from_torch_distributed(ctx, dev)
     in_rows_local = sum(len(runs[q]["key"]) for q in mine)
     enc_bytes_local = sum(int(runs[q]["table"].sizes.sum()) for q in mine)
 
@@ -63,10 +73,11 @@ def main():
     def step():
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         ev[0].record(stream)
-        dec = {q: decode_run(ctx, runs[q]["table"], 0, 1, [2, 3, 4], device=dev, device_image_ptr=images[q].data_ptr())
-               for q in mine}
+        dec = {q: decode_run(ctx, runs[q]["table"], 0, 1, [2, 3, 4], device=dev, batch=batches[q], check_rowkey=False) for q in mine}
         ev[1].record(stream)
-        if world > 1:
+        if comm is not None:
+            res, _, recv_rows = merge_decoded_distributed(ctx, comm, dec, args.runs, 3)
+        elif world > 1:
             res, _, recv_rows = distributed_major_merge(dec, args.runs, 3, lambda rs: merge_decoded(ctx, rs))
         else:
             res = merge_decoded(ctx, [dec[q] for q in range(args.runs)])
@@ -109,8 +120,19 @@ def main():
                                        f"10 % duplicated rowkeys (NOP cells), 2 % deletes; INT64 rowkey + 3 INT64 payload",
                            "input_rows": tot[0], "output_rows": tot[1], "dropped_deletes": tot[2], "fused_rows": tot[3],
                            "encoded_bytes": tot[4], "gen_seconds": round(t_gen, 1)},
+                "higher_is_better": True, "vs_baseline": None, "dtype": "int64", "data": "synthetic",
                 "phases_ms": {"decode_runs": dec_mean, "exchange_plus_merge": mrg_mean,
+                              "exchange": "ncclAllGather + grouped ncclSend / ncclRecv inside libobgpu_scan.so" if comm is not None else
+                                          ("torch.distributed from Python" if world > 1 else "none (one rank)"),
                               "timing": "wall clock per step incl. host orchestration; phases by CUDA events, max over ranks"}}
+        peak, peak_src = bench.measured_peak_gbs()
+        # bytes the merge has to move per step (SURVEY 8d style): encoded blocks read once, decoded cells (36 B / row: rowkey,
+        # flag, 3 payload values + ext bytes) written by the decode and read by the merge, merged rows written (35 B / row)
+        alg = tot[4] + 2 * 36 * tot[0] + 35 * tot[1]
+        kern_ms = dec_mean + mrg_mean
+        line["roofline"] = {"bound": "hbm", "achieved": alg / (kern_ms * 1e-3) / 1e9 / world, "peak": peak, "unit": "GB/s",
+                            "frac": alg / (kern_ms * 1e-3) / 1e9 / world / peak, "alg_bytes_per_step": alg, "kernel_ms": kern_ms,
+                            "peak_source": peak_src, "note": "per GPU: whole-job bytes / (N x max-over-ranks device time)"}
         if args.verify:
             import oracle_binding as ora
             want = ora.major_merge(runs, 3)
@@ -122,6 +144,10 @@ def main():
                               "value_checksums_match": sums_ok}
         print(json.dumps(line))
     res.free()
+    for b in batches.values():
+        b.close()
+    if comm is not None:
+        comm.close()
     ctx.close()
     if world > 1:
         dist.barrier()
