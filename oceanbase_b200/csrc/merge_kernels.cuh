@@ -14,6 +14,7 @@
 // HBM-bound: (rowkey, source) pairs are read and written once per pass (16 B per row per pass),
 // payload cells are gathered once.
 #pragma once
+#include <cub/device/device_radix_sort.cuh>
 
 namespace mrg {
 
@@ -153,6 +154,155 @@ __global__ void __launch_bounds__(kThreads) pass_kernel(const int64_t *__restric
   for (int k = tid; k < total; k += kThreads) {
     kout[pr.out0 + d0 + k] = s_key[k];
     sout[pr.out0 + d0 + k] = s_src[k];
+  }
+}
+
+// ---- single-pass K-way merge (single-column rowkeys) ------------------------------------------------------------------
+// The pairwise passes above read and write every (rowkey, source) pair ceil(log2 K) times. For a single rowkey column the
+// K runs are merged in ONE pass instead, the device form of a K-way merge-path partition:
+//   1. every run contributes the first rowkey of each chunk of S rows as a sample; the samples are radix-sorted;
+//   2. every m-th sorted sample is a splitter: bucket b holds the rows of all runs with splitter[b] <= rowkey < splitter[b + 1]
+//      (lower_bound of every splitter in every run). Rowkeys are unique inside a run, so a bucket holds at most
+//      (m + 2 K) S rows -- m S on average -- and all rows of one rowkey, whichever runs they come from, share a bucket;
+//   3. one CTA per bucket stages the K sorted segments in shared memory, ranks every row by binary searches in the other
+//      segments (equal rowkeys: newer run first, the loser tree's pop order) and writes the bucket in merged order.
+// S K = 1024 and m S = 1024: buckets average 1024 rows and never exceed 3072 (48 KB of rowkeys + sources).
+constexpr int kBucketMean = 1024;
+constexpr int kBucketCap = 3 * kBucketMean;
+constexpr int kBucketThreads = 256;
+constexpr int kBucketPer = kBucketCap / kBucketThreads;
+constexpr int kMaxRuns = 64;
+
+struct BucketRuns {
+  const int64_t *key[kMaxRuns];
+  int64_t n[kMaxRuns];
+  int64_t smp_off[kMaxRuns + 1];   // first sample of run r in the sample array
+  int32_t n_runs, chunk;           // chunk = S
+};
+
+__global__ void __launch_bounds__(256) bucket_sample_kernel(const __grid_constant__ BucketRuns br, int64_t n_samples, int64_t *__restrict__ smp) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_samples) return;
+  int r = 0;
+  while (r + 1 < br.n_runs && br.smp_off[r + 1] <= j) ++r;
+  smp[j] = br.key[r][(j - br.smp_off[r]) * br.chunk];
+}
+
+// bounds[b * K + r] = first row of run r in bucket b (b = 0 .. B; bucket B is the end sentinel)
+__global__ void __launch_bounds__(256) bucket_bounds_kernel(const __grid_constant__ BucketRuns br, const int64_t *__restrict__ sorted, int every,
+                                                            int64_t n_buckets, int64_t *__restrict__ bounds) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int K = br.n_runs;
+  if (t >= (n_buckets + 1) * K) return;
+  const int64_t b = t / K;
+  const int r = (int)(t % K);
+  int64_t lo = 0, hi = br.n[r];
+  if (b == 0) hi = 0;
+  else if (b == n_buckets) lo = hi;
+  else {
+    const int64_t q = sorted[b * every];
+    const int64_t *k = br.key[r];
+    while (lo < hi) {
+      const int64_t mid = (lo + hi) >> 1;
+      if (k[mid] < q) lo = mid + 1; else hi = mid;
+    }
+  }
+  bounds[t] = lo;
+}
+
+__global__ void __launch_bounds__(256) bucket_size_kernel(const int64_t *__restrict__ bounds, int K, int64_t n_buckets, uint32_t *__restrict__ size,
+                                                          int *__restrict__ status) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n_buckets) return;
+  int64_t tot = 0;
+  for (int r = 0; r < K; ++r) tot += bounds[(b + 1) * K + r] - bounds[b * K + r];
+  if (tot > kBucketCap) {   // impossible with unique rowkeys inside every run: the input breaks the merge's contract
+    atomicOr(status, ST_CORRUPT);
+    tot = 0;
+  }
+  size[b] = (uint32_t)tot;
+}
+
+__global__ void __launch_bounds__(kBucketThreads) bucket_merge_kernel(const __grid_constant__ BucketRuns br, const int64_t *__restrict__ bounds,
+                                                                      const uint32_t *__restrict__ size, const int64_t *__restrict__ out0,
+                                                                      int64_t *__restrict__ kout, uint64_t *__restrict__ sout) {
+  extern __shared__ __align__(16) uint8_t bk_smem[];
+  int64_t *s_key = reinterpret_cast<int64_t *>(bk_smem);
+  uint64_t *s_src = reinterpret_cast<uint64_t *>(bk_smem + (size_t)kBucketCap * 8);
+  uint8_t *s_run = bk_smem + (size_t)kBucketCap * 16;
+  __shared__ int s_off[kMaxRuns + 1];
+  __shared__ int64_t s_lb[kMaxRuns];
+  const int tid = threadIdx.x, K = br.n_runs;
+  const int64_t b = blockIdx.x;
+  const int total = (int)size[b];
+  if (total == 0) return;
+  if (tid < 32) {   // segment offsets: a warp scans the K <= 64 segment lengths
+    int acc = 0;
+    for (int r0 = 0; r0 < K; r0 += 32) {
+      const int r = r0 + tid;
+      const int64_t lb = r < K ? bounds[b * K + r] : 0;
+      const int len = r < K ? (int)(bounds[(b + 1) * K + r] - lb) : 0;
+      int inc = len;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, inc, o);
+        if (tid >= o) inc += u;
+      }
+      if (r < K) { s_off[r] = acc + inc - len; s_lb[r] = lb; }
+      acc += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (tid == 0) s_off[K] = acc;
+  }
+  __syncthreads();
+  for (int r = 0; r < K; ++r) {
+    const int o = s_off[r], len = s_off[r + 1] - o;
+    const int64_t *k = br.key[r] + s_lb[r];
+    for (int i = tid; i < len; i += kBucketThreads) {
+      s_key[o + i] = k[i];
+      s_run[o + i] = (uint8_t)r;
+    }
+  }
+  __syncthreads();
+  int64_t mykey[kBucketPer];
+  uint64_t mysrc[kBucketPer];
+  int myrank[kBucketPer];
+#pragma unroll
+  for (int e = 0; e < kBucketPer; ++e) {
+    const int p = tid + e * kBucketThreads;
+    myrank[e] = -1;
+    if (p < total) {
+      const int64_t k = s_key[p];
+      const int r = s_run[p];
+      int rank = p - s_off[r];
+      for (int q = 0; q < K; ++q) {
+        int lo = s_off[q], hi = s_off[q + 1];
+        if (q == r || lo == hi) continue;
+        const int base = lo;
+        if (q > r) {   // a newer run's row of the same rowkey goes first
+          while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_key[mid] <= k) lo = mid + 1; else hi = mid; }
+        } else {
+          while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_key[mid] < k) lo = mid + 1; else hi = mid; }
+        }
+        rank += lo - base;
+      }
+      mykey[e] = k;
+      mysrc[e] = ((uint64_t)r << kSrcShift) | (uint64_t)(s_lb[r] + (p - s_off[r]));
+      myrank[e] = rank;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int e = 0; e < kBucketPer; ++e) {
+    if (myrank[e] >= 0) {
+      s_key[myrank[e]] = mykey[e];
+      s_src[myrank[e]] = mysrc[e];
+    }
+  }
+  __syncthreads();
+  const int64_t o0 = out0[b];
+  for (int i = tid; i < total; i += kBucketThreads) {
+    kout[o0 + i] = s_key[i];
+    sout[o0 + i] = s_src[i];
   }
 }
 
@@ -513,8 +663,10 @@ int obgpu_merge_decoded(obgpu_ctx *ctx, const obgpu_merge_run *runs, int32_t n_r
   // ---- arena -----------------------------------------------------------------------------------------
   auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
   size_t o = 0;
-  const size_t o_k0 = o; o += al((size_t)N * 8);
-  const size_t o_s0 = o; o += al((size_t)N * 8);
+  // single-column rowkeys merge in one pass (bucket_merge_kernel) and need no ping-pong buffers
+  const bool bucket_path = n_more == 0 && n_runs >= 2 && n_runs <= mrg::kMaxRuns && N > 0 && getenv("OBGPU_MERGE_PAIRWISE") == nullptr;
+  const size_t o_k0 = o; o += al(bucket_path ? 0 : (size_t)N * 8);
+  const size_t o_s0 = o; o += al(bucket_path ? 0 : (size_t)N * 8);
   const size_t o_k1 = o; o += al((size_t)N * 8);
   const size_t o_s1 = o; o += al((size_t)N * 8);
   const size_t o_emit = o; o += al((size_t)N);
@@ -535,6 +687,34 @@ int obgpu_merge_decoded(obgpu_ctx *ctx, const obgpu_merge_run *runs, int32_t n_r
   for (int c = 0; c < n_cols; ++c) { o_on[(size_t)c] = o; o += al((size_t)N); }
   std::vector<size_t> o_om((size_t)n_more);
   for (int c = 0; c < n_more; ++c) { o_om[(size_t)c] = o; o += al((size_t)N * 8); }
+  // single-pass K-way merge (single-column rowkeys, see bucket_merge_kernel): samples, splitter bounds, bucket offsets
+  int bk_chunk = 1;
+  while (bk_chunk * 2 * n_runs <= mrg::kBucketMean) bk_chunk *= 2;
+  const int bk_every = mrg::kBucketMean / bk_chunk;
+  int64_t n_samples = 0;
+  mrg::BucketRuns br{};
+  if (bucket_path) {
+    br.n_runs = n_runs;
+    br.chunk = bk_chunk;
+    for (int r = 0; r < n_runs; ++r) {
+      br.key[r] = runs[r].key;
+      br.n[r] = runs[r].n;
+      br.smp_off[r] = n_samples;
+      n_samples += (runs[r].n + bk_chunk - 1) / bk_chunk;
+    }
+    br.smp_off[n_runs] = n_samples;
+  }
+  const int64_t n_buckets = bucket_path ? std::max<int64_t>(1, (n_samples + bk_every - 1) / bk_every) : 0;
+  size_t sort_tmp = 0;
+  if (bucket_path) cub::DeviceRadixSort::SortKeys(nullptr, sort_tmp, (const int64_t *)nullptr, (int64_t *)nullptr, n_samples, 0, 64, ctx->stream);
+  const size_t o_smp = o; o += al((size_t)n_samples * 8);
+  const size_t o_sorted = o; o += al((size_t)n_samples * 8);
+  const size_t o_sorttmp = o; o += al(sort_tmp);
+  const size_t o_bounds = o; o += al((size_t)(n_buckets + 1) * (size_t)n_runs * 8);
+  const size_t o_bsize = o; o += al((size_t)(n_buckets + 1) * 4);
+  const size_t o_bout = o; o += al((size_t)(n_buckets + 2) * 8);
+  const size_t n_bchunks = (size_t)((n_buckets + kPrefixChunk - 1) / kPrefixChunk);
+  const size_t o_bchunk = o; o += al((n_bchunks + 1) * 8);
   cudaError_t e = cudaMallocAsync(&res->arena, o + 256, ctx->stream);
   if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); delete res; return OBGPU_ALLOCATE_MEMORY_FAILED; }
   uint8_t *a = (uint8_t *)res->arena;
@@ -616,7 +796,26 @@ int obgpu_merge_decoded(obgpu_ctx *ctx, const obgpu_merge_run *runs, int32_t n_r
   e = cudaStreamSynchronize(ctx->stream);
   if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); obgpu_merge_result_free(res); return OBGPU_ERR_SYS; }
   // ---- launches ----------------------------------------------------------------------------------------------
-  for (int r = 0; r < n_runs; ++r) {
+  if (bucket_path) {
+    static bool attr_set = false;   // 51 KB of dynamic shared memory per CTA
+    const size_t bk_smem = (size_t)mrg::kBucketCap * 17;
+    if (!attr_set) {
+      cudaFuncSetAttribute(mrg::bucket_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bk_smem);
+      attr_set = true;
+    }
+    int64_t *smp = (int64_t *)(a + o_smp), *sorted = (int64_t *)(a + o_sorted), *bounds = (int64_t *)(a + o_bounds), *bout = (int64_t *)(a + o_bout);
+    uint32_t *bsize = (uint32_t *)(a + o_bsize);
+    mrg::bucket_sample_kernel<<<(unsigned)((n_samples + 255) / 256), 256, 0, ctx->stream>>>(br, n_samples, smp);
+    cub::DeviceRadixSort::SortKeys(a + o_sorttmp, sort_tmp, (const int64_t *)smp, sorted, n_samples, 0, 64, ctx->stream);
+    const int64_t nb_threads = (n_buckets + 1) * n_runs;
+    mrg::bucket_bounds_kernel<<<(unsigned)((nb_threads + 255) / 256), 256, 0, ctx->stream>>>(br, sorted, bk_every, n_buckets, bounds);
+    mrg::bucket_size_kernel<<<(unsigned)((n_buckets + 255) / 256), 256, 0, ctx->stream>>>(bounds, n_runs, n_buckets, bsize, res->d_status);
+    obgpu_prefix_local_kernel<<<(int)n_bchunks, 256, 0, ctx->stream>>>(bsize, (int)n_buckets, bout, (unsigned long long *)(a + o_bchunk));
+    obgpu_prefix_fix_kernel<<<(int)n_bchunks + 1, 256, 0, ctx->stream>>>((int)n_buckets, (int)n_bchunks, bout, (const unsigned long long *)(a + o_bchunk));
+    mrg::bucket_merge_kernel<<<(unsigned)n_buckets, mrg::kBucketThreads, bk_smem, ctx->stream>>>(br, bounds, bsize, bout, k1, s1);
+    ctx->launches += 9;
+  }
+  for (int r = 0; r < n_runs && !bucket_path; ++r) {
     if (runs[r].n == 0) continue;
     mrg::init_kernel<<<(unsigned)((runs[r].n + 255) / 256), 256, 0, ctx->stream>>>(runs[r].key, runs[r].n, (uint64_t)r,
                                                                                  k0 + segs[(size_t)r].begin, s0 + segs[(size_t)r].begin);
@@ -633,7 +832,11 @@ int obgpu_merge_decoded(obgpu_ctx *ctx, const obgpu_merge_run *runs, int32_t n_r
   rd.n_more = n_more;
   int64_t *kin = k0, *kout = k1;
   uint64_t *sin = s0, *sout = s1;
-  for (size_t ps = 0; ps < passes.size(); ++ps) {
+  if (bucket_path) {   // already merged, in k1 / s1
+    kin = k1;
+    sin = s1;
+  }
+  for (size_t ps = 0; ps < passes.size() && !bucket_path; ++ps) {
     const int n_pairs = (int)passes[ps].size() - 1;
     const int64_t tiles = passes[ps].back().tile0;
     if (tiles > 0) {

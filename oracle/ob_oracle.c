@@ -230,6 +230,8 @@ static uint64_t crc64_sse42(uint64_t crc, const uint8_t *p, int64_t len) {
 static void fmt_i64(int64_t v, int16_t *cs) { for (int i = 0; i < 4; i++) *cs = (int16_t)(*cs ^ ((v >> (i * 16)) & 0xFFFF)); }
 static void fmt_i32(int32_t v, int16_t *cs) { for (int i = 0; i < 2; i++) *cs = (int16_t)(*cs ^ ((v >> (i * 16)) & 0xFFFF)); }
 
+uint64_t ora_crc64_sse42(uint64_t crc, const void *p, int64_t len) { return crc64_sse42(crc, (const uint8_t *)p, len); }
+
 /* check_header_checksum / check_payload_checksum (ob_micro_block_header.cpp:236-285) */
 int ora_block_verify_checksums(const ora_block *b) {
   const uint8_t *p = b->buf;
@@ -678,15 +680,31 @@ static int col_dec_init(const ora_block *b, int32_t col, col_dec *c) {
   return ORA_SUCCESS;
 }
 
+/* ObIntegerArray<T>::lower_bound / upper_bound (encoding/ob_integer_array.h:38-51, ObIntArrayFuncTable :117-139) over an
+ * ascending array of `byte`-wide unsigned integers: first index in [begin, end) whose element is >= key / > key */
+int64_t ora_int_array_lower_bound(const void *array, int64_t byte, int64_t begin, int64_t end, int64_t key) {
+  const uint8_t *a = (const uint8_t *)array;
+  int64_t lo = begin, hi = end;
+  while (lo < hi) {
+    const int64_t mid = lo + (hi - lo) / 2;
+    if (rd_len(a + mid * byte, (int)byte) < (uint64_t)key) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+int64_t ora_int_array_upper_bound(const void *array, int64_t byte, int64_t begin, int64_t end, int64_t key) {
+  const uint8_t *a = (const uint8_t *)array;
+  int64_t lo = begin, hi = end;
+  while (lo < hi) {
+    const int64_t mid = lo + (hi - lo) / 2;
+    if (rd_len(a + mid * byte, (int)byte) <= (uint64_t)key) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
 /* CONST: ref of a row = exception ref if the row is in the sorted exception list, else the
  * constant's ref (ObConstDecoder::decode, ob_const_decoder.cpp:93-121: lower_bound over row ids) */
 static int64_t const_row_ref(const col_dec *c, int64_t row) {
-  int64_t lo = 0, hi = c->const_count;
-  while (lo < hi) {
-    const int64_t mid = (lo + hi) / 2;
-    if ((int64_t)rd_len(c->const_row_ids + mid * c->const_row_id_byte, c->const_row_id_byte) < row) lo = mid + 1;
-    else hi = mid;
-  }
+  const int64_t lo = ora_int_array_lower_bound(c->const_row_ids, c->const_row_id_byte, 0, c->const_count, row);
   if (lo < c->const_count &&
       (int64_t)rd_len(c->const_row_ids + lo * c->const_row_id_byte, c->const_row_id_byte) == row)
     return c->const_refs[lo];
@@ -695,13 +713,7 @@ static int64_t const_row_ref(const col_dec *c, int64_t row) {
 
 /* upper_bound over the RLE run-start array (ObIntArrayFuncTable::upper_bound_) */
 static int64_t rle_upper_bound(const col_dec *c, int64_t row) {
-  int64_t lo = 0, hi = c->rle_count;
-  while (lo < hi) {
-    const int64_t mid = (lo + hi) / 2;
-    if ((int64_t)rd_len(c->rle_row_ids + mid * c->rle_row_id_byte, c->rle_row_id_byte) <= row) lo = mid + 1;
-    else hi = mid;
-  }
-  return lo;
+  return ora_int_array_upper_bound(c->rle_row_ids, c->rle_row_id_byte, 0, c->rle_count, row);
 }
 static int64_t rle_ref_at(const col_dec *c, int64_t pos) {
   return (int64_t)rd_len(c->rle_refs + pos * c->rle_ref_byte, c->rle_ref_byte);

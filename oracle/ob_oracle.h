@@ -99,6 +99,11 @@ void ora_bs_set(uint8_t *buf, int64_t offset, int64_t cnt, uint64_t value);
 int ora_block_init(ora_block *blk, const void *buf, int64_t size);
 /* data checksum / header checksum verification (ob_micro_block_header.cpp:236-285) */
 int ora_block_verify_checksums(const ora_block *blk);
+/* building blocks pinned one by one to the compiled reference (tests/test_checksum_ref_kat.py): the payload checksum
+ * (ob_crc64_sse42: crc32c, seed as given, no final xor) and the integer-array searches of the RLE / CONST / row-index lookups */
+uint64_t ora_crc64_sse42(uint64_t crc, const void *p, int64_t len);
+int64_t ora_int_array_lower_bound(const void *array, int64_t byte, int64_t begin, int64_t end, int64_t key);
+int64_t ora_int_array_upper_bound(const void *array, int64_t byte, int64_t begin, int64_t end, int64_t key);
 int ora_decode_cell(const ora_block *blk, int32_t col, int64_t row, ora_datum *out);
 /* dictionary surface of a dictionary-coded column (DICT / RLE / CONST with exceptions / CS INT_DICT / STR_DICT):
  * distinct count, entry `ref` decoded like a cell, refs of rows (NULL / NOP rows: the distinct count) */

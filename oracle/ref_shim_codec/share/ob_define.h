@@ -1,0 +1,1 @@
+#include "ob_codec_shim.h"

@@ -12,6 +12,7 @@ ORACLE_LIB = os.path.join(ORACLE_DIR, "libob_oracle.so")
 REF_LIB = os.path.join(ORACLE_DIR, "_ref", "libref_bitstream.so")
 REF_CODEC_LIB = os.path.join(ORACLE_DIR, "_ref", "libref_codec.so")
 REF_BITMAP_LIB = os.path.join(ORACLE_DIR, "_ref", "libref_bitmap.so")
+REF_MISC_LIB = os.path.join(ORACLE_DIR, "_ref", "libref_misc.so")
 
 
 def _cpu_stamp():
@@ -42,7 +43,7 @@ def build_oracle():
         subprocess.run(["make", "-B", "-C", ORACLE_DIR, "-s", "all"], check=True, capture_output=True)
         with open(stamp_file, "w") as f:
             f.write(stamp + "\n")
-    elif os.path.isdir("/root/reference") and not (os.path.exists(REF_LIB) and os.path.exists(REF_CODEC_LIB) and os.path.exists(REF_BITMAP_LIB)):
+    elif os.path.isdir("/root/reference") and not (os.path.exists(REF_LIB) and os.path.exists(REF_CODEC_LIB) and os.path.exists(REF_BITMAP_LIB) and os.path.exists(REF_MISC_LIB)):
         subprocess.run(["make", "-C", ORACLE_DIR, "-s", "ref"], check=True, capture_output=True)
     return ORACLE_LIB
 
@@ -106,6 +107,11 @@ def oracle():
         L.ora_block_init.argtypes = [P(OraBlock), vp, i64]
         L.ora_block_verify_checksums.argtypes = [P(OraBlock)]
         L.ora_decode_cell.argtypes = [P(OraBlock), i32, i64, P(OraDatum)]
+        L.ora_crc64_sse42.restype = u64
+        L.ora_crc64_sse42.argtypes = [u64, vp, i64]
+        for f in ("ora_int_array_lower_bound", "ora_int_array_upper_bound"):
+            getattr(L, f).restype = i64
+            getattr(L, f).argtypes = [vp, i64, i64, i64, i64]
         L.ora_dict_count.argtypes = [P(OraBlock), i32, P(i64)]
         L.ora_dict_entry.argtypes = [P(OraBlock), i32, i64, P(OraDatum)]
         L.ora_dict_refs.argtypes = [P(OraBlock), i32, C.c_void_p, i64, C.c_void_p]

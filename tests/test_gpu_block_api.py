@@ -170,7 +170,7 @@ def test_datum_format_get_rows(ob, ctx):
     strs = [bytes(rng.integers(97, 123, size=rng.integers(1, 12), dtype=np.uint8)) for _ in range(40)]
     nl = (rng.random(n) < 0.2).astype(np.uint8)
     cols = [ob.Column(ob.OBJ_INT, ob.ENC_DICT, rng.integers(-9, 9, size=n) * 10 ** 10, nulls=nl),
-            ob.Column(ob.OBJ_INT32, ob.ENC_RAW, rng.integers(-(1 << 31), 1 << 31, size=n), nulls=nl),
+            ob.Column(ob.OBJ_DATE, ob.ENC_RAW, rng.integers(-(1 << 31), 1 << 31, size=n), nulls=nl),   # the 4-byte datum class
             ob.Column(ob.OBJ_VARCHAR, ob.ENC_DICT, [strs[i] for i in rng.integers(0, 40, size=n)], nulls=nl)]
     table = ob.encode_table(cols, 800)
     batch = ctx.open_batch(table)
