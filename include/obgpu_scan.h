@@ -65,6 +65,9 @@ enum {
   OBGPU_ENC_RLE = 2,
   OBGPU_ENC_CONST = 3,
   OBGPU_ENC_INTEGER_BASE_DIFF = 4,
+  OBGPU_ENC_STRING_DIFF = 5,
+  OBGPU_ENC_HEX_PACKING = 6,
+  OBGPU_ENC_STRING_PREFIX = 7,
   /* writer only: columns of a CS_ENCODING_ROW_STORE block (ObCSColumnHeader::Type) */
   OBGPU_ENC_CS_INTEGER = 16,
   OBGPU_ENC_CS_INT_DICT = 17,
@@ -354,6 +357,26 @@ int obgpu_block_group_by(obgpu_batch *batch, int32_t block, int32_t group_col, c
  * [host_group_off[b], host_group_off[b + 1]) of the group axis (host_group_off: n_blocks + 1 entries, may be NULL). */
 int obgpu_result_group_by(obgpu_result *res, int32_t group_col, const obgpu_group_agg *aggs, int32_t n_aggs,
                           int64_t *host_group_off, int64_t *host_out, int64_t out_cap_groups, int64_t *total_groups);
+
+/* =============================================================================================
+ * String cells as BYTES. HEX_PACKING / STRING_DIFF / STRING_PREFIX columns rebuild their values (ObHexStringDecoder,
+ * ObStringDiffDecoder, ObStringPrefixDecoder decode into allocator memory, encoding/ob_hex_string_decoder.cpp:33-127 ...): such a
+ * value is not part of the caller's block, so the (pointer, length) outputs of obgpu_scan / obgpu_project_discrete cannot address
+ * it. The device rebuilds these columns once per page batch (at obgpu_batch_open); filters and aggregates over them work like on
+ * any string column; their BYTES come back through the two calls below (which work for every string column).
+ * ============================================================================================= */
+/* 1 when some block of the batch holds column `col` in one of those codecs (its projected pointers are then not usable). */
+int obgpu_batch_column_materialised(const obgpu_batch *batch, int32_t col, int32_t *materialised);
+/* Rows [row_begin, row_begin + row_count) of projected string column i of a scan: host_off[k] .. host_off[k + 1] of host_heap are the
+ * bytes of row k (NULL rows: empty; the NULL bits come from obgpu_result_fetch_col). *heap_bytes is always set; OBGPU_BUF_NOT_ENOUGH
+ * when it exceeds heap_cap (host_off is valid then: call again with a larger heap). */
+int obgpu_result_fetch_strings(obgpu_result *res, int32_t i, int64_t row_begin, int64_t row_count, void *host_heap,
+                               int64_t heap_cap, int64_t *host_off, int64_t *heap_bytes);
+/* One block, the rows of row_ids (the reference call shape of a VEC_DISCRETE / VEC_CONTINUOUS decode): same outputs + the
+ * ObBitVector NULL image (host_nulls, has_null may be NULL). */
+int obgpu_project_strings(obgpu_batch *batch, int32_t block, int32_t col, const int32_t *row_ids, int64_t row_cap,
+                          void *host_heap, int64_t heap_cap, int64_t *host_off, uint64_t *host_nulls, int32_t *has_null,
+                          int64_t *heap_bytes);
 
 /* Library self-description (build id, arch) for logs. */
 const char *obgpu_version(void);

@@ -16,7 +16,7 @@ OB_INVALID_DATA = -4070
 
 (WHITE_OP_EQ, WHITE_OP_LE, WHITE_OP_LT, WHITE_OP_GE, WHITE_OP_GT, WHITE_OP_NE, WHITE_OP_BT,
  WHITE_OP_IN, WHITE_OP_NU, WHITE_OP_NN) = range(10)
-ENC_RAW, ENC_DICT, ENC_RLE, ENC_CONST, ENC_INTEGER_BASE_DIFF = range(5)
+ENC_RAW, ENC_DICT, ENC_RLE, ENC_CONST, ENC_INTEGER_BASE_DIFF, ENC_STRING_DIFF, ENC_HEX_PACKING, ENC_STRING_PREFIX = range(8)
 ENC_CS_INTEGER, ENC_CS_INT_DICT, ENC_CS_STRING, ENC_CS_STR_DICT = 16, 17, 18, 19  # columns of a CS_ENCODING_ROW_STORE block
 OBJ_TINYINT, OBJ_SMALLINT, OBJ_MEDIUMINT, OBJ_INT32, OBJ_INT = 1, 2, 3, 4, 5
 OBJ_UTINYINT, OBJ_USMALLINT, OBJ_UMEDIUMINT, OBJ_UINT32, OBJ_UINT64 = 6, 7, 8, 9, 10
@@ -176,6 +176,9 @@ def declared_signatures():
         "obgpu_project_discrete": (C.c_int, [vp, i32, i32, vp, i64, i64, u64, vp, vp, vp, P(i32)]),
         "obgpu_project_datums": (C.c_int, [vp, i32, i32, vp, i64, i64, u64, vp]),
         "obgpu_result_fetch_datums": (C.c_int, [vp, i32, i64, i64, vp, vp]),
+        "obgpu_batch_column_materialised": (C.c_int, [vp, i32, P(i32)]),
+        "obgpu_result_fetch_strings": (C.c_int, [vp, i32, i64, i64, vp, i64, vp, P(i64)]),
+        "obgpu_project_strings": (C.c_int, [vp, i32, i32, vp, i64, vp, i64, vp, vp, P(i32), P(i64)]),
         "obgpu_batch_column_type": (C.c_int, [vp, i32, P(i32), P(i32)]),
         "obgpu_block_distinct_count": (C.c_int, [vp, i32, i32, P(i64)]),
         "obgpu_block_read_distinct": (C.c_int, [vp, i32, i32, u64, vp, vp, i64, P(i64)]),

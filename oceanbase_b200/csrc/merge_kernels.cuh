@@ -14,6 +14,8 @@
 // HBM-bound: (rowkey, source) pairs are read and written once per pass (16 B per row per pass),
 // payload cells are gathered once.
 #pragma once
+#include <functional>
+
 #include <cub/device/device_radix_sort.cuh>
 
 namespace mrg {
@@ -170,7 +172,7 @@ __global__ void __launch_bounds__(kThreads) pass_kernel(const int64_t *__restric
 constexpr int kBucketMean = 1024;
 constexpr int kBucketCap = 3 * kBucketMean;
 constexpr int kBucketThreads = 256;
-constexpr int kBucketPer = kBucketCap / kBucketThreads;
+constexpr int kBucketPer = 13;   // consecutive rows per thread (odd: no shared-memory bank conflicts); 256 x 13 >= kBucketCap
 constexpr int kMaxRuns = 64;
 
 struct BucketRuns {
@@ -223,19 +225,42 @@ __global__ void __launch_bounds__(256) bucket_size_kernel(const int64_t *__restr
   size[b] = (uint32_t)tot;
 }
 
-__global__ void __launch_bounds__(kBucketThreads) bucket_merge_kernel(const __grid_constant__ BucketRuns br, const int64_t *__restrict__ bounds,
-                                                                      const uint32_t *__restrict__ size, const int64_t *__restrict__ out0,
-                                                                      int64_t *__restrict__ kout, uint64_t *__restrict__ sout) {
+__device__ __forceinline__ int flag_of(const RunsDev &r, uint64_t src) {
+  const int run = (int)(src >> kSrcShift);
+  const uint8_t *f = r.flag[run];
+  return f ? (int)f[src & ((1ull << kSrcShift) - 1)] : OBGPU_DF_INSERT;
+}
+
+// One CTA per bucket: stage the K sorted segments in shared memory and merge them with ceil(log2 K) PAIRWISE merge-path levels that
+// never leave shared memory (a thread produces kBucketPer consecutive outputs of a level: one binary search for its diagonal, then a
+// serial two-way merge; equal rowkeys: the newer run first, the loser tree's pop order). The rows travel as (rowkey, position in the
+// staged bucket); the source (run, row) is rebuilt from the position at the end. Then, still in shared memory: rowkey groups (they never
+// straddle buckets), emit / drop from the newest existing row of each group, the rank of every emitting head inside the bucket.
+// Written once: (rowkey, source, rank-or-0xffff) per row, cnt[b] = rows the bucket emits.
+constexpr uint16_t kNoEmit = 0xffffu;
+
+__global__ void __launch_bounds__(kBucketThreads) bucket_merge_kernel(const __grid_constant__ BucketRuns br, RunsDev runs,
+                                                                      const int64_t *__restrict__ bounds, const uint32_t *__restrict__ size,
+                                                                      const int64_t *__restrict__ out0, int64_t *__restrict__ kout,
+                                                                      uint64_t *__restrict__ sout, uint16_t *__restrict__ erank, uint32_t *__restrict__ cnt,
+                                                                      unsigned long long *__restrict__ stats, int *__restrict__ status) {
   extern __shared__ __align__(16) uint8_t bk_smem[];
-  int64_t *s_key = reinterpret_cast<int64_t *>(bk_smem);
-  uint64_t *s_src = reinterpret_cast<uint64_t *>(bk_smem + (size_t)kBucketCap * 8);
-  uint8_t *s_run = bk_smem + (size_t)kBucketCap * 16;
+  int64_t *s_k0 = reinterpret_cast<int64_t *>(bk_smem);
+  int64_t *s_k1 = reinterpret_cast<int64_t *>(bk_smem + (size_t)kBucketCap * 8);
+  uint16_t *s_t0 = reinterpret_cast<uint16_t *>(bk_smem + (size_t)kBucketCap * 16);
+  uint16_t *s_t1 = reinterpret_cast<uint16_t *>(bk_smem + (size_t)kBucketCap * 18);
+  uint8_t *s_run = bk_smem + (size_t)kBucketCap * 20;
   __shared__ int s_off[kMaxRuns + 1];
   __shared__ int64_t s_lb[kMaxRuns];
-  const int tid = threadIdx.x, K = br.n_runs;
+  __shared__ uint32_t s_wsum[kBucketThreads / 32];
+  __shared__ const uint8_t *s_flag[kMaxRuns];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, K = br.n_runs;
   const int64_t b = blockIdx.x;
   const int total = (int)size[b];
-  if (total == 0) return;
+  if (total == 0) {
+    if (tid == 0) cnt[b] = 0;
+    return;
+  }
   if (tid < 32) {   // segment offsets: a warp scans the K <= 64 segment lengths
     int acc = 0;
     for (int r0 = 0; r0 < K; r0 += 32) {
@@ -248,7 +273,7 @@ __global__ void __launch_bounds__(kBucketThreads) bucket_merge_kernel(const __gr
         const int u = __shfl_up_sync(0xffffffffu, inc, o);
         if (tid >= o) inc += u;
       }
-      if (r < K) { s_off[r] = acc + inc - len; s_lb[r] = lb; }
+      if (r < K) { s_off[r] = acc + inc - len; s_lb[r] = lb; s_flag[r] = runs.flag[r]; }
       acc += __shfl_sync(0xffffffffu, inc, 31);
     }
     if (tid == 0) s_off[K] = acc;
@@ -258,58 +283,237 @@ __global__ void __launch_bounds__(kBucketThreads) bucket_merge_kernel(const __gr
     const int o = s_off[r], len = s_off[r + 1] - o;
     const int64_t *k = br.key[r] + s_lb[r];
     for (int i = tid; i < len; i += kBucketThreads) {
-      s_key[o + i] = k[i];
+      s_k0[o + i] = k[i];
+      s_t0[o + i] = (uint16_t)(o + i);
       s_run[o + i] = (uint8_t)r;
     }
   }
   __syncthreads();
-  int64_t mykey[kBucketPer];
-  uint64_t mysrc[kBucketPer];
-  int myrank[kBucketPer];
-#pragma unroll
-  for (int e = 0; e < kBucketPer; ++e) {
-    const int p = tid + e * kBucketThreads;
-    myrank[e] = -1;
-    if (p < total) {
-      const int64_t k = s_key[p];
-      const int r = s_run[p];
-      int rank = p - s_off[r];
-      for (int q = 0; q < K; ++q) {
-        int lo = s_off[q], hi = s_off[q + 1];
-        if (q == r || lo == hi) continue;
-        const int base = lo;
-        if (q > r) {   // a newer run's row of the same rowkey goes first
-          while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_key[mid] <= k) lo = mid + 1; else hi = mid; }
-        } else {
-          while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_key[mid] < k) lo = mid + 1; else hi = mid; }
-        }
-        rank += lo - base;
+  int64_t *kin = s_k0, *kdst = s_k1;
+  uint16_t *tin = s_t0, *tdst = s_t1;
+  // every thread takes the same share of the bucket (an odd number of rows: no shared-memory bank conflicts between the lanes'
+  // strided accesses): 5 rows for the average bucket, 13 for a full one -- short serial chains, all warps busy
+  const int per = ((total + kBucketThreads - 1) / kBucketThreads) | 1;
+  const int x_begin = tid * per < total ? tid * per : total;
+  const int x_end = x_begin + per < total ? x_begin + per : total;
+  for (int w = 1; w < K; w <<= 1) {
+    int x = x_begin;
+    while (x < x_end) {
+      // the segment holding position x (segments may be empty: last one starting at or before x), then its group of 2 w segments
+      int lo = 0, hi = K;
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (s_off[mid] <= x) lo = mid; else hi = mid;
       }
-      mykey[e] = k;
-      mysrc[e] = ((uint64_t)r << kSrcShift) | (uint64_t)(s_lb[r] + (p - s_off[r]));
-      myrank[e] = rank;
+      const int g0 = (lo / (2 * w)) * (2 * w);
+      const int a0 = s_off[g0], a1 = s_off[g0 + w < K ? g0 + w : K], b1 = s_off[g0 + 2 * w < K ? g0 + 2 * w : K];
+      const int na = a1 - a0, nb = b1 - a1;
+      const int d = x - a0;
+      int l = d > nb ? d - nb : 0, h = d < na ? d : na;   // merge path: rows of A among the first d outputs, B first on equal rowkeys
+      while (l < h) {
+        const int mid = (l + h) >> 1;
+        if (kin[a0 + mid] < kin[a1 + d - 1 - mid]) l = mid + 1; else h = mid;
+      }
+      int ia = l, ib = d - l;
+      const int stop = x_end < b1 ? x_end : b1;
+      for (; x < stop; ++x) {
+        const bool take_b = ib < nb && (ia >= na || !(kin[a0 + ia] < kin[a1 + ib]));
+        const int at = take_b ? a1 + ib : a0 + ia;
+        kdst[x] = kin[at];
+        tdst[x] = tin[at];
+        if (take_b) ++ib; else ++ia;
+      }
+    }
+    __syncthreads();
+    int64_t *tk = kin; kin = kdst; kdst = tk;
+    uint16_t *tt = tin; tin = tdst; tdst = tt;
+  }
+  // kin / tin: the bucket in merged order. Group heads: the newest EXISTING row of the rowkey decides (delete -> the rowkey is dropped).
+  uint32_t my_emit = 0, my_mask = 0;
+  for (int x = x_begin; x < x_end; ++x) {
+    const int64_t key = kin[x];
+    if (x == 0 || kin[x - 1] != key) {
+      bool decided = false;
+      for (int j = x; j < total && kin[j] == key && !decided; ++j) {
+        const int p = tin[j], r = s_run[p];
+        const uint8_t *fl = s_flag[r];
+        const int f = fl ? (int)fl[s_lb[r] + (p - s_off[r])] : OBGPU_DF_INSERT;
+        if (f == OBGPU_DF_NOT_EXIST) continue;
+        decided = true;
+        if (f == OBGPU_DF_DELETE) atomicAdd(&stats[0], 1ull);
+        else if (f == OBGPU_DF_INSERT || f == OBGPU_DF_UPDATE) { my_mask |= 1u << (x - x_begin); ++my_emit; }
+        else atomicOr(status, ST_CORRUPT);
+      }
     }
   }
-  __syncthreads();
+  // exclusive scan of the per-thread emit counts (threads own consecutive rows: the scan order is the merged order)
+  uint32_t inc = my_emit;
 #pragma unroll
-  for (int e = 0; e < kBucketPer; ++e) {
-    if (myrank[e] >= 0) {
-      s_key[myrank[e]] = mykey[e];
-      s_src[myrank[e]] = mysrc[e];
-    }
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += u;
+  }
+  if (lane == 31) s_wsum[warp] = inc;
+  __syncthreads();
+  uint32_t woff = 0, tot = 0;
+#pragma unroll
+  for (int k = 0; k < kBucketThreads / 32; ++k) {
+    woff += k < warp ? s_wsum[k] : 0u;
+    tot += s_wsum[k];
+  }
+  uint32_t rank = woff + inc - my_emit;
+  for (int x = x_begin; x < x_end; ++x) {   // tdst is free: the ranks go there for the coalesced write below
+    const bool e = (my_mask >> (x - x_begin)) & 1u;
+    tdst[x] = e ? (uint16_t)rank : kNoEmit;
+    rank += e;
   }
   __syncthreads();
   const int64_t o0 = out0[b];
   for (int i = tid; i < total; i += kBucketThreads) {
-    kout[o0 + i] = s_key[i];
-    sout[o0 + i] = s_src[i];
+    const int p = tin[i], r = s_run[p];
+    kout[o0 + i] = kin[i];
+    sout[o0 + i] = ((uint64_t)r << kSrcShift) | (uint64_t)(s_lb[r] + (p - s_off[r]));
+    erank[o0 + i] = tdst[i];
+  }
+  if (tid == 0) cnt[b] = tot;
+}
+
+// Fuse of one bucket's emitting heads (the groups of a bucket are complete inside it, every head knows its rank). No CTA barriers.
+// Pass 1, a thread takes kFusePer rows at a time and requests everything they need together -- rank, rowkey, source, the next
+// rowkey, then every column's ext byte and value -- before the first use: a head whose rowkey lives in one run only (nine in ten in
+// a major merge) is finished there; a head that shares its rowkey is appended to its warp's list instead of being fused in place
+// (one lane in ten would otherwise drag the whole warp through the general fold). Pass 2: the warp fuses its listed heads, a lane
+// each, newest to oldest.
+constexpr int kFusePer = 4;
+constexpr int kFuseListCap = 512;   // listed heads per warp before an early flush
+__device__ __forceinline__ void fuse_general_row(const RunsDev &runs, const int64_t *__restrict__ keys, const uint64_t *__restrict__ src,
+                                                 int64_t i, int64_t end, int64_t o, const int64_t *__restrict__ default_vals,
+                                                 const uint8_t *__restrict__ default_null, int64_t *const *__restrict__ out_vals,
+                                                 uint8_t *const *__restrict__ out_null) {
+  const uint64_t idx_mask = (1ull << kSrcShift) - 1;
+  const int n_cols = runs.n_cols;
+  const int64_t key = keys[i];
+  int64_t jend = i;
+  bool open = true;     // no delete row met yet
+  for (int64_t j = i; j < end && keys[j] == key; ++j) {
+    if (open) {
+      if (flag_of(runs, src[j]) == OBGPU_DF_DELETE) open = false;
+      else jend = j + 1;
+    }
+  }
+  for (int c = 0; c < n_cols; ++c) {
+    int64_t v = 0;
+    uint8_t st = 2;  // NOP until a cell is found
+    for (int64_t j = i; j < jend && st == 2; ++j) {
+      const uint64_t s = src[j];
+      if (flag_of(runs, s) == OBGPU_DF_NOT_EXIST) continue;
+      const int run = (int)(s >> kSrcShift);
+      const int64_t at = (int64_t)(s & idx_mask);
+      const uint8_t x = runs.ext[run * n_cols + c][at];
+      if (x != 2) {
+        st = x;
+        v = x ? 0 : runs.vals[run * n_cols + c][at];
+      }
+    }
+    if (st == 2) {  // ObMajorPartitionMergeFuser::end_fuse_row: the default row
+      const bool dn = default_null ? default_null[c] != 0 : true;
+      st = dn ? 1 : 0;
+      v = dn ? 0 : (default_vals ? default_vals[c] : 0);
+    }
+    out_vals[c][o] = v;
+    out_null[c][o] = st;
   }
 }
 
-__device__ __forceinline__ int flag_of(const RunsDev &r, uint64_t src) {
-  const int run = (int)(src >> kSrcShift);
-  const uint8_t *f = r.flag[run];
-  return f ? (int)f[src & ((1ull << kSrcShift) - 1)] : OBGPU_DF_INSERT;
+__global__ void __launch_bounds__(256) fuse_bucket_kernel(const int64_t *__restrict__ keys, const uint64_t *__restrict__ src, RunsDev runs,
+                                                          const uint16_t *__restrict__ erank, const int64_t *__restrict__ seg0,
+                                                          const int64_t *__restrict__ out_off, const int64_t *__restrict__ default_vals,
+                                                          const uint8_t *__restrict__ default_null, int64_t *__restrict__ out_key,
+                                                          int64_t *const *__restrict__ out_vals, uint8_t *const *__restrict__ out_null,
+                                                          unsigned long long *__restrict__ stats) {
+  __shared__ uint16_t s_list[8][kFuseListCap];   // per warp: bucket-relative positions of the heads that need the general fold
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t begin = seg0[blockIdx.x], end = seg0[blockIdx.x + 1];
+  const int64_t base_out = out_off[blockIdx.x];
+  if (out_off[blockIdx.x + 1] == base_out) return;   // nothing to emit in this bucket
+  const uint64_t idx_mask = (1ull << kSrcShift) - 1;
+  const int n_cols = runs.n_cols;
+  int n_list = 0;   // warp-uniform
+  auto flush = [&]() {
+    __syncwarp();
+    for (int k = lane; k < n_list; k += 32) {
+      const int64_t i = begin + s_list[warp][k];
+      fuse_general_row(runs, keys, src, i, end, base_out + erank[i], default_vals, default_null, out_vals, out_null);
+    }
+    if (lane == 0 && n_list) atomicAdd(&stats[1], (unsigned long long)n_list);
+    __syncwarp();
+    n_list = 0;
+  };
+  for (int64_t w0 = begin + warp * 32; w0 < end; w0 += 256 * kFusePer) {   // warp-uniform trip count
+    const int64_t i0 = w0 + lane;
+    uint16_t rk[kFusePer];
+    int64_t key[kFusePer], nkey[kFusePer];
+    uint64_t ks[kFusePer];
+#pragma unroll
+    for (int u = 0; u < kFusePer; ++u) {
+      const int64_t i = i0 + 256 * u;
+      rk[u] = i < end ? erank[i] : kNoEmit;
+    }
+#pragma unroll
+    for (int u = 0; u < kFusePer; ++u) {
+      const int64_t i = i0 + 256 * u;
+      if (rk[u] != kNoEmit) {
+        key[u] = keys[i];
+        ks[u] = src[i];
+        nkey[u] = i + 1 < end ? keys[i + 1] : ~key[u];   // the bucket's last row has no successor: any value that differs
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kFusePer; ++u) {
+      const int64_t i = i0 + 256 * u;
+      const bool emits = rk[u] != kNoEmit;
+      const bool general = emits && nkey[u] == key[u];
+      const uint32_t gb = __ballot_sync(0xffffffffu, general);
+      if (general) s_list[warp][n_list + __popc(gb & ((1u << lane) - 1u))] = (uint16_t)(i - begin);
+      n_list += __popc(gb);
+      if (emits) {
+        const int64_t o = base_out + rk[u];
+        out_key[o] = key[u];
+        if (!general) {   // the rowkey lives in one run: that row exists (it emitted) and nothing is fused
+          const int run = (int)(ks[u] >> kSrcShift);
+          const int64_t at = (int64_t)(ks[u] & idx_mask);
+          for (int c0 = 0; c0 < n_cols; c0 += 4) {
+            uint8_t x[4];
+            int64_t v[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              if (c0 + q < n_cols) {
+                x[q] = runs.ext[run * n_cols + c0 + q][at];
+                v[q] = runs.vals[run * n_cols + c0 + q][at];
+              }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              if (c0 + q < n_cols) {
+                const int c = c0 + q;
+                uint8_t st = x[q];
+                int64_t val = st ? 0 : v[q];
+                if (st == 2) {   // NOP everywhere: the default row (ObMajorPartitionMergeFuser::end_fuse_row)
+                  const bool dn = default_null ? default_null[c] != 0 : true;
+                  st = dn ? 1 : 0;
+                  val = dn ? 0 : (default_vals ? default_vals[c] : 0);
+                }
+                out_vals[c][o] = val;
+                out_null[c][o] = st;
+              }
+            }
+          }
+        }
+      }
+      if (n_list > kFuseListCap - 32) flush();
+    }
+  }
+  flush();
 }
 
 // Per element: is it the head of its rowkey group, and does the group emit a row? (decided by the
@@ -669,11 +873,7 @@ int obgpu_merge_decoded(obgpu_ctx *ctx, const obgpu_merge_run *runs, int32_t n_r
   const size_t o_s0 = o; o += al(bucket_path ? 0 : (size_t)N * 8);
   const size_t o_k1 = o; o += al((size_t)N * 8);
   const size_t o_s1 = o; o += al((size_t)N * 8);
-  const size_t o_emit = o; o += al((size_t)N);
-  const size_t o_cnt = o; o += al(((size_t)n_tiles + 1) * 4);
-  const size_t o_off = o; o += al(((size_t)n_tiles + 2) * 8);
-  const size_t n_chunks = (size_t)((n_tiles + kPrefixChunk - 1) / kPrefixChunk);
-  const size_t o_chunk = o; o += al((n_chunks + 1) * 8);
+  const size_t o_emit = o; o += al((size_t)N * (bucket_path ? 2 : 1));   // emit flags, or the emitting heads' ranks inside their bucket
   const size_t o_stats = o; o += al(64);
   const size_t tbl_entries = (size_t)n_runs * 2 + (size_t)n_runs * n_cols * 2 + (size_t)n_cols * 2 + (size_t)n_runs * n_more + (size_t)n_more;
   const size_t o_tbl = o; o += al(tbl_entries * 8);
@@ -715,6 +915,12 @@ int obgpu_merge_decoded(obgpu_ctx *ctx, const obgpu_merge_run *runs, int32_t n_r
   const size_t o_bout = o; o += al((size_t)(n_buckets + 2) * 8);
   const size_t n_bchunks = (size_t)((n_buckets + kPrefixChunk - 1) / kPrefixChunk);
   const size_t o_bchunk = o; o += al((n_bchunks + 1) * 8);
+  const int64_t n_units = bucket_path ? n_buckets : n_tiles;   // emit counts / output offsets per bucket (single pass) or per tile
+  const size_t o_cnt = o; o += al(((size_t)n_units + 1) * 4);
+  const size_t o_off = o; o += al(((size_t)n_units + 2) * 8);
+  const size_t n_chunks = (size_t)((n_units + kPrefixChunk - 1) / kPrefixChunk);
+  const size_t o_chunk = o; o += al((n_chunks + 1) * 8);
+  if (bucket_path) res->n_tiles = n_units;
   cudaError_t e = cudaMallocAsync(&res->arena, o + 256, ctx->stream);
   if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); delete res; return OBGPU_ALLOCATE_MEMORY_FAILED; }
   uint8_t *a = (uint8_t *)res->arena;
@@ -796,9 +1002,10 @@ int obgpu_merge_decoded(obgpu_ctx *ctx, const obgpu_merge_run *runs, int32_t n_r
   e = cudaStreamSynchronize(ctx->stream);
   if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); obgpu_merge_result_free(res); return OBGPU_ERR_SYS; }
   // ---- launches ----------------------------------------------------------------------------------------------
+  std::function<void(const mrg::RunsDev &)> bk_launch;
   if (bucket_path) {
-    static bool attr_set = false;   // 51 KB of dynamic shared memory per CTA
-    const size_t bk_smem = (size_t)mrg::kBucketCap * 17;
+    static bool attr_set = false;   // 63 KB of dynamic shared memory per CTA
+    const size_t bk_smem = (size_t)mrg::kBucketCap * 21;
     if (!attr_set) {
       cudaFuncSetAttribute(mrg::bucket_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bk_smem);
       attr_set = true;
@@ -812,7 +1019,10 @@ int obgpu_merge_decoded(obgpu_ctx *ctx, const obgpu_merge_run *runs, int32_t n_r
     mrg::bucket_size_kernel<<<(unsigned)((n_buckets + 255) / 256), 256, 0, ctx->stream>>>(bounds, n_runs, n_buckets, bsize, res->d_status);
     obgpu_prefix_local_kernel<<<(int)n_bchunks, 256, 0, ctx->stream>>>(bsize, (int)n_buckets, bout, (unsigned long long *)(a + o_bchunk));
     obgpu_prefix_fix_kernel<<<(int)n_bchunks + 1, 256, 0, ctx->stream>>>((int)n_buckets, (int)n_bchunks, bout, (const unsigned long long *)(a + o_bchunk));
-    mrg::bucket_merge_kernel<<<(unsigned)n_buckets, mrg::kBucketThreads, bk_smem, ctx->stream>>>(br, bounds, bsize, bout, k1, s1);
+    bk_launch = [=](const mrg::RunsDev &rd_) {   // after the pointer tables are described (rd below)
+      mrg::bucket_merge_kernel<<<(unsigned)n_buckets, mrg::kBucketThreads, bk_smem, ctx->stream>>>(
+          br, rd_, bounds, bsize, bout, k1, s1, (uint16_t *)emit, tile_cnt, res->d_stats, res->d_status);
+    };
     ctx->launches += 9;
   }
   for (int r = 0; r < n_runs && !bucket_path; ++r) {
@@ -850,7 +1060,17 @@ int obgpu_merge_decoded(obgpu_ctx *ctx, const obgpu_merge_run *runs, int32_t n_r
     std::swap(kin, kout);
     std::swap(sin, sout);
   }
-  if (N > 0) {
+  if (bucket_path) {
+    bk_launch(rd);
+    const int nc = (int)n_chunks;
+    obgpu_prefix_local_kernel<<<nc, 256, 0, ctx->stream>>>(tile_cnt, (int)n_buckets, res->d_tile_off, (unsigned long long *)(a + o_chunk));
+    obgpu_prefix_fix_kernel<<<nc + 1, 256, 0, ctx->stream>>>((int)n_buckets, nc, res->d_tile_off, (const unsigned long long *)(a + o_chunk));
+    mrg::fuse_bucket_kernel<<<(unsigned)n_buckets, 256, 0, ctx->stream>>>(
+        kin, sin, rd, (const uint16_t *)emit, (const int64_t *)(a + o_bout), res->d_tile_off, (const int64_t *)(a + o_def),
+        (const uint8_t *)(a + o_def + (size_t)n_cols * 8), res->d_out_key, (int64_t *const *)(d_tbl + t_ov), (uint8_t *const *)(d_tbl + t_on),
+        res->d_stats);
+    ctx->launches += 3;
+  } else if (N > 0) {
     mrg::head_kernel<<<(unsigned)n_tiles, 256, 0, ctx->stream>>>(kin, sin, N, rd, emit, tile_cnt, res->d_stats, res->d_status);
     const int nc = (int)n_chunks;
     obgpu_prefix_local_kernel<<<nc, 256, 0, ctx->stream>>>(tile_cnt, (int)n_tiles, res->d_tile_off,

@@ -1009,6 +1009,8 @@ __global__ void __launch_bounds__(256) obgpu_index_kernel(const uint8_t *image, 
     if (is_dict_kind(d)) atomicMax(&col_span[max_cols + col], d.dict_count + 2u);
     // bytes a projection of the column stages (scan_small.cuh: VARCHAR dictionaries without their string bytes)
     atomicMax(&col_span[5 * max_cols + col], proj_ranges_bytes(d, b));
+    // strings that exist only in this batch's copy of the block (HEX_PACKING / STRING_DIFF / STRING_PREFIX, mat_codecs.cuh)
+    if (d.kind == K_CSSTR && !b.is_cs) atomicMax(&col_span[6 * max_cols + col], 1u);
   }
   if (b.ok && (uint32_t)col < b.column_count) {
     // per-column facts the host keeps for a batch: ObObjType (min / max over the blocks: equal when the blocks
@@ -1713,6 +1715,7 @@ __global__ void __launch_bounds__(kThreads) obgpu_bitmap_row_ids_kernel(const ui
 
 #include "scan_small.cuh"
 #include "stream_codecs.cuh"
+#include "mat_codecs.cuh"
 
 // =================================================================================================
 // Host side
@@ -1777,6 +1780,8 @@ struct obgpu_batch {
   // CS stream codecs: blocks restated as RAW at open (stream_codecs.cuh); nullptr when nothing had to be decoded
   obcs::XformRec *d_xf = nullptr;
   int64_t restated_blocks = 0, decoded_streams = 0;
+  std::vector<uint8_t> col_mat;        // per store index: 1 when some block rebuilt the column's strings at open (mat_codecs.cuh)
+  int64_t materialised_cols = 0;   // (block, column) pairs whose strings were rebuilt at open (mat_codecs.cuh)
 };
 
 struct ResultCol {
@@ -1808,6 +1813,7 @@ struct obgpu_result {
   obgpu_result_info info{};
   int32_t has_null[kMaxProj] = {0};
   int32_t status = 0;
+  uint64_t string_base = 0;   // of the scan spec: where projected string pointers were expressed (obgpu_result_fetch_strings undoes it)
 };
 
 static thread_local std::string g_last_global_err;
@@ -2020,6 +2026,114 @@ static int cs_restate_batch(obgpu_ctx *ctx, obgpu_batch *b) {
   return OBGPU_SUCCESS;
 }
 
+// PAX blocks with HEX_PACKING / STRING_DIFF / STRING_PREFIX columns -> a copy of the batch's image in which every such column has
+// its strings materialised behind the block (mat_codecs.cuh). Runs after cs_restate_batch (the two compose: a batch may hold both
+// kinds of blocks); synchronises.
+static int pax_materialise_batch(obgpu_ctx *ctx, obgpu_batch *b) {
+  const int32_t n = b->n_blocks;
+  uint32_t *d_flag = nullptr;
+  uint32_t flag = 0;
+  CUDA_TRY(ctx, cudaMallocAsync((void **)&d_flag, 16, ctx->stream));
+  cudaError_t e = cudaMemsetAsync(d_flag, 0, 16, ctx->stream);
+  if (e == cudaSuccess) {
+    obmat::mat_probe_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(b->d_image, b->d_blk_off, b->d_blk_size, n, d_flag);
+    ctx->launches++;
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&flag, d_flag, 4, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFreeAsync(d_flag, ctx->stream);
+  if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return OBGPU_ERR_SYS; }
+  if (!(flag & obmat::MF_ANY)) return OBGPU_SUCCESS;
+  uint32_t *d_sv = nullptr;
+  std::vector<uint32_t> sv((size_t)n * 4);
+  CUDA_TRY(ctx, cudaMallocAsync((void **)&d_sv, (size_t)n * 16, ctx->stream));
+  obmat::mat_survey_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(b->d_image, b->d_blk_off, b->d_blk_size, n, d_sv);
+  ctx->launches++;
+  e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(sv.data(), d_sv, (size_t)n * 16, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFreeAsync(d_sv, ctx->stream);
+  if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return OBGPU_ERR_SYS; }
+  std::vector<uint64_t> tab((size_t)n * 2);   // [new_off][job_base]
+  std::vector<uint32_t> nsz((size_t)n);
+  uint64_t pos = 0, jobs = 0;
+  for (int32_t i = 0; i < n; ++i) {
+    tab[(size_t)i] = pos;
+    tab[(size_t)n + i] = jobs;
+    nsz[(size_t)i] = sv[(size_t)4 * i];
+    pos += ((uint64_t)sv[(size_t)4 * i] + 127) & ~127ull;
+    jobs += sv[(size_t)4 * i + 1];
+  }
+  if (jobs == 0) return OBGPU_SUCCESS;   // every such column was refused: the index kernel leaves them unsupported
+  uint8_t *d_new = nullptr;
+  uint64_t *d_tab = nullptr;
+  uint32_t *d_nsz = nullptr;
+  obmat::MatJob *d_jobs = nullptr;
+  int *d_status = nullptr;
+  obcs::XformRec *d_xf = nullptr;
+  std::vector<obcs::XformRec> xf((size_t)n);
+  auto cleanup = [&]() {
+    if (d_tab) cudaFreeAsync(d_tab, ctx->stream);
+    if (d_nsz) cudaFreeAsync(d_nsz, ctx->stream);
+    if (d_jobs) cudaFreeAsync(d_jobs, ctx->stream);
+    if (d_status) cudaFreeAsync(d_status, ctx->stream);
+  };
+  // where the caller's image has every block (string pointers of the untouched columns keep addressing it): carried over from
+  // the CS restatement when that ran
+  if (b->d_xf) {
+    e = cudaMemcpyAsync(xf.data(), b->d_xf, (size_t)n * sizeof(obcs::XformRec), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return OBGPU_ERR_SYS; }
+  } else {
+    for (int32_t i = 0; i < n; ++i) { xf[(size_t)i].orig_off = (uint64_t)b->offsets[(size_t)i]; xf[(size_t)i].str_delta = 0; }
+  }
+  e = cudaMallocAsync((void **)&d_new, (size_t)pos + 64, ctx->stream);
+  if (e == cudaSuccess) e = cudaMallocAsync((void **)&d_tab, (size_t)n * 16, ctx->stream);
+  if (e == cudaSuccess) e = cudaMallocAsync((void **)&d_nsz, (size_t)n * 4, ctx->stream);
+  if (e == cudaSuccess) e = cudaMallocAsync((void **)&d_jobs, (size_t)(jobs + 1) * sizeof(obmat::MatJob), ctx->stream);
+  if (e == cudaSuccess) e = cudaMallocAsync((void **)&d_status, 16, ctx->stream);
+  if (e == cudaSuccess && !b->d_xf) e = cudaMallocAsync((void **)&d_xf, (size_t)n * sizeof(obcs::XformRec), ctx->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_status, 0, 16, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_new, 0, (size_t)pos + 64, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_tab, tab.data(), (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_nsz, nsz.data(), (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) {
+    obmat::mat_rewrite_kernel<<<(unsigned)(((int64_t)n * 32 + 127) / 128), 128, 0, ctx->stream>>>(b->d_image, b->d_blk_off, b->d_blk_size, n, d_new,
+                                                                                             d_tab, d_nsz, d_tab + n, d_jobs);
+    obmat::mat_decode_kernel<<<(unsigned)(((int64_t)jobs * 32 + 127) / 128), 128, 0, ctx->stream>>>(b->d_image, d_new, d_jobs, (int64_t)jobs, d_status);
+    ctx->launches += 2;
+    e = cudaGetLastError();
+  }
+  int st = 0;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&st, d_status, 4, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(b->d_blk_off, tab.data(), (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(b->d_blk_size, nsz.data(), (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess && d_xf) e = cudaMemcpyAsync(d_xf, xf.data(), (size_t)n * sizeof(obcs::XformRec), cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cleanup();
+  if (e != cudaSuccess || st != 0) {
+    if (d_new) cudaFreeAsync(d_new, ctx->stream);
+    if (d_xf) cudaFreeAsync(d_xf, ctx->stream);
+    if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return e == cudaErrorMemoryAllocation ? OBGPU_ALLOCATE_MEMORY_FAILED : OBGPU_ERR_SYS; }
+    ctx->err = "HEX_PACKING / STRING_DIFF / STRING_PREFIX column does not decode (corrupt micro block)";
+    return OBGPU_INVALID_DATA;
+  }
+  if (b->own_image && b->d_image) cudaFreeAsync((void *)b->d_image, ctx->stream);
+  b->d_image = d_new;
+  b->own_image = true;
+  b->image_size = (int64_t)pos;
+  if (d_xf) b->d_xf = d_xf;
+  b->max_block_bytes = 0;
+  for (int32_t i = 0; i < n; ++i) {
+    b->offsets[(size_t)i] = (int64_t)tab[(size_t)i];
+    b->sizes[(size_t)i] = nsz[(size_t)i];
+    b->max_block_bytes = std::max<uint32_t>(b->max_block_bytes, (nsz[(size_t)i] + 15u) & ~15u);
+  }
+  b->materialised_cols = (int64_t)jobs;
+  return OBGPU_SUCCESS;
+}
+
 static uint32_t rd32h(const uint8_t *p) { uint32_t v; memcpy(&v, p, 4); return v; }
 static uint16_t rd16h(const uint8_t *p) { uint16_t v; memcpy(&v, p, 2); return v; }
 
@@ -2047,7 +2161,7 @@ int obgpu_batch_open(obgpu_ctx *ctx, const void *image, int64_t image_size, cons
   b->col_count.resize((size_t)n_blocks);
   b->bm_word_off.resize((size_t)n_blocks + 1);
   int ret = OBGPU_SUCCESS;
-  bool any_cs = false;
+  bool any_cs = false, any_mat = false;
   for (int32_t i = 0; i < n_blocks; ++i) {
     const int64_t off = offsets[i], sz = sizes[i];
     if (off < 0 || (off & 15) || sz < 64 || sz > 0x7fffffffll || off + sz > image_size) { ret = OBGPU_INVALID_ARGUMENT; break; }
@@ -2112,9 +2226,15 @@ int obgpu_batch_open(obgpu_ctx *ctx, const void *image, int64_t image_size, cons
       b->row_count[(size_t)i] = rows;
       b->col_count[(size_t)i] = ncol;
       any_cs = any_cs || is_cs;
+      if (!is_cs && !any_mat)
+        for (uint32_t c = 0; c < ncol; ++c) {
+          const uint8_t t = p[header_size + 16u * c + 1];
+          if (t == obf::COL_STRING_DIFF || t == obf::COL_HEX_PACKING || t == obf::COL_STRING_PREFIX) { any_mat = true; break; }
+        }
     }
   } else {
     any_cs = true;   // no host view: the survey kernel of the restatement looks at every block's store type
+    any_mat = true;  // ... and the probe kernel of the materialisation at every block's column types
     if (!image_on_device) { ret = OBGPU_INVALID_ARGUMENT; }
     uint32_t *d_sv = nullptr;
     std::vector<uint32_t> sv((size_t)n_blocks * 2);
@@ -2196,6 +2316,14 @@ int obgpu_batch_open(obgpu_ctx *ctx, const void *image, int64_t image_size, cons
       return rret;
     }
   }
+  // PAX string codecs that rebuild their values (HEX_PACKING / STRING_DIFF / STRING_PREFIX): materialised once, here
+  if (e == cudaSuccess && any_mat) {
+    const int mret = pax_materialise_batch(ctx, b);
+    if (mret != OBGPU_SUCCESS) {
+      obgpu_batch_close(b);
+      return mret;
+    }
+  }
   // decode plans: one thread per (block, column)
   if (e == cudaSuccess && b->max_cols > 128) {
     ctx->err = "more than 128 columns in a micro block";
@@ -2207,14 +2335,14 @@ int obgpu_batch_open(obgpu_ctx *ctx, const void *image, int64_t image_size, cons
     void *dp = nullptr;
     const size_t rows_bytes = ((size_t)n_blocks * 4 + 63) & ~(size_t)63;
     const size_t rec_bytes = (size_t)n_blocks * sizeof(BlockRec);
-    e = cudaMallocAsync(&dp, plan_bytes + rows_bytes + rec_bytes + (size_t)b->max_cols * 24 + 64, ctx->stream);
+    e = cudaMallocAsync(&dp, plan_bytes + rows_bytes + rec_bytes + (size_t)b->max_cols * 28 + 64, ctx->stream);
     if (e == cudaSuccess) {
       b->d_plans = (ColDesc *)dp;
       b->d_rows = (uint32_t *)((uint8_t *)dp + plan_bytes);
       b->d_recs = (BlockRec *)((uint8_t *)dp + plan_bytes + rows_bytes);
       uint32_t *d_span = (uint32_t *)((uint8_t *)dp + plan_bytes + rows_bytes + rec_bytes);
-      // per-column reductions of the index kernel: [region span][dictionary size][type min][type max][RLE runs][projection span]
-      e = cudaMemsetAsync(d_span, 0, (size_t)b->max_cols * 24, ctx->stream);
+      // per-column reductions of the index kernel: [region span][dictionary size][type min][type max][RLE runs][projection span][materialised]
+      e = cudaMemsetAsync(d_span, 0, (size_t)b->max_cols * 28, ctx->stream);
       if (e == cudaSuccess) e = cudaMemsetAsync(d_span + 2 * (size_t)b->max_cols, 0xff, (size_t)b->max_cols * 4, ctx->stream);
       const int64_t nthreads = (int64_t)n_blocks * b->max_cols;
       obgpu_index_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, ctx->stream>>>(
@@ -2222,16 +2350,18 @@ int obgpu_batch_open(obgpu_ctx *ctx, const void *image, int64_t image_size, cons
           b->d_rows, b->d_recs, d_span);
       if (e == cudaSuccess) e = cudaGetLastError();
       ctx->launches++;
-      b->col_span.assign((size_t)b->max_cols * 6, 0);
+      b->col_span.assign((size_t)b->max_cols * 7, 0);
       if (e == cudaSuccess)
-        e = cudaMemcpyAsync(b->col_span.data(), d_span, (size_t)b->max_cols * 24, cudaMemcpyDeviceToHost, ctx->stream);
+        e = cudaMemcpyAsync(b->col_span.data(), d_span, (size_t)b->max_cols * 28, cudaMemcpyDeviceToHost, ctx->stream);
     }
   }
   // `stage` is pageable: the copy above is staged synchronously by the runtime before returning
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-  if (e == cudaSuccess && b->col_span.size() == (size_t)b->max_cols * 6) {
+  if (e == cudaSuccess && b->col_span.size() == (size_t)b->max_cols * 7) {
     const size_t mc = b->max_cols;
     b->col_pspan.assign(b->col_span.begin() + 5 * mc, b->col_span.begin() + 6 * mc);
+    b->col_mat.assign(mc, 0);
+    for (size_t c = 0; c < mc; ++c) b->col_mat[c] = b->col_span[6 * mc + c] ? 1 : 0;
     for (size_t c = 0; c < mc; ++c) {
       b->col_max_dict[c] = b->col_span[mc + c];
       const uint32_t tmin = b->col_span[2 * mc + c], tmax = b->col_span[3 * mc + c];
@@ -2784,6 +2914,7 @@ int obgpu_scan(obgpu_batch *b, const obgpu_scan_spec *spec, obgpu_result **out) 
   p.n_proj = spec->n_proj;
   p.want_row_ids = spec->want_row_ids ? 1 : 0;
   p.string_base = spec->string_base;
+  r->string_base = spec->string_base;
   // the caller's selectivity estimate (max_selected_rows): when it says at most 1/16 of the rows survive, most
   // blocks will be sparse and the warp-per-block kernel takes them
   p.sparse_split = (p.n_nodes > 0 && r->cap * 16 <= b->total_rows) ? 1 : 0;
@@ -3415,6 +3546,9 @@ int obgpu_project_datums(obgpu_batch *batch, int32_t block, int32_t col, const i
 }
 
 }  // extern "C"
+
+// ---- string cells as bytes (dense heap): scan results and the per-block entry ------------------------------------------
+#include "result_strings.cuh"
 
 // ---- dictionary surface: distinct values, references, black filter on one dictionary column, GROUP BY ----
 #include "dict_ops.cuh"

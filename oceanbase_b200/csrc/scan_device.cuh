@@ -332,8 +332,13 @@ __device__ __forceinline__ void parse_block(const uint8_t *s, uint32_t size, Blo
   b.row_index_off = 0;
   if (b.ok && b.row_index_byte > 0) {
     const uint32_t need = (uint32_t)b.row_index_byte * (b.row_count + 1);
-    if (need > size - b.row_data_off) b.ok = 0;
-    else b.row_index_off = size - need;
+    // the row index closes the block PROPER, header_size_ + data_length_ bytes; a page batch's own copy of a block may carry
+    // materialised string areas behind it (mat_codecs.cuh), so `size` can be larger than that
+    uint32_t end = size;
+    const uint32_t logical = b.header_size + ld32(s, 40);
+    if (logical < size && logical >= b.row_data_off) end = logical;
+    if (need > end - b.row_data_off) b.ok = 0;
+    else b.row_index_off = end - need;
   }
 }
 
@@ -794,8 +799,29 @@ __device__ __forceinline__ void build_col_desc(const BlockView &b, int col, ColD
       d.ok = 1;
       return;
     }
+    case COL_STRING_DIFF:
+    case COL_HEX_PACKING:
+    case COL_STRING_PREFIX: {
+      // Values these codecs rebuild are materialised once per page batch (mat_codecs.cuh): in the batch's copy of the block the
+      // codec header says where the column's area [NULL bits][END offset u32 x rows][strings] lies. Without that marker (a block
+      // opened some other way) the column stays unsupported and the caller falls back.
+      if (sc != 5 || length < 13 || meta + length > b.size || s[meta] != 0xA5) return;
+      const uint32_t pf = meta + (d.type == COL_HEX_PACKING ? 1u : (d.type == COL_STRING_DIFF ? 4u : 2u));
+      const uint32_t area = (uint32_t)ld_bytes(s, pf, 4), rows = b.row_count, nwords = (rows + 31u) / 32u;
+      if ((area & 15u) || area < meta + length || (uint64_t)area + nwords * 4ull + rows * 4ull > b.size) return;
+      d.kind = K_CSSTR;
+      d.ext_bit = 1;
+      d.ext_bit_off = area * 8u;
+      d.dict_payload = area + nwords * 4u;
+      d.dict_data_size = 4;
+      d.dict_var = d.dict_payload + rows * 4u;
+      d.dict_end = d.dict_var + (uint32_t)ld_bytes(s, d.dict_payload + (rows - 1u) * 4u, 4);
+      if (d.dict_end > b.size || d.dict_end < d.dict_var) return;
+      d.ok = 1;
+      return;
+    }
     default:
-      return;  // STRING_DIFF / HEX / PREFIX / span columns: caller falls back
+      return;  // span columns (COLUMN_EQUAL / COLUMN_SUBSTR): caller falls back
   }
 }
 
@@ -827,6 +853,10 @@ __device__ __forceinline__ bool col_region(const ColDesc &d, const BlockView &bv
       break;
     case K_RLE:
       a = d.rle_row_ids_bit >> 3;
+      b = d.dict_end;
+      break;
+    case K_CSSTR:   // a materialised PAX string column: NULL bits, END offsets and strings are one contiguous area (mat_codecs.cuh)
+      a = d.ext_bit_off >> 3;
       b = d.dict_end;
       break;
     case K_CONST: {

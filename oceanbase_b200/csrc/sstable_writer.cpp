@@ -136,6 +136,39 @@ struct ColOut {
   bool is_var = false;          // var-length cells live in the row data
   int var_int_size = 0;         // integer column turned into a var-stored one: bytes per non-NULL cell
   bool need_ext_in_row = false; // var column with NULLs: ext bits inside each row
+  // string codecs with their own meta header (HEX_PACKING / STRING_DIFF / STRING_PREFIX): the column header keeps the meta's
+  // position; a var-stored column's row position goes into the codec header's offset_ / length_ fields (set_data_pos), and its
+  // cells are encoded bytes (cell_off[r] .. cell_off[r + 1] of cell_heap), not the strings themselves
+  bool own_meta = false;
+  size_t pos_field_at = 0;      // offset inside `meta` of the codec header's offset_ field (length_ follows it)
+  std::vector<uint8_t> cell_heap;
+  std::vector<int64_t> cell_off;
+};
+
+// ObHexStringMap / ObHexStringPacker (encoding/ob_hex_string_encoder.h:26-107): at most 16 distinct bytes, two per stored byte,
+// the first one in the high nibble; indexes are assigned in byte order (build_index, ob_hex_string_encoder.cpp:30-43).
+struct HexMap {
+  int size = 0;
+  uint8_t map[256] = {0};
+  void mark(uint8_t c) { if (size <= 16 && map[c] == 0) map[c] = (uint8_t)++size; }
+  bool can_packing() const { return size <= 16; }
+  void build_index(uint8_t *arr) {
+    int idx = 0;
+    for (int i = 0; i < 256 && idx < size; ++i)
+      if (map[i]) { map[i] = (uint8_t)idx; arr[idx++] = (uint8_t)i; }
+  }
+};
+struct HexPacker {
+  const HexMap &m;
+  std::vector<uint8_t> &out;
+  size_t base;
+  uint64_t pos = 0;
+  HexPacker(const HexMap &m_, std::vector<uint8_t> &o) : m(m_), out(o), base(o.size()) {}
+  void pack(uint8_t c) {
+    if (base + pos / 2 >= out.size()) out.push_back(0);
+    out[base + pos / 2] = (uint8_t)(out[base + pos / 2] | (m.map[c] << (((pos + 1) % 2) * 4)));
+    ++pos;
+  }
 };
 
 // Fixed column store: [ext bits][bit packed] then byte aligned fixed values.
@@ -388,6 +421,10 @@ struct BlockBuilder {
   int encode_rle(int i);
   int encode_base_diff(int i);
   int encode_const(int i);
+  int encode_hex(int i);
+  int encode_string_diff(int i);
+  int encode_string_prefix(int i);
+  void store_ext_then_fixed_cells(int i, int64_t cell_len);
   int build_cs(std::vector<uint8_t> &block, int64_t original);
   int build(std::vector<uint8_t> &block);
 };
@@ -547,6 +584,269 @@ int BlockBuilder::encode_rle(int i) {
   o.hdr.attr_ = 0;
   o.hdr.offset_ = (uint32_t)meta_at;
   o.hdr.length_ = (uint32_t)(meta.size() - meta_at);
+  return OBGPU_SUCCESS;
+}
+
+// ---- string codecs that materialise their values (a10): HEX_PACKING, STRING_DIFF, STRING_PREFIX ----------------------------------
+// Fixed store of encoded cells: [ext bits][nrows x cell_len bytes] after the codec meta (fill_column_store of these encoders).
+void BlockBuilder::store_ext_then_fixed_cells(int i, int64_t cell_len) {
+  ColCtx &c = ctx[(size_t)i];
+  ColOut &o = out[(size_t)i];
+  const bool has_null = c.null_cnt > 0;
+  const int64_t bits_size = has_null ? ((int64_t)ext_bit * nrows + 7) / 8 : 0;
+  uint8_t *buf = meta.grow((size_t)(bits_size + cell_len * nrows));
+  if (has_null)
+    for (int64_t r = 0; r < nrows; ++r)
+      if (c.is_null(r)) put_bits(buf, r * ext_bit, ext_bit, c.ext_val(r));
+  uint8_t *p = buf + bits_size;
+  for (int64_t r = 0; r < nrows; ++r, p += cell_len)
+    if (!c.is_null(r)) memcpy(p, o.cell_heap.data() + o.cell_off[(size_t)r], (size_t)cell_len);
+  o.cell_heap.clear();
+  o.cell_off.clear();
+}
+
+// HEX_PACKING (ObHexStringEncoder, encoding/ob_hex_string_encoder.cpp:83-262): strings over an alphabet of <= 16 bytes, two per byte.
+//   meta: ObHexStringHeader {version u8, offset u32, length u32, max_string_size u32} + the alphabet (column header length = 13 + size)
+//   fixed store (every value max_string_size long): (max + 1) / 2 bytes per row; var store: [odd u8][packed] in the row data
+int BlockBuilder::encode_hex(int i) {
+  ColCtx &c = ctx[(size_t)i];
+  ColOut &o = out[(size_t)i];
+  if (c.sc != 5) return OBGPU_NOT_SUPPORTED;
+  o.hdr.type_ = COL_HEX_PACKING;
+  o.own_meta = true;
+  HexMap hm;
+  int64_t min_len = INT64_MAX, max_len = -1;
+  for (int64_t r = 0; r < nrows; ++r) {
+    if (c.is_null(r)) continue;
+    const StrRef v = c.sval(r);
+    min_len = std::min(min_len, v.len);
+    max_len = std::max(max_len, v.len);
+    for (int64_t k = 0; k < v.len; ++k) hm.mark((uint8_t)v.p[k]);
+  }
+  if (!hm.can_packing() || max_len < 0) return OBGPU_NOT_SUPPORTED;   // the reference's "not suitable"
+  bool fix_store = min_len == max_len;
+  if (fix_store && c.null_cnt * ((max_len + 1) / 2) > (2 + 1) * nrows) fix_store = false;   // ext cells waste more than var indexes
+  const bool has_null = c.null_cnt > 0;
+  if (has_null) o.hdr.attr_ |= ATTR_HAS_EXTEND_VALUE;
+  o.hdr.offset_ = (uint32_t)meta.size();
+  o.hdr.length_ = (uint32_t)(13 + hm.size);
+  uint8_t *h = meta.grow((size_t)(13 + hm.size));
+  const uint32_t mx = (uint32_t)max_len;
+  memcpy(h + 9, &mx, 4);
+  hm.build_index(h + 13);
+  o.pos_field_at = o.hdr.offset_ + 1;
+  o.cell_off.assign((size_t)nrows + 1, 0);
+  for (int64_t r = 0; r < nrows; ++r) {
+    if (!c.is_null(r)) {
+      const StrRef v = c.sval(r);
+      if (!fix_store) o.cell_heap.push_back((uint8_t)(v.len % 2));   // ObVarHexCellHeader::odd_
+      HexPacker pk(hm, o.cell_heap);
+      for (int64_t k = 0; k < v.len; ++k) pk.pack((uint8_t)v.p[k]);
+    }
+    o.cell_off[(size_t)r + 1] = (int64_t)o.cell_heap.size();
+  }
+  if (fix_store) {
+    o.hdr.attr_ |= ATTR_FIX_LENGTH;
+    const uint32_t len = (uint32_t)((max_len + 1) / 2);
+    memcpy(meta.d.data() + o.hdr.offset_ + 5, &len, 4);   // header_->length_ (store_fix_data)
+    store_ext_then_fixed_cells(i, len);
+  } else {
+    o.is_var = true;
+    o.need_ext_in_row = has_null;
+  }
+  return OBGPU_SUCCESS;
+}
+
+// STRING_DIFF (ObStringDiffEncoder, encoding/ob_string_diff_encoder.cpp:77-330): equal-length strings that share most positions.
+//   meta: ObStringDiffHeader {version u8, hex_char_array_size u8, string_size u16, offset u32, length u32, diff_desc_cnt u8}
+//         + DiffDesc[cnt] {diff:1, count:7} + alphabet (hex packing of the differing bytes) + the common bytes
+//   per row: the differing bytes only (hex packed when <= 16 distinct bytes and more than one differs), fixed or var store
+int BlockBuilder::encode_string_diff(int i) {
+  ColCtx &c = ctx[(size_t)i];
+  ColOut &o = out[(size_t)i];
+  if (c.sc != 5) return OBGPU_NOT_SUPPORTED;
+  o.hdr.type_ = COL_STRING_DIFF;
+  o.own_meta = true;
+  int64_t string_size = -1;
+  const char *first = nullptr;
+  std::vector<uint8_t> diff;
+  for (int64_t r = 0; r < nrows; ++r) {
+    if (c.is_null(r)) continue;
+    const StrRef v = c.sval(r);
+    if (string_size < 0) {
+      if (v.len <= 0 || v.len >= 0xffff) return OBGPU_NOT_SUPPORTED;
+      string_size = v.len;
+      first = v.p;
+      diff.assign((size_t)v.len, 0);
+    } else if (v.len != string_size) {
+      return OBGPU_NOT_SUPPORTED;
+    } else {
+      for (int64_t k = 0; k < string_size; ++k) if (v.p[k] != first[k]) diff[(size_t)k] = 1;
+    }
+  }
+  if (string_size < 0 || c.null_cnt + 2 >= nrows) return OBGPU_NOT_SUPPORTED;
+  HexMap hm;
+  for (int64_t r = 0; r < nrows; ++r) {
+    if (c.is_null(r)) continue;
+    const StrRef v = c.sval(r);
+    for (int64_t k = 0; k < string_size; ++k) if (diff[(size_t)k]) hm.mark((uint8_t)v.p[k]);
+  }
+  struct Desc { uint8_t diff, count; };
+  std::vector<Desc> descs;
+  int64_t common_size = 0;
+  {
+    int64_t begin = 0;
+    uint8_t cur = diff[0];
+    for (int64_t k = 0; k <= string_size; ++k) {
+      if (k == string_size || diff[(size_t)k] != cur || k - begin == 0x7f) {
+        descs.push_back(Desc{cur, (uint8_t)((k - begin) & 0x7f)});
+        if (!cur) common_size += k - begin;
+        begin = k;
+        if (k < string_size) cur = diff[(size_t)k];
+      }
+    }
+  }
+  if (common_size == string_size || common_size == 0 || descs.size() > 255) return OBGPU_NOT_SUPPORTED;
+  int64_t row_store = string_size - common_size;
+  const bool hex = row_store > 1 && hm.can_packing();
+  if (hex) row_store = (row_store + 1) / 2;
+  const bool var_store = row_store * c.null_cnt > 2 * nrows;
+  const bool has_null = c.null_cnt > 0;
+  if (has_null) o.hdr.attr_ |= ATTR_HAS_EXTEND_VALUE;
+  const size_t meta_size = 13 + descs.size() + (hex ? (size_t)hm.size : 0) + (size_t)common_size;
+  o.hdr.offset_ = (uint32_t)meta.size();
+  o.hdr.length_ = (uint32_t)meta_size;
+  uint8_t *h = meta.grow(meta_size);
+  h[1] = hex ? (uint8_t)hm.size : 0;
+  const uint16_t ss = (uint16_t)string_size;
+  memcpy(h + 2, &ss, 2);
+  h[12] = (uint8_t)descs.size();
+  for (size_t k = 0; k < descs.size(); ++k) h[13 + k] = (uint8_t)((descs[k].diff & 1) | (descs[k].count << 1));
+  uint8_t *arr = h + 13 + descs.size();
+  if (hex) hm.build_index(arr);
+  uint8_t *common = arr + (hex ? hm.size : 0);
+  for (int64_t k = 0, q = 0; k < string_size; ++k) if (!diff[(size_t)k]) common[q++] = (uint8_t)first[k];
+  o.pos_field_at = o.hdr.offset_ + 4;
+  o.cell_off.assign((size_t)nrows + 1, 0);
+  for (int64_t r = 0; r < nrows; ++r) {
+    if (!c.is_null(r)) {
+      const StrRef v = c.sval(r);
+      const size_t at = o.cell_heap.size();
+      if (hex) {
+        HexPacker pk(hm, o.cell_heap);
+        for (int64_t k = 0; k < string_size; ++k) if (diff[(size_t)k]) pk.pack((uint8_t)v.p[k]);
+      } else {
+        for (int64_t k = 0; k < string_size; ++k) if (diff[(size_t)k]) o.cell_heap.push_back((uint8_t)v.p[k]);
+      }
+      o.cell_heap.resize(at + (size_t)row_store, 0);
+    }
+    o.cell_off[(size_t)r + 1] = (int64_t)o.cell_heap.size();
+  }
+  if (!var_store) {
+    o.hdr.attr_ |= ATTR_FIX_LENGTH;
+    const uint32_t len = (uint32_t)row_store;
+    memcpy(meta.d.data() + o.hdr.offset_ + 8, &len, 4);
+    store_ext_then_fixed_cells(i, row_store);
+  } else {
+    o.is_var = true;
+    o.need_ext_in_row = has_null;
+  }
+  return OBGPU_SUCCESS;
+}
+
+// STRING_PREFIX (ObStringPrefixEncoder, encoding/ob_string_prefix_encoder.cpp:75-300): up to 16 shared prefixes in the meta, per row
+// [ref:4 | odd:4][common length u16][rest of the string, hex packed when the rests use <= 16 distinct bytes]; always var-stored.
+//   meta: ObStringPrefixMetaHeader {version u8, count u8, offset u32, length u32, max_string_size u32, {prefix_index_byte:2,
+//         hex_char_array_size:5} u8} + alphabet + (count - 1) x prefix_index_byte start offsets + the prefixes
+// The reference picks the prefixes with a multi-prefix tree (ob_multi_prefix_tree.cpp); any choice decodes the same way. Here: the
+// longest common prefix of every group of strings that start with the same byte, the 16 largest groups.
+int BlockBuilder::encode_string_prefix(int i) {
+  ColCtx &c = ctx[(size_t)i];
+  ColOut &o = out[(size_t)i];
+  if (c.sc != 5) return OBGPU_NOT_SUPPORTED;
+  o.hdr.type_ = COL_STRING_PREFIX;
+  o.own_meta = true;
+  struct Group { int64_t rows = 0; const char *p = nullptr; int64_t lcp = 0; };
+  Group groups[256];
+  int64_t max_len = 0;
+  for (int64_t r = 0; r < nrows; ++r) {
+    if (c.is_null(r)) continue;
+    const StrRef v = c.sval(r);
+    max_len = std::max(max_len, v.len);
+    if (v.len == 0) continue;
+    Group &g = groups[(uint8_t)v.p[0]];
+    if (g.rows++ == 0) { g.p = v.p; g.lcp = std::min<int64_t>(v.len, 0xffff); }
+    else {
+      int64_t k = 0;
+      while (k < g.lcp && k < v.len && v.p[k] == g.p[k]) ++k;
+      g.lcp = k;
+    }
+  }
+  std::vector<int> order;
+  for (int b = 0; b < 256; ++b) if (groups[b].rows > 1) order.push_back(b);
+  std::sort(order.begin(), order.end(), [&](int x, int y) { return groups[x].rows > groups[y].rows; });
+  if (order.size() > 16) order.resize(16);
+  if (order.empty()) return OBGPU_NOT_SUPPORTED;
+  int ref_of_byte[256];
+  for (int b = 0; b < 256; ++b) ref_of_byte[b] = -1;
+  int64_t prefix_length = 0;
+  for (size_t k = 0; k < order.size(); ++k) { ref_of_byte[order[k]] = (int)k; prefix_length += groups[order[k]].lcp; }
+  if (prefix_length > 0xffff) return OBGPU_NOT_SUPPORTED;
+  const int pib = prefix_length <= 0xff ? 1 : 2;
+  // hex packing of the rests
+  HexMap hm;
+  for (int64_t r = 0; r < nrows; ++r) {
+    if (c.is_null(r)) continue;
+    const StrRef v = c.sval(r);
+    const int ref = v.len ? ref_of_byte[(uint8_t)v.p[0]] : -1;
+    const int64_t common = ref >= 0 ? groups[order[(size_t)ref]].lcp : 0;
+    for (int64_t k = common; k < v.len; ++k) hm.mark((uint8_t)v.p[k]);
+  }
+  const bool hex = hm.can_packing() && hm.size > 0;
+  const bool has_null = c.null_cnt > 0;
+  if (has_null) o.hdr.attr_ |= ATTR_HAS_EXTEND_VALUE;
+  const size_t cnt = order.size();
+  const size_t meta_size = 15 + (hex ? (size_t)hm.size : 0) + (cnt - 1) * (size_t)pib + (size_t)prefix_length;
+  o.hdr.offset_ = (uint32_t)meta.size();
+  o.hdr.length_ = (uint32_t)meta_size;
+  uint8_t *h = meta.grow(meta_size);
+  h[1] = (uint8_t)cnt;
+  const uint32_t mx = (uint32_t)max_len;
+  memcpy(h + 10, &mx, 4);
+  h[14] = (uint8_t)((pib & 3) | ((hex ? hm.size : 0) << 2));
+  uint8_t *arr = h + 15;
+  if (hex) hm.build_index(arr);
+  uint8_t *idx = arr + (hex ? hm.size : 0);
+  uint8_t *pdata = idx + (cnt - 1) * (size_t)pib;
+  int64_t off = 0;
+  for (size_t k = 0; k < cnt; ++k) {
+    if (k > 0) { const uint32_t o32 = (uint32_t)off; memcpy(idx + (k - 1) * (size_t)pib, &o32, (size_t)pib); }
+    memcpy(pdata + off, groups[order[k]].p, (size_t)groups[order[k]].lcp);
+    off += groups[order[k]].lcp;
+  }
+  o.pos_field_at = o.hdr.offset_ + 2;
+  o.cell_off.assign((size_t)nrows + 1, 0);
+  for (int64_t r = 0; r < nrows; ++r) {
+    if (!c.is_null(r)) {
+      const StrRef v = c.sval(r);
+      const int ref = v.len ? ref_of_byte[(uint8_t)v.p[0]] : -1;
+      const int64_t common = ref >= 0 ? groups[order[(size_t)ref]].lcp : 0;
+      const int64_t rest = v.len - common;
+      const uint16_t cl = (uint16_t)common;
+      o.cell_heap.push_back((uint8_t)(((ref >= 0 ? ref : 0) & 0xf) | ((hex ? (rest % 2) : 0) << 4)));
+      o.cell_heap.push_back((uint8_t)(cl & 0xff));
+      o.cell_heap.push_back((uint8_t)(cl >> 8));
+      if (hex) {
+        HexPacker pk(hm, o.cell_heap);
+        for (int64_t k = common; k < v.len; ++k) pk.pack((uint8_t)v.p[k]);
+      } else {
+        o.cell_heap.insert(o.cell_heap.end(), (const uint8_t *)v.p + common, (const uint8_t *)v.p + v.len);
+      }
+    }
+    o.cell_off[(size_t)r + 1] = (int64_t)o.cell_heap.size();
+  }
+  o.is_var = true;
+  o.need_ext_in_row = has_null;
   return OBGPU_SUCCESS;
 }
 
@@ -721,6 +1021,9 @@ int BlockBuilder::build(std::vector<uint8_t> &block) {
       case OBGPU_ENC_RLE: ret = encode_rle(i); break;
       case OBGPU_ENC_INTEGER_BASE_DIFF: ret = encode_base_diff(i); break;
       case OBGPU_ENC_CONST: ret = encode_const(i); break;
+      case OBGPU_ENC_HEX_PACKING: ret = encode_hex(i); break;
+      case OBGPU_ENC_STRING_DIFF: ret = encode_string_diff(i); break;
+      case OBGPU_ENC_STRING_PREFIX: ret = encode_string_prefix(i); break;
       default: ret = OBGPU_NOT_SUPPORTED;
     }
     if (ret != OBGPU_SUCCESS) return ret;
@@ -738,9 +1041,15 @@ int BlockBuilder::build(std::vector<uint8_t> &block) {
   }
   const int64_t fix_data_size = (ext_bits_in_row + 7) / 8;
   for (size_t k = 0; k < var_cols.size(); ++k) {
-    ColumnHeader &h = out[(size_t)var_cols[k]].hdr;
-    h.offset_ = (uint32_t)fix_data_size;  // row_offset_
-    h.length_ = (uint32_t)k;              // index among the var columns
+    ColOut &vo = out[(size_t)var_cols[k]];
+    const uint32_t row_off = (uint32_t)fix_data_size, var_idx = (uint32_t)k;   // set_data_pos(fix_data_size, i)
+    if (vo.own_meta) {   // the codec's own header carries the row position; the column header keeps pointing at the meta
+      memcpy(meta.d.data() + vo.pos_field_at, &row_off, 4);
+      memcpy(meta.d.data() + vo.pos_field_at + 4, &var_idx, 4);
+    } else {
+      vo.hdr.offset_ = row_off;   // row_offset_
+      vo.hdr.length_ = var_idx;   // index among the var columns
+    }
   }
   if (!var_cols.empty()) out[(size_t)var_cols.back()].hdr.attr_ |= ATTR_LAST_VAR_FIELD;
 
@@ -760,7 +1069,8 @@ int BlockBuilder::build(std::vector<uint8_t> &block) {
       for (size_t k = 0; k < nv; ++k) {
         const ColCtx &c = ctx[(size_t)var_cols[k]];
         const int vis = out[(size_t)var_cols[k]].var_int_size;
-        lens[k] = c.is_null(r) ? 0 : (vis > 0 ? (int64_t)vis : c.sval(r).len);
+        const ColOut &vo = out[(size_t)var_cols[k]];
+        lens[k] = c.is_null(r) ? 0 : (vo.own_meta ? vo.cell_off[(size_t)r + 1] - vo.cell_off[(size_t)r] : (vis > 0 ? (int64_t)vis : c.sval(r).len));
         if (k > 0 && k == nv - 1) col_idx_byte = var_size <= 0xff ? 1 : (var_size <= 0xffff ? 2 : 4);
         var_size += lens[k];
       }
@@ -786,6 +1096,9 @@ int BlockBuilder::build(std::vector<uint8_t> &block) {
         } else if (out[(size_t)var_cols[k]].var_int_size > 0) {
           const uint64_t v = c.uval(r);   // low bytes of the datum (MEMCPY(buf, datum.ptr_, len))
           memcpy(var + off, &v, (size_t)std::min<int64_t>(lens[k], 8));
+        } else if (out[(size_t)var_cols[k]].own_meta) {
+          const ColOut &vo = out[(size_t)var_cols[k]];
+          if (lens[k] > 0) memcpy(var + off, vo.cell_heap.data() + vo.cell_off[(size_t)r], (size_t)lens[k]);
         } else if (lens[k] > 0) {
           memcpy(var + off, c.sval(r).p, (size_t)lens[k]);
         }

@@ -262,6 +262,29 @@ class PageBatch:
                                        datums.ctypes.data), "obgpu_project_datums", self.ctx._h)
         return datums
 
+    # ---- string cells as bytes (columns whose values the device rebuilt: HEX_PACKING / STRING_DIFF / STRING_PREFIX) ----
+    def column_materialised(self, col) -> bool:
+        m = C.c_int32(0)
+        check(lib.obgpu_batch_column_materialised(self._h, col, C.byref(m)), "obgpu_batch_column_materialised", self.ctx._h)
+        return bool(m.value)
+
+    def project_strings(self, block, col, row_ids):
+        """obgpu_project_strings: (heap uint8, offsets int64 [n + 1], nulls words) of the listed rows of one block."""
+        rid = np.ascontiguousarray(row_ids, dtype=np.int32)
+        n = len(rid)
+        off = np.zeros(n + 1, dtype=np.int64)
+        nulls = np.zeros(max((n + 63) // 64, 1), dtype=np.uint64)
+        need, hn = C.c_int64(0), C.c_int32(0)
+        heap = np.zeros(1, dtype=np.uint8)
+        rc = lib.obgpu_project_strings(self._h, block, col, rid.ctypes.data, n, heap.ctypes.data, 0, off.ctypes.data, nulls.ctypes.data,
+                                       C.byref(hn), C.byref(need))
+        if rc == capi.OB_BUF_NOT_ENOUGH:
+            heap = np.zeros(max(need.value, 1), dtype=np.uint8)
+            rc = lib.obgpu_project_strings(self._h, block, col, rid.ctypes.data, n, heap.ctypes.data, heap.size, off.ctypes.data,
+                                           nulls.ctypes.data, C.byref(hn), C.byref(need))
+        check(rc, "obgpu_project_strings", self.ctx._h)
+        return heap[:need.value], off, nulls
+
     # ---- dictionary surface (pushdown GROUP BY, black filter on one dictionary column) ----
     def distinct_count(self, block, col) -> int:
         """ObIMicroBlockReader::get_distinct_count."""
@@ -364,6 +387,20 @@ class ScanResult:
                                          aux.ctypes.data if aux is not None else None, nulls.ctypes.data),
               "obgpu_result_fetch_col", self.batch.ctx._h)
         return data[:row_count], (aux[:row_count] if aux is not None else None), nulls[:(row_count + 63) // 64]
+
+    def fetch_strings(self, i, row_begin=0, row_count=None):
+        """obgpu_result_fetch_strings: (heap uint8, offsets int64 [n + 1]) -- the bytes of projected string column i."""
+        if row_count is None:
+            row_count = self.selected_rows - row_begin
+        off = np.zeros(row_count + 1, dtype=np.int64)
+        need = C.c_int64(0)
+        heap = np.zeros(1, dtype=np.uint8)
+        rc = lib.obgpu_result_fetch_strings(self._h, i, row_begin, row_count, heap.ctypes.data, 0, off.ctypes.data, C.byref(need))
+        if rc == capi.OB_BUF_NOT_ENOUGH:
+            heap = np.zeros(max(need.value, 1), dtype=np.uint8)
+            rc = lib.obgpu_result_fetch_strings(self._h, i, row_begin, row_count, heap.ctypes.data, heap.size, off.ctypes.data, C.byref(need))
+        check(rc, "obgpu_result_fetch_strings", self.batch.ctx._h)
+        return heap[:need.value], off
 
     def group_by(self, group_col, aggs):
         """GROUP BY over every block of the scan, the rows the filter selected (one launch): returns (group_off int64

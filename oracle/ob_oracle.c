@@ -14,7 +14,7 @@
 #include <string.h>
 
 /* ---- layout constants (ob_micro_block_header.h:97-153, ob_block_sstable_struct.h:201-264) ---- */
-enum { T_RAW = 0, T_DICT = 1, T_RLE = 2, T_CONST = 3, T_BASE_DIFF = 4, T_CS_INTEGER = 100, T_CS_STRING = 101, T_CS_INT_DICT = 102, T_CS_STR_DICT = 103 /* CS block: 100 + ObCSColumnHeader::Type */ };
+enum { T_RAW = 0, T_DICT = 1, T_RLE = 2, T_CONST = 3, T_BASE_DIFF = 4, T_STRING_DIFF = 5, T_HEX = 6, T_STRING_PREFIX = 7, T_CS_INTEGER = 100, T_CS_STRING = 101, T_CS_INT_DICT = 102, T_CS_STR_DICT = 103 /* CS block: 100 + ObCSColumnHeader::Type */ };
 enum { A_FIX = 0x1, A_EXT = 0x2, A_BITPACK = 0x4, A_LASTVAR = 0x8 };
 enum { EXT_NOT = 0, EXT_NULL = 1, EXT_NOPE = 2 };
 #define MAGIC 1005
@@ -443,7 +443,42 @@ typedef struct col_dec {
   const uint8_t *cs_off;           /* END offsets: one per row (STRING) or per dictionary entry (STR_DICT) */
   int cs_off_w;
   int cs_zero_len_null;
+  /* HEX_PACKING / STRING_DIFF / STRING_PREFIX: the codec's own header (position of var cells in the row: offset / length) */
+  col_hdr mat_pos;              /* {offset_, length_} of the codec header + the column's attr (LAST_VAR_FIELD) */
+  const uint8_t *mat_hex;       /* alphabet (NULL: no hex packing) */
+  uint32_t mat_max;             /* max_string_size / string_size */
+  const uint8_t *mat_descs;     /* STRING_DIFF: DiffDesc[mat_desc_cnt] */
+  int mat_desc_cnt;
+  const uint8_t *mat_common;    /* STRING_DIFF: common bytes; STRING_PREFIX: prefix bytes */
+  const uint8_t *mat_index;     /* STRING_PREFIX: (count - 1) start offsets */
+  int mat_index_byte, mat_count;
 } col_dec;
+
+/* Strings that HEX_PACKING / STRING_DIFF / STRING_PREFIX rebuild do not exist in the block: the reference decodes them into memory
+ * of the decoder's allocator (ctx.allocator_->alloc, ob_hex_string_decoder.cpp:87-93). The oracle's equivalent: a thread-local bump
+ * arena that lives until ora_arena_reset(). */
+typedef struct arena_chunk { struct arena_chunk *next; size_t used, cap; } arena_chunk;
+static __thread arena_chunk *g_arena = 0;
+static uint8_t *arena_alloc(size_t n) {
+  n = (n + 15) & ~(size_t)15;
+  if (!g_arena || g_arena->used + n > g_arena->cap) {
+    const size_t cap = n > (1u << 20) ? n : (1u << 20);
+    arena_chunk *c = (arena_chunk *)malloc(sizeof(arena_chunk) + cap);
+    if (!c) return 0;
+    c->next = g_arena; c->used = 0; c->cap = cap;
+    g_arena = c;
+  }
+  uint8_t *p = (uint8_t *)(g_arena + 1) + g_arena->used;
+  g_arena->used += n;
+  return p;
+}
+void ora_arena_reset(void) {
+  while (g_arena) { arena_chunk *n = g_arena->next; free(g_arena); g_arena = n; }
+}
+/* ObHexStringUnpacker::unpack (ob_hex_string_encoder.h:86-91): nibble `pos` of the packed bytes, even positions in the high half */
+static inline uint8_t hex_at(const uint8_t *map, const uint8_t *data, int64_t pos) {
+  return map[(data[pos / 2] >> (((pos + 1) % 2) * 4)) & 0xf];
+}
 
 /* ObStringStreamMeta, serialized (ob_stream_encoding_struct.cpp:255-283) */
 typedef struct str_stream_meta { uint8_t attr; uint32_t uncompressed_len, fixed_len; int64_t meta_len; } str_stream_meta;
@@ -657,6 +692,36 @@ static int col_dec_init(const ora_block *b, int32_t col, col_dec *c) {
       if (c->sc == 1 && mask != 0 && (c->base & (mask >> 1))) c->base |= mask;
       break;
     }
+    case T_HEX: { /* ObHexStringHeader {version, offset u32, length u32, max_string_size u32} + alphabet (ob_hex_string_encoder.h:139-152) */
+      if (c->sc != 5 || c->h.length < 13 || c->meta[0] != 0) return ORA_ERR_UNEXPECTED;
+      c->mat_pos.offset = rd32(c->meta + 1); c->mat_pos.length = rd32(c->meta + 5); c->mat_pos.attr = c->h.attr;
+      c->mat_max = rd32(c->meta + 9);
+      c->mat_hex = c->meta + 13;
+      break;
+    }
+    case T_STRING_DIFF: { /* ObStringDiffHeader (ob_string_diff_encoder.h:27-104) */
+      if (c->sc != 5 || c->h.length < 13 || c->meta[0] != 0) return ORA_ERR_UNEXPECTED;
+      const int hex_size = c->meta[1];
+      c->mat_max = rd16(c->meta + 2);
+      c->mat_pos.offset = rd32(c->meta + 4); c->mat_pos.length = rd32(c->meta + 8); c->mat_pos.attr = c->h.attr;
+      c->mat_desc_cnt = c->meta[12];
+      c->mat_descs = c->meta + 13;
+      c->mat_hex = hex_size ? c->mat_descs + c->mat_desc_cnt : 0;
+      c->mat_common = c->mat_descs + c->mat_desc_cnt + hex_size;
+      break;
+    }
+    case T_STRING_PREFIX: { /* ObStringPrefixMetaHeader (ob_string_prefix_encoder.h:72-107) */
+      if (c->sc != 5 || c->h.length < 15 || c->meta[0] != 0) return ORA_ERR_UNEXPECTED;
+      c->mat_count = c->meta[1];
+      c->mat_pos.offset = rd32(c->meta + 2); c->mat_pos.length = rd32(c->meta + 6); c->mat_pos.attr = c->h.attr;
+      c->mat_max = rd32(c->meta + 10);
+      c->mat_index_byte = c->meta[14] & 3;
+      const int hex_size = (c->meta[14] >> 2) & 0x1f;
+      c->mat_hex = hex_size ? c->meta + 15 : 0;
+      c->mat_index = c->meta + 15 + hex_size;
+      c->mat_common = c->mat_index + (int64_t)(c->mat_count > 0 ? c->mat_count - 1 : 0) * c->mat_index_byte;
+      break;
+    }
     case T_CS_INTEGER:
     case T_CS_STRING:
     case T_CS_INT_DICT:
@@ -771,6 +836,65 @@ static int decode_cell(const ora_block *b, const col_dec *c, int64_t row, ora_da
       }
       if (c->sc == 5) { out->ptr = cell; out->len = (uint32_t)cell_len; out->is_null = 0; out->ival = 0; }
       else load_int(c->h.obj_type, cell, cell_len, out);
+      return ORA_SUCCESS;
+    }
+    case T_HEX:
+    case T_STRING_DIFF:
+    case T_STRING_PREFIX: {
+      /* ext bits and cell location are shared by the three decoders (ob_hex_string_decoder.cpp:33-90, ob_string_diff_decoder.cpp:
+       * 34-95, ob_string_prefix_decoder.cpp:30-70): fixed store = [ext bits][cells] after the meta, var store = a cell of the row */
+      const int fixed = (c->h.attr & A_FIX) != 0;
+      const uint8_t *col_data = c->meta + c->h.length;
+      const uint8_t *row_data = 0, *cell = 0;
+      int64_t row_len = 0, cell_len = 0, data_offset = 0;
+      uint64_t ext = EXT_NOT;
+      if (!fixed) locate_row(b, row, &row_data, &row_len);
+      if (c->h.attr & A_EXT) {
+        if (fixed) {
+          data_offset = ((int64_t)b->row_count * b->extend_value_bit + 7) / 8;
+          ext = ora_bs_get(col_data, row * b->extend_value_bit, b->extend_value_bit);
+        } else {
+          ext = ora_bs_get(row_data, c->h.ext_index, b->extend_value_bit);
+        }
+      }
+      if (ext != EXT_NOT) { set_null(out); if (ext == EXT_NOPE) out->is_null = 2; return ORA_SUCCESS; }
+      if (fixed) { cell = col_data + data_offset + row * (int64_t)c->mat_pos.length; cell_len = c->mat_pos.length; }
+      else locate_var_cell(b, &c->mat_pos, row_data, row_len, &cell, &cell_len);
+      uint8_t *buf = arena_alloc(c->mat_max > 128 ? c->mat_max : 128);
+      if (!buf) return ORA_ERR_UNEXPECTED;
+      int64_t len = 0;
+      if (c->h.type == T_HEX) {
+        len = c->mat_max;
+        if (!fixed) { len = (cell_len - 1) * 2 - cell[0]; cell += 1; }   /* ObVarHexCellHeader::odd_ */
+        for (int64_t i = 0; i < len; ++i) buf[i] = hex_at(c->mat_hex, cell, i);
+      } else if (c->h.type == T_STRING_DIFF) {
+        len = c->mat_max;
+        int64_t fpos = 0, cpos = 0, ppos = 0;   /* position in the string, in the common bytes, in the row's part */
+        for (int i = 0; i < c->mat_desc_cnt; ++i) {
+          const int diff = c->mat_descs[i] & 1, cnt = c->mat_descs[i] >> 1;
+          for (int k = 0; k < cnt; ++k, ++fpos) {
+            if (!diff) buf[fpos] = c->mat_common[cpos++];
+            else { buf[fpos] = c->mat_hex ? hex_at(c->mat_hex, cell, ppos) : cell[ppos]; ++ppos; }
+          }
+        }
+      } else {
+        if (cell_len < 3) return ORA_ERR_UNEXPECTED;
+        const int ref = cell[0] & 0xf, odd = cell[0] >> 4;
+        const int64_t common = rd16(cell + 1);
+        const int64_t poff = ref ? (int64_t)rd_len(c->mat_index + (int64_t)(ref - 1) * c->mat_index_byte, c->mat_index_byte) : 0;
+        if (ref >= c->mat_count || common > c->mat_max) return ORA_ERR_UNEXPECTED;
+        memcpy(buf, c->mat_common + poff, (size_t)common);
+        cell += 3; cell_len -= 3;
+        if (c->mat_hex) {
+          const int64_t rest = cell_len * 2 - odd;
+          for (int64_t i = 0; i < rest; ++i) buf[common + i] = hex_at(c->mat_hex, cell, i);
+          len = common + rest;
+        } else {
+          memcpy(buf + common, cell, (size_t)cell_len);
+          len = common + cell_len;
+        }
+      }
+      out->ptr = buf; out->len = (uint32_t)len; out->is_null = 0; out->ival = 0;
       return ORA_SUCCESS;
     }
     case T_DICT:
@@ -1331,7 +1455,10 @@ int ora_scan_blocks(const void *image, const int64_t *offsets, const int64_t *si
           uint64_t *dp = (uint64_t *)out->data[p];
           for (int64_t i = 0; i < cnt; ++i) {
             const int isnull = (nulls[i / 64] >> (i % 64)) & 1;
-            dp[nsel + i] = isnull ? 0 : out->string_base + (uint64_t)(ptrs[i] - (const uint8_t *)image);
+            /* a string a codec rebuilt (HEX / STRING_DIFF / STRING_PREFIX) lives in the oracle's arena, not in the image: its
+             * absolute address is reported (the reference's datum points into allocator memory there, too) */
+            const int in_block = !isnull && ptrs[i] >= (const uint8_t *)b.buf && ptrs[i] < (const uint8_t *)b.buf + b.size;
+            dp[nsel + i] = isnull ? 0 : (in_block ? out->string_base + (uint64_t)(ptrs[i] - (const uint8_t *)image) : (uint64_t)(uintptr_t)ptrs[i]);
             if (out->lens && out->lens[p]) out->lens[p][nsel + i] = isnull ? 0 : lens[i];
             if (isnull && out->nulls && out->nulls[p]) bitvec_set(out->nulls[p], nsel + i);
           }

@@ -105,6 +105,9 @@ uint64_t ora_crc64_sse42(uint64_t crc, const void *p, int64_t len);
 int64_t ora_int_array_lower_bound(const void *array, int64_t byte, int64_t begin, int64_t end, int64_t key);
 int64_t ora_int_array_upper_bound(const void *array, int64_t byte, int64_t begin, int64_t end, int64_t key);
 int ora_decode_cell(const ora_block *blk, int32_t col, int64_t row, ora_datum *out);
+/* Strings rebuilt by HEX_PACKING / STRING_DIFF / STRING_PREFIX live in a thread-local arena of the oracle until this call
+ * (the reference: the decoder's allocator). Pointers the oracle returned for such cells are invalid afterwards. */
+void ora_arena_reset(void);
 /* dictionary surface of a dictionary-coded column (DICT / RLE / CONST with exceptions / CS INT_DICT / STR_DICT):
  * distinct count, entry `ref` decoded like a cell, refs of rows (NULL / NOP rows: the distinct count) */
 int ora_dict_count(const ora_block *blk, int32_t col, int64_t *count);

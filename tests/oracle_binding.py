@@ -112,6 +112,8 @@ def oracle():
         for f in ("ora_int_array_lower_bound", "ora_int_array_upper_bound"):
             getattr(L, f).restype = i64
             getattr(L, f).argtypes = [vp, i64, i64, i64, i64]
+        L.ora_arena_reset.restype = None
+        L.ora_arena_reset.argtypes = []
         L.ora_dict_count.argtypes = [P(OraBlock), i32, P(i64)]
         L.ora_dict_entry.argtypes = [P(OraBlock), i32, i64, P(OraDatum)]
         L.ora_dict_refs.argtypes = [P(OraBlock), i32, C.c_void_p, i64, C.c_void_p]
@@ -248,6 +250,8 @@ class Block:
             return None
         if d.ptr:
             off = d.ptr - self.buf.ctypes.data
+            if off < 0 or off + d.len > self.buf.size:   # a string a codec rebuilt: it lives in the oracle's arena
+                return C.string_at(d.ptr, d.len)
             return bytes(self.buf[off:off + d.len])
         if d.len and d.ival == 0 and False:
             return 0
@@ -292,7 +296,7 @@ class Block:
                   "ora_get_rows_fixed")
         return data, nulls, hn.value
 
-    def get_rows_discrete(self, col, row_ids, vec_offset=0):
+    def get_rows_discrete(self, col, row_ids, vec_offset=0, absolute=False):
         rid = np.ascontiguousarray(row_ids, dtype=np.int32)
         total = vec_offset + len(rid)
         ptrs = np.zeros(total, dtype=np.uint64)
@@ -302,6 +306,8 @@ class Block:
         ora_check(oracle().ora_get_rows_discrete(C.byref(self.b), col, rid.ctypes.data, len(rid), vec_offset,
                                                  ptrs.ctypes.data, lens.ctypes.data, nulls.ctypes.data, C.byref(hn)),
                   "ora_get_rows_discrete")
+        if absolute:   # strings a codec rebuilt live in the oracle's arena: no block offset exists for them
+            return ptrs, lens, nulls, hn.value
         # pointers -> offsets inside the block buffer
         offs = np.where(ptrs != 0, ptrs - np.uint64(self.buf.ctypes.data), 0).astype(np.uint64)
         return offs, lens, nulls, hn.value
@@ -369,6 +375,28 @@ def scan_table(table, filter_expr, proj_cols, proj_is_string, proj_elem_len, bat
             "lens": [(l[:n] if l is not None else None) for l in lens],
             "nulls": [x[:(n + 63) // 64] for x in nulls], "has_null": has_null[:n_proj].copy(),
             "row_ids": row_ids[:n], "sel_offset": sel_off}
+
+
+def scan_strings(table, res, p, string_base=0):
+    """Bytes of string column p of a scan_table() result (None for NULL rows): cells inside the image through string_base,
+    strings a codec rebuilt (HEX / STRING_DIFF / STRING_PREFIX) through their absolute address in the oracle's arena."""
+    out = []
+    ptrs, lens, nulls = res["data"][p], res["lens"][p], res["nulls"][p]
+    for i in range(res["selected"]):
+        if (int(nulls[i // 64]) >> (i % 64)) & 1:
+            out.append(None)
+            continue
+        a, n = int(ptrs[i]), int(lens[i])
+        off = a - string_base
+        if 0 <= off and off + n <= table.image.size:
+            out.append(bytes(table.image[off:off + n]))
+        else:
+            out.append(C.string_at(a, n))
+    return out
+
+
+def arena_reset():
+    oracle().ora_arena_reset()
 
 
 def scan_table_mt(table, filter_expr, proj_cols, batch_size=256, n_threads=1, block_limit=None):

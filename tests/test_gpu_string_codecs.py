@@ -1,0 +1,118 @@
+"""HEX_PACKING / STRING_DIFF / STRING_PREFIX on the device (mat_codecs.cuh: rebuilt once per page batch at open) vs the oracle:
+per-block white filters and string projection, whole-table scans with such columns filtered AND projected (bytes through
+obgpu_result_fetch_strings), next to ordinary columns, page batches opened from the host and from a device image."""
+import numpy as np
+import pytest
+
+import oracle_binding as ora
+from test_string_codecs import CASES
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ob():
+    import oceanbase_b200
+    return oceanbase_b200
+
+
+@pytest.fixture(scope="module")
+def ctx(ob):
+    c = ob.ScanContext(0)
+    yield c
+    c.close()
+
+
+def heap_strings(heap, off, nulls):
+    out = []
+    for k in range(len(off) - 1):
+        if (int(nulls[k // 64]) >> (k % 64)) & 1:
+            out.append(None)
+        else:
+            out.append(bytes(heap[off[k]:off[k + 1]]))
+    return out
+
+
+@pytest.mark.parametrize("case", range(len(CASES)), ids=[c[0] for c in CASES])
+def test_block_filters_and_projection(ob, ctx, case):
+    name, enc, vals, nulls = CASES[case]
+    n = len(vals)
+    cols = [ob.Column(ob.OBJ_INT, ob.ENC_RAW, np.arange(n, dtype=np.int64)),
+            ob.Column(ob.OBJ_VARCHAR, ob.ENC_RAW, [b"x" * (i % 5) for i in range(n)]),
+            ob.Column(ob.OBJ_VARCHAR, enc, vals, nulls=nulls), ob.Column(ob.OBJ_INT, ob.ENC_DICT, np.arange(n, dtype=np.int64) % 7)]
+    table = ob.encode_table(cols, 110)
+    batch = ctx.open_batch(table)
+    assert batch.column_materialised(2) and not batch.column_materialised(1) and not batch.column_materialised(0)
+    isnull = np.zeros(n, dtype=bool) if nulls is None else nulls.astype(bool)
+    present = sorted({v for v, z in zip(vals, isnull) if not z})
+    lo, hi = present[len(present) // 4], present[3 * len(present) // 4]
+    row0 = 0
+    for b in range(table.n_blocks):
+        blk = ora.Block(table.block(b))
+        rows = blk.row_count
+        for flt in (ob.White(2, ob.WHITE_OP_EQ, (present[2],)), ob.White(2, ob.WHITE_OP_NE, (present[2],)), ob.White(2, ob.WHITE_OP_GE, (lo,)),
+                    ob.White(2, ob.WHITE_OP_BT, (lo, hi)), ob.White(2, ob.WHITE_OP_IN, (present[0], present[-1], b"nope")),
+                    ob.White(2, ob.WHITE_OP_NU, ()), ob.White(2, ob.WHITE_OP_NN, ()),
+                    ob.And([ob.White(3, ob.WHITE_OP_LT, (5,)), ob.Or([ob.White(2, ob.WHITE_OP_LT, (lo,)), ob.White(1, ob.WHITE_OP_EQ, (b"xx",))])])):
+            for start, count in ((0, None), (7, rows - 20)):
+                assert np.array_equal(batch.filter_tree(b, flt, start, count), blk.filter_tree(flt, start, count)), (name, b)
+        rid = np.concatenate([np.arange(0, rows, 2), np.arange(rows - 1, 0, -9)]).astype(np.int32)
+        heap, off, nl = batch.project_strings(b, 2, rid)
+        want = [None if isnull[row0 + r] else vals[row0 + r] for r in rid]
+        assert heap_strings(heap, off, nl) == want, (name, b)
+        heap, off, nl = batch.project_strings(b, 1, rid)     # an ordinary string column through the same call
+        assert heap_strings(heap, off, nl) == [b"x" * ((row0 + r) % 5) for r in rid]
+        row0 += rows
+    batch.close()
+    ora.arena_reset()
+
+
+@pytest.mark.parametrize("case", [0, 2, 5, 7, 10, 11, 12, 14], ids=lambda i: CASES[i][0])
+@pytest.mark.parametrize("on_device", [False, True])
+def test_scan_filters_and_projects_rebuilt_strings(ob, ctx, case, on_device):
+    import torch
+    name, enc, vals, nulls = CASES[case]
+    reps = 40
+    vals = vals * reps
+    nulls = None if nulls is None else np.tile(nulls, reps)
+    n = len(vals)
+    k = np.arange(n, dtype=np.int64)
+    cols = [ob.Column(ob.OBJ_INT, ob.ENC_INTEGER_BASE_DIFF, k), ob.Column(ob.OBJ_VARCHAR, enc, vals, nulls=nulls),
+            ob.Column(ob.OBJ_VARCHAR, ob.ENC_DICT, [b"d%d" % (i % 11) for i in range(n)])]
+    table = ob.encode_table(cols, 700)
+    base = table.image.ctypes.data
+    if on_device:
+        d = torch.empty(table.image.size + 64, dtype=torch.uint8, device="cuda:0")
+        d[:table.image.size].copy_(torch.from_numpy(table.image))
+        d[table.image.size:].zero_()
+        torch.cuda.synchronize()
+        batch = ctx.open_batch(table, device_image_ptr=d.data_ptr(), host_view=False, image_size=table.image.size)
+    else:
+        batch = ctx.open_batch(table)
+    isnull = np.zeros(n, dtype=bool) if nulls is None else nulls.astype(bool)
+    present = sorted({v for v, z in zip(vals, isnull) if not z})
+    lo, hi = present[len(present) // 3], present[2 * len(present) // 3]
+    for flt in (None, ob.White(1, ob.WHITE_OP_BT, (lo, hi)), ob.And([ob.White(0, ob.WHITE_OP_GE, (n // 5,)), ob.White(1, ob.WHITE_OP_NE, (present[1],))]),
+                ob.Or([ob.White(1, ob.WHITE_OP_NU, ()), ob.White(2, ob.WHITE_OP_EQ, (b"d3",))])):
+        want = ora.scan_table(table, flt, [0, 1, 2], [False, True, True], [8, 8, 8], string_base=base)
+        res = batch.scan(flt, [0, 1, 2], string_base=base)
+        assert res.selected_rows == want["selected"], (name, flt)
+        data, _, nl0 = res.fetch_col(0)
+        assert np.array_equal(data, want["data"][0])
+        _, lens, nl1 = res.fetch_col(1)
+        assert np.array_equal(nl1[:len(want["nulls"][1])], want["nulls"][1]) and np.array_equal(lens, want["lens"][1])
+        heap, off = res.fetch_strings(1)
+        assert heap_strings(heap, off, nl1) == ora.scan_strings(table, want, 1, base), (name, flt)
+        # the ordinary dictionary column: pointers into the caller's image, and the same bytes through fetch_strings
+        p2, l2, nl2 = res.fetch_col(2)
+        assert np.array_equal(p2, want["data"][2]) and np.array_equal(l2, want["lens"][2])
+        heap, off = res.fetch_strings(2)
+        assert heap_strings(heap, off, nl2) == ora.scan_strings(table, want, 2, base)
+        # a window of the rows
+        if res.selected_rows > 50:
+            heap, off = res.fetch_strings(1, 17, 30)
+            full = ora.scan_strings(table, want, 1, base)[17:47]
+            assert [bytes(heap[off[i]:off[i + 1]]) for i in range(30)] == [b"" if v is None else v for v in full]
+        res.free()
+        ora.arena_reset()
+    batch.close()
