@@ -156,6 +156,18 @@ int obgpu_pipeline_scan(obgpu_pipeline *p, const obgpu_host_scan_spec *s, obgpu_
         ret = obgpu_batch_set_agg_rows(batch, s->agg_rows, s->agg_off + b0);
         if (ret != OBGPU_SUCCESS) { fail(ret); return; }
       }
+      if (!s->no_row_output) {
+        // a string column whose values the device rebuilt (HEX_PACKING / STRING_DIFF / STRING_PREFIX) has no bytes in the caller's
+        // image to point at: such projections go through obgpu_scan + obgpu_result_fetch_strings, not through this entry
+        for (int32_t c = 0; c < s->n_proj; ++c) {
+          int32_t rebuilt = 0;
+          if (obgpu_batch_column_materialised(batch, s->proj_cols[c], &rebuilt) == OBGPU_SUCCESS && rebuilt) {
+            ctx->err = "projected string column is HEX_PACKING / STRING_DIFF / STRING_PREFIX coded: use obgpu_result_fetch_strings";
+            fail(OBGPU_NOT_SUPPORTED);
+            return;
+          }
+        }
+      }
       obgpu_scan_spec spec{};
       spec.filter = s->filter;
       spec.proj_cols = s->proj_cols;

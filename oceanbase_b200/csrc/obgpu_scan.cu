@@ -2482,6 +2482,19 @@ static int build_filter(obgpu_ctx *ctx, const obgpu_batch *b, const obgpu_filter
       }
       nd.n_params = (int16_t)kept;
       if (null_param || (src.op == OBGPU_WHITE_OP_IN && kept == 0)) nd.op = OP_FALSE;
+      if ((size_t)src.col < b->col_types.size() && obf::store_class_of(b->col_types[(size_t)src.col]) == 5 &&
+          (src.op == OBGPU_WHITE_OP_EQ || src.op == OBGPU_WHITE_OP_NE || src.op == OBGPU_WHITE_OP_IN)) {
+        // equality on strings: two 64-bit screens over the constants -- which lengths (mod 64) and which first bytes (mod 64) occur --
+        // let a dictionary entry skip the constant list with two bit tests (lo / span are otherwise unused on string leaves)
+        uint64_t len_mask = 0, b0_mask = 0;
+        for (int k = 0; k < kept; ++k) {
+          const ParamDev &q = p.params[nd.param_begin + k];
+          len_mask |= 1ull << (q.len & 63u);
+          if (q.len == 0) b0_mask = ~0ull; else b0_mask |= 1ull << ((uint64_t)q.i64 & 63u);
+        }
+        nd.lo = len_mask;
+        nd.span = b0_mask;
+      }
       // integer compares reduce to one unsigned range test on the compare image (cmp_image: the datum's low
       // bytes, sign-extended for signed classes)
       {

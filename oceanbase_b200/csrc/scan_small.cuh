@@ -135,7 +135,9 @@ __device__ __forceinline__ void lean_bitset_str_eq(const ScanParams &p, const Fi
       }
       const uint32_t pl = len < 8u ? len : 8u;
       const uint64_t pre = pl ? sbits(sbit + cell * 8u, pl * 8u) : 0ull;
-      for (int k = 0; k < nd.n_params && !r; ++k) {
+      // screens built on the host: does any constant have this length / this first byte? (most entries stop here)
+      const bool cand = ((nd.lo >> (len & 63u)) & 1ull) && (len == 0u || ((nd.span >> (pre & 63ull)) & 1ull));
+      for (int k = 0; cand && k < nd.n_params && !r; ++k) {
         const ParamDev &pp = p.params[nd.param_begin + k];
         if (pp.len != len || (uint64_t)pp.i64 != pre) continue;
         bool same = true;
@@ -201,7 +203,8 @@ __device__ __forceinline__ uint32_t lean_survivor_str(const ScanParams &p, const
         const uint32_t pl = len < 8u ? len : 8u;
         const uint64_t pre = pl ? sbits(sbit + cell * 8u, pl * 8u) : 0ull;
         bool hit = false;
-        for (int k = 0; k < nd.n_params && !hit; ++k) {
+        const bool cand = ((nd.lo >> (len & 63u)) & 1ull) && (len == 0u || ((nd.span >> (pre & 63ull)) & 1ull));
+        for (int k = 0; cand && k < nd.n_params && !hit; ++k) {
           const ParamDev &pp = p.params[nd.param_begin + k];
           hit = pp.len == len && (uint64_t)pp.i64 == pre && (len <= 8u || str_cmp(s, cell, len, p.param_heap + pp.heap_off, pp.len) == 0);
         }

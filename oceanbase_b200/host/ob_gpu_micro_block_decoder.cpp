@@ -18,6 +18,7 @@ ObGpuScanRuntime::~ObGpuScanRuntime() {
 
 // ---- ObGpuMicroBlockDecoder ------------------------------------------------------------------------
 void ObGpuMicroBlockDecoder::reset() {
+  str_arena_.clear();
   if (batch_) obgpu_batch_close(batch_);
   batch_ = nullptr;
   row_count_ = column_count_ = 0;
@@ -97,6 +98,29 @@ int ObGpuMicroBlockDecoder::get_rows(const int32_t col, const int32_t *row_ids, 
   if (!batch_) return OB_NOT_INIT;
   if ((int64_t)vec.ptrs_.size() < vec_offset + row_cap) return OB_BUF_NOT_ENOUGH;
   int32_t has_null = 0;
+  int32_t rebuilt = 0;
+  if (obgpu_batch_column_materialised(batch_, col, &rebuilt) == OB_SUCCESS && rebuilt) {
+    // HEX_PACKING / STRING_DIFF / STRING_PREFIX: the values do not exist in the block. The reference decodes them into memory of the
+    // decoder's allocator (ob_hex_string_decoder.cpp:87-93); here they land in an arena this decoder owns until its next init / reset.
+    std::vector<int64_t> off((size_t)row_cap + 1);
+    std::vector<uint64_t> nulls((size_t)(row_cap + 63) / 64, 0);
+    int64_t need = 0;
+    int ret = obgpu_project_strings(batch_, 0, col, row_ids, row_cap, nullptr, 0, off.data(), nulls.data(), &has_null, &need);
+    if (ret == OB_BUF_NOT_ENOUGH) {
+      str_arena_.emplace_back((size_t)need + 1);
+      ret = obgpu_project_strings(batch_, 0, col, row_ids, row_cap, str_arena_.back().data(), need, off.data(), nulls.data(), &has_null, &need);
+    }
+    if (ret != OB_SUCCESS) return ret;
+    char *heap = str_arena_.empty() ? nullptr : str_arena_.back().data();
+    for (int64_t i = 0; i < row_cap; ++i) {
+      const int64_t at = vec_offset + i;
+      if ((nulls[(size_t)i / 64] >> (i % 64)) & 1) { vec.nulls_[(size_t)at / 64] |= 1ull << (at % 64); continue; }   // slot left as it was
+      vec.ptrs_[(size_t)at] = heap + off[(size_t)i];
+      vec.lens_[(size_t)at] = (int32_t)(off[(size_t)i + 1] - off[(size_t)i]);
+    }
+    if (has_null) vec.has_null_ = true;
+    return OB_SUCCESS;
+  }
   // string pointers land in the CALLER's block buffer (zero-copy like the reference, rule 8c.6)
   const int ret = obgpu_project_discrete(batch_, 0, col, row_ids, row_cap, vec_offset, (uint64_t)(uintptr_t)host_buf_,
                                          reinterpret_cast<uint64_t *>(vec.ptrs_.data()), vec.lens_.data(),

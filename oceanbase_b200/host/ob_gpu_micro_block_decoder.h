@@ -256,6 +256,7 @@ private:
   ObGpuScanRuntime &rt_;
   obgpu_batch *batch_ = nullptr;
   std::vector<char> padded_;  // block copy padded to the 16-byte TMA granularity
+  std::vector<std::vector<char>> str_arena_;  // strings a codec rebuilt (HEX_PACKING / STRING_DIFF / STRING_PREFIX), one chunk per get_rows
   const char *host_buf_ = nullptr;
   int64_t row_count_ = 0, column_count_ = 0;
 };
@@ -352,6 +353,76 @@ private:
   ObMicroIndexInfo *index_infos_ = nullptr;
   int32_t n_index_infos_ = 0;
   int64_t skip_false_ = 0, skip_true_ = 0;
+};
+
+// blocksstable::ObDatumRow (storage/blocksstable/ob_datum_row.h), the slice a row iterator hands out: one storage datum per
+// projected column.
+struct ObDatumRow {
+  std::vector<common::ObStorageDatum> storage_datums_;
+  int64_t count_ = 0;
+  int64_t get_column_count() const { return count_; }
+};
+
+// storage::ObIStoreRowIterator / ObStoreRowIterator (access/ob_store_row_iterator.h:34-185) over the page-batch scanner: the
+// row-at-a-time contract the merge layer (ObMultipleMerge) and the compaction iterators pull through --
+// get_next_row(const ObDatumRow *&) until OB_ITER_END, reuse() to rescan, reset() to release. The row handed out stays valid until
+// the next call, string datums point into the scanned image (or the scanner's host buffers in pipelined mode).
+class ObGpuStoreRowIterator {
+public:
+  explicit ObGpuStoreRowIterator(ObGpuScanRuntime &rt) : scanner_(rt) {}
+  int init(const void *image, int64_t image_size, const int64_t *offsets, const int64_t *sizes, int32_t n_blocks,
+           sql::ObPushdownFilterExecutor *filter, const std::vector<int32_t> &proj, int64_t batch_size = 256) {
+    image_ = image; image_size_ = image_size; offsets_ = offsets; sizes_ = sizes; n_blocks_ = n_blocks; filter_ = filter; proj_ = proj;
+    batch_size_ = batch_size;
+    row_.storage_datums_.assign(proj.size(), common::ObStorageDatum());
+    row_.count_ = (int64_t)proj.size();
+    at_ = 0;
+    batch_ = ObGpuSSTableBatchScanner::Batch();
+    inited_ = true;
+    return scanner_.init(image, image_size, offsets, sizes, n_blocks, filter, proj, batch_size);
+  }
+  ObGpuSSTableBatchScanner &scanner() { return scanner_; }   // set_reverse_scan / set_limit / set_index_infos / set_pipelined before init
+  bool can_blockscan() const { return true; }
+  bool can_batch_scan() const { return true; }
+  bool is_sstable_iter() const { return true; }
+  int get_next_row(const ObDatumRow *&row) {
+    if (!inited_) return common::OB_NOT_INIT;
+    while (at_ >= batch_.count) {
+      const int ret = scanner_.get_next_rows(batch_);
+      if (ret != common::OB_SUCCESS) return ret;   // OB_ITER_END after the last row
+      at_ = 0;
+    }
+    for (size_t c = 0; c < proj_.size(); ++c) {
+      common::ObStorageDatum &d = row_.storage_datums_[c];
+      if (batch_.is_null[c][(size_t)at_]) d.set_null();
+      else if (!batch_.str_ptrs[c].empty()) d.set_string(batch_.str_ptrs[c][(size_t)at_], (uint32_t)batch_.str_lens[c][(size_t)at_]);
+      else d.set_int(batch_.ints[c][(size_t)at_]);
+    }
+    ++at_;
+    row = &row_;
+    return common::OB_SUCCESS;
+  }
+  // ObStoreRowIterator::reuse: the same scan again from its first row
+  int reuse() {
+    if (!inited_) return common::OB_NOT_INIT;
+    scanner_.reset();
+    at_ = 0;
+    batch_ = ObGpuSSTableBatchScanner::Batch();
+    return scanner_.init(image_, image_size_, offsets_, sizes_, n_blocks_, filter_, proj_, batch_size_);
+  }
+  void reset() { scanner_.reset(); inited_ = false; at_ = 0; batch_ = ObGpuSSTableBatchScanner::Batch(); }
+private:
+  ObGpuSSTableBatchScanner scanner_;
+  ObGpuSSTableBatchScanner::Batch batch_;
+  ObDatumRow row_;
+  int64_t at_ = 0;
+  bool inited_ = false;
+  const void *image_ = nullptr;
+  int64_t image_size_ = 0, batch_size_ = 256;
+  const int64_t *offsets_ = nullptr, *sizes_ = nullptr;
+  int32_t n_blocks_ = 0;
+  sql::ObPushdownFilterExecutor *filter_ = nullptr;
+  std::vector<int32_t> proj_;
 };
 
 }  // namespace blocksstable

@@ -309,6 +309,34 @@ static void test_filter_tree_and_batch_scanner(ObGpuScanRuntime &rt) {
   ASSERT_EQ(OB_ITER_END, scanner.get_next_rows(batch));
   (void)expect_total;
 
+  // (2b) the row-at-a-time contract (ObIStoreRowIterator::get_next_row until OB_ITER_END, reuse() rescans): same rows, same order
+  {
+    ObGpuStoreRowIterator iter(rt);
+    ASSERT_EQ(OB_SUCCESS, iter.init(image.data(), image_size, offs.data(), sizes.data(), nb, &andf, {1, 2, 0}, 256));
+    for (int pass = 0; pass < 2; ++pass) {
+      const ObDatumRow *row = nullptr;
+      int64_t cursor = 0, rows = 0;
+      int r2;
+      while ((r2 = iter.get_next_row(row)) == OB_SUCCESS) {
+        while (cursor < n && !(!nulls[(size_t)cursor] && (a[(size_t)cursor] < 100 || a[(size_t)cursor] >= 900) &&
+               heap.compare((size_t)off[(size_t)cursor], (size_t)(off[(size_t)cursor + 1] - off[(size_t)cursor]), "k3") == 0)) ++cursor;
+        ASSERT_EQ(3, row->get_column_count());
+        ASSERT_EQ(a[(size_t)cursor], row->storage_datums_[0].get_int());
+        ASSERT_EQ(2, row->storage_datums_[1].len_);
+        ASSERT_EQ(0, memcmp(row->storage_datums_[1].ptr_, "k3", 2));
+        ASSERT_EQ(b[(size_t)cursor], row->storage_datums_[2].get_int());
+        ++cursor;
+        ++rows;
+      }
+      ASSERT_EQ(OB_ITER_END, r2);
+      ASSERT_EQ(seen, rows);
+      if (pass == 0) ASSERT_EQ(OB_SUCCESS, iter.reuse());
+    }
+    iter.reset();
+    const ObDatumRow *row = nullptr;
+    ASSERT_EQ(OB_NOT_INIT, iter.get_next_row(row));
+  }
+
   // (3) skip index: b (column 0) is the row number, so BETWEEN on it is decided by min / max for all but the two
   // boundary blocks; same rows come back, the index infos carry the verdicts, pruned blocks are counted
   int32_t agg_cols[1] = {0};
@@ -416,6 +444,39 @@ static void test_filter_tree_and_batch_scanner(ObGpuScanRuntime &rt) {
   }
 }
 
+// HEX_PACKING / STRING_PREFIX columns through the adapter: the white filter popcounts of the reference layout and VEC_DISCRETE
+// get_rows whose pointers land in the decoder's own arena (the values do not exist in the block).
+static void test_rebuilt_string_codecs(ObGpuScanRuntime &rt) {
+  const int encs[] = {OBGPU_ENC_HEX_PACKING, OBGPU_ENC_STRING_PREFIX};
+  for (int enc : encs) {
+    Rows r = layout({{0, ROW_CNT - 40}, {1, 10}, {2, 10}, {3, 10}, {-1, 10}});
+    std::vector<uint8_t> blk = build_block(r, OBGPU_ENC_DICT, enc);
+    ObGpuMicroBlockDecoder dec(rt);
+    ObMicroBlockData data{(const char *)blk.data(), (int64_t)blk.size()};
+    ASSERT_EQ(OB_SUCCESS, dec.init(data));
+    ASSERT_EQ(ROW_CNT - 40, pushdown_popcnt(dec, 2, sql::WHITE_OP_EQ, {0}, 1, 0, ROW_CNT));
+    ASSERT_EQ(20, pushdown_popcnt(dec, 2, sql::WHITE_OP_IN, {1, 2, 5}, 1, 0, ROW_CNT));
+    ASSERT_EQ(10, pushdown_popcnt(dec, 2, sql::WHITE_OP_GT, {2}, 1, 0, ROW_CNT));
+    ASSERT_EQ(10, pushdown_popcnt(dec, 2, sql::WHITE_OP_NU, {}, 1, 0, ROW_CNT));
+    ASSERT_EQ(5, pushdown_popcnt(dec, 2, sql::WHITE_OP_NU, {}, 1, ROW_CNT - 35, 30));
+    std::vector<int32_t> rid;
+    for (int32_t i = 1; i < ROW_CNT; i += 3) rid.push_back(i);
+    ObDiscreteVector vec;
+    vec.reserve_rows((int64_t)rid.size() + 2);
+    ASSERT_EQ(OB_SUCCESS, dec.get_rows(2, rid.data(), (int64_t)rid.size(), 2, vec));
+    for (size_t i = 0; i < rid.size(); ++i) {
+      const int32_t row = rid[i];
+      ASSERT_EQ(r.nulls[(size_t)row] != 0, vec.is_null((int64_t)i + 2));
+      if (!r.nulls[(size_t)row]) {
+        ASSERT_EQ((long long)r.strs[(size_t)row].size(), vec.lens_[i + 2]);
+        ASSERT_EQ(0, memcmp(vec.ptrs_[i + 2], r.strs[(size_t)row].data(), r.strs[(size_t)row].size()));
+        const bool inside = vec.ptrs_[i + 2] >= (const char *)blk.data() && vec.ptrs_[i + 2] < (const char *)blk.data() + blk.size();
+        ASSERT_EQ(0, inside);   // not a pointer into the block: there is nothing to point at
+      }
+    }
+  }
+}
+
 // Black filter on one dictionary column + the group-by surface (test_dict_decoder.cpp's batch black-filter / group-by
 // cases in shape): the expression is only known to the caller, here "value % 2000 == 7 or NULL" / "string ends in an odd digit".
 struct OddSeedFilter : public sql::ObBlackFilterExecutor {
@@ -501,6 +562,7 @@ int main() {
   test_get_rows_vs_oracle(rt);
   test_filter_tree_and_batch_scanner(rt);
   test_black_filter_and_group_by_surface(rt);
+  test_rebuilt_string_codecs(rt);
   if (g_fail) { printf("%d assertion(s) failed\n", g_fail); return 1; }
   printf("host adapter tests passed\n");
   return 0;
