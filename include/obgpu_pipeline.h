@@ -56,6 +56,12 @@ typedef struct obgpu_host_scan_spec {
   int32_t no_row_output;      /* 1: only aggregates (and counts) come back */
   const obgpu_host_agg *aggs;
   int32_t n_aggs;
+  /* 1: do not stage the image in HBM. `image` must be pinned, device-accessible host memory (cudaHostAlloc / cudaHostRegister: with
+   * unified addressing the same pointer is valid on the device); the kernels then pull only what they reference -- headers, the
+   * filter columns' regions, the projected columns' regions -- straight over PCIe, instead of the library copying every byte of every
+   * block first. Pays off when the scan references a fraction of the columns; CS blocks with encoded streams and HEX / STRING_DIFF /
+   * STRING_PREFIX columns are still read in full once (their restatement at open). */
+  int32_t zero_copy;
 } obgpu_host_scan_spec;
 
 typedef struct obgpu_host_scan_result {

@@ -285,6 +285,94 @@ def write_merged_sstable(res: MergeResult, rows_per_block: int = 1400, payload_e
 
 
 # ---- multi-GPU: range partition + one exchange step ----------------------------------------------------
+# ---- runs larger than device memory: range by range, copies of the next range under the merge of this one ---------------------
+def streamed_major_merge(tables: Sequence[object], end_keys: Sequence[np.ndarray], key_col: int,
+                         flag_col: Optional[int], cols: Sequence[int], n_ranges: int, sink: Callable[[int, "MergeResult"], None],
+                         device=None, default_vals=None, default_null=None, n_workers: int = 2):
+    """Major merge of runs that do not fit in device memory together (ObPartitionMajorMerger over a tablet whose tables exceed HBM).
+    tables[q]: the run's SSTable in HOST memory (oldest first); end_keys[q][b]: last rowkey of its micro-block b (the index rows).
+    The rowkey space is cut into n_ranges ranges at quantiles of the block end keys (the reference cuts parallel-merge ranges at
+    macro-block boundaries the same way, ob_partition_parallel_merge_ctx.cpp:187-424). A range is one unit of work: the micro-blocks
+    of every run that can hold its rowkeys are opened as a page batch straight from host memory (the host->device copy), decoded,
+    cut to the range with a binary search on the decoded rowkeys, merged, and handed to sink(range_index, MergeResult) (which
+    fetches / encodes the rows: the device->host side). n_workers ranges are in flight, each on its own ctx / stream, so the copies
+    of range i + 1 run under the merge and the fetch of range i; device memory holds n_workers ranges at a time.
+    Ranges come back in order: sink is called with 0, 1, 2 ... (rowkey order of the whole output)."""
+    import threading
+    import torch
+    from .sstable import TableImage
+    device = device or torch.device("cuda", torch.cuda.current_device())
+    allk = np.sort(np.concatenate([np.asarray(e, dtype=np.int64) for e in end_keys]))
+    cuts = [int(allk[min(len(allk) - 1, (len(allk) * (i + 1)) // n_ranges)]) for i in range(n_ranges - 1)]
+    cuts = sorted(set(cuts))
+    bounds = [None] + cuts + [None]          # range i = (bounds[i], bounds[i + 1]]  (None: open)
+    n_ranges = len(bounds) - 1
+    results = [None] * n_ranges
+    errors = []
+    done = [threading.Event() for _ in range(n_ranges)]
+    next_range = [0]
+    lock = threading.Lock()
+
+    def work():
+        from .scan import ScanContext
+        torch.cuda.set_device(device)
+        stream = torch.cuda.Stream(device=device)          # this worker's stream: torch tensors and the library's launches share it
+        ctx = ScanContext(device.index if device.index is not None else 0, stream=stream.cuda_stream)
+        try:
+            while True:
+                with lock:
+                    i = next_range[0]
+                    next_range[0] += 1
+                if i >= n_ranges:
+                    break
+                lo, hi = bounds[i], bounds[i + 1]
+                runs = []
+                with torch.cuda.stream(stream):
+                    for q, tb in enumerate(tables):
+                        ek = np.asarray(end_keys[q], dtype=np.int64)
+                        b0 = 0 if lo is None else int(np.searchsorted(ek, lo, side="right"))     # first block whose last key > lo
+                        b1 = len(ek) if hi is None else min(len(ek), int(np.searchsorted(ek, hi, side="left")) + 1)
+                        if b0 >= b1:
+                            runs.append(DecodedRun(torch.empty(0, dtype=torch.int64, device=device), None if flag_col is None else
+                                                   torch.empty(0, dtype=torch.uint8, device=device),
+                                                   [torch.empty(0, dtype=torch.int64, device=device) for _ in cols],
+                                                   [torch.empty(0, dtype=torch.uint8, device=device) for _ in cols]))
+                            continue
+                        o0 = int(tb.offsets[b0])
+                        o1 = int(tb.offsets[b1 - 1]) + int(tb.sizes[b1 - 1])
+                        sub = TableImage(tb.image[o0:o1], np.asarray(tb.offsets[b0:b1]) - o0, tb.sizes[b0:b1], 0, tb.n_cols)
+                        d = decode_run(ctx, sub, key_col, flag_col, cols, device=device)
+                        ctx.synchronize()
+                        r0 = 0 if lo is None else int(torch.searchsorted(d.key, torch.tensor([lo], device=device), right=True)[0])
+                        r1 = d.n if hi is None else int(torch.searchsorted(d.key, torch.tensor([hi], device=device), right=True)[0])
+                        runs.append(d.slice(r0, r1))
+                    res = merge_decoded(ctx, runs, default_vals, default_null)
+                    res.info()
+                # hand the ranges over in order
+                if i > 0:
+                    done[i - 1].wait()
+                if not errors:
+                    sink(i, res)
+                res.free()
+                del runs
+                done[i].set()
+        except Exception as e:   # pragma: no cover
+            errors.append(e)
+            for ev in done:
+                ev.set()
+        finally:
+            ctx.close()
+
+    threads = [threading.Thread(target=work) for _ in range(max(1, n_workers))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    return n_ranges
+
+
 def choose_splitters(candidates, world: int):
     """world-1 splitters at the quantiles of the gathered rowkey samples (sorted, duplicates kept)."""
     import torch

@@ -150,7 +150,10 @@ int obgpu_pipeline_scan(obgpu_pipeline *p, const obgpu_host_scan_spec *s, obgpu_
         if (r) obgpu_result_free(r);
         if (batch) obgpu_batch_close(batch);
       };
-      int ret = obgpu_batch_open(ctx, (const uint8_t *)s->image + lo, hi - lo, offs.data(), s->sizes + b0, b1 - b0, 0, nullptr, &batch);
+      int ret = s->zero_copy
+                    ? obgpu_batch_open(ctx, (const uint8_t *)s->image + lo, hi - lo, offs.data(), s->sizes + b0, b1 - b0, 1,
+                                       (const uint8_t *)s->image + lo, &batch)   // the pinned host image IS the device image
+                    : obgpu_batch_open(ctx, (const uint8_t *)s->image + lo, hi - lo, offs.data(), s->sizes + b0, b1 - b0, 0, nullptr, &batch);
       if (ret != OBGPU_SUCCESS) { fail(ret); return; }
       if (s->agg_rows && s->agg_off) {   // offsets keep their table-wide base: the entry rebases them
         ret = obgpu_batch_set_agg_rows(batch, s->agg_rows, s->agg_off + b0);
@@ -247,7 +250,7 @@ int obgpu_pipeline_scan(obgpu_pipeline *p, const obgpu_host_scan_spec *s, obgpu_
         res->batch_rows[b] = n;
         res->total_rows += info.total_rows;
         res->selected_rows += n;
-        res->h2d_bytes += hi - lo;
+        if (!s->zero_copy) res->h2d_bytes += hi - lo;   // zero copy: the kernels read what they reference, the library copies nothing
         res->d2h_bytes += d2h;
         for (int a = 0; a < s->n_aggs; ++a) {
           const int kind = s->aggs[a].kind;

@@ -161,7 +161,7 @@ class HostScanPipeline:
              outputs: Optional[HostOutputs] = None, string_base: int = 0, ramp: int = 0,
              agg_rows: Optional[np.ndarray] = None, agg_off: Optional[np.ndarray] = None,
              aggs: Sequence[tuple] = (), no_row_output: bool = False, proj_is_string: Optional[Sequence[bool]] = None,
-             proj_elem_len: Optional[Sequence[int]] = None):
+             proj_elem_len: Optional[Sequence[int]] = None, zero_copy: bool = False):
         """One pipelined scan of a host table. outputs=None: buffers are allocated here (pageable; spare room for every
         row, so slices that outgrow the selectivity hint always find a place). aggs: (kind, col_a, col_b) over the
         projected columns. Returns HostScanOutput; .batches views the output buffers."""
@@ -182,6 +182,7 @@ class HostScanPipeline:
             spec.out_data, spec.out_lens, spec.out_nulls = od, ol, on
             spec.out_cap_rows = outputs.cap_rows
         spec.no_row_output = 1 if no_row_output else 0
+        spec.zero_copy = 1 if zero_copy else 0   # table.image must then be pinned host memory (the kernels read it over PCIe)
         if aggs:
             arr = (capi.HostAgg * len(aggs))()
             for i, (kind, a, b) in enumerate(aggs):

@@ -336,3 +336,43 @@ def test_distributed_entry_on_one_rank(ob, env):
     assert_merge_equal(res, ora.major_merge(runs, 3), 3)
     res.free()
     comm.close()
+
+
+def test_streamed_merge_of_runs_that_do_not_fit_together():
+    """Range by range (host -> device copy, decode, cut, merge, fetch; two ranges in flight): the concatenated ranges equal the
+    one-shot merge of the same runs."""
+    import torch
+    import oceanbase_b200 as ob
+    from oceanbase_b200.synth import make_config5_runs
+    from oceanbase_b200.compaction import decode_run, merge_decoded, streamed_major_merge
+    runs = make_config5_runs(n_runs=5, window=60_000, seed=9, rows_per_block=700)
+    ctx = ob.ScanContext(0)
+    dec = [decode_run(ctx, r["table"], 0, 1, [2, 3, 4]) for r in runs]
+    whole = merge_decoded(ctx, dec)
+    n = whole.info().out_rows
+    want = [whole.fetch(c) for c in (-1, 0, 1, 2)]
+    end_keys = [r["key"][np.minimum(np.arange(699, len(r["key"]) + 699, 700), len(r["key"]) - 1)] for r in runs]
+    for q, r in enumerate(runs):
+        assert len(end_keys[q]) == r["table"].n_blocks
+    got = {c: [] for c in (-1, 0, 1, 2)}
+    order, stats = [], [0, 0]
+
+    def sink(i, res):
+        order.append(i)
+        info = res.info()
+        stats[0] += info.dropped_deletes
+        stats[1] += info.fused_rows
+        for c in got:
+            got[c].append(res.fetch(c))
+
+    n_ranges = streamed_major_merge([r["table"] for r in runs], end_keys, 0, 1, [2, 3, 4], 7, sink, device=torch.device("cuda", 0))
+    assert order == list(range(n_ranges)) and n_ranges >= 5
+    for k, c in enumerate((-1, 0, 1, 2)):
+        v = np.concatenate([x[0] for x in got[c]])
+        nl = np.concatenate([x[1] for x in got[c]])
+        assert len(v) == n
+        assert np.array_equal(nl, want[k][1])
+        assert np.array_equal(v[nl == 0], want[k][0][want[k][1] == 0])
+    assert stats[0] == whole.info().dropped_deletes and stats[1] == whole.info().fused_rows
+    whole.free()
+    ctx.close()

@@ -88,3 +88,33 @@ def test_pipeline_strings_and_pushed_down_aggregates():
     assert only.aggregates[0] == out.aggregates[3] and only.selected_rows == out.selected_rows
     assert only.d2h_bytes == 16 * len(only.batches)
     pipe.close()
+
+
+def test_pipeline_zero_copy_reads_pinned_host_memory():
+    """zero_copy: the table image stays in pinned host memory and the kernels read what they reference over PCIe; same rows
+    as the staged pipeline and as the oracle, and the library reports no host->device copy of its own."""
+    import torch
+    import oceanbase_b200 as ob
+    from oceanbase_b200.pipeline import HostScanPipeline
+    from oceanbase_b200.synth import make_config3_like
+    w = make_config3_like(rows=30_000, rows_per_block=133, seed=4)
+    pinned = torch.empty(w.table.image.size + 256, dtype=torch.uint8).pin_memory()
+    img = pinned.numpy()
+    img[:w.table.image.size] = w.table.image
+    img[w.table.image.size:] = 0
+    table = ob.TableImage(img[:w.table.image.size], w.table.offsets, w.table.sizes, w.table.total_rows, w.table.n_cols)
+    base = table.image.ctypes.data
+    pipe = HostScanPipeline(0, n_workers=3)
+    kw = dict(blocks_per_batch=50, selectivity_hint=0.14, ramp=2, string_base=base, proj_is_string=w.proj_is_string, proj_elem_len=w.proj_elem_len)
+    zc = pipe.scan(table, w.filter, w.proj, zero_copy=True, **kw)
+    st = pipe.scan(table, w.filter, w.proj, zero_copy=False, **kw)
+    want = ora.scan_table(table, w.filter, w.proj, w.proj_is_string, w.proj_elem_len, string_base=base)
+    assert zc.selected_rows == st.selected_rows == want["selected"]
+    assert zc.h2d_bytes == 0 and st.h2d_bytes >= int(w.table.sizes.sum())
+    for c in range(len(w.proj)):
+        got = np.concatenate([b.cols[c] for b in zc.batches])
+        assert np.array_equal(got, want["data"][c]), c
+        assert np.array_equal(got, np.concatenate([b.cols[c] for b in st.batches]))
+        if w.proj_is_string[c]:
+            assert np.array_equal(np.concatenate([b.lens[c] for b in zc.batches]), want["lens"][c])
+    pipe.close()
