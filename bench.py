@@ -231,7 +231,10 @@ def cpu_reference_leg(w, steps, warmup, n_threads, sample_blocks):
 def cfg3_shape(args, world):
     """(rows per GPU, tiles, segment rows): rows per GPU = total / world, cut into `tiles` copies of one segment."""
     per_gpu = args.rows // max(world, 1)
-    tiles = max(1, -(-per_gpu // args.segment_rows))
+    # the host threads are shared by the ranks (cgroup quota / world each): generate a smaller segment per rank on wide jobs so that
+    # the untimed set-up stays around half a minute (a tile is still several hundred MB, far beyond L2)
+    seg_cap = max(2_000_000, args.segment_rows // max(1, world // 2))
+    tiles = max(1, -(-per_gpu // seg_cap))
     seg = per_gpu // tiles
     return seg * tiles, tiles, seg
 

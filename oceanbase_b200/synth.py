@@ -168,7 +168,7 @@ def make_config3_like(rows=100_000, rows_per_block=1100, seed=3, row_start=0, n_
 
 # ---- config 5: K sorted runs with overlapping rowkey ranges (major compaction input) -----------------
 def make_config5_runs(n_runs=8, window=100_000, seed=5, rows_per_block=1400, dup_pct=10, delete_pct=2,
-                      nop_pct=50, null_pct=5, n_threads=0, encode=True):
+                      nop_pct=50, null_pct=5, n_threads=0, encode=True, only=None):
     """Run r (0 = oldest table) covers rowkey indexes [r * window / 2, r * window / 2 + window): adjacent runs
     overlap by 50 %. A rowkey index lives in one covering run (its home, chosen by hash); dup_pct % of the
     indexes are present in EVERY covering run (newer copies are DF_UPDATE rows whose payload cells are NOP
@@ -178,6 +178,9 @@ def make_config5_runs(n_runs=8, window=100_000, seed=5, rows_per_block=1400, dup
     `table` (TableImage) when encode."""
     runs = []
     for r in range(n_runs):
+        if only is not None and r not in only:   # a rank of a multi-GPU job generates the runs it holds (a run is a pure function of r)
+            runs.append(None)
+            continue
         lo = r * (window // 2)
         i = np.arange(lo, lo + window, dtype=np.int64)
         h = splitmix64(_col_seed(seed, 100), int(lo), window)           # pure function of the rowkey index

@@ -46,9 +46,9 @@ def run(args):
     torch.cuda.set_stream(stream)
     ctx = ob.ScanContext(local, stream=stream.cuda_stream)
     t0 = time.perf_counter()
-    runs = make_config5_runs(n_runs=args.runs, window=args.window, seed=5, n_threads=max(1, bench.host_cpus() // world),
-                             encode=True)
     mine = [q for q in range(args.runs) if q % world == rank]
+    runs = make_config5_runs(n_runs=args.runs, window=args.window, seed=5, n_threads=max(1, bench.host_cpus() // world),
+                             encode=True, only=None if (args.verify or world == 1) else set(mine))
     t_gen = time.perf_counter() - t0
     if getattr(args, "stream_ranges", 0) > 0:
         return run_streamed(args, runs, t_gen, dev, local)
@@ -163,6 +163,7 @@ def run_streamed(args, runs, t_gen, dev, local):
     and fetches the merged rows into host buffers."""
     import torch
     import oceanbase_b200 as ob
+    from oceanbase_b200 import capi
     from oceanbase_b200.compaction import streamed_major_merge
     rpb = 1400
     tables, end_keys = [], []
@@ -179,17 +180,17 @@ def run_streamed(args, runs, t_gen, dev, local):
     enc = sum(int(t.sizes.sum()) for t in tables)
     out_cap = in_rows
     host_out = [torch.empty(out_cap, dtype=torch.int64).pin_memory().numpy() for _ in range(4)]
-    host_nl = [np.empty(out_cap, dtype=np.uint8) for _ in range(4)]
+    host_nl = [torch.empty(out_cap, dtype=torch.uint8).pin_memory().numpy() for _ in range(4)]
     state = {"rows": 0, "dropped": 0, "fused": 0}
 
     def sink(i, res):
         info = res.info()
         n = info.out_rows
         at = state["rows"]
-        for k, c in enumerate((-1, 0, 1, 2)):
-            v, nl = res.fetch(c)
-            host_out[k][at:at + n] = v
-            host_nl[k][at:at + n] = nl
+        for k, c in enumerate((-1, 0, 1, 2)):   # straight into the pinned output buffers (no pageable staging)
+            if n > 0:
+                capi.check(capi.lib.obgpu_merge_result_fetch(res._h, c, 0, n, host_out[k][at:].ctypes.data, host_nl[k][at:].ctypes.data),
+                           "obgpu_merge_result_fetch", res.ctx._h)
         state["rows"] += n
         state["dropped"] += info.dropped_deletes
         state["fused"] += info.fused_rows
