@@ -433,6 +433,14 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return t.tolist()
 
+    # every rank pins its host buffers next to ITS GPU: report all of them, not rank 0's
+    numa_all = [numa_node if numa_node is not None else -1]
+    if world > 1:
+        t = torch.full((world,), -2, device=dev, dtype=torch.int64)
+        t[rank] = numa_all[0]
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        numa_all = t.tolist()
+
     peak, peak_src = measured_peak_gbs()
     line = None
     if args.workload == "cfg3":
@@ -486,7 +494,7 @@ def run_ours(args):
                     "tiling": f"one seeded {seg.total_rows}-row segment per rank, generated on the host and copied {tiles}x into "
                               f"HBM (physically distinct tiles, one page batch of {table.n_blocks} micro-blocks)",
                     "l2_policy": "every tile (~2 GB) is larger than L2 (126 MB); no flush needed",
-                    "gen_seconds": round(t_gen, 1), "host_numa_node": numa_node}),
+                    "gen_seconds": round(t_gen, 1), "host_numa_node": numa_node, "host_numa_nodes": numa_all}),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": measured_traffic("r2_traffic_cfg3.json", table.total_rows), "peak_source": peak_src,
                              "alg_bytes_per_launch": int(alg), "alg_bytes_in": int(b_in), "alg_bytes_out": int(selected * out_per_row),
@@ -561,7 +569,7 @@ def run_ours(args):
                            "micro_blocks_per_gpu": table.n_blocks, "encoded_bytes_per_gpu": int(table.sizes.sum()),
                            "selectivity": selected / table.total_rows, "parallelism": f"shard{world}",
                            "l2_policy": "input image (1.2 GB) larger than L2 (126 MB); no flush needed",
-                           "gen_seconds": round(t_gen, 1), "host_numa_node": numa_node},
+                           "gen_seconds": round(t_gen, 1), "host_numa_node": numa_node, "host_numa_nodes": numa_all},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": measured_traffic("r1_traffic.json", table.total_rows), "peak_source": peak_src,
                              "alg_bytes_per_launch": alg, "kernel_ms": kern_ms,

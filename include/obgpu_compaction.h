@@ -145,6 +145,27 @@ int obgpu_merge_decoded_distributed(obgpu_ctx *ctx, obgpu_comm *comm, const obgp
                                     int32_t samples_per_run, obgpu_merge_result **out, int64_t *splitters_out,
                                     int64_t *recv_rows_out);
 
+/* ---- runs larger than device memory: the merge range by range, copies of the next range under the merge of this one ----------
+ * One run = its SSTable in HOST memory (pinned for full copy overlap) + the last rowkey of every micro-block (what the index rows
+ * hold). The rowkey space is cut into n_ranges ranges at quantiles of the block end keys (ObParallelMergeCtx cuts parallel-merge
+ * ranges at block boundaries of the index tree the same way, compaction/ob_partition_parallel_merge_ctx.cpp:187-424); for every
+ * range the blocks of each run that can hold its rowkeys are copied, decoded, cut to the range and merged, and sink(arg, range, result)
+ * is called with ranges 0, 1, 2 ... in rowkey order (the result is only valid inside the call: fetch / encode the rows there).
+ * n_streams ranges are in flight on their own streams; device memory holds n_streams ranges whatever the size of the runs.
+ * Single INT64 rowkey column, integer payload columns. */
+typedef struct obgpu_stream_run {
+  const void *image;         /* host memory, blocks 16-byte aligned */
+  const int64_t *offsets;    /* [n_blocks] */
+  const int64_t *sizes;      /* [n_blocks] */
+  const int64_t *end_keys;   /* [n_blocks] last rowkey of every micro-block, ascending */
+  int32_t n_blocks;
+} obgpu_stream_run;
+typedef int (*obgpu_merge_sink)(void *arg, int32_t range, obgpu_merge_result *result);
+int obgpu_merge_runs_streamed(int device, int32_t n_streams, const obgpu_stream_run *runs, int32_t n_runs, int32_t rowkey_col,
+                              int32_t flag_col /* -1: every row DF_INSERT */, const int32_t *cols, int32_t n_cols,
+                              const int64_t *default_vals, const uint8_t *default_null, int32_t n_ranges, obgpu_merge_sink sink,
+                              void *sink_arg, int32_t *ranges_done);
+
 #ifdef __cplusplus
 }
 #endif

@@ -85,6 +85,13 @@ class HostScanResult(C.Structure):
                 ("d2h_bytes", C.c_int64), ("kernel_launches", C.c_int64)]
 
 
+class StreamRun(C.Structure):
+    _fields_ = [("image", C.c_void_p), ("offsets", C.c_void_p), ("sizes", C.c_void_p), ("end_keys", C.c_void_p), ("n_blocks", C.c_int32)]
+
+
+MERGE_SINK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int32, C.c_void_p)
+
+
 class ColInput(C.Structure):
     _fields_ = [("obj_type", C.c_int32), ("encoding", C.c_int32), ("i64", C.c_void_p), ("is_null", C.c_void_p),
                 ("str_heap", C.c_void_p), ("str_off", C.c_void_p), ("byte_packing_only", C.c_int32),
@@ -192,6 +199,7 @@ def declared_signatures():
         "obgpu_batch_decode_columns": (C.c_int, [vp, i32, vp, vp, vp]),
         "obgpu_batch_decode_columns_tagged": (C.c_int, [vp, i32, vp, i32, vp, vp]),
         "obgpu_merge_result_set_string_images": (C.c_int, [vp, vp, vp, i32]),
+        "obgpu_merge_runs_streamed": (C.c_int, [i32, i32, vp, i32, i32, i32, vp, i32, vp, vp, i32, MERGE_SINK, vp, P(i32)]),
         "obgpu_merge_result_fetch_strings": (C.c_int, [vp, i32, i64, i64, vp, i64, vp, vp, P(i64)]),
         "obgpu_merge_decoded": (C.c_int, [vp, P(MergeRun), i32, i32, vp, vp, P(vp)]),
         "obgpu_merge_runs": (C.c_int, [vp, P(vp), i32, i32, i32, vp, i32, vp, vp, P(vp)]),

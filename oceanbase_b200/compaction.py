@@ -373,6 +373,50 @@ def streamed_major_merge(tables: Sequence[object], end_keys: Sequence[np.ndarray
     return n_ranges
 
 
+def merge_runs_streamed(device: int, tables: Sequence[object], end_keys: Sequence[np.ndarray], key_col: int, flag_col: Optional[int],
+                        cols: Sequence[int], n_ranges: int, sink: Callable[[int, "MergeResult"], None], n_streams: int = 2,
+                        default_vals=None, default_null=None) -> int:
+    """obgpu_merge_runs_streamed: the range loop of streamed_major_merge inside the library (worker threads, one ctx / stream each).
+    sink(range_index, MergeResult) is called in rowkey order; the result is only valid inside the call."""
+    arr = (capi.StreamRun * len(tables))()
+    keep = []
+    for q, tb in enumerate(tables):
+        offs = np.ascontiguousarray(tb.offsets, dtype=np.int64)
+        sizes = np.ascontiguousarray(tb.sizes, dtype=np.int64)
+        ek = np.ascontiguousarray(end_keys[q], dtype=np.int64)
+        keep += [offs, sizes, ek]
+        arr[q].image, arr[q].offsets, arr[q].sizes, arr[q].end_keys = tb.image.ctypes.data, offs.ctypes.data, sizes.ctypes.data, ek.ctypes.data
+        arr[q].n_blocks = len(offs)
+    ci = (C.c_int32 * max(len(cols), 1))(*cols)
+    dv = None if default_vals is None else np.ascontiguousarray(default_vals, dtype=np.int64)
+    dn = None if default_null is None else np.ascontiguousarray(default_null, dtype=np.uint8)
+    errors = []
+
+    class _Ctx:   # the result's ctx is the worker's: only what MergeResult.fetch needs
+        _h = None
+
+    def cb(_arg, rng, res_h):
+        try:
+            r = MergeResult(_Ctx, C.c_void_p(res_h), len(cols), None)
+            sink(int(rng), r)
+            r._h = C.c_void_p()     # owned by the library
+            return capi.OB_SUCCESS
+        except Exception as e:      # pragma: no cover
+            errors.append(e)
+            return capi.OB_ERR_SYS
+
+    cfn = capi.MERGE_SINK(cb)
+    done = C.c_int32(0)
+    code = lib.obgpu_merge_runs_streamed(device, n_streams, arr, len(tables), key_col, -1 if flag_col is None else flag_col, ci, len(cols),
+                                        dv.ctypes.data if dv is not None else None, dn.ctypes.data if dn is not None else None,
+                                        n_ranges, cfn, None, C.byref(done))
+    if errors:
+        raise errors[0]
+    if code != capi.OB_SUCCESS:
+        raise capi.ObGpuError(code, "obgpu_merge_runs_streamed", "")
+    return done.value
+
+
 def choose_splitters(candidates, world: int):
     """world-1 splitters at the quantiles of the gathered rowkey samples (sorted, duplicates kept)."""
     import torch

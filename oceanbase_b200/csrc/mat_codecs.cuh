@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(128) mat_survey_kernel(const uint8_t *image, c
       flags |= MF_ANY;
     }
   }
-  out[4 * i] = total;
+  out[4 * i] = jobs ? total : size;   // an untouched block keeps its exact size (a CS block finds its stream offsets from its end)
   out[4 * i + 1] = jobs;
   out[4 * i + 2] = flags;
   out[4 * i + 3] = 0;
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(128) mat_rewrite_kernel(const uint8_t *image, 
   uint4 *d4 = reinterpret_cast<uint4 *>(d);
   for (uint32_t k = (uint32_t)lane; k < padded / 16u; k += 32u) d4[k] = s4[k];   // blocks are 16-byte aligned and padded in both images
   __syncwarp();
-  if (lane != 0 || new_size[i] == padded) return;
+  if (lane != 0 || new_size[i] <= padded) return;   // nothing materialised in this block
   BlockView b;
   parse_block(s, size, b);
   uint32_t at = padded;

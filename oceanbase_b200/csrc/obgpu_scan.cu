@@ -3570,6 +3570,7 @@ int obgpu_project_datums(obgpu_batch *batch, int32_t block, int32_t col, const i
 #include "../../include/obgpu_compaction.h"
 #include "merge_kernels.cuh"
 #include "merge_exchange.cuh"
+#include "merge_streamed.cuh"
 
 // ---- host-buffer scan pipeline (include/obgpu_pipeline.h) ------------------------------------------------
 #include "host_pipeline.h"

@@ -367,6 +367,17 @@ def test_streamed_merge_of_runs_that_do_not_fit_together():
 
     n_ranges = streamed_major_merge([r["table"] for r in runs], end_keys, 0, 1, [2, 3, 4], 7, sink, device=torch.device("cuda", 0))
     assert order == list(range(n_ranges)) and n_ranges >= 5
+    py_side = ({c: [(v.copy(), nl.copy()) for v, nl in got[c]] for c in got}, list(stats))
+    # the same through the library's own range loop (obgpu_merge_runs_streamed: worker threads, one stream each)
+    from oceanbase_b200.compaction import merge_runs_streamed
+    got = {c: [] for c in (-1, 0, 1, 2)}
+    order.clear()
+    stats[0] = stats[1] = 0
+    n_c = merge_runs_streamed(0, [r["table"] for r in runs], end_keys, 0, 1, [2, 3, 4], 7, sink, n_streams=3)
+    assert n_c == n_ranges and order == list(range(n_ranges))
+    assert stats == py_side[1]
+    for c in got:
+        assert np.array_equal(np.concatenate([x[0] for x in got[c]]), np.concatenate([x[0] for x in py_side[0][c]]))
     for k, c in enumerate((-1, 0, 1, 2)):
         v = np.concatenate([x[0] for x in got[c]])
         nl = np.concatenate([x[1] for x in got[c]])
@@ -376,3 +387,36 @@ def test_streamed_merge_of_runs_that_do_not_fit_together():
     assert stats[0] == whole.info().dropped_deletes and stats[1] == whole.info().fused_rows
     whole.free()
     ctx.close()
+
+
+@pytest.mark.parametrize("k_runs,seed", [(2, 1), (3, 2), (5, 3), (8, 4), (13, 5), (33, 6), (64, 7)])
+def test_single_pass_merge_shapes(env, k_runs, seed, monkeypatch):
+    """The bucket merge (single-column rowkeys) over run counts that are not powers of two, runs of very different sizes, empty runs,
+    rowkeys shared by every run, dense and sparse key ranges; every case also through the pairwise passes (OBGPU_MERGE_PAIRWISE)."""
+    from oceanbase_b200.compaction import merge_decoded
+    ctx, torch = env
+    rng = np.random.default_rng(seed)
+    runs = []
+    shared = np.sort(rng.choice(1 << 20, size=300, replace=False)).astype(np.int64) * 7
+    for r in range(k_runs):
+        n = int(rng.choice([0, 1, 17, 900, 5000, 40000]))
+        span = int(rng.choice([1 << 12, 1 << 22, 1 << 40]))
+        key = np.unique(rng.integers(-span, span, size=n, dtype=np.int64))
+        if r % 3 == 0 and n > 0:
+            key = np.unique(np.concatenate([key, shared]))      # the same rowkeys in many runs: long groups
+        m = len(key)
+        flag = rng.choice([0, 2, 3, 3, 3, 4], size=m).astype(np.uint8)      # NOT_EXIST / UPDATE / INSERT / DELETE
+        vals = [rng.integers(-(1 << 50), 1 << 50, size=m, dtype=np.int64) for _ in range(2)]
+        ext = [rng.choice([0, 0, 0, 1, 2], size=m).astype(np.uint8) for _ in range(2)]
+        for c in range(2):
+            vals[c][ext[c] != 0] = 0
+        runs.append({"key": key, "flag": flag, "vals": vals, "ext": ext})
+    want = ora.major_merge(runs, 2, [5, 6], [0, 1])
+    for pairwise in (False, True):
+        if pairwise:
+            monkeypatch.setenv("OBGPU_MERGE_PAIRWISE", "1")
+        else:
+            monkeypatch.delenv("OBGPU_MERGE_PAIRWISE", raising=False)
+        res = merge_decoded(ctx, [to_dev(torch, r) for r in runs], [5, 6], [0, 1])
+        assert_merge_equal(res, want, 2)
+        res.free()

@@ -121,3 +121,54 @@ def test_scan_filters_and_projects_rebuilt_strings(ob, ctx, case, on_device):
         res.free()
         ora.arena_reset()
     batch.close()
+
+
+def test_batch_with_cs_coded_streams_and_rebuilt_pax_strings(ob, ctx):
+    """One page batch holding CS blocks whose integer streams are codec-coded (restated at open) AND PAX blocks with HEX_PACKING /
+    STRING_PREFIX columns (materialised at open): the two passes compose -- string pointers of the untouched columns keep addressing
+    the caller's image, rebuilt strings come back as bytes."""
+    import ctypes as C
+    rng = np.random.default_rng(21)
+    n = 2600
+    k = np.arange(n, dtype=np.int64) * 3
+    hexs = [bytes(np.frombuffer(b"0123456789abcdef", dtype=np.uint8)[rng.integers(0, 16, size=rng.integers(1, 14))]) for _ in range(n)]
+    plain = [b"p%d" % (i % 13) for i in range(n)]
+    nl = (rng.random(n) < 0.1).astype(np.uint8)
+    pax = ob.encode_table([ob.Column(ob.OBJ_INT, ob.ENC_INTEGER_BASE_DIFF, k), ob.Column(ob.OBJ_VARCHAR, ob.ENC_HEX_PACKING, hexs, nulls=nl),
+                           ob.Column(ob.OBJ_VARCHAR, ob.ENC_DICT, plain)], 400)
+    cs_cols = [ob.Column(ob.OBJ_INT, ob.ENC_CS_INTEGER, k), ob.Column(ob.OBJ_VARCHAR, ob.ENC_CS_STRING, hexs, nulls=nl),
+               ob.Column(ob.OBJ_VARCHAR, ob.ENC_CS_STR_DICT, plain)]
+    cs_raw = ob.encode_table(cs_cols, 400)                  # what the oracle reads: the same blocks with RAW streams
+    ob.capi.lib.obgpu_writer_set_cs_stream_encoding(0)      # detect: the sorted key column takes a delta codec
+    try:
+        cs = ob.encode_table(cs_cols, 400)
+    finally:
+        ob.capi.lib.obgpu_writer_set_cs_stream_encoding(1)
+    assert cs.image.size < cs_raw.image.size                # some stream really is coded
+
+    def interleave(cs_t):   # the two tables' blocks alternate in one image
+        image = np.concatenate([pax.image, cs_t.image])
+        offs = np.concatenate([pax.offsets, cs_t.offsets + pax.image.size])
+        sizes = np.concatenate([pax.sizes, cs_t.sizes])
+        order = np.argsort(np.concatenate([np.arange(pax.n_blocks) * 2, np.arange(cs_t.n_blocks) * 2 + 1]), kind="stable")
+        return ob.TableImage(image, offs[order], sizes[order], pax.total_rows + cs_t.total_rows, 3)
+
+    table, otable = interleave(cs), interleave(cs_raw)
+    base, obase = table.image.ctypes.data, otable.image.ctypes.data
+    batch = ctx.open_batch(table)
+    assert batch.column_materialised(1)
+    for flt in (None, ob.And([ob.White(0, ob.WHITE_OP_GE, (900,)), ob.White(1, ob.WHITE_OP_NE, (hexs[5],))]), ob.White(2, ob.WHITE_OP_IN, (b"p3", b"p7"))):
+        want = ora.scan_table(otable, flt, [0, 1, 2], [False, True, True], [8, 8, 8], string_base=obase)
+        res = batch.scan(flt, [0, 1, 2], string_base=base)
+        assert res.selected_rows == want["selected"]
+        assert np.array_equal(res.fetch_col(0)[0], want["data"][0])
+        _, l1, n1 = res.fetch_col(1)
+        heap, off = res.fetch_strings(1)
+        assert heap_strings(heap, off, n1) == ora.scan_strings(otable, want, 1, obase)
+        p2, l2, n2 = res.fetch_col(2)
+        assert np.array_equal(l2, want["lens"][2])
+        got2 = [C.string_at(int(p), int(l)) for p, l in zip(p2, l2)]        # still pointers into the caller's image
+        assert got2 == ora.scan_strings(otable, want, 2, obase)
+        res.free()
+        ora.arena_reset()
+    batch.close()

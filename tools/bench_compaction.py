@@ -195,9 +195,14 @@ def run_streamed(args, runs, t_gen, dev, local):
         state["dropped"] += info.dropped_deletes
         state["fused"] += info.fused_rows
 
+    from oceanbase_b200.compaction import merge_runs_streamed
+
     def step():
         state.update(rows=0, dropped=0, fused=0)
-        streamed_major_merge(tables, end_keys, 0, 1, [2, 3, 4], args.stream_ranges, sink, device=dev)
+        if getattr(args, "stream_python", False):   # the Python orchestration of the same loop
+            streamed_major_merge(tables, end_keys, 0, 1, [2, 3, 4], args.stream_ranges, sink, device=dev)
+        else:
+            merge_runs_streamed(local, tables, end_keys, 0, 1, [2, 3, 4], args.stream_ranges, sink, n_streams=3)
 
     for _ in range(args.warmup):
         step()
@@ -211,7 +216,7 @@ def run_streamed(args, runs, t_gen, dev, local):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "scaling": "strong", "higher_is_better": True,
             "vs_baseline": None, "dtype": "int64", "data": "synthetic",
             "config": {"workload": f"cfg5 stand-in, STREAMED: {args.runs} host-resident runs, window {args.window}, merged in "
-                                   f"{args.stream_ranges} rowkey ranges (2 in flight), rows fetched back to host buffers",
+                                   f"{args.stream_ranges} rowkey ranges (obgpu_merge_runs_streamed, 3 in flight), rows fetched back to pinned host buffers",
                        "input_rows": in_rows, "output_rows": state["rows"], "dropped_deletes": state["dropped"], "fused_rows": state["fused"],
                        "encoded_bytes": enc, "gen_seconds": round(t_gen, 1)},
             "e2e": {"value": in_rows / (ms * 1e-3), "unit": "rows/s", "h2d_bytes_per_step": int(enc), "d2h_bytes_per_step": int(state["rows"] * 36),
