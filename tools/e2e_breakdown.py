@@ -53,7 +53,8 @@ def main():
     ap.add_argument("--reps", type=int, default=3)
     args = ap.parse_args()
     import torch
-    from oceanbase_b200.pipeline import HostScanPipeline, split_table
+    import oceanbase_b200 as ob
+    from oceanbase_b200.pipeline import split_table
 
     bench.bind_to_gpu_numa_node(0)
     w, _pin = bench.build_workload(args.rows, 0, 1234, pinned=True)
@@ -68,7 +69,11 @@ def main():
         keep.append(bufs + nbufs)
         out_np.append([t.numpy().view(np.uint64) for t in bufs])
         null_np.append([t.numpy().view(np.uint64) for t in nbufs])
-    pipe = HostScanPipeline(0, n_workers=args.workers)
+    # the round-1 Python pipeline's shape rebuilt here on purpose: the phases of obgpu_pipeline_scan (open / scan / fetch per page batch,
+    # one ctx = one stream per worker) timed separately
+    class _Pipe:
+        ctxs = [ob.ScanContext(0) for _ in range(args.workers)]
+    pipe = _Pipe()
 
     def run(kind, resident=None, log=None):
         lock = threading.Lock()
@@ -167,7 +172,8 @@ def main():
     out["full_fetch_ms_mean"] = float(np.mean([d - c for c, d in d2h]) * 1e3)
     out["first_d2h_start_ms"] = (min(c for c, _ in d2h) - t0) * 1e3
     out["last_h2d_end_ms"] = (max(b for _, b in h2d) - t0) * 1e3
-    pipe.close()
+    for c in pipe.ctxs:
+        c.close()
     print(json.dumps(out))
 
 
