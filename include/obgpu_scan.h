@@ -378,6 +378,28 @@ int obgpu_project_strings(obgpu_batch *batch, int32_t block, int32_t col, const 
                           void *host_heap, int64_t heap_cap, int64_t *host_off, uint64_t *host_nulls, int32_t *has_null,
                           int64_t *heap_bytes);
 
+/* =============================================================================================
+ * Column groups (column-store tables: every column group is its own SSTable with its own micro-blocks). The reference evaluates
+ * each pushed-down filter on ITS column group (ObCGScanner::apply_filter, column_store/ob_cg_scanner.cpp:273), combines the groups'
+ * results in an ObCGBitmap over the row range (column_store/ob_cg_bitmap.h: bit_and / bit_or / set_bitmap at start_row_id
+ * offsets) and projects the other groups by that bitmap (ObCGRowScanner::get_next_rows(count, capacity, bitmap), :614).
+ * obgpu_cg_bitmap is that range bitmap, device resident; page batches of different groups (any block boundaries) meet in it.
+ * All objects of one flow live on one ctx (stream).
+ * ============================================================================================= */
+typedef struct obgpu_cg_bitmap obgpu_cg_bitmap;
+int obgpu_cg_bitmap_create(obgpu_ctx *ctx, int64_t n_rows, int32_t all_true, obgpu_cg_bitmap **out);
+void obgpu_cg_bitmap_free(obgpu_cg_bitmap *bm);
+enum { OBGPU_CG_SET = 0, OBGPU_CG_AND = 1, OBGPU_CG_OR = 2 };
+/* The selection of a (filter) scan -> rows [row_offset, row_offset + rows of the result's batch) of the range bitmap. */
+int obgpu_cg_bitmap_apply_result(obgpu_cg_bitmap *bm, obgpu_result *filter_result, int64_t row_offset, int32_t op);
+int obgpu_cg_bitmap_popcnt(obgpu_cg_bitmap *bm, int64_t from, int64_t to, int64_t *count);
+/* rows [from, from + count) as ObBitmap bytes (0x00 / 0x01) */
+int obgpu_cg_bitmap_fetch(obgpu_cg_bitmap *bm, int64_t from, int64_t count, uint8_t *host_bitmap_bytes);
+/* obgpu_scan whose selection is the range bitmap (spec->filter must be NULL): row r of the batch is selected when bit
+ * row_offset + r of the bitmap is set. Results, per-block tables, aggregates, GROUP BY work as after a filter scan. */
+int obgpu_scan_bitmap(obgpu_batch *batch, const obgpu_cg_bitmap *bm, int64_t row_offset, const obgpu_scan_spec *spec,
+                      obgpu_result **out);
+
 /* Library self-description (build id, arch) for logs. */
 const char *obgpu_version(void);
 

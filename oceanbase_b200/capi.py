@@ -183,6 +183,12 @@ def declared_signatures():
         "obgpu_project_discrete": (C.c_int, [vp, i32, i32, vp, i64, i64, u64, vp, vp, vp, P(i32)]),
         "obgpu_project_datums": (C.c_int, [vp, i32, i32, vp, i64, i64, u64, vp]),
         "obgpu_result_fetch_datums": (C.c_int, [vp, i32, i64, i64, vp, vp]),
+        "obgpu_cg_bitmap_create": (C.c_int, [vp, i64, i32, P(vp)]),
+        "obgpu_cg_bitmap_free": (None, [vp]),
+        "obgpu_cg_bitmap_apply_result": (C.c_int, [vp, vp, i64, i32]),
+        "obgpu_cg_bitmap_popcnt": (C.c_int, [vp, i64, i64, P(i64)]),
+        "obgpu_cg_bitmap_fetch": (C.c_int, [vp, i64, i64, vp]),
+        "obgpu_scan_bitmap": (C.c_int, [vp, vp, i64, vp, P(vp)]),
         "obgpu_batch_column_materialised": (C.c_int, [vp, i32, P(i32)]),
         "obgpu_result_fetch_strings": (C.c_int, [vp, i32, i64, i64, vp, i64, vp, P(i64)]),
         "obgpu_project_strings": (C.c_int, [vp, i32, i32, vp, i64, vp, i64, vp, vp, P(i32), P(i64)]),

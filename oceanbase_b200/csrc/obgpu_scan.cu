@@ -2897,10 +2897,55 @@ static int check_status(obgpu_ctx *ctx, int status) {
   return OBGPU_SUCCESS;
 }
 
+// ---- ObCGBitmap: the selection of a row range shared by the column groups of a table ------------------------------------------
+struct obgpu_cg_bitmap {
+  obgpu_ctx *ctx = nullptr;
+  uint32_t *d_words = nullptr;   // bit r of the range at word r / 32, LSB first; 2 words of slack behind the last one
+  int64_t n_rows = 0;
+};
+
+// 32 bits of a bit array starting at an arbitrary bit position
+__device__ __forceinline__ uint32_t bits_at(const uint32_t *__restrict__ w, int64_t bit) {
+  const int64_t i = bit >> 5;
+  const uint32_t sh = (uint32_t)(bit & 31);
+  return __funnelshift_r(w[i], w[i + 1], sh);
+}
+
+// One warp per block: the block's rows in the range bitmap -> its packed selection words + selected count (what the count kernel
+// produces from a filter)
+__global__ void __launch_bounds__(128) obgpu_bitmap_slice_kernel(const uint32_t *__restrict__ cg_words, int64_t cg_rows, int64_t row_offset,
+                                                                 const int64_t *__restrict__ row_start, const uint32_t *__restrict__ rows,
+                                                                 const int64_t *__restrict__ bm_word_off, int n_blocks,
+                                                                 uint32_t *__restrict__ bitmap_words, uint32_t *__restrict__ counts) {
+  const int blk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (blk >= n_blocks) return;
+  const uint32_t n = rows[blk];
+  const int64_t g0 = row_offset + row_start[blk];
+  uint32_t cnt = 0;
+  for (uint32_t w = (uint32_t)lane; w < (n + 31u) / 32u; w += 32u) {
+    const int64_t g = g0 + 32ll * w;
+    uint32_t v = (g >= 0 && g < cg_rows) ? bits_at(cg_words, g) : 0u;
+    const uint32_t valid = n - 32u * w >= 32u ? 0xffffffffu : ((1u << (n - 32u * w)) - 1u);
+    v &= valid;
+    if (g + 32 > cg_rows && g < cg_rows) v &= (uint32_t)((1ull << (cg_rows - g)) - 1ull);
+    bitmap_words[bm_word_off[blk] + w] = v;
+    cnt += __popc(v);
+  }
+  cnt = __reduce_add_sync(0xffffffffu, cnt);
+  if (lane == 0) counts[blk] = cnt;
+}
+
+static int scan_common(obgpu_batch *b, const obgpu_scan_spec *spec, const obgpu_cg_bitmap *ext_bm, int64_t ext_row_offset, obgpu_result **out);
+
 extern "C" {
 
-int obgpu_scan(obgpu_batch *b, const obgpu_scan_spec *spec, obgpu_result **out) {
+int obgpu_scan(obgpu_batch *b, const obgpu_scan_spec *spec, obgpu_result **out) { return scan_common(b, spec, nullptr, 0, out); }
+
+}  // extern "C"
+
+static int scan_common(obgpu_batch *b, const obgpu_scan_spec *spec, const obgpu_cg_bitmap *ext_bm, int64_t ext_row_offset, obgpu_result **out) {
   if (!b || !spec || !out) return OBGPU_INVALID_ARGUMENT;
+  if (ext_bm && spec->filter && spec->filter->n_nodes > 0) return OBGPU_INVALID_ARGUMENT;   // the bitmap IS the selection
   obgpu_ctx *ctx = b->ctx;
   if (spec->n_proj < 0 || spec->n_proj > kMaxProj || (spec->n_proj > 0 && !spec->proj_cols))
     return spec->n_proj > kMaxProj ? OBGPU_NOT_SUPPORTED : OBGPU_INVALID_ARGUMENT;
@@ -2930,8 +2975,9 @@ int obgpu_scan(obgpu_batch *b, const obgpu_scan_spec *spec, obgpu_result **out) 
   r->string_base = spec->string_base;
   // the caller's selectivity estimate (max_selected_rows): when it says at most 1/16 of the rows survive, most
   // blocks will be sparse and the warp-per-block kernel takes them
-  p.sparse_split = (p.n_nodes > 0 && r->cap * 16 <= b->total_rows) ? 1 : 0;
-  if (const char *e = getenv("OBGPU_SPARSE_SPLIT")) p.sparse_split = atoi(e) ? (p.n_nodes > 0 ? 1 : 0) : 0;  // testing knob
+  const bool selects = p.n_nodes > 0 || ext_bm != nullptr;   // some rows may be dropped: bitmap words + counts exist
+  p.sparse_split = (selects && r->cap * 16 <= b->total_rows) ? 1 : 0;
+  if (const char *e = getenv("OBGPU_SPARSE_SPLIT")) p.sparse_split = atoi(e) ? (selects ? 1 : 0) : 0;  // testing knob
   layout_smem_scan(b, p, ctx->max_smem_optin);
   layout_pipe(b, p, ctx->max_smem_optin);
   if ((int)p.smem_total > ctx->max_smem_optin && !p.pipe_project) {
@@ -3005,7 +3051,7 @@ int obgpu_scan(obgpu_batch *b, const obgpu_scan_spec *spec, obgpu_result **out) 
   r->d_sel_offset = p.sel_offset;
   r->d_bitmap = p.bitmap_words;
   r->d_row_ids = p.row_ids;
-  r->no_filter = p.n_nodes == 0;
+  r->no_filter = !selects;
   r->d_skip_counters = (unsigned long long *)(a + o_misc + 16);
   // ---- launches: [skip index ->] count (filter) -> prefix -> project --------------------------------
   const int pslot = (int)(ctx->prof_count % obgpu_ctx::kProfRing);
@@ -3017,7 +3063,11 @@ int obgpu_scan(obgpu_batch *b, const obgpu_scan_spec *spec, obgpu_result **out) 
     p.blk_const = a + o_blk_const;
     p.leaf_const = a + o_leaf_const;
   }
-  if (p.n_nodes > 0) {
+  if (ext_bm) {   // ObCGRowScanner::get_next_rows(bitmap): another column group's filter already chose the rows
+    obgpu_bitmap_slice_kernel<<<(unsigned)(((int64_t)n * 32 + 127) / 128), 128, 0, ctx->stream>>>(
+        ext_bm->d_words, ext_bm->n_rows, ext_row_offset, b->d_row_start, b->d_rows, b->d_bm_word_off, n, p.bitmap_words, p.counts);
+    ctx->launches++;
+  } else if (p.n_nodes > 0) {
     const uint32_t cw_total = p.cw_bytes * (uint32_t)kWarps;
     if ((int)cw_total > ctx->max_smem_optin) {
       ctx->err = "filter working set exceeds shared memory";
@@ -3037,7 +3087,7 @@ int obgpu_scan(obgpu_batch *b, const obgpu_scan_spec *spec, obgpu_result **out) 
   }
   {
     const int n_chunks = (n + kPrefixChunk - 1) / kPrefixChunk;
-    const uint32_t *cnts = p.n_nodes > 0 ? p.counts : b->d_rows;
+    const uint32_t *cnts = selects ? p.counts : b->d_rows;
     obgpu_prefix_local_kernel<<<n_chunks, 256, 0, ctx->stream>>>(cnts, n, p.sel_offset, (unsigned long long *)(a + o_chunk));
     obgpu_prefix_fix_kernel<<<n_chunks + 1, 256, 0, ctx->stream>>>(n, n_chunks, p.sel_offset, (const unsigned long long *)(a + o_chunk));
     ctx->launches += 2;
@@ -3068,6 +3118,8 @@ int obgpu_scan(obgpu_batch *b, const obgpu_scan_spec *spec, obgpu_result **out) 
   *out = r;
   return OBGPU_SUCCESS;
 }
+
+extern "C" {
 
 int obgpu_batch_set_agg_rows(obgpu_batch *b, const void *agg_rows, const int64_t *agg_off) {
   if (!b) return OBGPU_INVALID_ARGUMENT;
@@ -3559,6 +3611,9 @@ int obgpu_project_datums(obgpu_batch *batch, int32_t block, int32_t col, const i
 }
 
 }  // extern "C"
+
+// ---- ObCGBitmap: range bitmaps shared by the column groups of a table ----------------------------------------------------
+#include "cg_bitmap.cuh"
 
 // ---- string cells as bytes (dense heap): scan results and the per-block entry ------------------------------------------
 #include "result_strings.cuh"

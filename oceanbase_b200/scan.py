@@ -193,6 +193,20 @@ class PageBatch:
         check(lib.obgpu_scan(self._h, C.byref(spec), C.byref(h)), "obgpu_scan", self.ctx._h)
         return ScanResult(self, h, len(proj_cols))
 
+    def scan_bitmap(self, bitmap: "CGBitmap", proj_cols: Sequence[int], row_offset: int = 0, want_row_ids=False, string_base=0,
+                    max_selected_rows=0) -> "ScanResult":
+        """obgpu_scan_bitmap: project the rows a range bitmap selects (ObCGRowScanner::get_next_rows(count, capacity, bitmap))."""
+        proj = (C.c_int32 * max(len(proj_cols), 1))(*proj_cols)
+        spec = capi.ScanSpec()
+        spec.filter = None
+        spec.proj_cols, spec.n_proj = proj, len(proj_cols)
+        spec.want_row_ids = 1 if want_row_ids else 0
+        spec.string_base = string_base
+        spec.max_selected_rows = max_selected_rows
+        h = C.c_void_p()
+        check(lib.obgpu_scan_bitmap(self._h, bitmap._h, row_offset, C.byref(spec), C.byref(h)), "obgpu_scan_bitmap", self.ctx._h)
+        return ScanResult(self, h, len(proj_cols))
+
     # ---- skip index (include/obgpu_skip_index.h) ---------------------------------------------------
     def set_agg_rows(self, agg_rows: Optional[np.ndarray], agg_off: Optional[np.ndarray] = None):
         """Attach the blocks' serialized aggregate rows (block b: agg_rows[agg_off[b]:agg_off[b + 1]]); None detaches.
@@ -343,6 +357,41 @@ class PageBatch:
     def __del__(self):
         try:
             self.close()
+        except Exception:
+            pass
+
+
+class CGBitmap:
+    """obgpu_cg_bitmap: ObCGBitmap of a row range, device resident (column-store tables: filters of different column groups meet here)."""
+
+    def __init__(self, ctx: "ScanContext", n_rows: int, all_true: bool = False):
+        self.ctx, self.n_rows = ctx, n_rows
+        self._h = C.c_void_p()
+        check(lib.obgpu_cg_bitmap_create(ctx._h, n_rows, 1 if all_true else 0, C.byref(self._h)), "obgpu_cg_bitmap_create", ctx._h)
+
+    def apply(self, result: "ScanResult", row_offset: int = 0, op: str = "and"):
+        code = {"set": 0, "and": 1, "or": 2}[op]
+        check(lib.obgpu_cg_bitmap_apply_result(self._h, result._h, row_offset, code), "obgpu_cg_bitmap_apply_result", self.ctx._h)
+
+    def popcnt(self, lo: int = 0, hi: Optional[int] = None) -> int:
+        n = C.c_int64(0)
+        check(lib.obgpu_cg_bitmap_popcnt(self._h, lo, self.n_rows if hi is None else hi, C.byref(n)), "obgpu_cg_bitmap_popcnt", self.ctx._h)
+        return n.value
+
+    def fetch(self, lo: int = 0, count: Optional[int] = None) -> np.ndarray:
+        count = self.n_rows - lo if count is None else count
+        out = np.zeros(max(count, 1), dtype=np.uint8)
+        check(lib.obgpu_cg_bitmap_fetch(self._h, lo, count, out.ctypes.data), "obgpu_cg_bitmap_fetch", self.ctx._h)
+        return out[:count]
+
+    def free(self):
+        if self._h and self.ctx._h:
+            lib.obgpu_cg_bitmap_free(self._h)
+        self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
         except Exception:
             pass
 
