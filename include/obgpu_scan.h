@@ -68,6 +68,8 @@ enum {
   OBGPU_ENC_STRING_DIFF = 5,
   OBGPU_ENC_HEX_PACKING = 6,
   OBGPU_ENC_STRING_PREFIX = 7,
+  OBGPU_ENC_COLUMN_EQUAL = 8,   /* span columns: obgpu_col_input.ref_col names the referenced column */
+  OBGPU_ENC_COLUMN_SUBSTR = 9,
   /* writer only: columns of a CS_ENCODING_ROW_STORE block (ObCSColumnHeader::Type) */
   OBGPU_ENC_CS_INTEGER = 16,
   OBGPU_ENC_CS_INT_DICT = 17,

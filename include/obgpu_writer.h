@@ -34,7 +34,7 @@ typedef struct obgpu_col_input {
   const char *str_heap;    /* string classes: bytes                                            */
   const int64_t *str_off;  /*   nrows + 1 offsets into str_heap                                */
   int32_t byte_packing_only; /* 1 => ObMicroBlockEncoderOpt.enable_bit_packing_ == false       */
-  int32_t reserved;
+  int32_t ref_col;         /* OBGPU_ENC_COLUMN_EQUAL / COLUMN_SUBSTR: the column this one refers to      */
 } obgpu_col_input;
 
 /* Upper bound of the encoded size of a block of nrows rows. */

@@ -9,7 +9,7 @@ from .capi import (  # noqa: F401
     OB_INVALID_DATA, OB_ERR_SYS,
     WHITE_OP_EQ, WHITE_OP_LE, WHITE_OP_LT, WHITE_OP_GE, WHITE_OP_GT, WHITE_OP_NE, WHITE_OP_BT,
     WHITE_OP_IN, WHITE_OP_NU, WHITE_OP_NN,
-    ENC_RAW, ENC_DICT, ENC_RLE, ENC_CONST, ENC_INTEGER_BASE_DIFF, ENC_STRING_DIFF, ENC_HEX_PACKING, ENC_STRING_PREFIX, ENC_CS_INTEGER, ENC_CS_INT_DICT, ENC_CS_STRING, ENC_CS_STR_DICT,
+    ENC_RAW, ENC_DICT, ENC_RLE, ENC_CONST, ENC_INTEGER_BASE_DIFF, ENC_STRING_DIFF, ENC_HEX_PACKING, ENC_STRING_PREFIX, ENC_COLUMN_EQUAL, ENC_COLUMN_SUBSTR, ENC_CS_INTEGER, ENC_CS_INT_DICT, ENC_CS_STRING, ENC_CS_STR_DICT,
     OBJ_INT, OBJ_INT32, OBJ_UINT64, OBJ_VARCHAR, OBJ_DATE, OBJ_TINYINT, OBJ_SMALLINT, OBJ_UINT32,
     DF_NOT_EXIST, DF_LOCK, DF_UPDATE, DF_INSERT, DF_DELETE,
     AGG_COUNT, AGG_SUM, AGG_SUM_PRODUCT, AGG_MIN, AGG_MAX,

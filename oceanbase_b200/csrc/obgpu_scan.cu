@@ -2048,7 +2048,7 @@ static int pax_materialise_batch(obgpu_ctx *ctx, obgpu_batch *b) {
   uint32_t *d_sv = nullptr;
   std::vector<uint32_t> sv((size_t)n * 4);
   CUDA_TRY(ctx, cudaMallocAsync((void **)&d_sv, (size_t)n * 16, ctx->stream));
-  obmat::mat_survey_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(b->d_image, b->d_blk_off, b->d_blk_size, n, d_sv);
+  obmat::mat_survey_kernel<<<(unsigned)(((int64_t)n * 32 + 127) / 128), 128, 0, ctx->stream>>>(b->d_image, b->d_blk_off, b->d_blk_size, n, d_sv);
   ctx->launches++;
   e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaMemcpyAsync(sv.data(), d_sv, (size_t)n * 16, cudaMemcpyDeviceToHost, ctx->stream);
@@ -2229,7 +2229,11 @@ int obgpu_batch_open(obgpu_ctx *ctx, const void *image, int64_t image_size, cons
       if (!is_cs && !any_mat)
         for (uint32_t c = 0; c < ncol; ++c) {
           const uint8_t t = p[header_size + 16u * c + 1];
-          if (t == obf::COL_STRING_DIFF || t == obf::COL_HEX_PACKING || t == obf::COL_STRING_PREFIX) { any_mat = true; break; }
+          if (t == obf::COL_STRING_DIFF || t == obf::COL_HEX_PACKING || t == obf::COL_STRING_PREFIX || t == obf::COL_COLUMN_EQUAL ||
+              t == obf::COL_COLUMN_SUBSTR) {
+            any_mat = true;
+            break;
+          }
         }
     }
   } else {

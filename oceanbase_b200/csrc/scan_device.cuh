@@ -606,8 +606,9 @@ __device__ __forceinline__ void build_col_desc(const BlockView &b, int col, ColD
   }
   const uint32_t ch = b.header_size + 16u * (uint32_t)col;
   const uint32_t w0 = ld32(s, ch);
-  if ((w0 & 0xff) != 0) return;  // version
   d.type = (uint8_t)((w0 >> 8) & 0xff);
+  const bool span_area = (w0 & 0xff) == 0xA5 && (d.type == COL_COLUMN_EQUAL || d.type == COL_COLUMN_SUBSTR);
+  if ((w0 & 0xff) != 0 && !span_area) return;  // version
   d.attr = (uint8_t)((w0 >> 16) & 0xff);
   d.obj_type = (uint8_t)(w0 >> 24);
   d.ext_index = ld32(s, ch + 4);
@@ -617,6 +618,32 @@ __device__ __forceinline__ void build_col_desc(const BlockView &b, int col, ColD
   d.sc = (uint8_t)sc;
   d.elem_len = (uint8_t)datum_len_of(d.obj_type);
   d.int_mask = integer_mask_of(d.obj_type);
+  if (span_area) {
+    // A span column (COLUMN_EQUAL / COLUMN_SUBSTR) whose values the page batch rebuilt at open (mat_codecs.cuh): in the batch's copy
+    // of the block the column header (version byte 0xA5) points at the area, offset_ from the block start, length_ bytes.
+    const uint32_t area = offset, rows = b.row_count, nwords = (rows + 31u) / 32u;
+    if ((area & 15u) || area > b.size || length > b.size - area || rows == 0) return;
+    d.ext_bit = 1;
+    d.ext_bit_off = area * 8u;
+    if (sc == 5) {   // [NULL bits][END offset u32 x rows][strings]: the plan of a CS STRING column
+      if ((uint64_t)nwords * 4u + (uint64_t)rows * 4u > length) return;
+      d.kind = K_CSSTR;
+      d.dict_payload = area + nwords * 4u;
+      d.dict_data_size = 4;
+      d.dict_var = d.dict_payload + rows * 4u;
+      d.dict_end = d.dict_var + (uint32_t)ld_bytes(s, d.dict_payload + (rows - 1u) * 4u, 4);
+      if (d.dict_end > area + length || d.dict_end < d.dict_var) return;
+    } else {         // [NULL bits, padded to 8 bytes][8-byte value image x rows]: the plan of a RAW fixed-length column
+      const uint32_t vals = area + ((nwords * 4u + 7u) & ~7u);
+      if ((uint64_t)(vals - area) + (uint64_t)rows * 8u > length || (uint64_t)vals * 8u + (uint64_t)rows * 64u > 0xffffffffull) return;
+      d.kind = K_BITS;
+      d.width = 64;
+      d.stride = 64;
+      d.val_bit = vals * 8u;
+    }
+    d.ok = 1;
+    return;
+  }
   if (offset > b.size || b.meta_off > b.size - offset) return;   // untrusted: no wrap-around in meta_off + offset
   const uint32_t meta = b.meta_off + offset;
   const bool has_ext = d.attr & ATTR_HAS_EXTEND_VALUE;

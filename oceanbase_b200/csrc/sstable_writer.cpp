@@ -424,6 +424,9 @@ struct BlockBuilder {
   int encode_hex(int i);
   int encode_string_diff(int i);
   int encode_string_prefix(int i);
+  int encode_column_equal(int i);
+  int encode_column_substr(int i);
+  int span_ref_of(int i) const;
   void store_ext_then_fixed_cells(int i, int64_t cell_len);
   int build_cs(std::vector<uint8_t> &block, int64_t original);
   int build(std::vector<uint8_t> &block);
@@ -850,6 +853,197 @@ int BlockBuilder::encode_string_prefix(int i) {
   return OBGPU_SUCCESS;
 }
 
+// ---- span columns (a10): COLUMN_EQUAL, COLUMN_SUBSTR -----------------------------------------------------------------------------
+// Exception rows of a span column: ObBitMapMetaWriter (encoding/ob_encoding_bitset.h:163-557).
+//   ObBitMapMetaHeader {ext_offset u8, index_offset u8, data_offset u8, {bit_packing_len | fix_data_cnt | index_byte} u8}
+//   + BitSet of the exception rows (64-bit words over every row of the block) + 2 ext bits per exception (only when one of them is
+//   NULL / NOP) + (count - 1) start offsets (var-length exceptions) + the exception values (bit packed / fixed / var);
+//   an extend value keeps its slot in the bit-packed and fixed layouts and takes no bytes in the var layout.
+// Returns false when the reference's writer calls the column "not suitable" (the three offsets are uint8).
+struct ExcMeta {
+  std::vector<uint8_t> bytes;
+  bool bit_packing = false;
+};
+bool build_exc_meta(const ColCtx &c, const std::vector<int64_t> &exc, ExcMeta &m) {
+  const int64_t count = (int64_t)exc.size();
+  bool has_ext = false, var_store = false, bp = false;
+  int64_t total = 0, fix = -1, index_byte = 0;
+  uint64_t max_integer = 0;
+  for (int64_t rid : exc) {
+    if (c.is_null(rid)) { has_ext = true; continue; }
+    if (c.sc == 5) {
+      const int64_t len = c.sval(rid).len;
+      total += len;
+      if (!var_store) {
+        if (fix < 0) fix = len;
+        else if (len != fix) { fix = -1; var_store = true; }
+      }
+    } else {
+      max_integer = std::max(max_integer, c.uval(rid));
+    }
+  }
+  if (c.sc != 5) {   // fill_param<ObIntSC>: get_packing_size with its default enable_bit_packing
+    fix = packing_size(&bp, max_integer, true);
+    total = fix * count;
+    if (bp) total = (total + 7) / 8;
+  } else if (fix < 0) {
+    index_byte = total <= 0xff ? 1 : total <= 0xffff ? 2 : total <= 0xffffffffll ? 4 : 8;
+  } else {
+    total = fix * count;
+  }
+  const int64_t ext_len = (c.nrows + 63) / 64 * 8;
+  const int64_t bs_len = has_ext ? (count * 2 + 7) / 8 : 0;
+  const int64_t index_len = fix < 0 ? (count - 1) * index_byte : 0;
+  if (ext_len + bs_len + index_len > 0xff) return false;
+  m.bit_packing = bp;
+  m.bytes.assign((size_t)(4 + ext_len + bs_len + index_len + total + 8), 0);   // 8: the reference's safety bytes for bit packing
+  uint8_t *h = m.bytes.data(), *buf = h + 4;
+  h[0] = (uint8_t)ext_len;
+  h[1] = (uint8_t)(ext_len + bs_len);
+  h[2] = (uint8_t)(ext_len + bs_len + index_len);
+  h[3] = (uint8_t)(bp ? fix : (fix < 0 ? index_byte : count));
+  uint8_t *data = buf + h[2];
+  int64_t offset = 0;
+  for (int64_t ref = 0; ref < count; ++ref) {
+    const int64_t rid = exc[(size_t)ref];
+    buf[rid / 8] |= (uint8_t)(1u << (rid % 8));   // BitSet::set on little-endian 64-bit words
+    const bool ext = c.is_null(rid);
+    if (has_ext && ext) put_bits(buf + h[0], ref * 2, 2, c.ext_val(rid));
+    if (c.sc != 5) {
+      if (!ext) {
+        if (bp) put_bits(data, offset, (int)fix, c.ival(rid) & low_mask((int)fix));
+        else { const uint64_t v = (uint64_t)c.ival(rid); memcpy(data + offset, &v, (size_t)fix); }
+      }
+      offset += fix;
+    } else if (fix < 0) {
+      if (ref > 0) { const uint64_t o = (uint64_t)offset; memcpy(buf + h[1] + (ref - 1) * index_byte, &o, (size_t)index_byte); }
+      if (!ext) { const StrRef v = c.sval(rid); if (v.len) memcpy(data + offset, v.p, (size_t)v.len); offset += v.len; }
+    } else {
+      if (!ext && fix) memcpy(data + offset, c.sval(rid).p, (size_t)fix);
+      offset += fix;
+    }
+  }
+  m.bytes.resize(m.bytes.size() - 8);
+  return true;
+}
+
+// the column a span column refers to: an ordinary column of the same type
+int BlockBuilder::span_ref_of(int i) const {
+  const int ref = cols[i].ref_col;
+  if (ref < 0 || ref >= ncol || ref == i || cols[ref].obj_type != cols[i].obj_type) return -1;
+  if (cols[ref].encoding == OBGPU_ENC_COLUMN_EQUAL || cols[ref].encoding == OBGPU_ENC_COLUMN_SUBSTR) return -1;
+  return ref;
+}
+
+// COLUMN_EQUAL (ObColumnEqualEncoder, encoding/ob_column_equal_encoder.cpp:84-301): the column equals column ref_col_idx in every
+// row but the exception rows.  meta: ObColumnEqualMetaHeader {version u8, ref_col_idx u16} (+ the exception meta); nothing else.
+// At most min(100, rows / 10 + 1) exceptions (ObSpanColumnEncoder::MAX_EXC_CNT / EXC_THRESHOLD_PCT, ob_icolumn_encoder.cpp:94-95).
+int BlockBuilder::encode_column_equal(int i) {
+  ColCtx &c = ctx[(size_t)i];
+  ColOut &o = out[(size_t)i];
+  const int ref = span_ref_of(i);
+  if (ref < 0) return OBGPU_INVALID_ARGUMENT;
+  const ColCtx &rc = ctx[(size_t)ref];
+  std::vector<int64_t> exc;
+  for (int64_t r = 0; r < nrows; ++r) {   // is_datum_equal (ob_column_equal_encoder.h:90-110)
+    const int le = c.is_null(r) ? (int)c.ext_val(r) : 0, re = rc.is_null(r) ? (int)rc.ext_val(r) : 0;
+    bool equal;
+    if (le != re) equal = false;
+    else if (le) equal = true;
+    else if (c.sc != 5) equal = c.ival(r) == rc.ival(r);
+    else { const StrRef a = c.sval(r), b = rc.sval(r); equal = a.len == b.len && (a.len == 0 || memcmp(a.p, b.p, (size_t)a.len) == 0); }
+    if (!equal) exc.push_back(r);
+  }
+  if ((int64_t)exc.size() > std::min<int64_t>(100, nrows * 10 / 100 + 1)) return OBGPU_NOT_SUPPORTED;
+  ExcMeta em;
+  if (!exc.empty() && !build_exc_meta(c, exc, em)) return OBGPU_NOT_SUPPORTED;
+  o.hdr.type_ = COL_COLUMN_EQUAL;
+  o.hdr.attr_ = em.bit_packing ? ATTR_BIT_PACKING : 0;
+  o.hdr.offset_ = (uint32_t)meta.size();
+  o.hdr.length_ = (uint32_t)(3 + em.bytes.size());
+  uint8_t *h = meta.grow(3 + em.bytes.size());
+  const uint16_t r16 = (uint16_t)ref;
+  memcpy(h + 1, &r16, 2);
+  if (!em.bytes.empty()) memcpy(h + 3, em.bytes.data(), em.bytes.size());
+  return OBGPU_SUCCESS;
+}
+
+// COLUMN_SUBSTR (ObInterColSubStrEncoder, encoding/ob_inter_column_substring_encoder.cpp:103-395): every value is a substring of
+// the same row's value in column ref_col_idx (first occurrence, memmem), but the exception rows.
+//   meta: ObInterColSubStrMetaHeader {version u8, {start_pos_byte:2, val_len_byte:2, is_same_start_pos:1, is_fix_length:1} u8,
+//         start_pos u16, length u16, ref_col_idx u16} (+ the exception meta)
+//   fixed store after the meta, no ext bits: per row [start_pos, start_pos_byte bytes][value length, val_len_byte bytes]; a field
+//   every row shares lives in the header instead. Both cells NULL / NOP: start 0, length 0; exception rows: start -2.
+int BlockBuilder::encode_column_substr(int i) {
+  ColCtx &c = ctx[(size_t)i];
+  ColOut &o = out[(size_t)i];
+  const int ref = span_ref_of(i);
+  if (ref < 0) return OBGPU_INVALID_ARGUMENT;
+  if (c.sc != 5) return OBGPU_NOT_SUPPORTED;
+  const ColCtx &rc = ctx[(size_t)ref];
+  std::vector<int64_t> exc, start((size_t)nrows, 0);
+  int64_t same_start = -1, fix_size = -1, max_start = 0, max_len = 0;
+  bool is_same = true, var_data = false;
+  for (int64_t r = 0; r < nrows; ++r) {
+    const bool ce = c.is_null(r), re = rc.is_null(r);
+    if (!ce) max_len = std::max(max_len, c.sval(r).len);
+    if (ce && re) continue;   // EXT_START_POS: recorded as 0, excluded from the same-start / fixed-length tests
+    int64_t sp = -2;          // EXCEPTION_START_POS
+    if (!ce && !re) {
+      const StrRef v = c.sval(r), w = rc.sval(r);
+      if (v.len <= w.len) {
+        const void *found = v.len == 0 ? (const void *)w.p : memmem(w.p, (size_t)w.len, v.p, (size_t)v.len);
+        if (found) sp = (const char *)found - w.p;
+      }
+    }
+    start[(size_t)r] = sp;
+    if (sp < 0) { exc.push_back(r); continue; }
+    max_start = std::max(max_start, sp);
+    if (is_same) {
+      if (same_start == -1) same_start = sp;
+      else if (!(is_same = (same_start == sp))) same_start = -1;
+    }
+    if (!var_data) {
+      const int64_t len = c.sval(r).len;
+      if (fix_size < 0) fix_size = len;
+      else if (len != fix_size) { fix_size = -1; var_data = true; }
+    }
+  }
+  if (max_start >= 0xffff || max_len >= 0xffff) return OBGPU_NOT_SUPPORTED;
+  if ((int64_t)exc.size() > std::min<int64_t>(100, nrows * 10 / 100 + 1)) return OBGPU_NOT_SUPPORTED;
+  ExcMeta em;
+  if (!exc.empty() && !build_exc_meta(c, exc, em)) return OBGPU_NOT_SUPPORTED;
+  int spb = 0, vlb = 0;
+  if (!(fix_size > 0 && same_start >= 0)) {
+    if (same_start < 0) spb = max_start <= 0xff ? 1 : 2;
+    if (fix_size < 0) vlb = max_len <= 0xff ? 1 : 2;
+  }
+  o.hdr.type_ = COL_COLUMN_SUBSTR;
+  o.hdr.attr_ = ATTR_FIX_LENGTH;
+  o.hdr.offset_ = (uint32_t)meta.size();
+  o.hdr.length_ = (uint32_t)(8 + em.bytes.size());
+  uint8_t *h = meta.grow(8 + em.bytes.size());
+  uint8_t attr = 0;
+  uint16_t sp16 = 0, len16 = 0;
+  const uint16_t r16 = (uint16_t)ref;
+  if (same_start >= 0) { sp16 = (uint16_t)same_start; attr |= 1u << 4; } else attr |= (uint8_t)(spb & 3);
+  if (fix_size >= 0) { len16 = (uint16_t)fix_size; attr |= 1u << 5; } else attr |= (uint8_t)((vlb & 3) << 2);
+  h[1] = attr;
+  memcpy(h + 2, &sp16, 2);
+  memcpy(h + 4, &len16, 2);
+  memcpy(h + 6, &r16, 2);
+  if (!em.bytes.empty()) memcpy(h + 8, em.bytes.data(), em.bytes.size());
+  if (spb + vlb > 0) {
+    uint8_t *p = meta.grow((size_t)((spb + vlb) * nrows));
+    for (int64_t r = 0; r < nrows; ++r, p += spb + vlb) {
+      if (spb) memcpy(p, &start[(size_t)r], (size_t)spb);
+      const int64_t vl = c.is_null(r) ? 0 : c.sval(r).len;   // an extend value's length is forced to 0
+      if (vlb) memcpy(p + spb, &vl, (size_t)vlb);
+    }
+  }
+  return OBGPU_SUCCESS;
+}
+
 // CONST: one dominant value (or NULL) + at most 32 exception rows
 // (ob_const_encoder.cpp:58-131 traverse / suitability, :154-196 no-exception meta, :296-356 meta with
 // exceptions: [header][count x u8 ref][count x row_id_byte row ids][sorted dict meta]).
@@ -1024,6 +1218,8 @@ int BlockBuilder::build(std::vector<uint8_t> &block) {
       case OBGPU_ENC_HEX_PACKING: ret = encode_hex(i); break;
       case OBGPU_ENC_STRING_DIFF: ret = encode_string_diff(i); break;
       case OBGPU_ENC_STRING_PREFIX: ret = encode_string_prefix(i); break;
+      case OBGPU_ENC_COLUMN_EQUAL: ret = encode_column_equal(i); break;
+      case OBGPU_ENC_COLUMN_SUBSTR: ret = encode_column_substr(i); break;
       default: ret = OBGPU_NOT_SUPPORTED;
     }
     if (ret != OBGPU_SUCCESS) return ret;

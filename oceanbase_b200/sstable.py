@@ -22,6 +22,7 @@ class Column:
     values: object = None
     nulls: Optional[np.ndarray] = None
     byte_packing_only: bool = False
+    ref_col: int = 0   # ENC_COLUMN_EQUAL / ENC_COLUMN_SUBSTR: index of the referenced column
     str_heap: Optional[np.ndarray] = None
     str_off: Optional[np.ndarray] = None
     _keep: list = field(default_factory=list, repr=False)
@@ -34,6 +35,7 @@ class Column:
         ci.obj_type = self.obj_type
         ci.encoding = self.encoding
         ci.byte_packing_only = 1 if self.byte_packing_only else 0
+        ci.ref_col = int(self.ref_col)
         if self.is_string():
             if self.str_heap is None:
                 vals = [b"" if v is None else bytes(v) for v in self.values]

@@ -14,7 +14,7 @@
 #include <string.h>
 
 /* ---- layout constants (ob_micro_block_header.h:97-153, ob_block_sstable_struct.h:201-264) ---- */
-enum { T_RAW = 0, T_DICT = 1, T_RLE = 2, T_CONST = 3, T_BASE_DIFF = 4, T_STRING_DIFF = 5, T_HEX = 6, T_STRING_PREFIX = 7, T_CS_INTEGER = 100, T_CS_STRING = 101, T_CS_INT_DICT = 102, T_CS_STR_DICT = 103 /* CS block: 100 + ObCSColumnHeader::Type */ };
+enum { T_RAW = 0, T_DICT = 1, T_RLE = 2, T_CONST = 3, T_BASE_DIFF = 4, T_STRING_DIFF = 5, T_HEX = 6, T_STRING_PREFIX = 7, T_COLUMN_EQUAL = 8, T_COLUMN_SUBSTR = 9, T_CS_INTEGER = 100, T_CS_STRING = 101, T_CS_INT_DICT = 102, T_CS_STR_DICT = 103 /* CS block: 100 + ObCSColumnHeader::Type */ };
 enum { A_FIX = 0x1, A_EXT = 0x2, A_BITPACK = 0x4, A_LASTVAR = 0x8 };
 enum { EXT_NOT = 0, EXT_NULL = 1, EXT_NOPE = 2 };
 #define MAGIC 1005
@@ -452,6 +452,13 @@ typedef struct col_dec {
   const uint8_t *mat_common;    /* STRING_DIFF: common bytes; STRING_PREFIX: prefix bytes */
   const uint8_t *mat_index;     /* STRING_PREFIX: (count - 1) start offsets */
   int mat_index_byte, mat_count;
+  /* span columns (COLUMN_EQUAL / COLUMN_SUBSTR): the decoder of the referenced column, the exception meta (NULL: none) */
+  const struct col_dec *span_ref;
+  const uint8_t *span_exc;
+  int64_t span_exc_len;
+  const uint8_t *sub_rows;      /* COLUMN_SUBSTR: per-row [start_pos][length] behind the meta */
+  int sub_pos_byte, sub_len_byte, sub_same_pos, sub_fix_len;
+  uint32_t sub_start, sub_length;
 } col_dec;
 
 /* Strings that HEX_PACKING / STRING_DIFF / STRING_PREFIX rebuild do not exist in the block: the reference decodes them into memory
@@ -722,6 +729,32 @@ static int col_dec_init(const ora_block *b, int32_t col, col_dec *c) {
       c->mat_common = c->mat_index + (int64_t)(c->mat_count > 0 ? c->mat_count - 1 : 0) * c->mat_index_byte;
       break;
     }
+    case T_COLUMN_EQUAL:     /* ObColumnEqualMetaHeader {version u8, ref_col_idx u16} (ob_column_equal_encoder.h:25-39) */
+    case T_COLUMN_SUBSTR: {  /* ObInterColSubStrMetaHeader {version, attr, start_pos u16, length u16, ref_col_idx u16} (ob_inter_column_substring_encoder.h:26-60) */
+      const int hdr = c->h.type == T_COLUMN_EQUAL ? 3 : 8;
+      if ((int64_t)c->h.length < hdr || c->meta[0] != 0) return ORA_ERR_UNEXPECTED;
+      if (c->h.type == T_COLUMN_SUBSTR && c->sc != 5) return ORA_ERR_UNEXPECTED;
+      const int32_t ref = rd16(c->meta + (c->h.type == T_COLUMN_EQUAL ? 1 : 6));
+      col_hdr rh;
+      if (ref == col || get_col(b, ref, &rh) || rh.type == T_COLUMN_EQUAL || rh.type == T_COLUMN_SUBSTR || rh.obj_type != c->h.obj_type)
+        return ORA_ERR_UNEXPECTED;   /* the referenced column is an ordinary column of the same type */
+      col_dec *rc = (col_dec *)arena_alloc(sizeof(col_dec));
+      if (!rc) return ORA_ERR_UNEXPECTED;
+      memset(rc, 0, sizeof(*rc));
+      ret = col_dec_init(b, ref, rc);
+      if (ret) return ret;
+      c->span_ref = rc;
+      c->span_exc = (int64_t)c->h.length > hdr ? c->meta + hdr : 0;   /* has_exc (ob_column_equal_decoder.h:60-61) */
+      c->span_exc_len = (int64_t)c->h.length - hdr;
+      if (c->h.type == T_COLUMN_SUBSTR) {
+        const uint8_t attr = c->meta[1];
+        c->sub_pos_byte = attr & 3; c->sub_len_byte = (attr >> 2) & 3;
+        c->sub_same_pos = (attr >> 4) & 1; c->sub_fix_len = (attr >> 5) & 1;
+        c->sub_start = rd16(c->meta + 2); c->sub_length = rd16(c->meta + 4);
+        c->sub_rows = c->meta + c->h.length;
+      }
+      break;
+    }
     case T_CS_INTEGER:
     case T_CS_STRING:
     case T_CS_INT_DICT:
@@ -797,6 +830,58 @@ static int64_t dict_row_ref(const ora_block *b, const col_dec *c, int64_t row) {
 static uint64_t fixed_ext(const ora_block *b, const col_dec *c, const uint8_t *col_data, int64_t row) {
   if (!(c->h.attr & A_EXT)) return EXT_NOT;
   return ora_bs_get(col_data, row * b->extend_value_bit, b->extend_value_bit);
+}
+
+/* BitSet::get_ref (ob_encoding_bitset.h:68-71, count_before :131-149): -1 when bit `pos` of the 64-bit words is clear, else the
+ * number of set bits below it */
+int64_t ora_bitset_get_ref(const void *words, int64_t pos) {
+  const uint8_t *buf = (const uint8_t *)words;
+  if (!((rd64(buf + pos / 64 * 8) >> (pos % 64)) & 1)) return -1;
+  int64_t r = 0;
+  for (int64_t w = 0; w < pos / 64; ++w) r += __builtin_popcountll(rd64(buf + w * 8));
+  return r + __builtin_popcountll(rd64(buf + pos / 64 * 8) & ((1ull << (pos % 64)) - 1));
+}
+
+/* Exception rows of a span column: ObBitMapMetaReader<StoreClass>::read / read_exc_cell (encoding/ob_encoding_bitset.h:574-760).
+ *   ObBitMapMetaHeader {ext_offset u8, index_offset u8, data_offset u8, {bit_packing_len | fix_data_cnt | index_byte} u8}, then the
+ *   BitSet over the block's rows (64-bit words); *ref = -1 when `row` is no exception, else its rank among the exception rows
+ *   (BitSet::get_ref, :68-71) and *out = its value. `len` = bytes of the whole exception meta. */
+static int bitmap_meta_read(const uint8_t *buf, int bit_packing, int64_t row, int64_t len, int sc, uint8_t obj_type, int64_t *ref,
+                            ora_datum *out) {
+  if (len <= 4) return ORA_INVALID_ARGUMENT;
+  const uint8_t ext_offset = buf[0], index_offset = buf[1], data_offset = buf[2], u = buf[3];
+  buf += 4;
+  const int64_t r = ora_bitset_get_ref(buf, row);
+  *ref = r;
+  if (r < 0) return ORA_SUCCESS;
+  uint64_t ext = EXT_NOT;
+  if (index_offset > ext_offset) ext = ora_bs_get(buf + ext_offset, r * 2, 2);   /* has_ext_val */
+  if (ext != EXT_NOT) { set_null(out); if (ext == EXT_NOPE) out->is_null = 2; return ORA_SUCCESS; }
+  const int64_t data_len = len - 4 - data_offset;
+  const uint8_t *data = buf + data_offset;
+  if (sc != 5) {
+    if (bit_packing) {   /* MEMCPY(datum.ptr_, &v, datum_len): no sign extension, a bit-packed image never has its top bit set */
+      set_int(obj_type, ora_bs_get(data, r * u, u), out);
+    } else {
+      if (u == 0) return ORA_ERR_UNEXPECTED;
+      const int64_t cell_len = data_len / u;   /* get_fix_data_size: fix_data_cnt_ = number of exceptions */
+      if (cell_len < 0 || cell_len > 8) return ORA_ERR_UNEXPECTED;
+      load_int(obj_type, data + r * cell_len, cell_len, out);
+    }
+    return ORA_SUCCESS;
+  }
+  int64_t offset = 0, cell_len = 0;
+  if (data_offset == index_offset) {   /* !is_var_exc */
+    if (u == 0) return ORA_ERR_UNEXPECTED;
+    cell_len = data_len / u;
+    offset = r * cell_len;
+  } else {
+    const int64_t exc_cnt = (data_offset - index_offset) / u + 1;   /* get_var_cnt */
+    if (r != 0) offset = (int64_t)rd_len(buf + index_offset + (r - 1) * u, u);
+    cell_len = (r == exc_cnt - 1 ? data_len : (int64_t)rd_len(buf + index_offset + r * u, u)) - offset;
+  }
+  out->ptr = data + offset; out->len = (uint32_t)cell_len; out->is_null = 0; out->ival = 0;
+  return ORA_SUCCESS;
 }
 
 /* One cell: ObRawDecoder::decode (ob_raw_decoder.cpp:243-326), ObDictDecoder::decode (:214-241),
@@ -895,6 +980,28 @@ static int decode_cell(const ora_block *b, const col_dec *c, int64_t row, ora_da
         }
       }
       out->ptr = buf; out->len = (uint32_t)len; out->is_null = 0; out->ival = 0;
+      return ORA_SUCCESS;
+    }
+    case T_COLUMN_EQUAL:
+    case T_COLUMN_SUBSTR: {
+      /* ObColumnEqualDecoder::decode (ob_column_equal_decoder.cpp:32-133), ObInterColSubStrDecoder::decode
+       * (ob_inter_column_substring_decoder.cpp:32-93): an exception row reads its value from the exception meta, every other
+       * row from the referenced column (whole value / the bytes [start_pos, start_pos + length) of it) */
+      int64_t ref = -1;
+      if (c->span_exc) {
+        const int ret = bitmap_meta_read(c->span_exc, (c->h.attr & A_BITPACK) != 0, row, c->span_exc_len,
+                                         c->h.type == T_COLUMN_SUBSTR ? 5 : c->sc, c->h.obj_type, &ref, out);
+        if (ret) return ret;
+      }
+      if (ref != -1) return ORA_SUCCESS;
+      const int ret = decode_cell(b, c->span_ref, row, out);
+      if (ret || c->h.type == T_COLUMN_EQUAL || out->is_null) return ret;
+      const uint8_t *cell = c->sub_rows + row * (int64_t)(c->sub_pos_byte + c->sub_len_byte);
+      const int64_t start = c->sub_same_pos ? c->sub_start : (int64_t)rd_len(cell, c->sub_pos_byte);
+      const int64_t len = c->sub_fix_len ? c->sub_length : (int64_t)rd_len(cell + c->sub_pos_byte, c->sub_len_byte);
+      if (start + len > out->len) return ORA_ERR_UNEXPECTED;
+      out->ptr = (const uint8_t *)out->ptr + start;
+      out->len = (uint32_t)len;
       return ORA_SUCCESS;
     }
     case T_DICT:

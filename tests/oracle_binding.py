@@ -112,6 +112,8 @@ def oracle():
         for f in ("ora_int_array_lower_bound", "ora_int_array_upper_bound"):
             getattr(L, f).restype = i64
             getattr(L, f).argtypes = [vp, i64, i64, i64, i64]
+        L.ora_bitset_get_ref.restype = i64
+        L.ora_bitset_get_ref.argtypes = [vp, i64]
         L.ora_arena_reset.restype = None
         L.ora_arena_reset.argtypes = []
         L.ora_dict_count.argtypes = [P(OraBlock), i32, P(i64)]
