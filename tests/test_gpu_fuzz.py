@@ -99,6 +99,26 @@ def random_case(ob, seed):
                 rng.choice([ob.ENC_RAW, ob.ENC_DICT, ob.ENC_RLE, ob.ENC_CONST, ob.ENC_INTEGER_BASE_DIFF])
         cols.append(ob.Column(t, int(enc), v, nulls=nulls))
         meta.append((t, is_str, v, nulls))
+    # a span column next to some PAX tables: an integer COLUMN_EQUAL over one of the integer columns, a few exception rows (values,
+    # NULL <-> value flips). Its own generator, so the tables of the seeds above stay what they were.
+    srng = np.random.default_rng(770000 + seed)
+    ints = [j for j, m in enumerate(meta) if not m[1]]
+    if not cs and ints and srng.integers(0, 3) == 0:
+        j = int(srng.choice(ints))
+        t, _, v, nulls = meta[j]
+        v2 = np.array(v, dtype=np.int64).copy()
+        n2 = np.zeros(n, dtype=np.uint8) if nulls is None else nulls.copy()
+        ex = srng.choice(n, size=max(1, n // 150), replace=False)
+        v2[ex] = random_int_values(srng, len(ex), t, ob)
+        flip = ex[:len(ex) // 3]
+        n2[flip] ^= 1
+        n2 = n2 if n2.any() else None
+        try:   # the span encoder's own limits (exceptions per block, the BitSet's uint8 offsets) decide whether the column exists
+            ob.encode_table([ob.Column(t, ob.ENC_RAW, v, nulls=nulls), ob.Column(t, ob.ENC_COLUMN_EQUAL, v2, nulls=n2, ref_col=0)], rpb)
+            cols.append(ob.Column(t, ob.ENC_COLUMN_EQUAL, v2, nulls=n2, ref_col=j))
+            meta.append((t, False, v2, n2))
+        except ob.ObGpuError:
+            pass
     return rng, cs, n, rpb, cols, meta
 
 
