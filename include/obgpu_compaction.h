@@ -166,6 +166,53 @@ int obgpu_merge_runs_streamed(int device, int32_t n_streams, const obgpu_stream_
                               const int64_t *default_vals, const uint8_t *default_null, int32_t n_ranges, obgpu_merge_sink sink,
                               void *sink_arg, int32_t *ranges_done);
 
+/* =============================================================================================
+ * Phase B of the compaction: the merged rows leave the device as SSTable bytes, not as rows.
+ *   blocksstable/encoding/ob_micro_block_encoder.cpp:561-721   ObMicroBlockEncoder::build_block (PAX layout)
+ *   blocksstable/encoding/ob_raw_encoder.cpp:95-155            ObRawEncoder::traverse (width: bit / byte packing, ext bits)
+ *   blocksstable/encoding/ob_encoding_util.cpp:37-73           get_packing_size
+ *   blocksstable/ob_micro_block_header.cpp:193-233             header checksum; payload checksum = ob_crc64_sse42 (crc32c)
+ *   blocksstable/ob_micro_block_checksum_helper.cpp:127-257    cal_column_checksum: per column, the wrapping int64 sum
+ *                                                              over the rows of ObDatum::checksum(0) (share/datum/ob_datum.h:849)
+ *   column_store/ob_co_merge_writer.cpp:67-117                 ObWriteHelper::project / append: one merged stream replayed into
+ *                                                              the writer of every column group
+ * Integer-class columns (device arrays of 8-byte value images + optional NULL bytes, 1 => NULL), every column RAW
+ * (ObRawEncoder): consecutive blocks of rows_per_block rows, block i at offsets[i] (aligned to `align`, a power of two
+ * >= 16, padding zeroed) -- byte for byte what obgpu_writer_encode_table (include/obgpu_writer.h) produces for the same
+ * rows with OBGPU_ENC_RAW forced on every column. A block in which a column would be stored as var-length cells (NULLs
+ * dominate, ob_raw_encoder.cpp:106-110) is left to the host writer: its size reads 0.
+ * ============================================================================================= */
+typedef struct obgpu_encode_col {
+  const int64_t *dev_vals;   /* [total_rows] value image of the datum (low type_store_size bytes are stored) */
+  const uint8_t *dev_null;   /* [total_rows] 1 => NULL; NULL pointer: no NULL cell                           */
+  int32_t obj_type;          /* OBGPU_OBJ_* (integer classes)                                                */
+  int32_t byte_packing_only; /* 1 => ObMicroBlockEncoderOpt.enable_bit_packing_ == false                     */
+} obgpu_encode_col;
+typedef struct obgpu_encoded obgpu_encoded;
+int obgpu_encode_columns(obgpu_ctx *ctx, const obgpu_encode_col *cols, int32_t n_cols, int32_t rowkey_col_cnt,
+                         int64_t total_rows, int64_t rows_per_block, int32_t align, obgpu_encoded **out);
+/* The same over a merge result: result_cols[i] = -1 the rowkey, -2, -3 ...: the following rowkey columns, >= 0 a payload
+ * column (a column group of a column-oriented merge is one call with the group's columns: ObWriteHelper::project). */
+int obgpu_merge_result_encode(obgpu_merge_result *res, const int32_t *result_cols, const int32_t *obj_types, int32_t n_cols,
+                              int32_t rowkey_col_cnt, int64_t rows_per_block, int32_t align, obgpu_encoded **out);
+typedef struct obgpu_encoded_info {
+  int64_t image_size;    /* bytes of the image (aligned block slots)          */
+  int64_t total_rows;
+  int32_t n_blocks;
+  int32_t n_host_blocks; /* blocks left to the host writer (size 0)           */
+} obgpu_encoded_info;
+int obgpu_encoded_get_info(obgpu_encoded *enc, obgpu_encoded_info *info);
+/* Image + per block offset / size to host memory; any of the three may be NULL. */
+int obgpu_encoded_fetch(obgpu_encoded *enc, void *host_image, int64_t image_cap, int64_t *host_offsets, int64_t *host_sizes,
+                        int32_t blocks_cap);
+/* The device image itself (valid until obgpu_encoded_free), e.g. to re-open it as a page batch without a host round trip. */
+int obgpu_encoded_device_image(obgpu_encoded *enc, const void **dev_image, const int64_t **dev_offsets, const uint32_t **dev_sizes);
+/* Column checksums (K16) of the encoded rows, n_cols values in host memory. */
+int obgpu_encoded_column_checksums(obgpu_encoded *enc, int64_t *host_checksums);
+void obgpu_encoded_free(obgpu_encoded *enc);
+/* Column checksums of plain device columns (no encode). */
+int obgpu_column_checksums(obgpu_ctx *ctx, const obgpu_encode_col *cols, int32_t n_cols, int64_t total_rows, int64_t *host_checksums);
+
 #ifdef __cplusplus
 }
 #endif

@@ -114,6 +114,14 @@ class MergeRun(C.Structure):
                 ("ext", C.POINTER(C.c_void_p)), ("more_keys", C.POINTER(C.c_void_p)), ("n_more_keys", C.c_int32)]
 
 
+class EncodeCol(C.Structure):
+    _fields_ = [("dev_vals", C.c_void_p), ("dev_null", C.c_void_p), ("obj_type", C.c_int32), ("byte_packing_only", C.c_int32)]
+
+
+class EncodedInfo(C.Structure):
+    _fields_ = [("image_size", C.c_int64), ("total_rows", C.c_int64), ("n_blocks", C.c_int32), ("n_host_blocks", C.c_int32)]
+
+
 class MergeInfo(C.Structure):
     _fields_ = [("in_rows", C.c_int64), ("out_rows", C.c_int64), ("dropped_deletes", C.c_int64),
                 ("fused_rows", C.c_int64)]
@@ -214,6 +222,14 @@ def declared_signatures():
         "obgpu_merge_result_info": (C.c_int, [vp, P(MergeInfo)]),
         "obgpu_merge_result_cols": (C.c_int, [vp, P(vp), P(P(vp)), P(P(vp))]),
         "obgpu_merge_result_fetch": (C.c_int, [vp, i32, i64, i64, vp, vp]),
+        "obgpu_encode_columns": (C.c_int, [vp, P(EncodeCol), i32, i32, i64, i64, i32, P(vp)]),
+        "obgpu_merge_result_encode": (C.c_int, [vp, vp, vp, i32, i32, i64, i32, P(vp)]),
+        "obgpu_encoded_get_info": (C.c_int, [vp, P(EncodedInfo)]),
+        "obgpu_encoded_fetch": (C.c_int, [vp, vp, i64, vp, vp, i32]),
+        "obgpu_encoded_device_image": (C.c_int, [vp, P(vp), P(vp), P(vp)]),
+        "obgpu_encoded_column_checksums": (C.c_int, [vp, vp]),
+        "obgpu_encoded_free": (None, [vp]),
+        "obgpu_column_checksums": (C.c_int, [vp, P(EncodeCol), i32, i64, vp]),
         # include/obgpu_skip_index.h
         "obgpu_batch_set_agg_rows": (C.c_int, [vp, vp, vp]),
         "obgpu_batch_skip_index_filter": (C.c_int, [vp, P(Filter), vp]),

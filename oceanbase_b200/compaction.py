@@ -284,6 +284,104 @@ def write_merged_sstable(res: MergeResult, rows_per_block: int = 1400, payload_e
     return encode_table(cols, rows_per_block, rowkey_cnt=1, n_threads=n_threads)
 
 
+# ---- phase B on the device: merged columns -> SSTable bytes + column checksums -------------------------------------------
+class Encoded:
+    """Device-encoded micro-blocks (obgpu_encoded): PAX blocks, every column RAW, byte for byte what the host writer
+    produces (ObMicroBlockEncoder::build_block with ObRawEncoder on every column)."""
+
+    def __init__(self, ctx, handle, n_cols, keep=None):
+        self.ctx, self._h, self.n_cols, self._keep = ctx, handle, n_cols, keep
+
+    def info(self) -> capi.EncodedInfo:
+        info = capi.EncodedInfo()
+        check(lib.obgpu_encoded_get_info(self._h, C.byref(info)), "obgpu_encoded_get_info", self.ctx._h)
+        return info
+
+    def fetch(self):
+        """(image uint8, offsets int64, sizes int64); a size of 0 marks a block left to the host writer."""
+        info = self.info()
+        img = np.zeros(max(info.image_size, 1), dtype=np.uint8)
+        off = np.zeros(info.n_blocks, dtype=np.int64)
+        sz = np.zeros(info.n_blocks, dtype=np.int64)
+        check(lib.obgpu_encoded_fetch(self._h, img.ctypes.data, img.size, off.ctypes.data, sz.ctypes.data, info.n_blocks),
+              "obgpu_encoded_fetch", self.ctx._h)
+        return img[:info.image_size], off, sz
+
+    def device_image(self):
+        """(device pointer of the image, of the int64 offsets, of the uint32 sizes) -- valid until free()."""
+        a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        check(lib.obgpu_encoded_device_image(self._h, C.byref(a), C.byref(b), C.byref(c)), "obgpu_encoded_device_image", self.ctx._h)
+        return a.value, b.value, c.value
+
+    def column_checksums(self) -> np.ndarray:
+        out = np.zeros(self.n_cols, dtype=np.int64)
+        check(lib.obgpu_encoded_column_checksums(self._h, out.ctypes.data), "obgpu_encoded_column_checksums", self.ctx._h)
+        return out
+
+    def free(self):
+        if self._h and self.ctx._h:
+            lib.obgpu_encoded_free(self._h)
+        self._h = C.c_void_p()
+        self._keep = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def _encode_cols(cols):
+    arr = (capi.EncodeCol * len(cols))()
+    for i, (vals_ptr, null_ptr, obj_type, byte_only) in enumerate(cols):
+        arr[i].dev_vals = vals_ptr
+        arr[i].dev_null = null_ptr
+        arr[i].obj_type = obj_type
+        arr[i].byte_packing_only = 1 if byte_only else 0
+    return arr
+
+
+def encode_columns(ctx, cols, total_rows: int, rows_per_block: int, rowkey_cnt: int = 0, align: int = 128, keep=None) -> Encoded:
+    """cols: (device pointer of the int64 value images, device pointer of the NULL bytes or None, OBJ_* type, byte_packing_only)."""
+    h = C.c_void_p()
+    arr = _encode_cols(cols)
+    check(lib.obgpu_encode_columns(ctx._h, arr, len(cols), rowkey_cnt, total_rows, rows_per_block, align, C.byref(h)),
+          "obgpu_encode_columns", ctx._h)
+    return Encoded(ctx, h, len(cols), keep)
+
+
+def column_checksums(ctx, cols, total_rows: int) -> np.ndarray:
+    out = np.zeros(len(cols), dtype=np.int64)
+    arr = _encode_cols(cols)
+    check(lib.obgpu_column_checksums(ctx._h, arr, len(cols), total_rows, out.ctypes.data), "obgpu_column_checksums", ctx._h)
+    return out
+
+
+def encode_merge_result(res: MergeResult, result_cols: Sequence[int], obj_types: Sequence[int], rows_per_block: int,
+                        rowkey_cnt: int = 1, align: int = 128) -> Encoded:
+    """One column group of the merged stream (-1: the rowkey, -2 ...: further rowkey columns, >= 0 payload columns)."""
+    rc = np.ascontiguousarray(result_cols, dtype=np.int32)
+    ot = np.ascontiguousarray(obj_types, dtype=np.int32)
+    h = C.c_void_p()
+    check(lib.obgpu_merge_result_encode(res._h, rc.ctypes.data, ot.ctypes.data, len(rc), rowkey_cnt, rows_per_block, align,
+                                        C.byref(h)), "obgpu_merge_result_encode", res.ctx._h)
+    return Encoded(res.ctx, h, len(rc), res)
+
+
+def co_merge_write(res: MergeResult, column_groups: Sequence[Sequence[int]], obj_types: Dict[int, int], rows_per_block: int,
+                   align: int = 128) -> List[Encoded]:
+    """Column-oriented merge, writer side (ObCOMergeLogReplayer::replay_merge_log -> ObCOMergeWriter -> ObWriteHelper::project /
+    append, column_store/ob_column_oriented_merger.cpp:722-745, ob_co_merge_writer.cpp:67-117): the merged stream is produced
+    ONCE and replayed into the writer of every column group; here every group is one obgpu_merge_result_encode over the columns
+    the group projects. A group that holds the rowkey (-1 first) is written with rowkey_cnt 1, a pure column group with 0."""
+    out = []
+    for cg in column_groups:
+        cg = list(cg)
+        rk = 1 if cg and cg[0] == -1 else 0
+        out.append(encode_merge_result(res, cg, [obj_types[c] for c in cg], rows_per_block, rowkey_cnt=rk, align=align))
+    return out
+
+
 # ---- multi-GPU: range partition + one exchange step ----------------------------------------------------
 # ---- runs larger than device memory: range by range, copies of the next range under the merge of this one ---------------------
 def streamed_major_merge(tables: Sequence[object], end_keys: Sequence[np.ndarray], key_col: int,

@@ -3630,6 +3630,7 @@ int obgpu_project_datums(obgpu_batch *batch, int32_t block, int32_t col, const i
 #include "merge_kernels.cuh"
 #include "merge_exchange.cuh"
 #include "merge_streamed.cuh"
+#include "encode_kernels.cuh"   // phase B: merged columns -> SSTable bytes + column checksums
 
 // ---- host-buffer scan pipeline (include/obgpu_pipeline.h) ------------------------------------------------
 #include "host_pipeline.h"

@@ -232,6 +232,23 @@ static void fmt_i32(int32_t v, int16_t *cs) { for (int i = 0; i < 2; i++) *cs = 
 
 uint64_t ora_crc64_sse42(uint64_t crc, const void *p, int64_t len) { return crc64_sse42(crc, (const uint8_t *)p, len); }
 
+/* Column checksum of a run of integer-class cells: ObMicroBlockChecksumHelper::cal_column_checksum
+ * (blocksstable/ob_micro_block_checksum_helper.cpp:127-146; the portable loop cal_column_checksum_normal and the sse4.2
+ * loop :149-257 add the same value per cell) = wrapping int64 sum over the rows of ObDatum::checksum(0)
+ * (share/datum/ob_datum.h:849-856): crc of the 4 pack_ bytes {len_:29, flag_:2, null_:1} (ob_datum.h:142-158), then of the
+ * len_ value bytes; a NULL datum has len_ 0 and null_ 1. */
+int64_t ora_column_checksum(const int64_t *vals, const uint8_t *nulls, int64_t n, int32_t datum_len) {
+  int64_t sum = 0;
+  for (int64_t r = 0; r < n; r++) {
+    const int is_null = nulls && nulls[r] != 0;
+    const uint32_t pack = is_null ? 0x80000000u : (uint32_t)datum_len;
+    uint64_t c = crc64_sse42(0, (const uint8_t *)&pack, 4);
+    if (!is_null && datum_len > 0) c = crc64_sse42(c, (const uint8_t *)&vals[r], datum_len);
+    sum = (int64_t)((uint64_t)sum + c);
+  }
+  return sum;
+}
+
 /* check_header_checksum / check_payload_checksum (ob_micro_block_header.cpp:236-285) */
 int ora_block_verify_checksums(const ora_block *b) {
   const uint8_t *p = b->buf;

@@ -109,6 +109,8 @@ def oracle():
         L.ora_decode_cell.argtypes = [P(OraBlock), i32, i64, P(OraDatum)]
         L.ora_crc64_sse42.restype = u64
         L.ora_crc64_sse42.argtypes = [u64, vp, i64]
+        L.ora_column_checksum.restype = i64
+        L.ora_column_checksum.argtypes = [vp, vp, i64, i32]
         for f in ("ora_int_array_lower_bound", "ora_int_array_upper_bound"):
             getattr(L, f).restype = i64
             getattr(L, f).argtypes = [vp, i64, i64, i64, i64]
