@@ -17,7 +17,7 @@
 
 namespace enc {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 128;
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxCols = 64;
 constexpr uint32_t kCrcPoly = 0x82f63b78u;   // CRC-32C (Castagnoli), reflected
@@ -103,19 +103,22 @@ __global__ void __launch_bounds__(kThreads) obgpu_encode_blocks_kernel(const __g
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   if (tid == 0) s_blk = atomicAdd(p.ticket, 1);
-  {   // crc tables (slicing by 4): tab[k * 256 + i] = crc of byte i followed by k zero bytes
-    uint32_t c = (uint32_t)tid;
+  // zero image (cells are OR-ed in; padding up to the aligned slot must be zero): before anything else, under the ticket's round trip
+  for (uint32_t i = (uint32_t)tid; i < p.slot_cap / 16u; i += kThreads) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+  // crc tables (slicing by 4): tab[k * 256 + i] = crc of byte i followed by k zero bytes
+  for (int i = tid; i < 256; i += kThreads) {
+    uint32_t c = (uint32_t)i;
 #pragma unroll
     for (int k = 0; k < 8; ++k) c = (c & 1u) ? kCrcPoly ^ (c >> 1) : c >> 1;
-    tab[tid] = c;
+    tab[i] = c;
   }
   __syncthreads();
-  {
-    uint32_t c = tab[tid];
+  for (int i = tid; i < 256; i += kThreads) {
+    uint32_t c = tab[i];
 #pragma unroll
     for (int k = 1; k < 4; ++k) {
       c = (c >> 8) ^ tab[c & 0xffu];
-      tab[k * 256 + tid] = c;
+      tab[k * 256 + i] = c;
     }
   }
   const int blk = s_blk;
@@ -124,98 +127,139 @@ __global__ void __launch_bounds__(kThreads) obgpu_encode_blocks_kernel(const __g
   const int nc = p.n_cols;
   __syncthreads();
 
-  // ---- stats (+ column checksums) --------------------------------------------------------------------------------------
-  for (int c = 0; c < nc; ++c) {
-    const ColSpec &cs = p.col[c];
-    const int64_t *v = cs.vals + row0;
-    const uint8_t *nl = cs.nulls ? cs.nulls + row0 : nullptr;
-    unsigned long long mx = 0, sum = 0;
-    uint32_t nn = 0;
-    uint32_t len_crc = 0, null_crc = 0;
-    if (CKSUM) {   // crc32c of the 4 pack_ bytes: {len_:29, flag_:2, null_:1}
-      len_crc = crc_word(tab, 0u, (uint32_t)cs.datum_len);
-      null_crc = crc_word(tab, 0u, 0x80000000u);
+  // ---- stats (+ column checksums): four columns at a time, their loads in flight together ---------------------------------
+  for (int c0 = 0; c0 < nc; c0 += 4) {
+    unsigned long long mx[4] = {0, 0, 0, 0}, sum[4] = {0, 0, 0, 0};
+    uint32_t nn[4] = {0, 0, 0, 0};
+    // ObDatum::checksum(0) starts with the crc32c of the 4 pack_ bytes {len_:29, flag_:2, null_:1}: two values per column
+    uint32_t len_crc[4] = {0, 0, 0, 0};
+    const uint32_t null_crc = CKSUM ? crc_word(tab, 0u, 0x80000000u) : 0u;
+    if (CKSUM) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) len_crc[j] = crc_word(tab, 0u, (uint32_t)p.col[min(c0 + j, nc - 1)].datum_len);
     }
     for (uint32_t r = (uint32_t)tid; r < nrows; r += kThreads) {
-      const bool is_null = nl && nl[r] != 0;
-      const unsigned long long x = (unsigned long long)v[r];
-      if (is_null) ++nn;
-      else mx = max(mx, x & cs.store_mask);
-      if (CKSUM) {
-        uint32_t crc = null_crc;
-        if (!is_null) {
-          crc = len_crc;
-          if (cs.datum_len == 8) {
-            crc = crc_word(tab, crc, (uint32_t)x);
-            crc = crc_word(tab, crc, (uint32_t)(x >> 32));
-          } else if (cs.datum_len == 4) {
-            crc = crc_word(tab, crc, (uint32_t)x);
-          } else {
-            for (uint32_t k = 0; k < cs.datum_len; ++k) crc = crc_byte(tab, crc, (uint32_t)(x >> (8u * k)) & 0xffu);
+      unsigned long long x[4];
+      uint32_t nlb[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = min(c0 + j, nc - 1);   // the tail repeats the last column (its results are dropped below)
+        x[j] = (unsigned long long)p.col[c].vals[row0 + r];
+        nlb[j] = p.col[c].nulls ? p.col[c].nulls[row0 + r] : 0u;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const ColSpec &cs = p.col[min(c0 + j, nc - 1)];
+        const bool is_null = nlb[j] != 0;
+        if (is_null) ++nn[j];
+        else mx[j] = max(mx[j], x[j] & cs.store_mask);
+        if (CKSUM) {   // ... then the crc of the value bytes
+          uint32_t crc = is_null ? null_crc : len_crc[j];
+          if (!is_null) {
+            if (cs.datum_len == 8) {
+              crc = crc_word(tab, crc, (uint32_t)x[j]);
+              crc = crc_word(tab, crc, (uint32_t)(x[j] >> 32));
+            } else if (cs.datum_len == 4) {
+              crc = crc_word(tab, crc, (uint32_t)x[j]);
+            } else {
+              for (uint32_t k = 0; k < cs.datum_len; ++k) crc = crc_byte(tab, crc, (uint32_t)(x[j] >> (8u * k)) & 0xffu);
+            }
           }
+          sum[j] += crc;
         }
-        sum += crc;
       }
     }
+    // warp reductions through redux.sync (one instruction per 32-bit value): 64-bit max as (high word, then the low words of
+    // the lanes that hold it); the checksum sum (< 2^32 * rows per lane) as 16-bit digits that cannot overflow 32 bits
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-      nn += __shfl_xor_sync(0xffffffffu, nn, o);
-      if (CKSUM) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    }
-    if (lane == 0) {
-      s_wmax[warp * nc + c] = mx;
-      s_wnull[warp * nc + c] = nn;
-      if (CKSUM && sum != 0) atomicAdd(p.checksums + c, sum);
+    for (int j = 0; j < 4; ++j) {
+      if (c0 + j >= nc) break;
+      const uint32_t hi = (uint32_t)(mx[j] >> 32), hmax = __reduce_max_sync(0xffffffffu, hi);
+      const uint32_t lmax = __reduce_max_sync(0xffffffffu, hi == hmax ? (uint32_t)mx[j] : 0u);
+      const uint32_t nsum = __reduce_add_sync(0xffffffffu, nn[j]);
+      unsigned long long tot = 0;
+      if (CKSUM) {
+#pragma unroll
+        for (int d = 0; d < 4; ++d) tot += (unsigned long long)__reduce_add_sync(0xffffffffu, (uint32_t)(sum[j] >> (16 * d)) & 0xffffu) << (16 * d);
+      }
+      if (lane == 0) {
+        s_wmax[warp * nc + c0 + j] = ((unsigned long long)hmax << 32) | lmax;
+        s_wnull[warp * nc + c0 + j] = nsum;
+        if (CKSUM && tot != 0) atomicAdd(p.checksums + c0 + j, tot);
+      }
     }
   }
   __syncthreads();
 
-  // ---- plan ------------------------------------------------------------------------------------------------------------
-  if (tid == 0) {
-    uint32_t ext_bit = 0;
-    for (int c = 0; c < nc; ++c) {
-      uint32_t nn = 0;
-      for (int w = 0; w < kWarps; ++w) nn += s_wnull[w * nc + c];
-      s_wnull[c] = nn;
-      if (nn) ext_bit = 1;   // ob_micro_block_encoder.cpp:507-517 (a major merge has no NOP cell left: never 2 bits)
-    }
+  // ---- plan: warp 0, one lane per column (two rounds for more than 32 columns) -------------------------------------------
+  if (warp == 0) {
     uint32_t at = kHeaderSize + 16u * (uint32_t)nc;
     unsigned long long original = 0;
     bool host = false;
-    for (int c = 0; c < nc; ++c) {
-      unsigned long long mx = 0;
-      for (int w = 0; w < kWarps; ++w) mx = max(mx, s_wmax[w * nc + c]);
-      const uint32_t nn = s_wnull[c];
-      bool bp;
-      const uint32_t size = packing_size(mx, p.col[c].byte_only == 0, bp);
-      // ObRawEncoder::traverse (ob_raw_encoder.cpp:106-110,150-155): NULLs dominate -> var-stored column
-      if (bp ? (unsigned long long)size * nn > (unsigned long long)nrows * 16ull : (unsigned long long)size * nn > (unsigned long long)nrows * 2ull) host = true;
-      ColLayout l;
-      l.has_null = nn != 0;
-      l.bp = bp;
-      l.size = (uint8_t)size;
-      l.attr = (uint8_t)(0x1u /*FIX_LENGTH*/ | (nn ? 0x2u /*HAS_EXTEND_VALUE*/ : 0u) | (bp ? 0x4u /*BIT_PACKING*/ : 0u));
-      l.store_off = at;
-      const unsigned long long bits = (nn ? (unsigned long long)ext_bit * nrows : 0ull) + (bp ? (unsigned long long)size * nrows : 0ull);
-      l.bits_size = (uint32_t)((bits + 7ull) / 8ull);
-      at += l.bits_size + (bp ? 0u : size * nrows);
-      s_lay[c] = l;
-      original += (unsigned long long)(nrows - nn) * p.col[c].datum_len;
+    // ext bits: 1 as soon as any column has a NULL (ob_micro_block_encoder.cpp:507-517; a major merge leaves no NOP cell)
+    bool any_null = false;
+    for (int c = lane; c < nc; c += 32) {
+      uint32_t n = 0;
+      for (int w = 0; w < kWarps; ++w) n += s_wnull[w * nc + c];
+      any_null = any_null || n != 0;
     }
-    s_size = host ? 0u : at;
-    s_original = (uint32_t)min(original, 0x7fffffffull);
-    s_ext_bit = ext_bit;
-    s_host = host;
-    // ---- output offset: decoupled look-back over the aligned sizes. The size is known here, long before the block is
-    // packed, so every CTA publishes early and the wait on its predecessors hides behind its own pack.
-    // flag word: bits 63..62 state (1 aggregate, 2 inclusive prefix), low 62 bits bytes
-    const unsigned long long slot0 = host ? 0ull : (unsigned long long)((at + p.align - 1u) & ~(p.align - 1u));
+    const uint32_t ext_bit = __any_sync(0xffffffffu, any_null) ? 1u : 0u;
+    for (int cb = 0; cb < nc; cb += 32) {
+      const int c = cb + lane;
+      uint32_t bytes = 0, nn = 0;
+      ColLayout l{};
+      bool var = false;
+      if (c < nc) {
+        unsigned long long mx = 0;
+        for (int w = 0; w < kWarps; ++w) { mx = max(mx, s_wmax[w * nc + c]); nn += s_wnull[w * nc + c]; }
+        bool bp;
+        const uint32_t size = packing_size(mx, p.col[c].byte_only == 0, bp);
+        // ObRawEncoder::traverse (ob_raw_encoder.cpp:106-110,150-155): NULLs dominate -> var-stored column
+        var = bp ? (unsigned long long)size * nn > (unsigned long long)nrows * 16ull : (unsigned long long)size * nn > (unsigned long long)nrows * 2ull;
+        l.has_null = nn != 0;
+        l.bp = bp;
+        l.size = (uint8_t)size;
+        l.attr = (uint8_t)(0x1u /*FIX_LENGTH*/ | (nn ? 0x2u /*HAS_EXTEND_VALUE*/ : 0u) | (bp ? 0x4u /*BIT_PACKING*/ : 0u));
+        const unsigned long long bits = (nn ? (unsigned long long)ext_bit * nrows : 0ull) + (bp ? (unsigned long long)size * nrows : 0ull);
+        l.bits_size = (uint32_t)((bits + 7ull) / 8ull);
+        bytes = l.bits_size + (bp ? 0u : size * nrows);
+      }
+      uint32_t incl = bytes;   // column stores back to back: exclusive prefix over the columns
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += u;
+      }
+      if (c < nc) {
+        l.store_off = at + incl - bytes;
+        s_lay[c] = l;
+      }
+      at += __shfl_sync(0xffffffffu, incl, 31);
+      host = host || __any_sync(0xffffffffu, var);
+      const uint32_t cells = c < nc ? (nrows - nn) * p.col[c].datum_len : 0u;
+      original += __reduce_add_sync(0xffffffffu, cells);
+    }
+    if (lane == 0) {
+      s_size = host ? 0u : at;
+      s_original = (uint32_t)min(original, 0x7fffffffull);
+      s_ext_bit = ext_bit;
+      s_host = host;
+      // publish the aligned size at once: the look-backs of the following blocks can pass over this one without waiting
+      if (blk > 0) {
+        volatile unsigned long long *flags = p.flags;
+        flags[blk] = (1ull << 62) | (host ? 0ull : (unsigned long long)((at + p.align - 1u) & ~(p.align - 1u)));
+      }
+    }
+  }
+  __syncthreads();
+  const uint32_t size = s_size;
+  const uint32_t slot = (size + p.align - 1u) & ~(p.align - 1u);
+  if (tid == 0) {
+    // ---- output offset: decoupled look-back over the aligned sizes (flag word: bits 63..62 state -- 1 aggregate, 2 inclusive
+    // prefix --, low 62 bits bytes). Tickets are handed out in scheduling order, so every predecessor is running or done.
     volatile unsigned long long *flags = p.flags;
     unsigned long long excl = 0;
     if (blk > 0) {
-      flags[blk] = (1ull << 62) | slot0;
-      __threadfence();
       int j = blk - 1;
       for (;;) {
         unsigned long long f;
@@ -225,22 +269,17 @@ __global__ void __launch_bounds__(kThreads) obgpu_encode_blocks_kernel(const __g
         --j;
       }
     }
-    flags[blk] = (2ull << 62) | (excl + slot0);
+    flags[blk] = (2ull << 62) | (excl + slot);
     s_off = (long long)excl;
     p.blk_off[blk] = (int64_t)excl;
-    p.blk_size[blk] = host ? 0u : at;
-    if (blk == p.n_blocks - 1) p.totals[0] = excl + slot0;
-    if (host) atomicAdd(p.totals + 1, 1ull);
+    p.blk_size[blk] = size;
+    if (blk == p.n_blocks - 1) p.totals[0] = excl + slot;
+    if (s_host) atomicAdd(p.totals + 1, 1ull);
   }
-  __syncthreads();
-  const uint32_t size = s_size;
-  const uint32_t slot = (size + p.align - 1u) & ~(p.align - 1u);
 
   if (size != 0) {
     // ---- pack ------------------------------------------------------------------------------------------------------------
-    for (uint32_t i = (uint32_t)tid; i < slot / 16u; i += kThreads) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
-    __syncthreads();
-    const uint32_t ext_bit = s_ext_bit;
+    const uint32_t ext_bit = s_ext_bit;   // (the image was zeroed at the start of the kernel)
     if (tid < nc) {   // ObColumnHeader: version_, type_ (RAW = 0), attr_, obj_type_, extend_value_index_, offset_ (from the meta start), length_
       const ColLayout l = s_lay[tid];
       uint32_t *h = img32 + (kHeaderSize + 16u * (uint32_t)tid) / 4u;
@@ -256,7 +295,6 @@ __global__ void __launch_bounds__(kThreads) obgpu_encode_blocks_kernel(const __g
       const uint8_t *nl = (cs.nulls && l.has_null) ? cs.nulls + row0 : nullptr;
       const uint32_t bit0 = l.store_off * 8u;                                    // block bit address of the bit area
       const uint32_t val0 = bit0 + (l.has_null ? ext_bit * nrows : 0u);         // bit-packed values follow the ext bits
-      uint8_t *fix = smem + l.store_off + l.bits_size;
       for (uint32_t r = (uint32_t)tid; r < nrows; r += kThreads) {
         if (nl && nl[r] != 0) {
           const uint32_t b = bit0 + r * ext_bit;   // STORED_NULL = 1
@@ -264,17 +302,14 @@ __global__ void __launch_bounds__(kThreads) obgpu_encode_blocks_kernel(const __g
           continue;
         }
         const unsigned long long x = (unsigned long long)v[r] & cs.store_mask;
-        if (l.bp) {
-          const uint32_t w = l.size, b = val0 + r * w, sh = b & 31u;
-          const unsigned long long xm = w >= 64u ? x : (x & ((1ull << w) - 1ull));
-          uint32_t *q = img32 + (b >> 5);
-          atomicOr(q, (uint32_t)(xm << sh));
-          if (sh + w > 32u) atomicOr(q + 1, (uint32_t)(xm >> (32u - sh)));
-          if (sh + w > 64u) atomicOr(q + 2, (uint32_t)(xm >> (64u - sh)));
-        } else {
-          uint8_t *q = fix + (size_t)r * l.size;
-          for (uint32_t k = 0; k < l.size; ++k) q[k] = (uint8_t)(x >> (8u * k));
-        }
+        // bit-packed cells: size bits each behind the ext bits; byte-packed cells: 8 * size bits each behind the bit area
+        const uint32_t w = l.bp ? l.size : 8u * l.size;
+        const uint32_t b = (l.bp ? val0 : (l.store_off + l.bits_size) * 8u) + r * w, sh = b & 31u;
+        const unsigned long long xm = w >= 64u ? x : (x & ((1ull << w) - 1ull));
+        uint32_t *q = img32 + (b >> 5);
+        atomicOr(q, (uint32_t)(xm << sh));
+        if (sh + w > 32u) atomicOr(q + 1, (uint32_t)(xm >> (32u - sh)));
+        if (sh + w > 64u) atomicOr(q + 2, (uint32_t)(xm >> (64u - sh)));
       }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // pack writes -> visible to the bulk copy issued by thread 0
@@ -283,12 +318,12 @@ __global__ void __launch_bounds__(kThreads) obgpu_encode_blocks_kernel(const __g
     const uint32_t len = size - kHeaderSize, W = len >> 2;
     uint32_t lw = (W + kThreads - 1u) / kThreads;
     lw |= 1u;   // odd word stride between the threads' chunks: bank-conflict free
-    const int64_t padw = (int64_t)kThreads * lw - (int64_t)W;
+    const int padw = (int)(kThreads * lw) - (int)W;   // leading zero words of the conceptual message
     const uint32_t *pay = img32 + kHeaderSize / 4u;
     uint32_t crc = 0;
-    for (uint32_t k = 0; k < lw; ++k) {
-      const int64_t w = (int64_t)tid * lw + k - padw;
-      if (w >= 0) crc = crc_word(tab, crc, pay[w]);
+    {
+      const int w0 = tid * (int)lw - padw;
+      for (int w = max(w0, 0); w < w0 + (int)lw; ++w) crc = crc_word(tab, crc, pay[w]);
     }
     if (crc != 0) crc = gf2_mulmod(crc, p.xpow32[(uint32_t)(kThreads - 1 - tid) * lw]);
 #pragma unroll
@@ -343,7 +378,8 @@ __global__ void __launch_bounds__(kThreads) obgpu_encode_blocks_kernel(const __g
 }
 
 // Column checksums alone (ObMicroBlockChecksumHelper::cal_column_checksum over plain columns).
-__global__ void __launch_bounds__(kThreads) obgpu_column_checksum_kernel(const __grid_constant__ Params p) {
+constexpr int kCkThreads = 256;
+__global__ void __launch_bounds__(kCkThreads) obgpu_column_checksum_kernel(const __grid_constant__ Params p) {
   __shared__ uint32_t tab[1024];
   const int tid = threadIdx.x, lane = tid & 31;
   {
@@ -362,12 +398,12 @@ __global__ void __launch_bounds__(kThreads) obgpu_column_checksum_kernel(const _
     }
   }
   __syncthreads();
-  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  const int64_t stride = (int64_t)gridDim.x * kCkThreads;
   for (int c = 0; c < p.n_cols; ++c) {
     const ColSpec &cs = p.col[c];
     const uint32_t len_crc = crc_word(tab, 0u, (uint32_t)cs.datum_len), null_crc = crc_word(tab, 0u, 0x80000000u);
     unsigned long long sum = 0;
-    for (int64_t r = (int64_t)blockIdx.x * kThreads + tid; r < p.total_rows; r += stride) {
+    for (int64_t r = (int64_t)blockIdx.x * kCkThreads + tid; r < p.total_rows; r += stride) {
       uint32_t crc = null_crc;
       if (!(cs.nulls && cs.nulls[r] != 0)) {
         const unsigned long long x = (unsigned long long)cs.vals[r];
@@ -584,9 +620,9 @@ int obgpu_column_checksums(obgpu_ctx *ctx, const obgpu_encode_col *cols, int32_t
   cudaMemsetAsync(d, 0, (size_t)n_cols * 8, ctx->stream);
   p.total_rows = total_rows;
   p.checksums = d;
-  const int64_t want = (total_rows + enc::kThreads * 8 - 1) / (enc::kThreads * 8);
+  const int64_t want = (total_rows + enc::kCkThreads * 8 - 1) / (enc::kCkThreads * 8);
   const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)ctx->sm_count * 8));
-  enc::obgpu_column_checksum_kernel<<<grid, enc::kThreads, 0, ctx->stream>>>(p);
+  enc::obgpu_column_checksum_kernel<<<grid, enc::kCkThreads, 0, ctx->stream>>>(p);
   ctx->launches++;
   cudaError_t err = cudaMemcpyAsync(host_checksums, d, (size_t)n_cols * 8, cudaMemcpyDeviceToHost, ctx->stream);
   if (err == cudaSuccess) err = cudaStreamSynchronize(ctx->stream);

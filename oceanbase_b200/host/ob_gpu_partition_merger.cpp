@@ -111,5 +111,82 @@ int ObGpuPartitionMajorMerger::get_next_rows(int64_t max_rows, ObGpuMergedRows &
   return ret;
 }
 
+int ObGpuPartitionMajorMerger::write_column_groups(const std::vector<ObGpuColumnGroup> &groups, int64_t rows_per_block, int32_t align,
+                                                   std::vector<ObGpuEncodedColumnGroup> &out) {
+  int ret = OB_SUCCESS;
+  if (!merged_) {
+    ret = OB_NOT_INIT;
+  } else if (groups.empty() || rows_per_block <= 0 || info_.out_rows <= 0) {
+    ret = OB_INVALID_ARGUMENT;
+  }
+  out.clear();
+  out.resize(OB_SUCCESS == ret ? groups.size() : 0);
+  // every group is enqueued before the first one is fetched: the encodes run back to back on the ctx stream
+  std::vector<obgpu_encoded *> enc(groups.size(), nullptr);
+  for (size_t g = 0; OB_SUCCESS == ret && g < groups.size(); ++g) {
+    const ObGpuColumnGroup &cg = groups[g];
+    if (cg.cols_.empty() || cg.cols_.size() != cg.obj_types_.size()) ret = OB_INVALID_ARGUMENT;
+    else ret = obgpu_merge_result_encode(result_, cg.cols_.data(), cg.obj_types_.data(), (int32_t)cg.cols_.size(), cg.rowkey_col_cnt_,
+                                         rows_per_block, align, &enc[g]);
+  }
+  for (size_t g = 0; OB_SUCCESS == ret && g < groups.size(); ++g) {
+    const ObGpuColumnGroup &cg = groups[g];
+    ObGpuEncodedColumnGroup &o = out[g];
+    obgpu_encoded_info info{};
+    ret = obgpu_encoded_get_info(enc[g], &info);
+    if (OB_SUCCESS != ret) break;
+    o.row_count_ = info.total_rows;
+    o.host_encoded_blocks_ = info.n_host_blocks;
+    o.offsets_.resize((size_t)info.n_blocks);
+    o.sizes_.resize((size_t)info.n_blocks);
+    o.image_.resize((size_t)info.image_size);
+    o.column_checksums_.resize(cg.cols_.size());
+    ret = obgpu_encoded_fetch(enc[g], o.image_.data(), info.image_size, o.offsets_.data(), o.sizes_.data(), info.n_blocks);
+    if (OB_SUCCESS == ret) ret = obgpu_encoded_column_checksums(enc[g], o.column_checksums_.data());
+    if (OB_SUCCESS == ret && info.n_host_blocks > 0) {
+      // the blocks the device left out (ObRawEncoder stores a NULL-dominated column as var-length cells): their rows come
+      // back as rows and go through the host writer; the image is laid out again with them in place
+      std::vector<uint8_t> image;
+      std::vector<int64_t> offsets((size_t)info.n_blocks);
+      std::vector<int64_t> vals;
+      std::vector<uint8_t> nulls;
+      for (int32_t b = 0; OB_SUCCESS == ret && b < info.n_blocks; ++b) {
+        const size_t at = image.size();
+        offsets[(size_t)b] = (int64_t)at;
+        if (o.sizes_[(size_t)b] != 0) {
+          image.insert(image.end(), o.image_.begin() + o.offsets_[(size_t)b], o.image_.begin() + o.offsets_[(size_t)b] + o.sizes_[(size_t)b]);
+        } else {
+          const int64_t row0 = (int64_t)b * rows_per_block, n = std::min(rows_per_block, info.total_rows - row0);
+          const size_t nc = cg.cols_.size();
+          vals.assign(nc * (size_t)n, 0);
+          nulls.assign(nc * (size_t)n, 0);
+          std::vector<obgpu_col_input> in(nc);
+          for (size_t c = 0; OB_SUCCESS == ret && c < nc; ++c) {
+            ret = obgpu_merge_result_fetch(result_, cg.cols_[c], row0, n, vals.data() + c * (size_t)n,
+                                           cg.cols_[c] >= 0 ? nulls.data() + c * (size_t)n : nullptr);
+            in[c] = obgpu_col_input{};
+            in[c].obj_type = cg.obj_types_[c];
+            in[c].encoding = OBGPU_ENC_RAW;
+            in[c].i64 = vals.data() + c * (size_t)n;
+            in[c].is_null = nulls.data() + c * (size_t)n;
+          }
+          if (OB_SUCCESS == ret) {
+            const int64_t bound = obgpu_writer_block_bound(in.data(), (int32_t)nc, 0, n);
+            image.resize(at + (size_t)bound);
+            int64_t sz = 0;
+            ret = obgpu_writer_encode_block(in.data(), (int32_t)nc, cg.rowkey_col_cnt_, 0, n, image.data() + at, bound, &sz);
+            if (OB_SUCCESS == ret) { image.resize(at + (size_t)sz); o.sizes_[(size_t)b] = sz; }
+          }
+        }
+        image.resize((image.size() + (size_t)align - 1) / (size_t)align * (size_t)align, 0);
+      }
+      if (OB_SUCCESS == ret) { o.image_.swap(image); o.offsets_.swap(offsets); }
+    }
+  }
+  for (obgpu_encoded *e : enc) obgpu_encoded_free(e);
+  if (OB_SUCCESS != ret) out.clear();
+  return ret;
+}
+
 }  // namespace compaction
 }  // namespace oceanbase

@@ -10,6 +10,7 @@
 
 extern "C" {
 #include "../../include/obgpu_compaction.h"
+#include "../../include/obgpu_writer.h"
 }
 #include "ob_gpu_micro_block_decoder.h"
 
@@ -49,6 +50,23 @@ struct ObGpuMergedRows {
   std::vector<std::vector<int64_t>> offsets_;
 };
 
+// One column group of a column-oriented merge (ObStorageColumnGroupSchema): which columns of the merged row it stores, in
+// row order of the group. -1 = the rowkey, -2, -3 ... = the following rowkey columns, >= 0 = payload column index.
+struct ObGpuColumnGroup {
+  std::vector<int32_t> cols_;
+  std::vector<int32_t> obj_types_;   // OBGPU_OBJ_* of every column (integer classes)
+  int32_t rowkey_col_cnt_ = 0;       // > 0 for the group that carries the rowkey (all-column / rowkey group)
+};
+
+// What the writer of one column group produced: the micro-blocks of its SSTable + the column checksums of its rows.
+struct ObGpuEncodedColumnGroup {
+  std::vector<uint8_t> image_;
+  std::vector<int64_t> offsets_, sizes_;
+  std::vector<int64_t> column_checksums_;
+  int64_t row_count_ = 0;
+  int32_t host_encoded_blocks_ = 0;  // blocks the device left to the host writer (a NULL-dominated column stored as var cells)
+};
+
 class ObGpuPartitionMajorMerger {
 public:
   ObGpuPartitionMajorMerger() = default;
@@ -66,6 +84,13 @@ public:
   int64_t get_fused_row_count() const { return info_.fused_rows; }
   // Next window of at most max_rows merged rows in rowkey order; OB_ITER_END after the last one.
   int get_next_rows(int64_t max_rows, ObGpuMergedRows &rows);
+  // Column-oriented merge, writer side (ObCOMergeLogReplayer::replay_merge_log -> ObCOMergeWriter::replay_mergelog ->
+  // ObWriteHelper::project / append, column_store/ob_column_oriented_merger.cpp:722-745, ob_co_merge_writer.cpp:67-117,345):
+  // the merged stream -- produced once by merge_partition -- is replayed into the writer of every column group. Here a
+  // writer is the device encoder (obgpu_merge_result_encode): the rows never leave the device as rows, each group comes back
+  // as reference-format micro-blocks (every column RAW) + its column checksums. rows_per_block cuts the blocks.
+  int write_column_groups(const std::vector<ObGpuColumnGroup> &groups, int64_t rows_per_block, int32_t align,
+                          std::vector<ObGpuEncodedColumnGroup> &out);
   void reset();
 
 private:

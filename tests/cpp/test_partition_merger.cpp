@@ -116,6 +116,50 @@ static void check_against_oracle(std::vector<Run> &runs, const std::vector<int64
   }
   ASSERT_EQ(ret, OB_ITER_END);
   ASSERT_EQ(at, orows);
+  // ---- column-oriented merge, writer side: the same merged stream replayed into three column groups on the device
+  // (ObCOMergeLogReplayer / ObWriteHelper::project): every group's blocks must be the host writer's blocks over the ORACLE's
+  // merged rows, pass the oracle's checksum checks, and carry the oracle's column checksums
+  {
+    std::vector<ObGpuColumnGroup> groups(3);
+    groups[0].cols_ = {-1, 0, 1, 2}; groups[0].obj_types_.assign(4, OBGPU_OBJ_INT); groups[0].rowkey_col_cnt_ = 1;   // all-column group
+    groups[1].cols_ = {1}; groups[1].obj_types_ = {OBGPU_OBJ_INT};
+    groups[2].cols_ = {2, 0}; groups[2].obj_types_.assign(2, OBGPU_OBJ_INT);
+    std::vector<ObGpuEncodedColumnGroup> enc;
+    const int64_t rpb = 700;
+    ASSERT_EQ(merger.write_column_groups(groups, rpb, 128, enc), OB_SUCCESS);
+    ASSERT_EQ((long long)enc.size(), 3);
+    for (size_t g = 0; g < enc.size() && g_fail < 10; ++g) {
+      const ObGpuColumnGroup &cg = groups[g];
+      std::vector<obgpu_col_input> in(cg.cols_.size());
+      for (size_t c = 0; c < cg.cols_.size(); ++c) {
+        memset(&in[c], 0, sizeof(in[c]));
+        in[c].obj_type = OBGPU_OBJ_INT; in[c].encoding = OBGPU_ENC_RAW;
+        in[c].i64 = cg.cols_[c] < 0 ? okey.data() : ov[(size_t)cg.cols_[c]].data();
+        in[c].is_null = cg.cols_[c] < 0 ? nullptr : on[(size_t)cg.cols_[c]].data();
+        const int64_t want = ora_column_checksum(in[c].i64, in[c].is_null, orows, 8);
+        ASSERT_EQ(enc[g].column_checksums_[c], want);
+      }
+      obgpu_table_image *img = nullptr;
+      ASSERT_EQ(obgpu_writer_encode_table(in.data(), (int32_t)in.size(), cg.rowkey_col_cnt_, orows, rpb, 128, 2, &img), 0);
+      int64_t size = 0; int32_t nb = 0;
+      obgpu_table_image_info(img, &size, &nb);
+      std::vector<uint8_t> want((size_t)size);
+      std::vector<int64_t> woff((size_t)nb), wsz((size_t)nb);
+      obgpu_table_image_export(img, want.data(), size, woff.data(), wsz.data(), nb);
+      obgpu_table_image_free(img);
+      ASSERT_EQ(enc[g].row_count_, orows);
+      ASSERT_EQ((long long)enc[g].offsets_.size(), nb);
+      ASSERT_EQ((long long)enc[g].image_.size(), size);
+      if (enc[g].image_.size() == want.size()) ASSERT_EQ(memcmp(enc[g].image_.data(), want.data(), want.size()), 0);
+      for (int32_t b = 0; b < nb && g_fail < 10; ++b) {
+        ASSERT_EQ(enc[g].offsets_[(size_t)b], woff[(size_t)b]);
+        ASSERT_EQ(enc[g].sizes_[(size_t)b], wsz[(size_t)b]);
+        ora_block blk;
+        ASSERT_EQ(ora_block_init(&blk, enc[g].image_.data() + enc[g].offsets_[(size_t)b], enc[g].sizes_[(size_t)b]), 0);
+        ASSERT_EQ(ora_block_verify_checksums(&blk), 0);
+      }
+    }
+  }
 }
 
 int main() {
@@ -158,6 +202,29 @@ int main() {
     }
     check_against_oracle(runs, {}, {});
     check_against_oracle(runs, {11, 22, 33}, {0, 1, 0});
+  }
+  // ---- two runs whose second payload column is NULL in 60 % of the rows with 60-bit values: ObRawEncoder stores such a
+  // column as var-length cells, the device leaves those blocks to the host writer (write_column_groups splices them in) ----
+  {
+    std::vector<Run> runs(2);
+    for (int r = 0; r < 2; ++r) {
+      Run &run = runs[r];
+      run.vals.assign(3, {}); run.ext.assign(3, {});
+      for (int64_t i = 0; i < 4000; ++i) {
+        const uint64_t h = mix((uint64_t)i * 131u + (uint64_t)r);
+        if (h % 3 == 0) continue;
+        run.key.push_back(500 + i * 2 + r);   // disjoint rowkeys: nothing fuses
+        run.flag.push_back(OBGPU_DF_INSERT);
+        for (int c = 0; c < 3; ++c) {
+          const uint64_t hv = mix(h + (uint64_t)c * 977u);
+          const uint8_t e = (c == 1 && hv % 100 < 60) ? 1 : 0;
+          run.vals[c].push_back(e ? 0 : (int64_t)(hv >> 4));
+          run.ext[c].push_back(e);
+        }
+      }
+      encode(run, 900);
+    }
+    check_against_oracle(runs, {}, {});
   }
   // ---- the reference's test_fuse_nomal as five single-row tables (rows listed newest first there) ----------
   {
