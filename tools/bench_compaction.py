@@ -39,7 +39,8 @@ def run(args):
         dist.barrier()
     import oceanbase_b200 as ob
     from oceanbase_b200.synth import make_config5_runs
-    from oceanbase_b200.compaction import decode_run, merge_decoded, distributed_major_merge, merge_decoded_distributed, Comm
+    from oceanbase_b200.compaction import decode_run, merge_decoded, distributed_major_merge, merge_decoded_distributed, Comm, encode_merge_result
+    from oceanbase_b200 import capi
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     stream = torch.cuda.Stream(device=dev)
@@ -74,8 +75,11 @@ def run(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    ENC_ROWS_PER_BLOCK = 500
+    phase_b = {}
+
     def step():
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         ev[0].record(stream)
         dec = {q: decode_run(ctx, runs[q]["table"], 0, 1, [2, 3, 4], device=dev, batch=batches[q], check_rowkey=False) for q in mine}
         ev[1].record(stream)
@@ -88,19 +92,29 @@ def run(args):
             recv_rows = None
         info = res.info()
         ev[2].record(stream)
+        # phase B: the merged rows leave the device as SSTable bytes (PAX blocks, every column RAW) + column checksums
+        enc = encode_merge_result(res, [-1, 0, 1, 2], [capi.OBJ_INT] * 4, ENC_ROWS_PER_BLOCK, rowkey_cnt=1) if info.out_rows else None
+        ev[3].record(stream)
         torch.cuda.synchronize()
-        return res, info, ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])
+        phase_b["image_bytes"] = enc.info().image_size if enc else 0
+        phase_b["n_blocks"] = enc.info().n_blocks if enc else 0
+        phase_b["host_blocks"] = enc.info().n_host_blocks if enc else 0
+        phase_b["checksums"] = [int(x) for x in enc.column_checksums()] if enc else [0] * 4
+        if enc:
+            enc.free()
+        return res, info, ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), ev[2].elapsed_time(ev[3])
 
     for _ in range(args.warmup):
-        r, _, _, _ = step()
+        r = step()[0]
         r.free()
     barrier()
     t0 = time.perf_counter()
-    dec_ms, mrg_ms = [], []
+    dec_ms, mrg_ms, enc_ms = [], [], []
     for _ in range(args.steps):
-        res, info, a, b = step()
+        res, info, a, b, c_ms = step()
         dec_ms.append(a)
         mrg_ms.append(b)
+        enc_ms.append(c_ms)
         if _ + 1 < args.steps:
             res.free()
     barrier()
@@ -109,13 +123,17 @@ def run(args):
     ksum = int(res.fetch(-1)[0].astype(np.uint64).sum()) if out_rows else 0
     vsum = [int(res.fetch(c)[0].astype(np.uint64).sum()) for c in range(3)]
     nsum = [int(res.fetch(c)[1].sum()) for c in range(3)]
-    t = torch.tensor([step_ms, float(np.mean(dec_ms)), float(np.mean(mrg_ms))], device=dev, dtype=torch.float64)
+    t = torch.tensor([step_ms, float(np.mean(dec_ms)), float(np.mean(mrg_ms)), float(np.mean(enc_ms))], device=dev, dtype=torch.float64)
+    pb = torch.tensor([phase_b["image_bytes"], phase_b["n_blocks"], phase_b["host_blocks"]] + [c % (1 << 56) for c in phase_b["checksums"]],
+                      device=dev, dtype=torch.int64)
     tot = torch.tensor([in_rows_local, out_rows, info.dropped_deletes, info.fused_rows, enc_bytes_local, ksum % (1 << 62)]
                        + [v % (1 << 62) for v in vsum] + nsum, device=dev, dtype=torch.int64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    step_ms, dec_mean, mrg_mean = t.tolist()
+        dist.all_reduce(pb, op=dist.ReduceOp.SUM)
+    step_ms, dec_mean, mrg_mean, enc_mean = t.tolist()
+    pb = pb.tolist()
     tot = tot.tolist()
     if rank == 0:
         line = {"metric": "major-compaction merged input rows/sec", "value": tot[0] / (step_ms * 1e-3), "unit": "rows/s",
@@ -130,6 +148,14 @@ def run(args):
                                           ("torch.distributed from Python" if world > 1 else "none (one rank)"),
                               "timing": "wall clock per step incl. host orchestration; phases by CUDA events, max over ranks"}}
         peak, peak_src = bench.measured_peak_gbs()
+        # phase B (device encoder): merged columns read once (8 B x 4 columns + 3 NULL bytes per row), image written once
+        enc_alg = 35 * tot[1] + pb[0]
+        line["phase_b"] = {"what": f"merged rows -> PAX micro-blocks of {ENC_ROWS_PER_BLOCK} rows (rowkey + 3 payload columns, every column RAW) "
+                                   "+ column checksums, on the device (obgpu_merge_result_encode); inside ms_per_step",
+                           "encode_ms": enc_mean, "image_bytes": pb[0], "n_blocks": pb[1], "host_encoded_blocks": pb[2],
+                           "alg_gbps_per_gpu": enc_alg / (enc_mean * 1e-3) / 1e9 / world if enc_mean > 0 else None,
+                           "frac": enc_alg / (enc_mean * 1e-3) / 1e9 / world / peak if enc_mean > 0 else None,
+                           "d2h_bytes_as_blocks": pb[0], "d2h_bytes_as_rows": 35 * tot[1]}
         # bytes the merge has to move per step (SURVEY 8d style): encoded blocks read once, decoded cells (36 B / row: rowkey,
         # flag, 3 payload values + ext bytes) written by the decode and read by the merge, merged rows written (35 B / row)
         alg = tot[4] + 2 * 36 * tot[0] + 35 * tot[1]
@@ -143,6 +169,12 @@ def run(args):
             M = 1 << 62
             u = lambda a: int(a.astype(np.uint64).sum()) % M
             sums_ok = tot[5] % M == u(want["key"]) and all(tot[6 + c] % M == u(want["vals"][c]) for c in range(3))
+            o = ora.oracle()
+            M56 = 1 << 56   # column checksums add up over the ranks' ranges (wrapping int64 sums): compared modulo 2^56
+            want_ck = [o.ora_column_checksum(want["key"].ctypes.data, None, len(want["key"]), 8) % M56] + \
+                      [o.ora_column_checksum(np.ascontiguousarray(want["vals"][c]).ctypes.data, np.ascontiguousarray(want["null"][c]).ctypes.data,
+                                             len(want["key"]), 8) % M56 for c in range(3)]
+            line["phase_b"]["column_checksums_match"] = [c % M56 for c in pb[3:7]] == want_ck
             line["parity"] = {"rows_match": tot[1] == len(want["key"]), "dropped_match": tot[2] == want["dropped"],
                               "fused_match": tot[3] == want["fused"], "null_counts_match": tot[9:12] == [int(x.sum()) for x in want["null"]],
                               "value_checksums_match": sums_ok}
