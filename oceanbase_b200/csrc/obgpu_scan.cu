@@ -55,6 +55,16 @@ struct FilterNodeDev {
   uint64_t span;
 };
 
+// String-equality leaves (EQ / NE / IN): slot of a (length, first 8 bytes) pair in a 64-slot hash. When one of the multipliers
+// maps the leaf's constants to distinct slots (FilterNodeDev::pad = multiplier index + 1), the constants are stored in slot
+// order and FilterNodeDev::span is the occupancy mask: a dictionary entry finds the ONLY constant it can equal with one
+// popcount instead of walking the list.
+__host__ __device__ __forceinline__ uint32_t str_eq_slot(uint64_t pre, uint32_t len, int m) {
+  const uint64_t mult = 0xD6E8FEB86659FD93ull + 2ull * (uint64_t)m * 0x9E3779B97F4A7C15ull;   // odd
+  return (uint32_t)(((pre ^ ((uint64_t)len * 0x9E3779B97F4A7C15ull)) * mult) >> 58);
+}
+constexpr int kStrEqHashTries = 8;
+
 struct ParamDev {
   int64_t i64;
   uint32_t heap_off;
@@ -2498,6 +2508,23 @@ static int build_filter(obgpu_ctx *ctx, const obgpu_batch *b, const obgpu_filter
         }
         nd.lo = len_mask;
         nd.span = b0_mask;
+        // hash slots instead of the first-byte screen when the constants are distinct under one of the multipliers
+        for (int m = 0; m < kStrEqHashTries && kept >= 1 && kept <= 32 && nd.pad == 0; ++m) {
+          uint64_t occ = 0;
+          bool clash = false;
+          for (int k = 0; k < kept && !clash; ++k) {
+            const ParamDev &q = p.params[nd.param_begin + k];
+            const uint64_t bit = 1ull << str_eq_slot((uint64_t)q.i64, q.len, m);
+            clash = (occ & bit) != 0;
+            occ |= bit;
+          }
+          if (clash) continue;
+          std::sort(p.params + nd.param_begin, p.params + nd.param_begin + kept, [m](const ParamDev &x, const ParamDev &y) {
+            return str_eq_slot((uint64_t)x.i64, x.len, m) < str_eq_slot((uint64_t)y.i64, y.len, m);
+          });
+          nd.span = occ;
+          nd.pad = (int16_t)(m + 1);
+        }
       }
       // integer compares reduce to one unsigned range test on the compare image (cmp_image: the datum's low
       // bytes, sign-extended for signed classes)

@@ -119,6 +119,7 @@ __device__ __forceinline__ void lean_bitset_str_eq(const ScanParams &p, const Fi
                                                    uint32_t *bits, int lane) {
   const uint32_t n = d.dict_count, ib8 = d.dict_data_size * 8u, ibit = sbit + d.dict_payload * 8u, heap_len = d.dict_end - d.dict_var;
   const bool fixed = d.dict_fixed != 0, ne = nd.op == OP_NE;
+  const int hm = nd.pad;   // 0: first-byte screen + constant list; m + 1: hash slots under multiplier m
   for (uint32_t b0 = 0; b0 < n + 2u; b0 += 32u) {
     const uint32_t idx = b0 + (uint32_t)lane;
     bool r = false;
@@ -135,9 +136,17 @@ __device__ __forceinline__ void lean_bitset_str_eq(const ScanParams &p, const Fi
       }
       const uint32_t pl = len < 8u ? len : 8u;
       const uint64_t pre = pl ? sbits(sbit + cell * 8u, pl * 8u) : 0ull;
-      // screens built on the host: does any constant have this length / this first byte? (most entries stop here)
-      const bool cand = ((nd.lo >> (len & 63u)) & 1ull) && (len == 0u || ((nd.span >> (pre & 63ull)) & 1ull));
-      for (int k = 0; cand && k < nd.n_params && !r; ++k) {
+      // screens built on the host: does any constant have this length (most entries stop here), then either the hash slot of
+      // (length, first 8 bytes) -- it names the only constant the entry can equal -- or the first-byte screen + the list
+      const bool len_ok = (nd.lo >> (len & 63u)) & 1ull;
+      int k0 = 0, k1 = 0;
+      if (len_ok && hm) {
+        const uint32_t h = str_eq_slot(pre, len, hm - 1);
+        if ((nd.span >> h) & 1ull) { k0 = __popcll(nd.span & ((1ull << h) - 1ull)); k1 = k0 + 1; }
+      } else if (len_ok && (len == 0u || ((nd.span >> (pre & 63ull)) & 1ull))) {
+        k1 = nd.n_params;
+      }
+      for (int k = k0; k < k1 && !r; ++k) {
         const ParamDev &pp = p.params[nd.param_begin + k];
         if (pp.len != len || (uint64_t)pp.i64 != pre) continue;
         bool same = true;
@@ -203,8 +212,15 @@ __device__ __forceinline__ uint32_t lean_survivor_str(const ScanParams &p, const
         const uint32_t pl = len < 8u ? len : 8u;
         const uint64_t pre = pl ? sbits(sbit + cell * 8u, pl * 8u) : 0ull;
         bool hit = false;
-        const bool cand = ((nd.lo >> (len & 63u)) & 1ull) && (len == 0u || ((nd.span >> (pre & 63ull)) & 1ull));
-        for (int k = 0; cand && k < nd.n_params && !hit; ++k) {
+        const bool len_ok = (nd.lo >> (len & 63u)) & 1ull;
+        int k0 = 0, k1 = 0;
+        if (len_ok && nd.pad) {
+          const uint32_t h = str_eq_slot(pre, len, nd.pad - 1);
+          if ((nd.span >> h) & 1ull) { k0 = __popcll(nd.span & ((1ull << h) - 1ull)); k1 = k0 + 1; }
+        } else if (len_ok && (len == 0u || ((nd.span >> (pre & 63ull)) & 1ull))) {
+          k1 = nd.n_params;
+        }
+        for (int k = k0; k < k1 && !hit; ++k) {
           const ParamDev &pp = p.params[nd.param_begin + k];
           hit = pp.len == len && (uint64_t)pp.i64 == pre && (len <= 8u || str_cmp(s, cell, len, p.param_heap + pp.heap_off, pp.len) == 0);
         }
