@@ -94,6 +94,36 @@ int obgpu_writer_table_agg_rows(const obgpu_col_input *cols, int32_t n_cols, con
  * 8 XOR_FIXED_PFOR). The CS writer encodes its column streams with: mode 1 RAW (default); 0 the codec
  * ObIntegerStreamEncoder::choose_stream_codec would detect (smallest on a sample, cs_encoding/ob_integer_stream_encoder.h:
  * 195-400); 2..8 that codec wherever it is not larger than RAW. Process-wide setting. */
+/* =============================================================================================
+ * Macro blocks: encoded micro-blocks packed into fixed-size (2 MiB) macro blocks the way ObMacroBlock does
+ *   blocksstable/ob_macro_block.cpp:455-520   reserve_header / write_macro_header: [ObMacroBlockCommonHeader (24 B)]
+ *                                             [ObSSTableMacroBlockHeader: FixedHeader (128 B) + column types / orders /
+ *                                             checksums + is_normal_cg_] then the micro-blocks back to back
+ *   blocksstable/ob_macro_block.cpp:264-303   write_micro_block: micro header + data appended; row_count_, micro_block_count_,
+ *                                             micro_block_data_size_, occupy_size_ and the running data_checksum_ (crc of the
+ *                                             micro headers' data_checksum_ fields)
+ *   ob_macro_block_common_header.h:20-112, ob_sstable_macro_block_header.h:30-113
+ * The leaf index block and the macro meta block that follow the data in the reference (idx_block_*, meta_block_*) are not
+ * written (index rows are outside the path): their fields stay 0, which FixedHeader::is_valid() accepts. Every macro block
+ * occupies macro_block_size bytes of `out` (zero padded), like a block slot on disk.
+ * ============================================================================================= */
+typedef struct obgpu_macro_spec {
+  uint64_t tablet_id;           /* != 0 */
+  int64_t logical_version;
+  int64_t first_data_seq;       /* data_seq_ of macro block i = first_data_seq + i */
+  int32_t header_version;       /* 1: type / order arrays for every column, 2: for the rowkey columns only */
+  int32_t is_cg;                /* is_normal_cg_ */
+  int32_t rowkey_col_cnt;
+  int32_t n_cols;
+  const uint8_t *col_metas;     /* n_cols x 4 bytes (ObObjMeta: type_, cs_level_, cs_type_, scale_)              */
+  const int32_t *col_orders;    /* n_cols ObOrderType values (ASC 0, DESC -1); NULL: all ASC                      */
+  int64_t macro_block_size;     /* 2 MiB (OB_DEFAULT_MACRO_BLOCK_SIZE)                                            */
+} obgpu_macro_spec;
+/* first_micro (optional): n_macro + 1 entries, micro-blocks [first_micro[i], first_micro[i + 1]) live in macro block i. */
+int obgpu_writer_build_macro_blocks(const void *micro_image, const int64_t *offsets, const int64_t *sizes, int32_t n_blocks,
+                                    const obgpu_macro_spec *spec, void *out, int64_t out_cap, int64_t *out_size,
+                                    int32_t *n_macro, int32_t *first_micro, int32_t first_micro_cap);
+
 int obgpu_writer_set_cs_stream_encoding(int32_t mode);
 /* The codec bytes alone (no ObIntegerStreamMeta) for count values of width_bytes (low bytes of vals[i]); type 0 =
  * detect. out == NULL: only *out_len. Byte-exact with the reference encoders (ObCodec::encode). */

@@ -114,6 +114,12 @@ class MergeRun(C.Structure):
                 ("ext", C.POINTER(C.c_void_p)), ("more_keys", C.POINTER(C.c_void_p)), ("n_more_keys", C.c_int32)]
 
 
+class MacroSpec(C.Structure):
+    _fields_ = [("tablet_id", C.c_uint64), ("logical_version", C.c_int64), ("first_data_seq", C.c_int64), ("header_version", C.c_int32),
+                ("is_cg", C.c_int32), ("rowkey_col_cnt", C.c_int32), ("n_cols", C.c_int32), ("col_metas", C.c_void_p),
+                ("col_orders", C.c_void_p), ("macro_block_size", C.c_int64)]
+
+
 class EncodeCol(C.Structure):
     _fields_ = [("dev_vals", C.c_void_p), ("dev_null", C.c_void_p), ("obj_type", C.c_int32), ("byte_packing_only", C.c_int32)]
 
@@ -142,6 +148,7 @@ def writer_signatures():
         "obgpu_writer_block_agg_row": (C.c_int, [P(ColInput), i32, vp, i32, i64, i64, vp, i64, P(i64)]),
         "obgpu_writer_table_agg_rows": (C.c_int, [P(ColInput), i32, vp, i32, i64, i64, vp, i64, vp, P(i64)]),
         "obgpu_writer_set_cs_stream_encoding": (C.c_int, [i32]),
+        "obgpu_writer_build_macro_blocks": (C.c_int, [vp, vp, vp, i32, P(MacroSpec), vp, i64, P(i64), P(i32), vp, i32]),
         "obgpu_writer_stream_encode": (C.c_int, [i32, i32, vp, i64, vp, i64, P(i64)]),
     }
 

@@ -2083,6 +2083,127 @@ int obgpu_writer_table_agg_rows(const obgpu_col_input *cols, int32_t n_cols, con
 }
 
 
+// ---- macro blocks (ObMacroBlock: reserve_header / write_micro_block / write_macro_header, ob_macro_block.cpp:264-303,455-520) ----
+namespace {
+uint32_t crc32c_update(uint32_t c, const uint8_t *p, size_t len) {
+  static uint32_t tab[256];
+  static std::atomic<int> ready{0};
+  if (!ready.load(std::memory_order_acquire)) {
+    uint32_t t[256];
+    for (uint32_t n = 0; n < 256; ++n) {
+      uint32_t cc = n;
+      for (int k = 0; k < 8; ++k) cc = (cc & 1) ? 0x82f63b78u ^ (cc >> 1) : cc >> 1;
+      t[n] = cc;
+    }
+    memcpy(tab, t, sizeof(t));
+    ready.store(1, std::memory_order_release);
+  }
+  for (size_t k = 0; k < len; ++k) c = tab[(c ^ p[k]) & 0xff] ^ (c >> 8);
+  return c;
+}
+#pragma pack(push, 1)
+struct MacroCommonHeader {   // ObMacroBlockCommonHeader, ob_macro_block_common_header.h:100-106
+  int32_t header_size_, version_, magic_, attr_, payload_size_, payload_checksum_;
+};
+#pragma pack(pop)
+struct MacroFixedHeader {    // ObSSTableMacroBlockHeader::FixedHeader, ob_sstable_macro_block_header.h:48-71 (natural alignment: 128 bytes)
+  uint32_t header_size_;
+  uint16_t version_, magic_;
+  uint64_t tablet_id_;
+  int64_t logical_version_, data_seq_;
+  int32_t column_count_, rowkey_column_count_, row_store_type_, row_count_, occupy_size_, micro_block_count_,
+      micro_block_data_offset_, micro_block_data_size_, idx_block_offset_, idx_block_size_, meta_block_offset_, meta_block_size_;
+  int64_t data_checksum_, encrypt_id_, master_key_id_;
+  uint8_t compressor_type_;
+  char encrypt_key_[16];
+};
+static_assert(sizeof(MacroCommonHeader) == 24, "ObMacroBlockCommonHeader is 24 bytes");
+static_assert(sizeof(MacroFixedHeader) == 128, "FixedHeader is 128 bytes");
+}  // namespace
+
+int obgpu_writer_build_macro_blocks(const void *micro_image, const int64_t *offsets, const int64_t *sizes, int32_t n_blocks,
+                                    const obgpu_macro_spec *spec, void *out, int64_t out_cap, int64_t *out_size, int32_t *n_macro,
+                                    int32_t *first_micro, int32_t first_micro_cap) {
+  if (!micro_image || !offsets || !sizes || n_blocks <= 0 || !spec || !out || !out_size || !n_macro || spec->tablet_id == 0 ||
+      spec->n_cols <= 0 || spec->rowkey_col_cnt < 0 || spec->rowkey_col_cnt > spec->n_cols || !spec->col_metas ||
+      (spec->header_version != 1 && spec->header_version != 2) || spec->macro_block_size < 4096 || spec->macro_block_size > 0x7fffffffll)
+    return OBGPU_INVALID_ARGUMENT;
+  const int64_t n_type_cols = spec->header_version == 2 ? spec->rowkey_col_cnt : spec->n_cols;
+  // get_serialize_size: fixed header + ObObjMeta[] + ObOrderType[] + int64 checksum per column + is_normal_cg_
+  const int64_t mh_size = (int64_t)sizeof(MacroFixedHeader) + n_type_cols * 4 + n_type_cols * 4 + (int64_t)spec->n_cols * 8 + 1;
+  const int64_t data_base = (int64_t)sizeof(MacroCommonHeader) + mh_size;
+  const uint8_t *img = (const uint8_t *)micro_image;
+  uint8_t *o = (uint8_t *)out;
+  int64_t at = 0;
+  int32_t nm = 0, b = 0;
+  while (b < n_blocks) {
+    if (at + spec->macro_block_size > out_cap) return OBGPU_BUF_NOT_ENOUGH;
+    if (first_micro && nm < first_micro_cap) first_micro[nm] = b;
+    uint8_t *m = o + at;
+    memset(m, 0, (size_t)spec->macro_block_size);
+    MacroFixedHeader fh{};
+    fh.header_size_ = (uint32_t)mh_size;
+    fh.version_ = (uint16_t)spec->header_version;
+    fh.magic_ = 1007;   // SSTABLE_MACRO_BLOCK_HEADER_MAGIC
+    fh.tablet_id_ = spec->tablet_id;
+    fh.logical_version_ = spec->logical_version;
+    fh.data_seq_ = spec->first_data_seq + nm;
+    fh.column_count_ = spec->n_cols;
+    fh.rowkey_column_count_ = spec->rowkey_col_cnt;
+    fh.micro_block_data_offset_ = (int32_t)data_base;
+    fh.encrypt_id_ = 0;
+    fh.master_key_id_ = 0;   // the spec's store desc has no encryption (FixedHeader::reset leaves -1 only until init)
+    fh.compressor_type_ = 1;  // NONE_COMPRESSOR
+    int64_t len = data_base;
+    uint64_t data_ck = 0;
+    while (b < n_blocks) {
+      const int64_t sz = sizes[b];
+      if (sz < 64 || offsets[b] < 0) return OBGPU_INVALID_ARGUMENT;
+      if (data_base + sz > spec->macro_block_size) return OBGPU_NOT_SUPPORTED;   // a micro block larger than a macro block
+      if (len + sz > spec->macro_block_size) break;                              // check_micro_block: no room left
+      const uint8_t *mb = img + offsets[b];
+      memcpy(m + len, mb, (size_t)sz);
+      len += sz;
+      fh.micro_block_count_ += 1;
+      uint32_t rows;
+      memcpy(&rows, mb + 16, 4);
+      fh.row_count_ += (int32_t)rows;
+      fh.row_store_type_ = mb[20];
+      data_ck = crc32c_update((uint32_t)data_ck, mb + 48, 8);   // ob_crc64_sse42(data_checksum_, &header->data_checksum_, 8)
+      ++b;
+    }
+    fh.micro_block_data_size_ = (int32_t)(len - data_base);
+    fh.occupy_size_ = (int32_t)len;
+    fh.data_checksum_ = (int64_t)data_ck;
+    uint8_t *p = m + sizeof(MacroCommonHeader);
+    memcpy(p, &fh, sizeof(fh));
+    p += sizeof(fh);
+    memcpy(p, spec->col_metas, (size_t)n_type_cols * 4);
+    p += n_type_cols * 4;
+    for (int64_t i = 0; i < n_type_cols; ++i) {
+      const int32_t ord = spec->col_orders ? spec->col_orders[i] : 0;
+      memcpy(p + i * 4, &ord, 4);
+    }
+    p += n_type_cols * 4;
+    p += (int64_t)spec->n_cols * 8;   // column checksums: "for compatibility, fill 0" (ob_sstable_macro_block_header.cpp:347-350)
+    *p = spec->is_cg ? 1 : 0;
+    MacroCommonHeader ch{};
+    ch.header_size_ = (int32_t)sizeof(MacroCommonHeader);
+    ch.version_ = 1;
+    ch.magic_ = 1001;
+    ch.attr_ = 1;   // SSTableData
+    ch.payload_size_ = (int32_t)(len - (int64_t)sizeof(MacroCommonHeader));
+    ch.payload_checksum_ = (int32_t)crc32c_update(0, m + sizeof(MacroCommonHeader), (size_t)ch.payload_size_);   // (int32_t)ob_crc64(payload)
+    memcpy(m, &ch, sizeof(ch));
+    at += spec->macro_block_size;
+    ++nm;
+  }
+  if (first_micro && nm < first_micro_cap) first_micro[nm] = n_blocks;
+  *out_size = at;
+  *n_macro = nm;
+  return OBGPU_SUCCESS;
+}
+
 int obgpu_writer_set_cs_stream_encoding(int32_t mode) {
   if (mode < 0 || mode > 8 || mode == obstream::T_UNIVERSAL) return OBGPU_INVALID_ARGUMENT;
   g_cs_stream_mode.store(mode);

@@ -132,6 +132,41 @@ def encode_table(cols: List[Column], rows_per_block: int, rowkey_cnt=0, align=12
     return TableImage(image, offsets, sizes, total, len(cols))
 
 
+# ---- macro blocks (ObMacroBlock, blocksstable/ob_macro_block.cpp) ---------------------------------------------------------------
+@dataclass
+class MacroImage:
+    """Fixed-size macro blocks holding the micro-blocks of a TableImage back to back (no alignment inside a macro block)."""
+    image: np.ndarray          # uint8, n_macro * macro_block_size
+    macro_block_size: int
+    n_macro: int
+    first_micro: np.ndarray    # int32 [n_macro + 1]
+
+
+def build_macro_blocks(table: TableImage, col_types: Sequence[int], rowkey_cnt: int, tablet_id: int = 200001, logical_version: int = 1,
+                       first_data_seq: int = 0, header_version: int = 1, is_cg: bool = False, macro_block_size: int = 2 << 20,
+                       col_orders: Optional[Sequence[int]] = None) -> MacroImage:
+    """ObMacroBlock::write_micro_block / write_macro_header over the micro-blocks of `table`."""
+    n_cols = len(col_types)
+    metas = np.zeros((n_cols, 4), dtype=np.uint8)
+    metas[:, 0] = col_types
+    orders = np.ascontiguousarray(col_orders if col_orders is not None else [0] * n_cols, dtype=np.int32)
+    spec = capi.MacroSpec(tablet_id, logical_version, first_data_seq, header_version, 1 if is_cg else 0, rowkey_cnt, n_cols,
+                          metas.ctypes.data, orders.ctypes.data, macro_block_size)
+    img = np.ascontiguousarray(table.image)
+    off = np.ascontiguousarray(table.offsets, dtype=np.int64)
+    sz = np.ascontiguousarray(table.sizes, dtype=np.int64)
+    # every macro block holds at least one micro-block: n_blocks macro blocks is the upper bound
+    data_per_macro = macro_block_size - 24 - 128 - 16 * n_cols - 1
+    est = int(sz.sum() // max(data_per_macro - int(sz.max()), 1)) + 2
+    out = np.zeros(min(est, table.n_blocks) * macro_block_size, dtype=np.uint8)
+    first = np.zeros(table.n_blocks + 1, dtype=np.int32)
+    size, nm = C.c_int64(0), C.c_int32(0)
+    check(lib.obgpu_writer_build_macro_blocks(img.ctypes.data, off.ctypes.data, sz.ctypes.data, table.n_blocks, C.byref(spec),
+                                              out.ctypes.data, out.size, C.byref(size), C.byref(nm), first.ctypes.data, first.size),
+          "obgpu_writer_build_macro_blocks")
+    return MacroImage(out[:size.value], macro_block_size, nm.value, first[:nm.value + 1].copy())
+
+
 # ---- skip index: aggregate rows (include/obgpu_skip_index.h) -------------------------------------------------
 def agg_row_write(cells, version: int = 3) -> np.ndarray:
     """ObAggRowWriter: cells = [(col_idx, col_type, value)] with value None (not stored), bytes, or

@@ -249,6 +249,69 @@ int64_t ora_column_checksum(const int64_t *vals, const uint8_t *nulls, int64_t n
   return sum;
 }
 
+/* Macro block: [ObMacroBlockCommonHeader 24 B][ObSSTableMacroBlockHeader][micro blocks back to back] (ob_macro_block.cpp:455-520).
+ * ObMacroBlockCommonHeader::deserialize + check_integrity (ob_macro_block_common_header.cpp:54-69,118-143),
+ * ObSSTableMacroBlockHeader::deserialize + FixedHeader::is_valid (ob_sstable_macro_block_header.cpp:118-140,216-273).
+ * fields[] as the reference door lists them (oracle/ref_macro_wrap.cpp). The payload checksum ((int32_t)ob_crc64(payload) = crc32c)
+ * and the running data checksum over the micro headers (ob_macro_block.cpp:301-303) are verified when verify != 0. */
+int ora_macro_block_parse(const uint8_t *buf, int64_t len, int64_t *f, int32_t verify) {
+  if (!buf || len < 24 + 128 || !f) return ORA_INVALID_ARGUMENT;
+  for (int i = 0; i < 6; i++) f[i] = (int32_t)rd32(buf + 4 * i);
+  if (!(f[0] == 24 && f[1] == 1 && f[2] == 1001)) return ORA_INVALID_DATA;          /* is_integrity */
+  if (!(f[3] >= 0 && f[3] < 10)) return ORA_INVALID_DATA;                              /* is_valid: attr in [None, MaxMacroType) */
+  const uint8_t *h = buf + 24;
+  f[6] = rd32(h); f[7] = rd16(h + 4); f[8] = rd16(h + 6); f[9] = (int64_t)rd64(h + 8); f[10] = (int64_t)rd64(h + 16); f[11] = (int64_t)rd64(h + 24);
+  for (int i = 0; i < 12; i++) f[12 + i] = (int32_t)rd32(h + 32 + 4 * i);
+  f[24] = (int64_t)rd64(h + 80);
+  const int64_t encrypt_id = (int64_t)rd64(h + 88), master_key_id = (int64_t)rd64(h + 96);
+  f[25] = h[104];
+  const int64_t type_cols = f[7] == 2 ? f[13] : f[12];
+  const int64_t ck_off = 24 + 128 + type_cols * 8;
+  if (ck_off + f[12] * 8 + 1 > len) return ORA_INVALID_DATA;
+  f[27] = ck_off;
+  f[26] = buf[ck_off + f[12] * 8];
+  f[6] = 128 + type_cols * 8 + f[12] * 8 + 1;                                           /* header_size_ = get_serialize_size() */
+  if (!(f[7] >= 1 && f[7] <= 2 && f[8] == 1007 && f[9] != 0 && f[10] >= 0 && f[13] >= 0 && f[14] >= 0 && f[15] > 0 && f[16] > 0 &&
+        f[17] > 0 && f[18] > 0 && f[19] > 0 && f[24] >= 0 && encrypt_id >= 0 && master_key_id >= -1 && f[25] > 0))
+    return ORA_INVALID_DATA;
+  if (verify) {
+    if (24 + f[4] > len || f[4] < 0) return ORA_INVALID_DATA;
+    if ((int32_t)crc64_sse42(0, buf + 24, f[4]) != (int32_t)f[5]) return ORA_INVALID_DATA;
+  }
+  return ORA_SUCCESS;
+}
+
+/* The micro blocks of a macro block: micro_block_count_ headers walked from micro_block_data_offset_, each block
+ * header_size_ + data_zlength_ bytes long (ob_micro_block_header.h:95-153); the walk must end exactly at
+ * micro_block_data_offset_ + micro_block_data_size_. */
+int ora_macro_block_micro_blocks(const uint8_t *buf, int64_t len, int64_t *offs, int64_t *sizes, int32_t cap, int32_t *n_out, int32_t verify) {
+  int64_t f[28];
+  int ret = ora_macro_block_parse(buf, len, f, verify);
+  if (ret != ORA_SUCCESS) return ret;
+  if (f[17] > cap) return ORA_BUF_NOT_ENOUGH;
+  int64_t at = f[18];
+  const int64_t end = f[18] + f[19];
+  if (end > len) return ORA_INVALID_DATA;
+  uint64_t ck = 0;
+  int64_t rows = 0;
+  for (int64_t i = 0; i < f[17]; i++) {
+    if (at + 64 > end) return ORA_INVALID_DATA;
+    const uint8_t *m = buf + at;
+    if ((int16_t)rd16(m) != 1005) return ORA_INVALID_DATA;
+    const int64_t sz = (int64_t)rd32(m + 4) + (int32_t)rd32(m + 44);
+    if (sz < 64 || at + sz > end) return ORA_INVALID_DATA;
+    offs[i] = at;
+    sizes[i] = sz;
+    rows += rd32(m + 16);
+    ck = crc64_sse42(ck, m + 48, 8);
+    at += sz;
+  }
+  if (at != end || rows != f[15]) return ORA_INVALID_DATA;
+  if (verify && (int64_t)ck != f[24]) return ORA_INVALID_DATA;
+  *n_out = (int32_t)f[17];
+  return ORA_SUCCESS;
+}
+
 /* check_header_checksum / check_payload_checksum (ob_micro_block_header.cpp:236-285) */
 int ora_block_verify_checksums(const ora_block *b) {
   const uint8_t *p = b->buf;

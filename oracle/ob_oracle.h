@@ -102,6 +102,9 @@ int ora_block_verify_checksums(const ora_block *blk);
 /* building blocks pinned one by one to the compiled reference (tests/test_checksum_ref_kat.py): the payload checksum
  * (ob_crc64_sse42: crc32c, seed as given, no final xor) and the integer-array searches of the RLE / CONST / row-index lookups */
 uint64_t ora_crc64_sse42(uint64_t crc, const void *p, int64_t len);
+/* macro block headers (fields[28]: see oracle/ref_macro_wrap.cpp) and the walk over its micro blocks */
+int ora_macro_block_parse(const uint8_t *buf, int64_t len, int64_t *fields, int32_t verify);
+int ora_macro_block_micro_blocks(const uint8_t *buf, int64_t len, int64_t *offs, int64_t *sizes, int32_t cap, int32_t *n_out, int32_t verify);
 /* column checksum (K16) of n integer-class cells: sum over the rows of ObDatum::checksum(0) */
 int64_t ora_column_checksum(const int64_t *vals, const uint8_t *nulls, int64_t n, int32_t datum_len);
 /* BitSet::get_ref (encoding/ob_encoding_bitset.h:68-71): rank of bit `pos` among the set bits, -1 when clear */
