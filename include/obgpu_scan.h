@@ -143,6 +143,16 @@ void obgpu_batch_close(obgpu_batch *batch);
 int obgpu_batch_block_info(const obgpu_batch *batch, int32_t block, int64_t *row_count,
                            int32_t *column_count);
 int obgpu_batch_total_rows(const obgpu_batch *batch, int64_t *total_rows);
+/* Disk-format bytes into the block cache: n_macro_blocks macro blocks of macro_block_size bytes each (ObMacroBlock,
+ * blocksstable/ob_macro_block.cpp:455-520: ObMacroBlockCommonHeader, ObSSTableMacroBlockHeader, micro-blocks back to back) are
+ * validated and walked ON THE DEVICE (ObMacroBlockCommonHeader::check_integrity ob_macro_block_common_header.cpp:54-69,
+ * FixedHeader::is_valid ob_sstable_macro_block_header.cpp:118-140, the micro headers' header_size_ + data_zlength_ chain) and
+ * their micro-blocks re-laid into an aligned image that the returned page batch owns -- what ObMacroBlockReader /
+ * ObMicroBlockBareIterator (blocksstable/ob_micro_block_bare_iterator.cpp) do block by block on the CPU. The macro image may be
+ * host memory (copied once) or device memory. Compressed / encrypted macro blocks: OBGPU_NOT_SUPPORTED; broken headers or
+ * chains: OBGPU_INVALID_DATA. The payload checksum is not re-computed here (the IO layer's job in the reference). */
+int obgpu_batch_open_macro_blocks(obgpu_ctx *ctx, const void *macro_image, int64_t image_size, int64_t macro_block_size,
+                                  int32_t n_macro_blocks, int32_t image_on_device, obgpu_batch **out, int32_t *n_micro_out);
 
 /* =============================================================================================
  * Filter tree = sql::ObPushdownFilterExecutor tree flattened in post-order

@@ -229,6 +229,7 @@ def declared_signatures():
         "obgpu_merge_result_info": (C.c_int, [vp, P(MergeInfo)]),
         "obgpu_merge_result_cols": (C.c_int, [vp, P(vp), P(P(vp)), P(P(vp))]),
         "obgpu_merge_result_fetch": (C.c_int, [vp, i32, i64, i64, vp, vp]),
+        "obgpu_batch_open_macro_blocks": (C.c_int, [vp, vp, i64, i64, i32, i32, P(vp), P(i32)]),
         "obgpu_encode_columns": (C.c_int, [vp, P(EncodeCol), i32, i32, i64, i64, i32, P(vp)]),
         "obgpu_merge_result_encode": (C.c_int, [vp, vp, vp, i32, i32, i64, i32, P(vp)]),
         "obgpu_encoded_get_info": (C.c_int, [vp, P(EncodedInfo)]),

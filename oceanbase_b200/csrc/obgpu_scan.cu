@@ -3644,6 +3644,7 @@ int obgpu_project_datums(obgpu_batch *batch, int32_t block, int32_t col, const i
 }  // extern "C"
 
 // ---- ObCGBitmap: range bitmaps shared by the column groups of a table ----------------------------------------------------
+#include "macro_blocks.cuh"   // macro blocks (disk format) -> page batch, parsed and re-laid on the device
 #include "cg_bitmap.cuh"
 
 // ---- string cells as bytes (dense heap): scan results and the per-block entry ------------------------------------------

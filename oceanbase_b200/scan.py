@@ -174,6 +174,30 @@ class PageBatch:
         check(lib.obgpu_batch_total_rows(self._h, C.byref(tr)), "obgpu_batch_total_rows", ctx._h)
         self.total_rows = tr.value
 
+    @classmethod
+    def from_macro_blocks(cls, ctx: "ScanContext", macro_image, macro_block_size: int, n_macro: int, device_ptr: Optional[int] = None,
+                          table=None) -> "PageBatch":
+        """obgpu_batch_open_macro_blocks: disk-format macro blocks (sstable.build_macro_blocks) parsed and re-laid on the device.
+        macro_image: host uint8 array, or None with device_ptr naming a device-resident copy of n_macro * macro_block_size bytes."""
+        self = cls.__new__(cls)
+        self.ctx = ctx
+        self.table = table
+        self._h = C.c_void_p()
+        n_micro = C.c_int32(0)
+        size = n_macro * macro_block_size
+        if device_ptr is None:
+            img = np.ascontiguousarray(macro_image, dtype=np.uint8)
+            code = lib.obgpu_batch_open_macro_blocks(ctx._h, img.ctypes.data, size, macro_block_size, n_macro, 0, C.byref(self._h), C.byref(n_micro))
+        else:
+            code = lib.obgpu_batch_open_macro_blocks(ctx._h, C.c_void_p(device_ptr), size, macro_block_size, n_macro, 1, C.byref(self._h),
+                                                     C.byref(n_micro))
+        check(code, "obgpu_batch_open_macro_blocks", ctx._h)
+        self.n_blocks = n_micro.value
+        tr = C.c_int64(0)
+        check(lib.obgpu_batch_total_rows(self._h, C.byref(tr)), "obgpu_batch_total_rows", ctx._h)
+        self.total_rows = tr.value
+        return self
+
     def block_info(self, i):
         rc, cc = C.c_int64(0), C.c_int32(0)
         check(lib.obgpu_batch_block_info(self._h, i, C.byref(rc), C.byref(cc)), "obgpu_batch_block_info", self.ctx._h)
