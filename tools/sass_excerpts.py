@@ -7,12 +7,13 @@ so = os.path.join(ROOT, "oceanbase_b200", "csrc", "libobgpu_scan.so")
 lines = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout.split("\n")
 starts = [(i, l.split("Function : ")[1].strip()) for i, l in enumerate(lines) if "Function :" in l]
 want = ["obgpu_count_pipe_kernel", "obgpu_project_pipe_kernel", "obgpu_count_kernel", "obgpu_project_kernelILb0", "obgpu_index_kernel",
-        "pass_kernel", "kway_kernel", "fuse_kernel", "cs_decode_kernel"]
+        "pass_kernel", "kway_kernel", "fuse_kernel", "cs_decode_kernel", "obgpu_encode_blocks_kernel", "obgpu_macro_realign_kernel",
+        "obgpu_macro_walk_kernel"]
 out = ["cuobjdump -sass oceanbase_b200/csrc/libobgpu_scan.so (sm_100a).",
        "UBLKCP = cp.async.bulk (TMA bulk copy global->shared), SYNCS = mbarrier ops (arrive.expect_tx / try_wait), LDGSTS = cp.async (global->shared",
        "without registers), LDS/STS = shared loads/stores, SHF = funnel shift (the bit-granular load path), VOTE = ballot, LDL/STL = local memory.", ""]
 keys = ["UBLKCP", "SYNCS", "LDGSTS", "LDGDEPBAR", "DEPBAR", "LDG", "STG", "LDS", "STS", "SHF", "VOTE", "POPC", "SHFL", "REDUX", "ATOMS", "ATOMG", "RED",
-        "BAR", "LDL", "STL", "BRA"]
+        "BAR", "LDL", "STL", "BRA", "UBLKCP.S", "FENCE", "MEMBAR"]
 for k, (i, name) in enumerate(starts):
     if not any(w in name for w in want):
         continue
