@@ -13,6 +13,7 @@ REF_LIB = os.path.join(ORACLE_DIR, "_ref", "libref_bitstream.so")
 REF_CODEC_LIB = os.path.join(ORACLE_DIR, "_ref", "libref_codec.so")
 REF_BITMAP_LIB = os.path.join(ORACLE_DIR, "_ref", "libref_bitmap.so")
 REF_MISC_LIB = os.path.join(ORACLE_DIR, "_ref", "libref_misc.so")
+REF_MACRO_LIB = os.path.join(ORACLE_DIR, "_ref", "libref_macro.so")
 
 
 def _cpu_stamp():
@@ -43,7 +44,7 @@ def build_oracle():
         subprocess.run(["make", "-B", "-C", ORACLE_DIR, "-s", "all"], check=True, capture_output=True)
         with open(stamp_file, "w") as f:
             f.write(stamp + "\n")
-    elif os.path.isdir("/root/reference") and not (os.path.exists(REF_LIB) and os.path.exists(REF_CODEC_LIB) and os.path.exists(REF_BITMAP_LIB) and os.path.exists(REF_MISC_LIB)):
+    elif os.path.isdir("/root/reference") and not (os.path.exists(REF_LIB) and os.path.exists(REF_CODEC_LIB) and os.path.exists(REF_BITMAP_LIB) and os.path.exists(REF_MISC_LIB) and os.path.exists(REF_MACRO_LIB)):
         subprocess.run(["make", "-C", ORACLE_DIR, "-s", "ref"], check=True, capture_output=True)
     return ORACLE_LIB
 

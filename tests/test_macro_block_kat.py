@@ -12,7 +12,7 @@ import pytest
 
 import oracle_binding as ora
 
-REF_MACRO_LIB = os.path.join(ora.ORACLE_DIR, "_ref", "libref_macro.so")
+REF_MACRO_LIB = ora.REF_MACRO_LIB
 
 
 def _ref():
