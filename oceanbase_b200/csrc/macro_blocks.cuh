@@ -49,6 +49,7 @@ __device__ __forceinline__ int32_t parse_headers(const uint8_t *m, int64_t macro
   const int64_t type_cols = version == 2 ? rowkey_cnt : column_count;
   if (f.data_off != 24 + 128 + type_cols * 8 + (int64_t)column_count * 8 + 1) return kStBadFixed;
   if ((int64_t)f.data_off + f.data_size > macro_size || occupy != f.data_off + f.data_size) return kStBadFixed;
+  if ((int64_t)f.micro_count * 64 > f.data_size) return kStBadFixed;   // a micro-block is at least its 64-byte header
   if (compressor != 1 /*NONE_COMPRESSOR*/ || encrypt_id != 0) return kStCompressed;
   return kStOk;
 }
