@@ -74,7 +74,10 @@ enum {
   OBGPU_ENC_CS_INTEGER = 16,
   OBGPU_ENC_CS_INT_DICT = 17,
   OBGPU_ENC_CS_STRING = 18,
-  OBGPU_ENC_CS_STR_DICT = 19
+  OBGPU_ENC_CS_STR_DICT = 19,
+  /* writer only: the codec of the column is chosen per micro-block the way ObMicroBlockEncoder::choose_encoder does
+   * (encoding/ob_micro_block_encoder.cpp:1318-1366,1603-1823) among RAW / DICT / RLE / CONST / INTEGER_BASE_DIFF */
+  OBGPU_ENC_AUTO = 32
 };
 
 /* ---- ObObjType values the path accepts (common/object/ob_obj_type.h) ------------------------ */

@@ -1176,6 +1176,167 @@ int BlockBuilder::encode_base_diff(int i) {
   return OBGPU_SUCCESS;
 }
 
+// ---- encoder selection (OBGPU_ENC_AUTO) ------------------------------------------------------------------------------------------
+// ObMicroBlockEncoder::encoder_detection -> fast_encoder_detect / choose_encoder (ob_micro_block_encoder.cpp:1259-1366,1603-1823) for
+// the first micro-block of an SSTable (no previous-block hints, try_previous_encoder :1445-1497 has nothing to try) over the codecs
+// whose size estimates depend on the column alone: RAW, DICT, RLE, CONST, INTEGER_BASE_DIFF. Span columns (COLUMN_EQUAL / SUBSTR need
+// the cross-column detection) and the string transforms (STRING_DIFF / PREFIX / HEX) are only written when the caller names them.
+// Every estimate is the encoder's own calc_size() over the column's ObColumnEncodingCtx (build_column_encoding_ctx,
+// ob_encoding_hash_util.cpp:374-470), restated; a candidate replaces the choice only when STRICTLY smaller, in the reference's order,
+// and the search stops once the choice is within a quarter of the RAW size.
+int choose_auto_encoding(const ColCtx &c, int ext_bit) {
+  const int64_t n = c.nrows;
+  const bool is_int = c.sc == 1 || c.sc == 2;
+  const int64_t ts = is_int ? type_store_size((uint8_t)c.in->obj_type) : 0;
+  const int64_t null_cnt = c.null_cnt - c.nope_cnt, nope_cnt = c.nope_cnt, ext_cnt = c.null_cnt;
+  // ---- ObColumnEncodingCtx: distinct values in first-occurrence order (the hash table's dict refs), per-row refs ----------------
+  std::vector<uint32_t> refs;
+  std::vector<int64_t> value_rows;   // rows per distinct value
+  int64_t distinct = 0, fix_data_size = ts, dict_var_data_size = 0, var_data_size = 0;
+  uint64_t max_integer = 0;
+  if (is_int) {
+    IntDict d;
+    build_int_dict(c, false, d);
+    refs.swap(d.refs);
+    distinct = (int64_t)d.values.size();
+    max_integer = d.max_integer;
+  } else {
+    StrDict d;
+    build_str_dict(c, false, d);
+    refs.swap(d.refs);
+    distinct = (int64_t)d.values.size();
+    fix_data_size = -1;
+    bool var_store = false;
+    for (const StrRef &v : d.values) {
+      dict_var_data_size += v.len;
+      if (!var_store) {
+        if (fix_data_size < 0) fix_data_size = v.len;
+        else if (v.len != fix_data_size) { fix_data_size = -1; var_store = true; }
+      }
+    }
+    for (int64_t r = 0; r < n; ++r) if (!c.is_null(r)) var_data_size += c.sval(r).len;
+  }
+  value_rows.assign((size_t)distinct + 2, 0);
+  for (int64_t r = 0; r < n; ++r) value_rows[refs[(size_t)r]]++;
+  const int64_t ext_store = (ext_cnt > 0) ? (n * ext_bit + 1) / 8 : 0;
+  // ---- ObRawEncoder::traverse + calc_size (ob_raw_encoder.cpp:88-165,256-273) -----------------------------------------------------
+  int64_t raw_size;
+  {
+    int64_t bp_len = 0, fix_len = 0, raw_var = 0;
+    bool is_var = false;
+    if (is_int) {
+      bool bp = false;
+      const int64_t size = packing_size(&bp, max_integer, c.enable_bp);
+      if (bp) {
+        if (size * ext_cnt > n * 2 * 8) { is_var = true; raw_var = (size / 8 + 1) * (n - ext_cnt); }
+        else bp_len = size;
+      } else {
+        fix_len = size;
+      }
+    } else if (fix_data_size < 0) {
+      is_var = true;
+      raw_var = var_data_size;
+    } else {
+      fix_len = fix_data_size;
+      raw_var = var_data_size;
+    }
+    if (fix_len > 0 && bp_len == 0 && fix_len * ext_cnt > n * 2) { is_var = true; fix_len = 0; }   // (integers: var_data_size_ stays 0 here, :147-152)
+    raw_size = bp_len > 0 ? bp_len * n / 8 + 1 : (!is_var ? fix_len * n : raw_var + n * 2);
+    raw_size += ext_store;
+  }
+  // ---- ObDictEncoder::traverse / calc_meta_size / calc_size (ob_dict_encoder.cpp:83-133, ob_dict_encoder.h:98-125) ----------------
+  int64_t dict_fix = is_int ? (c.enable_bp ? int_size_bytes(max_integer) : byte_packed_int_size(max_integer)) : fix_data_size;
+  const bool var_dict = dict_fix < 0 || dict_fix > 0xffff;
+  const int64_t dict_index_byte = dict_var_data_size <= 0xff ? 1 : (dict_var_data_size <= 0xffff ? 2 : 4);
+  const int64_t dict_meta = 9 /*ObDictMetaHeader*/ + (var_dict ? dict_index_byte * (distinct - 1) + dict_var_data_size : dict_fix * distinct);
+  int64_t dict_size;
+  {
+    int64_t max_ref = distinct - 1;
+    if (null_cnt > 0) max_ref = distinct;
+    if (nope_cnt > 0) max_ref = distinct + 1;
+    bool bp = false;
+    const int64_t size = packing_size(&bp, (uint64_t)std::max<int64_t>(max_ref, 0), c.enable_bp);
+    dict_size = dict_meta + (bp ? (n * size + 7) / 8 : n * size);
+  }
+  // ---- ObConstEncoder::traverse / calc_size (ob_const_encoder.cpp:57-160): the most frequent value is the constant ---------------
+  bool const_ok = true;
+  int64_t const_size = 0;
+  {
+    int64_t max_cnt = 0, const_ref = 0;
+    for (int64_t v = 0; v < distinct; ++v) if (value_rows[(size_t)v] > max_cnt) { max_cnt = value_rows[(size_t)v]; const_ref = v; }
+    if (null_cnt > max_cnt) { max_cnt = null_cnt; const_ref = distinct; }
+    if (nope_cnt > max_cnt) { max_cnt = nope_cnt; const_ref = distinct + 1; }
+    const int64_t exc = n - max_cnt;
+    if (nope_cnt - 1 > 32 + 1 || exc > 32 || exc > std::max<int64_t>(n * 10 / 100, 1)) {   // MAX_EXCEPTION_SIZE / MAX_EXCEPTION_PCT
+      const_ok = false;
+    } else if (exc == 0) {
+      int64_t cell = 0;
+      if (null_cnt == 0 && nope_cnt == 0) cell = is_int ? ts : (n > 0 ? c.sval(0).len : 0);   // get_cell_len of the constant
+      const_size = cell + 6 /*ObConstMetaHeader*/;
+    } else {
+      int64_t max_row_id = 0;
+      for (int64_t r = n - 1; r >= 0; --r) if ((int64_t)refs[(size_t)r] != const_ref) { max_row_id = r; break; }
+      const_size = 6 + dict_meta + exc * (byte_packed_int_size((uint64_t)max_row_id) + 1);
+    }
+  }
+  // ---- fast_encoder_detect (:1318-1366): at most one distinct value -> CONST when it is suitable -----------------------------------
+  if (distinct <= 1 && const_ok) return OBGPU_ENC_CONST;
+  int choose = OBGPU_ENC_RAW;
+  int64_t choose_size = raw_size;
+  const int64_t acceptable = raw_size / 4;
+  if (dict_size < choose_size) { choose = OBGPU_ENC_DICT; choose_size = dict_size; }
+  bool try_more = true;
+  // (previous-block encodings, COLUMN_EQUAL, COLUMN_SUBSTR: nothing to try here)
+  if (try_more && distinct <= n / 2) {   // "try rle and const" (:1686-1713)
+    int64_t runs = n > 0 ? 1 : 0, max_rle_row_id = 0;
+    for (int64_t r = 1; r < n; ++r) if (refs[(size_t)r] != refs[(size_t)r - 1]) { ++runs; max_rle_row_id = r; }
+    int64_t max_ref = distinct - 1;
+    if (null_cnt > 0) max_ref = distinct;
+    if (nope_cnt > 0) max_ref = distinct + 1;
+    const int64_t rle_size = 10 /*ObRLEMetaHeader*/ + dict_meta +
+        runs * (byte_packed_int_size((uint64_t)max_rle_row_id) + byte_packed_int_size((uint64_t)std::max<int64_t>(max_ref, 0)));
+    if (rle_size < choose_size) { choose = OBGPU_ENC_RLE; choose_size = rle_size; }
+    if (const_ok && const_size < choose_size) { choose = OBGPU_ENC_CONST; choose_size = const_size; }
+  }
+  if (try_more && choose_size <= acceptable) try_more = false;
+  if (try_more && is_int) {   // ObIntegerBaseDiffEncoder::traverse / calc_size (ob_integer_base_diff_encoder.cpp:163-224,254-265)
+    // ObIntegerData<T>::traverse_cell / max_delta / max_unsign_value (:43-73): min / max over the stored images, sign-extended for
+    // the signed class; a negative minimum makes the "original" width 64 bits
+    bool any = false;
+    int64_t smin = INT64_MAX, smax = INT64_MIN;
+    uint64_t umin = UINT64_MAX, umax = 0;
+    const uint64_t rev = ~low_mask((uint32_t)ts * 8);
+    for (int64_t r = 0; r < n; ++r) {
+      if (c.is_null(r)) continue;
+      any = true;
+      uint64_t v = c.uval(r);
+      if (c.sc == 1) {
+        if (rev != 0 && (v & (rev >> 1))) v |= rev;
+        smin = std::min(smin, (int64_t)v);
+        smax = std::max(smax, (int64_t)v);
+      } else {
+        umin = std::min(umin, v);
+        umax = std::max(umax, v);
+      }
+    }
+    const uint64_t delta = !any ? 0 : (c.sc == 1 ? (smin < smax ? (uint64_t)smax - (uint64_t)smin : 0) : (umin < umax ? umax - umin : 0));
+    const uint64_t max_unsigned = !any ? 0 : (c.sc == 1 ? (smin < 0 ? ~0ull : (uint64_t)smax) : umax);
+    if (delta != 0) {
+      bool bp = false;
+      int64_t orig = packing_size(&bp, max_unsigned, true);
+      if (!bp) orig *= 8;
+      bp = false;
+      int64_t dsz = packing_size(&bp, delta, true);
+      if (!bp) dsz *= 8;
+      if ((orig - dsz) * n > (2 /*header*/ + ts) * 8) {
+        const int64_t bd_size = (bp ? (n * dsz + 7) / 8 : n * (dsz / 8)) + 2 + ts;
+        if (bd_size < choose_size) { choose = OBGPU_ENC_INTEGER_BASE_DIFF; choose_size = bd_size; }
+      }
+    }
+  }
+  return choose;
+}
+
 int BlockBuilder::build(std::vector<uint8_t> &block) {
   if (ncol <= 0 || nrows <= 0 || nrows > 0x7fffffff || rowkey_cnt < 0 || rowkey_cnt > ncol)
     return OBGPU_INVALID_ARGUMENT;
@@ -1202,14 +1363,15 @@ int BlockBuilder::build(std::vector<uint8_t> &block) {
   }
   {
     int n_cs = 0;
-    for (int i = 0; i < ncol; ++i) n_cs += cols[i].encoding >= OBGPU_ENC_CS_INTEGER;
+    for (int i = 0; i < ncol; ++i) n_cs += cols[i].encoding >= OBGPU_ENC_CS_INTEGER && cols[i].encoding <= OBGPU_ENC_CS_STR_DICT;
     if (n_cs == ncol) return build_cs(block, original);
     if (n_cs != 0) return OBGPU_INVALID_ARGUMENT;  // one row store type per block
   }
   for (int i = 0; i < ncol; ++i) {
     out[(size_t)i].hdr.obj_type_ = (uint8_t)cols[i].obj_type;
     int ret;
-    switch (cols[i].encoding) {
+    const int enc = cols[i].encoding == OBGPU_ENC_AUTO ? choose_auto_encoding(ctx[(size_t)i], ext_bit) : cols[i].encoding;
+    switch (enc) {
       case OBGPU_ENC_RAW: ret = encode_raw(i); break;
       case OBGPU_ENC_DICT: ret = encode_dict(i); break;
       case OBGPU_ENC_RLE: ret = encode_rle(i); break;
