@@ -5,12 +5,16 @@
 //     check_integrity
 //   * ObSSTableMacroBlockHeader (storage/blocksstable/ob_sstable_macro_block_header.{h,cpp}): FixedHeader + column type / order /
 //     checksum arrays + is_normal_cg_, init / serialize / deserialize / is_valid
+//   * ObMicroBlockHeader (storage/blocksstable/ob_micro_block_header.{h,cpp}): the 64-byte micro-block header -- init / set_header_checksum /
+//     serialize, and deserialize_and_check_record = is_valid + header checksum (format_i32 / format_i64 of common/ob_record_header.h,
+//     the real ones) + payload checksum over a whole micro-block
 //   * ob_crc64 (deps/oblib/src/lib/checksum/ob_crc64.cpp), the payload checksum of the common header (ob_macro_block.cpp:516):
 //     crc32c again (ob_crc64 -> ob_crc64_sse42)
 // tests/test_macro_block_kat.py pins the writer's macro blocks and the oracle's parser to them.
 #include "lib/checksum/ob_crc64.h"
 #include "storage/blocksstable/ob_macro_block_common_header.h"
 #include "storage/blocksstable/ob_data_store_desc.h"
+#include "storage/blocksstable/ob_micro_block_header.h"
 #define private public
 #include "storage/blocksstable/ob_sstable_macro_block_header.h"
 #undef private
@@ -20,7 +24,10 @@ using namespace oceanbase::common;
 using namespace oceanbase::blocksstable;
 
 extern "C" {
-unsigned int crc32_iscsi(unsigned char *, int, unsigned int) { abort(); }   // never reached (vendor dispatch)
+// ob_crc64_sse42's vendor dispatch (ob_crc64.cpp:1113-1140) selects ISA-L's crc32_iscsi on Intel CPUs. ISA-L is an external assembly
+// library that is not in the tree; its crc32_iscsi(buf, len, init) is crc32c over buf starting from init without inversions, i.e. the
+// function the in-tree crc64_sse42 (crc32 instruction) computes -- tests/test_checksum_ref_kat.py holds the three in-tree versions equal.
+unsigned int crc32_iscsi(unsigned char *buf, int len, unsigned int init) { return (unsigned int)crc64_sse42(init, (const char *)buf, len); }
 
 // ob_crc64(pv, cb) (ob_crc64.cpp:348-364) is ob_crc64_sse42(0, pv, cb): the vendor dispatch picks ISA-L's crc32_iscsi, the crc32
 // instruction or the table version -- one function, crc32c with seed 0 and no final xor (tests/test_checksum_ref_kat.py holds the
@@ -78,6 +85,35 @@ int64_t ref_macro_headers_build(uint16_t version, uint64_t tablet_id, int64_t lo
   common.set_payload_checksum(payload_checksum);
   if (common.build_serialized_header(out, cap) != OB_SUCCESS) return -6;
   return chs + pos;
+}
+
+// The reference's own integrity check of one whole micro-block (header + payload): ObMicroBlockHeader::deserialize_and_check_record
+// (ob_micro_block_header.cpp:279-369: deserialize, is_valid, check_header_checksum, check_payload_checksum). Returns an OB code.
+int ref_micro_block_check(const char *block, int64_t size) {
+  return ObMicroBlockHeader::deserialize_and_check_record(block, size, MICRO_BLOCK_HEADER_MAGIC);
+}
+
+// A micro-block header built by the reference: init (version 3, magic, header size), the layout facts of the block, then
+// set_header_checksum and serialize. flag16 carries all_lob_in_row_ etc. as the writer sets them. Returns bytes written (< 0: error).
+int64_t ref_micro_header_build(int32_t column_count, int32_t rowkey_column_count, int32_t row_store_type, uint16_t flag16, uint32_t row_count,
+                               uint8_t opt, uint16_t opt2, uint32_t row_offset, int32_t original_length, int64_t max_merged_trans_version,
+                               int32_t data_length, int32_t data_zlength, int64_t data_checksum, char *out, int64_t cap) {
+  ObMicroBlockHeader h;
+  if (h.init(0, column_count, rowkey_column_count, (ObRowStoreType)row_store_type, false) != OB_SUCCESS) return -1;
+  h.flag16_ = flag16;
+  h.row_count_ = row_count;
+  h.opt_ = opt;
+  h.opt2_ = opt2;
+  h.row_offset_ = row_offset;
+  h.original_length_ = original_length;
+  h.max_merged_trans_version_ = max_merged_trans_version;
+  h.data_length_ = data_length;
+  h.data_zlength_ = data_zlength;
+  h.data_checksum_ = data_checksum;
+  h.set_header_checksum();
+  int64_t pos = 0;
+  if (h.serialize(out, cap, pos) != OB_SUCCESS) return -2;
+  return pos;
 }
 
 // Deserialises both headers with the reference's code; fields[]: 0 common header_size, 1 version, 2 magic, 3 attr, 4 payload_size,
