@@ -19,6 +19,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 import oracle_binding as ora  # noqa: E402
 
 CODEC_TYPES = (1, 2, 3, 4, 5, 6, 8)
@@ -153,3 +154,42 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+# ---- second fixture: micro-blocks of every codec as this repo's writer emits them today (regression anchors) -------------------------
+# Not reference output (the reference ships no golden blocks and its encoder cannot be built here): these pin the writer's bytes against
+# accidental format drift. Every block in the file passed the REAL reference's ObMicroBlockHeader::deserialize_and_check_record when it
+# was generated (asserted below), and tests/test_golden_blocks.py requires the oracle to decode the bytes to the recorded cells.
+def make_blocks():
+    import test_micro_header_ref_kat as mk
+    L = C.CDLL(ora.REF_MACRO_LIB)
+    L.ref_micro_block_check.argtypes = [C.c_void_p, C.c_int64]
+    out = {}
+    names = []
+    for name, b in mk.blocks():
+        b = np.ascontiguousarray(b)
+        assert L.ref_micro_block_check(b.ctypes.data, b.size) == 0, name
+        blk = ora.Block(b)
+        names.append(name)
+        out[f"block_{name}"] = b
+        rows = list(range(0, blk.row_count, max(1, blk.row_count // 40))) + [blk.row_count - 1]
+        out[f"rows_{name}"] = np.array(rows, dtype=np.int32)
+        for c in range(blk.column_count):
+            cells = [blk.cell(c, r) for r in rows]
+            is_null = np.array([x is None for x in cells], dtype=np.uint8)
+            if any(isinstance(x, (bytes, bytearray)) for x in cells):
+                heap = b"".join(b"" if x is None else bytes(x) for x in cells)
+                lens = np.array([0 if x is None else len(x) for x in cells], dtype=np.int64)
+                out[f"str_{name}_{c}"] = np.frombuffer(heap + b"\0", dtype=np.uint8).copy()
+                out[f"len_{name}_{c}"] = lens
+            else:
+                out[f"int_{name}_{c}"] = np.array([0 if x is None else (x & 0xffffffffffffffff) for x in cells], dtype=np.uint64)
+            out[f"null_{name}_{c}"] = is_null
+    out["names"] = np.array(names)
+    path = os.path.join(HERE, "writer_blocks.npz")
+    np.savez_compressed(path, **out)
+    print(path, os.path.getsize(path), "bytes;", len(names), "blocks")
+
+
+if __name__ == "__main__":
+    make_blocks()
