@@ -2,14 +2,17 @@
 // blocks the host writer (sstable_writer.cpp: BlockBuilder::encode_raw / build / finish_header) produces for the same rows,
 // plus the column checksums of the rows (K16). One kernel, one CTA per micro-block, input read once, output written once:
 //
-//   stats   : per column max of the stored value image + NULL count (and, fused, the column checksum of the cells)
-//   plan    : thread 0 lays the block out (ObRawEncoder::traverse width rules, ext bits, column stores back to back)
-//   pack    : cells -> shared-memory image of the block (ext bits / bit-packed values through shared atomicOr, byte-packed
-//             values as byte stores); the second read of the cells hits L2 (the same CTA read them a moment ago)
+//   stats   : per column max of the stored value image + NULL count (and, fused, the column checksum of the cells); four
+//             columns' loads in flight together, warp reductions through redux.sync
+//   plan    : warp 0, one lane per column, lays the block out (ObRawEncoder::traverse width rules, ext bits, column stores back
+//             to back by a warp scan) and publishes the aligned block size for the look-back at once
+//   pack    : cells -> shared-memory image of the block (ext bits, bit-packed and byte-packed values are all "w bits at bit
+//             address b": at most three shared atomicOr per cell); the second read of the cells hits L2
 //   crc32c  : payload checksum in parallel -- every thread the raw CRC of an odd-word-stride chunk (slicing by 4, tables in
 //             shared memory), shifted to its position by ONE carry-less multiplication with x^(32 * words after it) mod P
 //             (host-built table) and XOR-reduced; leading zero words cost nothing with init 0 / no final xor
-//   offset  : decoupled look-back over the aligned block sizes (tickets in scheduling order, one 64-bit flag per block)
+//   offset  : decoupled look-back over the aligned block sizes (tickets in scheduling order, one 64-bit flag per block), resolved
+//             by thread 0 while the other warps pack
 //   store   : header + checksums, then ONE bulk copy (TMA, cp.async.bulk shared -> global) of the aligned slot
 #pragma once
 #include <map>
