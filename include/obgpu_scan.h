@@ -77,7 +77,10 @@ enum {
   OBGPU_ENC_CS_STR_DICT = 19,
   /* writer only: the codec of the column is chosen per micro-block the way ObMicroBlockEncoder::choose_encoder does
    * (encoding/ob_micro_block_encoder.cpp:1318-1366,1603-1823) among RAW / DICT / RLE / CONST / INTEGER_BASE_DIFF */
-  OBGPU_ENC_AUTO = 32
+  OBGPU_ENC_AUTO = 32,
+  /* writer only, CS blocks: INTEGER vs INT_DICT / STRING vs STR_DICT per micro-block like ObMicroBlockCSEncoder::choose_encoder_
+   * (cs_encoding/ob_micro_block_cs_encoder.cpp:2246-2375) from the column encoders' estimate_store_size() */
+  OBGPU_ENC_CS_AUTO = 33
 };
 
 /* ---- ObObjType values the path accepts (common/object/ob_obj_type.h) ------------------------ */

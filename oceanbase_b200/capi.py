@@ -18,6 +18,7 @@ OB_INVALID_DATA = -4070
  WHITE_OP_IN, WHITE_OP_NU, WHITE_OP_NN) = range(10)
 ENC_RAW, ENC_DICT, ENC_RLE, ENC_CONST, ENC_INTEGER_BASE_DIFF, ENC_STRING_DIFF, ENC_HEX_PACKING, ENC_STRING_PREFIX, ENC_COLUMN_EQUAL, ENC_COLUMN_SUBSTR = range(10)
 ENC_CS_INTEGER, ENC_CS_INT_DICT, ENC_CS_STRING, ENC_CS_STR_DICT = 16, 17, 18, 19  # columns of a CS_ENCODING_ROW_STORE block
+ENC_CS_AUTO = 33  # writer only, CS blocks: INTEGER vs INT_DICT / STRING vs STR_DICT (ObMicroBlockCSEncoder::choose_encoder_)
 ENC_AUTO = 32  # writer only: codec chosen per micro-block (ObMicroBlockEncoder::choose_encoder)
 OBJ_TINYINT, OBJ_SMALLINT, OBJ_MEDIUMINT, OBJ_INT32, OBJ_INT = 1, 2, 3, 4, 5
 OBJ_UTINYINT, OBJ_USMALLINT, OBJ_UMEDIUMINT, OBJ_UINT32, OBJ_UINT64 = 6, 7, 8, 9, 10

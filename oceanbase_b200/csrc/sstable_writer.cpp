@@ -1363,7 +1363,7 @@ int BlockBuilder::build(std::vector<uint8_t> &block) {
   }
   {
     int n_cs = 0;
-    for (int i = 0; i < ncol; ++i) n_cs += cols[i].encoding >= OBGPU_ENC_CS_INTEGER && cols[i].encoding <= OBGPU_ENC_CS_STR_DICT;
+    for (int i = 0; i < ncol; ++i) n_cs += (cols[i].encoding >= OBGPU_ENC_CS_INTEGER && cols[i].encoding <= OBGPU_ENC_CS_STR_DICT) || cols[i].encoding == OBGPU_ENC_CS_AUTO;
     if (n_cs == ncol) return build_cs(block, original);
     if (n_cs != 0) return OBGPU_INVALID_ARGUMENT;  // one row store type per block
   }
@@ -1700,7 +1700,147 @@ static int cs_str_dict_column(const ColCtx &c, CSColumnHeader &ch, Buf &body, Bu
   return OBGPU_SUCCESS;
 }
 
+// ---- CS encoder selection (OBGPU_ENC_CS_AUTO): ObMicroBlockCSEncoder::choose_encoder_for_integer_ / _for_string_
+// (cs_encoding/ob_micro_block_cs_encoder.cpp:2289-2375, data version > 4.3.5.0): the dictionary form is used when its estimate is
+// below 70 % of the plain one, or below it with fewer than rows / 2 distinct values. Estimates: ObIntegerColumnEncoder::
+// estimate_store_size (ob_integer_column_encoder.cpp:296-314: bits(range) x rows / 8 + NULL bitmap when NULL cannot be replaced),
+// ObIntDictColumnEncoder / ObStrDictColumnEncoder (ob_int_dict_column_encoder.cpp:262-279, ob_str_dict_column_encoder.cpp:170-196:
+// meta + dictionary + bits(max ref stream value) x ref rows / 8, the const-encoded ref form of ob_dict_column_encoder.cpp:150-186
+// included), ObStringColumnEncoder (ob_string_column_encoder.cpp:195-218).
+static int64_t cs_bit_size(uint64_t v) { return v == 0 ? 1 : 64 - __builtin_clzll(v); }   // ObCSEncodingUtil::get_bit_size
+
+int choose_cs_auto_encoding(const ColCtx &c) {
+  const int64_t n = c.nrows;
+  const bool is_int = c.sc == 1 || c.sc == 2;
+  if (!is_int && c.sc != 5) return -1;
+  // dictionary refs (first occurrence order is enough: only counts and frequencies matter)
+  std::vector<uint32_t> refs;
+  int64_t distinct = 0;
+  int64_t dict_var = 0, var_all = 0, fix_len = -1;
+  uint64_t dict_range = 0;
+  if (is_int) {
+    IntDict d;
+    build_int_dict(c, false, d);
+    refs.swap(d.refs);
+    distinct = (int64_t)d.values.size();
+    if (distinct > 0) {   // ObIntDictColumnEncoder: the dictionary is an integer stream over [min, max] with a base when negative
+      const int ts = type_store_size((uint8_t)c.in->obj_type);
+      const uint64_t rev = ~low_mask((uint32_t)ts * 8);
+      if (c.sc == 1) {
+        int64_t mn = INT64_MAX, mx = INT64_MIN;
+        for (uint64_t v : d.values) { if (rev != 0 && (v & (rev >> 1))) v |= rev; mn = std::min(mn, (int64_t)v); mx = std::max(mx, (int64_t)v); }
+        dict_range = mn < 0 ? (uint64_t)mx - (uint64_t)mn : (uint64_t)mx;
+      } else {
+        dict_range = d.max_integer;
+      }
+    }
+  } else {
+    StrDict d;
+    build_str_dict(c, false, d);
+    refs.swap(d.refs);
+    distinct = (int64_t)d.values.size();
+    bool var = false;
+    for (const StrRef &v : d.values) {
+      dict_var += v.len;
+      if (!var) { if (fix_len < 0) fix_len = v.len; else if (fix_len != v.len) { fix_len = -1; var = true; } }
+    }
+    for (int64_t r = 0; r < n; ++r) if (!c.is_null(r)) var_all += c.sval(r).len;
+  }
+  const bool has_null = c.null_cnt > 0;
+  // ---- the ref stream of the dictionary forms (ObDictColumnEncoder::try_const_encoding_ref_, ob_dict_column_encoder.cpp:150-186) ----
+  int64_t ref_rows = n;
+  uint64_t ref_max = has_null ? (uint64_t)distinct : (uint64_t)std::max<int64_t>(distinct - 1, 0);
+  if (distinct > 0) {
+    std::vector<int64_t> freq((size_t)distinct + 2, 0);
+    for (uint32_t r : refs) ++freq[r];
+    int64_t max_cnt = 0, const_ref = 0;
+    for (int64_t k = 0; k < distinct; ++k) if (freq[(size_t)k] > max_cnt) { max_cnt = freq[(size_t)k]; const_ref = k; }
+    if (freq[(size_t)distinct] > max_cnt) { max_cnt = freq[(size_t)distinct]; const_ref = distinct; }
+    const int64_t exc = n - max_cnt;
+    if (exc == 0) { ref_rows = 2; ref_max = (uint64_t)std::max<int64_t>(exc, const_ref); }
+    else if (exc <= 64 && exc < n * 10 / 100) {
+      int64_t max_row = 0;
+      for (int64_t r = n - 1; r >= 0; --r) if ((int64_t)refs[(size_t)r] != const_ref) { max_row = r; break; }
+      ref_rows = 2 + 2 * exc;
+      ref_max = std::max<uint64_t>(std::max<uint64_t>((uint64_t)exc, (uint64_t)max_row), ref_max);
+    }
+  }
+  const int64_t bitmap = (n + 7) / 8;
+  if (is_int) {
+    // ---- plain INTEGER: range after the NULL replacement rules (build_signed / unsigned_encoder_ctx_, ob_integer_column_encoder.cpp:177-287)
+    const int ts = type_store_size((uint8_t)c.in->obj_type);
+    const uint64_t mask = low_mask((uint32_t)ts * 8);
+    bool any = false, need_bitmap = false;
+    int64_t smin = 0, smax = 0;
+    uint64_t umin = 0, umax = 0;
+    for (int64_t r = 0; r < n; ++r) {
+      if (c.is_null(r)) continue;
+      const int64_t sv = c.ival(r);
+      const uint64_t uv = (uint64_t)sv & mask;
+      if (!any) { smin = smax = sv; umin = umax = uv; any = true; }
+      else { smin = std::min(smin, sv); smax = std::max(smax, sv); umin = std::min(umin, uv); umax = std::max(umax, uv); }
+    }
+    uint64_t range;
+    if (c.sc == 1) {
+      const uint64_t rmask = ~mask;
+      const int64_t type_min = rmask == 0 ? INT64_MIN : (int64_t)(rmask | (rmask >> 1)), type_max = (int64_t)(mask >> 1);
+      int64_t nmin = smin, nmax = smax;
+      if (has_null) {
+        if (!any) nmin = nmax = 0;
+        if (nmin == 0) { if (nmax != type_max) nmax += 1; else nmin = -1; }
+        else if (nmin == type_min) { if (nmax != type_max) nmax += 1; else need_bitmap = true; }
+        else nmin -= 1;
+      }
+      range = nmin < 0 ? (uint64_t)nmax - (uint64_t)nmin : (uint64_t)nmax;
+    } else {
+      uint64_t nmin = umin, nmax = umax;
+      if (has_null) {
+        if (!any) nmin = nmax = 0;
+        if (nmin == 0) { if (nmax != mask) nmax += 1; else need_bitmap = true; }
+        else nmin -= 1;
+      }
+      (void)nmin;
+      range = nmax;
+    }
+    const int64_t int_est = cs_bit_size(range) * n / 8 + (need_bitmap ? bitmap : 0);
+    int64_t dict_est = (int64_t)sizeof(DictEncodingMeta);
+    if (distinct > 0) dict_est += cs_bit_size(dict_range) * distinct / 8 + cs_bit_size(ref_max) * ref_rows / 8;
+    const bool use_dict = dict_est < int_est * 70 / 100 || (dict_est < int_est && distinct < n * 50 / 100);
+    return use_dict ? OBGPU_ENC_CS_INT_DICT : OBGPU_ENC_CS_INTEGER;
+  }
+  int64_t str_est;
+  if (fix_len >= 0 && distinct > 0) str_est = fix_len * n;
+  else str_est = var_all + cs_bit_size((uint64_t)(n > 0 ? var_all / n : 0)) * n / 8;
+  if (has_null) str_est += bitmap;
+  int64_t dict_est = (int64_t)sizeof(DictEncodingMeta);
+  if (distinct > 0) {
+    if (fix_len >= 0) dict_est += fix_len * distinct;
+    else dict_est += dict_var + cs_bit_size((uint64_t)(dict_var / distinct)) * distinct / 8;
+    dict_est += cs_bit_size(ref_max) * ref_rows / 8;
+  }
+  const bool use_dict = dict_est < str_est * 70 / 100 || (dict_est < str_est && distinct < n * 50 / 100);
+  return use_dict ? OBGPU_ENC_CS_STR_DICT : OBGPU_ENC_CS_STRING;
+}
+
 int BlockBuilder::build_cs(std::vector<uint8_t> &block, int64_t original) {
+  // OBGPU_ENC_CS_AUTO columns are resolved first; the rest of the function sees concrete column types
+  std::vector<obgpu_col_input> resolved;
+  for (int i = 0; i < ncol; ++i) {
+    if (cols[i].encoding != OBGPU_ENC_CS_AUTO) continue;
+    if (resolved.empty()) resolved.assign(cols, cols + ncol);
+    const int enc = choose_cs_auto_encoding(ctx[(size_t)i]);
+    if (enc < 0) return OBGPU_NOT_SUPPORTED;
+    resolved[(size_t)i].encoding = enc;
+  }
+  if (!resolved.empty()) {
+    const obgpu_col_input *saved = cols;
+    cols = resolved.data();
+    for (int i = 0; i < ncol; ++i) ctx[(size_t)i].in = &cols[i];
+    const int ret = build_cs(block, original);
+    cols = saved;
+    for (int i = 0; i < ncol; ++i) ctx[(size_t)i].in = &cols[i];
+    return ret;
+  }
   const uint32_t header_size = (uint32_t)sizeof(MicroBlockHeader);
   Buf body;  // everything after the micro header
   body.grow(sizeof(AllColumnHeader) + sizeof(CSColumnHeader) * (size_t)ncol);

@@ -113,3 +113,57 @@ def test_random_tables_round_trip():
             else:
                 assert (cell & 0xffffffffffffffff) == (int(v[r]) & 0xffffffffffffffff), (trial, r)
     assert seen >= {0, 1, 2, 3, 4}, seen
+
+
+CS_NAMES = {0: "INTEGER", 1: "STRING", 2: "INT_DICT", 3: "STR_DICT"}
+
+
+def cs_col_type(block, i, ncol):
+    # [micro header 64][ObAllColumnHeader 12][ObCSColumnHeader x ncol: version_, type_, attrs_, obj_type_]
+    return int(block[64 + 12 + 4 * i + 1])
+
+
+def test_cs_auto_integer_vs_dict_and_string_vs_dict():
+    """OBGPU_ENC_CS_AUTO: ObMicroBlockCSEncoder::choose_encoder_for_integer_ / _for_string_ (ob_micro_block_cs_encoder.cpp:2289-2375) over the
+    column encoders' estimate_store_size(): dictionary form below 70 % of the plain estimate, or below it with < rows / 2 distinct values."""
+    from oceanbase_b200 import capi
+    from oceanbase_b200.sstable import Column, encode_block
+    rng = np.random.default_rng(14)
+    n = 1200
+    big = rng.integers(1 << 40, 1 << 41, size=6, dtype=np.int64)
+    words = [b"north", b"south-south", b"east", b"westwestwest"]
+    nl = (rng.random(n) < 0.2).astype(np.uint8)
+    shapes = [
+        ("low_card_wide", capi.OBJ_INT, big[rng.integers(0, 6, size=n)], None, "INT_DICT"),
+        ("unique_wide", capi.OBJ_INT, rng.integers(0, 1 << 41, size=n, dtype=np.int64), None, "INTEGER"),
+        ("constant", capi.OBJ_INT, np.full(n, 777_777, dtype=np.int64), None, "INT_DICT"),
+        ("two_bit_values", capi.OBJ_INT, rng.integers(0, 4, size=n, dtype=np.int64), None, "INTEGER"),
+        ("low_card_with_nulls", capi.OBJ_INT, big[rng.integers(0, 3, size=n)], nl, "INT_DICT"),
+        ("negative_narrow_range", capi.OBJ_INT, rng.integers(-40, 40, size=n, dtype=np.int64), None, "INTEGER"),
+        ("low_card_strings", capi.OBJ_VARCHAR, [words[i] for i in rng.integers(0, 4, size=n)], None, "STR_DICT"),
+        ("unique_strings", capi.OBJ_VARCHAR, [b"row-%06d-%s" % (i, b"y" * int(rng.integers(0, 7))) for i in range(n)], None, "STRING"),
+        ("strings_with_nulls", capi.OBJ_VARCHAR, [words[i] for i in rng.integers(0, 2, size=n)], nl, "STR_DICT"),
+    ]
+    forced = {"INTEGER": capi.ENC_CS_INTEGER, "INT_DICT": capi.ENC_CS_INT_DICT, "STRING": capi.ENC_CS_STRING, "STR_DICT": capi.ENC_CS_STR_DICT}
+    for name, t, v, nulls, want in shapes:
+        block = encode_block([Column(t, capi.ENC_CS_AUTO, v, nulls=nulls)])
+        got = CS_NAMES[cs_col_type(block, 0, 1)]
+        assert got == want, (name, got, want)
+        assert np.array_equal(block, encode_block([Column(t, forced[got], v, nulls=nulls)])), name
+        blk = ora.Block(block)
+        assert blk.verify_checksums() == 0
+        for r in list(range(0, n, 53)) + [n - 1]:
+            cell = blk.cell(0, r)
+            if nulls is not None and nulls[r]:
+                assert cell is None, (name, r)
+            elif isinstance(v, list):
+                assert bytes(cell) == v[r], (name, r)
+            else:
+                assert (cell & 0xffffffffffffffff) == int(v[r]) & 0xffffffffffffffff, (name, r)
+    # a whole table: every column resolved independently, per micro-block
+    from oceanbase_b200.sstable import encode_table
+    cols = [Column(t, capi.ENC_CS_AUTO, v, nulls=nulls) for (_n, t, v, nulls, _w) in shapes]
+    table = encode_table(cols, 400)
+    for b in range(table.n_blocks):
+        got = [CS_NAMES[cs_col_type(table.block(b), i, len(cols))] for i in range(len(cols))]
+        assert got == [w for (*_x, w) in shapes], (b, got)
